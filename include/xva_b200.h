@@ -1,0 +1,131 @@
+/* libxva_b200 -- C ABI of the B200-native FastPitch 1.1 / HiFi-GAN training hot path.
+ *
+ * The reference (DanRuta/xva-trainer) has no FFI of its own: its operator API is Python (nn.Module methods and
+ * free functions). Each entry point below names the reference interface it stands in for (file:line relative to
+ * the reference tree); the Python host side in xva-trainer_b200/ keeps the reference's names and signatures and
+ * calls these through ctypes (see INTEGRATION.md for the binding a maintainer would add).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch's caching allocator in practice), unless the
+ *     parameter name ends in _host; the library allocates no device memory and keeps no pointer after return;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); nothing synchronises the device;
+ *   - return 0 on success, negative on failure; the message is in xva_last_error() (thread-local);
+ *   - activations are channels-last: [batch, time, channels], fp32; "lens" are int32;
+ *   - there is no CPU fallback: on a device that is not compute capability 10.x every op fails.
+ */
+#ifndef XVA_B200_H_
+#define XVA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XVA_ABI_VERSION 1
+#define XVA_MAX_TAPS 48
+
+int xva_abi_version(void);
+const char* xva_last_error(void);
+/* 0 if `device` is a compute-capability 10.x GPU, negative otherwise. */
+int xva_device_check(int device);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Tap-GEMM: the one dense-contraction kernel family (tcgen05 + TMA, tf32 operands, fp32 accumulate in TMEM).
+ *
+ *  mode 0  out[z,r,n] = alpha * sum_j sum_k A[z, r+shift[j], k] * B[zb, n, k]      zb = j*b_tap_z + z*b_batch_z
+ *          replaces nn.Linear / nn.Conv1d forward: fastpitch/transformer.py:46-52,109,138 ; common/layers.py:94 ;
+ *          fastpitch/model.py:118-122,386 ; hifigan/models.py:21-37,87,111 ; and torch.bmm(q, k^T) transformer.py:118
+ *  mode 1  out[z,r,n] = alpha * sum_j sum_k A[z, r+shift[j], k] * B[zb, k, n]
+ *          replaces the autograd input-gradient of the same layers and torch.bmm(attn_prob, v) transformer.py:130
+ *  mode 2  out[zo,j,m,n] (+)= sum_{zr<ZR} sum_t A[z,t,m] * B[z, t+shift[j], n]        z = zo*ZR + zr
+ *          replaces the autograd weight-gradient of the same layers, and dK / dV of the attention
+ *
+ *  Rows addressed outside an operand's [0, rows) read as zero -- this is the Conv1d zero padding.
+ *  Epilogue (mode 0/1), in order: alpha, +bias[n], ReLU, gate (ReLU / leaky-ReLU backward), dropout(pre),
+ *  +residual, [LayerNorm(gamma,beta) over n, dropout(post)], zero rows >= lens[z].
+ * ---------------------------------------------------------------------------------------------------------- */
+enum {
+  XVA_GEMM_RELU = 1 << 0,
+  XVA_GEMM_LN = 1 << 1,
+  XVA_GEMM_DROP_PRE = 1 << 2,
+  XVA_GEMM_DROP_POST = 1 << 3,
+  XVA_GEMM_ATOMIC = 1 << 4,
+  XVA_GEMM_LRELU_GATE = 1 << 5
+};
+
+typedef struct xva_gemm_args {
+  int32_t mode;
+  int32_t Z;      /* batch items */
+  int32_t R;      /* rows per item: output rows (mode 0/1) or contraction rows (mode 2) */
+  int32_t M;      /* mode 2: output rows */
+  int32_t N;      /* output columns */
+  int32_t K;      /* mode 0/1: contraction length per tap */
+  int32_t taps;
+  int32_t shift[XVA_MAX_TAPS];
+  int32_t ZR;     /* mode 2: consecutive z reduced into one output batch */
+  int32_t split;  /* mode 2: CTAs sharing one output tile (needs XVA_GEMM_ATOMIC when > 1) */
+
+  const float* a;
+  int64_t a_rs, a_zs; /* element strides: row, batch item */
+  int32_t a_rows;     /* valid rows of A per item (0 = R) */
+  int32_t _pad0;
+  const float* b;
+  int64_t b_rs, b_zs;
+  int32_t b_rows;     /* mode 2: valid rows of B per item (0 = R) */
+  int32_t b_nz;       /* z slices in B */
+  int32_t b_tap_z, b_batch_z;
+
+  float* out;
+  int64_t o_rs, o_zs, o_js;
+
+  float alpha;
+  int32_t flags;
+  const float* bias;
+  const float* residual;
+  int64_t r_rs, r_zs;
+  const float* gate;
+  int64_t g_rs, g_zs;
+  float gate_slope;
+  int32_t _pad1;
+  const int32_t* lens;
+  const float* gamma;
+  const float* beta;
+  float ln_eps;
+  int32_t _pad2;
+  float* out_pre;   /* pre-LayerNorm value, same strides as out (optional) */
+  float* ln_mean;   /* [Z*R] (optional) */
+  float* ln_rstd;
+  float drop_p;
+  int32_t _pad3;
+  uint64_t seed;
+} xva_gemm_args;
+
+/* sizeof(xva_gemm_args) as compiled into the library, so a binding can verify its struct layout. */
+int xva_sizeof_gemm_args(void);
+int xva_gemm(const xva_gemm_args* args, void* stream);
+/* Same contract on CUDA cores in exact fp32: a checker for the tests, never used by the product path. */
+int xva_gemm_ref(const xva_gemm_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Length regulator -- replaces regulate_len(), fastpitch/model.py:59-79 (integer index path, bit-exact).
+ *   scan : reps = trunc(durs*pace + 0.5); cum[b,0..Tt] = exclusive int32 prefix sum; dec_lens[b] = min(sum, mel_max_len)
+ *          (mel_max_len < 0: no clamp)
+ *   fwd  : out[b,t,:] = enc[b,j,:] with cum[b,j] <= t < cum[b,j+1], zero for t >= cum[b,Tt]; idx[b,t] = j or -1 (optional)
+ *   bwd  : denc[b,j,:] (+)= sum_{t in token j, t < T_out} dout[b,t,:]
+ * ---------------------------------------------------------------------------------------------------------- */
+int xva_regulate_len_scan(const float* durs, int B, int Tt, float pace, int mel_max_len, int32_t* cum,
+                          int32_t* dec_lens, void* stream);
+int xva_regulate_len_fwd(const float* enc, const int32_t* cum, int B, int Tt, int C, int T_out, float* out,
+                         int32_t* idx, void* stream);
+int xva_regulate_len_bwd(const float* dout, const int32_t* cum, int B, int Tt, int C, int T_out, float* denc,
+                         int accumulate, void* stream);
+
+/* average_pitch(), fastpitch/model.py:82-100: per-token mean of the non-zero frame values. pitch [B,F,Tm],
+ * durs [B,Tt] -> out [B,F,Tt]. */
+int xva_average_pitch(const float* pitch, const float* durs, int B, int F, int Tm, int Tt, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XVA_B200_H_ */

@@ -1,0 +1,253 @@
+"""Parity of the tcgen05 tap-GEMM (xva_gemm) against (a) plain torch fp32 math with TF32 off and (b) the exact-fp32
+SIMT checker xva_gemm_ref, for every mode / epilogue the FastPitch and HiFi-GAN layers use.
+
+Tolerance: operands are read as tf32 (10-bit mantissa) with fp32 accumulation, so the bar for the tensor-core
+kernel is relative L2 error <= 2e-3 per tensor; the SIMT checker must agree with torch to 1e-5.
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TOL_TC = 2e-3
+TOL_REF = 2e-5
+
+
+def rel(a, b):
+    r = ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+    if not (r < TOL_TC):
+        _describe(a, b)
+    return r
+
+
+def _describe(got, want):
+    """Error anatomy printed on failure: which rows / columns are off tells descriptor bugs from wiring bugs."""
+    try:
+        g, w = got.reshape(-1, got.shape[-1]).float(), want.reshape(-1, want.shape[-1]).float()
+        print(f"\n[describe] shape {tuple(got.shape)} max|got| {g.abs().max():.4g} max|want| {w.abs().max():.4g} "
+              f"nan {int(torch.isnan(g).sum())} zeros {(g == 0).float().mean():.3f}")
+        err = (g - w).abs()
+        rows = err.mean(1)
+        cols = err.mean(0)
+        print("[describe] row-mean err, first 16 rows:", [f"{v:.2g}" for v in rows[:16].tolist()])
+        print("[describe] row-mean err by row%8      :", [f"{rows[i::8].mean():.2g}" for i in range(8)])
+        nb = (cols.numel() + 31) // 32
+        print("[describe] col-mean err per 32-col blk:", [f"{cols[i * 32:(i + 1) * 32].mean():.2g}" for i in range(min(nb, 16))])
+        print("[describe] col-mean err by col%8 (blk0):", [f"{cols[i:32:8].mean():.2g}" for i in range(8)])
+        rb = (rows.numel() + 127) // 128
+        print("[describe] row-mean err per 128-row blk:", [f"{rows[i * 128:(i + 1) * 128].mean():.2g}" for i in range(min(rb, 12))])
+    except Exception as e:  # pragma: no cover
+        print("[describe] failed:", e)
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _strict_fp32(lib):
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+
+
+def _ops():
+    from xva_trainer_b200 import ops
+
+    return ops
+
+
+def conv_ref(x, wp, shifts):
+    """out[b,t,n] = sum_j x[b,t+s_j,:] @ wp[j].T with zero rows outside [0,T)."""
+    B, T, K = x.shape
+    out = torch.zeros(B, T, wp.shape[1], device=x.device, dtype=torch.float64)
+    xd, wd = x.double(), wp.double()
+    for j, s in enumerate(shifts):
+        lo, hi = max(0, -s), min(T, T - s)
+        if hi > lo:
+            out[:, lo:hi] += xd[:, lo + s:hi + s] @ wd[j].T
+    return out.float()
+
+
+def gen(*shape, seed=0, scale=1.0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return torch.randn(*shape, device="cuda", generator=g) * scale
+
+
+@pytest.mark.parametrize("B,T,K,N,shifts", [
+    (2, 200, 64, 64, (0,)),
+    (3, 130, 384, 192, (0,)),          # qkv projection shape
+    (2, 257, 384, 80, (0,)),           # proj 384 -> 80
+    (2, 300, 384, 1536, (-1, 0, 1)),   # ConvFF first conv
+    (2, 140, 1536, 384, (-1, 0, 1)),   # ConvFF second conv
+    (2, 96, 80, 512, (-3, -2, -1, 0, 1, 2, 3)),  # conv_pre k7, K not a multiple of 32
+    (1, 500, 128, 128, (-5, 0, 5)),    # dilated k3 d5
+    (2, 64, 32, 32, (-1, 0, 1)),
+])
+def test_conv_fwd(B, T, K, N, shifts):
+    ops = _ops()
+    x, w = gen(B, T, K, seed=1), gen(len(shifts), N, K, seed=2, scale=K ** -0.5)
+    bias = gen(N, seed=3)
+    want = conv_ref(x, w, shifts) + bias
+    got_ref = ops.conv_fwd(x, w, shifts, bias=bias, ref=True)
+    got = ops.conv_fwd(x, w, shifts, bias=bias)
+    torch.cuda.synchronize()
+    assert rel(got_ref, want) < TOL_REF
+    assert rel(got, want) < TOL_TC, f"tcgen05 rel err {rel(got, want)}"
+
+
+def test_conv_fwd_relu_lens_strided():
+    ops = _ops()
+    B, T, K, N = 3, 200, 384, 256
+    big = gen(B, T, K + 64, seed=4)
+    x = big[:, :, 32:32 + K]  # strided view: row stride K+64
+    w = gen(3, N, K, seed=5, scale=K ** -0.5)
+    lens = torch.tensor([200, 77, 128], device="cuda", dtype=torch.int32)
+    want = torch.relu(conv_ref(x.contiguous(), w, (-1, 0, 1)))
+    mask = (torch.arange(T, device="cuda")[None, :] < lens[:, None]).float()[..., None]
+    want = want * mask
+    got = ops.conv_fwd(x, w, (-1, 0, 1), relu=True, lens=lens)
+    got_ref = ops.conv_fwd(x, w, (-1, 0, 1), relu=True, lens=lens, ref=True)
+    assert rel(got_ref, want) < TOL_REF
+    assert rel(got, want) < TOL_TC
+
+
+@pytest.mark.parametrize("N,K,shifts", [(384, 64, (0,)), (384, 1536, (-1, 0, 1)), (256, 384, (-1, 0, 1))])
+def test_conv_fwd_layernorm(N, K, shifts):
+    ops = _ops()
+    B, T = 2, 150
+    x = gen(B, T, K, seed=6)
+    w = gen(len(shifts), N, K, seed=7, scale=K ** -0.5)
+    bias, res = gen(N, seed=8), gen(B, T, N, seed=9)
+    gamma, beta = 1 + 0.1 * gen(N, seed=10), 0.1 * gen(N, seed=11)
+    lens = torch.tensor([150, 99], device="cuda", dtype=torch.int32)
+    pre = conv_ref(x, w, shifts) + bias + res
+    mask = (torch.arange(T, device="cuda")[None, :] < lens[:, None]).float()[..., None]
+    want = torch.nn.functional.layer_norm(pre, (N,), gamma, beta, 1e-5) * mask
+    for ref in (True, False):
+        got, extra = ops.conv_fwd(x, w, shifts, bias=bias, residual=res, ln=(gamma, beta), lens=lens, save_ln=True,
+                                  ref=ref)
+        tol = TOL_REF if ref else TOL_TC
+        assert rel(got, want) < tol, f"ref={ref} out {rel(got, want)}"
+        assert rel(extra["pre"], pre) < tol
+        assert rel(extra["mean"].view(B, T), pre.mean(-1)) < 5e-3 + tol
+        assert rel(extra["rstd"].view(B, T), (pre.var(-1, unbiased=False) + 1e-5).rsqrt()) < tol
+
+
+def test_relu_then_layernorm_predictor():
+    # ConvReLUNorm: LN(relu(conv(x)+b))  (common/layers.py:94-97)
+    ops = _ops()
+    B, T, K, N = 2, 160, 384, 256
+    x, w, bias = gen(B, T, K, seed=12), gen(3, N, K, seed=13, scale=K ** -0.5), gen(N, seed=14)
+    gamma, beta = 1 + 0.1 * gen(N, seed=15), 0.1 * gen(N, seed=16)
+    want = torch.nn.functional.layer_norm(torch.relu(conv_ref(x, w, (-1, 0, 1)) + bias), (N,), gamma, beta, 1e-5)
+    got = ops.conv_fwd(x, w, (-1, 0, 1), bias=bias, relu=True, ln=(gamma, beta))
+    assert rel(got, want) < TOL_TC
+
+
+@pytest.mark.parametrize("B,T,K,N,shifts", [
+    (2, 200, 384, 1536, (-1, 0, 1)),
+    (2, 300, 64, 384, (0,)),
+    (3, 130, 384, 192, (0,)),
+    (1, 400, 128, 128, (-3, 0, 3)),
+])
+def test_conv_dgrad(B, T, K, N, shifts):
+    ops = _ops()
+    dy, w = gen(B, T, N, seed=20), gen(len(shifts), N, K, seed=21, scale=N ** -0.5)
+    x = gen(B, T, K, seed=22).requires_grad_(True)
+    (conv_ref_autograd(x, w, shifts) * dy).sum().backward()
+    want = x.grad
+    got_ref = ops.conv_dgrad(dy, w, shifts, ref=True)
+    got = ops.conv_dgrad(dy, w, shifts)
+    assert rel(got_ref, want) < TOL_REF
+    assert rel(got, want) < TOL_TC, f"dgrad rel err {rel(got, want)}"
+
+
+def conv_ref_autograd(x, wp, shifts):
+    B, T, K = x.shape
+    out = 0
+    for j, s in enumerate(shifts):
+        xs = torch.zeros_like(x)
+        lo, hi = max(0, -s), min(T, T - s)
+        pad = torch.nn.functional.pad(x, (0, 0, max(0, -s), max(0, s)))
+        xs = pad[:, max(0, s):max(0, s) + T]
+        out = out + xs @ wp[j].T
+    return out
+
+
+def test_dgrad_relu_gate_residual():
+    ops = _ops()
+    B, T, K, N = 2, 130, 1536, 384
+    dy, w = gen(B, T, N, seed=23), gen(3, N, K, seed=24, scale=N ** -0.5)
+    h = gen(B, T, K, seed=25)
+    want = conv_ref(dy, w.transpose(1, 2).contiguous(), (1, 0, -1)) * (h > 0).float()
+    got = ops.conv_dgrad(dy, w, (-1, 0, 1), gate=h)
+    got_ref = ops.conv_dgrad(dy, w, (-1, 0, 1), gate=h, ref=True)
+    assert rel(got_ref, want) < TOL_REF
+    assert rel(got, want) < TOL_TC
+
+
+@pytest.mark.parametrize("B,T,K,N,shifts,split", [
+    (4, 200, 384, 1536, (-1, 0, 1), 2),
+    (2, 300, 64, 384, (0,), 1),
+    (3, 130, 384, 192, (0,), 3),
+    (2, 90, 1536, 384, (-1, 0, 1), None),
+])
+def test_conv_wgrad(B, T, K, N, shifts, split):
+    ops = _ops()
+    dy, x = gen(B, T, N, seed=30), gen(B, T, K, seed=31)
+    w = gen(len(shifts), N, K, seed=32).requires_grad_(True)
+    (conv_ref_autograd(x, w, shifts) * dy).sum().backward()
+    want = w.grad
+    got_ref = ops.conv_wgrad(dy, x, shifts, ref=True)
+    got = ops.conv_wgrad(dy, x, shifts, split=split)
+    assert rel(got_ref, want) < TOL_REF
+    assert rel(got, want) < TOL_TC, f"wgrad rel err {rel(got, want)}"
+
+
+def test_attention_bmms_on_qkv_slices():
+    ops = _ops()
+    B, T, D = 3, 200, 64
+    qkv = gen(B, T, 3 * D, seed=40)
+    q, k, v = qkv[..., :D], qkv[..., D:2 * D], qkv[..., 2 * D:]
+    s_want = torch.bmm(q, k.transpose(1, 2)) * 0.125
+    s_got = ops.bmm_nt(q, k, alpha=0.125)
+    assert rel(s_got, s_want) < TOL_TC
+    p = torch.softmax(s_want, -1)
+    o_want = torch.bmm(p, v)
+    o_got = ops.bmm_nn(p, v)
+    assert rel(o_got, o_want) < TOL_TC
+    do = gen(B, T, D, seed=41)
+    dv_want = torch.bmm(p.transpose(1, 2), do)
+    dv_got = ops.bmm_tn(p, do)
+    assert rel(dv_got, dv_want) < TOL_TC
+    for fn, want in ((lambda r: ops.bmm_nt(q, k, alpha=0.125, ref=r), s_want), (lambda r: ops.bmm_nn(p, v, ref=r), o_want),
+                     (lambda r: ops.bmm_tn(p, do, ref=r), dv_want)):
+        assert rel(fn(True), want) < TOL_REF
+
+
+def test_dropout_matches_checker_and_keeps_scale():
+    ops = _ops()
+    B, T, K, N = 2, 256, 384, 384
+    x, w = gen(B, T, K, seed=50), gen(1, N, K, seed=51, scale=K ** -0.5)
+    a = ops.conv_fwd(x, w, (0,), drop_p=0.1, seed=1234)
+    b = ops.conv_fwd(x, w, (0,), drop_p=0.1, seed=1234, ref=True)
+    full = ops.conv_fwd(x, w, (0,), ref=True)
+    assert torch.equal(a == 0, b == 0)           # same counter-based mask in both implementations
+    frac = (a == 0).float().mean().item()
+    assert 0.08 < frac < 0.12
+    kept = a != 0
+    assert rel(a[kept], full[kept] / 0.9) < TOL_TC
+    c = ops.conv_fwd(x, w, (0,), drop_p=0.1, seed=99)
+    assert not torch.equal(a == 0, c == 0)
+
+
+def test_full_size_linearity_property():
+    """BASELINE size (B=32, T=880): f(x1 + x2) == f(x1) + f(x2) for the k3 conv, checked without any reference."""
+    ops = _ops()
+    B, T, K, N = 32, 880, 384, 1536
+    x1, x2 = gen(B, T, K, seed=60), gen(B, T, K, seed=61)
+    w = gen(3, N, K, seed=62, scale=K ** -0.5)
+    y12 = ops.conv_fwd(x1 + x2, w, (-1, 0, 1))
+    y1, y2 = ops.conv_fwd(x1, w, (-1, 0, 1)), ops.conv_fwd(x2, w, (-1, 0, 1))
+    assert rel(y12, y1 + y2) < TOL_TC
+    # and a sampled exact check of 64 rows against fp64 math
+    rows = torch.randint(0, T, (64,), device="cuda")
+    want = conv_ref(x1[:2], w, (-1, 0, 1))[:, rows]
+    assert rel(y1[:2][:, rows], want) < TOL_TC

@@ -1,0 +1,96 @@
+"""ctypes binding of libxva_b200.so (C ABI declared in include/xva_b200.h).
+
+This is the only place that touches the shared library. Every function raises XvaError on a non-zero status;
+there is no fallback implementation: if the library is missing or the device is not sm_100 the call fails.
+"""
+import ctypes as C
+import os
+
+from . import build as _build
+
+XVA_MAX_TAPS = 48
+
+GEMM_RELU = 1 << 0
+GEMM_LN = 1 << 1
+GEMM_DROP_PRE = 1 << 2
+GEMM_DROP_POST = 1 << 3
+GEMM_ATOMIC = 1 << 4
+
+c_float_p = C.c_void_p  # device pointers travel as integers
+
+
+class XvaError(RuntimeError):
+    pass
+
+
+class GemmArgs(C.Structure):
+    """Mirror of struct xva_gemm_args (include/xva_b200.h)."""
+    _fields_ = [
+        ("mode", C.c_int32), ("Z", C.c_int32), ("R", C.c_int32), ("M", C.c_int32), ("N", C.c_int32),
+        ("K", C.c_int32), ("taps", C.c_int32), ("shift", C.c_int32 * XVA_MAX_TAPS), ("ZR", C.c_int32),
+        ("split", C.c_int32),
+        ("a", C.c_void_p), ("a_rs", C.c_int64), ("a_zs", C.c_int64), ("a_rows", C.c_int32), ("_pad0", C.c_int32),
+        ("b", C.c_void_p), ("b_rs", C.c_int64), ("b_zs", C.c_int64), ("b_rows", C.c_int32), ("b_nz", C.c_int32),
+        ("b_tap_z", C.c_int32), ("b_batch_z", C.c_int32),
+        ("out", C.c_void_p), ("o_rs", C.c_int64), ("o_zs", C.c_int64), ("o_js", C.c_int64),
+        ("alpha", C.c_float), ("flags", C.c_int32),
+        ("bias", C.c_void_p), ("residual", C.c_void_p), ("r_rs", C.c_int64), ("r_zs", C.c_int64),
+        ("gate", C.c_void_p), ("g_rs", C.c_int64), ("g_zs", C.c_int64), ("gate_slope", C.c_float),
+        ("_pad1", C.c_int32),
+        ("lens", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("ln_eps", C.c_float),
+        ("_pad2", C.c_int32),
+        ("out_pre", C.c_void_p), ("ln_mean", C.c_void_p), ("ln_rstd", C.c_void_p), ("drop_p", C.c_float),
+        ("_pad3", C.c_int32), ("seed", C.c_uint64),
+    ]
+
+
+# name -> (restype, argtypes); must list every symbol include/xva_b200.h declares (tests/test_abi.py checks it)
+_I, _F, _P = C.c_int, C.c_float, C.c_void_p
+PROTOTYPES = {
+    "xva_abi_version": (_I, []),
+    "xva_last_error": (C.c_char_p, []),
+    "xva_device_check": (_I, [_I]),
+    "xva_sizeof_gemm_args": (_I, []),
+    "xva_gemm": (_I, [C.POINTER(GemmArgs), _P]),
+    "xva_gemm_ref": (_I, [C.POINTER(GemmArgs), _P]),
+    "xva_regulate_len_scan": (_I, [_P, _I, _I, _F, _I, _P, _P, _P]),
+    "xva_regulate_len_fwd": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),
+    "xva_regulate_len_bwd": (_I, [_P, _P, _I, _I, _I, _I, _P, _I, _P]),
+    "xva_average_pitch": (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),
+}
+
+_lib = None
+
+
+def lib_path():
+    return _build.LIB
+
+
+def load():
+    """Load (once) and return the ctypes handle. Raises if the library has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise XvaError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` first "
+                       "(there is no CPU / eager fallback)")
+    lib = C.CDLL(path)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.xva_sizeof_gemm_args() != C.sizeof(GemmArgs):
+        raise XvaError(f"xva_gemm_args layout mismatch: C {lib.xva_sizeof_gemm_args()} vs ctypes {C.sizeof(GemmArgs)}")
+    _lib = lib
+    return lib
+
+
+def check(status, what=""):
+    if status != 0:
+        msg = load().xva_last_error()
+        raise XvaError(f"{what} failed ({status}): {msg.decode() if msg else '?'}")
+
+
+def call(name, *args):
+    check(getattr(load(), name)(*args), name)

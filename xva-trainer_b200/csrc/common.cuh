@@ -1,0 +1,64 @@
+// Shared host-side helpers for libxva_b200: error reporting across the C ABI, launch checks.
+#pragma once
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cuda_runtime.h>
+
+namespace xva {
+
+// Thread-local last-error text returned by xva_last_error() (see include/xva_b200.h).
+void set_error(const char* fmt, ...);
+const char* last_error();
+
+// Error codes of the C ABI (negative = failure).
+enum : int {
+  XVA_OK = 0,
+  XVA_ERR_ARG = -1,      // invalid argument / unsupported shape
+  XVA_ERR_CUDA = -2,     // CUDA runtime or driver failure (text in xva_last_error)
+  XVA_ERR_DEVICE = -3,   // not a compute-capability 10.x device
+};
+
+#define XVA_CHECK_ARG(cond, ...)            \
+  do {                                      \
+    if (!(cond)) {                          \
+      ::xva::set_error(__VA_ARGS__);        \
+      return ::xva::XVA_ERR_ARG;            \
+    }                                       \
+  } while (0)
+
+#define XVA_CHECK_CUDA(expr)                                                                   \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      ::xva::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return ::xva::XVA_ERR_CUDA;                                                              \
+    }                                                                                          \
+  } while (0)
+
+#define XVA_CHECK_LAUNCH() XVA_CHECK_CUDA(cudaGetLastError())
+
+int num_sms();  // SM count of the current device (cached)
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline long ceil_div_l(long a, long b) { return (a + b - 1) / b; }
+static inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
+
+// Counter-based RNG shared by every kernel that applies dropout: the keep/drop decision for element
+// `idx` of a tensor is a pure function of (seed, idx), so backward re-derives the mask instead of storing it.
+__host__ __device__ __forceinline__ uint32_t hash_u32(uint64_t seed, uint64_t idx) {
+  uint64_t x = idx * 0x9E3779B97F4A7C15ull + seed;
+  x ^= x >> 32;
+  x *= 0xD6E8FEB86659FD93ull;
+  x ^= x >> 32;
+  x *= 0xD6E8FEB86659FD93ull;
+  x ^= x >> 32;
+  return static_cast<uint32_t>(x);
+}
+// Returns the multiplier of inverted dropout: 0 if dropped, 1/(1-p) if kept.  thresh = p * 2^32.
+__host__ __device__ __forceinline__ float dropout_scale(uint64_t seed, uint64_t idx, uint32_t thresh,
+                                                        float inv_keep) {
+  return hash_u32(seed, idx) >= thresh ? inv_keep : 0.0f;
+}
+
+}  // namespace xva

@@ -1,0 +1,240 @@
+"""Tensor-level wrappers over the C ABI: torch tensors in, torch tensors out, kernels from libxva_b200.so.
+
+torch is used for device memory and the current stream only. All tensors are fp32, channels-last [batch, time,
+channels] with a contiguous last dimension (row / batch strides are passed through, so slices such as the q, k, v
+thirds of a fused qkv projection are used in place).
+"""
+import ctypes as C
+
+import torch
+
+from . import capi
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _check3(t, name):
+    if t.dtype != torch.float32 or t.dim() != 3 or t.stride(2) != 1 or not t.is_cuda:
+        raise ValueError(f"{name}: expected a CUDA fp32 [batch, rows, cols] tensor with contiguous last dim, got "
+                         f"{t.dtype} {tuple(t.shape)} strides {t.stride()}")
+
+
+def gemm_launch(args, ref=False):
+    """Launch one tap-GEMM described by a filled capi.GemmArgs."""
+    capi.call("xva_gemm_ref" if ref else "xva_gemm", C.byref(args), _stream())
+
+
+def _base_args(mode, shifts):
+    g = capi.GemmArgs()
+    g.mode = mode
+    g.taps = len(shifts)
+    for j, s in enumerate(shifts):
+        g.shift[j] = int(s)
+    g.ZR = 1
+    g.split = 1
+    g.b_nz = 1
+    g.alpha = 1.0
+    g.ln_eps = 1e-5
+    return g
+
+
+def _epilogue(g, out, bias=None, relu=False, gate=None, gate_slope=0.0, residual=None, lens=None, ln=None,
+              ln_eps=1e-5, save_ln=False, drop_p=0.0, drop_post=False, seed=0, alpha=1.0):
+    keep = [out, bias, gate, residual, lens]
+    g.out, g.o_rs, g.o_zs = _p(out), out.stride(1), out.stride(0)
+    g.alpha = alpha
+    flags = 0
+    if bias is not None:
+        g.bias = _p(bias)
+    if relu:
+        flags |= capi.GEMM_RELU
+    if gate is not None:
+        _check3(gate, "gate")
+        g.gate, g.g_rs, g.g_zs, g.gate_slope = _p(gate), gate.stride(1), gate.stride(0), gate_slope
+    if residual is not None:
+        _check3(residual, "residual")
+        g.residual, g.r_rs, g.r_zs = _p(residual), residual.stride(1), residual.stride(0)
+    if lens is not None:
+        assert lens.dtype == torch.int32
+        g.lens = _p(lens)
+    extra = {}
+    if ln is not None:
+        gamma, beta = ln
+        flags |= capi.GEMM_LN
+        g.gamma, g.beta, g.ln_eps = _p(gamma), _p(beta), ln_eps
+        keep += [gamma, beta]
+        if save_ln:
+            pre = torch.empty_like(out)
+            mean = torch.empty(out.shape[0] * out.shape[1], device=out.device, dtype=torch.float32)
+            rstd = torch.empty_like(mean)
+            assert pre.stride() == out.stride()
+            g.out_pre, g.ln_mean, g.ln_rstd = _p(pre), _p(mean), _p(rstd)
+            extra = {"pre": pre, "mean": mean, "rstd": rstd}
+    if drop_p > 0.0:
+        flags |= capi.GEMM_DROP_POST if drop_post else capi.GEMM_DROP_PRE
+        g.drop_p, g.seed = drop_p, seed
+    g.flags = flags
+    return keep, extra
+
+
+def conv_fwd(x, wp, shifts=(0,), out=None, ref=False, **epi):
+    """out[b,t,n] = sum_j sum_k x[b, t+shifts[j], k] * wp[j, n, k]  (+ epilogue).  x [B,T,K], wp [taps,N,K]."""
+    _check3(x, "x")
+    _check3(wp, "wp")
+    B, T, K = x.shape
+    taps, N, K2 = wp.shape
+    assert K2 == K and taps == len(shifts)
+    if out is None:
+        out = torch.empty(B, T, N, device=x.device, dtype=torch.float32)
+    g = _base_args(0, shifts)
+    g.Z, g.R, g.N, g.K = B, T, N, K
+    g.a, g.a_rs, g.a_zs = _p(x), x.stride(1), x.stride(0)
+    g.b, g.b_rs, g.b_zs, g.b_nz, g.b_tap_z = _p(wp), wp.stride(1), wp.stride(0), taps, 1
+    keep, extra = _epilogue(g, out, **epi)
+    gemm_launch(g, ref)
+    return (out, extra) if extra else out
+
+
+def conv_dgrad(dy, wp, shifts=(0,), out=None, ref=False, **epi):
+    """dx[b,t,k] = sum_j sum_n dy[b, t-shifts[j], n] * wp[j, n, k]: input gradient of conv_fwd, same packed weights
+    read MN-major (no transposed copy).  dy [B,T,N], wp [taps,N,K]."""
+    _check3(dy, "dy")
+    _check3(wp, "wp")
+    B, T, N = dy.shape
+    taps, N2, K = wp.shape
+    assert N2 == N and taps == len(shifts)
+    if out is None:
+        out = torch.empty(B, T, K, device=dy.device, dtype=torch.float32)
+    g = _base_args(1, [-s for s in shifts])
+    g.Z, g.R, g.N, g.K = B, T, K, N
+    g.a, g.a_rs, g.a_zs = _p(dy), dy.stride(1), dy.stride(0)
+    g.b, g.b_rs, g.b_zs, g.b_nz, g.b_tap_z = _p(wp), wp.stride(1), wp.stride(0), taps, 1
+    keep, extra = _epilogue(g, out, **epi)
+    gemm_launch(g, ref)
+    return (out, extra) if extra else out
+
+
+def conv_wgrad(dy, x, shifts=(0,), out=None, accumulate=False, split=None, ref=False):
+    """dw[j,n,k] (+)= sum_b sum_t dy[b,t,n] * x[b, t+shifts[j], k]: weight gradient of conv_fwd in the packed layout.
+    dy [B,T,N], x [B,T,K] -> dw [taps,N,K].  N and K must be multiples of 32."""
+    _check3(dy, "dy")
+    _check3(x, "x")
+    B, T, N = dy.shape
+    B2, T2, K = x.shape
+    assert B2 == B
+    taps = len(shifts)
+    if out is None:
+        out = torch.zeros(taps, N, K, device=dy.device, dtype=torch.float32)
+        accumulate = True
+    g = _base_args(2, shifts)
+    g.Z, g.R, g.M, g.N, g.ZR = B, T, N, K, B
+    g.a, g.a_rs, g.a_zs, g.a_rows = _p(dy), dy.stride(1), dy.stride(0), T
+    g.b, g.b_rs, g.b_zs, g.b_rows = _p(x), x.stride(1), x.stride(0), T2
+    g.out, g.o_rs, g.o_zs, g.o_js = _p(out), out.stride(1), 0, out.stride(0)
+    if split is None:
+        tiles = taps * ((N + 127) // 128) * ((K + 255) // 256)
+        split = max(1, min(B, (2 * 148) // max(tiles, 1)))
+    g.split = split if accumulate else 1
+    g.flags = capi.GEMM_ATOMIC if accumulate else 0
+    gemm_launch(g, ref)
+    return out
+
+
+def bmm_nt(a, b, alpha=1.0, out=None, ref=False):
+    """out[z,m,n] = alpha * sum_k a[z,m,k] * b[z,n,k]   (torch.bmm(a, b.transpose(1,2)))."""
+    _check3(a, "a")
+    _check3(b, "b")
+    Z, M, K = a.shape
+    N = b.shape[1]
+    if out is None:
+        out = torch.empty(Z, M, N, device=a.device, dtype=torch.float32)
+    g = _base_args(0, (0,))
+    g.Z, g.R, g.N, g.K = Z, M, N, K
+    g.a, g.a_rs, g.a_zs = _p(a), a.stride(1), a.stride(0)
+    g.b, g.b_rs, g.b_zs, g.b_nz, g.b_batch_z = _p(b), b.stride(1), b.stride(0), Z, 1
+    _epilogue(g, out, alpha=alpha)
+    gemm_launch(g, ref)
+    return out
+
+
+def bmm_nn(a, b, alpha=1.0, out=None, ref=False):
+    """out[z,m,n] = alpha * sum_k a[z,m,k] * b[z,k,n]   (torch.bmm(a, b)); n must be a multiple of 32."""
+    _check3(a, "a")
+    _check3(b, "b")
+    Z, M, K = a.shape
+    N = b.shape[2]
+    if out is None:
+        out = torch.empty(Z, M, N, device=a.device, dtype=torch.float32)
+    g = _base_args(1, (0,))
+    g.Z, g.R, g.N, g.K = Z, M, N, K
+    g.a, g.a_rs, g.a_zs = _p(a), a.stride(1), a.stride(0)
+    g.b, g.b_rs, g.b_zs, g.b_nz, g.b_batch_z = _p(b), b.stride(1), b.stride(0), Z, 1
+    _epilogue(g, out, alpha=alpha)
+    gemm_launch(g, ref)
+    return out
+
+
+def bmm_tn(a, b, alpha=1.0, out=None, ref=False):
+    """out[z,m,n] = alpha * sum_t a[z,t,m] * b[z,t,n]   (torch.bmm(a.transpose(1,2), b)); m, n multiples of 32."""
+    _check3(a, "a")
+    _check3(b, "b")
+    Z, T, M = a.shape
+    N = b.shape[2]
+    if out is None:
+        out = torch.empty(Z, M, N, device=a.device, dtype=torch.float32)
+    g = _base_args(2, (0,))
+    g.Z, g.R, g.M, g.N, g.ZR = Z, T, M, N, 1
+    g.a, g.a_rs, g.a_zs, g.a_rows = _p(a), a.stride(1), a.stride(0), T
+    g.b, g.b_rs, g.b_zs, g.b_rows = _p(b), b.stride(1), b.stride(0), T
+    g.out, g.o_rs, g.o_zs, g.o_js = _p(out), out.stride(1), out.stride(0), 0
+    g.alpha = alpha
+    gemm_launch(g, ref)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- length regulator
+def duration_scan(durs, pace=1.0, mel_max_len=None):
+    """-> (cum int32 [B,Tt+1], dec_lens int32 [B])   fastpitch/model.py:62-65,76-78."""
+    B, Tt = durs.shape
+    d = durs.float().contiguous()
+    cum = torch.empty(B, Tt + 1, device=d.device, dtype=torch.int32)
+    dec = torch.empty(B, device=d.device, dtype=torch.int32)
+    capi.call("xva_regulate_len_scan", _p(d), B, Tt, float(pace), -1 if mel_max_len is None else int(mel_max_len),
+              _p(cum), _p(dec), _stream())
+    return cum, dec
+
+
+def regulate_gather(enc, cum, T_out, want_idx=False):
+    B, Tt, Cc = enc.shape
+    enc = enc.contiguous()
+    out = torch.empty(B, T_out, Cc, device=enc.device, dtype=torch.float32)
+    idx = torch.empty(B, T_out, device=enc.device, dtype=torch.int32) if want_idx else None
+    capi.call("xva_regulate_len_fwd", _p(enc), _p(cum), B, Tt, Cc, T_out, _p(out), _p(idx), _stream())
+    return (out, idx) if want_idx else out
+
+
+def regulate_scatter(dout, cum, Tt, out=None):
+    B, T_out, Cc = dout.shape
+    dout = dout.contiguous()
+    acc = out is not None
+    if out is None:
+        out = torch.empty(B, Tt, Cc, device=dout.device, dtype=torch.float32)
+    capi.call("xva_regulate_len_bwd", _p(dout), _p(cum), B, Tt, Cc, T_out, _p(out), int(acc), _stream())
+    return out
+
+
+def average_pitch(pitch, durs):
+    """fastpitch/model.py:82-100.  pitch [B,F,Tm], durs [B,Tt] -> [B,F,Tt]."""
+    B, F, Tm = pitch.shape
+    Tt = durs.shape[1]
+    pitch = pitch.float().contiguous()
+    d = durs.float().contiguous()
+    out = torch.empty(B, F, Tt, device=pitch.device, dtype=torch.float32)
+    capi.call("xva_average_pitch", _p(pitch), _p(d), B, F, Tm, Tt, _p(out), _stream())
+    return out
