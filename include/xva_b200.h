@@ -125,6 +125,71 @@ int xva_regulate_len_bwd(const float* dout, const int32_t* cum, int B, int Tt, i
  * durs [B,Tt] -> out [B,F,Tt]. */
 int xva_average_pitch(const float* pitch, const float* durs, int B, int F, int Tm, int Tt, float* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Attention softmax -- replaces masked_fill + F.softmax + dropatt, fastpitch/transformer.py:120-127, and its autograd.
+ *   fwd : s [Z,R,N] = alpha*q.k^T (from xva_gemm) -> p (softmax over n with keys n >= lens[z] masked), and
+ *         pd = p * dropout (optional; pass NULL when drop_p == 0 and use p for the P*V product)
+ *   bwd : dpd [Z,R,N] (gradient wrt pd) is overwritten with alpha * ds (gradient wrt q.k^T)
+ * ---------------------------------------------------------------------------------------------------------- */
+int xva_softmax_fwd(const float* s, const int32_t* lens, int Z, int R, int N, float* p, float* pd, float drop_p,
+                    uint64_t seed, void* stream);
+int xva_softmax_bwd(const float* p, float* dpd, int Z, int R, int N, float alpha, float drop_p, uint64_t seed,
+                    void* stream);
+
+/* LayerNorm backward for the LayerNorm epilogue of xva_gemm (nn.LayerNorm autograd, transformer.py:75,148 and
+ * common/layers.py:96). x/mean/rstd are the out_pre/ln_mean/ln_rstd the forward saved; rows >= lens[z] get zero.
+ * dx_drop (optional) = dx * dropout(pre) mask of the forward; dgamma/dbeta/dbias (optional) are ACCUMULATED. */
+int xva_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
+                      const int32_t* lens, int Z, int R, int C, float* dx, float* dx_drop, float* dgamma,
+                      float* dbeta, float* dbias, float drop_post_p, uint64_t seed_post, float drop_pre_p,
+                      uint64_t seed_pre, void* stream);
+
+/* out[n] += sum over rows of x[row*ld + n]   (bias gradients). */
+int xva_colsum(const float* x, int64_t rows, int C, int64_t ld, float* out, void* stream);
+
+/* FFTransformer input stage, transformer.py:212-227: out = (tokens ? emb[tokens] : in) + pos_emb(t)*mask.
+ * Encoder: tokens int64 [B,T] + emb [n,C] (mask = token != 0). Decoder: in [B,T,C] + lens (mask = t < lens[b]). */
+int xva_embed_pos(const int64_t* tokens, const float* emb, const float* in, const int32_t* lens,
+                  const float* inv_freq, int B, int T, int C, float* out, void* stream);
+int xva_embed_bwd(const int64_t* tokens, const float* dout, int B, int T, int C, float* demb, void* stream);
+
+/* pitch_emb / energy_emb = nn.Conv1d(1, C, 3, padding=1), model.py:403-404,417-418:
+ *   io[b,t,:] += bias + sum_j w[:,j] * x[b,t+j-1] ; bwd accumulates dw [C,3] and dbias [C]. */
+int xva_scalar_conv_add(float* io, const float* x, const float* w, const float* bias, int B, int T, int C, void* stream);
+int xva_scalar_conv_bwd(const float* dout, const float* x, int B, int T, int C, float* dw, float* dbias, void* stream);
+
+/* TemporalPredictor.fc (C -> 1) * mask, model.py:121. bwd writes dx and ACCUMULATES dw [C], db [1]. */
+int xva_rowdot_fwd(const float* x, const float* w, const float* bias, const int32_t* lens, int Z, int R, int C,
+                   float* out, void* stream);
+int xva_rowdot_bwd(const float* dout, const float* x, const float* w, const int32_t* lens, int Z, int R, int C,
+                   float* dx, float* dw, float* db, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * FastPitchLoss masked MSE terms, fastpitch/loss_function.py:81-136. acc is double[2] = {sum sq err, mask count},
+ * ACCUMULATED (zero it first); loss = acc[0]/acc[1]. The grad kernels write scale * d(loss)/d(pred).
+ *   mel : pred [B,T_out,C] (rows >= T_out count as zero), tgt [B,C,Tm], mask = tgt != 0; dpred row stride ldd >= C
+ *   lens: pred,tgt [B,T], mask = t < lens[b]; log1p_tgt = 1 compares against log(tgt + 1) (duration loss)
+ * ---------------------------------------------------------------------------------------------------------- */
+int xva_mel_mse(const float* pred, const float* tgt, int B, int T_out, int Tm, int C, double* acc, void* stream);
+int xva_mel_mse_grad(const float* pred, const float* tgt, int B, int T_out, int Tm, int C, int ldd, const double* acc,
+                     float scale, float* dpred, void* stream);
+int xva_lens_mse(const float* pred, const float* tgt, const int32_t* lens, int B, int T, int log1p_tgt, double* acc,
+                 void* stream);
+int xva_lens_mse_grad(const float* pred, const float* tgt, const int32_t* lens, int B, int T, int log1p_tgt,
+                      const double* acc, float scale, float* dpred, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Multi-tensor LAMB -- replaces Lamb.step, fastpitch1_1/lamb.py:40-106, plus clip_grad_norm_ (xva_train.py:857).
+ * p/g/m/v are flat fp32 arenas; `chunks` is a device array of {int64 start; int32 len; int32 tensor} records (one
+ * CUDA block each; every chunk lies inside one tensor). norms is double[2*n_tensors], zeroed by the caller.
+ * gnorm_sq (optional) = sum of squared gradients from xva_grad_sqnorm: gradients are scaled by
+ * min(1, max_norm/(sqrt(gnorm_sq)+1e-6)) on the fly. lr is read from device memory (CUDA-graph friendly).
+ * ---------------------------------------------------------------------------------------------------------- */
+int xva_grad_sqnorm(const float* g, const void* chunks, int n_chunks, double* out, void* stream);
+int xva_lamb_step(float* p, const float* g, float* m, float* v, const void* chunks, int n_chunks, double* norms,
+                  const double* gnorm_sq, float max_norm, const float* lr_dev, float beta1, float beta2, float eps,
+                  float weight_decay, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

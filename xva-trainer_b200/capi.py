@@ -45,7 +45,7 @@ class GemmArgs(C.Structure):
 
 
 # name -> (restype, argtypes); must list every symbol include/xva_b200.h declares (tests/test_abi.py checks it)
-_I, _F, _P = C.c_int, C.c_float, C.c_void_p
+_I, _F, _P, _U64, _I64 = C.c_int, C.c_float, C.c_void_p, C.c_uint64, C.c_int64
 PROTOTYPES = {
     "xva_abi_version": (_I, []),
     "xva_last_error": (C.c_char_p, []),
@@ -57,6 +57,22 @@ PROTOTYPES = {
     "xva_regulate_len_fwd": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "xva_regulate_len_bwd": (_I, [_P, _P, _I, _I, _I, _I, _P, _I, _P]),
     "xva_average_pitch": (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),
+    "xva_softmax_fwd": (_I, [_P, _P, _I, _I, _I, _P, _P, _F, _U64, _P]),
+    "xva_softmax_bwd": (_I, [_P, _P, _I, _I, _I, _F, _F, _U64, _P]),
+    "xva_layernorm_bwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _F, _U64, _F, _U64, _P]),
+    "xva_colsum": (_I, [_P, _I64, _I, _I64, _P, _P]),
+    "xva_embed_pos": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P]),
+    "xva_embed_bwd": (_I, [_P, _P, _I, _I, _I, _P, _P]),
+    "xva_scalar_conv_add": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
+    "xva_scalar_conv_bwd": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
+    "xva_rowdot_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P]),
+    "xva_rowdot_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
+    "xva_mel_mse": (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),
+    "xva_mel_mse_grad": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _F, _P, _P]),
+    "xva_lens_mse": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
+    "xva_lens_mse_grad": (_I, [_P, _P, _P, _I, _I, _I, _P, _F, _P, _P]),
+    "xva_grad_sqnorm": (_I, [_P, _P, _I, _P, _P]),
+    "xva_lamb_step": (_I, [_P, _P, _P, _P, _P, _I, _P, _P, _F, _P, _F, _F, _F, _F, _P]),
 }
 
 _lib = None

@@ -57,4 +57,85 @@ int xva_average_pitch(const float* pitch, const float* durs, int B, int F, int T
   return average_pitch(pitch, durs, B, F, Tm, Tt, out, S(stream));
 }
 
+int xva_softmax_fwd(const float* s, const int32_t* lens, int Z, int R, int N, float* p, float* pd, float drop_p,
+                    uint64_t seed, void* stream) {
+  return softmax_fwd(s, lens, Z, R, N, p, pd, drop_p, seed, S(stream));
+}
+
+int xva_softmax_bwd(const float* p, float* dpd, int Z, int R, int N, float alpha, float drop_p, uint64_t seed,
+                    void* stream) {
+  return softmax_bwd(p, dpd, Z, R, N, alpha, drop_p, seed, S(stream));
+}
+
+int xva_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
+                      const int32_t* lens, int Z, int R, int C, float* dx, float* dx_drop, float* dgamma,
+                      float* dbeta, float* dbias, float drop_post_p, uint64_t seed_post, float drop_pre_p,
+                      uint64_t seed_pre, void* stream) {
+  return layernorm_bwd(dy, x, mean, rstd, gamma, lens, Z, R, C, dx, dx_drop, dgamma, dbeta, dbias, drop_post_p,
+                       seed_post, drop_pre_p, seed_pre, S(stream));
+}
+
+int xva_colsum(const float* x, int64_t rows, int C, int64_t ld, float* out, void* stream) {
+  return colsum(x, rows, C, ld, out, S(stream));
+}
+
+int xva_embed_pos(const int64_t* tokens, const float* emb, const float* in, const int32_t* lens,
+                  const float* inv_freq, int B, int T, int C, float* out, void* stream) {
+  return embed_pos(reinterpret_cast<const long long*>(tokens), emb, in, lens, inv_freq, B, T, C, out, S(stream));
+}
+
+int xva_embed_bwd(const int64_t* tokens, const float* dout, int B, int T, int C, float* demb, void* stream) {
+  return embed_bwd(reinterpret_cast<const long long*>(tokens), dout, B, T, C, demb, S(stream));
+}
+
+int xva_scalar_conv_add(float* io, const float* x, const float* w, const float* bias, int B, int T, int C,
+                        void* stream) {
+  return scalar_conv_add(io, x, w, bias, B, T, C, S(stream));
+}
+
+int xva_scalar_conv_bwd(const float* dout, const float* x, int B, int T, int C, float* dw, float* dbias,
+                        void* stream) {
+  return scalar_conv_bwd(dout, x, B, T, C, dw, dbias, S(stream));
+}
+
+int xva_rowdot_fwd(const float* x, const float* w, const float* bias, const int32_t* lens, int Z, int R, int C,
+                   float* out, void* stream) {
+  return rowdot_fwd(x, w, bias, lens, Z, R, C, out, S(stream));
+}
+
+int xva_rowdot_bwd(const float* dout, const float* x, const float* w, const int32_t* lens, int Z, int R, int C,
+                   float* dx, float* dw, float* db, void* stream) {
+  return rowdot_bwd(dout, x, w, lens, Z, R, C, dx, dw, db, S(stream));
+}
+
+int xva_mel_mse(const float* pred, const float* tgt, int B, int T_out, int Tm, int C, double* acc, void* stream) {
+  return mel_mse(pred, tgt, B, T_out, Tm, C, acc, S(stream));
+}
+
+int xva_mel_mse_grad(const float* pred, const float* tgt, int B, int T_out, int Tm, int C, int ldd, const double* acc,
+                     float scale, float* dpred, void* stream) {
+  return mel_mse_grad(pred, tgt, B, T_out, Tm, C, ldd, acc, scale, dpred, S(stream));
+}
+
+int xva_lens_mse(const float* pred, const float* tgt, const int32_t* lens, int B, int T, int log1p_tgt, double* acc,
+                 void* stream) {
+  return lens_mse(pred, tgt, lens, B, T, log1p_tgt, acc, S(stream));
+}
+
+int xva_lens_mse_grad(const float* pred, const float* tgt, const int32_t* lens, int B, int T, int log1p_tgt,
+                      const double* acc, float scale, float* dpred, void* stream) {
+  return lens_mse_grad(pred, tgt, lens, B, T, log1p_tgt, acc, scale, dpred, S(stream));
+}
+
+int xva_grad_sqnorm(const float* g, const void* chunks, int n_chunks, double* out, void* stream) {
+  return grad_sqnorm(g, chunks, n_chunks, out, S(stream));
+}
+
+int xva_lamb_step(float* p, const float* g, float* m, float* v, const void* chunks, int n_chunks, double* norms,
+                  const double* gnorm_sq, float max_norm, const float* lr_dev, float beta1, float beta2, float eps,
+                  float weight_decay, void* stream) {
+  return lamb_step(p, g, m, v, chunks, n_chunks, norms, gnorm_sq, max_norm, lr_dev, beta1, beta2, eps, weight_decay,
+                   S(stream));
+}
+
 }  // extern "C"

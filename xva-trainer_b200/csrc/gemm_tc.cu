@@ -9,6 +9,7 @@
 // The k-tap convolution is a sum of `taps` GEMMs whose A tiles are the same activation rows shifted by
 // shift[j]; the shift is a TMA coordinate, the zero padding is TMA out-of-bounds fill: no im2col, no halo copy.
 #include <cuda.h>
+#include <cstdlib>
 #include <mutex>
 #include "gemm.cuh"
 #include "ptx.cuh"
@@ -30,6 +31,7 @@ struct GemmDev {
   int mode, Z, R, M, N, K, taps, ZR, split, zper;
   int n_tile, n_sub, n_mma, tiles_n, tiles_m, k_chunks, stages, acc_stages, num_tiles;
   int b_tap_z, b_batch_z;
+  uint32_t mn_layout, mn_lbo, mn_sbo;  // MN-major descriptor constants (debug-overridable, see gemm_tc_launch)
   int shift[kMaxTaps];
   float* out;
   long o_rs, o_zs, o_js;
@@ -91,16 +93,19 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmDev& p, int t) {
   return c;
 }
 
-// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout): 128B swizzle, version 1.
-//   K-major : 8-row groups of 128B rows, SBO = 1024 B between groups, LBO unused (1).
-//   MN-major: atoms of 8 k-rows x 128 B; LBO = byte distance between 32-element MN chunks, SBO = 1024 B.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout), version 1.
+//   K-major : SWIZZLE_128B (layout type 2); 8-row groups of 128B rows, SBO = 1024 B between groups, LBO unused (1).
+//   MN-major: 32-bit operands only exist as SWIZZLE_128B_BASE32B (layout type 1; TMA 128B_ATOM_32B): atoms of
+//             4 k-rows x 128 B whose 32-byte chunks are XOR-ed with (row & 3); LBO = byte distance between
+//             32-element MN chunks, SBO = 512 B between 4-row k groups.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout_type) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
   d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= static_cast<uint64_t>(1) << 46;  // descriptor version (Blackwell)
-  d |= static_cast<uint64_t>(2) << 61;  // SWIZZLE_128B
+  d |= static_cast<uint64_t>(layout_type) << 61;
   return d;
 }
 
@@ -206,8 +211,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       const uint32_t idesc = make_idesc(p.n_sub, a_mn ? 1 : 0, b_mn ? 1 : 0);
-      const uint32_t a_lbo = a_mn ? kBlockK * 128 : 16;
-      const uint32_t b_lbo = b_mn ? kBlockK * 128 : 16;
+      const uint32_t a_lbo = a_mn ? p.mn_lbo : 16;
+      const uint32_t b_lbo = b_mn ? p.mn_lbo : 16;
       const uint32_t a_kstep = a_mn ? 1024 : kUmmaK * 4;  // bytes to advance per UMMA_K
       const uint32_t b_kstep = b_mn ? 1024 : kUmmaK * 4;
       const uint32_t b_sub_bytes = b_mn ? (p.n_sub / 32) * (kBlockK * 128) : p.n_sub * kBlockK * 4;
@@ -228,9 +233,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const uint32_t sb = sa + kATileBytes;
 #pragma unroll
           for (int k4 = 0; k4 < kBlockK / kUmmaK; ++k4) {
-            const uint64_t da = make_smem_desc(sa + k4 * a_kstep, a_lbo, 1024);
+            const uint64_t da = make_smem_desc(sa + k4 * a_kstep, a_lbo, a_mn ? p.mn_sbo : 1024, a_mn ? p.mn_layout : 2);
             for (int sub = 0; sub < p.n_mma; ++sub) {
-              const uint64_t db = make_smem_desc(sb + sub * b_sub_bytes + k4 * b_kstep, b_lbo, 1024);
+              const uint64_t db = make_smem_desc(sb + sub * b_sub_bytes + k4 * b_kstep, b_lbo, b_mn ? p.mn_sbo : 1024, b_mn ? p.mn_layout : 2);
               ptx::mma_tf32(tmem_acc + sub * p.n_sub, da, db, idesc, (it > 0 || k4 > 0) ? 1u : 0u);
             }
           }
@@ -430,10 +435,10 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// fp32 tensor map with 128B swizzle and zero out-of-bounds fill. dims/strides in elements, innermost first;
+// fp32 tensor map, zero out-of-bounds fill; 128B swizzle (K-major tiles) or 128B swizzle with 32B atoms (MN-major tiles). dims/strides in elements, innermost first;
 // strides[0] is implicit (1).
 int encode_map(CUtensorMap* map, const float* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
-               const uint32_t* box) {
+               const uint32_t* box, int swizzle) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled entry point not available");
@@ -458,7 +463,9 @@ int encode_map(CUtensorMap* map, const float* base, int rank, const uint64_t* di
     return XVA_ERR_ARG;
   }
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<float*>(base), gdim, gstride, gbox, estride,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  static_cast<CUtensorMapSwizzle>(swizzle),
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu %llu %llu box %u %u %u)", (int)r, rank,
@@ -542,6 +549,23 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
     p.num_tiles = (g.Z / g.ZR) * p.split * g.taps * p.tiles_m * p.tiles_n;
   }
 
+  // MN-major tiles: SWIZZLE_128B_BASE32B descriptors + TMA 128B_ATOM_32B. XVA_MN_DEBUG=layout:lbo:sbo:tma_swizzle
+  // overrides the four constants (bring-up aid for tests/gpu_mn_probe.py; unset in production).
+  p.mn_layout = 1;
+  p.mn_lbo = kBlockK * 128;
+  p.mn_sbo = 512;
+  int mn_swizzle = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+  if (const char* dbg = getenv("XVA_MN_DEBUG")) {
+    unsigned a, b, c;
+    int d;
+    if (sscanf(dbg, "%u:%u:%u:%d", &a, &b, &c, &d) == 4) {
+      p.mn_layout = a;
+      p.mn_lbo = b;
+      p.mn_sbo = c;
+      mn_swizzle = d;
+    }
+  }
+
   // ---- tensor maps
   CUtensorMap map_a, map_b;
   int rc;
@@ -551,34 +575,34 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
     uint64_t str[3] = {1, (uint64_t)g.a_rs, (uint64_t)g.a_zs};
     uint32_t box[3] = {kBlockK, kBlockM, 1};
     if (g.Z == 1 || str[2] == 0) str[2] = (uint64_t)g.a_rs * a_rows;
-    if ((rc = encode_map(&map_a, g.a, 3, dims, str, box)) != XVA_OK) return rc;
+    if ((rc = encode_map(&map_a, g.a, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) != XVA_OK) return rc;
   } else {
     uint64_t dims[4] = {32, (uint64_t)a_rows, (uint64_t)(g.M / 32), (uint64_t)g.Z};
     uint64_t str[4] = {1, (uint64_t)g.a_rs, 32, (uint64_t)g.a_zs};
     uint32_t box[4] = {32, kBlockK, kBlockM / 32, 1};
     if (g.Z == 1 || str[3] == 0) str[3] = (uint64_t)g.a_rs * a_rows;
-    if ((rc = encode_map(&map_a, g.a, 4, dims, str, box)) != XVA_OK) return rc;
+    if ((rc = encode_map(&map_a, g.a, 4, dims, str, box, mn_swizzle)) != XVA_OK) return rc;
   }
   if (g.mode == 0) {
     uint64_t dims[3] = {(uint64_t)g.K, (uint64_t)g.N, (uint64_t)g.b_nz};
     uint64_t str[3] = {1, (uint64_t)g.b_rs, (uint64_t)g.b_zs};
     uint32_t box[3] = {kBlockK, (uint32_t)p.n_sub, 1};
     if (g.b_nz == 1 || str[2] == 0) str[2] = (uint64_t)g.b_rs * g.N;
-    if ((rc = encode_map(&map_b, g.b, 3, dims, str, box)) != XVA_OK) return rc;
+    if ((rc = encode_map(&map_b, g.b, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) != XVA_OK) return rc;
   } else if (g.mode == 1) {
     XVA_CHECK_ARG(g.N % 32 == 0, "gemm: MN-major B needs N %% 32 == 0 (N=%d)", g.N);
     uint64_t dims[4] = {32, (uint64_t)g.K, (uint64_t)(g.N / 32), (uint64_t)g.b_nz};
     uint64_t str[4] = {1, (uint64_t)g.b_rs, 32, (uint64_t)g.b_zs};
     uint32_t box[4] = {32, kBlockK, (uint32_t)(p.n_tile / 32), 1};
     if (g.b_nz == 1 || str[3] == 0) str[3] = (uint64_t)g.b_rs * g.K;
-    if ((rc = encode_map(&map_b, g.b, 4, dims, str, box)) != XVA_OK) return rc;
+    if ((rc = encode_map(&map_b, g.b, 4, dims, str, box, mn_swizzle)) != XVA_OK) return rc;
   } else {
     const int b_rows = g.b_rows ? g.b_rows : g.R;
     uint64_t dims[4] = {32, (uint64_t)b_rows, (uint64_t)(g.N / 32), (uint64_t)g.Z};
     uint64_t str[4] = {1, (uint64_t)g.b_rs, 32, (uint64_t)g.b_zs};
     uint32_t box[4] = {32, kBlockK, (uint32_t)(p.n_tile / 32), 1};
     if (g.Z == 1 || str[3] == 0) str[3] = (uint64_t)g.b_rs * b_rows;
-    if ((rc = encode_map(&map_b, g.b, 4, dims, str, box)) != XVA_OK) return rc;
+    if ((rc = encode_map(&map_b, g.b, 4, dims, str, box, mn_swizzle)) != XVA_OK) return rc;
   }
 
   // ---- epilogue

@@ -1,0 +1,495 @@
+// Row-wise HBM-bound kernels around the tap-GEMM: masked softmax (+dropout) forward/backward, LayerNorm backward,
+// column sums (bias gradients), token embedding + sinusoidal positions, the 1->C k3 "scalar" conv used by
+// pitch_emb / energy_emb, and the C->1 projection of the temporal predictors.
+//
+// Layout everywhere: [rows, C] fp32 with C contiguous; one warp per row, lanes stride over columns so every
+// global access is a coalesced 128-byte line; reductions are warp shuffles; cross-row reductions (dgamma, dbeta,
+// dbias, dW of the tiny convs) are accumulated per thread over a grid-stride loop of rows, combined through shared
+// memory once per block, then one fp32 atomicAdd per column per block.
+#include "common.cuh"
+#include "ops.cuh"
+
+namespace xva {
+
+namespace {
+
+constexpr int kWarpsPerBlock = 8;
+constexpr int kMaxColsPerLane = 32;  // rows up to 1024 columns are held in registers (softmax)
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+
+// Sum per-thread column accumulators (thread owns columns lane + 32*i) over the warps of the block and add the
+// block total to dst[0..C) with one atomic per column. `red` is reused across calls (leading __syncthreads()).
+template <int kColsPerLane>
+__device__ __forceinline__ void block_colsum_atomic(const float (&acc)[kColsPerLane],
+                                                    float (*red)[32 * kColsPerLane + 1], int C, float* dst, int stride) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < kColsPerLane; ++i) red[warp][lane + 32 * i] = acc[i];
+  __syncthreads();
+  if (dst == nullptr) return;
+  for (int n = threadIdx.x; n < C; n += blockDim.x) {
+    float a = 0.0f;
+#pragma unroll
+    for (int w = 0; w < kWarpsPerBlock; ++w) a += red[w][n];
+    atomicAdd(dst + static_cast<long>(n) * stride, a);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ softmax
+// transformer.py:120-127: masked_fill(key >= len, -inf) -> softmax(dim=2) -> dropout.
+// s [Z,R,N] holds alpha*q.k (written by the tap-GEMM); p_out gets softmax, pd_out (optional) softmax*dropout.
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+softmax_fwd_kernel(const float* __restrict__ s, const int* __restrict__ lens, int R, int N, long rows,
+                   float* __restrict__ p_out, float* __restrict__ pd_out, uint64_t seed, uint32_t thresh,
+                   float inv_keep) {
+  const int lane = threadIdx.x & 31;
+  const long row = static_cast<long>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int z = static_cast<int>(row / R);
+  const int nk = lens ? min(lens[z], N) : N;
+  const float* src = s + row * N;
+  float v[kMaxColsPerLane];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < kMaxColsPerLane; ++i) {
+    const int n = lane + 32 * i;
+    v[i] = (n < nk) ? src[n] : -INFINITY;
+    mx = fmaxf(mx, v[i]);
+  }
+  mx = warp_max(mx);
+  float sum = 0.0f;
+#pragma unroll
+  for (int i = 0; i < kMaxColsPerLane; ++i) {
+    v[i] = (lane + 32 * i < nk) ? expf(v[i] - mx) : 0.0f;
+    sum += v[i];
+  }
+  sum = warp_sum(sum);
+  const float inv = 1.0f / sum;
+#pragma unroll
+  for (int i = 0; i < kMaxColsPerLane; ++i) {
+    const int n = lane + 32 * i;
+    if (n < N) {
+      const float p = v[i] * inv;
+      p_out[row * N + n] = p;
+      if (pd_out) pd_out[row * N + n] = p * dropout_scale(seed, static_cast<uint64_t>(row) * N + n, thresh, inv_keep);
+    }
+  }
+}
+
+// ds = p * (g - sum_n g*p) with g = dpd * dropout_scale   (in place on dpd)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+softmax_bwd_kernel(const float* __restrict__ p, float* __restrict__ dpd, int N, long rows, float alpha, uint64_t seed,
+                   uint32_t thresh, float inv_keep) {
+  const int lane = threadIdx.x & 31;
+  const long row = static_cast<long>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float pv[kMaxColsPerLane], gv[kMaxColsPerLane];
+  float dot = 0.0f;
+#pragma unroll
+  for (int i = 0; i < kMaxColsPerLane; ++i) {
+    const int n = lane + 32 * i;
+    if (n < N) {
+      pv[i] = p[row * N + n];
+      gv[i] = dpd[row * N + n] * dropout_scale(seed, static_cast<uint64_t>(row) * N + n, thresh, inv_keep);
+    } else {
+      pv[i] = 0.0f;
+      gv[i] = 0.0f;
+    }
+    dot += pv[i] * gv[i];
+  }
+  dot = warp_sum(dot);
+#pragma unroll
+  for (int i = 0; i < kMaxColsPerLane; ++i) {
+    const int n = lane + 32 * i;
+    if (n < N) dpd[row * N + n] = alpha * pv[i] * (gv[i] - dot);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm bwd
+// y = (LN(x)*gamma + beta) [* post-dropout] * rowmask ; given dy and the saved pre-LN x, mean, rstd:
+//   dx = rstd * (g - mean_n(g) - xhat * mean_n(g*xhat)),  g = dy_eff * gamma
+//   dgamma += sum_rows dy_eff * xhat ; dbeta += sum_rows dy_eff
+// dx_drop (optional) = dx * pre-dropout scale: the gradient of the GEMM branch when dropout sat between the GEMM
+// and the residual add (transformer.py:51,139); dbias (optional) += column sums of that branch gradient.
+template <int kColsPerLane>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
+                     const float* __restrict__ rstd, const float* __restrict__ gamma, const int* __restrict__ lens,
+                     int R, int C, long rows, float* __restrict__ dx, float* __restrict__ dx_drop,
+                     float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias,
+                     uint64_t seed_post, uint32_t thresh_post, float inv_keep_post, uint64_t seed_pre,
+                     uint32_t thresh_pre, float inv_keep_pre) {
+  __shared__ float red[kWarpsPerBlock][32 * kColsPerLane + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float gm[kColsPerLane], acc_g[kColsPerLane], acc_b[kColsPerLane], acc_bias[kColsPerLane];
+#pragma unroll
+  for (int i = 0; i < kColsPerLane; ++i) {
+    const int n = lane + 32 * i;
+    gm[i] = n < C ? gamma[n] : 0.0f;
+    acc_g[i] = acc_b[i] = acc_bias[i] = 0.0f;
+  }
+  const float inv_c = 1.0f / static_cast<float>(C);
+  for (long row = static_cast<long>(blockIdx.x) * kWarpsPerBlock + warp; row < rows;
+       row += static_cast<long>(gridDim.x) * kWarpsPerBlock) {
+    const int z = static_cast<int>(row / R), r = static_cast<int>(row - static_cast<long>(z) * R);
+    const bool live = (lens == nullptr) || (r < lens[z]);
+    const float mu = mean[row], rs = rstd[row];
+    float xh[kColsPerLane], g[kColsPerLane];
+    float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+    for (int i = 0; i < kColsPerLane; ++i) {
+      const int n = lane + 32 * i;
+      float d = 0.0f;
+      xh[i] = 0.0f;
+      if (n < C && live) {
+        d = dy[row * C + n] * dropout_scale(seed_post, static_cast<uint64_t>(row) * C + n, thresh_post, inv_keep_post);
+        xh[i] = (x[row * C + n] - mu) * rs;
+      }
+      acc_g[i] += d * xh[i];
+      acc_b[i] += d;
+      g[i] = d * gm[i];
+      s1 += g[i];
+      s2 += g[i] * xh[i];
+    }
+    s1 = warp_sum(s1) * inv_c;
+    s2 = warp_sum(s2) * inv_c;
+#pragma unroll
+    for (int i = 0; i < kColsPerLane; ++i) {
+      const int n = lane + 32 * i;
+      if (n < C) {
+        const float v = rs * (g[i] - s1 - xh[i] * s2);
+        dx[row * C + n] = v;
+        if (dx_drop) {
+          const float vd = v * dropout_scale(seed_pre, static_cast<uint64_t>(row) * C + n, thresh_pre, inv_keep_pre);
+          dx_drop[row * C + n] = vd;
+          acc_bias[i] += vd;
+        } else {
+          acc_bias[i] += v;
+        }
+      }
+    }
+  }
+  block_colsum_atomic<kColsPerLane>(acc_g, red, C, dgamma, 1);
+  block_colsum_atomic<kColsPerLane>(acc_b, red, C, dbeta, 1);
+  block_colsum_atomic<kColsPerLane>(acc_bias, red, C, dbias, 1);
+}
+
+// ------------------------------------------------------------------------------------------------ column sums
+// out[n] += sum_rows x[row, n]   (bias gradients). Thread per column within a 32-column strip, rows strided over
+// blockIdx.y; coalesced 128-byte reads.
+__global__ void __launch_bounds__(256)
+colsum_kernel(const float* __restrict__ x, long rows, int C, long ld, float* __restrict__ out) {
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + lane;
+  float acc = 0.0f;
+  if (n < C)
+    for (long r = static_cast<long>(blockIdx.y) * 8 + warp; r < rows; r += static_cast<long>(gridDim.y) * 8)
+      acc += x[r * ld + n];
+  red[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0 && n < C) {
+    float s = 0.0f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][lane];
+    atomicAdd(out + n, s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ embedding
+// out[b,t,:] = (tokens ? emb[tok] : in[b,t,:]) + pos(t) * live     transformer.py:212-227 (conditioning = 0)
+//   pos(t)[c] = sin(t*f[c]) for c < C/2, cos(t*f[c-C/2]) otherwise (transformer.py:28-35)
+//   live = tok != 0 (encoder) or t < lens[b] (decoder)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+embed_pos_kernel(const long long* __restrict__ tokens, const float* __restrict__ emb, const float* __restrict__ in,
+                 const int* __restrict__ lens, const float* __restrict__ inv_freq, int T, int C, long rows,
+                 float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long row = static_cast<long>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int b = static_cast<int>(row / T), t = static_cast<int>(row - static_cast<long>(b) * T);
+  const float* src;
+  bool live;
+  if (tokens) {
+    const long long tok = tokens[row];
+    src = emb + tok * C;
+    live = tok != 0;
+  } else {
+    src = in + row * C;
+    live = t < lens[b];
+  }
+  const int half = C >> 1;
+  const float tf = static_cast<float>(t);
+  for (int c = lane; c < C; c += 32) {
+    float v = src[c];
+    if (live) {
+      const float ang = tf * inv_freq[c < half ? c : c - half];
+      v += (c < half) ? sinf(ang) : cosf(ang);
+    }
+    out[row * C + c] = v;
+  }
+}
+
+// d_emb[tok] += dout[row]  (tok != padding 0)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+embed_bwd_kernel(const long long* __restrict__ tokens, const float* __restrict__ dout, int C, long rows,
+                 float* __restrict__ demb) {
+  const int lane = threadIdx.x & 31;
+  const long row = static_cast<long>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const long long tok = tokens[row];
+  if (tok == 0) return;
+  for (int c = lane; c < C; c += 32) atomicAdd(demb + tok * C + c, dout[row * C + c]);
+}
+
+// ------------------------------------------------------------------------------------------------ scalar conv
+// io[b,t,c] += bias[c] + sum_j w[c,j] * x[b, t+j-1]     pitch_emb / energy_emb: Conv1d(1, C, 3, padding=1)
+// (model.py:403-404,417-418). x [B,T]; w [C,3].
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+scalar_conv_add_kernel(float* __restrict__ io, const float* __restrict__ x, const float* __restrict__ w,
+                       const float* __restrict__ bias, int T, int C, long rows) {
+  const int lane = threadIdx.x & 31;
+  const long row = static_cast<long>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int t = static_cast<int>(row % T);
+  const float x0 = t > 0 ? x[row - 1] : 0.0f, x1 = x[row], x2 = t + 1 < T ? x[row + 1] : 0.0f;
+  for (int c = lane; c < C; c += 32)
+    io[row * C + c] += bias[c] + w[c * 3] * x0 + w[c * 3 + 1] * x1 + w[c * 3 + 2] * x2;
+}
+
+// dw[c,j] += sum_rows dout[row,c] * x[row+j-1] ; dbias[c] += sum_rows dout[row,c]
+template <int kColsPerLane>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+scalar_conv_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ x, int T, int C, long rows,
+                       float* __restrict__ dw, float* __restrict__ dbias) {
+  __shared__ float red[kWarpsPerBlock][32 * kColsPerLane + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float a[4][kColsPerLane];
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int i = 0; i < kColsPerLane; ++i) a[q][i] = 0.0f;
+  for (long row = static_cast<long>(blockIdx.x) * kWarpsPerBlock + warp; row < rows;
+       row += static_cast<long>(gridDim.x) * kWarpsPerBlock) {
+    const int t = static_cast<int>(row % T);
+    const float x0 = t > 0 ? x[row - 1] : 0.0f, x1 = x[row], x2 = t + 1 < T ? x[row + 1] : 0.0f;
+#pragma unroll
+    for (int i = 0; i < kColsPerLane; ++i) {
+      const int c = lane + 32 * i;
+      if (c < C) {
+        const float d = dout[row * C + c];
+        a[0][i] += d * x0;
+        a[1][i] += d * x1;
+        a[2][i] += d * x2;
+        a[3][i] += d;
+      }
+    }
+  }
+  block_colsum_atomic<kColsPerLane>(a[0], red, C, dw, 3);
+  block_colsum_atomic<kColsPerLane>(a[1], red, C, dw + 1, 3);
+  block_colsum_atomic<kColsPerLane>(a[2], red, C, dw + 2, 3);
+  block_colsum_atomic<kColsPerLane>(a[3], red, C, dbias, 1);
+}
+
+// ------------------------------------------------------------------------------------------------ C -> 1 projection
+// out[row] = (dot(x[row,:], w) + b) * live      TemporalPredictor.fc + mask, model.py:121
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+rowdot_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                  const int* __restrict__ lens, int R, int C, long rows, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long row = static_cast<long>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float acc = 0.0f;
+  for (int c = lane; c < C; c += 32) acc += x[row * C + c] * w[c];
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    const int z = static_cast<int>(row / R), r = static_cast<int>(row - static_cast<long>(z) * R);
+    out[row] = (lens == nullptr || r < lens[z]) ? acc + bias[0] : 0.0f;
+  }
+}
+
+// dx[row,:] = g*w ; dw += sum g*x[row,:] ; db += sum g,   g = dout[row]*live
+template <int kColsPerLane>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+rowdot_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ x, const float* __restrict__ w,
+                  const int* __restrict__ lens, int R, int C, long rows, float* __restrict__ dx,
+                  float* __restrict__ dw, float* __restrict__ db) {
+  __shared__ float red[kWarpsPerBlock][32 * kColsPerLane + 1];
+  __shared__ float redb[kWarpsPerBlock];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float a[kColsPerLane];
+  float ab = 0.0f;
+#pragma unroll
+  for (int i = 0; i < kColsPerLane; ++i) a[i] = 0.0f;
+  for (long row = static_cast<long>(blockIdx.x) * kWarpsPerBlock + warp; row < rows;
+       row += static_cast<long>(gridDim.x) * kWarpsPerBlock) {
+    const int z = static_cast<int>(row / R), r = static_cast<int>(row - static_cast<long>(z) * R);
+    const float g = (lens == nullptr || r < lens[z]) ? dout[row] : 0.0f;
+    ab += g;
+#pragma unroll
+    for (int i = 0; i < kColsPerLane; ++i) {
+      const int c = lane + 32 * i;
+      if (c < C) {
+        a[i] += g * x[row * C + c];
+        dx[row * C + c] = g * w[c];
+      }
+    }
+  }
+  if (lane == 0) redb[warp] = ab;
+  block_colsum_atomic<kColsPerLane>(a, red, C, dw, 1);
+  if (threadIdx.x == 0) {
+    float s = 0.0f;
+    for (int wv = 0; wv < kWarpsPerBlock; ++wv) s += redb[wv];
+    atomicAdd(db, s);
+  }
+}
+
+inline void drop_consts(float p, uint32_t* thresh, float* inv_keep) {
+  if (p > 0.0f) {
+    *thresh = static_cast<uint32_t>(static_cast<double>(p) * 4294967296.0);
+    *inv_keep = 1.0f / (1.0f - p);
+  } else {
+    *thresh = 0;
+    *inv_keep = 1.0f;
+  }
+}
+
+inline int row_blocks(long rows) { return static_cast<int>(ceil_div_l(rows, kWarpsPerBlock)); }
+
+}  // namespace
+
+int softmax_fwd(const float* s, const int* lens, int Z, int R, int N, float* p_out, float* pd_out, float drop_p,
+                uint64_t seed, cudaStream_t stream) {
+  XVA_CHECK_ARG(N >= 1 && N <= 32 * kMaxColsPerLane, "softmax: N=%d out of range (max %d)", N, 32 * kMaxColsPerLane);
+  XVA_CHECK_ARG(drop_p >= 0.0f && drop_p < 1.0f, "softmax: dropout p=%f", drop_p);
+  uint32_t th;
+  float ik;
+  drop_consts(pd_out ? drop_p : 0.0f, &th, &ik);
+  const long rows = static_cast<long>(Z) * R;
+  softmax_fwd_kernel<<<row_blocks(rows), kWarpsPerBlock * 32, 0, stream>>>(s, lens, R, N, rows, p_out, pd_out, seed, th, ik);
+  XVA_CHECK_LAUNCH();
+  return XVA_OK;
+}
+
+int softmax_bwd(const float* p, float* dpd, int Z, int R, int N, float alpha, float drop_p, uint64_t seed,
+                cudaStream_t stream) {
+  XVA_CHECK_ARG(N >= 1 && N <= 32 * kMaxColsPerLane, "softmax bwd: N=%d out of range", N);
+  uint32_t th;
+  float ik;
+  drop_consts(drop_p, &th, &ik);
+  const long rows = static_cast<long>(Z) * R;
+  softmax_bwd_kernel<<<row_blocks(rows), kWarpsPerBlock * 32, 0, stream>>>(p, dpd, N, rows, alpha, seed, th, ik);
+  XVA_CHECK_LAUNCH();
+  return XVA_OK;
+}
+
+int layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
+                  const int* lens, int Z, int R, int C, float* dx, float* dx_drop, float* dgamma, float* dbeta,
+                  float* dbias, float drop_post_p, uint64_t seed_post, float drop_pre_p, uint64_t seed_pre,
+                  cudaStream_t stream) {
+  XVA_CHECK_ARG(C >= 1 && C <= 512, "layernorm bwd: C=%d (max 512)", C);
+  uint32_t th_post, th_pre;
+  float ik_post, ik_pre;
+  drop_consts(drop_post_p, &th_post, &ik_post);
+  drop_consts(dx_drop ? drop_pre_p : 0.0f, &th_pre, &ik_pre);
+  const long rows = static_cast<long>(Z) * R;
+  int grid = static_cast<int>(ceil_div_l(rows, kWarpsPerBlock * 4));
+  if (grid > 4 * num_sms()) grid = 4 * num_sms();
+  if (grid < 1) grid = 1;
+#define XVA_LN_BWD(CPL)                                                                                           \
+  layernorm_bwd_kernel<CPL><<<grid, kWarpsPerBlock * 32, 0, stream>>>(dy, x, mean, rstd, gamma, lens, R, C, rows, \
+                                                                      dx, dx_drop, dgamma, dbeta, dbias, seed_post, \
+                                                                      th_post, ik_post, seed_pre, th_pre, ik_pre)
+  if (C <= 256) XVA_LN_BWD(8);
+  else if (C <= 384) XVA_LN_BWD(12);
+  else XVA_LN_BWD(16);
+#undef XVA_LN_BWD
+  XVA_CHECK_LAUNCH();
+  return XVA_OK;
+}
+
+int colsum(const float* x, long rows, int C, long ld, float* out, cudaStream_t stream) {
+  XVA_CHECK_ARG(rows >= 0 && C >= 1, "colsum: rows=%ld C=%d", rows, C);
+  if (rows == 0) return XVA_OK;
+  int gy = static_cast<int>(ceil_div_l(rows, 8 * 16));
+  const int strips = ceil_div(C, 32);
+  const int cap = ceil_div(8 * num_sms(), strips);
+  if (gy > cap) gy = cap;
+  if (gy < 1) gy = 1;
+  colsum_kernel<<<dim3(strips, gy), 256, 0, stream>>>(x, rows, C, ld, out);
+  XVA_CHECK_LAUNCH();
+  return XVA_OK;
+}
+
+int embed_pos(const long long* tokens, const float* emb, const float* in, const int* lens, const float* inv_freq,
+              int B, int T, int C, float* out, cudaStream_t stream) {
+  XVA_CHECK_ARG((tokens && emb) || (in && lens), "embed_pos: need tokens+emb or in+lens");
+  XVA_CHECK_ARG(C % 2 == 0, "embed_pos: C=%d must be even", C);
+  const long rows = static_cast<long>(B) * T;
+  embed_pos_kernel<<<row_blocks(rows), kWarpsPerBlock * 32, 0, stream>>>(tokens, emb, in, lens, inv_freq, T, C, rows, out);
+  XVA_CHECK_LAUNCH();
+  return XVA_OK;
+}
+
+int embed_bwd(const long long* tokens, const float* dout, int B, int T, int C, float* demb, cudaStream_t stream) {
+  const long rows = static_cast<long>(B) * T;
+  embed_bwd_kernel<<<row_blocks(rows), kWarpsPerBlock * 32, 0, stream>>>(tokens, dout, C, rows, demb);
+  XVA_CHECK_LAUNCH();
+  return XVA_OK;
+}
+
+int scalar_conv_add(float* io, const float* x, const float* w, const float* bias, int B, int T, int C,
+                    cudaStream_t stream) {
+  const long rows = static_cast<long>(B) * T;
+  scalar_conv_add_kernel<<<row_blocks(rows), kWarpsPerBlock * 32, 0, stream>>>(io, x, w, bias, T, C, rows);
+  XVA_CHECK_LAUNCH();
+  return XVA_OK;
+}
+
+int scalar_conv_bwd(const float* dout, const float* x, int B, int T, int C, float* dw, float* dbias,
+                    cudaStream_t stream) {
+  XVA_CHECK_ARG(C <= 512, "scalar_conv bwd: C=%d (max 512)", C);
+  const long rows = static_cast<long>(B) * T;
+  int grid = static_cast<int>(ceil_div_l(rows, kWarpsPerBlock * 8));
+  if (grid > 2 * num_sms()) grid = 2 * num_sms();
+  if (grid < 1) grid = 1;
+  if (C <= 384) scalar_conv_bwd_kernel<12><<<grid, kWarpsPerBlock * 32, 0, stream>>>(dout, x, T, C, rows, dw, dbias);
+  else scalar_conv_bwd_kernel<16><<<grid, kWarpsPerBlock * 32, 0, stream>>>(dout, x, T, C, rows, dw, dbias);
+  XVA_CHECK_LAUNCH();
+  return XVA_OK;
+}
+
+int rowdot_fwd(const float* x, const float* w, const float* bias, const int* lens, int Z, int R, int C, float* out,
+               cudaStream_t stream) {
+  const long rows = static_cast<long>(Z) * R;
+  rowdot_fwd_kernel<<<row_blocks(rows), kWarpsPerBlock * 32, 0, stream>>>(x, w, bias, lens, R, C, rows, out);
+  XVA_CHECK_LAUNCH();
+  return XVA_OK;
+}
+
+int rowdot_bwd(const float* dout, const float* x, const float* w, const int* lens, int Z, int R, int C, float* dx,
+               float* dw, float* db, cudaStream_t stream) {
+  XVA_CHECK_ARG(C <= 512, "rowdot bwd: C=%d (max 512)", C);
+  const long rows = static_cast<long>(Z) * R;
+  int grid = static_cast<int>(ceil_div_l(rows, kWarpsPerBlock * 8));
+  if (grid > 2 * num_sms()) grid = 2 * num_sms();
+  if (grid < 1) grid = 1;
+  if (C <= 256) rowdot_bwd_kernel<8><<<grid, kWarpsPerBlock * 32, 0, stream>>>(dout, x, w, lens, R, C, rows, dx, dw, db);
+  else rowdot_bwd_kernel<16><<<grid, kWarpsPerBlock * 32, 0, stream>>>(dout, x, w, lens, R, C, rows, dx, dw, db);
+  XVA_CHECK_LAUNCH();
+  return XVA_OK;
+}
+
+}  // namespace xva
