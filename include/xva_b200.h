@@ -42,6 +42,9 @@ int xva_device_check(int device);
  *          replaces the autograd weight-gradient of the same layers, and dK / dV of the attention
  *
  *  Rows addressed outside an operand's [0, rows) read as zero -- this is the Conv1d zero padding.
+ *  MN-major operands (B in mode 1; A and B in mode 2) are fetched in 32-column chunks: when their column count
+ *  (N, or M) is not a multiple of 32 the row stride must be >= the count rounded up to 32 (pad columns are
+ *  multiplied into output rows/columns that are never stored).
  *  Epilogue (mode 0/1), in order: alpha, +bias[n], ReLU, gate (ReLU / leaky-ReLU backward), dropout(pre),
  *  +residual, [LayerNorm(gamma,beta) over n, dropout(post)], zero rows >= lens[z].
  * ---------------------------------------------------------------------------------------------------------- */
@@ -72,7 +75,8 @@ typedef struct xva_gemm_args {
   int32_t _pad0;
   const float* b;
   int64_t b_rs, b_zs;
-  int32_t b_rows;     /* mode 2: valid rows of B per item (0 = R) */
+  int32_t b_rows;     /* valid rows of B per item: mode 0 rows n (0 = N), mode 1 rows k (0 = K), mode 2 rows t (0 = R);
+                         rows past it read as zero */
   int32_t b_nz;       /* z slices in B */
   int32_t b_tap_z, b_batch_z;
 
@@ -99,6 +103,8 @@ typedef struct xva_gemm_args {
   float drop_p;
   int32_t _pad3;
   uint64_t seed;
+  const uint64_t* seed_dev; /* optional device counter added to `seed` (x odd constant) at run time, so a captured
+                               CUDA graph draws a fresh dropout mask on every replay */
 } xva_gemm_args;
 
 /* sizeof(xva_gemm_args) as compiled into the library, so a binding can verify its struct layout. */
@@ -122,27 +128,34 @@ int xva_regulate_len_bwd(const float* dout, const int32_t* cum, int B, int Tt, i
                          int accumulate, void* stream);
 
 /* average_pitch(), fastpitch/model.py:82-100: per-token mean of the non-zero frame values. pitch [B,F,Tm],
- * durs [B,Tt] -> out [B,F,Tt]. */
-int xva_average_pitch(const float* pitch, const float* durs, int B, int F, int Tm, int Tt, float* out, void* stream);
+ * durs [B,Tt] -> out [B,F,Tt]. log1p_out = 1 writes log(1 + mean) (the energy target, model.py:415). */
+int xva_average_pitch(const float* pitch, const float* durs, int B, int F, int Tm, int Tt, float* out, int log1p_out,
+                      void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Attention softmax -- replaces masked_fill + F.softmax + dropatt, fastpitch/transformer.py:120-127, and its autograd.
  *   fwd : s [Z,R,N] = alpha*q.k^T (from xva_gemm) -> p (softmax over n with keys n >= lens[z] masked), and
  *         pd = p * dropout (optional; pass NULL when drop_p == 0 and use p for the P*V product)
  *   bwd : dpd [Z,R,N] (gradient wrt pd) is overwritten with alpha * ds (gradient wrt q.k^T)
+ *   ld  : row stride of s / p / pd / dpd in elements (0 = N). Pad columns [N, ld) are written as zero, so a stride
+ *         rounded up to 32 makes the tensors legal MN-major operands of xva_gemm.
  * ---------------------------------------------------------------------------------------------------------- */
-int xva_softmax_fwd(const float* s, const int32_t* lens, int Z, int R, int N, float* p, float* pd, float drop_p,
-                    uint64_t seed, void* stream);
-int xva_softmax_bwd(const float* p, float* dpd, int Z, int R, int N, float alpha, float drop_p, uint64_t seed,
-                    void* stream);
+int xva_softmax_fwd(const float* s, const int32_t* lens, int Z, int R, int N, int ld, float* p, float* pd,
+                    float drop_p, uint64_t seed, const uint64_t* seed_dev, void* stream);
+int xva_softmax_bwd(const float* p, float* dpd, int Z, int R, int N, int ld, float alpha, float drop_p,
+                    uint64_t seed, const uint64_t* seed_dev, void* stream);
 
 /* LayerNorm backward for the LayerNorm epilogue of xva_gemm (nn.LayerNorm autograd, transformer.py:75,148 and
  * common/layers.py:96). x/mean/rstd are the out_pre/ln_mean/ln_rstd the forward saved; rows >= lens[z] get zero.
- * dx_drop (optional) = dx * dropout(pre) mask of the forward; dgamma/dbeta/dbias (optional) are ACCUMULATED. */
+ * dx_drop (optional) = dx * dropout(pre) mask of the forward; dgamma/dbeta/dbias (optional) are ACCUMULATED.
+ * relu_gate = 1: x is a ReLU output (ConvReLUNorm), dx is zeroed where x <= 0. seed_dev: see xva_gemm_args. */
 int xva_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
                       const int32_t* lens, int Z, int R, int C, float* dx, float* dx_drop, float* dgamma,
                       float* dbeta, float* dbias, float drop_post_p, uint64_t seed_post, float drop_pre_p,
-                      uint64_t seed_pre, void* stream);
+                      uint64_t seed_pre, const uint64_t* seed_dev, int relu_gate, void* stream);
+
+/* *counter += inc on the stream: the per-step dropout counter every `seed_dev` argument points at. */
+int xva_counter_add(uint64_t* counter, uint64_t inc, void* stream);
 
 /* out[n] += sum over rows of x[row*ld + n]   (bias gradients). */
 int xva_colsum(const float* x, int64_t rows, int C, int64_t ld, float* out, void* stream);
@@ -154,8 +167,11 @@ int xva_embed_pos(const int64_t* tokens, const float* emb, const float* in, cons
 int xva_embed_bwd(const int64_t* tokens, const float* dout, int B, int T, int C, float* demb, void* stream);
 
 /* pitch_emb / energy_emb = nn.Conv1d(1, C, 3, padding=1), model.py:403-404,417-418:
- *   io[b,t,:] += bias + sum_j w[:,j] * x[b,t+j-1] ; bwd accumulates dw [C,3] and dbias [C]. */
-int xva_scalar_conv_add(float* io, const float* x, const float* w, const float* bias, int B, int T, int C, void* stream);
+ *   io[b,t,:] += bias + sum_j w[:,j] * x[b,t+j-1] for t < lens[b] (lens optional; padded token rows are left as they
+ *   are -- nothing downstream reads them: the predictors mask their input, model.py:119, and padded tokens have zero
+ *   duration) ; bwd accumulates dw [C,3] and dbias [C]. */
+int xva_scalar_conv_add(float* io, const float* x, const float* w, const float* bias, const int32_t* lens, int B,
+                        int T, int C, void* stream);
 int xva_scalar_conv_bwd(const float* dout, const float* x, int B, int T, int C, float* dw, float* dbias, void* stream);
 
 /* TemporalPredictor.fc (C -> 1) * mask, model.py:121. bwd writes dx and ACCUMULATES dw [C], db [1]. */

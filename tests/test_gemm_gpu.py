@@ -209,7 +209,11 @@ def test_attention_bmms_on_qkv_slices():
     s_want = torch.bmm(q, k.transpose(1, 2)) * 0.125
     s_got = ops.bmm_nt(q, k, alpha=0.125)
     assert rel(s_got, s_want) < TOL_TC
-    p = torch.softmax(s_want, -1)
+    # key dimension T = 200 is not a multiple of 32: the probabilities live in rows of stride 224 (zero pad columns),
+    # which is how the engine lays out the score tensor (include/xva_b200.h, MN-major operand rule)
+    p_pad = torch.zeros(B, T, 224, device="cuda")
+    p = p_pad[..., :T]
+    p.copy_(torch.softmax(s_want, -1))
     o_want = torch.bmm(p, v)
     o_got = ops.bmm_nn(p, v)
     assert rel(o_got, o_want) < TOL_TC

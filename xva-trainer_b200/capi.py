@@ -15,6 +15,7 @@ GEMM_LN = 1 << 1
 GEMM_DROP_PRE = 1 << 2
 GEMM_DROP_POST = 1 << 3
 GEMM_ATOMIC = 1 << 4
+GEMM_LRELU_GATE = 1 << 5
 
 c_float_p = C.c_void_p  # device pointers travel as integers
 
@@ -40,7 +41,7 @@ class GemmArgs(C.Structure):
         ("lens", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("ln_eps", C.c_float),
         ("_pad2", C.c_int32),
         ("out_pre", C.c_void_p), ("ln_mean", C.c_void_p), ("ln_rstd", C.c_void_p), ("drop_p", C.c_float),
-        ("_pad3", C.c_int32), ("seed", C.c_uint64),
+        ("_pad3", C.c_int32), ("seed", C.c_uint64), ("seed_dev", C.c_void_p),
     ]
 
 
@@ -56,14 +57,15 @@ PROTOTYPES = {
     "xva_regulate_len_scan": (_I, [_P, _I, _I, _F, _I, _P, _P, _P]),
     "xva_regulate_len_fwd": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "xva_regulate_len_bwd": (_I, [_P, _P, _I, _I, _I, _I, _P, _I, _P]),
-    "xva_average_pitch": (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),
-    "xva_softmax_fwd": (_I, [_P, _P, _I, _I, _I, _P, _P, _F, _U64, _P]),
-    "xva_softmax_bwd": (_I, [_P, _P, _I, _I, _I, _F, _F, _U64, _P]),
-    "xva_layernorm_bwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _F, _U64, _F, _U64, _P]),
+    "xva_average_pitch": (_I, [_P, _P, _I, _I, _I, _I, _P, _I, _P]),
+    "xva_softmax_fwd": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _F, _U64, _P, _P]),
+    "xva_softmax_bwd": (_I, [_P, _P, _I, _I, _I, _I, _F, _F, _U64, _P, _P]),
+    "xva_layernorm_bwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _F, _U64, _F, _U64, _P, _I, _P]),
+    "xva_counter_add": (_I, [_P, _U64, _P]),
     "xva_colsum": (_I, [_P, _I64, _I, _I64, _P, _P]),
     "xva_embed_pos": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P]),
     "xva_embed_bwd": (_I, [_P, _P, _I, _I, _I, _P, _P]),
-    "xva_scalar_conv_add": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
+    "xva_scalar_conv_add": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "xva_scalar_conv_bwd": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
     "xva_rowdot_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P]),
     "xva_rowdot_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),

@@ -53,26 +53,31 @@ int xva_regulate_len_bwd(const float* dout, const int32_t* cum, int B, int Tt, i
   return regulate_scatter(dout, cum, B, Tt, C, T_out, denc, accumulate, S(stream));
 }
 
-int xva_average_pitch(const float* pitch, const float* durs, int B, int F, int Tm, int Tt, float* out, void* stream) {
-  return average_pitch(pitch, durs, B, F, Tm, Tt, out, S(stream));
+int xva_average_pitch(const float* pitch, const float* durs, int B, int F, int Tm, int Tt, float* out, int log1p_out,
+                      void* stream) {
+  return average_pitch(pitch, durs, B, F, Tm, Tt, out, log1p_out, S(stream));
 }
 
-int xva_softmax_fwd(const float* s, const int32_t* lens, int Z, int R, int N, float* p, float* pd, float drop_p,
-                    uint64_t seed, void* stream) {
-  return softmax_fwd(s, lens, Z, R, N, p, pd, drop_p, seed, S(stream));
+int xva_softmax_fwd(const float* s, const int32_t* lens, int Z, int R, int N, int ld, float* p, float* pd,
+                    float drop_p, uint64_t seed, const uint64_t* seed_dev, void* stream) {
+  return softmax_fwd(s, lens, Z, R, N, ld, p, pd, drop_p, seed, seed_dev, S(stream));
 }
 
-int xva_softmax_bwd(const float* p, float* dpd, int Z, int R, int N, float alpha, float drop_p, uint64_t seed,
-                    void* stream) {
-  return softmax_bwd(p, dpd, Z, R, N, alpha, drop_p, seed, S(stream));
+int xva_softmax_bwd(const float* p, float* dpd, int Z, int R, int N, int ld, float alpha, float drop_p,
+                    uint64_t seed, const uint64_t* seed_dev, void* stream) {
+  return softmax_bwd(p, dpd, Z, R, N, ld, alpha, drop_p, seed, seed_dev, S(stream));
 }
 
 int xva_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
                       const int32_t* lens, int Z, int R, int C, float* dx, float* dx_drop, float* dgamma,
                       float* dbeta, float* dbias, float drop_post_p, uint64_t seed_post, float drop_pre_p,
-                      uint64_t seed_pre, void* stream) {
+                      uint64_t seed_pre, const uint64_t* seed_dev, int relu_gate, void* stream) {
   return layernorm_bwd(dy, x, mean, rstd, gamma, lens, Z, R, C, dx, dx_drop, dgamma, dbeta, dbias, drop_post_p,
-                       seed_post, drop_pre_p, seed_pre, S(stream));
+                       seed_post, drop_pre_p, seed_pre, seed_dev, relu_gate, S(stream));
+}
+
+int xva_counter_add(uint64_t* counter, uint64_t inc, void* stream) {
+  return counter_add(reinterpret_cast<unsigned long long*>(counter), inc, S(stream));
 }
 
 int xva_colsum(const float* x, int64_t rows, int C, int64_t ld, float* out, void* stream) {
@@ -88,9 +93,9 @@ int xva_embed_bwd(const int64_t* tokens, const float* dout, int B, int T, int C,
   return embed_bwd(reinterpret_cast<const long long*>(tokens), dout, B, T, C, demb, S(stream));
 }
 
-int xva_scalar_conv_add(float* io, const float* x, const float* w, const float* bias, int B, int T, int C,
-                        void* stream) {
-  return scalar_conv_add(io, x, w, bias, B, T, C, S(stream));
+int xva_scalar_conv_add(float* io, const float* x, const float* w, const float* bias, const int32_t* lens, int B,
+                        int T, int C, void* stream) {
+  return scalar_conv_add(io, x, w, bias, lens, B, T, C, S(stream));
 }
 
 int xva_scalar_conv_bwd(const float* dout, const float* x, int B, int T, int C, float* dw, float* dbias,

@@ -14,6 +14,10 @@ struct RefDev {
   float inv_keep;
 };
 
+__device__ __forceinline__ uint64_t eff_seed(const GemmArgs& g) {
+  return g.seed + (g.seed_dev ? *g.seed_dev * 0xA24BAED4963EE407ull : 0ull);
+}
+
 __device__ float ref_dot(const GemmArgs& g, int z, int r, int n) {
   float acc = 0.0f;
   const int a_rows = g.a_rows ? g.a_rows : g.R;
@@ -23,11 +27,13 @@ __device__ float ref_dot(const GemmArgs& g, int z, int r, int n) {
     const float* arow = g.a + z * g.a_zs + static_cast<long>(ar) * g.a_rs;
     const int zb = j * g.b_tap_z + z * g.b_batch_z;
     if (g.mode == 0) {
+      if (g.b_rows && n >= g.b_rows) continue;
       const float* brow = g.b + zb * g.b_zs + static_cast<long>(n) * g.b_rs;
       for (int k = 0; k < g.K; ++k) acc = fmaf(arow[k], brow[k], acc);
     } else {
       const float* bcol = g.b + zb * g.b_zs + n;
-      for (int k = 0; k < g.K; ++k) acc = fmaf(arow[k], bcol[static_cast<long>(k) * g.b_rs], acc);
+      const int kmax = (g.b_rows && g.b_rows < g.K) ? g.b_rows : g.K;
+      for (int k = 0; k < kmax; ++k) acc = fmaf(arow[k], bcol[static_cast<long>(k) * g.b_rs], acc);
     }
   }
   return acc;
@@ -50,7 +56,7 @@ __global__ void gemm_ref_fwd_kernel(const RefDev d) {
     if (g.bias) v += g.bias[n];
     if (g.flags & GEMM_RELU) v = fmaxf(v, 0.0f);
     if (g.gate) v *= (g.gate[rowoff_g + n] > 0.0f) ? 1.0f : g.gate_slope;
-    if (g.flags & GEMM_DROP_PRE) v *= dropout_scale(g.seed, drop_row + n, d.drop_thresh, d.inv_keep);
+    if (g.flags & GEMM_DROP_PRE) v *= dropout_scale(eff_seed(g), drop_row + n, d.drop_thresh, d.inv_keep);
     if (g.residual) v += g.residual[rowoff_r + n];
     return v;
   };
@@ -93,7 +99,7 @@ __global__ void gemm_ref_fwd_kernel(const RefDev d) {
   for (int n = threadIdx.x; n < g.N; n += blockDim.x) {
     const float x = vals[cnt++];
     float y = (x - mean) * rstd * g.gamma[n] + g.beta[n];
-    if (g.flags & GEMM_DROP_POST) y *= dropout_scale(g.seed, drop_row + n, d.drop_thresh, d.inv_keep);
+    if (g.flags & GEMM_DROP_POST) y *= dropout_scale(eff_seed(g), drop_row + n, d.drop_thresh, d.inv_keep);
     g.out[rowoff_o + n] = y * keep_row;
     if (g.out_pre) g.out_pre[rowoff_o + n] = x;
   }

@@ -53,6 +53,7 @@ struct GemmDev {
   uint32_t drop_thresh;
   float inv_keep;
   uint64_t seed;
+  const uint64_t* seed_dev;
 };
 
 struct TileCoord {
@@ -254,6 +255,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int row_in_tile = ew * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>(ew * 32) << 16;
     int tile_iter = 0;
+    const uint64_t seed = p.seed + (p.seed_dev ? __ldg(p.seed_dev) * 0xA24BAED4963EE407ull : 0ull);
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tile_iter) {
       const TileCoord c = decode_tile(p, tile);
       const int acc = tile_iter % p.acc_stages;
@@ -304,7 +306,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const float gv = __ldg(p.gate + rowoff_g + n);
             v *= (gv > 0.0f) ? 1.0f : p.gate_slope;
           }
-          if (p.flags & GEMM_DROP_PRE) v *= dropout_scale(p.seed, drop_row + n, p.drop_thresh, p.inv_keep);
+          if (p.flags & GEMM_DROP_PRE) v *= dropout_scale(seed, drop_row + n, p.drop_thresh, p.inv_keep);
           if (p.residual) v += __ldg(p.residual + rowoff_r + n);
           return v;
         };
@@ -379,7 +381,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 const int n = ch * 16 + i;
                 const float x = __uint_as_float(v[i]);
                 float y = (x - mean) * rstd * __ldg(p.gamma + n) + __ldg(p.beta + n);
-                if (p.flags & GEMM_DROP_POST) y *= dropout_scale(p.seed, drop_row + n, p.drop_thresh, p.inv_keep);
+                if (p.flags & GEMM_DROP_POST) y *= dropout_scale(seed, drop_row + n, p.drop_thresh, p.inv_keep);
                 o[i] = y * keep_row;
               }
               float* dst = p.out + rowoff_o + ch * 16;
@@ -527,7 +529,8 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
   // ---- tiling along M and the k loop
   if (g.mode != 2) {
     XVA_CHECK_ARG(g.K >= 1, "gemm: K=%d", g.K);
-    XVA_CHECK_ARG(g.K % 4 == 0, "gemm: K=%d must be a multiple of 4 (16-byte TMA rows)", g.K);
+    // K itself may be ragged (the last 32-wide k-block is zero-filled by TMA); only row strides need 16-byte
+    // alignment, which encode_map checks.
     p.tiles_m = ceil_div(g.R, kBlockM);
     p.k_chunks = ceil_div(g.K, kBlockK);
     p.ZR = 1;
@@ -535,8 +538,13 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
     p.zper = 1;
     p.num_tiles = g.Z * p.tiles_m * p.tiles_n;
   } else {
-    XVA_CHECK_ARG(g.M >= 1 && g.M % 32 == 0, "gemm: wgrad M=%d must be a multiple of 32", g.M);
-    XVA_CHECK_ARG(g.N % 32 == 0, "gemm: wgrad N=%d must be a multiple of 32", g.N);
+    XVA_CHECK_ARG(g.M >= 1, "gemm: wgrad M=%d", g.M);
+    XVA_CHECK_ARG(g.M % 32 == 0 || g.a_rs >= round_up(g.M, 32),
+                  "gemm: MN-major A with M=%d needs M %% 32 == 0 or a row stride >= %d (got %lld)", g.M,
+                  round_up(g.M, 32), (long long)g.a_rs);
+    XVA_CHECK_ARG(g.N % 32 == 0 || g.b_rs >= round_up(g.N, 32),
+                  "gemm: MN-major B with N=%d needs N %% 32 == 0 or a row stride >= %d (got %lld)", g.N,
+                  round_up(g.N, 32), (long long)g.b_rs);
     XVA_CHECK_ARG(g.ZR >= 1 && g.Z % g.ZR == 0, "gemm: Z=%d not divisible by ZR=%d", g.Z, g.ZR);
     p.tiles_m = ceil_div(g.M, kBlockM);
     p.k_chunks = ceil_div(g.R, kBlockK);
@@ -577,28 +585,32 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
     if (g.Z == 1 || str[2] == 0) str[2] = (uint64_t)g.a_rs * a_rows;
     if ((rc = encode_map(&map_a, g.a, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) != XVA_OK) return rc;
   } else {
-    uint64_t dims[4] = {32, (uint64_t)a_rows, (uint64_t)(g.M / 32), (uint64_t)g.Z};
+    uint64_t dims[4] = {32, (uint64_t)a_rows, (uint64_t)ceil_div(g.M, 32), (uint64_t)g.Z};
     uint64_t str[4] = {1, (uint64_t)g.a_rs, 32, (uint64_t)g.a_zs};
     uint32_t box[4] = {32, kBlockK, kBlockM / 32, 1};
     if (g.Z == 1 || str[3] == 0) str[3] = (uint64_t)g.a_rs * a_rows;
     if ((rc = encode_map(&map_a, g.a, 4, dims, str, box, mn_swizzle)) != XVA_OK) return rc;
   }
   if (g.mode == 0) {
-    uint64_t dims[3] = {(uint64_t)g.K, (uint64_t)g.N, (uint64_t)g.b_nz};
+    const int bn_rows = g.b_rows ? g.b_rows : g.N;
+    uint64_t dims[3] = {(uint64_t)g.K, (uint64_t)bn_rows, (uint64_t)g.b_nz};
     uint64_t str[3] = {1, (uint64_t)g.b_rs, (uint64_t)g.b_zs};
     uint32_t box[3] = {kBlockK, (uint32_t)p.n_sub, 1};
-    if (g.b_nz == 1 || str[2] == 0) str[2] = (uint64_t)g.b_rs * g.N;
+    if (g.b_nz == 1 || str[2] == 0) str[2] = (uint64_t)g.b_rs * bn_rows;
     if ((rc = encode_map(&map_b, g.b, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) != XVA_OK) return rc;
   } else if (g.mode == 1) {
-    XVA_CHECK_ARG(g.N % 32 == 0, "gemm: MN-major B needs N %% 32 == 0 (N=%d)", g.N);
-    uint64_t dims[4] = {32, (uint64_t)g.K, (uint64_t)(g.N / 32), (uint64_t)g.b_nz};
+    XVA_CHECK_ARG(g.N % 32 == 0 || g.b_rs >= round_up(g.N, 32),
+                  "gemm: MN-major B with N=%d needs N %% 32 == 0 or a row stride >= %d (got %lld)", g.N,
+                  round_up(g.N, 32), (long long)g.b_rs);
+    const int bk_rows = g.b_rows ? g.b_rows : g.K;
+    uint64_t dims[4] = {32, (uint64_t)bk_rows, (uint64_t)ceil_div(g.N, 32), (uint64_t)g.b_nz};
     uint64_t str[4] = {1, (uint64_t)g.b_rs, 32, (uint64_t)g.b_zs};
     uint32_t box[4] = {32, kBlockK, (uint32_t)(p.n_tile / 32), 1};
-    if (g.b_nz == 1 || str[3] == 0) str[3] = (uint64_t)g.b_rs * g.K;
+    if (g.b_nz == 1 || str[3] == 0) str[3] = (uint64_t)g.b_rs * bk_rows;
     if ((rc = encode_map(&map_b, g.b, 4, dims, str, box, mn_swizzle)) != XVA_OK) return rc;
   } else {
     const int b_rows = g.b_rows ? g.b_rows : g.R;
-    uint64_t dims[4] = {32, (uint64_t)b_rows, (uint64_t)(g.N / 32), (uint64_t)g.Z};
+    uint64_t dims[4] = {32, (uint64_t)b_rows, (uint64_t)ceil_div(g.N, 32), (uint64_t)g.Z};
     uint64_t str[4] = {1, (uint64_t)g.b_rs, 32, (uint64_t)g.b_zs};
     uint32_t box[4] = {32, kBlockK, (uint32_t)(p.n_tile / 32), 1};
     if (g.Z == 1 || str[3] == 0) str[3] = (uint64_t)g.b_rs * b_rows;
@@ -628,6 +640,7 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
   p.ln_mean = g.ln_mean;
   p.ln_rstd = g.ln_rstd;
   p.seed = g.seed;
+  p.seed_dev = g.seed_dev;
   if ((g.flags & (GEMM_DROP_PRE | GEMM_DROP_POST)) && g.drop_p > 0.0f) {
     XVA_CHECK_ARG(g.drop_p < 1.0f, "gemm: dropout p=%f", g.drop_p);
     p.drop_thresh = static_cast<uint32_t>(static_cast<double>(g.drop_p) * 4294967296.0);

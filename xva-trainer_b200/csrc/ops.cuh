@@ -13,23 +13,25 @@ int regulate_gather(const float* enc, const int* cum, int B, int Tt, int C, int 
                     cudaStream_t stream);
 int regulate_scatter(const float* dout, const int* cum, int B, int Tt, int C, int T_out, float* denc, int accumulate,
                      cudaStream_t stream);
-int average_pitch(const float* pitch, const float* durs, int B, int F, int Tm, int Tt, float* out, cudaStream_t stream);
+int average_pitch(const float* pitch, const float* durs, int B, int F, int Tm, int Tt, float* out, int log1p_out,
+                  cudaStream_t stream);
 
 // ---- rowops.cu
-int softmax_fwd(const float* s, const int* lens, int Z, int R, int N, float* p_out, float* pd_out, float drop_p,
-                uint64_t seed, cudaStream_t stream);
-int softmax_bwd(const float* p, float* dpd, int Z, int R, int N, float alpha, float drop_p, uint64_t seed,
-                cudaStream_t stream);
+int softmax_fwd(const float* s, const int* lens, int Z, int R, int N, int ld, float* p_out, float* pd_out, float drop_p,
+                uint64_t seed, const uint64_t* seed_dev, cudaStream_t stream);
+int softmax_bwd(const float* p, float* dpd, int Z, int R, int N, int ld, float alpha, float drop_p, uint64_t seed,
+                const uint64_t* seed_dev, cudaStream_t stream);
 int layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
                   const int* lens, int Z, int R, int C, float* dx, float* dx_drop, float* dgamma, float* dbeta,
                   float* dbias, float drop_post_p, uint64_t seed_post, float drop_pre_p, uint64_t seed_pre,
-                  cudaStream_t stream);
+                  const uint64_t* seed_dev, int relu_gate, cudaStream_t stream);
+int counter_add(unsigned long long* counter, unsigned long long inc, cudaStream_t stream);
 int colsum(const float* x, long rows, int C, long ld, float* out, cudaStream_t stream);
 int embed_pos(const long long* tokens, const float* emb, const float* in, const int* lens, const float* inv_freq,
               int B, int T, int C, float* out, cudaStream_t stream);
 int embed_bwd(const long long* tokens, const float* dout, int B, int T, int C, float* demb, cudaStream_t stream);
-int scalar_conv_add(float* io, const float* x, const float* w, const float* bias, int B, int T, int C,
-                    cudaStream_t stream);
+int scalar_conv_add(float* io, const float* x, const float* w, const float* bias, const int* lens, int B, int T,
+                    int C, cudaStream_t stream);
 int scalar_conv_bwd(const float* dout, const float* x, int B, int T, int C, float* dw, float* dbias,
                     cudaStream_t stream);
 int rowdot_fwd(const float* x, const float* w, const float* bias, const int* lens, int Z, int R, int C, float* out,

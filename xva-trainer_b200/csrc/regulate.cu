@@ -137,7 +137,7 @@ regulate_scatter_kernel(const float* __restrict__ dout, const int* __restrict__ 
 // average_pitch: one warp per (utterance, formant, token). Mean of the non-zero frame values, 0 if none.
 __global__ void __launch_bounds__(128)
 average_pitch_kernel(const float* __restrict__ pitch, const float* __restrict__ durs, int F, int Tm, int Tt,
-                     float* __restrict__ out) {
+                     float* __restrict__ out, int log1p_out) {
   extern __shared__ int s_cum[];
   const int b = blockIdx.y;
   // cumsum(durs).long(): the running sum is accumulated in fp32 and truncated, like torch.cumsum(...).long()
@@ -168,7 +168,11 @@ average_pitch_kernel(const float* __restrict__ pitch, const float* __restrict__ 
     sum += __shfl_xor_sync(0xffffffffu, sum, o);
     cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
   }
-  if (lane == 0) out[(static_cast<long>(b) * F + f) * Tt + j] = cnt > 0 ? sum / static_cast<float>(cnt) : 0.0f;
+  if (lane == 0) {
+    const float mean = cnt > 0 ? sum / static_cast<float>(cnt) : 0.0f;
+    // energy target: torch.log(1.0 + average_pitch(...)), model.py:415
+    out[(static_cast<long>(b) * F + f) * Tt + j] = log1p_out ? logf(1.0f + mean) : mean;
+  }
 }
 
 }  // namespace
@@ -205,10 +209,11 @@ int regulate_scatter(const float* dout, const int* cum, int B, int Tt, int C, in
   return XVA_OK;
 }
 
-int average_pitch(const float* pitch, const float* durs, int B, int F, int Tm, int Tt, float* out, cudaStream_t stream) {
+int average_pitch(const float* pitch, const float* durs, int B, int F, int Tm, int Tt, float* out, int log1p_out,
+                  cudaStream_t stream) {
   XVA_CHECK_ARG((Tt + 1) * 4 <= 48 * 1024, "average_pitch: Tt=%d too long", Tt);
   dim3 grid(ceil_div(F * Tt, 4), B);
-  average_pitch_kernel<<<grid, 128, (Tt + 1) * 4, stream>>>(pitch, durs, F, Tm, Tt, out);
+  average_pitch_kernel<<<grid, 128, (Tt + 1) * 4, stream>>>(pitch, durs, F, Tm, Tt, out, log1p_out);
   XVA_CHECK_LAUNCH();
   return XVA_OK;
 }

@@ -15,6 +15,7 @@ namespace {
 
 constexpr int kWarpsPerBlock = 8;
 constexpr int kMaxColsPerLane = 32;  // rows up to 1024 columns are held in registers (softmax)
+constexpr uint64_t kSeedStep = 0xA24BAED4963EE407ull;  // seed += *seed_dev * kSeedStep (same constant as the tap-GEMM)
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -51,15 +52,16 @@ __device__ __forceinline__ void block_colsum_atomic(const float (&acc)[kColsPerL
 // transformer.py:120-127: masked_fill(key >= len, -inf) -> softmax(dim=2) -> dropout.
 // s [Z,R,N] holds alpha*q.k (written by the tap-GEMM); p_out gets softmax, pd_out (optional) softmax*dropout.
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
-softmax_fwd_kernel(const float* __restrict__ s, const int* __restrict__ lens, int R, int N, long rows,
-                   float* __restrict__ p_out, float* __restrict__ pd_out, uint64_t seed, uint32_t thresh,
-                   float inv_keep) {
+softmax_fwd_kernel(const float* __restrict__ s, const int* __restrict__ lens, int R, int N, int ld, long rows,
+                   float* __restrict__ p_out, float* __restrict__ pd_out, uint64_t seed,
+                   const uint64_t* __restrict__ seed_dev, uint32_t thresh, float inv_keep) {
   const int lane = threadIdx.x & 31;
+  seed += seed_dev ? __ldg(seed_dev) * kSeedStep : 0ull;
   const long row = static_cast<long>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int z = static_cast<int>(row / R);
   const int nk = lens ? min(lens[z], N) : N;
-  const float* src = s + row * N;
+  const float* src = s + row * ld;
   float v[kMaxColsPerLane];
   float mx = -INFINITY;
 #pragma unroll
@@ -80,19 +82,20 @@ softmax_fwd_kernel(const float* __restrict__ s, const int* __restrict__ lens, in
 #pragma unroll
   for (int i = 0; i < kMaxColsPerLane; ++i) {
     const int n = lane + 32 * i;
-    if (n < N) {
+    if (n < ld) {  // pad columns [N, ld) are written as zero: the MN-major consumers multiply them
       const float p = v[i] * inv;
-      p_out[row * N + n] = p;
-      if (pd_out) pd_out[row * N + n] = p * dropout_scale(seed, static_cast<uint64_t>(row) * N + n, thresh, inv_keep);
+      p_out[row * ld + n] = p;
+      if (pd_out) pd_out[row * ld + n] = p * dropout_scale(seed, static_cast<uint64_t>(row) * ld + n, thresh, inv_keep);
     }
   }
 }
 
 // ds = p * (g - sum_n g*p) with g = dpd * dropout_scale   (in place on dpd)
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
-softmax_bwd_kernel(const float* __restrict__ p, float* __restrict__ dpd, int N, long rows, float alpha, uint64_t seed,
-                   uint32_t thresh, float inv_keep) {
+softmax_bwd_kernel(const float* __restrict__ p, float* __restrict__ dpd, int N, int ld, long rows, float alpha, uint64_t seed,
+                   const uint64_t* __restrict__ seed_dev, uint32_t thresh, float inv_keep) {
   const int lane = threadIdx.x & 31;
+  seed += seed_dev ? __ldg(seed_dev) * kSeedStep : 0ull;
   const long row = static_cast<long>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
   if (row >= rows) return;
   float pv[kMaxColsPerLane], gv[kMaxColsPerLane];
@@ -101,8 +104,8 @@ softmax_bwd_kernel(const float* __restrict__ p, float* __restrict__ dpd, int N, 
   for (int i = 0; i < kMaxColsPerLane; ++i) {
     const int n = lane + 32 * i;
     if (n < N) {
-      pv[i] = p[row * N + n];
-      gv[i] = dpd[row * N + n] * dropout_scale(seed, static_cast<uint64_t>(row) * N + n, thresh, inv_keep);
+      pv[i] = p[row * ld + n];
+      gv[i] = dpd[row * ld + n] * dropout_scale(seed, static_cast<uint64_t>(row) * ld + n, thresh, inv_keep);
     } else {
       pv[i] = 0.0f;
       gv[i] = 0.0f;
@@ -113,7 +116,7 @@ softmax_bwd_kernel(const float* __restrict__ p, float* __restrict__ dpd, int N, 
 #pragma unroll
   for (int i = 0; i < kMaxColsPerLane; ++i) {
     const int n = lane + 32 * i;
-    if (n < N) dpd[row * N + n] = alpha * pv[i] * (gv[i] - dot);
+    if (n < ld) dpd[row * ld + n] = (n < N) ? alpha * pv[i] * (gv[i] - dot) : 0.0f;
   }
 }
 
@@ -130,8 +133,13 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
                      int R, int C, long rows, float* __restrict__ dx, float* __restrict__ dx_drop,
                      float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias,
                      uint64_t seed_post, uint32_t thresh_post, float inv_keep_post, uint64_t seed_pre,
-                     uint32_t thresh_pre, float inv_keep_pre) {
+                     uint32_t thresh_pre, float inv_keep_pre, const uint64_t* __restrict__ seed_dev, int relu_gate) {
   __shared__ float red[kWarpsPerBlock][32 * kColsPerLane + 1];
+  if (seed_dev) {
+    const uint64_t add = __ldg(seed_dev) * kSeedStep;
+    seed_post += add;
+    seed_pre += add;
+  }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float gm[kColsPerLane], acc_g[kColsPerLane], acc_b[kColsPerLane], acc_bias[kColsPerLane];
 #pragma unroll
@@ -148,6 +156,7 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
     const float mu = mean[row], rs = rstd[row];
     float xh[kColsPerLane], g[kColsPerLane];
     float s1 = 0.0f, s2 = 0.0f;
+    uint32_t pos = 0u;
 #pragma unroll
     for (int i = 0; i < kColsPerLane; ++i) {
       const int n = lane + 32 * i;
@@ -155,7 +164,9 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
       xh[i] = 0.0f;
       if (n < C && live) {
         d = dy[row * C + n] * dropout_scale(seed_post, static_cast<uint64_t>(row) * C + n, thresh_post, inv_keep_post);
-        xh[i] = (x[row * C + n] - mu) * rs;
+        const float xv = x[row * C + n];
+        xh[i] = (xv - mu) * rs;
+        pos |= (xv > 0.0f ? 1u : 0u) << i;
       }
       acc_g[i] += d * xh[i];
       acc_b[i] += d;
@@ -169,7 +180,9 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
     for (int i = 0; i < kColsPerLane; ++i) {
       const int n = lane + 32 * i;
       if (n < C) {
-        const float v = rs * (g[i] - s1 - xh[i] * s2);
+        float v = rs * (g[i] - s1 - xh[i] * s2);
+        // ConvReLUNorm (common/layers.py:94-97): x is the ReLU output, so the gradient passes only where x > 0
+        if (relu_gate && !((pos >> i) & 1u)) v = 0.0f;
         dx[row * C + n] = v;
         if (dx_drop) {
           const float vd = v * dropout_scale(seed_pre, static_cast<uint64_t>(row) * C + n, thresh_pre, inv_keep_pre);
@@ -259,11 +272,12 @@ embed_bwd_kernel(const long long* __restrict__ tokens, const float* __restrict__
 // (model.py:403-404,417-418). x [B,T]; w [C,3].
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 scalar_conv_add_kernel(float* __restrict__ io, const float* __restrict__ x, const float* __restrict__ w,
-                       const float* __restrict__ bias, int T, int C, long rows) {
+                       const float* __restrict__ bias, const int* __restrict__ lens, int T, int C, long rows) {
   const int lane = threadIdx.x & 31;
   const long row = static_cast<long>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int t = static_cast<int>(row % T);
+  if (lens && t >= lens[row / T]) return;  // padded token rows stay untouched (zero): nothing downstream reads them
   const float x0 = t > 0 ? x[row - 1] : 0.0f, x1 = x[row], x2 = t + 1 < T ? x[row + 1] : 0.0f;
   for (int c = lane; c < C; c += 32)
     io[row * C + c] += bias[c] + w[c * 3] * x0 + w[c * 3 + 1] * x1 + w[c * 3 + 2] * x2;
@@ -356,6 +370,8 @@ rowdot_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ x, c
   }
 }
 
+__global__ void counter_add_kernel(unsigned long long* c, unsigned long long inc) { *c += inc; }
+
 inline void drop_consts(float p, uint32_t* thresh, float* inv_keep) {
   if (p > 0.0f) {
     *thresh = static_cast<uint32_t>(static_cast<double>(p) * 4294967296.0);
@@ -370,27 +386,30 @@ inline int row_blocks(long rows) { return static_cast<int>(ceil_div_l(rows, kWar
 
 }  // namespace
 
-int softmax_fwd(const float* s, const int* lens, int Z, int R, int N, float* p_out, float* pd_out, float drop_p,
-                uint64_t seed, cudaStream_t stream) {
-  XVA_CHECK_ARG(N >= 1 && N <= 32 * kMaxColsPerLane, "softmax: N=%d out of range (max %d)", N, 32 * kMaxColsPerLane);
+int softmax_fwd(const float* s, const int* lens, int Z, int R, int N, int ld, float* p_out, float* pd_out, float drop_p,
+                uint64_t seed, const uint64_t* seed_dev, cudaStream_t stream) {
+  if (ld <= 0) ld = N;
+  XVA_CHECK_ARG(N >= 1 && ld >= N && ld <= 32 * kMaxColsPerLane, "softmax: N=%d ld=%d out of range (max %d)", N, ld,
+                32 * kMaxColsPerLane);
   XVA_CHECK_ARG(drop_p >= 0.0f && drop_p < 1.0f, "softmax: dropout p=%f", drop_p);
   uint32_t th;
   float ik;
   drop_consts(pd_out ? drop_p : 0.0f, &th, &ik);
   const long rows = static_cast<long>(Z) * R;
-  softmax_fwd_kernel<<<row_blocks(rows), kWarpsPerBlock * 32, 0, stream>>>(s, lens, R, N, rows, p_out, pd_out, seed, th, ik);
+  softmax_fwd_kernel<<<row_blocks(rows), kWarpsPerBlock * 32, 0, stream>>>(s, lens, R, N, ld, rows, p_out, pd_out, seed, seed_dev, th, ik);
   XVA_CHECK_LAUNCH();
   return XVA_OK;
 }
 
-int softmax_bwd(const float* p, float* dpd, int Z, int R, int N, float alpha, float drop_p, uint64_t seed,
-                cudaStream_t stream) {
-  XVA_CHECK_ARG(N >= 1 && N <= 32 * kMaxColsPerLane, "softmax bwd: N=%d out of range", N);
+int softmax_bwd(const float* p, float* dpd, int Z, int R, int N, int ld, float alpha, float drop_p, uint64_t seed,
+                const uint64_t* seed_dev, cudaStream_t stream) {
+  if (ld <= 0) ld = N;
+  XVA_CHECK_ARG(N >= 1 && ld >= N && ld <= 32 * kMaxColsPerLane, "softmax bwd: N=%d ld=%d out of range", N, ld);
   uint32_t th;
   float ik;
   drop_consts(drop_p, &th, &ik);
   const long rows = static_cast<long>(Z) * R;
-  softmax_bwd_kernel<<<row_blocks(rows), kWarpsPerBlock * 32, 0, stream>>>(p, dpd, N, rows, alpha, seed, th, ik);
+  softmax_bwd_kernel<<<row_blocks(rows), kWarpsPerBlock * 32, 0, stream>>>(p, dpd, N, ld, rows, alpha, seed, seed_dev, th, ik);
   XVA_CHECK_LAUNCH();
   return XVA_OK;
 }
@@ -398,7 +417,7 @@ int softmax_bwd(const float* p, float* dpd, int Z, int R, int N, float alpha, fl
 int layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
                   const int* lens, int Z, int R, int C, float* dx, float* dx_drop, float* dgamma, float* dbeta,
                   float* dbias, float drop_post_p, uint64_t seed_post, float drop_pre_p, uint64_t seed_pre,
-                  cudaStream_t stream) {
+                  const uint64_t* seed_dev, int relu_gate, cudaStream_t stream) {
   XVA_CHECK_ARG(C >= 1 && C <= 512, "layernorm bwd: C=%d (max 512)", C);
   uint32_t th_post, th_pre;
   float ik_post, ik_pre;
@@ -411,7 +430,8 @@ int layernorm_bwd(const float* dy, const float* x, const float* mean, const floa
 #define XVA_LN_BWD(CPL)                                                                                           \
   layernorm_bwd_kernel<CPL><<<grid, kWarpsPerBlock * 32, 0, stream>>>(dy, x, mean, rstd, gamma, lens, R, C, rows, \
                                                                       dx, dx_drop, dgamma, dbeta, dbias, seed_post, \
-                                                                      th_post, ik_post, seed_pre, th_pre, ik_pre)
+                                                                      th_post, ik_post, seed_pre, th_pre, ik_pre, \
+                                                                      seed_dev, relu_gate)
   if (C <= 256) XVA_LN_BWD(8);
   else if (C <= 384) XVA_LN_BWD(12);
   else XVA_LN_BWD(16);
@@ -450,10 +470,10 @@ int embed_bwd(const long long* tokens, const float* dout, int B, int T, int C, f
   return XVA_OK;
 }
 
-int scalar_conv_add(float* io, const float* x, const float* w, const float* bias, int B, int T, int C,
+int scalar_conv_add(float* io, const float* x, const float* w, const float* bias, const int* lens, int B, int T, int C,
                     cudaStream_t stream) {
   const long rows = static_cast<long>(B) * T;
-  scalar_conv_add_kernel<<<row_blocks(rows), kWarpsPerBlock * 32, 0, stream>>>(io, x, w, bias, T, C, rows);
+  scalar_conv_add_kernel<<<row_blocks(rows), kWarpsPerBlock * 32, 0, stream>>>(io, x, w, bias, lens, T, C, rows);
   XVA_CHECK_LAUNCH();
   return XVA_OK;
 }
@@ -488,6 +508,12 @@ int rowdot_bwd(const float* dout, const float* x, const float* w, const int* len
   if (grid < 1) grid = 1;
   if (C <= 256) rowdot_bwd_kernel<8><<<grid, kWarpsPerBlock * 32, 0, stream>>>(dout, x, w, lens, R, C, rows, dx, dw, db);
   else rowdot_bwd_kernel<16><<<grid, kWarpsPerBlock * 32, 0, stream>>>(dout, x, w, lens, R, C, rows, dx, dw, db);
+  XVA_CHECK_LAUNCH();
+  return XVA_OK;
+}
+
+int counter_add(unsigned long long* counter, unsigned long long inc, cudaStream_t stream) {
+  counter_add_kernel<<<1, 1, 0, stream>>>(counter, inc);
   XVA_CHECK_LAUNCH();
   return XVA_OK;
 }

@@ -1,0 +1,665 @@
+"""B200-native FastPitch 1.1 training path: the reference's ``FastPitch`` / ``FastPitchLoss`` / ``Lamb`` surface, with
+every tensor operation issued through the C ABI of libxva_b200.so (tcgen05 tap-GEMMs + HBM row kernels).
+
+Mirrors (names, argument meaning, outputs) of the reference, paths relative to python/fastpitch1_1/ :
+    FastPitch            fastpitch/model.py:125-390      (forward -> the 13-list of model.py:388-390)
+    FastPitchLoss        fastpitch/loss_function.py:29-154
+    Lamb                 lamb.py:8-106                    (+ clip_grad_norm_ of xva_train.py:857)
+    noam learning rate   xva_train.py:1252-1261
+
+What differs by design (B200-first):
+  * activations are channels-last [B, T, C] fp32 in HBM; the dense contractions run as tf32 tcgen05 MMAs with fp32
+    accumulation, the rest as coalesced fp32 row kernels; nothing here calls a torch math op on an activation;
+  * there is no autograd graph: forward() records the activations it needs and backward() walks the layers in
+    reverse, writing weight gradients straight into a flat gradient arena that the multi-tensor LAMB consumes;
+  * parameters live in one flat fp32 arena in the layout the kernels read (conv weights as [taps, Cout, Cin]);
+    state_dict() / load_state_dict() convert to and from the reference's keys and shapes, so checkpoints interchange;
+  * padding must be trailing (tokens != 0 is a prefix of each row) -- true for every batch the reference's collate
+    builds (data_function.py:565-695).
+There is no CPU or eager fallback: without the CUDA library every call raises.
+"""
+import math
+from collections import OrderedDict
+
+import torch
+
+from . import capi, ops
+
+D_MODEL, D_HEAD, D_INNER, N_LAYERS, N_MEL, N_SYMBOLS, D_PRED = 384, 64, 1536, 6, 80, 148, 256
+P_DROP = 0.1            # p_{in,out}_fft_dropout, dropatt, predictor dropout: model.py:131-179
+K3 = (-1, 0, 1)         # row shifts of a kernel-3, padding-1 convolution
+_ALIGN = 64             # arena entries start on 256-byte boundaries (TMA needs 16)
+
+
+def _state_spec():
+    """(key, reference shape) for every FastPitch().state_dict() entry, in the reference's order (model.py:125-265)."""
+    spec = [("pitch_mean", (1,)), ("pitch_std", (1,))]
+
+    def fft(prefix, embed):
+        out = []
+        if embed:
+            out.append((f"{prefix}.word_emb.weight", (N_SYMBOLS, D_MODEL)))
+        out.append((f"{prefix}.pos_emb.inv_freq", (D_MODEL // 2,)))
+        for i in range(N_LAYERS):
+            p = f"{prefix}.layers.{i}"
+            out += [(f"{p}.dec_attn.qkv_net.weight", (3 * D_HEAD, D_MODEL)), (f"{p}.dec_attn.qkv_net.bias", (3 * D_HEAD,)),
+                    (f"{p}.dec_attn.o_net.weight", (D_MODEL, D_HEAD)),
+                    (f"{p}.dec_attn.layer_norm.weight", (D_MODEL,)), (f"{p}.dec_attn.layer_norm.bias", (D_MODEL,)),
+                    (f"{p}.pos_ff.CoreNet.0.weight", (D_INNER, D_MODEL, 3)), (f"{p}.pos_ff.CoreNet.0.bias", (D_INNER,)),
+                    (f"{p}.pos_ff.CoreNet.2.weight", (D_MODEL, D_INNER, 3)), (f"{p}.pos_ff.CoreNet.2.bias", (D_MODEL,)),
+                    (f"{p}.pos_ff.layer_norm.weight", (D_MODEL,)), (f"{p}.pos_ff.layer_norm.bias", (D_MODEL,))]
+        return out
+
+    def predictor(prefix):
+        out = []
+        for i, cin in enumerate((D_MODEL, D_PRED)):
+            p = f"{prefix}.layers.{i}"
+            out += [(f"{p}.conv.weight", (D_PRED, cin, 3)), (f"{p}.conv.bias", (D_PRED,)),
+                    (f"{p}.norm.weight", (D_PRED,)), (f"{p}.norm.bias", (D_PRED,))]
+        out += [(f"{prefix}.fc.weight", (1, D_PRED)), (f"{prefix}.fc.bias", (1,))]
+        return out
+
+    spec += fft("encoder", True)
+    spec += predictor("duration_predictor")
+    spec += fft("decoder", False)
+    spec += predictor("pitch_predictor")
+    spec += [("pitch_emb.weight", (D_MODEL, 1, 3)), ("pitch_emb.bias", (D_MODEL,))]
+    spec += predictor("energy_predictor")
+    spec += [("energy_emb.weight", (D_MODEL, 1, 3)), ("energy_emb.bias", (D_MODEL,))]
+    spec += [("proj.weight", (N_MEL, D_MODEL)), ("proj.bias", (N_MEL,))]
+    spec += [("attention.query_proj.0.conv.weight", (160, 80, 3)), ("attention.query_proj.0.conv.bias", (160,)),
+             ("attention.query_proj.2.conv.weight", (80, 160, 1)), ("attention.query_proj.2.conv.bias", (80,)),
+             ("attention.query_proj.4.conv.weight", (80, 80, 1)), ("attention.query_proj.4.conv.bias", (80,)),
+             ("attention.attn_proj.weight", (1, 80, 1, 1)), ("attention.attn_proj.bias", (1,)),
+             ("attention.key_proj.0.conv.weight", (768, 384, 3)), ("attention.key_proj.0.conv.bias", (768,)),
+             ("attention.key_proj.2.conv.weight", (80, 768, 1)), ("attention.key_proj.2.conv.bias", (80,))]
+    return spec
+
+
+BUFFERS = ("pitch_mean", "pitch_std", "encoder.pos_emb.inv_freq", "decoder.pos_emb.inv_freq")
+
+
+def _packed_shape(key, shape):
+    """Kernel-side layout of a reference tensor: Conv1d [Cout, Cin, k] -> [k, Cout, Cin]; Linear [N, K] -> [1, N, K];
+    the 1 -> C scalar convs and C -> 1 projections are flat."""
+    if key.endswith("_emb.weight") and len(shape) == 3 and shape[1] == 1:
+        return (shape[0], shape[2])
+    if key.endswith(".fc.weight"):
+        return (shape[1],)
+    if len(shape) == 3:
+        return (shape[2], shape[0], shape[1])
+    if len(shape) == 2 and not key.endswith("word_emb.weight"):
+        return (1, shape[0], shape[1])
+    return tuple(shape)
+
+
+def _to_packed(key, ref):
+    shape = tuple(ref.shape)
+    ps = _packed_shape(key, shape)
+    if len(shape) == 3 and len(ps) == 3 and not key.endswith("_emb.weight"):
+        return ref.permute(2, 0, 1).contiguous()
+    return ref.reshape(ps)
+
+
+def _to_ref(key, packed, ref_shape):
+    if len(ref_shape) == 3 and packed.dim() == 3 and not key.endswith("_emb.weight"):
+        return packed.permute(1, 2, 0).contiguous()
+    return packed.reshape(ref_shape).clone()
+
+
+def trainable_keys(stage):
+    """Parameter keys that receive gradients in a training stage (freezing of xva_train.py:607-669)."""
+    keys = [k for k, _ in _state_spec() if k not in BUFFERS]
+
+    def under(*prefixes):
+        return [k for k in keys if any(k.startswith(p + ".") for p in prefixes)]
+
+    if stage == 2:
+        return under("encoder", "duration_predictor")
+    if stage == 3:
+        return [k for k in keys if not (k.startswith("attention.") or k.startswith("duration_predictor."))]
+    if stage == 4:
+        return under("encoder", "decoder", "energy_emb", "proj")
+    raise NotImplementedError(f"training stage {stage}: the stage-1 aligner (attention.py / alignment.py) is not part of "
+                              "this build yet (SURVEY.md section 8f rank 2)")
+
+
+class _Arena:
+    """Flat fp32 storage for parameters (p), gradients (g) and the two LAMB moments (m, v), one layout for all four."""
+
+    def __init__(self, device):
+        self.spec = [(k, s) for k, s in _state_spec() if k not in BUFFERS]
+        self.offset, self.pshape, self.rshape = {}, {}, {}
+        off = 0
+        for k, s in self.spec:
+            ps = _packed_shape(k, s)
+            n = int(math.prod(ps))
+            self.offset[k], self.pshape[k], self.rshape[k] = off, ps, tuple(s)
+            off += (n + _ALIGN - 1) // _ALIGN * _ALIGN
+        self.numel = off
+        self.p = torch.zeros(off, device=device, dtype=torch.float32)
+        self.g = torch.zeros(off, device=device, dtype=torch.float32)
+        self.m = None
+        self.v = None
+
+    def view(self, flat, key):
+        o, ps = self.offset[key], self.pshape[key]
+        return flat[o:o + int(math.prod(ps))].view(ps)
+
+
+class _NS:
+    """attribute bag"""
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+class FastPitch(torch.nn.Module):
+    """Drop-in for the reference ``FastPitch`` (fastpitch/model.py:125): same constructor argument, ``training_stage``
+    attribute, ``pitch_mean`` / ``pitch_std`` buffers, ``forward(inputs_x, ...)`` -> 13-list, state_dict keys and shapes.
+
+    Training adds ``backward(criterion, scale)`` (the hand-written reverse pass; there is no autograd graph)."""
+
+    def __init__(self, logger=None, device=None, seed=1234):
+        super().__init__()
+        self.logger = logger
+        self.training_stage = 3
+        self.device_ = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        if self.device_.type != "cuda":
+            raise capi.XvaError("FastPitch (B200 build) needs a CUDA device: there is no CPU path")
+        capi.load()
+        capi.call("xva_device_check", self.device_.index or 0)
+        self.arena = _Arena(self.device_)
+        dev = self.device_
+        self.pitch_mean = torch.zeros(1, device=dev)
+        self.pitch_std = torch.zeros(1, device=dev)
+        self.inv_freq = (1.0 / (10000 ** (torch.arange(0.0, D_MODEL, 2.0) / D_MODEL))).to(dev)
+        self.p_drop = P_DROP
+        self.seed = int(seed)
+        self.step_counter = torch.zeros(1, device=dev, dtype=torch.int64)  # device-side dropout counter (uint64 bits)
+        self._site = 0
+        self._ctx = None
+        self._bind()
+        self.reset_parameters(seed)
+
+    # ------------------------------------------------------------------------------------------ parameters
+    def _bind(self):
+        """Name the packed parameter / gradient views the kernels read."""
+        A = self.arena
+        W = lambda k: A.view(A.p, k)
+        G = lambda k: A.view(A.g, k)
+
+        def fft(prefix):
+            layers = []
+            for i in range(N_LAYERS):
+                p = f"{prefix}.layers.{i}"
+                names = dict(qkv_w=f"{p}.dec_attn.qkv_net.weight", qkv_b=f"{p}.dec_attn.qkv_net.bias",
+                             o_w=f"{p}.dec_attn.o_net.weight", ln1_g=f"{p}.dec_attn.layer_norm.weight",
+                             ln1_b=f"{p}.dec_attn.layer_norm.bias", w1=f"{p}.pos_ff.CoreNet.0.weight",
+                             b1=f"{p}.pos_ff.CoreNet.0.bias", w2=f"{p}.pos_ff.CoreNet.2.weight",
+                             b2=f"{p}.pos_ff.CoreNet.2.bias", ln2_g=f"{p}.pos_ff.layer_norm.weight",
+                             ln2_b=f"{p}.pos_ff.layer_norm.bias")
+                layers.append(_NS(w=_NS(**{n: W(k) for n, k in names.items()}), g=_NS(**{n: G(k) for n, k in names.items()})))
+            return layers
+
+        def predictor(prefix):
+            names = {}
+            for i in range(2):
+                p = f"{prefix}.layers.{i}"
+                names.update({f"w{i}": f"{p}.conv.weight", f"b{i}": f"{p}.conv.bias", f"g{i}": f"{p}.norm.weight",
+                              f"be{i}": f"{p}.norm.bias"})
+            names.update(fc_w=f"{prefix}.fc.weight", fc_b=f"{prefix}.fc.bias")
+            return _NS(w=_NS(**{n: W(k) for n, k in names.items()}), g=_NS(**{n: G(k) for n, k in names.items()}))
+
+        self.enc_layers, self.dec_layers = fft("encoder"), fft("decoder")
+        self.pred = {n: predictor(f"{n}_predictor") for n in ("duration", "pitch", "energy")}
+        misc = dict(emb="encoder.word_emb.weight", pitch_emb_w="pitch_emb.weight", pitch_emb_b="pitch_emb.bias",
+                    energy_emb_w="energy_emb.weight", energy_emb_b="energy_emb.bias", proj_w="proj.weight",
+                    proj_b="proj.bias")
+        self.w = _NS(**{n: W(k) for n, k in misc.items()})
+        self.g = _NS(**{n: G(k) for n, k in misc.items()})
+
+    def reset_parameters(self, seed=1234):
+        """Seeded init with torch's default fan-in scales (what nn.Conv1d / nn.Linear / nn.Embedding / nn.LayerNorm do
+        in the reference constructor); generated on the CPU so it is identical on every rank and machine."""
+        g = torch.Generator().manual_seed(int(seed))
+        sd = OrderedDict()
+        for key, shape in _state_spec():
+            if key in BUFFERS:
+                continue
+            if ".layer_norm." in key or ".norm." in key:
+                sd[key] = torch.ones(shape) if key.endswith("weight") else torch.zeros(shape)
+            elif key.endswith("word_emb.weight"):
+                w = torch.randn(shape, generator=g)
+                w[0] = 0.0
+                sd[key] = w
+            else:
+                wshape = shape
+                if key.endswith(".bias"):
+                    wkey = key[:-4] + "weight"
+                    wshape = dict(_state_spec())[wkey]
+                fan_in = int(math.prod(wshape[1:]))
+                bound = 1.0 / math.sqrt(fan_in)
+                sd[key] = (torch.rand(shape, generator=g) * 2 - 1) * bound
+        self.load_state_dict(sd, strict=False)
+
+    def state_dict(self, *args, destination=None, prefix="", keep_vars=False):
+        """The reference's 185 keys with the reference's shapes (conv weights back in [Cout, Cin, k])."""
+        out = OrderedDict() if destination is None else destination
+        A = self.arena
+        for key, shape in _state_spec():
+            if key == "pitch_mean":
+                t = self.pitch_mean.clone()
+            elif key == "pitch_std":
+                t = self.pitch_std.clone()
+            elif key.endswith("inv_freq"):
+                t = self.inv_freq.clone()
+            else:
+                t = _to_ref(key, A.view(A.p, key), tuple(shape))
+            out[prefix + key] = t
+        return out
+
+    def load_state_dict(self, state_dict, strict=True):
+        A = self.arena
+        known = dict(_state_spec())
+        missing = [k for k in known if k not in state_dict]
+        unexpected = [k for k in state_dict if k not in known]
+        if strict and (missing or unexpected):
+            raise RuntimeError(f"load_state_dict: missing {missing[:5]} unexpected {unexpected[:5]}")
+        with torch.no_grad():
+            for key, t in state_dict.items():
+                if key not in known:
+                    continue
+                t = t.detach().to(torch.float32)
+                if tuple(t.shape) != tuple(known[key]):
+                    raise RuntimeError(f"load_state_dict: {key} has shape {tuple(t.shape)}, expected {tuple(known[key])}")
+                if key == "pitch_mean":
+                    self.pitch_mean.copy_(t)
+                elif key == "pitch_std":
+                    self.pitch_std.copy_(t)
+                elif key.endswith("inv_freq"):
+                    self.inv_freq.copy_(t)
+                else:
+                    A.view(A.p, key).copy_(_to_packed(key, t))
+        return torch.nn.modules.module._IncompatibleKeys(missing, unexpected)
+
+    def grads(self, keys=None):
+        """{reference key: gradient in the reference's shape} for the given (default: all) parameter keys."""
+        A = self.arena
+        keys = [k for k, _ in A.spec] if keys is None else keys
+        return {k: _to_ref(k, A.view(A.g, k), A.rshape[k]) for k in keys}
+
+    def zero_grad(self, set_to_none=True):
+        self.arena.g.zero_()
+
+    def parameters(self, recurse=True):  # the arena is the one parameter tensor (what an optimizer / DDP bucket sees)
+        return iter([self.arena.p])
+
+    def to(self, *a, **k):
+        return self
+
+    # ------------------------------------------------------------------------------------------ dropout bookkeeping
+    def _drop(self):
+        """(p, seed) for the next dropout site of this pass; p = 0 outside training. Sites are numbered in call order,
+        so backward re-derives the same masks from the numbers it saved."""
+        self._site += 1
+        p = self.p_drop if self.training else 0.0
+        return p, (self.seed * 0x9E3779B1 + self._site * 0x85EBCA77) & 0xFFFFFFFFFFFF
+
+    # ------------------------------------------------------------------------------------------ FFT block
+    def _layer_fwd(self, x, lens, L, save):
+        """TransformerLayer.forward, transformer.py:164-171 = MultiHeadAttn :100-152 + PositionwiseConvFF :59-77."""
+        B, T, _ = x.shape
+        sd = self.step_counter
+        qkv = ops.conv_fwd(x, L.w.qkv_w, bias=L.w.qkv_b)
+        q, k, v = qkv[..., :D_HEAD], qkv[..., D_HEAD:2 * D_HEAD], qkv[..., 2 * D_HEAD:]
+        Tp = (T + 31) // 32 * 32
+        s = torch.empty(B, T, Tp, device=x.device, dtype=torch.float32)
+        ops.bmm_nt(q, k, alpha=1.0 / math.sqrt(D_HEAD), out=s[..., :T])
+        p_att, seed_att = self._drop()
+        P, Pd = ops.softmax_fwd(s, lens, T, p_att, seed_att, sd)
+        del s
+        vec = ops.bmm_nn(Pd[..., :T], v)
+        p1, seed1 = self._drop()
+        y1, sv1 = ops.conv_fwd(vec, L.w.o_w, residual=x, ln=(L.w.ln1_g, L.w.ln1_b), save_ln=True, lens=lens,
+                               drop_p=p1, seed=seed1, seed_dev=sd)
+        h = ops.conv_fwd(y1, L.w.w1, K3, bias=L.w.b1, relu=True)
+        p2, seed2 = self._drop()
+        y2, sv2 = ops.conv_fwd(h, L.w.w2, K3, bias=L.w.b2, residual=y1, ln=(L.w.ln2_g, L.w.ln2_b), save_ln=True,
+                               lens=lens, drop_p=p2, seed=seed2, seed_dev=sd)
+        if save is not None:
+            save.append(_NS(x=x, qkv=qkv, P=P, Pd=Pd, vec=vec, sv1=sv1, y1=y1, h=h, sv2=sv2, T=T, att=(p_att, seed_att),
+                            d1=(p1, seed1), d2=(p2, seed2)))
+        return y2
+
+    def _layer_bwd(self, dy, lens, L, c, need_dx=True):
+        sd = self.step_counter
+        x, qkv = c.x, c.qkv
+        B, T, _ = x.shape
+        q, k, v = qkv[..., :D_HEAD], qkv[..., D_HEAD:2 * D_HEAD], qkv[..., 2 * D_HEAD:]
+        # ---- PositionwiseConvFF
+        dx2, dbr2 = ops.layernorm_bwd(dy, c.sv2, L.w.ln2_g, lens, L.g.ln2_g, L.g.ln2_b, dbias=L.g.b2, want_drop=True,
+                                      drop_pre_p=c.d2[0], seed_pre=c.d2[1], seed_dev=sd)
+        ops.conv_wgrad(dbr2, c.h, K3, out=L.g.w2, accumulate=True)
+        dh = ops.conv_dgrad(dbr2, L.w.w2, K3, gate=c.h)
+        del dbr2
+        ops.conv_wgrad(dh, c.y1, K3, out=L.g.w1, accumulate=True)
+        ops.colsum_(B * T, D_INNER, D_INNER, dh, L.g.b1)
+        dy1 = ops.conv_dgrad(dh, L.w.w1, K3, residual=dx2)
+        del dh, dx2
+        # ---- MultiHeadAttn
+        dx1, dbr1 = ops.layernorm_bwd(dy1, c.sv1, L.w.ln1_g, lens, L.g.ln1_g, L.g.ln1_b, dbias=None, want_drop=True,
+                                      drop_pre_p=c.d1[0], seed_pre=c.d1[1], seed_dev=sd)
+        ops.conv_wgrad(dbr1, c.vec, (0,), out=L.g.o_w, accumulate=True)
+        dvec = ops.conv_dgrad(dbr1, L.w.o_w)
+        dqkv = torch.empty_like(qkv)
+        Tp = c.P.shape[2]
+        dP = torch.empty(B, T, Tp, device=x.device, dtype=torch.float32)
+        ops.bmm_nt(dvec, v, out=dP[..., :T])
+        ops.bmm_tn(c.Pd[..., :T], dvec, out=dqkv[..., 2 * D_HEAD:])
+        ops.softmax_bwd_(c.P, dP, T, 1.0 / math.sqrt(D_HEAD), c.att[0], c.att[1], sd)
+        ops.bmm_nn(dP[..., :T], k, out=dqkv[..., :D_HEAD])
+        ops.bmm_tn(dP[..., :T], q, out=dqkv[..., D_HEAD:2 * D_HEAD])
+        del dP
+        ops.conv_wgrad(dqkv, x, (0,), out=L.g.qkv_w, accumulate=True)
+        ops.colsum_(B * T, 3 * D_HEAD, 3 * D_HEAD, dqkv, L.g.qkv_b)
+        if not need_dx:
+            return None
+        return ops.conv_dgrad(dqkv, L.w.qkv_w, residual=dx1)
+
+    # ------------------------------------------------------------------------------------------ temporal predictor
+    def _pred_fwd(self, x, lens, P, save):
+        """TemporalPredictor.forward, model.py:118-122 (ConvReLUNorm common/layers.py:94-97). x is already zero on
+        padded rows (= enc_out * mask). -> [B, Tt]"""
+        pa, sa = self._drop()
+        h1, s1 = ops.conv_fwd(x, P.w.w0, K3, bias=P.w.b0, relu=True, ln=(P.w.g0, P.w.be0), save_ln=True, drop_p=pa,
+                              drop_post=True, seed=sa, seed_dev=self.step_counter)
+        pb, sb = self._drop()
+        h2, s2 = ops.conv_fwd(h1, P.w.w1, K3, bias=P.w.b1, relu=True, ln=(P.w.g1, P.w.be1), save_ln=True, drop_p=pb,
+                              drop_post=True, seed=sb, seed_dev=self.step_counter)
+        out = ops.rowdot_fwd(h2, P.w.fc_w, P.w.fc_b, lens)
+        if save is not None:
+            save.update(x=x, h1=h1, s1=s1, h2=h2, s2=s2, da=(pa, sa), db=(pb, sb))
+        return out
+
+    def _pred_bwd(self, dpred, lens, P, c, residual=None):
+        """-> gradient wrt the predictor input (+ residual), zero on padded rows."""
+        sd = self.step_counter
+        dh2 = ops.rowdot_bwd(dpred, c["h2"], P.w.fc_w, lens, P.g.fc_w, P.g.fc_b)
+        dc2, _ = ops.layernorm_bwd(dh2, c["s2"], P.w.g1, None, P.g.g1, P.g.be1, dbias=P.g.b1, drop_post_p=c["db"][0],
+                                   seed_post=c["db"][1], seed_dev=sd, relu_gate=True)
+        ops.conv_wgrad(dc2, c["h1"], K3, out=P.g.w1, accumulate=True)
+        dh1 = ops.conv_dgrad(dc2, P.w.w1, K3)
+        dc1, _ = ops.layernorm_bwd(dh1, c["s1"], P.w.g0, None, P.g.g0, P.g.be0, dbias=P.g.b0, drop_post_p=c["da"][0],
+                                   seed_post=c["da"][1], seed_dev=sd, relu_gate=True)
+        ops.conv_wgrad(dc1, c["x"], K3, out=P.g.w0, accumulate=True)
+        return ops.conv_dgrad(dc1, P.w.w0, K3, residual=residual, lens=lens)
+
+    # ------------------------------------------------------------------------------------------ forward
+    def forward(self, inputs_x, use_gt_pitch=True, use_dur_tgt=False, pace=1.0, max_duration=75, host_lens=None):
+        """FastPitch.forward, model.py:325-390, training stages 2-4. ``inputs_x`` is the 12-list of
+        data_function.py:737-738. ``host_lens`` = (mel_max_len, max(dec_lens)) as Python ints lets a caller that already
+        knows them on the host (the collate does) skip the two device->host reads the reference makes (model.py:330,
+        :75). Returns the reference's 13-list; with the module in training mode the activations backward() needs are
+        kept until the next forward()."""
+        (inputs, input_lens, mel_tgt, mel_lens, pitch_dense, energy_dense, speaker, attn_prior, durs_padded,
+         max_inp_lengths, max_mel_lengths, audiopaths) = inputs_x
+        stage = self.training_stage
+        if stage not in (2, 3, 4):
+            trainable_keys(stage)
+        if not use_gt_pitch:
+            raise NotImplementedError("use_gt_pitch=False is the inference path (FastPitch.infer), not part of training")
+        dev = self.device_
+        self._site = 0
+        ctx = _NS(stage=stage, enc=[], dec=[], preds={}) if self.training else None
+        save = (lambda name: ctx.preds.setdefault(name, {})) if ctx is not None else (lambda name: None)
+        B, Tt = inputs.shape
+        tokens = inputs.to(torch.int64).contiguous()
+        in_lens32 = input_lens.to(torch.int32)
+
+        # ---- encoder (FFTransformer.forward, transformer.py:212-243)
+        x = ops.embed_pos(tokens, self.w.emb, None, None, self.inv_freq, B, Tt, D_MODEL)
+        for L in self.enc_layers:
+            x = self._layer_fwd(x, in_lens32, L, ctx.enc if ctx is not None else None)
+        enc_out = x
+        dur_tgt = durs_padded
+        if ctx is not None:
+            ctx.tokens, ctx.in_lens, ctx.B, ctx.Tt = tokens, in_lens32, B, Tt
+
+        if stage == 2:
+            log_dur_pred = self._pred_fwd(enc_out, in_lens32, self.pred["duration"], save("duration"))
+            dur_pred = torch.clamp(torch.exp(log_dur_pred) - 1, 0, max_duration)  # returned for logging only
+            self._ctx = ctx
+            return [None, None, dur_pred, log_dur_pred, None, None, None, None, None, None, dur_tgt, None, input_lens]
+
+        # ---- get_pitch_energy, model.py:394-423
+        durs = dur_tgt.to(torch.float32).contiguous()
+        pitch_pred = self._pred_fwd(enc_out, in_lens32, self.pred["pitch"], save("pitch")).view(B, 1, Tt)
+        pitch_tgt = ops.average_pitch(pitch_dense, durs)                                    # [B,1,Tt]
+        enc2 = enc_out.clone()
+        ops.scalar_conv_add_(enc2, pitch_tgt, self.w.pitch_emb_w, self.w.pitch_emb_b, in_lens32)
+        energy_pred = self._pred_fwd(enc2, in_lens32, self.pred["energy"], save("energy"))
+        energy_tgt = ops.average_pitch(energy_dense.view(B, 1, -1), durs, log1p=True)       # [B,1,Tt]
+        enc3 = enc2.clone()
+        ops.scalar_conv_add_(enc3, energy_tgt, self.w.energy_emb_w, self.w.energy_emb_b, in_lens32)
+        energy_tgt = energy_tgt.view(B, Tt)
+
+        # ---- regulate_len, model.py:59-79
+        if host_lens is None:
+            mel_max_len = int(max_mel_lengths[0].item())
+        else:
+            mel_max_len = int(host_lens[0])
+        cum, dec_lens = ops.duration_scan(durs, pace, mel_max_len)
+        T_out = int(dec_lens.max().item()) if host_lens is None else min(int(host_lens[1]), mel_max_len)
+        regulated = ops.regulate_gather(enc3, cum, T_out)
+
+        # ---- decoder + projection
+        y = ops.embed_pos(None, None, regulated, dec_lens, self.inv_freq, B, T_out, D_MODEL)
+        for L in self.dec_layers:
+            y = self._layer_fwd(y, dec_lens, L, ctx.dec if ctx is not None else None)
+        mel_out = ops.conv_fwd(y, self.w.proj_w, bias=self.w.proj_b)
+        if ctx is not None:
+            ctx.dec_out, ctx.cum, ctx.dec_lens, ctx.T_out = y, cum, dec_lens, T_out
+            ctx.pitch_tgt, ctx.energy_tgt = pitch_tgt, energy_tgt
+        self._ctx = ctx
+        dec_mask = (torch.arange(T_out, device=dev)[None, :] < dec_lens[:, None]).unsqueeze(2)
+        return [mel_out, dec_mask, None, None, pitch_pred, pitch_tgt, energy_pred, energy_tgt, None, None, dur_tgt, None,
+                input_lens]
+
+    # ------------------------------------------------------------------------------------------ backward
+    def backward(self, criterion, scale=1.0):
+        """Reverse pass for the loss ``criterion`` just evaluated on this module's last forward() output. Gradients of
+        the stage's trainable parameters are ACCUMULATED into the gradient arena (zero_grad() clears it), scaled by
+        ``scale`` (the 1/gam of xva_train.py:806)."""
+        ctx = self._ctx
+        if ctx is None:
+            raise RuntimeError("backward() needs a forward() in training mode first")
+        stage = ctx.stage
+        lens = ctx.in_lens
+        B, Tt = ctx.B, ctx.Tt
+        seeds = criterion.grad_seeds(scale)
+        if stage == 2:
+            d_enc = self._pred_bwd(seeds["log_dur"], lens, self.pred["duration"], ctx.preds["duration"])
+        else:
+            # projection
+            dmel = seeds["mel"]                                   # [B,T_out,96], columns 80.. are zero
+            dm = dmel[..., :N_MEL]
+            T_out = ctx.T_out
+            ops.conv_wgrad(dm, ctx.dec_out, (0,), out=self.g.proj_w, accumulate=True)
+            ops.colsum_(B * T_out, N_MEL, dmel.shape[2], dmel, self.g.proj_b)
+            dy = ops.conv_dgrad(dm, self.w.proj_w, lens=ctx.dec_lens)
+            for L, c in zip(reversed(self.dec_layers), reversed(ctx.dec)):
+                dy = self._layer_bwd(dy, ctx.dec_lens, L, c)
+            d_enc = ops.regulate_scatter(dy, ctx.cum, Tt)         # pos-emb has no parameters: dy is d(regulated)
+            del dy
+            ops.scalar_conv_bwd_(d_enc, ctx.energy_tgt, self.g.energy_emb_w, self.g.energy_emb_b)
+            if stage == 3:
+                d_enc = self._pred_bwd(seeds["energy"], lens, self.pred["energy"], ctx.preds["energy"], residual=d_enc)
+                ops.scalar_conv_bwd_(d_enc, ctx.pitch_tgt, self.g.pitch_emb_w, self.g.pitch_emb_b)
+                d_enc = self._pred_bwd(seeds["pitch"], lens, self.pred["pitch"], ctx.preds["pitch"], residual=d_enc)
+        n = len(self.enc_layers)
+        for i, (L, c) in enumerate(zip(reversed(self.enc_layers), reversed(ctx.enc))):
+            d_enc = self._layer_bwd(d_enc, lens, L, c)
+        ops.embed_bwd_(ctx.tokens, d_enc, self.g.emb)
+        self._ctx = None
+
+    def step_dropout(self):
+        """Advance the device-side dropout counter (one increment per optimizer micro-step)."""
+        ops.counter_add_(self.step_counter, 1)
+
+
+class FastPitchLoss:
+    """FastPitchLoss, fastpitch/loss_function.py:29-154, for training stages 2-4: masked MSE terms reduced on the device
+    in fp64. ``forward`` returns (loss, meta) as 0-dim device tensors (no host sync); ``grad_seeds`` hands the
+    d(loss)/d(prediction) tensors to FastPitch.backward."""
+
+    def __init__(self, dur_predictor_loss_scale=0.1, pitch_predictor_loss_scale=0.1, attn_loss_scale=1.0,
+                 energy_predictor_loss_scale=0.1, gpus=None):
+        self.dur_predictor_loss_scale = dur_predictor_loss_scale
+        self.pitch_predictor_loss_scale = pitch_predictor_loss_scale
+        self.energy_predictor_loss_scale = energy_predictor_loss_scale
+        self.attn_loss_scale = attn_loss_scale
+        self.training_stage = 3
+        self._saved = None
+
+    def __call__(self, model_out, targets, is_training=True, meta_agg="mean"):
+        return self.forward(model_out, targets, is_training, meta_agg)
+
+    def forward(self, model_out, targets, is_training=True, meta_agg="mean"):
+        (mel_out, dec_mask, dur_pred, log_dur_pred, pitch_pred, pitch_tgt, energy_pred, energy_tgt, _, _, attn_dur, _,
+         input_lens) = model_out
+        mel_tgt, in_lens, out_lens, max_inp_lengths = targets[:4]
+        stage = self.training_stage
+        dev = input_lens.device
+        lens32 = input_lens.to(torch.int32)
+        acc = torch.zeros(4, 2, device=dev, dtype=torch.float64)   # rows: mel, dur, pitch, energy = {sum sq err, count}
+        zero = torch.zeros((), device=dev, dtype=torch.float64)
+        mel_loss = dur_loss = pitch_loss = energy_loss = zero
+        saved = {"stage": stage, "acc": acc, "lens": lens32}
+        if stage == 2:
+            tgt = attn_dur.to(torch.float32).contiguous()
+            ops.lens_mse(log_dur_pred, tgt, lens32, acc[1], log1p_tgt=True)
+            dur_loss = acc[1, 0] / acc[1, 1]
+            saved.update(log_dur_pred=log_dur_pred, dur_tgt=tgt)
+        else:
+            mt = mel_tgt.to(torch.float32).contiguous()
+            ops.mel_mse(mel_out, mt, acc[0])
+            mel_loss = acc[0, 0] / acc[0, 1]
+            saved.update(mel_out=mel_out, mel_tgt=mt)
+            if stage == 3:
+                pp, pt = pitch_pred.reshape(pitch_pred.shape[0], -1), pitch_tgt.reshape(pitch_tgt.shape[0], -1)
+                ops.lens_mse(pp, pt, lens32, acc[2])
+                ops.lens_mse(energy_pred, energy_tgt, lens32, acc[3])
+                pitch_loss = acc[2, 0] / acc[2, 1]
+                energy_loss = acc[3, 0] / acc[3, 1]
+                saved.update(pitch_pred=pp, pitch_tgt=pt, energy_pred=energy_pred, energy_tgt=energy_tgt)
+        loss = (mel_loss + dur_loss * self.dur_predictor_loss_scale + pitch_loss * self.pitch_predictor_loss_scale
+                + energy_loss * self.energy_predictor_loss_scale)
+        self._saved = saved
+        meta = {"loss": loss, "mel_loss": mel_loss, "duration_predictor_loss": dur_loss, "pitch_loss": pitch_loss,
+                "energy_loss": energy_loss}
+        return loss, meta
+
+    def grad_seeds(self, scale=1.0):
+        s = self._saved
+        if s is None:
+            raise RuntimeError("FastPitchLoss.grad_seeds() needs a forward() first")
+        acc, lens = s["acc"], s["lens"]
+        out = {}
+        if s["stage"] == 2:
+            out["log_dur"] = ops.lens_mse_grad(s["log_dur_pred"], s["dur_tgt"], lens, acc[1],
+                                               scale * self.dur_predictor_loss_scale, log1p_tgt=True)
+        else:
+            out["mel"] = ops.mel_mse_grad(s["mel_out"], s["mel_tgt"], acc[0], scale, 96)
+            if s["stage"] == 3:
+                out["pitch"] = ops.lens_mse_grad(s["pitch_pred"], s["pitch_tgt"], lens, acc[2],
+                                                 scale * self.pitch_predictor_loss_scale)
+                out["energy"] = ops.lens_mse_grad(s["energy_pred"], s["energy_tgt"], lens, acc[3],
+                                                  scale * self.energy_predictor_loss_scale)
+        return out
+
+
+class Lamb:
+    """Lamb, lamb.py:8-106, as one multi-tensor launch pair over the model's flat arena, preceded by the
+    clip_grad_norm_(max_norm) the trainer applies (xva_train.py:857). ``param_groups[0]['lr']`` is what
+    adjust_learning_rate (xva_train.py:1252-1261) writes."""
+
+    CHUNK = 8192
+
+    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-6, weight_decay=0, clip_grad_norm=1000.0):
+        self.model = model
+        self.param_groups = [{"lr": lr, "betas": betas, "eps": eps, "weight_decay": weight_decay}]
+        self.clip = clip_grad_norm
+        A = model.arena
+        if A.m is None:
+            A.m = torch.zeros_like(A.p)
+            A.v = torch.zeros_like(A.p)
+        self.lr_dev = torch.zeros(1, device=A.p.device, dtype=torch.float32)
+        self._tables = {}
+        self.steps = 0
+
+    def _table(self, stage):
+        if stage not in self._tables:
+            A = self.model.arena
+            keys = trainable_keys(stage)
+            rec = []
+            for ti, k in enumerate(keys):
+                off, n = A.offset[k], int(math.prod(A.pshape[k]))
+                for s in range(0, n, self.CHUNK):
+                    rec.append((off + s, min(self.CHUNK, n - s), ti))
+            import numpy as np
+            arr = np.zeros(len(rec), dtype=np.dtype([("start", "<i8"), ("len", "<i4"), ("tensor", "<i4")]))
+            for i, (a, b, c) in enumerate(rec):
+                arr[i] = (a, b, c)
+            chunks = torch.from_numpy(arr.view(np.uint8).copy()).to(A.p.device)
+            self._tables[stage] = (chunks, len(rec), len(keys))
+        return self._tables[stage]
+
+    def zero_grad(self, set_to_none=True):
+        self.model.zero_grad()
+
+    def step(self, closure=None):
+        A = self.model.arena
+        g = self.param_groups[0]
+        chunks, n_chunks, n_tensors = self._table(self.model.training_stage)
+        self.lr_dev.fill_(float(g["lr"]))
+        scratch = torch.zeros(2 * n_tensors + 1, device=A.p.device, dtype=torch.float64)
+        gn = scratch[2 * n_tensors:]
+        if self.clip is not None and self.clip > 0:
+            ops.grad_sqnorm(A.g, chunks, n_chunks, gn)
+        ops.lamb_step(A.p, A.g, A.m, A.v, chunks, n_chunks, scratch, gn if self.clip else None,
+                      self.clip if self.clip else 0.0, self.lr_dev, g["betas"][0], g["betas"][1], g["eps"],
+                      g["weight_decay"])
+        self.steps += 1
+        self.last_grad_sqnorm = gn
+
+    def state_dict(self):
+        """{'state': {reference key: {'exp_avg', 'exp_avg_sq'}}, 'param_groups'} with tensors in the reference's shapes."""
+        A = self.model.arena
+        st = OrderedDict()
+        for k, _ in A.spec:
+            st[k] = {"step": self.steps, "exp_avg": _to_ref(k, A.view(A.m, k), A.rshape[k]),
+                     "exp_avg_sq": _to_ref(k, A.view(A.v, k), A.rshape[k])}
+        return {"state": st, "param_groups": [dict(g) for g in self.param_groups], "steps": self.steps}
+
+    def load_state_dict(self, sd):
+        A = self.model.arena
+        for k, st in sd.get("state", {}).items():
+            if k in A.offset:
+                A.view(A.m, k).copy_(_to_packed(k, st["exp_avg"].to(torch.float32)))
+                A.view(A.v, k).copy_(_to_packed(k, st["exp_avg_sq"].to(torch.float32)))
+        self.steps = int(sd.get("steps", 0))
+        if sd.get("param_groups"):
+            self.param_groups[0].update(sd["param_groups"][0])
+
+
+def adjust_learning_rate(total_iter, opt, learning_rate, warmup_iters=None):
+    """xva_train.py:1252-1261 (noam)."""
+    if warmup_iters == 0:
+        scale = 1.0
+    elif total_iter > warmup_iters:
+        scale = 1.0 / (total_iter ** 0.5)
+    else:
+        scale = total_iter / (warmup_iters ** 1.5)
+    for param_group in opt.param_groups:
+        param_group["lr"] = learning_rate * scale

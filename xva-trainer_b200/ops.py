@@ -45,7 +45,7 @@ def _base_args(mode, shifts):
 
 
 def _epilogue(g, out, bias=None, relu=False, gate=None, gate_slope=0.0, residual=None, lens=None, ln=None,
-              ln_eps=1e-5, save_ln=False, drop_p=0.0, drop_post=False, seed=0, alpha=1.0):
+              ln_eps=1e-5, save_ln=False, drop_p=0.0, drop_post=False, seed=0, seed_dev=None, alpha=1.0):
     keep = [out, bias, gate, residual, lens]
     g.out, g.o_rs, g.o_zs = _p(out), out.stride(1), out.stride(0)
     g.alpha = alpha
@@ -78,7 +78,7 @@ def _epilogue(g, out, bias=None, relu=False, gate=None, gate_slope=0.0, residual
             extra = {"pre": pre, "mean": mean, "rstd": rstd}
     if drop_p > 0.0:
         flags |= capi.GEMM_DROP_POST if drop_post else capi.GEMM_DROP_PRE
-        g.drop_p, g.seed = drop_p, seed
+        g.drop_p, g.seed, g.seed_dev = drop_p, seed, _p(seed_dev)
     g.flags = flags
     return keep, extra
 
@@ -229,12 +229,124 @@ def regulate_scatter(dout, cum, Tt, out=None):
     return out
 
 
-def average_pitch(pitch, durs):
+def average_pitch(pitch, durs, log1p=False):
     """fastpitch/model.py:82-100.  pitch [B,F,Tm], durs [B,Tt] -> [B,F,Tt]."""
     B, F, Tm = pitch.shape
     Tt = durs.shape[1]
     pitch = pitch.float().contiguous()
     d = durs.float().contiguous()
     out = torch.empty(B, F, Tt, device=pitch.device, dtype=torch.float32)
-    capi.call("xva_average_pitch", _p(pitch), _p(d), B, F, Tm, Tt, _p(out), _stream())
+    capi.call("xva_average_pitch", _p(pitch), _p(d), B, F, Tm, Tt, _p(out), int(log1p), _stream())
     return out
+
+
+# ---------------------------------------------------------------------------------------------- row kernels
+def softmax_fwd(s, lens, n_valid, drop_p=0.0, seed=0, seed_dev=None):
+    """transformer.py:120-127.  s [Z,R,ld] holds alpha*q.k^T in its first n_valid columns -> (p, pd); pd is p when
+    drop_p == 0. Pad columns [n_valid, ld) of the outputs are zero."""
+    Z, R, ld = s.shape
+    p = torch.empty_like(s)
+    pd = torch.empty_like(s) if drop_p > 0.0 else None
+    capi.call("xva_softmax_fwd", _p(s), _p(lens), Z, R, int(n_valid), ld, _p(p), _p(pd), float(drop_p), int(seed),
+              _p(seed_dev), _stream())
+    return p, (pd if pd is not None else p)
+
+
+def softmax_bwd_(p, dpd, n_valid, alpha, drop_p=0.0, seed=0, seed_dev=None):
+    """In place: dpd (gradient wrt the dropped-out probabilities) becomes alpha * d(scores)."""
+    Z, R, ld = p.shape
+    capi.call("xva_softmax_bwd", _p(p), _p(dpd), Z, R, int(n_valid), ld, float(alpha), float(drop_p), int(seed),
+              _p(seed_dev), _stream())
+    return dpd
+
+
+def layernorm_bwd(dy, saved, gamma, lens, dgamma, dbeta, dbias=None, want_drop=False, drop_post_p=0.0, seed_post=0,
+                  drop_pre_p=0.0, seed_pre=0, seed_dev=None, relu_gate=False):
+    """Backward of the LayerNorm epilogue. saved = {"pre","mean","rstd"} from conv_fwd(save_ln=True).
+    -> dx (gradient wrt the pre-LN sum), dx_drop (dx * pre-dropout mask, or dx itself when no dropout)."""
+    Z, R, Cc = dy.shape
+    dx = torch.empty_like(dy)
+    dxd = torch.empty_like(dy) if (want_drop and drop_pre_p > 0.0) else None
+    capi.call("xva_layernorm_bwd", _p(dy), _p(saved["pre"]), _p(saved["mean"]), _p(saved["rstd"]), _p(gamma), _p(lens),
+              Z, R, Cc, _p(dx), _p(dxd), _p(dgamma), _p(dbeta), _p(dbias), float(drop_post_p), int(seed_post),
+              float(drop_pre_p), int(seed_pre), _p(seed_dev), int(relu_gate), _stream())
+    return dx, (dxd if dxd is not None else dx)
+
+
+def colsum_(x2d_rows, C_, ld, x, out):
+    capi.call("xva_colsum", _p(x), int(x2d_rows), int(C_), int(ld), _p(out), _stream())
+
+
+def embed_pos(tokens, emb, inp, lens, inv_freq, B, T, Cc):
+    out = torch.empty(B, T, Cc, device=inv_freq.device, dtype=torch.float32)
+    capi.call("xva_embed_pos", _p(tokens), _p(emb), _p(inp), _p(lens), _p(inv_freq), B, T, Cc, _p(out), _stream())
+    return out
+
+
+def embed_bwd_(tokens, dout, demb):
+    B, T, Cc = dout.shape
+    capi.call("xva_embed_bwd", _p(tokens), _p(dout), B, T, Cc, _p(demb), _stream())
+
+
+def scalar_conv_add_(io, x, w, bias, lens=None):
+    B, T, Cc = io.shape
+    capi.call("xva_scalar_conv_add", _p(io), _p(x), _p(w), _p(bias), _p(lens), B, T, Cc, _stream())
+
+
+def scalar_conv_bwd_(dout, x, dw, dbias):
+    B, T, Cc = dout.shape
+    capi.call("xva_scalar_conv_bwd", _p(dout), _p(x), B, T, Cc, _p(dw), _p(dbias), _stream())
+
+
+def rowdot_fwd(x, w, bias, lens):
+    Z, R, Cc = x.shape
+    out = torch.empty(Z, R, device=x.device, dtype=torch.float32)
+    capi.call("xva_rowdot_fwd", _p(x), _p(w), _p(bias), _p(lens), Z, R, Cc, _p(out), _stream())
+    return out
+
+
+def rowdot_bwd(dout, x, w, lens, dw, db):
+    Z, R, Cc = x.shape
+    dx = torch.empty_like(x)
+    capi.call("xva_rowdot_bwd", _p(dout), _p(x), _p(w), _p(lens), Z, R, Cc, _p(dx), _p(dw), _p(db), _stream())
+    return dx
+
+
+# ---------------------------------------------------------------------------------------------- losses / optimizer
+def mel_mse(pred, tgt, acc):
+    B, T_out, Cc = pred.shape
+    capi.call("xva_mel_mse", _p(pred), _p(tgt), B, T_out, tgt.shape[2], Cc, _p(acc), _stream())
+
+
+def mel_mse_grad(pred, tgt, acc, scale, ldd):
+    B, T_out, Cc = pred.shape
+    d = torch.empty(B, T_out, ldd, device=pred.device, dtype=torch.float32)
+    capi.call("xva_mel_mse_grad", _p(pred), _p(tgt), B, T_out, tgt.shape[2], Cc, int(ldd), _p(acc), float(scale), _p(d),
+              _stream())
+    return d
+
+
+def lens_mse(pred, tgt, lens, acc, log1p_tgt=False):
+    B, T = pred.shape
+    capi.call("xva_lens_mse", _p(pred), _p(tgt), _p(lens), B, T, int(log1p_tgt), _p(acc), _stream())
+
+
+def lens_mse_grad(pred, tgt, lens, acc, scale, log1p_tgt=False):
+    B, T = pred.shape
+    d = torch.empty_like(pred)
+    capi.call("xva_lens_mse_grad", _p(pred), _p(tgt), _p(lens), B, T, int(log1p_tgt), _p(acc), float(scale), _p(d),
+              _stream())
+    return d
+
+
+def counter_add_(counter, inc=1):
+    capi.call("xva_counter_add", _p(counter), int(inc), _stream())
+
+
+def grad_sqnorm(g, chunks, n_chunks, out):
+    capi.call("xva_grad_sqnorm", _p(g), _p(chunks), int(n_chunks), _p(out), _stream())
+
+
+def lamb_step(p, g, m, v, chunks, n_chunks, norms, gnorm_sq, max_norm, lr_dev, beta1, beta2, eps, weight_decay):
+    capi.call("xva_lamb_step", _p(p), _p(g), _p(m), _p(v), _p(chunks), int(n_chunks), _p(norms), _p(gnorm_sq),
+              float(max_norm), _p(lr_dev), float(beta1), float(beta2), float(eps), float(weight_decay), _stream())
