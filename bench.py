@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""Benchmark of the FastPitch 1.1 fine-tune step (BASELINE.json configs[1]: batch 32, 80-bin mels, 880 frames and
+160 tokens per utterance) through the B200-native engine: forward + FastPitchLoss + backward + clip + LAMB, dropout on.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--stage 3|4]
+
+Prints ONE JSON line (rank 0). `value` = mel-frames/s of the whole job with the batch resident in HBM; `e2e` = the same
+step driven from pinned HOST buffers (host->device copy of the batch and a device->host read of the loss inside the
+timed region). `roofline` is for the dominant kernel (the tcgen05 tap-GEMM): algorithmic FLOPs of every tap-GEMM launch
+of one step / their summed device time, measured with CUDA events on the launching stream in one instrumented step
+that follows the timed region. `cpu_baseline` = the CPU oracle (a PyTorch-CPU restatement of the reference step, pinned
+to the reference's outputs by tests/) timed on this box's host cores on a bounded sample of the same workload.
+`--impl reference` times that CPU path alone on the same metric (the tier's reference arm).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+B, TT, TM = 32, 160, 880
+METRIC, UNIT = "mel-frames/s (FastPitch 1.1 fine-tune step)", "frames/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--stage", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=B)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-batch", type=int, default=4)
+    ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
+    return ap.parse_args()
+
+
+def config(args, world):
+    return {"workload": f"FastPitch1.1 fine-tune stage {args.stage}, batch={args.batch}/GPU, 80-bin mel, {TM} frames/utt, "
+                        f"{TT} tokens/utt, synthetic text+mel pairs (BASELINE.json configs[1])",
+            "global_batch": args.batch * world, "frames_per_utt": TM, "tokens_per_utt": TT,
+            "step": "forward + FastPitchLoss + backward + clip_grad_norm(1000) + LAMB, dropout 0.1 on, gam=1",
+            "parallelism": f"dp{world}", "l2": "per-step working set (~5 GB of activations) exceeds the 126 MB L2; no flush"}
+
+
+# ---------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi sampled every 200 ms while the timed region runs (B200_PROFILING.md clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------- CPU reference / baseline
+def cpu_step_rate(stage, batch, steps, warmup):
+    """frames/s of the CPU oracle's training step (oracle/fastpitch.py: forward, FastPitchLoss, autograd backward,
+    clip, LAMB; fp32, dropout on) on all host cores."""
+    import torch
+    from oracle import fastpitch as ofp
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    x, y = ofp.synthetic_batch(batch, TT, TM, seed=1234)
+    sd = ofp.make_state(1234, perturb=False)
+    opt = {}
+    frames = int(x[3].sum())
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        ofp.train_step(sd, x, y, stage, ofp.noam_lr(50000 + i), opt, drop=0.1, training=True)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    per = sum(times) / len(times)
+    return frames / per, per, cores, frames
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    bs = args.cpu_sample_batch
+    steps, warm = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+    rate, per, cores, frames = cpu_step_rate(args.stage, bs, steps, warm)
+    sample = (f"oracle train_step (PyTorch-CPU restatement of the reference step), batch {bs} x {TM} frames of the "
+              f"batch-{args.batch} workload, {warm} warm-up + {steps} timed steps, {cores} threads")
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warm, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config(args, 1),
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------- native arm
+def gemm_flops(g):
+    """Algorithmic FLOPs of one tap-GEMM launch (2 * rows * cols * contraction)."""
+    if g.mode == 2:
+        return 2.0 * g.Z * g.R * g.M * g.N * g.taps
+    return 2.0 * g.Z * g.R * g.N * g.K * g.taps
+
+
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as ge
+    ge.build()
+    from oracle import fastpitch as ofp  # synthetic batch generator + cpu_baseline leg only
+    from xva_trainer_b200 import capi, fastpitch as fp, ops, parallel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    capi.call("xva_device_check", local)
+
+    model = fp.FastPitch(device=dev, seed=1234)          # identical weights on every rank
+    model.training_stage = args.stage
+    model.train()
+    crit = fp.FastPitchLoss()
+    crit.training_stage = args.stage
+    opt = fp.Lamb(model, lr=0.1, betas=(0.9, 0.98), eps=1e-9, weight_decay=1e-6)
+    ddp = parallel.GradSync(model, world) if world > 1 else None
+
+    x_cpu, y_cpu = ofp.synthetic_batch(args.batch, TT, TM, seed=1234 + rank)
+    frames = int(x_cpu[3].sum())
+    host_lens = (TM, int(x_cpu[3].max()))
+    pin = [t.pin_memory() if torch.is_tensor(t) else t for t in x_cpu]
+    h2d_bytes = sum(t.numel() * t.element_size() for t in pin if torch.is_tensor(t))
+
+    def to_dev(src):
+        return [t.to(dev, non_blocking=True) if torch.is_tensor(t) else t for t in src]
+
+    state = {"it": 50000}
+
+    def step(x):
+        y = [x[2], x[1], x[3], x[9]]
+        state["it"] += 1
+        fp.adjust_learning_rate(state["it"], opt, 0.1, 1000)
+        model.zero_grad()
+        out = model(x, host_lens=host_lens)
+        loss, meta = crit(out, y)
+        model.backward(crit, 1.0, grad_sync=ddp) if ddp is not None else model.backward(crit, 1.0)
+        if ddp is not None:
+            ddp.finish()
+        opt.step()
+        model.step_dropout()
+        return loss
+
+    x_dev = to_dev(pin)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up
+    for _ in range(max(args.warmup, 3)):
+        loss = step(x_dev)
+    barrier()
+
+    # ---- timed region 1: batch resident in HBM
+    clocks = ClockSampler(local)
+    clocks.start()
+    capi.reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        loss = step(x_dev)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = capi.launch_count()
+    clk = clocks.stop()
+
+    # ---- timed region 2: end to end from pinned host buffers, loss read back every step
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        xb = to_dev(pin)
+        loss = step(xb)
+        loss_host = float(loss)           # device -> host read of the step's result
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    if not (loss_host == loss_host):
+        raise RuntimeError("loss is NaN")
+
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+
+    # ---- instrumented step: CUDA events around every tap-GEMM launch (after the timed regions)
+    roof = None
+    if rank == 0:
+        rec = []
+        orig = ops.gemm_launch
+
+        def timed_launch(g, ref=False):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            orig(g, ref)
+            b.record()
+            rec.append((a, b, gemm_flops(g), (g.mode, g.Z, g.R, g.M, g.N, g.K, g.taps, g.flags, g.split)))
+
+        ops.gemm_launch = timed_launch
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        # park the GPU (~60 ms spin) so the host enqueues the whole step ahead of it: the event pairs then bracket
+        # device time only, not host launch gaps
+        torch.cuda._sleep(int(0.06 * 1.9e9))
+        s0.record()
+        step(x_dev)
+        s1.record()
+        torch.cuda.synchronize()
+        ops.gemm_launch = orig
+        gemm_ms = sum(r[0].elapsed_time(r[1]) for r in rec)
+        flops = sum(r[2] for r in rec)
+        table_path = os.environ.get("XVA_BENCH_GEMM_TABLE")
+        if table_path:  # per-shape breakdown of the instrumented step (diagnostic; not part of the JSON line)
+            agg = {}
+            for a, b, f, shape in rec:
+                e = agg.setdefault(shape, [0, 0.0, 0.0])
+                e[0] += 1
+                e[1] += a.elapsed_time(b)
+                e[2] += f
+            rows = sorted(agg.items(), key=lambda kv: -kv[1][1])
+            with open(table_path, "w") as fh:
+                fh.write("mode Z R M N K taps flags split | launches ms GFLOP TFLOP/s\n")
+                for shape, (n, t, f) in rows:
+                    fh.write(" ".join(str(v) for v in shape) + f" | {n} {t:.3f} {f / 1e9:.1f} {f / (t * 1e-3) / 1e12:.1f}\n")
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
+            os.path.join(ROOT, "MEASURED_PEAKS.json")) else None
+        bf16_peak = peaks["bf16_tflops_sustained"] if peaks else 1400.0
+        peak = bf16_peak / 2.0
+        achieved = flops / (gemm_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 kind::tf32 tap-GEMM)", "achieved": achieved,
+                "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "launches_per_step": len(rec), "flops_per_step": flops, "kernel_ms_per_step": gemm_ms,
+                "share_of_step": gemm_ms / s0.elapsed_time(s1),
+                "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained / 2 (kind::tf32 runs at half the bf16 rate), "
+                                "of measured") if peaks else "fallback 1.4 PFLOP/s / 2, of fallback"}
+
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        rate, per, cores, fr = cpu_step_rate(args.stage, args.cpu_sample_batch, 2, 1)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"oracle train_step, batch {args.cpu_sample_batch} x {TM} frames of the batch-{args.batch} workload, "
+                         f"1 warm-up + 2 timed steps ({per:.1f} s/step), {cores} threads"}
+
+    total_frames = frames * world  # every rank draws a batch with the same frame count (lengths are fixed)
+    line = {"metric": METRIC, "value": total_frames * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32 (fp32 storage/accumulate)",
+            "data": "synthetic", "config": config(args, world), "clocks": clk,
+            "e2e": {"value": total_frames * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+                    "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "loss": loss_host}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

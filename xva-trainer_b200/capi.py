@@ -110,5 +110,23 @@ def check(status, what=""):
         raise XvaError(f"{what} failed ({status}): {msg.decode() if msg else '?'}")
 
 
+# kernels enqueued per successful call (everything not listed launches exactly one)
+_LAUNCHES = {"xva_lamb_step": 2, "xva_abi_version": 0, "xva_last_error": 0, "xva_device_check": 0,
+             "xva_sizeof_gemm_args": 0}
+_launch_count = 0
+
+
+def reset_launch_count():
+    global _launch_count
+    _launch_count = 0
+
+
+def launch_count():
+    """CUDA kernels of this library launched through call() since the last reset (bench.py's gpu_launches)."""
+    return _launch_count
+
+
 def call(name, *args):
+    global _launch_count
     check(getattr(load(), name)(*args), name)
+    _launch_count += _LAUNCHES.get(name, 1)

@@ -9,6 +9,7 @@
 // The k-tap convolution is a sum of `taps` GEMMs whose A tiles are the same activation rows shifted by
 // shift[j]; the shift is a TMA coordinate, the zero padding is TMA out-of-bounds fill: no im2col, no halo copy.
 #include <cuda.h>
+#include <cstdio>
 #include <cstdlib>
 #include <mutex>
 #include "gemm.cuh"
@@ -23,9 +24,15 @@ constexpr int kBlockK = 32;         // fp32 elements per k-block = one 128-byte 
 constexpr int kUmmaK = 8;           // tf32 MMA K
 constexpr int kMaxStages = 8;
 constexpr int kTmemCols = 512;
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;        // 4 control warps (TMA, MMA, TMEM alloc, spare) + 8 epilogue warps
 constexpr int kATileBytes = kBlockM * kBlockK * 4;  // 16 KiB
-constexpr int kSmemBudget = 220 * 1024;
+constexpr int kEpiSmemBytes = 8 * 4096;  // one 32x32 fp32 transpose tile per epilogue warp
+constexpr int kSmemBudget = 192 * 1024;   // operand ring; + kEpiSmemBytes + 1 KiB alignment slack <= 227 KiB
+constexpr int kLnSmemBytes = 2 * 4 * 32 * 2 * 4;
+constexpr int kBarSmemBytes = (2 * kMaxStages + 4) * 8 + 8;
+constexpr int kAlignSlack = 768;
+constexpr int kTailSmemBytes = kEpiSmemBytes + kLnSmemBytes + kBarSmemBytes + kAlignSlack;
+enum { EPI_WGRAD = 0, EPI_PLAIN = 1, EPI_FULL = 2, EPI_LN = 3 };
 
 struct GemmDev {
   int mode, Z, R, M, N, K, taps, ZR, split, zper;
@@ -54,6 +61,7 @@ struct GemmDev {
   float inv_keep;
   uint64_t seed;
   const uint64_t* seed_dev;
+  int vec_ok;  // every epilogue pointer is 16-byte aligned and every stride a multiple of 4: float4 accesses
 };
 
 struct TileCoord {
@@ -123,22 +131,31 @@ __device__ __forceinline__ uint32_t make_idesc(int n, int a_mn_major, int b_mn_m
   return d;
 }
 
-__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
+template <int kEpi>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ GemmDev p) {
+  // One dynamic allocation, carved by hand (the ring + staging leave < 1 KiB of the 227 KiB an SM offers):
+  //   [operand ring: stages * stage_bytes, 1024-aligned][epilogue transpose tiles 32 KiB][LN exchange 2 KiB][barriers]
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_full[kMaxStages];
-  __shared__ __align__(8) uint64_t bar_empty[kMaxStages];
-  __shared__ __align__(8) uint64_t bar_tmem_full[2];
-  __shared__ __align__(8) uint64_t bar_tmem_empty[2];
-  __shared__ uint32_t tmem_base_slot;
 
   // 1024-byte alignment of the tile ring (SWIZZLE_128B atoms are 1024 B).
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  if (threadIdx.x == 0 && (smem - smem_raw) > kAlignSlack) {
+    printf("gemm_tc_kernel: dynamic shared memory base needs %d B of alignment slack (have %d)\n",
+           static_cast<int>(smem - smem_raw), kAlignSlack);
+    __trap();
+  }
   const int b_tile_bytes = p.n_tile * kBlockK * 4;
   const int stage_bytes = kATileBytes + b_tile_bytes;
+  uint8_t* tail = smem + p.stages * stage_bytes + kEpiSmemBytes;
+  float (*ln_part)[4][32][2] = reinterpret_cast<float (*)[4][32][2]>(tail);  // LayerNorm (mean, M2) exchange
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(tail + kLnSmemBytes);
+  uint64_t* bar_empty = bar_full + kMaxStages;
+  uint64_t* bar_tmem_full = bar_empty + kMaxStages;
+  uint64_t* bar_tmem_empty = bar_tmem_full + 2;
+  uint32_t& tmem_base_slot = *reinterpret_cast<uint32_t*>(bar_tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -154,7 +171,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&bar_tmem_full[a], 1);
-      ptx::mbar_init(&bar_tmem_empty[a], 4);
+      ptx::mbar_init(&bar_tmem_empty[a], 8);
     }
     ptx::fence_mbar_init();
   }
@@ -250,12 +267,70 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------------ epilogue (128 threads <-> 128 TMEM lanes)
-    const int ew = warp & 3;
-    const int row_in_tile = ew * 32 + lane;
-    const uint32_t lane_base = static_cast<uint32_t>(ew * 32) << 16;
+    // ------------------------------------------------------------------ epilogue (8 warps)
+    // TMEM lanes 32q..32q+31 are only visible to warps with (warp & 3) == q, so two warps share each 32-row quarter
+    // and split the tile's 32-column chunks between them (even / odd). A 32x32 block is read with one tcgen05.ld
+    // (thread = row), transposed through a 4 KiB XOR-swizzled shared-memory tile, and from there on every thread
+    // holds float4 pieces in a COALESCED layout: lane l <-> columns 4*(l&7)..+3 of rows 4k + (l>>3), k = 0..7, so
+    // eight consecutive lanes cover one full 128-byte line of a row for every global load (bias, gate, residual),
+    // store and reduction. All global loads of a chunk are issued before the first use (8 x 16 B in flight per
+    // lane): the epilogue of the memory-bound launches is a bandwidth problem, not a latency chain.
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
+    const int c4 = lane & 7, rsub = lane >> 3;
+    const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
+    float4* tbuf = reinterpret_cast<float4*>(smem + p.stages * stage_bytes) + (warp - 4) * 256;
     int tile_iter = 0;
     const uint64_t seed = p.seed + (p.seed_dev ? __ldg(p.seed_dev) * 0xA24BAED4963EE407ull : 0ull);
+    const bool vec = p.vec_ok != 0;
+
+    auto load_chunk = [&](uint32_t taddr, float4 (&t)[8]) {
+      uint32_t v[32];
+      ptx::tmem_ld32(taddr, v);
+      ptx::tmem_wait_ld();
+      __syncwarp();  // everyone has finished reading the previous block out of tbuf
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        tbuf[lane * 8 + (c ^ (lane & 7))] = make_float4(__uint_as_float(v[4 * c]), __uint_as_float(v[4 * c + 1]),
+                                                        __uint_as_float(v[4 * c + 2]), __uint_as_float(v[4 * c + 3]));
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int r = 4 * k + rsub;
+        t[k] = tbuf[r * 8 + (c4 ^ (r & 7))];
+      }
+    };
+    // Batched access to one float4 column slot of the 8 rows this lane owns. `full`: all four columns valid and
+    // float4-aligned (the common case); otherwise `nv` (< 4 or unaligned) columns are touched one by one.
+    auto load8 = [&](const float* base, long rs, int row0, int row_limit, bool full, int nv, float4 (&o)[8]) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int row = row0 + 4 * k;
+        o[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < row_limit) {
+          const float* ptr = base + static_cast<long>(row) * rs;
+          if (full) {
+            o[k] = __ldg(reinterpret_cast<const float4*>(ptr));
+          } else {
+            if (nv > 0) o[k].x = __ldg(ptr);
+            if (nv > 1) o[k].y = __ldg(ptr + 1);
+            if (nv > 2) o[k].z = __ldg(ptr + 2);
+            if (nv > 3) o[k].w = __ldg(ptr + 3);
+          }
+        }
+      }
+    };
+    auto store1 = [&](float* ptr, bool full, int nv, const float4 v) {
+      if (full) {
+        *reinterpret_cast<float4*>(ptr) = v;
+      } else {
+        if (nv > 0) ptr[0] = v.x;
+        if (nv > 1) ptr[1] = v.y;
+        if (nv > 2) ptr[2] = v.z;
+        if (nv > 3) ptr[3] = v.w;
+      }
+    };
+
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tile_iter) {
       const TileCoord c = decode_tile(p, tile);
       const int acc = tile_iter % p.acc_stages;
@@ -264,153 +339,243 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       ptx::tc_fence_after();
       const uint32_t tacc = tmem_base + acc * 256 + lane_base;
 
-      const int row = c.m0 + row_in_tile;
-      const int row_limit = (p.mode == 2) ? p.M : p.R;
-      const bool row_ok = row < row_limit;
+      const int row_limit = (kEpi == EPI_WGRAD) ? p.M : p.R;
       const int n_cols = (p.N - c.n0) < p.n_tile ? (p.N - c.n0) : p.n_tile;  // valid columns of this tile
-      const int n_chunks = (n_cols + 15) / 16;
+      const int n_chunks = (n_cols + 31) / 32;
+      const int row0 = c.m0 + q * 32 + rsub;  // this lane's rows are row0 + 4k
+      const int last_ch = ((n_chunks - 1 - half) & ~1) + half;  // last chunk of this warp (< half: none)
+      bool released = false;
+      auto release_tmem = [&]() {  // accumulator fully read: the MMA warp may start the next tile into it
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&bar_tmem_empty[acc]);
+        released = true;
+      };
 
-      if (p.mode == 2) {
-        float* orow = p.out + c.zo * p.o_zs + c.j * p.o_js + static_cast<long>(row) * p.o_rs + c.n0;
-        for (int ch = 0; ch < n_chunks; ++ch) {
-          uint32_t v[16];
-          ptx::tmem_ld16(tacc + ch * 16, v);
-          ptx::tmem_wait_ld();
-          if (row_ok) {
+      if constexpr (kEpi == EPI_WGRAD) {
+        float* obase = p.out + c.zo * p.o_zs + c.j * p.o_js + c.n0;
+        for (int ch = half; ch < n_chunks; ch += 2) {
+          float4 t[8];
+          load_chunk(tacc + ch * 32, t);
+          if (ch == last_ch) release_tmem();
+          const int n = ch * 32 + 4 * c4;
+          const int nv = n < n_cols ? ((n_cols - n) < 4 ? (n_cols - n) : 4) : 0;
+          const bool full = vec && nv == 4;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int n = ch * 16 + i;
-              if (n < n_cols) {
-                const float val = p.alpha * __uint_as_float(v[i]);
-                if (p.flags & GEMM_ATOMIC) atomicAdd(orow + n, val);
-                else orow[n] = val;
+          for (int k = 0; k < 8; ++k) {
+            const int row = row0 + 4 * k;
+            if (row >= row_limit || nv == 0) continue;
+            float* dst = obase + static_cast<long>(row) * p.o_rs + n;
+            const float4 o = make_float4(p.alpha * t[k].x, p.alpha * t[k].y, p.alpha * t[k].z, p.alpha * t[k].w);
+            if (p.flags & GEMM_ATOMIC) {
+              if (full) {
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(o.x), "f"(o.y), "f"(o.z),
+                             "f"(o.w)
+                             : "memory");
+              } else {
+                if (nv > 0) atomicAdd(dst, o.x);
+                if (nv > 1) atomicAdd(dst + 1, o.y);
+                if (nv > 2) atomicAdd(dst + 2, o.z);
+                if (nv > 3) atomicAdd(dst + 3, o.w);
               }
+            } else {
+              store1(dst, full, nv, o);
             }
           }
         }
       } else {
-        const long rowoff_o = c.z * p.o_zs + static_cast<long>(row) * p.o_rs + c.n0;
-        const long rowoff_r = c.z * p.r_zs + static_cast<long>(row) * p.r_rs + c.n0;
-        const long rowoff_g = c.z * p.g_zs + static_cast<long>(row) * p.g_rs + c.n0;
-        const float keep_row = (p.lens == nullptr || row < p.lens[c.z]) ? 1.0f : 0.0f;
-        const uint64_t drop_row = (static_cast<uint64_t>(c.z) * p.R + row) * static_cast<uint64_t>(p.N) + c.n0;
-        const bool vec_ok = ((p.o_rs & 3) == 0) && ((c.n0 & 3) == 0) &&
-                            ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
+        const int len_z = p.lens ? p.lens[c.z] : 0x7fffffff;
+        const long zoff_o = c.z * p.o_zs + c.n0, zoff_r = c.z * p.r_zs + c.n0, zoff_g = c.z * p.g_zs + c.n0;
 
-        // v = alpha*acc + bias -> relu -> gate -> dropout(pre) -> + residual      (column n of this row)
-        auto pre_value = [&](float accv, int n) -> float {
-          float v = p.alpha * accv;
-          if (p.bias) v += __ldg(p.bias + c.n0 + n);
-          if (p.flags & GEMM_RELU) v = fmaxf(v, 0.0f);
-          if (p.gate) {
-            const float gv = __ldg(p.gate + rowoff_g + n);
-            v *= (gv > 0.0f) ? 1.0f : p.gate_slope;
+        // x = alpha*acc + bias -> relu -> gate -> dropout(pre) -> + residual   for the 8 float4 of one chunk
+        auto finish_chunk = [&](float4 (&t)[8], int n, bool full, int nv) {
+          float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias && nv) {
+            const float* bp = p.bias + c.n0 + n;
+            if (full) b = __ldg(reinterpret_cast<const float4*>(bp));
+            else {
+              b.x = __ldg(bp);
+              if (nv > 1) b.y = __ldg(bp + 1);
+              if (nv > 2) b.z = __ldg(bp + 2);
+              if (nv > 3) b.w = __ldg(bp + 3);
+            }
           }
-          if (p.flags & GEMM_DROP_PRE) v *= dropout_scale(seed, drop_row + n, p.drop_thresh, p.inv_keep);
-          if (p.residual) v += __ldg(p.residual + rowoff_r + n);
-          return v;
+          float4 gv[8], rv[8];
+          if constexpr (kEpi != EPI_PLAIN) {
+            if (p.gate) load8(p.gate + zoff_g + n, p.g_rs, row0, row_limit, full, nv, gv);
+            if (p.residual) load8(p.residual + zoff_r + n, p.r_rs, row0, row_limit, full, nv, rv);
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            float4 x = make_float4(p.alpha * t[k].x + b.x, p.alpha * t[k].y + b.y, p.alpha * t[k].z + b.z,
+                                   p.alpha * t[k].w + b.w);
+            if (p.flags & GEMM_RELU) {
+              x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f);
+            }
+            if constexpr (kEpi != EPI_PLAIN) {
+              if (p.gate) {
+                x.x *= gv[k].x > 0.f ? 1.f : p.gate_slope;
+                x.y *= gv[k].y > 0.f ? 1.f : p.gate_slope;
+                x.z *= gv[k].z > 0.f ? 1.f : p.gate_slope;
+                x.w *= gv[k].w > 0.f ? 1.f : p.gate_slope;
+              }
+              if (p.flags & GEMM_DROP_PRE) {
+                const uint64_t di = (static_cast<uint64_t>(c.z) * p.R + (row0 + 4 * k)) * static_cast<uint64_t>(p.N) + c.n0 + n;
+                x.x *= dropout_scale(seed, di, p.drop_thresh, p.inv_keep);
+                x.y *= dropout_scale(seed, di + 1, p.drop_thresh, p.inv_keep);
+                x.z *= dropout_scale(seed, di + 2, p.drop_thresh, p.inv_keep);
+                x.w *= dropout_scale(seed, di + 3, p.drop_thresh, p.inv_keep);
+              }
+              if (p.residual) {
+                x.x += rv[k].x; x.y += rv[k].y; x.z += rv[k].z; x.w += rv[k].w;
+              }
+            }
+            t[k] = x;
+          }
         };
 
-        if (!(p.flags & GEMM_LN)) {
-          for (int ch = 0; ch < n_chunks; ++ch) {
-            uint32_t v[16];
-            ptx::tmem_ld16(tacc + ch * 16, v);
-            ptx::tmem_wait_ld();
-            if (row_ok) {
-              float o[16];
+        if constexpr (kEpi != EPI_LN) {
+          for (int ch = half; ch < n_chunks; ch += 2) {
+            float4 t[8];
+            load_chunk(tacc + ch * 32, t);
+            if (ch == last_ch) release_tmem();
+            const int n = ch * 32 + 4 * c4;
+            const int nv = n < n_cols ? ((n_cols - n) < 4 ? (n_cols - n) : 4) : 0;
+            const bool full = vec && nv == 4;
+            finish_chunk(t, n, full, nv);
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const int n = ch * 16 + i;
-                o[i] = (n < n_cols) ? pre_value(__uint_as_float(v[i]), n) * keep_row : 0.0f;
-              }
-              float* dst = p.out + rowoff_o + ch * 16;
-              if (vec_ok && (ch * 16 + 16 <= n_cols)) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                  *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
-              } else {
-#pragma unroll
-                for (int i = 0; i < 16; ++i)
-                  if (ch * 16 + i < n_cols) dst[i] = o[i];
-              }
+            for (int k = 0; k < 8; ++k) {
+              const int row = row0 + 4 * k;
+              if (row >= row_limit || nv == 0) continue;
+              if (row >= len_z) t[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+              store1(p.out + zoff_o + static_cast<long>(row) * p.o_rs + n, full, nv, t[k]);
             }
           }
         } else {
-          // LayerNorm over the n_cols (= N) columns held by this thread's TMEM lane. Three TMEM passes:
-          // (1) finish the pre-LN value in place and sum it, (2) centred second moment, (3) normalise + store.
-          float sum = 0.0f;
-          for (int ch = 0; ch < n_chunks; ++ch) {
-            uint32_t v[16];
-            ptx::tmem_ld16(tacc + ch * 16, v);
-            ptx::tmem_wait_ld();
+          // LayerNorm over the n_cols (= N) columns of each row. Pass 1 finishes the pre-LN value, stores it (to
+          // out_pre, or to out as scratch) and accumulates moments about the first element this warp sees of each
+          // row (shifted sums: no cancellation when |mean| >> std). The two warps of a quarter then merge their
+          // (count, mean, M2) through shared memory, and pass 2 re-reads the values this same thread wrote
+          // (L2-resident), normalises and stores. The accumulator is released between the passes.
+          float* pre_dst = p.out_pre ? p.out_pre : p.out;
+          float s1[8], s2[8], x0[8];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float x = row_ok ? pre_value(__uint_as_float(v[i]), ch * 16 + i) : 0.0f;
-              sum += x;
-              v[i] = __float_as_uint(x);
+          for (int k = 0; k < 8; ++k) s1[k] = s2[k] = x0[k] = 0.0f;
+          int cnt = 0;  // columns this warp has accumulated per row
+          for (int ch = half; ch < n_chunks; ch += 2) {
+            float4 t[8];
+            load_chunk(tacc + ch * 32, t);
+            if (ch == last_ch) release_tmem();
+            const int n = ch * 32 + 4 * c4;
+            const int nv = n < n_cols ? ((n_cols - n) < 4 ? (n_cols - n) : 4) : 0;
+            const bool full = vec && nv == 4;
+            finish_chunk(t, n, full, nv);
+            cnt += (n_cols - ch * 32) < 32 ? (n_cols - ch * 32) : 32;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const int row = row0 + 4 * k;
+              if (row < row_limit && nv) store1(pre_dst + zoff_o + static_cast<long>(row) * p.o_rs + n, full, nv, t[k]);
+              if (ch == half) x0[k] = __shfl_sync(0xffffffffu, t[k].x, lane & ~7);
+              const float d0 = nv > 0 ? t[k].x - x0[k] : 0.f, d1 = nv > 1 ? t[k].y - x0[k] : 0.f;
+              const float d2 = nv > 2 ? t[k].z - x0[k] : 0.f, d3 = nv > 3 ? t[k].w - x0[k] : 0.f;
+              s1[k] += (d0 + d1) + (d2 + d3);
+              s2[k] += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
             }
-            ptx::tmem_st16(tacc + ch * 16, v);
           }
-          ptx::tmem_wait_st();
-          const float mean = sum / static_cast<float>(n_cols);
-          float sq = 0.0f;
-          for (int ch = 0; ch < n_chunks; ++ch) {
-            uint32_t v[16];
-            ptx::tmem_ld16(tacc + ch * 16, v);
-            ptx::tmem_wait_ld();
+          if (!released) release_tmem();
+          // per-warp (count, mean, M2) per row -> shared memory -> merge with the partner warp (Chan et al.)
+          float mean[8], rstd[8];
+          float* my = ln_part[half][q][0];
+          const float* other = ln_part[half ^ 1][q][0];
+          const float fc = static_cast<float>(cnt);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float d = __uint_as_float(v[i]) - mean;
-              sq += d * d;
+          for (int k = 0; k < 8; ++k) {
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {
+              s1[k] += __shfl_xor_sync(0xffffffffu, s1[k], o);
+              s2[k] += __shfl_xor_sync(0xffffffffu, s2[k], o);
+            }
+            const float md = cnt ? s1[k] / fc : 0.f;
+            mean[k] = x0[k] + md;
+            rstd[k] = fmaxf(s2[k] - s1[k] * md, 0.f);  // M2 for now
+            if (c4 == 0) {
+              my[(4 * k + rsub) * 2] = mean[k];
+              my[(4 * k + rsub) * 2 + 1] = rstd[k];
             }
           }
-          const float rstd = rsqrtf(sq / static_cast<float>(n_cols) + p.ln_eps);
-          if (row_ok) {
-            const long srow = static_cast<long>(c.z) * p.R + row;
-            if (p.ln_mean) p.ln_mean[srow] = mean;
-            if (p.ln_rstd) p.ln_rstd[srow] = rstd;
+          asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+          const int cnt_o = n_cols - cnt;
+          const float fo = static_cast<float>(cnt_o), fn = static_cast<float>(n_cols);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float mo = other[(4 * k + rsub) * 2], m2o = other[(4 * k + rsub) * 2 + 1];
+            float m = mean[k], m2 = rstd[k];
+            if (cnt_o > 0) {
+              const float delta = mo - m;
+              m2 = m2 + m2o + delta * delta * (fc * fo / fn);
+              m = (fc * m + fo * mo) / fn;
+            }
+            mean[k] = m;
+            rstd[k] = rsqrtf(m2 / fn + p.ln_eps);
+            const int row = row0 + 4 * k;
+            if (half == 0 && c4 == 0 && row < row_limit) {
+              const long srow = static_cast<long>(c.z) * p.R + row;
+              if (p.ln_mean) p.ln_mean[srow] = mean[k];
+              if (p.ln_rstd) p.ln_rstd[srow] = rstd[k];
+            }
           }
-          for (int ch = 0; ch < n_chunks; ++ch) {
-            uint32_t v[16];
-            ptx::tmem_ld16(tacc + ch * 16, v);
-            ptx::tmem_wait_ld();
-            if (row_ok) {
-              float o[16];
+          asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");  // partner has read my stats: slot reusable
+          for (int ch = half; ch < n_chunks; ch += 2) {
+            const int n = ch * 32 + 4 * c4;
+            const int nv = n < n_cols ? ((n_cols - n) < 4 ? (n_cols - n) : 4) : 0;
+            if (nv == 0) continue;
+            const bool full = vec && nv == 4;
+            float4 gm = make_float4(0.f, 0.f, 0.f, 0.f), bt = gm;
+            if (full) {
+              gm = __ldg(reinterpret_cast<const float4*>(p.gamma + n));
+              bt = __ldg(reinterpret_cast<const float4*>(p.beta + n));
+            } else {
+              gm.x = p.gamma[n]; bt.x = p.beta[n];
+              if (nv > 1) { gm.y = p.gamma[n + 1]; bt.y = p.beta[n + 1]; }
+              if (nv > 2) { gm.z = p.gamma[n + 2]; bt.z = p.beta[n + 2]; }
+              if (nv > 3) { gm.w = p.gamma[n + 3]; bt.w = p.beta[n + 3]; }
+            }
+            float4 x[8];
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const int n = ch * 16 + i;
-                const float x = __uint_as_float(v[i]);
-                float y = (x - mean) * rstd * __ldg(p.gamma + n) + __ldg(p.beta + n);
-                if (p.flags & GEMM_DROP_POST) y *= dropout_scale(seed, drop_row + n, p.drop_thresh, p.inv_keep);
-                o[i] = y * keep_row;
-              }
-              float* dst = p.out + rowoff_o + ch * 16;
-              float* dpre = p.out_pre ? p.out_pre + rowoff_o + ch * 16 : nullptr;
-              if (vec_ok) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                  *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
-                if (dpre) {
-#pragma unroll
-                  for (int q = 0; q < 4; ++q)
-                    *reinterpret_cast<float4*>(dpre + 4 * q) =
-                        make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
-                                    __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
-                }
-              } else {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                  dst[i] = o[i];
-                  if (dpre) dpre[i] = __uint_as_float(v[i]);
+            for (int k = 0; k < 8; ++k) {  // plain (coherent) loads: these addresses were written by this thread
+              const int row = row0 + 4 * k;
+              x[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (row < row_limit) {
+                const float* ptr = pre_dst + zoff_o + static_cast<long>(row) * p.o_rs + n;
+                if (full) x[k] = *reinterpret_cast<const float4*>(ptr);
+                else {
+                  x[k].x = ptr[0];
+                  if (nv > 1) x[k].y = ptr[1];
+                  if (nv > 2) x[k].z = ptr[2];
+                  if (nv > 3) x[k].w = ptr[3];
                 }
               }
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const int row = row0 + 4 * k;
+              if (row >= row_limit) continue;
+              float4 y = make_float4((x[k].x - mean[k]) * rstd[k] * gm.x + bt.x, (x[k].y - mean[k]) * rstd[k] * gm.y + bt.y,
+                                     (x[k].z - mean[k]) * rstd[k] * gm.z + bt.z, (x[k].w - mean[k]) * rstd[k] * gm.w + bt.w);
+              if (p.flags & GEMM_DROP_POST) {
+                const uint64_t di = (static_cast<uint64_t>(c.z) * p.R + row) * static_cast<uint64_t>(p.N) + c.n0 + n;
+                y.x *= dropout_scale(seed, di, p.drop_thresh, p.inv_keep);
+                y.y *= dropout_scale(seed, di + 1, p.drop_thresh, p.inv_keep);
+                y.z *= dropout_scale(seed, di + 2, p.drop_thresh, p.inv_keep);
+                y.w *= dropout_scale(seed, di + 3, p.drop_thresh, p.inv_keep);
+              }
+              if (row >= len_z) y = make_float4(0.f, 0.f, 0.f, 0.f);
+              store1(p.out + zoff_o + static_cast<long>(row) * p.o_rs + n, full, nv, y);
             }
           }
         }
       }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&bar_tmem_empty[acc]);
+      if (!released) release_tmem();
     }
   }
 
@@ -524,7 +689,7 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
   p.stages = kSmemBudget / stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   XVA_CHECK_ARG(p.stages >= 2, "gemm: tile too large for shared memory");
-  const int smem_bytes = p.stages * stage_bytes + 1024;
+  const int smem_bytes = p.stages * stage_bytes + kTailSmemBytes;
 
   // ---- tiling along M and the k loop
   if (g.mode != 2) {
@@ -651,15 +816,41 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
     p.inv_keep = 1.0f;
   }
 
+  {
+    auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    auto m4 = [](long v) { return (v & 3) == 0; };
+    bool ok = al(g.out) && m4(g.o_rs) && m4(g.o_zs) && m4(g.o_js);
+    if (g.bias) ok = ok && al(g.bias);
+    if (g.residual) ok = ok && al(g.residual) && m4(g.r_rs) && m4(g.r_zs);
+    if (g.gate) ok = ok && al(g.gate) && m4(g.g_rs) && m4(g.g_zs);
+    if (g.out_pre) ok = ok && al(g.out_pre);
+    if (g.flags & GEMM_LN) ok = ok && al(g.gamma) && al(g.beta);
+    p.vec_ok = ok ? 1 : 0;
+  }
+
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + 1024);
+    const int mx = kSmemBudget + kTailSmemBytes;
+    attr_err = cudaFuncSetAttribute(gemm_tc_kernel<EPI_WGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(gemm_tc_kernel<EPI_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(gemm_tc_kernel<EPI_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(gemm_tc_kernel<EPI_LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
   });
   XVA_CHECK_CUDA(attr_err);
 
   int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-  gemm_tc_kernel<<<grid, kThreads, smem_bytes, stream>>>(map_a, map_b, p);
+  if (g.mode == 2)
+    gemm_tc_kernel<EPI_WGRAD><<<grid, kThreads, smem_bytes, stream>>>(map_a, map_b, p);
+  else if (p.flags & GEMM_LN)
+    gemm_tc_kernel<EPI_LN><<<grid, kThreads, smem_bytes, stream>>>(map_a, map_b, p);
+  else if (p.gate || p.residual || (p.flags & GEMM_DROP_PRE))
+    gemm_tc_kernel<EPI_FULL><<<grid, kThreads, smem_bytes, stream>>>(map_a, map_b, p);
+  else
+    gemm_tc_kernel<EPI_PLAIN><<<grid, kThreads, smem_bytes, stream>>>(map_a, map_b, p);
   XVA_CHECK_LAUNCH();
   return XVA_OK;
 }

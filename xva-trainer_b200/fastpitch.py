@@ -467,11 +467,15 @@ class FastPitch(torch.nn.Module):
                 input_lens]
 
     # ------------------------------------------------------------------------------------------ backward
-    def backward(self, criterion, scale=1.0):
+    def backward(self, criterion, scale=1.0, grad_sync=None):
         """Reverse pass for the loss ``criterion`` just evaluated on this module's last forward() output. Gradients of
         the stage's trainable parameters are ACCUMULATED into the gradient arena (zero_grad() clears it), scaled by
-        ``scale`` (the 1/gam of xva_train.py:806)."""
+        ``scale`` (the 1/gam of xva_train.py:806). ``grad_sync`` (parallel.GradSync) is told which arena slices are
+        final as the pass proceeds, so their all-reduce overlaps the rest of the backward."""
         ctx = self._ctx
+        if grad_sync is not None:
+            scale = scale * grad_sync.loss_scale
+        ready = (lambda *p, flush=False: grad_sync.ready(list(p), flush)) if grad_sync is not None else (lambda *p, flush=False: None)
         if ctx is None:
             raise RuntimeError("backward() needs a forward() in training mode first")
         stage = ctx.stage
@@ -480,6 +484,7 @@ class FastPitch(torch.nn.Module):
         seeds = criterion.grad_seeds(scale)
         if stage == 2:
             d_enc = self._pred_bwd(seeds["log_dur"], lens, self.pred["duration"], ctx.preds["duration"])
+            ready("duration_predictor", flush=True)
         else:
             # projection
             dmel = seeds["mel"]                                   # [B,T_out,96], columns 80.. are zero
@@ -488,8 +493,9 @@ class FastPitch(torch.nn.Module):
             ops.conv_wgrad(dm, ctx.dec_out, (0,), out=self.g.proj_w, accumulate=True)
             ops.colsum_(B * T_out, N_MEL, dmel.shape[2], dmel, self.g.proj_b)
             dy = ops.conv_dgrad(dm, self.w.proj_w, lens=ctx.dec_lens)
-            for L, c in zip(reversed(self.dec_layers), reversed(ctx.dec)):
+            for i, (L, c) in enumerate(zip(reversed(self.dec_layers), reversed(ctx.dec))):
                 dy = self._layer_bwd(dy, ctx.dec_lens, L, c)
+                ready(f"decoder.layers.{N_LAYERS - 1 - i}")
             d_enc = ops.regulate_scatter(dy, ctx.cum, Tt)         # pos-emb has no parameters: dy is d(regulated)
             del dy
             ops.scalar_conv_bwd_(d_enc, ctx.energy_tgt, self.g.energy_emb_w, self.g.energy_emb_b)
@@ -497,10 +503,14 @@ class FastPitch(torch.nn.Module):
                 d_enc = self._pred_bwd(seeds["energy"], lens, self.pred["energy"], ctx.preds["energy"], residual=d_enc)
                 ops.scalar_conv_bwd_(d_enc, ctx.pitch_tgt, self.g.pitch_emb_w, self.g.pitch_emb_b)
                 d_enc = self._pred_bwd(seeds["pitch"], lens, self.pred["pitch"], ctx.preds["pitch"], residual=d_enc)
-        n = len(self.enc_layers)
+            # the tail of the arena (pitch/energy predictors + embeddings, proj) is final, touched or not
+            ready("pitch_predictor", "pitch_emb", "energy_predictor", "energy_emb", "proj", flush=True)
         for i, (L, c) in enumerate(zip(reversed(self.enc_layers), reversed(ctx.enc))):
             d_enc = self._layer_bwd(d_enc, lens, L, c)
+            if i < N_LAYERS - 1:
+                ready(f"encoder.layers.{N_LAYERS - 1 - i}")
         ops.embed_bwd_(ctx.tokens, d_enc, self.g.emb)
+        ready("encoder.layers.0", "encoder.word_emb", flush=True)
         self._ctx = None
 
     def step_dropout(self):

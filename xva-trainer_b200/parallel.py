@@ -1,0 +1,74 @@
+"""Data-parallel gradient exchange: one process per GPU, the utterance batch sharded across ranks, and ONE collective
+on the path -- an all-reduce (SUM) of the gradient arena before the optimizer step (the reference
+itself only has single-process nn.DataParallel, xva_train.py:465-466).
+
+The gradient arena is one flat fp32 buffer laid out in state_dict order, and backward() finishes it from the top of the
+network down, so the exchange is bucketed by construction: as soon as a contiguous slice is final (a decoder layer, the
+predictor / projection tail, an encoder layer) backward() calls ``ready(prefixes)`` and that slice is all-reduced in
+place on NCCL's own stream while the remaining backward kernels keep the SMs busy. ``finish()`` joins the streams before
+LAMB reads the arena. Loss gradients are pre-scaled by 1/world, so SUM yields the mean and every rank applies the
+same update (replicas stay bit-identical without a broadcast).
+"""
+import math
+
+import torch
+import torch.distributed as dist
+
+
+class GradSync:
+    def __init__(self, model_or_arena, world, group=None, min_bucket_elems=1 << 20):
+        self.arena = getattr(model_or_arena, "arena", model_or_arena)
+        self.world = int(world)
+        self.group = group
+        self.min_bucket = int(min_bucket_elems)
+        self.pending = []
+        self._lo = None
+        self._hi = None
+        self.buckets_sent = 0
+        self.elems_sent = 0
+
+    @property
+    def loss_scale(self):
+        return 1.0 / self.world
+
+    def _range(self, prefixes):
+        A = self.arena
+        lo, hi = None, None
+        for k in A.offset:
+            if any(k == p or k.startswith(p + ".") for p in prefixes):
+                a = A.offset[k]
+                b = a + int(math.prod(A.pshape[k]))
+                lo = a if lo is None else min(lo, a)
+                hi = b if hi is None else max(hi, b)
+        if lo is None:
+            raise KeyError(f"no arena entry under {prefixes}")
+        return lo, hi
+
+    def ready(self, prefixes, flush=False):
+        """The gradients of every parameter under ``prefixes`` are final. Adjacent ready slices are merged until a
+        bucket reaches min_bucket elements (or ``flush``), then all-reduced asynchronously."""
+        lo, hi = self._range(prefixes)
+        if self._lo is not None and (hi == self._lo or lo == self._hi or (lo <= self._hi and hi >= self._lo)):
+            self._lo, self._hi = min(lo, self._lo), max(hi, self._hi)
+        else:
+            self._send()
+            self._lo, self._hi = lo, hi
+        if flush or (self._hi - self._lo) >= self.min_bucket:
+            self._send()
+
+    def _send(self):
+        if self._lo is None:
+            return
+        sl = self.arena.g[self._lo:self._hi]
+        if self.world > 1:
+            self.pending.append(dist.all_reduce(sl, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        self.buckets_sent += 1
+        self.elems_sent += self._hi - self._lo
+        self._lo = self._hi = None
+
+    def finish(self):
+        """Join: the current stream waits for every outstanding all-reduce."""
+        self._send()
+        for w in self.pending:
+            w.wait()
+        self.pending = []
