@@ -110,6 +110,9 @@ typedef struct xva_gemm_args {
 /* sizeof(xva_gemm_args) as compiled into the library, so a binding can verify its struct layout. */
 int xva_sizeof_gemm_args(void);
 int xva_gemm(const xva_gemm_args* args, void* stream);
+/* Bring-up aid: eight cycle counters of CTA 0 from the last xva_gemm launched with XVA_GEMM_DBG & 32 in the
+ * environment (role wait / work times; layout in csrc/gemm_tc.cu). Synchronises the device. */
+int xva_gemm_debug_counters(long long* out8_host);
 /* Same contract on CUDA cores in exact fp32: a checker for the tests, never used by the product path. */
 int xva_gemm_ref(const xva_gemm_args* args, void* stream);
 

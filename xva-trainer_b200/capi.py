@@ -54,6 +54,7 @@ PROTOTYPES = {
     "xva_sizeof_gemm_args": (_I, []),
     "xva_gemm": (_I, [C.POINTER(GemmArgs), _P]),
     "xva_gemm_ref": (_I, [C.POINTER(GemmArgs), _P]),
+    "xva_gemm_debug_counters": (_I, [C.POINTER(C.c_longlong * 8)]),
     "xva_regulate_len_scan": (_I, [_P, _I, _I, _F, _I, _P, _P, _P]),
     "xva_regulate_len_fwd": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "xva_regulate_len_bwd": (_I, [_P, _P, _I, _I, _I, _I, _P, _I, _P]),
@@ -111,7 +112,7 @@ def check(status, what=""):
 
 
 # kernels enqueued per successful call (everything not listed launches exactly one)
-_LAUNCHES = {"xva_lamb_step": 2, "xva_abi_version": 0, "xva_last_error": 0, "xva_device_check": 0,
+_LAUNCHES = {"xva_lamb_step": 2, "xva_gemm_debug_counters": 0, "xva_abi_version": 0, "xva_last_error": 0, "xva_device_check": 0,
              "xva_sizeof_gemm_args": 0}
 _launch_count = 0
 

@@ -33,6 +33,8 @@ int xva_gemm(const xva_gemm_args* args, void* stream) {
   return gemm_tc_launch(*args, S(stream));
 }
 
+int xva_gemm_debug_counters(long long* out8) { return gemm_debug_counters(out8); }
+
 int xva_gemm_ref(const xva_gemm_args* args, void* stream) {
   XVA_CHECK_ARG(args != nullptr, "xva_gemm_ref: null args");
   return gemm_ref_launch(*args, S(stream));

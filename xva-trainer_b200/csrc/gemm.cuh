@@ -47,6 +47,8 @@ inline GemmArgs gemm_args() {
 
 // tcgen05 + TMA implementation (the product path).
 int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream);
+// Bring-up: cycle counters of CTA 0 from the last launch made with XVA_GEMM_DBG & 32 (see gemm_tc.cu).
+int gemm_debug_counters(long long* out8);
 // Plain fp32 SIMT implementation of the same contract; used by the tests to separate "descriptor/layout bug"
 // from "host wiring bug". Never called by the product path.
 int gemm_ref_launch(const GemmArgs& g, cudaStream_t stream);

@@ -38,6 +38,7 @@ struct GemmDev {
   int mode, Z, R, M, N, K, taps, ZR, split, zper;
   int n_tile, n_sub, n_mma, tiles_n, tiles_m, k_chunks, stages, acc_stages, num_tiles;
   int b_tap_z, b_batch_z;
+  int row_tiles;  // Z * tiles_m: 128-row tiles of the output (mode 0/1)
   uint32_t mn_layout, mn_lbo, mn_sbo;  // MN-major descriptor constants (debug-overridable, see gemm_tc_launch)
   int shift[kMaxTaps];
   float* out;
@@ -61,6 +62,7 @@ struct GemmDev {
   float inv_keep;
   uint64_t seed;
   const uint64_t* seed_dev;
+  int dbg;     // bring-up knobs (XVA_GEMM_DBG): 1 = no epilogue stores, 2 = no TMA after the first ring fill, 4 = no MMA
   int vec_ok;  // every epilogue pointer is 16-byte aligned and every stride a multiple of 4: float4 accesses
 };
 
@@ -72,12 +74,24 @@ struct TileCoord {
   int m0;     // first output row of the tile
   int n0;     // first output column of the tile
   int iters;  // k-iterations of the main loop
+  bool dup;   // CTA pair, odd row-tile count: this CTA repeats its partner's rows and stores nothing
 };
 
-__device__ __forceinline__ TileCoord decode_tile(const GemmDev& p, int t) {
+// kCG = 2: a tile belongs to a CTA pair; the two CTAs take consecutive 128-row tiles (possibly of different batch
+// items -- they only have to share the B operand) and the same n tile.
+template <int kCG>
+__device__ __forceinline__ TileCoord decode_tile(const GemmDev& p, int t, int cta_rank) {
   TileCoord c;
+  c.dup = false;
   int n_t = t % p.tiles_n;
   t /= p.tiles_n;
+  if (kCG == 2) {
+    t = 2 * t + cta_rank;
+    if (t >= p.row_tiles) {
+      t = p.row_tiles - 1;
+      c.dup = true;
+    }
+  }
   int m_t = t % p.tiles_m;
   t /= p.tiles_m;
   c.n0 = n_t * p.n_tile;
@@ -107,6 +121,11 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmDev& p, int t) {
 //   MN-major: 32-bit operands only exist as SWIZZLE_128B_BASE32B (layout type 1; TMA 128B_ATOM_32B): atoms of
 //             4 k-rows x 128 B whose 32-byte chunks are XOR-ed with (row & 3); LBO = byte distance between
 //             32-element MN chunks, SBO = 512 B between 4-row k groups.
+// Bring-up counters (XVA_GEMM_DBG & 32): cycles CTA 0 spends in each role state, summed over its tiles.
+//  [0] MMA warp waiting for a free accumulator   [1] MMA warp waiting for operands   [2] MMA warp issuing
+//  [3] epilogue warp 4 waiting for an accumulator [4] epilogue warp 4 working        [5] tiles of CTA 0   [6] total
+__device__ long long g_gemm_dbg[8];
+
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
                                                    uint32_t layout_type) {
   uint64_t d = 0;
@@ -119,7 +138,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
 }
 
 // Instruction descriptor (cute::UMMA::InstrDescriptor): tf32 x tf32 -> f32, M = 128, runtime N.
-__device__ __forceinline__ uint32_t make_idesc(int n, int a_mn_major, int b_mn_major) {
+__device__ __forceinline__ uint32_t make_idesc(int n, int a_mn_major, int b_mn_major, int m) {
   uint32_t d = 0;
   d |= 1u << 4;                                   // c_format = F32
   d |= 2u << 7;                                   // a_format = TF32
@@ -127,12 +146,12 @@ __device__ __forceinline__ uint32_t make_idesc(int n, int a_mn_major, int b_mn_m
   d |= static_cast<uint32_t>(a_mn_major) << 15;   // a_major
   d |= static_cast<uint32_t>(b_mn_major) << 16;   // b_major
   d |= static_cast<uint32_t>(n >> 3) << 17;       // n_dim
-  d |= static_cast<uint32_t>(kBlockM >> 4) << 24; // m_dim
+  d |= static_cast<uint32_t>(m >> 4) << 24;       // m_dim (256 = both CTAs of a pair)
   return d;
 }
 
 
-template <int kEpi>
+template <int kEpi, int kCG>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ GemmDev p) {
@@ -147,8 +166,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
            static_cast<int>(smem - smem_raw), kAlignSlack);
     __trap();
   }
-  const int b_tile_bytes = p.n_tile * kBlockK * 4;
+  const int b_tile_bytes = p.n_tile * kBlockK * 4 / kCG;  // a CTA pair splits every B tile along n
   const int stage_bytes = kATileBytes + b_tile_bytes;
+  const uint32_t cta_rank = (kCG == 2) ? ptx::cluster_ctarank() : 0u;
+  const int cta_id = (kCG == 2) ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int n_ctas = (kCG == 2) ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   uint8_t* tail = smem + p.stages * stage_bytes + kEpiSmemBytes;
   float (*ln_part)[4][32][2] = reinterpret_cast<float (*)[4][32][2]>(tail);  // LayerNorm (mean, M2) exchange
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(tail + kLnSmemBytes);
@@ -171,16 +193,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&bar_tmem_full[a], 1);
-      ptx::mbar_init(&bar_tmem_empty[a], 8);
+      ptx::mbar_init(&bar_tmem_empty[a], 8 * kCG);
     }
     ptx::fence_mbar_init();
   }
   if (warp == 2) {
-    ptx::tmem_alloc(&tmem_base_slot, kTmemCols);
-    ptx::tmem_relinquish();
+    if (kCG == 2) {
+      ptx::tmem_alloc_cg2(&tmem_base_slot, kTmemCols);
+      ptx::tmem_relinquish_cg2();
+    } else {
+      ptx::tmem_alloc(&tmem_base_slot, kTmemCols);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if (kCG == 2) ptx::cluster_sync_all();  // the peer's barriers must exist before anything is signalled across
+  else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
@@ -189,81 +217,154 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    {
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const TileCoord c = decode_tile(p, tile);
-        for (int it = 0; it < c.iters; ++it) {
-          ptx::mbar_wait(&bar_empty[s], ph ^ 1);
-          uint8_t* sa = smem + s * stage_bytes;
-          uint8_t* sb = sa + kATileBytes;
-          ptx::mbar_arrive_expect_tx(&bar_full[s], stage_bytes);
-          if (p.mode != 2) {
-            const int j = it / p.k_chunks;
-            const int kc = it - j * p.k_chunks;
-            const int zb = j * p.b_tap_z + c.z * p.b_batch_z;
-            ptx::tma_load_3d(sa, &tmap_a, &bar_full[s], kc * kBlockK, c.m0 + p.shift[j], c.z);
-            if (p.mode == 0) {
-              for (int sub = 0; sub < p.n_mma; ++sub)
-                ptx::tma_load_3d(sb + sub * p.n_sub * kBlockK * 4, &tmap_b, &bar_full[s], kc * kBlockK,
-                                 c.n0 + sub * p.n_sub, zb);
+      for (int tile = cta_id; tile < p.num_tiles; tile += n_ctas) {
+        const TileCoord c = decode_tile<kCG>(p, tile, cta_rank);
+        if (p.dbg & 16) continue;  // probe: raw MMA issue rate, no operand pipeline at all
+        // outer index: tap (mode 0/1) or batch item of the reduced range (mode 2); inner: 32-wide k block
+        const int n_outer = c.iters / p.k_chunks;
+        int it = 0;
+        for (int jo = 0; jo < n_outer; ++jo) {
+          const int shift_j = (p.mode != 2) ? p.shift[jo] : p.shift[c.j];
+          for (int kc = 0; kc < p.k_chunks; ++kc, ++it) {
+            ptx::mbar_wait(&bar_empty[s], ph ^ 1);
+            uint8_t* sa = smem + s * stage_bytes;
+            uint8_t* sb = sa + kATileBytes;
+            if (!ptx::elect_one()) {
+            } else if ((p.dbg & 2) && (tile != cta_id || it >= p.stages)) {
+              if (kCG == 1 || cta_rank == 0) ptx::mbar_arrive(&bar_full[s]);
+            } else if constexpr (kCG == 2) {
+              // Both CTAs load into their own shared memory; all completion bytes land on the LEADER's full
+              // barrier, which alone expects them (its MMA thread is the only consumer).
+              if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&bar_full[s], 2 * stage_bytes);
+              const uint32_t full = ptx::mapa(ptx::smem_u32(&bar_full[s]), 0);
+              const int zb = jo * p.b_tap_z;
+              const int half_n = p.n_sub >> 1;
+              ptx::tma_load_3d_cg2(sa, &tmap_a, full, kc * kBlockK, c.m0 + shift_j, c.z);
+              for (int sub = 0; sub < p.n_mma; ++sub) {
+                const int nb = c.n0 + sub * p.n_sub + static_cast<int>(cta_rank) * half_n;
+                if (p.mode == 0)
+                  ptx::tma_load_3d_cg2(sb + sub * half_n * kBlockK * 4, &tmap_b, full, kc * kBlockK, nb, zb);
+                else
+                  ptx::tma_load_4d_cg2(sb + sub * half_n * kBlockK * 4, &tmap_b, full, 0, kc * kBlockK, nb / 32, zb);
+              }
+            } else if (p.mode != 2) {
+              ptx::mbar_arrive_expect_tx(&bar_full[s], stage_bytes);
+              const int zb = jo * p.b_tap_z + c.z * p.b_batch_z;
+              ptx::tma_load_3d(sa, &tmap_a, &bar_full[s], kc * kBlockK, c.m0 + shift_j, c.z);
+              if (p.mode == 0) {
+                for (int sub = 0; sub < p.n_mma; ++sub)
+                  ptx::tma_load_3d(sb + sub * p.n_sub * kBlockK * 4, &tmap_b, &bar_full[s], kc * kBlockK,
+                                   c.n0 + sub * p.n_sub, zb);
+              } else {
+                ptx::tma_load_4d(sb, &tmap_b, &bar_full[s], 0, kc * kBlockK, c.n0 / 32, zb);
+              }
             } else {
-              ptx::tma_load_4d(sb, &tmap_b, &bar_full[s], 0, kc * kBlockK, c.n0 / 32, zb);
+              ptx::mbar_arrive_expect_tx(&bar_full[s], stage_bytes);
+              const int z = c.z + jo;
+              ptx::tma_load_4d(sa, &tmap_a, &bar_full[s], 0, kc * kBlockK, c.m0 / 32, z);
+              ptx::tma_load_4d(sb, &tmap_b, &bar_full[s], 0, kc * kBlockK + shift_j, c.n0 / 32, z);
             }
-          } else {
-            const int zi = it / p.k_chunks;
-            const int tc = it - zi * p.k_chunks;
-            const int z = c.z + zi;
-            ptx::tma_load_4d(sa, &tmap_a, &bar_full[s], 0, tc * kBlockK, c.m0 / 32, z);
-            ptx::tma_load_4d(sb, &tmap_b, &bar_full[s], 0, tc * kBlockK + p.shift[c.j], c.n0 / 32, z);
-          }
-          if (++s == p.stages) {
-            s = 0;
-            ph ^= 1;
+            __syncwarp();
+            if (++s == p.stages) {
+              s = 0;
+              ph ^= 1;
+            }
           }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(p.n_sub, a_mn ? 1 : 0, b_mn ? 1 : 0);
-      const uint32_t a_lbo = a_mn ? p.mn_lbo : 16;
-      const uint32_t b_lbo = b_mn ? p.mn_lbo : 16;
-      const uint32_t a_kstep = a_mn ? 1024 : kUmmaK * 4;  // bytes to advance per UMMA_K
-      const uint32_t b_kstep = b_mn ? 1024 : kUmmaK * 4;
-      const uint32_t b_sub_bytes = b_mn ? (p.n_sub / 32) * (kBlockK * 128) : p.n_sub * kBlockK * 4;
+    if (cta_rank == 0) {  // whole warp, uniform control flow; one elected lane issues
+      const uint32_t idesc = make_idesc(p.n_sub, a_mn ? 1 : 0, b_mn ? 1 : 0, kBlockM * kCG);
+      // descriptor = constant fields | (shared address >> 4); advancing along k only touches the address field
+      const uint64_t da_hi = make_smem_desc(0, a_mn ? p.mn_lbo : 16, a_mn ? p.mn_sbo : 1024, a_mn ? p.mn_layout : 2);
+      const uint64_t db_hi = make_smem_desc(0, b_mn ? p.mn_lbo : 16, b_mn ? p.mn_sbo : 1024, b_mn ? p.mn_layout : 2);
+      const uint32_t a_kstep = (a_mn ? 1024 : kUmmaK * 4) >> 4;  // address-field units (16 B) per UMMA_K
+      const uint32_t b_kstep = (b_mn ? 1024 : kUmmaK * 4) >> 4;
+      const uint32_t b_sub = ((b_mn ? (p.n_sub / 32) * (kBlockK * 128) : p.n_sub * kBlockK * 4) / kCG) >> 4;
+      const uint32_t ring = ptx::smem_u32(smem) >> 4;
+      const uint32_t stage_u = static_cast<uint32_t>(stage_bytes) >> 4;
+      const int n_mma = p.n_mma, n_sub = p.n_sub, dbg = p.dbg;
       int s = 0;
       uint32_t ph = 0;
+      uint32_t a_lo = ring;  // address field (16-byte units) of the current stage's A tile
       int tile_iter = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tile_iter) {
-        const TileCoord c = decode_tile(p, tile);
+      long long cyc_wait_acc = 0, cyc_wait_ops = 0;
+      const long long t_start = clock64();
+      for (int tile = cta_id; tile < p.num_tiles; tile += n_ctas, ++tile_iter) {
+        const TileCoord c = decode_tile<kCG>(p, tile, 0);
         const int acc = tile_iter % p.acc_stages;
         const uint32_t acc_ph = (tile_iter / p.acc_stages) & 1;
+        long long t_a = clock64();
         ptx::mbar_wait(&bar_tmem_empty[acc], acc_ph ^ 1);
         ptx::tc_fence_after();
+        long long t_b = clock64();
+        cyc_wait_acc += t_b - t_a;
         const uint32_t tmem_acc = tmem_base + acc * 256;
         for (int it = 0; it < c.iters; ++it) {
-          ptx::mbar_wait(&bar_full[s], ph);
-          ptx::tc_fence_after();
-          const uint32_t sa = ptx::smem_u32(smem + s * stage_bytes);
-          const uint32_t sb = sa + kATileBytes;
-#pragma unroll
-          for (int k4 = 0; k4 < kBlockK / kUmmaK; ++k4) {
-            const uint64_t da = make_smem_desc(sa + k4 * a_kstep, a_lbo, a_mn ? p.mn_sbo : 1024, a_mn ? p.mn_layout : 2);
-            for (int sub = 0; sub < p.n_mma; ++sub) {
-              const uint64_t db = make_smem_desc(sb + sub * b_sub_bytes + k4 * b_kstep, b_lbo, b_mn ? p.mn_sbo : 1024, b_mn ? p.mn_layout : 2);
-              ptx::mma_tf32(tmem_acc + sub * p.n_sub, da, db, idesc, (it > 0 || k4 > 0) ? 1u : 0u);
-            }
+          if (!(dbg & 16)) {
+            long long t_c = clock64();
+            ptx::mbar_wait(&bar_full[s], ph);
+            ptx::tc_fence_after();
+            cyc_wait_ops += clock64() - t_c;
           }
-          ptx::mma_commit(&bar_empty[s]);  // frees the smem stage once these MMAs have read it
+          if (ptx::elect_one()) {
+            // straight-line issue: 4 k-slices x n_mma column halves, descriptors differ only in the address field
+            const uint64_t da0 = da_hi | static_cast<uint64_t>(a_lo);
+            const uint64_t db0 = db_hi | static_cast<uint64_t>(a_lo + (kATileBytes >> 4));
+            const uint32_t first = it > 0 ? 1u : 0u;
+            if (dbg & 4) {
+            } else if (n_mma == 1) {
+#pragma unroll
+              for (int k4 = 0; k4 < kBlockK / kUmmaK; ++k4) {
+                if (kCG == 2) ptx::mma_tf32_cg2(tmem_acc, da0 + k4 * a_kstep, db0 + k4 * b_kstep, idesc, k4 ? 1u : first);
+                else ptx::mma_tf32(tmem_acc, da0 + k4 * a_kstep, db0 + k4 * b_kstep, idesc, k4 ? 1u : first);
+              }
+            } else {
+#pragma unroll
+              for (int k4 = 0; k4 < kBlockK / kUmmaK; ++k4) {
+#pragma unroll
+                for (int sub = 0; sub < 2; ++sub) {
+                  if (kCG == 2)
+                    ptx::mma_tf32_cg2(tmem_acc + sub * n_sub, da0 + k4 * a_kstep, db0 + sub * b_sub + k4 * b_kstep, idesc,
+                                      k4 ? 1u : first);
+                  else
+                    ptx::mma_tf32(tmem_acc + sub * n_sub, da0 + k4 * a_kstep, db0 + sub * b_sub + k4 * b_kstep, idesc,
+                                  k4 ? 1u : first);
+                }
+              }
+            }
+            // frees the smem stage (in both CTAs of a pair) once these MMAs have read it
+            if (dbg & 16) {
+            } else if (kCG == 2) ptx::mma_commit_cg2(&bar_empty[s], 3);
+            else ptx::mma_commit(&bar_empty[s]);
+          }
+          __syncwarp();
+          a_lo += stage_u;
           if (++s == p.stages) {
             s = 0;
             ph ^= 1;
+            a_lo = ring;
           }
         }
-        ptx::mma_commit(&bar_tmem_full[acc]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue warps (of both CTAs)
+        if (ptx::elect_one()) {
+          if (kCG == 2) ptx::mma_commit_cg2(&bar_tmem_full[acc], 3);
+          else ptx::mma_commit(&bar_tmem_full[acc]);
+        }
+        __syncwarp();
+      }
+      if ((dbg & 32) && blockIdx.x == 0 && lane == 0) {
+        const long long total = clock64() - t_start;
+        g_gemm_dbg[0] = cyc_wait_acc;
+        g_gemm_dbg[1] = cyc_wait_ops;
+        g_gemm_dbg[2] = total - cyc_wait_acc - cyc_wait_ops;
+        g_gemm_dbg[5] = tile_iter;
+        g_gemm_dbg[6] = total;
       }
     }
   } else if (warp >= 4) {
@@ -281,6 +382,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
     float4* tbuf = reinterpret_cast<float4*>(smem + p.stages * stage_bytes) + (warp - 4) * 256;
     int tile_iter = 0;
+    long long epi_wait = 0, epi_work = 0;
     const uint64_t seed = p.seed + (p.seed_dev ? __ldg(p.seed_dev) * 0xA24BAED4963EE407ull : 0ull);
     const bool vec = p.vec_ok != 0;
 
@@ -331,15 +433,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
     };
 
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tile_iter) {
-      const TileCoord c = decode_tile(p, tile);
+    for (int tile = cta_id; tile < p.num_tiles; tile += n_ctas, ++tile_iter) {
+      const TileCoord c = decode_tile<kCG>(p, tile, cta_rank);
       const int acc = tile_iter % p.acc_stages;
       const uint32_t acc_ph = (tile_iter / p.acc_stages) & 1;
+      const long long t_e0 = clock64();
       ptx::mbar_wait(&bar_tmem_full[acc], acc_ph);
       ptx::tc_fence_after();
+      const long long t_e1 = clock64();
+      epi_wait += t_e1 - t_e0;
       const uint32_t tacc = tmem_base + acc * 256 + lane_base;
 
-      const int row_limit = (kEpi == EPI_WGRAD) ? p.M : p.R;
+      const int row_limit = (c.dup || (p.dbg & 1)) ? 0 : ((kEpi == EPI_WGRAD) ? p.M : p.R);
       const int n_cols = (p.N - c.n0) < p.n_tile ? (p.N - c.n0) : p.n_tile;  // valid columns of this tile
       const int n_chunks = (n_cols + 31) / 32;
       const int row0 = c.m0 + q * 32 + rsub;  // this lane's rows are row0 + 4k
@@ -348,7 +453,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       auto release_tmem = [&]() {  // accumulator fully read: the MMA warp may start the next tile into it
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&bar_tmem_empty[acc]);
+        if (lane == 0) {
+          if (kCG == 2) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bar_tmem_empty[acc]), 0));
+          else ptx::mbar_arrive(&bar_tmem_empty[acc]);
+        }
         released = true;
       };
 
@@ -576,12 +684,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
       }
       if (!released) release_tmem();
+      epi_work += clock64() - t_e1;
+    }
+    if ((p.dbg & 32) && blockIdx.x == 0 && warp == 4 && lane == 0) {
+      g_gemm_dbg[3] = epi_wait;
+      g_gemm_dbg[4] = epi_work;
     }
   }
 
   ptx::tc_fence_before();
-  __syncthreads();
-  if (warp == 2) ptx::tmem_dealloc(tmem_base, kTmemCols);
+  if (kCG == 2) {
+    ptx::cluster_sync_all();  // neither CTA may retire (or free TMEM) while the pair's MMAs can still touch it
+    if (warp == 2) ptx::tmem_dealloc_cg2(tmem_base, kTmemCols);
+  } else {
+    __syncthreads();
+    if (warp == 2) ptx::tmem_dealloc(tmem_base, kTmemCols);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------- host side
@@ -645,6 +763,11 @@ int encode_map(CUtensorMap* map, const float* base, int rank, const uint64_t* di
 
 }  // namespace
 
+int gemm_debug_counters(long long* out8) {
+  XVA_CHECK_CUDA(cudaMemcpyFromSymbol(out8, g_gemm_dbg, sizeof(long long) * 8));
+  return XVA_OK;
+}
+
 int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
   XVA_CHECK_ARG(g.mode >= 0 && g.mode <= 2, "gemm: bad mode %d", g.mode);
   XVA_CHECK_ARG(g.taps >= 1 && g.taps <= kMaxTaps, "gemm: taps %d out of range", g.taps);
@@ -673,7 +796,9 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
     p.n_tile = round_up(g.N, n_gran);
     p.tiles_n = 1;
   } else {
-    p.tiles_n = ceil_div(g.N, 256);
+    int nt_max = 256;
+    if (const char* e = getenv("XVA_GEMM_NTILE")) nt_max = atoi(e) >= 16 ? atoi(e) : 256;
+    p.tiles_n = ceil_div(g.N, nt_max);
     p.n_tile = round_up(ceil_div(g.N, p.tiles_n), n_gran);
   }
   p.n_mma = ceil_div(p.n_tile, 256);
@@ -685,9 +810,28 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
   XVA_CHECK_ARG(p.n_tile <= 512 && p.n_sub <= 256 && p.n_sub % 16 == 0, "gemm: bad n tiling %d/%d", p.n_tile, p.n_sub);
   p.acc_stages = (p.n_tile <= 256) ? 2 : 1;
 
-  const int stage_bytes = kATileBytes + p.n_tile * kBlockK * 4;
+  // ---- CTA pair (cta_group::2): two 128-row tiles share one B tile, each CTA stages half of it. Halves the B bytes
+  // every SM pulls through L2 (the fp32 operand stream is L2-bandwidth-bound at 128x256 tiles). Needs a B operand
+  // that does not depend on the batch item (weights), and half-tiles that are whole swizzle atoms / 32-column chunks.
+  int dbg_stages = 0;
+  static const bool pair_enabled = [] {
+    const char* e = getenv("XVA_GEMM_PAIR");
+    return !(e && e[0] == '0');
+  }();
+  const int row_tiles = (g.mode != 2) ? g.Z * ceil_div(g.R, kBlockM) : 0;
+  const bool pair = pair_enabled && g.mode != 2 && g.b_batch_z == 0 && row_tiles >= 2 &&
+                    (g.mode == 0 ? (p.n_sub % 16 == 0) : (p.n_sub % 64 == 0));
+  const int cg = pair ? 2 : 1;
+  p.row_tiles = row_tiles;
+  if (const char* e = getenv("XVA_GEMM_DBG")) p.dbg = atoi(e);
+  if (const char* e = getenv("XVA_GEMM_STAGES")) {
+    if (atoi(e) >= 2) dbg_stages = atoi(e);
+  }
+
+  const int stage_bytes = kATileBytes + p.n_tile * kBlockK * 4 / cg;
   p.stages = kSmemBudget / stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
+  if (dbg_stages && dbg_stages < p.stages) p.stages = dbg_stages;
   XVA_CHECK_ARG(p.stages >= 2, "gemm: tile too large for shared memory");
   const int smem_bytes = p.stages * stage_bytes + kTailSmemBytes;
 
@@ -701,7 +845,7 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
     p.ZR = 1;
     p.split = 1;
     p.zper = 1;
-    p.num_tiles = g.Z * p.tiles_m * p.tiles_n;
+    p.num_tiles = (pair ? ceil_div(row_tiles, 2) : row_tiles) * p.tiles_n;
   } else {
     XVA_CHECK_ARG(g.M >= 1, "gemm: wgrad M=%d", g.M);
     XVA_CHECK_ARG(g.M % 32 == 0 || g.a_rs >= round_up(g.M, 32),
@@ -760,7 +904,7 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
     const int bn_rows = g.b_rows ? g.b_rows : g.N;
     uint64_t dims[3] = {(uint64_t)g.K, (uint64_t)bn_rows, (uint64_t)g.b_nz};
     uint64_t str[3] = {1, (uint64_t)g.b_rs, (uint64_t)g.b_zs};
-    uint32_t box[3] = {kBlockK, (uint32_t)p.n_sub, 1};
+    uint32_t box[3] = {kBlockK, (uint32_t)(p.n_sub / cg), 1};
     if (g.b_nz == 1 || str[2] == 0) str[2] = (uint64_t)g.b_rs * bn_rows;
     if ((rc = encode_map(&map_b, g.b, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) != XVA_OK) return rc;
   } else if (g.mode == 1) {
@@ -770,7 +914,7 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
     const int bk_rows = g.b_rows ? g.b_rows : g.K;
     uint64_t dims[4] = {32, (uint64_t)bk_rows, (uint64_t)ceil_div(g.N, 32), (uint64_t)g.b_nz};
     uint64_t str[4] = {1, (uint64_t)g.b_rs, 32, (uint64_t)g.b_zs};
-    uint32_t box[4] = {32, kBlockK, (uint32_t)(p.n_tile / 32), 1};
+    uint32_t box[4] = {32, kBlockK, (uint32_t)(pair ? p.n_sub / 64 : p.n_tile / 32), 1};
     if (g.b_nz == 1 || str[3] == 0) str[3] = (uint64_t)g.b_rs * bk_rows;
     if ((rc = encode_map(&map_b, g.b, 4, dims, str, box, mn_swizzle)) != XVA_OK) return rc;
   } else {
@@ -832,25 +976,46 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
     const int mx = kSmemBudget + kTailSmemBytes;
-    attr_err = cudaFuncSetAttribute(gemm_tc_kernel<EPI_WGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(gemm_tc_kernel<EPI_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(gemm_tc_kernel<EPI_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(gemm_tc_kernel<EPI_LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    const void* fns[] = {(const void*)gemm_tc_kernel<EPI_WGRAD, 1>, (const void*)gemm_tc_kernel<EPI_PLAIN, 1>,
+                         (const void*)gemm_tc_kernel<EPI_FULL, 1>,  (const void*)gemm_tc_kernel<EPI_LN, 1>,
+                         (const void*)gemm_tc_kernel<EPI_PLAIN, 2>, (const void*)gemm_tc_kernel<EPI_FULL, 2>,
+                         (const void*)gemm_tc_kernel<EPI_LN, 2>};
+    for (const void* f : fns)
+      if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
   });
   XVA_CHECK_CUDA(attr_err);
 
-  int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-  if (g.mode == 2)
-    gemm_tc_kernel<EPI_WGRAD><<<grid, kThreads, smem_bytes, stream>>>(map_a, map_b, p);
-  else if (p.flags & GEMM_LN)
-    gemm_tc_kernel<EPI_LN><<<grid, kThreads, smem_bytes, stream>>>(map_a, map_b, p);
-  else if (p.gate || p.residual || (p.flags & GEMM_DROP_PRE))
-    gemm_tc_kernel<EPI_FULL><<<grid, kThreads, smem_bytes, stream>>>(map_a, map_b, p);
-  else
-    gemm_tc_kernel<EPI_PLAIN><<<grid, kThreads, smem_bytes, stream>>>(map_a, map_b, p);
+  const int epi = (g.mode == 2) ? EPI_WGRAD
+                  : (p.flags & GEMM_LN) ? EPI_LN
+                  : (p.gate || p.residual || (p.flags & GEMM_DROP_PRE)) ? EPI_FULL : EPI_PLAIN;
+  if (!pair) {
+    const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+    switch (epi) {
+      case EPI_WGRAD: gemm_tc_kernel<EPI_WGRAD, 1><<<grid, kThreads, smem_bytes, stream>>>(map_a, map_b, p); break;
+      case EPI_LN: gemm_tc_kernel<EPI_LN, 1><<<grid, kThreads, smem_bytes, stream>>>(map_a, map_b, p); break;
+      case EPI_FULL: gemm_tc_kernel<EPI_FULL, 1><<<grid, kThreads, smem_bytes, stream>>>(map_a, map_b, p); break;
+      default: gemm_tc_kernel<EPI_PLAIN, 1><<<grid, kThreads, smem_bytes, stream>>>(map_a, map_b, p); break;
+    }
+  } else {
+    const int pairs = num_sms() / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * (p.num_tiles < pairs ? p.num_tiles : pairs));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    switch (epi) {
+      case EPI_LN: XVA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<EPI_LN, 2>, map_a, map_b, p)); break;
+      case EPI_FULL: XVA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<EPI_FULL, 2>, map_a, map_b, p)); break;
+      default: XVA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<EPI_PLAIN, 2>, map_a, map_b, p)); break;
+    }
+  }
   XVA_CHECK_LAUNCH();
   return XVA_OK;
 }
