@@ -46,7 +46,10 @@ int xva_device_check(int device);
  *  (N, or M) is not a multiple of 32 the row stride must be >= the count rounded up to 32 (pad columns are
  *  multiplied into output rows/columns that are never stored).
  *  Epilogue (mode 0/1), in order: alpha, +bias[n], ReLU, gate (ReLU / leaky-ReLU backward), dropout(pre),
- *  +residual, [LayerNorm(gamma,beta) over n, dropout(post)], zero rows >= lens[z].
+ *  +residual, [LayerNorm(gamma,beta) over n, dropout(post)], zero rows >= lens[z], [round to tf32].
+ *  Operand precision: the MMA reads fp32 operands as tf32 by TRUNCATION. Every producer of a GEMM operand in this
+ *  library (XVA_GEMM_ROUND_OUT, the softmax / LayerNorm-backward / embedding / loss-gradient kernels, and the tf32
+ *  weight copy kept by xva_lamb_step / xva_round_tf32) therefore stores it already rounded to nearest.
  * ---------------------------------------------------------------------------------------------------------- */
 enum {
   XVA_GEMM_RELU = 1 << 0,
@@ -54,7 +57,8 @@ enum {
   XVA_GEMM_DROP_PRE = 1 << 2,
   XVA_GEMM_DROP_POST = 1 << 3,
   XVA_GEMM_ATOMIC = 1 << 4,
-  XVA_GEMM_LRELU_GATE = 1 << 5
+  XVA_GEMM_LRELU_GATE = 1 << 5,
+  XVA_GEMM_ROUND_OUT = 1 << 6 /* store `out` rounded to tf32 (nearest): set when the result is a later GEMM operand */
 };
 
 typedef struct xva_gemm_args {
@@ -157,6 +161,14 @@ int xva_layernorm_bwd(const float* dy, const float* x, const float* mean, const 
                       float* dbeta, float* dbias, float drop_post_p, uint64_t seed_post, float drop_pre_p,
                       uint64_t seed_pre, const uint64_t* seed_dev, int relu_gate, void* stream);
 
+/* Test switch, default on: 0 makes every kernel store GEMM operands unrounded (and xva_round_tf32 a plain copy), so
+ * that the exact-fp32 checker xva_gemm_ref reproduces an fp32 reference to rounding. Not for production use:
+ * the tensor-core path then truncates its operands. Synchronous (cudaMemcpyToSymbol). */
+int xva_set_operand_rounding(int on);
+
+/* dst[i] = tf32-rounded src[i] (round to nearest): refreshes the GEMM-operand copy of the parameters after a load. */
+int xva_round_tf32(const float* src, float* dst, int64_t n, void* stream);
+
 /* *counter += inc on the stream: the per-step dropout counter every `seed_dev` argument points at. */
 int xva_counter_add(uint64_t* counter, uint64_t inc, void* stream);
 
@@ -203,11 +215,12 @@ int xva_lens_mse_grad(const float* pred, const float* tgt, const int32_t* lens, 
  * CUDA block each; every chunk lies inside one tensor). norms is double[2*n_tensors], zeroed by the caller.
  * gnorm_sq (optional) = sum of squared gradients from xva_grad_sqnorm: gradients are scaled by
  * min(1, max_norm/(sqrt(gnorm_sq)+1e-6)) on the fly. lr is read from device memory (CUDA-graph friendly).
+ * p_tf32 (optional, same layout as p) receives the updated parameters rounded to tf32: the copy the GEMMs read.
  * ---------------------------------------------------------------------------------------------------------- */
 int xva_grad_sqnorm(const float* g, const void* chunks, int n_chunks, double* out, void* stream);
 int xva_lamb_step(float* p, const float* g, float* m, float* v, const void* chunks, int n_chunks, double* norms,
                   const double* gnorm_sq, float max_norm, const float* lr_dev, float beta1, float beta2, float eps,
-                  float weight_decay, void* stream);
+                  float weight_decay, float* p_tf32, void* stream);
 
 #ifdef __cplusplus
 }

@@ -16,6 +16,7 @@ GEMM_DROP_PRE = 1 << 2
 GEMM_DROP_POST = 1 << 3
 GEMM_ATOMIC = 1 << 4
 GEMM_LRELU_GATE = 1 << 5
+GEMM_ROUND_OUT = 1 << 6
 
 c_float_p = C.c_void_p  # device pointers travel as integers
 
@@ -75,7 +76,9 @@ PROTOTYPES = {
     "xva_lens_mse": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
     "xva_lens_mse_grad": (_I, [_P, _P, _P, _I, _I, _I, _P, _F, _P, _P]),
     "xva_grad_sqnorm": (_I, [_P, _P, _I, _P, _P]),
-    "xva_lamb_step": (_I, [_P, _P, _P, _P, _P, _I, _P, _P, _F, _P, _F, _F, _F, _F, _P]),
+    "xva_lamb_step": (_I, [_P, _P, _P, _P, _P, _I, _P, _P, _F, _P, _F, _F, _F, _F, _P, _P]),
+    "xva_round_tf32": (_I, [_P, _P, _I64, _P]),
+    "xva_set_operand_rounding": (_I, [_I]),
 }
 
 _lib = None
@@ -112,7 +115,7 @@ def check(status, what=""):
 
 
 # kernels enqueued per successful call (everything not listed launches exactly one)
-_LAUNCHES = {"xva_lamb_step": 2, "xva_gemm_debug_counters": 0, "xva_abi_version": 0, "xva_last_error": 0, "xva_device_check": 0,
+_LAUNCHES = {"xva_lamb_step": 2, "xva_gemm_debug_counters": 0, "xva_set_operand_rounding": 0, "xva_abi_version": 0, "xva_last_error": 0, "xva_device_check": 0,
              "xva_sizeof_gemm_args": 0}
 _launch_count = 0
 

@@ -78,6 +78,18 @@ int xva_layernorm_bwd(const float* dy, const float* x, const float* mean, const 
                        seed_post, drop_pre_p, seed_pre, seed_dev, relu_gate, S(stream));
 }
 
+int xva_set_operand_rounding(int on) {
+  int rc;
+  if ((rc = set_operand_rounding_gemm_tc(on)) != XVA_OK) return rc;
+  if ((rc = set_operand_rounding_gemm_ref(on)) != XVA_OK) return rc;
+  if ((rc = set_operand_rounding_rowops(on)) != XVA_OK) return rc;
+  return set_operand_rounding_loss_optim(on);
+}
+
+int xva_round_tf32(const float* src, float* dst, int64_t n, void* stream) {
+  return round_tf32(src, dst, static_cast<long>(n), S(stream));
+}
+
 int xva_counter_add(uint64_t* counter, uint64_t inc, void* stream) {
   return counter_add(reinterpret_cast<unsigned long long*>(counter), inc, S(stream));
 }
@@ -140,9 +152,9 @@ int xva_grad_sqnorm(const float* g, const void* chunks, int n_chunks, double* ou
 
 int xva_lamb_step(float* p, const float* g, float* m, float* v, const void* chunks, int n_chunks, double* norms,
                   const double* gnorm_sq, float max_norm, const float* lr_dev, float beta1, float beta2, float eps,
-                  float weight_decay, void* stream) {
+                  float weight_decay, float* p_tf32, void* stream) {
   return lamb_step(p, g, m, v, chunks, n_chunks, norms, gnorm_sq, max_norm, lr_dev, beta1, beta2, eps, weight_decay,
-                   S(stream));
+                   p_tf32, S(stream));
 }
 
 }  // extern "C"

@@ -44,6 +44,28 @@ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline long ceil_div_l(long a, long b) { return (a + b - 1) / b; }
 static inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
 
+// Round-to-nearest (ties away) fp32 -> tf32, returned as fp32 with the low 13 mantissa bits cleared. The tensor core
+// TRUNCATES fp32 operands to tf32; storing every GEMM operand pre-rounded makes the conversion unbiased, so operand
+// rounding errors average out over a dot product instead of accumulating as a systematic -2^-12 relative bias.
+// Test switch (xva_set_operand_rounding): with rounding off the fp32 checker GEMM reproduces a strict-fp32 reference to fp32
+// rounding, which is how the tests prove the wiring independently of tensor-core precision. One copy per
+// translation unit (the library is built without relocatable device code); XVA_DEFINE_ROUNDING_SWITCH(tag) emits
+// the setter each .cu that rounds registers with capi.cu.
+static __device__ int g_xva_round_operands = 1;
+#define XVA_DEFINE_ROUNDING_SWITCH(tag)                                                        \
+  int set_operand_rounding_##tag(int on) {                                                     \
+    XVA_CHECK_CUDA(cudaMemcpyToSymbol(g_xva_round_operands, &on, sizeof(int)));                \
+    return XVA_OK;                                                                             \
+  }
+__device__ __forceinline__ float tf32_rn(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return g_xva_round_operands ? __uint_as_float(r) : x;
+}
+__device__ __forceinline__ float4 tf32_rn4(float4 v) {
+  return make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
+}
+
 // Counter-based RNG shared by every kernel that applies dropout: the keep/drop decision for element
 // `idx` of a tensor is a pure function of (seed, idx), so backward re-derives the mask instead of storing it.
 __host__ __device__ __forceinline__ uint32_t hash_u32(uint64_t seed, uint64_t idx) {

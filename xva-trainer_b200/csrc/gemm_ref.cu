@@ -62,7 +62,10 @@ __global__ void gemm_ref_fwd_kernel(const RefDev d) {
   };
 
   if (!ln) {
-    for (int n = threadIdx.x; n < g.N; n += blockDim.x) g.out[rowoff_o + n] = pre_value(n) * keep_row;
+    for (int n = threadIdx.x; n < g.N; n += blockDim.x) {
+      const float v = pre_value(n) * keep_row;
+      g.out[rowoff_o + n] = (g.flags & GEMM_ROUND_OUT) ? tf32_rn(v) : v;
+    }
     return;
   }
   // LayerNorm: N <= 512, each thread owns up to 4 columns.
@@ -100,7 +103,7 @@ __global__ void gemm_ref_fwd_kernel(const RefDev d) {
     const float x = vals[cnt++];
     float y = (x - mean) * rstd * g.gamma[n] + g.beta[n];
     if (g.flags & GEMM_DROP_POST) y *= dropout_scale(eff_seed(g), drop_row + n, d.drop_thresh, d.inv_keep);
-    g.out[rowoff_o + n] = y * keep_row;
+    g.out[rowoff_o + n] = (g.flags & GEMM_ROUND_OUT) ? tf32_rn(y * keep_row) : y * keep_row;
     if (g.out_pre) g.out_pre[rowoff_o + n] = x;
   }
 }
@@ -127,7 +130,7 @@ __global__ void gemm_ref_wgrad_kernel(const RefDev d) {
   }
   float* o = g.out + zo * g.o_zs + j * g.o_js + static_cast<long>(m) * g.o_rs + n;
   if (g.flags & GEMM_ATOMIC) *o += g.alpha * acc;  // each element has exactly one writer here
-  else *o = g.alpha * acc;
+  else *o = (g.flags & GEMM_ROUND_OUT) ? tf32_rn(g.alpha * acc) : g.alpha * acc;
 }
 
 }  // namespace
@@ -156,5 +159,7 @@ int gemm_ref_launch(const GemmArgs& g, cudaStream_t stream) {
   XVA_CHECK_LAUNCH();
   return XVA_OK;
 }
+
+XVA_DEFINE_ROUNDING_SWITCH(gemm_ref)
 
 }  // namespace xva

@@ -487,7 +487,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 if (nv > 3) atomicAdd(dst + 3, o.w);
               }
             } else {
-              store1(dst, full, nv, o);
+              store1(dst, full, nv, (p.flags & GEMM_ROUND_OUT) ? tf32_rn4(o) : o);
             }
           }
         }
@@ -556,6 +556,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               const int row = row0 + 4 * k;
               if (row >= row_limit || nv == 0) continue;
               if (row >= len_z) t[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (p.flags & GEMM_ROUND_OUT) t[k] = tf32_rn4(t[k]);
               store1(p.out + zoff_o + static_cast<long>(row) * p.o_rs + n, full, nv, t[k]);
             }
           }
@@ -678,6 +679,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 y.w *= dropout_scale(seed, di + 3, p.drop_thresh, p.inv_keep);
               }
               if (row >= len_z) y = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (p.flags & GEMM_ROUND_OUT) y = tf32_rn4(y);
               store1(p.out + zoff_o + static_cast<long>(row) * p.o_rs + n, full, nv, y);
             }
           }
@@ -1019,5 +1021,7 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
   XVA_CHECK_LAUNCH();
   return XVA_OK;
 }
+
+XVA_DEFINE_ROUNDING_SWITCH(gemm_tc)
 
 }  // namespace xva

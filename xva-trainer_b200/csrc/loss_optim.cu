@@ -65,7 +65,7 @@ mel_mse_grad_kernel(const float* __restrict__ pred, const float* __restrict__ tg
     float g = 0.0f;
     if (c < C) {
       const float y = tgt[(static_cast<long>(b) * C + c) * Tm + t];
-      if (y != 0.0f) g = k * (pred[(static_cast<long>(b) * T_out + t) * C + c] - y);
+      if (y != 0.0f) g = tf32_rn(k * (pred[(static_cast<long>(b) * T_out + t) * C + c] - y));  // operand of proj dgrad/wgrad
     }
     dpred[i] = g;
   }
@@ -171,7 +171,7 @@ lamb_stage1_kernel(const float* __restrict__ p, const float* __restrict__ g, flo
 __global__ void __launch_bounds__(256)
 lamb_stage2_kernel(float* __restrict__ p, const float* __restrict__ m, const float* __restrict__ v,
                    const LambChunk* __restrict__ chunks, const double* __restrict__ norms,
-                   const float* __restrict__ lr_dev, float eps, float wd) {
+                   const float* __restrict__ lr_dev, float eps, float wd, float* __restrict__ p_tf32) {
   const LambChunk ck = chunks[blockIdx.x];
   const float wn = fminf(static_cast<float>(sqrt(norms[2 * ck.tensor])), 10.0f);
   const float rn = static_cast<float>(sqrt(norms[2 * ck.tensor + 1]));
@@ -181,7 +181,9 @@ lamb_stage2_kernel(float* __restrict__ p, const float* __restrict__ m, const flo
     const long long k = ck.start + i;
     const float pi = p[k];
     const float r = m[k] / (sqrtf(v[k]) + eps) + wd * pi;
-    p[k] = pi - step * r;
+    const float pn = pi - step * r;
+    p[k] = pn;
+    if (p_tf32) p_tf32[k] = tf32_rn(pn);
   }
 }
 
@@ -237,14 +239,16 @@ int grad_sqnorm(const float* g, const void* chunks, int n_chunks, double* out, c
 
 int lamb_step(float* p, const float* g, float* m, float* v, const void* chunks, int n_chunks, double* norms,
               const double* gnorm_sq, float max_norm, const float* lr_dev, float b1, float b2, float eps, float wd,
-              cudaStream_t stream) {
+              float* p_tf32, cudaStream_t stream) {
   if (n_chunks == 0) return XVA_OK;
   const LambChunk* ck = static_cast<const LambChunk*>(chunks);
   lamb_stage1_kernel<<<n_chunks, 256, 0, stream>>>(p, g, m, v, ck, norms, gnorm_sq, max_norm, b1, b2, eps, wd);
   XVA_CHECK_LAUNCH();
-  lamb_stage2_kernel<<<n_chunks, 256, 0, stream>>>(p, m, v, ck, norms, lr_dev, eps, wd);
+  lamb_stage2_kernel<<<n_chunks, 256, 0, stream>>>(p, m, v, ck, norms, lr_dev, eps, wd, p_tf32);
   XVA_CHECK_LAUNCH();
   return XVA_OK;
 }
+
+XVA_DEFINE_ROUNDING_SWITCH(loss_optim)
 
 }  // namespace xva

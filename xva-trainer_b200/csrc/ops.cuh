@@ -6,6 +6,12 @@
 
 namespace xva {
 
+// ---- test switch for the tf32 operand rounding, one setter per translation unit (common.cuh)
+int set_operand_rounding_gemm_tc(int on);
+int set_operand_rounding_gemm_ref(int on);
+int set_operand_rounding_rowops(int on);
+int set_operand_rounding_loss_optim(int on);
+
 // ---- regulate.cu
 int duration_scan(const float* durs, int B, int Tt, float pace, int mel_max_len, int* cum, int* dec_lens,
                   cudaStream_t stream);
@@ -26,6 +32,7 @@ int layernorm_bwd(const float* dy, const float* x, const float* mean, const floa
                   float* dbias, float drop_post_p, uint64_t seed_post, float drop_pre_p, uint64_t seed_pre,
                   const uint64_t* seed_dev, int relu_gate, cudaStream_t stream);
 int counter_add(unsigned long long* counter, unsigned long long inc, cudaStream_t stream);
+int round_tf32(const float* src, float* dst, long n, cudaStream_t stream);
 int colsum(const float* x, long rows, int C, long ld, float* out, cudaStream_t stream);
 int embed_pos(const long long* tokens, const float* emb, const float* in, const int* lens, const float* inv_freq,
               int B, int T, int C, float* out, cudaStream_t stream);
@@ -50,6 +57,6 @@ int lens_mse_grad(const float* pred, const float* tgt, const int* lens, int B, i
 int grad_sqnorm(const float* g, const void* chunks, int n_chunks, double* out, cudaStream_t stream);
 int lamb_step(float* p, const float* g, float* m, float* v, const void* chunks, int n_chunks, double* norms,
               const double* gnorm_sq, float max_norm, const float* lr_dev, float b1, float b2, float eps, float wd,
-              cudaStream_t stream);
+              float* p_tf32, cudaStream_t stream);
 
 }  // namespace xva

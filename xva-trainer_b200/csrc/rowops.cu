@@ -83,9 +83,9 @@ softmax_fwd_kernel(const float* __restrict__ s, const int* __restrict__ lens, in
   for (int i = 0; i < kMaxColsPerLane; ++i) {
     const int n = lane + 32 * i;
     if (n < ld) {  // pad columns [N, ld) are written as zero: the MN-major consumers multiply them
-      const float p = v[i] * inv;
+      const float p = tf32_rn(v[i] * inv);  // both outputs are GEMM operands (P*V, dV = P^T dO)
       p_out[row * ld + n] = p;
-      if (pd_out) pd_out[row * ld + n] = p * dropout_scale(seed, static_cast<uint64_t>(row) * ld + n, thresh, inv_keep);
+      if (pd_out) pd_out[row * ld + n] = tf32_rn(p * dropout_scale(seed, static_cast<uint64_t>(row) * ld + n, thresh, inv_keep));
     }
   }
 }
@@ -116,7 +116,7 @@ softmax_bwd_kernel(const float* __restrict__ p, float* __restrict__ dpd, int N, 
 #pragma unroll
   for (int i = 0; i < kMaxColsPerLane; ++i) {
     const int n = lane + 32 * i;
-    if (n < ld) dpd[row * ld + n] = (n < N) ? alpha * pv[i] * (gv[i] - dot) : 0.0f;
+    if (n < ld) dpd[row * ld + n] = (n < N) ? tf32_rn(alpha * pv[i] * (gv[i] - dot)) : 0.0f;  // operand of dQ, dK
   }
 }
 
@@ -183,12 +183,15 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
         float v = rs * (g[i] - s1 - xh[i] * s2);
         // ConvReLUNorm (common/layers.py:94-97): x is the ReLU output, so the gradient passes only where x > 0
         if (relu_gate && !((pos >> i) & 1u)) v = 0.0f;
-        dx[row * C + n] = v;
+        // the tensor that feeds the dgrad / wgrad GEMMs (dx_drop if there is one, else dx) is stored tf32-rounded
         if (dx_drop) {
-          const float vd = v * dropout_scale(seed_pre, static_cast<uint64_t>(row) * C + n, thresh_pre, inv_keep_pre);
+          dx[row * C + n] = v;
+          const float vd = tf32_rn(v * dropout_scale(seed_pre, static_cast<uint64_t>(row) * C + n, thresh_pre, inv_keep_pre));
           dx_drop[row * C + n] = vd;
           acc_bias[i] += vd;
         } else {
+          v = tf32_rn(v);
+          dx[row * C + n] = v;
           acc_bias[i] += v;
         }
       }
@@ -251,7 +254,7 @@ embed_pos_kernel(const long long* __restrict__ tokens, const float* __restrict__
       const float ang = tf * inv_freq[c < half ? c : c - half];
       v += (c < half) ? sinf(ang) : cosf(ang);
     }
-    out[row * C + c] = v;
+    out[row * C + c] = tf32_rn(v);  // first GEMM operand of the FFT stack
   }
 }
 
@@ -279,8 +282,8 @@ scalar_conv_add_kernel(float* __restrict__ io, const float* __restrict__ x, cons
   const int t = static_cast<int>(row % T);
   if (lens && t >= lens[row / T]) return;  // padded token rows stay untouched (zero): nothing downstream reads them
   const float x0 = t > 0 ? x[row - 1] : 0.0f, x1 = x[row], x2 = t + 1 < T ? x[row + 1] : 0.0f;
-  for (int c = lane; c < C; c += 32)
-    io[row * C + c] += bias[c] + w[c * 3] * x0 + w[c * 3 + 1] * x1 + w[c * 3 + 2] * x2;
+  for (int c = lane; c < C; c += 32)  // the sum feeds the predictor convs and the length regulator -> decoder GEMMs
+    io[row * C + c] = tf32_rn(io[row * C + c] + bias[c] + w[c * 3] * x0 + w[c * 3 + 1] * x1 + w[c * 3 + 2] * x2);
 }
 
 // dw[c,j] += sum_rows dout[row,c] * x[row+j-1] ; dbias[c] += sum_rows dout[row,c]
@@ -368,6 +371,12 @@ rowdot_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ x, c
     for (int wv = 0; wv < kWarpsPerBlock; ++wv) s += redb[wv];
     atomicAdd(db, s);
   }
+}
+
+__global__ void __launch_bounds__(256)
+round_tf32_kernel(const float* __restrict__ src, float* __restrict__ dst, long n) {
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x)
+    dst[i] = tf32_rn(src[i]);
 }
 
 __global__ void counter_add_kernel(unsigned long long* c, unsigned long long inc) { *c += inc; }
@@ -512,10 +521,21 @@ int rowdot_bwd(const float* dout, const float* x, const float* w, const int* len
   return XVA_OK;
 }
 
+int round_tf32(const float* src, float* dst, long n, cudaStream_t stream) {
+  if (n <= 0) return XVA_OK;
+  long b = ceil_div_l(n, 256 * 8);
+  if (b > 16L * num_sms()) b = 16L * num_sms();
+  round_tf32_kernel<<<static_cast<int>(b), 256, 0, stream>>>(src, dst, n);
+  XVA_CHECK_LAUNCH();
+  return XVA_OK;
+}
+
 int counter_add(unsigned long long* counter, unsigned long long inc, cudaStream_t stream) {
   counter_add_kernel<<<1, 1, 0, stream>>>(counter, inc);
   XVA_CHECK_LAUNCH();
   return XVA_OK;
 }
+
+XVA_DEFINE_ROUNDING_SWITCH(rowops)
 
 }  // namespace xva

@@ -137,7 +137,8 @@ class _Arena:
             self.offset[k], self.pshape[k], self.rshape[k] = off, ps, tuple(s)
             off += (n + _ALIGN - 1) // _ALIGN * _ALIGN
         self.numel = off
-        self.p = torch.zeros(off, device=device, dtype=torch.float32)
+        self.p = torch.zeros(off, device=device, dtype=torch.float32)   # fp32 master parameters (what LAMB updates)
+        self.w = torch.zeros(off, device=device, dtype=torch.float32)   # the same, rounded to tf32: GEMM B operands
         self.g = torch.zeros(off, device=device, dtype=torch.float32)
         self.m = None
         self.v = None
@@ -186,8 +187,13 @@ class FastPitch(torch.nn.Module):
     def _bind(self):
         """Name the packed parameter / gradient views the kernels read."""
         A = self.arena
-        W = lambda k: A.view(A.p, k)
         G = lambda k: A.view(A.g, k)
+
+        def W(k):
+            """Weight matrices that are tensor-core operands are read from the tf32-rounded copy (the MMA would
+            otherwise truncate them); biases, LayerNorm parameters and the small non-GEMM weights stay fp32."""
+            is_gemm_operand = k.endswith(".weight") and len(A.pshape[k]) == 3
+            return A.view(A.w if is_gemm_operand else A.p, k)
 
         def fft(prefix):
             layers = []
@@ -281,6 +287,7 @@ class FastPitch(torch.nn.Module):
                     self.inv_freq.copy_(t)
                 else:
                     A.view(A.p, key).copy_(_to_packed(key, t))
+            ops.round_tf32_(A.p, A.w)
         return torch.nn.modules.module._IncompatibleKeys(missing, unexpected)
 
     def grads(self, keys=None):
@@ -311,7 +318,7 @@ class FastPitch(torch.nn.Module):
         """TransformerLayer.forward, transformer.py:164-171 = MultiHeadAttn :100-152 + PositionwiseConvFF :59-77."""
         B, T, _ = x.shape
         sd = self.step_counter
-        qkv = ops.conv_fwd(x, L.w.qkv_w, bias=L.w.qkv_b)
+        qkv = ops.conv_fwd(x, L.w.qkv_w, bias=L.w.qkv_b, round_out=True)
         q, k, v = qkv[..., :D_HEAD], qkv[..., D_HEAD:2 * D_HEAD], qkv[..., 2 * D_HEAD:]
         Tp = (T + 31) // 32 * 32
         s = torch.empty(B, T, Tp, device=x.device, dtype=torch.float32)
@@ -319,14 +326,14 @@ class FastPitch(torch.nn.Module):
         p_att, seed_att = self._drop()
         P, Pd = ops.softmax_fwd(s, lens, T, p_att, seed_att, sd)
         del s
-        vec = ops.bmm_nn(Pd[..., :T], v)
+        vec = ops.bmm_nn(Pd[..., :T], v, round_out=True)
         p1, seed1 = self._drop()
         y1, sv1 = ops.conv_fwd(vec, L.w.o_w, residual=x, ln=(L.w.ln1_g, L.w.ln1_b), save_ln=True, lens=lens,
-                               drop_p=p1, seed=seed1, seed_dev=sd)
-        h = ops.conv_fwd(y1, L.w.w1, K3, bias=L.w.b1, relu=True)
+                               drop_p=p1, seed=seed1, seed_dev=sd, round_out=True)
+        h = ops.conv_fwd(y1, L.w.w1, K3, bias=L.w.b1, relu=True, round_out=True)
         p2, seed2 = self._drop()
         y2, sv2 = ops.conv_fwd(h, L.w.w2, K3, bias=L.w.b2, residual=y1, ln=(L.w.ln2_g, L.w.ln2_b), save_ln=True,
-                               lens=lens, drop_p=p2, seed=seed2, seed_dev=sd)
+                               lens=lens, drop_p=p2, seed=seed2, seed_dev=sd, round_out=True)
         if save is not None:
             save.append(_NS(x=x, qkv=qkv, P=P, Pd=Pd, vec=vec, sv1=sv1, y1=y1, h=h, sv2=sv2, T=T, att=(p_att, seed_att),
                             d1=(p1, seed1), d2=(p2, seed2)))
@@ -341,7 +348,7 @@ class FastPitch(torch.nn.Module):
         dx2, dbr2 = ops.layernorm_bwd(dy, c.sv2, L.w.ln2_g, lens, L.g.ln2_g, L.g.ln2_b, dbias=L.g.b2, want_drop=True,
                                       drop_pre_p=c.d2[0], seed_pre=c.d2[1], seed_dev=sd)
         ops.conv_wgrad(dbr2, c.h, K3, out=L.g.w2, accumulate=True)
-        dh = ops.conv_dgrad(dbr2, L.w.w2, K3, gate=c.h)
+        dh = ops.conv_dgrad(dbr2, L.w.w2, K3, gate=c.h, round_out=True)
         del dbr2
         ops.conv_wgrad(dh, c.y1, K3, out=L.g.w1, accumulate=True)
         ops.colsum_(B * T, D_INNER, D_INNER, dh, L.g.b1)
@@ -351,15 +358,15 @@ class FastPitch(torch.nn.Module):
         dx1, dbr1 = ops.layernorm_bwd(dy1, c.sv1, L.w.ln1_g, lens, L.g.ln1_g, L.g.ln1_b, dbias=None, want_drop=True,
                                       drop_pre_p=c.d1[0], seed_pre=c.d1[1], seed_dev=sd)
         ops.conv_wgrad(dbr1, c.vec, (0,), out=L.g.o_w, accumulate=True)
-        dvec = ops.conv_dgrad(dbr1, L.w.o_w)
+        dvec = ops.conv_dgrad(dbr1, L.w.o_w, round_out=True)
         dqkv = torch.empty_like(qkv)
         Tp = c.P.shape[2]
         dP = torch.empty(B, T, Tp, device=x.device, dtype=torch.float32)
         ops.bmm_nt(dvec, v, out=dP[..., :T])
-        ops.bmm_tn(c.Pd[..., :T], dvec, out=dqkv[..., 2 * D_HEAD:])
+        ops.bmm_tn(c.Pd[..., :T], dvec, out=dqkv[..., 2 * D_HEAD:], round_out=True)
         ops.softmax_bwd_(c.P, dP, T, 1.0 / math.sqrt(D_HEAD), c.att[0], c.att[1], sd)
-        ops.bmm_nn(dP[..., :T], k, out=dqkv[..., :D_HEAD])
-        ops.bmm_tn(dP[..., :T], q, out=dqkv[..., D_HEAD:2 * D_HEAD])
+        ops.bmm_nn(dP[..., :T], k, out=dqkv[..., :D_HEAD], round_out=True)
+        ops.bmm_tn(dP[..., :T], q, out=dqkv[..., D_HEAD:2 * D_HEAD], round_out=True)
         del dP
         ops.conv_wgrad(dqkv, x, (0,), out=L.g.qkv_w, accumulate=True)
         ops.colsum_(B * T, 3 * D_HEAD, 3 * D_HEAD, dqkv, L.g.qkv_b)
@@ -373,7 +380,7 @@ class FastPitch(torch.nn.Module):
         padded rows (= enc_out * mask). -> [B, Tt]"""
         pa, sa = self._drop()
         h1, s1 = ops.conv_fwd(x, P.w.w0, K3, bias=P.w.b0, relu=True, ln=(P.w.g0, P.w.be0), save_ln=True, drop_p=pa,
-                              drop_post=True, seed=sa, seed_dev=self.step_counter)
+                              drop_post=True, seed=sa, seed_dev=self.step_counter, round_out=True)
         pb, sb = self._drop()
         h2, s2 = ops.conv_fwd(h1, P.w.w1, K3, bias=P.w.b1, relu=True, ln=(P.w.g1, P.w.be1), save_ln=True, drop_p=pb,
                               drop_post=True, seed=sb, seed_dev=self.step_counter)
@@ -639,7 +646,7 @@ class Lamb:
             ops.grad_sqnorm(A.g, chunks, n_chunks, gn)
         ops.lamb_step(A.p, A.g, A.m, A.v, chunks, n_chunks, scratch, gn if self.clip else None,
                       self.clip if self.clip else 0.0, self.lr_dev, g["betas"][0], g["betas"][1], g["eps"],
-                      g["weight_decay"])
+                      g["weight_decay"], p_tf32=A.w)
         self.steps += 1
         self.last_grad_sqnorm = gn
 

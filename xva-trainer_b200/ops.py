@@ -45,7 +45,8 @@ def _base_args(mode, shifts):
 
 
 def _epilogue(g, out, bias=None, relu=False, gate=None, gate_slope=0.0, residual=None, lens=None, ln=None,
-              ln_eps=1e-5, save_ln=False, drop_p=0.0, drop_post=False, seed=0, seed_dev=None, alpha=1.0):
+              ln_eps=1e-5, save_ln=False, drop_p=0.0, drop_post=False, seed=0, seed_dev=None, alpha=1.0,
+              round_out=False):
     keep = [out, bias, gate, residual, lens]
     g.out, g.o_rs, g.o_zs = _p(out), out.stride(1), out.stride(0)
     g.alpha = alpha
@@ -79,6 +80,8 @@ def _epilogue(g, out, bias=None, relu=False, gate=None, gate_slope=0.0, residual
     if drop_p > 0.0:
         flags |= capi.GEMM_DROP_POST if drop_post else capi.GEMM_DROP_PRE
         g.drop_p, g.seed, g.seed_dev = drop_p, seed, _p(seed_dev)
+    if round_out:
+        flags |= capi.GEMM_ROUND_OUT
     g.flags = flags
     return keep, extra
 
@@ -146,7 +149,7 @@ def conv_wgrad(dy, x, shifts=(0,), out=None, accumulate=False, split=None, ref=F
     return out
 
 
-def bmm_nt(a, b, alpha=1.0, out=None, ref=False):
+def bmm_nt(a, b, alpha=1.0, out=None, ref=False, round_out=False):
     """out[z,m,n] = alpha * sum_k a[z,m,k] * b[z,n,k]   (torch.bmm(a, b.transpose(1,2)))."""
     _check3(a, "a")
     _check3(b, "b")
@@ -158,12 +161,12 @@ def bmm_nt(a, b, alpha=1.0, out=None, ref=False):
     g.Z, g.R, g.N, g.K = Z, M, N, K
     g.a, g.a_rs, g.a_zs = _p(a), a.stride(1), a.stride(0)
     g.b, g.b_rs, g.b_zs, g.b_nz, g.b_batch_z = _p(b), b.stride(1), b.stride(0), Z, 1
-    _epilogue(g, out, alpha=alpha)
+    _epilogue(g, out, alpha=alpha, round_out=round_out)
     gemm_launch(g, ref)
     return out
 
 
-def bmm_nn(a, b, alpha=1.0, out=None, ref=False):
+def bmm_nn(a, b, alpha=1.0, out=None, ref=False, round_out=False):
     """out[z,m,n] = alpha * sum_k a[z,m,k] * b[z,k,n]   (torch.bmm(a, b)); n must be a multiple of 32."""
     _check3(a, "a")
     _check3(b, "b")
@@ -175,12 +178,12 @@ def bmm_nn(a, b, alpha=1.0, out=None, ref=False):
     g.Z, g.R, g.N, g.K = Z, M, N, K
     g.a, g.a_rs, g.a_zs = _p(a), a.stride(1), a.stride(0)
     g.b, g.b_rs, g.b_zs, g.b_nz, g.b_batch_z = _p(b), b.stride(1), b.stride(0), Z, 1
-    _epilogue(g, out, alpha=alpha)
+    _epilogue(g, out, alpha=alpha, round_out=round_out)
     gemm_launch(g, ref)
     return out
 
 
-def bmm_tn(a, b, alpha=1.0, out=None, ref=False):
+def bmm_tn(a, b, alpha=1.0, out=None, ref=False, round_out=False):
     """out[z,m,n] = alpha * sum_t a[z,t,m] * b[z,t,n]   (torch.bmm(a.transpose(1,2), b)); m, n multiples of 32."""
     _check3(a, "a")
     _check3(b, "b")
@@ -194,6 +197,7 @@ def bmm_tn(a, b, alpha=1.0, out=None, ref=False):
     g.b, g.b_rs, g.b_zs, g.b_rows = _p(b), b.stride(1), b.stride(0), T
     g.out, g.o_rs, g.o_zs, g.o_js = _p(out), out.stride(1), out.stride(0), 0
     g.alpha = alpha
+    g.flags = capi.GEMM_ROUND_OUT if round_out else 0
     gemm_launch(g, ref)
     return out
 
@@ -347,6 +351,13 @@ def grad_sqnorm(g, chunks, n_chunks, out):
     capi.call("xva_grad_sqnorm", _p(g), _p(chunks), int(n_chunks), _p(out), _stream())
 
 
-def lamb_step(p, g, m, v, chunks, n_chunks, norms, gnorm_sq, max_norm, lr_dev, beta1, beta2, eps, weight_decay):
+def lamb_step(p, g, m, v, chunks, n_chunks, norms, gnorm_sq, max_norm, lr_dev, beta1, beta2, eps, weight_decay,
+              p_tf32=None):
     capi.call("xva_lamb_step", _p(p), _p(g), _p(m), _p(v), _p(chunks), int(n_chunks), _p(norms), _p(gnorm_sq),
-              float(max_norm), _p(lr_dev), float(beta1), float(beta2), float(eps), float(weight_decay), _stream())
+              float(max_norm), _p(lr_dev), float(beta1), float(beta2), float(eps), float(weight_decay), _p(p_tf32),
+              _stream())
+
+
+def round_tf32_(src, dst):
+    """dst = src rounded to tf32 (nearest); flat fp32 tensors of equal length."""
+    capi.call("xva_round_tf32", _p(src), _p(dst), int(src.numel()), _stream())
