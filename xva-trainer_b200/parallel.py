@@ -16,6 +16,8 @@ import torch.distributed as dist
 
 
 class GradSync:
+    MAX_GAP = 256  # elements; the arena aligns tensors to 64 floats
+
     def __init__(self, model_or_arena, world, group=None, min_bucket_elems=1 << 20):
         self.arena = getattr(model_or_arena, "arena", model_or_arena)
         self.world = int(world)
@@ -48,7 +50,8 @@ class GradSync:
         """The gradients of every parameter under ``prefixes`` are final. Adjacent ready slices are merged until a
         bucket reaches min_bucket elements (or ``flush``), then all-reduced asynchronously."""
         lo, hi = self._range(prefixes)
-        if self._lo is not None and (hi == self._lo or lo == self._hi or (lo <= self._hi and hi >= self._lo)):
+        # slices separated only by the arena's alignment padding (never written, always zero) count as adjacent
+        if self._lo is not None and lo <= self._hi + self.MAX_GAP and hi >= self._lo - self.MAX_GAP:
             self._lo, self._hi = min(lo, self._lo), max(hi, self._hi)
         else:
             self._send()
