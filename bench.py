@@ -246,6 +246,8 @@ def run_native(args):
 
     # ---- instrumented step: CUDA events around every tap-GEMM launch (after the timed regions)
     roof = None
+    if rank != 0 and world > 1:
+        step(x_dev)          # the instrumented step below contains the gradient all-reduce: every rank must run it
     if rank == 0:
         rec = []
         orig = ops.gemm_launch

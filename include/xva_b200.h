@@ -45,8 +45,9 @@ int xva_device_check(int device);
  *  MN-major operands (B in mode 1; A and B in mode 2) are fetched in 32-column chunks: when their column count
  *  (N, or M) is not a multiple of 32 the row stride must be >= the count rounded up to 32 (pad columns are
  *  multiplied into output rows/columns that are never stored).
- *  Epilogue (mode 0/1), in order: alpha, +bias[n], ReLU, gate (ReLU / leaky-ReLU backward), dropout(pre),
- *  +residual, [LayerNorm(gamma,beta) over n, dropout(post)], zero rows >= lens[z], [round to tf32].
+ *  Epilogue (mode 0/1), in order: alpha, +bias[n], (leaky) ReLU, gate ((leaky-)ReLU backward), dropout(pre),
+ *  +residual, [LayerNorm(gamma,beta) over n, dropout(post)], [tanh], zero rows >= lens[z], [round to tf32];
+ *  out_act (optional) additionally receives leaky_relu(out).
  *  Operand precision: the MMA reads fp32 operands as tf32 by TRUNCATION. Every producer of a GEMM operand in this
  *  library (XVA_GEMM_ROUND_OUT, the softmax / LayerNorm-backward / embedding / loss-gradient kernels, and the tf32
  *  weight copy kept by xva_lamb_step / xva_round_tf32) therefore stores it already rounded to nearest.
@@ -58,6 +59,7 @@ enum {
   XVA_GEMM_DROP_POST = 1 << 3,
   XVA_GEMM_ATOMIC = 1 << 4,
   XVA_GEMM_LRELU_GATE = 1 << 5,
+  XVA_GEMM_TANH = 1 << 7,     /* out = tanh(value) as the last step (Generator.forward, hifigan/models.py:126) */
   XVA_GEMM_ROUND_OUT = 1 << 6 /* store `out` rounded to tf32 (nearest): set when the result is a later GEMM operand */
 };
 
@@ -95,7 +97,7 @@ typedef struct xva_gemm_args {
   const float* gate;
   int64_t g_rs, g_zs;
   float gate_slope;
-  int32_t _pad1;
+  float act_slope;    /* XVA_GEMM_RELU computes v > 0 ? v : act_slope * v (0 = ReLU, 0.1 = the HiFi-GAN leaky ReLU) */
   const int32_t* lens;
   const float* gamma;
   const float* beta;
@@ -105,8 +107,12 @@ typedef struct xva_gemm_args {
   float* ln_mean;   /* [Z*R] (optional) */
   float* ln_rstd;
   float drop_p;
-  int32_t _pad3;
+  float out_act_slope;
   uint64_t seed;
+  float* out_act;   /* optional second output, same strides as out: leaky_relu(out, out_act_slope) rounded to tf32 --
+                       the operand the next convolution reads (ResBlock1.forward, hifigan/models.py:41-48) */
+  int32_t a_col[XVA_MAX_TAPS]; /* mode 0/1: column offset of A added per tap (strided convolutions on a
+                                  [T/stride, stride*C] view of the input: tap = (row shift, phase*C)) */
   const uint64_t* seed_dev; /* optional device counter added to `seed` (x odd constant) at run time, so a captured
                                CUDA graph draws a fresh dropout mask on every replay */
 } xva_gemm_args;
@@ -221,6 +227,44 @@ int xva_grad_sqnorm(const float* g, const void* chunks, int n_chunks, double* ou
 int xva_lamb_step(float* p, const float* g, float* m, float* v, const void* chunks, int n_chunks, double* norms,
                   const double* gnorm_sq, float max_norm, const float* lr_dev, float beta1, float beta2, float eps,
                   float weight_decay, float* p_tf32, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * HiFi-GAN element-wise steps (hifigan/models.py:110-128) and optimizer (hifigan/xva_train.py:298-300).
+ *   mean3_lrelu : out = leaky_relu((y0 + y1 + y2) / 3, slope)   -- `x = xs / num_kernels` followed by the leaky ReLU of
+ *                 the next stage (slope 0.1, models.py:115) or of conv_post (slope 0.01, models.py:124); tf32-rounded
+ *   sum3        : out = a + b + c, tf32-rounded (gradient of a tensor read by the three ResBlocks of a stage)
+ *   tanh_bwd    : out[r, 0] = dy[r] * (1 - y[r]^2), out[r, 1..ld) = 0   (models.py:126; ld pads the single channel so
+ *                 the buffer is a legal MN-major wgrad operand)
+ *   adamw_step  : torch.optim.AdamW over a flat arena; step is 1-based, lr read from device memory
+ * ---------------------------------------------------------------------------------------------------------- */
+int xva_mean3_lrelu(const float* y0, const float* y1, const float* y2, int64_t n, float slope, float* out, void* stream);
+int xva_sum3(const float* a, const float* b, const float* c, int64_t n, float* out, void* stream);
+int xva_tanh_bwd(const float* dy, const float* y, int64_t rows, int ld, float* out, void* stream);
+int xva_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, const float* lr_dev, float beta1, float beta2,
+                   float eps, float weight_decay, int step, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Mel-spectrogram extractor -- mel_spectrogram(), hifigan/meldataset.py:217-240 (forward and the backward the 45 * L1
+ * mel loss needs, hifigan/xva_train.py:480,504). The STFT and the mel projection are xva_gemm launches (a 4-tap GEMM
+ * over the [len/hop, hop] view of the padded signal, and a plain GEMM); these are the steps around them.
+ *   reflect_pad : out[b, i] = y[b, reflect(i - pad)], length n + 2 pad (F.pad mode='reflect', meldataset.py:229), tf32
+ *   spec_mag    : mag[r, c] = sqrt(re^2 + im^2 + eps) for c < nb, 0 for nb <= c < ld_m; spec rows hold re in columns
+ *                 [0, nb) and im in [nb, 2 nb) (meldataset.py:235)
+ *   log_clamp   : out = log(max(x, lo))  (spectral_normalize_torch, meldataset.py:238); bwd: dy / x where x >= lo
+ *   reduce_loss : kind 0: acc += sum |a - b| (F.l1_loss, feature_loss models.py:263-269); kind 1: acc += sum (c - a)^2
+ *                 (discriminator_loss / generator_loss, models.py:272-294). acc is a device double.
+ *   loss_grad   : kind 0: out (+)= scale * sign(b - a) (gradient wrt b); kind 1: out (+)= 2 scale (a - c) (wrt a)
+ * ---------------------------------------------------------------------------------------------------------- */
+int xva_reflect_pad_fwd(const float* y, int B, int64_t n, int pad, float* out, void* stream);
+int xva_reflect_pad_bwd(const float* dyp, int B, int64_t n, int pad, float* dy, void* stream);
+int xva_spec_mag_fwd(const float* spec, int64_t rows, int nb, int ld_s, int ld_m, float eps, float* mag, void* stream);
+int xva_spec_mag_bwd(const float* dmag, const float* spec, int64_t rows, int nb, int ld_s, int ld_m, float eps,
+                     float* dspec, void* stream);
+int xva_log_clamp_fwd(const float* x, int64_t n, float lo, float* out, void* stream);
+int xva_log_clamp_bwd(const float* dy, const float* x, int64_t n, float lo, float* dx, void* stream);
+int xva_reduce_loss(const float* a, const float* b, int64_t n, int kind, float c, double* acc, void* stream);
+int xva_loss_grad(const float* a, const float* b, int64_t n, int kind, float c, float scale, int accumulate, float* out,
+                  void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,171 @@
+"""Oracle (test infrastructure, see oracle/__init__.py): functional fp32 restatement of the HiFi-GAN v1 training path of
+the reference, written against plain ``{state_dict key: tensor}`` mappings with the reference's keys
+(``weight_g`` / ``weight_v`` / ``bias`` per weight-normed conv).
+
+Reference files restated (paths relative to the reference tree, python/hifigan/...):
+  models.py       ResBlock1 :17-54, Generator :81-137, DiscriminatorP :140-173, MultiPeriodDiscriminator :176-200,
+                  DiscriminatorS :203-228, MultiScaleDiscriminator :231-260, feature_loss :263-269,
+                  discriminator_loss :272-283, generator_loss :286-294
+  meldataset.py   mel_spectrogram :217-240 (librosa 0.8.1 Slaney mel filterbank restated in mel_filterbank())
+  utils.py        get_padding :35-36, init_weights :23-26
+  config_v1.json  upsample rates 8,8,2,2 / kernels 16,16,4,4 / initial channel 512 / resblock kernels 3,7,11 /
+                  dilations (1,3,5) / segment 8192 / n_fft 1024 / hop 256 / win 1024 / 80 mels / 22050 Hz
+  xva_train.py    HiFiTrainer.iteration :467-515 (D step then G step, mel loss x45, AdamW lr 2e-4 betas .8/.99)
+
+Pinned against outputs of the imported reference by tests/golden/make_golden_hifigan.py -> tests/test_oracle_golden.py.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+LRELU_SLOPE = 0.1
+UP_RATES, UP_KERNELS, UP_INIT = (8, 8, 2, 2), (16, 16, 4, 4), 512
+RB_KERNELS, RB_DILATIONS = (3, 7, 11), ((1, 3, 5), (1, 3, 5), (1, 3, 5))
+N_FFT, HOP, WIN, N_MELS, SR, FMIN, FMAX, FMAX_LOSS = 1024, 256, 1024, 80, 22050, 0, 8000, None
+PERIODS = (2, 3, 5, 7, 11)
+
+
+def get_padding(kernel_size, dilation=1):
+    return int((kernel_size * dilation - dilation) / 2)
+
+
+# ------------------------------------------------------------------------------------------------ parameters
+def generator_spec():
+    """(key, shape) of Generator(h).state_dict() for config_v1 (models.py:82-108): 234 keys, 13 936 130 parameters."""
+    spec = []
+
+    def wn(prefix, shape, transposed=False):
+        g_shape = (shape[0], 1, 1)
+        return [(f"{prefix}.bias", (shape[1] if transposed else shape[0],)), (f"{prefix}.weight_g", g_shape),
+                (f"{prefix}.weight_v", shape)]
+
+    spec += wn("conv_pre", (UP_INIT, 80, 7))
+    for i, (u, k) in enumerate(zip(UP_RATES, UP_KERNELS)):
+        spec += wn(f"ups.{i}", (UP_INIT // 2 ** i, UP_INIT // 2 ** (i + 1), k), transposed=True)
+    for i in range(len(UP_RATES)):
+        ch = UP_INIT // 2 ** (i + 1)
+        for j, k in enumerate(RB_KERNELS):
+            for name in ("convs1", "convs2"):
+                for m in range(3):
+                    spec += wn(f"resblocks.{i * 3 + j}.{name}.{m}", (ch, ch, k))
+    spec += wn("conv_post", (1, UP_INIT // 2 ** len(UP_RATES), 7))
+    return spec
+
+
+def make_generator_state(seed=1234, scale=1.0):
+    """Seeded weights in the reference's parameterisation. ``scale`` > 1 moves the N(0, 0.01) init of the reference
+    (utils.py:23-26) to magnitudes where every layer contributes visibly to the output, which makes parity tests
+    sensitive to each of them."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for key, shape in generator_spec():
+        if key.endswith("weight_v"):
+            fan_in = shape[1] * shape[2]
+            std = scale / math.sqrt(fan_in) if scale != 1.0 else 0.01
+            if key.startswith("conv_pre") and scale == 1.0:
+                std = 1.0 / math.sqrt(3 * fan_in)
+            sd[key] = torch.randn(shape, generator=g) * std
+        elif key.endswith("weight_g"):
+            v = sd.get(key[:-1] + "v")
+            sd[key] = None  # filled below (the state_dict order has g before v)
+        else:
+            sd[key] = (torch.rand(shape, generator=g) * 2 - 1) * 0.05
+    for key in list(sd):
+        if key.endswith("weight_g"):
+            v = sd[key[:-1] + "v"]
+            sd[key] = v.flatten(1).norm(dim=1).view(-1, 1, 1) * (1.0 + 0.1 * torch.rand(v.shape[0], 1, 1, generator=g))
+    return {k: sd[k] for k, _ in generator_spec()}
+
+
+def wn_weight(sd, prefix):
+    """torch.nn.utils.weight_norm (dim=0): w = g * v / ||v|| with the norm over all dims but the first."""
+    v, g = sd[f"{prefix}.weight_v"], sd[f"{prefix}.weight_g"]
+    return v * (g / v.flatten(1).norm(dim=1).view(-1, 1, 1))
+
+
+# ------------------------------------------------------------------------------------------------ generator
+def resblock1(x, sd, prefix, k, dilations=(1, 3, 5)):
+    """models.py:41-48"""
+    for m, d in enumerate(dilations):
+        xt = F.leaky_relu(x, LRELU_SLOPE)
+        xt = F.conv1d(xt, wn_weight(sd, f"{prefix}.convs1.{m}"), sd[f"{prefix}.convs1.{m}.bias"], dilation=d,
+                      padding=get_padding(k, d))
+        xt = F.leaky_relu(xt, LRELU_SLOPE)
+        xt = F.conv1d(xt, wn_weight(sd, f"{prefix}.convs2.{m}"), sd[f"{prefix}.convs2.{m}.bias"], padding=get_padding(k, 1))
+        x = xt + x
+    return x
+
+
+def generator(sd, mel):
+    """Generator.forward, models.py:110-128. mel [B, 80, T] -> [B, 1, 256 T]."""
+    x = F.conv1d(mel, wn_weight(sd, "conv_pre"), sd["conv_pre.bias"], padding=3)
+    for i, (u, k) in enumerate(zip(UP_RATES, UP_KERNELS)):
+        x = F.leaky_relu(x, LRELU_SLOPE)
+        x = F.conv_transpose1d(x, wn_weight(sd, f"ups.{i}"), sd[f"ups.{i}.bias"], stride=u, padding=(k - u) // 2)
+        xs = None
+        for j, rk in enumerate(RB_KERNELS):
+            r = resblock1(x, sd, f"resblocks.{i * 3 + j}", rk, RB_DILATIONS[j])
+            xs = r if xs is None else xs + r
+        x = xs / len(RB_KERNELS)
+    x = F.leaky_relu(x)  # default slope 0.01 (models.py:124)
+    x = F.conv1d(x, wn_weight(sd, "conv_post"), sd["conv_post.bias"], padding=3)
+    return torch.tanh(x)
+
+
+# ------------------------------------------------------------------------------------------------ mel spectrogram
+def _hz_to_mel(f):
+    f = np.asanyarray(f, dtype=np.float64)
+    f_sp = 200.0 / 3
+    mels = f / f_sp
+    min_log_hz, logstep = 1000.0, np.log(6.4) / 27.0
+    min_log_mel = min_log_hz / f_sp
+    return np.where(f >= min_log_hz, min_log_mel + np.log(np.maximum(f, 1e-10) / min_log_hz) / logstep, mels)
+
+
+def _mel_to_hz(m):
+    m = np.asanyarray(m, dtype=np.float64)
+    f_sp = 200.0 / 3
+    min_log_hz, logstep = 1000.0, np.log(6.4) / 27.0
+    min_log_mel = min_log_hz / f_sp
+    return np.where(m >= min_log_mel, min_log_hz * np.exp(logstep * (m - min_log_mel)), f_sp * m)
+
+
+def mel_filterbank(sr=SR, n_fft=N_FFT, n_mels=N_MELS, fmin=FMIN, fmax=FMAX):
+    """librosa.filters.mel of librosa 0.8.1 (htk=False, norm='slaney'): the call at meldataset.py:225. librosa is not
+    installed in the build image; this restates its published algorithm (triangles on the Slaney mel scale, each
+    normalised by 2 / bandwidth). float32 like librosa's return value."""
+    if fmax is None:
+        fmax = sr / 2.0
+    fftfreqs = np.linspace(0, sr / 2.0, 1 + n_fft // 2)
+    mel_f = _mel_to_hz(np.linspace(_hz_to_mel(fmin), _hz_to_mel(fmax), n_mels + 2))
+    fdiff = np.diff(mel_f)
+    ramps = np.subtract.outer(mel_f, fftfreqs)
+    weights = np.zeros((n_mels, 1 + n_fft // 2))
+    for i in range(n_mels):
+        lower = -ramps[i] / fdiff[i]
+        upper = ramps[i + 2] / fdiff[i + 1]
+        weights[i] = np.maximum(0, np.minimum(lower, upper))
+    enorm = 2.0 / (mel_f[2:n_mels + 2] - mel_f[:n_mels])
+    weights *= enorm[:, None]
+    return torch.from_numpy(weights.astype(np.float32))
+
+
+def mel_spectrogram(y, fmax=FMAX, n_fft=N_FFT, hop=HOP, win=WIN, n_mels=N_MELS, sr=SR, fmin=FMIN):
+    """meldataset.py:217-240. y [B, N] -> [B, 80, N / 256]."""
+    basis = mel_filterbank(sr, n_fft, n_mels, fmin, fmax).to(y.device)
+    pad = int((n_fft - hop) / 2)
+    yp = F.pad(y.unsqueeze(1), (pad, pad), mode="reflect").squeeze(1)
+    spec = torch.stft(yp, n_fft, hop_length=hop, win_length=win, window=torch.hann_window(win, device=y.device), center=False,
+                      pad_mode="reflect", normalized=False, onesided=True, return_complex=True)
+    mag = torch.sqrt(spec.real ** 2 + spec.imag ** 2 + 1e-9)
+    return torch.log(torch.clamp(torch.matmul(basis, mag), min=1e-5))
+
+
+# ------------------------------------------------------------------------------------------------ synthetic inputs
+def synthetic_batch(B, frames, seed=1234):
+    """audio = 0.95 tanh(N(0, 0.3)), x = mel(audio, fmax 8000), y_mel = mel(audio, fmax None)."""
+    g = torch.Generator().manual_seed(seed)
+    y = 0.95 * torch.tanh(torch.randn(B, frames * HOP, generator=g) * 0.3)
+    return mel_spectrogram(y, FMAX), y, mel_spectrogram(y, FMAX_LOSS)

@@ -1,0 +1,162 @@
+"""HiFi-GAN generator (xva-trainer_b200/hifigan.py, all math through libxva_b200.so) vs the CPU oracle (pinned to the
+reference by tests/test_oracle_golden.py) and vs the golden fixture recorded from the reference's Generator.
+
+Tolerances: tf32 tensor-core operands (rounded to nearest), fp32 accumulation. Forward waveform: relative L2 <= 2e-3
+(49 convolutions deep). Parameter gradients: <= 6e-2 per tensor, <= 2e-2 on the global vector (the backward
+signal passes through up to 98 tf32 products before it reaches conv_pre); with the exact-fp32
+checker GEMM and operand rounding off (wiring check): forward <= 1e-5, gradients <= 1e-4 (leaky ReLU has no dead zone, so
+there is no gate-flip noise floor here as there is for FastPitch's ReLU)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import hifigan as ohg
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+class _H(dict):
+    __getattr__ = dict.__getitem__
+
+
+def _config():
+    h = _H(resblock="1", upsample_rates=[8, 8, 2, 2], upsample_kernel_sizes=[16, 16, 4, 4], upsample_initial_channel=512,
+           resblock_kernel_sizes=[3, 7, 11], resblock_dilation_sizes=[[1, 3, 5], [1, 3, 5], [1, 3, 5]])
+    return h
+
+
+def _generator(lib, sd):
+    from xva_trainer_b200 import hifigan as hg
+
+    g = hg.Generator(_config(), device="cuda:0")
+    missing = g.load_state_dict({k: v for k, v in sd.items()})
+    assert not missing.missing_keys and not missing.unexpected_keys
+    g.train()
+    return g
+
+
+def test_state_dict_keys_match_reference(lib):
+    ref = json.load(open(os.path.join(GOLD, "hifigan_keys.json")))
+    g = _generator(lib, ohg.make_generator_state(1))
+    assert [[k, list(v.shape)] for k, v in g.state_dict().items()] == ref
+
+
+def _run(g, sd, mel, w):
+    y = g(mel.cuda())
+    g.zero_grad()
+    g.backward(w.cuda())
+    torch.cuda.synchronize()
+    grads = {k: p.grad.detach().cpu() for k, p in g.named_parameters()}
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    yo = ohg.generator(leaves, mel)
+    (yo * w).sum().backward()
+    return y, yo.detach(), grads, {k: p.grad for k, p in leaves.items()}
+
+
+@pytest.mark.parametrize("T,seed", [(6, 3), (9, 4)])
+def test_generator_matches_oracle(lib, T, seed):
+    sd = ohg.make_generator_state(seed, scale=0.7)
+    g = _generator(lib, sd)
+    gen = torch.Generator().manual_seed(seed)
+    mel = torch.randn(2, 80, T, generator=gen)
+    w = torch.randn(2, 1, 256 * T, generator=gen)
+    y, yo, grads, want = _run(g, sd, mel, w)
+    assert y.shape == yo.shape
+    assert rel(y, yo) < 2e-3, rel(y, yo)
+    num = den = 0.0
+    for k, gr in grads.items():
+        e = rel(gr, want[k])
+        assert e < 6e-2, (k, e)
+        num += float((gr.double() - want[k].double()).pow(2).sum())
+        den += float(want[k].double().pow(2).sum())
+    assert (num / den) ** 0.5 < 2e-2, (num / den) ** 0.5
+
+
+def test_generator_wiring_exact(lib, monkeypatch):
+    from xva_trainer_b200 import capi, ops
+
+    orig = ops.gemm_launch
+    monkeypatch.setattr(ops, "gemm_launch", lambda args, ref=False: orig(args, True))
+    capi.call("xva_set_operand_rounding", 0)
+    try:
+        sd = ohg.make_generator_state(11, scale=0.7)
+        g = _generator(lib, sd)
+        gen = torch.Generator().manual_seed(11)
+        mel = torch.randn(1, 80, 5, generator=gen)
+        w = torch.randn(1, 1, 256 * 5, generator=gen)
+        y, yo, grads, want = _run(g, sd, mel, w)
+        assert rel(y, yo) < 1e-5, rel(y, yo)
+        for k, gr in grads.items():
+            assert rel(gr, want[k]) < 1e-4, (k, rel(gr, want[k]))
+    finally:
+        capi.call("xva_set_operand_rounding", 1)
+
+
+def test_generator_matches_reference_golden(lib):
+    gold = np.load(os.path.join(GOLD, "hifigan_small.npz"))
+    sd = ohg.make_generator_state(1234, scale=1.0)
+    g = _generator(lib, sd)
+    y = g(torch.from_numpy(gold["gen/mel"]).cuda())
+    assert rel(y, torch.from_numpy(gold["gen/y"])) < 2e-3
+    g.zero_grad()
+    g.backward(torch.from_numpy(gold["gen/w"]).cuda())
+    for k, p in g.named_parameters():
+        want_norm = float(gold[f"gen/grad/{k}/norm"])
+        assert abs(float(p.grad.double().norm()) - want_norm) <= 3e-2 * want_norm + 1e-12, (k, float(p.grad.norm()), want_norm)
+
+
+# ------------------------------------------------------------------------------------------------ mel spectrogram
+@pytest.mark.parametrize("fmax", [8000, None])
+def test_mel_spectrogram_matches_oracle_and_golden(lib, fmax):
+    """Forward vs the reference fixture and the oracle; backward vs torch autograd through the oracle. The log-mel is
+    compared in absolute terms (values span about [-11.5, 2]); tolerance 5e-3 absolute = tf32 DFT of a signal whose
+    spectrum spans several decades, then log."""
+    from xva_trainer_b200 import hifigan as hg
+
+    gold = np.load(os.path.join(GOLD, "hifigan_small.npz"))
+    audio = torch.from_numpy(gold["mel/audio"])
+    ms = hg.MelSpectrogram(fmax=fmax, device="cuda:0")
+    got = ms(audio.cuda()).transpose(1, 2).cpu()
+    want = torch.from_numpy(gold[f"mel/{'none' if fmax is None else '8000'}"])
+    assert got.shape == want.shape
+    assert float((got - want).abs().max()) < 5e-3, float((got - want).abs().max())
+    assert rel(got, want) < 1e-3
+    # gradient of a random linear functional of the mel
+    g = torch.Generator().manual_seed(3)
+    w = torch.randn(want.shape, generator=g)
+    a = audio.clone().requires_grad_(True)
+    (ohg.mel_spectrogram(a, fmax) * w).sum().backward()
+    d = ms.backward(w.transpose(1, 2).contiguous().cuda()).cpu()
+    assert rel(d, a.grad) < 1e-2, rel(d, a.grad)
+
+
+def test_reflect_pad_and_losses(lib):
+    from xva_trainer_b200 import ops
+
+    g = torch.Generator().manual_seed(0)
+    y = torch.randn(3, 700, generator=g).cuda()
+    yp = ops.reflect_pad(y, 384)
+    want = torch.nn.functional.pad(y.unsqueeze(1), (384, 384), mode="reflect").squeeze(1)
+    assert rel(yp, want) < 3e-4          # tf32-rounded copy
+    d = torch.randn(3, 700 + 768, generator=g).cuda()
+    yy = y.clone().requires_grad_(True)
+    (torch.nn.functional.pad(yy.unsqueeze(1), (384, 384), mode="reflect").squeeze(1) * d).sum().backward()
+    assert rel(ops.reflect_pad_bwd(d, 700, 384), yy.grad) < 1e-6
+    a, b = torch.randn(1000, generator=g).cuda(), torch.randn(1000, generator=g).cuda()
+    acc = torch.zeros(2, device="cuda", dtype=torch.float64)
+    ops.reduce_l1(a, b, acc[0:1])
+    ops.reduce_sq(a, 1.0, acc[1:2])
+    assert abs(float(acc[0]) - float((a - b).abs().sum())) < 1e-3
+    assert abs(float(acc[1]) - float(((1 - a) ** 2).sum())) < 1e-3
+    assert torch.equal(ops.l1_grad(a, b, 0.5), 0.5 * torch.sign(b - a))
+    assert rel(ops.sq_grad(a, 1.0, 0.25), 0.5 * (a - 1.0)) < 1e-6

@@ -17,6 +17,7 @@ GEMM_DROP_POST = 1 << 3
 GEMM_ATOMIC = 1 << 4
 GEMM_LRELU_GATE = 1 << 5
 GEMM_ROUND_OUT = 1 << 6
+GEMM_TANH = 1 << 7
 
 c_float_p = C.c_void_p  # device pointers travel as integers
 
@@ -38,11 +39,12 @@ class GemmArgs(C.Structure):
         ("alpha", C.c_float), ("flags", C.c_int32),
         ("bias", C.c_void_p), ("residual", C.c_void_p), ("r_rs", C.c_int64), ("r_zs", C.c_int64),
         ("gate", C.c_void_p), ("g_rs", C.c_int64), ("g_zs", C.c_int64), ("gate_slope", C.c_float),
-        ("_pad1", C.c_int32),
+        ("act_slope", C.c_float),
         ("lens", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("ln_eps", C.c_float),
         ("_pad2", C.c_int32),
         ("out_pre", C.c_void_p), ("ln_mean", C.c_void_p), ("ln_rstd", C.c_void_p), ("drop_p", C.c_float),
-        ("_pad3", C.c_int32), ("seed", C.c_uint64), ("seed_dev", C.c_void_p),
+        ("out_act_slope", C.c_float), ("seed", C.c_uint64), ("out_act", C.c_void_p),
+        ("a_col", C.c_int32 * XVA_MAX_TAPS), ("seed_dev", C.c_void_p),
     ]
 
 
@@ -79,6 +81,18 @@ PROTOTYPES = {
     "xva_lamb_step": (_I, [_P, _P, _P, _P, _P, _I, _P, _P, _F, _P, _F, _F, _F, _F, _P, _P]),
     "xva_round_tf32": (_I, [_P, _P, _I64, _P]),
     "xva_set_operand_rounding": (_I, [_I]),
+    "xva_reflect_pad_fwd": (_I, [_P, _I, _I64, _I, _P, _P]),
+    "xva_reflect_pad_bwd": (_I, [_P, _I, _I64, _I, _P, _P]),
+    "xva_spec_mag_fwd": (_I, [_P, _I64, _I, _I, _I, _F, _P, _P]),
+    "xva_spec_mag_bwd": (_I, [_P, _P, _I64, _I, _I, _I, _F, _P, _P]),
+    "xva_log_clamp_fwd": (_I, [_P, _I64, _F, _P, _P]),
+    "xva_log_clamp_bwd": (_I, [_P, _P, _I64, _F, _P, _P]),
+    "xva_reduce_loss": (_I, [_P, _P, _I64, _I, _F, _P, _P]),
+    "xva_loss_grad": (_I, [_P, _P, _I64, _I, _F, _F, _I, _P, _P]),
+    "xva_mean3_lrelu": (_I, [_P, _P, _P, _I64, _F, _P, _P]),
+    "xva_sum3": (_I, [_P, _P, _P, _I64, _P, _P]),
+    "xva_tanh_bwd": (_I, [_P, _P, _I64, _I, _P, _P]),
+    "xva_adamw_step": (_I, [_P, _P, _P, _P, _I64, _P, _F, _F, _F, _F, _I, _P]),
 }
 
 _lib = None

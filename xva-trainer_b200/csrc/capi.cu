@@ -83,6 +83,8 @@ int xva_set_operand_rounding(int on) {
   if ((rc = set_operand_rounding_gemm_tc(on)) != XVA_OK) return rc;
   if ((rc = set_operand_rounding_gemm_ref(on)) != XVA_OK) return rc;
   if ((rc = set_operand_rounding_rowops(on)) != XVA_OK) return rc;
+  if ((rc = set_operand_rounding_elemwise(on)) != XVA_OK) return rc;
+  if ((rc = set_operand_rounding_melspec(on)) != XVA_OK) return rc;
   return set_operand_rounding_loss_optim(on);
 }
 
@@ -155,6 +157,50 @@ int xva_lamb_step(float* p, const float* g, float* m, float* v, const void* chun
                   float weight_decay, float* p_tf32, void* stream) {
   return lamb_step(p, g, m, v, chunks, n_chunks, norms, gnorm_sq, max_norm, lr_dev, beta1, beta2, eps, weight_decay,
                    p_tf32, S(stream));
+}
+
+int xva_mean3_lrelu(const float* y0, const float* y1, const float* y2, int64_t n, float slope, float* out, void* stream) {
+  return mean3_lrelu(y0, y1, y2, static_cast<long>(n), slope, out, S(stream));
+}
+
+int xva_sum3(const float* a, const float* b, const float* c, int64_t n, float* out, void* stream) {
+  return sum3(a, b, c, static_cast<long>(n), out, S(stream));
+}
+
+int xva_tanh_bwd(const float* dy, const float* y, int64_t rows, int ld, float* out, void* stream) {
+  return tanh_bwd(dy, y, static_cast<long>(rows), ld, out, S(stream));
+}
+
+int xva_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, const float* lr_dev, float beta1, float beta2,
+                   float eps, float weight_decay, int step, void* stream) {
+  return adamw_step(p, g, m, v, static_cast<long>(n), lr_dev, beta1, beta2, eps, weight_decay, step, S(stream));
+}
+
+int xva_reflect_pad_fwd(const float* y, int B, int64_t n, int pad, float* out, void* stream) {
+  return reflect_pad_fwd(y, B, static_cast<long>(n), pad, out, S(stream));
+}
+int xva_reflect_pad_bwd(const float* dyp, int B, int64_t n, int pad, float* dy, void* stream) {
+  return reflect_pad_bwd(dyp, B, static_cast<long>(n), pad, dy, S(stream));
+}
+int xva_spec_mag_fwd(const float* spec, int64_t rows, int nb, int ld_s, int ld_m, float eps, float* mag, void* stream) {
+  return spec_mag_fwd(spec, static_cast<long>(rows), nb, ld_s, ld_m, eps, mag, S(stream));
+}
+int xva_spec_mag_bwd(const float* dmag, const float* spec, int64_t rows, int nb, int ld_s, int ld_m, float eps,
+                     float* dspec, void* stream) {
+  return spec_mag_bwd(dmag, spec, static_cast<long>(rows), nb, ld_s, ld_m, eps, dspec, S(stream));
+}
+int xva_log_clamp_fwd(const float* x, int64_t n, float lo, float* out, void* stream) {
+  return log_clamp_fwd(x, static_cast<long>(n), lo, out, S(stream));
+}
+int xva_log_clamp_bwd(const float* dy, const float* x, int64_t n, float lo, float* dx, void* stream) {
+  return log_clamp_bwd(dy, x, static_cast<long>(n), lo, dx, S(stream));
+}
+int xva_reduce_loss(const float* a, const float* b, int64_t n, int kind, float c, double* acc, void* stream) {
+  return reduce_loss(a, b, static_cast<long>(n), kind, c, acc, S(stream));
+}
+int xva_loss_grad(const float* a, const float* b, int64_t n, int kind, float c, float scale, int accumulate, float* out,
+                  void* stream) {
+  return loss_grad(a, b, static_cast<long>(n), kind, c, scale, accumulate, out, S(stream));
 }
 
 }  // extern "C"

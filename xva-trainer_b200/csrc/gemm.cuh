@@ -28,6 +28,7 @@ enum GemmFlags : int {
   GEMM_DROP_POST = XVA_GEMM_DROP_POST,    // dropout after LN (ConvReLUNorm: common/layers.py:94-97)
   GEMM_ATOMIC = XVA_GEMM_ATOMIC,          // mode 2: accumulate into `out` with fp32 atomics (split-z)
   GEMM_LRELU_GATE = XVA_GEMM_LRELU_GATE,  // reserved
+  GEMM_TANH = XVA_GEMM_TANH,
   GEMM_ROUND_OUT = XVA_GEMM_ROUND_OUT,    // out is a later GEMM operand: store it rounded to tf32
 };
 

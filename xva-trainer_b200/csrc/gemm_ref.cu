@@ -24,7 +24,7 @@ __device__ float ref_dot(const GemmArgs& g, int z, int r, int n) {
   for (int j = 0; j < g.taps; ++j) {
     const int ar = r + g.shift[j];
     if (ar < 0 || ar >= a_rows) continue;
-    const float* arow = g.a + z * g.a_zs + static_cast<long>(ar) * g.a_rs;
+    const float* arow = g.a + z * g.a_zs + static_cast<long>(ar) * g.a_rs + g.a_col[j];
     const int zb = j * g.b_tap_z + z * g.b_batch_z;
     if (g.mode == 0) {
       if (g.b_rows && n >= g.b_rows) continue;
@@ -54,7 +54,7 @@ __global__ void gemm_ref_fwd_kernel(const RefDev d) {
   auto pre_value = [&](int n) -> float {
     float v = g.alpha * ref_dot(g, z, r, n);
     if (g.bias) v += g.bias[n];
-    if (g.flags & GEMM_RELU) v = fmaxf(v, 0.0f);
+    if (g.flags & GEMM_RELU) v = v > 0.0f ? v : g.act_slope * v;
     if (g.gate) v *= (g.gate[rowoff_g + n] > 0.0f) ? 1.0f : g.gate_slope;
     if (g.flags & GEMM_DROP_PRE) v *= dropout_scale(eff_seed(g), drop_row + n, d.drop_thresh, d.inv_keep);
     if (g.residual) v += g.residual[rowoff_r + n];
@@ -63,7 +63,10 @@ __global__ void gemm_ref_fwd_kernel(const RefDev d) {
 
   if (!ln) {
     for (int n = threadIdx.x; n < g.N; n += blockDim.x) {
-      const float v = pre_value(n) * keep_row;
+      float v = pre_value(n);
+      if (g.flags & GEMM_TANH) v = tanhf(v);
+      v *= keep_row;
+      if (g.out_act) g.out_act[rowoff_o + n] = tf32_rn(v > 0.0f ? v : g.out_act_slope * v);
       g.out[rowoff_o + n] = (g.flags & GEMM_ROUND_OUT) ? tf32_rn(v) : v;
     }
     return;

@@ -51,6 +51,10 @@ struct GemmDev {
   const float* gate;
   long g_rs, g_zs;
   float gate_slope;
+  float act_slope;
+  float out_act_slope;
+  float* out_act;
+  int a_col[kMaxTaps];
   const int* lens;
   const float* gamma;
   const float* beta;
@@ -228,6 +232,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         int it = 0;
         for (int jo = 0; jo < n_outer; ++jo) {
           const int shift_j = (p.mode != 2) ? p.shift[jo] : p.shift[c.j];
+          const int acol_j = (p.mode != 2) ? p.a_col[jo] : 0;
           for (int kc = 0; kc < p.k_chunks; ++kc, ++it) {
             ptx::mbar_wait(&bar_empty[s], ph ^ 1);
             uint8_t* sa = smem + s * stage_bytes;
@@ -242,7 +247,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               const uint32_t full = ptx::mapa(ptx::smem_u32(&bar_full[s]), 0);
               const int zb = jo * p.b_tap_z;
               const int half_n = p.n_sub >> 1;
-              ptx::tma_load_3d_cg2(sa, &tmap_a, full, kc * kBlockK, c.m0 + shift_j, c.z);
+              ptx::tma_load_3d_cg2(sa, &tmap_a, full, acol_j + kc * kBlockK, c.m0 + shift_j, c.z);
               for (int sub = 0; sub < p.n_mma; ++sub) {
                 const int nb = c.n0 + sub * p.n_sub + static_cast<int>(cta_rank) * half_n;
                 if (p.mode == 0)
@@ -253,7 +258,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             } else if (p.mode != 2) {
               ptx::mbar_arrive_expect_tx(&bar_full[s], stage_bytes);
               const int zb = jo * p.b_tap_z + c.z * p.b_batch_z;
-              ptx::tma_load_3d(sa, &tmap_a, &bar_full[s], kc * kBlockK, c.m0 + shift_j, c.z);
+              ptx::tma_load_3d(sa, &tmap_a, &bar_full[s], acol_j + kc * kBlockK, c.m0 + shift_j, c.z);
               if (p.mode == 0) {
                 for (int sub = 0; sub < p.n_mma; ++sub)
                   ptx::tma_load_3d(sb + sub * p.n_sub * kBlockK * 4, &tmap_b, &bar_full[s], kc * kBlockK,
@@ -518,7 +523,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             float4 x = make_float4(p.alpha * t[k].x + b.x, p.alpha * t[k].y + b.y, p.alpha * t[k].z + b.z,
                                    p.alpha * t[k].w + b.w);
             if (p.flags & GEMM_RELU) {
-              x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f);
+              x.x = x.x > 0.f ? x.x : p.act_slope * x.x; x.y = x.y > 0.f ? x.y : p.act_slope * x.y;
+              x.z = x.z > 0.f ? x.z : p.act_slope * x.z; x.w = x.w > 0.f ? x.w : p.act_slope * x.w;
             }
             if constexpr (kEpi != EPI_PLAIN) {
               if (p.gate) {
@@ -555,7 +561,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             for (int k = 0; k < 8; ++k) {
               const int row = row0 + 4 * k;
               if (row >= row_limit || nv == 0) continue;
+              if (p.flags & GEMM_TANH) t[k] = make_float4(tanhf(t[k].x), tanhf(t[k].y), tanhf(t[k].z), tanhf(t[k].w));
               if (row >= len_z) t[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (p.out_act) {
+                const float sl = p.out_act_slope;
+                const float4 a = make_float4(t[k].x > 0.f ? t[k].x : sl * t[k].x, t[k].y > 0.f ? t[k].y : sl * t[k].y,
+                                             t[k].z > 0.f ? t[k].z : sl * t[k].z, t[k].w > 0.f ? t[k].w : sl * t[k].w);
+                store1(p.out_act + zoff_o + static_cast<long>(row) * p.o_rs + n, full, nv, tf32_rn4(a));
+              }
               if (p.flags & GEMM_ROUND_OUT) t[k] = tf32_rn4(t[k]);
               store1(p.out + zoff_o + static_cast<long>(row) * p.o_rs + n, full, nv, t[k]);
             }
@@ -890,7 +903,10 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
   int rc;
   const int a_rows = g.a_rows ? g.a_rows : g.R;
   if (g.mode != 2) {
-    uint64_t dims[3] = {(uint64_t)g.K, (uint64_t)a_rows, (uint64_t)g.Z};
+    int a_cols = g.K;  // with per-tap column offsets each tap reads columns [a_col, a_col + K) of a wider row
+    for (int j = 0; j < g.taps; ++j) a_cols = g.a_col[j] + g.K > a_cols ? g.a_col[j] + g.K : a_cols;
+    // (a ragged last k-block then reads real neighbouring columns of A; they meet zero-filled rows of B)
+    uint64_t dims[3] = {(uint64_t)a_cols, (uint64_t)a_rows, (uint64_t)g.Z};
     uint64_t str[3] = {1, (uint64_t)g.a_rs, (uint64_t)g.a_zs};
     uint32_t box[3] = {kBlockK, kBlockM, 1};
     if (g.Z == 1 || str[2] == 0) str[2] = (uint64_t)g.a_rs * a_rows;
@@ -943,6 +959,10 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
   p.g_rs = g.g_rs;
   p.g_zs = g.g_zs;
   p.gate_slope = g.gate_slope;
+  p.act_slope = g.act_slope;
+  p.out_act_slope = g.out_act_slope;
+  p.out_act = g.out_act;
+  for (int j = 0; j < g.taps; ++j) p.a_col[j] = g.a_col[j];
   p.lens = g.lens;
   p.gamma = g.gamma;
   p.beta = g.beta;
@@ -970,6 +990,7 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
     if (g.residual) ok = ok && al(g.residual) && m4(g.r_rs) && m4(g.r_zs);
     if (g.gate) ok = ok && al(g.gate) && m4(g.g_rs) && m4(g.g_zs);
     if (g.out_pre) ok = ok && al(g.out_pre);
+    if (g.out_act) ok = ok && al(g.out_act);
     if (g.flags & GEMM_LN) ok = ok && al(g.gamma) && al(g.beta);
     p.vec_ok = ok ? 1 : 0;
   }

@@ -11,6 +11,8 @@ int set_operand_rounding_gemm_tc(int on);
 int set_operand_rounding_gemm_ref(int on);
 int set_operand_rounding_rowops(int on);
 int set_operand_rounding_loss_optim(int on);
+int set_operand_rounding_elemwise(int on);
+int set_operand_rounding_melspec(int on);
 
 // ---- regulate.cu
 int duration_scan(const float* durs, int B, int Tt, float pace, int mel_max_len, int* cum, int* dec_lens,
@@ -45,6 +47,25 @@ int rowdot_fwd(const float* x, const float* w, const float* bias, const int* len
                cudaStream_t stream);
 int rowdot_bwd(const float* dout, const float* x, const float* w, const int* lens, int Z, int R, int C, float* dx,
                float* dw, float* db, cudaStream_t stream);
+
+// ---- elemwise.cu
+int mean3_lrelu(const float* y0, const float* y1, const float* y2, long n, float slope, float* out, cudaStream_t stream);
+int sum3(const float* a, const float* b, const float* c, long n, float* out, cudaStream_t stream);
+int tanh_bwd(const float* dy, const float* y, long rows, int ld, float* out, cudaStream_t stream);
+int adamw_step(float* p, const float* g, float* m, float* v, long n, const float* lr_dev, float b1, float b2, float eps,
+               float wd, int step, cudaStream_t stream);
+
+// ---- melspec.cu
+int reflect_pad_fwd(const float* y, int B, long n, int pad, float* out, cudaStream_t stream);
+int reflect_pad_bwd(const float* dyp, int B, long n, int pad, float* dy, cudaStream_t stream);
+int spec_mag_fwd(const float* spec, long rows, int nb, int ld_s, int ld_m, float eps, float* mag, cudaStream_t stream);
+int spec_mag_bwd(const float* dmag, const float* spec, long rows, int nb, int ld_s, int ld_m, float eps, float* dspec,
+                 cudaStream_t stream);
+int log_clamp_fwd(const float* x, long n, float lo, float* out, cudaStream_t stream);
+int log_clamp_bwd(const float* dy, const float* x, long n, float lo, float* dx, cudaStream_t stream);
+int reduce_loss(const float* a, const float* b, long n, int kind, float c, double* acc, cudaStream_t stream);
+int loss_grad(const float* a, const float* b, long n, int kind, float c, float scale, int accumulate, float* out,
+              cudaStream_t stream);
 
 // ---- loss_optim.cu
 int mel_mse(const float* pred, const float* tgt, int B, int T_out, int Tm, int C, double* acc, cudaStream_t stream);

@@ -1,0 +1,370 @@
+"""B200-native HiFi-GAN v1 training path: the reference's ``Generator`` (python/hifigan/models.py:81-137) with every
+tensor operation issued through the C ABI of libxva_b200.so.
+
+Same constructor argument (the config ``h``), same ``state_dict`` keys and shapes as the reference (``weight_g`` /
+``weight_v`` / ``bias`` of every weight-normed conv: 234 keys), same ``forward(x)`` signature ([B, 80, T] mel ->
+[B, 1, 256 T] waveform). Training adds ``backward(dy)``: there is no autograd graph over activations.
+
+Design:
+  * activations are channels-last [B, T, C] fp32; every conv is the tcgen05 tap-GEMM (k taps = k shifted TMA loads,
+    dilation = shift stride, zero padding = TMA out-of-bounds fill);
+  * each ResBlock1 step `x = c2(lrelu(c1(lrelu(x)))) + x` (models.py:41-48) is two launches: conv1 with the leaky ReLU
+    in its epilogue, conv2 with the residual add in its epilogue and a second output leaky_relu(x) that is the next
+    conv's operand -- no standalone activation or add kernels;
+  * ConvTranspose1d(k = 2u, stride u) is two 2-tap GEMMs (output phases below / above u/2) writing column slices of
+    the [B, T, u*Cout] view of the [B, u*T, Cout] output: no zero insertion, no col2im;
+  * the weight-norm reparametrisation (w = g v / ||v||) and the re-packing of w into the kernel layout stay in PyTorch
+    (tiny tensors; autograd carries dL/dw back to weight_g / weight_v), as SURVEY.md section 7 recommends.
+"""
+import math
+
+import torch
+from torch import nn
+
+from . import capi, ops
+
+LRELU_SLOPE = 0.1
+
+
+class _WNConv(nn.Module):
+    """Parameters of one weight-normed Conv1d / ConvTranspose1d with the reference's names (bias, weight_g, weight_v)."""
+
+    def __init__(self, cin, cout, k, dilation=1, transposed=False, stride=1):
+        super().__init__()
+        self.cin, self.cout, self.k, self.dilation, self.transposed, self.stride = cin, cout, k, dilation, transposed, stride
+        shape = (cin, cout, k) if transposed else (cout, cin, k)
+        self.bias = nn.Parameter(torch.zeros(cout))
+        self.weight_g = nn.Parameter(torch.ones(shape[0], 1, 1))
+        self.weight_v = nn.Parameter(torch.zeros(shape))
+
+    def weight(self):
+        v = self.weight_v
+        return v * (self.weight_g / v.flatten(1).norm(dim=1).view(-1, 1, 1))
+
+    @property
+    def shifts(self):
+        half = (self.k - 1) // 2
+        return tuple((j - half) * self.dilation for j in range(self.k))
+
+
+class ResBlock1(nn.Module):
+    def __init__(self, h, channels, kernel_size=3, dilation=(1, 3, 5)):
+        super().__init__()
+        self.convs1 = nn.ModuleList([_WNConv(channels, channels, kernel_size, d) for d in dilation])
+        self.convs2 = nn.ModuleList([_WNConv(channels, channels, kernel_size, 1) for _ in dilation])
+
+
+class Generator(nn.Module):
+    """Drop-in for hifigan/models.py:81 ``Generator(h)`` (config_v1: resblock '1')."""
+
+    def __init__(self, h, device=None, seed=1234):
+        super().__init__()
+        self.h = h
+        self.num_kernels = len(h.resblock_kernel_sizes)
+        self.num_upsamples = len(h.upsample_rates)
+        if str(h.resblock) != "1":
+            raise NotImplementedError("only ResBlock1 (config_v1.json) is built")
+        c0 = h.upsample_initial_channel
+        self.conv_pre = _WNConv(80, c0, 7)
+        self.ups = nn.ModuleList()
+        for i, (u, k) in enumerate(zip(h.upsample_rates, h.upsample_kernel_sizes)):
+            if k != 2 * u or u % 2:
+                raise NotImplementedError(f"upsample kernel {k} / rate {u}: only k = 2u with even u is built")
+            self.ups.append(_WNConv(c0 // 2 ** i, c0 // 2 ** (i + 1), k, transposed=True, stride=u))
+        self.resblocks = nn.ModuleList()
+        for i in range(len(self.ups)):
+            ch = c0 // 2 ** (i + 1)
+            for k, d in zip(h.resblock_kernel_sizes, h.resblock_dilation_sizes):
+                self.resblocks.append(ResBlock1(h, ch, k, tuple(d)))
+        self.conv_post = _WNConv(ch, 1, 7)
+        self.reset_parameters(seed)
+        dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        if dev.type != "cuda":
+            raise capi.XvaError("Generator (B200 build) needs a CUDA device: there is no CPU path")
+        capi.load()
+        capi.call("xva_device_check", dev.index or 0)
+        self.to(dev)
+        self._ctx = None
+        self._packed = None
+
+    def reset_parameters(self, seed=1234):
+        """Reference init: N(0, 0.01) weights for ups / resblocks / conv_post (utils.py:23-26), torch default for
+        conv_pre, g = ||v|| (what weight_norm does at wrap time); generated on the CPU from one seed."""
+        g = torch.Generator().manual_seed(int(seed))
+        with torch.no_grad():
+            for name, m in self.named_modules():
+                if not isinstance(m, _WNConv):
+                    continue
+                fan_in = m.weight_v.shape[1] * m.weight_v.shape[2]
+                if name == "conv_pre":
+                    bound = 1.0 / math.sqrt(fan_in)
+                    m.weight_v.copy_((torch.rand(m.weight_v.shape, generator=g) * 2 - 1) * bound)
+                else:
+                    m.weight_v.copy_(torch.randn(m.weight_v.shape, generator=g) * 0.01)
+                m.weight_g.copy_(m.weight_v.flatten(1).norm(dim=1).view(-1, 1, 1))
+                m.bias.copy_((torch.rand(m.bias.shape, generator=g) * 2 - 1) / math.sqrt(fan_in))
+
+    # ------------------------------------------------------------------------------------------ weights
+    def _pack(self):
+        """Effective weights in the kernel layout [taps, Cout, Cin] (tf32-rounded by the GEMM's own operand rule: the
+        packed copies are produced by torch here and rounded by xva_round_tf32), under autograd so that
+        backward() can hand dL/d(packed) back to weight_g / weight_v."""
+        packed = {}
+        for name, m in self.named_modules():
+            if not isinstance(m, _WNConv):
+                continue
+            w = m.weight()
+            if not m.transposed:
+                packed[name] = (w.permute(2, 0, 1).contiguous(),)
+            else:
+                u, p = m.stride, m.stride // 2
+                wk = w.permute(2, 1, 0)                                   # [k, Cout, Cin]
+                cat = lambda a, b: torch.stack([a.reshape(-1, m.cin), b.reshape(-1, m.cin)]).contiguous()
+                # phases r' < u - p: taps (shift 0, shift -1) = kernel columns (r'+p, r'+p+u)
+                lo = cat(wk[p:u], wk[p + u:2 * u])
+                # phases r' >= u - p: taps (shift +1, shift 0) = kernel columns (r'+p-u, r'+p)
+                hi = cat(wk[0:p], wk[u:u + p])
+                packed[name] = (lo, hi)
+        return packed
+
+    def _rounded(self, t):
+        out = torch.empty_like(t)
+        ops.round_tf32_(t.detach().reshape(-1), out.reshape(-1))
+        return out
+
+    # ------------------------------------------------------------------------------------------ forward
+    def forward(self, x, cond_emb=None):
+        """Generator.forward, models.py:110-128. x [B, 80, T] -> [B, 1, 256 T]. In training mode the tensors backward()
+        needs are kept until the next forward()."""
+        if cond_emb is not None:
+            raise NotImplementedError("USE_EMB_CONDITIONING is off in config_v1.json")
+        B, _, T = x.shape
+        keep = self.training
+        packed = self._pack()
+        W = {k: tuple(self._rounded(t) for t in v) for k, v in packed.items()}
+        # [B, T, 80] channels-last operand in rows of 96 floats (zero tail): the weight-gradient GEMM reads it MN-major
+        # in 32-column chunks
+        melp = torch.zeros(B, T, 96, device=x.device, dtype=torch.float32)
+        mel = melp[..., :80]
+        mel.copy_(x.to(torch.float32).transpose(1, 2))
+        ops.round_tf32_(melp.reshape(-1), melp.reshape(-1))
+        ctx = {"mel": mel, "stages": [], "W": W, "packed": packed, "B": B}
+        # conv_pre; only leaky_relu(conv_pre(x)) is ever read (models.py:111,115)
+        a = ops.conv_fwd(mel, W["conv_pre"][0], self.conv_pre.shifts, bias=self.conv_pre.bias.detach(),
+                         act_slope=LRELU_SLOPE, round_out=True)
+        for i in range(self.num_upsamples):
+            up = self.ups[i]
+            u, p, cout = up.stride, up.stride // 2, up.cout
+            Tin = a.shape[1]
+            bias_rep = up.bias.detach().repeat(u)
+            xu = torch.empty(B, Tin, u * cout, device=a.device, dtype=torch.float32)  # = [B, u*Tin, cout]
+            au = torch.empty_like(xu)
+            nlo = (u - p) * cout
+            ops.conv_fwd(a, W[f"ups.{i}"][0], (0, -1), out=xu[..., :nlo], bias=bias_rep[:nlo], out_act=au[..., :nlo],
+                         out_act_slope=LRELU_SLOPE)
+            ops.conv_fwd(a, W[f"ups.{i}"][1], (1, 0), out=xu[..., nlo:], bias=bias_rep[nlo:], out_act=au[..., nlo:],
+                         out_act_slope=LRELU_SLOPE)
+            x0 = xu.view(B, Tin * u, cout)
+            a0 = au.view(B, Tin * u, cout)
+            stage = {"a_in": a, "a0": a0, "blocks": []}
+            ys = []
+            for j in range(self.num_kernels):
+                rb = self.resblocks[i * self.num_kernels + j]
+                name = f"resblocks.{i * self.num_kernels + j}"
+                xr, ar = x0, a0
+                saved = []
+                for m in range(3):
+                    c1, c2 = rb.convs1[m], rb.convs2[m]
+                    t = ops.conv_fwd(ar, W[f"{name}.convs1.{m}"][0], c1.shifts, bias=c1.bias.detach(),
+                                     act_slope=LRELU_SLOPE, round_out=True)
+                    last = m == 2
+                    xn = torch.empty_like(xr)
+                    an = None if last else torch.empty_like(xr)
+                    ops.conv_fwd(t, W[f"{name}.convs2.{m}"][0], c2.shifts, out=xn, bias=c2.bias.detach(), residual=xr,
+                                 out_act=an, out_act_slope=LRELU_SLOPE)
+                    saved.append((ar, t))
+                    xr, ar = xn, an
+                ys.append(xr)
+                stage["blocks"].append(saved)
+            slope = LRELU_SLOPE if i + 1 < self.num_upsamples else 0.01               # models.py:115 vs :124
+            a = ops.mean3_lrelu(ys[0], ys[1], ys[2], slope)
+            ctx["stages"].append(stage)
+        y = ops.conv_fwd(a, W["conv_post"][0], self.conv_post.shifts, bias=self.conv_post.bias.detach(), tanh=True)
+        ctx["a_last"], ctx["y"] = a, y
+        self._ctx = ctx if keep else None
+        return y.view(B, 1, -1)
+
+    # ------------------------------------------------------------------------------------------ backward
+    def backward(self, dy):
+        """dy = dL/d(output) [B, 1, 256 T]. Accumulates .grad of every parameter (bias directly, weight_g / weight_v
+        through the autograd graph of the weight-norm reparametrisation)."""
+        ctx = self._ctx
+        if ctx is None:
+            raise RuntimeError("backward() needs a forward() in training mode first")
+        B, W = ctx["B"], ctx["W"]
+        gW = {k: tuple(torch.zeros_like(t) for t in v) for k, v in W.items()}
+        gb = {}
+
+        def bias_grad(name, d, cols, ld=None):
+            out = torch.zeros(cols, device=d.device, dtype=torch.float32)
+            ops.colsum_(d.shape[0] * d.shape[1], cols, ld if ld is not None else d.shape[2], d, out)
+            gb[name] = out
+
+        # conv_post + tanh
+        y, a = ctx["y"], ctx["a_last"]
+        Tl = a.shape[1]
+        dpre = ops.tanh_bwd(dy.reshape(-1).to(torch.float32).contiguous(), y.reshape(-1), 32).view(B, Tl, 32)
+        dp1 = dpre[..., :1]
+        ops.conv_wgrad(dp1, a, self.conv_post.shifts, out=gW["conv_post"][0], accumulate=True)
+        bias_grad("conv_post", dpre, 1, 32)
+        for i in reversed(range(self.num_upsamples)):
+            stage = ctx["stages"][i]
+            slope = LRELU_SLOPE if i + 1 < self.num_upsamples else 0.01
+            # gradient wrt each ResBlock output y_j: (1/3) * lrelu'(mean) * d(a); a carries the sign of the mean
+            if i + 1 == self.num_upsamples:
+                dyj = ops.conv_dgrad(dp1, W["conv_post"][0], self.conv_post.shifts, gate=a, gate_slope=slope,
+                                     alpha=1.0 / 3.0, round_out=True)
+            else:
+                dyj = self._ups_dgrad(i + 1, d_up, a, slope, W)
+            a0 = stage["a0"]
+            dx_blocks = []
+            for j in range(self.num_kernels):
+                rb = self.resblocks[i * self.num_kernels + j]
+                name = f"resblocks.{i * self.num_kernels + j}"
+                G = dyj
+                for m in reversed(range(3)):
+                    c1, c2 = rb.convs1[m], rb.convs2[m]
+                    ar, t = stage["blocks"][j][m]
+                    bias_grad(f"{name}.convs2.{m}", G, c2.cout)
+                    ops.conv_wgrad(G, t, c2.shifts, out=gW[f"{name}.convs2.{m}"][0], accumulate=True)
+                    dt = ops.conv_dgrad(G, W[f"{name}.convs2.{m}"][0], c2.shifts, gate=t, gate_slope=LRELU_SLOPE,
+                                        round_out=True)
+                    bias_grad(f"{name}.convs1.{m}", dt, c1.cout)
+                    ops.conv_wgrad(dt, ar, c1.shifts, out=gW[f"{name}.convs1.{m}"][0], accumulate=True)
+                    G = ops.conv_dgrad(dt, W[f"{name}.convs1.{m}"][0], c1.shifts, gate=ar, gate_slope=LRELU_SLOPE,
+                                       residual=G, round_out=True)
+                dx_blocks.append(G)
+            d_up = ops.sum3(dx_blocks[0], dx_blocks[1], dx_blocks[2])       # dL/d(ups[i] output), [B, u*Tin, cout]
+            a = stage["a_in"]
+            up = self.ups[i]
+            u, p, cout = up.stride, up.stride // 2, up.cout
+            Tin = a.shape[1]
+            dv = d_up.view(B, Tin, u * cout)
+            nlo = (u - p) * cout
+            ops.conv_wgrad(dv[..., :nlo], a, (0, -1), out=gW[f"ups.{i}"][0], accumulate=True)
+            ops.conv_wgrad(dv[..., nlo:], a, (1, 0), out=gW[f"ups.{i}"][1], accumulate=True)
+            bias_grad(f"ups.{i}", d_up, cout)
+        # ups[0] input is leaky_relu(conv_pre(x)): gate by its sign, then conv_pre's own gradients
+        dpre0 = self._ups_dgrad(0, d_up, a, LRELU_SLOPE, W, alpha=1.0)
+        ops.conv_wgrad(dpre0, ctx["mel"], self.conv_pre.shifts, out=gW["conv_pre"][0], accumulate=True)
+        bias_grad("conv_pre", dpre0, self.conv_pre.cout)
+
+        # hand the packed-weight gradients to autograd (weight norm + re-packing), biases directly
+        tensors, grads = [], []
+        for k, v in ctx["packed"].items():
+            for t, g_ in zip(v, gW[k]):
+                tensors.append(t)
+                grads.append(g_)
+        torch.autograd.backward(tensors, grads)
+        for name, m in self.named_modules():
+            if isinstance(m, _WNConv):
+                g_ = gb[name]
+                m.bias.grad = g_ if m.bias.grad is None else m.bias.grad + g_
+        self._ctx = None
+
+    def _ups_dgrad(self, i, d_up, a_in, slope, W, alpha=1.0 / 3.0):
+        """Input gradient of ups[i] (two 2-tap dgrads, summed through the residual slot), times the derivative of the
+        leaky ReLU that produced its input (gate = a_in) and the 1/3 of the MRF mean that precedes it."""
+        up = self.ups[i]
+        u, p, cout = up.stride, up.stride // 2, up.cout
+        B, Tin, _ = a_in.shape
+        dv = d_up.view(B, Tin, u * cout)
+        nlo = (u - p) * cout
+        # alpha and the gate are linear, so they can be applied to both halves separately; the residual slot adds the
+        # first half's (already scaled and gated) result
+        lo = ops.conv_dgrad(dv[..., :nlo], W[f"ups.{i}"][0], (0, -1), gate=a_in, gate_slope=slope, alpha=alpha)
+        return ops.conv_dgrad(dv[..., nlo:], W[f"ups.{i}"][1], (1, 0), gate=a_in, gate_slope=slope, alpha=alpha,
+                              residual=lo, round_out=True)
+
+
+# ------------------------------------------------------------------------------------------------ mel spectrogram
+def _slaney_mel_filterbank(sr, n_fft, n_mels, fmin, fmax):
+    """librosa.filters.mel(sr, n_fft, n_mels, fmin, fmax) of librosa 0.8.1 (Slaney scale, Slaney norm), the call the
+    reference makes at meldataset.py:225 -- restated (librosa is a third-party dependency of the reference)."""
+    import numpy as np
+
+    if fmax is None:
+        fmax = sr / 2.0
+    f_sp, min_log_hz, logstep = 200.0 / 3, 1000.0, math.log(6.4) / 27.0
+    min_log_mel = min_log_hz / f_sp
+    hz2mel = lambda f: np.where(f >= min_log_hz, min_log_mel + np.log(np.maximum(f, 1e-10) / min_log_hz) / logstep, f / f_sp)
+    mel2hz = lambda m: np.where(m >= min_log_mel, min_log_hz * np.exp(logstep * (m - min_log_mel)), f_sp * m)
+    fftfreqs = np.linspace(0, sr / 2.0, 1 + n_fft // 2)
+    mel_f = mel2hz(np.linspace(hz2mel(np.float64(fmin)), hz2mel(np.float64(fmax)), n_mels + 2))
+    fdiff = np.diff(mel_f)
+    ramps = np.subtract.outer(mel_f, fftfreqs)
+    w = np.zeros((n_mels, 1 + n_fft // 2))
+    for i in range(n_mels):
+        w[i] = np.maximum(0, np.minimum(-ramps[i] / fdiff[i], ramps[i + 2] / fdiff[i + 1]))
+    w *= (2.0 / (mel_f[2:n_mels + 2] - mel_f[:n_mels]))[:, None]
+    return torch.from_numpy(w.astype(np.float32))
+
+
+class MelSpectrogram:
+    """mel_spectrogram(), hifigan/meldataset.py:217-240, with its backward. ``forward(y [B, N])`` returns the log-mel
+    in channels-last layout [B, N / hop, n_mels] (transpose(1, 2) of the reference's [B, n_mels, frames]);
+    ``backward(dmel)`` returns dL/dy [B, N]. Unlike the reference (which rebuilds the filterbank with librosa on the
+    CPU at every call, meldataset.py:224-226) the DFT and mel bases are built once and stay on the device."""
+
+    EPS, LOG_MIN = 1e-9, 1e-5
+
+    def __init__(self, n_fft=1024, num_mels=80, sampling_rate=22050, hop_size=256, win_size=1024, fmin=0, fmax=8000,
+                 device="cuda"):
+        if n_fft % hop_size or win_size != n_fft:
+            raise NotImplementedError("built for win_size == n_fft and n_fft a multiple of hop_size (config_v1.json)")
+        self.n_fft, self.hop, self.n_mels = n_fft, hop_size, num_mels
+        self.taps = n_fft // hop_size
+        self.nb = n_fft // 2 + 1
+        self.pad = (n_fft - hop_size) // 2
+        self.ld_s = (2 * self.nb + 3) // 4 * 4          # spectrum row stride (16-byte rows)
+        self.ld_m = (self.nb + 31) // 32 * 32           # magnitude row stride / padded K of the mel projection
+        dev = torch.device(device)
+        n = torch.arange(n_fft, dtype=torch.float64)
+        window = torch.hann_window(win_size, periodic=True, dtype=torch.float64)
+        ang = 2.0 * math.pi * torch.outer(torch.arange(self.nb, dtype=torch.float64), n) / n_fft
+        basis = torch.cat([torch.cos(ang), -torch.sin(ang)], 0) * window[None, :]                # [2 nb, n_fft]
+        bw = basis.view(2 * self.nb, self.taps, hop_size).permute(1, 0, 2).contiguous().float()  # [taps, 2 nb, hop]
+        self.dft = torch.empty_like(bw, device=dev)
+        ops.round_tf32_(bw.to(dev).reshape(-1), self.dft.reshape(-1))
+        mel = torch.zeros(1, num_mels, self.ld_m)
+        mel[0, :, :self.nb] = _slaney_mel_filterbank(sampling_rate, n_fft, num_mels, fmin, fmax)
+        self.mel = torch.empty_like(mel, device=dev)
+        ops.round_tf32_(mel.to(dev).reshape(-1), self.mel.reshape(-1))
+        self._ctx = None
+
+    def forward(self, y):
+        B, N = y.shape
+        if N % self.hop:
+            raise ValueError(f"signal length {N} is not a multiple of the hop size {self.hop}")
+        F_ = N // self.hop
+        yp = ops.reflect_pad(y.to(torch.float32).contiguous(), self.pad)              # [B, N + n_fft - hop]
+        view = yp.view(B, F_ + self.taps - 1, self.hop)
+        spec = torch.empty(B, F_, self.ld_s, device=y.device, dtype=torch.float32)
+        if self.ld_s > 2 * self.nb:
+            spec[..., 2 * self.nb:].zero_()
+        ops.conv_fwd(view, self.dft, tuple(range(self.taps)), out=spec[..., :2 * self.nb], out_rows=F_)
+        mag = ops.spec_mag(spec, self.nb, self.ld_m, self.EPS)
+        lin = ops.conv_fwd(mag[..., :self.nb], self.mel[..., :self.nb])
+        out = ops.log_clamp(lin, self.LOG_MIN)
+        self._ctx = (B, N, F_, spec, lin)
+        return out
+
+    __call__ = forward
+
+    def backward(self, dmel):
+        B, N, F_, spec, lin = self._ctx
+        dlin = ops.log_clamp_bwd(dmel.contiguous(), lin, self.LOG_MIN)
+        dmag = ops.conv_dgrad(dlin, self.mel)                                        # [B, F, ld_m]
+        dspec = ops.spec_mag_bwd(dmag, spec, self.nb, self.EPS)
+        dview = ops.conv_dgrad(dspec[..., :2 * self.nb], self.dft, tuple(range(self.taps)), out_rows=F_ + self.taps - 1)
+        return ops.reflect_pad_bwd(dview.view(B, -1), N, self.pad)

@@ -46,15 +46,22 @@ def _base_args(mode, shifts):
 
 def _epilogue(g, out, bias=None, relu=False, gate=None, gate_slope=0.0, residual=None, lens=None, ln=None,
               ln_eps=1e-5, save_ln=False, drop_p=0.0, drop_post=False, seed=0, seed_dev=None, alpha=1.0,
-              round_out=False):
+              round_out=False, act_slope=0.0, out_act=None, out_act_slope=0.0, tanh=False):
     keep = [out, bias, gate, residual, lens]
     g.out, g.o_rs, g.o_zs = _p(out), out.stride(1), out.stride(0)
     g.alpha = alpha
     flags = 0
     if bias is not None:
         g.bias = _p(bias)
-    if relu:
+    if relu or act_slope != 0.0:
         flags |= capi.GEMM_RELU
+        g.act_slope = act_slope
+    if tanh:
+        flags |= capi.GEMM_TANH
+    if out_act is not None:
+        assert out_act.stride() == out.stride()
+        g.out_act, g.out_act_slope = _p(out_act), out_act_slope
+        keep.append(out_act)
     if gate is not None:
         _check3(gate, "gate")
         g.gate, g.g_rs, g.g_zs, g.gate_slope = _p(gate), gate.stride(1), gate.stride(0), gate_slope
@@ -86,25 +93,32 @@ def _epilogue(g, out, bias=None, relu=False, gate=None, gate_slope=0.0, residual
     return keep, extra
 
 
-def conv_fwd(x, wp, shifts=(0,), out=None, ref=False, **epi):
-    """out[b,t,n] = sum_j sum_k x[b, t+shifts[j], k] * wp[j, n, k]  (+ epilogue).  x [B,T,K], wp [taps,N,K]."""
+def conv_fwd(x, wp, shifts=(0,), out=None, ref=False, a_cols=None, out_rows=None, **epi):
+    """out[b,t,n] = sum_j sum_k x[b, t+shifts[j], a_cols[j]+k] * wp[j, n, k]  (+ epilogue).
+    x [B,T,Kx], wp [taps,N,K]; a_cols (per-tap column offsets into x's rows, default 0) lets a strided convolution
+    run on the [T/stride, stride*C] view of its input."""
     _check3(x, "x")
     _check3(wp, "wp")
-    B, T, K = x.shape
-    taps, N, K2 = wp.shape
-    assert K2 == K and taps == len(shifts)
+    B, T, Kx = x.shape
+    taps, N, K = wp.shape
+    assert taps == len(shifts) and (a_cols is not None or Kx == K)
+    R = T if out_rows is None else int(out_rows)   # output rows per item; x keeps its own row count (a_rows)
     if out is None:
-        out = torch.empty(B, T, N, device=x.device, dtype=torch.float32)
+        out = torch.empty(B, R, N, device=x.device, dtype=torch.float32)
     g = _base_args(0, shifts)
-    g.Z, g.R, g.N, g.K = B, T, N, K
-    g.a, g.a_rs, g.a_zs = _p(x), x.stride(1), x.stride(0)
+    if a_cols is not None:
+        for j, c in enumerate(a_cols):
+            assert c + K <= Kx
+            g.a_col[j] = int(c)
+    g.Z, g.R, g.N, g.K = B, R, N, K
+    g.a, g.a_rs, g.a_zs, g.a_rows = _p(x), x.stride(1), x.stride(0), T
     g.b, g.b_rs, g.b_zs, g.b_nz, g.b_tap_z = _p(wp), wp.stride(1), wp.stride(0), taps, 1
     keep, extra = _epilogue(g, out, **epi)
     gemm_launch(g, ref)
     return (out, extra) if extra else out
 
 
-def conv_dgrad(dy, wp, shifts=(0,), out=None, ref=False, **epi):
+def conv_dgrad(dy, wp, shifts=(0,), out=None, ref=False, out_rows=None, **epi):
     """dx[b,t,k] = sum_j sum_n dy[b, t-shifts[j], n] * wp[j, n, k]: input gradient of conv_fwd, same packed weights
     read MN-major (no transposed copy).  dy [B,T,N], wp [taps,N,K]."""
     _check3(dy, "dy")
@@ -112,11 +126,12 @@ def conv_dgrad(dy, wp, shifts=(0,), out=None, ref=False, **epi):
     B, T, N = dy.shape
     taps, N2, K = wp.shape
     assert N2 == N and taps == len(shifts)
+    R = T if out_rows is None else int(out_rows)
     if out is None:
-        out = torch.empty(B, T, K, device=dy.device, dtype=torch.float32)
+        out = torch.empty(B, R, K, device=dy.device, dtype=torch.float32)
     g = _base_args(1, [-s for s in shifts])
-    g.Z, g.R, g.N, g.K = B, T, K, N
-    g.a, g.a_rs, g.a_zs = _p(dy), dy.stride(1), dy.stride(0)
+    g.Z, g.R, g.N, g.K = B, R, K, N
+    g.a, g.a_rs, g.a_zs, g.a_rows = _p(dy), dy.stride(1), dy.stride(0), T
     g.b, g.b_rs, g.b_zs, g.b_nz, g.b_tap_z = _p(wp), wp.stride(1), wp.stride(0), taps, 1
     keep, extra = _epilogue(g, out, **epi)
     gemm_launch(g, ref)
@@ -361,3 +376,99 @@ def lamb_step(p, g, m, v, chunks, n_chunks, norms, gnorm_sq, max_norm, lr_dev, b
 def round_tf32_(src, dst):
     """dst = src rounded to tf32 (nearest); flat fp32 tensors of equal length."""
     capi.call("xva_round_tf32", _p(src), _p(dst), int(src.numel()), _stream())
+
+
+# ---------------------------------------------------------------------------------------------- HiFi-GAN element-wise
+def mean3_lrelu(y0, y1, y2, slope):
+    out = torch.empty_like(y0)
+    capi.call("xva_mean3_lrelu", _p(y0), _p(y1), _p(y2), y0.numel(), float(slope), _p(out), _stream())
+    return out
+
+
+def sum3(a, b, c):
+    out = torch.empty_like(a)
+    capi.call("xva_sum3", _p(a), _p(b), _p(c), a.numel(), _p(out), _stream())
+    return out
+
+
+def tanh_bwd(dy, y, ld=32):
+    """dy, y [rows] -> [rows, ld] with d(pre-tanh) in column 0 and zeros elsewhere."""
+    rows = y.numel()
+    out = torch.empty(rows, ld, device=y.device, dtype=torch.float32)
+    capi.call("xva_tanh_bwd", _p(dy), _p(y), rows, int(ld), _p(out), _stream())
+    return out
+
+
+def adamw_step_(p, g, m, v, lr_dev, beta1, beta2, eps, weight_decay, step):
+    capi.call("xva_adamw_step", _p(p), _p(g), _p(m), _p(v), p.numel(), _p(lr_dev), float(beta1), float(beta2),
+              float(eps), float(weight_decay), int(step), _stream())
+
+
+# ---------------------------------------------------------------------------------------------- mel / losses
+def reflect_pad(y, pad):
+    B, n = y.shape
+    out = torch.empty(B, n + 2 * pad, device=y.device, dtype=torch.float32)
+    capi.call("xva_reflect_pad_fwd", _p(y), B, n, int(pad), _p(out), _stream())
+    return out
+
+
+def reflect_pad_bwd(dyp, n, pad):
+    B = dyp.shape[0]
+    dy = torch.empty(B, n, device=dyp.device, dtype=torch.float32)
+    capi.call("xva_reflect_pad_bwd", _p(dyp), B, int(n), int(pad), _p(dy), _stream())
+    return dy
+
+
+def spec_mag(spec, nb, ld_m, eps):
+    rows = spec.numel() // spec.shape[-1]
+    mag = torch.empty(*spec.shape[:-1], ld_m, device=spec.device, dtype=torch.float32)
+    capi.call("xva_spec_mag_fwd", _p(spec), rows, int(nb), spec.shape[-1], int(ld_m), float(eps), _p(mag), _stream())
+    return mag
+
+
+def spec_mag_bwd(dmag, spec, nb, eps):
+    rows = spec.numel() // spec.shape[-1]
+    dspec = torch.empty_like(spec)
+    capi.call("xva_spec_mag_bwd", _p(dmag), _p(spec), rows, int(nb), spec.shape[-1], dmag.shape[-1], float(eps), _p(dspec),
+              _stream())
+    return dspec
+
+
+def log_clamp(x, lo):
+    out = torch.empty_like(x)
+    capi.call("xva_log_clamp_fwd", _p(x), x.numel(), float(lo), _p(out), _stream())
+    return out
+
+
+def log_clamp_bwd(dy, x, lo):
+    dx = torch.empty_like(x)
+    capi.call("xva_log_clamp_bwd", _p(dy), _p(x), x.numel(), float(lo), _p(dx), _stream())
+    return dx
+
+
+def reduce_l1(a, b, acc):
+    """acc (device double, 0-dim or 1-element view) += sum |a - b|"""
+    capi.call("xva_reduce_loss", _p(a), _p(b), a.numel(), 0, 0.0, _p(acc), _stream())
+
+
+def reduce_sq(a, c, acc):
+    """acc += sum (c - a)^2"""
+    capi.call("xva_reduce_loss", _p(a), None, a.numel(), 1, float(c), _p(acc), _stream())
+
+
+def l1_grad(a, b, scale, out=None):
+    """scale * d(sum |a - b|)/db = scale * sign(b - a); accumulated into ``out`` when given."""
+    acc = out is not None
+    if out is None:
+        out = torch.empty_like(b)
+    capi.call("xva_loss_grad", _p(a), _p(b), b.numel(), 0, 0.0, float(scale), int(acc), _p(out), _stream())
+    return out
+
+
+def sq_grad(a, c, scale, out=None):
+    """scale * d(sum (c - a)^2)/da = 2 scale (a - c); accumulated into ``out`` when given."""
+    acc = out is not None
+    if out is None:
+        out = torch.empty_like(a)
+    capi.call("xva_loss_grad", _p(a), None, a.numel(), 1, float(c), float(scale), int(acc), _p(out), _stream())
+    return out
