@@ -31,7 +31,7 @@ METRIC, UNIT = "mel-frames/s (FastPitch 1.1 fine-tune step)", "frames/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--stage", type=int, default=3)
@@ -52,7 +52,7 @@ def config(args, world):
 
 # ---------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """nvidia-smi sampled every 200 ms while the timed region runs (B200_PROFILING.md clocks line)."""
+    """nvidia-smi sampled every 100 ms while the timed region runs (B200_PROFILING.md clocks line)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -62,7 +62,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()

@@ -111,8 +111,9 @@ typedef struct xva_gemm_args {
   uint64_t seed;
   float* out_act;   /* optional second output, same strides as out: leaky_relu(out, out_act_slope) rounded to tf32 --
                        the operand the next convolution reads (ResBlock1.forward, hifigan/models.py:41-48) */
-  int32_t a_col[XVA_MAX_TAPS]; /* mode 0/1: column offset of A added per tap (strided convolutions on a
-                                  [T/stride, stride*C] view of the input: tap = (row shift, phase*C)) */
+  int32_t a_col[XVA_MAX_TAPS]; /* per-tap column offset of the activation operand (A in mode 0/1, B in mode 2, there a
+                                  multiple of 32): strided convolutions read a [T/stride, stride*C] view of their
+                                  input, tap = (row shift, phase*C + group offset) */
   const uint64_t* seed_dev; /* optional device counter added to `seed` (x odd constant) at run time, so a captured
                                CUDA graph draws a fresh dropout mask on every replay */
 } xva_gemm_args;
@@ -253,7 +254,8 @@ int xva_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, cons
  *   log_clamp   : out = log(max(x, lo))  (spectral_normalize_torch, meldataset.py:238); bwd: dy / x where x >= lo
  *   reduce_loss : kind 0: acc += sum |a - b| (F.l1_loss, feature_loss models.py:263-269); kind 1: acc += sum (c - a)^2
  *                 (discriminator_loss / generator_loss, models.py:272-294). acc is a device double.
- *   loss_grad   : kind 0: out (+)= scale * sign(b - a) (gradient wrt b); kind 1: out (+)= 2 scale (a - c) (wrt a)
+ *   loss_grad   : kind 0: out (+)= scale * sign(b - a) (gradient wrt b), times gate_slope where b <= 0 (b a leaky-ReLU
+ *                 output: gradient wrt its pre-activation; pass 1 for none); kind 1: out (+)= 2 scale (a - c) (wrt a)
  * ---------------------------------------------------------------------------------------------------------- */
 int xva_reflect_pad_fwd(const float* y, int B, int64_t n, int pad, float* out, void* stream);
 int xva_reflect_pad_bwd(const float* dyp, int B, int64_t n, int pad, float* dy, void* stream);
@@ -263,8 +265,31 @@ int xva_spec_mag_bwd(const float* dmag, const float* spec, int64_t rows, int nb,
 int xva_log_clamp_fwd(const float* x, int64_t n, float lo, float* out, void* stream);
 int xva_log_clamp_bwd(const float* dy, const float* x, int64_t n, float lo, float* dx, void* stream);
 int xva_reduce_loss(const float* a, const float* b, int64_t n, int kind, float c, double* acc, void* stream);
-int xva_loss_grad(const float* a, const float* b, int64_t n, int kind, float c, float scale, int accumulate, float* out,
-                  void* stream);
+int xva_loss_grad(const float* a, const float* b, int64_t n, int kind, float c, float scale, float gate_slope,
+                  int accumulate, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * HiFi-GAN discriminators, the parts that are not GEMMs (hifigan/models.py:140-260).
+ *   conv_c1_* : first convolution of a discriminator (one input channel) applied to Z = B*P sequences cut out of the
+ *               raw waveform: element q of sequence (b, c) is sample q*xs_q + c*xs_c of item b (reflected about the last
+ *               sample when >= Lsrc: the period padding of DiscriminatorP.forward, models.py:159-163). MPD period p:
+ *               P = p, xs_q = p, xs_c = 1, L = ceil(Lsrc / p); MSD: P = 1, xs_q = 1, xs_c = 0, L = Lsrc.
+ *               out [Z, Lout_p, Cout] = leaky_relu(conv + bias) for rows < Lout, zero rows up to Lout_p (tf32-rounded).
+ *               bwd_w accumulates dw [Cout, k], db [Cout] from dpre (gradient wrt the pre-activation); bwd_x ACCUMULATES
+ *               scale * dL/d(waveform) with atomics (every discriminator adds into the same buffer).
+ *   avgpool4  : AvgPool1d(4, 2, padding=2) (models.py:241) on [B, L] -> [B, L/2 + 1]; bwd overwrites dx.
+ *   zero_tail_rows : x[z, Lvalid.., :] = 0 for x [Z, Lp, C].
+ * ---------------------------------------------------------------------------------------------------------- */
+int xva_conv_c1_fwd(const float* x, int64_t xs_b, int xs_q, int xs_c, int P, int Lsrc, int L, const float* w,
+                    const float* bias, int k, int s, int pad, int Z, int Lout, int Lout_p, int Cout, float slope, float* out,
+                    void* stream);
+int xva_conv_c1_bwd_w(const float* dpre, const float* x, int64_t xs_b, int xs_q, int xs_c, int P, int Lsrc, int L, int k,
+                      int s, int pad, int Z, int Lout, int Lout_p, int Cout, float* dw, float* db, void* stream);
+int xva_conv_c1_bwd_x(const float* dpre, const float* w, int64_t xs_b, int xs_q, int xs_c, int P, int Lsrc, int L, int k,
+                      int s, int pad, int Z, int Lout, int Lout_p, int Cout, float scale, float* dx, void* stream);
+int xva_avgpool4_fwd(const float* x, int B, int L, float* out, void* stream);
+int xva_avgpool4_bwd(const float* dout, int B, int L, float* dx, void* stream);
+int xva_zero_tail_rows(float* x, int Z, int Lp, int Lvalid, int C, void* stream);
 
 #ifdef __cplusplus
 }

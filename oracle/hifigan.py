@@ -169,3 +169,158 @@ def synthetic_batch(B, frames, seed=1234):
     g = torch.Generator().manual_seed(seed)
     y = 0.95 * torch.tanh(torch.randn(B, frames * HOP, generator=g) * 0.3)
     return mel_spectrogram(y, FMAX), y, mel_spectrogram(y, FMAX_LOSS)
+
+
+# ------------------------------------------------------------------------------------------------ discriminators
+P_SPECS = [(1, 32, 5, 3, 2, 1), (32, 128, 5, 3, 2, 1), (128, 512, 5, 3, 2, 1), (512, 1024, 5, 3, 2, 1), (1024, 1024, 5, 1, 2, 1)]
+S_SPECS = [(1, 128, 15, 1, 7, 1), (128, 128, 41, 2, 20, 4), (128, 256, 41, 2, 20, 16), (256, 512, 41, 4, 20, 16),
+           (512, 1024, 41, 4, 20, 16), (1024, 1024, 41, 1, 20, 16), (1024, 1024, 5, 1, 2, 1)]
+POST = (1024, 1, 3, 1, 1, 1)
+
+
+def mpd_spec():
+    """(key, shape) of MultiPeriodDiscriminator().state_dict() (models.py:176-186): 90 keys."""
+    spec = []
+    for d in range(len(PERIODS)):
+        for name, (cin, cout, k, s, p, g) in [(f"convs.{i}", sp) for i, sp in enumerate(P_SPECS)] + [("conv_post", POST)]:
+            pre = f"discriminators.{d}.{name}"
+            spec += [(f"{pre}.bias", (cout,)), (f"{pre}.weight_g", (cout, 1, 1, 1)), (f"{pre}.weight_v", (cout, cin // g, k, 1))]
+    return spec
+
+
+def msd_spec():
+    """(key, shape) of MultiScaleDiscriminator().state_dict() (models.py:231-243): 80 keys; disc 0 is spectral-normed."""
+    spec = []
+    for d in range(3):
+        for name, (cin, cout, k, s, p, g) in [(f"convs.{i}", sp) for i, sp in enumerate(S_SPECS)] + [("conv_post", POST)]:
+            pre = f"discriminators.{d}.{name}"
+            if d == 0:
+                spec += [(f"{pre}.bias", (cout,)), (f"{pre}.weight_orig", (cout, cin // g, k)), (f"{pre}.weight_u", (cout,)),
+                         (f"{pre}.weight_v", (cin // g * k,))]
+            else:
+                spec += [(f"{pre}.bias", (cout,)), (f"{pre}.weight_g", (cout, 1, 1)), (f"{pre}.weight_v", (cout, cin // g, k))]
+    return spec
+
+
+def make_disc_state(spec, seed):
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for key, shape in spec:
+        if key.endswith("weight_u") or (key.endswith("weight_v") and len(shape) == 1):
+            sd[key] = F.normalize(torch.randn(shape, generator=g), dim=0)
+        elif key.endswith("weight_v") or key.endswith("weight_orig"):
+            fan_in = int(np.prod(shape[1:]))
+            sd[key] = torch.randn(shape, generator=g) / math.sqrt(fan_in)
+        elif key.endswith("weight_g"):
+            sd[key] = None
+        else:
+            sd[key] = (torch.rand(shape, generator=g) * 2 - 1) * 0.05
+    for key in list(sd):
+        if key.endswith("weight_g"):
+            v = sd[key[:-1] + "v"]
+            sd[key] = v.flatten(1).norm(dim=1).view(sd_shape(spec, key)) * (1.0 + 0.1 * torch.rand(v.shape[0], generator=g).view(sd_shape(spec, key)))
+    return {k: sd[k] for k, _ in spec}
+
+
+def sd_shape(spec, key):
+    return dict(spec)[key]
+
+
+def _disc_weight(sd, pre, training, state):
+    """weight_norm (dim 0) or spectral_norm (one power iteration per training forward, torch.nn.utils.spectral_norm).
+    ``state`` carries the evolving u vectors across calls within one oracle evaluation."""
+    if f"{pre}.weight_g" in sd:
+        v, g = sd[f"{pre}.weight_v"], sd[f"{pre}.weight_g"]
+        return v * (g / v.flatten(1).norm(dim=1).view((-1,) + (1,) * (v.dim() - 1)))
+    wo = sd[f"{pre}.weight_orig"]
+    mat = wo.reshape(wo.shape[0], -1)
+    u = state.setdefault(f"{pre}.u", sd[f"{pre}.weight_u"].clone())
+    v = state.setdefault(f"{pre}.v", sd[f"{pre}.weight_v"].clone())
+    if training:
+        with torch.no_grad():
+            v = F.normalize(torch.mv(mat.t(), u), dim=0, eps=1e-12)
+            u = F.normalize(torch.mv(mat, v), dim=0, eps=1e-12)
+            state[f"{pre}.u"], state[f"{pre}.v"] = u, v
+    return wo / torch.dot(u, torch.mv(mat, v))
+
+
+def discriminator_p(sd, pre, x, period, training=True, state=None):
+    """DiscriminatorP.forward, models.py:154-173. x [B, 1, T] -> (flattened score, fmaps)"""
+    state = {} if state is None else state
+    fmap = []
+    b, c, t = x.shape
+    if t % period != 0:
+        n_pad = period - (t % period)
+        x = F.pad(x, (0, n_pad), "reflect")
+        t = t + n_pad
+    x = x.view(b, c, t // period, period)
+    for i, (cin, cout, k, s, p, g) in enumerate(P_SPECS):
+        x = F.conv2d(x, _disc_weight(sd, f"{pre}.convs.{i}", training, state), sd[f"{pre}.convs.{i}.bias"], stride=(s, 1), padding=(p, 0))
+        x = F.leaky_relu(x, LRELU_SLOPE)
+        fmap.append(x)
+    x = F.conv2d(x, _disc_weight(sd, f"{pre}.conv_post", training, state), sd[f"{pre}.conv_post.bias"], padding=(1, 0))
+    fmap.append(x)
+    return torch.flatten(x, 1, -1), fmap
+
+
+def discriminator_s(sd, pre, x, training=True, state=None):
+    """DiscriminatorS.forward, models.py:218-228."""
+    state = {} if state is None else state
+    fmap = []
+    for i, (cin, cout, k, s, p, g) in enumerate(S_SPECS):
+        x = F.conv1d(x, _disc_weight(sd, f"{pre}.convs.{i}", training, state), sd[f"{pre}.convs.{i}.bias"], stride=s, padding=p, groups=g)
+        x = F.leaky_relu(x, LRELU_SLOPE)
+        fmap.append(x)
+    x = F.conv1d(x, _disc_weight(sd, f"{pre}.conv_post", training, state), sd[f"{pre}.conv_post.bias"], padding=1)
+    fmap.append(x)
+    return torch.flatten(x, 1, -1), fmap
+
+
+def mpd(sd, y, y_hat, training=True, state=None):
+    """MultiPeriodDiscriminator.forward, models.py:187-200."""
+    state = {} if state is None else state
+    rs, gs, frs, fgs = [], [], [], []
+    for i, p in enumerate(PERIODS):
+        r, fr = discriminator_p(sd, f"discriminators.{i}", y, p, training, state)
+        g_, fg = discriminator_p(sd, f"discriminators.{i}", y_hat, p, training, state)
+        rs.append(r); gs.append(g_); frs.append(fr); fgs.append(fg)
+    return rs, gs, frs, fgs
+
+
+def msd(sd, y, y_hat, training=True, state=None):
+    """MultiScaleDiscriminator.forward, models.py:244-260."""
+    state = {} if state is None else state
+    rs, gs, frs, fgs = [], [], [], []
+    for i in range(3):
+        if i != 0:
+            y = F.avg_pool1d(y, 4, 2, padding=2)
+            y_hat = F.avg_pool1d(y_hat, 4, 2, padding=2)
+        r, fr = discriminator_s(sd, f"discriminators.{i}", y, training, state)
+        g_, fg = discriminator_s(sd, f"discriminators.{i}", y_hat, training, state)
+        rs.append(r); gs.append(g_); frs.append(fr); fgs.append(fg)
+    return rs, gs, frs, fgs
+
+
+def feature_loss(fmap_r, fmap_g):
+    """models.py:263-269"""
+    loss = 0
+    for dr, dg in zip(fmap_r, fmap_g):
+        for rl, gl in zip(dr, dg):
+            loss = loss + torch.mean(torch.abs(rl - gl))
+    return loss * 2
+
+
+def discriminator_loss(rs, gs):
+    """models.py:272-283"""
+    loss = 0
+    for dr, dg in zip(rs, gs):
+        loss = loss + torch.mean((1 - dr) ** 2) + torch.mean(dg ** 2)
+    return loss
+
+
+def generator_loss(gs):
+    """models.py:286-294"""
+    loss = 0
+    for dg in gs:
+        loss = loss + torch.mean((1 - dg) ** 2)
+    return loss

@@ -86,3 +86,37 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def disc_goldens():
+    """Scores and feature-map norms of the reference MPD / MSD (training mode: one spectral-norm power iteration per
+    forward) on a fixed pair of waveforms, with weights from oracle.hifigan.make_disc_state."""
+    from python.hifigan.models import MultiPeriodDiscriminator, MultiScaleDiscriminator
+
+    out = {}
+    g = torch.Generator().manual_seed(9)
+    y = 0.9 * torch.tanh(torch.randn(2, 1, 2048, generator=g))
+    yh = 0.9 * torch.tanh(torch.randn(2, 1, 2048, generator=g))
+    out["disc/y"], out["disc/y_hat"] = y.numpy(), yh.numpy()
+    for name, cls, spec, seed in (("mpd", MultiPeriodDiscriminator, ohg.mpd_spec(), 21), ("msd", MultiScaleDiscriminator, ohg.msd_spec(), 22)):
+        torch.manual_seed(0)
+        m = cls()
+        keys = [[k, list(v.shape)] for k, v in m.state_dict().items()]
+        json.dump(keys, open(os.path.join(HERE, f"hifigan_{name}_keys.json"), "w"))
+        m.load_state_dict(ohg.make_disc_state(spec, seed))
+        m.train()
+        rs, gs, frs, fgs = m(y, yh)
+        for i, (r, g_) in enumerate(zip(rs, gs)):
+            out[f"disc/{name}/r{i}"], out[f"disc/{name}/g{i}"] = r.detach().numpy(), g_.detach().numpy()
+            out[f"disc/{name}/fnorm_r{i}"] = np.array([float(f.detach().double().norm()) for f in frs[i]])
+            out[f"disc/{name}/fnorm_g{i}"] = np.array([float(f.detach().double().norm()) for f in fgs[i]])
+    return out
+
+
+if __name__ == "__main__":
+    extra = disc_goldens()
+    path = os.path.join(HERE, "hifigan_small.npz")
+    base = dict(np.load(path))
+    base.update(extra)
+    np.savez_compressed(path, **base)
+    print("added", len(extra), "discriminator arrays")

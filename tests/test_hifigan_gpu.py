@@ -160,3 +160,87 @@ def test_reflect_pad_and_losses(lib):
     assert abs(float(acc[1]) - float(((1 - a) ** 2).sum())) < 1e-3
     assert torch.equal(ops.l1_grad(a, b, 0.5), 0.5 * torch.sign(b - a))
     assert rel(ops.sq_grad(a, 1.0, 0.25), 0.5 * (a - 1.0)) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ discriminators
+def _disc_models(lib, name):
+    from xva_trainer_b200 import hifigan as hg
+
+    spec, seed = (ohg.mpd_spec(), 21) if name == "mpd" else (ohg.msd_spec(), 22)
+    sd = ohg.make_disc_state(spec, seed)
+    m = (hg.MultiPeriodDiscriminator if name == "mpd" else hg.MultiScaleDiscriminator)(device="cuda:0")
+    res = m.load_state_dict(sd)
+    assert not res.missing_keys and not res.unexpected_keys
+    m.train()
+    return hg, m, sd
+
+
+def _to_ref_layout(f, B):
+    """engine fmap [B*P, Lp, C] (channels-last, P period columns) -> reference [B, C, L, P] (or [B, C, L] when P = 1)"""
+    Z, L, Cc = f.shape
+    P = Z // B
+    t = f.view(B, P, L, Cc).permute(0, 3, 2, 1)
+    return t if P > 1 else t[..., 0]
+
+
+@pytest.mark.parametrize("name", ["mpd", "msd"])
+def test_discriminator_forward_matches_oracle_and_golden(lib, name):
+    hg, m, sd = _disc_models(lib, name)
+    gold = np.load(os.path.join(GOLD, "hifigan_small.npz"))
+    y, yh = torch.from_numpy(gold["disc/y"]), torch.from_numpy(gold["disc/y_hat"])
+    rs, gs, frs, fgs = m(y.cuda(), yh.cuda())
+    ors, ogs, ofrs, ofgs = (ohg.mpd if name == "mpd" else ohg.msd)(sd, y, yh, training=True)
+    B = y.shape[0]
+    for i in range(len(rs)):
+        want_r = torch.from_numpy(gold[f"disc/{name}/r{i}"])
+        got_r = _to_ref_layout(rs[i], B).reshape(B, -1).cpu()
+        assert rel(got_r, want_r) < 3e-3, (i, rel(got_r, want_r))
+        assert rel(_to_ref_layout(gs[i], B).reshape(B, -1).cpu(), ogs[i]) < 3e-3
+        for l, (f, of) in enumerate(zip(fgs[i], ofgs[i])):
+            got = _to_ref_layout(f, B)[:, :, :of.shape[2]].cpu()
+            assert got.shape == of.shape, (i, l, got.shape, of.shape)
+            assert rel(got, of) < 3e-3, (i, l, rel(got, of))
+            assert float(f[:, of.shape[2]:].abs().max() if f.shape[1] > of.shape[2] else 0.0) == 0.0   # alignment rows stay zero
+
+
+@pytest.mark.parametrize("name", ["mpd", "msd"])
+def test_discriminator_step_gradients(lib, name):
+    """D step: discriminator_loss and every parameter gradient; G step: generator_loss + feature_loss and the gradient
+    wrt the generated waveform. Oracle = torch autograd through oracle/hifigan.py."""
+    hg, m, sd = _disc_models(lib, name)
+    g = torch.Generator().manual_seed(31)
+    B, T = 2, 1536
+    y = 0.9 * torch.tanh(torch.randn(B, 1, T, generator=g))
+    yh = 0.9 * torch.tanh(torch.randn(B, 1, T, generator=g))
+    fn = ohg.mpd if name == "mpd" else ohg.msd
+    # ---- D step
+    leaves = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and not k.endswith("weight_u") and not (k.endswith("weight_v") and v.dim() == 1) else v.clone())
+              for k, v in sd.items()}
+    ors, ogs, _, _ = fn(leaves, y, yh, training=True)
+    want_loss = ohg.discriminator_loss(ors, ogs)
+    want_loss.backward()
+    m.zero_grad()
+    rs, gs, frs, fgs = m(y.cuda(), yh.cuda())
+    loss = hg.discriminator_loss_backward(m, rs, gs)
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(want_loss)) < 2e-3 * abs(float(want_loss))
+    num = den = 0.0
+    for k, p in m.named_parameters():
+        w = leaves[k].grad
+        e = rel(p.grad, w)
+        num += float((p.grad.cpu().double() - w.double()).pow(2).sum())
+        den += float(w.double().pow(2).sum())
+        assert e < 6e-2, (k, e)
+    assert (num / den) ** 0.5 < 2e-2
+    # ---- G step (fresh spectral-norm state in both: reload)
+    hg, m, sd = _disc_models(lib, name)
+    yh_leaf = yh.clone().requires_grad_(True)
+    ors, ogs, ofrs, ofgs = fn(sd, y, yh_leaf, training=True)
+    want = ohg.generator_loss(ogs) + ohg.feature_loss(ofrs, ofgs)
+    want.backward()
+    rs, gs, frs, fgs = m(y.cuda(), yh.cuda())
+    dwave = torch.zeros(B, T, device="cuda")
+    lg, lf = hg.generator_adv_loss_backward(m, gs, frs, fgs, dwave, pools=(name == "msd"))
+    torch.cuda.synchronize()
+    assert abs(float(lg + lf) - float(want)) < 2e-3 * abs(float(want)), (float(lg), float(lf), float(want))
+    assert rel(dwave.cpu(), yh_leaf.grad.reshape(B, T)) < 3e-2, rel(dwave.cpu(), yh_leaf.grad.reshape(B, T))

@@ -88,7 +88,13 @@ PROTOTYPES = {
     "xva_log_clamp_fwd": (_I, [_P, _I64, _F, _P, _P]),
     "xva_log_clamp_bwd": (_I, [_P, _P, _I64, _F, _P, _P]),
     "xva_reduce_loss": (_I, [_P, _P, _I64, _I, _F, _P, _P]),
-    "xva_loss_grad": (_I, [_P, _P, _I64, _I, _F, _F, _I, _P, _P]),
+    "xva_loss_grad": (_I, [_P, _P, _I64, _I, _F, _F, _F, _I, _P, _P]),
+    "xva_conv_c1_fwd": (_I, [_P, _I64, _I, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P, _P]),
+    "xva_conv_c1_bwd_w": (_I, [_P, _P, _I64, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "xva_conv_c1_bwd_x": (_I, [_P, _P, _I64, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P, _P]),
+    "xva_avgpool4_fwd": (_I, [_P, _I, _I, _P, _P]),
+    "xva_avgpool4_bwd": (_I, [_P, _I, _I, _P, _P]),
+    "xva_zero_tail_rows": (_I, [_P, _I, _I, _I, _I, _P]),
     "xva_mean3_lrelu": (_I, [_P, _P, _P, _I64, _F, _P, _P]),
     "xva_sum3": (_I, [_P, _P, _P, _I64, _P, _P]),
     "xva_tanh_bwd": (_I, [_P, _P, _I64, _I, _P, _P]),

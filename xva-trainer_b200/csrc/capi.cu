@@ -85,6 +85,7 @@ int xva_set_operand_rounding(int on) {
   if ((rc = set_operand_rounding_rowops(on)) != XVA_OK) return rc;
   if ((rc = set_operand_rounding_elemwise(on)) != XVA_OK) return rc;
   if ((rc = set_operand_rounding_melspec(on)) != XVA_OK) return rc;
+  if ((rc = set_operand_rounding_disc(on)) != XVA_OK) return rc;
   return set_operand_rounding_loss_optim(on);
 }
 
@@ -198,9 +199,31 @@ int xva_log_clamp_bwd(const float* dy, const float* x, int64_t n, float lo, floa
 int xva_reduce_loss(const float* a, const float* b, int64_t n, int kind, float c, double* acc, void* stream) {
   return reduce_loss(a, b, static_cast<long>(n), kind, c, acc, S(stream));
 }
-int xva_loss_grad(const float* a, const float* b, int64_t n, int kind, float c, float scale, int accumulate, float* out,
-                  void* stream) {
-  return loss_grad(a, b, static_cast<long>(n), kind, c, scale, accumulate, out, S(stream));
+int xva_loss_grad(const float* a, const float* b, int64_t n, int kind, float c, float scale, float gate_slope,
+                  int accumulate, float* out, void* stream) {
+  return loss_grad(a, b, static_cast<long>(n), kind, c, scale, gate_slope, accumulate, out, S(stream));
+}
+
+int xva_conv_c1_fwd(const float* x, int64_t xs_b, int xs_q, int xs_c, int P, int Lsrc, int L, const float* w,
+                    const float* bias, int k, int s, int pad, int Z, int Lout, int Lout_p, int Cout, float slope, float* out,
+                    void* stream) {
+  return conv_c1_fwd(x, static_cast<long>(xs_b), xs_q, xs_c, P, Lsrc, L, w, bias, k, s, pad, Z, Lout, Lout_p, Cout, slope,
+                     out, S(stream));
+}
+int xva_conv_c1_bwd_w(const float* dpre, const float* x, int64_t xs_b, int xs_q, int xs_c, int P, int Lsrc, int L, int k,
+                      int s, int pad, int Z, int Lout, int Lout_p, int Cout, float* dw, float* db, void* stream) {
+  return conv_c1_bwd_w(dpre, x, static_cast<long>(xs_b), xs_q, xs_c, P, Lsrc, L, k, s, pad, Z, Lout, Lout_p, Cout, dw, db,
+                       S(stream));
+}
+int xva_conv_c1_bwd_x(const float* dpre, const float* w, int64_t xs_b, int xs_q, int xs_c, int P, int Lsrc, int L, int k,
+                      int s, int pad, int Z, int Lout, int Lout_p, int Cout, float scale, float* dx, void* stream) {
+  return conv_c1_bwd_x(dpre, w, static_cast<long>(xs_b), xs_q, xs_c, P, Lsrc, L, k, s, pad, Z, Lout, Lout_p, Cout, scale, dx,
+                       S(stream));
+}
+int xva_avgpool4_fwd(const float* x, int B, int L, float* out, void* stream) { return avgpool4_fwd(x, B, L, out, S(stream)); }
+int xva_avgpool4_bwd(const float* dout, int B, int L, float* dx, void* stream) { return avgpool4_bwd(dout, B, L, dx, S(stream)); }
+int xva_zero_tail_rows(float* x, int Z, int Lp, int Lvalid, int C, void* stream) {
+  return zero_tail_rows(x, Z, Lp, Lvalid, C, S(stream));
 }
 
 }  // extern "C"

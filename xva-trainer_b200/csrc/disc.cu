@@ -1,0 +1,242 @@
+// HiFi-GAN discriminator pieces that are not GEMM-shaped (hifigan/models.py:140-260):
+//   conv_c1_*      the first convolution of every discriminator (one input channel: Conv2d(1, 32, (5,1), (3,1)) per
+//                  period column in DiscriminatorP :144, Conv1d(1, 128, 15) in DiscriminatorS :207), including the
+//                  period reshape and its reflect padding (:159-163) as index arithmetic on the raw waveform;
+//   avgpool4_*     AvgPool1d(4, 2, padding=2) between the scales of MultiScaleDiscriminator (:240-243);
+//   zero_tail_rows clears the alignment rows of an activation buffer so they can be read as conv zero padding.
+// All HBM-bound: one pass over the waveform / the [rows, Cout] output.
+#include "common.cuh"
+#include "ops.cuh"
+
+namespace xva {
+
+namespace {
+
+struct C1 {
+  long xs_b;      // waveform stride between batch items
+  int xs_q, xs_c; // sample index of element q of sequence (b, c) = q * xs_q + c * xs_c, reflected when >= Lsrc
+  int P;          // sequences per batch item (period columns)
+  int Lsrc;       // valid samples per batch item
+  int L;          // logical sequence length (after the reflect padding)
+  int k, s, pad;  // kernel size, stride, zero padding
+  int Lout, Lout_p, Cout;
+  float slope;
+};
+
+__device__ __forceinline__ long c1_src(const C1& p, int z, int q) {
+  const int b = z / p.P, c = z - b * p.P;
+  int idx = q * p.xs_q + c * p.xs_c;
+  if (idx >= p.Lsrc) idx = 2 * (p.Lsrc - 1) - idx;
+  return static_cast<long>(b) * p.xs_b + idx;
+}
+
+constexpr int kMaxK = 16;
+
+// one warp per output row (z, t): lanes over output channels
+__global__ void __launch_bounds__(256)
+conv_c1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, C1 p, long rows,
+                   float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long row = static_cast<long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int z = static_cast<int>(row / p.Lout_p), t = static_cast<int>(row - static_cast<long>(z) * p.Lout_p);
+  float* o = out + row * p.Cout;
+  if (t >= p.Lout) {
+    for (int co = lane; co < p.Cout; co += 32) o[co] = 0.0f;
+    return;
+  }
+  float xv[kMaxK];
+#pragma unroll
+  for (int j = 0; j < kMaxK; ++j) {
+    const int q = t * p.s + j - p.pad;
+    xv[j] = (j < p.k && q >= 0 && q < p.L) ? x[c1_src(p, z, q)] : 0.0f;
+  }
+  for (int co = lane; co < p.Cout; co += 32) {
+    float acc = bias[co];
+#pragma unroll
+    for (int j = 0; j < kMaxK; ++j)
+      if (j < p.k) acc = fmaf(w[co * p.k + j], xv[j], acc);
+    o[co] = tf32_rn(acc > 0.0f ? acc : p.slope * acc);  // operand of the next (tensor-core) convolution
+  }
+}
+
+// dw[co, j] += sum_rows dpre[row, co] * x(row, j) ; db[co] += sum_rows dpre[row, co].  Cout <= 128: one thread per co.
+__global__ void __launch_bounds__(128)
+conv_c1_bwd_w_kernel(const float* __restrict__ dpre, const float* __restrict__ x, C1 p, long rows, float* __restrict__ dw,
+                     float* __restrict__ db) {
+  const int co = threadIdx.x;
+  float acc[kMaxK + 1];
+#pragma unroll
+  for (int j = 0; j <= kMaxK; ++j) acc[j] = 0.0f;
+  __shared__ float xs[kMaxK];
+  for (long row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int z = static_cast<int>(row / p.Lout_p), t = static_cast<int>(row - static_cast<long>(z) * p.Lout_p);
+    if (t >= p.Lout) continue;
+    __syncthreads();
+    if (threadIdx.x < p.k) {
+      const int q = t * p.s + threadIdx.x - p.pad;
+      xs[threadIdx.x] = (q >= 0 && q < p.L) ? x[c1_src(p, z, q)] : 0.0f;
+    }
+    __syncthreads();
+    if (co < p.Cout) {
+      const float d = dpre[row * p.Cout + co];
+#pragma unroll
+      for (int j = 0; j < kMaxK; ++j)
+        if (j < p.k) acc[j] = fmaf(d, xs[j], acc[j]);
+      acc[kMaxK] += d;
+    }
+  }
+  if (co < p.Cout) {
+    for (int j = 0; j < p.k; ++j) atomicAdd(dw + co * p.k + j, acc[j]);
+    atomicAdd(db + co, acc[kMaxK]);
+  }
+}
+
+// dx[src(z, q)] += sum_{t, j : t*s + j - pad = q} dot(dpre[z, t, :], w[:, j]) ; one warp per (z, q)
+__global__ void __launch_bounds__(256)
+conv_c1_bwd_x_kernel(const float* __restrict__ dpre, const float* __restrict__ w, C1 p, long items, float scale,
+                     float* __restrict__ dx) {
+  const int lane = threadIdx.x & 31;
+  const long item = static_cast<long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (item >= items) return;
+  const int z = static_cast<int>(item / p.L), q = static_cast<int>(item - static_cast<long>(z) * p.L);
+  float acc = 0.0f;
+  for (int j = 0; j < p.k; ++j) {
+    const int num = q + p.pad - j;
+    if (num < 0 || num % p.s) continue;
+    const int t = num / p.s;
+    if (t >= p.Lout) continue;
+    const float* d = dpre + (static_cast<long>(z) * p.Lout_p + t) * p.Cout;
+    for (int co = lane; co < p.Cout; co += 32) acc = fmaf(d[co], w[co * p.k + j], acc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) atomicAdd(dx + c1_src(p, z, q), scale * acc);
+}
+
+// AvgPool1d(4, 2, padding=2), count_include_pad: out[i] = (x[2i-2] + x[2i-1] + x[2i] + x[2i+1]) / 4
+__global__ void __launch_bounds__(256)
+avgpool4_fwd_kernel(const float* __restrict__ x, int L, int Lout, long total, float* __restrict__ out) {
+  for (long n = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; n < total; n += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long b = n / Lout;
+    const int i = static_cast<int>(n - b * Lout);
+    const float* r = x + b * L;
+    float s = 0.0f;
+#pragma unroll
+    for (int d = -2; d <= 1; ++d) {
+      const int m = 2 * i + d;
+      if (m >= 0 && m < L) s += r[m];
+    }
+    out[n] = 0.25f * s;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+avgpool4_bwd_kernel(const float* __restrict__ dout, int L, int Lout, long total, float* __restrict__ dx) {
+  for (long n = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; n < total; n += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long b = n / L;
+    const int m = static_cast<int>(n - b * L);
+    const float* r = dout + b * Lout;
+    float s = 0.0f;
+    // 2i + d = m, d in {-2,-1,0,1}  ->  i in {(m+2)/2, (m+1)/2, m/2, (m-1)/2} where the division is exact
+#pragma unroll
+    for (int d = -2; d <= 1; ++d) {
+      const int num = m - d;
+      if (num >= 0 && (num & 1) == 0 && (num >> 1) < Lout) s += r[num >> 1];
+    }
+    dx[n] = 0.25f * s;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+zero_tail_rows_kernel(float* __restrict__ x, int Lp, int Lvalid, int C, long total) {
+  const int tail = (Lp - Lvalid) * C;
+  for (long n = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; n < total; n += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long z = n / tail;
+    x[(z * Lp + Lvalid) * C + (n - z * tail)] = 0.0f;
+  }
+}
+
+inline int grid_for(long n) {
+  long b = ceil_div_l(n, 256 * 4);
+  const long cap = 16L * num_sms();
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return static_cast<int>(b);
+}
+
+inline int fill(C1* p, long xs_b, int xs_q, int xs_c, int P, int Lsrc, int L, int k, int s, int pad, int Lout, int Lout_p,
+                int Cout, float slope) {
+  XVA_CHECK_ARG(k >= 1 && k <= kMaxK, "conv_c1: kernel size %d (max %d)", k, kMaxK);
+  XVA_CHECK_ARG(s >= 1 && Lout <= Lout_p && Cout >= 1, "conv_c1: stride %d Lout %d/%d Cout %d", s, Lout, Lout_p, Cout);
+  XVA_CHECK_ARG(L - Lsrc < Lsrc, "conv_c1: reflect padding %d longer than the signal %d", L - Lsrc, Lsrc);
+  p->xs_b = xs_b; p->xs_q = xs_q; p->xs_c = xs_c; p->P = P; p->Lsrc = Lsrc; p->L = L; p->k = k; p->s = s; p->pad = pad;
+  p->Lout = Lout; p->Lout_p = Lout_p; p->Cout = Cout; p->slope = slope;
+  return XVA_OK;
+}
+
+}  // namespace
+
+int conv_c1_fwd(const float* x, long xs_b, int xs_q, int xs_c, int P, int Lsrc, int L, const float* w, const float* bias,
+                int k, int s, int pad, int Z, int Lout, int Lout_p, int Cout, float slope, float* out, cudaStream_t stream) {
+  C1 p;
+  int rc = fill(&p, xs_b, xs_q, xs_c, P, Lsrc, L, k, s, pad, Lout, Lout_p, Cout, slope);
+  if (rc != XVA_OK) return rc;
+  const long rows = static_cast<long>(Z) * Lout_p;
+  conv_c1_fwd_kernel<<<static_cast<int>(ceil_div_l(rows, 8)), 256, 0, stream>>>(x, w, bias, p, rows, out);
+  XVA_CHECK_LAUNCH();
+  return XVA_OK;
+}
+
+int conv_c1_bwd_w(const float* dpre, const float* x, long xs_b, int xs_q, int xs_c, int P, int Lsrc, int L, int k, int s,
+                  int pad, int Z, int Lout, int Lout_p, int Cout, float* dw, float* db, cudaStream_t stream) {
+  XVA_CHECK_ARG(Cout <= 128, "conv_c1 bwd: Cout=%d (max 128)", Cout);
+  C1 p;
+  int rc = fill(&p, xs_b, xs_q, xs_c, P, Lsrc, L, k, s, pad, Lout, Lout_p, Cout, 0.0f);
+  if (rc != XVA_OK) return rc;
+  const long rows = static_cast<long>(Z) * Lout_p;
+  long grid = rows < 8L * num_sms() ? rows : 8L * num_sms();
+  conv_c1_bwd_w_kernel<<<static_cast<int>(grid), 128, 0, stream>>>(dpre, x, p, rows, dw, db);
+  XVA_CHECK_LAUNCH();
+  return XVA_OK;
+}
+
+int conv_c1_bwd_x(const float* dpre, const float* w, long xs_b, int xs_q, int xs_c, int P, int Lsrc, int L, int k, int s,
+                  int pad, int Z, int Lout, int Lout_p, int Cout, float scale, float* dx, cudaStream_t stream) {
+  C1 p;
+  int rc = fill(&p, xs_b, xs_q, xs_c, P, Lsrc, L, k, s, pad, Lout, Lout_p, Cout, 0.0f);
+  if (rc != XVA_OK) return rc;
+  const long items = static_cast<long>(Z) * L;
+  conv_c1_bwd_x_kernel<<<static_cast<int>(ceil_div_l(items, 8)), 256, 0, stream>>>(dpre, w, p, items, scale, dx);
+  XVA_CHECK_LAUNCH();
+  return XVA_OK;
+}
+
+int avgpool4_fwd(const float* x, int B, int L, float* out, cudaStream_t stream) {
+  const int Lout = L / 2 + 1;
+  const long total = static_cast<long>(B) * Lout;
+  avgpool4_fwd_kernel<<<grid_for(total), 256, 0, stream>>>(x, L, Lout, total, out);
+  XVA_CHECK_LAUNCH();
+  return XVA_OK;
+}
+
+int avgpool4_bwd(const float* dout, int B, int L, float* dx, cudaStream_t stream) {
+  const int Lout = L / 2 + 1;
+  const long total = static_cast<long>(B) * L;
+  avgpool4_bwd_kernel<<<grid_for(total), 256, 0, stream>>>(dout, L, Lout, total, dx);
+  XVA_CHECK_LAUNCH();
+  return XVA_OK;
+}
+
+int zero_tail_rows(float* x, int Z, int Lp, int Lvalid, int C, cudaStream_t stream) {
+  XVA_CHECK_ARG(Lvalid <= Lp, "zero_tail_rows: %d > %d", Lvalid, Lp);
+  if (Lvalid == Lp) return XVA_OK;
+  const long total = static_cast<long>(Z) * (Lp - Lvalid) * C;
+  zero_tail_rows_kernel<<<grid_for(total), 256, 0, stream>>>(x, Lp, Lvalid, C, total);
+  XVA_CHECK_LAUNCH();
+  return XVA_OK;
+}
+
+XVA_DEFINE_ROUNDING_SWITCH(disc)
+
+}  // namespace xva

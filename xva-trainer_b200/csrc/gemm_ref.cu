@@ -127,7 +127,7 @@ __global__ void gemm_ref_wgrad_kernel(const RefDev d) {
     for (int t = 0; t < g.R && t < a_rows; ++t) {
       const int bt = t + g.shift[j];
       if (bt < 0 || bt >= b_rows) continue;
-      acc = fmaf(g.a[z * g.a_zs + static_cast<long>(t) * g.a_rs + m], g.b[z * g.b_zs + static_cast<long>(bt) * g.b_rs + n],
+      acc = fmaf(g.a[z * g.a_zs + static_cast<long>(t) * g.a_rs + m], g.b[z * g.b_zs + static_cast<long>(bt) * g.b_rs + g.a_col[j] + n],
                  acc);
     }
   }

@@ -270,7 +270,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               ptx::mbar_arrive_expect_tx(&bar_full[s], stage_bytes);
               const int z = c.z + jo;
               ptx::tma_load_4d(sa, &tmap_a, &bar_full[s], 0, kc * kBlockK, c.m0 / 32, z);
-              ptx::tma_load_4d(sb, &tmap_b, &bar_full[s], 0, kc * kBlockK + shift_j, c.n0 / 32, z);
+              ptx::tma_load_4d(sb, &tmap_b, &bar_full[s], 0, kc * kBlockK + shift_j, (c.n0 + p.a_col[c.j]) / 32, z);
             }
             __syncwarp();
             if (++s == p.stages) {
@@ -937,7 +937,12 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
     if ((rc = encode_map(&map_b, g.b, 4, dims, str, box, mn_swizzle)) != XVA_OK) return rc;
   } else {
     const int b_rows = g.b_rows ? g.b_rows : g.R;
-    uint64_t dims[4] = {32, (uint64_t)b_rows, (uint64_t)ceil_div(g.N, 32), (uint64_t)g.Z};
+    int b_cols = g.N;  // mode 2: a_col[j] offsets the columns of B per tap (strided convolution views); 32-aligned
+    for (int j = 0; j < g.taps; ++j) {
+      XVA_CHECK_ARG(g.a_col[j] % 32 == 0, "gemm: wgrad column offset %d of tap %d is not a multiple of 32", g.a_col[j], j);
+      b_cols = g.a_col[j] + g.N > b_cols ? g.a_col[j] + g.N : b_cols;
+    }
+    uint64_t dims[4] = {32, (uint64_t)b_rows, (uint64_t)ceil_div(b_cols, 32), (uint64_t)g.Z};
     uint64_t str[4] = {1, (uint64_t)g.b_rs, 32, (uint64_t)g.b_zs};
     uint32_t box[4] = {32, kBlockK, (uint32_t)(p.n_tile / 32), 1};
     if (g.Z == 1 || str[3] == 0) str[3] = (uint64_t)g.b_rs * b_rows;

@@ -133,12 +133,13 @@ reduce_loss_kernel(const float* __restrict__ a, const float* __restrict__ b, lon
 // kind 1: out = scale * 2 (a - c)    (gradient of scale * sum (c - a)^2 wrt a)
 __global__ void __launch_bounds__(256)
 loss_grad_kernel(const float* __restrict__ a, const float* __restrict__ b, long n, int kind, float c, float scale,
-                 int accumulate, float* __restrict__ out) {
+                 float gate_slope, int accumulate, float* __restrict__ out) {
   for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x) {
     float g;
     if (kind == 0) {
       const float d = b[i] - a[i];
       g = d > 0.0f ? scale : (d < 0.0f ? -scale : 0.0f);
+      if (!(b[i] > 0.0f)) g *= gate_slope;  // b is a leaky-ReLU output: gradient wrt its pre-activation
     } else {
       g = scale * 2.0f * (a[i] - c);
     }
@@ -199,11 +200,11 @@ int reduce_loss(const float* a, const float* b, long n, int kind, float c, doubl
   return XVA_OK;
 }
 
-int loss_grad(const float* a, const float* b, long n, int kind, float c, float scale, int accumulate, float* out,
-              cudaStream_t stream) {
+int loss_grad(const float* a, const float* b, long n, int kind, float c, float scale, float gate_slope, int accumulate,
+              float* out, cudaStream_t stream) {
   XVA_CHECK_ARG(kind == 0 || kind == 1, "loss_grad: kind=%d", kind);
   if (n == 0) return XVA_OK;
-  loss_grad_kernel<<<grid_for(n), 256, 0, stream>>>(a, b, n, kind, c, scale, accumulate, out);
+  loss_grad_kernel<<<grid_for(n), 256, 0, stream>>>(a, b, n, kind, c, scale, gate_slope, accumulate, out);
   XVA_CHECK_LAUNCH();
   return XVA_OK;
 }

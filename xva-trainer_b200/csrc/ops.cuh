@@ -13,6 +13,7 @@ int set_operand_rounding_rowops(int on);
 int set_operand_rounding_loss_optim(int on);
 int set_operand_rounding_elemwise(int on);
 int set_operand_rounding_melspec(int on);
+int set_operand_rounding_disc(int on);
 
 // ---- regulate.cu
 int duration_scan(const float* durs, int B, int Tt, float pace, int mel_max_len, int* cum, int* dec_lens,
@@ -64,8 +65,19 @@ int spec_mag_bwd(const float* dmag, const float* spec, long rows, int nb, int ld
 int log_clamp_fwd(const float* x, long n, float lo, float* out, cudaStream_t stream);
 int log_clamp_bwd(const float* dy, const float* x, long n, float lo, float* dx, cudaStream_t stream);
 int reduce_loss(const float* a, const float* b, long n, int kind, float c, double* acc, cudaStream_t stream);
-int loss_grad(const float* a, const float* b, long n, int kind, float c, float scale, int accumulate, float* out,
-              cudaStream_t stream);
+int loss_grad(const float* a, const float* b, long n, int kind, float c, float scale, float gate_slope, int accumulate,
+              float* out, cudaStream_t stream);
+
+// ---- disc.cu
+int conv_c1_fwd(const float* x, long xs_b, int xs_q, int xs_c, int P, int Lsrc, int L, const float* w, const float* bias,
+                int k, int s, int pad, int Z, int Lout, int Lout_p, int Cout, float slope, float* out, cudaStream_t stream);
+int conv_c1_bwd_w(const float* dpre, const float* x, long xs_b, int xs_q, int xs_c, int P, int Lsrc, int L, int k, int s,
+                  int pad, int Z, int Lout, int Lout_p, int Cout, float* dw, float* db, cudaStream_t stream);
+int conv_c1_bwd_x(const float* dpre, const float* w, long xs_b, int xs_q, int xs_c, int P, int Lsrc, int L, int k, int s,
+                  int pad, int Z, int Lout, int Lout_p, int Cout, float scale, float* dx, cudaStream_t stream);
+int avgpool4_fwd(const float* x, int B, int L, float* out, cudaStream_t stream);
+int avgpool4_bwd(const float* dout, int B, int L, float* dx, cudaStream_t stream);
+int zero_tail_rows(float* x, int Z, int Lp, int Lvalid, int C, cudaStream_t stream);
 
 // ---- loss_optim.cu
 int mel_mse(const float* pred, const float* tgt, int B, int T_out, int Tm, int C, double* acc, cudaStream_t stream);

@@ -268,8 +268,10 @@ class Generator(nn.Module):
         torch.autograd.backward(tensors, grads)
         for name, m in self.named_modules():
             if isinstance(m, _WNConv):
-                g_ = gb[name]
-                m.bias.grad = g_ if m.bias.grad is None else m.bias.grad + g_
+                if m.bias.grad is None:
+                    m.bias.grad = gb[name]
+                else:
+                    m.bias.grad.add_(gb[name])
         self._ctx = None
 
     def _ups_dgrad(self, i, d_up, a_in, slope, W, alpha=1.0 / 3.0):
@@ -368,3 +370,429 @@ class MelSpectrogram:
         dspec = ops.spec_mag_bwd(dmag, spec, self.nb, self.EPS)
         dview = ops.conv_dgrad(dspec[..., :2 * self.nb], self.dft, tuple(range(self.taps)), out_rows=F_ + self.taps - 1)
         return ops.reflect_pad_bwd(dview.view(B, -1), N, self.pad)
+
+
+# ================================================================================================ discriminators
+def _round_up(a, b):
+    return (a + b - 1) // b * b
+
+
+class _DiscConv(nn.Module):
+    """Parameters of one discriminator convolution with the reference's names: weight-normed (bias, weight_g, weight_v)
+    or spectral-normed (bias, weight_orig, weight_u, weight_v; torch.nn.utils.spectral_norm, one power iteration per
+    training forward). ``conv2d`` keeps the trailing singleton kernel dimension of DiscriminatorP's Conv2d weights."""
+
+    def __init__(self, cin, cout, k, stride, pad, groups=1, spectral=False, conv2d=False):
+        super().__init__()
+        self.cin, self.cout, self.k, self.stride, self.pad, self.groups = cin, cout, k, stride, pad, groups
+        self.spectral, self.conv2d = spectral, conv2d
+        shape = (cout, cin // groups, k) + ((1,) if conv2d else ())
+        self.bias = nn.Parameter(torch.zeros(cout))
+        if spectral:
+            self.weight_orig = nn.Parameter(torch.zeros(shape))
+            self.register_buffer("weight_u", torch.zeros(cout))
+            self.register_buffer("weight_v", torch.zeros(int(math.prod(shape[1:]))))
+        else:
+            self.weight_g = nn.Parameter(torch.ones((cout,) + (1,) * (len(shape) - 1)))
+            self.weight_v = nn.Parameter(torch.zeros(shape))
+
+    def weight(self):
+        """Effective [Cout, Cin/groups, k] weight under autograd (and, in training mode, the spectral-norm power
+        iteration on the u / v buffers exactly as torch's forward pre-hook does it)."""
+        if not self.spectral:
+            v = self.weight_v
+            w = v * (self.weight_g / v.flatten(1).norm(dim=1).view((-1,) + (1,) * (v.dim() - 1)))
+        else:
+            wo = self.weight_orig
+            mat = wo.reshape(self.cout, -1)
+            u, v = self.weight_u, self.weight_v
+            if self.training:
+                with torch.no_grad():
+                    v = torch.nn.functional.normalize(torch.mv(mat.t(), u), dim=0, eps=1e-12, out=v)
+                    u = torch.nn.functional.normalize(torch.mv(mat, v), dim=0, eps=1e-12, out=u)
+                    u, v = u.clone(), v.clone()
+            sigma = torch.dot(u, torch.mv(mat, v))
+            w = wo / sigma
+        return w.reshape(self.cout, self.cin // self.groups, self.k)
+
+    # ---- tap geometry of the (strided) convolution on the [L/stride, stride*Cin] view of its input
+    def taps(self):
+        """[(j, row shift, phase)] ordered by phase so that the taps of one phase are consecutive in the packed weight."""
+        t = []
+        for j in range(self.k):
+            o = j - self.pad
+            t.append((j, o // self.stride, o % self.stride))
+        return sorted(t, key=lambda e: (e[2], e[0]))
+
+    def out_len(self, L):
+        return (L + 2 * self.pad - self.k) // self.stride + 1
+
+
+class _Disc(nn.Module):
+    """One sub-discriminator: convs[0] reads the raw waveform (one channel), convs[1:] and conv_post are tap-GEMMs."""
+
+    def __init__(self, specs, post, period=None, spectral=False):
+        super().__init__()
+        c2d = period is not None
+        self.period = period
+        self.convs = nn.ModuleList([_DiscConv(*s, spectral=spectral, conv2d=c2d) for s in specs])
+        self.conv_post = _DiscConv(*post, spectral=spectral, conv2d=c2d)
+
+    # geometry of the Z = B*P sequences inside the waveform [B, T]
+    def _geom(self, T):
+        if self.period is None:
+            return (T, 1, 0, 1, T, T)
+        p = self.period
+        return (T, p, 1, p, T, (T + p - 1) // p)
+
+    def _packed(self):
+        """per layer: list over groups of packed weights [k (phase-major), Og, max(Cg, 32)] (autograd), for layers >= 1
+        and conv_post; layer 0 uses its [Cout, k] weight directly."""
+        out = []
+        for li, m in enumerate(list(self.convs) + [self.conv_post]):
+            w = m.weight()
+            if li == 0:
+                out.append(w.reshape(m.cout, m.k).contiguous())
+                continue
+            order = [j for j, _, _ in m.taps()]
+            G, Og, Cg = m.groups, m.cout // m.groups, m.cin // m.groups
+            Cgp = max(Cg, 32)
+            per_group = []
+            for g_ in range(G):
+                wg = w[g_ * Og:(g_ + 1) * Og][:, :, order].permute(2, 0, 1)            # [k, Og, Cg]
+                if Cgp != Cg:
+                    wg = torch.nn.functional.pad(wg, (0, Cgp - Cg))
+                per_group.append(wg.contiguous())
+            out.append(per_group)
+        return out
+
+    def forward(self, wave, keep=True):
+        """wave [B, T] fp32 -> (score [Z, L, 1], fmaps [activation buffers + score], ctx)."""
+        B, T = wave.shape
+        geom = self._geom(T)
+        P, L = geom[3], geom[5]
+        Z = B * P
+        packed = self._packed()
+        rounded = lambda t: _rounded(t)
+        layers = list(self.convs)
+        m0 = layers[0]
+        L0 = m0.out_len(L)
+        nxt = layers[1].stride
+        X = ops.conv_c1_fwd(wave, geom, packed[0].detach(), m0.bias.detach(), m0.k, m0.stride, m0.pad, Z, L0,
+                            _round_up(L0, nxt), m0.cout, LRELU_SLOPE)
+        acts, lens_v = [X], [L0]
+        Wr = [None]
+        for li in range(1, len(layers)):
+            m = layers[li]
+            Lin = lens_v[-1]
+            Lout = m.out_len(Lin)
+            s_next = layers[li + 1].stride if li + 1 < len(layers) else 1
+            Lp_out = _round_up(Lout, s_next)
+            out = torch.empty(Z, Lp_out, m.cout, device=wave.device, dtype=torch.float32)
+            lens_t = torch.full((Z,), Lout, device=wave.device, dtype=torch.int32)
+            wr = [rounded(w) for w in packed[li]]
+            Wr.append(wr)
+            self._layer_fwd(m, X, wr, out, Lp_out, lens_t)
+            X = out
+            acts.append(X)
+            lens_v.append(Lout)
+        mp = self.conv_post
+        wrp = [rounded(w) for w in packed[-1]]
+        Wr.append(wrp)
+        Lf = lens_v[-1]
+        score = torch.empty(Z, Lf, 1, device=wave.device, dtype=torch.float32)
+        taps = mp.taps()
+        ops.conv_fwd(X, wrp[0][..., :mp.cin], [sh for _, sh, _ in taps], out=score, out_rows=Lf, bias=mp.bias.detach())
+        ctx = dict(wave=wave, geom=geom, Z=Z, acts=acts, lens=lens_v, packed=packed, Wr=Wr, score=score) if keep else None
+        return score, acts + [score], ctx
+
+    def _layer_fwd(self, m, X, wr, out, Lp_out, lens_t):
+        Z, Lp_in, Cin = X.shape
+        s = m.stride
+        xv = X.view(Z, Lp_in // s, s * Cin)
+        taps = m.taps()
+        shifts = [sh for _, sh, _ in taps]
+        G, Og, Cg = m.groups, m.cout // m.groups, m.cin // m.groups
+        bias = m.bias.detach()
+        for g_ in range(G):
+            ops.conv_fwd(xv[..., g_ * Cg:], wr[g_][..., :Cg], shifts, a_cols=[ph * Cin for _, _, ph in taps],
+                         out=out[..., g_ * Og:(g_ + 1) * Og], out_rows=Lp_out, lens=lens_t, bias=bias[g_ * Og:(g_ + 1) * Og],
+                         act_slope=LRELU_SLOPE, round_out=True)
+
+    def backward(self, ctx, dscore, dfeat, need_w, dwave=None, wave_scale=1.0):
+        """dscore [Z, L, 1]: gradient wrt the score; dfeat[l]: gradient wrt the PRE-activation of acts[l] coming from the
+        feature loss (already gated), or None. Accumulates parameter gradients when need_w, and dL/d(waveform) into dwave
+        when given."""
+        Z, acts, lens_v, Wr = ctx["Z"], ctx["acts"], ctx["lens"], ctx["Wr"]
+        layers = list(self.convs)
+        dev = dscore.device
+        gW = [None] + [[torch.zeros_like(w) for w in Wr[li]] for li in range(1, len(Wr))] if need_w else None
+        gb = {}
+        # conv_post: pad the single score channel to 32 columns (MN-major operand rule)
+        mp = self.conv_post
+        Lf = lens_v[-1]
+        dp = torch.zeros(Z, Lf, 32, device=dev, dtype=torch.float32)
+        dp[..., 0] = dscore[..., 0]
+        ops.round_tf32_(dp.reshape(-1), dp.reshape(-1))
+        d1 = dp[..., :1]
+        X = acts[-1]
+        taps = mp.taps()
+        shifts = [sh for _, sh, _ in taps]
+        if need_w:
+            ops.conv_wgrad(d1, X, shifts, out=gW[-1][0][..., :mp.cin], accumulate=True, dy_rows=Lf)
+            gb[len(layers)] = dscore.sum().reshape(1)
+        lens_t = torch.full((Z,), Lf, device=dev, dtype=torch.int32)
+        dpre = ops.conv_dgrad(d1, Wr[-1][0][..., :mp.cin], shifts, out_rows=X.shape[1], gate=X, gate_slope=LRELU_SLOPE,
+                              residual=dfeat[len(layers) - 1], lens=lens_t, round_out=True)
+        for li in range(len(layers) - 1, 0, -1):
+            m = layers[li]
+            Xin = acts[li - 1]
+            Zz, Lp_in, Cin = Xin.shape
+            s = m.stride
+            xv = Xin.view(Z, Lp_in // s, s * Cin)
+            taps = m.taps()
+            G, Og, Cg = m.groups, m.cout // m.groups, m.cin // m.groups
+            if need_w:
+                gb_l = torch.zeros(m.cout, device=dev, dtype=torch.float32)
+                ops.colsum_(dpre.shape[0] * dpre.shape[1], m.cout, m.cout, dpre, gb_l)
+                gb[li] = gb_l
+                for g_ in range(G):
+                    ops.conv_wgrad(dpre[..., g_ * Og:(g_ + 1) * Og], xv[..., g_ * Cg:], [sh for _, sh, _ in taps],
+                                   x_cols=[ph * Cin for _, _, ph in taps], n_cols=Cg, out=gW[li][g_][..., :Cg], accumulate=True)
+            if li == 1 and dwave is None and not need_w:
+                break
+            dX = torch.empty_like(Xin)
+            dxv = dX.view(Z, Lp_in // s, s * Cin)
+            res = dfeat[li - 1]
+            resv = res.view(Z, Lp_in // s, s * Cin) if res is not None else None
+            for ph in range(s):
+                idx = [i for i, (_, _, p_) in enumerate(taps) if p_ == ph]
+                lo, hi = idx[0], idx[-1] + 1
+                shifts = [taps[i][1] for i in idx]
+                for g_ in range(G):
+                    c0 = ph * Cin + g_ * Cg
+                    ops.conv_dgrad(dpre[..., g_ * Og:(g_ + 1) * Og], Wr[li][g_][lo:hi][..., :Cg], shifts,
+                                   out=dxv[..., c0:c0 + Cg], out_rows=Lp_in // s, gate=xv[..., c0:c0 + Cg],
+                                   gate_slope=LRELU_SLOPE, residual=None if resv is None else resv[..., c0:c0 + Cg],
+                                   round_out=True)
+            ops.zero_tail_rows_(dX, lens_v[li - 1])
+            dpre = dX
+        # first layer (raw waveform)
+        m0 = layers[0]
+        w0 = ctx["packed"][0]
+        if need_w:
+            dw0 = torch.zeros(m0.cout, m0.k, device=dev, dtype=torch.float32)
+            db0 = torch.zeros(m0.cout, device=dev, dtype=torch.float32)
+            ops.conv_c1_bwd_w(dpre, ctx["wave"], ctx["geom"], m0.k, m0.stride, m0.pad, lens_v[0], dw0, db0)
+            gb[0] = db0
+        if dwave is not None:
+            ops.conv_c1_bwd_x(dpre, w0.detach(), ctx["geom"], m0.k, m0.stride, m0.pad, lens_v[0], wave_scale, dwave)
+        if need_w:
+            tensors, grads = [w0], [dw0]
+            for li in range(1, len(Wr)):
+                for t, g_ in zip(ctx["packed"][li], gW[li]):
+                    tensors.append(t)
+                    grads.append(g_)
+            torch.autograd.backward(tensors, grads)
+            for li, m in enumerate(layers + [mp]):
+                if m.bias.grad is None:
+                    m.bias.grad = gb[li]
+                else:
+                    m.bias.grad.add_(gb[li])
+
+
+def _rounded(t):
+    out = torch.empty_like(t)
+    ops.round_tf32_(t.detach().reshape(-1), out.reshape(-1))
+    return out
+
+
+class DiscriminatorP(_Disc):
+    """hifigan/models.py:140-173"""
+
+    def __init__(self, period, kernel_size=5, stride=3, use_spectral_norm=False):
+        specs = [(1, 32, kernel_size, stride, 2), (32, 128, kernel_size, stride, 2), (128, 512, kernel_size, stride, 2),
+                 (512, 1024, kernel_size, stride, 2), (1024, 1024, kernel_size, 1, 2)]
+        super().__init__(specs, (1024, 1, 3, 1, 1), period=period, spectral=use_spectral_norm)
+
+
+class DiscriminatorS(_Disc):
+    """hifigan/models.py:203-228"""
+
+    def __init__(self, use_spectral_norm=False):
+        specs = [(1, 128, 15, 1, 7), (128, 128, 41, 2, 20, 4), (128, 256, 41, 2, 20, 16), (256, 512, 41, 4, 20, 16),
+                 (512, 1024, 41, 4, 20, 16), (1024, 1024, 41, 1, 20, 16), (1024, 1024, 5, 1, 2)]
+        super().__init__(specs, (1024, 1, 3, 1, 1), period=None, spectral=use_spectral_norm)
+
+
+class MultiPeriodDiscriminator(nn.Module):
+    """hifigan/models.py:176-200. forward(y, y_hat) -> (y_d_rs, y_d_gs, fmap_rs, fmap_gs) with channels-last fmaps
+    [B*p, L, C]; ctxs are kept on the module for backward."""
+
+    def __init__(self, device=None, seed=1234):
+        super().__init__()
+        self.discriminators = nn.ModuleList([DiscriminatorP(p) for p in (2, 3, 5, 7, 11)])
+        _init_disc(self, seed, device)
+
+    def forward(self, y, y_hat):
+        return _multi_forward(self, y, y_hat, pools=0)
+
+
+class MultiScaleDiscriminator(nn.Module):
+    """hifigan/models.py:231-260"""
+
+    def __init__(self, device=None, seed=1234):
+        super().__init__()
+        self.discriminators = nn.ModuleList([DiscriminatorS(use_spectral_norm=True), DiscriminatorS(), DiscriminatorS()])
+        _init_disc(self, seed + 1, device)
+
+    def forward(self, y, y_hat):
+        return _multi_forward(self, y, y_hat, pools=1)
+
+
+def _init_disc(model, seed, device):
+    g = torch.Generator().manual_seed(int(seed))
+    with torch.no_grad():
+        for m in model.modules():
+            if not isinstance(m, _DiscConv):
+                continue
+            w = m.weight_orig if m.spectral else m.weight_v
+            fan_in = int(math.prod(w.shape[1:]))
+            bound = 1.0 / math.sqrt(fan_in)
+            w.copy_((torch.rand(w.shape, generator=g) * 2 - 1) * bound)
+            m.bias.copy_((torch.rand(m.bias.shape, generator=g) * 2 - 1) * bound)
+            if m.spectral:
+                m.weight_u.copy_(torch.nn.functional.normalize(torch.randn(m.weight_u.shape, generator=g), dim=0))
+                m.weight_v.copy_(torch.nn.functional.normalize(torch.randn(m.weight_v.shape, generator=g), dim=0))
+            else:
+                m.weight_g.copy_(w.flatten(1).norm(dim=1).view(m.weight_g.shape))
+    dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+    if dev.type != "cuda":
+        raise capi.XvaError("the discriminators (B200 build) need a CUDA device: there is no CPU path")
+    capi.load()
+    model.to(dev)
+
+
+def _multi_forward(model, y, y_hat, pools):
+    """Shared by MPD / MSD: every sub-discriminator on the real and the generated waveform ([B, 1, T] or [B, T])."""
+    yr = y.reshape(y.shape[0], -1).to(torch.float32).contiguous()
+    yg = y_hat.reshape(y_hat.shape[0], -1).to(torch.float32).contiguous()
+    model._ctx = []
+    y_d_rs, y_d_gs, fmap_rs, fmap_gs = [], [], [], []
+    for i, d in enumerate(model.discriminators):
+        pooled_from = None
+        if pools and i != 0:
+            pooled_from = (yr.shape[1], yg.shape[1])
+            yr, yg = ops.avgpool4(yr), ops.avgpool4(yg)
+        sr, fr, cr = d(yr)
+        sg, fg, cg = d(yg)
+        y_d_rs.append(sr)
+        y_d_gs.append(sg)
+        fmap_rs.append(fr)
+        fmap_gs.append(fg)
+        model._ctx.append((cr, cg, pooled_from))
+    return y_d_rs, y_d_gs, fmap_rs, fmap_gs
+
+
+# ================================================================================================ losses / steps
+def discriminator_loss_backward(model, y_d_rs, y_d_gs):
+    """discriminator_loss (models.py:272-283) on the outputs of ``model(y, y_hat.detach())`` plus the backward into the
+    discriminator's parameters (hifigan/xva_train.py:486-497). Returns the loss as a 0-dim device tensor."""
+    dev = y_d_rs[0].device
+    acc = torch.zeros(2 * len(y_d_rs), device=dev, dtype=torch.float64)
+    loss = torch.zeros((), device=dev, dtype=torch.float64)
+    for i, (d, (cr, cg, _)) in enumerate(zip(model.discriminators, model._ctx)):
+        dr, dg = y_d_rs[i], y_d_gs[i]
+        n = dr.numel()
+        ops.reduce_sq(dr, 1.0, acc[2 * i:2 * i + 1])
+        ops.reduce_sq(dg, 0.0, acc[2 * i + 1:2 * i + 2])
+        loss = loss + (acc[2 * i] + acc[2 * i + 1]) / n
+        none = [None] * len(cr["acts"])
+        d.backward(cr, ops.sq_grad(dr, 1.0, 1.0 / n), none, need_w=True)
+        d.backward(cg, ops.sq_grad(dg, 0.0, 1.0 / n), none, need_w=True)
+    return loss
+
+
+def generator_adv_loss_backward(model, y_d_gs, fmap_rs, fmap_gs, dwave, pools):
+    """generator_loss + feature_loss (models.py:263-269, 286-294) on the outputs of ``model(y, y_hat)`` and their
+    gradient wrt the generated waveform, ACCUMULATED into dwave [B, T] (hifigan/xva_train.py:506-513). The
+    discriminator weights get no gradient here: the reference computes and then discards it (its zero_grad at
+    :468-469 / :483 clears it before any optimizer step reads it)."""
+    dev = dwave.device
+    n_d = len(y_d_gs)
+    acc = torch.zeros(n_d * 16, device=dev, dtype=torch.float64)
+    loss_gen = torch.zeros((), device=dev, dtype=torch.float64)
+    loss_fm = torch.zeros((), device=dev, dtype=torch.float64)
+    levels = [dwave]
+    for i in range(1, n_d):
+        if pools:
+            L = levels[-1].shape[1]
+            levels.append(torch.zeros(dwave.shape[0], L // 2 + 1, device=dev, dtype=torch.float32))
+    for i in reversed(range(n_d)):
+        d = model.discriminators[i]
+        cr, cg, _ = model._ctx[i]
+        dg = y_d_gs[i]
+        n = dg.numel()
+        ops.reduce_sq(dg, 1.0, acc[16 * i:16 * i + 1])
+        loss_gen = loss_gen + acc[16 * i] / n
+        dscore = ops.sq_grad(dg, 1.0, 1.0 / n)
+        dfeat = []
+        n_act = len(cg["acts"])
+        for l, (fr, fg) in enumerate(zip(fmap_rs[i], fmap_gs[i])):
+            valid = cg["Z"] * (cg["lens"][l] if l < n_act else cg["lens"][-1]) * fg.shape[2]
+            a = acc[16 * i + 1 + l:16 * i + 2 + l]
+            ops.reduce_l1(fr, fg, a)
+            loss_fm = loss_fm + 2.0 * a[0] / valid
+            if l < n_act:
+                dfeat.append(ops.l1_grad(fr, fg, 2.0 / valid, gate_slope=LRELU_SLOPE))
+            else:
+                ops.l1_grad(fr, fg, 2.0 / valid, out=dscore)     # conv_post output is the last feature map too
+        tgt = levels[i] if pools else dwave
+        d.backward(cg, dscore, dfeat, need_w=False, dwave=tgt)
+    if pools:
+        for i in reversed(range(1, n_d)):
+            up = ops.avgpool4_bwd(levels[i], levels[i - 1].shape[1])
+            levels[i - 1].add_(up)
+    return loss_gen, loss_fm
+
+
+class AdamW:
+    """torch.optim.AdamW(params, lr, betas) of hifigan/xva_train.py:298-300 as ONE launch over a flat arena: at
+    construction the parameters are moved into one contiguous fp32 buffer (they become views of it) and their .grad
+    fields are bound to views of a second one, so backward writes the arena directly."""
+
+    def __init__(self, params, lr=2e-4, betas=(0.8, 0.99), eps=1e-8, weight_decay=0.01):
+        self.params = [p for p in params]
+        self.param_groups = [{"lr": lr, "betas": betas, "eps": eps, "weight_decay": weight_decay}]
+        dev = self.params[0].device
+        n = sum(p.numel() for p in self.params)
+        self.p = torch.empty(n, device=dev, dtype=torch.float32)
+        self.g = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.m = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.v = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.lr_dev = torch.zeros(1, device=dev, dtype=torch.float32)
+        off = 0
+        with torch.no_grad():
+            for p in self.params:
+                k = p.numel()
+                self.p[off:off + k].copy_(p.reshape(-1))
+                p.data = self.p[off:off + k].view(p.shape)
+                p.grad = self.g[off:off + k].view(p.shape)
+                off += k
+        self.steps = 0
+
+    def zero_grad(self, set_to_none=False):
+        self.g.zero_()
+        off = 0
+        for p in self.params:       # re-bind in case something replaced a .grad tensor
+            k = p.numel()
+            if p.grad is None or p.grad.data_ptr() != self.g[off:off + k].data_ptr():
+                p.grad = self.g[off:off + k].view(p.shape)
+            off += k
+
+    def step(self):
+        g = self.param_groups[0]
+        self.steps += 1
+        self.lr_dev.fill_(float(g["lr"]))
+        ops.adamw_step_(self.p, self.g, self.m, self.v, self.lr_dev, g["betas"][0], g["betas"][1], g["eps"],
+                        g["weight_decay"], self.steps)

@@ -138,7 +138,8 @@ def conv_dgrad(dy, wp, shifts=(0,), out=None, ref=False, out_rows=None, **epi):
     return (out, extra) if extra else out
 
 
-def conv_wgrad(dy, x, shifts=(0,), out=None, accumulate=False, split=None, ref=False):
+def conv_wgrad(dy, x, shifts=(0,), out=None, accumulate=False, split=None, ref=False, x_cols=None, n_cols=None,
+               dy_rows=None):
     """dw[j,n,k] (+)= sum_b sum_t dy[b,t,n] * x[b, t+shifts[j], k]: weight gradient of conv_fwd in the packed layout.
     dy [B,T,N], x [B,T,K] -> dw [taps,N,K].  N and K must be multiples of 32."""
     _check3(dy, "dy")
@@ -147,12 +148,17 @@ def conv_wgrad(dy, x, shifts=(0,), out=None, accumulate=False, split=None, ref=F
     B2, T2, K = x.shape
     assert B2 == B
     taps = len(shifts)
+    if n_cols is not None:      # x_cols[j] + [0, n_cols) are the columns of x tap j contracts with
+        K = int(n_cols)
     if out is None:
         out = torch.zeros(taps, N, K, device=dy.device, dtype=torch.float32)
         accumulate = True
     g = _base_args(2, shifts)
+    if x_cols is not None:
+        for j, c in enumerate(x_cols):
+            g.a_col[j] = int(c)
     g.Z, g.R, g.M, g.N, g.ZR = B, T, N, K, B
-    g.a, g.a_rs, g.a_zs, g.a_rows = _p(dy), dy.stride(1), dy.stride(0), T
+    g.a, g.a_rs, g.a_zs, g.a_rows = _p(dy), dy.stride(1), dy.stride(0), (T if dy_rows is None else int(dy_rows))
     g.b, g.b_rs, g.b_zs, g.b_rows = _p(x), x.stride(1), x.stride(0), T2
     g.out, g.o_rs, g.o_zs, g.o_js = _p(out), out.stride(1), 0, out.stride(0)
     if split is None:
@@ -456,12 +462,14 @@ def reduce_sq(a, c, acc):
     capi.call("xva_reduce_loss", _p(a), None, a.numel(), 1, float(c), _p(acc), _stream())
 
 
-def l1_grad(a, b, scale, out=None):
-    """scale * d(sum |a - b|)/db = scale * sign(b - a); accumulated into ``out`` when given."""
+def l1_grad(a, b, scale, out=None, gate_slope=1.0):
+    """scale * d(sum |a - b|)/db = scale * sign(b - a), times gate_slope where b <= 0; accumulated into ``out`` when
+    given."""
     acc = out is not None
     if out is None:
         out = torch.empty_like(b)
-    capi.call("xva_loss_grad", _p(a), _p(b), b.numel(), 0, 0.0, float(scale), int(acc), _p(out), _stream())
+    capi.call("xva_loss_grad", _p(a), _p(b), b.numel(), 0, 0.0, float(scale), float(gate_slope), int(acc), _p(out),
+              _stream())
     return out
 
 
@@ -470,5 +478,48 @@ def sq_grad(a, c, scale, out=None):
     acc = out is not None
     if out is None:
         out = torch.empty_like(a)
-    capi.call("xva_loss_grad", _p(a), None, a.numel(), 1, float(c), float(scale), int(acc), _p(out), _stream())
+    capi.call("xva_loss_grad", _p(a), None, a.numel(), 1, float(c), float(scale), 1.0, int(acc), _p(out), _stream())
     return out
+
+
+# ---------------------------------------------------------------------------------------------- discriminator pieces
+def conv_c1_fwd(wave, geom, w, bias, k, s, pad, Z, Lout, Lout_p, Cout, slope):
+    """geom = (xs_b, xs_q, xs_c, P, Lsrc, L): how the Z = B*P sequences are cut out of wave [B, Lsrc] (include/xva_b200.h)."""
+    out = torch.empty(Z, Lout_p, Cout, device=wave.device, dtype=torch.float32)
+    xs_b, xs_q, xs_c, P, Lsrc, L = geom
+    capi.call("xva_conv_c1_fwd", _p(wave), xs_b, xs_q, xs_c, P, Lsrc, L, _p(w), _p(bias), k, s, pad, Z, Lout, Lout_p, Cout,
+              float(slope), _p(out), _stream())
+    return out
+
+
+def conv_c1_bwd_w(dpre, wave, geom, k, s, pad, Lout, dw, db):
+    Z, Lout_p, Cout = dpre.shape
+    xs_b, xs_q, xs_c, P, Lsrc, L = geom
+    capi.call("xva_conv_c1_bwd_w", _p(dpre), _p(wave), xs_b, xs_q, xs_c, P, Lsrc, L, k, s, pad, Z, Lout, Lout_p, Cout,
+              _p(dw), _p(db), _stream())
+
+
+def conv_c1_bwd_x(dpre, w, geom, k, s, pad, Lout, scale, dwave):
+    Z, Lout_p, Cout = dpre.shape
+    xs_b, xs_q, xs_c, P, Lsrc, L = geom
+    capi.call("xva_conv_c1_bwd_x", _p(dpre), _p(w), xs_b, xs_q, xs_c, P, Lsrc, L, k, s, pad, Z, Lout, Lout_p, Cout,
+              float(scale), _p(dwave), _stream())
+
+
+def avgpool4(x):
+    B, L = x.shape
+    out = torch.empty(B, L // 2 + 1, device=x.device, dtype=torch.float32)
+    capi.call("xva_avgpool4_fwd", _p(x), B, L, _p(out), _stream())
+    return out
+
+
+def avgpool4_bwd(dout, L):
+    B = dout.shape[0]
+    dx = torch.empty(B, L, device=dout.device, dtype=torch.float32)
+    capi.call("xva_avgpool4_bwd", _p(dout), B, L, _p(dx), _stream())
+    return dx
+
+
+def zero_tail_rows_(x, Lvalid):
+    Z, Lp, Cc = x.shape
+    capi.call("xva_zero_tail_rows", _p(x), Z, Lp, int(Lvalid), Cc, _stream())
