@@ -324,3 +324,64 @@ def generator_loss(gs):
     for dg in gs:
         loss = loss + torch.mean((1 - dg) ** 2)
     return loss
+
+
+# ------------------------------------------------------------------------------------------------ training step
+def adamw_step(params, grads, state, lr=2e-4, betas=(0.8, 0.99), eps=1e-8, weight_decay=0.01):
+    """torch.optim.AdamW (decoupled weight decay, bias correction), the optimizer of xva_train.py:298-300."""
+    b1, b2 = betas
+    for k, g in grads.items():
+        if g is None:
+            continue
+        p = params[k]
+        st = state.setdefault(k, {"m": torch.zeros_like(p), "v": torch.zeros_like(p), "t": 0})
+        st["t"] += 1
+        p.mul_(1 - lr * weight_decay)
+        st["m"].mul_(b1).add_(g, alpha=1 - b1)
+        st["v"].mul_(b2).addcmul_(g, g, value=1 - b2)
+        denom = (st["v"].sqrt() / math.sqrt(1 - b2 ** st["t"])).add_(eps)
+        p.addcdiv_(st["m"], denom, value=-lr / (1 - b1 ** st["t"]))
+
+
+def _leaves(sd):
+    is_buf = lambda k, v: k.endswith("weight_u") or (k.endswith("weight_v") and v.dim() == 1)
+    return {k: (v if is_buf(k, v) else v.detach().requires_grad_(True)) for k, v in sd.items()}
+
+
+def train_step(sd_g, sd_mpd, sd_msd, x, y, y_mel, opt_state, lr=2e-4):
+    """HiFiTrainer.iteration body, xva_train.py:467-515. Updates the three state dicts in place (including the
+    spectral-norm u / v buffers: four power iterations per step, two per msd call). Returns the loss terms."""
+    y = y.unsqueeze(1) if y.dim() == 2 else y
+    lg, lp, ls = _leaves(sd_g), _leaves(sd_mpd), _leaves(sd_msd)
+    sn_state = {}
+    y_g_hat = generator(lg, x)
+    y_g_hat_mel = mel_spectrogram(y_g_hat.squeeze(1), FMAX_LOSS)
+    # D step
+    rs, gs, _, _ = mpd(lp, y, y_g_hat.detach(), True, sn_state)
+    loss_disc_f = discriminator_loss(rs, gs)
+    rs, gs, _, _ = msd(ls, y, y_g_hat.detach(), True, sn_state)
+    loss_disc_s = discriminator_loss(rs, gs)
+    loss_disc_all = loss_disc_s + loss_disc_f
+    d_keys = [(ls, k) for k, v in ls.items() if v.requires_grad] + [(lp, k) for k, v in lp.items() if v.requires_grad]
+    d_grads = torch.autograd.grad(loss_disc_all, [s[k] for s, k in d_keys])
+    with torch.no_grad():
+        adamw_step({("s" if s is ls else "p", k): (sd_msd if s is ls else sd_mpd)[k] for s, k in d_keys},
+                   {("s" if s is ls else "p", k): g for (s, k), g in zip(d_keys, d_grads)}, opt_state.setdefault("d", {}), lr)
+    # G step (discriminators now hold the updated weights; fresh leaves)
+    lp, ls = _leaves(sd_mpd), _leaves(sd_msd)
+    loss_mel = F.l1_loss(y_mel, y_g_hat_mel) * 45
+    rs, gs, frs, fgs = mpd(lp, y, y_g_hat, True, sn_state)
+    loss_fm_f, loss_gen_f = feature_loss(frs, fgs), generator_loss(gs)
+    rs, gs, frs, fgs = msd(ls, y, y_g_hat, True, sn_state)
+    loss_fm_s, loss_gen_s = feature_loss(frs, fgs), generator_loss(gs)
+    loss_gen_all = loss_gen_s + loss_gen_f + loss_fm_s + loss_fm_f + loss_mel
+    g_keys = [k for k, v in lg.items()]
+    g_grads = torch.autograd.grad(loss_gen_all, [lg[k] for k in g_keys])
+    with torch.no_grad():
+        adamw_step({k: sd_g[k] for k in g_keys}, dict(zip(g_keys, g_grads)), opt_state.setdefault("g", {}), lr)
+        for k in sd_msd:        # persist the power-iteration vectors like the module buffers do
+            if k.endswith("weight_u") and f"{k[:-9]}.u" in sn_state:
+                sd_msd[k] = sn_state[f"{k[:-9]}.u"].clone()
+                sd_msd[k[:-1] + "v"] = sn_state[f"{k[:-9]}.v"].clone()
+    return {"loss_gen_all": loss_gen_all.detach(), "loss_disc_all": loss_disc_all.detach(), "loss_mel": loss_mel.detach(),
+            "loss_fm": (loss_fm_s + loss_fm_f).detach(), "loss_gen": (loss_gen_s + loss_gen_f).detach()}, dict(zip(g_keys, g_grads))

@@ -796,3 +796,56 @@ class AdamW:
         self.lr_dev.fill_(float(g["lr"]))
         ops.adamw_step_(self.p, self.g, self.m, self.v, self.lr_dev, g["betas"][0], g["betas"][1], g["eps"],
                         g["weight_decay"], self.steps)
+
+
+class HiFiGANStep:
+    """The body of HiFiTrainer.iteration (hifigan/xva_train.py:467-515): generator forward, mel of the generated audio,
+    D step (MPD + MSD on (y, y_hat.detach()) -> discriminator_loss -> AdamW), G step (45 * L1 mel + feature + adversarial
+    losses -> AdamW). ``step(x, y, y_mel)`` takes the reference's batch tensors (x [B, 80, T] input mel, y [B, 8192]
+    audio, y_mel [B, 80, T] loss mel) and returns the losses as 0-dim device tensors (no host sync)."""
+
+    def __init__(self, generator, mpd, msd, h, lr=None, betas=None):
+        self.generator, self.mpd, self.msd, self.h = generator, mpd, msd, h
+        lr = h.learning_rate if lr is None else lr
+        betas = (h.adam_b1, h.adam_b2) if betas is None else betas
+        dev = next(generator.parameters()).device
+        self.mel = MelSpectrogram(h.n_fft, h.num_mels, h.sampling_rate, h.hop_size, h.win_size, h.fmin, h.fmax_for_loss,
+                                  device=dev)
+        self.optim_g = AdamW(generator.parameters(), lr, betas)
+        self.optim_d = AdamW(list(msd.parameters()) + list(mpd.parameters()), lr, betas)   # itertools.chain order of :300
+        self.steps = 0
+
+    def step(self, x, y, y_mel):
+        G, mpd, msd = self.generator, self.mpd, self.msd
+        B = y.shape[0]
+        y = y.reshape(B, -1).to(torch.float32).contiguous()
+        y_g_hat = G(x)                                                       # :479
+        wave = y_g_hat.reshape(B, -1)
+        mel_hat = self.mel(wave)                                             # :480, channels-last [B, F, 80]
+        mel_tgt = y_mel.to(torch.float32).transpose(1, 2).contiguous()
+
+        # ---- discriminators (:483-498); y_hat is detached: no gradient reaches the generator here
+        self.optim_d.zero_grad()
+        rs, gs, _, _ = mpd(y, wave)
+        loss_disc_f = discriminator_loss_backward(mpd, rs, gs)
+        rs, gs, _, _ = msd(y, wave)
+        loss_disc_s = discriminator_loss_backward(msd, rs, gs)
+        self.optim_d.step()
+
+        # ---- generator (:501-515)
+        self.optim_g.zero_grad()
+        n = mel_hat.numel()
+        acc = torch.zeros(1, device=y.device, dtype=torch.float64)
+        ops.reduce_l1(mel_tgt, mel_hat, acc)
+        loss_mel = 45.0 * acc[0] / n
+        dwave = self.mel.backward(ops.l1_grad(mel_tgt, mel_hat, 45.0 / n))
+        rs, gs, frs, fgs = mpd(y, wave)
+        loss_gen_f, loss_fm_f = generator_adv_loss_backward(mpd, gs, frs, fgs, dwave, pools=False)
+        rs, gs, frs, fgs = msd(y, wave)
+        loss_gen_s, loss_fm_s = generator_adv_loss_backward(msd, gs, frs, fgs, dwave, pools=True)
+        G.backward(dwave.view(B, 1, -1))
+        self.optim_g.step()
+        self.steps += 1
+        loss_gen_all = loss_gen_s + loss_gen_f + loss_fm_s + loss_fm_f + loss_mel
+        return {"loss_gen_all": loss_gen_all, "loss_disc_all": loss_disc_s + loss_disc_f, "loss_mel": loss_mel,
+                "mel_error": loss_mel / 45.0, "loss_fm": loss_fm_s + loss_fm_f, "loss_gen": loss_gen_s + loss_gen_f}
