@@ -236,13 +236,14 @@ int xva_lamb_step(float* p, const float* g, float* m, float* v, const void* chun
  *   sum3        : out = a + b + c, tf32-rounded (gradient of a tensor read by the three ResBlocks of a stage)
  *   tanh_bwd    : out[r, 0] = dy[r] * (1 - y[r]^2), out[r, 1..ld) = 0   (models.py:126; ld pads the single channel so
  *                 the buffer is a legal MN-major wgrad operand)
- *   adamw_step  : torch.optim.AdamW over a flat arena; step is 1-based, lr read from device memory
+ *   adamw_step  : torch.optim.AdamW over a flat arena; step is 1-based (taken from *step_dev when that is given, so a
+ *                 captured CUDA graph advances it with xva_counter_add), lr read from device memory
  * ---------------------------------------------------------------------------------------------------------- */
 int xva_mean3_lrelu(const float* y0, const float* y1, const float* y2, int64_t n, float slope, float* out, void* stream);
 int xva_sum3(const float* a, const float* b, const float* c, int64_t n, float* out, void* stream);
 int xva_tanh_bwd(const float* dy, const float* y, int64_t rows, int ld, float* out, void* stream);
 int xva_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, const float* lr_dev, float beta1, float beta2,
-                   float eps, float weight_decay, int step, void* stream);
+                   float eps, float weight_decay, int step, const uint64_t* step_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Mel-spectrogram extractor -- mel_spectrogram(), hifigan/meldataset.py:217-240 (forward and the backward the 45 * L1

@@ -26,22 +26,30 @@ def main():
     msd = hg.MultiScaleDiscriminator(device="cuda:0"); msd.train()
     step = hg.HiFiGANStep(G, mpd, msd, h)
     x, y, y_mel = (t.cuda() for t in ohg.synthetic_batch(B, 32, seed=1))
+    use_graph = os.environ.get("XVA_NO_GRAPH") is None
+    if use_graph:
+        from xva_trainer_b200 import graph
+        step.optim_g.lr_on_device = step.optim_d.lr_on_device = True
+        gs = graph.GraphedStep(lambda a, b, c: step.step(a, b, c), [x, y, y_mel], warmup=3)
+        run = lambda: gs()
+    else:
+        run = lambda: step.step(x, y, y_mel)
     for _ in range(3):
-        out = step.step(x, y, y_mel)
+        out = run()
     torch.cuda.synchronize()
     capi.reset_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record()
     for _ in range(steps):
-        out = step.step(x, y, y_mel)
+        out = run()
     e1.record()
     host_s = time.perf_counter() - t0
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
     print(json.dumps({"metric": "audio-samples/s (HiFi-GAN v1 G+MPD+MSD train step)", "value": B * 8192 / (ms * 1e-3),
                       "unit": "samples/s", "ms_per_step": ms, "host_enqueue_ms_per_step": host_s * 1e3 / steps, "batch": B,
-                      "segment": 8192, "gpu_launches_per_step": capi.launch_count() / steps,
+                      "segment": 8192, "gpu_launches_per_step": capi.launch_count() / steps, "cuda_graph": use_graph,
                       "losses": {k: float(v) for k, v in out.items()}}))
 
 

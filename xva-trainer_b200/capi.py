@@ -98,7 +98,7 @@ PROTOTYPES = {
     "xva_mean3_lrelu": (_I, [_P, _P, _P, _I64, _F, _P, _P]),
     "xva_sum3": (_I, [_P, _P, _P, _I64, _P, _P]),
     "xva_tanh_bwd": (_I, [_P, _P, _I64, _I, _P, _P]),
-    "xva_adamw_step": (_I, [_P, _P, _P, _P, _I64, _P, _F, _F, _F, _F, _I, _P]),
+    "xva_adamw_step": (_I, [_P, _P, _P, _P, _I64, _P, _F, _F, _F, _F, _I, _P, _P]),
 }
 
 _lib = None

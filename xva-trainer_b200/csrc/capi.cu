@@ -173,8 +173,9 @@ int xva_tanh_bwd(const float* dy, const float* y, int64_t rows, int ld, float* o
 }
 
 int xva_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, const float* lr_dev, float beta1, float beta2,
-                   float eps, float weight_decay, int step, void* stream) {
-  return adamw_step(p, g, m, v, static_cast<long>(n), lr_dev, beta1, beta2, eps, weight_decay, step, S(stream));
+                   float eps, float weight_decay, int step, const uint64_t* step_dev, void* stream) {
+  return adamw_step(p, g, m, v, static_cast<long>(n), lr_dev, beta1, beta2, eps, weight_decay, step,
+                    reinterpret_cast<const unsigned long long*>(step_dev), S(stream));
 }
 
 int xva_reflect_pad_fwd(const float* y, int B, int64_t n, int pad, float* out, void* stream) {

@@ -52,8 +52,14 @@ tanh_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, long 
 // p = p*(1 - lr*wd) - lr * mhat / (sqrt(vhat) + eps), mhat = m/(1-b1^t), vhat = v/(1-b2^t)    (torch AdamW)
 __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long n,
-             const float* __restrict__ lr_dev, float b1, float b2, float eps, float wd, float bc1, float bc2) {
+             const float* __restrict__ lr_dev, float b1, float b2, float eps, float wd, float bc1, float bc2,
+             const unsigned long long* __restrict__ step_dev) {
   const float lr = lr_dev[0];
+  if (step_dev) {  // step count kept on the device (CUDA-graph replay): bias corrections computed here
+    const float t = static_cast<float>(*step_dev);
+    bc1 = 1.0f - powf(b1, t);
+    bc2 = 1.0f - powf(b2, t);
+  }
   for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x) {
     const float gi = g[i];
     const float mi = b1 * m[i] + (1.0f - b1) * gi;
@@ -103,11 +109,12 @@ int tanh_bwd(const float* dy, const float* y, long rows, int ld, float* out, cud
 }
 
 int adamw_step(float* p, const float* g, float* m, float* v, long n, const float* lr_dev, float b1, float b2, float eps,
-               float wd, int step, cudaStream_t stream) {
-  XVA_CHECK_ARG(step >= 1, "adamw: step=%d (1-based)", step);
+               float wd, int step, const unsigned long long* step_dev, cudaStream_t stream) {
+  XVA_CHECK_ARG(step >= 1 || step_dev, "adamw: step=%d (1-based)", step);
+  if (step < 1) step = 1;
   if (n == 0) return XVA_OK;
   const float bc1 = 1.0f - powf(b1, static_cast<float>(step)), bc2 = 1.0f - powf(b2, static_cast<float>(step));
-  adamw_kernel<<<grid_for(n), 256, 0, stream>>>(p, g, m, v, n, lr_dev, b1, b2, eps, wd, bc1, bc2);
+  adamw_kernel<<<grid_for(n), 256, 0, stream>>>(p, g, m, v, n, lr_dev, b1, b2, eps, wd, bc1, bc2, step_dev);
   XVA_CHECK_LAUNCH();
   return XVA_OK;
 }

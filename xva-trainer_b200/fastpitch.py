@@ -612,6 +612,7 @@ class Lamb:
             A.m = torch.zeros_like(A.p)
             A.v = torch.zeros_like(A.p)
         self.lr_dev = torch.zeros(1, device=A.p.device, dtype=torch.float32)
+        self.lr_on_device = False   # True: lr_dev is maintained by the caller (CUDA-graph replay), step() leaves it
         self._tables = {}
         self.steps = 0
 
@@ -639,7 +640,8 @@ class Lamb:
         A = self.model.arena
         g = self.param_groups[0]
         chunks, n_chunks, n_tensors = self._table(self.model.training_stage)
-        self.lr_dev.fill_(float(g["lr"]))
+        if not self.lr_on_device:
+            self.lr_dev.fill_(float(g["lr"]))
         scratch = torch.zeros(2 * n_tensors + 1, device=A.p.device, dtype=torch.float64)
         gn = scratch[2 * n_tensors:]
         if self.clip is not None and self.clip > 0:

@@ -454,12 +454,14 @@ class _Disc(nn.Module):
             if li == 0:
                 out.append(w.reshape(m.cout, m.k).contiguous())
                 continue
-            order = [j for j, _, _ in m.taps()]
+            if getattr(m, "_order_idx", None) is None or m._order_idx.device != w.device:
+                m._order_idx = torch.tensor([j for j, _, _ in m.taps()], device=w.device, dtype=torch.long)
+            order = m._order_idx          # cached on the device: no host->device copy inside a captured step
             G, Og, Cg = m.groups, m.cout // m.groups, m.cin // m.groups
             Cgp = max(Cg, 32)
             per_group = []
             for g_ in range(G):
-                wg = w[g_ * Og:(g_ + 1) * Og][:, :, order].permute(2, 0, 1)            # [k, Og, Cg]
+                wg = w[g_ * Og:(g_ + 1) * Og].index_select(2, order).permute(2, 0, 1)   # [k, Og, Cg]
                 if Cgp != Cg:
                     wg = torch.nn.functional.pad(wg, (0, Cgp - Cg))
                 per_group.append(wg.contiguous())
@@ -770,7 +772,9 @@ class AdamW:
         self.g = torch.zeros(n, device=dev, dtype=torch.float32)
         self.m = torch.zeros(n, device=dev, dtype=torch.float32)
         self.v = torch.zeros(n, device=dev, dtype=torch.float32)
-        self.lr_dev = torch.zeros(1, device=dev, dtype=torch.float32)
+        self.lr_dev = torch.full((1,), float(lr), device=dev, dtype=torch.float32)
+        self.step_dev = torch.zeros(1, device=dev, dtype=torch.int64)   # device-side step count (graph replay)
+        self.lr_on_device = False   # True: lr_dev is maintained by the caller (CUDA-graph replay), step() leaves it
         off = 0
         with torch.no_grad():
             for p in self.params:
@@ -793,9 +797,11 @@ class AdamW:
     def step(self):
         g = self.param_groups[0]
         self.steps += 1
-        self.lr_dev.fill_(float(g["lr"]))
+        if not self.lr_on_device:
+            self.lr_dev.fill_(float(g["lr"]))
+        ops.counter_add_(self.step_dev, 1)
         ops.adamw_step_(self.p, self.g, self.m, self.v, self.lr_dev, g["betas"][0], g["betas"][1], g["eps"],
-                        g["weight_decay"], self.steps)
+                        g["weight_decay"], self.steps, self.step_dev)
 
 
 class HiFiGANStep:

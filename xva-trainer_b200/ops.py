@@ -405,9 +405,9 @@ def tanh_bwd(dy, y, ld=32):
     return out
 
 
-def adamw_step_(p, g, m, v, lr_dev, beta1, beta2, eps, weight_decay, step):
+def adamw_step_(p, g, m, v, lr_dev, beta1, beta2, eps, weight_decay, step, step_dev=None):
     capi.call("xva_adamw_step", _p(p), _p(g), _p(m), _p(v), p.numel(), _p(lr_dev), float(beta1), float(beta2),
-              float(eps), float(weight_decay), int(step), _stream())
+              float(eps), float(weight_decay), int(step), _p(step_dev), _stream())
 
 
 # ---------------------------------------------------------------------------------------------- mel / losses
