@@ -1,0 +1,80 @@
+"""Facade test: a fake websocket records send() strings, a temp output_path collects the
+files the Electron UI reads; asserts names / JSON schemas / protocol strings of the reference's trainers."""
+import asyncio
+import json
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+class FakeSocket:
+    def __init__(self):
+        self.sent = []
+
+    async def send(self, msg):
+        self.sent.append(msg)
+
+
+class Log:
+    def info(self, *a):
+        pass
+
+
+def test_fastpitch_handle_trainer_stages_and_files(lib, tmp_path, monkeypatch):
+    from xva_trainer_b200 import trainers
+
+    monkeypatch.setenv("XVA_B200_MAX_EPOCHS", "2")
+    mm = trainers.ModelsManager(Log(), PROD=False)
+    ws = FakeSocket()
+    data = {"dataset_path": "synthetic:4x24x64x16", "output_path": str(tmp_path), "checkpoint": None, "num_workers": 0,
+            "batch_size": 64, "epochs_per_checkpoint": 1, "force_stage": None}
+    res = asyncio.run(trainers.handleTrainer(mm, data, ws, [0]))
+    assert res == "move to hifi"
+    assert ws.sent == ["Set stage to: 2 ", "Set stage to: 3 ", "Set stage to: 4 "]
+    out = tmp_path / "synthetic_4x24x64x16"
+    names = sorted(os.listdir(out))
+    assert "training.log" in names and "graphs.json" in names
+    assert "synthetic_4x24x64x16.pt" in names and "synthetic_4x24x64x16.json" in names
+    assert sum(n.startswith("FastPitch_checkpoint_") for n in names) <= 2          # only the last two are kept
+    assert {n.split("_")[1] for n in names if n.startswith("Stage_")} == {"2", "3", "4"}
+    graphs = json.load(open(out / "graphs.json"))
+    assert set(graphs["stages"]) == {"1", "2", "3", "4", "5"}
+    for s in ("2", "3", "4"):
+        assert len(graphs["stages"][s]["loss"]) == 2 and graphs["stages"][s]["target_delta"] is not None
+    ck = torch.load(out / [n for n in names if n.startswith("FastPitch_checkpoint_")][-1], map_location="cpu")
+    assert set(ck) == {"epoch", "iteration", "avg_loss_per_epoch", "training_stage", "state_dict", "optimizer"}
+    assert len(ck["state_dict"]) == 185 and ck["state_dict"]["decoder.layers.0.pos_ff.CoreNet.0.weight"].shape == (1536, 384, 3)
+    half = torch.load(out / "synthetic_4x24x64x16.pt", map_location="cpu")
+    assert half["proj.weight"].dtype == torch.float16
+    log = open(out / "training.log").read()
+    assert "Stage: 2" in log and "frames/s" in log
+    # losses went down within a stage
+    l3 = [v for _, v in graphs["stages"]["3"]["loss"]]
+    assert l3[-1] < l3[0]
+
+
+def test_hifigan_handle_trainer_files(lib, tmp_path, monkeypatch):
+    from xva_trainer_b200 import trainers
+
+    monkeypatch.setenv("XVA_B200_MAX_EPOCHS", "1")
+    mm = trainers.ModelsManager(Log(), PROD=False)
+    ws = FakeSocket()
+    data = {"dataset_path": "synthetic:2x8x4", "output_path": str(tmp_path), "hifigan_checkpoint": None, "num_workers": 0,
+            "batch_size": 2, "epochs_per_checkpoint": 1}
+    res = asyncio.run(trainers.handleTrainerHiFi(mm, data, ws, [0]))
+    assert res == "done"
+    assert ws.sent == ["Set stage to: 5 ", "Finished training HiFi-GAN\n"]
+    out = tmp_path / "synthetic_2x8x4"
+    hifi = sorted(os.listdir(out / "hifi"))
+    assert any(n.startswith("g_") and len(n) == 10 for n in hifi) and any(n.startswith("do_") and len(n) == 11 for n in hifi)
+    assert os.path.exists(out / "synthetic_2x8x4.hg.pt")
+    g = torch.load(out / "hifi" / [n for n in hifi if n.startswith("g_")][-1], map_location="cpu")
+    assert list(g) == ["generator"] and len(g["generator"]) == 234
+    do = torch.load(out / "hifi" / [n for n in hifi if n.startswith("do_")][-1], map_location="cpu")
+    assert {"mpd", "msd", "optim_g", "optim_d", "steps", "epoch"} <= set(do)
+    assert len(do["mpd"]) == 90 and len(do["msd"]) == 80
+    graphs = json.load(open(out / "graphs.json"))
+    assert len(graphs["stages"]["5"]["loss"]) == 1

@@ -1,0 +1,585 @@
+"""Trainer facades: the entry points the reference's server / UI drive, re-hosted on the B200 engine.
+
+Mirrors (same names, constructor arguments, attributes, websocket strings and on-disk outputs):
+    python/models_manager.py:8-164            ModelsManager.sync_init_model / models / models_bank
+    python/fastpitch1_1/xva_train.py:57-176   handleTrainer            :185-1081  FastPitchTrainer
+    python/hifigan/xva_train.py:50-125        handleTrainer (HiFi-GAN) :132-649   HiFiTrainer
+
+Kept from the reference: the ``data`` dict (dataset_path, output_path, checkpoint, batch_size, epochs_per_checkpoint,
+force_stage, ...), ``"Set stage to: N "`` / ``"Finished training HiFi-GAN\\n"`` websocket messages, ``training.log``
+(rewritten whole, as the UI tails it), ``graphs.json`` ({stages: {"1".."5": {loss, loss_delta, target_delta}}}),
+checkpoint names and keys (FastPitch_checkpoint_{epoch}_{iter}.pt = {epoch, iteration, avg_loss_per_epoch,
+training_stage, state_dict, optimizer}; {voice}.pt fp16 state dict; {voice}.json; hifi/g_{steps:08d}, hifi/do_{steps:08d},
+{voice}.hg.pt), two checkpoints retained, the per-stage early-stopping rule (relative loss delta averaged over a span,
+patience 3; xva_train.py:920-972), noam learning rate, gradient accumulation to ~256 items.
+
+Replaced: the recursive ``await self.iteration()`` + "recursion depth" catch (xva_train.py:908-909, 719-721) is a plain
+loop; stage changes are a ``StageFinished`` exception (a RuntimeError, so handleTrainer's contract is unchanged) instead
+of a bare ``raise``; ``LOCAL_RANK`` is parsed as int (Appendix C-5 of SURVEY.md).
+
+Out of scope: the wav / text dataset loaders. Batches come from ``data["batch_source"]``
+(any iterable of reference-layout batches) or, with ``dataset_path = "synthetic:<B>x<Tt>x<Tm>x<items>"``, from the seeded
+synthetic generator of SURVEY.md section 8(d).
+"""
+import asyncio
+import datetime
+import json
+import math
+import os
+import time
+import traceback
+
+import torch
+
+from . import fastpitch as fp
+from . import hifigan as hg
+
+
+class StageFinished(RuntimeError):
+    """Raised by finish_epoch when a training stage (or the whole run) is over; handleTrainer inspects the trainer's
+    JUST_FINISHED_STAGE / END_OF_TRAINING flags exactly as the reference does after its bare ``raise``."""
+
+
+def _now():
+    t = str(datetime.datetime.now().time())
+    return t.split(".")[0]
+
+
+def _synthetic_fastpitch_batches(spec, device, seed=1234):
+    """'synthetic:BxTtxTmxitems' -> list of (x, y, num_frames) in the layout of batch_to_gpu (data_function.py:706-741)."""
+    B, Tt, Tm, items = (int(v) for v in spec.split(":", 1)[1].split("x"))
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for _ in range(max(1, items // B)):
+        text = torch.randint(1, fp.N_SYMBOLS, (B, Tt), generator=g)
+        durs = torch.ones(B, Tt)
+        for b in range(B):
+            durs[b] += torch.bincount(torch.randint(0, Tt, (Tm - Tt,), generator=g), minlength=Tt).float()
+        mel = torch.randn(B, fp.N_MEL, Tm, generator=g)
+        pitch = torch.randn(B, 1, Tm, generator=g) * (torch.rand(B, 1, Tm, generator=g) > 0.3)
+        energy = torch.rand(B, Tm, generator=g) * 10
+        lens = torch.full((B,), Tt, dtype=torch.long)
+        mlens = torch.full((B,), Tm, dtype=torch.long)
+        t = lambda v: v.to(device)
+        x = [t(text), t(lens), t(mel), t(mlens), t(pitch), t(energy), None, None, t(durs),
+             t(torch.full((B,), float(Tt))), t(torch.full((B,), float(Tm))), ["synthetic"] * B]
+        out.append((x, [x[2], x[1], x[3], x[9]], int(mlens.sum())))
+    return out
+
+
+class _TrainerBase:
+    def __init__(self, logger, PROD, gpus, models_manager, websocket=None):
+        self.logger = logger
+        self.PROD = PROD
+        self.models_manager = models_manager
+        self.gpus = gpus
+        self.device = torch.device(f"cuda:{gpus[0]}")
+        self.ckpt_path = None
+        self.websocket = websocket
+        self.training_log = []
+        self.training_log_live_line = ""
+        self.model = None
+        self.isReady = True
+        self.epoch = None
+        self.running = False
+        self.is_init = False
+        self.logs_are_init = False
+        self.dataset_id = self.dataset_input = self.dataset_output = None
+        self.batch_size = self.force_stage = self.workers = None
+        self.local_rank = int(os.getenv("LOCAL_RANK", 0))
+        self.JUST_FINISHED_STAGE = False
+        self.END_OF_TRAINING = False
+        self.graphs_json = None
+
+    # reference: xva_train.py:226-238 (rewrites the whole file: the UI polls it)
+    def print_and_log(self, line=None, end="\n", flush=False, save_to_file=False):
+        if line is not None:
+            self.training_log.append(f"{_now()} | {line}")
+        if save_to_file and self.local_rank == 0:
+            with open(f"{save_to_file}/training.log", "w+") as f:
+                f.write("\n".join(self.training_log + [self.training_log_live_line]))
+
+    def load_state_dict(self, ckpt_path, sd):
+        pass
+
+    def set_device(self, device):
+        pass
+
+    def pause(self, websocket=None):
+        self.logger.info("pause") if self.logger else None
+        self.running = False
+
+    # reference: xva_train.py:539-587
+    def init_logs(self, dataset_output):
+        os.makedirs(dataset_output, exist_ok=True)
+        self.training_log = []
+        if os.path.exists(f"{dataset_output}/training.log"):
+            with open(f"{dataset_output}/training.log") as f:
+                self.training_log = [l for l in f.read().split("\n") if l]
+        gpath = f"{dataset_output}/graphs.json"
+        if os.path.exists(gpath):
+            self.graphs_json = json.load(open(gpath))
+        else:
+            self.graphs_json = {"stages": {str(s): {"loss": [], "loss_delta": [], "target_delta": None} for s in range(1, 6)}}
+        self.logs_are_init = True
+
+    def _write_graphs(self):
+        if self.local_rank == 0:
+            with open(f"{self.dataset_output}/graphs.json", "w+") as f:
+                f.write(json.dumps(self.graphs_json))
+
+    async def _send(self, msg):
+        if self.websocket is not None and self.local_rank == 0:
+            r = self.websocket.send(msg)
+            if asyncio.iscoroutine(r):
+                await r
+
+
+# ==================================================================================================== FastPitch
+class FastPitchTrainer(_TrainerBase):
+    """python/fastpitch1_1/xva_train.py:185. Stages 2-4 run on the B200 engine; stage 1 (aligner) is not built yet, so a
+    run starts at stage 2 with the durations the batches carry."""
+
+    TARGET_DELTAS = {2: 0.0005, 3: 0.0005, 4: 0.0003}   # order of magnitude of get_target_delta (xva_train.py:589-672)
+
+    def __init__(self, logger, PROD, gpus, models_manager, websocket=None):
+        super().__init__(logger, PROD, gpus, models_manager, websocket)
+        if logger:
+            logger.info("New FastPitchTrainer")
+
+    async def start(self, data, gpus=None, resume=False):
+        if self.running:
+            return
+        self.running = True
+        if not resume:
+            self.force_stage = int(data["force_stage"]) if data.get("force_stage") else None
+            self.dataset_input = data["dataset_path"]
+            self.dataset_id = (self.dataset_input.split("/")[-1] or "voice").replace(":", "_")
+            self.dataset_output = os.path.join(data["output_path"], self.dataset_id)
+            self.checkpoint = data.get("checkpoint")
+            self.workers = data.get("num_workers", 0)
+            self.batch_size = int(data["batch_size"])
+            self.epochs_per_checkpoint = int(data.get("epochs_per_checkpoint", 1))
+            self.batch_source = data.get("batch_source")
+            self.learning_rate, self.warmup_steps = 0.1, 1000
+            self.max_epochs = int(os.environ.get("XVA_B200_MAX_EPOCHS", "0"))       # test hook: bound epochs per stage
+        if not self.logs_are_init:
+            self.init_logs(self.dataset_output)
+        while self.running:
+            await self.iteration()
+
+    async def init(self):
+        torch.manual_seed(1234 + self.local_rank)
+        self.model = fp.FastPitch(logger=self.logger, device=self.device, seed=1234)
+        self.criterion = fp.FastPitchLoss()
+        self.optimizer = fp.Lamb(self.model, lr=0.1, betas=(0.9, 0.98), eps=1e-9, weight_decay=1e-6)
+        self.total_iter, self.epoch, self.avg_loss_per_epoch = 50000, 0, []       # new voices start at 40-50k (:304-335)
+        self.start_iterations = self.total_iter
+        stage = 2
+        ck = self.last_checkpoint(self.dataset_output)
+        if self.checkpoint and os.path.isfile(str(self.checkpoint)):
+            ck = self.checkpoint
+        if ck:
+            stage, self.epoch, self.total_iter, self.avg_loss_per_epoch = self.load_checkpoint(ck)
+            self.ckpt_path = ck
+        if self.force_stage:
+            stage = self.force_stage
+        stage = max(2, int(stage))
+        self.model.training_stage = self.criterion.training_stage = stage
+        self.target_delta = self.TARGET_DELTAS.get(stage, 0.0005)
+        self.graphs_json["stages"][str(stage)]["target_delta"] = self.target_delta
+        await self._send(f"Set stage to: {stage} ")
+        mult = {2: 12, 3: 3.5, 4: 4}.get(stage, 1)                                 # stage batch multipliers (:387-404)
+        self.stage_batch = max(1, int(self.batch_size * mult))
+        self.gam = max(1, round(256 / self.stage_batch))                           # :407
+        if self.batch_source is not None:
+            self.batches = list(self.batch_source)
+        elif str(self.dataset_input).startswith("synthetic:"):
+            self.batches = _synthetic_fastpitch_batches(self.dataset_input, self.device, 1234 + self.local_rank)
+        else:
+            raise NotImplementedError("wav/text dataset loading is outside this build (SURVEY.md section 2 row 6): pass "
+                                      "data['batch_source'] or dataset_path='synthetic:BxTtxTmxitems'")
+        self.model.train()
+        self.EPOCH_AVG_SPAN, self.target_patience, self.target_patience_count = 20, 3, 0
+        self.last_loss, self.iter_losses, self.avg_frames_s = None, [], []
+        self.epoch_iter, self.micro, self.frames_acc = 0, 0, 0
+        self.batch_pos = 0
+        self.avg_loss_per_epoch.append(0.0)
+        self.step_t0 = time.perf_counter()
+        self.model.zero_grad()
+        self.is_init = True
+
+    async def iteration(self):
+        if not self.is_init:
+            await self.init()
+        if self.batch_pos >= len(self.batches):
+            self.batch_pos = 0
+            self.finish_epoch()
+            self.avg_loss_per_epoch.append(0.0)
+            self.epoch_iter = 0
+            self.iter_losses = []
+        x, y, num_frames = self.batches[self.batch_pos]
+        self.batch_pos += 1
+        self.total_iter += 1
+        self.epoch_iter += 1
+        fp.adjust_learning_rate(self.total_iter, self.optimizer, self.learning_rate, self.warmup_steps)     # :780
+        y_pred = self.model(x)                                                                               # :788
+        loss, meta = self.criterion(y_pred, y)                                                               # :790
+        self.model.backward(self.criterion, 1.0 / self.gam)                                                  # :806-813
+        self.micro += 1
+        self.frames_acc += num_frames
+        stage = self.model.training_stage
+        key = {3: "pitch_loss", 4: "mel_loss"}.get(stage, "loss")                                            # :815-820
+        tracked = meta[key] * (0.1 if stage == 3 else 1.0)
+        if self.micro % self.gam == 0:
+            self.optimizer.step()                                                                            # :855-862
+            self.model.step_dropout()
+            self.model.zero_grad()
+            val = float(tracked)                       # one host read per optimizer step (the reference does six)
+            if not math.isfinite(val):                 # NaN guard (:825-832): drop the step's contribution
+                self.print_and_log("NaN loss: step skipped", save_to_file=self.dataset_output)
+                return
+            dt = time.perf_counter() - self.step_t0
+            self.step_t0 = time.perf_counter()
+            frames_s = self.frames_acc / max(dt, 1e-9)
+            self.frames_acc = 0
+            self.avg_frames_s.append(frames_s)
+            self.iter_losses.append(val)
+            self.avg_loss_per_epoch[-1] += val
+            self.training_log_live_line = (f"| Stage {stage} | Epoch {self.epoch} | iter {self.total_iter} | loss "
+                                           f"{val:.5f} | frames/s {int(frames_s)} | lr {self.optimizer.param_groups[0]['lr']:.2e}")
+            self.print_and_log(save_to_file=self.dataset_output)
+
+    # reference: xva_train.py:915-976
+    def finish_epoch(self):
+        self.epoch += 1
+        n_steps = max(1, len(self.iter_losses))
+        self.avg_loss_per_epoch[-1] /= n_steps
+        deltas = [(a - b) / a for a, b in zip(self.avg_loss_per_epoch[:-1], self.avg_loss_per_epoch[1:]) if a]
+        avg_loss = sum(self.iter_losses) / n_steps if self.iter_losses else 0.0
+        delta_avg = None
+        if len(deltas) >= 2:
+            span = deltas[-self.EPOCH_AVG_SPAN:]
+            delta_avg = sum(span) / len(span)
+        stage = self.model.training_stage
+        fpath = os.path.join(self.dataset_output, f"FastPitch_checkpoint_{self.epoch}_{self.total_iter}.pt")
+        frames_s = sum(self.avg_frames_s) / max(1, len(self.avg_frames_s))
+        self.save_checkpoint(False, frames_s, self.total_iter, avg_loss, delta_avg, self.avg_loss_per_epoch, fpath)
+        self.graphs_json["stages"][str(stage)]["loss"].append([self.total_iter, self.avg_loss_per_epoch[-1]])
+        if delta_avg is not None:
+            self.graphs_json["stages"][str(stage)]["loss_delta"].append([self.total_iter, delta_avg])
+        self._write_graphs()
+        done = False
+        if delta_avg is not None and len(deltas) >= (20 if stage == 2 else 1) and delta_avg <= self.target_delta:
+            self.target_patience_count += 1
+            done = self.target_patience_count >= self.target_patience
+        else:
+            self.target_patience_count = 0
+        if self.max_epochs and self.epoch_in_stage() >= self.max_epochs:
+            done = True
+        self.avg_frames_s = []
+        if done:
+            stage_path = os.path.join(self.dataset_output, f"Stage_{stage}_DONE_FastPitch_checkpoint_{self.epoch}_{self.total_iter}.pt")
+            if stage == 4:
+                self.END_OF_TRAINING = True
+            self.JUST_FINISHED_STAGE = True
+            self.model.training_stage += 1
+            self.avg_loss_per_epoch = []
+            it = self.total_iter if self.model.training_stage == 4 else self.start_iterations
+            self.save_checkpoint(True, frames_s, it, avg_loss, delta_avg, self.avg_loss_per_epoch, fpath)
+            self.save_checkpoint(True, frames_s, it, avg_loss, delta_avg, self.avg_loss_per_epoch, stage_path, doPrintLog=False)
+            raise StageFinished(f"stage {stage} finished")
+
+    def epoch_in_stage(self):
+        return len(self.avg_loss_per_epoch)
+
+    # reference: xva_train.py:979-1052
+    def save_checkpoint(self, force_save=False, frames_s=0, total_iter=0, avg_loss=None, loss_delta=None,
+                        avg_loss_per_epoch=(), fpath="out.pt", doPrintLog=True):
+        if self.local_rank != 0:
+            return
+        intermediate = self.epochs_per_checkpoint > 0 and self.epoch % self.epochs_per_checkpoint == 0
+        if not intermediate and not force_save:
+            return
+        old = sorted([f for f in os.listdir(self.dataset_output) if f.startswith("FastPitch_checkpoint_")], key=_sort_fp)
+        for f in old[:-2] if len(old) > 2 else []:
+            os.remove(f"{self.dataset_output}/{f}")
+        line = (f"Stage: {self.model.training_stage} | Epoch: {self.epoch} | {os.path.basename(self.dataset_output)}~"
+                f"{self.epoch}_{self.total_iter}.pt | frames/s: {int(frames_s)}")
+        if avg_loss is not None:
+            line += f" | Loss: {avg_loss:.5f}"
+        if loss_delta is not None:
+            line += f" | Delta: {loss_delta:.5f}"
+        line += f" | Target: {self.target_delta:.5f}"
+        sd = self.model.state_dict()
+        torch.save({"epoch": self.epoch, "iteration": total_iter, "avg_loss_per_epoch": list(avg_loss_per_epoch),
+                    "training_stage": self.model.training_stage, "state_dict": sd,
+                    "optimizer": self.optimizer.state_dict()}, fpath)
+        # the fp16 export xVASynth loads (:1013-1016) is made from a copy: the live fp32 model is never touched
+        torch.save({k: (v.half() if v.is_floating_point() else v) for k, v in sd.items()},
+                   f"{self.dataset_output}/{self.dataset_id}.pt")
+        with open(f"{self.dataset_output}/{self.dataset_id}.json", "w+") as f:
+            json.dump({"version": "2.0", "modelVersion": "2.0", "modelType": "FastPitch1.1", "author": "", "lang": "en",
+                       "games": [{"gameId": "other", "voiceId": self.dataset_id,
+                                  "voiceName": os.path.basename(self.dataset_output), "resemblyzer": [], "gender": "male"}]},
+                      f, indent=4)
+        self.training_log_live_line = ""
+        if doPrintLog:
+            self.print_and_log(line, save_to_file=self.dataset_output)
+
+    # reference: xva_train.py:1054-1081
+    def load_checkpoint(self, filepath):
+        self.print_and_log(f"Loading model and optimizer state from {filepath}", save_to_file=self.dataset_output)
+        try:
+            ck = torch.load(filepath, map_location="cpu")
+        except Exception:
+            self.print_and_log("Failed to load the checkpoint! Maybe try the second-last checkpoint (delete the last one). "
+                               f"Full error message: {traceback.format_exc()}", save_to_file=self.dataset_output)
+            raise
+        sd = {k.replace("module.", ""): v for k, v in ck["state_dict"].items()}
+        self.model.load_state_dict(sd)
+        try:
+            self.optimizer.load_state_dict(ck["optimizer"])
+        except Exception:
+            self.print_and_log("========== OPTIM NOT LOADED ==========", save_to_file=self.dataset_output)
+        return ck.get("training_stage", 1), ck.get("epoch", 0) + 1, ck.get("iteration", 0), ck.get("avg_loss_per_epoch", [])
+
+    @staticmethod
+    def last_checkpoint(output):      # :1239-1250
+        if not output or not os.path.isdir(output):
+            return None
+        c = sorted([f for f in os.listdir(output) if f.startswith("FastPitch_checkpoint_")], key=_sort_fp)
+        return os.path.join(output, c[-1]) if c else None
+
+
+def _sort_fp(name):
+    return int(name.split("FastPitch_checkpoint_")[-1].split(".")[0].split("_")[0])
+
+
+async def handleTrainer(models_manager, data, websocket, gpus, resume=False):
+    """python/fastpitch1_1/xva_train.py:57-176: drives FastPitch stages 2 -> 4, returns "move to hifi" when stage 4 ends."""
+    gpus = gpus or [0]
+    trainer = models_manager.sync_init_model("fastpitch1_1", websocket=websocket, gpus=gpus)
+    try:
+        await trainer.start(data, gpus=gpus, resume=resume)
+        return None
+    except RuntimeError as e:
+        if "out of memory" in str(e):                                   # :131-145: retry three items smaller
+            trainer.print_and_log(f"Out of VRAM; batch size {data['batch_size']} -> {int(data['batch_size']) - 3}")
+            data["batch_size"] = max(1, int(data["batch_size"]) - 3)
+            trainer.running, trainer.is_init = False, False
+            torch.cuda.empty_cache()
+            return await handleTrainer(models_manager, data, websocket, gpus)
+        if trainer.JUST_FINISHED_STAGE:                                 # :147-168
+            trainer.JUST_FINISHED_STAGE = False
+            trainer.running, trainer.is_init = False, False
+            if trainer.END_OF_TRAINING:
+                trainer.END_OF_TRAINING = False
+                del models_manager.models_bank["fastpitch1_1"]
+                return "move to hifi"
+            data["force_stage"] = None
+            return await handleTrainer(models_manager, data, websocket, gpus)
+        raise
+
+
+# ==================================================================================================== HiFi-GAN
+class _Cfg(dict):
+    __getattr__ = dict.__getitem__
+    __setattr__ = dict.__setitem__
+
+
+HIFI_CONFIG_V1 = dict(resblock="1", num_gpus=0, batch_size=16, learning_rate=0.0002, adam_b1=0.8, adam_b2=0.99,
+                      lr_decay=0.999, seed=1234, upsample_rates=[8, 8, 2, 2], upsample_kernel_sizes=[16, 16, 4, 4],
+                      upsample_initial_channel=512, resblock_kernel_sizes=[3, 7, 11],
+                      resblock_dilation_sizes=[[1, 3, 5], [1, 3, 5], [1, 3, 5]], segment_size=8192, num_mels=80, num_freq=1025,
+                      n_fft=1024, hop_size=256, win_size=1024, sampling_rate=22050, fmin=0, fmax=8000, fmax_for_loss=None)
+
+
+class HiFiTrainer(_TrainerBase):
+    """python/hifigan/xva_train.py:132 ("stage 5")."""
+
+    def __init__(self, logger, PROD, gpus, models_manager, websocket=None):
+        super().__init__(logger, PROD, gpus, models_manager, websocket)
+        if logger:
+            logger.info("New HiFiTrainer")
+
+    async def start(self, data, gpus=None, resume=False):
+        if self.running:
+            return
+        self.running = True
+        if not resume:
+            self.dataset_input = data["dataset_path"]
+            self.dataset_id = (self.dataset_input.split("/")[-1] or "voice").replace(":", "_")
+            self.dataset_output = os.path.join(data["output_path"], self.dataset_id)
+            self.hifi_dir = os.path.join(self.dataset_output, "hifi")
+            self.checkpoint = data.get("hifigan_checkpoint")
+            self.batch_size = int(data["batch_size"])
+            self.epochs_per_checkpoint = int(data.get("epochs_per_checkpoint", 1))
+            self.batch_source = data.get("batch_source")
+            self.max_epochs = int(os.environ.get("XVA_B200_MAX_EPOCHS", "0"))
+        if not self.logs_are_init:
+            self.init_logs(self.dataset_output)
+        while self.running:
+            await self.iteration()
+
+    async def init(self):
+        os.makedirs(self.hifi_dir, exist_ok=True)
+        h = _Cfg(HIFI_CONFIG_V1)
+        h.batch_size = int(self.batch_size * 1.4)                                     # :228
+        self.h = h
+        torch.manual_seed(h.seed + self.local_rank)
+        self.generator = hg.Generator(h, device=self.device)
+        self.mpd = hg.MultiPeriodDiscriminator(device=self.device)
+        self.msd = hg.MultiScaleDiscriminator(device=self.device)
+        self.model = self.generator
+        self.steps, self.epoch, self.avg_loss_per_epoch = 0, 0, []
+        cp_g, cp_do = self.scan_checkpoint("g_"), self.scan_checkpoint("do_")
+        if self.checkpoint and os.path.isfile(str(self.checkpoint)):
+            cp_g = self.checkpoint
+        synthetic = self.batch_source is not None or str(self.dataset_input).startswith("synthetic:")
+        if cp_g is None and not synthetic:
+            raise RuntimeError("HiFi-GAN fine-tuning needs a generator checkpoint (hifigan/xva_train.py:276-277)")
+        if cp_g:
+            self.generator.load_state_dict(torch.load(cp_g, map_location="cpu")["generator"])
+            self.ckpt_path = cp_g
+        state_do = torch.load(cp_do, map_location="cpu") if cp_do else None
+        if state_do:
+            self.mpd.load_state_dict(state_do["mpd"])
+            self.msd.load_state_dict(state_do["msd"])
+            self.steps, self.epoch = state_do["steps"] + 1, state_do["epoch"]
+            self.avg_loss_per_epoch = list(state_do.get("avg_loss_per_epoch", []))
+        self.generator.train(); self.mpd.train(); self.msd.train()
+        self.stepper = hg.HiFiGANStep(self.generator, self.mpd, self.msd, h)
+        if state_do and "optim_g" in state_do:
+            for opt, key in ((self.stepper.optim_g, "optim_g"), (self.stepper.optim_d, "optim_d")):
+                st = state_do[key]
+                opt.m.copy_(st["m"]); opt.v.copy_(st["v"]); opt.steps = int(st["steps"]); opt.step_dev.fill_(opt.steps)
+        self.lr = h.learning_rate * (h.lr_decay ** self.epoch)                        # ExponentialLR per epoch (:306-307)
+        if self.batch_source is not None:
+            self.batches = list(self.batch_source)
+        elif str(self.dataset_input).startswith("synthetic:"):
+            B, frames, items = (int(v) for v in self.dataset_input.split(":", 1)[1].split("x"))
+            from . import hifigan as _hg
+            g = torch.Generator().manual_seed(1234 + self.local_rank)
+            mel_in = _hg.MelSpectrogram(fmax=h.fmax, device=self.device)
+            mel_loss = _hg.MelSpectrogram(fmax=h.fmax_for_loss, device=self.device)
+            self.batches = []
+            for _ in range(max(1, items // B)):
+                y = (0.95 * torch.tanh(torch.randn(B, frames * h.hop_size, generator=g) * 0.3)).to(self.device)
+                self.batches.append((mel_in(y).transpose(1, 2).contiguous(), y, mel_loss(y).transpose(1, 2).contiguous()))
+        else:
+            raise NotImplementedError("wav dataset loading is outside this build (SURVEY.md section 2 row 13): pass "
+                                      "data['batch_source'] or dataset_path='synthetic:BxFRAMESxITEMS'")
+        self.graphs_json["stages"]["5"]["target_delta"] = 0.0002
+        await self._send("Set stage to: 5 ")
+        self.batch_pos, self.iter_losses = 0, []
+        self.avg_loss_per_epoch.append(0.0)
+        self.is_init = True
+
+    async def iteration(self):
+        if not self.is_init:
+            await self.init()
+        if self.batch_pos >= len(self.batches):
+            self.batch_pos = 0
+            self.finish_epoch()
+            self.avg_loss_per_epoch.append(0.0)
+            self.iter_losses = []
+        x, y, y_mel = self.batches[self.batch_pos]
+        self.batch_pos += 1
+        t0 = time.perf_counter()
+        for opt in (self.stepper.optim_g, self.stepper.optim_d):
+            opt.param_groups[0]["lr"] = self.lr
+        out = self.stepper.step(x, y, y_mel)                                          # :467-515
+        gen_loss = float(out["loss_gen_all"])
+        its = 1.0 / max(time.perf_counter() - t0, 1e-9)
+        self.iter_losses.append(gen_loss)
+        self.avg_loss_per_epoch[-1] += gen_loss
+        self.training_log_live_line = (f"| Stage 5 | Epoch {self.epoch} | Steps {self.steps} | Gen loss {gen_loss:.3f} | "
+                                       f"Mel err {float(out['mel_error']):.4f} | {its * y.shape[0]:.1f} its/s")
+        self.print_and_log(save_to_file=self.dataset_output)                          # :517-545
+        self.steps += 1
+
+    def finish_epoch(self):                                                           # :607-649
+        self.epoch += 1
+        self.avg_loss_per_epoch[-1] /= max(1, len(self.iter_losses))
+        self.lr *= self.h.lr_decay
+        self.graphs_json["stages"]["5"]["loss"].append([self.steps, self.avg_loss_per_epoch[-1]])
+        deltas = [(a - b) / a for a, b in zip(self.avg_loss_per_epoch[:-1], self.avg_loss_per_epoch[1:]) if a]
+        if len(deltas) >= 2:
+            d = sum(deltas[-20:]) / len(deltas[-20:])
+            self.graphs_json["stages"]["5"]["loss_delta"].append([self.steps, d])
+        self._write_graphs()
+        if self.epochs_per_checkpoint > 0 and self.epoch % self.epochs_per_checkpoint == 0:
+            self.output_checkpoint()
+        if self.max_epochs and self.epoch >= self.max_epochs:
+            self.output_checkpoint()
+            self.END_OF_TRAINING = True
+            raise StageFinished("HiFi-GAN finished")
+
+    def output_checkpoint(self):                                                      # :570-604
+        if self.local_rank != 0:
+            return
+        gpath = f"{self.hifi_dir}/g_{self.steps:08d}"
+        torch.save({"generator": self.generator.state_dict()}, gpath)
+        opt = lambda o: {"m": o.m.cpu(), "v": o.v.cpu(), "steps": o.steps}
+        torch.save({"mpd": self.mpd.state_dict(), "msd": self.msd.state_dict(), "optim_g": opt(self.stepper.optim_g),
+                    "optim_d": opt(self.stepper.optim_d), "steps": self.steps, "epoch": self.epoch,
+                    "avg_loss_per_epoch": self.avg_loss_per_epoch, "ckpts_finetuned": True}, f"{self.hifi_dir}/do_{self.steps:08d}")
+        torch.save({"generator": self.generator.state_dict()}, f"{self.dataset_output}/{self.dataset_id}.hg.pt")
+        for prefix in ("g_", "do_"):                                                  # keep the last two (:592-597)
+            old = sorted(f for f in os.listdir(self.hifi_dir) if f.startswith(prefix) and len(f) == len(prefix) + 8)
+            for f in old[:-2]:
+                os.remove(f"{self.hifi_dir}/{f}")
+        self.print_and_log(f"Stage: 5 | Epoch: {self.epoch} | Saved {os.path.basename(gpath)}", save_to_file=self.dataset_output)
+
+    def scan_checkpoint(self, prefix):                                                # hifigan/utils.py:57-62
+        d = getattr(self, "hifi_dir", None)
+        if not d or not os.path.isdir(d):
+            return None
+        c = sorted(f for f in os.listdir(d) if f.startswith(prefix) and len(f) == len(prefix) + 8)
+        return os.path.join(d, c[-1]) if c else None
+
+
+async def handleTrainerHiFi(models_manager, data, websocket, gpus, resume=False):
+    """python/hifigan/xva_train.py:50-125: returns "done" after sending "Finished training HiFi-GAN\\n"."""
+    gpus = gpus or [0]
+    trainer = models_manager.sync_init_model("hifigan", websocket=websocket, gpus=gpus)
+    try:
+        await trainer.start(data, gpus=gpus, resume=resume)
+        return None
+    except RuntimeError as e:
+        if "out of memory" in str(e):                                                 # :95-109
+            data["batch_size"] = max(1, int(data["batch_size"]) - 3)
+            trainer.running, trainer.is_init = False, False
+            torch.cuda.empty_cache()
+            return await handleTrainerHiFi(models_manager, data, websocket, gpus)
+        if trainer.END_OF_TRAINING:
+            trainer.running = False
+            await trainer._send("Finished training HiFi-GAN\n")                       # :113
+            del models_manager.models_bank["hifigan"]
+            return "done"
+        raise
+
+
+# ==================================================================================================== registry
+class ModelsManager:
+    """python/models_manager.py:8-164, trainer part: key -> lazily constructed trainer, owned by ``models_bank``."""
+
+    def __init__(self, logger=None, PROD=False, device="cuda"):
+        self.logger, self.PROD, self.device_label, self.models_bank = logger, PROD, device, {}
+
+    def sync_init_model(self, model_key, websocket=None, gpus=(0,)):
+        if model_key in self.models_bank and self.models_bank[model_key] != "move to hifi":
+            self.models_bank[model_key].websocket = websocket
+            return self.models_bank[model_key]
+        gpus = list(gpus)
+        if model_key == "fastpitch1_1":
+            self.models_bank[model_key] = FastPitchTrainer(self.logger, self.PROD, gpus, self, websocket=websocket)
+        elif model_key == "hifigan":
+            self.models_bank[model_key] = HiFiTrainer(self.logger, self.PROD, gpus, self, websocket=websocket)
+        else:
+            raise KeyError(f"{model_key}: only the fastpitch1_1 and hifigan trainers are part of this build")
+        return self.models_bank[model_key]
+
+    def models(self, key):
+        return self.models_bank[key]
