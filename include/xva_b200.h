@@ -116,6 +116,15 @@ typedef struct xva_gemm_args {
                                   input, tap = (row shift, phase*C + group offset) */
   const uint64_t* seed_dev; /* optional device counter added to `seed` (x odd constant) at run time, so a captured
                                CUDA graph draws a fresh dropout mask on every replay */
+  int32_t groups;   /* grouped convolution (DiscriminatorS, hifigan/models.py:207-213) in ONE launch; 0 / 1 = dense.
+                       With G = groups the output-tile index along n (mode 0/1) or m (mode 2) is the group g:
+                         mode 0: N = G*Og, K = Cg.  out[.., g*Og+n] contracts A columns a_col[j] + g*grp_step + [0,K)
+                                 with B rows g*Og+n (B = packed weights [taps, N, K]); Og % 16 == 0, Og <= 256
+                         mode 1: N = G*Cg, K = Og.  out[.., g*Cg+n] contracts A columns a_col[j] + g*K + [0,K) with B rows
+                                 g*K + [0,K), B columns [0,Cg) (B = the same packed weights); K % 32 == 0, Cg % 32 == 0
+                         mode 2: M = G*Og, N = Cg.  out[j, g*Og+m, n] contracts A columns g*Og+m with B columns
+                                 a_col[j] + g*grp_step + n; Og % 32 == 0, Og <= 128, grp_step % 32 == 0 */
+  int32_t grp_step; /* column step per group in the activation operand (mode 0: Cg of the input; mode 2: Cg) */
 } xva_gemm_args;
 
 /* sizeof(xva_gemm_args) as compiled into the library, so a binding can verify its struct layout. */

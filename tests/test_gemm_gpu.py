@@ -255,3 +255,107 @@ def test_full_size_linearity_property():
     rows = torch.randint(0, T, (64,), device="cuda")
     want = conv_ref(x1[:2], w, (-1, 0, 1))[:, rows]
     assert rel(y1[:2][:, rows], want) < TOL_TC
+
+
+# ------------------------------------------------------------------------------------------------ segmented row tiles
+@pytest.mark.parametrize("B,T,K,N,shifts", [
+    (32, 160, 384, 192, (0,)),            # FastPitch encoder: 160 tokens = 5 segments of 32, tiles span items
+    (9, 160, 96, 256, (-1, 0, 1)),        # odd item count: last tile half empty, CTA-pair duplicate
+    (22, 10, 128, 128, (-2, -1, 0, 1, 2)),  # DiscriminatorP period 11: 10 rows per sequence
+    (7, 51, 64, 96, (-1, 0, 1)),          # 51 rows -> 64-row segments
+    (5, 83, 64, 64, (-1, 0, 1)),          # 83 rows -> three 32-row segments
+])
+def test_segmented_tiles(B, T, K, N, shifts):
+    """Short sequences share 128-row tiles (segments of 32 / 64 rows): conv halo stays per item (TMA zero fill per
+    segment), every epilogue input (bias, gate, residual, lens) follows the row's own item."""
+    ops = _ops()
+    x, w = gen(B, T, K, seed=41), gen(len(shifts), N, K, seed=42, scale=K ** -0.5)
+    bias, res, gate = gen(N, seed=43), gen(B, T, N, seed=44), gen(B, T, N, seed=45)
+    lens = torch.randint(1, T + 1, (B,), device="cuda", generator=torch.Generator(device="cuda").manual_seed(46)).int()
+    mask = (torch.arange(T, device="cuda")[None, :] < lens[:, None]).float()[..., None]
+    want = ((conv_ref(x, w, shifts) + bias) * torch.where(gate > 0, 1.0, 0.1) + res) * mask
+    got_ref = ops.conv_fwd(x, w, shifts, bias=bias, residual=res, gate=gate, gate_slope=0.1, lens=lens, ref=True)
+    got = ops.conv_fwd(x, w, shifts, bias=bias, residual=res, gate=gate, gate_slope=0.1, lens=lens)
+    assert rel(got_ref, want) < TOL_REF
+    assert rel(got, want) < TOL_TC
+    # dgrad through the same tiles (MN-major B)
+    dy = gen(B, T, N, seed=47)
+    want_dx = conv_ref(dy, w.transpose(1, 2).contiguous(), [-s for s in shifts])
+    got_dx = ops.conv_dgrad(dy, w, shifts)
+    assert rel(got_dx, want_dx) < TOL_TC
+    # LayerNorm epilogue
+    if N % 16 == 0:
+        gamma, beta = 1 + 0.1 * gen(N, seed=48), 0.1 * gen(N, seed=49)
+        pre = conv_ref(x, w, shifts) + bias + res
+        want_ln = torch.nn.functional.layer_norm(pre, (N,), gamma, beta, 1e-5) * mask
+        got_ln, sv = ops.conv_fwd(x, w, shifts, bias=bias, residual=res, ln=(gamma, beta), save_ln=True, lens=lens)
+        assert rel(got_ln, want_ln) < TOL_TC
+        assert rel(sv["pre"], pre) < TOL_TC
+        assert rel(sv["mean"].view(B, T), pre.mean(-1)) < 2e-3 + 1e-3
+
+
+# ------------------------------------------------------------------------------------------------ grouped convolutions
+def _grouped_case(Cin, Cout, G, k, stride, seed):
+    """DiscriminatorS-style grouped strided conv: returns everything the three launches need plus the torch result."""
+    import math
+    B, L = 3, 4 * 97
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = torch.randn(B, L, Cin, device="cuda", generator=g)
+    w = torch.randn(Cout, Cin // G, k, device="cuda", generator=g) * (Cin // G * k) ** -0.5
+    pad = (k - 1) // 2
+    y = torch.nn.functional.conv1d(x.transpose(1, 2), w, None, stride=stride, padding=pad, groups=G).transpose(1, 2).contiguous()
+    return B, L, x, w, pad, y
+
+
+@pytest.mark.parametrize("Cin,Cout,G,k,stride", [(128, 128, 4, 41, 2), (128, 256, 16, 41, 2), (256, 512, 16, 41, 4),
+                                                   (64, 128, 2, 5, 1)])
+def test_grouped_conv_single_launch(Cin, Cout, G, k, stride):
+    """Grouped conv forward / input gradient / weight gradient, one launch each (xva_gemm_args.groups), through the
+    packing hifigan._Disc uses (phase-major taps on the [L/stride, stride*Cin] view, groups with < 32 channels merged
+    into block-diagonal super-groups) vs torch's grouped conv1d and its autograd."""
+    from xva_trainer_b200 import hifigan as hg
+    ops = _ops()
+    B, L, x, w, pad, y = _grouped_case(Cin, Cout, G, k, stride, seed=50 + G)
+    m = hg._DiscConv(Cin, Cout, k, stride, pad, groups=G).cuda()
+    Gp, Ogp, Cgp, f = hg._Disc._group_geom(None, m)
+    taps = m.taps()
+    order = torch.tensor([j for j, _, _ in taps], device="cuda")
+    Og, Cg = Cout // G, Cin // G
+    wk = w.index_select(2, order).permute(2, 0, 1)
+    if f > 1:
+        slot = (torch.arange(Cout, device="cuda") // Og) % f
+        mask = (slot[:, None] == torch.arange(f, device="cuda")[None, :]).float()[:, :, None]
+        wk = (wk.unsqueeze(2) * mask).reshape(k, Cout, Cgp)
+    wk = wk.contiguous()
+    xv = x.view(B, L // stride, stride * Cin)
+    shifts = [sh for _, sh, _ in taps]
+    a_cols = [ph * Cin for _, _, ph in taps]
+    Lout = y.shape[1]
+    kw = dict(a_cols=a_cols, out_rows=Lout, groups=Gp, grp_step=Cgp)
+    got_ref = ops.conv_fwd(xv, wk, shifts, ref=True, **kw)
+    got = ops.conv_fwd(xv, wk, shifts, **kw)
+    assert rel(got_ref, y) < TOL_REF
+    assert rel(got, y) < TOL_TC
+    # gradients
+    dy = gen(B, Lout, Cout, seed=60)
+    xl, wl = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    yy = torch.nn.functional.conv1d(xl.transpose(1, 2), wl, None, stride=stride, padding=pad, groups=G).transpose(1, 2)
+    (yy * dy).sum().backward()
+    for ref in (True, False):
+        tol = TOL_REF if ref else TOL_TC
+        dx = torch.zeros_like(x)
+        dxv = dx.view(B, L // stride, stride * Cin)
+        for ph in range(stride):
+            idx = [i for i, (_, _, p_) in enumerate(taps) if p_ == ph]
+            if not idx:
+                continue
+            ops.conv_dgrad(dy, wk[idx[0]:idx[-1] + 1], [taps[i][1] for i in idx], out=dxv[..., ph * Cin:(ph + 1) * Cin],
+                           out_rows=L // stride, groups=Gp, ref=ref)
+        assert rel(dx, xl.grad) < tol, ("dgrad", ref)
+        dw = ops.conv_wgrad(dy, xv, shifts, x_cols=a_cols, n_cols=Cgp, groups=Gp, grp_step=Cgp, ref=ref)   # [k, Cout, Cgp]
+        # un-pack: diagonal blocks of the super-groups, taps back in kernel order
+        if f > 1:
+            dw = (dw.view(k, Cout, f, Cg) * mask).sum(2)
+        dw_ref_layout = torch.empty_like(w)
+        dw_ref_layout[:, :, order] = dw.permute(1, 2, 0)
+        assert rel(dw_ref_layout, wl.grad) < tol, ("wgrad", ref)

@@ -45,6 +45,7 @@ class GemmArgs(C.Structure):
         ("out_pre", C.c_void_p), ("ln_mean", C.c_void_p), ("ln_rstd", C.c_void_p), ("drop_p", C.c_float),
         ("out_act_slope", C.c_float), ("seed", C.c_uint64), ("out_act", C.c_void_p),
         ("a_col", C.c_int32 * XVA_MAX_TAPS), ("seed_dev", C.c_void_p),
+        ("groups", C.c_int32), ("grp_step", C.c_int32),
     ]
 
 

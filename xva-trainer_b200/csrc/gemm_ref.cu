@@ -21,15 +21,23 @@ __device__ __forceinline__ uint64_t eff_seed(const GemmArgs& g) {
 __device__ float ref_dot(const GemmArgs& g, int z, int r, int n) {
   float acc = 0.0f;
   const int a_rows = g.a_rows ? g.a_rows : g.R;
+  // grouped launch (xva_gemm_args.groups): column n belongs to group grp
+  const int G = g.groups > 1 ? g.groups : 1;
+  const int n_per = g.N / G;
+  const int grp = G > 1 ? n / n_per : 0;
+  const int a_goff = G > 1 ? grp * (g.mode == 0 ? g.grp_step : g.K) : 0;
   for (int j = 0; j < g.taps; ++j) {
     const int ar = r + g.shift[j];
     if (ar < 0 || ar >= a_rows) continue;
-    const float* arow = g.a + z * g.a_zs + static_cast<long>(ar) * g.a_rs + g.a_col[j];
+    const float* arow = g.a + z * g.a_zs + static_cast<long>(ar) * g.a_rs + g.a_col[j] + a_goff;
     const int zb = j * g.b_tap_z + z * g.b_batch_z;
     if (g.mode == 0) {
       if (g.b_rows && n >= g.b_rows) continue;
       const float* brow = g.b + zb * g.b_zs + static_cast<long>(n) * g.b_rs;
       for (int k = 0; k < g.K; ++k) acc = fmaf(arow[k], brow[k], acc);
+    } else if (G > 1) {
+      const float* bcol = g.b + zb * g.b_zs + static_cast<long>(grp) * g.K * g.b_rs + (n - grp * n_per);
+      for (int k = 0; k < g.K; ++k) acc = fmaf(arow[k], bcol[static_cast<long>(k) * g.b_rs], acc);
     } else {
       const float* bcol = g.b + zb * g.b_zs + n;
       const int kmax = (g.b_rows && g.b_rows < g.K) ? g.b_rows : g.K;
@@ -122,13 +130,14 @@ __global__ void gemm_ref_wgrad_kernel(const RefDev d) {
   const int b_rows = g.b_rows ? g.b_rows : g.R;
   const int a_rows = g.a_rows ? g.a_rows : g.R;
   float acc = 0.0f;
+  const int goff = g.groups > 1 ? (m / (g.M / g.groups)) * g.grp_step : 0;
   for (int zr = 0; zr < g.ZR; ++zr) {
     const int z = zo * g.ZR + zr;
     for (int t = 0; t < g.R && t < a_rows; ++t) {
       const int bt = t + g.shift[j];
       if (bt < 0 || bt >= b_rows) continue;
-      acc = fmaf(g.a[z * g.a_zs + static_cast<long>(t) * g.a_rs + m], g.b[z * g.b_zs + static_cast<long>(bt) * g.b_rs + g.a_col[j] + n],
-                 acc);
+      acc = fmaf(g.a[z * g.a_zs + static_cast<long>(t) * g.a_rs + m],
+                 g.b[z * g.b_zs + static_cast<long>(bt) * g.b_rs + g.a_col[j] + goff + n], acc);
     }
   }
   float* o = g.out + zo * g.o_zs + j * g.o_js + static_cast<long>(m) * g.o_rs + n;

@@ -39,6 +39,14 @@ struct GemmDev {
   int n_tile, n_sub, n_mma, tiles_n, tiles_m, k_chunks, stages, acc_stages, num_tiles;
   int b_tap_z, b_batch_z;
   int row_tiles;  // Z * tiles_m: 128-row tiles of the output (mode 0/1)
+  int groups;     // > 1: grouped convolution, the n tile (mode 0/1) or m tile (mode 2) index is the group
+  int grp_a;      // mode 0/1: A column step per group; mode 2: B column step per group
+  int grp_bk;     // mode 1: B row (contraction) step per group
+  int m_step;     // mode 2: output rows between consecutive m tiles (kBlockM, or Og when grouped)
+  // Segmented row tiles (mode 0/1): a 128-row tile is made of 128/seg segments of `seg` consecutive rows, taken in
+  // (item, segment) order, so short sequences (R = 160 tokens, or the 10..83-row period columns of DiscriminatorP)
+  // share tiles instead of padding each item to a multiple of 128 rows. seg = 128: one segment = the classic tile.
+  int seg, segs, tot_segs;  // rows per segment (32 / 64 / 128), segments per item, Z * segs
   uint32_t mn_layout, mn_lbo, mn_sbo;  // MN-major descriptor constants (debug-overridable, see gemm_tc_launch)
   int shift[kMaxTaps];
   float* out;
@@ -78,6 +86,8 @@ struct TileCoord {
   int m0;     // first output row of the tile
   int n0;     // first output column of the tile
   int iters;  // k-iterations of the main loop
+  int g;      // group (0 when the launch is not grouped)
+  int s0;     // segmented tiles: first segment (in item-major order) of this tile
   bool dup;   // CTA pair, odd row-tile count: this CTA repeats its partner's rows and stores nothing
 };
 
@@ -96,10 +106,19 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmDev& p, int t, int ct
       c.dup = true;
     }
   }
-  int m_t = t % p.tiles_m;
-  t /= p.tiles_m;
+  c.s0 = 0;
+  int m_t;
+  if (p.seg < kBlockM && p.mode != 2) {  // tile t covers segments [t * 128/seg, (t+1) * 128/seg)
+    c.s0 = t * (kBlockM / p.seg);
+    m_t = 0;
+    t = 0;  // c.z / c.m0 are per segment (see seg_coord)
+  } else {
+    m_t = t % p.tiles_m;
+    t /= p.tiles_m;
+  }
   c.n0 = n_t * p.n_tile;
-  c.m0 = m_t * kBlockM;
+  c.m0 = (p.mode != 2) ? m_t * kBlockM : m_t * p.m_step;
+  c.g = (p.groups > 1) ? ((p.mode != 2) ? n_t : m_t) : 0;
   if (p.mode != 2) {
     c.z = t;
     c.z_end = t + 1;
@@ -118,6 +137,13 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmDev& p, int t, int ct
     c.iters = (c.z_end - c.z) * p.k_chunks;
   }
   return c;
+}
+
+// Segment S (item-major) -> (item, first row). Segments past the last item map to item Z: TMA zero-fills them and
+// the epilogue skips them.
+__device__ __forceinline__ void seg_coord(const GemmDev& p, int S, int& z, int& r0) {
+  z = S / p.segs;
+  r0 = (S - z * p.segs) * p.seg;
 }
 
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout), version 1.
@@ -229,6 +255,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (p.dbg & 16) continue;  // probe: raw MMA issue rate, no operand pipeline at all
         // outer index: tap (mode 0/1) or batch item of the reduced range (mode 2); inner: 32-wide k block
         const int n_outer = c.iters / p.k_chunks;
+        // grouped mode 1: the group's contraction rows start at g*K of B and its B columns at 0 (not at n0)
+        const int bk0 = c.g * p.grp_bk;
+        const int bn0 = (p.groups > 1 && p.mode == 1) ? 0 : c.n0;
+        const int n_seg = (p.mode != 2) ? kBlockM / p.seg : 1;
+        int seg_z[4], seg_r[4];
+        seg_z[0] = c.z;
+        seg_r[0] = c.m0;
+        if (n_seg > 1) {
+#pragma unroll
+          for (int sg = 0; sg < 4; ++sg)
+            if (sg < n_seg) seg_coord(p, c.s0 + sg, seg_z[sg], seg_r[sg]);
+        }
+        const int seg_bytes = p.seg * kBlockK * 4;
         int it = 0;
         for (int jo = 0; jo < n_outer; ++jo) {
           const int shift_j = (p.mode != 2) ? p.shift[jo] : p.shift[c.j];
@@ -247,30 +286,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               const uint32_t full = ptx::mapa(ptx::smem_u32(&bar_full[s]), 0);
               const int zb = jo * p.b_tap_z;
               const int half_n = p.n_sub >> 1;
-              ptx::tma_load_3d_cg2(sa, &tmap_a, full, acol_j + kc * kBlockK, c.m0 + shift_j, c.z);
+#pragma unroll
+              for (int sg = 0; sg < 4; ++sg)
+                if (sg < n_seg)
+                  ptx::tma_load_3d_cg2(sa + sg * seg_bytes, &tmap_a, full, acol_j + c.g * p.grp_a + kc * kBlockK,
+                                       seg_r[sg] + shift_j, seg_z[sg]);
               for (int sub = 0; sub < p.n_mma; ++sub) {
-                const int nb = c.n0 + sub * p.n_sub + static_cast<int>(cta_rank) * half_n;
+                const int nb = bn0 + sub * p.n_sub + static_cast<int>(cta_rank) * half_n;
                 if (p.mode == 0)
                   ptx::tma_load_3d_cg2(sb + sub * half_n * kBlockK * 4, &tmap_b, full, kc * kBlockK, nb, zb);
                 else
-                  ptx::tma_load_4d_cg2(sb + sub * half_n * kBlockK * 4, &tmap_b, full, 0, kc * kBlockK, nb / 32, zb);
+                  ptx::tma_load_4d_cg2(sb + sub * half_n * kBlockK * 4, &tmap_b, full, 0, bk0 + kc * kBlockK, nb / 32, zb);
               }
             } else if (p.mode != 2) {
               ptx::mbar_arrive_expect_tx(&bar_full[s], stage_bytes);
               const int zb = jo * p.b_tap_z + c.z * p.b_batch_z;
-              ptx::tma_load_3d(sa, &tmap_a, &bar_full[s], acol_j + kc * kBlockK, c.m0 + shift_j, c.z);
+#pragma unroll
+              for (int sg = 0; sg < 4; ++sg)
+                if (sg < n_seg)
+                  ptx::tma_load_3d(sa + sg * seg_bytes, &tmap_a, &bar_full[s], acol_j + c.g * p.grp_a + kc * kBlockK,
+                                   seg_r[sg] + shift_j, seg_z[sg]);
               if (p.mode == 0) {
                 for (int sub = 0; sub < p.n_mma; ++sub)
                   ptx::tma_load_3d(sb + sub * p.n_sub * kBlockK * 4, &tmap_b, &bar_full[s], kc * kBlockK,
                                    c.n0 + sub * p.n_sub, zb);
               } else {
-                ptx::tma_load_4d(sb, &tmap_b, &bar_full[s], 0, kc * kBlockK, c.n0 / 32, zb);
+                ptx::tma_load_4d(sb, &tmap_b, &bar_full[s], 0, bk0 + kc * kBlockK, bn0 / 32, zb);
               }
             } else {
               ptx::mbar_arrive_expect_tx(&bar_full[s], stage_bytes);
               const int z = c.z + jo;
               ptx::tma_load_4d(sa, &tmap_a, &bar_full[s], 0, kc * kBlockK, c.m0 / 32, z);
-              ptx::tma_load_4d(sb, &tmap_b, &bar_full[s], 0, kc * kBlockK + shift_j, (c.n0 + p.a_col[c.j]) / 32, z);
+              ptx::tma_load_4d(sb, &tmap_b, &bar_full[s], 0, kc * kBlockK + shift_j,
+                               (c.n0 + p.a_col[c.j] + c.g * p.grp_a) / 32, z);
             }
             __syncwarp();
             if (++s == p.stages) {
@@ -449,10 +497,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       epi_wait += t_e1 - t_e0;
       const uint32_t tacc = tmem_base + acc * 256 + lane_base;
 
-      const int row_limit = (c.dup || (p.dbg & 1)) ? 0 : ((kEpi == EPI_WGRAD) ? p.M : p.R);
+      int row_limit = (c.dup || (p.dbg & 1)) ? 0 : ((kEpi == EPI_WGRAD) ? p.M : p.R);
+      if (kEpi == EPI_WGRAD && p.groups > 1 && row_limit > c.m0 + p.m_step) row_limit = c.m0 + p.m_step;
       const int n_cols = (p.N - c.n0) < p.n_tile ? (p.N - c.n0) : p.n_tile;  // valid columns of this tile
       const int n_chunks = (n_cols + 31) / 32;
-      const int row0 = c.m0 + q * 32 + rsub;  // this lane's rows are row0 + 4k
+      // item and first row of this warp's 32-row quarter (a quarter never straddles a segment: seg % 32 == 0)
+      int zq = c.z, rq0 = c.m0 + q * 32;
+      if (kEpi != EPI_WGRAD && p.seg < kBlockM) {
+        seg_coord(p, c.s0 + (q * 32) / p.seg, zq, rq0);
+        rq0 += (q * 32) % p.seg;
+        if (zq >= p.Z) {
+          zq = 0;
+          row_limit = 0;
+        }
+      }
+      const int row0 = rq0 + rsub;  // this lane's rows are row0 + 4k
       const int last_ch = ((n_chunks - 1 - half) & ~1) + half;  // last chunk of this warp (< half: none)
       bool released = false;
       auto release_tmem = [&]() {  // accumulator fully read: the MMA warp may start the next tile into it
@@ -497,8 +556,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
         }
       } else {
-        const int len_z = p.lens ? p.lens[c.z] : 0x7fffffff;
-        const long zoff_o = c.z * p.o_zs + c.n0, zoff_r = c.z * p.r_zs + c.n0, zoff_g = c.z * p.g_zs + c.n0;
+        const int len_z = p.lens ? p.lens[zq] : 0x7fffffff;
+        const long zoff_o = zq * p.o_zs + c.n0, zoff_r = zq * p.r_zs + c.n0, zoff_g = zq * p.g_zs + c.n0;
 
         // x = alpha*acc + bias -> relu -> gate -> dropout(pre) -> + residual   for the 8 float4 of one chunk
         auto finish_chunk = [&](float4 (&t)[8], int n, bool full, int nv) {
@@ -534,7 +593,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 x.w *= gv[k].w > 0.f ? 1.f : p.gate_slope;
               }
               if (p.flags & GEMM_DROP_PRE) {
-                const uint64_t di = (static_cast<uint64_t>(c.z) * p.R + (row0 + 4 * k)) * static_cast<uint64_t>(p.N) + c.n0 + n;
+                const uint64_t di = (static_cast<uint64_t>(zq) * p.R + (row0 + 4 * k)) * static_cast<uint64_t>(p.N) + c.n0 + n;
                 x.x *= dropout_scale(seed, di, p.drop_thresh, p.inv_keep);
                 x.y *= dropout_scale(seed, di + 1, p.drop_thresh, p.inv_keep);
                 x.z *= dropout_scale(seed, di + 2, p.drop_thresh, p.inv_keep);
@@ -641,7 +700,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             rstd[k] = rsqrtf(m2 / fn + p.ln_eps);
             const int row = row0 + 4 * k;
             if (half == 0 && c4 == 0 && row < row_limit) {
-              const long srow = static_cast<long>(c.z) * p.R + row;
+              const long srow = static_cast<long>(zq) * p.R + row;
               if (p.ln_mean) p.ln_mean[srow] = mean[k];
               if (p.ln_rstd) p.ln_rstd[srow] = rstd[k];
             }
@@ -685,7 +744,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               float4 y = make_float4((x[k].x - mean[k]) * rstd[k] * gm.x + bt.x, (x[k].y - mean[k]) * rstd[k] * gm.y + bt.y,
                                      (x[k].z - mean[k]) * rstd[k] * gm.z + bt.z, (x[k].w - mean[k]) * rstd[k] * gm.w + bt.w);
               if (p.flags & GEMM_DROP_POST) {
-                const uint64_t di = (static_cast<uint64_t>(c.z) * p.R + row) * static_cast<uint64_t>(p.N) + c.n0 + n;
+                const uint64_t di = (static_cast<uint64_t>(zq) * p.R + row) * static_cast<uint64_t>(p.N) + c.n0 + n;
                 y.x *= dropout_scale(seed, di, p.drop_thresh, p.inv_keep);
                 y.y *= dropout_scale(seed, di + 1, p.drop_thresh, p.inv_keep);
                 y.z *= dropout_scale(seed, di + 2, p.drop_thresh, p.inv_keep);
@@ -800,6 +859,46 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
   for (int j = 0; j < g.taps; ++j) p.shift[j] = g.shift[j];
   p.b_tap_z = g.b_tap_z;
   p.b_batch_z = g.b_batch_z;
+  const int G = g.groups > 1 ? g.groups : 1;
+  p.groups = G;
+  p.m_step = kBlockM;
+  if (G > 1) {
+    XVA_CHECK_ARG(!(g.flags & GEMM_LN) && g.b_batch_z == 0, "gemm: groups with LayerNorm / batched B");
+    if (g.mode == 0) {
+      XVA_CHECK_ARG(g.N % G == 0 && (g.N / G) % 16 == 0 && g.N / G <= 256, "gemm: grouped fwd needs N/G %% 16 == 0, <= 256 (N=%d G=%d)", g.N, G);
+      p.grp_a = g.grp_step;
+    } else if (g.mode == 1) {
+      XVA_CHECK_ARG(g.N % G == 0 && (g.N / G) % 32 == 0 && g.N / G <= 256 && g.K % 32 == 0,
+                    "gemm: grouped dgrad needs N/G %% 32 == 0, <= 256 and K %% 32 == 0 (N=%d K=%d G=%d)", g.N, g.K, G);
+      p.grp_a = g.K;
+      p.grp_bk = g.K;
+    } else {
+      XVA_CHECK_ARG(g.M % G == 0 && (g.M / G) % 32 == 0 && g.M / G <= kBlockM && g.grp_step % 32 == 0 && g.N <= 256,
+                    "gemm: grouped wgrad needs M/G %% 32 == 0, <= 128, grp_step %% 32 == 0, N <= 256 (M=%d N=%d G=%d)", g.M, g.N, G);
+      p.grp_a = g.grp_step;
+      p.m_step = g.M / G;
+    }
+  }
+
+  // ---- segmented row tiles (mode 0/1, B shared by all items): pick the segment length that needs the fewest tiles
+  p.seg = kBlockM;
+  p.segs = ceil_div(g.R, kBlockM);
+  int row_tiles = (g.mode != 2) ? g.Z * ceil_div(g.R, kBlockM) : 0;
+  static const bool seg_enabled = [] {
+    const char* e = getenv("XVA_GEMM_SEG");
+    return !(e && e[0] == '0');
+  }();
+  if (seg_enabled && g.mode != 2 && g.b_batch_z == 0 && g.Z > 1) {
+    for (int sg = 64; sg >= 32; sg >>= 1) {
+      const int t = ceil_div(g.Z * ceil_div(g.R, sg), kBlockM / sg);
+      if (t < row_tiles) {
+        row_tiles = t;
+        p.seg = sg;
+        p.segs = ceil_div(g.R, sg);
+      }
+    }
+  }
+  p.tot_segs = g.Z * p.segs;
 
   // ---- tile shape along N
   const bool ln = (g.flags & GEMM_LN) != 0;
@@ -813,8 +912,15 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
   } else {
     int nt_max = 256;
     if (const char* e = getenv("XVA_GEMM_NTILE")) nt_max = atoi(e) >= 16 ? atoi(e) : 256;
+    // small problems: narrower n tiles until every SM has one (a 128x64 tile still feeds the MMA from one A stage)
+    if (g.mode != 2)
+      while (nt_max > 64 && row_tiles * ceil_div(g.N, nt_max) < num_sms()) nt_max >>= 1;
     p.tiles_n = ceil_div(g.N, nt_max);
     p.n_tile = round_up(ceil_div(g.N, p.tiles_n), n_gran);
+    if (G > 1 && g.mode != 2) {  // one n tile per group
+      p.tiles_n = G;
+      p.n_tile = g.N / G;
+    }
   }
   p.n_mma = ceil_div(p.n_tile, 256);
   p.n_sub = p.n_tile / p.n_mma;
@@ -833,7 +939,6 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
     const char* e = getenv("XVA_GEMM_PAIR");
     return !(e && e[0] == '0');
   }();
-  const int row_tiles = (g.mode != 2) ? g.Z * ceil_div(g.R, kBlockM) : 0;
   const bool pair = pair_enabled && g.mode != 2 && g.b_batch_z == 0 && row_tiles >= 2 &&
                     (g.mode == 0 ? (p.n_sub % 16 == 0) : (p.n_sub % 64 == 0));
   const int cg = pair ? 2 : 1;
@@ -870,7 +975,7 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
                   "gemm: MN-major B with N=%d needs N %% 32 == 0 or a row stride >= %d (got %lld)", g.N,
                   round_up(g.N, 32), (long long)g.b_rs);
     XVA_CHECK_ARG(g.ZR >= 1 && g.Z % g.ZR == 0, "gemm: Z=%d not divisible by ZR=%d", g.Z, g.ZR);
-    p.tiles_m = ceil_div(g.M, kBlockM);
+    p.tiles_m = (G > 1) ? G : ceil_div(g.M, kBlockM);
     p.k_chunks = ceil_div(g.R, kBlockK);
     p.ZR = g.ZR;
     int split = g.split < 1 ? 1 : g.split;
@@ -905,10 +1010,11 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
   if (g.mode != 2) {
     int a_cols = g.K;  // with per-tap column offsets each tap reads columns [a_col, a_col + K) of a wider row
     for (int j = 0; j < g.taps; ++j) a_cols = g.a_col[j] + g.K > a_cols ? g.a_col[j] + g.K : a_cols;
+    a_cols += (G - 1) * p.grp_a;
     // (a ragged last k-block then reads real neighbouring columns of A; they meet zero-filled rows of B)
     uint64_t dims[3] = {(uint64_t)a_cols, (uint64_t)a_rows, (uint64_t)g.Z};
     uint64_t str[3] = {1, (uint64_t)g.a_rs, (uint64_t)g.a_zs};
-    uint32_t box[3] = {kBlockK, kBlockM, 1};
+    uint32_t box[3] = {kBlockK, (uint32_t)p.seg, 1};
     if (g.Z == 1 || str[2] == 0) str[2] = (uint64_t)g.a_rs * a_rows;
     if ((rc = encode_map(&map_a, g.a, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) != XVA_OK) return rc;
   } else {
@@ -929,8 +1035,8 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
     XVA_CHECK_ARG(g.N % 32 == 0 || g.b_rs >= round_up(g.N, 32),
                   "gemm: MN-major B with N=%d needs N %% 32 == 0 or a row stride >= %d (got %lld)", g.N,
                   round_up(g.N, 32), (long long)g.b_rs);
-    const int bk_rows = g.b_rows ? g.b_rows : g.K;
-    uint64_t dims[4] = {32, (uint64_t)bk_rows, (uint64_t)ceil_div(g.N, 32), (uint64_t)g.b_nz};
+    const int bk_rows = g.b_rows ? g.b_rows : g.K * G;
+    uint64_t dims[4] = {32, (uint64_t)bk_rows, (uint64_t)ceil_div(G > 1 ? g.N / G : g.N, 32), (uint64_t)g.b_nz};
     uint64_t str[4] = {1, (uint64_t)g.b_rs, 32, (uint64_t)g.b_zs};
     uint32_t box[4] = {32, kBlockK, (uint32_t)(pair ? p.n_sub / 64 : p.n_tile / 32), 1};
     if (g.b_nz == 1 || str[3] == 0) str[3] = (uint64_t)g.b_rs * bk_rows;
@@ -942,6 +1048,7 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
       XVA_CHECK_ARG(g.a_col[j] % 32 == 0, "gemm: wgrad column offset %d of tap %d is not a multiple of 32", g.a_col[j], j);
       b_cols = g.a_col[j] + g.N > b_cols ? g.a_col[j] + g.N : b_cols;
     }
+    b_cols += (G - 1) * p.grp_a;
     uint64_t dims[4] = {32, (uint64_t)b_rows, (uint64_t)ceil_div(b_cols, 32), (uint64_t)g.Z};
     uint64_t str[4] = {1, (uint64_t)g.b_rs, 32, (uint64_t)g.b_zs};
     uint32_t box[4] = {32, kBlockK, (uint32_t)(p.n_tile / 32), 1};

@@ -202,13 +202,22 @@ class Generator(nn.Module):
         if ctx is None:
             raise RuntimeError("backward() needs a forward() in training mode first")
         B, W = ctx["B"], ctx["W"]
-        gW = {k: tuple(torch.zeros_like(t) for t in v) for k, v in W.items()}
-        gb = {}
+        # one zero-filled buffer for every packed-weight gradient (a single fill instead of one per convolution)
+        flat = torch.zeros(sum(t.numel() for v in W.values() for t in v), device=dy.device, dtype=torch.float32)
+        gW, off = {}, 0
+        for k, v in W.items():
+            views = []
+            for t in v:
+                views.append(flat[off:off + t.numel()].view(t.shape))
+                off += t.numel()
+            gW[k] = tuple(views)
+        mods = dict(self.named_modules())
 
         def bias_grad(name, d, cols, ld=None):
-            out = torch.zeros(cols, device=d.device, dtype=torch.float32)
-            ops.colsum_(d.shape[0] * d.shape[1], cols, ld if ld is not None else d.shape[2], d, out)
-            gb[name] = out
+            b = mods[name].bias
+            if b.grad is None:
+                b.grad = torch.zeros_like(b)
+            ops.colsum_(d.shape[0] * d.shape[1], cols, ld if ld is not None else d.shape[2], d, b.grad)
 
         # conv_post + tanh
         y, a = ctx["y"], ctx["a_last"]
@@ -266,12 +275,6 @@ class Generator(nn.Module):
                 tensors.append(t)
                 grads.append(g_)
         torch.autograd.backward(tensors, grads)
-        for name, m in self.named_modules():
-            if isinstance(m, _WNConv):
-                if m.bias.grad is None:
-                    m.bias.grad = gb[name]
-                else:
-                    m.bias.grad.add_(gb[name])
         self._ctx = None
 
     def _ups_dgrad(self, i, d_up, a_in, slope, W, alpha=1.0 / 3.0):
@@ -445,9 +448,19 @@ class _Disc(nn.Module):
         p = self.period
         return (T, p, 1, p, T, (T + p - 1) // p)
 
+    def _group_geom(self, m):
+        """(Gp, Ogp, Cgp): launch-level grouping of a layer. Groups with fewer than 32 input channels are merged f at
+        a time into super-groups with a block-diagonal filter (zeros off the diagonal), so that every k-block the
+        tensor core reads is 32 real channels wide and one launch covers the whole layer (xva_gemm_args.groups)."""
+        G, Og, Cg = m.groups, m.cout // m.groups, m.cin // m.groups
+        f = max(1, 32 // Cg) if G > 1 else 1
+        if G % f:
+            raise NotImplementedError(f"groups={G} with {Cg} channels per group")
+        return G // f, Og * f, Cg * f, f
+
     def _packed(self):
-        """per layer: list over groups of packed weights [k (phase-major), Og, max(Cg, 32)] (autograd), for layers >= 1
-        and conv_post; layer 0 uses its [Cout, k] weight directly."""
+        """per layer: packed weight [k (phase-major), Cout, Cgp] (autograd) for layers >= 1 and conv_post; layer 0 uses
+        its [Cout, k] weight directly."""
         out = []
         for li, m in enumerate(list(self.convs) + [self.conv_post]):
             w = m.weight()
@@ -456,26 +469,33 @@ class _Disc(nn.Module):
                 continue
             if getattr(m, "_order_idx", None) is None or m._order_idx.device != w.device:
                 m._order_idx = torch.tensor([j for j, _, _ in m.taps()], device=w.device, dtype=torch.long)
+                Gp, Ogp, Cgp, f = self._group_geom(m)
+                Og = m.cout // m.groups
+                slot = (torch.arange(m.cout, device=w.device) // Og) % f
+                m._slot_mask = (slot[:, None] == torch.arange(f, device=w.device)[None, :]).to(torch.float32)[:, :, None]
             order = m._order_idx          # cached on the device: no host->device copy inside a captured step
-            G, Og, Cg = m.groups, m.cout // m.groups, m.cin // m.groups
-            Cgp = max(Cg, 32)
-            per_group = []
-            for g_ in range(G):
-                wg = w[g_ * Og:(g_ + 1) * Og].index_select(2, order).permute(2, 0, 1)   # [k, Og, Cg]
-                if Cgp != Cg:
-                    wg = torch.nn.functional.pad(wg, (0, Cgp - Cg))
-                per_group.append(wg.contiguous())
-            out.append(per_group)
+            Gp, Ogp, Cgp, f = self._group_geom(m)
+            wk = w.index_select(2, order).permute(2, 0, 1)                       # [k, Cout, Cg]
+            if f > 1:
+                wk = (wk.unsqueeze(2) * m._slot_mask).reshape(m.k, m.cout, Cgp)  # block-diagonal super-groups
+            out.append(wk.contiguous())
         return out
 
-    def forward(self, wave, keep=True):
+    def _lens(self, Z, L, dev):
+        key = (Z, L)
+        cache = self.__dict__.setdefault("_lens_cache", {})
+        if key not in cache:
+            cache[key] = torch.full((Z,), L, device=dev, dtype=torch.int32)
+        return cache[key]
+
+    def forward(self, wave, keep=True, weight_grad=True):
         """wave [B, T] fp32 -> (score [Z, L, 1], fmaps [activation buffers + score], ctx)."""
         B, T = wave.shape
         geom = self._geom(T)
         P, L = geom[3], geom[5]
         Z = B * P
-        packed = self._packed()
-        rounded = lambda t: _rounded(t)
+        with torch.set_grad_enabled(weight_grad and torch.is_grad_enabled()):
+            packed = self._packed()
         layers = list(self.convs)
         m0 = layers[0]
         L0 = m0.out_len(L)
@@ -491,20 +511,19 @@ class _Disc(nn.Module):
             s_next = layers[li + 1].stride if li + 1 < len(layers) else 1
             Lp_out = _round_up(Lout, s_next)
             out = torch.empty(Z, Lp_out, m.cout, device=wave.device, dtype=torch.float32)
-            lens_t = torch.full((Z,), Lout, device=wave.device, dtype=torch.int32)
-            wr = [rounded(w) for w in packed[li]]
+            wr = _rounded(packed[li])
             Wr.append(wr)
-            self._layer_fwd(m, X, wr, out, Lp_out, lens_t)
+            self._layer_fwd(m, X, wr, out, Lp_out, self._lens(Z, Lout, wave.device))
             X = out
             acts.append(X)
             lens_v.append(Lout)
         mp = self.conv_post
-        wrp = [rounded(w) for w in packed[-1]]
+        wrp = _rounded(packed[-1])
         Wr.append(wrp)
         Lf = lens_v[-1]
         score = torch.empty(Z, Lf, 1, device=wave.device, dtype=torch.float32)
         taps = mp.taps()
-        ops.conv_fwd(X, wrp[0][..., :mp.cin], [sh for _, sh, _ in taps], out=score, out_rows=Lf, bias=mp.bias.detach())
+        ops.conv_fwd(X, wrp, [sh for _, sh, _ in taps], out=score, out_rows=Lf, bias=mp.bias.detach())
         ctx = dict(wave=wave, geom=geom, Z=Z, acts=acts, lens=lens_v, packed=packed, Wr=Wr, score=score) if keep else None
         return score, acts + [score], ctx
 
@@ -513,13 +532,19 @@ class _Disc(nn.Module):
         s = m.stride
         xv = X.view(Z, Lp_in // s, s * Cin)
         taps = m.taps()
-        shifts = [sh for _, sh, _ in taps]
-        G, Og, Cg = m.groups, m.cout // m.groups, m.cin // m.groups
-        bias = m.bias.detach()
-        for g_ in range(G):
-            ops.conv_fwd(xv[..., g_ * Cg:], wr[g_][..., :Cg], shifts, a_cols=[ph * Cin for _, _, ph in taps],
-                         out=out[..., g_ * Og:(g_ + 1) * Og], out_rows=Lp_out, lens=lens_t, bias=bias[g_ * Og:(g_ + 1) * Og],
-                         act_slope=LRELU_SLOPE, round_out=True)
+        Gp, Ogp, Cgp, _ = self._group_geom(m)
+        ops.conv_fwd(xv, wr, [sh for _, sh, _ in taps], a_cols=[ph * Cin for _, _, ph in taps], out=out, out_rows=Lp_out,
+                     lens=lens_t, bias=m.bias.detach(), act_slope=LRELU_SLOPE, round_out=True, groups=Gp, grp_step=Cgp)
+
+    @staticmethod
+    def slice_ctx(ctx, lo, hi):
+        """The part of a batched pass that belongs to sequences [lo, hi) (e.g. the generated half of a real + generated
+        batch): views, nothing is copied."""
+        P = ctx["geom"][3]
+        out = dict(ctx)
+        out.update(Z=hi - lo, acts=[a[lo:hi] for a in ctx["acts"]], score=ctx["score"][lo:hi],
+                   wave=ctx["wave"][lo // P:hi // P])
+        return out
 
     def backward(self, ctx, dscore, dfeat, need_w, dwave=None, wave_scale=1.0):
         """dscore [Z, L, 1]: gradient wrt the score; dfeat[l]: gradient wrt the PRE-activation of acts[l] coming from the
@@ -528,8 +553,20 @@ class _Disc(nn.Module):
         Z, acts, lens_v, Wr = ctx["Z"], ctx["acts"], ctx["lens"], ctx["Wr"]
         layers = list(self.convs)
         dev = dscore.device
-        gW = [None] + [[torch.zeros_like(w) for w in Wr[li]] for li in range(1, len(Wr))] if need_w else None
-        gb = {}
+        gW = None
+        if need_w:   # one zero-filled buffer for every packed-weight gradient of this sub-discriminator
+            sizes = [w.numel() for w in Wr[1:]]
+            flat = torch.zeros(sum(sizes), device=dev, dtype=torch.float32)
+            gW, off = [None], 0
+            for w, n in zip(Wr[1:], sizes):
+                gW.append(flat[off:off + n].view(w.shape))
+                off += n
+
+        def bias_grad(m, d, cols, ld):
+            if m.bias.grad is None:
+                m.bias.grad = torch.zeros_like(m.bias)
+            ops.colsum_(d.shape[0] * d.shape[1], cols, ld, d, m.bias.grad)
+
         # conv_post: pad the single score channel to 32 columns (MN-major operand rule)
         mp = self.conv_post
         Lf = lens_v[-1]
@@ -541,11 +578,10 @@ class _Disc(nn.Module):
         taps = mp.taps()
         shifts = [sh for _, sh, _ in taps]
         if need_w:
-            ops.conv_wgrad(d1, X, shifts, out=gW[-1][0][..., :mp.cin], accumulate=True, dy_rows=Lf)
-            gb[len(layers)] = dscore.sum().reshape(1)
-        lens_t = torch.full((Z,), Lf, device=dev, dtype=torch.int32)
-        dpre = ops.conv_dgrad(d1, Wr[-1][0][..., :mp.cin], shifts, out_rows=X.shape[1], gate=X, gate_slope=LRELU_SLOPE,
-                              residual=dfeat[len(layers) - 1], lens=lens_t, round_out=True)
+            ops.conv_wgrad(d1, X, shifts, out=gW[-1], accumulate=True, dy_rows=Lf)
+            bias_grad(mp, dscore.contiguous(), 1, 1)
+        dpre = ops.conv_dgrad(d1, Wr[-1], shifts, out_rows=X.shape[1], gate=X, gate_slope=LRELU_SLOPE,
+                              residual=dfeat[len(layers) - 1], lens=self._lens(Z, Lf, dev), round_out=True)
         for li in range(len(layers) - 1, 0, -1):
             m = layers[li]
             Xin = acts[li - 1]
@@ -553,14 +589,11 @@ class _Disc(nn.Module):
             s = m.stride
             xv = Xin.view(Z, Lp_in // s, s * Cin)
             taps = m.taps()
-            G, Og, Cg = m.groups, m.cout // m.groups, m.cin // m.groups
+            Gp, Ogp, Cgp, _ = self._group_geom(m)
             if need_w:
-                gb_l = torch.zeros(m.cout, device=dev, dtype=torch.float32)
-                ops.colsum_(dpre.shape[0] * dpre.shape[1], m.cout, m.cout, dpre, gb_l)
-                gb[li] = gb_l
-                for g_ in range(G):
-                    ops.conv_wgrad(dpre[..., g_ * Og:(g_ + 1) * Og], xv[..., g_ * Cg:], [sh for _, sh, _ in taps],
-                                   x_cols=[ph * Cin for _, _, ph in taps], n_cols=Cg, out=gW[li][g_][..., :Cg], accumulate=True)
+                bias_grad(m, dpre, m.cout, m.cout)
+                ops.conv_wgrad(dpre, xv, [sh for _, sh, _ in taps], x_cols=[ph * Cin for _, _, ph in taps], n_cols=Cgp,
+                               out=gW[li], accumulate=True, groups=Gp, grp_step=Cgp)
             if li == 1 and dwave is None and not need_w:
                 break
             dX = torch.empty_like(Xin)
@@ -570,37 +603,25 @@ class _Disc(nn.Module):
             for ph in range(s):
                 idx = [i for i, (_, _, p_) in enumerate(taps) if p_ == ph]
                 lo, hi = idx[0], idx[-1] + 1
-                shifts = [taps[i][1] for i in idx]
-                for g_ in range(G):
-                    c0 = ph * Cin + g_ * Cg
-                    ops.conv_dgrad(dpre[..., g_ * Og:(g_ + 1) * Og], Wr[li][g_][lo:hi][..., :Cg], shifts,
-                                   out=dxv[..., c0:c0 + Cg], out_rows=Lp_in // s, gate=xv[..., c0:c0 + Cg],
-                                   gate_slope=LRELU_SLOPE, residual=None if resv is None else resv[..., c0:c0 + Cg],
-                                   round_out=True)
-            ops.zero_tail_rows_(dX, lens_v[li - 1])
+                c0, c1 = ph * Cin, (ph + 1) * Cin
+                ops.conv_dgrad(dpre, Wr[li][lo:hi], [taps[i][1] for i in idx], out=dxv[..., c0:c1], out_rows=Lp_in // s,
+                               gate=xv[..., c0:c1], gate_slope=LRELU_SLOPE,
+                               residual=None if resv is None else resv[..., c0:c1], round_out=True, groups=Gp)
+            if Lp_in > lens_v[li - 1]:
+                ops.zero_tail_rows_(dX, lens_v[li - 1])
             dpre = dX
         # first layer (raw waveform)
         m0 = layers[0]
         w0 = ctx["packed"][0]
         if need_w:
             dw0 = torch.zeros(m0.cout, m0.k, device=dev, dtype=torch.float32)
-            db0 = torch.zeros(m0.cout, device=dev, dtype=torch.float32)
-            ops.conv_c1_bwd_w(dpre, ctx["wave"], ctx["geom"], m0.k, m0.stride, m0.pad, lens_v[0], dw0, db0)
-            gb[0] = db0
+            if m0.bias.grad is None:
+                m0.bias.grad = torch.zeros_like(m0.bias)
+            ops.conv_c1_bwd_w(dpre, ctx["wave"], ctx["geom"], m0.k, m0.stride, m0.pad, lens_v[0], dw0, m0.bias.grad)
         if dwave is not None:
             ops.conv_c1_bwd_x(dpre, w0.detach(), ctx["geom"], m0.k, m0.stride, m0.pad, lens_v[0], wave_scale, dwave)
         if need_w:
-            tensors, grads = [w0], [dw0]
-            for li in range(1, len(Wr)):
-                for t, g_ in zip(ctx["packed"][li], gW[li]):
-                    tensors.append(t)
-                    grads.append(g_)
-            torch.autograd.backward(tensors, grads)
-            for li, m in enumerate(layers + [mp]):
-                if m.bias.grad is None:
-                    m.bias.grad = gb[li]
-                else:
-                    m.bias.grad.add_(gb[li])
+            torch.autograd.backward([w0] + list(ctx["packed"][1:]), [dw0] + gW[1:])
 
 
 def _rounded(t):
@@ -636,8 +657,8 @@ class MultiPeriodDiscriminator(nn.Module):
         self.discriminators = nn.ModuleList([DiscriminatorP(p) for p in (2, 3, 5, 7, 11)])
         _init_disc(self, seed, device)
 
-    def forward(self, y, y_hat):
-        return _multi_forward(self, y, y_hat, pools=0)
+    def forward(self, y, y_hat, weight_grad=True):
+        return _multi_forward(self, y, y_hat, pools=0, weight_grad=weight_grad)
 
 
 class MultiScaleDiscriminator(nn.Module):
@@ -648,8 +669,8 @@ class MultiScaleDiscriminator(nn.Module):
         self.discriminators = nn.ModuleList([DiscriminatorS(use_spectral_norm=True), DiscriminatorS(), DiscriminatorS()])
         _init_disc(self, seed + 1, device)
 
-    def forward(self, y, y_hat):
-        return _multi_forward(self, y, y_hat, pools=1)
+    def forward(self, y, y_hat, weight_grad=True):
+        return _multi_forward(self, y, y_hat, pools=1, weight_grad=weight_grad)
 
 
 def _init_disc(model, seed, device):
@@ -675,24 +696,36 @@ def _init_disc(model, seed, device):
     model.to(dev)
 
 
-def _multi_forward(model, y, y_hat, pools):
-    """Shared by MPD / MSD: every sub-discriminator on the real and the generated waveform ([B, 1, T] or [B, T])."""
-    yr = y.reshape(y.shape[0], -1).to(torch.float32).contiguous()
-    yg = y_hat.reshape(y_hat.shape[0], -1).to(torch.float32).contiguous()
+def _multi_forward(model, y, y_hat, pools, weight_grad=True):
+    """Shared by MPD / MSD: every sub-discriminator on the real and the generated waveform ([B, 1, T] or [B, T]).
+    Weight-normed sub-discriminators see both waveforms as ONE batch of 2B sequences (one launch per layer instead of
+    two); the spectral-normed one (MSD scale 0) runs them one after the other because torch's spectral_norm hook does a
+    power iteration per call, so the reference's two calls (models.py:251-252) use two different weights.
+    model._ctx[i] = list of passes (ctx, rows of the real sequences or None, rows of the generated ones or None)."""
+    yr = y.reshape(y.shape[0], -1).to(torch.float32)
+    yg = y_hat.reshape(y_hat.shape[0], -1).to(torch.float32)
+    B = yr.shape[0]
+    both = torch.cat([yr, yg], 0)
     model._ctx = []
     y_d_rs, y_d_gs, fmap_rs, fmap_gs = [], [], [], []
     for i, d in enumerate(model.discriminators):
-        pooled_from = None
         if pools and i != 0:
-            pooled_from = (yr.shape[1], yg.shape[1])
-            yr, yg = ops.avgpool4(yr), ops.avgpool4(yg)
-        sr, fr, cr = d(yr)
-        sg, fg, cg = d(yg)
+            both = ops.avgpool4(both)
+        if any(m.spectral for m in d.convs):
+            sr, fr, cr = d(both[:B], weight_grad=weight_grad)
+            sg, fg, cg = d(both[B:], weight_grad=weight_grad)
+            passes = [(cr, (0, cr["Z"]), None), (cg, None, (0, cg["Z"]))]
+        else:
+            s2, f2, c2 = d(both, weight_grad=weight_grad)
+            Z = c2["Z"] // 2
+            sr, sg = s2[:Z], s2[Z:]
+            fr, fg = [f[:Z] for f in f2], [f[Z:] for f in f2]
+            passes = [(c2, (0, Z), (Z, 2 * Z))]
         y_d_rs.append(sr)
         y_d_gs.append(sg)
         fmap_rs.append(fr)
         fmap_gs.append(fg)
-        model._ctx.append((cr, cg, pooled_from))
+        model._ctx.append(passes)
     return y_d_rs, y_d_gs, fmap_rs, fmap_gs
 
 
@@ -703,15 +736,19 @@ def discriminator_loss_backward(model, y_d_rs, y_d_gs):
     dev = y_d_rs[0].device
     acc = torch.zeros(2 * len(y_d_rs), device=dev, dtype=torch.float64)
     loss = torch.zeros((), device=dev, dtype=torch.float64)
-    for i, (d, (cr, cg, _)) in enumerate(zip(model.discriminators, model._ctx)):
+    for i, (d, passes) in enumerate(zip(model.discriminators, model._ctx)):
         dr, dg = y_d_rs[i], y_d_gs[i]
         n = dr.numel()
         ops.reduce_sq(dr, 1.0, acc[2 * i:2 * i + 1])
         ops.reduce_sq(dg, 0.0, acc[2 * i + 1:2 * i + 2])
         loss = loss + (acc[2 * i] + acc[2 * i + 1]) / n
-        none = [None] * len(cr["acts"])
-        d.backward(cr, ops.sq_grad(dr, 1.0, 1.0 / n), none, need_w=True)
-        d.backward(cg, ops.sq_grad(dg, 0.0, 1.0 / n), none, need_w=True)
+        for ctx, rr, gr in passes:
+            dscore = torch.empty_like(ctx["score"])
+            if rr is not None:
+                ops.sq_grad(dr, 1.0, 1.0 / n, out=dscore[rr[0]:rr[1]], accumulate=False)
+            if gr is not None:
+                ops.sq_grad(dg, 0.0, 1.0 / n, out=dscore[gr[0]:gr[1]], accumulate=False)
+            d.backward(ctx, dscore, [None] * len(ctx["acts"]), need_w=True)
     return loss
 
 
@@ -732,7 +769,10 @@ def generator_adv_loss_backward(model, y_d_gs, fmap_rs, fmap_gs, dwave, pools):
             levels.append(torch.zeros(dwave.shape[0], L // 2 + 1, device=dev, dtype=torch.float32))
     for i in reversed(range(n_d)):
         d = model.discriminators[i]
-        cr, cg, _ = model._ctx[i]
+        cg = None
+        for ctx, rr, gr in model._ctx[i]:          # the pass (or the half of the batched pass) of the generated waveform
+            if gr is not None:
+                cg = ctx if rr is None else _Disc.slice_ctx(ctx, gr[0], gr[1])
         dg = y_d_gs[i]
         n = dg.numel()
         ops.reduce_sq(dg, 1.0, acc[16 * i:16 * i + 1])
@@ -845,9 +885,9 @@ class HiFiGANStep:
         ops.reduce_l1(mel_tgt, mel_hat, acc)
         loss_mel = 45.0 * acc[0] / n
         dwave = self.mel.backward(ops.l1_grad(mel_tgt, mel_hat, 45.0 / n))
-        rs, gs, frs, fgs = mpd(y, wave)
+        rs, gs, frs, fgs = mpd(y, wave, weight_grad=False)
         loss_gen_f, loss_fm_f = generator_adv_loss_backward(mpd, gs, frs, fgs, dwave, pools=False)
-        rs, gs, frs, fgs = msd(y, wave)
+        rs, gs, frs, fgs = msd(y, wave, weight_grad=False)
         loss_gen_s, loss_fm_s = generator_adv_loss_backward(msd, gs, frs, fgs, dwave, pools=True)
         G.backward(dwave.view(B, 1, -1))
         self.optim_g.step()

@@ -93,24 +93,26 @@ def _epilogue(g, out, bias=None, relu=False, gate=None, gate_slope=0.0, residual
     return keep, extra
 
 
-def conv_fwd(x, wp, shifts=(0,), out=None, ref=False, a_cols=None, out_rows=None, **epi):
+def conv_fwd(x, wp, shifts=(0,), out=None, ref=False, a_cols=None, out_rows=None, groups=1, grp_step=0, **epi):
     """out[b,t,n] = sum_j sum_k x[b, t+shifts[j], a_cols[j]+k] * wp[j, n, k]  (+ epilogue).
     x [B,T,Kx], wp [taps,N,K]; a_cols (per-tap column offsets into x's rows, default 0) lets a strided convolution
-    run on the [T/stride, stride*C] view of its input."""
+    run on the [T/stride, stride*C] view of its input. groups > 1: grouped convolution in one launch -- output columns
+    [g*N/groups, (g+1)*N/groups) read x columns a_cols[j] + g*grp_step + [0, K) (xva_gemm_args.groups)."""
     _check3(x, "x")
     _check3(wp, "wp")
     B, T, Kx = x.shape
     taps, N, K = wp.shape
-    assert taps == len(shifts) and (a_cols is not None or Kx == K)
+    assert taps == len(shifts) and (a_cols is not None or groups > 1 or Kx == K)
     R = T if out_rows is None else int(out_rows)   # output rows per item; x keeps its own row count (a_rows)
     if out is None:
         out = torch.empty(B, R, N, device=x.device, dtype=torch.float32)
     g = _base_args(0, shifts)
     if a_cols is not None:
         for j, c in enumerate(a_cols):
-            assert c + K <= Kx
+            assert c + (groups - 1) * grp_step + K <= Kx
             g.a_col[j] = int(c)
     g.Z, g.R, g.N, g.K = B, R, N, K
+    g.groups, g.grp_step = int(groups), int(grp_step)
     g.a, g.a_rs, g.a_zs, g.a_rows = _p(x), x.stride(1), x.stride(0), T
     g.b, g.b_rs, g.b_zs, g.b_nz, g.b_tap_z = _p(wp), wp.stride(1), wp.stride(0), taps, 1
     keep, extra = _epilogue(g, out, **epi)
@@ -118,9 +120,10 @@ def conv_fwd(x, wp, shifts=(0,), out=None, ref=False, a_cols=None, out_rows=None
     return (out, extra) if extra else out
 
 
-def conv_dgrad(dy, wp, shifts=(0,), out=None, ref=False, out_rows=None, **epi):
+def conv_dgrad(dy, wp, shifts=(0,), out=None, ref=False, out_rows=None, groups=1, **epi):
     """dx[b,t,k] = sum_j sum_n dy[b, t-shifts[j], n] * wp[j, n, k]: input gradient of conv_fwd, same packed weights
-    read MN-major (no transposed copy).  dy [B,T,N], wp [taps,N,K]."""
+    read MN-major (no transposed copy).  dy [B,T,N], wp [taps,N,K]. groups > 1: wp's rows [g*N/groups, ...) are group
+    g's filters and its K columns the group's input channels; dx has groups*K columns."""
     _check3(dy, "dy")
     _check3(wp, "wp")
     B, T, N = dy.shape
@@ -128,9 +131,10 @@ def conv_dgrad(dy, wp, shifts=(0,), out=None, ref=False, out_rows=None, **epi):
     assert N2 == N and taps == len(shifts)
     R = T if out_rows is None else int(out_rows)
     if out is None:
-        out = torch.empty(B, R, K, device=dy.device, dtype=torch.float32)
+        out = torch.empty(B, R, K * groups, device=dy.device, dtype=torch.float32)
     g = _base_args(1, [-s for s in shifts])
-    g.Z, g.R, g.N, g.K = B, R, K, N
+    g.Z, g.R, g.N, g.K = B, R, K * groups, N // groups
+    g.groups = int(groups)
     g.a, g.a_rs, g.a_zs, g.a_rows = _p(dy), dy.stride(1), dy.stride(0), T
     g.b, g.b_rs, g.b_zs, g.b_nz, g.b_tap_z = _p(wp), wp.stride(1), wp.stride(0), taps, 1
     keep, extra = _epilogue(g, out, **epi)
@@ -139,7 +143,7 @@ def conv_dgrad(dy, wp, shifts=(0,), out=None, ref=False, out_rows=None, **epi):
 
 
 def conv_wgrad(dy, x, shifts=(0,), out=None, accumulate=False, split=None, ref=False, x_cols=None, n_cols=None,
-               dy_rows=None):
+               dy_rows=None, groups=1, grp_step=0):
     """dw[j,n,k] (+)= sum_b sum_t dy[b,t,n] * x[b, t+shifts[j], k]: weight gradient of conv_fwd in the packed layout.
     dy [B,T,N], x [B,T,K] -> dw [taps,N,K].  N and K must be multiples of 32."""
     _check3(dy, "dy")
@@ -161,8 +165,9 @@ def conv_wgrad(dy, x, shifts=(0,), out=None, accumulate=False, split=None, ref=F
     g.a, g.a_rs, g.a_zs, g.a_rows = _p(dy), dy.stride(1), dy.stride(0), (T if dy_rows is None else int(dy_rows))
     g.b, g.b_rs, g.b_zs, g.b_rows = _p(x), x.stride(1), x.stride(0), T2
     g.out, g.o_rs, g.o_zs, g.o_js = _p(out), out.stride(1), 0, out.stride(0)
+    g.groups, g.grp_step = int(groups), int(grp_step)
     if split is None:
-        tiles = taps * ((N + 127) // 128) * ((K + 255) // 256)
+        tiles = taps * (groups if groups > 1 else (N + 127) // 128) * ((K + 255) // 256)
         split = max(1, min(B, (2 * 148) // max(tiles, 1)))
     g.split = split if accumulate else 1
     g.flags = capi.GEMM_ATOMIC if accumulate else 0
@@ -473,9 +478,9 @@ def l1_grad(a, b, scale, out=None, gate_slope=1.0):
     return out
 
 
-def sq_grad(a, c, scale, out=None):
-    """scale * d(sum (c - a)^2)/da = 2 scale (a - c); accumulated into ``out`` when given."""
-    acc = out is not None
+def sq_grad(a, c, scale, out=None, accumulate=True):
+    """scale * d(sum (c - a)^2)/da = 2 scale (a - c); accumulated into ``out`` when given (unless accumulate=False)."""
+    acc = out is not None and accumulate
     if out is None:
         out = torch.empty_like(a)
     capi.call("xva_loss_grad", _p(a), None, a.numel(), 1, float(c), float(scale), 1.0, int(acc), _p(out), _stream())
