@@ -177,6 +177,13 @@ int xva_layernorm_bwd(const float* dy, const float* x, const float* mean, const 
                       float* dbeta, float* dbias, float drop_post_p, uint64_t seed_post, float drop_pre_p,
                       uint64_t seed_pre, const uint64_t* seed_dev, int relu_gate, void* stream);
 
+/* nn.LayerNorm forward (transformer.py:75,148) on a stored pre-LN tensor x [Z,R,C] (C % 4 == 0, <= 512):
+ * y = ((x - mean) * rstd * gamma + beta) for rows r < lens[z] (lens optional), zero otherwise, stored tf32-rounded (it is
+ * the next GEMM's operand); mean / rstd [Z*R] are saved for xva_layernorm_bwd. The FFT blocks use this after a GEMM
+ * whose epilogue did bias + dropout + residual: un-fused, the GEMM keeps double-buffered accumulators. */
+int xva_layernorm_fwd(const float* x, const float* gamma, const float* beta, const int32_t* lens, int Z, int R, int C,
+                      float eps, float* y, float* mean, float* rstd, void* stream);
+
 /* Test switch, default on: 0 makes every kernel store GEMM operands unrounded (and xva_round_tf32 a plain copy), so
  * that the exact-fp32 checker xva_gemm_ref reproduces an fp32 reference to rounding. Not for production use:
  * the tensor-core path then truncates its operands. Synchronous (cudaMemcpyToSymbol). */

@@ -66,6 +66,7 @@ PROTOTYPES = {
     "xva_softmax_fwd": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _F, _U64, _P, _P]),
     "xva_softmax_bwd": (_I, [_P, _P, _I, _I, _I, _I, _F, _F, _U64, _P, _P]),
     "xva_layernorm_bwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _F, _U64, _F, _U64, _P, _I, _P]),
+    "xva_layernorm_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _F, _P, _P, _P, _P]),
     "xva_counter_add": (_I, [_P, _U64, _P]),
     "xva_colsum": (_I, [_P, _I64, _I, _I64, _P, _P]),
     "xva_embed_pos": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P]),

@@ -78,6 +78,11 @@ int xva_layernorm_bwd(const float* dy, const float* x, const float* mean, const 
                        seed_post, drop_pre_p, seed_pre, seed_dev, relu_gate, S(stream));
 }
 
+int xva_layernorm_fwd(const float* x, const float* gamma, const float* beta, const int32_t* lens, int Z, int R, int C,
+                      float eps, float* y, float* mean, float* rstd, void* stream) {
+  return layernorm_fwd(x, gamma, beta, lens, Z, R, C, eps, y, mean, rstd, S(stream));
+}
+
 int xva_set_operand_rounding(int on) {
   int rc;
   if ((rc = set_operand_rounding_gemm_tc(on)) != XVA_OK) return rc;

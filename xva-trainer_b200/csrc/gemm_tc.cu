@@ -42,7 +42,9 @@ struct GemmDev {
   int groups;     // > 1: grouped convolution, the n tile (mode 0/1) or m tile (mode 2) index is the group
   int grp_a;      // mode 0/1: A column step per group; mode 2: B column step per group
   int grp_bk;     // mode 1: B row (contraction) step per group
-  int m_step;     // mode 2: output rows between consecutive m tiles (kBlockM, or Og when grouped)
+  int gpt;        // grouped mode 2: groups per 128-row m tile (= 128 / Og); the tile computes the dense
+                  // [gpt*Og, gpt*Cg] product of its groups and stores only the gpt diagonal [Og, Cg] blocks
+  int og, cg;     // grouped mode 2: output rows / columns per group
   // Segmented row tiles (mode 0/1): a 128-row tile is made of 128/seg segments of `seg` consecutive rows, taken in
   // (item, segment) order, so short sequences (R = 160 tokens, or the 10..83-row period columns of DiscriminatorP)
   // share tiles instead of padding each item to a multiple of 128 rows. seg = 128: one segment = the classic tile.
@@ -117,8 +119,8 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmDev& p, int t, int ct
     t /= p.tiles_m;
   }
   c.n0 = n_t * p.n_tile;
-  c.m0 = (p.mode != 2) ? m_t * kBlockM : m_t * p.m_step;
-  c.g = (p.groups > 1) ? ((p.mode != 2) ? n_t : m_t) : 0;
+  c.m0 = m_t * kBlockM;
+  c.g = (p.groups > 1) ? ((p.mode != 2) ? n_t : m_t * p.gpt) : 0;
   if (p.mode != 2) {
     c.z = t;
     c.z_end = t + 1;
@@ -498,7 +500,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const uint32_t tacc = tmem_base + acc * 256 + lane_base;
 
       int row_limit = (c.dup || (p.dbg & 1)) ? 0 : ((kEpi == EPI_WGRAD) ? p.M : p.R);
-      if (kEpi == EPI_WGRAD && p.groups > 1 && row_limit > c.m0 + p.m_step) row_limit = c.m0 + p.m_step;
       const int n_cols = (p.N - c.n0) < p.n_tile ? (p.N - c.n0) : p.n_tile;  // valid columns of this tile
       const int n_chunks = (n_cols + 31) / 32;
       // item and first row of this warp's 32-row quarter (a quarter never straddles a segment: seg % 32 == 0)
@@ -526,7 +527,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
       if constexpr (kEpi == EPI_WGRAD) {
         float* obase = p.out + c.zo * p.o_zs + c.j * p.o_js + c.n0;
+        // grouped: this warp's 32 rows belong to group gi of the tile; only its diagonal block is stored
+        int ch_lo = 0, ch_hi = n_chunks, col_shift = 0;
+        if (p.groups > 1) {
+          const int gi = (q * 32) / p.og;
+          ch_lo = gi * p.cg / 32;
+          ch_hi = ch_lo + p.cg / 32;
+          col_shift = gi * p.cg;
+        }
         for (int ch = half; ch < n_chunks; ch += 2) {
+          if (ch < ch_lo || ch >= ch_hi) continue;  // warp-uniform
           float4 t[8];
           load_chunk(tacc + ch * 32, t);
           if (ch == last_ch) release_tmem();
@@ -537,7 +547,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           for (int k = 0; k < 8; ++k) {
             const int row = row0 + 4 * k;
             if (row >= row_limit || nv == 0) continue;
-            float* dst = obase + static_cast<long>(row) * p.o_rs + n;
+            float* dst = obase + static_cast<long>(row) * p.o_rs + (n - col_shift);
             const float4 o = make_float4(p.alpha * t[k].x, p.alpha * t[k].y, p.alpha * t[k].z, p.alpha * t[k].w);
             if (p.flags & GEMM_ATOMIC) {
               if (full) {
@@ -594,10 +604,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               }
               if (p.flags & GEMM_DROP_PRE) {
                 const uint64_t di = (static_cast<uint64_t>(zq) * p.R + (row0 + 4 * k)) * static_cast<uint64_t>(p.N) + c.n0 + n;
-                x.x *= dropout_scale(seed, di, p.drop_thresh, p.inv_keep);
-                x.y *= dropout_scale(seed, di + 1, p.drop_thresh, p.inv_keep);
-                x.z *= dropout_scale(seed, di + 2, p.drop_thresh, p.inv_keep);
-                x.w *= dropout_scale(seed, di + 3, p.drop_thresh, p.inv_keep);
+                const float4 ds = dropout_scale4(seed, di, p.drop_thresh, p.inv_keep);
+                x.x *= ds.x; x.y *= ds.y; x.z *= ds.z; x.w *= ds.w;
               }
               if (p.residual) {
                 x.x += rv[k].x; x.y += rv[k].y; x.z += rv[k].z; x.w += rv[k].w;
@@ -745,10 +753,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                                      (x[k].z - mean[k]) * rstd[k] * gm.z + bt.z, (x[k].w - mean[k]) * rstd[k] * gm.w + bt.w);
               if (p.flags & GEMM_DROP_POST) {
                 const uint64_t di = (static_cast<uint64_t>(zq) * p.R + row) * static_cast<uint64_t>(p.N) + c.n0 + n;
-                y.x *= dropout_scale(seed, di, p.drop_thresh, p.inv_keep);
-                y.y *= dropout_scale(seed, di + 1, p.drop_thresh, p.inv_keep);
-                y.z *= dropout_scale(seed, di + 2, p.drop_thresh, p.inv_keep);
-                y.w *= dropout_scale(seed, di + 3, p.drop_thresh, p.inv_keep);
+                const float4 ds = dropout_scale4(seed, di, p.drop_thresh, p.inv_keep);
+                y.x *= ds.x; y.y *= ds.y; y.z *= ds.z; y.w *= ds.w;
               }
               if (row >= len_z) y = make_float4(0.f, 0.f, 0.f, 0.f);
               if (p.flags & GEMM_ROUND_OUT) y = tf32_rn4(y);
@@ -861,7 +867,6 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
   p.b_batch_z = g.b_batch_z;
   const int G = g.groups > 1 ? g.groups : 1;
   p.groups = G;
-  p.m_step = kBlockM;
   if (G > 1) {
     XVA_CHECK_ARG(!(g.flags & GEMM_LN) && g.b_batch_z == 0, "gemm: groups with LayerNorm / batched B");
     if (g.mode == 0) {
@@ -873,10 +878,16 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
       p.grp_a = g.K;
       p.grp_bk = g.K;
     } else {
-      XVA_CHECK_ARG(g.M % G == 0 && (g.M / G) % 32 == 0 && g.M / G <= kBlockM && g.grp_step % 32 == 0 && g.N <= 256,
-                    "gemm: grouped wgrad needs M/G %% 32 == 0, <= 128, grp_step %% 32 == 0, N <= 256 (M=%d N=%d G=%d)", g.M, g.N, G);
+      const int og = g.M / G;
+      XVA_CHECK_ARG(g.M % G == 0 && (og == 32 || og == 64 || og == 128) && g.grp_step == g.N && g.N % 32 == 0 &&
+                        (kBlockM / og) * g.N <= 256,
+                    "gemm: grouped wgrad needs M/G in {32, 64, 128}, N %% 32 == 0, grp_step == N, (128/Og)*N <= 256 "
+                    "(M=%d N=%d G=%d grp_step=%d)", g.M, g.N, G, g.grp_step);
       p.grp_a = g.grp_step;
-      p.m_step = g.M / G;
+      p.og = og;
+      p.cg = g.N;
+      p.gpt = kBlockM / og;
+      p.N = p.gpt * g.N;  // columns of one tile: the groups of a 128-row m tile side by side
     }
   }
 
@@ -912,11 +923,31 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
   } else {
     int nt_max = 256;
     if (const char* e = getenv("XVA_GEMM_NTILE")) nt_max = atoi(e) >= 16 ? atoi(e) : 256;
-    // small problems: narrower n tiles until every SM has one (a 128x64 tile still feeds the MMA from one A stage)
-    if (g.mode != 2)
-      while (nt_max > 64 && row_tiles * ceil_div(g.N, nt_max) < num_sms()) nt_max >>= 1;
-    p.tiles_n = ceil_div(g.N, nt_max);
-    p.n_tile = round_up(ceil_div(g.N, p.tiles_n), n_gran);
+    // Small problems leave SMs idle at 256-wide tiles. Narrower tiles add parallelism but re-read A once per n tile,
+    // so pick the width that minimises  waves x k-step time,  k-step = max(operand fetch, MMA) in SM clocks:
+    // fetch = (16 KiB of A + the B tile, halved when a CTA pair shares it) at ~64 B/clk from L2; MMA = 2 clk per column.
+    static const bool fill_enabled = [] {
+      const char* e = getenv("XVA_GEMM_FILL");
+      return !(e && e[0] == '0');
+    }();
+    if (g.mode != 2 && fill_enabled && !getenv("XVA_GEMM_NTILE")) {
+      const bool can_pair = g.b_batch_z == 0 && row_tiles >= 2;
+      const int slots = can_pair ? num_sms() / 2 : num_sms();
+      const int units = can_pair ? ceil_div(row_tiles, 2) : row_tiles;
+      long best = -1;
+      for (int cand = 256; cand >= 64; cand >>= 1) {
+        const int tn = ceil_div(g.N, cand);
+        const int nt = round_up(ceil_div(g.N, tn), n_gran);
+        const long fetch = 256 + (can_pair ? nt : 2 * nt), mma = 2L * nt;
+        const long cost = static_cast<long>(ceil_div(units * tn, slots)) * (fetch > mma ? fetch : mma);
+        if (best < 0 || cost < best) {
+          best = cost;
+          nt_max = cand;
+        }
+      }
+    }
+    p.tiles_n = ceil_div(p.N, nt_max);
+    p.n_tile = round_up(ceil_div(p.N, p.tiles_n), n_gran);
     if (G > 1 && g.mode != 2) {  // one n tile per group
       p.tiles_n = G;
       p.n_tile = g.N / G;
@@ -975,7 +1006,7 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
                   "gemm: MN-major B with N=%d needs N %% 32 == 0 or a row stride >= %d (got %lld)", g.N,
                   round_up(g.N, 32), (long long)g.b_rs);
     XVA_CHECK_ARG(g.ZR >= 1 && g.Z % g.ZR == 0, "gemm: Z=%d not divisible by ZR=%d", g.Z, g.ZR);
-    p.tiles_m = (G > 1) ? G : ceil_div(g.M, kBlockM);
+    p.tiles_m = ceil_div(g.M, kBlockM);
     p.k_chunks = ceil_div(g.R, kBlockK);
     p.ZR = g.ZR;
     int split = g.split < 1 ? 1 : g.split;

@@ -202,6 +202,287 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
   block_colsum_atomic<kColsPerLane>(acc_bias, red, C, dbias, 1);
 }
 
+// ------------------------------------------------------------------------------------------------ float4 variants
+// Same math as the scalar kernels above with 16-byte accesses (lane l owns float4 l + 32 i of its row) and one
+// dropout hash per float4. Used whenever the row stride is a multiple of 4 and the pointers are 16-byte aligned.
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+template <int kV4>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+softmax_fwd_v4_kernel(const float* __restrict__ s, const int* __restrict__ lens, int R, int N, int ld, long rows,
+                      float* __restrict__ p_out, float* __restrict__ pd_out, uint64_t seed,
+                      const uint64_t* __restrict__ seed_dev, uint32_t thresh, float inv_keep) {
+  const int lane = threadIdx.x & 31;
+  seed += seed_dev ? __ldg(seed_dev) * kSeedStep : 0ull;
+  const long row = static_cast<long>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int z = static_cast<int>(row / R);
+  const int nk = lens ? min(lens[z], N) : N;
+  const float* src = s + row * ld;
+  float4 v[kV4];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < kV4; ++i) {
+    const int n = 4 * (lane + 32 * i);
+    v[i] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    if (n < nk) {  // columns >= nk (masked keys, and the never-written pad columns) are not used
+      const float4 t = ld4(src + n);
+      v[i].x = t.x;
+      if (n + 1 < nk) v[i].y = t.y;
+      if (n + 2 < nk) v[i].z = t.z;
+      if (n + 3 < nk) v[i].w = t.w;
+    }
+    mx = fmaxf(fmaxf(mx, fmaxf(v[i].x, v[i].y)), fmaxf(v[i].z, v[i].w));
+  }
+  mx = warp_max(mx);
+  float sum = 0.0f;
+#pragma unroll
+  for (int i = 0; i < kV4; ++i) {  // expf(-inf) = 0 for the masked columns
+    v[i] = make_float4(expf(v[i].x - mx), expf(v[i].y - mx), expf(v[i].z - mx), expf(v[i].w - mx));
+    sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  sum = warp_sum(sum);
+  const float inv = 1.0f / sum;
+#pragma unroll
+  for (int i = 0; i < kV4; ++i) {
+    const int n = 4 * (lane + 32 * i);
+    if (n < ld) {  // pad columns [N, ld) are written as zero: the MN-major consumers multiply them
+      const float4 pr = tf32_rn4(make_float4(v[i].x * inv, v[i].y * inv, v[i].z * inv, v[i].w * inv));
+      st4(p_out + row * ld + n, pr);
+      if (pd_out) {
+        const float4 d = dropout_scale4(seed, static_cast<uint64_t>(row) * ld + n, thresh, inv_keep);
+        st4(pd_out + row * ld + n, tf32_rn4(make_float4(pr.x * d.x, pr.y * d.y, pr.z * d.z, pr.w * d.w)));
+      }
+    }
+  }
+}
+
+template <int kV4>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+softmax_bwd_v4_kernel(const float* __restrict__ p, float* __restrict__ dpd, int N, int ld, long rows, float alpha,
+                      uint64_t seed, const uint64_t* __restrict__ seed_dev, uint32_t thresh, float inv_keep) {
+  const int lane = threadIdx.x & 31;
+  seed += seed_dev ? __ldg(seed_dev) * kSeedStep : 0ull;
+  const long row = static_cast<long>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float4 pv[kV4], gv[kV4];
+  float dot = 0.0f;
+#pragma unroll
+  for (int i = 0; i < kV4; ++i) {
+    const int n = 4 * (lane + 32 * i);
+    pv[i] = gv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n < N) {  // p is exactly zero in the pad columns; dpd's pad columns hold nothing
+      pv[i] = ld4(p + row * ld + n);
+      const float4 g = ld4(dpd + row * ld + n);
+      const float4 d = dropout_scale4(seed, static_cast<uint64_t>(row) * ld + n, thresh, inv_keep);
+      gv[i].x = g.x * d.x;
+      if (n + 1 < N) gv[i].y = g.y * d.y;
+      if (n + 2 < N) gv[i].z = g.z * d.z;
+      if (n + 3 < N) gv[i].w = g.w * d.w;
+    }
+    dot += (pv[i].x * gv[i].x + pv[i].y * gv[i].y) + (pv[i].z * gv[i].z + pv[i].w * gv[i].w);
+  }
+  dot = warp_sum(dot);
+#pragma unroll
+  for (int i = 0; i < kV4; ++i) {
+    const int n = 4 * (lane + 32 * i);
+    if (n < ld)  // operand of dQ, dK; pv = 0 in the pad columns makes them zero
+      st4(dpd + row * ld + n, tf32_rn4(make_float4(alpha * pv[i].x * (gv[i].x - dot), alpha * pv[i].y * (gv[i].y - dot),
+                                                   alpha * pv[i].z * (gv[i].z - dot), alpha * pv[i].w * (gv[i].w - dot))));
+  }
+}
+
+// column = 4 * (lane + 32 i) + e  <->  acc[4 i + e]
+template <int kV4>
+__device__ __forceinline__ void block_colsum_atomic_v4(const float (&acc)[4 * kV4], float (*red)[128 * kV4 + 4], int C,
+                                                       float* dst) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < kV4; ++i)
+    *reinterpret_cast<float4*>(&red[warp][4 * (lane + 32 * i)]) = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+  __syncthreads();
+  if (dst == nullptr) return;
+  for (int n = threadIdx.x; n < C; n += blockDim.x) {
+    float a = 0.0f;
+#pragma unroll
+    for (int w = 0; w < kWarpsPerBlock; ++w) a += red[w][n];
+    atomicAdd(dst + n, a);
+  }
+}
+
+template <int kV4>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+layernorm_bwd_v4_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
+                        const float* __restrict__ rstd, const float* __restrict__ gamma, const int* __restrict__ lens,
+                        int R, int C, long rows, float* __restrict__ dx, float* __restrict__ dx_drop,
+                        float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias,
+                        uint64_t seed_post, uint32_t thresh_post, float inv_keep_post, uint64_t seed_pre,
+                        uint32_t thresh_pre, float inv_keep_pre, const uint64_t* __restrict__ seed_dev, int relu_gate) {
+  __shared__ __align__(16) float red[kWarpsPerBlock][128 * kV4 + 4];
+  if (seed_dev) {
+    const uint64_t add = __ldg(seed_dev) * kSeedStep;
+    seed_post += add;
+    seed_pre += add;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4 gm[kV4];
+  float acc_g[4 * kV4], acc_b[4 * kV4], acc_bias[4 * kV4];
+#pragma unroll
+  for (int i = 0; i < kV4; ++i) {
+    const int n = 4 * (lane + 32 * i);
+    gm[i] = n < C ? ld4(gamma + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc_g[4 * i + e] = acc_b[4 * i + e] = acc_bias[4 * i + e] = 0.0f;
+  }
+  const float inv_c = 1.0f / static_cast<float>(C);
+  for (long row = static_cast<long>(blockIdx.x) * kWarpsPerBlock + warp; row < rows;
+       row += static_cast<long>(gridDim.x) * kWarpsPerBlock) {
+    const int z = static_cast<int>(row / R), r = static_cast<int>(row - static_cast<long>(z) * R);
+    const bool live = (lens == nullptr) || (r < lens[z]);
+    const float mu = mean[row], rs = rstd[row];
+    float4 xh[kV4], g[kV4];
+    float s1 = 0.0f, s2 = 0.0f;
+    uint32_t pos = 0u;
+#pragma unroll
+    for (int i = 0; i < kV4; ++i) {
+      const int n = 4 * (lane + 32 * i);
+      float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+      xh[i] = d;
+      if (n < C && live) {
+        d = ld4(dy + row * C + n);
+        const float4 sc = dropout_scale4(seed_post, static_cast<uint64_t>(row) * C + n, thresh_post, inv_keep_post);
+        d = make_float4(d.x * sc.x, d.y * sc.y, d.z * sc.z, d.w * sc.w);
+        const float4 xv = ld4(x + row * C + n);
+        xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+        pos |= ((xv.x > 0.f ? 1u : 0u) | (xv.y > 0.f ? 2u : 0u) | (xv.z > 0.f ? 4u : 0u) | (xv.w > 0.f ? 8u : 0u)) << (4 * i);
+      }
+      acc_g[4 * i] += d.x * xh[i].x; acc_g[4 * i + 1] += d.y * xh[i].y; acc_g[4 * i + 2] += d.z * xh[i].z; acc_g[4 * i + 3] += d.w * xh[i].w;
+      acc_b[4 * i] += d.x; acc_b[4 * i + 1] += d.y; acc_b[4 * i + 2] += d.z; acc_b[4 * i + 3] += d.w;
+      g[i] = make_float4(d.x * gm[i].x, d.y * gm[i].y, d.z * gm[i].z, d.w * gm[i].w);
+      s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
+      s2 += (g[i].x * xh[i].x + g[i].y * xh[i].y) + (g[i].z * xh[i].z + g[i].w * xh[i].w);
+    }
+    s1 = warp_sum(s1) * inv_c;
+    s2 = warp_sum(s2) * inv_c;
+#pragma unroll
+    for (int i = 0; i < kV4; ++i) {
+      const int n = 4 * (lane + 32 * i);
+      if (n < C) {
+        float4 v = make_float4(rs * (g[i].x - s1 - xh[i].x * s2), rs * (g[i].y - s1 - xh[i].y * s2),
+                               rs * (g[i].z - s1 - xh[i].z * s2), rs * (g[i].w - s1 - xh[i].w * s2));
+        if (relu_gate) {  // ConvReLUNorm (common/layers.py:94-97): the gradient passes only where the ReLU output > 0
+          const uint32_t m = pos >> (4 * i);
+          if (!(m & 1u)) v.x = 0.f;
+          if (!(m & 2u)) v.y = 0.f;
+          if (!(m & 4u)) v.z = 0.f;
+          if (!(m & 8u)) v.w = 0.f;
+        }
+        // the tensor that feeds the dgrad / wgrad GEMMs (dx_drop if there is one, else dx) is stored tf32-rounded
+        if (dx_drop) {
+          st4(dx + row * C + n, v);
+          const float4 sc = dropout_scale4(seed_pre, static_cast<uint64_t>(row) * C + n, thresh_pre, inv_keep_pre);
+          v = tf32_rn4(make_float4(v.x * sc.x, v.y * sc.y, v.z * sc.z, v.w * sc.w));
+          st4(dx_drop + row * C + n, v);
+        } else {
+          v = tf32_rn4(v);
+          st4(dx + row * C + n, v);
+        }
+        acc_bias[4 * i] += v.x; acc_bias[4 * i + 1] += v.y; acc_bias[4 * i + 2] += v.z; acc_bias[4 * i + 3] += v.w;
+      }
+    }
+  }
+  block_colsum_atomic_v4<kV4>(acc_g, red, C, dgamma);
+  block_colsum_atomic_v4<kV4>(acc_b, red, C, dbeta);
+  block_colsum_atomic_v4<kV4>(acc_bias, red, C, dbias);
+}
+
+// LayerNorm forward on a stored pre-LN tensor (the un-fused path of the FFT blocks: the producing GEMM keeps narrow,
+// double-buffered n tiles and this pass costs one read + one write at HBM speed).
+//   y = ((x - mean) * rstd * gamma + beta) * (r < lens[z]), tf32-rounded (next GEMM operand); mean / rstd saved.
+template <int kV4>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+layernorm_fwd_v4_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                        const int* __restrict__ lens, int R, int C, long rows, float eps, float* __restrict__ y,
+                        float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  const int lane = threadIdx.x & 31;
+  const long row = static_cast<long>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int z = static_cast<int>(row / R), r = static_cast<int>(row - static_cast<long>(z) * R);
+  const bool live = (lens == nullptr) || (r < lens[z]);
+  float4 v[kV4];
+  float s = 0.0f;
+#pragma unroll
+  for (int i = 0; i < kV4; ++i) {
+    const int n = 4 * (lane + 32 * i);
+    v[i] = n < C ? ld4(x + row * C + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mu = warp_sum(s) / static_cast<float>(C);
+  float q = 0.0f;
+#pragma unroll
+  for (int i = 0; i < kV4; ++i) {
+    const int n = 4 * (lane + 32 * i);
+    if (n < C) {
+      const float a = v[i].x - mu, b = v[i].y - mu, c = v[i].z - mu, d = v[i].w - mu;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+  const float rs = rsqrtf(warp_sum(q) / static_cast<float>(C) + eps);
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mu;
+    if (rstd_out) rstd_out[row] = rs;
+  }
+#pragma unroll
+  for (int i = 0; i < kV4; ++i) {
+    const int n = 4 * (lane + 32 * i);
+    if (n < C) {
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (live) {
+        const float4 gmv = ld4(gamma + n), bt = ld4(beta + n);
+        o = tf32_rn4(make_float4((v[i].x - mu) * rs * gmv.x + bt.x, (v[i].y - mu) * rs * gmv.y + bt.y,
+                                 (v[i].z - mu) * rs * gmv.z + bt.z, (v[i].w - mu) * rs * gmv.w + bt.w));
+      }
+      st4(y + row * C + n, o);
+    }
+  }
+}
+
+// out[n] += sum_rows x[row, n], 16-byte loads: a block owns a 128-column strip, its 8 warps take rows 8 apart, four
+// rows in flight per lane.
+__global__ void __launch_bounds__(256)
+colsum_v4_kernel(const float* __restrict__ x, long rows, int C, long ld, float* __restrict__ out) {
+  __shared__ __align__(16) float red[8][132];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = blockIdx.x * 128 + 4 * lane;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (n < C) {
+    const long step = static_cast<long>(gridDim.y) * 8;
+    long r = static_cast<long>(blockIdx.y) * 8 + warp;
+    for (; r + 3 * step < rows; r += 4 * step) {
+      const float4 a = ld4(x + r * ld + n), b = ld4(x + (r + step) * ld + n), c = ld4(x + (r + 2 * step) * ld + n),
+                   d = ld4(x + (r + 3 * step) * ld + n);
+      acc.x += (a.x + b.x) + (c.x + d.x);
+      acc.y += (a.y + b.y) + (c.y + d.y);
+      acc.z += (a.z + b.z) + (c.z + d.z);
+      acc.w += (a.w + b.w) + (c.w + d.w);
+    }
+    for (; r < rows; r += step) {
+      const float4 a = ld4(x + r * ld + n);
+      acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+    }
+  }
+  *reinterpret_cast<float4*>(&red[warp][4 * lane]) = acc;
+  __syncthreads();
+  if (threadIdx.x < 128 && blockIdx.x * 128 + threadIdx.x < C) {
+    float sum = 0.0f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) sum += red[w][threadIdx.x];
+    atomicAdd(out + blockIdx.x * 128 + threadIdx.x, sum);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ column sums
 // out[n] += sum_rows x[row, n]   (bias gradients). Thread per column within a 32-column strip, rows strided over
 // blockIdx.y; coalesced 128-byte reads.
@@ -392,6 +673,7 @@ inline void drop_consts(float p, uint32_t* thresh, float* inv_keep) {
 }
 
 inline int row_blocks(long rows) { return static_cast<int>(ceil_div_l(rows, kWarpsPerBlock)); }
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }  // nullptr counts as aligned
 
 }  // namespace
 
@@ -405,7 +687,12 @@ int softmax_fwd(const float* s, const int* lens, int Z, int R, int N, int ld, fl
   float ik;
   drop_consts(pd_out ? drop_p : 0.0f, &th, &ik);
   const long rows = static_cast<long>(Z) * R;
-  softmax_fwd_kernel<<<row_blocks(rows), kWarpsPerBlock * 32, 0, stream>>>(s, lens, R, N, ld, rows, p_out, pd_out, seed, seed_dev, th, ik);
+  if (ld % 4 == 0 && aligned16(s) && aligned16(p_out) && aligned16(pd_out)) {
+    if (ld <= 512) softmax_fwd_v4_kernel<4><<<row_blocks(rows), kWarpsPerBlock * 32, 0, stream>>>(s, lens, R, N, ld, rows, p_out, pd_out, seed, seed_dev, th, ik);
+    else softmax_fwd_v4_kernel<8><<<row_blocks(rows), kWarpsPerBlock * 32, 0, stream>>>(s, lens, R, N, ld, rows, p_out, pd_out, seed, seed_dev, th, ik);
+  } else {
+    softmax_fwd_kernel<<<row_blocks(rows), kWarpsPerBlock * 32, 0, stream>>>(s, lens, R, N, ld, rows, p_out, pd_out, seed, seed_dev, th, ik);
+  }
   XVA_CHECK_LAUNCH();
   return XVA_OK;
 }
@@ -418,7 +705,12 @@ int softmax_bwd(const float* p, float* dpd, int Z, int R, int N, int ld, float a
   float ik;
   drop_consts(drop_p, &th, &ik);
   const long rows = static_cast<long>(Z) * R;
-  softmax_bwd_kernel<<<row_blocks(rows), kWarpsPerBlock * 32, 0, stream>>>(p, dpd, N, ld, rows, alpha, seed, seed_dev, th, ik);
+  if (ld % 4 == 0 && aligned16(p) && aligned16(dpd)) {
+    if (ld <= 512) softmax_bwd_v4_kernel<4><<<row_blocks(rows), kWarpsPerBlock * 32, 0, stream>>>(p, dpd, N, ld, rows, alpha, seed, seed_dev, th, ik);
+    else softmax_bwd_v4_kernel<8><<<row_blocks(rows), kWarpsPerBlock * 32, 0, stream>>>(p, dpd, N, ld, rows, alpha, seed, seed_dev, th, ik);
+  } else {
+    softmax_bwd_kernel<<<row_blocks(rows), kWarpsPerBlock * 32, 0, stream>>>(p, dpd, N, ld, rows, alpha, seed, seed_dev, th, ik);
+  }
   XVA_CHECK_LAUNCH();
   return XVA_OK;
 }
@@ -441,10 +733,33 @@ int layernorm_bwd(const float* dy, const float* x, const float* mean, const floa
                                                                       dx, dx_drop, dgamma, dbeta, dbias, seed_post, \
                                                                       th_post, ik_post, seed_pre, th_pre, ik_pre, \
                                                                       seed_dev, relu_gate)
-  if (C <= 256) XVA_LN_BWD(8);
+#define XVA_LN_BWD4(V4)                                                                                             \
+  layernorm_bwd_v4_kernel<V4><<<grid, kWarpsPerBlock * 32, 0, stream>>>(dy, x, mean, rstd, gamma, lens, R, C, rows, \
+                                                                        dx, dx_drop, dgamma, dbeta, dbias, seed_post, \
+                                                                        th_post, ik_post, seed_pre, th_pre, ik_pre, \
+                                                                        seed_dev, relu_gate)
+  if (C % 4 == 0 && aligned16(dy) && aligned16(x) && aligned16(gamma) && aligned16(dx) && aligned16(dx_drop)) {
+    if (C <= 256) XVA_LN_BWD4(2);
+    else if (C <= 384) XVA_LN_BWD4(3);
+    else XVA_LN_BWD4(4);
+  } else if (C <= 256) XVA_LN_BWD(8);
   else if (C <= 384) XVA_LN_BWD(12);
   else XVA_LN_BWD(16);
+#undef XVA_LN_BWD4
 #undef XVA_LN_BWD
+  XVA_CHECK_LAUNCH();
+  return XVA_OK;
+}
+
+int layernorm_fwd(const float* x, const float* gamma, const float* beta, const int* lens, int Z, int R, int C, float eps,
+                  float* y, float* mean, float* rstd, cudaStream_t stream) {
+  XVA_CHECK_ARG(C >= 4 && C <= 512 && C % 4 == 0, "layernorm fwd: C=%d (multiple of 4, max 512)", C);
+  XVA_CHECK_ARG(aligned16(x) && aligned16(y) && aligned16(gamma) && aligned16(beta), "layernorm fwd: pointers must be 16-byte aligned");
+  const long rows = static_cast<long>(Z) * R;
+  if (rows == 0) return XVA_OK;
+  if (C <= 256) layernorm_fwd_v4_kernel<2><<<row_blocks(rows), kWarpsPerBlock * 32, 0, stream>>>(x, gamma, beta, lens, R, C, rows, eps, y, mean, rstd);
+  else if (C <= 384) layernorm_fwd_v4_kernel<3><<<row_blocks(rows), kWarpsPerBlock * 32, 0, stream>>>(x, gamma, beta, lens, R, C, rows, eps, y, mean, rstd);
+  else layernorm_fwd_v4_kernel<4><<<row_blocks(rows), kWarpsPerBlock * 32, 0, stream>>>(x, gamma, beta, lens, R, C, rows, eps, y, mean, rstd);
   XVA_CHECK_LAUNCH();
   return XVA_OK;
 }
@@ -452,6 +767,16 @@ int layernorm_bwd(const float* dy, const float* x, const float* mean, const floa
 int colsum(const float* x, long rows, int C, long ld, float* out, cudaStream_t stream) {
   XVA_CHECK_ARG(rows >= 0 && C >= 1, "colsum: rows=%ld C=%d", rows, C);
   if (rows == 0) return XVA_OK;
+  if (C % 4 == 0 && ld % 4 == 0 && aligned16(x)) {
+    const int strips4 = ceil_div(C, 128);
+    int gy4 = static_cast<int>(ceil_div_l(rows, 8 * 16));
+    const int cap4 = ceil_div(6 * num_sms(), strips4);
+    if (gy4 > cap4) gy4 = cap4;
+    if (gy4 < 1) gy4 = 1;
+    colsum_v4_kernel<<<dim3(strips4, gy4), 256, 0, stream>>>(x, rows, C, ld, out);
+    XVA_CHECK_LAUNCH();
+    return XVA_OK;
+  }
   int gy = static_cast<int>(ceil_div_l(rows, 8 * 16));
   const int strips = ceil_div(C, 32);
   const int cap = ceil_div(8 * num_sms(), strips);

@@ -19,6 +19,7 @@ What differs by design (B200-first):
 There is no CPU or eager fallback: without the CUDA library every call raises.
 """
 import math
+import os
 from collections import OrderedDict
 
 import torch
@@ -176,6 +177,7 @@ class FastPitch(torch.nn.Module):
         self.pitch_std = torch.zeros(1, device=dev)
         self.inv_freq = (1.0 / (10000 ** (torch.arange(0.0, D_MODEL, 2.0) / D_MODEL))).to(dev)
         self.p_drop = P_DROP
+        self.fuse_ln = os.environ.get("XVA_FUSE_LN", "0") == "1"   # LayerNorm inside the GEMM epilogue (measured slower)
         self.seed = int(seed)
         self.step_counter = torch.zeros(1, device=dev, dtype=torch.int64)  # device-side dropout counter (uint64 bits)
         self._site = 0
@@ -328,12 +330,23 @@ class FastPitch(torch.nn.Module):
         del s
         vec = ops.bmm_nn(Pd[..., :T], v, round_out=True)
         p1, seed1 = self._drop()
-        y1, sv1 = ops.conv_fwd(vec, L.w.o_w, residual=x, ln=(L.w.ln1_g, L.w.ln1_b), save_ln=True, lens=lens,
-                               drop_p=p1, seed=seed1, seed_dev=sd, round_out=True)
+        # The post-LN of both sub-blocks is a separate HBM pass (xva_layernorm_fwd) over the pre-LN sum the GEMM epilogue
+        # wrote (bias + dropout + residual): a 384-column LayerNorm epilogue needs the whole row in one accumulator, which
+        # cannot be double-buffered in TMEM and left 54 % (T = 160) or 27 % (T = 880) of the SMs without a tile.
+        if self.fuse_ln:
+            y1, sv1 = ops.conv_fwd(vec, L.w.o_w, residual=x, ln=(L.w.ln1_g, L.w.ln1_b), save_ln=True, lens=lens,
+                                   drop_p=p1, seed=seed1, seed_dev=sd, round_out=True)
+        else:
+            pre1 = ops.conv_fwd(vec, L.w.o_w, residual=x, drop_p=p1, seed=seed1, seed_dev=sd)
+            y1, sv1 = ops.layernorm_fwd(pre1, L.w.ln1_g, L.w.ln1_b, lens)
         h = ops.conv_fwd(y1, L.w.w1, K3, bias=L.w.b1, relu=True, round_out=True)
         p2, seed2 = self._drop()
-        y2, sv2 = ops.conv_fwd(h, L.w.w2, K3, bias=L.w.b2, residual=y1, ln=(L.w.ln2_g, L.w.ln2_b), save_ln=True,
-                               lens=lens, drop_p=p2, seed=seed2, seed_dev=sd, round_out=True)
+        if self.fuse_ln:
+            y2, sv2 = ops.conv_fwd(h, L.w.w2, K3, bias=L.w.b2, residual=y1, ln=(L.w.ln2_g, L.w.ln2_b), save_ln=True,
+                                   lens=lens, drop_p=p2, seed=seed2, seed_dev=sd, round_out=True)
+        else:
+            pre2 = ops.conv_fwd(h, L.w.w2, K3, bias=L.w.b2, residual=y1, drop_p=p2, seed=seed2, seed_dev=sd)
+            y2, sv2 = ops.layernorm_fwd(pre2, L.w.ln2_g, L.w.ln2_b, lens)
         if save is not None:
             save.append(_NS(x=x, qkv=qkv, P=P, Pd=Pd, vec=vec, sv1=sv1, y1=y1, h=h, sv2=sv2, T=T, att=(p_att, seed_att),
                             d1=(p1, seed1), d2=(p2, seed2)))

@@ -167,7 +167,7 @@ def conv_wgrad(dy, x, shifts=(0,), out=None, accumulate=False, split=None, ref=F
     g.out, g.o_rs, g.o_zs, g.o_js = _p(out), out.stride(1), 0, out.stride(0)
     g.groups, g.grp_step = int(groups), int(grp_step)
     if split is None:
-        tiles = taps * (groups if groups > 1 else (N + 127) // 128) * ((K + 255) // 256)
+        tiles = taps * ((N + 127) // 128) * ((K + 255) // 256)
         split = max(1, min(B, (2 * 148) // max(tiles, 1)))
     g.split = split if accumulate else 1
     g.flags = capi.GEMM_ATOMIC if accumulate else 0
@@ -301,6 +301,18 @@ def layernorm_bwd(dy, saved, gamma, lens, dgamma, dbeta, dbias=None, want_drop=F
               Z, R, Cc, _p(dx), _p(dxd), _p(dgamma), _p(dbeta), _p(dbias), float(drop_post_p), int(seed_post),
               float(drop_pre_p), int(seed_pre), _p(seed_dev), int(relu_gate), _stream())
     return dx, (dxd if dxd is not None else dx)
+
+
+def layernorm_fwd(pre, gamma, beta, lens, eps=1e-5):
+    """LayerNorm of a stored pre-LN tensor [Z,R,C] -> (y, {"pre", "mean", "rstd"}); rows >= lens[z] of y are zero."""
+    Z, R, Cc = pre.shape
+    assert pre.is_contiguous()
+    y = torch.empty_like(pre)
+    mean = torch.empty(Z * R, device=pre.device, dtype=torch.float32)
+    rstd = torch.empty_like(mean)
+    capi.call("xva_layernorm_fwd", _p(pre), _p(gamma), _p(beta), _p(lens), Z, R, Cc, float(eps), _p(y), _p(mean), _p(rstd),
+              _stream())
+    return y, {"pre": pre, "mean": mean, "rstd": rstd}
 
 
 def colsum_(x2d_rows, C_, ld, x, out):
