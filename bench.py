@@ -39,6 +39,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-batch", type=int, default=4)
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-hifigan", action="store_true", help="skip the second half of the metric (HiFi-GAN samples/s)")
+    ap.add_argument("--hifigan-steps", type=int, default=20)
     return ap.parse_args()
 
 
@@ -145,6 +147,111 @@ def gemm_flops(g):
     if g.mode == 2:
         return 2.0 * g.Z * g.R * g.M * g.N * g.taps
     return 2.0 * g.Z * g.R * g.N * g.K * g.taps
+
+
+class _H(dict):
+    __getattr__ = dict.__getitem__
+
+
+def run_hifigan(args, dev, world, rank, peak_tf32):
+    """Second half of BASELINE.json's metric: audio-samples/s of the HiFi-GAN v1 training step (configs[2]: G + MPD + MSD,
+    batch 16 x 8192-sample segments per GPU; D step + G step, both AdamW updates). Same protocol as the FastPitch half:
+    `value` with the batch resident in HBM, `e2e` from pinned host buffers with a loss read back every step, tap-GEMM
+    roofline from one instrumented step. Returns the dict that goes under "hifigan" in the JSON line."""
+    import torch
+    import torch.distributed as dist
+    from oracle import hifigan as ohg           # synthetic batch generator only
+    from xva_trainer_b200 import capi, graph, hifigan as hg, ops
+
+    Bh, frames = 16, 32
+    h = _H(resblock="1", upsample_rates=[8, 8, 2, 2], upsample_kernel_sizes=[16, 16, 4, 4], upsample_initial_channel=512,
+           resblock_kernel_sizes=[3, 7, 11], resblock_dilation_sizes=[[1, 3, 5]] * 3, learning_rate=2e-4, adam_b1=0.8,
+           adam_b2=0.99, n_fft=1024, num_mels=80, sampling_rate=22050, hop_size=256, win_size=1024, fmin=0, fmax=8000,
+           fmax_for_loss=None)
+    G = hg.Generator(h, device=dev); G.train()
+    mpd = hg.MultiPeriodDiscriminator(device=dev); mpd.train()
+    msd = hg.MultiScaleDiscriminator(device=dev); msd.train()
+    stepper = hg.HiFiGANStep(G, mpd, msd, h, world=world)
+    host = [t.pin_memory() for t in ohg.synthetic_batch(Bh, frames, seed=1 + rank)]
+    h2d = sum(t.numel() * t.element_size() for t in host)
+    x, y, y_mel = (t.to(dev, non_blocking=True) for t in host)
+    steps = args.hifigan_steps
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    use_graph = world == 1 and not args.no_graph
+    capi.reset_launch_count()
+    if use_graph:
+        stepper.optim_g.lr_on_device = stepper.optim_d.lr_on_device = True
+        gs = graph.GraphedStep(lambda a, b, c: stepper.step(a, b, c), [x, y, y_mel], warmup=3)
+        per_step = capi.launch_count() // 4
+        run = lambda src=None: gs(*src) if src is not None else gs()
+    else:
+        for _ in range(3):
+            stepper.step(x, y, y_mel)
+        per_step = capi.launch_count() // 3
+        run = lambda src=None: stepper.step(*[t.to(dev, non_blocking=True) for t in src]) if src is not None else stepper.step(x, y, y_mel)
+    for _ in range(3):
+        out = run()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = run()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(steps):
+        out = run(host)
+        loss_host = float(out["loss_gen_all"])
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    # instrumented eager step (every rank runs it: it contains the gradient all-reduces)
+    rec = []
+    orig = ops.gemm_launch
+
+    def timed_launch(g, ref=False):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        orig(g, ref)
+        b.record()
+        rec.append((a, b, gemm_flops(g)))
+
+    stepper.optim_g.lr_on_device = stepper.optim_d.lr_on_device = False
+    ops.gemm_launch = timed_launch
+    torch.cuda.synchronize()
+    torch.cuda._sleep(int(0.3 * 1.9e9))
+    stepper.step(x, y, y_mel)
+    torch.cuda.synchronize()
+    ops.gemm_launch = orig
+    gemm_ms = sum(a.elapsed_time(b) for a, b, _ in rec)
+    flops = sum(f for _, _, f in rec)
+    achieved = flops / (gemm_ms * 1e-3) / 1e12
+    samples = Bh * frames * 256 * world
+    return {"metric": "audio-samples/s (HiFi-GAN v1 G+MPD+MSD train step)", "value": samples * steps / (ms * 1e-3),
+            "unit": "samples/s", "ms_per_step": ms / steps, "steps": steps, "n_gpus": world,
+            "config": {"workload": "HiFi-GAN v1 G+MPD+MSD train step, batch=16/GPU, 8192-sample segments, synthetic "
+                                   "(BASELINE.json configs[2])", "global_batch": Bh * world,
+                       "step": "G fwd + mel + D step (MPD + MSD, AdamW) + G step (45 L1 mel + feature + adversarial, AdamW)",
+                       "launch": "one CUDA-graph replay per step" if use_graph else "eager launches"},
+            "e2e": {"value": samples * steps / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e / steps},
+            "gpu_launches_per_step": per_step,
+            "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 kind::tf32 tap-GEMM)", "achieved": achieved,
+                         "peak": peak_tf32, "unit": "TFLOP/s", "frac": achieved / peak_tf32, "traffic": None,
+                         "launches_per_step": len(rec), "flops_per_step": flops, "kernel_ms_per_step": gemm_ms,
+                         "share_of_step": gemm_ms / (ms / steps)},
+            "loss_gen_all": loss_host}
 
 
 def run_native(args):
@@ -327,6 +434,12 @@ def run_native(args):
                 "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained / 2 (kind::tf32 runs at half the bf16 rate), "
                                 "of measured") if peaks else "fallback 1.4 PFLOP/s / 2, of fallback"}
 
+    hifi = None
+    if not args.no_hifigan:
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
+            os.path.join(ROOT, "MEASURED_PEAKS.json")) else None
+        hifi = run_hifigan(args, dev, world, rank, (pk["bf16_tflops_sustained"] if pk else 1400.0) / 2.0)
+
     if world > 1:
         dist.barrier()
     if rank != 0:
@@ -348,7 +461,7 @@ def run_native(args):
             "data": "synthetic", "config": config(args, world), "clocks": clk,
             "e2e": {"value": total_frames * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "loss": loss_host}
+            "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "loss": loss_host, "hifigan": hifi}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

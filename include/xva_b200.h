@@ -308,6 +308,36 @@ int xva_avgpool4_fwd(const float* x, int B, int L, float* out, void* stream);
 int xva_avgpool4_bwd(const float* dout, int B, int L, float* dx, void* stream);
 int xva_zero_tail_rows(float* x, int Z, int Lp, int Lvalid, int C, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Weight-norm reparametrisation + packing of every convolution of a model in one launch -- replaces the
+ * torch.nn.utils.weight_norm forward hook of each conv (hifigan/models.py:21-38, 87-105, 144-150, 207-215:
+ * w = g * v / ||v||, norm over all dims but 0) plus the re-layout of w into the tap-GEMM's operand format, and their
+ * autograd. One descriptor per convolution, the table lives in device memory.
+ *   element (r, c, j) of v [rows, inner / k, k] goes, scaled by g[r] / ||v[r]|| and tf32-rounded, to
+ *     dst[tap_off[j] + r * ld + ((r / og) % f) * cg + c]      (Conv1d / Conv2d; f > 1: block-diagonal super-groups)
+ *     dst[tap_off[j] + c * ld + r]                            (XVA_WN_TRANSPOSED: ConvTranspose1d, v is [Cin, Cout, k])
+ *   bwd: dv (+)= g/||v|| * (dW - v (v.dW)/||v||^2), dg (+)= (v.dW)/||v||, with dW gathered from ddst (same layout as dst).
+ * max_inner = the largest `inner` of the table (shared-memory staging of one row; <= 12288).
+ * ---------------------------------------------------------------------------------------------------------- */
+#define XVA_WN_TRANSPOSED 1
+#define XVA_WN_NO_ROUND 2
+typedef struct xva_wn_desc {
+  const float* v;
+  const float* g;
+  float* dv;          /* accumulated (bwd) */
+  float* dg;
+  float* dst;         /* packed-weight arena base (fwd) */
+  const float* ddst;  /* gradient arena base (bwd) */
+  int32_t rows, inner, k, flags;
+  int32_t ld, og, f, cg;
+  int32_t row_start;  /* sum of `rows` of the preceding descriptors */
+  int32_t _pad;
+  int64_t tap_off[XVA_MAX_TAPS];
+} xva_wn_desc;
+int xva_sizeof_wn_desc(void);
+int xva_wn_pack_fwd(const xva_wn_desc* table_dev, int n_desc, int total_rows, int max_inner, void* stream);
+int xva_wn_pack_bwd(const xva_wn_desc* table_dev, int n_desc, int total_rows, int max_inner, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

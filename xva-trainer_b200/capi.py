@@ -49,6 +49,20 @@ class GemmArgs(C.Structure):
     ]
 
 
+class WnDesc(C.Structure):
+    """Mirror of struct xva_wn_desc (include/xva_b200.h)."""
+    _fields_ = [
+        ("v", C.c_void_p), ("g", C.c_void_p), ("dv", C.c_void_p), ("dg", C.c_void_p), ("dst", C.c_void_p),
+        ("ddst", C.c_void_p),
+        ("rows", C.c_int32), ("inner", C.c_int32), ("k", C.c_int32), ("flags", C.c_int32),
+        ("ld", C.c_int32), ("og", C.c_int32), ("f", C.c_int32), ("cg", C.c_int32),
+        ("row_start", C.c_int32), ("_pad", C.c_int32),
+        ("tap_off", C.c_int64 * XVA_MAX_TAPS),
+    ]
+
+
+WN_TRANSPOSED, WN_NO_ROUND = 1, 2
+
 # name -> (restype, argtypes); must list every symbol include/xva_b200.h declares (tests/test_abi.py checks it)
 _I, _F, _P, _U64, _I64 = C.c_int, C.c_float, C.c_void_p, C.c_uint64, C.c_int64
 PROTOTYPES = {
@@ -100,6 +114,9 @@ PROTOTYPES = {
     "xva_mean3_lrelu": (_I, [_P, _P, _P, _I64, _F, _P, _P]),
     "xva_sum3": (_I, [_P, _P, _P, _I64, _P, _P]),
     "xva_tanh_bwd": (_I, [_P, _P, _I64, _I, _P, _P]),
+    "xva_sizeof_wn_desc": (_I, []),
+    "xva_wn_pack_fwd": (_I, [_P, _I, _I, _I, _P]),
+    "xva_wn_pack_bwd": (_I, [_P, _I, _I, _I, _P]),
     "xva_adamw_step": (_I, [_P, _P, _P, _P, _I64, _P, _F, _F, _F, _F, _I, _P, _P]),
 }
 
@@ -124,6 +141,8 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
+    if lib.xva_sizeof_wn_desc() != C.sizeof(WnDesc):
+        raise XvaError(f"xva_wn_desc layout mismatch: C {lib.xva_sizeof_wn_desc()} vs ctypes {C.sizeof(WnDesc)}")
     if lib.xva_sizeof_gemm_args() != C.sizeof(GemmArgs):
         raise XvaError(f"xva_gemm_args layout mismatch: C {lib.xva_sizeof_gemm_args()} vs ctypes {C.sizeof(GemmArgs)}")
     _lib = lib
@@ -138,7 +157,7 @@ def check(status, what=""):
 
 # kernels enqueued per successful call (everything not listed launches exactly one)
 _LAUNCHES = {"xva_lamb_step": 2, "xva_gemm_debug_counters": 0, "xva_set_operand_rounding": 0, "xva_abi_version": 0, "xva_last_error": 0, "xva_device_check": 0,
-             "xva_sizeof_gemm_args": 0}
+             "xva_sizeof_gemm_args": 0, "xva_sizeof_wn_desc": 0}
 _launch_count = 0
 
 

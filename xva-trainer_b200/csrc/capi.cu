@@ -91,6 +91,7 @@ int xva_set_operand_rounding(int on) {
   if ((rc = set_operand_rounding_elemwise(on)) != XVA_OK) return rc;
   if ((rc = set_operand_rounding_melspec(on)) != XVA_OK) return rc;
   if ((rc = set_operand_rounding_disc(on)) != XVA_OK) return rc;
+  if ((rc = set_operand_rounding_wnpack(on)) != XVA_OK) return rc;
   return set_operand_rounding_loss_optim(on);
 }
 
@@ -181,6 +182,14 @@ int xva_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, cons
                    float eps, float weight_decay, int step, const uint64_t* step_dev, void* stream) {
   return adamw_step(p, g, m, v, static_cast<long>(n), lr_dev, beta1, beta2, eps, weight_decay, step,
                     reinterpret_cast<const unsigned long long*>(step_dev), S(stream));
+}
+
+int xva_sizeof_wn_desc(void) { return static_cast<int>(sizeof(xva_wn_desc)); }
+int xva_wn_pack_fwd(const xva_wn_desc* table_dev, int n_desc, int total_rows, int max_inner, void* stream) {
+  return wn_pack(table_dev, n_desc, total_rows, max_inner, 0, S(stream));
+}
+int xva_wn_pack_bwd(const xva_wn_desc* table_dev, int n_desc, int total_rows, int max_inner, void* stream) {
+  return wn_pack(table_dev, n_desc, total_rows, max_inner, 1, S(stream));
 }
 
 int xva_reflect_pad_fwd(const float* y, int B, int64_t n, int pad, float* out, void* stream) {

@@ -3,6 +3,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#include "../../include/xva_b200.h"
 
 namespace xva {
 
@@ -14,6 +15,7 @@ int set_operand_rounding_loss_optim(int on);
 int set_operand_rounding_elemwise(int on);
 int set_operand_rounding_melspec(int on);
 int set_operand_rounding_disc(int on);
+int set_operand_rounding_wnpack(int on);
 
 // ---- regulate.cu
 int duration_scan(const float* durs, int B, int Tt, float pace, int mel_max_len, int* cum, int* dec_lens,
@@ -55,6 +57,7 @@ int rowdot_bwd(const float* dout, const float* x, const float* w, const int* len
 int mean3_lrelu(const float* y0, const float* y1, const float* y2, long n, float slope, float* out, cudaStream_t stream);
 int sum3(const float* a, const float* b, const float* c, long n, float* out, cudaStream_t stream);
 int tanh_bwd(const float* dy, const float* y, long rows, int ld, float* out, cudaStream_t stream);
+int wn_pack(const xva_wn_desc* table_dev, int n_desc, int total_rows, int max_inner, int backward, cudaStream_t stream);
 int adamw_step(float* p, const float* g, float* m, float* v, long n, const float* lr_dev, float b1, float b2, float eps,
                float wd, int step, const unsigned long long* step_dev, cudaStream_t stream);
 

@@ -47,6 +47,109 @@ class _WNConv(nn.Module):
         return tuple((j - half) * self.dilation for j in range(self.k))
 
 
+class _WnPacker:
+    """Effective weights w = g * v / ||v|| of a set of weight-normed convolutions, written by ONE kernel launch
+    (xva_wn_pack_fwd) into a flat arena in the layouts the tap-GEMM reads, and the way back (xva_wn_pack_bwd: gradient
+    arena -> .grad of weight_g / weight_v) in one more. Replaces ~20 PyTorch launches per convolution and step."""
+
+    def __init__(self):
+        self.items = []          # (module, flags, ld, og, f, cg, tap_off list (arena-relative))
+        self.layout = {}         # key -> [(offset, shape)]
+        self.size = 0
+        self.table = None
+        self._ptrs = None
+
+    def _alloc(self, key, shape):
+        off = self.size
+        n = int(math.prod(shape))
+        self.size += (n + 63) // 64 * 64          # 256-byte alignment (TMA needs 16)
+        self.layout.setdefault(key, []).append((off, tuple(shape)))
+        return off
+
+    def add_conv(self, key, m, cout, cg, k, order=None, og=None, f=1):
+        """Conv weight v [cout, cg, k] -> [k (in `order`), cout, f * cg] with group r's columns at ((r / og) % f) * cg."""
+        off = self._alloc(key, (k, cout, f * cg))
+        order = list(range(k)) if order is None else list(order)
+        taps = [0] * k
+        for pos, j in enumerate(order):
+            taps[j] = off + pos * cout * f * cg
+        self.items.append((m, 0, f * cg, og if og else cout, f, cg, taps))
+
+    def add_flat(self, key, m, cout, k):
+        """First discriminator layer (one input channel): [cout, k], not rounded (it runs on CUDA cores in fp32)."""
+        off = self._alloc(key, (cout, k))
+        self.items.append((m, capi.WN_NO_ROUND, k, cout, 1, 0, [off + j for j in range(k)]))
+
+    def add_transposed(self, key, m, cin, cout, u):
+        """ConvTranspose1d(k = 2u, stride u) weight v [cin, cout, 2u] -> the two 2-tap phase groups of Generator.forward."""
+        p = u // 2
+        lo = self._alloc(key, (2, (u - p) * cout, cin))
+        hi = self._alloc(key, (2, p * cout, cin))
+        mat = cout * cin
+        taps = [0] * (2 * u)
+        for kk in range(2 * u):
+            if p <= kk < u:
+                taps[kk] = lo + (kk - p) * mat
+            elif kk >= p + u:
+                taps[kk] = lo + (u - p) * mat + (kk - p - u) * mat
+            elif kk < p:
+                taps[kk] = hi + kk * mat
+            else:
+                taps[kk] = hi + p * mat + (kk - u) * mat
+        self.items.append((m, capi.WN_TRANSPOSED, cin, 1, 1, 0, taps))
+
+    def finalize(self, device):
+        self.arena = torch.zeros(self.size, device=device, dtype=torch.float32)    # off-diagonal blocks stay zero
+        self.garena = torch.zeros(self.size, device=device, dtype=torch.float32)
+        view = lambda a: {k: tuple(a[o:o + int(math.prod(sh))].view(sh) for o, sh in v) for k, v in self.layout.items()}
+        self.W, self.gW = view(self.arena), view(self.garena)
+        self.rows = sum(m.weight_v.shape[0] for m, *_ in self.items)
+        self.max_inner = max(m.weight_v.numel() // m.weight_v.shape[0] for m, *_ in self.items)
+
+    def _sync(self, grads):
+        ptrs = []
+        for m, *_ in self.items:
+            if grads:
+                for prm in (m.weight_v, m.weight_g):
+                    if prm.grad is None:
+                        prm.grad = torch.zeros_like(prm)
+            ptrs.append((m.weight_v.data_ptr(), m.weight_g.data_ptr(),
+                         m.weight_v.grad.data_ptr() if m.weight_v.grad is not None else 0,
+                         m.weight_g.grad.data_ptr() if m.weight_g.grad is not None else 0))
+        if ptrs == self._ptrs:
+            return
+        import ctypes as C
+        arr = (capi.WnDesc * len(self.items))()
+        row = 0
+        for d, (m, flags, ld, og, f, cg, taps), (pv, pg, pdv, pdg) in zip(arr, self.items, ptrs):
+            v = m.weight_v
+            assert v.is_contiguous() and m.weight_g.is_contiguous()
+            d.v, d.g, d.dv, d.dg = pv, pg, pdv, pdg
+            d.dst, d.ddst = self.arena.data_ptr(), self.garena.data_ptr()
+            d.rows, d.inner, d.k, d.flags = v.shape[0], v.numel() // v.shape[0], len(taps), flags
+            d.ld, d.og, d.f, d.cg = ld, og, f, cg
+            d.row_start = row
+            row += v.shape[0]
+            for j, t in enumerate(taps):
+                d.tap_off[j] = t
+        host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+        self.table = host.to(self.arena.device)
+        self._ptrs = ptrs
+
+    def pack(self):
+        self._sync(False)
+        capi.call("xva_wn_pack_fwd", ops._p(self.table), len(self.items), self.rows, self.max_inner, ops._stream())
+        return self.W
+
+    def zero_grads(self):
+        self.garena.zero_()
+        return self.gW
+
+    def unpack_grads(self):
+        self._sync(True)
+        capi.call("xva_wn_pack_bwd", ops._p(self.table), len(self.items), self.rows, self.max_inner, ops._stream())
+
+
 class ResBlock1(nn.Module):
     def __init__(self, h, channels, kernel_size=3, dilation=(1, 3, 5)):
         super().__init__()
@@ -85,7 +188,21 @@ class Generator(nn.Module):
         capi.call("xva_device_check", dev.index or 0)
         self.to(dev)
         self._ctx = None
-        self._packed = None
+        self._packer = None
+
+    def _get_packer(self):
+        if self._packer is None:
+            pk = _WnPacker()
+            for name, m in self.named_modules():
+                if not isinstance(m, _WNConv):
+                    continue
+                if m.transposed:
+                    pk.add_transposed(name, m, m.cin, m.cout, m.stride)
+                else:
+                    pk.add_conv(name, m, m.cout, m.cin, m.k)
+            pk.finalize(self.conv_pre.weight_v.device)
+            self._packer = pk
+        return self._packer
 
     def reset_parameters(self, seed=1234):
         """Reference init: N(0, 0.01) weights for ups / resblocks / conv_post (utils.py:23-26), torch default for
@@ -140,15 +257,14 @@ class Generator(nn.Module):
             raise NotImplementedError("USE_EMB_CONDITIONING is off in config_v1.json")
         B, _, T = x.shape
         keep = self.training
-        packed = self._pack()
-        W = {k: tuple(self._rounded(t) for t in v) for k, v in packed.items()}
+        W = self._get_packer().pack()      # tf32-rounded effective weights of all 86 convolutions, one launch
         # [B, T, 80] channels-last operand in rows of 96 floats (zero tail): the weight-gradient GEMM reads it MN-major
         # in 32-column chunks
         melp = torch.zeros(B, T, 96, device=x.device, dtype=torch.float32)
         mel = melp[..., :80]
         mel.copy_(x.to(torch.float32).transpose(1, 2))
         ops.round_tf32_(melp.reshape(-1), melp.reshape(-1))
-        ctx = {"mel": mel, "stages": [], "W": W, "packed": packed, "B": B}
+        ctx = {"mel": mel, "stages": [], "W": W, "B": B}
         # conv_pre; only leaky_relu(conv_pre(x)) is ever read (models.py:111,115)
         a = ops.conv_fwd(mel, W["conv_pre"][0], self.conv_pre.shifts, bias=self.conv_pre.bias.detach(),
                          act_slope=LRELU_SLOPE, round_out=True)
@@ -202,15 +318,7 @@ class Generator(nn.Module):
         if ctx is None:
             raise RuntimeError("backward() needs a forward() in training mode first")
         B, W = ctx["B"], ctx["W"]
-        # one zero-filled buffer for every packed-weight gradient (a single fill instead of one per convolution)
-        flat = torch.zeros(sum(t.numel() for v in W.values() for t in v), device=dy.device, dtype=torch.float32)
-        gW, off = {}, 0
-        for k, v in W.items():
-            views = []
-            for t in v:
-                views.append(flat[off:off + t.numel()].view(t.shape))
-                off += t.numel()
-            gW[k] = tuple(views)
+        gW = self._get_packer().zero_grads()      # packed-weight gradients: one arena, one fill
         mods = dict(self.named_modules())
 
         def bias_grad(name, d, cols, ld=None):
@@ -268,13 +376,8 @@ class Generator(nn.Module):
         ops.conv_wgrad(dpre0, ctx["mel"], self.conv_pre.shifts, out=gW["conv_pre"][0], accumulate=True)
         bias_grad("conv_pre", dpre0, self.conv_pre.cout)
 
-        # hand the packed-weight gradients to autograd (weight norm + re-packing), biases directly
-        tensors, grads = [], []
-        for k, v in ctx["packed"].items():
-            for t, g_ in zip(v, gW[k]):
-                tensors.append(t)
-                grads.append(g_)
-        torch.autograd.backward(tensors, grads)
+        # packed-weight gradients -> weight_g / weight_v (.grad accumulated), one launch
+        self._get_packer().unpack_grads()
         self._ctx = None
 
     def _ups_dgrad(self, i, d_up, a_in, slope, W, alpha=1.0 / 3.0):
@@ -488,22 +591,39 @@ class _Disc(nn.Module):
             cache[key] = torch.full((Z,), L, device=dev, dtype=torch.int32)
         return cache[key]
 
-    def forward(self, wave, keep=True, weight_grad=True):
-        """wave [B, T] fp32 -> (score [Z, L, 1], fmaps [activation buffers + score], ctx)."""
+    def register_weights(self, packer, prefix):
+        """Describe this sub-discriminator's convolutions to a _WnPacker (same layouts as _packed())."""
+        for li, m in enumerate(list(self.convs) + [self.conv_post]):
+            key = f"{prefix}.{li}"
+            if li == 0:
+                packer.add_flat(key, m, m.cout, m.k)
+            else:
+                Gp, Ogp, Cgp, f = self._group_geom(m)
+                packer.add_conv(key, m, m.cout, m.cin // m.groups, m.k, order=[j for j, _, _ in m.taps()],
+                                og=m.cout // m.groups, f=f)
+
+    def forward(self, wave, keep=True, weight_grad=True, W=None, gW=None):
+        """wave [B, T] fp32 -> (score [Z, L, 1], fmaps [activation buffers + score], ctx). W / gW: this
+        sub-discriminator's packed weights and their gradient buffers when the model packs all weights in one launch
+        (_WnPacker); otherwise they are produced here with PyTorch ops under autograd (the spectral-norm path)."""
         B, T = wave.shape
         geom = self._geom(T)
         P, L = geom[3], geom[5]
         Z = B * P
-        with torch.set_grad_enabled(weight_grad and torch.is_grad_enabled()):
-            packed = self._packed()
+        if W is None:
+            with torch.set_grad_enabled(weight_grad and torch.is_grad_enabled()):
+                packed = self._packed()
+        else:
+            packed = None
         layers = list(self.convs)
         m0 = layers[0]
         L0 = m0.out_len(L)
         nxt = layers[1].stride
-        X = ops.conv_c1_fwd(wave, geom, packed[0].detach(), m0.bias.detach(), m0.k, m0.stride, m0.pad, Z, L0,
+        w0 = packed[0].detach() if W is None else W[0]
+        X = ops.conv_c1_fwd(wave, geom, w0, m0.bias.detach(), m0.k, m0.stride, m0.pad, Z, L0,
                             _round_up(L0, nxt), m0.cout, LRELU_SLOPE)
         acts, lens_v = [X], [L0]
-        Wr = [None]
+        Wr = [w0]
         for li in range(1, len(layers)):
             m = layers[li]
             Lin = lens_v[-1]
@@ -511,20 +631,20 @@ class _Disc(nn.Module):
             s_next = layers[li + 1].stride if li + 1 < len(layers) else 1
             Lp_out = _round_up(Lout, s_next)
             out = torch.empty(Z, Lp_out, m.cout, device=wave.device, dtype=torch.float32)
-            wr = _rounded(packed[li])
+            wr = _rounded(packed[li]) if W is None else W[li]
             Wr.append(wr)
             self._layer_fwd(m, X, wr, out, Lp_out, self._lens(Z, Lout, wave.device))
             X = out
             acts.append(X)
             lens_v.append(Lout)
         mp = self.conv_post
-        wrp = _rounded(packed[-1])
+        wrp = _rounded(packed[-1]) if W is None else W[-1]
         Wr.append(wrp)
         Lf = lens_v[-1]
         score = torch.empty(Z, Lf, 1, device=wave.device, dtype=torch.float32)
         taps = mp.taps()
         ops.conv_fwd(X, wrp, [sh for _, sh, _ in taps], out=score, out_rows=Lf, bias=mp.bias.detach())
-        ctx = dict(wave=wave, geom=geom, Z=Z, acts=acts, lens=lens_v, packed=packed, Wr=Wr, score=score) if keep else None
+        ctx = dict(wave=wave, geom=geom, Z=Z, acts=acts, lens=lens_v, packed=packed, Wr=Wr, score=score, gW=gW) if keep else None
         return score, acts + [score], ctx
 
     def _layer_fwd(self, m, X, wr, out, Lp_out, lens_t):
@@ -554,7 +674,10 @@ class _Disc(nn.Module):
         layers = list(self.convs)
         dev = dscore.device
         gW = None
-        if need_w:   # one zero-filled buffer for every packed-weight gradient of this sub-discriminator
+        shared = ctx.get("gW") is not None       # gradient views of the model-level _WnPacker (already zeroed)
+        if need_w and shared:
+            gW = list(ctx["gW"])
+        elif need_w:   # one zero-filled buffer for every packed-weight gradient of this sub-discriminator
             sizes = [w.numel() for w in Wr[1:]]
             flat = torch.zeros(sum(sizes), device=dev, dtype=torch.float32)
             gW, off = [None], 0
@@ -612,15 +735,15 @@ class _Disc(nn.Module):
             dpre = dX
         # first layer (raw waveform)
         m0 = layers[0]
-        w0 = ctx["packed"][0]
+        w0 = Wr[0] if shared else ctx["packed"][0]
         if need_w:
-            dw0 = torch.zeros(m0.cout, m0.k, device=dev, dtype=torch.float32)
+            dw0 = gW[0] if shared else torch.zeros(m0.cout, m0.k, device=dev, dtype=torch.float32)
             if m0.bias.grad is None:
                 m0.bias.grad = torch.zeros_like(m0.bias)
             ops.conv_c1_bwd_w(dpre, ctx["wave"], ctx["geom"], m0.k, m0.stride, m0.pad, lens_v[0], dw0, m0.bias.grad)
         if dwave is not None:
             ops.conv_c1_bwd_x(dpre, w0.detach(), ctx["geom"], m0.k, m0.stride, m0.pad, lens_v[0], wave_scale, dwave)
-        if need_w:
+        if need_w and not shared:
             torch.autograd.backward([w0] + list(ctx["packed"][1:]), [dw0] + gW[1:])
 
 
@@ -707,6 +830,16 @@ def _multi_forward(model, y, y_hat, pools, weight_grad=True):
     B = yr.shape[0]
     both = torch.cat([yr, yg], 0)
     model._ctx = []
+    pk = getattr(model, "_packer", None)
+    if pk is None:
+        pk = _WnPacker()
+        for i, d in enumerate(model.discriminators):
+            if not any(m.spectral for m in d.convs):
+                d.register_weights(pk, str(i))
+        pk.finalize(both.device)
+        model._packer = pk
+    Wall = pk.pack()                      # every weight-normed convolution of the model: one launch
+    n_layers = lambda d: len(d.convs) + 1
     y_d_rs, y_d_gs, fmap_rs, fmap_gs = [], [], [], []
     for i, d in enumerate(model.discriminators):
         if pools and i != 0:
@@ -716,7 +849,8 @@ def _multi_forward(model, y, y_hat, pools, weight_grad=True):
             sg, fg, cg = d(both[B:], weight_grad=weight_grad)
             passes = [(cr, (0, cr["Z"]), None), (cg, None, (0, cg["Z"]))]
         else:
-            s2, f2, c2 = d(both, weight_grad=weight_grad)
+            s2, f2, c2 = d(both, weight_grad=weight_grad, W=[Wall[f"{i}.{li}"][0] for li in range(n_layers(d))],
+                           gW=[pk.gW[f"{i}.{li}"][0] for li in range(n_layers(d))])
             Z = c2["Z"] // 2
             sr, sg = s2[:Z], s2[Z:]
             fr, fg = [f[:Z] for f in f2], [f[Z:] for f in f2]
@@ -736,6 +870,7 @@ def discriminator_loss_backward(model, y_d_rs, y_d_gs):
     dev = y_d_rs[0].device
     acc = torch.zeros(2 * len(y_d_rs), device=dev, dtype=torch.float64)
     loss = torch.zeros((), device=dev, dtype=torch.float64)
+    model._packer.zero_grads()
     for i, (d, passes) in enumerate(zip(model.discriminators, model._ctx)):
         dr, dg = y_d_rs[i], y_d_gs[i]
         n = dr.numel()
@@ -749,6 +884,7 @@ def discriminator_loss_backward(model, y_d_rs, y_d_gs):
             if gr is not None:
                 ops.sq_grad(dg, 0.0, 1.0 / n, out=dscore[gr[0]:gr[1]], accumulate=False)
             d.backward(ctx, dscore, [None] * len(ctx["acts"]), need_w=True)
+    model._packer.unpack_grads()          # packed-weight gradients -> weight_g / weight_v of every sub-discriminator
     return loss
 
 
@@ -850,8 +986,11 @@ class HiFiGANStep:
     losses -> AdamW). ``step(x, y, y_mel)`` takes the reference's batch tensors (x [B, 80, T] input mel, y [B, 8192]
     audio, y_mel [B, 80, T] loss mel) and returns the losses as 0-dim device tensors (no host sync)."""
 
-    def __init__(self, generator, mpd, msd, h, lr=None, betas=None):
+    def __init__(self, generator, mpd, msd, h, lr=None, betas=None, world=1, group=None):
+        """world > 1: one process per GPU, each on its own shard of the utterance batch; the two gradient arenas are
+        all-reduced (mean) right before their optimizer steps -- the only collectives on the path."""
         self.generator, self.mpd, self.msd, self.h = generator, mpd, msd, h
+        self.world, self.group = int(world), group
         lr = h.learning_rate if lr is None else lr
         betas = (h.adam_b1, h.adam_b2) if betas is None else betas
         dev = next(generator.parameters()).device
@@ -860,6 +999,12 @@ class HiFiGANStep:
         self.optim_g = AdamW(generator.parameters(), lr, betas)
         self.optim_d = AdamW(list(msd.parameters()) + list(mpd.parameters()), lr, betas)   # itertools.chain order of :300
         self.steps = 0
+
+    def _all_reduce(self, flat_grad):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=self.group)
+            flat_grad.mul_(1.0 / self.world)
 
     def step(self, x, y, y_mel):
         G, mpd, msd = self.generator, self.mpd, self.msd
@@ -876,6 +1021,7 @@ class HiFiGANStep:
         loss_disc_f = discriminator_loss_backward(mpd, rs, gs)
         rs, gs, _, _ = msd(y, wave)
         loss_disc_s = discriminator_loss_backward(msd, rs, gs)
+        self._all_reduce(self.optim_d.g)
         self.optim_d.step()
 
         # ---- generator (:501-515)
@@ -890,6 +1036,7 @@ class HiFiGANStep:
         rs, gs, frs, fgs = msd(y, wave, weight_grad=False)
         loss_gen_s, loss_fm_s = generator_adv_loss_backward(msd, gs, frs, fgs, dwave, pools=True)
         G.backward(dwave.view(B, 1, -1))
+        self._all_reduce(self.optim_g.g)
         self.optim_g.step()
         self.steps += 1
         loss_gen_all = loss_gen_s + loss_gen_f + loss_fm_s + loss_fm_f + loss_mel
