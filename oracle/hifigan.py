@@ -163,6 +163,22 @@ def mel_spectrogram(y, fmax=FMAX, n_fft=N_FFT, hop=HOP, win=WIN, n_mels=N_MELS, 
     return torch.log(torch.clamp(torch.matmul(basis, mag), min=1e-5))
 
 
+def tacotron_mel(y, n_fft=N_FFT, hop=HOP, n_mels=N_MELS, sr=SR, fmin=FMIN, fmax=FMAX):
+    """TacotronSTFT.mel_spectrogram, fastpitch1_1/common/layers.py:121-138 with STFT.transform, common/stft.py:86-114
+    (the FastPitch dataset's mel extractor): reflect-pad n_fft/2, windowed-DFT-basis conv1d with stride
+    hop, sqrt(re^2 + im^2) (no epsilon), Slaney mel basis, log(clamp(., 1e-5)). y [B, N] in [-1, 1] -> [B, 80, N/256 + 1]."""
+    assert float(y.min()) >= -1 and float(y.max()) <= 1
+    nb = n_fft // 2 + 1
+    fb = np.fft.fft(np.eye(n_fft))
+    basis = torch.from_numpy(np.vstack([np.real(fb[:nb]), np.imag(fb[:nb])])).float()            # stft.py:63-69
+    basis = basis[:, None, :] * torch.hann_window(n_fft, periodic=True).float()                 # stft.py:75-81 (fftbins=True)
+    yp = F.pad(y[:, None, None, :], (n_fft // 2, n_fft // 2, 0, 0), mode="reflect").squeeze(1)  # stft.py:93-98
+    ft = F.conv1d(yp, basis, stride=hop)
+    mag = torch.sqrt(ft[:, :nb] ** 2 + ft[:, nb:] ** 2)
+    mel = torch.matmul(mel_filterbank(sr, n_fft, n_mels, fmin, fmax), mag)
+    return torch.log(torch.clamp(mel, min=1e-5))                                                # audio_processing: C = 1
+
+
 # ------------------------------------------------------------------------------------------------ synthetic inputs
 def synthetic_batch(B, frames, seed=1234):
     """audio = 0.95 tanh(N(0, 0.3)), x = mel(audio, fmax 8000), y_mel = mel(audio, fmax None)."""

@@ -16,6 +16,8 @@ b1, b2 = r(1536), r(384)
 gam, bet = 1 + 0.1 * r(384), 0.1 * r(384)
 lens = torch.full((B,), T, device="cuda", dtype=torch.int32)
 K3 = (-1, 0, 1)
+scores = torch.empty(B, T, 896, device="cuda")
+wo = r(1, 384, 64) * 0.1
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 for _ in range(reps):
@@ -29,5 +31,11 @@ for _ in range(reps):
         ops.conv_dgrad(h, w1, K3, residual=x)
     if which in ("all", "wgrad1"):
         ops.conv_wgrad(h, x, K3)
+    if which in ("qk",):          # attention scores: K = 64, the launch is all epilogue (101 MB written)
+        ops.bmm_nt(x[..., :64], x[..., 64:128], alpha=0.125, out=scores[..., :T])
+    if which in ("onet",):        # o_net: K = 64, residual + dropout epilogue
+        ops.conv_fwd(x[..., :64], wo, residual=x, drop_p=0.1, seed=1)
+    if which in ("conv2",):       # ConvFF second conv, un-fused: bias + dropout + residual
+        ops.conv_fwd(h, w2, K3, bias=b2, residual=x, drop_p=0.1, seed=1)
 torch.cuda.synchronize()
 print("done")

@@ -194,6 +194,22 @@ def test_mel_spectrogram_matches_oracle_and_golden(lib, fmax):
     assert rel(d, a.grad) < 1e-2, rel(d, a.grad)
 
 
+def test_tacotron_stft_variant_matches_reference_golden(lib):
+    """TacotronSTFT.mel_spectrogram (reflect pad n_fft / 2, no epsilon, N / 256 + 1 frames) vs the
+    fixture recorded from the reference and vs the oracle. Same tolerance as the HiFi-GAN variant (5e-3 absolute on the
+    log-mel; tf32 DFT)."""
+    from xva_trainer_b200 import hifigan as hg
+
+    gold = np.load(os.path.join(GOLD, "tacotron_stft.npz"))
+    audio = torch.from_numpy(gold["audio"])
+    ms = hg.MelSpectrogram.tacotron(device="cuda:0")
+    got = ms(audio.cuda()).transpose(1, 2).cpu()
+    want = torch.from_numpy(gold["mel"])
+    assert got.shape == want.shape, (got.shape, want.shape)
+    assert float((got - want).abs().max()) < 5e-3, float((got - want).abs().max())
+    assert rel(got, ohg.tacotron_mel(audio)) < 1e-3
+
+
 def test_reflect_pad_and_losses(lib):
     from xva_trainer_b200 import ops
 

@@ -17,6 +17,8 @@
 
 namespace xva {
 
+static int g_round_host = 1;  // host mirror of g_xva_round_operands: travels to the kernel as GemmDev::round_on
+
 namespace {
 
 constexpr int kBlockM = 128;        // accumulator rows per tile (= TMEM lanes)
@@ -78,6 +80,7 @@ struct GemmDev {
   const uint64_t* seed_dev;
   int dbg;     // bring-up knobs (XVA_GEMM_DBG): 1 = no epilogue stores, 2 = no TMA after the first ring fill, 4 = no MMA
   int vec_ok;  // every epilogue pointer is 16-byte aligned and every stride a multiple of 4: float4 accesses
+  int round_on;  // host mirror of the operand-rounding test switch (xva_set_operand_rounding), read once per tile
 };
 
 struct TileCoord {
@@ -569,53 +572,91 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int len_z = p.lens ? p.lens[zq] : 0x7fffffff;
         const long zoff_o = zq * p.o_zs + c.n0, zoff_r = zq * p.r_zs + c.n0, zoff_g = zq * p.g_zs + c.n0;
 
+        // Every feature test below is uniform over the launch: it is evaluated once per tile and each feature is its own
+        // loop over the lane's 8 rows. (With the tests inside one fused per-row loop the epilogue executed ~19 thread
+        // instructions per output element and the epilogue-bound launches -- attention scores, o_net, gated input
+        // gradients -- ran instruction-bound at ~1.8 TB/s of stores: profiles/r01_epilogue_stalls.txt.)
+        const int flags = p.flags;
+        const bool f_bias = p.bias != nullptr, f_relu = (flags & GEMM_RELU) != 0, f_tanh = (flags & GEMM_TANH) != 0;
+        const bool f_round = (flags & GEMM_ROUND_OUT) != 0 && p.round_on != 0, f_lens = p.lens != nullptr;
+        const bool f_act = p.out_act != nullptr, f_scale = p.alpha != 1.0f;
+        const bool f_gate = (kEpi != EPI_PLAIN) && p.gate != nullptr, f_res = (kEpi != EPI_PLAIN) && p.residual != nullptr;
+        const bool f_drop = (kEpi != EPI_PLAIN) && (flags & GEMM_DROP_PRE) != 0;
+        const float alpha = p.alpha, act_slope = p.act_slope, gate_slope = p.gate_slope;
+        auto cvt4 = [](float4 v) {  // fp32 -> tf32, round to nearest (the switch was read once: f_round)
+          uint32_t a, b, c2, d;
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(a) : "f"(v.x));
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(b) : "f"(v.y));
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(c2) : "f"(v.z));
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(d) : "f"(v.w));
+          return make_float4(__uint_as_float(a), __uint_as_float(b), __uint_as_float(c2), __uint_as_float(d));
+        };
+
         // x = alpha*acc + bias -> relu -> gate -> dropout(pre) -> + residual   for the 8 float4 of one chunk
         auto finish_chunk = [&](float4 (&t)[8], int n, bool full, int nv) {
-          float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.bias && nv) {
-            const float* bp = p.bias + c.n0 + n;
-            if (full) b = __ldg(reinterpret_cast<const float4*>(bp));
-            else {
-              b.x = __ldg(bp);
-              if (nv > 1) b.y = __ldg(bp + 1);
-              if (nv > 2) b.z = __ldg(bp + 2);
-              if (nv > 3) b.w = __ldg(bp + 3);
-            }
-          }
-          float4 gv[8], rv[8];
+          // One auxiliary row set: the gate (or, without a gate, the residual) is requested before the arithmetic on
+          // the accumulator so its latency overlaps; with both, the residual is fetched after the gate is consumed
+          // (two live sets next to the accumulator spill at 168 registers).
+          float4 aux[8];
           if constexpr (kEpi != EPI_PLAIN) {
-            if (p.gate) load8(p.gate + zoff_g + n, p.g_rs, row0, row_limit, full, nv, gv);
-            if (p.residual) load8(p.residual + zoff_r + n, p.r_rs, row0, row_limit, full, nv, rv);
+            if (f_gate) load8(p.gate + zoff_g + n, p.g_rs, row0, row_limit, full, nv, aux);
+            else if (f_res) load8(p.residual + zoff_r + n, p.r_rs, row0, row_limit, full, nv, aux);
           }
+          if (f_bias) {
+            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (nv) {
+              const float* bp = p.bias + c.n0 + n;
+              if (full) b = __ldg(reinterpret_cast<const float4*>(bp));
+              else {
+                b.x = __ldg(bp);
+                if (nv > 1) b.y = __ldg(bp + 1);
+                if (nv > 2) b.z = __ldg(bp + 2);
+                if (nv > 3) b.w = __ldg(bp + 3);
+              }
+            }
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            float4 x = make_float4(p.alpha * t[k].x + b.x, p.alpha * t[k].y + b.y, p.alpha * t[k].z + b.z,
-                                   p.alpha * t[k].w + b.w);
-            if (p.flags & GEMM_RELU) {
-              x.x = x.x > 0.f ? x.x : p.act_slope * x.x; x.y = x.y > 0.f ? x.y : p.act_slope * x.y;
-              x.z = x.z > 0.f ? x.z : p.act_slope * x.z; x.w = x.w > 0.f ? x.w : p.act_slope * x.w;
+            for (int k = 0; k < 8; ++k)
+              t[k] = make_float4(alpha * t[k].x + b.x, alpha * t[k].y + b.y, alpha * t[k].z + b.z, alpha * t[k].w + b.w);
+          } else if (f_scale) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) t[k] = make_float4(alpha * t[k].x, alpha * t[k].y, alpha * t[k].z, alpha * t[k].w);
+          }
+          if (f_relu) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              t[k].x = t[k].x > 0.f ? t[k].x : act_slope * t[k].x; t[k].y = t[k].y > 0.f ? t[k].y : act_slope * t[k].y;
+              t[k].z = t[k].z > 0.f ? t[k].z : act_slope * t[k].z; t[k].w = t[k].w > 0.f ? t[k].w : act_slope * t[k].w;
             }
-            if constexpr (kEpi != EPI_PLAIN) {
-              if (p.gate) {
-                x.x *= gv[k].x > 0.f ? 1.f : p.gate_slope;
-                x.y *= gv[k].y > 0.f ? 1.f : p.gate_slope;
-                x.z *= gv[k].z > 0.f ? 1.f : p.gate_slope;
-                x.w *= gv[k].w > 0.f ? 1.f : p.gate_slope;
+          }
+          if constexpr (kEpi != EPI_PLAIN) {
+            if (f_gate) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                t[k].x *= aux[k].x > 0.f ? 1.f : gate_slope; t[k].y *= aux[k].y > 0.f ? 1.f : gate_slope;
+                t[k].z *= aux[k].z > 0.f ? 1.f : gate_slope; t[k].w *= aux[k].w > 0.f ? 1.f : gate_slope;
               }
-              if (p.flags & GEMM_DROP_PRE) {
-                const uint64_t di = (static_cast<uint64_t>(zq) * p.R + (row0 + 4 * k)) * static_cast<uint64_t>(p.N) + c.n0 + n;
-                const float4 ds = dropout_scale4(seed, di, p.drop_thresh, p.inv_keep);
-                x.x *= ds.x; x.y *= ds.y; x.z *= ds.z; x.w *= ds.w;
-              }
-              if (p.residual) {
-                x.x += rv[k].x; x.y += rv[k].y; x.z += rv[k].z; x.w += rv[k].w;
+              if (f_res) load8(p.residual + zoff_r + n, p.r_rs, row0, row_limit, full, nv, aux);
+            }
+            if (f_drop) {
+              const uint64_t d0 = (static_cast<uint64_t>(zq) * p.R + row0) * static_cast<uint64_t>(p.N) + c.n0 + n;
+              const uint64_t dstep = 4ull * static_cast<uint64_t>(p.N);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const float4 ds = dropout_scale4(seed, d0 + k * dstep, p.drop_thresh, p.inv_keep);
+                t[k].x *= ds.x; t[k].y *= ds.y; t[k].z *= ds.z; t[k].w *= ds.w;
               }
             }
-            t[k] = x;
+            if (f_res) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                t[k].x += aux[k].x; t[k].y += aux[k].y; t[k].z += aux[k].z; t[k].w += aux[k].w;
+              }
+            }
           }
         };
 
         if constexpr (kEpi != EPI_LN) {
+          const long ostep = 4L * p.o_rs;
           for (int ch = half; ch < n_chunks; ch += 2) {
             float4 t[8];
             load_chunk(tacc + ch * 32, t);
@@ -624,20 +665,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const int nv = n < n_cols ? ((n_cols - n) < 4 ? (n_cols - n) : 4) : 0;
             const bool full = vec && nv == 4;
             finish_chunk(t, n, full, nv);
+            if (f_tanh) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const int row = row0 + 4 * k;
-              if (row >= row_limit || nv == 0) continue;
-              if (p.flags & GEMM_TANH) t[k] = make_float4(tanhf(t[k].x), tanhf(t[k].y), tanhf(t[k].z), tanhf(t[k].w));
-              if (row >= len_z) t[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (p.out_act) {
-                const float sl = p.out_act_slope;
-                const float4 a = make_float4(t[k].x > 0.f ? t[k].x : sl * t[k].x, t[k].y > 0.f ? t[k].y : sl * t[k].y,
-                                             t[k].z > 0.f ? t[k].z : sl * t[k].z, t[k].w > 0.f ? t[k].w : sl * t[k].w);
-                store1(p.out_act + zoff_o + static_cast<long>(row) * p.o_rs + n, full, nv, tf32_rn4(a));
+              for (int k = 0; k < 8; ++k) t[k] = make_float4(tanhf(t[k].x), tanhf(t[k].y), tanhf(t[k].z), tanhf(t[k].w));
+            }
+            if (f_lens) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k)
+                if (row0 + 4 * k >= len_z) t[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            // rows this lane may store: k < kmax (none for an empty column slot)
+            const int kmax = nv == 0 ? 0 : (row_limit - row0 + 3) / 4;
+            const long off0 = zoff_o + static_cast<long>(row0) * p.o_rs + n;
+            if (f_act) {
+              const float sl = p.out_act_slope;
+              float* ap = p.out_act + off0;
+#pragma unroll
+              for (int k = 0; k < 8; ++k, ap += ostep) {
+                if (k >= kmax) continue;
+                float4 a = make_float4(t[k].x > 0.f ? t[k].x : sl * t[k].x, t[k].y > 0.f ? t[k].y : sl * t[k].y,
+                                       t[k].z > 0.f ? t[k].z : sl * t[k].z, t[k].w > 0.f ? t[k].w : sl * t[k].w);
+                if (p.round_on) a = cvt4(a);
+                store1(ap, full, nv, a);
               }
-              if (p.flags & GEMM_ROUND_OUT) t[k] = tf32_rn4(t[k]);
-              store1(p.out + zoff_o + static_cast<long>(row) * p.o_rs + n, full, nv, t[k]);
+            }
+            if (f_round) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) t[k] = cvt4(t[k]);
+            }
+            float* op = p.out + off0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k, op += ostep) {
+              if (k < kmax) store1(op, full, nv, t[k]);
             }
           }
         } else {
@@ -1136,6 +1195,7 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
     if (g.out_act) ok = ok && al(g.out_act);
     if (g.flags & GEMM_LN) ok = ok && al(g.gamma) && al(g.beta);
     p.vec_ok = ok ? 1 : 0;
+    p.round_on = g_round_host;
   }
 
   static std::once_flag attr_once;
@@ -1186,6 +1246,10 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
   return XVA_OK;
 }
 
-XVA_DEFINE_ROUNDING_SWITCH(gemm_tc)
+int set_operand_rounding_gemm_tc(int on) {
+  XVA_CHECK_CUDA(cudaMemcpyToSymbol(g_xva_round_operands, &on, sizeof(int)));
+  g_round_host = on;
+  return XVA_OK;
+}
 
 }  // namespace xva

@@ -427,13 +427,20 @@ class MelSpectrogram:
     EPS, LOG_MIN = 1e-9, 1e-5
 
     def __init__(self, n_fft=1024, num_mels=80, sampling_rate=22050, hop_size=256, win_size=1024, fmin=0, fmax=8000,
-                 device="cuda"):
+                 device="cuda", pad=None, mag_eps=None):
+        """pad / mag_eps select the variant: the defaults are hifigan/meldataset.py's
+        (reflect (n_fft - hop) / 2, sqrt(re^2 + im^2 + 1e-9)); ``MelSpectrogram.tacotron()`` gives the FastPitch dataset's
+        TacotronSTFT (reflect n_fft / 2, no epsilon, N / hop + 1 frames)."""
         if n_fft % hop_size or win_size != n_fft:
             raise NotImplementedError("built for win_size == n_fft and n_fft a multiple of hop_size (config_v1.json)")
         self.n_fft, self.hop, self.n_mels = n_fft, hop_size, num_mels
         self.taps = n_fft // hop_size
         self.nb = n_fft // 2 + 1
-        self.pad = (n_fft - hop_size) // 2
+        self.pad = (n_fft - hop_size) // 2 if pad is None else int(pad)
+        if mag_eps is not None:
+            self.EPS = float(mag_eps)
+        if (2 * self.pad) % hop_size:
+            raise NotImplementedError("2 * pad must be a multiple of the hop size")
         self.ld_s = (2 * self.nb + 3) // 4 * 4          # spectrum row stride (16-byte rows)
         self.ld_m = (self.nb + 31) // 32 * 32           # magnitude row stride / padded K of the mel projection
         dev = torch.device(device)
@@ -454,8 +461,8 @@ class MelSpectrogram:
         B, N = y.shape
         if N % self.hop:
             raise ValueError(f"signal length {N} is not a multiple of the hop size {self.hop}")
-        F_ = N // self.hop
-        yp = ops.reflect_pad(y.to(torch.float32).contiguous(), self.pad)              # [B, N + n_fft - hop]
+        F_ = (N + 2 * self.pad - self.n_fft) // self.hop + 1                          # N / hop, or N / hop + 1 (tacotron)
+        yp = ops.reflect_pad(y.to(torch.float32).contiguous(), self.pad)              # [B, N + 2 pad]
         view = yp.view(B, F_ + self.taps - 1, self.hop)
         spec = torch.empty(B, F_, self.ld_s, device=y.device, dtype=torch.float32)
         if self.ld_s > 2 * self.nb:
@@ -468,6 +475,15 @@ class MelSpectrogram:
         return out
 
     __call__ = forward
+
+    @classmethod
+    def tacotron(cls, filter_length=1024, hop_length=256, win_length=1024, n_mel_channels=80, sampling_rate=22050,
+                 mel_fmin=0.0, mel_fmax=8000.0, device="cuda"):
+        """TacotronSTFT(...).mel_spectrogram of fastpitch1_1/common/layers.py:102-138 (+ common/stft.py:86-114), the mel
+        extractor of the FastPitch dataset (data_function.py:226-228): same constructor arguments; ``forward(y [B, N])``
+        -> [B, N / hop + 1, n_mels] (channels-last; the reference returns its transpose)."""
+        return cls(filter_length, n_mel_channels, sampling_rate, hop_length, win_length, mel_fmin, mel_fmax, device=device,
+                   pad=filter_length // 2, mag_eps=0.0)
 
     def backward(self, dmel):
         B, N, F_, spec, lin = self._ctx
