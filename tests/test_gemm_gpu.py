@@ -264,6 +264,8 @@ def test_full_size_linearity_property():
     (22, 10, 128, 128, (-2, -1, 0, 1, 2)),  # DiscriminatorP period 11: 10 rows per sequence
     (7, 51, 64, 96, (-1, 0, 1)),          # 51 rows -> 64-row segments
     (5, 83, 64, 64, (-1, 0, 1)),          # 83 rows -> three 32-row segments
+    (8, 48, 64, 96, (-1, 0, 1)),          # 48 rows -> two 32-row segments, the second half empty
+    (8, 880, 32, 64, (-2, 0, 2)),         # FastPitch decoder rows (880 = 6 x 128 + 112)
 ])
 def test_segmented_tiles(B, T, K, N, shifts):
     """Short sequences share 128-row tiles (segments of 32 / 64 rows): conv halo stays per item (TMA zero fill per
