@@ -155,6 +155,16 @@ int xva_regulate_len_bwd(const float* dout, const int32_t* cum, int B, int Tt, i
 int xva_average_pitch(const float* pitch, const float* durs, int B, int F, int Tm, int Tt, float* out, int log1p_out,
                       void* stream);
 
+/* Monotonic alignment search -- replaces b_mas / mas_width1, fastpitch/alignment.py:79-118 (called through
+ * FastPitch.binarize_attention_parallel, model.py:283-294, after a device->host copy; training stage 1): Viterbi path
+ * through the soft alignment attn [B, Tm, Tt] (mel x text, the reference's [B, 1, Tm, Tt]) restricted to
+ * [out_lens[b], in_lens[b]]. hard [B, Tm, Tt] gets the 0/1 alignment (zero elsewhere), durs [B, Tt] its column sums
+ * (attn_hard.sum(2), model.py:318) as int32. is_log = 0: attn holds probabilities (the reference's input; log taken in
+ * double and rounded to fp32); is_log = 1: attn holds fp32 log-probabilities and the path is bit-identical to the
+ * reference recurrence on the same values. Tm x ceil(Tt/32) x 4 bytes of shared memory (<= 200 KiB). */
+int xva_mas_width1(const float* attn, const int32_t* in_lens, const int32_t* out_lens, int B, int Tm, int Tt, int is_log,
+                   float* hard, int32_t* durs, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Attention softmax -- replaces masked_fill + F.softmax + dropatt, fastpitch/transformer.py:120-127, and its autograd.
  *   fwd : s [Z,R,N] = alpha*q.k^T (from xva_gemm) -> p (softmax over n with keys n >= lens[z] masked), and

@@ -77,6 +77,7 @@ PROTOTYPES = {
     "xva_regulate_len_fwd": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "xva_regulate_len_bwd": (_I, [_P, _P, _I, _I, _I, _I, _P, _I, _P]),
     "xva_average_pitch": (_I, [_P, _P, _I, _I, _I, _I, _P, _I, _P]),
+    "xva_mas_width1": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "xva_softmax_fwd": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _F, _U64, _P, _P]),
     "xva_softmax_bwd": (_I, [_P, _P, _I, _I, _I, _I, _F, _F, _U64, _P, _P]),
     "xva_layernorm_bwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _F, _U64, _F, _U64, _P, _I, _P]),

@@ -60,6 +60,11 @@ int xva_average_pitch(const float* pitch, const float* durs, int B, int F, int T
   return average_pitch(pitch, durs, B, F, Tm, Tt, out, log1p_out, S(stream));
 }
 
+int xva_mas_width1(const float* attn, const int32_t* in_lens, const int32_t* out_lens, int B, int Tm, int Tt, int is_log,
+                   float* hard, int32_t* durs, void* stream) {
+  return mas_width1(attn, in_lens, out_lens, B, Tm, Tt, is_log, hard, durs, S(stream));
+}
+
 int xva_softmax_fwd(const float* s, const int32_t* lens, int Z, int R, int N, int ld, float* p, float* pd,
                     float drop_p, uint64_t seed, const uint64_t* seed_dev, void* stream) {
   return softmax_fwd(s, lens, Z, R, N, ld, p, pd, drop_p, seed, seed_dev, S(stream));

@@ -32,63 +32,92 @@ __device__ __forceinline__ long c1_src(const C1& p, int z, int q) {
 
 constexpr int kMaxK = 16;
 
-// one warp per output row (z, t): lanes over output channels
+constexpr int kRowsFwd = 64;    // output rows per block (forward)
+constexpr int kRowsBwdW = 256;  // output rows per block (weight gradient)
+constexpr int kMaxWin = (kRowsBwdW - 1) * 4 + kMaxK;  // input window of a row tile (stride <= 4)
+
+// A block owns kRowsFwd consecutive output rows of one sequence: the input window ((rows-1)*s + k samples, gathered
+// through the period reshape / reflect padding once) and the transposed filter bank [k][Cout] sit in shared memory;
+// thread = (row, channel) with the channel fastest, so filter reads are conflict-free, the window read is a broadcast
+// and the [rows, Cout] store is fully coalesced.
 __global__ void __launch_bounds__(256)
-conv_c1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, C1 p, long rows,
-                   float* __restrict__ out) {
-  const int lane = threadIdx.x & 31;
-  const long row = static_cast<long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const int z = static_cast<int>(row / p.Lout_p), t = static_cast<int>(row - static_cast<long>(z) * p.Lout_p);
-  float* o = out + row * p.Cout;
-  if (t >= p.Lout) {
-    for (int co = lane; co < p.Cout; co += 32) o[co] = 0.0f;
-    return;
+conv_c1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, C1 p,
+                   int tiles_per_seq, float* __restrict__ out) {
+  __shared__ float xs[(kRowsFwd - 1) * 4 + kMaxK];
+  __shared__ float ws[kMaxK * 128 + 128];  // [k][Cout] then bias[Cout]
+  const int z = blockIdx.x / tiles_per_seq, t0 = (blockIdx.x - z * tiles_per_seq) * kRowsFwd;
+  const int win = (kRowsFwd - 1) * p.s + p.k;
+  for (int i = threadIdx.x; i < win; i += blockDim.x) {
+    const int q = t0 * p.s - p.pad + i;
+    xs[i] = (q >= 0 && q < p.L) ? x[c1_src(p, z, q)] : 0.0f;
   }
-  float xv[kMaxK];
-#pragma unroll
-  for (int j = 0; j < kMaxK; ++j) {
-    const int q = t * p.s + j - p.pad;
-    xv[j] = (j < p.k && q >= 0 && q < p.L) ? x[c1_src(p, z, q)] : 0.0f;
+  for (int i = threadIdx.x; i < p.Cout * p.k; i += blockDim.x) {
+    const int co = i / p.k, j = i - co * p.k;
+    ws[j * p.Cout + co] = w[i];
   }
-  for (int co = lane; co < p.Cout; co += 32) {
-    float acc = bias[co];
+  float* bs = ws + p.k * p.Cout;
+  for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) bs[i] = bias[i];
+  __syncthreads();
+  const int rows = min(kRowsFwd, p.Lout_p - t0);
+  float* o = out + (static_cast<long>(z) * p.Lout_p + t0) * p.Cout;
+  for (int i = threadIdx.x; i < rows * p.Cout; i += blockDim.x) {
+    const int r = i / p.Cout, co = i - r * p.Cout;
+    float acc = 0.0f;
+    if (t0 + r < p.Lout) {  // alignment rows [Lout, Lout_p) stay zero
+      acc = bs[co];
+      const float* xw = xs + r * p.s;
 #pragma unroll
-    for (int j = 0; j < kMaxK; ++j)
-      if (j < p.k) acc = fmaf(w[co * p.k + j], xv[j], acc);
-    o[co] = tf32_rn(acc > 0.0f ? acc : p.slope * acc);  // operand of the next (tensor-core) convolution
+      for (int j = 0; j < kMaxK; ++j)
+        if (j < p.k) acc = fmaf(ws[j * p.Cout + co], xw[j], acc);
+      acc = tf32_rn(acc > 0.0f ? acc : p.slope * acc);  // operand of the next (tensor-core) convolution
+    }
+    o[i] = acc;
   }
 }
 
-// dw[co, j] += sum_rows dpre[row, co] * x(row, j) ; db[co] += sum_rows dpre[row, co].  Cout <= 128: one thread per co.
-__global__ void __launch_bounds__(128)
-conv_c1_bwd_w_kernel(const float* __restrict__ dpre, const float* __restrict__ x, C1 p, long rows, float* __restrict__ dw,
-                     float* __restrict__ db) {
-  const int co = threadIdx.x;
+// dw[co, j] += sum_rows dpre[row, co] * x(row, j) ; db[co] += sum_rows dpre[row, co].
+// A block owns kRowsBwdW rows of one sequence (input window in shared memory); thread = (channel, row slice): the
+// Cout channels are spread over the lanes (coalesced dpre rows), 256 / Cout row slices run in parallel and are summed
+// through shared memory before one atomic per (co, j) per block.
+__global__ void __launch_bounds__(256)
+conv_c1_bwd_w_kernel(const float* __restrict__ dpre, const float* __restrict__ x, C1 p, int tiles_per_seq,
+                     float* __restrict__ dw, float* __restrict__ db) {
+  __shared__ float xs[kMaxWin];
+  __shared__ float red[256 * (kMaxK + 1)];
+  const int z = blockIdx.x / tiles_per_seq, t0 = (blockIdx.x - z * tiles_per_seq) * kRowsBwdW;
+  const int rows = min(kRowsBwdW, p.Lout - t0);
+  const int win = (kRowsBwdW - 1) * p.s + p.k;
+  for (int i = threadIdx.x; i < win; i += blockDim.x) {
+    const int q = t0 * p.s - p.pad + i;
+    xs[i] = (q >= 0 && q < p.L) ? x[c1_src(p, z, q)] : 0.0f;
+  }
+  __syncthreads();
+  const int co = threadIdx.x % p.Cout, slice = threadIdx.x / p.Cout, n_slices = blockDim.x / p.Cout;
   float acc[kMaxK + 1];
 #pragma unroll
   for (int j = 0; j <= kMaxK; ++j) acc[j] = 0.0f;
-  __shared__ float xs[kMaxK];
-  for (long row = blockIdx.x; row < rows; row += gridDim.x) {
-    const int z = static_cast<int>(row / p.Lout_p), t = static_cast<int>(row - static_cast<long>(z) * p.Lout_p);
-    if (t >= p.Lout) continue;
-    __syncthreads();
-    if (threadIdx.x < p.k) {
-      const int q = t * p.s + threadIdx.x - p.pad;
-      xs[threadIdx.x] = (q >= 0 && q < p.L) ? x[c1_src(p, z, q)] : 0.0f;
-    }
-    __syncthreads();
-    if (co < p.Cout) {
-      const float d = dpre[row * p.Cout + co];
+  if (slice < n_slices) {
+    const float* d = dpre + (static_cast<long>(z) * p.Lout_p + t0) * p.Cout + co;
+    for (int r = slice; r < rows; r += n_slices) {
+      const float g = d[static_cast<long>(r) * p.Cout];
+      const float* xw = xs + r * p.s;
 #pragma unroll
       for (int j = 0; j < kMaxK; ++j)
-        if (j < p.k) acc[j] = fmaf(d, xs[j], acc[j]);
-      acc[kMaxK] += d;
+        if (j < p.k) acc[j] = fmaf(g, xw[j], acc[j]);
+      acc[kMaxK] += g;
     }
   }
-  if (co < p.Cout) {
-    for (int j = 0; j < p.k; ++j) atomicAdd(dw + co * p.k + j, acc[j]);
-    atomicAdd(db + co, acc[kMaxK]);
+#pragma unroll
+  for (int j = 0; j <= kMaxK; ++j) red[j * 256 + threadIdx.x] = acc[j];
+  __syncthreads();
+  // (co, j) sums over the slices: thread i handles pairs i, i + 256, ...
+  for (int i = threadIdx.x; i < p.Cout * (p.k + 1); i += blockDim.x) {
+    const int c = i % p.Cout, j = i / p.Cout;  // j == k: the bias column
+    const int jj = j < p.k ? j : kMaxK;
+    float sum = 0.0f;
+    for (int sl = 0; sl < n_slices; ++sl) sum += red[jj * 256 + sl * p.Cout + c];
+    if (j < p.k) atomicAdd(dw + c * p.k + j, sum);
+    else atomicAdd(db + c, sum);
   }
 }
 
@@ -182,21 +211,21 @@ int conv_c1_fwd(const float* x, long xs_b, int xs_q, int xs_c, int P, int Lsrc, 
   C1 p;
   int rc = fill(&p, xs_b, xs_q, xs_c, P, Lsrc, L, k, s, pad, Lout, Lout_p, Cout, slope);
   if (rc != XVA_OK) return rc;
-  const long rows = static_cast<long>(Z) * Lout_p;
-  conv_c1_fwd_kernel<<<static_cast<int>(ceil_div_l(rows, 8)), 256, 0, stream>>>(x, w, bias, p, rows, out);
+  XVA_CHECK_ARG(Cout <= 128 && s <= 4, "conv_c1 fwd: Cout=%d (max 128), stride=%d (max 4)", Cout, s);
+  const int tiles = ceil_div(Lout_p, kRowsFwd);
+  conv_c1_fwd_kernel<<<Z * tiles, 256, 0, stream>>>(x, w, bias, p, tiles, out);
   XVA_CHECK_LAUNCH();
   return XVA_OK;
 }
 
 int conv_c1_bwd_w(const float* dpre, const float* x, long xs_b, int xs_q, int xs_c, int P, int Lsrc, int L, int k, int s,
                   int pad, int Z, int Lout, int Lout_p, int Cout, float* dw, float* db, cudaStream_t stream) {
-  XVA_CHECK_ARG(Cout <= 128, "conv_c1 bwd: Cout=%d (max 128)", Cout);
+  XVA_CHECK_ARG(Cout <= 128 && s <= 4, "conv_c1 bwd: Cout=%d (max 128), stride=%d (max 4)", Cout, s);
   C1 p;
   int rc = fill(&p, xs_b, xs_q, xs_c, P, Lsrc, L, k, s, pad, Lout, Lout_p, Cout, 0.0f);
   if (rc != XVA_OK) return rc;
-  const long rows = static_cast<long>(Z) * Lout_p;
-  long grid = rows < 8L * num_sms() ? rows : 8L * num_sms();
-  conv_c1_bwd_w_kernel<<<static_cast<int>(grid), 128, 0, stream>>>(dpre, x, p, rows, dw, db);
+  const int tiles = ceil_div(Lout, kRowsBwdW);
+  conv_c1_bwd_w_kernel<<<Z * tiles, 256, 0, stream>>>(dpre, x, p, tiles, dw, db);
   XVA_CHECK_LAUNCH();
   return XVA_OK;
 }

@@ -970,6 +970,23 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
   }
   p.tot_segs = g.Z * p.segs;
 
+  // ---- CTA pair (cta_group::2): two 128-row tiles share one B tile, each CTA stages half of it. Halves the B bytes
+  // every SM pulls through L2 (the fp32 operand stream is L2-bandwidth-bound at 128x256 tiles). Needs a B operand
+  // that does not depend on the batch item (weights). Measured per shape on B200: it pays for long main loops over at
+  // least two waves of tiles (decoder ConvFF: 4-7 % faster) and costs 7-15 % on short-K or single-wave launches.
+  static const bool pair_enabled = [] {
+    const char* e = getenv("XVA_GEMM_PAIR");
+    return !(e && e[0] == '0');
+  }();
+  static const bool pair_forced = [] {
+    const char* e = getenv("XVA_GEMM_PAIR");
+    return e && e[0] == '2';
+  }();
+  auto want_pair = [&](long tiles, long iters) {
+    if (!pair_enabled || g.mode == 2 || g.b_batch_z != 0 || row_tiles < 2) return false;
+    return pair_forced || (tiles >= 2L * num_sms() && iters >= 16);
+  };
+
   // ---- tile shape along N
   const bool ln = (g.flags & GEMM_LN) != 0;
   const int n_gran = (g.mode == 0) ? 16 : 32;  // MN-major B tiles are made of 32-element chunks
@@ -982,28 +999,36 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
   } else {
     int nt_max = 256;
     if (const char* e = getenv("XVA_GEMM_NTILE")) nt_max = atoi(e) >= 16 ? atoi(e) : 256;
-    // Small problems leave SMs idle at 256-wide tiles. Narrower tiles add parallelism but re-read A once per n tile,
-    // so pick the width that minimises  waves x k-step time,  k-step = max(operand fetch, MMA) in SM clocks:
-    // fetch = (16 KiB of A + the B tile, halved when a CTA pair shares it) at ~64 B/clk from L2; MMA = 2 clk per column.
+    // Small problems leave SMs idle at 256-wide tiles; narrower tiles add parallelism but re-read A once per n tile;
+    // a 257..512-column tile reads A once but its accumulator cannot be double-buffered (the epilogue is exposed).
+    // Pick the width that minimises  waves x (k-steps x max(operand fetch, MMA) + exposed epilogue)  in SM clocks:
+    // fetch = (16 KiB of A + the B tile, halved when a CTA pair shares it) at ~64 B/clk from L2; MMA = 2 clk per column;
+    // exposed epilogue ~ 40 clk per column of a 128-row tile. (Measured, B = 32 x 880: N = 384, K = 3 x 1536 runs 12 %
+    // faster as one 384-column tile than as two 192-column tiles; N = 1536 is fastest at 256.)
     static const bool fill_enabled = [] {
       const char* e = getenv("XVA_GEMM_FILL");
       return !(e && e[0] == '0');
     }();
-    if (g.mode != 2 && fill_enabled && !getenv("XVA_GEMM_NTILE")) {
-      const bool can_pair = g.b_batch_z == 0 && row_tiles >= 2;
-      const int slots = can_pair ? num_sms() / 2 : num_sms();
-      const int units = can_pair ? ceil_div(row_tiles, 2) : row_tiles;
+    if (g.mode != 2 && fill_enabled && G == 1 && !getenv("XVA_GEMM_NTILE")) {
+      const long iters = static_cast<long>(g.taps) * ceil_div(g.K, kBlockK);
       long best = -1;
-      for (int cand = 256; cand >= 64; cand >>= 1) {
+      for (int cand = 512; cand >= 64; cand >>= 1) {
         const int tn = ceil_div(g.N, cand);
         const int nt = round_up(ceil_div(g.N, tn), n_gran);
-        const long fetch = 256 + (can_pair ? nt : 2 * nt), mma = 2L * nt;
-        const long cost = static_cast<long>(ceil_div(units * tn, slots)) * (fetch > mma ? fetch : mma);
+        if (cand == 512 && (nt <= 256 || round_up(nt / 2, g.mode == 0 ? 16 : 64) * 2 > 512)) continue;
+        const bool pr = want_pair(row_tiles * tn, iters);
+        const int slots = pr ? num_sms() / 2 : num_sms();
+        const int units = pr ? ceil_div(row_tiles, 2) : row_tiles;
+        const long fetch = 256 + (pr ? nt : 2 * nt), mma = 2L * nt;
+        const long cost = static_cast<long>(ceil_div(units * tn, slots)) *
+                          (iters * (fetch > mma ? fetch : mma) + (nt > 256 ? 40L * nt : 0));
         if (best < 0 || cost < best) {
           best = cost;
           nt_max = cand;
         }
       }
+    } else if (g.mode == 2 && G == 1 && g.N > 256 && g.N <= 512 && !getenv("XVA_GEMM_NTILE")) {
+      nt_max = 512;  // weight gradient with 257..512 columns: one tile (the dy operand is read once)
     }
     p.tiles_n = ceil_div(p.N, nt_max);
     p.n_tile = round_up(ceil_div(p.N, p.tiles_n), n_gran);
@@ -1021,15 +1046,10 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
   XVA_CHECK_ARG(p.n_tile <= 512 && p.n_sub <= 256 && p.n_sub % 16 == 0, "gemm: bad n tiling %d/%d", p.n_tile, p.n_sub);
   p.acc_stages = (p.n_tile <= 256) ? 2 : 1;
 
-  // ---- CTA pair (cta_group::2): two 128-row tiles share one B tile, each CTA stages half of it. Halves the B bytes
-  // every SM pulls through L2 (the fp32 operand stream is L2-bandwidth-bound at 128x256 tiles). Needs a B operand
-  // that does not depend on the batch item (weights), and half-tiles that are whole swizzle atoms / 32-column chunks.
+  // (half-tiles of a pair must be whole swizzle atoms / 32-column chunks)
   int dbg_stages = 0;
-  static const bool pair_enabled = [] {
-    const char* e = getenv("XVA_GEMM_PAIR");
-    return !(e && e[0] == '0');
-  }();
-  const bool pair = pair_enabled && g.mode != 2 && g.b_batch_z == 0 && row_tiles >= 2 &&
+  const bool pair = g.mode != 2 &&
+                    want_pair(static_cast<long>(row_tiles) * p.tiles_n, static_cast<long>(g.taps) * ceil_div(g.K, kBlockK)) &&
                     (g.mode == 0 ? (p.n_sub % 16 == 0) : (p.n_sub % 64 == 0));
   const int cg = pair ? 2 : 1;
   p.row_tiles = row_tiles;

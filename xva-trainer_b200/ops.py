@@ -270,6 +270,19 @@ def average_pitch(pitch, durs, log1p=False):
     return out
 
 
+def mas_width1(attn, in_lens, out_lens, is_log=False):
+    """b_mas, fastpitch/alignment.py:110-118. attn [B, 1, Tm, Tt] (or [B, Tm, Tt]) soft alignment, in_lens / out_lens [B]
+    -> (attn_hard, same shape, 0/1 floats; durations int32 [B, Tt] = attn_hard.sum over mel)."""
+    shape = attn.shape
+    a = attn.reshape(shape[0], shape[-2], shape[-1]).to(torch.float32).contiguous()
+    B, Tm, Tt = a.shape
+    hard = torch.empty_like(a)
+    durs = torch.empty(B, Tt, device=a.device, dtype=torch.int32)
+    capi.call("xva_mas_width1", _p(a), _p(in_lens.to(torch.int32).contiguous()), _p(out_lens.to(torch.int32).contiguous()),
+              B, Tm, Tt, int(is_log), _p(hard), _p(durs), _stream())
+    return hard.view(shape), durs
+
+
 # ---------------------------------------------------------------------------------------------- row kernels
 def softmax_fwd(s, lens, n_valid, drop_p=0.0, seed=0, seed_dev=None):
     """transformer.py:120-127.  s [Z,R,ld] holds alpha*q.k^T in its first n_valid columns -> (p, pd); pd is p when
