@@ -60,6 +60,10 @@ enum {
   XVA_GEMM_ATOMIC = 1 << 4,
   XVA_GEMM_LRELU_GATE = 1 << 5,
   XVA_GEMM_TANH = 1 << 7,     /* out = tanh(value) as the last step (Generator.forward, hifigan/models.py:126) */
+  XVA_GEMM_SOFTMAX_BWD = 1 << 8, /* softmax + attention-dropout backward fused into the dP = dO.V^T product
+                                    (autograd of transformer.py:120-128): out = alpha * P * (acc * dropmask - rowvec[row])
+                                    with P read through the `gate` slot, rowvec[z*R + r] = sum_j P_d[r,j] dP_d[r,j] = dO[r].O[r],
+                                    the dropout mask of xva_softmax_fwd (element index (z*R + r) * drop_ld + n) */
   XVA_GEMM_ROUND_OUT = 1 << 6 /* store `out` rounded to tf32 (nearest): set when the result is a later GEMM operand */
 };
 
@@ -125,6 +129,9 @@ typedef struct xva_gemm_args {
                          mode 2: M = G*Og, N = Cg.  out[j, g*Og+m, n] contracts A columns g*Og+m with B columns
                                  a_col[j] + g*grp_step + n; Og % 32 == 0, Og <= 128, grp_step % 32 == 0 */
   int32_t grp_step; /* column step per group in the activation operand (mode 0: Cg of the input; mode 2: Cg) */
+  const float* rowvec; /* XVA_GEMM_SOFTMAX_BWD: per-row scalar [Z*R] */
+  int32_t drop_ld;     /* XVA_GEMM_SOFTMAX_BWD: row pitch of the dropout element index (0 = N) */
+  int32_t _pad3;
 } xva_gemm_args;
 
 /* sizeof(xva_gemm_args) as compiled into the library, so a binding can verify its struct layout. */
@@ -154,6 +161,10 @@ int xva_regulate_len_bwd(const float* dout, const int32_t* cum, int B, int Tt, i
  * durs [B,Tt] -> out [B,F,Tt]. log1p_out = 1 writes log(1 + mean) (the energy target, model.py:415). */
 int xva_average_pitch(const float* pitch, const float* durs, int B, int F, int Tm, int Tt, float* out, int log1p_out,
                       void* stream);
+
+/* out[row] = dot(a[row, 0..C), b[row, 0..C)) with row pitches a_ld / b_ld: the per-row term of the fused softmax backward
+ * (XVA_GEMM_SOFTMAX_BWD): sum_j P_d[r,j] * dP_d[r,j] = dO[r] . O[r] for O = P_d V. */
+int xva_rowdot2(const float* a, const float* b, int64_t rows, int C, int64_t a_ld, int64_t b_ld, float* out, void* stream);
 
 /* Monotonic alignment search -- replaces b_mas / mas_width1, fastpitch/alignment.py:79-118 (called through
  * FastPitch.binarize_attention_parallel, model.py:283-294, after a device->host copy; training stage 1): Viterbi path

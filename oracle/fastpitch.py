@@ -363,3 +363,44 @@ def synthetic_batch(B, Tt, Tm, seed=1234, ragged=False, device="cpu"):
          t(torch.full((B,), float(Tt))), t(torch.full((B,), float(Tm))), ["synthetic"] * B]
     y = [t(mel), t(in_lens), t(mel_lens), x[9]]
     return x, y
+
+
+# ------------------------------------------------------------------------------------------------ stage-1 MAS
+def mas_width1(attn_map, is_log=False):
+    """mas_width1, fastpitch/alignment.py:79-108, restated in numpy (the reference JIT-compiles it with numba).
+    attn_map [Tm, Tt] fp32 probabilities (or log-probabilities with is_log) -> 0/1 matrix of the same shape."""
+    import numpy as np
+
+    a = np.asarray(attn_map, dtype=np.float32)
+    opt = np.zeros_like(a)
+    with np.errstate(divide="ignore"):
+        la = a.copy() if is_log else np.log(a)                       # alignment.py:85
+    la[0, 1:] = -np.inf                                                # :86
+    log_p = np.zeros_like(la)
+    log_p[0, :] = la[0, :]
+    prev_ind = np.zeros(la.shape, dtype=np.int64)
+    Tm, Tt = la.shape
+    for i in range(1, Tm):                                             # :90-100, one mel row at a time (vectorised over j)
+        stay = log_p[i - 1]
+        adv = np.concatenate([np.array([-np.inf], dtype=np.float32), log_p[i - 1, :-1]])
+        take = adv >= stay
+        take[0] = False
+        log_p[i] = la[i] + np.where(take, adv, stay)
+        prev_ind[i] = np.arange(Tt) - take.astype(np.int64)
+    cur = Tt - 1
+    for i in range(Tm - 1, -1, -1):                                    # :103-107
+        opt[i, cur] = 1
+        cur = prev_ind[i, cur]
+    opt[0, cur] = 1                                                    # :108
+    return opt
+
+
+def b_mas(b_attn_map, in_lens, out_lens, is_log=False):
+    """b_mas, fastpitch/alignment.py:110-118. b_attn_map [B, 1, Tm, Tt] -> hard alignment of the same shape."""
+    import numpy as np
+
+    a = np.asarray(b_attn_map, dtype=np.float32)
+    out = np.zeros_like(a)
+    for b in range(a.shape[0]):
+        out[b, 0, :out_lens[b], :in_lens[b]] = mas_width1(a[b, 0, :out_lens[b], :in_lens[b]], is_log)
+    return out

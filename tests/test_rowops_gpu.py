@@ -111,3 +111,44 @@ def test_colsum(lib, rows, C, ld):
     out = torch.ones(C, device="cuda")
     ops.colsum_(rows, C, ld, x, out)
     assert rel(out, 1 + x[:, :C].double().sum(0).float()) < 1e-5
+
+
+@pytest.mark.parametrize("Z,T,p", [(3, 200, 0.0), (2, 880, 0.1), (4, 160, 0.25)])
+def test_fused_softmax_backward_matches_unfused(lib, Z, T, p):
+    """XVA_GEMM_SOFTMAX_BWD (dS computed in the epilogue of dP = dO.V^T, row term dO.O) vs the two-kernel path
+    (xva_gemm + xva_softmax_bwd) and vs torch autograd through softmax (no dropout case). Same dropout mask by
+    construction (same seed and element index); tolerance: tf32 products."""
+    import math
+    from xva_trainer_b200 import ops
+    d = 64
+    alpha = 1.0 / math.sqrt(d)
+    q, k, v, dvec = (gen(Z, T, d, seed=s) for s in (31, 32, 33, 34))
+    lens = torch.tensor([T, max(1, T // 2), T - 3, T][:Z], device="cuda", dtype=torch.int32)
+    ld = (T + 31) // 32 * 32
+    S = torch.empty(Z, T, ld, device="cuda")
+    ops.bmm_nt(q, k, alpha=alpha, out=S[..., :T])
+    seed = 777
+    P, Pd = ops.softmax_fwd(S, lens, T, p, seed)
+    vec = ops.bmm_nn(Pd[..., :T], v)
+    # two-kernel path
+    dP = torch.empty(Z, T, ld, device="cuda")
+    ops.bmm_nt(dvec, v, out=dP[..., :T])
+    ops.softmax_bwd_(P, dP, T, alpha, p, seed)
+    # fused
+    dS = torch.full((Z, T, ld), float("nan"), device="cuda")
+    dS[..., T:].zero_()
+    D = ops.rowdot2(dvec, vec)
+    ops.bmm_nt(dvec, v, alpha=alpha, out=dS[..., :T], round_out=True, softmax_bwd=(P, D, p, seed, None))
+    assert rel(dS[..., :T], dP[..., :T]) < 3e-3, rel(dS[..., :T], dP[..., :T])
+    dS_ref = torch.empty(Z, T, ld, device="cuda")
+    ops.bmm_nt(dvec, v, alpha=alpha, out=dS_ref[..., :T], round_out=True, softmax_bwd=(P, D, p, seed, None), ref=True)
+    assert rel(dS[..., :T], dS_ref[..., :T]) < 2e-3
+    if p == 0.0:
+        torch.backends.cuda.matmul.allow_tf32 = False
+        ql = q.clone().requires_grad_(True)
+        mask = torch.arange(T, device="cuda")[None, None, :] >= lens[:, None, None]
+        s = (ql @ k.transpose(1, 2)) * alpha
+        pr = torch.softmax(s.masked_fill(mask, float("-inf")), -1)
+        ((pr @ v) * dvec).sum().backward()
+        dq = ops.bmm_nn(dS[..., :T], k)
+        assert rel(dq, ql.grad) < 3e-3, rel(dq, ql.grad)

@@ -18,6 +18,7 @@ GEMM_ATOMIC = 1 << 4
 GEMM_LRELU_GATE = 1 << 5
 GEMM_ROUND_OUT = 1 << 6
 GEMM_TANH = 1 << 7
+GEMM_SOFTMAX_BWD = 1 << 8
 
 c_float_p = C.c_void_p  # device pointers travel as integers
 
@@ -46,6 +47,7 @@ class GemmArgs(C.Structure):
         ("out_act_slope", C.c_float), ("seed", C.c_uint64), ("out_act", C.c_void_p),
         ("a_col", C.c_int32 * XVA_MAX_TAPS), ("seed_dev", C.c_void_p),
         ("groups", C.c_int32), ("grp_step", C.c_int32),
+        ("rowvec", C.c_void_p), ("drop_ld", C.c_int32), ("_pad3", C.c_int32),
     ]
 
 
@@ -77,6 +79,7 @@ PROTOTYPES = {
     "xva_regulate_len_fwd": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "xva_regulate_len_bwd": (_I, [_P, _P, _I, _I, _I, _I, _P, _I, _P]),
     "xva_average_pitch": (_I, [_P, _P, _I, _I, _I, _I, _P, _I, _P]),
+    "xva_rowdot2": (_I, [_P, _P, _I64, _I, _I64, _I64, _P, _P]),
     "xva_mas_width1": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "xva_softmax_fwd": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _F, _U64, _P, _P]),
     "xva_softmax_bwd": (_I, [_P, _P, _I, _I, _I, _I, _F, _F, _U64, _P, _P]),

@@ -60,6 +60,10 @@ int xva_average_pitch(const float* pitch, const float* durs, int B, int F, int T
   return average_pitch(pitch, durs, B, F, Tm, Tt, out, log1p_out, S(stream));
 }
 
+int xva_rowdot2(const float* a, const float* b, int64_t rows, int C, int64_t a_ld, int64_t b_ld, float* out, void* stream) {
+  return rowdot2(a, b, static_cast<long>(rows), C, static_cast<long>(a_ld), static_cast<long>(b_ld), out, S(stream));
+}
+
 int xva_mas_width1(const float* attn, const int32_t* in_lens, const int32_t* out_lens, int B, int Tm, int Tt, int is_log,
                    float* hard, int32_t* durs, void* stream) {
   return mas_width1(attn, in_lens, out_lens, B, Tm, Tt, is_log, hard, durs, S(stream));

@@ -60,6 +60,12 @@ __global__ void gemm_ref_fwd_kernel(const RefDev d) {
   const bool ln = g.flags & GEMM_LN;
 
   auto pre_value = [&](int n) -> float {
+    if (g.flags & GEMM_SOFTMAX_BWD) {
+      const int ld = g.drop_ld > 0 ? g.drop_ld : g.N;
+      const uint64_t di = (static_cast<uint64_t>(z) * g.R + r) * static_cast<uint64_t>(ld) + n;
+      const float dp = ref_dot(g, z, r, n) * dropout_scale(eff_seed(g), di, d.drop_thresh, d.inv_keep);
+      return g.alpha * g.gate[rowoff_g + n] * (dp - g.rowvec[static_cast<long>(z) * g.R + r]);
+    }
     float v = g.alpha * ref_dot(g, z, r, n);
     if (g.bias) v += g.bias[n];
     if (g.flags & GEMM_RELU) v = v > 0.0f ? v : g.act_slope * v;
@@ -152,7 +158,7 @@ int gemm_ref_launch(const GemmArgs& g, cudaStream_t stream) {
   XVA_CHECK_ARG(g.taps >= 1 && g.taps <= kMaxTaps, "gemm_ref: taps %d", g.taps);
   RefDev d;
   d.g = g;
-  if ((g.flags & (GEMM_DROP_PRE | GEMM_DROP_POST)) && g.drop_p > 0.0f) {
+  if ((g.flags & (GEMM_DROP_PRE | GEMM_DROP_POST | GEMM_SOFTMAX_BWD)) && g.drop_p > 0.0f) {
     d.drop_thresh = static_cast<uint32_t>(static_cast<double>(g.drop_p) * 4294967296.0);
     d.inv_keep = 1.0f / (1.0f - g.drop_p);
   } else {

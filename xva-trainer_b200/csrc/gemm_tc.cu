@@ -78,6 +78,8 @@ struct GemmDev {
   float inv_keep;
   uint64_t seed;
   const uint64_t* seed_dev;
+  const float* rowvec;  // GEMM_SOFTMAX_BWD: per-row scalar
+  int drop_ld;          // GEMM_SOFTMAX_BWD: row pitch of the dropout index
   int dbg;     // bring-up knobs (XVA_GEMM_DBG): 1 = no epilogue stores, 2 = no TMA after the first ring fill, 4 = no MMA
   int vec_ok;  // every epilogue pointer is 16-byte aligned and every stride a multiple of 4: float4 accesses
   int round_on;  // host mirror of the operand-rounding test switch (xva_set_operand_rounding), read once per tile
@@ -582,6 +584,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const bool f_act = p.out_act != nullptr, f_scale = p.alpha != 1.0f;
         const bool f_gate = (kEpi != EPI_PLAIN) && p.gate != nullptr, f_res = (kEpi != EPI_PLAIN) && p.residual != nullptr;
         const bool f_drop = (kEpi != EPI_PLAIN) && (flags & GEMM_DROP_PRE) != 0;
+        const bool f_sbwd = (kEpi != EPI_PLAIN) && (flags & GEMM_SOFTMAX_BWD) != 0;
         const float alpha = p.alpha, act_slope = p.act_slope, gate_slope = p.gate_slope;
         auto cvt4 = [](float4 v) {  // fp32 -> tf32, round to nearest (the switch was read once: f_round)
           uint32_t a, b, c2, d;
@@ -601,6 +604,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           if constexpr (kEpi != EPI_PLAIN) {
             if (f_gate) load8(p.gate + zoff_g + n, p.g_rs, row0, row_limit, full, nv, aux);
             else if (f_res) load8(p.residual + zoff_r + n, p.r_rs, row0, row_limit, full, nv, aux);
+          }
+          if constexpr (kEpi != EPI_PLAIN) {
+            if (f_sbwd) {  // dS = alpha * P * (dP_dropped * mask - D[row]); aux holds P (requested above via the gate slot)
+              const uint64_t d0 = (static_cast<uint64_t>(zq) * p.R + row0) * static_cast<uint64_t>(p.drop_ld) + c.n0 + n;
+              const uint64_t dstep = 4ull * static_cast<uint64_t>(p.drop_ld);
+              const float* dv = p.rowvec + static_cast<long>(zq) * p.R;
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const int row = row0 + 4 * k;
+                const float dr = row < row_limit ? __ldg(dv + row) : 0.0f;
+                const float4 ds = dropout_scale4(seed, d0 + k * dstep, p.drop_thresh, p.inv_keep);
+                t[k] = make_float4(alpha * aux[k].x * (t[k].x * ds.x - dr), alpha * aux[k].y * (t[k].y * ds.y - dr),
+                                   alpha * aux[k].z * (t[k].z * ds.z - dr), alpha * aux[k].w * (t[k].w * ds.w - dr));
+              }
+              return;
+            }
           }
           if (f_bias) {
             float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -973,7 +992,7 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
   // ---- CTA pair (cta_group::2): two 128-row tiles share one B tile, each CTA stages half of it. Halves the B bytes
   // every SM pulls through L2 (the fp32 operand stream is L2-bandwidth-bound at 128x256 tiles). Needs a B operand
   // that does not depend on the batch item (weights). Measured per shape on B200: it pays for long main loops over at
-  // least two waves of tiles (decoder ConvFF: 4-7 % faster) and costs 7-15 % on short-K or single-wave launches.
+  // least one wave of row tiles (decoder ConvFF: 4-7 % faster) and costs 7-15 % on short-K or sub-wave launches.
   static const bool pair_enabled = [] {
     const char* e = getenv("XVA_GEMM_PAIR");
     return !(e && e[0] == '0');
@@ -982,9 +1001,9 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
     const char* e = getenv("XVA_GEMM_PAIR");
     return e && e[0] == '2';
   }();
-  auto want_pair = [&](long tiles, long iters) {
+  auto want_pair = [&](long iters) {  // at least one full wave of row tiles and a main loop worth sharing B for
     if (!pair_enabled || g.mode == 2 || g.b_batch_z != 0 || row_tiles < 2) return false;
-    return pair_forced || (tiles >= 2L * num_sms() && iters >= 16);
+    return pair_forced || (row_tiles >= num_sms() && iters >= 16);
   };
 
   // ---- tile shape along N
@@ -1016,7 +1035,7 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
         const int tn = ceil_div(g.N, cand);
         const int nt = round_up(ceil_div(g.N, tn), n_gran);
         if (cand == 512 && (nt <= 256 || round_up(nt / 2, g.mode == 0 ? 16 : 64) * 2 > 512)) continue;
-        const bool pr = want_pair(row_tiles * tn, iters);
+        const bool pr = want_pair(iters);
         const int slots = pr ? num_sms() / 2 : num_sms();
         const int units = pr ? ceil_div(row_tiles, 2) : row_tiles;
         const long fetch = 256 + (pr ? nt : 2 * nt), mma = 2L * nt;
@@ -1049,7 +1068,7 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
   // (half-tiles of a pair must be whole swizzle atoms / 32-column chunks)
   int dbg_stages = 0;
   const bool pair = g.mode != 2 &&
-                    want_pair(static_cast<long>(row_tiles) * p.tiles_n, static_cast<long>(g.taps) * ceil_div(g.K, kBlockK)) &&
+                    want_pair(static_cast<long>(g.taps) * ceil_div(g.K, kBlockK)) &&
                     (g.mode == 0 ? (p.n_sub % 16 == 0) : (p.n_sub % 64 == 0));
   const int cg = pair ? 2 : 1;
   p.row_tiles = row_tiles;
@@ -1194,7 +1213,11 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
   p.ln_rstd = g.ln_rstd;
   p.seed = g.seed;
   p.seed_dev = g.seed_dev;
-  if ((g.flags & (GEMM_DROP_PRE | GEMM_DROP_POST)) && g.drop_p > 0.0f) {
+  p.rowvec = g.rowvec;
+  p.drop_ld = g.drop_ld > 0 ? g.drop_ld : g.N;
+  if (g.flags & GEMM_SOFTMAX_BWD)
+    XVA_CHECK_ARG(g.mode != 2 && g.gate && g.rowvec && !(g.flags & GEMM_LN), "gemm: SOFTMAX_BWD needs gate (P), rowvec, mode 0/1");
+  if ((g.flags & (GEMM_DROP_PRE | GEMM_DROP_POST | GEMM_SOFTMAX_BWD)) && g.drop_p > 0.0f) {
     XVA_CHECK_ARG(g.drop_p < 1.0f, "gemm: dropout p=%f", g.drop_p);
     p.drop_thresh = static_cast<uint32_t>(static_cast<double>(g.drop_p) * 4294967296.0);
     p.inv_keep = 1.0f / (1.0f - g.drop_p);

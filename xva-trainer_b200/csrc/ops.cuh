@@ -42,6 +42,7 @@ int layernorm_fwd(const float* x, const float* gamma, const float* beta, const i
                   float* y, float* mean, float* rstd, cudaStream_t stream);
 int counter_add(unsigned long long* counter, unsigned long long inc, cudaStream_t stream);
 int round_tf32(const float* src, float* dst, long n, cudaStream_t stream);
+int rowdot2(const float* a, const float* b, long rows, int C, long a_ld, long b_ld, float* out, cudaStream_t stream);
 int colsum(const float* x, long rows, int C, long ld, float* out, cudaStream_t stream);
 int embed_pos(const long long* tokens, const float* emb, const float* in, const int* lens, const float* inv_freq,
               int B, int T, int C, float* out, cudaStream_t stream);

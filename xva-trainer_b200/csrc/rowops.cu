@@ -654,6 +654,19 @@ rowdot_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ x, c
   }
 }
 
+// out[row] = dot(a[row, :], b[row, :])   (the softmax-backward row term dO . O, see XVA_GEMM_SOFTMAX_BWD)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+rowdot2_kernel(const float* __restrict__ a, const float* __restrict__ b, long rows, int C, long a_ld, long b_ld,
+               float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long row = static_cast<long>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float acc = 0.0f;
+  for (int c = lane; c < C; c += 32) acc = fmaf(a[row * a_ld + c], b[row * b_ld + c], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) out[row] = acc;
+}
+
 __global__ void __launch_bounds__(256)
 round_tf32_kernel(const float* __restrict__ src, float* __restrict__ dst, long n) {
   for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x)
@@ -842,6 +855,13 @@ int rowdot_bwd(const float* dout, const float* x, const float* w, const int* len
   if (grid < 1) grid = 1;
   if (C <= 256) rowdot_bwd_kernel<8><<<grid, kWarpsPerBlock * 32, 0, stream>>>(dout, x, w, lens, R, C, rows, dx, dw, db);
   else rowdot_bwd_kernel<16><<<grid, kWarpsPerBlock * 32, 0, stream>>>(dout, x, w, lens, R, C, rows, dx, dw, db);
+  XVA_CHECK_LAUNCH();
+  return XVA_OK;
+}
+
+int rowdot2(const float* a, const float* b, long rows, int C, long a_ld, long b_ld, float* out, cudaStream_t stream) {
+  if (rows <= 0) return XVA_OK;
+  rowdot2_kernel<<<row_blocks(rows), kWarpsPerBlock * 32, 0, stream>>>(a, b, rows, C, a_ld, b_ld, out);
   XVA_CHECK_LAUNCH();
   return XVA_OK;
 }

@@ -178,6 +178,7 @@ class FastPitch(torch.nn.Module):
         self.inv_freq = (1.0 / (10000 ** (torch.arange(0.0, D_MODEL, 2.0) / D_MODEL))).to(dev)
         self.p_drop = P_DROP
         self.fuse_ln = os.environ.get("XVA_FUSE_LN", "0") == "1"   # LayerNorm inside the GEMM epilogue (measured slower)
+        self.fuse_softmax_bwd = os.environ.get("XVA_FUSE_SOFTMAX_BWD", "1") == "1"
         self.seed = int(seed)
         self.step_counter = torch.zeros(1, device=dev, dtype=torch.int64)  # device-side dropout counter (uint64 bits)
         self._site = 0
@@ -375,9 +376,20 @@ class FastPitch(torch.nn.Module):
         dqkv = torch.empty_like(qkv)
         Tp = c.P.shape[2]
         dP = torch.empty(B, T, Tp, device=x.device, dtype=torch.float32)
-        ops.bmm_nt(dvec, v, out=dP[..., :T])
-        ops.bmm_tn(c.Pd[..., :T], dvec, out=dqkv[..., 2 * D_HEAD:], round_out=True)
-        ops.softmax_bwd_(c.P, dP, T, 1.0 / math.sqrt(D_HEAD), c.att[0], c.att[1], sd)
+        if self.fuse_softmax_bwd:
+            # softmax + attention-dropout backward inside the epilogue of dP = dO.V^T: the row term sum_j P_d dP_d
+            # equals dO.O (O = P_d V = vec), so dS is element-wise in the tile and the score-sized tensor is written
+            # once instead of written, read twice and written again.
+            if Tp > T:
+                dP[..., T:].zero_()
+            D = ops.rowdot2(dvec, c.vec)
+            ops.bmm_nt(dvec, v, alpha=1.0 / math.sqrt(D_HEAD), out=dP[..., :T], round_out=True,
+                       softmax_bwd=(c.P, D, c.att[0], c.att[1], sd))
+            ops.bmm_tn(c.Pd[..., :T], dvec, out=dqkv[..., 2 * D_HEAD:], round_out=True)
+        else:
+            ops.bmm_nt(dvec, v, out=dP[..., :T])
+            ops.bmm_tn(c.Pd[..., :T], dvec, out=dqkv[..., 2 * D_HEAD:], round_out=True)
+            ops.softmax_bwd_(c.P, dP, T, 1.0 / math.sqrt(D_HEAD), c.att[0], c.att[1], sd)
         ops.bmm_nn(dP[..., :T], k, out=dqkv[..., :D_HEAD], round_out=True)
         ops.bmm_tn(dP[..., :T], q, out=dqkv[..., D_HEAD:2 * D_HEAD], round_out=True)
         del dP
@@ -414,6 +426,17 @@ class FastPitch(torch.nn.Module):
                                    seed_post=c["da"][1], seed_dev=sd, relu_gate=True)
         ops.conv_wgrad(dc1, c["x"], K3, out=P.g.w0, accumulate=True)
         return ops.conv_dgrad(dc1, P.w.w0, K3, residual=residual, lens=lens)
+
+    # ------------------------------------------------------------------------------------------ stage-1 alignment
+    def binarize_attention_parallel(self, attn, in_lens, out_lens):
+        """FastPitch.binarize_attention_parallel, model.py:283-294: hard (Viterbi) alignment of the soft attention
+        attn [B, 1, max_mel_len, max_text_len]. The reference copies attn to the host, runs numba's b_mas and copies the
+        result back; here it is one kernel on the device (xva_mas_width1), bit-identical path on the same fp32 values."""
+        with torch.no_grad():
+            hard, _ = ops.mas_width1(attn, in_lens, out_lens)
+        return hard
+
+    binarize_attention = binarize_attention_parallel          # model.py:267-281: the same result, item by item
 
     # ------------------------------------------------------------------------------------------ forward
     def forward(self, inputs_x, use_gt_pitch=True, use_dur_tgt=False, pace=1.0, max_duration=75, host_lens=None):

@@ -175,8 +175,11 @@ def conv_wgrad(dy, x, shifts=(0,), out=None, accumulate=False, split=None, ref=F
     return out
 
 
-def bmm_nt(a, b, alpha=1.0, out=None, ref=False, round_out=False):
-    """out[z,m,n] = alpha * sum_k a[z,m,k] * b[z,n,k]   (torch.bmm(a, b.transpose(1,2)))."""
+def bmm_nt(a, b, alpha=1.0, out=None, ref=False, round_out=False, softmax_bwd=None):
+    """out[z,m,n] = alpha * sum_k a[z,m,k] * b[z,n,k]   (torch.bmm(a, b.transpose(1,2))).
+    softmax_bwd = (P [Z,M,ld], rowvec [Z*M], drop_p, seed, seed_dev): the product is dP_dropped = dO.V^T and the epilogue
+    turns it into alpha * dS = alpha * P * (dP_dropped * mask - rowvec) (XVA_GEMM_SOFTMAX_BWD); out's pad columns
+    [N, ld) must already be zero."""
     _check3(a, "a")
     _check3(b, "b")
     Z, M, K = a.shape
@@ -187,8 +190,26 @@ def bmm_nt(a, b, alpha=1.0, out=None, ref=False, round_out=False):
     g.Z, g.R, g.N, g.K = Z, M, N, K
     g.a, g.a_rs, g.a_zs = _p(a), a.stride(1), a.stride(0)
     g.b, g.b_rs, g.b_zs, g.b_nz, g.b_batch_z = _p(b), b.stride(1), b.stride(0), Z, 1
-    _epilogue(g, out, alpha=alpha, round_out=round_out)
+    if softmax_bwd is None:
+        _epilogue(g, out, alpha=alpha, round_out=round_out)
+    else:
+        P, rowvec, drop_p, seed, seed_dev = softmax_bwd
+        _epilogue(g, out, alpha=alpha, round_out=round_out, gate=P[..., :N])
+        g.flags |= capi.GEMM_SOFTMAX_BWD
+        g.rowvec, g.drop_ld = _p(rowvec), P.stride(1)
+        g.drop_p, g.seed, g.seed_dev = float(drop_p), int(seed), _p(seed_dev)
     gemm_launch(g, ref)
+    return out
+
+
+def rowdot2(a, b):
+    """[Z,R,C] x [Z,R,C] -> [Z*R] row-wise dot products (contiguous last dim; row pitches are passed through)."""
+    _check3(a, "a")
+    _check3(b, "b")
+    Z, R, Cc = a.shape
+    assert a.stride(0) == R * a.stride(1) and b.stride(0) == R * b.stride(1)
+    out = torch.empty(Z * R, device=a.device, dtype=torch.float32)
+    capi.call("xva_rowdot2", _p(a), _p(b), Z * R, Cc, a.stride(1), b.stride(1), _p(out), _stream())
     return out
 
 
