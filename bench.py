@@ -39,6 +39,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-batch", type=int, default=4)
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--ragged", action="store_true", help="utterance lengths drawn below the maximum (realistic padding) "
+                    "instead of the BASELINE config's full-length batch; frames/s then counts valid frames only")
     ap.add_argument("--no-hifigan", action="store_true", help="skip the second half of the metric (HiFi-GAN samples/s)")
     ap.add_argument("--hifigan-steps", type=int, default=20)
     return ap.parse_args()
@@ -49,6 +51,7 @@ def config(args, world):
                         f"{TT} tokens/utt, synthetic text+mel pairs (BASELINE.json configs[1])",
             "global_batch": args.batch * world, "frames_per_utt": TM, "tokens_per_utt": TT,
             "step": "forward + FastPitchLoss + backward + clip_grad_norm(1000) + LAMB, dropout 0.1 on, gam=1",
+            "lengths": "ragged (valid frames counted)" if args.ragged else "every utterance at the maximum length",
             "launch": "one CUDA-graph replay per step" if (world == 1 and not args.no_graph) else "eager launches",
             "parallelism": f"dp{world}", "l2": "per-step working set (~5 GB of activations) exceeds the 126 MB L2; no flush"}
 
@@ -123,6 +126,28 @@ def cpu_step_rate(stage, batch, steps, warmup):
     return frames / per, per, cores, frames
 
 
+def cpu_hifigan_rate(batch, steps, warmup):
+    """samples/s of the CPU oracle's HiFi-GAN training step (oracle/hifigan.py: D step + G step, AdamW; fp32) on all host
+    cores, on a bounded sample (batch x 8192 samples) of the batch-16 workload."""
+    import torch
+    from oracle import hifigan as ohg
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd_g = ohg.make_generator_state(1234)
+    sd_p = ohg.make_disc_state(ohg.mpd_spec(), 21)
+    sd_s = ohg.make_disc_state(ohg.msd_spec(), 22)
+    x, y, y_mel = ohg.synthetic_batch(batch, 32, seed=1)
+    opt, times = {}, []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        ohg.train_step(sd_g, sd_p, sd_s, x, y, y_mel, opt)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    per = sum(times) / len(times)
+    return batch * 8192 / per, per, cores
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -132,12 +157,18 @@ def run_reference(args):
     rate, per, cores, frames = cpu_step_rate(args.stage, bs, steps, warm)
     sample = (f"oracle train_step (PyTorch-CPU restatement of the reference step), batch {bs} x {TM} frames of the "
               f"batch-{args.batch} workload, {warm} warm-up + {steps} timed steps, {cores} threads")
+    hifi = None
+    if not args.no_hifigan:
+        hr, hper, _ = cpu_hifigan_rate(2, 1, 1)
+        hifi = {"metric": "audio-samples/s (HiFi-GAN v1 G+MPD+MSD train step)", "value": hr, "unit": "samples/s",
+                "ms_per_step": hper * 1e3, "cpu_baseline": {"value": hr, "unit": "samples/s", "cores": cores, "kind": "port",
+                "sample": f"oracle train_step, batch 2 x 8192 samples of the batch-16 workload, 1 warm-up + 1 timed step, {cores} threads"}}
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": warm, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": config(args, 1),
             "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "gpu_launches": 0, "hifigan": hifi}
     print(json.dumps(line), flush=True)
 
 
@@ -280,7 +311,7 @@ def run_native(args):
     opt = fp.Lamb(model, lr=0.1, betas=(0.9, 0.98), eps=1e-9, weight_decay=1e-6)
     ddp = parallel.GradSync(model, world) if world > 1 else None
 
-    x_cpu, y_cpu = ofp.synthetic_batch(args.batch, TT, TM, seed=1234 + rank)
+    x_cpu, y_cpu = ofp.synthetic_batch(args.batch, TT, TM, seed=1234 + rank, ragged=args.ragged)
     frames = int(x_cpu[3].sum())
     host_lens = (TM, int(x_cpu[3].max()))
     pin = [t.pin_memory() if torch.is_tensor(t) else t for t in x_cpu]
@@ -453,6 +484,11 @@ def run_native(args):
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"oracle train_step, batch {args.cpu_sample_batch} x {TM} frames of the batch-{args.batch} workload, "
                          f"1 warm-up + 2 timed steps ({per:.1f} s/step), {cores} threads"}
+        if hifi is not None:
+            hr, hper, _ = cpu_hifigan_rate(2, 1, 1)
+            hifi["cpu_baseline"] = {"value": hr, "unit": "samples/s", "cores": cores, "kind": "port",
+                                    "sample": f"oracle train_step, batch 2 x 8192 samples of the batch-16 workload, 1 warm-up + "
+                                              f"1 timed step ({hper:.1f} s/step), {cores} threads"}
 
     total_frames = frames * world  # every rank draws a batch with the same frame count (lengths are fixed)
     line = {"metric": METRIC, "value": total_frames * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,

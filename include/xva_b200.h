@@ -318,6 +318,10 @@ int xva_loss_grad(const float* a, const float* b, int64_t n, int kind, float c, 
  *   avgpool4  : AvgPool1d(4, 2, padding=2) (models.py:241) on [B, L] -> [B, L/2 + 1]; bwd overwrites dx.
  *   zero_tail_rows : x[z, Lvalid.., :] = 0 for x [Z, Lp, C].
  * ---------------------------------------------------------------------------------------------------------- */
+/* feature_loss term and its gradient in one pass (models.py:263-269): *acc += sum |a - b|, out = scale * sign(b - a),
+ * times gate_slope where b <= 0 (b a leaky-ReLU output: gradient wrt its pre-activation; pass 1 for none). */
+int xva_l1_loss_grad(const float* a, const float* b, int64_t n, float scale, float gate_slope, double* acc, float* out,
+                     void* stream);
 int xva_conv_c1_fwd(const float* x, int64_t xs_b, int xs_q, int xs_c, int P, int Lsrc, int L, const float* w,
                     const float* bias, int k, int s, int pad, int Z, int Lout, int Lout_p, int Cout, float slope, float* out,
                     void* stream);

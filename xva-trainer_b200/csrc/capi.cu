@@ -194,6 +194,10 @@ int xva_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, cons
 }
 
 int xva_sizeof_wn_desc(void) { return static_cast<int>(sizeof(xva_wn_desc)); }
+int xva_l1_loss_grad(const float* a, const float* b, int64_t n, float scale, float gate_slope, double* acc, float* out,
+                     void* stream) {
+  return l1_loss_grad(a, b, static_cast<long>(n), scale, gate_slope, acc, out, S(stream));
+}
 int xva_wn_pack_fwd(const xva_wn_desc* table_dev, int n_desc, int total_rows, int max_inner, void* stream) {
   return wn_pack(table_dev, n_desc, total_rows, max_inner, 0, S(stream));
 }

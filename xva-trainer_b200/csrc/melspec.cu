@@ -147,7 +147,33 @@ loss_grad_kernel(const float* __restrict__ a, const float* __restrict__ b, long 
   }
 }
 
+// feature_loss term + its gradient in one pass (models.py:263-269): acc += sum |a - b| ; out = scale * sign(b - a),
+// times gate_slope where b <= 0 (b is a leaky-ReLU output: gradient wrt its pre-activation).
+__global__ void __launch_bounds__(256)
+l1_loss_grad_kernel(const float* __restrict__ a, const float* __restrict__ b, long n, float scale, float gate_slope,
+                    double* __restrict__ acc, float* __restrict__ out) {
+  __shared__ double sh[8];
+  double s = 0.0;
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const float bv = b[i], d = bv - a[i];
+    s += static_cast<double>(fabsf(d));
+    float g = d > 0.0f ? scale : (d < 0.0f ? -scale : 0.0f);
+    if (!(bv > 0.0f)) g *= gate_slope;
+    out[i] = g;
+  }
+  s = block_sum_d(s, sh);
+  if (threadIdx.x == 0) atomicAdd(acc, s);
+}
+
 }  // namespace
+
+int l1_loss_grad(const float* a, const float* b, long n, float scale, float gate_slope, double* acc, float* out,
+                 cudaStream_t stream) {
+  if (n == 0) return XVA_OK;
+  l1_loss_grad_kernel<<<grid_for(n), 256, 0, stream>>>(a, b, n, scale, gate_slope, acc, out);
+  XVA_CHECK_LAUNCH();
+  return XVA_OK;
+}
 
 int reflect_pad_fwd(const float* y, int B, long n, int pad, float* out, cudaStream_t stream) {
   XVA_CHECK_ARG(pad >= 0 && pad < n, "reflect_pad: pad=%d must be < n=%ld", pad, n);

@@ -935,12 +935,12 @@ def generator_adv_loss_backward(model, y_d_gs, fmap_rs, fmap_gs, dwave, pools):
         for l, (fr, fg) in enumerate(zip(fmap_rs[i], fmap_gs[i])):
             valid = cg["Z"] * (cg["lens"][l] if l < n_act else cg["lens"][-1]) * fg.shape[2]
             a = acc[16 * i + 1 + l:16 * i + 2 + l]
-            ops.reduce_l1(fr, fg, a)
-            loss_fm = loss_fm + 2.0 * a[0] / valid
             if l < n_act:
-                dfeat.append(ops.l1_grad(fr, fg, 2.0 / valid, gate_slope=LRELU_SLOPE))
+                dfeat.append(ops.l1_loss_grad(fr, fg, 2.0 / valid, a, gate_slope=LRELU_SLOPE))   # loss term + gradient
             else:
+                ops.reduce_l1(fr, fg, a)
                 ops.l1_grad(fr, fg, 2.0 / valid, out=dscore)     # conv_post output is the last feature map too
+            loss_fm = loss_fm + 2.0 * a[0] / valid
         tgt = levels[i] if pools else dwave
         d.backward(cg, dscore, dfeat, need_w=False, dwave=tgt)
     if pools:

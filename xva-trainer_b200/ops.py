@@ -299,8 +299,8 @@ def mas_width1(attn, in_lens, out_lens, is_log=False):
     B, Tm, Tt = a.shape
     hard = torch.empty_like(a)
     durs = torch.empty(B, Tt, device=a.device, dtype=torch.int32)
-    capi.call("xva_mas_width1", _p(a), _p(in_lens.to(torch.int32).contiguous()), _p(out_lens.to(torch.int32).contiguous()),
-              B, Tm, Tt, int(is_log), _p(hard), _p(durs), _stream())
+    il, ol = in_lens.to(torch.int32).contiguous(), out_lens.to(torch.int32).contiguous()   # keep both alive for the call
+    capi.call("xva_mas_width1", _p(a), _p(il), _p(ol), B, Tm, Tt, int(is_log), _p(hard), _p(durs), _stream())
     return hard.view(shape), durs
 
 
@@ -521,6 +521,13 @@ def l1_grad(a, b, scale, out=None, gate_slope=1.0):
         out = torch.empty_like(b)
     capi.call("xva_loss_grad", _p(a), _p(b), b.numel(), 0, 0.0, float(scale), float(gate_slope), int(acc), _p(out),
               _stream())
+    return out
+
+
+def l1_loss_grad(a, b, scale, acc, gate_slope=1.0):
+    """acc += sum |a - b| and returns scale * sign(b - a) (times gate_slope where b <= 0) in one pass."""
+    out = torch.empty_like(b)
+    capi.call("xva_l1_loss_grad", _p(a), _p(b), b.numel(), float(scale), float(gate_slope), _p(acc), _p(out), _stream())
     return out
 
 
