@@ -361,3 +361,49 @@ def test_grouped_conv_single_launch(Cin, Cout, G, k, stride):
         dw_ref_layout = torch.empty_like(w)
         dw_ref_layout[:, :, order] = dw.permute(1, 2, 0)
         assert rel(dw_ref_layout, wl.grad) < tol, ("wgrad", ref)
+
+
+@pytest.mark.parametrize("B,T,N,K,shifts,split", [(2, 4096, 32, 32, (-5, 0, 5), 24), (3, 1000, 64, 96, (-1, 0, 1), 9),
+                                                  (1, 2048, 128, 128, (0,), 8)])
+def test_conv_wgrad_row_chunked_split(B, T, N, K, shifts, split):
+    """More CTAs per output tile than items: every item's contraction rows are cut into chunks (few long sequences, the
+    HiFi-GAN generator's case); the tap shift still reads across chunk boundaries and zero-fills only at the item's ends."""
+    ops = _ops()
+    dy, x = gen(B, T, N, seed=71), gen(B, T, K, seed=72)
+    want = torch.zeros(len(shifts), N, K, device="cuda", dtype=torch.float64)
+    for j, s in enumerate(shifts):
+        lo, hi = max(0, -s), min(T, T - s)
+        want[j] = torch.einsum("btn,btk->nk", dy[:, lo:hi].double(), x[:, lo + s:hi + s].double())
+    got = ops.conv_wgrad(dy, x, shifts, split=split)
+    assert rel(got, want.float()) < TOL_TC
+
+
+@pytest.mark.parametrize("B,T,K,N,shifts", [
+    (2, 256, 96, 128, (-1, 0, 1)),                                   # rows a multiple of 128: un-segmented tiles
+    (1, 1000, 64, 64, tuple(5 * (j - 5) for j in range(11))),        # HiFi-GAN ResBlock k = 11, dilation 5 (halo 25 rows)
+    (1, 700, 128, 32, tuple(3 * (j - 3) for j in range(7))),         # k = 7, dilation 3
+    (3, 384, 1536, 384, (-1, 0, 1)),                                 # ConvFF second conv: N = 384 single tile
+    (16, 1280, 192, 256, (-1, 0, 1)),                                # a full wave of row tiles: CTA pairs
+    (1, 300, 80, 512, (-3, -2, -1, 0, 1, 2, 3)),                     # conv_pre k = 7, K not a multiple of 32
+    (2, 128, 64, 64, (0, -1)),                                       # transposed-conv phase group (two taps)
+])
+def test_halo_mode_taps_from_one_activation_tile(B, T, K, N, shifts):
+    """k-tap convolutions on un-segmented tiles load the activation tile once per k-block with halo rows and read every tap
+    through a row-shifted descriptor: forward, input gradient (negated shifts, MN-major weights), gated / residual / LN
+    epilogues, per-item zero padding at both ends."""
+    ops = _ops()
+    x, w = gen(B, T, K, seed=81), gen(len(shifts), N, K, seed=82, scale=(K * len(shifts)) ** -0.5)
+    bias, res, gate = gen(N, seed=83), gen(B, T, N, seed=84), gen(B, T, N, seed=85)
+    want = (conv_ref(x, w, shifts) + bias) * torch.where(gate > 0, 1.0, 0.1) + res
+    got = ops.conv_fwd(x, w, shifts, bias=bias, residual=res, gate=gate, gate_slope=0.1)
+    got_ref = ops.conv_fwd(x, w, shifts, bias=bias, residual=res, gate=gate, gate_slope=0.1, ref=True)
+    assert rel(got_ref, want) < TOL_REF
+    assert rel(got, want) < TOL_TC
+    dy = gen(B, T, N, seed=86)
+    want_dx = conv_ref(dy, w.transpose(1, 2).contiguous(), [-s for s in shifts])
+    assert rel(ops.conv_dgrad(dy, w, shifts), want_dx) < TOL_TC
+    if N % 16 == 0 and N <= 512:
+        gamma, beta = 1 + 0.1 * gen(N, seed=87), 0.1 * gen(N, seed=88)
+        pre = conv_ref(x, w, shifts) + bias + res
+        got_ln = ops.conv_fwd(x, w, shifts, bias=bias, residual=res, ln=(gamma, beta))
+        assert rel(got_ln, torch.nn.functional.layer_norm(pre, (N,), gamma, beta, 1e-5)) < TOL_TC

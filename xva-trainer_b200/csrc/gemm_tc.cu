@@ -31,13 +31,21 @@ constexpr int kATileBytes = kBlockM * kBlockK * 4;  // 16 KiB
 constexpr int kEpiSmemBytes = 8 * 4096;  // one 32x32 fp32 transpose tile per epilogue warp
 constexpr int kSmemBudget = 192 * 1024;   // operand ring; + kEpiSmemBytes + 1 KiB alignment slack <= 227 KiB
 constexpr int kLnSmemBytes = 2 * 4 * 32 * 2 * 4;
-constexpr int kBarSmemBytes = (2 * kMaxStages + 4) * 8 + 8;
+constexpr int kMaxStagesA = 4;       // activation ring of the halo mode
+constexpr int kBarSmemBytes = (2 * kMaxStages + 4) * 8 + 8 + 2 * kMaxStagesA * 8;
 constexpr int kAlignSlack = 768;
 constexpr int kTailSmemBytes = kEpiSmemBytes + kLnSmemBytes + kBarSmemBytes + kAlignSlack;
 enum { EPI_WGRAD = 0, EPI_PLAIN = 1, EPI_FULL = 2, EPI_LN = 3 };
 
 struct GemmDev {
   int mode, Z, R, M, N, K, taps, ZR, split, zper;
+  // Halo mode (mode 0/1, k-tap convolutions on un-segmented tiles): the activation tile of a k-block is loaded ONCE with
+  // hp halo rows on either side and every tap reads it through a descriptor whose start address is advanced by
+  // (hp + shift) rows (SWIZZLE_128B is a function of the absolute shared-memory address, so any row offset is legal with
+  // base offset 0: scripts/rowshift_probe.cu). The weights keep their own ring, one stage per (tap, k-block).
+  int halo, hp, a_rows, stages_a, ring_bytes;
+  int rsplit, chunk_rows;  // mode 2: every item's R contraction rows are cut into rsplit chunks of chunk_rows (a multiple
+                           // of 32); the reduction units (item, chunk) -- ZR of them per output -- are what `split` divides
   int n_tile, n_sub, n_mma, tiles_n, tiles_m, k_chunks, stages, acc_stages, num_tiles;
   int b_tap_z, b_batch_z;
   int row_tiles;  // Z * tiles_m: 128-row tiles of the output (mode 0/1)
@@ -208,13 +216,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const uint32_t cta_rank = (kCG == 2) ? ptx::cluster_ctarank() : 0u;
   const int cta_id = (kCG == 2) ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int n_ctas = (kCG == 2) ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
-  uint8_t* tail = smem + p.stages * stage_bytes + kEpiSmemBytes;
+  uint8_t* tail = smem + p.ring_bytes + kEpiSmemBytes;
   float (*ln_part)[4][32][2] = reinterpret_cast<float (*)[4][32][2]>(tail);  // LayerNorm (mean, M2) exchange
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(tail + kLnSmemBytes);
   uint64_t* bar_empty = bar_full + kMaxStages;
   uint64_t* bar_tmem_full = bar_empty + kMaxStages;
   uint64_t* bar_tmem_empty = bar_tmem_full + 2;
   uint32_t& tmem_base_slot = *reinterpret_cast<uint32_t*>(bar_tmem_empty + 2);
+  uint64_t* bar_afull = bar_tmem_empty + 3;
+  uint64_t* bar_aempty = bar_afull + kMaxStagesA;
+  const int a_stage_bytes = p.a_rows * kBlockK * 4;               // halo mode
+  uint8_t* ring_b = smem + p.stages_a * a_stage_bytes;            // halo mode: the weight ring follows the activation ring
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -231,6 +243,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&bar_tmem_full[a], 1);
       ptx::mbar_init(&bar_tmem_empty[a], 8 * kCG);
+    }
+    for (int a = 0; a < p.stages_a; ++a) {
+      ptx::mbar_init(&bar_afull[a], 1);
+      ptx::mbar_init(&bar_aempty[a], 1);
     }
     ptx::fence_mbar_init();
   }
@@ -249,10 +265,76 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) touches no
+  // global memory and may overlap the tail of the previous kernel in the stream; from here on this grid reads and
+  // writes tensors, so it waits for the previous grid to complete and flush. The trigger lets the next kernel's CTAs
+  // start their own prologue on SMs this grid no longer occupies (a no-op pair when launched without the attribute).
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
   const bool a_mn = (p.mode == 2);
   const bool b_mn = (p.mode != 0);
 
-  if (warp == 0) {
+  if (warp == 0 && p.halo) {
+    // ------------------------------------------------------------------ TMA producer, halo mode
+    int s = 0, sa_i = 0;
+    uint32_t ph = 0, pha = 0;
+    for (int tile = cta_id; tile < p.num_tiles; tile += n_ctas) {
+      const TileCoord c = decode_tile<kCG>(p, tile, cta_rank);
+      for (int kc = 0; kc < p.k_chunks; ++kc) {
+        ptx::mbar_wait(&bar_aempty[sa_i], pha ^ 1);
+        if (ptx::elect_one()) {
+          uint8_t* sa = smem + sa_i * a_stage_bytes;
+          if constexpr (kCG == 2) {
+            if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&bar_afull[sa_i], 2 * a_stage_bytes);
+            const uint32_t full = ptx::mapa(ptx::smem_u32(&bar_afull[sa_i]), 0);
+            ptx::tma_load_3d_cg2(sa, &tmap_a, full, p.a_col[0] + kc * kBlockK, c.m0 - p.hp, c.z);
+          } else {
+            ptx::mbar_arrive_expect_tx(&bar_afull[sa_i], a_stage_bytes);
+            ptx::tma_load_3d(sa, &tmap_a, &bar_afull[sa_i], p.a_col[0] + kc * kBlockK, c.m0 - p.hp, c.z);
+          }
+        }
+        __syncwarp();
+        if (++sa_i == p.stages_a) {
+          sa_i = 0;
+          pha ^= 1;
+        }
+        for (int j = 0; j < p.taps; ++j) {
+          ptx::mbar_wait(&bar_empty[s], ph ^ 1);
+          if (ptx::elect_one()) {
+            uint8_t* sb = ring_b + s * b_tile_bytes;
+            const int zb = j * p.b_tap_z;
+            if constexpr (kCG == 2) {
+              if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&bar_full[s], 2 * b_tile_bytes);
+              const uint32_t full = ptx::mapa(ptx::smem_u32(&bar_full[s]), 0);
+              const int half_n = p.n_sub >> 1;
+              for (int sub = 0; sub < p.n_mma; ++sub) {
+                const int nb = c.n0 + sub * p.n_sub + static_cast<int>(cta_rank) * half_n;
+                if (p.mode == 0)
+                  ptx::tma_load_3d_cg2(sb + sub * half_n * kBlockK * 4, &tmap_b, full, kc * kBlockK, nb, zb);
+                else
+                  ptx::tma_load_4d_cg2(sb + sub * half_n * kBlockK * 4, &tmap_b, full, 0, kc * kBlockK, nb / 32, zb);
+              }
+            } else {
+              ptx::mbar_arrive_expect_tx(&bar_full[s], b_tile_bytes);
+              if (p.mode == 0) {
+                for (int sub = 0; sub < p.n_mma; ++sub)
+                  ptx::tma_load_3d(sb + sub * p.n_sub * kBlockK * 4, &tmap_b, &bar_full[s], kc * kBlockK,
+                                   c.n0 + sub * p.n_sub, zb);
+              } else {
+                ptx::tma_load_4d(sb, &tmap_b, &bar_full[s], 0, kc * kBlockK, c.n0 / 32, zb);
+              }
+            }
+          }
+          __syncwarp();
+          if (++s == p.stages) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     {
       int s = 0;
@@ -322,9 +404,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               }
             } else {
               ptx::mbar_arrive_expect_tx(&bar_full[s], stage_bytes);
-              const int z = c.z + jo;
-              ptx::tma_load_4d(sa, &tmap_a, &bar_full[s], 0, kc * kBlockK, c.m0 / 32, z);
-              ptx::tma_load_4d(sb, &tmap_b, &bar_full[s], 0, kc * kBlockK + shift_j,
+              const int u = c.z + jo;  // reduction unit = (item, row chunk)
+              const int z = u / p.rsplit;
+              const int r0 = (u - z * p.rsplit) * p.chunk_rows + kc * kBlockK;
+              ptx::tma_load_4d(sa, &tmap_a, &bar_full[s], 0, r0, c.m0 / 32, z);
+              ptx::tma_load_4d(sb, &tmap_b, &bar_full[s], 0, r0 + shift_j,
                                (c.n0 + p.a_col[c.j] + c.g * p.grp_a) / 32, z);
             }
             __syncwarp();
@@ -355,6 +439,68 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       int tile_iter = 0;
       long long cyc_wait_acc = 0, cyc_wait_ops = 0;
       const long long t_start = clock64();
+      if (p.halo) {
+        // halo mode: k-block outer (one activation stage), taps inner (one weight stage each); tap j reads the
+        // activation stage starting (hp + shift_j) rows in
+        const uint32_t ring_b_u = ptx::smem_u32(ring_b) >> 4;
+        const uint32_t bstage_u = static_cast<uint32_t>(b_tile_bytes) >> 4;
+        const uint32_t astage_u = static_cast<uint32_t>(a_stage_bytes) >> 4;
+        int sa_i = 0;
+        uint32_t pha = 0;
+        for (int tile = cta_id; tile < p.num_tiles; tile += n_ctas, ++tile_iter) {
+          const int acc = tile_iter % p.acc_stages;
+          const uint32_t acc_ph = (tile_iter / p.acc_stages) & 1;
+          ptx::mbar_wait(&bar_tmem_empty[acc], acc_ph ^ 1);
+          ptx::tc_fence_after();
+          const uint32_t tmem_acc = tmem_base + acc * 256;
+          for (int kc = 0; kc < p.k_chunks; ++kc) {
+            ptx::mbar_wait(&bar_afull[sa_i], pha);
+            ptx::tc_fence_after();
+            for (int j = 0; j < p.taps; ++j) {
+              ptx::mbar_wait(&bar_full[s], ph);
+              ptx::tc_fence_after();
+              if (ptx::elect_one()) {
+                const uint32_t a_u = ring + sa_i * astage_u + static_cast<uint32_t>((p.hp + p.shift[j]) * (kBlockK * 4 / 16));
+                const uint64_t da0 = da_hi | static_cast<uint64_t>(a_u);
+                const uint64_t db0 = db_hi | static_cast<uint64_t>(ring_b_u + s * bstage_u);
+                const uint32_t first = (kc > 0 || j > 0) ? 1u : 0u;
+#pragma unroll
+                for (int k4 = 0; k4 < kBlockK / kUmmaK; ++k4) {
+                  for (int sub = 0; sub < n_mma; ++sub) {
+                    if (kCG == 2)
+                      ptx::mma_tf32_cg2(tmem_acc + sub * n_sub, da0 + k4 * a_kstep, db0 + sub * b_sub + k4 * b_kstep, idesc,
+                                        k4 ? 1u : first);
+                    else
+                      ptx::mma_tf32(tmem_acc + sub * n_sub, da0 + k4 * a_kstep, db0 + sub * b_sub + k4 * b_kstep, idesc,
+                                    k4 ? 1u : first);
+                  }
+                }
+                if (kCG == 2) ptx::mma_commit_cg2(&bar_empty[s], 3);
+                else ptx::mma_commit(&bar_empty[s]);
+              }
+              __syncwarp();
+              if (++s == p.stages) {
+                s = 0;
+                ph ^= 1;
+              }
+            }
+            if (ptx::elect_one()) {  // every tap of this k-block has been issued: the activation stage frees with them
+              if (kCG == 2) ptx::mma_commit_cg2(&bar_aempty[sa_i], 3);
+              else ptx::mma_commit(&bar_aempty[sa_i]);
+            }
+            __syncwarp();
+            if (++sa_i == p.stages_a) {
+              sa_i = 0;
+              pha ^= 1;
+            }
+          }
+          if (ptx::elect_one()) {
+            if (kCG == 2) ptx::mma_commit_cg2(&bar_tmem_full[acc], 3);
+            else ptx::mma_commit(&bar_tmem_full[acc]);
+          }
+          __syncwarp();
+        }
+      } else
       for (int tile = cta_id; tile < p.num_tiles; tile += n_ctas, ++tile_iter) {
         const TileCoord c = decode_tile<kCG>(p, tile, 0);
         const int acc = tile_iter % p.acc_stages;
@@ -440,7 +586,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int half = (warp - 4) >> 2;
     const int c4 = lane & 7, rsub = lane >> 3;
     const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
-    float4* tbuf = reinterpret_cast<float4*>(smem + p.stages * stage_bytes) + (warp - 4) * 256;
+    float4* tbuf = reinterpret_cast<float4*>(smem + p.ring_bytes) + (warp - 4) * 256;
     int tile_iter = 0;
     long long epi_wait = 0, epi_work = 0;
     const uint64_t seed = p.seed + (p.seed_dev ? __ldg(p.seed_dev) * 0xA24BAED4963EE407ull : 0ull);
@@ -1082,7 +1228,42 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   if (dbg_stages && dbg_stages < p.stages) p.stages = dbg_stages;
   XVA_CHECK_ARG(p.stages >= 2, "gemm: tile too large for shared memory");
-  const int smem_bytes = p.stages * stage_bytes + kTailSmemBytes;
+  p.ring_bytes = p.stages * stage_bytes;
+  p.a_rows = kBlockM;
+  p.stages_a = 0;
+
+  // ---- halo mode: a k-tap convolution on un-segmented tiles whose taps all read the same columns fetches its activation
+  // tile once per k-block (with halo rows) instead of once per tap -- the fp32 operand stream of these launches is
+  // L2 -> SM bandwidth bound, and the activation tile is 1/2 (3 taps, 256 columns) to 9/10 (11 taps, 32 columns) of it.
+  static const bool halo_enabled = [] {
+    const char* e = getenv("XVA_GEMM_HALO");
+    return !(e && e[0] == '0');
+  }();
+  if (halo_enabled && g.mode != 2 && g.taps > 1 && G == 1 && p.seg == kBlockM && g.b_batch_z == 0 && p.dbg == 0) {
+    int h = 0;
+    bool same_cols = true;
+    for (int j = 0; j < g.taps; ++j) {
+      const int a = g.shift[j] < 0 ? -g.shift[j] : g.shift[j];
+      h = a > h ? a : h;
+      same_cols = same_cols && g.a_col[j] == g.a_col[0];
+    }
+    const int hp = round_up(h, 4);
+    const int a_rows = kBlockM + 2 * hp;
+    const int b_tile = p.n_tile * kBlockK * 4 / cg;
+    const int stages_a = 3;
+    const int a_ring = stages_a * a_rows * kBlockK * 4;
+    int stages_b = (kSmemBudget - a_ring) / b_tile;
+    if (stages_b > kMaxStages) stages_b = kMaxStages;
+    if (same_cols && a_rows <= 256 && stages_b >= 3) {
+      p.halo = 1;
+      p.hp = hp;
+      p.a_rows = a_rows;
+      p.stages_a = stages_a;
+      p.stages = stages_b;
+      p.ring_bytes = a_ring + stages_b * b_tile;
+    }
+  }
+  const int smem_bytes = p.ring_bytes + kTailSmemBytes;
 
   // ---- tiling along M and the k loop
   if (g.mode != 2) {
@@ -1094,6 +1275,8 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
     p.ZR = 1;
     p.split = 1;
     p.zper = 1;
+    p.rsplit = 1;
+    p.chunk_rows = 0;
     p.num_tiles = (pair ? ceil_div(row_tiles, 2) : row_tiles) * p.tiles_n;
   } else {
     XVA_CHECK_ARG(g.M >= 1, "gemm: wgrad M=%d", g.M);
@@ -1105,12 +1288,22 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
                   round_up(g.N, 32), (long long)g.b_rs);
     XVA_CHECK_ARG(g.ZR >= 1 && g.Z % g.ZR == 0, "gemm: Z=%d not divisible by ZR=%d", g.Z, g.ZR);
     p.tiles_m = ceil_div(g.M, kBlockM);
-    p.k_chunks = ceil_div(g.R, kBlockK);
-    p.ZR = g.ZR;
+    // A caller asking for more CTAs per output tile than there are items gets the contraction rows of every item cut
+    // into chunks too (few long sequences: the HiFi-GAN generator has 16 items x 8192..225 280 rows)
     int split = g.split < 1 ? 1 : g.split;
-    if (split > g.ZR) split = g.ZR;
-    p.zper = ceil_div(g.ZR, split);
-    p.split = ceil_div(g.ZR, p.zper);
+    p.rsplit = 1;
+    p.chunk_rows = round_up(g.R, kBlockK);
+    if (split > g.ZR) {
+      const int want = ceil_div(split, g.ZR);
+      p.chunk_rows = round_up(ceil_div(g.R, want), kBlockK);
+      if (p.chunk_rows < 8 * kBlockK) p.chunk_rows = 8 * kBlockK;  // at least 8 k-steps per unit
+      p.rsplit = ceil_div(g.R, p.chunk_rows);
+    }
+    p.k_chunks = p.chunk_rows / kBlockK;
+    p.ZR = g.ZR * p.rsplit;
+    if (split > p.ZR) split = p.ZR;
+    p.zper = ceil_div(p.ZR, split);
+    p.split = ceil_div(p.ZR, p.zper);
     XVA_CHECK_ARG(p.split == 1 || (g.flags & GEMM_ATOMIC), "gemm: split > 1 needs GEMM_ATOMIC");
     p.num_tiles = (g.Z / g.ZR) * p.split * g.taps * p.tiles_m * p.tiles_n;
   }
@@ -1143,7 +1336,7 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
     // (a ragged last k-block then reads real neighbouring columns of A; they meet zero-filled rows of B)
     uint64_t dims[3] = {(uint64_t)a_cols, (uint64_t)a_rows, (uint64_t)g.Z};
     uint64_t str[3] = {1, (uint64_t)g.a_rs, (uint64_t)g.a_zs};
-    uint32_t box[3] = {kBlockK, (uint32_t)p.seg, 1};
+    uint32_t box[3] = {kBlockK, (uint32_t)(p.halo ? p.a_rows : p.seg), 1};
     if (g.Z == 1 || str[2] == 0) str[2] = (uint64_t)g.a_rs * a_rows;
     if ((rc = encode_map(&map_a, g.a, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) != XVA_OK) return rc;
   } else {
@@ -1257,28 +1450,42 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
   const int epi = (g.mode == 2) ? EPI_WGRAD
                   : (p.flags & GEMM_LN) ? EPI_LN
                   : (p.gate || p.residual || (p.flags & GEMM_DROP_PRE)) ? EPI_FULL : EPI_PLAIN;
+  // measured: no gain under CUDA-graph replay (13.87 vs 13.91 ms/step), so opt-in
+  static const bool pdl_enabled = [] {
+    const char* e = getenv("XVA_GEMM_PDL");
+    return e && e[0] == '1';
+  }();
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int n_attr = 0;
+  if (pair) {
+    attr[n_attr].id = cudaLaunchAttributeClusterDimension;
+    attr[n_attr].val.clusterDim.x = 2;
+    attr[n_attr].val.clusterDim.y = 1;
+    attr[n_attr].val.clusterDim.z = 1;
+    ++n_attr;
+  }
+  if (pdl_enabled) {
+    attr[n_attr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n_attr].val.programmaticStreamSerializationAllowed = 1;
+    ++n_attr;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n_attr;
   if (!pair) {
-    const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+    cfg.gridDim = dim3(p.num_tiles < num_sms() ? p.num_tiles : num_sms());
     switch (epi) {
-      case EPI_WGRAD: gemm_tc_kernel<EPI_WGRAD, 1><<<grid, kThreads, smem_bytes, stream>>>(map_a, map_b, p); break;
-      case EPI_LN: gemm_tc_kernel<EPI_LN, 1><<<grid, kThreads, smem_bytes, stream>>>(map_a, map_b, p); break;
-      case EPI_FULL: gemm_tc_kernel<EPI_FULL, 1><<<grid, kThreads, smem_bytes, stream>>>(map_a, map_b, p); break;
-      default: gemm_tc_kernel<EPI_PLAIN, 1><<<grid, kThreads, smem_bytes, stream>>>(map_a, map_b, p); break;
+      case EPI_WGRAD: XVA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<EPI_WGRAD, 1>, map_a, map_b, p)); break;
+      case EPI_LN: XVA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<EPI_LN, 1>, map_a, map_b, p)); break;
+      case EPI_FULL: XVA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<EPI_FULL, 1>, map_a, map_b, p)); break;
+      default: XVA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<EPI_PLAIN, 1>, map_a, map_b, p)); break;
     }
   } else {
     const int pairs = num_sms() / 2;
-    cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * (p.num_tiles < pairs ? p.num_tiles : pairs));
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = smem_bytes;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
     switch (epi) {
       case EPI_LN: XVA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<EPI_LN, 2>, map_a, map_b, p)); break;
       case EPI_FULL: XVA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<EPI_FULL, 2>, map_a, map_b, p)); break;

@@ -168,6 +168,9 @@ def conv_wgrad(dy, x, shifts=(0,), out=None, accumulate=False, split=None, ref=F
     g.groups, g.grp_step = int(groups), int(grp_step)
     if split is None:
         tiles = taps * ((N + 127) // 128) * ((K + 255) // 256)
+        # CTAs per output tile: up to two waves in total, at most one per item. (The kernel can also cut every item's
+        # rows into chunks -- pass split > B -- but measured on the HiFi-GAN generator that is slower: the per-tap tiles
+        # of a small-channel weight gradient are HBM-bound on re-reading dy / x once per tap, not short of CTAs.)
         split = max(1, min(B, (2 * 148) // max(tiles, 1)))
     g.split = split if accumulate else 1
     g.flags = capi.GEMM_ATOMIC if accumulate else 0
