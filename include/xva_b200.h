@@ -60,6 +60,9 @@ enum {
   XVA_GEMM_ATOMIC = 1 << 4,
   XVA_GEMM_LRELU_GATE = 1 << 5,
   XVA_GEMM_TANH = 1 << 7,     /* out = tanh(value) as the last step (Generator.forward, hifigan/models.py:126) */
+  XVA_GEMM_HALO = 1 << 9,     /* k-tap convolution (mode 0/1, un-segmented tiles, equal a_col): fetch the activation tile once
+                                 per k-block with halo rows and read the taps through row-shifted descriptors. Parity-green
+                                 but measured 5 % SLOWER than one fetch per tap on B200 (13.76 vs 14.33 ms/step), so opt-in */
   XVA_GEMM_SOFTMAX_BWD = 1 << 8, /* softmax + attention-dropout backward fused into the dP = dO.V^T product
                                     (autograd of transformer.py:120-128): out = alpha * P * (acc * dropmask - rowvec[row])
                                     with P read through the `gate` slot, rowvec[z*R + r] = sum_j P_d[r,j] dP_d[r,j] = dO[r].O[r],

@@ -388,22 +388,23 @@ def test_conv_wgrad_row_chunked_split(B, T, N, K, shifts, split):
     (2, 128, 64, 64, (0, -1)),                                       # transposed-conv phase group (two taps)
 ])
 def test_halo_mode_taps_from_one_activation_tile(B, T, K, N, shifts):
-    """k-tap convolutions on un-segmented tiles load the activation tile once per k-block with halo rows and read every tap
+    """(opt-in path, XVA_GEMM_HALO) k-tap convolutions on un-segmented tiles load the activation tile once per k-block with halo rows and read every tap
     through a row-shifted descriptor: forward, input gradient (negated shifts, MN-major weights), gated / residual / LN
     epilogues, per-item zero padding at both ends."""
     ops = _ops()
     x, w = gen(B, T, K, seed=81), gen(len(shifts), N, K, seed=82, scale=(K * len(shifts)) ** -0.5)
     bias, res, gate = gen(N, seed=83), gen(B, T, N, seed=84), gen(B, T, N, seed=85)
     want = (conv_ref(x, w, shifts) + bias) * torch.where(gate > 0, 1.0, 0.1) + res
-    got = ops.conv_fwd(x, w, shifts, bias=bias, residual=res, gate=gate, gate_slope=0.1)
+    got = ops.conv_fwd(x, w, shifts, bias=bias, residual=res, gate=gate, gate_slope=0.1, halo=True)
     got_ref = ops.conv_fwd(x, w, shifts, bias=bias, residual=res, gate=gate, gate_slope=0.1, ref=True)
     assert rel(got_ref, want) < TOL_REF
     assert rel(got, want) < TOL_TC
-    dy = gen(B, T, N, seed=86)
-    want_dx = conv_ref(dy, w.transpose(1, 2).contiguous(), [-s for s in shifts])
-    assert rel(ops.conv_dgrad(dy, w, shifts), want_dx) < TOL_TC
+    if K % 32 == 0:      # the input gradient reads the weights MN-major: rows of 32-column chunks
+        dy = gen(B, T, N, seed=86)
+        want_dx = conv_ref(dy, w.transpose(1, 2).contiguous(), [-s for s in shifts])
+        assert rel(ops.conv_dgrad(dy, w, shifts, halo=True), want_dx) < TOL_TC
     if N % 16 == 0 and N <= 512:
         gamma, beta = 1 + 0.1 * gen(N, seed=87), 0.1 * gen(N, seed=88)
         pre = conv_ref(x, w, shifts) + bias + res
-        got_ln = ops.conv_fwd(x, w, shifts, bias=bias, residual=res, ln=(gamma, beta))
+        got_ln = ops.conv_fwd(x, w, shifts, bias=bias, residual=res, ln=(gamma, beta), halo=True)
         assert rel(got_ln, torch.nn.functional.layer_norm(pre, (N,), gamma, beta, 1e-5)) < TOL_TC

@@ -19,6 +19,7 @@ GEMM_LRELU_GATE = 1 << 5
 GEMM_ROUND_OUT = 1 << 6
 GEMM_TANH = 1 << 7
 GEMM_SOFTMAX_BWD = 1 << 8
+GEMM_HALO = 1 << 9
 
 c_float_p = C.c_void_p  # device pointers travel as integers
 

@@ -29,7 +29,8 @@ enum GemmFlags : int {
   GEMM_ATOMIC = XVA_GEMM_ATOMIC,          // mode 2: accumulate into `out` with fp32 atomics (split-z)
   GEMM_LRELU_GATE = XVA_GEMM_LRELU_GATE,  // reserved
   GEMM_TANH = XVA_GEMM_TANH,
-  GEMM_SOFTMAX_BWD = XVA_GEMM_SOFTMAX_BWD,  // see include/xva_b200.h
+  GEMM_SOFTMAX_BWD = XVA_GEMM_SOFTMAX_BWD,
+  GEMM_HALO = XVA_GEMM_HALO,  // see include/xva_b200.h
   GEMM_ROUND_OUT = XVA_GEMM_ROUND_OUT,    // out is a later GEMM operand: store it rounded to tf32
 };
 

@@ -1235,11 +1235,15 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
   // ---- halo mode: a k-tap convolution on un-segmented tiles whose taps all read the same columns fetches its activation
   // tile once per k-block (with halo rows) instead of once per tap -- the fp32 operand stream of these launches is
   // L2 -> SM bandwidth bound, and the activation tile is 1/2 (3 taps, 256 columns) to 9/10 (11 taps, 32 columns) of it.
+  // Measured on B200 (same box, back to back): FastPitch step 13.76 ms without, 14.33-14.47 ms with (either halo
+  // alignment); HiFi-GAN generator at 880 frames 95 -> 123 ms. The launches are bound by the latency x bytes-in-flight
+  // of the operand stream rather than by the bytes themselves, and one large activation box per k-block pipelines worse
+  // than three small ones. Kept behind XVA_GEMM_HALO (flag) / XVA_GEMM_HALO=1 (environment) with its tests.
   static const bool halo_enabled = [] {
     const char* e = getenv("XVA_GEMM_HALO");
-    return !(e && e[0] == '0');
+    return e && e[0] == '1';
   }();
-  if (halo_enabled && g.mode != 2 && g.taps > 1 && G == 1 && p.seg == kBlockM && g.b_batch_z == 0 && p.dbg == 0) {
+  if ((halo_enabled || (g.flags & GEMM_HALO)) && g.mode != 2 && g.taps > 1 && G == 1 && p.seg == kBlockM && g.b_batch_z == 0 && p.dbg == 0) {
     int h = 0;
     bool same_cols = true;
     for (int j = 0; j < g.taps; ++j) {
@@ -1247,7 +1251,9 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
       h = a > h ? a : h;
       same_cols = same_cols && g.a_col[j] == g.a_col[0];
     }
-    const int hp = round_up(h, 4);
+    int hp_align = 4;
+    if (const char* e = getenv("XVA_GEMM_HALO_ALIGN")) hp_align = atoi(e) >= 4 ? atoi(e) : 4;
+    const int hp = round_up(h, hp_align);
     const int a_rows = kBlockM + 2 * hp;
     const int b_tile = p.n_tile * kBlockK * 4 / cg;
     const int stages_a = 3;

@@ -46,7 +46,7 @@ def _base_args(mode, shifts):
 
 def _epilogue(g, out, bias=None, relu=False, gate=None, gate_slope=0.0, residual=None, lens=None, ln=None,
               ln_eps=1e-5, save_ln=False, drop_p=0.0, drop_post=False, seed=0, seed_dev=None, alpha=1.0,
-              round_out=False, act_slope=0.0, out_act=None, out_act_slope=0.0, tanh=False):
+              round_out=False, act_slope=0.0, out_act=None, out_act_slope=0.0, tanh=False, halo=False):
     keep = [out, bias, gate, residual, lens]
     g.out, g.o_rs, g.o_zs = _p(out), out.stride(1), out.stride(0)
     g.alpha = alpha
@@ -89,6 +89,8 @@ def _epilogue(g, out, bias=None, relu=False, gate=None, gate_slope=0.0, residual
         g.drop_p, g.seed, g.seed_dev = drop_p, seed, _p(seed_dev)
     if round_out:
         flags |= capi.GEMM_ROUND_OUT
+    if halo:
+        flags |= capi.GEMM_HALO
     g.flags = flags
     return keep, extra
 
