@@ -408,3 +408,27 @@ def test_halo_mode_taps_from_one_activation_tile(B, T, K, N, shifts):
         pre = conv_ref(x, w, shifts) + bias + res
         got_ln = ops.conv_fwd(x, w, shifts, bias=bias, residual=res, ln=(gamma, beta), halo=True)
         assert rel(got_ln, torch.nn.functional.layer_norm(pre, (N,), gamma, beta, 1e-5)) < TOL_TC
+
+
+@pytest.mark.parametrize("B,T,N,K,shifts", [
+    (2, 4096, 32, 32, tuple(j - 5 for j in range(11))),            # ResBlock k = 11 at 32 channels: all 11 taps in one tile
+    (3, 1500, 64, 64, tuple(3 * (j - 3) for j in range(7))),         # 64 channels, k = 7 dilation 3: taps in two groups
+    (2, 900, 128, 128, tuple(5 * (j - 5) for j in range(11))),       # 128 channels, k = 11 dilation 5: three groups
+    (4, 700, 1, 32, (-3, -2, -1, 0, 1, 2, 3)),                       # conv_post: one output channel
+])
+def test_conv_wgrad_multi_tap_tiles(B, T, N, K, shifts):
+    """Small-channel weight gradients accumulate several taps side by side in TMEM (dy fetched once per k-block for all of
+    them) and split the rows of every item over the SMs; vs the fp64 einsum."""
+    ops = _ops()
+    ld = 32 if N < 32 else N
+    dyp = torch.zeros(B, T, ld, device="cuda")
+    dyp[..., :N] = gen(B, T, N, seed=91)
+    dy, x = dyp[..., :N], gen(B, T, K, seed=92)
+    want = torch.zeros(len(shifts), N, K, device="cuda", dtype=torch.float64)
+    for j, s in enumerate(shifts):
+        lo, hi = max(0, -s), min(T, T - s)
+        want[j] = torch.einsum("btn,btk->nk", dy[:, lo:hi].double(), x[:, lo + s:hi + s].double())
+    got = ops.conv_wgrad(dy, x, shifts)
+    got_ref = ops.conv_wgrad(dy, x, shifts, ref=True)
+    assert rel(got_ref, want.float()) < TOL_REF
+    assert rel(got, want.float()) < TOL_TC

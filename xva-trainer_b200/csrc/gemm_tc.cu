@@ -44,6 +44,10 @@ struct GemmDev {
   // (hp + shift) rows (SWIZZLE_128B is a function of the absolute shared-memory address, so any row offset is legal with
   // base offset 0: scripts/rowshift_probe.cu). The weights keep their own ring, one stage per (tap, k-block).
   int halo, hp, a_rows, stages_a, ring_bytes;
+  // mode 2, multi-tap tiles: one tile accumulates tp taps side by side in TMEM (tap jj at columns jj * n_tile), so dy is
+  // fetched once per k-block for all of them and the tap-shifted windows of x hit L2 -- a small-channel weight gradient
+  // (HiFi-GAN ResBlocks: 32 / 64 channels, 3..11 taps) was HBM-bound on re-reading both operands once per tap.
+  int tp, tgroups;
   int rsplit, chunk_rows;  // mode 2: every item's R contraction rows are cut into rsplit chunks of chunk_rows (a multiple
                            // of 32); the reduction units (item, chunk) -- ZR of them per output -- are what `split` divides
   int n_tile, n_sub, n_mma, tiles_n, tiles_m, k_chunks, stages, acc_stages, num_tiles;
@@ -141,8 +145,8 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmDev& p, int t, int ct
     c.j = 0;
     c.iters = p.taps * p.k_chunks;
   } else {
-    c.j = t % p.taps;
-    t /= p.taps;
+    c.j = (t % p.tgroups) * p.tp;  // first tap of the tile's tap group (tp = 1: the tap)
+    t /= p.tgroups;
     int s = t % p.split;
     c.zo = t / p.split;
     c.z = c.zo * p.ZR + s * p.zper;
@@ -212,7 +216,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     __trap();
   }
   const int b_tile_bytes = p.n_tile * kBlockK * 4 / kCG;  // a CTA pair splits every B tile along n
-  const int stage_bytes = kATileBytes + b_tile_bytes;
+  const int stage_bytes = kATileBytes + b_tile_bytes * (p.mode == 2 ? p.tp : 1);  // multi-tap wgrad: tp B tiles per stage
   const uint32_t cta_rank = (kCG == 2) ? ptx::cluster_ctarank() : 0u;
   const int cta_id = (kCG == 2) ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int n_ctas = (kCG == 2) ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
@@ -403,13 +407,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 ptx::tma_load_4d(sb, &tmap_b, &bar_full[s], 0, bk0 + kc * kBlockK, bn0 / 32, zb);
               }
             } else {
-              ptx::mbar_arrive_expect_tx(&bar_full[s], stage_bytes);
+              const int nt_here = (p.taps - c.j) < p.tp ? (p.taps - c.j) : p.tp;
+              ptx::mbar_arrive_expect_tx(&bar_full[s], kATileBytes + nt_here * b_tile_bytes);
               const int u = c.z + jo;  // reduction unit = (item, row chunk)
               const int z = u / p.rsplit;
               const int r0 = (u - z * p.rsplit) * p.chunk_rows + kc * kBlockK;
               ptx::tma_load_4d(sa, &tmap_a, &bar_full[s], 0, r0, c.m0 / 32, z);
-              ptx::tma_load_4d(sb, &tmap_b, &bar_full[s], 0, r0 + shift_j,
-                               (c.n0 + p.a_col[c.j] + c.g * p.grp_a) / 32, z);
+              for (int jj = 0; jj < nt_here; ++jj)
+                ptx::tma_load_4d(sb + jj * b_tile_bytes, &tmap_b, &bar_full[s], 0, r0 + p.shift[c.j + jj],
+                                 (c.n0 + p.a_col[c.j + jj] + c.g * p.grp_a) / 32, z);
             }
             __syncwarp();
             if (++s == p.stages) {
@@ -525,10 +531,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const uint32_t first = it > 0 ? 1u : 0u;
             if (dbg & 4) {
             } else if (n_mma == 1) {
+              // (multi-tap weight gradient: the stage holds one B tile per tap of the group, each with its own accumulator)
+              const int nt_here = (p.mode == 2 && p.tp > 1) ? ((p.taps - c.j) < p.tp ? (p.taps - c.j) : p.tp) : 1;
+              const uint32_t btile_u = static_cast<uint32_t>(b_tile_bytes) >> 4;
+              for (int jj = 0; jj < nt_here; ++jj) {
 #pragma unroll
-              for (int k4 = 0; k4 < kBlockK / kUmmaK; ++k4) {
-                if (kCG == 2) ptx::mma_tf32_cg2(tmem_acc, da0 + k4 * a_kstep, db0 + k4 * b_kstep, idesc, k4 ? 1u : first);
-                else ptx::mma_tf32(tmem_acc, da0 + k4 * a_kstep, db0 + k4 * b_kstep, idesc, k4 ? 1u : first);
+                for (int k4 = 0; k4 < kBlockK / kUmmaK; ++k4) {
+                  if (kCG == 2)
+                    ptx::mma_tf32_cg2(tmem_acc + jj * p.n_tile, da0 + k4 * a_kstep, db0 + jj * btile_u + k4 * b_kstep, idesc,
+                                      k4 ? 1u : first);
+                  else
+                    ptx::mma_tf32(tmem_acc + jj * p.n_tile, da0 + k4 * a_kstep, db0 + jj * btile_u + k4 * b_kstep, idesc,
+                                  k4 ? 1u : first);
+                }
               }
             } else {
 #pragma unroll
@@ -677,7 +692,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       };
 
       if constexpr (kEpi == EPI_WGRAD) {
-        float* obase = p.out + c.zo * p.o_zs + c.j * p.o_js + c.n0;
+        float* obase = p.out + c.zo * p.o_zs + c.j * p.o_js + c.n0;  // tap c.j; re-pointed per tap of a multi-tap tile
         // grouped: this warp's 32 rows belong to group gi of the tile; only its diagonal block is stored
         int ch_lo = 0, ch_hi = n_chunks, col_shift = 0;
         if (p.groups > 1) {
@@ -686,11 +701,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           ch_hi = ch_lo + p.cg / 32;
           col_shift = gi * p.cg;
         }
-        for (int ch = half; ch < n_chunks; ch += 2) {
+        const int nt_here = (p.tp > 1) ? ((p.taps - c.j) < p.tp ? (p.taps - c.j) : p.tp) : 1;
+        for (int qi = half; qi < nt_here * n_chunks; qi += 2) {
+          const int jj = qi / n_chunks, ch = qi - jj * n_chunks;  // tap of the group, 32-column chunk of its accumulator
           if (ch < ch_lo || ch >= ch_hi) continue;  // warp-uniform
           float4 t[8];
-          load_chunk(tacc + ch * 32, t);
-          if (ch == last_ch) release_tmem();
+          load_chunk(tacc + jj * p.n_tile + ch * 32, t);
+          if (p.tp == 1 && ch == last_ch) release_tmem();
+          obase = p.out + c.zo * p.o_zs + (c.j + jj) * p.o_js + c.n0;
           const int n = ch * 32 + 4 * c4;
           const int nv = n < n_cols ? ((n_cols - n) < 4 ? (n_cols - n) : 4) : 0;
           const bool full = vec && nv == 4;
@@ -1223,7 +1241,28 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
     if (atoi(e) >= 2) dbg_stages = atoi(e);
   }
 
-  const int stage_bytes = kATileBytes + p.n_tile * kBlockK * 4 / cg;
+  // ---- multi-tap weight-gradient tiles (see GemmDev::tp)
+  p.tp = 1;
+  p.tgroups = g.taps;
+  static const bool mtap_enabled = [] {
+    const char* e = getenv("XVA_GEMM_MTAP");
+    return !(e && e[0] == '0');
+  }();
+  if (mtap_enabled && g.mode == 2 && G == 1 && g.taps > 1 && p.tiles_n == 1 && p.n_tile <= 128) {
+    int tp = kTmemCols / p.n_tile;
+    const int smem_tp = (kSmemBudget / 2 - kATileBytes) / (p.n_tile * kBlockK * 4);  // at least two stages
+    if (tp > smem_tp) tp = smem_tp;
+    if (tp > g.taps) tp = g.taps;
+    // spread the taps evenly over the groups (11 taps, 8 per tile -> 6 + 5)
+    const int groups = ceil_div(g.taps, tp);
+    tp = ceil_div(g.taps, groups);
+    if (tp > 1) {
+      p.tp = tp;
+      p.tgroups = groups;
+      if (tp * p.n_tile > 256) p.acc_stages = 1;
+    }
+  }
+  const int stage_bytes = kATileBytes + p.tp * p.n_tile * kBlockK * 4 / cg;
   p.stages = kSmemBudget / stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   if (dbg_stages && dbg_stages < p.stages) p.stages = dbg_stages;
@@ -1297,6 +1336,10 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
     // A caller asking for more CTAs per output tile than there are items gets the contraction rows of every item cut
     // into chunks too (few long sequences: the HiFi-GAN generator has 16 items x 8192..225 280 rows)
     int split = g.split < 1 ? 1 : g.split;
+    if (p.tp > 1 && (g.flags & GEMM_ATOMIC)) {  // fewer, fatter tiles: keep every SM busy by splitting the rows further
+      const int want = ceil_div(num_sms(), p.tgroups * p.tiles_m);
+      if (split < want) split = want;
+    }
     p.rsplit = 1;
     p.chunk_rows = round_up(g.R, kBlockK);
     if (split > g.ZR) {
@@ -1311,7 +1354,7 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
     p.zper = ceil_div(p.ZR, split);
     p.split = ceil_div(p.ZR, p.zper);
     XVA_CHECK_ARG(p.split == 1 || (g.flags & GEMM_ATOMIC), "gemm: split > 1 needs GEMM_ATOMIC");
-    p.num_tiles = (g.Z / g.ZR) * p.split * g.taps * p.tiles_m * p.tiles_n;
+    p.num_tiles = (g.Z / g.ZR) * p.split * p.tgroups * p.tiles_m * p.tiles_n;
   }
 
   // MN-major tiles: SWIZZLE_128B_BASE32B descriptors + TMA 128B_ATOM_32B. XVA_MN_DEBUG=layout:lbo:sbo:tma_swizzle
