@@ -458,10 +458,21 @@ def run_native(args):
         bf16_peak = peaks["bf16_tflops_sustained"] if peaks else 1400.0
         peak = bf16_peak / 2.0
         achieved = flops / (gemm_ms * 1e-3) / 1e12
+        # the launch shape that takes the most time, on its own
+        by_shape = {}
+        for a, b, f, shape in rec:
+            e = by_shape.setdefault(shape, [0, 0.0, 0.0])
+            e[0] += 1
+            e[1] += a.elapsed_time(b)
+            e[2] += f
+        top_shape, (top_n, top_ms, top_f) = max(by_shape.items(), key=lambda kv: kv[1][1])
+        dominant = {"shape": dict(zip(("mode", "Z", "R", "M", "N", "K", "taps", "flags", "split"), top_shape)),
+                    "launches_per_step": top_n, "us_per_launch": 1e3 * top_ms / top_n, "gflop_per_launch": top_f / top_n / 1e9,
+                    "achieved": top_f / (top_ms * 1e-3) / 1e12, "frac": top_f / (top_ms * 1e-3) / 1e12 / peak}
         roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 kind::tf32 tap-GEMM)", "achieved": achieved,
                 "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
                 "launches_per_step": len(rec), "flops_per_step": flops, "kernel_ms_per_step": gemm_ms,
-                "share_of_step": gemm_ms / (ms / args.steps),
+                "share_of_step": gemm_ms / (ms / args.steps), "dominant_launch": dominant,
                 "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained / 2 (kind::tf32 runs at half the bf16 rate), "
                                 "of measured") if peaks else "fallback 1.4 PFLOP/s / 2, of fallback"}
 

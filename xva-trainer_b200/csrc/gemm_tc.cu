@@ -44,6 +44,7 @@ struct GemmDev {
   // (hp + shift) rows (SWIZZLE_128B is a function of the absolute shared-memory address, so any row offset is legal with
   // base offset 0: scripts/rowshift_probe.cu). The weights keep their own ring, one stage per (tap, k-block).
   int halo, hp, a_rows, stages_a, ring_bytes;
+  int tap_inner;  // mode 0/1 loop order of the operand stream: k-block outer, tap inner (see the producer)
   // mode 2, multi-tap tiles: one tile accumulates tp taps side by side in TMEM (tap jj at columns jj * n_tile), so dy is
   // fetched once per k-block for all of them and the tap-shifted windows of x hit L2 -- a small-channel weight gradient
   // (HiFi-GAN ResBlocks: 32 / 64 channels, 3..11 taps) was HBM-bound on re-reading both operands once per tap.
@@ -362,10 +363,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
         const int seg_bytes = p.seg * kBlockK * 4;
         int it = 0;
-        for (int jo = 0; jo < n_outer; ++jo) {
-          const int shift_j = (p.mode != 2) ? p.shift[jo] : p.shift[c.j];
-          const int acol_j = (p.mode != 2) ? p.a_col[jo] : 0;
-          for (int kc = 0; kc < p.k_chunks; ++kc, ++it) {
+        // Loop order. Mode 2: reduction unit outer, k-block inner. Mode 0/1 with p.tap_inner: k-block outer, TAP INNER --
+        // the taps of one k-block re-read the same activation lines (shifted by a row) back to back, so they hit L2; with
+        // the tap outer, a CTA streams its whole 128 x K row block once per tap and at K = 1536 the 148 CTAs push 116 MB
+        // through the 126 MB L2 between two reads of a line (ncu: 459 MB read from DRAM for 223 MB of operands).
+        const bool tap_inner = (p.mode != 2) && p.tap_inner;
+        const int n1 = tap_inner ? p.k_chunks : n_outer, n2 = tap_inner ? n_outer : p.k_chunks;
+        for (int o1 = 0; o1 < n1; ++o1) {
+          for (int o2 = 0; o2 < n2; ++o2, ++it) {
+            const int jo = tap_inner ? o2 : o1, kc = tap_inner ? o1 : o2;
+            const int shift_j = (p.mode != 2) ? p.shift[jo] : p.shift[c.j];
+            const int acol_j = (p.mode != 2) ? p.a_col[jo] : 0;
             ptx::mbar_wait(&bar_empty[s], ph ^ 1);
             uint8_t* sa = smem + s * stage_bytes;
             uint8_t* sb = sa + kATileBytes;
@@ -1240,6 +1248,12 @@ int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
   if (const char* e = getenv("XVA_GEMM_STAGES")) {
     if (atoi(e) >= 2) dbg_stages = atoi(e);
   }
+
+  static const bool tap_inner_enabled = [] {
+    const char* e = getenv("XVA_GEMM_TAP_INNER");
+    return !(e && e[0] == '0');
+  }();
+  p.tap_inner = tap_inner_enabled ? 1 : 0;
 
   // ---- multi-tap weight-gradient tiles (see GemmDev::tp)
   p.tp = 1;
