@@ -179,6 +179,42 @@ int xva_rowdot2(const float* a, const float* b, int64_t rows, int C, int64_t a_l
 int xva_mas_width1(const float* attn, const int32_t* in_lens, const int32_t* out_lens, int B, int Tm, int Tt, int is_log,
                    float* hard, int32_t* durs, void* stream);
 
+/* Stage-1 aligner score -- replaces the body of ConvAttention.forward after the two projection stacks,
+ * fastpitch/attention.py:203-219. q [B, Tm, C] (row pitch ldq) = query_proj(mel), k [B, Tt, C] (row pitch ldk) =
+ * key_proj(text embedding), prior [B, Tm, Tt], in_lens [B] (the key mask of model.py:303):
+ *   logprob[b,t,j] = log_softmax_j(-0.0005 * sum_c (q[b,t,c] - k[b,j,c])^2) + log(prior[b,t,j] + 1e-8)    (attn_logprob)
+ *   soft[b,t,j]    = softmax over j < in_lens[b] of logprob[b,t,:], 0 for the padded keys                 (attn_soft)
+ * both [B, Tm, Tt] (the reference's [B, 1, Tm, Tt]). C <= 96, Tt <= 512; the keys of one utterance sit in shared memory.
+ * bwd: g = d(loss)/d(logprob) with every contribution summed (xva_attn_grad_combine) -> dD (the gradient of the raw
+ * score, [B, Tm, Tt], may alias g), dq [B, Tm, C] (row pitch lddq), dk [B, Tt, C] (row pitch lddk); two launches. */
+int xva_attn_score_fwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* prior, const int32_t* in_lens,
+                       int B, int Tm, int Tt, int C, float* logprob, float* soft, void* stream);
+int xva_attn_score_bwd(const float* g, const float* logprob, const float* prior, const float* q, int64_t ldq,
+                       const float* k, int64_t ldk, int B, int Tm, int Tt, int C, float* dD, float* dq, int64_t lddq,
+                       float* dk, int64_t lddk, void* stream);
+
+/* AttentionCTCLoss.forward, fastpitch/attn_loss_function.py:20-44, and its autograd, for the whole batch in one launch
+ * (the reference loops over the batch in Python: 32 F.ctc_loss calls and as many host syncs). Per utterance b, with
+ * L = in_lens[b], T = out_lens[b]: rows t < T of [blank_logprob, logprob[b,t,0..L)] are log_softmax-ed and scored by CTC
+ * against the target 1..L; cost[b] = -log p / max(L, 1) (nn.CTCLoss reduction 'mean' on a batch of one), 0 when the
+ * alignment is impossible (zero_infinity=True). The reference's loss is mean_b cost[b]; grad [B, Tm, Tt] receives
+ * d(mean_b cost[b]) / d logprob (zero outside [T, L]). workspace: xva_attn_ctc_workspace_bytes(B, Tm, Tt) bytes, 8-byte
+ * aligned (the fp64 forward variables, B x Tm x (2 Tt + 1)); caller-owned like every other buffer. */
+int64_t xva_attn_ctc_workspace_bytes(int B, int Tm, int Tt);
+int xva_attn_ctc(const float* logprob, const int32_t* in_lens, const int32_t* out_lens, int B, int Tm, int Tt,
+                 float blank_logprob, void* workspace, int64_t workspace_bytes, double* cost, float* grad, void* stream);
+
+/* AttentionBinarizationLoss.forward, fastpitch/attn_loss_function.py:47-54: acc (double[2], ACCUMULATED) +=
+ * {sum over hard == 1 of log(max(soft, eps)), sum of hard}; the loss is -acc[0] / acc[1]. hard, soft [rows, Tt]. */
+int xva_attn_bin_loss(const float* hard, const float* soft, int64_t rows, int Tt, float eps, double* acc, void* stream);
+
+/* d(loss)/d(logprob) of FastPitchTrainer.iteration's stage-1 loss, xva_train.py:790-798:
+ *   g = a * gctc + (bw / acc[1]) * (soft * rowsum(h') - h'),  h' = hard * [soft >= eps]
+ * a = loss scale * attn_loss_scale, bw = loss scale * kl_weight (the binarization term flows back through the masked
+ * softmax that produced soft). hard = NULL (or bw = 0): g = a * gctc. All [rows, Tt]. */
+int xva_attn_grad_combine(const float* gctc, const float* hard, const float* soft, const double* acc, float a, float bw,
+                          float eps, int64_t rows, int Tt, float* g, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Attention softmax -- replaces masked_fill + F.softmax + dropatt, fastpitch/transformer.py:120-127, and its autograd.
  *   fwd : s [Z,R,N] = alpha*q.k^T (from xva_gemm) -> p (softmax over n with keys n >= lens[z] masked), and
@@ -223,7 +259,8 @@ int xva_counter_add(uint64_t* counter, uint64_t inc, void* stream);
 int xva_colsum(const float* x, int64_t rows, int C, int64_t ld, float* out, void* stream);
 
 /* FFTransformer input stage, transformer.py:212-227: out = (tokens ? emb[tokens] : in) + pos_emb(t)*mask.
- * Encoder: tokens int64 [B,T] + emb [n,C] (mask = token != 0). Decoder: in [B,T,C] + lens (mask = t < lens[b]). */
+ * Encoder: tokens int64 [B,T] + emb [n,C] (mask = token != 0). Decoder: in [B,T,C] + lens (mask = t < lens[b]).
+ * inv_freq = NULL: no positional term -- the plain encoder.word_emb(inputs) the stage-1 aligner reads (model.py:299). */
 int xva_embed_pos(const int64_t* tokens, const float* emb, const float* in, const int32_t* lens,
                   const float* inv_freq, int B, int T, int C, float* out, void* stream);
 int xva_embed_bwd(const int64_t* tokens, const float* dout, int B, int T, int C, float* demb, void* stream);

@@ -9,8 +9,13 @@ Reference files restated (paths relative to the reference tree, python/fastpitch
   common/layers.py           ConvReLUNorm :85-97
   fastpitch/loss_function.py FastPitchLoss.forward :63-154 (the reference hard-codes cuda: placeholders; same math here)
   lamb.py                    Lamb.step :40-106
+  fastpitch/attention.py     ConvAttention.forward :171-220 ('3xconv' query encoder; ConvNorm common/layers.py:60-82)
+  fastpitch/attn_loss_function.py  AttentionCTCLoss :20-44, AttentionBinarizationLoss :47-54
+  fastpitch/model.py         get_alignment_durations :298-323 and the stage-1 return of forward :346-360
+  fastpitch/alignment.py     mas_width1 / b_mas :79-118
 
-Pinned against outputs of the imported reference by tests/golden/make_golden.py -> tests/test_oracle_golden.py.
+Pinned against outputs of the imported reference by tests/golden/make_golden.py (stages 2-4), make_golden_mas.py and
+make_golden_stage1.py (the aligner: ConvAttention, both attention losses, their gradients) -> tests/test_oracle_golden.py.
 """
 import math
 
@@ -109,6 +114,11 @@ def trainable_keys(stage):
     def under(*prefixes):
         return [k for k in keys if any(k.startswith(p + ".") for p in prefixes)]
 
+    if stage == 1:
+        # xva_train.py:607-669 leaves encoder + attention trainable, but the stage-1 loss only reaches the token
+        # embedding (the keys are encoder.word_emb(inputs), model.py:299 -- enc_out is unused) and the two projection
+        # stacks; every other parameter keeps grad = None, which Lamb.step skips (lamb.py:52-53: no decay either)
+        return ["encoder.word_emb.weight"] + [k for k in under("attention") if ".attn_proj." not in k]
     if stage == 2:
         return under("encoder", "duration_predictor")
     if stage == 3:
@@ -225,9 +235,11 @@ def temporal_predictor(enc_out, mask, sd, prefix, drop=0.0, training=False):
 
 # ------------------------------------------------------------------------------------------------ model
 def forward(sd, inputs_x, stage, use_gt_pitch=True, pace=1.0, max_duration=75, drop=0.0, training=False):
-    """FastPitch.forward, model.py:325-390, stages 2/3/4 (stage 1 = aligner, next tier). Returns the 13-list."""
+    """FastPitch.forward, model.py:325-390. Returns the 13-list."""
     (inputs, input_lens, mel_tgt, mel_lens, pitch_dense, energy_dense, speaker, attn_prior, durs_padded,
      max_inp_lengths, max_mel_lengths, audiopaths) = inputs_x
+    if stage == 1:
+        return forward_stage1(sd, inputs_x)
     mel_max_len = int(max_mel_lengths[0].item())
     enc_out, enc_mask = fftransformer(sd, "encoder", inputs, conditioning=0, drop=drop, dropatt=drop, training=training)
     dur_tgt = durs_padded
@@ -252,11 +264,21 @@ def forward(sd, inputs_x, stage, use_gt_pitch=True, pace=1.0, max_duration=75, d
             input_lens]
 
 
-def loss(model_out, targets, stage, dur_scale=0.1, pitch_scale=0.1, energy_scale=0.1):
-    """FastPitchLoss.forward, loss_function.py:63-154, stages 2-4. -> (loss, dict of detached terms)"""
-    (mel_out, dec_mask, dur_pred, log_dur_pred, pitch_pred, pitch_tgt, energy_pred, energy_tgt, _, _, attn_dur, _,
-     input_lens) = model_out
+def loss(model_out, targets, stage, dur_scale=0.1, pitch_scale=0.1, energy_scale=0.1, attn_scale=1.0, kl_weight=0.0):
+    """FastPitchLoss.forward, loss_function.py:63-154 (+ for stage 1 the binarization term the trainer adds,
+    xva_train.py:792-798, weighted by kl_weight). -> (loss, dict of detached terms)"""
+    (mel_out, dec_mask, dur_pred, log_dur_pred, pitch_pred, pitch_tgt, energy_pred, energy_tgt, attn_soft, attn_hard,
+     attn_dur, attn_logprob, input_lens) = model_out
     mel_tgt, in_lens, out_lens, max_inp_lengths = targets
+    if stage == 1:
+        attn_loss = attention_ctc_loss(attn_logprob, input_lens, out_lens)            # loss_function.py:74-82
+        total = attn_loss * attn_scale
+        meta = {"loss": total.detach(), "attn_loss": attn_loss.detach(), "kl_loss": torch.zeros(())}
+        if kl_weight:
+            kl = attention_binarization_loss(attn_hard, attn_soft)
+            meta["kl_loss"] = kl.detach() * kl_weight
+            total = total + kl_weight * kl
+        return total, meta
     dur_mask = mask_from_lens(input_lens, max_len=int(max_inp_lengths[0]))
     zero = torch.zeros(1, device=input_lens.device)
     mel_loss = pitch_loss = energy_loss = dur_loss = zero
@@ -313,7 +335,7 @@ def noam_lr(iteration, base_lr=0.1, warmup=1000):
     return base_lr * scale
 
 
-def train_step(sd, batch_x, batch_y, stage, lr, opt_state, drop=0.0, training=True, clip=1000.0):
+def train_step(sd, batch_x, batch_y, stage, lr, opt_state, drop=0.0, training=True, clip=1000.0, kl_weight=0.0):
     """One micro-batch with gam = 1 of FastPitchTrainer.iteration, xva_train.py:784-862 (fp32, no GradScaler):
     forward, loss, backward, clip_grad_norm_(1000), LAMB. Returns (loss terms, grads)."""
     keys = trainable_keys(stage)
@@ -321,7 +343,7 @@ def train_step(sd, batch_x, batch_y, stage, lr, opt_state, drop=0.0, training=Tr
     work = dict(sd)
     work.update(leaves)
     out = forward(work, batch_x, stage, drop=drop, training=training)
-    total, meta = loss(out, batch_y, stage)
+    total, meta = loss(out, batch_y, stage, kl_weight=kl_weight)
     grads = dict(zip(keys, torch.autograd.grad(total, [leaves[k] for k in keys], allow_unused=True)))
     gl = [g for g in grads.values() if g is not None]
     norm = torch.linalg.vector_norm(torch.stack([torch.linalg.vector_norm(g) for g in gl]))
@@ -333,8 +355,9 @@ def train_step(sd, batch_x, batch_y, stage, lr, opt_state, drop=0.0, training=Tr
 
 
 # ------------------------------------------------------------------------------------------------ synthetic batches
-def synthetic_batch(B, Tt, Tm, seed=1234, ragged=False, device="cpu"):
-    """SURVEY.md section 8(d) synthetic inputs, in the layout of batch_to_gpu (data_function.py:706-741)."""
+def synthetic_batch(B, Tt, Tm, seed=1234, ragged=False, device="cpu", prior=False):
+    """SURVEY.md section 8(d) synthetic inputs, in the layout of batch_to_gpu (data_function.py:706-741).
+    prior=True fills x[7] with a beta-binomial alignment prior per utterance (what stage 1 reads)."""
     g = torch.Generator().manual_seed(seed)
     if ragged:
         in_lens = torch.randint(max(1, (3 * Tt) // 5), Tt + 1, (B,), generator=g)
@@ -359,7 +382,14 @@ def synthetic_batch(B, Tt, Tm, seed=1234, ragged=False, device="cpu"):
         pitch[b, :, int(mel_lens[b]):] = 0
         energy[b, int(mel_lens[b]):] = 0
     t = lambda x: x.to(device)
-    x = [t(text), t(in_lens), t(mel), t(mel_lens), t(pitch), t(energy), None, None, t(durs),
+    attn_prior = None
+    if prior:
+        attn_prior = torch.zeros(B, Tm, Tt)
+        for b in range(B):
+            n, m = int(in_lens[b]), int(mel_lens[b])
+            attn_prior[b, :m, :n] = beta_binomial_prior(n, m)
+        attn_prior = t(attn_prior)
+    x = [t(text), t(in_lens), t(mel), t(mel_lens), t(pitch), t(energy), None, attn_prior, t(durs),
          t(torch.full((B,), float(Tt))), t(torch.full((B,), float(Tm))), ["synthetic"] * B]
     y = [t(mel), t(in_lens), t(mel_lens), x[9]]
     return x, y
@@ -404,3 +434,121 @@ def b_mas(b_attn_map, in_lens, out_lens, is_log=False):
     for b in range(a.shape[0]):
         out[b, 0, :out_lens[b], :in_lens[b]] = mas_width1(a[b, 0, :out_lens[b], :in_lens[b]], is_log)
     return out
+
+
+# ------------------------------------------------------------------------------------------------ stage-1 aligner
+def beta_binomial_prior(n_text, n_mel, scaling=1.0):
+    """The alignment prior the dataset caches per utterance (data_function.py:85-99: scipy.stats.betabinom(n_text, a, b)
+    with a = scaling * i, b = scaling * (n_mel + 1 - i) for mel frame i = 1..n_mel, its pmf at text positions
+    0..n_text-1). Restated with lgamma so the oracle needs no scipy; only used to give synthetic batches a realistic prior."""
+    i = torch.arange(1, n_mel + 1, dtype=torch.float64)[:, None]
+    k = torch.arange(0, n_text, dtype=torch.float64)[None, :]
+    n = float(n_text)
+    a, b = scaling * i, scaling * (n_mel + 1 - i)
+    lg = torch.lgamma
+    log_comb = lg(torch.tensor(n + 1.0, dtype=torch.float64)) - lg(k + 1) - lg(n - k + 1)
+    log_beta = lambda x, y: lg(x) + lg(y) - lg(x + y)
+    return torch.exp(log_comb + log_beta(k + a, n - k + b) - log_beta(a, b)).float()
+
+
+def conv_attention(sd, queries, keys, key_pad_mask, attn_prior):
+    """ConvAttention.forward, attention.py:171-220, with the reference's configuration (model.py:262-264: '3xconv'
+    query encoder, 80 attention channels). queries [B, 80, Tm] (the mel target), keys [B, 384, Tt] (token embedding),
+    key_pad_mask [B, Tt] True on padded tokens, attn_prior [B, Tm, Tt] or None.
+    -> (attn_soft, attn_logprob), both [B, 1, Tm, Tt]."""
+    p = "attention"
+    k = F.relu(F.conv1d(keys, sd[f"{p}.key_proj.0.conv.weight"], sd[f"{p}.key_proj.0.conv.bias"], padding=1))
+    k = F.conv1d(k, sd[f"{p}.key_proj.2.conv.weight"], sd[f"{p}.key_proj.2.conv.bias"])               # [B, 80, Tt]
+    q = F.relu(F.conv1d(queries, sd[f"{p}.query_proj.0.conv.weight"], sd[f"{p}.query_proj.0.conv.bias"], padding=1))
+    q = F.relu(F.conv1d(q, sd[f"{p}.query_proj.2.conv.weight"], sd[f"{p}.query_proj.2.conv.bias"]))
+    q = F.conv1d(q, sd[f"{p}.query_proj.4.conv.weight"], sd[f"{p}.query_proj.4.conv.bias"])           # [B, 80, Tm]
+    # isotropic Gaussian log-likelihood of every (frame, token) pair, :207-209
+    sq = (q.transpose(1, 2).unsqueeze(2) - k.transpose(1, 2).unsqueeze(1)).pow(2).sum(-1)             # [B, Tm, Tt]
+    score = (-0.0005 * sq).unsqueeze(1)
+    if attn_prior is not None:
+        score = F.log_softmax(score, dim=3) + torch.log(attn_prior.unsqueeze(1) + 1e-8)               # :210-211
+    attn_logprob = score.clone()
+    if key_pad_mask is not None:
+        # the reference fills score.data in place (:215-217); out of place here, same values and same gradient
+        score = score.masked_fill(key_pad_mask[:, None, None, :], float("-inf"))
+    return F.softmax(score, dim=3), attn_logprob
+
+
+def attention_ctc_loss(attn_logprob, in_lens, out_lens, blank_logprob=-1.0):
+    """AttentionCTCLoss.forward, attn_loss_function.py:20-44: one CTC per utterance over [blank, its own keys], target
+    = the token positions in order, nn.CTCLoss(zero_infinity=True) with its default 'mean' reduction, mean over B."""
+    B = attn_logprob.shape[0]
+    with_blank = F.pad(attn_logprob, (1, 0), value=blank_logprob)                                      # [B,1,Tm,Tt+1]
+    total = 0.0
+    for b in range(B):
+        n_key, n_query = int(in_lens[b]), int(out_lens[b])
+        lp = with_blank[b, 0, :n_query, :n_key + 1].log_softmax(dim=-1).unsqueeze(1)                   # [T, 1, L+1]
+        total = total + F.ctc_loss(lp, torch.arange(1, n_key + 1).unsqueeze(0), input_lengths=[n_query],
+                                   target_lengths=[n_key], blank=0, reduction="mean", zero_infinity=True)
+    return total / B
+
+
+def attention_binarization_loss(hard_attention, soft_attention, eps=1e-12):
+    """AttentionBinarizationLoss.forward, attn_loss_function.py:47-54."""
+    picked = soft_attention[hard_attention == 1].clamp(min=eps)
+    return -picked.log().sum() / hard_attention.sum()
+
+
+def forward_stage1(sd, inputs_x):
+    """Training stage 1 of FastPitch.forward: get_alignment_durations, model.py:298-323, and the return at :356-360.
+    The encoder FFT stack also runs in the reference (:345) but nothing returned depends on it."""
+    (inputs, input_lens, mel_tgt, mel_lens, _, _, _, attn_prior, _, max_inp_lengths, _, _) = inputs_x
+    text_emb = F.embedding(inputs, sd["encoder.word_emb.weight"], padding_idx=0)
+    key_pad = ~mask_from_lens(input_lens, int(max_inp_lengths[0]))
+    attn_soft, attn_logprob = conv_attention(sd, mel_tgt, text_emb.transpose(1, 2), key_pad, attn_prior)
+    hard = b_mas(attn_soft.detach().cpu().numpy(), input_lens.cpu().numpy(), mel_lens.cpu().numpy())
+    attn_hard = torch.from_numpy(hard).to(attn_soft.device)
+    attn_hard_dur = attn_hard.sum(2)[:, 0, :]
+    return [None, None, None, None, None, None, None, None, attn_soft, attn_hard, attn_hard_dur, attn_logprob,
+            input_lens]
+
+
+def ctc_recursion(lp, n_key, n_query, blank_logprob=-1.0):
+    """The CTC forward-backward of one utterance written out (numpy fp64), as csrc/align.cu evaluates it: independent of
+    torch's ctc_loss, which attention_ctc_loss above (and the reference) call. lp [Tm, Tt] = attn_logprob of the
+    utterance. Extended states s = 0..2L: blank for even s, key (s-1)/2 for odd s; the keys are all distinct, so the
+    skip s-2 -> s is open for every odd s >= 3. -> (cost = -log p / max(L, 1) or 0 if impossible, d cost / d lp)."""
+    import numpy as np
+
+    L, T = int(n_key), int(n_query)
+    S = 2 * L + 1
+    grad = np.zeros_like(lp, dtype=np.float64)
+    if T == 0:
+        return 0.0, grad
+    z = np.concatenate([np.full((T, 1), blank_logprob), np.asarray(lp, dtype=np.float64)[:T, :L]], axis=1)
+    n = z - np.log(np.exp(z - z.max(1, keepdims=True)).sum(1, keepdims=True)) - z.max(1, keepdims=True)
+    col = np.array([0 if s % 2 == 0 else (s + 1) // 2 for s in range(S)])
+    odd = (np.arange(S) % 2) == 1
+
+    def lse(*terms):
+        m = np.max(terms, axis=0)
+        safe = np.where(np.isfinite(m), m, 0.0)
+        with np.errstate(divide="ignore"):
+            return np.where(np.isfinite(m), safe + np.log(sum(np.exp(t - safe) for t in terms)), -np.inf)
+
+    ninf = np.full(S + 4, -np.inf)
+    alpha = np.full((T, S), -np.inf)
+    alpha[0, :min(S, 2)] = n[0, col[:min(S, 2)]]
+    for t in range(1, T):
+        p = ninf.copy()
+        p[2:S + 2] = alpha[t - 1]
+        alpha[t] = n[t, col] + lse(p[2:S + 2], p[1:S + 1], np.where(odd, p[0:S], -np.inf))
+    tail = alpha[T - 1, max(S - 2, 0):]
+    nll = -float(lse(*[np.array(v) for v in tail]))
+    if not np.isfinite(nll):
+        return 0.0, grad
+    beta = np.full((T, S), -np.inf)
+    beta[T - 1, max(S - 2, 0):] = n[T - 1, col[max(S - 2, 0):]]
+    for t in range(T - 2, -1, -1):
+        p = ninf.copy()
+        p[2:S + 2] = beta[t + 1]
+        beta[t] = n[t, col] + lse(p[2:S + 2], p[3:S + 3], np.where(odd, p[4:S + 4], -np.inf))
+    s_of_key = 2 * np.arange(L) + 1
+    post = np.exp(alpha[:, s_of_key] + beta[:, s_of_key] - n[:, 1:] + nll)
+    grad[:T, :L] = (np.exp(n[:, 1:]) - post) / max(L, 1)
+    return nll / max(L, 1), grad

@@ -56,6 +56,42 @@ def test_fastpitch_handle_trainer_stages_and_files(lib, tmp_path, monkeypatch):
     assert l3[-1] < l3[0]
 
 
+def test_fastpitch_handle_trainer_starts_at_the_aligner(lib, tmp_path, monkeypatch):
+    """Batches that carry the alignment prior start at stage 1 like a new voice in the reference; the durations stage 2
+    trains on are the aligner's (xva_train.py:1128-1160), not the ones the batches came with."""
+    from xva_trainer_b200 import trainers
+
+    monkeypatch.setenv("XVA_B200_MAX_EPOCHS", "2")
+    mm = trainers.ModelsManager(Log(), PROD=False)
+    ws = FakeSocket()
+    data = {"dataset_path": "synthetic:4x24x64x16:prior", "output_path": str(tmp_path), "checkpoint": None,
+            "num_workers": 0, "batch_size": 64, "epochs_per_checkpoint": 1, "force_stage": None}
+    seen = {}
+    orig = trainers.FastPitchTrainer.extract_durations
+
+    def spy(self):
+        before = [b[0][8].clone() for b in self.batches]
+        orig(self)
+        seen["changed"] = any(not torch.equal(a, b[0][8]) for a, b in zip(before, self.batches))
+        seen["sums"] = [b[0][8].sum(1).cpu() for b in self.batches]
+        seen["mel_lens"] = [b[0][3].cpu() for b in self.batches]
+
+    monkeypatch.setattr(trainers.FastPitchTrainer, "extract_durations", spy)
+    res = asyncio.run(trainers.handleTrainer(mm, data, ws, [0]))
+    assert res == "move to hifi"
+    assert ws.sent == ["Set stage to: 1 ", "Set stage to: 2 ", "Set stage to: 3 ", "Set stage to: 4 "]
+    assert seen["changed"]
+    for s_, l_ in zip(seen["sums"], seen["mel_lens"]):
+        assert torch.equal(s_.long(), l_)                       # a hard alignment: durations add up to the mel length
+    out = tmp_path / "synthetic_4x24x64x16_prior"
+    names = sorted(os.listdir(out))
+    assert {n.split("_")[1] for n in names if n.startswith("Stage_")} == {"1", "2", "3", "4"}
+    graphs = json.load(open(out / "graphs.json"))
+    assert len(graphs["stages"]["1"]["loss"]) == 2 and graphs["stages"]["1"]["target_delta"] is not None
+    log = open(out / "training.log").read()
+    assert "Stage 1: Pre-training only the alignment." in log and "Extracting durations from alignments" in log
+
+
 def test_hifigan_handle_trainer_files(lib, tmp_path, monkeypatch):
     from xva_trainer_b200 import trainers
 

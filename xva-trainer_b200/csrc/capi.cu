@@ -69,6 +69,35 @@ int xva_mas_width1(const float* attn, const int32_t* in_lens, const int32_t* out
   return mas_width1(attn, in_lens, out_lens, B, Tm, Tt, is_log, hard, durs, S(stream));
 }
 
+int xva_attn_score_fwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* prior, const int32_t* in_lens,
+                       int B, int Tm, int Tt, int C, float* logprob, float* soft, void* stream) {
+  return attn_score_fwd(q, static_cast<long>(ldq), k, static_cast<long>(ldk), prior, in_lens, B, Tm, Tt, C, logprob, soft,
+                        S(stream));
+}
+
+int xva_attn_score_bwd(const float* g, const float* logprob, const float* prior, const float* q, int64_t ldq,
+                       const float* k, int64_t ldk, int B, int Tm, int Tt, int C, float* dD, float* dq, int64_t lddq,
+                       float* dk, int64_t lddk, void* stream) {
+  return attn_score_bwd(g, logprob, prior, q, static_cast<long>(ldq), k, static_cast<long>(ldk), B, Tm, Tt, C, dD, dq,
+                        static_cast<long>(lddq), dk, static_cast<long>(lddk), S(stream));
+}
+
+int64_t xva_attn_ctc_workspace_bytes(int B, int Tm, int Tt) { return attn_ctc_workspace_bytes(B, Tm, Tt); }
+
+int xva_attn_ctc(const float* logprob, const int32_t* in_lens, const int32_t* out_lens, int B, int Tm, int Tt,
+                 float blank_logprob, void* workspace, int64_t workspace_bytes, double* cost, float* grad, void* stream) {
+  return attn_ctc(logprob, in_lens, out_lens, B, Tm, Tt, blank_logprob, workspace, workspace_bytes, cost, grad, S(stream));
+}
+
+int xva_attn_bin_loss(const float* hard, const float* soft, int64_t rows, int Tt, float eps, double* acc, void* stream) {
+  return attn_bin_loss(hard, soft, static_cast<long>(rows), Tt, eps, acc, S(stream));
+}
+
+int xva_attn_grad_combine(const float* gctc, const float* hard, const float* soft, const double* acc, float a, float bw,
+                          float eps, int64_t rows, int Tt, float* g, void* stream) {
+  return attn_grad_combine(gctc, hard, soft, acc, a, bw, eps, static_cast<long>(rows), Tt, g, S(stream));
+}
+
 int xva_softmax_fwd(const float* s, const int32_t* lens, int Z, int R, int N, int ld, float* p, float* pd,
                     float drop_p, uint64_t seed, const uint64_t* seed_dev, void* stream) {
   return softmax_fwd(s, lens, Z, R, N, ld, p, pd, drop_p, seed, seed_dev, S(stream));
@@ -101,6 +130,7 @@ int xva_set_operand_rounding(int on) {
   if ((rc = set_operand_rounding_melspec(on)) != XVA_OK) return rc;
   if ((rc = set_operand_rounding_disc(on)) != XVA_OK) return rc;
   if ((rc = set_operand_rounding_wnpack(on)) != XVA_OK) return rc;
+  if ((rc = set_operand_rounding_align(on)) != XVA_OK) return rc;
   return set_operand_rounding_loss_optim(on);
 }
 

@@ -16,6 +16,7 @@ int set_operand_rounding_elemwise(int on);
 int set_operand_rounding_melspec(int on);
 int set_operand_rounding_disc(int on);
 int set_operand_rounding_wnpack(int on);
+int set_operand_rounding_align(int on);
 
 // ---- regulate.cu
 int duration_scan(const float* durs, int B, int Tt, float pace, int mel_max_len, int* cum, int* dec_lens,
@@ -55,6 +56,19 @@ int rowdot_fwd(const float* x, const float* w, const float* bias, const int* len
                cudaStream_t stream);
 int rowdot_bwd(const float* dout, const float* x, const float* w, const int* lens, int Z, int R, int C, float* dx,
                float* dw, float* db, cudaStream_t stream);
+
+// ---- align.cu (FastPitch stage-1 aligner: score, CTC, binarization loss)
+int attn_score_fwd(const float* q, long ldq, const float* k, long ldk, const float* prior, const int* in_lens, int B,
+                   int Tm, int Tt, int C, float* logprob, float* soft, cudaStream_t stream);
+int attn_score_bwd(const float* g, const float* logprob, const float* prior, const float* q, long ldq, const float* k,
+                   long ldk, int B, int Tm, int Tt, int C, float* dD, float* dq, long lddq, float* dk, long lddk,
+                   cudaStream_t stream);
+long long attn_ctc_workspace_bytes(int B, int Tm, int Tt);
+int attn_ctc(const float* logprob, const int* in_lens, const int* out_lens, int B, int Tm, int Tt, float blank_logprob,
+             void* workspace, long long workspace_bytes, double* cost, float* grad, cudaStream_t stream);
+int attn_bin_loss(const float* hard, const float* soft, long rows, int Tt, float eps, double* acc, cudaStream_t stream);
+int attn_grad_combine(const float* gctc, const float* hard, const float* soft, const double* acc, float a, float bw,
+                      float eps, long rows, int Tt, float* g, cudaStream_t stream);
 
 // ---- elemwise.cu
 int mean3_lrelu(const float* y0, const float* y1, const float* y2, long n, float slope, float* out, cudaStream_t stream);

@@ -531,7 +531,7 @@ embed_pos_kernel(const long long* __restrict__ tokens, const float* __restrict__
   const float tf = static_cast<float>(t);
   for (int c = lane; c < C; c += 32) {
     float v = src[c];
-    if (live) {
+    if (live && inv_freq != nullptr) {
       const float ang = tf * inv_freq[c < half ? c : c - half];
       v += (c < half) ? sinf(ang) : cosf(ang);
     }

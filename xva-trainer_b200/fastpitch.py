@@ -4,6 +4,8 @@ every tensor operation issued through the C ABI of libxva_b200.so (tcgen05 tap-G
 Mirrors (names, argument meaning, outputs) of the reference, paths relative to python/fastpitch1_1/ :
     FastPitch            fastpitch/model.py:125-390      (forward -> the 13-list of model.py:388-390)
     FastPitchLoss        fastpitch/loss_function.py:29-154
+    stage-1 aligner      fastpitch/attention.py:171-220 (ConvAttention), fastpitch/alignment.py:79-118 (MAS),
+                         fastpitch/attn_loss_function.py:20-54 (AttentionCTCLoss, AttentionBinarizationLoss)
     Lamb                 lamb.py:8-106                    (+ clip_grad_norm_ of xva_train.py:857)
     noam learning rate   xva_train.py:1252-1261
 
@@ -115,14 +117,19 @@ def trainable_keys(stage):
     def under(*prefixes):
         return [k for k in keys if any(k.startswith(p + ".") for p in prefixes)]
 
+    if stage == 1:
+        # The trainer un-freezes encoder + attention (xva_train.py:607-620), but the stage-1 loss only reaches the token
+        # embedding (the keys are encoder.word_emb(inputs), model.py:299; enc_out is not used) and the two projection
+        # stacks: every other tensor keeps grad = None in the reference, and Lamb.step skips those (lamb.py:52-53) --
+        # no moment update, no weight decay. attention.attn_proj is never called by ConvAttention.forward.
+        return ["encoder.word_emb.weight"] + [k for k in under("attention") if ".attn_proj." not in k]
     if stage == 2:
         return under("encoder", "duration_predictor")
     if stage == 3:
         return [k for k in keys if not (k.startswith("attention.") or k.startswith("duration_predictor."))]
     if stage == 4:
         return under("encoder", "decoder", "energy_emb", "proj")
-    raise NotImplementedError(f"training stage {stage}: the stage-1 aligner (attention.py / alignment.py) is not part of "
-                              "this build yet (SURVEY.md section 8f rank 2)")
+    raise ValueError(f"training stage {stage}: FastPitch has stages 1-4")
 
 
 class _Arena:
@@ -229,6 +236,12 @@ class FastPitch(torch.nn.Module):
                     proj_b="proj.bias")
         self.w = _NS(**{n: W(k) for n, k in misc.items()})
         self.g = _NS(**{n: G(k) for n, k in misc.items()})
+        att = {}
+        for stack, idx in (("query_proj", (0, 2, 4)), ("key_proj", (0, 2))):
+            for i in idx:
+                att[f"{stack[0]}{i}_w"] = f"attention.{stack}.{i}.conv.weight"
+                att[f"{stack[0]}{i}_b"] = f"attention.{stack}.{i}.conv.bias"
+        self.att = _NS(w=_NS(**{n: W(k) for n, k in att.items()}), g=_NS(**{n: G(k) for n, k in att.items()}))
 
     def reset_parameters(self, seed=1234):
         """Seeded init with torch's default fan-in scales (what nn.Conv1d / nn.Linear / nn.Embedding / nn.LayerNorm do
@@ -441,17 +454,103 @@ class FastPitch(torch.nn.Module):
     binarize_attention = binarize_attention_parallel          # model.py:267-281: the same result, item by item
 
     # ------------------------------------------------------------------------------------------ forward
+    def _forward_stage1(self, inputs_x):
+        """Training stage 1: FastPitch.get_alignment_durations, model.py:298-323, and the return of model.py:356-360.
+        ConvAttention (attention.py:171-220): the two projection stacks on the tap-GEMM (channels-last, the k=3 halo and
+        the utterance boundaries are TMA zero fill), the Gaussian score + log_softmax + prior + masked softmax in one
+        kernel (xva_attn_score_fwd), the Viterbi alignment on the device (xva_mas_width1; the reference copies the
+        attention to the host for numba and back). The reference also runs the encoder stack here (model.py:345) but
+        returns nothing that depends on it in stage 1, so it is skipped."""
+        (inputs, input_lens, mel_tgt, mel_lens, _, _, _, attn_prior, _, max_inp_lengths, _, _) = inputs_x
+        if attn_prior is None:
+            raise ValueError("training stage 1 needs the alignment prior (inputs_x[7], data_function.py:88-99)")
+        dev = self.device_
+        B, Tt = inputs.shape
+        Tm = mel_tgt.shape[2]
+        tokens = inputs.to(torch.int64).contiguous()
+        in_lens32 = input_lens.to(torch.int32).contiguous()
+        out_lens32 = mel_lens.to(torch.int32).contiguous()
+        A = self.att.w
+        # 80-channel tensors live in rows of 96 floats with a zero tail: they are MN-major operands (read in 32-column
+        # chunks) of the weight-gradient GEMMs of the backward pass
+        wide = lambda rows: torch.zeros(B, rows, 96, device=dev, dtype=torch.float32)
+        # keys: key_proj(encoder.word_emb(inputs)) -- Conv1d(384, 768, 3) -> ReLU -> Conv1d(768, 80, 1), attention.py:95-107
+        text_emb = ops.embed_pos(tokens, self.w.emb, None, None, None, B, Tt, D_MODEL)
+        kh = ops.conv_fwd(text_emb, A.k0_w, K3, bias=A.k0_b, relu=True, round_out=True)
+        kbuf = wide(Tt)
+        k_enc = ops.conv_fwd(kh, A.k2_w, bias=A.k2_b, out=kbuf[..., :N_MEL])
+        # queries: query_proj(mel) -- Conv1d(80, 160, 3) -> ReLU -> Conv1d(160, 80, 1) -> ReLU -> Conv1d(80, 80, 1), :113-128
+        melp = wide(Tm)
+        mel = melp[..., :N_MEL]
+        mel.copy_(mel_tgt.to(torch.float32).transpose(1, 2))
+        ops.round_tf32_(melp.view(-1), melp.view(-1))
+        qh1 = ops.conv_fwd(mel, A.q0_w, K3, bias=A.q0_b, relu=True, round_out=True)
+        qh2 = ops.conv_fwd(qh1, A.q2_w, bias=A.q2_b, relu=True, round_out=True, out=wide(Tm)[..., :N_MEL])
+        q_enc = ops.conv_fwd(qh2, A.q4_w, bias=A.q4_b, out=wide(Tm)[..., :N_MEL])
+        # score, log_softmax + prior, masked softmax (attention.py:203-219)
+        logprob, soft, prior = ops.attn_score_fwd(q_enc, k_enc, attn_prior, in_lens32)
+        attn_hard, durs = ops.mas_width1(soft, in_lens32, out_lens32)
+        if self.training:
+            self._ctx = _NS(stage=1, B=B, Tt=Tt, Tm=Tm, tokens=tokens, in_lens=in_lens32, text_emb=text_emb, kh=kh, k=k_enc,
+                            mel=mel, qh1=qh1, qh2=qh2, q=q_enc, logprob=logprob, prior=prior)
+        else:
+            self._ctx = None
+        shape4 = (B, 1, Tm, Tt)
+        return [None, None, None, None, None, None, None, None, soft.view(shape4), attn_hard.view(shape4),
+                durs.to(torch.float32), logprob.view(shape4), input_lens]
+
+    def _backward_stage1(self, criterion, scale, kl, ready):
+        """Reverse of _forward_stage1 for loss = attn_loss_scale * ctc + kl_weight * binarization (xva_train.py:790-798)."""
+        ctx = self._ctx
+        A, G = self.att.w, self.att.g
+        B, Tt, Tm = ctx.B, ctx.Tt, ctx.Tm
+        gctc, a = criterion.grad_seeds(scale)["attn_logprob"]
+        if kl is not None and kl[1]:
+            g = ops.attn_grad_combine(gctc, a, *kl[0].saved(), bw=scale * float(kl[1]))
+        else:
+            g = ops.attn_grad_combine(gctc, a)
+        dq, dk = ops.attn_score_bwd(g, ctx.logprob, ctx.prior, ctx.q, ctx.k)
+        del g
+        # query_proj, last layer first. The 80 -> 80 layer's weight is copied into rows of 96 floats: the input-gradient
+        # GEMM reads it MN-major in 32-column chunks.
+        ops.conv_wgrad(dq, ctx.qh2, (0,), out=G.q4_w, accumulate=True)
+        ops.colsum_(B * Tm, N_MEL, dq.stride(1), dq, G.q4_b)
+        w4 = torch.zeros(1, N_MEL, 96, device=dq.device, dtype=torch.float32)
+        w4[..., :N_MEL].copy_(A.q4_w)
+        dh2 = ops.conv_dgrad(dq, w4[..., :N_MEL], gate=ctx.qh2, round_out=True,
+                             out=torch.zeros(B, Tm, 96, device=dq.device, dtype=torch.float32)[..., :N_MEL])
+        ops.conv_wgrad(dh2, ctx.qh1, (0,), out=G.q2_w, accumulate=True)
+        ops.colsum_(B * Tm, N_MEL, dh2.stride(1), dh2, G.q2_b)
+        dh1 = ops.conv_dgrad(dh2, A.q2_w, gate=ctx.qh1, round_out=True)
+        ops.conv_wgrad(dh1, ctx.mel, K3, out=G.q0_w, accumulate=True)
+        ops.colsum_(B * Tm, dh1.shape[2], dh1.shape[2], dh1, G.q0_b)
+        del dq, dh2, dh1
+        # key_proj and the token embedding
+        ops.conv_wgrad(dk, ctx.kh, (0,), out=G.k2_w, accumulate=True)
+        ops.colsum_(B * Tt, N_MEL, dk.stride(1), dk, G.k2_b)
+        dkh = ops.conv_dgrad(dk, A.k2_w, gate=ctx.kh, round_out=True)
+        ops.conv_wgrad(dkh, ctx.text_emb, K3, out=G.k0_w, accumulate=True)
+        ops.colsum_(B * Tt, dkh.shape[2], dkh.shape[2], dkh, G.k0_b)
+        demb = ops.conv_dgrad(dkh, A.k0_w, K3)
+        ops.embed_bwd_(ctx.tokens, demb, self.g.emb)
+        ready("attention", flush=True)              # two slices at opposite ends of the arena: sent separately
+        ready("encoder.word_emb", flush=True)
+        self._ctx = None
+
     def forward(self, inputs_x, use_gt_pitch=True, use_dur_tgt=False, pace=1.0, max_duration=75, host_lens=None):
-        """FastPitch.forward, model.py:325-390, training stages 2-4. ``inputs_x`` is the 12-list of
+        """FastPitch.forward, model.py:325-390, training stages 1-4. ``inputs_x`` is the 12-list of
         data_function.py:737-738. ``host_lens`` = (mel_max_len, max(dec_lens)) as Python ints lets a caller that already
         knows them on the host (the collate does) skip the two device->host reads the reference makes (model.py:330,
         :75). Returns the reference's 13-list; with the module in training mode the activations backward() needs are
         kept until the next forward()."""
         (inputs, input_lens, mel_tgt, mel_lens, pitch_dense, energy_dense, speaker, attn_prior, durs_padded,
          max_inp_lengths, max_mel_lengths, audiopaths) = inputs_x
-        stage = self.training_stage
-        if stage not in (2, 3, 4):
+        stage = int(self.training_stage)
+        if stage not in (1, 2, 3, 4):
             trainable_keys(stage)
+        self._site = 0
+        if stage == 1:
+            return self._forward_stage1(inputs_x)
         if not use_gt_pitch:
             raise NotImplementedError("use_gt_pitch=False is the inference path (FastPitch.infer), not part of training")
         dev = self.device_
@@ -512,11 +611,13 @@ class FastPitch(torch.nn.Module):
                 input_lens]
 
     # ------------------------------------------------------------------------------------------ backward
-    def backward(self, criterion, scale=1.0, grad_sync=None):
+    def backward(self, criterion, scale=1.0, grad_sync=None, kl=None):
         """Reverse pass for the loss ``criterion`` just evaluated on this module's last forward() output. Gradients of
         the stage's trainable parameters are ACCUMULATED into the gradient arena (zero_grad() clears it), scaled by
         ``scale`` (the 1/gam of xva_train.py:806). ``grad_sync`` (parallel.GradSync) is told which arena slices are
-        final as the pass proceeds, so their all-reduce overlaps the rest of the backward."""
+        final as the pass proceeds, so their all-reduce overlaps the rest of the backward. Stage 1 only: ``kl`` =
+        (AttentionBinarizationLoss already evaluated on this forward's attn_hard / attn_soft, kl_weight) adds the
+        binarization term of xva_train.py:792-798 to the loss being differentiated."""
         ctx = self._ctx
         if grad_sync is not None:
             scale = scale * grad_sync.loss_scale
@@ -524,6 +625,8 @@ class FastPitch(torch.nn.Module):
         if ctx is None:
             raise RuntimeError("backward() needs a forward() in training mode first")
         stage = ctx.stage
+        if stage == 1:
+            return self._backward_stage1(criterion, scale, kl, ready)
         lens = ctx.in_lens
         B, Tt = ctx.B, ctx.Tt
         seeds = criterion.grad_seeds(scale)
@@ -577,16 +680,28 @@ class FastPitchLoss:
         self.training_stage = 3
         self._saved = None
 
-    def __call__(self, model_out, targets, is_training=True, meta_agg="mean"):
-        return self.forward(model_out, targets, is_training, meta_agg)
+    def __call__(self, model_out, targets, is_training=True, meta_agg="mean", training_stage=None):
+        return self.forward(model_out, targets, is_training, meta_agg, training_stage)
 
-    def forward(self, model_out, targets, is_training=True, meta_agg="mean"):
-        (mel_out, dec_mask, dur_pred, log_dur_pred, pitch_pred, pitch_tgt, energy_pred, energy_tgt, _, _, attn_dur, _,
-         input_lens) = model_out
+    def forward(self, model_out, targets, is_training=True, meta_agg="mean", training_stage=None):
+        """``training_stage`` (the reference passes it per call, loss_function.py:63) overrides the attribute."""
+        (mel_out, dec_mask, dur_pred, log_dur_pred, pitch_pred, pitch_tgt, energy_pred, energy_tgt, _, _, attn_dur,
+         attn_logprob, input_lens) = model_out
         mel_tgt, in_lens, out_lens, max_inp_lengths = targets[:4]
+        if training_stage is not None:
+            self.training_stage = int(training_stage)
         stage = self.training_stage
         dev = input_lens.device
         lens32 = input_lens.to(torch.int32)
+        if stage == 1:
+            # AttentionCTCLoss over the whole batch in one launch (loss_function.py:74-82); the kernel also leaves
+            # d(mean cost)/d(attn_logprob), which grad_seeds() hands to FastPitch.backward
+            lp = attn_logprob.reshape(attn_logprob.shape[0], attn_logprob.shape[-2], attn_logprob.shape[-1])
+            cost, gctc = ops.attn_ctc(lp, lens32.contiguous(), out_lens.to(torch.int32).contiguous())
+            attn_loss = cost.mean()
+            loss = attn_loss * self.attn_loss_scale
+            self._saved = {"stage": 1, "gctc": gctc}
+            return loss, {"loss": loss, "attn_loss": attn_loss}
         acc = torch.zeros(4, 2, device=dev, dtype=torch.float64)   # rows: mel, dur, pitch, energy = {sum sq err, count}
         zero = torch.zeros((), device=dev, dtype=torch.float64)
         mel_loss = dur_loss = pitch_loss = energy_loss = zero
@@ -619,6 +734,8 @@ class FastPitchLoss:
         s = self._saved
         if s is None:
             raise RuntimeError("FastPitchLoss.grad_seeds() needs a forward() first")
+        if s["stage"] == 1:
+            return {"attn_logprob": (s["gctc"], scale * self.attn_loss_scale)}
         acc, lens = s["acc"], s["lens"]
         out = {}
         if s["stage"] == 2:
@@ -632,6 +749,32 @@ class FastPitchLoss:
                 out["energy"] = ops.lens_mse_grad(s["energy_pred"], s["energy_tgt"], lens, acc[3],
                                                   scale * self.energy_predictor_loss_scale)
         return out
+
+
+class AttentionBinarizationLoss:
+    """AttentionBinarizationLoss, fastpitch/attn_loss_function.py:47-54: -sum_{hard == 1} log(clamp(soft, eps)) / sum(hard),
+    reduced on the device in fp64. The trainer adds kl_weight times it to the stage-1 loss (xva_train.py:792-798); pass
+    ``kl=(this, kl_weight)`` to FastPitch.backward for its gradient."""
+
+    def __init__(self):
+        self._saved = None
+
+    def __call__(self, hard_attention, soft_attention, eps=1e-12):
+        return self.forward(hard_attention, soft_attention, eps)
+
+    def forward(self, hard_attention, soft_attention, eps=1e-12):
+        hard = hard_attention.to(torch.float32).contiguous()
+        soft = soft_attention.to(torch.float32).contiguous()
+        acc = torch.zeros(2, device=soft.device, dtype=torch.float64)
+        ops.attn_bin_loss(hard, soft, acc, eps)
+        self._saved = (hard, soft, acc, float(eps))
+        return -acc[0] / acc[1]
+
+    def saved(self):
+        """(hard, soft, acc) of the last forward, for ops.attn_grad_combine."""
+        if self._saved is None:
+            raise RuntimeError("AttentionBinarizationLoss.saved() needs a forward() first")
+        return self._saved[:3]
 
 
 class Lamb:

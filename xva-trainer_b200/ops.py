@@ -309,6 +309,66 @@ def mas_width1(attn, in_lens, out_lens, is_log=False):
     return hard.view(shape), durs
 
 
+def attn_score_fwd(q, k, prior, in_lens):
+    """ConvAttention.forward after the projections, fastpitch/attention.py:203-219. q [B,Tm,C], k [B,Tt,C] (row pitches
+    passed through), prior [B,Tm,Tt], in_lens int32 [B] -> (attn_logprob, attn_soft), both [B,Tm,Tt]."""
+    _check3(q, "q")
+    _check3(k, "k")
+    B, Tm, Cc = q.shape
+    Tt = k.shape[1]
+    assert q.stride(0) == Tm * q.stride(1) and k.stride(0) == Tt * k.stride(1) and in_lens.dtype == torch.int32
+    pr = prior.to(torch.float32).contiguous()
+    assert tuple(pr.shape) == (B, Tm, Tt), (tuple(pr.shape), (B, Tm, Tt))
+    logprob = torch.empty(B, Tm, Tt, device=q.device, dtype=torch.float32)
+    soft = torch.empty_like(logprob)
+    capi.call("xva_attn_score_fwd", _p(q), q.stride(1), _p(k), k.stride(1), _p(pr), _p(in_lens), B, Tm, Tt, Cc,
+              _p(logprob), _p(soft), _stream())
+    return logprob, soft, pr
+
+
+def attn_score_bwd(g, logprob, prior, q, k, ld=96):
+    """-> (dq [B,Tm,C], dk [B,Tt,C]) as views of zero-tailed buffers with row pitch ``ld`` (they are the MN-major
+    operands of the projection stacks' weight-gradient GEMMs). g [B,Tm,Tt] is overwritten with the raw-score gradient."""
+    B, Tm, Cc = q.shape
+    Tt = k.shape[1]
+    dq = torch.zeros(B, Tm, ld, device=q.device, dtype=torch.float32)
+    dk = torch.zeros(B, Tt, ld, device=q.device, dtype=torch.float32)
+    capi.call("xva_attn_score_bwd", _p(g), _p(logprob), _p(prior), _p(q), q.stride(1), _p(k), k.stride(1), B, Tm, Tt, Cc,
+              _p(g), _p(dq), ld, _p(dk), ld, _stream())
+    return dq[..., :Cc], dk[..., :Cc]
+
+
+def attn_ctc(logprob, in_lens, out_lens, blank_logprob=-1.0):
+    """AttentionCTCLoss, fastpitch/attn_loss_function.py:20-44, whole batch in one launch.
+    -> (cost double [B] per utterance, grad [B,Tm,Tt] = d(mean cost)/d(logprob))."""
+    B, Tm, Tt = logprob.shape
+    assert logprob.is_contiguous() and in_lens.dtype == torch.int32 and out_lens.dtype == torch.int32
+    nbytes = int(capi.load().xva_attn_ctc_workspace_bytes(B, Tm, Tt))
+    ws = torch.empty(nbytes // 8, device=logprob.device, dtype=torch.float64)
+    cost = torch.empty(B, device=logprob.device, dtype=torch.float64)
+    grad = torch.empty_like(logprob)
+    capi.call("xva_attn_ctc", _p(logprob), _p(in_lens), _p(out_lens), B, Tm, Tt, float(blank_logprob), _p(ws), nbytes,
+              _p(cost), _p(grad), _stream())
+    return cost, grad
+
+
+def attn_bin_loss(hard, soft, acc, eps=1e-12):
+    """acc (double[2]) += {sum_{hard==1} log(max(soft, eps)), sum(hard)}  (attn_loss_function.py:47-54)."""
+    assert hard.is_contiguous() and soft.is_contiguous() and hard.shape == soft.shape and acc.dtype == torch.float64
+    Tt = hard.shape[-1]
+    capi.call("xva_attn_bin_loss", _p(hard), _p(soft), hard.numel() // Tt, Tt, float(eps), _p(acc), _stream())
+
+
+def attn_grad_combine(gctc, a, hard=None, soft=None, acc=None, bw=0.0, eps=1e-12):
+    """g = a * gctc + (bw / acc[1]) * (soft * rowsum(h') - h'), h' = hard * [soft >= eps]; [.., Tt] tensors."""
+    Tt = gctc.shape[-1]
+    g = torch.empty_like(gctc)
+    use_kl = hard is not None and bw != 0.0
+    capi.call("xva_attn_grad_combine", _p(gctc), _p(hard) if use_kl else None, _p(soft) if use_kl else None,
+              _p(acc) if use_kl else None, float(a), float(bw), float(eps), gctc.numel() // Tt, Tt, _p(g), _stream())
+    return g
+
+
 # ---------------------------------------------------------------------------------------------- row kernels
 def softmax_fwd(s, lens, n_valid, drop_p=0.0, seed=0, seed_dev=None):
     """transformer.py:120-127.  s [Z,R,ld] holds alpha*q.k^T in its first n_valid columns -> (p, pd); pd is p when
@@ -359,7 +419,9 @@ def colsum_(x2d_rows, C_, ld, x, out):
 
 
 def embed_pos(tokens, emb, inp, lens, inv_freq, B, T, Cc):
-    out = torch.empty(B, T, Cc, device=inv_freq.device, dtype=torch.float32)
+    """inv_freq = None: the embedding lookup alone (no positional term)."""
+    dev = inv_freq.device if inv_freq is not None else (emb if emb is not None else inp).device
+    out = torch.empty(B, T, Cc, device=dev, dtype=torch.float32)
     capi.call("xva_embed_pos", _p(tokens), _p(emb), _p(inp), _p(lens), _p(inv_freq), B, T, Cc, _p(out), _stream())
     return out
 

@@ -45,9 +45,24 @@ def _now():
     return t.split(".")[0]
 
 
+def beta_binomial_prior_distribution(phoneme_count, mel_count, scaling_factor=1.0):
+    """data_function.py:85-99 (scipy.stats.betabinom(P, a, b).pmf(0..P-1) per mel frame) from lgamma, [M, P] fp32."""
+    i = torch.arange(1, mel_count + 1, dtype=torch.float64)[:, None]
+    k = torch.arange(0, phoneme_count, dtype=torch.float64)[None, :]
+    n = torch.tensor(float(phoneme_count), dtype=torch.float64)
+    a, b = scaling_factor * i, scaling_factor * (mel_count + 1 - i)
+    lg = torch.lgamma
+    log_beta = lambda u, v: lg(u) + lg(v) - lg(u + v)
+    return torch.exp(lg(n + 1) - lg(k + 1) - lg(n - k + 1) + log_beta(k + a, n - k + b) - log_beta(a, b)).float()
+
+
 def _synthetic_fastpitch_batches(spec, device, seed=1234):
-    """'synthetic:BxTtxTmxitems' -> list of (x, y, num_frames) in the layout of batch_to_gpu (data_function.py:706-741)."""
-    B, Tt, Tm, items = (int(v) for v in spec.split(":", 1)[1].split("x"))
+    """'synthetic:BxTtxTmxitems[:prior]' -> list of (x, y, num_frames) in the layout of batch_to_gpu
+    (data_function.py:706-741). With ':prior' every batch carries the beta-binomial alignment prior (x[7]) and a run
+    starts at training stage 1, like a new voice in the reference."""
+    body = spec.split(":", 1)[1]
+    with_prior = body.endswith(":prior")
+    B, Tt, Tm, items = (int(v) for v in body.split(":")[0].split("x"))
     g = torch.Generator().manual_seed(seed)
     out = []
     for _ in range(max(1, items // B)):
@@ -61,7 +76,8 @@ def _synthetic_fastpitch_batches(spec, device, seed=1234):
         lens = torch.full((B,), Tt, dtype=torch.long)
         mlens = torch.full((B,), Tm, dtype=torch.long)
         t = lambda v: v.to(device)
-        x = [t(text), t(lens), t(mel), t(mlens), t(pitch), t(energy), None, None, t(durs),
+        prior = t(beta_binomial_prior_distribution(Tt, Tm).unsqueeze(0).repeat(B, 1, 1)) if with_prior else None
+        x = [t(text), t(lens), t(mel), t(mlens), t(pitch), t(energy), None, prior, t(durs),
              t(torch.full((B,), float(Tt))), t(torch.full((B,), float(Tm))), ["synthetic"] * B]
         out.append((x, [x[2], x[1], x[3], x[9]], int(mlens.sum())))
     return out
@@ -137,10 +153,13 @@ class _TrainerBase:
 
 # ==================================================================================================== FastPitch
 class FastPitchTrainer(_TrainerBase):
-    """python/fastpitch1_1/xva_train.py:185. Stages 2-4 run on the B200 engine; stage 1 (aligner) is not built yet, so a
-    run starts at stage 2 with the durations the batches carry."""
+    """python/fastpitch1_1/xva_train.py:185. All four stages run on the B200 engine. A run starts at stage 1 (the
+    aligner) when its batches carry the alignment prior (x[7]), otherwise at stage 2 with the durations they carry;
+    when stage 1 ends, the durations of every batch are replaced by the aligner's (the in-memory equivalent of the
+    reference's duration extraction to durs_arpabet/*.npy, xva_train.py:1128-1160)."""
 
-    TARGET_DELTAS = {2: 0.0005, 3: 0.0005, 4: 0.0003}   # order of magnitude of get_target_delta (xva_train.py:589-672)
+    TARGET_DELTAS = {1: 0.0004, 2: 0.0005, 3: 0.0005, 4: 0.0003}   # order of magnitude of get_target_delta (xva_train.py:589-672)
+    KL_LOSS_START_EPOCH, KL_LOSS_WARMUP_EPOCHS, KL_LOSS_WEIGHT = 0, 100, 1.0    # xva_train.py:706-708
 
     def __init__(self, logger, PROD, gpus, models_manager, websocket=None):
         super().__init__(logger, PROD, gpus, models_manager, websocket)
@@ -172,10 +191,11 @@ class FastPitchTrainer(_TrainerBase):
         torch.manual_seed(1234 + self.local_rank)
         self.model = fp.FastPitch(logger=self.logger, device=self.device, seed=1234)
         self.criterion = fp.FastPitchLoss()
+        self.attention_kl_loss = fp.AttentionBinarizationLoss()                    # :342
         self.optimizer = fp.Lamb(self.model, lr=0.1, betas=(0.9, 0.98), eps=1e-9, weight_decay=1e-6)
         self.total_iter, self.epoch, self.avg_loss_per_epoch = 50000, 0, []       # new voices start at 40-50k (:304-335)
         self.start_iterations = self.total_iter
-        stage = 2
+        stage = None
         ck = self.last_checkpoint(self.dataset_output)
         if self.checkpoint and os.path.isfile(str(self.checkpoint)):
             ck = self.checkpoint
@@ -184,21 +204,32 @@ class FastPitchTrainer(_TrainerBase):
             self.ckpt_path = ck
         if self.force_stage:
             stage = self.force_stage
-        stage = max(2, int(stage))
-        self.model.training_stage = self.criterion.training_stage = stage
-        self.target_delta = self.TARGET_DELTAS.get(stage, 0.0005)
-        self.graphs_json["stages"][str(stage)]["target_delta"] = self.target_delta
-        await self._send(f"Set stage to: {stage} ")
-        mult = {2: 12, 3: 3.5, 4: 4}.get(stage, 1)                                 # stage batch multipliers (:387-404)
-        self.stage_batch = max(1, int(self.batch_size * mult))
-        self.gam = max(1, round(256 / self.stage_batch))                           # :407
-        if self.batch_source is not None:
+        source_key = (str(self.dataset_input), id(self.batch_source))
+        if getattr(self, "_batches_key", None) == source_key:
+            pass          # same trainer re-initialised for the next stage: keep the batches (and the extracted durations)
+        elif self.batch_source is not None:
             self.batches = list(self.batch_source)
         elif str(self.dataset_input).startswith("synthetic:"):
             self.batches = _synthetic_fastpitch_batches(self.dataset_input, self.device, 1234 + self.local_rank)
         else:
             raise NotImplementedError("wav/text dataset loading is outside this build (SURVEY.md section 2 row 6): pass "
                                       "data['batch_source'] or dataset_path='synthetic:BxTtxTmxitems'")
+        self._batches_key = source_key
+        has_prior = all(b[0][7] is not None for b in self.batches)
+        if stage is None:
+            stage = 1 if has_prior else 2
+        stage = min(4, max(1, int(stage)))
+        if stage == 1 and not has_prior:
+            raise ValueError("training stage 1 needs batches that carry the alignment prior (inputs_x[7])")
+        self.model.training_stage = self.criterion.training_stage = stage
+        self.target_delta = self.TARGET_DELTAS.get(stage, 0.0005)
+        self.graphs_json["stages"][str(stage)]["target_delta"] = self.target_delta
+        await self._send(f"Set stage to: {stage} ")
+        mult = {1: 1.5, 2: 12, 3: 3.5, 4: 4}.get(stage, 1)                         # stage batch multipliers (:387-404)
+        self.stage_batch = max(1, int(self.batch_size * mult))
+        self.gam = max(1, round(256 / self.stage_batch))                           # :407
+        if stage == 1:
+            self.print_and_log("Stage 1: Pre-training only the alignment.", save_to_file=self.dataset_output)   # :411-412
         self.model.train()
         self.EPOCH_AVG_SPAN, self.target_patience, self.target_patience_count = 20, 3, 0
         self.last_loss, self.iter_losses, self.avg_frames_s = None, [], []
@@ -225,10 +256,17 @@ class FastPitchTrainer(_TrainerBase):
         fp.adjust_learning_rate(self.total_iter, self.optimizer, self.learning_rate, self.warmup_steps)     # :780
         y_pred = self.model(x)                                                                               # :788
         loss, meta = self.criterion(y_pred, y)                                                               # :790
-        self.model.backward(self.criterion, 1.0 / self.gam)                                                  # :806-813
+        stage = self.model.training_stage
+        kl = None
+        if stage == 1 and self.KL_LOSS_START_EPOCH is not None and self.epoch >= self.KL_LOSS_START_EPOCH:   # :792-798
+            binarization_loss = self.attention_kl_loss(y_pred[9], y_pred[8])
+            kl_weight = min((self.epoch - self.KL_LOSS_START_EPOCH) / self.KL_LOSS_WARMUP_EPOCHS, 1.0) * self.KL_LOSS_WEIGHT
+            meta["kl_loss"] = binarization_loss * kl_weight
+            meta["loss"] = meta["loss"] + kl_weight * binarization_loss
+            kl = (self.attention_kl_loss, kl_weight)
+        self.model.backward(self.criterion, 1.0 / self.gam, kl=kl)                                           # :806-813
         self.micro += 1
         self.frames_acc += num_frames
-        stage = self.model.training_stage
         key = {3: "pitch_loss", 4: "mel_loss"}.get(stage, "loss")                                            # :815-820
         tracked = meta[key] * (0.1 if stage == 3 else 1.0)
         if self.micro % self.gam == 0:
@@ -283,6 +321,8 @@ class FastPitchTrainer(_TrainerBase):
             if stage == 4:
                 self.END_OF_TRAINING = True
             self.JUST_FINISHED_STAGE = True
+            if stage == 1:
+                self.extract_durations()
             self.model.training_stage += 1
             self.avg_loss_per_epoch = []
             it = self.total_iter if self.model.training_stage == 4 else self.start_iterations
@@ -292,6 +332,18 @@ class FastPitchTrainer(_TrainerBase):
 
     def epoch_in_stage(self):
         return len(self.avg_loss_per_epoch)
+
+    def extract_durations(self):
+        """End of stage 1 (xva_train.py:1128-1160): run the aligner over every batch without gradients and keep its hard
+        durations as the duration targets of stages 2-4. The reference writes them to durs_arpabet / durs_text .npy
+        files that its dataset reads back; batches here are in memory, so x[8] is replaced in place."""
+        self.print_and_log("Extracting durations from alignments...", save_to_file=self.dataset_output)
+        was_training = self.model.training
+        self.model.eval()
+        with torch.no_grad():
+            for x, _, _ in self.batches:
+                x[8] = self.model(x)[10]
+        self.model.train(was_training)
 
     # reference: xva_train.py:979-1052
     def save_checkpoint(self, force_save=False, frames_s=0, total_iter=0, avg_loss=None, loss_delta=None,
@@ -357,7 +409,7 @@ def _sort_fp(name):
 
 
 async def handleTrainer(models_manager, data, websocket, gpus, resume=False):
-    """python/fastpitch1_1/xva_train.py:57-176: drives FastPitch stages 2 -> 4, returns "move to hifi" when stage 4 ends."""
+    """python/fastpitch1_1/xva_train.py:57-176: drives FastPitch stages 1 -> 4, returns "move to hifi" when stage 4 ends."""
     gpus = gpus or [0]
     trainer = models_manager.sync_init_model("fastpitch1_1", websocket=websocket, gpus=gpus)
     try:
