@@ -178,6 +178,10 @@ int xva_rowdot2(const float* a, const float* b, int64_t rows, int C, int64_t a_l
  * reference recurrence on the same values. Tm x ceil(Tt/32) x 4 bytes of shared memory (<= 200 KiB). */
 int xva_mas_width1(const float* attn, const int32_t* in_lens, const int32_t* out_lens, int B, int Tm, int Tt, int is_log,
                    float* hard, int32_t* durs, void* stream);
+/* out[i] = (float) log((double) attn[i]), i < n: the logarithm xva_mas_width1 takes element by element with is_log = 0,
+ * as one parallel pass, so that the (sequential) search can run on log-probabilities (is_log = 1) with the identical
+ * result -- the double-precision log sat on the critical path of every one of its Tm steps. */
+int xva_mas_log(const float* attn, int64_t n, float* out, void* stream);
 
 /* Stage-1 aligner score -- replaces the body of ConvAttention.forward after the two projection stacks,
  * fastpitch/attention.py:203-219. q [B, Tm, C] (row pitch ldq) = query_proj(mel), k [B, Tt, C] (row pitch ldk) =
@@ -199,7 +203,9 @@ int xva_attn_score_bwd(const float* g, const float* logprob, const float* prior,
  * against the target 1..L; cost[b] = -log p / max(L, 1) (nn.CTCLoss reduction 'mean' on a batch of one), 0 when the
  * alignment is impossible (zero_infinity=True). The reference's loss is mean_b cost[b]; grad [B, Tm, Tt] receives
  * d(mean_b cost[b]) / d logprob (zero outside [T, L]). workspace: xva_attn_ctc_workspace_bytes(B, Tm, Tt) bytes, 8-byte
- * aligned (the fp64 forward variables, B x Tm x (2 Tt + 1)); caller-owned like every other buffer. */
+ * aligned (the fp64 forward and backward variables, 2 x B x Tm x (2 Tt + 1), and the row normalisers); caller-owned
+ * like every other buffer. Three launches: row normalisers, the alpha and beta recursions side by side (2 B blocks),
+ * the gradient. Tt <= 1023. */
 int64_t xva_attn_ctc_workspace_bytes(int B, int Tm, int Tt);
 int xva_attn_ctc(const float* logprob, const int32_t* in_lens, const int32_t* out_lens, int B, int Tm, int Tt,
                  float blank_logprob, void* workspace, int64_t workspace_bytes, double* cost, float* grad, void* stream);

@@ -88,6 +88,7 @@ PROTOTYPES = {
     "xva_attn_ctc": (_I, [_P, _P, _P, _I, _I, _I, _F, _P, _I64, _P, _P, _P]),
     "xva_attn_bin_loss": (_I, [_P, _P, _I64, _I, _F, _P, _P]),
     "xva_attn_grad_combine": (_I, [_P, _P, _P, _P, _F, _F, _F, _I64, _I, _P, _P]),
+    "xva_mas_log": (_I, [_P, _I64, _P, _P]),
     "xva_softmax_fwd": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _F, _U64, _P, _P]),
     "xva_softmax_bwd": (_I, [_P, _P, _I, _I, _I, _I, _F, _F, _U64, _P, _P]),
     "xva_layernorm_bwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _F, _U64, _F, _U64, _P, _I, _P]),
@@ -168,7 +169,7 @@ def check(status, what=""):
 
 
 # kernels enqueued per successful call (everything not listed launches exactly one)
-_LAUNCHES = {"xva_lamb_step": 2, "xva_attn_score_bwd": 2, "xva_gemm_debug_counters": 0, "xva_set_operand_rounding": 0, "xva_abi_version": 0, "xva_last_error": 0, "xva_device_check": 0,
+_LAUNCHES = {"xva_lamb_step": 2, "xva_attn_score_bwd": 2, "xva_attn_ctc": 3, "xva_gemm_debug_counters": 0, "xva_set_operand_rounding": 0, "xva_abi_version": 0, "xva_last_error": 0, "xva_device_check": 0,
              "xva_sizeof_gemm_args": 0, "xva_sizeof_wn_desc": 0}
 _launch_count = 0
 

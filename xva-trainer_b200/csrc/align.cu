@@ -237,6 +237,21 @@ attn_key_grad_kernel(const float* __restrict__ dD, const float* __restrict__ q, 
 }
 
 // ------------------------------------------------------------------------------------------------ CTC
+// Extended label sequence of the target 1..L: state s (0 <= s < S = 2L+1) is the blank for even s and key (s-1)/2 for
+// odd s; all keys are distinct, so the skip s-2 -> s is open for every odd s >= 3.
+//   z[t, .]    = [blank_logprob, logprob[t, 0..L)] ;  n[t, .] = log_softmax(z[t, .])       (attn_loss_function.py:28-36)
+//   alpha_t(s) = n[t, lab(s)] + lse(alpha_{t-1}(s), alpha_{t-1}(s-1), alpha_{t-1}(s-2)*),  alpha_0 = n[0, .] on s <= 1
+//   beta_t(s)  = n[t, lab(s)] + lse(beta_{t+1}(s),  beta_{t+1}(s+1),  beta_{t+1}(s+2)*),   beta_{T-1} = n[T-1, .] on s >= S-2
+//   nll        = -lse(alpha_{T-1}(S-1), alpha_{T-1}(S-2)),   cost = nll / max(L, 1)  (0 if nll is infinite: zero_infinity)
+//   d cost / d logprob[t, j] = (exp(n[t,j+1]) - exp(alpha_t(s) + beta_t(s) - n[t,j+1] + nll)) / max(L, 1),  s = 2j+1
+//   (the gradient of -log p through the row's log_softmax; the blank column is a constant).
+// Three launches. (1) the row normalisers lse[b,t], one warp per row. (2) the two recursions: they are independent, so
+// block (b, 0) walks alpha forward and block (b, 1) walks beta backward at the same time -- the mel axis is the only
+// sequential dimension of the whole stage, and this halves it; one thread per state, the emission of step t+1 is loaded
+// while step t is computed (the global-load latency was 1/3 of the first version's step time, the barrier another 1/3),
+// both tables go to the workspace in fp64. (3) the gradient, fully parallel over (b, t, j).
+// First version (one block per utterance doing normaliser, alpha, then beta + gradient): 2.35 ms at 32 x 880 x 160.
+
 // log(exp(a) + exp(b) + exp(c)): the maximum is carried in fp64, the (small) differences go through fp32 exp / log
 __device__ __forceinline__ double lse3(double a, double b, double c) {
   const double m = fmax(a, fmax(b, c));
@@ -245,112 +260,136 @@ __device__ __forceinline__ double lse3(double a, double b, double c) {
   return m + static_cast<double>(logf(s));
 }
 
-constexpr int kCtcThreads = 256;
+// lse[b,t] = log(exp(blank) + sum_{j < L} exp(logprob[b,t,j])) for t < T (0 elsewhere)
+__global__ void __launch_bounds__(kWarps * 32)
+ctc_row_lse_kernel(const float* __restrict__ logprob, const int* __restrict__ in_lens, const int* __restrict__ out_lens,
+                   int Tm, int Tt, float blank, long rows, float* __restrict__ lse) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long row = static_cast<long>(blockIdx.x) * kWarps + warp;
+  if (row >= rows) return;
+  const int b = static_cast<int>(row / Tm), t = static_cast<int>(row - static_cast<long>(b) * Tm);
+  const int L = min(max(in_lens[b], 0), Tt), T = min(max(out_lens[b], 0), Tm);
+  if (t >= T) {
+    if (lane == 0) lse[row] = 0.0f;
+    return;
+  }
+  const float* lp = logprob + row * Tt;
+  float mx = blank;
+  for (int j = lane; j < L; j += 32) mx = fmaxf(mx, lp[j]);
+  mx = warp_max(mx);
+  float se = (lane == 0) ? expf(blank - mx) : 0.0f;
+  for (int j = lane; j < L; j += 32) se += expf(lp[j] - mx);
+  se = warp_sum(se);
+  if (lane == 0) lse[row] = mx + logf(se);
+}
 
-// One block per utterance. Extended label sequence of the target 1..L: state s (0 <= s < S = 2L+1) is the blank for
-// even s and key (s-1)/2 for odd s; all keys are distinct, so s-2 -> s is allowed for every odd s >= 3.
-//   z[t, .]   = [blank_logprob, logprob[t, 0..L)] ;  n[t, .] = log_softmax(z[t, .])       (attn_loss_function.py:28-36)
-//   alpha_t(s) = n[t, lab(s)] + lse(alpha_{t-1}(s), alpha_{t-1}(s-1), alpha_{t-1}(s-2)*)
-//   nll        = -lse(alpha_{T-1}(S-1), alpha_{T-1}(S-2)),   cost = nll / max(L, 1)  (0 if nll is infinite)
-//   beta likewise from the end;  d cost / d logprob[t, j] = (exp(n[t,j+1]) - exp(alpha_t(s) + beta_t(s) - n[t,j+1] + nll))
-//   / max(L, 1) with s = 2j+1  (the gradient of -log p through the row's log_softmax; the blank column is a constant).
-// grad receives d(mean_b cost_b)/d logprob, i.e. the above times 1/B, zero outside [T, L].
-__global__ void __launch_bounds__(kCtcThreads)
-attn_ctc_kernel(const float* __restrict__ logprob, const int* __restrict__ in_lens, const int* __restrict__ out_lens,
-                int B, int Tm, int Tt, float blank, double* __restrict__ alpha_ws, double* __restrict__ cost,
-                float* __restrict__ grad) {
+constexpr int kCtcMaxThreads = 1024;
+constexpr int kCtcNS = 2;   // states per thread: S_max = 2 Tt + 1 <= 2 * 1024
+
+// blockIdx.y = 0: alpha, forward in time, -> table[0]; blockIdx.y = 1: beta, backward in time, -> table[1].
+// table[d][b][t][s] fp64, row pitch S_max. The alpha block also writes nll[b] and cost[b].
+__global__ void __launch_bounds__(kCtcMaxThreads)
+ctc_recursion_kernel(const float* __restrict__ logprob, const int* __restrict__ in_lens, const int* __restrict__ out_lens,
+                     const float* __restrict__ lse, int B, int Tm, int Tt, float blank, double* __restrict__ table,
+                     double* __restrict__ nll_out, double* __restrict__ cost) {
   extern __shared__ double smem_d[];
-  __shared__ double nll_s;
   const int b = blockIdx.x;
+  const bool fwd = blockIdx.y == 0;
   const int L = min(max(in_lens[b], 0), Tt), T = min(max(out_lens[b], 0), Tm);
   const int S = 2 * L + 1, S_max = 2 * Tt + 1;
   double* buf0 = smem_d;                       // [S_max + 4], state s at index s + 2, two -inf guards on either side
   double* buf1 = buf0 + (S_max + 4);
-  float* lse = reinterpret_cast<float*>(buf1 + (S_max + 4));   // [Tm]
   const float* lp = logprob + static_cast<long>(b) * Tm * Tt;
-  float* gr = grad + static_cast<long>(b) * Tm * Tt;
-  double* aw = alpha_ws + static_cast<long>(b) * Tm * S_max;
+  const float* ls = lse + static_cast<long>(b) * Tm;
+  double* tab = table + (static_cast<long>(fwd ? 0 : 1) * B + b) * Tm * S_max;
   const double ninf = -INFINITY;
-  for (long i = threadIdx.x; i < static_cast<long>(Tm) * Tt; i += blockDim.x) gr[i] = 0.0f;
   if (T == 0) {
-    if (threadIdx.x == 0) cost[b] = 0.0;
+    if (fwd && threadIdx.x == 0) {
+      nll_out[b] = 0.0;
+      cost[b] = 0.0;
+    }
     return;
-  }
-  // ---- per-row normaliser of [blank, keys < L]
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
-  for (int t = warp; t < T; t += n_warps) {
-    float mx = blank;
-    for (int j = lane; j < L; j += 32) mx = fmaxf(mx, lp[static_cast<long>(t) * Tt + j]);
-    mx = warp_max(mx);
-    float se = (lane == 0) ? expf(blank - mx) : 0.0f;
-    for (int j = lane; j < L; j += 32) se += expf(lp[static_cast<long>(t) * Tt + j] - mx);
-    se = warp_sum(se);
-    if (lane == 0) lse[t] = mx + logf(se);
   }
   for (int i = threadIdx.x; i < 2 * (S_max + 4); i += blockDim.x) buf0[i] = ninf;
   __syncthreads();
-  auto emit = [&](int t, int s) -> double {
-    const float v = (s & 1) ? lp[static_cast<long>(t) * Tt + (s >> 1)] : blank;
-    return static_cast<double>(v - lse[t]);
-  };
-  // ---- alpha
+  const int dt = fwd ? 1 : -1, t_first = fwd ? 0 : T - 1, off1 = fwd ? -1 : 1;
+  // raw emission of (t, s): logprob of key (s-1)/2 for odd s, the blank constant for even s; minus lse[t] when used
+  float raw[kCtcNS], raw_next[kCtcNS];
+  float lse_cur = ls[t_first], lse_next = 0.0f;
+#pragma unroll
+  for (int k = 0; k < kCtcNS; ++k) {
+    const int s = threadIdx.x + k * blockDim.x;
+    raw[k] = (s < S && (s & 1)) ? lp[static_cast<long>(t_first) * Tt + (s >> 1)] : blank;
+  }
   double* prev = buf0 + 2;
   double* cur = buf1 + 2;
-  for (int s = threadIdx.x; s < S; s += blockDim.x) {
-    const double v = (s <= 1) ? emit(0, s) : ninf;
-    prev[s] = v;
-    aw[s] = v;
-  }
-  __syncthreads();
-  for (int t = 1; t < T; ++t) {
-    for (int s = threadIdx.x; s < S; s += blockDim.x) {
-      const double c2 = (s & 1) ? prev[s - 2] : ninf;
-      const double v = emit(t, s) + lse3(prev[s], prev[s - 1], c2);
-      cur[s] = v;
-      aw[static_cast<long>(t) * S_max + s] = v;
+  for (int step = 0; step < T; ++step) {
+    const int t = t_first + step * dt;
+    const bool more = step + 1 < T;
+    if (more) {                                   // loads of the next step, in flight while this one is computed
+      lse_next = ls[t + dt];
+#pragma unroll
+      for (int k = 0; k < kCtcNS; ++k) {
+        const int s = threadIdx.x + k * blockDim.x;
+        raw_next[k] = (s < S && (s & 1)) ? lp[static_cast<long>(t + dt) * Tt + (s >> 1)] : blank;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kCtcNS; ++k) {
+      const int s = threadIdx.x + k * blockDim.x;
+      if (s < S) {
+        const double e = static_cast<double>(raw[k] - lse_cur);
+        double v;
+        if (step == 0) {
+          v = (fwd ? (s <= 1) : (s >= S - 2)) ? e : ninf;
+        } else {
+          const double c2 = (s & 1) ? prev[s + 2 * off1] : ninf;
+          v = e + lse3(prev[s], prev[s + off1], c2);
+        }
+        cur[s] = v;
+        tab[static_cast<long>(t) * S_max + s] = v;
+      }
     }
     __syncthreads();
     double* sw = prev;
     prev = cur;
     cur = sw;
+    lse_cur = lse_next;
+#pragma unroll
+    for (int k = 0; k < kCtcNS; ++k) raw[k] = raw_next[k];
   }
-  if (threadIdx.x == 0) nll_s = -lse3(prev[S - 1], prev[S - 2], ninf);   // S = 1: prev[-1] is a guard
-  __syncthreads();
-  const double nll = nll_s;
-  const double inv_len = 1.0 / static_cast<double>(max(L, 1));
-  if (!(nll < INFINITY) || nll != nll) {        // zero_infinity (nn.CTCLoss(zero_infinity=True)): no cost, no gradient
-    if (threadIdx.x == 0) cost[b] = 0.0;
-    return;
+  if (fwd && threadIdx.x == 0) {
+    const double nll = -lse3(prev[S - 1], prev[S - 2], ninf);   // S = 1: prev[-1] is a guard
+    const bool ok = nll < INFINITY && nll == nll;               // zero_infinity: no cost (and no gradient) otherwise
+    nll_out[b] = nll;
+    cost[b] = ok ? nll / static_cast<double>(max(L, 1)) : 0.0;
   }
-  if (threadIdx.x == 0) cost[b] = nll * inv_len;
-  const float w = static_cast<float>(inv_len / static_cast<double>(B));
-  // ---- beta and the gradient, last frame first. The buffers are reused: reset the guards' neighbours first.
-  __syncthreads();
-  for (int i = threadIdx.x; i < 2 * (S_max + 4); i += blockDim.x) buf0[i] = ninf;
-  __syncthreads();
-  double* nxt = buf0 + 2;
-  cur = buf1 + 2;
-  for (int t = T - 1; t >= 0; --t) {
-    for (int s = threadIdx.x; s < S; s += blockDim.x) {
-      double v;
-      if (t == T - 1) {
-        v = (s >= S - 2) ? emit(t, s) : ninf;
-      } else {
-        const double c2 = (s & 1) ? nxt[s + 2] : ninf;
-        v = emit(t, s) + lse3(nxt[s], nxt[s + 1], c2);
-      }
-      cur[s] = v;
-      if (s & 1) {
-        const int j = s >> 1;
-        const float n_tj = lp[static_cast<long>(t) * Tt + j] - lse[t];
-        const float post = expf(static_cast<float>(aw[static_cast<long>(t) * S_max + s] + v + nll) - n_tj);
-        gr[static_cast<long>(t) * Tt + j] = w * (expf(n_tj) - post);
-      }
+}
+
+// grad[b,t,j] = (1 / (B max(L,1))) * (exp(n) - exp(alpha_t(2j+1) + beta_t(2j+1) - n + nll)),  n = logprob[b,t,j] - lse[b,t];
+// zero outside [T, L] and for utterances whose alignment is impossible
+__global__ void __launch_bounds__(256)
+ctc_grad_kernel(const float* __restrict__ logprob, const int* __restrict__ in_lens, const int* __restrict__ out_lens,
+                const float* __restrict__ lse, const double* __restrict__ table, const double* __restrict__ nll_in, int B,
+                int Tm, int Tt, float* __restrict__ grad) {
+  const long total = static_cast<long>(B) * Tm * Tt;
+  const int S_max = 2 * Tt + 1;
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long row = i / Tt;
+    const int j = static_cast<int>(i - row * Tt);
+    const int b = static_cast<int>(row / Tm), t = static_cast<int>(row - static_cast<long>(b) * Tm);
+    const int L = min(max(in_lens[b], 0), Tt), T = min(max(out_lens[b], 0), Tm);
+    const double nll = nll_in[b];
+    float g = 0.0f;
+    if (t < T && j < L && nll < INFINITY && nll == nll) {
+      const long at = (static_cast<long>(b) * Tm + t) * S_max + 2 * j + 1;
+      const double al = table[at], be = table[static_cast<long>(B) * Tm * S_max + at];
+      const float n = logprob[i] - lse[row];
+      const float post = expf(static_cast<float>(al + be + nll) - n);
+      g = (expf(n) - post) / (static_cast<float>(B) * static_cast<float>(max(L, 1)));
     }
-    __syncthreads();
-    double* sw = nxt;
-    nxt = cur;
-    cur = sw;
+    grad[i] = g;
   }
 }
 
@@ -471,26 +510,38 @@ int attn_score_bwd(const float* g, const float* logprob, const float* prior, con
   return XVA_OK;
 }
 
+// workspace: alpha and beta tables (fp64, B x Tm x (2 Tt + 1) each), nll (fp64, B), the row normalisers (fp32, B x Tm)
 long long attn_ctc_workspace_bytes(int B, int Tm, int Tt) {
-  return static_cast<long long>(B) * Tm * (2LL * Tt + 1) * static_cast<long long>(sizeof(double));
+  const long long tables = 2LL * B * Tm * (2LL * Tt + 1) * static_cast<long long>(sizeof(double));
+  return tables + static_cast<long long>(B) * 8 + (static_cast<long long>(B) * Tm * 4 + 7) / 8 * 8;
 }
 
 int attn_ctc(const float* logprob, const int* in_lens, const int* out_lens, int B, int Tm, int Tt, float blank_logprob,
              void* workspace, long long workspace_bytes, double* cost, float* grad, cudaStream_t stream) {
   XVA_CHECK_ARG(logprob && in_lens && out_lens && workspace && cost && grad, "attn_ctc: null pointer");
   XVA_CHECK_ARG(B >= 1 && Tm >= 1 && Tt >= 1, "attn_ctc: B=%d Tm=%d Tt=%d", B, Tm, Tt);
+  XVA_CHECK_ARG(2 * Tt + 1 <= kCtcNS * kCtcMaxThreads, "attn_ctc: Tt=%d exceeds %d text positions", Tt,
+                (kCtcNS * kCtcMaxThreads - 1) / 2);
   XVA_CHECK_ARG(workspace_bytes >= attn_ctc_workspace_bytes(B, Tm, Tt), "attn_ctc: workspace of %lld bytes, need %lld",
                 workspace_bytes, attn_ctc_workspace_bytes(B, Tm, Tt));
   XVA_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 7) == 0, "attn_ctc: workspace not 8-byte aligned");
-  const size_t smem = 2 * (2 * static_cast<size_t>(Tt) + 5) * sizeof(double) + static_cast<size_t>(Tm) * sizeof(float);
-  XVA_CHECK_ARG(smem <= 200 * 1024, "attn_ctc: Tm=%d Tt=%d needs %zu bytes of shared memory (max 200 KiB)", Tm, Tt, smem);
-  static bool attr_done = false;
-  if (!attr_done) {
-    XVA_CHECK_CUDA(cudaFuncSetAttribute(attn_ctc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_done = true;
-  }
-  attn_ctc_kernel<<<B, kCtcThreads, smem, stream>>>(logprob, in_lens, out_lens, B, Tm, Tt, blank_logprob,
-                                                    static_cast<double*>(workspace), cost, grad);
+  const int S_max = 2 * Tt + 1;
+  double* table = static_cast<double*>(workspace);
+  double* nll = table + 2LL * B * Tm * S_max;
+  float* lse = reinterpret_cast<float*>(nll + B);
+  const long rows = static_cast<long>(B) * Tm;
+  ctc_row_lse_kernel<<<static_cast<unsigned>(ceil_div_l(rows, kWarps)), kWarps * 32, 0, stream>>>(
+      logprob, in_lens, out_lens, Tm, Tt, blank_logprob, rows, lse);
+  XVA_CHECK_LAUNCH();
+  const size_t smem = 2 * static_cast<size_t>(S_max + 4) * sizeof(double);
+  const int threads = S_max >= kCtcMaxThreads ? kCtcMaxThreads : round_up(S_max, 32);
+  ctc_recursion_kernel<<<dim3(B, 2), threads, smem, stream>>>(logprob, in_lens, out_lens, lse, B, Tm, Tt, blank_logprob,
+                                                              table, nll, cost);
+  XVA_CHECK_LAUNCH();
+  const long total = rows * Tt;
+  const long blocks = ceil_div_l(total, 256);
+  const int grid = static_cast<int>(blocks < 8L * num_sms() ? blocks : 8L * num_sms());
+  ctc_grad_kernel<<<grid, 256, 0, stream>>>(logprob, in_lens, out_lens, lse, table, nll, B, Tm, Tt, grad);
   XVA_CHECK_LAUNCH();
   return XVA_OK;
 }

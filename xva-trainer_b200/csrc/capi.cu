@@ -98,6 +98,10 @@ int xva_attn_grad_combine(const float* gctc, const float* hard, const float* sof
   return attn_grad_combine(gctc, hard, soft, acc, a, bw, eps, static_cast<long>(rows), Tt, g, S(stream));
 }
 
+int xva_mas_log(const float* attn, int64_t n, float* out, void* stream) {
+  return mas_log(attn, static_cast<long>(n), out, S(stream));
+}
+
 int xva_softmax_fwd(const float* s, const int32_t* lens, int Z, int R, int N, int ld, float* p, float* pd,
                     float drop_p, uint64_t seed, const uint64_t* seed_dev, void* stream) {
   return softmax_fwd(s, lens, Z, R, N, ld, p, pd, drop_p, seed, seed_dev, S(stream));

@@ -46,12 +46,18 @@ mas_kernel(const float* __restrict__ attn, const int* __restrict__ in_lens, cons
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
+  // the mel axis is sequential and each step is a handful of instructions, so a global load inside the step would be
+  // most of its latency: the value of row i + 1 (first 256 text positions) is fetched while row i is processed
+  const bool pre_lane = static_cast<int>(threadIdx.x) < n_txt;
+  float a_pre = (pre_lane && n_mel > 1) ? a[Tt + threadIdx.x] : 0.0f;
   for (int i = 1; i < n_mel; ++i) {
+    const float a_cur = a_pre;
+    if (pre_lane && i + 1 < n_mel) a_pre = a[static_cast<long>(i + 1) * Tt + threadIdx.x];
     for (int jb = 0; jb < n_txt; jb += blockDim.x) {       // uniform trip count: every thread reaches the ballot
       const int j = jb + threadIdx.x;
       bool take_adv = false;
       if (j < n_txt) {
-        const float la = lg(a[static_cast<long>(i) * Tt + j]);
+        const float la = lg(jb == 0 ? a_cur : a[static_cast<long>(i) * Tt + j]);
         const float stay = cur[j + 1], adv = cur[j];       // adv = log_p[i-1, j-1]
         take_adv = (j >= 1) && (adv >= stay);              // alignment.py:96
         nxt[j + 1] = __fadd_rn(la, take_adv ? adv : stay);
@@ -68,11 +74,17 @@ mas_kernel(const float* __restrict__ attn, const int* __restrict__ in_lens, cons
   if (threadIdx.x == 0) {
     int j = n_txt - 1;
     int* d = durs + static_cast<long>(b) * Tt;
+    int run = 0;                                            // marks in the current column (the path never returns to one)
     for (int i = n_mel - 1; i >= 0; --i) {
       h[static_cast<long>(i) * Tt + j] = 1.0f;
-      d[j] += 1;
-      if (i > 0 && ((bits[static_cast<size_t>(i) * words + (j >> 5)] >> (j & 31)) & 1u)) --j;
+      ++run;
+      if (i > 0 && ((bits[static_cast<size_t>(i) * words + (j >> 5)] >> (j & 31)) & 1u)) {
+        d[j] = run;                                         // stores only: a read-modify-write per frame was half the kernel
+        run = 0;
+        --j;
+      }
     }
+    d[j] = run;
     // alignment.py:106-108: prev_ind[0, :] is 0, so after the loop curr_text_idx = 0 and opt[0, 0] is set as well -- a
     // second mark in row 0 when the back-track did not reach text position 0 (fewer mel frames than tokens)
     if (h[0] == 0.0f) {
@@ -82,7 +94,22 @@ mas_kernel(const float* __restrict__ attn, const int* __restrict__ in_lens, cons
   }
 }
 
+// out = (float) log((double) a): the logarithm mas_kernel takes with is_log = 0, for every element at once
+__global__ void __launch_bounds__(256) mas_log_kernel(const float* __restrict__ a, long n, float* __restrict__ out) {
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x)
+    out[i] = static_cast<float>(log(static_cast<double>(a[i])));
+}
+
 }  // namespace
+
+int mas_log(const float* attn, long n, float* out, cudaStream_t stream) {
+  XVA_CHECK_ARG(attn && out && n >= 1, "mas_log: bad arguments (n=%ld)", n);
+  const long blocks = ceil_div_l(n, 256);
+  const int grid = static_cast<int>(blocks < 16L * num_sms() ? blocks : 16L * num_sms());
+  mas_log_kernel<<<grid, 256, 0, stream>>>(attn, n, out);
+  XVA_CHECK_LAUNCH();
+  return XVA_OK;
+}
 
 int mas_width1(const float* attn, const int* in_lens, const int* out_lens, int B, int Tm, int Tt, int is_log, float* hard,
                int* durs, cudaStream_t stream) {

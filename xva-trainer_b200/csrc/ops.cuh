@@ -39,6 +39,7 @@ int layernorm_bwd(const float* dy, const float* x, const float* mean, const floa
                   const uint64_t* seed_dev, int relu_gate, cudaStream_t stream);
 int mas_width1(const float* attn, const int* in_lens, const int* out_lens, int B, int Tm, int Tt, int is_log, float* hard,
                int* durs, cudaStream_t stream);
+int mas_log(const float* attn, long n, float* out, cudaStream_t stream);
 int layernorm_fwd(const float* x, const float* gamma, const float* beta, const int* lens, int Z, int R, int C, float eps,
                   float* y, float* mean, float* rstd, cudaStream_t stream);
 int counter_add(unsigned long long* counter, unsigned long long inc, cudaStream_t stream);

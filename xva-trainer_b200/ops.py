@@ -305,7 +305,13 @@ def mas_width1(attn, in_lens, out_lens, is_log=False):
     hard = torch.empty_like(a)
     durs = torch.empty(B, Tt, device=a.device, dtype=torch.int32)
     il, ol = in_lens.to(torch.int32).contiguous(), out_lens.to(torch.int32).contiguous()   # keep both alive for the call
-    capi.call("xva_mas_width1", _p(a), _p(il), _p(ol), B, Tm, Tt, int(is_log), _p(hard), _p(durs), _stream())
+    if not is_log:
+        # the logarithm the search takes of every probability, as one parallel pass (same function, same result) instead
+        # of a double-precision log inside each of the Tm sequential steps
+        la = torch.empty_like(a)
+        capi.call("xva_mas_log", _p(a), a.numel(), _p(la), _stream())
+        a = la
+    capi.call("xva_mas_width1", _p(a), _p(il), _p(ol), B, Tm, Tt, 1, _p(hard), _p(durs), _stream())
     return hard.view(shape), durs
 
 
