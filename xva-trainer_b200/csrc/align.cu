@@ -249,7 +249,7 @@ attn_key_grad_kernel(const float* __restrict__ dD, const float* __restrict__ q, 
 // block (b, 0) walks alpha forward and block (b, 1) walks beta backward at the same time -- the mel axis is the only
 // sequential dimension of the whole stage, and this halves it; one thread per state, the emission of step t+1 is loaded
 // while step t is computed (the global-load latency was 1/3 of the first version's step time, the barrier another 1/3),
-// both tables go to the workspace in fp64 (one step ahead: 0.45 ms; eight steps ahead hides the whole L2 latency). (3) the gradient, fully parallel over (b, t, j).
+// both tables go to the workspace in fp64. (3) the gradient, fully parallel over (b, t, j).
 // First version (one block per utterance doing normaliser, alpha, then beta + gradient): 2.35 ms at 32 x 880 x 160.
 
 // log(exp(a) + exp(b) + exp(c)): the maximum is carried in fp64, the (small) differences go through fp32 exp / log
@@ -285,7 +285,6 @@ ctc_row_lse_kernel(const float* __restrict__ logprob, const int* __restrict__ in
 
 constexpr int kCtcMaxThreads = 1024;
 constexpr int kCtcNS = 2;   // states per thread: S_max = 2 Tt + 1 <= 2 * 1024
-constexpr int kCtcPre = 8;  // steps of look-ahead held in registers
 
 // blockIdx.y = 0: alpha, forward in time, -> table[0]; blockIdx.y = 1: beta, backward in time, -> table[1].
 // table[d][b][t][s] fp64, row pitch S_max. The alpha block also writes nll[b] and cost[b].
@@ -314,60 +313,50 @@ ctc_recursion_kernel(const float* __restrict__ logprob, const int* __restrict__ 
   for (int i = threadIdx.x; i < 2 * (S_max + 4); i += blockDim.x) buf0[i] = ninf;
   __syncthreads();
   const int dt = fwd ? 1 : -1, t_first = fwd ? 0 : T - 1, off1 = fwd ? -1 : 1;
-  // raw emission of (t, s): logprob of key (s-1)/2 for odd s, the blank constant for even s; minus lse[t] when used.
-  // An L2 hit costs more than four steps of arithmetic, so the emissions of the next kCtcPre steps sit in a register
-  // ring that is refilled as it is consumed.
-  float ring[kCtcPre][kCtcNS], lring[kCtcPre];
-  auto fetch = [&](int slot_t, float (&dst)[kCtcNS], float& dl) {
-    dl = ls[slot_t];
+  // raw emission of (t, s): logprob of key (s-1)/2 for odd s, the blank constant for even s; minus lse[t] when used
+  float raw[kCtcNS], raw_next[kCtcNS];
+  float lse_cur = ls[t_first], lse_next = 0.0f;
 #pragma unroll
-    for (int k = 0; k < kCtcNS; ++k) {
-      const int s = threadIdx.x + k * blockDim.x;
-      dst[k] = (s < S && (s & 1)) ? lp[static_cast<long>(slot_t) * Tt + (s >> 1)] : blank;
-    }
-  };
-#pragma unroll
-  for (int r = 0; r < kCtcPre; ++r) {
-    lring[r] = 0.0f;
-#pragma unroll
-    for (int k = 0; k < kCtcNS; ++k) ring[r][k] = blank;
-    if (r < T) fetch(t_first + r * dt, ring[r], lring[r]);
+  for (int k = 0; k < kCtcNS; ++k) {
+    const int s = threadIdx.x + k * blockDim.x;
+    raw[k] = (s < S && (s & 1)) ? lp[static_cast<long>(t_first) * Tt + (s >> 1)] : blank;
   }
   double* prev = buf0 + 2;
   double* cur = buf1 + 2;
-  for (int step0 = 0; step0 < T; step0 += kCtcPre) {
+  for (int step = 0; step < T; ++step) {
+    const int t = t_first + step * dt;
+    const bool more = step + 1 < T;
+    if (more) {                                   // loads of the next step, in flight while this one is computed
+      lse_next = ls[t + dt];
 #pragma unroll
-    for (int r = 0; r < kCtcPre; ++r) {
-      const int step = step0 + r;
-      if (step < T) {                                   // block-uniform
-        const int t = t_first + step * dt;
-        float raw[kCtcNS];
-#pragma unroll
-        for (int k = 0; k < kCtcNS; ++k) raw[k] = ring[r][k];
-        const float lse_cur = lring[r];
-        if (step + kCtcPre < T) fetch(t + kCtcPre * dt, ring[r], lring[r]);
-#pragma unroll
-        for (int k = 0; k < kCtcNS; ++k) {
-          const int s = threadIdx.x + k * blockDim.x;
-          if (s < S) {
-            const double e = static_cast<double>(raw[k] - lse_cur);
-            double v;
-            if (step == 0) {
-              v = (fwd ? (s <= 1) : (s >= S - 2)) ? e : ninf;
-            } else {
-              const double c2 = (s & 1) ? prev[s + 2 * off1] : ninf;
-              v = e + lse3(prev[s], prev[s + off1], c2);
-            }
-            cur[s] = v;
-            tab[static_cast<long>(t) * S_max + s] = v;
-          }
-        }
-        __syncthreads();
-        double* sw = prev;
-        prev = cur;
-        cur = sw;
+      for (int k = 0; k < kCtcNS; ++k) {
+        const int s = threadIdx.x + k * blockDim.x;
+        raw_next[k] = (s < S && (s & 1)) ? lp[static_cast<long>(t + dt) * Tt + (s >> 1)] : blank;
       }
     }
+#pragma unroll
+    for (int k = 0; k < kCtcNS; ++k) {
+      const int s = threadIdx.x + k * blockDim.x;
+      if (s < S) {
+        const double e = static_cast<double>(raw[k] - lse_cur);
+        double v;
+        if (step == 0) {
+          v = (fwd ? (s <= 1) : (s >= S - 2)) ? e : ninf;
+        } else {
+          const double c2 = (s & 1) ? prev[s + 2 * off1] : ninf;
+          v = e + lse3(prev[s], prev[s + off1], c2);
+        }
+        cur[s] = v;
+        tab[static_cast<long>(t) * S_max + s] = v;
+      }
+    }
+    __syncthreads();
+    double* sw = prev;
+    prev = cur;
+    cur = sw;
+    lse_cur = lse_next;
+#pragma unroll
+    for (int k = 0; k < kCtcNS; ++k) raw[k] = raw_next[k];
   }
   if (fwd && threadIdx.x == 0) {
     const double nll = -lse3(prev[S - 1], prev[S - 2], ninf);   // S = 1: prev[-1] is a guard

@@ -18,7 +18,6 @@ namespace xva {
 namespace {
 
 constexpr int kMasThreads = 256;
-constexpr int kMasPre = 8;      // rows of look-ahead held in registers
 
 __global__ void __launch_bounds__(kMasThreads)
 mas_kernel(const float* __restrict__ attn, const int* __restrict__ in_lens, const int* __restrict__ out_lens, int Tm,
@@ -48,38 +47,28 @@ mas_kernel(const float* __restrict__ attn, const int* __restrict__ in_lens, cons
   __syncthreads();
   const int lane = threadIdx.x & 31;
   // the mel axis is sequential and each step is a handful of instructions, so a global load inside the step would be
-  // most of its latency (an L2 hit costs more than four steps of arithmetic): the values of the next kMasPre rows (first
-  // 256 text positions) sit in a register ring that is refilled as it is consumed
+  // most of its latency: the value of row i + 1 (first 256 text positions) is fetched while row i is processed
   const bool pre_lane = static_cast<int>(threadIdx.x) < n_txt;
-  float ring[kMasPre];
-#pragma unroll
-  for (int k = 0; k < kMasPre; ++k)
-    ring[k] = (pre_lane && 1 + k < n_mel) ? a[static_cast<long>(1 + k) * Tt + threadIdx.x] : 0.0f;
-  for (int i0 = 1; i0 < n_mel; i0 += kMasPre) {
-#pragma unroll
-    for (int k = 0; k < kMasPre; ++k) {
-      const int i = i0 + k;
-      if (i < n_mel) {                                     // block-uniform
-        const float a_cur = ring[k];
-        if (pre_lane && i + kMasPre < n_mel) ring[k] = a[static_cast<long>(i + kMasPre) * Tt + threadIdx.x];
-        for (int jb = 0; jb < n_txt; jb += blockDim.x) {   // uniform trip count: every thread reaches the ballot
-          const int j = jb + threadIdx.x;
-          bool take_adv = false;
-          if (j < n_txt) {
-            const float la = lg(jb == 0 ? a_cur : a[static_cast<long>(i) * Tt + j]);
-            const float stay = cur[j + 1], adv = cur[j];   // adv = log_p[i-1, j-1]
-            take_adv = (j >= 1) && (adv >= stay);          // alignment.py:96
-            nxt[j + 1] = __fadd_rn(la, take_adv ? adv : stay);
-          }
-          const unsigned int m = __ballot_sync(0xffffffffu, take_adv);
-          if (lane == 0 && j < n_txt) bits[static_cast<size_t>(i) * words + (j >> 5)] = m;
-        }
-        __syncthreads();
-        float* t = cur;
-        cur = nxt;
-        nxt = t;
+  float a_pre = (pre_lane && n_mel > 1) ? a[Tt + threadIdx.x] : 0.0f;
+  for (int i = 1; i < n_mel; ++i) {
+    const float a_cur = a_pre;
+    if (pre_lane && i + 1 < n_mel) a_pre = a[static_cast<long>(i + 1) * Tt + threadIdx.x];
+    for (int jb = 0; jb < n_txt; jb += blockDim.x) {       // uniform trip count: every thread reaches the ballot
+      const int j = jb + threadIdx.x;
+      bool take_adv = false;
+      if (j < n_txt) {
+        const float la = lg(jb == 0 ? a_cur : a[static_cast<long>(i) * Tt + j]);
+        const float stay = cur[j + 1], adv = cur[j];       // adv = log_p[i-1, j-1]
+        take_adv = (j >= 1) && (adv >= stay);              // alignment.py:96
+        nxt[j + 1] = __fadd_rn(la, take_adv ? adv : stay);
       }
+      const unsigned int m = __ballot_sync(0xffffffffu, take_adv);
+      if (lane == 0 && j < n_txt) bits[static_cast<size_t>(i) * words + (j >> 5)] = m;
     }
+    __syncthreads();
+    float* t = cur;
+    cur = nxt;
+    nxt = t;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
