@@ -250,6 +250,9 @@ attn_key_grad_kernel(const float* __restrict__ dD, const float* __restrict__ q, 
 // sequential dimension of the whole stage, and this halves it; one thread per state, the emission of step t+1 is loaded
 // while step t is computed (the global-load latency was 1/3 of the first version's step time, the barrier another 1/3),
 // both tables go to the workspace in fp64. (3) the gradient, fully parallel over (b, t, j).
+// Measured at 32 x 880 x 160: 0.45 ms for the three launches. An eight-step register look-ahead instead of one was not
+// faster (0.55 ms, scripts/gpu_call_v.sh): after the first prefetch the step is bound by the ~150 instructions per state
+// (three expf, one logf, fp64 adds) that one SM issues for the 11 warps of an utterance, not by load latency.
 // First version (one block per utterance doing normaliser, alpha, then beta + gradient): 2.35 ms at 32 x 880 x 160.
 
 // log(exp(a) + exp(b) + exp(c)): the maximum is carried in fp64, the (small) differences go through fp32 exp / log
