@@ -24,6 +24,28 @@ class _FakeArena:
         self.g = torch.full((off,), float(rank + 1))
 
 
+def _worker_stage1(rank, world, port, q):
+    """Stage 1 (the aligner): backward() finishes exactly two slices at opposite ends of the arena -- the attention
+    projection stacks and the token embedding -- and announces them separately (fastpitch.py::_backward_stage1)."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from xva_trainer_b200.parallel import GradSync
+
+    arena = _FakeArena(rank)
+    sync = GradSync(arena, world)
+    sync.ready(["attention"], flush=True)
+    sync.ready(["encoder.word_emb"], flush=True)
+    sync.finish()
+    total, own = float(sum(r + 1 for r in range(world))), float(rank + 1)
+    ok = True
+    for name, off in arena.offset.items():
+        touched = name.startswith("attention") or name.startswith("encoder.word_emb")
+        ok &= bool(torch.all(arena.g[off:off + 1000] == (total if touched else own)))
+    q.put((rank, ok, sync.buckets_sent, sync.elems_sent))
+    dist.destroy_process_group()
+
+
 def _worker(rank, world, port, q):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -64,3 +86,18 @@ def test_gradsync_two_ranks_gloo():
     for rank, ok, buckets in res:
         assert ok, f"rank {rank}: all-reduced arena is wrong"
         assert 2 <= buckets <= 6, buckets  # adjacent layer slices were merged into fewer, larger messages
+
+
+def test_gradsync_stage1_slices_two_ranks_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker_stage1, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, ok, buckets, elems in res:
+        assert ok, f"rank {rank}: all-reduced arena is wrong"
+        assert buckets == 2 and elems == 2000, (buckets, elems)   # only the two slices travel, not the arena between them
