@@ -5,7 +5,7 @@ Reference files restated (paths relative to the reference tree, python/fastpitch
   fastpitch/transformer.py   PositionalEmbedding :21-35, PositionwiseConvFF :38-77, MultiHeadAttn :80-152,
                              TransformerLayer :155-171, FFTransformer.forward :212-243, mask_from_lens :299-304
   fastpitch/model.py         regulate_len :59-79, average_pitch :82-100, TemporalPredictor :103-122,
-                             FastPitch.forward :325-390, get_pitch_energy :394-423
+                             FastPitch.forward :325-390, get_pitch_energy :394-423, FastPitch.infer :426-482
   common/layers.py           ConvReLUNorm :85-97
   fastpitch/loss_function.py FastPitchLoss.forward :63-154 (the reference hard-codes cuda: placeholders; same math here)
   lamb.py                    Lamb.step :40-106
@@ -262,6 +262,25 @@ def forward(sd, inputs_x, stage, use_gt_pitch=True, pace=1.0, max_duration=75, d
     mel_out = F.linear(dec_out, sd["proj.weight"], sd["proj.bias"])
     return [mel_out, dec_mask, None, None, pitch_pred, pitch_tgt, energy_pred, energy_tgt, None, None, dur_tgt, None,
             input_lens]
+
+
+def infer(sd, inputs, pace=1.0, dur_tgt=None, pitch_tgt=None, energy_tgt=None, max_duration=75):
+    """FastPitch.infer, model.py:426-482 (no speaker embedding, no pitch_transform): free-running synthesis -- predicted
+    durations, pitch and energy feed the length regulator and the decoder.
+    -> (mel_out [B, 80, T], dec_lens, dur_pred, pitch_pred [B, 1, Tt], energy_pred [B, Tt])."""
+    enc_out, enc_mask = fftransformer(sd, "encoder", inputs, conditioning=0)
+    log_dur_pred = temporal_predictor(enc_out, enc_mask, sd, "duration_predictor").squeeze(-1)
+    dur_pred = torch.clamp(torch.exp(log_dur_pred) - 1, 0, max_duration)
+    pitch_pred = temporal_predictor(enc_out, enc_mask, sd, "pitch_predictor").permute(0, 2, 1)
+    src = pitch_pred if pitch_tgt is None else pitch_tgt
+    enc_out = enc_out + F.conv1d(src, sd["pitch_emb.weight"], sd["pitch_emb.bias"], padding=1).transpose(1, 2)
+    energy_pred = temporal_predictor(enc_out, enc_mask, sd, "energy_predictor").squeeze(-1)
+    esrc = energy_pred.unsqueeze(1) if energy_tgt is None else energy_tgt
+    enc_out = enc_out + F.conv1d(esrc, sd["energy_emb.weight"], sd["energy_emb.bias"], padding=1).transpose(1, 2)
+    len_regulated, dec_lens = regulate_len(dur_pred if dur_tgt is None else dur_tgt, enc_out, pace, None)
+    dec_out, _ = fftransformer(sd, "decoder", len_regulated, seq_lens=dec_lens)
+    mel_out = F.linear(dec_out, sd["proj.weight"], sd["proj.bias"])
+    return mel_out.permute(0, 2, 1), dec_lens, dur_pred, pitch_pred, energy_pred
 
 
 def loss(model_out, targets, stage, dur_scale=0.1, pitch_scale=0.1, energy_scale=0.1, attn_scale=1.0, kl_weight=0.0):

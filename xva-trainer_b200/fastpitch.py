@@ -610,6 +610,56 @@ class FastPitch(torch.nn.Module):
         return [mel_out, dec_mask, None, None, pitch_pred, pitch_tgt, energy_pred, energy_tgt, None, None, dur_tgt, None,
                 input_lens]
 
+    # ------------------------------------------------------------------------------------------ inference
+    def infer(self, inputs, pace=1.0, dur_tgt=None, pitch_tgt=None, energy_tgt=None, pitch_transform=None, max_duration=75,
+              speaker=0):
+        """FastPitch.infer, model.py:426-482: free-running synthesis (what the UI's preview / export call). Same
+        arguments and 5-tuple: (mel_out [B, 80, T], dec_lens, dur_pred [B, Tt], pitch_pred [B, 1, Tt], energy_pred
+        [B, Tt]). There is no speaker embedding in this model (speaker_emb is None, model.py:188-199), so ``speaker`` is
+        ignored as in the reference. With ``energy_tgt`` the reference fails on an unbound ``energy_pred`` (:462-467,482);
+        here it is returned as None. Runs the forward kernels only; call ``eval()`` first, as the reference's callers do."""
+        B, Tt = inputs.shape
+        tokens = inputs.to(torch.int64).contiguous()
+        in_lens32 = (tokens != 0).sum(1).to(torch.int32)          # enc_mask = (tokens != 0), transformer.py:216-217
+        self._site = 0
+        x = ops.embed_pos(tokens, self.w.emb, None, None, self.inv_freq, B, Tt, D_MODEL)
+        for L in self.enc_layers:
+            x = self._layer_fwd(x, in_lens32, L, None)
+        enc_out = x
+        log_dur_pred = self._pred_fwd(enc_out, in_lens32, self.pred["duration"], None)
+        dur_pred = torch.clamp(torch.exp(log_dur_pred) - 1, 0, max_duration)
+        pitch_pred = self._pred_fwd(enc_out, in_lens32, self.pred["pitch"], None).view(B, 1, Tt)
+        if pitch_transform is not None:
+            if float(self.pitch_std[0]) == 0.0:
+                mean, std = 218.14, 67.24                         # model.py:447-449 (LJSpeech-1.1 defaults)
+            else:
+                mean, std = self.pitch_mean[0], self.pitch_std[0]
+            pitch_pred = pitch_transform(pitch_pred, in_lens32.to(torch.int64), mean, std)
+        src = pitch_pred if pitch_tgt is None else pitch_tgt
+        enc2 = enc_out.clone()
+        ops.scalar_conv_add_(enc2, src.to(torch.float32).reshape(B, 1, Tt).contiguous(), self.w.pitch_emb_w,
+                             self.w.pitch_emb_b, in_lens32)
+        energy_pred = None
+        if energy_tgt is None:
+            energy_pred = self._pred_fwd(enc2, in_lens32, self.pred["energy"], None)
+            esrc = energy_pred.view(B, 1, Tt)
+        else:
+            esrc = energy_tgt
+        enc3 = enc2.clone()
+        ops.scalar_conv_add_(enc3, esrc.to(torch.float32).reshape(B, 1, Tt).contiguous(), self.w.energy_emb_w,
+                             self.w.energy_emb_b, in_lens32)
+        durs = (dur_pred if dur_tgt is None else dur_tgt).to(torch.float32).contiguous()
+        cum, dec_lens = ops.duration_scan(durs, pace, None)       # regulate_len(..., mel_max_len=None), model.py:473-475
+        T_out = int(dec_lens.max().item())
+        if T_out <= 0:
+            raise ValueError("infer: every predicted duration rounds to zero frames")
+        regulated = ops.regulate_gather(enc3, cum, T_out)
+        y = ops.embed_pos(None, None, regulated, dec_lens, self.inv_freq, B, T_out, D_MODEL)
+        for L in self.dec_layers:
+            y = self._layer_fwd(y, dec_lens, L, None)
+        mel_out = ops.conv_fwd(y, self.w.proj_w, bias=self.w.proj_b)
+        return mel_out.permute(0, 2, 1), dec_lens.to(torch.int64), dur_pred, pitch_pred, energy_pred
+
     # ------------------------------------------------------------------------------------------ backward
     def backward(self, criterion, scale=1.0, grad_sync=None, kl=None):
         """Reverse pass for the loss ``criterion`` just evaluated on this module's last forward() output. Gradients of
