@@ -469,8 +469,19 @@ def run_native(args):
         dominant = {"shape": dict(zip(("mode", "Z", "R", "M", "N", "K", "taps", "flags", "split"), top_shape)),
                     "launches_per_step": top_n, "us_per_launch": 1e3 * top_ms / top_n, "gflop_per_launch": top_f / top_n / 1e9,
                     "achieved": top_f / (top_ms * 1e-3) / 1e12, "frac": top_f / (top_ms * 1e-3) / 1e12 / peak}
+        # DRAM bytes of the dominant launch from the committed ncu --set full capture of that exact shape (per launch)
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_s5_dominant_launch_traffic.json")))
+            if all(dominant["shape"].get(k) == v for k, v in tr["shape"].items()):
+                traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+                dominant["traffic"] = traffic
+                dominant["traffic_source"] = tr["source"]
+        except Exception:
+            traffic = None
         roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 kind::tf32 tap-GEMM)", "achieved": achieved,
-                "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_of": "dominant_launch (DRAM read + write bytes per launch, committed ncu --set full capture)" if traffic else None,
                 "launches_per_step": len(rec), "flops_per_step": flops, "kernel_ms_per_step": gemm_ms,
                 "share_of_step": gemm_ms / (ms / args.steps), "dominant_launch": dominant,
                 "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained / 2 (kind::tf32 runs at half the bf16 rate), "
