@@ -18,15 +18,19 @@ B, TT, TM, C = 32, 160, 880, 80
 
 
 def algorithmic_bytes():
-    """fp32 bytes each align.cu launch must move at least once (operands that fit in L2 counted once)."""
+    """fp32 bytes each operator must move at least once: its inputs read once, its outputs written once. Workspaces and
+    intermediates an implementation chooses to keep in HBM (the fp64 alpha / beta tables of the CTC kernels: 289 MB
+    written and read back; the raw-score gradient dD between the two backward kernels: 18 MB each way) are NOT counted,
+    so achieved / peak says how far each operator is from the one-pass HBM bound."""
     s = B * TM * TT * 4            # one score-sized tensor, 18.0 MB
     q, k = B * TM * C * 4, B * TT * C * 4
     return {"xva_attn_score_fwd": q + k + s + 2 * s,                 # q, k, prior -> logprob, soft
-            "xva_mas_width1": s + s + B * TT * 4,                    # soft -> hard, durations
-            "xva_attn_ctc": 3 * s + 2 * (2 * s + B * TM * 8) + 2 * s,  # logprob x3 passes, fp64 alpha written + read, grad zeroed + written
+            "xva_mas_width1": s + s + B * TT * 4,                    # log-probabilities -> hard, durations
+            "xva_mas_log": 2 * s,
+            "xva_attn_ctc": 2 * s + B * 8,                           # logprob -> gradient, cost
             "xva_attn_bin_loss": 2 * s,
             "xva_attn_grad_combine": 3 * s + s,
-            "xva_attn_score_bwd": (3 * s + q + k + s + q) + (s + q + k + k)}  # row kernel + key-gradient kernel
+            "xva_attn_score_bwd": 3 * s + q + k + q + k}             # g, logprob, prior, q, k -> dq, dk
 
 
 def main():

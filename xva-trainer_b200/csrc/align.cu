@@ -8,8 +8,9 @@
 //   attn_loss_function.py:47-54     AttentionBinarizationLoss: -sum_{hard == 1} log(clamp(soft, 1e-12)) / sum(hard)
 // and the autograd of all three. The reference builds a [B, C, Tm, Tt] broadcast difference (1.44 GB at 32 x 80 x 880 x
 // 160), loops over the batch in Python for the CTC calls and syncs 32 times; here the score is computed from the key
-// matrix held in shared memory (one pass over q, one write of each output), the CTC forward-backward of an utterance is
-// one block walking the mel axis with one thread per extended-label state, and the gradients come out of two kernels.
+// matrix held in shared memory (one pass over q, one write of each output), the CTC forward and backward recursions of an
+// utterance are two blocks walking the mel axis in opposite directions at the same time with one thread per
+// extended-label state, and the score gradients come out of two kernels.
 //
 // All of it is fp32 CUDA-core work on a 80-channel contraction (0.7 GFLOP per pass at 32 x 880 x 160) and a few 18 MB
 // tensors: HBM / latency bound, not a tensor-core shape. The differences q - k are formed explicitly in fp32, exactly as
