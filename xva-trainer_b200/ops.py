@@ -317,7 +317,8 @@ def mas_width1(attn, in_lens, out_lens, is_log=False):
 
 def attn_score_fwd(q, k, prior, in_lens):
     """ConvAttention.forward after the projections, fastpitch/attention.py:203-219. q [B,Tm,C], k [B,Tt,C] (row pitches
-    passed through), prior [B,Tm,Tt], in_lens int32 [B] -> (attn_logprob, attn_soft), both [B,Tm,Tt]."""
+    passed through), prior [B,Tm,Tt], in_lens int32 [B] -> (attn_logprob, attn_soft, prior as the contiguous fp32 tensor
+    the kernel read -- the backward needs the same values), all [B,Tm,Tt]."""
     _check3(q, "q")
     _check3(k, "k")
     B, Tm, Cc = q.shape
