@@ -1,0 +1,17 @@
+# round-2 opener: the two-stream backward experiment (XVA_BWD_STREAMS=1, fastpitch.py::_wgrad_side) -- parity, then A/B
+mkdir -p gpurun_out
+(XVA_TEST_EXPERIMENTAL=1 timeout 200 python -m pytest tests/test_fastpitch_gpu.py -m gpu -q -k two_stream 2>&1 | tail -20) > gpurun_out/r2_streams_test.log
+tail -3 gpurun_out/r2_streams_test.log
+for f in 0 1; do
+  XVA_BWD_STREAMS=$f timeout 200 python bench.py --no-hifigan --no-cpu-baseline --steps 30 --warmup 5 > gpurun_out/r2_streams_bench_$f.log 2>&1
+  XVA_BWD_STREAMS=$f timeout 200 python bench.py --no-hifigan --no-cpu-baseline --no-graph --steps 30 --warmup 5 > gpurun_out/r2_streams_bench_eager_$f.log 2>&1
+done
+python - <<'PY'
+import json
+for tag in ("0", "1", "eager_0", "eager_1"):
+    try:
+        d = json.loads(open(f"gpurun_out/r2_streams_bench_{tag}.log").read().strip().splitlines()[-1])
+        print("XVA_BWD_STREAMS", tag, round(d["ms_per_step"], 3), "ms/step", round(d["value"]), "frames/s")
+    except Exception as e:
+        print(tag, "failed", e)
+PY

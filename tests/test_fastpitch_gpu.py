@@ -256,3 +256,27 @@ def test_dropout_training_step_is_finite_and_replays(lib):
     m.step_dropout()
     g3 = run()
     assert rel(g3, g1) > 1e-2
+
+
+@pytest.mark.skipif(os.environ.get("XVA_TEST_EXPERIMENTAL") != "1",
+                    reason="two-stream backward is an unmeasured experiment (DESIGN.md section 7); set XVA_TEST_EXPERIMENTAL=1")
+def test_two_stream_backward_gives_the_same_gradients(lib, monkeypatch):
+    """XVA_BWD_STREAMS=1 issues the FFT-block weight gradients on a side stream; the gradient arena must come out the
+    same (to the rounding of the fp32 atomics the split weight gradient already uses)."""
+    B, Tt, Tm = 3, 32, 100
+    x, y = ofp.synthetic_batch(B, Tt, Tm, seed=5)
+    cx, cy = _cuda_batch(x, y)
+    grads = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("XVA_BWD_STREAMS", flag)
+        fp, m = _model(lib, ofp.make_state(99), 3)
+        assert m.bwd_streams == (flag == "1")
+        crit = fp.FastPitchLoss()
+        for _ in range(2):
+            out = m(cx)
+            crit(out, cy)
+            m.zero_grad()
+            m.backward(crit, 1.0)
+        torch.cuda.synchronize()
+        grads.append(m.arena.g.clone())
+    assert rel(grads[1], grads[0]) < 1e-5

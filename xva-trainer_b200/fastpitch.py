@@ -188,6 +188,14 @@ class FastPitch(torch.nn.Module):
         # softmax backward inside the dP GEMM epilogue: parity-green but measured slower (13.84 vs 13.59 ms/step: the
         # epilogue-bound GEMM gets heavier than the HBM-speed row kernel it replaces), so off by default
         self.fuse_softmax_bwd = os.environ.get("XVA_FUSE_SOFTMAX_BWD", "0") == "1"
+        # EXPERIMENT, off by default, not yet measured (round-2 item): issue every FFT-block weight
+        # gradient on a second stream. It only reads activations the forward saved and the layer's output gradient and
+        # accumulates into the gradient arena, so it is independent of the input-gradient GEMM that follows it on the main
+        # stream; the persistent CTAs of one kernel that run out of tiles (224 row tiles on 148 SMs = 1.51 waves) free
+        # their SMs for the other kernel instead of idling until the launch ends.
+        self.bwd_streams = os.environ.get("XVA_BWD_STREAMS", "0") == "1"
+        self._side = torch.cuda.Stream(device=dev) if self.bwd_streams else None
+        self._side_keep = []
         self.seed = int(seed)
         self.step_counter = torch.zeros(1, device=dev, dtype=torch.int64)  # device-side dropout counter (uint64 bits)
         self._site = 0
@@ -368,6 +376,22 @@ class FastPitch(torch.nn.Module):
                             d1=(p1, seed1), d2=(p2, seed2)))
         return y2
 
+    def _wgrad_side(self, fn, *inputs):
+        """Run ``fn`` (weight / bias gradient launches) on the side stream when the two-stream backward is on. ``inputs``
+        are kept alive until _join_side(): the caching allocator must not hand their memory to a main-stream kernel while
+        the side stream still reads it."""
+        if self._side is None:
+            return fn()
+        self._side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self._side):
+            fn()
+        self._side_keep.extend(inputs)
+
+    def _join_side(self):
+        if self._side is not None and self._side_keep:
+            torch.cuda.current_stream().wait_stream(self._side)
+            self._side_keep.clear()
+
     def _layer_bwd(self, dy, lens, L, c, need_dx=True):
         sd = self.step_counter
         x, qkv = c.x, c.qkv
@@ -376,17 +400,21 @@ class FastPitch(torch.nn.Module):
         # ---- PositionwiseConvFF
         dx2, dbr2 = ops.layernorm_bwd(dy, c.sv2, L.w.ln2_g, lens, L.g.ln2_g, L.g.ln2_b, dbias=L.g.b2, want_drop=True,
                                       drop_pre_p=c.d2[0], seed_pre=c.d2[1], seed_dev=sd)
-        ops.conv_wgrad(dbr2, c.h, K3, out=L.g.w2, accumulate=True)
+        self._wgrad_side(lambda: ops.conv_wgrad(dbr2, c.h, K3, out=L.g.w2, accumulate=True), dbr2)
         dh = ops.conv_dgrad(dbr2, L.w.w2, K3, gate=c.h, round_out=True)
         del dbr2
-        ops.conv_wgrad(dh, c.y1, K3, out=L.g.w1, accumulate=True)
-        ops.colsum_(B * T, D_INNER, D_INNER, dh, L.g.b1)
+
+        def w1_grads():
+            ops.conv_wgrad(dh, c.y1, K3, out=L.g.w1, accumulate=True)
+            ops.colsum_(B * T, D_INNER, D_INNER, dh, L.g.b1)
+
+        self._wgrad_side(w1_grads, dh)
         dy1 = ops.conv_dgrad(dh, L.w.w1, K3, residual=dx2)
         del dh, dx2
         # ---- MultiHeadAttn
         dx1, dbr1 = ops.layernorm_bwd(dy1, c.sv1, L.w.ln1_g, lens, L.g.ln1_g, L.g.ln1_b, dbias=None, want_drop=True,
                                       drop_pre_p=c.d1[0], seed_pre=c.d1[1], seed_dev=sd)
-        ops.conv_wgrad(dbr1, c.vec, (0,), out=L.g.o_w, accumulate=True)
+        self._wgrad_side(lambda: ops.conv_wgrad(dbr1, c.vec, (0,), out=L.g.o_w, accumulate=True), dbr1)
         dvec = ops.conv_dgrad(dbr1, L.w.o_w, round_out=True)
         dqkv = torch.empty_like(qkv)
         Tp = c.P.shape[2]
@@ -408,11 +436,14 @@ class FastPitch(torch.nn.Module):
         ops.bmm_nn(dP[..., :T], k, out=dqkv[..., :D_HEAD], round_out=True)
         ops.bmm_tn(dP[..., :T], q, out=dqkv[..., D_HEAD:2 * D_HEAD], round_out=True)
         del dP
-        ops.conv_wgrad(dqkv, x, (0,), out=L.g.qkv_w, accumulate=True)
-        ops.colsum_(B * T, 3 * D_HEAD, 3 * D_HEAD, dqkv, L.g.qkv_b)
-        if not need_dx:
-            return None
-        return ops.conv_dgrad(dqkv, L.w.qkv_w, residual=dx1)
+        def qkv_grads():
+            ops.conv_wgrad(dqkv, x, (0,), out=L.g.qkv_w, accumulate=True)
+            ops.colsum_(B * T, 3 * D_HEAD, 3 * D_HEAD, dqkv, L.g.qkv_b)
+
+        self._wgrad_side(qkv_grads, dqkv)
+        dx = ops.conv_dgrad(dqkv, L.w.qkv_w, residual=dx1) if need_dx else None
+        self._join_side()      # the layer's gradient slice is final (GradSync.ready / LAMB read it from the main stream)
+        return dx
 
     # ------------------------------------------------------------------------------------------ temporal predictor
     def _pred_fwd(self, x, lens, P, save):
