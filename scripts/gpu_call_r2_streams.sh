@@ -15,3 +15,10 @@ for tag in ("0", "1", "eager_0", "eager_1"):
     except Exception as e:
         print(tag, "failed", e)
 PY
+# the HiFi-GAN half (hifigan._Side): parity, then A/B of the replayed and the eager step
+(XVA_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_hifigan_gpu.py -m gpu -q -k two_stream 2>&1 | tail -20) > gpurun_out/r2_streams_hifigan_test.log
+tail -3 gpurun_out/r2_streams_hifigan_test.log
+for f in 0 1; do
+  XVA_BWD_STREAMS=$f timeout 300 python scripts/bench_hifigan.py 16 10 > gpurun_out/r2_streams_hifigan_$f.log 2>&1; tail -1 gpurun_out/r2_streams_hifigan_$f.log | cut -c1-160
+  XVA_BWD_STREAMS=$f XVA_NO_GRAPH=1 timeout 300 python scripts/bench_hifigan.py 16 10 > gpurun_out/r2_streams_hifigan_eager_$f.log 2>&1; tail -1 gpurun_out/r2_streams_hifigan_eager_$f.log | cut -c1-160
+done

@@ -17,6 +17,7 @@ Design:
     (tiny tensors; autograd carries dL/dw back to weight_g / weight_v), as SURVEY.md section 7 recommends.
 """
 import math
+import os
 
 import torch
 from torch import nn
@@ -24,6 +25,37 @@ from torch import nn
 from . import capi, ops
 
 LRELU_SLOPE = 0.1
+
+
+class _Side:
+    """EXPERIMENT, off by default (XVA_BWD_STREAMS=1), not yet measured: weight / bias gradient
+    launches go to a second stream. They only read tensors that already exist and accumulate into the packed gradient
+    arena / the bias .grad tensors, allocate nothing, and nothing on the main stream depends on them until the arena is
+    unpacked -- so the small-channel weight gradients (52 CTAs on 148 SMs, 160 us each at B = 16 x 8192) overlap the
+    input-gradient chain instead of serialising with it. Inputs are record_stream()-ed: their memory is not reused
+    before the side stream is done with it; join() runs where the gradients are consumed (_WnPacker.unpack_grads)."""
+    enabled = os.environ.get("XVA_BWD_STREAMS", "0") == "1"
+    stream = None
+    used = False
+
+    @classmethod
+    def run(cls, fn, *inputs):
+        if not cls.enabled:
+            return fn()
+        if cls.stream is None:
+            cls.stream = torch.cuda.Stream()
+        cls.stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(cls.stream):
+            fn()
+        for t in inputs:
+            t.record_stream(cls.stream)
+        cls.used = True
+
+    @classmethod
+    def join(cls):
+        if cls.enabled and cls.used:
+            torch.cuda.current_stream().wait_stream(cls.stream)
+            cls.used = False
 
 
 class _WNConv(nn.Module):
@@ -146,6 +178,7 @@ class _WnPacker:
         return self.gW
 
     def unpack_grads(self):
+        _Side.join()
         self._sync(True)
         capi.call("xva_wn_pack_bwd", ops._p(self.table), len(self.items), self.rows, self.max_inner, ops._stream())
 
@@ -325,14 +358,17 @@ class Generator(nn.Module):
             b = mods[name].bias
             if b.grad is None:
                 b.grad = torch.zeros_like(b)
-            ops.colsum_(d.shape[0] * d.shape[1], cols, ld if ld is not None else d.shape[2], d, b.grad)
+            _Side.run(lambda: ops.colsum_(d.shape[0] * d.shape[1], cols, ld if ld is not None else d.shape[2], d, b.grad), d)
+
+        def wgrad(dy_, x_, shifts, out):
+            _Side.run(lambda: ops.conv_wgrad(dy_, x_, shifts, out=out, accumulate=True), dy_, x_)
 
         # conv_post + tanh
         y, a = ctx["y"], ctx["a_last"]
         Tl = a.shape[1]
         dpre = ops.tanh_bwd(dy.reshape(-1).to(torch.float32).contiguous(), y.reshape(-1), 32).view(B, Tl, 32)
         dp1 = dpre[..., :1]
-        ops.conv_wgrad(dp1, a, self.conv_post.shifts, out=gW["conv_post"][0], accumulate=True)
+        wgrad(dp1, a, self.conv_post.shifts, gW["conv_post"][0])
         bias_grad("conv_post", dpre, 1, 32)
         for i in reversed(range(self.num_upsamples)):
             stage = ctx["stages"][i]
@@ -353,11 +389,11 @@ class Generator(nn.Module):
                     c1, c2 = rb.convs1[m], rb.convs2[m]
                     ar, t = stage["blocks"][j][m]
                     bias_grad(f"{name}.convs2.{m}", G, c2.cout)
-                    ops.conv_wgrad(G, t, c2.shifts, out=gW[f"{name}.convs2.{m}"][0], accumulate=True)
+                    wgrad(G, t, c2.shifts, gW[f"{name}.convs2.{m}"][0])
                     dt = ops.conv_dgrad(G, W[f"{name}.convs2.{m}"][0], c2.shifts, gate=t, gate_slope=LRELU_SLOPE,
                                         round_out=True)
                     bias_grad(f"{name}.convs1.{m}", dt, c1.cout)
-                    ops.conv_wgrad(dt, ar, c1.shifts, out=gW[f"{name}.convs1.{m}"][0], accumulate=True)
+                    wgrad(dt, ar, c1.shifts, gW[f"{name}.convs1.{m}"][0])
                     G = ops.conv_dgrad(dt, W[f"{name}.convs1.{m}"][0], c1.shifts, gate=ar, gate_slope=LRELU_SLOPE,
                                        residual=G, round_out=True)
                 dx_blocks.append(G)
@@ -368,12 +404,12 @@ class Generator(nn.Module):
             Tin = a.shape[1]
             dv = d_up.view(B, Tin, u * cout)
             nlo = (u - p) * cout
-            ops.conv_wgrad(dv[..., :nlo], a, (0, -1), out=gW[f"ups.{i}"][0], accumulate=True)
-            ops.conv_wgrad(dv[..., nlo:], a, (1, 0), out=gW[f"ups.{i}"][1], accumulate=True)
+            wgrad(dv[..., :nlo], a, (0, -1), gW[f"ups.{i}"][0])
+            wgrad(dv[..., nlo:], a, (1, 0), gW[f"ups.{i}"][1])
             bias_grad(f"ups.{i}", d_up, cout)
         # ups[0] input is leaky_relu(conv_pre(x)): gate by its sign, then conv_pre's own gradients
         dpre0 = self._ups_dgrad(0, d_up, a, LRELU_SLOPE, W, alpha=1.0)
-        ops.conv_wgrad(dpre0, ctx["mel"], self.conv_pre.shifts, out=gW["conv_pre"][0], accumulate=True)
+        wgrad(dpre0, ctx["mel"], self.conv_pre.shifts, gW["conv_pre"][0])
         bias_grad("conv_pre", dpre0, self.conv_pre.cout)
 
         # packed-weight gradients -> weight_g / weight_v (.grad accumulated), one launch
@@ -704,7 +740,7 @@ class _Disc(nn.Module):
         def bias_grad(m, d, cols, ld):
             if m.bias.grad is None:
                 m.bias.grad = torch.zeros_like(m.bias)
-            ops.colsum_(d.shape[0] * d.shape[1], cols, ld, d, m.bias.grad)
+            _Side.run(lambda: ops.colsum_(d.shape[0] * d.shape[1], cols, ld, d, m.bias.grad), d)
 
         # conv_post: pad the single score channel to 32 columns (MN-major operand rule)
         mp = self.conv_post
@@ -717,7 +753,7 @@ class _Disc(nn.Module):
         taps = mp.taps()
         shifts = [sh for _, sh, _ in taps]
         if need_w:
-            ops.conv_wgrad(d1, X, shifts, out=gW[-1], accumulate=True, dy_rows=Lf)
+            _Side.run(lambda: ops.conv_wgrad(d1, X, shifts, out=gW[-1], accumulate=True, dy_rows=Lf), d1, X)
             bias_grad(mp, dscore.contiguous(), 1, 1)
         dpre = ops.conv_dgrad(d1, Wr[-1], shifts, out_rows=X.shape[1], gate=X, gate_slope=LRELU_SLOPE,
                               residual=dfeat[len(layers) - 1], lens=self._lens(Z, Lf, dev), round_out=True)
@@ -731,8 +767,9 @@ class _Disc(nn.Module):
             Gp, Ogp, Cgp, _ = self._group_geom(m)
             if need_w:
                 bias_grad(m, dpre, m.cout, m.cout)
-                ops.conv_wgrad(dpre, xv, [sh for _, sh, _ in taps], x_cols=[ph * Cin for _, _, ph in taps], n_cols=Cgp,
-                               out=gW[li], accumulate=True, groups=Gp, grp_step=Cgp)
+                _Side.run(lambda dpre=dpre, xv=xv, taps=taps, Cin=Cin, Cgp=Cgp, Gp=Gp, li=li: ops.conv_wgrad(
+                    dpre, xv, [sh for _, sh, _ in taps], x_cols=[ph * Cin for _, _, ph in taps], n_cols=Cgp,
+                    out=gW[li], accumulate=True, groups=Gp, grp_step=Cgp), dpre, xv)
             if li == 1 and dwave is None and not need_w:
                 break
             dX = torch.empty_like(Xin)
@@ -760,6 +797,7 @@ class _Disc(nn.Module):
         if dwave is not None:
             ops.conv_c1_bwd_x(dpre, w0.detach(), ctx["geom"], m0.k, m0.stride, m0.pad, lens_v[0], wave_scale, dwave)
         if need_w and not shared:
+            _Side.join()
             torch.autograd.backward([w0] + list(ctx["packed"][1:]), [dw0] + gW[1:])
 
 
