@@ -22,3 +22,8 @@ for f in 0 1; do
   XVA_BWD_STREAMS=$f timeout 300 python scripts/bench_hifigan.py 16 10 > gpurun_out/r2_streams_hifigan_$f.log 2>&1; tail -1 gpurun_out/r2_streams_hifigan_$f.log | cut -c1-160
   XVA_BWD_STREAMS=$f XVA_NO_GRAPH=1 timeout 300 python scripts/bench_hifigan.py 16 10 > gpurun_out/r2_streams_hifigan_eager_$f.log 2>&1; tail -1 gpurun_out/r2_streams_hifigan_eager_$f.log | cut -c1-160
 done
+# sub-discriminators on parallel streams (hifigan._Branches), alone and with the side-stream weight gradients
+for n in 2 4 8; do
+  XVA_DISC_STREAMS=$n timeout 300 python scripts/bench_hifigan.py 16 10 > gpurun_out/r2_disc_streams_$n.log 2>&1; tail -1 gpurun_out/r2_disc_streams_$n.log | cut -c1-160
+done
+XVA_DISC_STREAMS=4 XVA_BWD_STREAMS=1 timeout 300 python scripts/bench_hifigan.py 16 10 > gpurun_out/r2_disc_streams_4_side.log 2>&1; tail -1 gpurun_out/r2_disc_streams_4_side.log | cut -c1-160

@@ -58,6 +58,61 @@ class _Side:
             cls.used = False
 
 
+class _Branches:
+    """EXPERIMENT, off by default (XVA_DISC_STREAMS=n), not yet measured: the sub-
+    discriminators of MPD / MSD are independent chains of small launches; with n > 0 sub-discriminator i runs -- forward,
+    loss gradients and backward -- on stream i mod n. Discipline that keeps the caching allocator safe without
+    record_stream: a branch starts by waiting for the main stream (fork) and everything in it, torch ops included, runs on
+    its stream; the main stream waits for every branch (join) before it touches what they produced; a tensor created in
+    a branch is freed in it or after the join; a main-stream tensor a branch reads is kept referenced until the join."""
+    n = int(os.environ.get("XVA_DISC_STREAMS", "0") or 0)
+    streams = []
+    open_streams = []
+
+    class _Ctx:
+        def __init__(self, stream):
+            self.stream = stream
+
+        def __enter__(self):
+            self.stream.wait_stream(torch.cuda.current_stream())
+            self.cm = torch.cuda.stream(self.stream)
+            self.cm.__enter__()
+
+        def __exit__(self, *exc):
+            self.cm.__exit__(*exc)
+            if self.stream not in _Branches.open_streams:
+                _Branches.open_streams.append(self.stream)
+            return False
+
+    class _Null:
+        def __enter__(self):
+            return None
+
+        def __exit__(self, *exc):
+            return False
+
+    @classmethod
+    def on(cls):
+        return cls.n > 0
+
+    @classmethod
+    def branch(cls, i):
+        if cls.n <= 0:
+            return cls._Null()
+        while len(cls.streams) < cls.n:
+            cls.streams.append(torch.cuda.Stream())
+        return cls._Ctx(cls.streams[i % cls.n])
+
+    @classmethod
+    def join(cls):
+        if not cls.open_streams:
+            return
+        main = torch.cuda.current_stream()
+        for st in cls.open_streams:
+            main.wait_stream(st)
+        cls.open_streams = []
+
+
 class _WNConv(nn.Module):
     """Parameters of one weight-normed Conv1d / ConvTranspose1d with the reference's names (bias, weight_g, weight_v)."""
 
@@ -895,25 +950,30 @@ def _multi_forward(model, y, y_hat, pools, weight_grad=True):
     Wall = pk.pack()                      # every weight-normed convolution of the model: one launch
     n_layers = lambda d: len(d.convs) + 1
     y_d_rs, y_d_gs, fmap_rs, fmap_gs = [], [], [], []
+    inputs = [both]                       # every pooled waveform stays referenced until the branches have been joined
     for i, d in enumerate(model.discriminators):
         if pools and i != 0:
             both = ops.avgpool4(both)
-        if any(m.spectral for m in d.convs):
-            sr, fr, cr = d(both[:B], weight_grad=weight_grad)
-            sg, fg, cg = d(both[B:], weight_grad=weight_grad)
-            passes = [(cr, (0, cr["Z"]), None), (cg, None, (0, cg["Z"]))]
-        else:
-            s2, f2, c2 = d(both, weight_grad=weight_grad, W=[Wall[f"{i}.{li}"][0] for li in range(n_layers(d))],
-                           gW=[pk.gW[f"{i}.{li}"][0] for li in range(n_layers(d))])
-            Z = c2["Z"] // 2
-            sr, sg = s2[:Z], s2[Z:]
-            fr, fg = [f[:Z] for f in f2], [f[Z:] for f in f2]
-            passes = [(c2, (0, Z), (Z, 2 * Z))]
+            inputs.append(both)
+        with _Branches.branch(i):
+            if any(m.spectral for m in d.convs):
+                sr, fr, cr = d(both[:B], weight_grad=weight_grad)
+                sg, fg, cg = d(both[B:], weight_grad=weight_grad)
+                passes = [(cr, (0, cr["Z"]), None), (cg, None, (0, cg["Z"]))]
+            else:
+                s2, f2, c2 = d(both, weight_grad=weight_grad, W=[Wall[f"{i}.{li}"][0] for li in range(n_layers(d))],
+                               gW=[pk.gW[f"{i}.{li}"][0] for li in range(n_layers(d))])
+                Z = c2["Z"] // 2
+                sr, sg = s2[:Z], s2[Z:]
+                fr, fg = [f[:Z] for f in f2], [f[Z:] for f in f2]
+                passes = [(c2, (0, Z), (Z, 2 * Z))]
         y_d_rs.append(sr)
         y_d_gs.append(sg)
         fmap_rs.append(fr)
         fmap_gs.append(fg)
         model._ctx.append(passes)
+    _Branches.join()
+    del inputs
     return y_d_rs, y_d_gs, fmap_rs, fmap_gs
 
 
@@ -925,19 +985,24 @@ def discriminator_loss_backward(model, y_d_rs, y_d_gs):
     acc = torch.zeros(2 * len(y_d_rs), device=dev, dtype=torch.float64)
     loss = torch.zeros((), device=dev, dtype=torch.float64)
     model._packer.zero_grads()
+    parts = []
     for i, (d, passes) in enumerate(zip(model.discriminators, model._ctx)):
-        dr, dg = y_d_rs[i], y_d_gs[i]
-        n = dr.numel()
-        ops.reduce_sq(dr, 1.0, acc[2 * i:2 * i + 1])
-        ops.reduce_sq(dg, 0.0, acc[2 * i + 1:2 * i + 2])
-        loss = loss + (acc[2 * i] + acc[2 * i + 1]) / n
-        for ctx, rr, gr in passes:
-            dscore = torch.empty_like(ctx["score"])
-            if rr is not None:
-                ops.sq_grad(dr, 1.0, 1.0 / n, out=dscore[rr[0]:rr[1]], accumulate=False)
-            if gr is not None:
-                ops.sq_grad(dg, 0.0, 1.0 / n, out=dscore[gr[0]:gr[1]], accumulate=False)
-            d.backward(ctx, dscore, [None] * len(ctx["acts"]), need_w=True)
+        with _Branches.branch(i):
+            dr, dg = y_d_rs[i], y_d_gs[i]
+            n = dr.numel()
+            ops.reduce_sq(dr, 1.0, acc[2 * i:2 * i + 1])
+            ops.reduce_sq(dg, 0.0, acc[2 * i + 1:2 * i + 2])
+            parts.append((acc[2 * i] + acc[2 * i + 1]) / n)
+            for ctx, rr, gr in passes:
+                dscore = torch.empty_like(ctx["score"])
+                if rr is not None:
+                    ops.sq_grad(dr, 1.0, 1.0 / n, out=dscore[rr[0]:rr[1]], accumulate=False)
+                if gr is not None:
+                    ops.sq_grad(dg, 0.0, 1.0 / n, out=dscore[gr[0]:gr[1]], accumulate=False)
+                d.backward(ctx, dscore, [None] * len(ctx["acts"]), need_w=True)
+    _Branches.join()
+    for part in parts:                    # same summation order as one sub-discriminator after the other
+        loss = loss + part
     model._packer.unpack_grads()          # packed-weight gradients -> weight_g / weight_v of every sub-discriminator
     return loss
 
@@ -957,30 +1022,45 @@ def generator_adv_loss_backward(model, y_d_gs, fmap_rs, fmap_gs, dwave, pools):
         if pools:
             L = levels[-1].shape[1]
             levels.append(torch.zeros(dwave.shape[0], L // 2 + 1, device=dev, dtype=torch.float32))
+    gen_parts, fm_parts, own_dwave = [], [], []
     for i in reversed(range(n_d)):
-        d = model.discriminators[i]
-        cg = None
-        for ctx, rr, gr in model._ctx[i]:          # the pass (or the half of the batched pass) of the generated waveform
-            if gr is not None:
-                cg = ctx if rr is None else _Disc.slice_ctx(ctx, gr[0], gr[1])
-        dg = y_d_gs[i]
-        n = dg.numel()
-        ops.reduce_sq(dg, 1.0, acc[16 * i:16 * i + 1])
-        loss_gen = loss_gen + acc[16 * i] / n
-        dscore = ops.sq_grad(dg, 1.0, 1.0 / n)
-        dfeat = []
-        n_act = len(cg["acts"])
-        for l, (fr, fg) in enumerate(zip(fmap_rs[i], fmap_gs[i])):
-            valid = cg["Z"] * (cg["lens"][l] if l < n_act else cg["lens"][-1]) * fg.shape[2]
-            a = acc[16 * i + 1 + l:16 * i + 2 + l]
-            if l < n_act:
-                dfeat.append(ops.l1_loss_grad(fr, fg, 2.0 / valid, a, gate_slope=LRELU_SLOPE))   # loss term + gradient
+        with _Branches.branch(i):
+            d = model.discriminators[i]
+            cg = None
+            for ctx, rr, gr in model._ctx[i]:      # the pass (or the half of the batched pass) of the generated waveform
+                if gr is not None:
+                    cg = ctx if rr is None else _Disc.slice_ctx(ctx, gr[0], gr[1])
+            dg = y_d_gs[i]
+            n = dg.numel()
+            ops.reduce_sq(dg, 1.0, acc[16 * i:16 * i + 1])
+            gen_parts.append(acc[16 * i] / n)
+            dscore = ops.sq_grad(dg, 1.0, 1.0 / n)
+            dfeat = []
+            n_act = len(cg["acts"])
+            for l, (fr, fg) in enumerate(zip(fmap_rs[i], fmap_gs[i])):
+                valid = cg["Z"] * (cg["lens"][l] if l < n_act else cg["lens"][-1]) * fg.shape[2]
+                a = acc[16 * i + 1 + l:16 * i + 2 + l]
+                if l < n_act:
+                    dfeat.append(ops.l1_loss_grad(fr, fg, 2.0 / valid, a, gate_slope=LRELU_SLOPE))   # loss term + gradient
+                else:
+                    ops.reduce_l1(fr, fg, a)
+                    ops.l1_grad(fr, fg, 2.0 / valid, out=dscore)     # conv_post output is the last feature map too
+                fm_parts.append(2.0 * a[0] / valid)
+            if pools:
+                tgt = levels[i]
+            elif _Branches.on():                   # concurrent branches must not accumulate into one tensor
+                tgt = torch.zeros_like(dwave)
+                own_dwave.append(tgt)
             else:
-                ops.reduce_l1(fr, fg, a)
-                ops.l1_grad(fr, fg, 2.0 / valid, out=dscore)     # conv_post output is the last feature map too
-            loss_fm = loss_fm + 2.0 * a[0] / valid
-        tgt = levels[i] if pools else dwave
-        d.backward(cg, dscore, dfeat, need_w=False, dwave=tgt)
+                tgt = dwave
+            d.backward(cg, dscore, dfeat, need_w=False, dwave=tgt)
+    _Branches.join()
+    for part in gen_parts:                # same summation order as one sub-discriminator after the other
+        loss_gen = loss_gen + part
+    for part in fm_parts:
+        loss_fm = loss_fm + part
+    for t in own_dwave:
+        dwave.add_(t)
     if pools:
         for i in reversed(range(1, n_d)):
             up = ops.avgpool4_bwd(levels[i], levels[i - 1].shape[1])
