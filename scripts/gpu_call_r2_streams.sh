@@ -27,3 +27,5 @@ for n in 2 4 8; do
   XVA_DISC_STREAMS=$n timeout 300 python scripts/bench_hifigan.py 16 10 > gpurun_out/r2_disc_streams_$n.log 2>&1; tail -1 gpurun_out/r2_disc_streams_$n.log | cut -c1-160
 done
 XVA_DISC_STREAMS=4 XVA_BWD_STREAMS=1 timeout 300 python scripts/bench_hifigan.py 16 10 > gpurun_out/r2_disc_streams_4_side.log 2>&1; tail -1 gpurun_out/r2_disc_streams_4_side.log | cut -c1-160
+XVA_GEN_STREAMS=1 timeout 300 python scripts/bench_hifigan.py 16 10 > gpurun_out/r2_gen_streams.log 2>&1; tail -1 gpurun_out/r2_gen_streams.log | cut -c1-160
+XVA_GEN_STREAMS=1 XVA_DISC_STREAMS=4 XVA_BWD_STREAMS=1 timeout 300 python scripts/bench_hifigan.py 16 10 > gpurun_out/r2_all_streams.log 2>&1; tail -1 gpurun_out/r2_all_streams.log | cut -c1-160

@@ -353,10 +353,10 @@ def test_full_hifigan_step_matches_oracle(lib):
 
 @pytest.mark.skipif(os.environ.get("XVA_TEST_EXPERIMENTAL") != "1",
                     reason="two-stream backward is an unmeasured experiment (DESIGN.md section 7); set XVA_TEST_EXPERIMENTAL=1")
-@pytest.mark.parametrize("mode", ["side_stream", "disc_branches", "both"])
+@pytest.mark.parametrize("mode", ["side_stream", "disc_branches", "gen_branches", "all"])
 def test_two_stream_backward_gives_the_same_step(lib, mode):
     """hifigan._Side (XVA_BWD_STREAMS=1): weight / bias gradients on a side stream; hifigan._Branches
-    (XVA_DISC_STREAMS=n): sub-discriminators on parallel streams. The same training step from the same state must
+    (XVA_DISC_STREAMS=n / XVA_GEN_STREAMS=1): sub-discriminators / the ResBlocks of an MRF stage on parallel streams. The same training step from the same state must
     produce the same losses and (to the rounding of the fp32 atomics) the same updated weights."""
     from xva_trainer_b200 import hifigan as hg
 
@@ -365,11 +365,12 @@ def test_two_stream_backward_gives_the_same_step(lib, mode):
              win_size=1024, fmin=0, fmax=8000, fmax_for_loss=None)
     x, y, y_mel = (t.cuda() for t in ohg.synthetic_batch(2, 8, seed=3))
     results = []
-    was = (hg._Side.enabled, hg._Branches.n)
+    was = (hg._Side.enabled, hg._Branches.n, hg._Branches.n_gen)
     try:
         for flag in (False, True):
-            hg._Side.enabled = flag and mode in ("side_stream", "both")
-            hg._Branches.n = 4 if (flag and mode in ("disc_branches", "both")) else 0
+            hg._Side.enabled = flag and mode in ("side_stream", "all")
+            hg._Branches.n = 4 if (flag and mode in ("disc_branches", "all")) else 0
+            hg._Branches.n_gen = 3 if (flag and mode in ("gen_branches", "all")) else 0
             G = _generator(lib, ohg.make_generator_state(5, scale=0.7))
             mpd = hg.MultiPeriodDiscriminator(device="cuda:0"); mpd.load_state_dict(ohg.make_disc_state(ohg.mpd_spec(), 21)); mpd.train()
             msd = hg.MultiScaleDiscriminator(device="cuda:0"); msd.load_state_dict(ohg.make_disc_state(ohg.msd_spec(), 22)); msd.train()
@@ -380,7 +381,7 @@ def test_two_stream_backward_gives_the_same_step(lib, mode):
             results.append(({k: float(v) for k, v in losses.items()},
                             {n: {k: v.clone() for k, v in m.state_dict().items()} for n, m in (("G", G), ("mpd", mpd), ("msd", msd))}))
     finally:
-        hg._Side.enabled, hg._Branches.n = was
+        hg._Side.enabled, hg._Branches.n, hg._Branches.n_gen = was
     (l0, s0), (l1, s1) = results
     for k in l0:
         assert abs(l0[k] - l1[k]) <= 1e-5 * abs(l0[k]) + 1e-7, (k, l0[k], l1[k])

@@ -66,6 +66,7 @@ class _Branches:
     its stream; the main stream waits for every branch (join) before it touches what they produced; a tensor created in
     a branch is freed in it or after the join; a main-stream tensor a branch reads is kept referenced until the join."""
     n = int(os.environ.get("XVA_DISC_STREAMS", "0") or 0)
+    n_gen = 3 if os.environ.get("XVA_GEN_STREAMS", "0") == "1" else 0   # same idea for the three ResBlocks of an MRF stage
     streams = []
     open_streams = []
 
@@ -96,12 +97,13 @@ class _Branches:
         return cls.n > 0
 
     @classmethod
-    def branch(cls, i):
-        if cls.n <= 0:
+    def branch(cls, i, n=None):
+        n = cls.n if n is None else n
+        if n <= 0:
             return cls._Null()
-        while len(cls.streams) < cls.n:
+        while len(cls.streams) < n:
             cls.streams.append(torch.cuda.Stream())
-        return cls._Ctx(cls.streams[i % cls.n])
+        return cls._Ctx(cls.streams[i % n])
 
     @classmethod
     def join(cls):
@@ -375,21 +377,23 @@ class Generator(nn.Module):
             for j in range(self.num_kernels):
                 rb = self.resblocks[i * self.num_kernels + j]
                 name = f"resblocks.{i * self.num_kernels + j}"
-                xr, ar = x0, a0
-                saved = []
-                for m in range(3):
-                    c1, c2 = rb.convs1[m], rb.convs2[m]
-                    t = ops.conv_fwd(ar, W[f"{name}.convs1.{m}"][0], c1.shifts, bias=c1.bias.detach(),
-                                     act_slope=LRELU_SLOPE, round_out=True)
-                    last = m == 2
-                    xn = torch.empty_like(xr)
-                    an = None if last else torch.empty_like(xr)
-                    ops.conv_fwd(t, W[f"{name}.convs2.{m}"][0], c2.shifts, out=xn, bias=c2.bias.detach(), residual=xr,
-                                 out_act=an, out_act_slope=LRELU_SLOPE)
-                    saved.append((ar, t))
-                    xr, ar = xn, an
+                with _Branches.branch(j, _Branches.n_gen):     # the ResBlocks of a stage only share their input
+                    xr, ar = x0, a0
+                    saved = []
+                    for m in range(3):
+                        c1, c2 = rb.convs1[m], rb.convs2[m]
+                        t = ops.conv_fwd(ar, W[f"{name}.convs1.{m}"][0], c1.shifts, bias=c1.bias.detach(),
+                                         act_slope=LRELU_SLOPE, round_out=True)
+                        last = m == 2
+                        xn = torch.empty_like(xr)
+                        an = None if last else torch.empty_like(xr)
+                        ops.conv_fwd(t, W[f"{name}.convs2.{m}"][0], c2.shifts, out=xn, bias=c2.bias.detach(), residual=xr,
+                                     out_act=an, out_act_slope=LRELU_SLOPE)
+                        saved.append((ar, t))
+                        xr, ar = xn, an
                 ys.append(xr)
                 stage["blocks"].append(saved)
+            _Branches.join()
             slope = LRELU_SLOPE if i + 1 < self.num_upsamples else 0.01               # models.py:115 vs :124
             a = ops.mean3_lrelu(ys[0], ys[1], ys[2], slope)
             ctx["stages"].append(stage)
@@ -439,19 +443,21 @@ class Generator(nn.Module):
             for j in range(self.num_kernels):
                 rb = self.resblocks[i * self.num_kernels + j]
                 name = f"resblocks.{i * self.num_kernels + j}"
-                G = dyj
-                for m in reversed(range(3)):
-                    c1, c2 = rb.convs1[m], rb.convs2[m]
-                    ar, t = stage["blocks"][j][m]
-                    bias_grad(f"{name}.convs2.{m}", G, c2.cout)
-                    wgrad(G, t, c2.shifts, gW[f"{name}.convs2.{m}"][0])
-                    dt = ops.conv_dgrad(G, W[f"{name}.convs2.{m}"][0], c2.shifts, gate=t, gate_slope=LRELU_SLOPE,
-                                        round_out=True)
-                    bias_grad(f"{name}.convs1.{m}", dt, c1.cout)
-                    wgrad(dt, ar, c1.shifts, gW[f"{name}.convs1.{m}"][0])
-                    G = ops.conv_dgrad(dt, W[f"{name}.convs1.{m}"][0], c1.shifts, gate=ar, gate_slope=LRELU_SLOPE,
-                                       residual=G, round_out=True)
+                with _Branches.branch(j, _Branches.n_gen):
+                    G = dyj
+                    for m in reversed(range(3)):
+                        c1, c2 = rb.convs1[m], rb.convs2[m]
+                        ar, t = stage["blocks"][j][m]
+                        bias_grad(f"{name}.convs2.{m}", G, c2.cout)
+                        wgrad(G, t, c2.shifts, gW[f"{name}.convs2.{m}"][0])
+                        dt = ops.conv_dgrad(G, W[f"{name}.convs2.{m}"][0], c2.shifts, gate=t, gate_slope=LRELU_SLOPE,
+                                            round_out=True)
+                        bias_grad(f"{name}.convs1.{m}", dt, c1.cout)
+                        wgrad(dt, ar, c1.shifts, gW[f"{name}.convs1.{m}"][0])
+                        G = ops.conv_dgrad(dt, W[f"{name}.convs1.{m}"][0], c1.shifts, gate=ar, gate_slope=LRELU_SLOPE,
+                                           residual=G, round_out=True)
                 dx_blocks.append(G)
+            _Branches.join()
             d_up = ops.sum3(dx_blocks[0], dx_blocks[1], dx_blocks[2])       # dL/d(ups[i] output), [B, u*Tin, cout]
             a = stage["a_in"]
             up = self.ups[i]
