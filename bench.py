@@ -46,13 +46,19 @@ def parse():
     return ap.parse_args()
 
 
+def graph_ok(args, world):
+    """One CUDA-graph replay per step: always on one GPU; with N > 1 only when XVA_BENCH_GRAPH_NCCL=1 asks for the
+    (not yet measured) capture of the NCCL all-reduces inside the graph -- the default multi-GPU step launches eagerly."""
+    return (world == 1 or os.environ.get("XVA_BENCH_GRAPH_NCCL") == "1") and not args.no_graph
+
+
 def config(args, world):
     return {"workload": f"FastPitch1.1 fine-tune stage {args.stage}, batch={args.batch}/GPU, 80-bin mel, {TM} frames/utt, "
                         f"{TT} tokens/utt, synthetic text+mel pairs (BASELINE.json configs[1])",
             "global_batch": args.batch * world, "frames_per_utt": TM, "tokens_per_utt": TT,
             "step": "forward + FastPitchLoss + backward + clip_grad_norm(1000) + LAMB, dropout 0.1 on, gam=1",
             "lengths": "ragged (valid frames counted)" if args.ragged else "every utterance at the maximum length",
-            "launch": "one CUDA-graph replay per step" if (world == 1 and not args.no_graph) else "eager launches",
+            "launch": "one CUDA-graph replay per step" if graph_ok(args, world) else "eager launches",
             "parallelism": f"dp{world}", "l2": "per-step working set (~5 GB of activations) exceeds the 126 MB L2; no flush"}
 
 
@@ -213,7 +219,7 @@ def run_hifigan(args, dev, world, rank, peak_tf32):
             dist.barrier()
         torch.cuda.synchronize()
 
-    use_graph = world == 1 and not args.no_graph
+    use_graph = graph_ok(args, world)
     capi.reset_launch_count()
     if use_graph:
         stepper.optim_g.lr_on_device = stepper.optim_d.lr_on_device = True
@@ -346,7 +352,7 @@ def run_native(args):
 
     # ---- CUDA-graph replay of the whole step (single-GPU; the multi-GPU step keeps NCCL outside a graph for now)
     eager_step = step
-    use_graph = (world == 1) and not args.no_graph
+    use_graph = graph_ok(args, world)
     launches_per_step = None
     if use_graph:
         tensor_idx = [i for i, t in enumerate(x_dev) if torch.is_tensor(t)]

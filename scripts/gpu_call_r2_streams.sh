@@ -29,3 +29,6 @@ done
 XVA_DISC_STREAMS=4 XVA_BWD_STREAMS=1 timeout 300 python scripts/bench_hifigan.py 16 10 > gpurun_out/r2_disc_streams_4_side.log 2>&1; tail -1 gpurun_out/r2_disc_streams_4_side.log | cut -c1-160
 XVA_GEN_STREAMS=1 timeout 300 python scripts/bench_hifigan.py 16 10 > gpurun_out/r2_gen_streams.log 2>&1; tail -1 gpurun_out/r2_gen_streams.log | cut -c1-160
 XVA_GEN_STREAMS=1 XVA_DISC_STREAMS=4 XVA_BWD_STREAMS=1 timeout 300 python scripts/bench_hifigan.py 16 10 > gpurun_out/r2_all_streams.log 2>&1; tail -1 gpurun_out/r2_all_streams.log | cut -c1-160
+# multi-GPU (run with gpurun --gpus 2): NCCL all-reduces captured inside the step graph
+#   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --no-cpu-baseline
+#   XVA_BENCH_GRAPH_NCCL=1 python -m torch.distributed.run ... (same line)
