@@ -114,3 +114,38 @@ def test_hifigan_handle_trainer_files(lib, tmp_path, monkeypatch):
     assert len(do["mpd"]) == 90 and len(do["msd"]) == 80
     graphs = json.load(open(out / "graphs.json"))
     assert len(graphs["stages"]["5"]["loss"]) == 1
+
+
+@pytest.mark.skipif(os.environ.get("XVA_TEST_EXPERIMENTAL") != "1",
+                    reason="voice-folder loader: host logic is covered by tests/test_wavdata_cpu.py; this end-to-end run has not "
+                           "been on a GPU yet (set XVA_TEST_EXPERIMENTAL=1)")
+def test_hifigan_trainer_on_a_voice_folder(lib, tmp_path, monkeypatch):
+    """HiFiTrainer on metadata.csv + wavs/ (hifigan/xva_train.py:309-325): crops assembled on the host, both mels per batch
+    on the device."""
+    import numpy as np
+    from scipy.io.wavfile import write as write_wav
+    from xva_trainer_b200 import trainers
+
+    voice = tmp_path / "voice"
+    (voice / "wavs").mkdir(parents=True)
+    rng = np.random.RandomState(1)
+    lines = []
+    for i in range(6):
+        n = int(rng.randint(6000, 40000))
+        t = np.arange(n) / 22050.0
+        x = (8000 * np.sin(2 * np.pi * (110 + 40 * i) * t) + 500 * rng.randn(n)).astype(np.int16)
+        write_wav(str(voice / "wavs" / f"u{i}.wav"), 22050, x)
+        lines.append(f"u{i}|line {i}")
+    (voice / "metadata.csv").write_text("\n".join(lines) + "\n")
+    monkeypatch.setenv("XVA_B200_MAX_EPOCHS", "1")
+    mm = trainers.ModelsManager(Log(), PROD=False)
+    ws = FakeSocket()
+    data = {"dataset_path": str(voice), "output_path": str(tmp_path / "out"), "hifigan_checkpoint": None, "num_workers": 0,
+            "batch_size": 3, "epochs_per_checkpoint": 1}
+    os.makedirs(tmp_path / "out", exist_ok=True)
+    res = asyncio.run(trainers.handleTrainerHiFi(mm, data, ws, [0]))
+    assert res == "done" and ws.sent == ["Set stage to: 5 ", "Finished training HiFi-GAN\n"]
+    log = open(tmp_path / "out" / "voice" / "training.log").read()
+    assert "Training items: 6 | Data multiplier: 167 | Not found: 0 | Total: 1002" in log
+    graphs = json.load(open(tmp_path / "out" / "voice" / "graphs.json"))
+    assert len(graphs["stages"]["5"]["loss"]) == 1 and np.isfinite(graphs["stages"]["5"]["loss"][0][1])

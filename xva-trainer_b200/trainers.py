@@ -507,6 +507,7 @@ class HiFiTrainer(_TrainerBase):
                 st = state_do[key]
                 opt.m.copy_(st["m"]); opt.v.copy_(st["v"]); opt.steps = int(st["steps"]); opt.step_dev.fill_(opt.steps)
         self.lr = h.learning_rate * (h.lr_decay ** self.epoch)                        # ExponentialLR per epoch (:306-307)
+        self.wav_segments = None
         if self.batch_source is not None:
             self.batches = list(self.batch_source)
         elif str(self.dataset_input).startswith("synthetic:"):
@@ -519,14 +520,33 @@ class HiFiTrainer(_TrainerBase):
             for _ in range(max(1, items // B)):
                 y = (0.95 * torch.tanh(torch.randn(B, frames * h.hop_size, generator=g) * 0.3)).to(self.device)
                 self.batches.append((mel_in(y).transpose(1, 2).contiguous(), y, mel_loss(y).transpose(1, 2).contiguous()))
+        elif os.path.isfile(os.path.join(str(self.dataset_input), "metadata.csv")):
+            # a voice folder (metadata.csv + wavs/): hifigan/xva_train.py:309-325 with the crops assembled on the host and
+            # both mel spectrograms computed per batch on the device (wavdata.py)
+            from . import hifigan as _hg, wavdata
+            files, not_found, dm = wavdata.get_dataset_filelist(f"{self.dataset_input}/metadata.csv", f"{self.dataset_input}/wavs")
+            self.print_and_log(f"Training items: {int(len(files) / dm)} | Data multiplier: {dm} | Not found: {not_found} | "
+                               f"Total: {len(files)}", save_to_file=self.dataset_output)                      # :313
+            self.wav_segments = wavdata.WavSegments(files, h.segment_size, h.sampling_rate)
+            self.mel_extractors = (_hg.MelSpectrogram(fmax=h.fmax, device=self.device),
+                                   _hg.MelSpectrogram(fmax=h.fmax_for_loss, device=self.device))
+            self.batches = self._wav_epoch()
         else:
-            raise NotImplementedError("wav dataset loading is outside this build (SURVEY.md section 2 row 13): pass "
-                                      "data['batch_source'] or dataset_path='synthetic:BxFRAMESxITEMS'")
+            raise NotImplementedError("dataset_path must be a voice folder (metadata.csv + wavs/), 'synthetic:BxFRAMESxITEMS', "
+                                      "or pass data['batch_source']")
         self.graphs_json["stages"]["5"]["target_delta"] = 0.0002
         await self._send("Set stage to: 5 ")
         self.batch_pos, self.iter_losses = 0, []
         self.avg_loss_per_epoch.append(0.0)
         self.is_init = True
+
+    def _wav_epoch(self):
+        """One epoch of batches from the voice folder: fresh permutation, fresh random crops (meldataset.py:358-362)."""
+        bs = int(self.h.batch_size)                                                   # DataLoader(batch_size=h.batch_size), :321
+        batches = list(self.wav_segments.batches(bs, self.device, *self.mel_extractors))
+        if not batches:
+            raise ValueError(f"batch size {bs} exceeds the {len(self.wav_segments)} training items")
+        return batches
 
     async def iteration(self):
         if not self.is_init:
@@ -536,6 +556,8 @@ class HiFiTrainer(_TrainerBase):
             self.finish_epoch()
             self.avg_loss_per_epoch.append(0.0)
             self.iter_losses = []
+            if getattr(self, "wav_segments", None) is not None:
+                self.batches = self._wav_epoch()
         x, y, y_mel = self.batches[self.batch_pos]
         self.batch_pos += 1
         t0 = time.perf_counter()
