@@ -21,3 +21,14 @@ def test_beta_binomial_prior_matches_scipy(P, M, scale):
     # rows are the pmf over 0..P (P + 1 outcomes) evaluated at 0..P-1: they sum to 1 minus the mass of outcome P
     tail = np.array([betabinom(P, scale * i, scale * (M + 1 - i)).pmf(P) for i in range(1, M + 1)])
     np.testing.assert_allclose(got.double().sum(1).numpy(), 1.0 - tail, rtol=1e-4, atol=1e-6)
+
+
+def test_target_delta_table_follows_the_reference():
+    """get_target_delta, xva_train.py:588-672: spot values computed by hand from the reference's branches."""
+    from xva_trainer_b200.trainers import get_target_delta as d
+
+    assert d(1, 5000) == 2e-5 and d(1, 3000) == 15e-5 and d(1, 1000) == 4e-4 and d(1, 100) == 4e-4 and d(1, 500) == 0
+    assert d(2, 5000) == 5e-5 * 1.5 and d(2, 3000) == 1e-4 * 1.5 and d(2, 1000) == 5e-4 * 1.5 and d(2, 499) == 4e-3 * 1.5
+    assert d(3, 5000) == 5e-5 * 2.5 and d(3, 1000) == 6e-4 * 2.5 and d(3, 300) == 1e-3 * 2.5 and d(3, 100) == 2e-3 * 2.5
+    assert d(4, 5000) == 35e-6 * 3 and d(4, 3000) == 1e-4 * 3 and d(4, 1000) == 25e-5 * 3 and d(4, 300) == 45e-5 * 3
+    assert d(4, 100) == 15e-4 * 3

@@ -56,6 +56,35 @@ def beta_binomial_prior_distribution(phoneme_count, mel_count, scaling_factor=1.
     return torch.exp(lg(n + 1) - lg(k + 1) - lg(n - k + 1) + log_beta(k + a, n - k + b) - log_beta(a, b)).float()
 
 
+def get_target_delta(training_stage, num_data_lines):
+    """FastPitchTrainer.get_target_delta, xva_train.py:588-672: the relative loss improvement per epoch below which a
+    training stage counts as converged, by stage and dataset size (the thresholds and multipliers are the reference's;
+    its first two stage-1 branches test the same bound, so 5e-5 is unreachable there as well). The parameter freezing the
+    reference does in the same function is trainable_keys(stage) here."""
+    n = num_data_lines
+    if training_stage == 1:
+        delta = 2e-5 if n > 4000 else 15e-5 if n > 2000 else 4e-4 if n > 500 else 0
+        if n < 500:
+            delta = 4e-4
+        return delta
+    if training_stage == 2:
+        delta = 5e-5 if n > 4000 else 1e-4 if n > 2000 else 5e-4
+        if n < 500:
+            delta = 4e-3
+        return delta * 1.5
+    if training_stage == 3:
+        delta = 5e-5 if n > 4000 else 1e-4 if n > 2000 else 6e-4
+        if n < 500:
+            delta = 2e-3 if n < 250 else 1e-3
+        return delta * 2.5
+    if training_stage == 4:
+        delta = 35e-6 if n > 4000 else 1e-4 if n > 2000 else 25e-5
+        if n < 500:
+            delta = 15e-4 if n < 250 else 45e-5
+        return delta * 1.5 * 2
+    return 0
+
+
 def _synthetic_fastpitch_batches(spec, device, seed=1234):
     """'synthetic:BxTtxTmxitems[:prior]' -> list of (x, y, num_frames) in the layout of batch_to_gpu
     (data_function.py:706-741). With ':prior' every batch carries the beta-binomial alignment prior (x[7]) and a run
@@ -158,7 +187,6 @@ class FastPitchTrainer(_TrainerBase):
     when stage 1 ends, the durations of every batch are replaced by the aligner's (the in-memory equivalent of the
     reference's duration extraction to durs_arpabet/*.npy, xva_train.py:1128-1160)."""
 
-    TARGET_DELTAS = {1: 0.0004, 2: 0.0005, 3: 0.0005, 4: 0.0003}   # order of magnitude of get_target_delta (xva_train.py:589-672)
     KL_LOSS_START_EPOCH, KL_LOSS_WARMUP_EPOCHS, KL_LOSS_WEIGHT = 0, 100, 1.0    # xva_train.py:706-708
 
     def __init__(self, logger, PROD, gpus, models_manager, websocket=None):
@@ -222,7 +250,8 @@ class FastPitchTrainer(_TrainerBase):
         if stage == 1 and not has_prior:
             raise ValueError("training stage 1 needs batches that carry the alignment prior (inputs_x[7])")
         self.model.training_stage = self.criterion.training_stage = stage
-        self.target_delta = self.TARGET_DELTAS.get(stage, 0.0005)
+        num_data_lines = sum(int(b[0][0].shape[0]) for b in self.batches)           # utterances in the dataset (:380)
+        self.target_delta = get_target_delta(stage, num_data_lines)
         self.graphs_json["stages"][str(stage)]["target_delta"] = self.target_delta
         await self._send(f"Set stage to: {stage} ")
         mult = {1: 1.5, 2: 12, 3: 3.5, 4: 4}.get(stage, 1)                         # stage batch multipliers (:387-404)
