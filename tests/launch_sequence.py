@@ -18,7 +18,32 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden", "launch_sequence.json")
 
 
-def record():
+class _FakeStream:
+    """Stand-in for torch.cuda.Stream in the host-only dry run of the stream experiments."""
+    waits = 0
+
+    def __init__(self, *a, **k):
+        pass
+
+    def wait_stream(self, other):
+        _FakeStream.waits += 1
+
+    def synchronize(self):
+        pass
+
+
+class _NullCtx:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+def record(streams=False):
+    """streams=True: the same steps with the (off by default) multi-stream experiments switched on -- XVA_BWD_STREAMS,
+    XVA_DISC_STREAMS, XVA_GEN_STREAMS -- and torch's CUDA stream API replaced by stand-ins: Python issues the launches in
+    the same order whatever stream they go to, so the sequence must not change."""
     if ROOT not in sys.path:
         sys.path.insert(0, ROOT)
     import torch
@@ -48,8 +73,17 @@ def record():
         return None if a is None else "ptr"
 
     saved = (capi.load, capi.call, ops._stream, ops._check3, ops.duration_scan)
+    saved_cuda = (torch.cuda.Stream, torch.cuda.stream, torch.cuda.current_stream, getattr(torch.Tensor, "record_stream", None))
+    saved_env = {k: os.environ.get(k) for k in ("XVA_BWD_STREAMS", "XVA_DISC_STREAMS", "XVA_GEN_STREAMS")}
     Tm = 40
     try:
+        if streams:
+            os.environ.update(XVA_BWD_STREAMS="1", XVA_DISC_STREAMS="4", XVA_GEN_STREAMS="1")
+            torch.cuda.Stream = _FakeStream
+            torch.cuda.stream = lambda s: _NullCtx()
+            torch.cuda.current_stream = lambda *a, **k: _FakeStream()
+            torch.Tensor.record_stream = lambda self, s: None
+            _FakeStream.waits = 0
         capi.load = lambda: types.SimpleNamespace(xva_attn_ctc_workspace_bytes=lambda B, T, Tt: 2 * B * T * (2 * Tt + 1) * 8 + B * 8 + (B * T * 4 + 7) // 8 * 8)
         capi.call = lambda name, *a: seq.append([name, [ser(x) for x in a]])
         ops._stream = lambda: None
@@ -111,6 +145,17 @@ def record():
         hg.HiFiGANStep(G, mpd, msd, h).step(xx, yy, y_mel)
     finally:
         capi.load, capi.call, ops._stream, ops._check3, ops.duration_scan = saved
+        torch.cuda.Stream, torch.cuda.stream, torch.cuda.current_stream = saved_cuda[:3]
+        if saved_cuda[3] is not None:
+            torch.Tensor.record_stream = saved_cuda[3]
+        for k, v in saved_env.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    if streams:
+        assert fp.FastPitch  # (modules were loaded with the experiments on)
+        assert _FakeStream.waits > 100, "the stream experiments were not active in the dry run"
     return seq
 
 

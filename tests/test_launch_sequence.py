@@ -16,3 +16,11 @@ def test_host_code_emits_the_gpu_validated_launch_sequence():
             f"launch sequence changed: {got['calls']} calls (validated: {want['calls']}); first differing entry point at call "
             f"{first}; first differing 50-call chunk {bad_chunk} (calls {None if bad_chunk is None else bad_chunk * 50}..). "
             "If the change is intended, re-run the GPU parity suite and then `python tests/launch_sequence.py --write`.")
+
+
+def test_stream_experiments_do_not_change_any_launch():
+    """XVA_BWD_STREAMS / XVA_DISC_STREAMS / XVA_GEN_STREAMS (off by default) only choose the stream a
+    launch goes to: with all three on, every entry point and every argument is the same as in the validated sequence."""
+    want = json.load(open(GOLDEN))
+    got = fingerprint(record(streams=True))
+    assert got["calls"] == want["calls"] and got["sha256"] == want["sha256"]
