@@ -114,6 +114,28 @@ def generator(sd, mel):
     return torch.tanh(x)
 
 
+def generator_vits(sd, z, g=None):
+    """HifiganGenerator.forward of the xVAPitch model (python/xvapitch/hifigan.py:234-262, configured at
+    xvapitch/model.py:134-149: 192 latent channels in, plain -- not weight-normed -- conv_pre and conv_post, no conv_post
+    bias, speaker conditioning cond_layer 512 -> 512 added after conv_pre). Groundwork for SURVEY.md section 8f rank 1:
+    apart from the input width and the per-utterance conditioning vector it is Generator.forward above -- same
+    transposed convolutions, same ResBlock1 stacks (xvapitch/hifigan.py:29-103), same MRF mean, same slopes -- so the
+    generator kernels carry over. z [B, 192, T], g [B, 512, 1] or None -> [B, 1, 256 T]."""
+    x = F.conv1d(z, sd["conv_pre.weight"], sd["conv_pre.bias"], padding=3)
+    if g is not None:
+        x = x + F.conv1d(g, sd["cond_layer.weight"], sd["cond_layer.bias"])
+    for i, (u, k) in enumerate(zip(UP_RATES, UP_KERNELS)):
+        x = F.leaky_relu(x, LRELU_SLOPE)
+        x = F.conv_transpose1d(x, wn_weight(sd, f"ups.{i}"), sd[f"ups.{i}.bias"], stride=u, padding=(k - u) // 2)
+        xs = None
+        for j, rk in enumerate(RB_KERNELS):
+            r = resblock1(x, sd, f"resblocks.{i * 3 + j}", rk, RB_DILATIONS[j])
+            xs = r if xs is None else xs + r
+        x = xs / len(RB_KERNELS)
+    x = F.leaky_relu(x)
+    return torch.tanh(F.conv1d(x, sd["conv_post.weight"], None, padding=3))
+
+
 # ------------------------------------------------------------------------------------------------ mel spectrogram
 def _hz_to_mel(f):
     f = np.asanyarray(f, dtype=np.float64)
