@@ -32,3 +32,10 @@ XVA_GEN_STREAMS=1 XVA_DISC_STREAMS=4 XVA_BWD_STREAMS=1 timeout 300 python script
 # multi-GPU (run with gpurun --gpus 2): NCCL all-reduces captured inside the step graph
 #   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --no-cpu-baseline
 #   XVA_BENCH_GRAPH_NCCL=1 python -m torch.distributed.run ... (same line)
+# warm-cache captures of the two sequential stage-1 kernels (the round-1 captures flushed the caches between replays)
+for k in ctc_recursion mas; do
+  timeout 200 ncu --set full --clock-control none --cache-control none --import-source on -k regex:${k}_kernel -s 2 -c 1 -f -o gpurun_out/r2_warm_$k python scripts/bench_stage1.py 1 --no-cpu > gpurun_out/r2_prof_warm_$k.log 2>&1
+done
+# voice-folder loader end to end (gated test) -- ungate it in tests/test_trainers_gpu.py once green
+(XVA_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_trainers_gpu.py -m gpu -q -k voice_folder 2>&1 | tail -15) > gpurun_out/r2_voice_folder.log
+tail -3 gpurun_out/r2_voice_folder.log
