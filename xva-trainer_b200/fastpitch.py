@@ -195,7 +195,7 @@ class FastPitch(torch.nn.Module):
         # their SMs for the other kernel instead of idling until the launch ends.
         self.bwd_streams = os.environ.get("XVA_BWD_STREAMS", "0") == "1"
         self._side = torch.cuda.Stream(device=dev) if self.bwd_streams else None
-        self._side_keep = []
+        self._side_used = False
         self.seed = int(seed)
         self.step_counter = torch.zeros(1, device=dev, dtype=torch.int64)  # device-side dropout counter (uint64 bits)
         self._site = 0
@@ -378,19 +378,23 @@ class FastPitch(torch.nn.Module):
 
     def _wgrad_side(self, fn, *inputs):
         """Run ``fn`` (weight / bias gradient launches) on the side stream when the two-stream backward is on. ``inputs``
-        are kept alive until _join_side(): the caching allocator must not hand their memory to a main-stream kernel while
-        the side stream still reads it."""
+        are record_stream()-ed: the caching allocator does not hand their memory to a main-stream kernel before the side
+        stream is done with it (inside a graph capture such blocks are simply not reused). The main stream does not wait
+        for the side stream until the gradients are consumed (_join_side)."""
         if self._side is None:
             return fn()
         self._side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self._side):
             fn()
-        self._side_keep.extend(inputs)
+        for t in inputs:
+            t.record_stream(self._side)
+        self._side_used = True
 
     def _join_side(self):
-        if self._side is not None and self._side_keep:
+        """Before anything reads the gradient arena from the main stream: GradSync.ready, the end of backward()."""
+        if self._side is not None and self._side_used:
             torch.cuda.current_stream().wait_stream(self._side)
-            self._side_keep.clear()
+            self._side_used = False
 
     def _layer_bwd(self, dy, lens, L, c, need_dx=True):
         sd = self.step_counter
@@ -441,9 +445,7 @@ class FastPitch(torch.nn.Module):
             ops.colsum_(B * T, 3 * D_HEAD, 3 * D_HEAD, dqkv, L.g.qkv_b)
 
         self._wgrad_side(qkv_grads, dqkv)
-        dx = ops.conv_dgrad(dqkv, L.w.qkv_w, residual=dx1) if need_dx else None
-        self._join_side()      # the layer's gradient slice is final (GradSync.ready / LAMB read it from the main stream)
-        return dx
+        return ops.conv_dgrad(dqkv, L.w.qkv_w, residual=dx1) if need_dx else None
 
     # ------------------------------------------------------------------------------------------ temporal predictor
     def _pred_fwd(self, x, lens, P, save):
@@ -702,7 +704,11 @@ class FastPitch(torch.nn.Module):
         ctx = self._ctx
         if grad_sync is not None:
             scale = scale * grad_sync.loss_scale
-        ready = (lambda *p, flush=False: grad_sync.ready(list(p), flush)) if grad_sync is not None else (lambda *p, flush=False: None)
+        def ready(*prefixes, flush=False):
+            if grad_sync is not None:
+                self._join_side()          # the slice must be final on the stream the all-reduce is ordered after
+                grad_sync.ready(list(prefixes), flush)
+
         if ctx is None:
             raise RuntimeError("backward() needs a forward() in training mode first")
         stage = ctx.stage
@@ -740,6 +746,7 @@ class FastPitch(torch.nn.Module):
                 ready(f"encoder.layers.{N_LAYERS - 1 - i}")
         ops.embed_bwd_(ctx.tokens, d_enc, self.g.emb)
         ready("encoder.layers.0", "encoder.word_emb", flush=True)
+        self._join_side()
         self._ctx = None
 
     def step_dropout(self):
