@@ -386,9 +386,11 @@ def _leaves(sd):
     return {k: (v if is_buf(k, v) else v.detach().requires_grad_(True)) for k, v in sd.items()}
 
 
-def train_step(sd_g, sd_mpd, sd_msd, x, y, y_mel, opt_state, lr=2e-4):
+def train_step(sd_g, sd_mpd, sd_msd, x, y, y_mel, opt_state, lr=2e-4, detail=None):
     """HiFiTrainer.iteration body, xva_train.py:467-515. Updates the three state dicts in place (including the
-    spectral-norm u / v buffers: four power iterations per step, two per msd call). Returns the loss terms."""
+    spectral-norm u / v buffers: four power iterations per step, two per msd call). Returns the loss terms. ``detail``
+    (a dict) additionally receives every loss term, the generated waveform and the D-step parameter gradients
+    ({"mpd": {key: grad}, "msd": {key: grad}}) -- what tests/golden/hifigan_step.npz records from the reference."""
     y = y.unsqueeze(1) if y.dim() == 2 else y
     lg, lp, ls = _leaves(sd_g), _leaves(sd_mpd), _leaves(sd_msd)
     sn_state = {}
@@ -405,6 +407,11 @@ def train_step(sd_g, sd_mpd, sd_msd, x, y, y_mel, opt_state, lr=2e-4):
     with torch.no_grad():
         adamw_step({("s" if s is ls else "p", k): (sd_msd if s is ls else sd_mpd)[k] for s, k in d_keys},
                    {("s" if s is ls else "p", k): g for (s, k), g in zip(d_keys, d_grads)}, opt_state.setdefault("d", {}), lr)
+    if detail is not None:
+        detail["dgrad"] = {"msd": {}, "mpd": {}}
+        for (s_, k), g_ in zip(d_keys, d_grads):
+            detail["dgrad"]["msd" if s_ is ls else "mpd"][k] = g_
+        detail["y_g_hat"] = y_g_hat.detach()
     # G step (discriminators now hold the updated weights; fresh leaves)
     lp, ls = _leaves(sd_mpd), _leaves(sd_msd)
     loss_mel = F.l1_loss(y_mel, y_g_hat_mel) * 45
@@ -415,6 +422,11 @@ def train_step(sd_g, sd_mpd, sd_msd, x, y, y_mel, opt_state, lr=2e-4):
     loss_gen_all = loss_gen_s + loss_gen_f + loss_fm_s + loss_fm_f + loss_mel
     g_keys = [k for k, v in lg.items()]
     g_grads = torch.autograd.grad(loss_gen_all, [lg[k] for k in g_keys])
+    if detail is not None:
+        detail["loss"] = {"loss_disc_f": loss_disc_f, "loss_disc_s": loss_disc_s, "loss_disc_all": loss_disc_all,
+                          "loss_mel": loss_mel, "loss_fm_f": loss_fm_f, "loss_fm_s": loss_fm_s, "loss_gen_f": loss_gen_f,
+                          "loss_gen_s": loss_gen_s, "loss_gen_all": loss_gen_all}
+        detail["loss"] = {k: float(v.detach()) for k, v in detail["loss"].items()}
     with torch.no_grad():
         adamw_step({k: sd_g[k] for k in g_keys}, dict(zip(g_keys, g_grads)), opt_state.setdefault("g", {}), lr)
         for k in sd_msd:        # persist the power-iteration vectors like the module buffers do
