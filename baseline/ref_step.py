@@ -316,7 +316,6 @@ def eager_b200(device="cuda:0", batch=32, stage=3, steps=10, warmup=3, hifigan=T
 def amp_error_table(device="cuda:0", B=4, Tt=40, Tm=150, stage=3):
     """How far the reference's OWN reduced-precision modes are from its strict-fp32 result on identical weights and
     inputs (dropout off): relative L2 error of mel_out, the losses and every parameter gradient."""
-    g = torch.Generator().manual_seed(11)
     x = fastpitch_batch(B, Tt, Tm, seed=11)
     x = _to(x, device)
     base = FastPitchRef(device, stage, "fp32_strict", dropout=False)
@@ -328,12 +327,13 @@ def amp_error_table(device="cuda:0", B=4, Tt=40, Tm=150, stage=3):
         y_pred, loss, meta = r.fwd_bwd(x)
         inv = 1.0 / r.scaler.get_scale() if r.amp else 1.0
         grads = {k: (p.grad.detach().double() * inv) for k, p in r.model.named_parameters() if p.grad is not None}
-        cur = {"mel_out": y_pred[0].detach().double(), "loss": loss.detach().double(),
-               "pitch_pred": y_pred[4].detach().double(), "energy_pred": y_pred[6].detach().double(), "grads": grads}
+        d = lambda t: None if t is None else t.detach().double()
+        cur = {"mel_out": d(y_pred[0]), "loss": d(loss), "pitch_pred": d(y_pred[4]), "energy_pred": d(y_pred[6]),
+               "grads": grads}
         if ref_out is None:
             ref_out = cur
             continue
-        rel = lambda a, b: float((a - b).norm() / b.norm().clamp_min(1e-30))
+        rel = lambda a, b: float("nan") if a is None or b is None else float((a - b).norm() / b.norm().clamp_min(1e-30))
         ge = {k: rel(v, ref_out["grads"][k]) for k, v in grads.items() if float(ref_out["grads"][k].norm()) > 0}
         num = sum(float((v - ref_out["grads"][k]).pow(2).sum()) for k, v in grads.items())
         den = sum(float(v.pow(2).sum()) for v in ref_out["grads"].values())

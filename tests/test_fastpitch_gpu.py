@@ -29,7 +29,10 @@ from oracle import fastpitch as ofp
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
-FWD_TOL, LOSS_TOL, GRAD_TOL, GRAD_GLOBAL_TOL = 2e-3, 1e-3, 5e-2, 2e-2
+# <= 2x the values measured on B200 at this shape (profiles/r02_parity_table.txt, 'toy 4x40x150'): forward tensors
+# <= 1.19e-3 (energy_pred), dur_pred 2.6e-3, losses <= 1.2e-4, gradients worst tensor 3.4e-2 (encoder.word_emb: a handful of
+# rows), global 9.0e-3. At the BASELINE shape every figure is 3-6x smaller (tests/test_parity_full_gpu.py).
+FWD_TOL, LOSS_TOL, GRAD_TOL, GRAD_GLOBAL_TOL = 2e-3, 2.4e-4, 5e-2, 1.8e-2
 
 
 def rel(a, b):
@@ -94,7 +97,7 @@ def test_step_matches_oracle(lib, stage, ragged):
         if w_.dtype == torch.bool:
             assert torch.equal(g_.cpu(), w_), n
         else:
-            tol = {"pitch_tgt": 1e-5, "energy_tgt": 1e-5, "mel_out": 1e-3, "dur_pred": 6e-3}.get(n, FWD_TOL)
+            tol = {"pitch_tgt": 1e-5, "energy_tgt": 1e-5, "mel_out": 1e-3, "dur_pred": 5.2e-3}.get(n, FWD_TOL)
             assert rel(g_, w_) < tol, (n, rel(g_, w_))
 
     opt_state = {}
@@ -258,11 +261,9 @@ def test_dropout_training_step_is_finite_and_replays(lib):
     assert rel(g3, g1) > 1e-2
 
 
-@pytest.mark.skipif(os.environ.get("XVA_TEST_EXPERIMENTAL") != "1",
-                    reason="two-stream backward is an unmeasured experiment (DESIGN.md section 7); set XVA_TEST_EXPERIMENTAL=1")
 def test_two_stream_backward_gives_the_same_gradients(lib, monkeypatch):
-    """XVA_BWD_STREAMS=1 issues the FFT-block weight gradients on a side stream; the gradient arena must come out the
-    same (to the rounding of the fp32 atomics the split weight gradient already uses)."""
+    """XVA_BWD_STREAMS=1 (the default inside a captured graph) issues the FFT-block weight gradients on a side stream; the
+    gradient arena must come out the same (to the rounding of the fp32 atomics the split weight gradient already uses)."""
     B, Tt, Tm = 3, 32, 100
     x, y = ofp.synthetic_batch(B, Tt, Tm, seed=5)
     cx, cy = _cuda_batch(x, y)
@@ -270,7 +271,7 @@ def test_two_stream_backward_gives_the_same_gradients(lib, monkeypatch):
     for flag in ("0", "1"):
         monkeypatch.setenv("XVA_BWD_STREAMS", flag)
         fp, m = _model(lib, ofp.make_state(99), 3)
-        assert m.bwd_streams == (flag == "1")
+        assert m._side_on() == (flag == "1")
         crit = fp.FastPitchLoss()
         for _ in range(2):
             out = m(cx)

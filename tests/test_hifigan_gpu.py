@@ -351,13 +351,13 @@ def test_full_hifigan_step_matches_oracle(lib):
         assert moved >= len(ref) * 0.9, (name, moved, len(ref))
 
 
-@pytest.mark.skipif(os.environ.get("XVA_TEST_EXPERIMENTAL") != "1",
-                    reason="two-stream backward is an unmeasured experiment (DESIGN.md section 7); set XVA_TEST_EXPERIMENTAL=1")
 @pytest.mark.parametrize("mode", ["side_stream", "disc_branches", "gen_branches", "all"])
 def test_two_stream_backward_gives_the_same_step(lib, mode):
-    """hifigan._Side (XVA_BWD_STREAMS=1): weight / bias gradients on a side stream; hifigan._Branches
-    (XVA_DISC_STREAMS=n / XVA_GEN_STREAMS=1): sub-discriminators / the ResBlocks of an MRF stage on parallel streams. The same training step from the same state must
-    produce the same losses and (to the rounding of the fp32 atomics) the same updated weights."""
+    """hifigan._Side (XVA_BWD_STREAMS): weight / bias gradients on a side stream; hifigan._Branches (XVA_DISC_STREAMS /
+    XVA_GEN_STREAMS): sub-discriminators / the ResBlocks of an MRF stage on parallel streams -- all three are the default
+    inside a captured graph. The same two training steps from the same state must produce the same losses and the same
+    updated weights up to the order of the fp32 atomic additions of the split weight gradients, which the streams
+    change: measured 1.1e-5 on a loss of the second step (B200, profiles/r02_streams_ab.txt), bound 1e-4."""
     from xva_trainer_b200 import hifigan as hg
 
     h = _config()
@@ -368,7 +368,7 @@ def test_two_stream_backward_gives_the_same_step(lib, mode):
     was = (hg._Side.enabled, hg._Branches.n, hg._Branches.n_gen)
     try:
         for flag in (False, True):
-            hg._Side.enabled = flag and mode in ("side_stream", "all")
+            hg._Side.enabled = bool(flag and mode in ("side_stream", "all"))
             hg._Branches.n = 4 if (flag and mode in ("disc_branches", "all")) else 0
             hg._Branches.n_gen = 3 if (flag and mode in ("gen_branches", "all")) else 0
             G = _generator(lib, ohg.make_generator_state(5, scale=0.7))
@@ -384,7 +384,7 @@ def test_two_stream_backward_gives_the_same_step(lib, mode):
         hg._Side.enabled, hg._Branches.n, hg._Branches.n_gen = was
     (l0, s0), (l1, s1) = results
     for k in l0:
-        assert abs(l0[k] - l1[k]) <= 1e-5 * abs(l0[k]) + 1e-7, (k, l0[k], l1[k])
+        assert abs(l0[k] - l1[k]) <= 1e-4 * abs(l0[k]) + 1e-7, (k, l0[k], l1[k])
     # weights after two AdamW steps: an entry whose gradient is within atomic-order rounding of zero moves by +-lr in
     # either run (the first AdamW steps are sign-like), so the bound is the one the oracle comparison above uses, not
     # rounding (measured on B200, side_stream mode: losses equal to 1e-5, worst tensor 1.3e-4)

@@ -116,9 +116,6 @@ def test_hifigan_handle_trainer_files(lib, tmp_path, monkeypatch):
     assert len(graphs["stages"]["5"]["loss"]) == 1
 
 
-@pytest.mark.skipif(os.environ.get("XVA_TEST_EXPERIMENTAL") != "1",
-                    reason="voice-folder loader: host logic is covered by tests/test_wavdata_cpu.py; this end-to-end run has not "
-                           "been on a GPU yet (set XVA_TEST_EXPERIMENTAL=1)")
 def test_hifigan_trainer_on_a_voice_folder(lib, tmp_path, monkeypatch):
     """HiFiTrainer on metadata.csv + wavs/ (hifigan/xva_train.py:309-325): crops assembled on the host, both mels per batch
     on the device."""
@@ -149,3 +146,110 @@ def test_hifigan_trainer_on_a_voice_folder(lib, tmp_path, monkeypatch):
     assert "Training items: 6 | Data multiplier: 167 | Not found: 0 | Total: 1002" in log
     graphs = json.load(open(tmp_path / "out" / "voice" / "graphs.json"))
     assert len(graphs["stages"]["5"]["loss"]) == 1 and np.isfinite(graphs["stages"]["5"]["loss"][0][1])
+
+
+# ------------------------------------------------------------------------------------------------ round-1 advisor findings
+def _fp_data(tmp_path, spec="synthetic:4x24x64x16", **kw):
+    d = {"dataset_path": spec, "output_path": str(tmp_path), "checkpoint": None, "num_workers": 0, "batch_size": 64,
+         "epochs_per_checkpoint": 1, "force_stage": None}
+    d.update(kw)
+    return d
+
+
+def test_fastpitch_base_checkpoint_is_only_the_starting_point(lib, tmp_path, monkeypatch):
+    """xva_train.py:284-288 + :380-385: a user-supplied base checkpoint seeds a run whose output folder is empty ("New
+    voice": stage and iteration restart, weights kept); after that the run's own newest checkpoint wins, so the stages
+    advance 2 -> 3 -> 4 instead of reloading the base (and its stage) at every stage change."""
+    from xva_trainer_b200 import trainers
+
+    monkeypatch.setenv("XVA_B200_MAX_EPOCHS", "1")
+    mm = trainers.ModelsManager(Log(), PROD=False)
+    res = asyncio.run(trainers.handleTrainer(mm, _fp_data(tmp_path / "a"), FakeSocket(), [0]))
+    assert res == "move to hifi"
+    a = tmp_path / "a" / "synthetic_4x24x64x16"
+    base = [n for n in os.listdir(a) if n.startswith("Stage_2_DONE_")]
+    assert len(base) == 1
+    base_ck = torch.load(a / base[0], map_location="cpu")
+    assert base_ck["training_stage"] == 3
+    ws = FakeSocket()
+    data = _fp_data(tmp_path / "b", spec="synthetic:4x24x64x32", checkpoint=str(a / base[0]))
+    res = asyncio.run(trainers.handleTrainer(mm, data, ws, [0]))
+    assert res == "move to hifi"
+    assert ws.sent == ["Set stage to: 2 ", "Set stage to: 3 ", "Set stage to: 4 "]
+    log = open(tmp_path / "b" / "synthetic_4x24x64x32" / "training.log").read()
+    assert log.count("New voice") == 1 and log.count(f"Checkpoint: {a / base[0]}") == 1
+    # a finished run on disk (training_stage 5) goes straight on to the vocoder (:356-359); so does force_stage 5
+    ws2 = FakeSocket()
+    assert asyncio.run(trainers.handleTrainer(mm, data, ws2, [0])) == "move to hifi"
+    assert ws2.sent == []
+    ws3 = FakeSocket()
+    d3 = _fp_data(tmp_path / "c", force_stage=5)
+    assert asyncio.run(trainers.handleTrainer(mm, d3, ws3, [0])) == "move to hifi" and ws3.sent == []
+
+
+def test_fastpitch_nan_batch_is_skipped_before_the_update(lib, tmp_path, monkeypatch):
+    """xva_train.py:825-832: a non-finite micro-batch is dropped BEFORE the optimizer step -- weights, LAMB moments and the
+    tf32 weight copy never see it."""
+    from xva_trainer_b200 import trainers
+
+    monkeypatch.setenv("XVA_B200_MAX_EPOCHS", "1")
+    batches = trainers._synthetic_fastpitch_batches("synthetic:4x24x64x16", torch.device("cuda:0"))
+    assert len(batches) == 4
+    batches[1][0][2][0, 3, 5] = float("nan")          # one NaN in the mel target of the second batch
+    mm = trainers.ModelsManager(Log(), PROD=False)
+    seen = {}
+    orig = trainers.FastPitchTrainer.finish_epoch
+
+    def spy(self):
+        A = self.model.arena
+        seen.setdefault("finite", []).append(bool(torch.isfinite(A.p).all() and torch.isfinite(A.m).all()
+                                                  and torch.isfinite(A.v).all() and torch.isfinite(A.w).all()))
+        seen["steps"] = self.optimizer.steps
+        return orig(self)
+
+    monkeypatch.setattr(trainers.FastPitchTrainer, "finish_epoch", spy)
+    data = _fp_data(tmp_path, force_stage=3, batch_source=batches)
+    with pytest.raises(RuntimeError):
+        # force_stage stays 3 for every re-entry of this hand-driven call: stop after the first stage
+        asyncio.run(_one_stage(trainers, mm, data))
+    assert seen["finite"] and all(seen["finite"])
+    assert seen["steps"] == 3                          # 4 batches, gam = 1, one skipped
+    log = open(tmp_path / "synthetic_4x24x64x16" / "training.log").read()
+    assert log.count("loss is NaN") == 1
+
+
+async def _one_stage(trainers, mm, data):
+    trainer = mm.sync_init_model("fastpitch1_1", websocket=None, gpus=[0])
+    await trainer.start(data, gpus=[0])
+
+
+def test_hifigan_optimizer_state_is_torch_adamw_format_and_resumes(lib, tmp_path, monkeypatch):
+    """do_ checkpoints carry optim_g / optim_d in torch.optim.AdamW's state_dict layout (hifigan/xva_train.py:583-584): a
+    stock AdamW over parameters of the same shapes loads them, and a second run resumes from them."""
+    from xva_trainer_b200 import trainers
+
+    monkeypatch.setenv("XVA_B200_MAX_EPOCHS", "1")
+    mm = trainers.ModelsManager(Log(), PROD=False)
+    data = {"dataset_path": "synthetic:2x8x4", "output_path": str(tmp_path), "hifigan_checkpoint": None, "num_workers": 0,
+            "batch_size": 2, "epochs_per_checkpoint": 1}
+    assert asyncio.run(trainers.handleTrainerHiFi(mm, data, FakeSocket(), [0])) == "done"
+    hifi = tmp_path / "synthetic_2x8x4" / "hifi"
+    do_name = sorted(n for n in os.listdir(hifi) if n.startswith("do_"))[-1]
+    do = torch.load(hifi / do_name, map_location="cpu")
+    g = torch.load(hifi / do_name.replace("do_", "g_"), map_location="cpu")["generator"]
+    for key in ("optim_g", "optim_d"):
+        assert set(do[key]) == {"state", "param_groups"} and do[key]["param_groups"][0]["betas"] == (0.8, 0.99)
+    # the generator's parameters in registration order = state_dict order without buffers (it has none)
+    params = [torch.nn.Parameter(v.clone().float()) for v in g.values()]
+    ref_opt = torch.optim.AdamW(params, 2e-4, betas=[0.8, 0.99])
+    ref_opt.load_state_dict(do["optim_g"])
+    st = ref_opt.state_dict()["state"]
+    assert len(st) == len(params) and all(st[i]["exp_avg"].shape == params[i].shape for i in range(len(params)))
+    assert float(st[0]["step"]) == 2.0                 # 4 items / batch 2 = 2 steps in the epoch
+    # resume: the second run starts from these files (steps continue, moments are loaded, nothing raises)
+    monkeypatch.setenv("XVA_B200_MAX_EPOCHS", "2")
+    assert asyncio.run(trainers.handleTrainerHiFi(mm, data, FakeSocket(), [0])) == "done"
+    do2 = torch.load(hifi / sorted(n for n in os.listdir(hifi) if n.startswith("do_"))[-1], map_location="cpu")
+    assert do2["steps"] > do["steps"] and float(do2["optim_g"]["state"][0]["step"]) == 4.0
+    log = open(tmp_path / "synthetic_2x8x4" / "training.log").read()
+    assert "OPTIM NOT LOADED" not in log

@@ -193,8 +193,8 @@ class FastPitch(torch.nn.Module):
         # accumulates into the gradient arena, so it is independent of the input-gradient GEMM that follows it on the main
         # stream; the persistent CTAs of one kernel that run out of tiles (224 row tiles on 148 SMs = 1.51 waves) free
         # their SMs for the other kernel instead of idling until the launch ends.
-        self.bwd_streams = os.environ.get("XVA_BWD_STREAMS", "0") == "1"
-        self._side = torch.cuda.Stream(device=dev) if self.bwd_streams else None
+        self.bwd_streams = None      # None: by XVA_BWD_STREAMS (default auto = inside CUDA-graph capture); bool: forced
+        self._side = None
         self._side_used = False
         self.seed = int(seed)
         self.step_counter = torch.zeros(1, device=dev, dtype=torch.int64)  # device-side dropout counter (uint64 bits)
@@ -381,14 +381,26 @@ class FastPitch(torch.nn.Module):
         are record_stream()-ed: the caching allocator does not hand their memory to a main-stream kernel before the side
         stream is done with it (inside a graph capture such blocks are simply not reused). The main stream does not wait
         for the side stream until the gradients are consumed (_join_side)."""
-        if self._side is None:
+        if not self._side_on():
             return fn()
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device_)
         self._side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self._side):
             fn()
         for t in inputs:
             t.record_stream(self._side)
         self._side_used = True
+
+    def _side_on(self):
+        """Two-stream backward: measured 14.07 -> 13.69 ms / step inside the replayed graph and 14.86 -> 14.34 launched
+        eagerly at 32 x 880 x 160 (profiles/r02_streams_ab.txt)."""
+        if self.bwd_streams is not None:
+            return bool(self.bwd_streams)
+        v = os.environ.get("XVA_BWD_STREAMS", "auto").strip().lower()
+        if v in ("", "auto"):
+            return ops.capturing()
+        return v not in ("0", "false", "off")
 
     def _join_side(self):
         """Before anything reads the gradient arena from the main stream: GradSync.ready, the end of backward()."""
@@ -767,6 +779,23 @@ class FastPitchLoss:
         self.attn_loss_scale = attn_loss_scale
         self.training_stage = 3
         self._saved = None
+        self.world, self.group = 1, None
+
+    def set_distributed(self, world, group=None):
+        """One process per GPU: every masked MSE becomes sum_global(err * mask) / sum_global(mask) -- what the
+        reference computes on the outputs nn.DataParallel gathered (xva_train.py:790, loss_function.py:90-117), and what
+        one GPU running the global batch computes -- instead of the mean of per-rank ratios: the {sum, count} pairs are
+        all-reduced (8 doubles) before the ratios and before grad_seeds() divides by the counts. Each rank then holds
+        d(global loss)/d(its own predictions), so the gradient all-reduce is a plain SUM (GradSync(mean=False)). The
+        stage-1 CTC term is a mean over utterances (equal batch per rank): mean of means, scaled by 1/world."""
+        self.world, self.group = int(world), group
+        return self
+
+    def _all_reduce(self, t):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
 
     def __call__(self, model_out, targets, is_training=True, meta_agg="mean", training_stage=None):
         return self.forward(model_out, targets, is_training, meta_agg, training_stage)
@@ -787,6 +816,8 @@ class FastPitchLoss:
             lp = attn_logprob.reshape(attn_logprob.shape[0], attn_logprob.shape[-2], attn_logprob.shape[-1])
             cost, gctc = ops.attn_ctc(lp, lens32.contiguous(), out_lens.to(torch.int32).contiguous())
             attn_loss = cost.mean()
+            if self.world > 1:
+                attn_loss = self._all_reduce(attn_loss.clone()) / self.world
             loss = attn_loss * self.attn_loss_scale
             self._saved = {"stage": 1, "gctc": gctc}
             return loss, {"loss": loss, "attn_loss": attn_loss}
@@ -797,20 +828,23 @@ class FastPitchLoss:
         if stage == 2:
             tgt = attn_dur.to(torch.float32).contiguous()
             ops.lens_mse(log_dur_pred, tgt, lens32, acc[1], log1p_tgt=True)
+            self._all_reduce(acc)
             dur_loss = acc[1, 0] / acc[1, 1]
             saved.update(log_dur_pred=log_dur_pred, dur_tgt=tgt)
         else:
             mt = mel_tgt.to(torch.float32).contiguous()
             ops.mel_mse(mel_out, mt, acc[0])
-            mel_loss = acc[0, 0] / acc[0, 1]
             saved.update(mel_out=mel_out, mel_tgt=mt)
             if stage == 3:
                 pp, pt = pitch_pred.reshape(pitch_pred.shape[0], -1), pitch_tgt.reshape(pitch_tgt.shape[0], -1)
                 ops.lens_mse(pp, pt, lens32, acc[2])
                 ops.lens_mse(energy_pred, energy_tgt, lens32, acc[3])
+                saved.update(pitch_pred=pp, pitch_tgt=pt, energy_pred=energy_pred, energy_tgt=energy_tgt)
+            self._all_reduce(acc)                      # global {sum, count} of every term, one 8-double message
+            mel_loss = acc[0, 0] / acc[0, 1]
+            if stage == 3:
                 pitch_loss = acc[2, 0] / acc[2, 1]
                 energy_loss = acc[3, 0] / acc[3, 1]
-                saved.update(pitch_pred=pp, pitch_tgt=pt, energy_pred=energy_pred, energy_tgt=energy_tgt)
         loss = (mel_loss + dur_loss * self.dur_predictor_loss_scale + pitch_loss * self.pitch_predictor_loss_scale
                 + energy_loss * self.energy_predictor_loss_scale)
         self._saved = saved
@@ -823,7 +857,7 @@ class FastPitchLoss:
         if s is None:
             raise RuntimeError("FastPitchLoss.grad_seeds() needs a forward() first")
         if s["stage"] == 1:
-            return {"attn_logprob": (s["gctc"], scale * self.attn_loss_scale)}
+            return {"attn_logprob": (s["gctc"], scale * self.attn_loss_scale / self.world)}
         acc, lens = s["acc"], s["lens"]
         out = {}
         if s["stage"] == 2:
@@ -846,6 +880,12 @@ class AttentionBinarizationLoss:
 
     def __init__(self):
         self._saved = None
+        self.world, self.group = 1, None
+
+    def set_distributed(self, world, group=None):
+        """Global {sum, count} across ranks, as FastPitchLoss.set_distributed."""
+        self.world, self.group = int(world), group
+        return self
 
     def __call__(self, hard_attention, soft_attention, eps=1e-12):
         return self.forward(hard_attention, soft_attention, eps)
@@ -855,6 +895,9 @@ class AttentionBinarizationLoss:
         soft = soft_attention.to(torch.float32).contiguous()
         acc = torch.zeros(2, device=soft.device, dtype=torch.float64)
         ops.attn_bin_loss(hard, soft, acc, eps)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=self.group)
         self._saved = (hard, soft, acc, float(eps))
         return -acc[0] / acc[1]
 

@@ -27,20 +27,38 @@ from . import capi, ops
 LRELU_SLOPE = 0.1
 
 
+def _auto_streams(env, width):
+    """Stream-level parallelism switch shared by _Side / _Branches / fastpitch.FastPitch: XVA_*_STREAMS = "0" off, a number
+    = forced width, unset / "auto" = ``width`` while a CUDA graph is being captured and 0 otherwise. Measured on B200
+    (profiles/r02_streams_ab.txt): inside a replayed graph the extra streams cost nothing on the host and win 2.6 %
+    (FastPitch) / 15.6 % (HiFi-GAN); launched eagerly the stream switches and event records make the host-bound HiFi-GAN
+    step 18 % slower, hence "auto"."""
+    v = os.environ.get(env, "auto").strip().lower()
+    if v in ("", "auto"):
+        return width if ops.capturing() else 0
+    try:
+        return max(0, int(v))
+    except ValueError:
+        return 0
+
+
 class _Side:
-    """EXPERIMENT, off by default (XVA_BWD_STREAMS=1), not yet measured: weight / bias gradient
-    launches go to a second stream. They only read tensors that already exist and accumulate into the packed gradient
+    """Weight / bias gradient launches go to a second stream (XVA_BWD_STREAMS: auto = inside graph capture, 0, 1). They only read tensors that already exist and accumulate into the packed gradient
     arena / the bias .grad tensors, allocate nothing, and nothing on the main stream depends on them until the arena is
     unpacked -- so the small-channel weight gradients (52 CTAs on 148 SMs, 160 us each at B = 16 x 8192) overlap the
     input-gradient chain instead of serialising with it. Inputs are record_stream()-ed: their memory is not reused
     before the side stream is done with it; join() runs where the gradients are consumed (_WnPacker.unpack_grads)."""
-    enabled = os.environ.get("XVA_BWD_STREAMS", "0") == "1"
+    enabled = None          # None: by XVA_BWD_STREAMS (default auto); True / False: forced (tests)
     stream = None
     used = False
 
     @classmethod
+    def on(cls):
+        return bool(_auto_streams("XVA_BWD_STREAMS", 1)) if cls.enabled is None else bool(cls.enabled)
+
+    @classmethod
     def run(cls, fn, *inputs):
-        if not cls.enabled:
+        if not cls.on():
             return fn()
         if cls.stream is None:
             cls.stream = torch.cuda.Stream()
@@ -53,20 +71,20 @@ class _Side:
 
     @classmethod
     def join(cls):
-        if cls.enabled and cls.used:
+        if cls.used:
             torch.cuda.current_stream().wait_stream(cls.stream)
             cls.used = False
 
 
 class _Branches:
-    """EXPERIMENT, off by default (XVA_DISC_STREAMS=n), not yet measured: the sub-
-    discriminators of MPD / MSD are independent chains of small launches; with n > 0 sub-discriminator i runs -- forward,
-    loss gradients and backward -- on stream i mod n. Discipline that keeps the caching allocator safe without
+    """The sub-discriminators of MPD / MSD are independent chains of small launches; with n > 0 sub-discriminator i runs
+    -- forward, loss gradients and backward -- on stream i mod n (XVA_DISC_STREAMS: auto = 8 inside graph capture, 0, n;
+    XVA_GEN_STREAMS the same for the three ResBlocks of an MRF stage). Discipline that keeps the caching allocator safe without
     record_stream: a branch starts by waiting for the main stream (fork) and everything in it, torch ops included, runs on
     its stream; the main stream waits for every branch (join) before it touches what they produced; a tensor created in
     a branch is freed in it or after the join; a main-stream tensor a branch reads is kept referenced until the join."""
-    n = int(os.environ.get("XVA_DISC_STREAMS", "0") or 0)
-    n_gen = 3 if os.environ.get("XVA_GEN_STREAMS", "0") == "1" else 0   # same idea for the three ResBlocks of an MRF stage
+    n = None                # None: by XVA_DISC_STREAMS (default auto); an int: forced (tests)
+    n_gen = None            # None: by XVA_GEN_STREAMS; an int: forced
     streams = []
     open_streams = []
 
@@ -93,12 +111,20 @@ class _Branches:
             return False
 
     @classmethod
+    def width(cls):
+        return _auto_streams("XVA_DISC_STREAMS", 8) if cls.n is None else int(cls.n)
+
+    @classmethod
+    def gen_width(cls):
+        return (3 if _auto_streams("XVA_GEN_STREAMS", 1) else 0) if cls.n_gen is None else int(cls.n_gen)
+
+    @classmethod
     def on(cls):
-        return cls.n > 0
+        return cls.width() > 0
 
     @classmethod
     def branch(cls, i, n=None):
-        n = cls.n if n is None else n
+        n = cls.width() if n is None else n
         if n <= 0:
             return cls._Null()
         while len(cls.streams) < n:
@@ -377,7 +403,7 @@ class Generator(nn.Module):
             for j in range(self.num_kernels):
                 rb = self.resblocks[i * self.num_kernels + j]
                 name = f"resblocks.{i * self.num_kernels + j}"
-                with _Branches.branch(j, _Branches.n_gen):     # the ResBlocks of a stage only share their input
+                with _Branches.branch(j, _Branches.gen_width()):     # the ResBlocks of a stage only share their input
                     xr, ar = x0, a0
                     saved = []
                     for m in range(3):
@@ -443,7 +469,7 @@ class Generator(nn.Module):
             for j in range(self.num_kernels):
                 rb = self.resblocks[i * self.num_kernels + j]
                 name = f"resblocks.{i * self.num_kernels + j}"
-                with _Branches.branch(j, _Branches.n_gen):
+                with _Branches.branch(j, _Branches.gen_width()):
                     G = dyj
                     for m in reversed(range(3)):
                         c1, c2 = rb.convs1[m], rb.convs2[m]
@@ -1109,6 +1135,52 @@ class AdamW:
             if p.grad is None or p.grad.data_ptr() != self.g[off:off + k].data_ptr():
                 p.grad = self.g[off:off + k].view(p.shape)
             off += k
+
+    def state_dict(self):
+        """torch.optim.AdamW.state_dict() layout: {'state': {i: {'step', 'exp_avg', 'exp_avg_sq'}}, 'param_groups': [...]}
+        with parameter i = the i-th parameter handed to the constructor, tensors on the CPU in the parameters' shapes."""
+        st, off = {}, 0
+        for i, p in enumerate(self.params):
+            k = p.numel()
+            if self.steps > 0:
+                st[i] = {"step": torch.tensor(float(self.steps)), "exp_avg": self.m[off:off + k].view(p.shape).cpu().clone(),
+                         "exp_avg_sq": self.v[off:off + k].view(p.shape).cpu().clone()}
+            off += k
+        g = self.param_groups[0]
+        group = {"lr": g["lr"], "betas": tuple(g["betas"]), "eps": g["eps"], "weight_decay": g["weight_decay"],
+                 "amsgrad": False, "maximize": False, "foreach": None, "capturable": False, "differentiable": False,
+                 "fused": None, "params": list(range(len(self.params)))}
+        return {"state": st, "param_groups": [group]}
+
+    def load_state_dict(self, sd):
+        """Accepts torch.optim.AdamW's state_dict (what the reference's do_ checkpoints hold) or this class's round-1 flat
+        layout ({'m', 'v', 'steps'})."""
+        if "m" in sd and "v" in sd and "state" not in sd:
+            self.m.copy_(sd["m"])
+            self.v.copy_(sd["v"])
+            self.steps = int(sd["steps"])
+        else:
+            state = sd["state"]
+            if len(state) not in (0, len(self.params)):
+                raise ValueError(f"optimizer state holds {len(state)} parameters, this model has {len(self.params)}")
+            off, steps = 0, 0
+            for i, p in enumerate(self.params):
+                k = p.numel()
+                e = state.get(i, state.get(str(i)))
+                if e is not None:
+                    if tuple(e["exp_avg"].shape) != tuple(p.shape):
+                        raise ValueError(f"optimizer state {i}: shape {tuple(e['exp_avg'].shape)} != {tuple(p.shape)}")
+                    self.m[off:off + k].copy_(e["exp_avg"].reshape(-1).to(torch.float32))
+                    self.v[off:off + k].copy_(e["exp_avg_sq"].reshape(-1).to(torch.float32))
+                    steps = max(steps, int(float(e["step"])))
+                off += k
+            self.steps = steps
+            if sd.get("param_groups"):
+                g0 = sd["param_groups"][0]
+                for key in ("lr", "betas", "eps", "weight_decay"):
+                    if key in g0:
+                        self.param_groups[0][key] = tuple(g0[key]) if key == "betas" else g0[key]
+        self.step_dev.fill_(self.steps)
 
     def step(self):
         g = self.param_groups[0]

@@ -11,6 +11,12 @@ import torch
 from . import capi
 
 
+def capturing():
+    """True while the current CUDA stream is being captured into a graph (False on a host without a CUDA context: the
+    launch-sequence dry run of tests/)."""
+    return torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 

@@ -6,8 +6,16 @@ The gradient arena is one flat fp32 buffer laid out in state_dict order, and bac
 network down, so the exchange is bucketed by construction: as soon as a contiguous slice is final (a decoder layer, the
 predictor / projection tail, an encoder layer) backward() calls ``ready(prefixes)`` and that slice is all-reduced in
 place on NCCL's own stream while the remaining backward kernels keep the SMs busy. ``finish()`` joins the streams before
-LAMB reads the arena. Loss gradients are pre-scaled by 1/world, so SUM yields the mean and every rank applies the
-same update (replicas stay bit-identical without a broadcast).
+LAMB reads the arena. Every rank applies the same update to the same all-reduced gradients, so replicas stay
+bit-identical without a broadcast.
+
+Loss normalisation. ``mean=True``: loss gradients are pre-scaled by 1/world and SUM yields the mean of the
+per-rank gradients -- exact for losses that are plain means over equal-sized shards. FastPitch's masked MSE terms are
+ratios sum(err * mask) / sum(mask) and the reference evaluates them on the GATHERED outputs of all GPUs
+(xva_train.py:790), which the mean of per-rank ratios only equals when every rank holds the same number of valid frames
+and tokens. ``mean=False`` + ``FastPitchLoss.set_distributed(world)``: the criterion all-reduces its {sum, count} pairs
+first, every rank back-propagates d(global loss)/d(its predictions), and the SUM of the gradients is exactly the gradient
+of one GPU running the global batch.
 """
 import math
 
@@ -18,11 +26,12 @@ import torch.distributed as dist
 class GradSync:
     MAX_GAP = 256  # elements; the arena aligns tensors to 64 floats
 
-    def __init__(self, model_or_arena, world, group=None, min_bucket_elems=1 << 20):
+    def __init__(self, model_or_arena, world, group=None, min_bucket_elems=1 << 20, mean=True):
         self.arena = getattr(model_or_arena, "arena", model_or_arena)
         self.world = int(world)
         self.group = group
         self.min_bucket = int(min_bucket_elems)
+        self.mean = bool(mean)
         self.pending = []
         self._lo = None
         self._hi = None
@@ -31,7 +40,7 @@ class GradSync:
 
     @property
     def loss_scale(self):
-        return 1.0 / self.world
+        return 1.0 / self.world if self.mean else 1.0
 
     def _range(self, prefixes):
         A = self.arena
@@ -75,3 +84,11 @@ class GradSync:
         for w in self.pending:
             w.wait()
         self.pending = []
+
+
+def shard_batches(batches, rank, world):
+    """Rank r takes items r, r + world, ... of the (already shuffled) list and every rank the same count (drop_last, as the
+    reference's DataLoader at xva_train.py:452): ranks must issue the same number of collectives per epoch."""
+    batches = list(batches)
+    n = (len(batches) // world) * world
+    return batches[rank:n:world]

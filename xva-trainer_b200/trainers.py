@@ -33,6 +33,7 @@ import torch
 
 from . import fastpitch as fp
 from . import hifigan as hg
+from . import parallel
 
 
 class StageFinished(RuntimeError):
@@ -118,7 +119,16 @@ class _TrainerBase:
         self.PROD = PROD
         self.models_manager = models_manager
         self.gpus = gpus
-        self.device = torch.device(f"cuda:{gpus[0]}")
+        # One process per GPU. The reference reaches multi-GPU as len(gpus) > 1 inside ONE process
+        # (nn.DataParallel, xva_train.py:465-466); here the same ``gpus`` list is served by WORLD_SIZE processes launched
+        # with torchrun, rank r driving gpus[LOCAL_RANK] -- LOCAL_RANK parsed as an int (the reference adds the string to
+        # 1234 and dies, Appendix C-5).
+        self.local_rank = int(os.getenv("LOCAL_RANK", 0))
+        self.world = int(os.getenv("WORLD_SIZE", "1"))
+        self.rank = int(os.getenv("RANK", "0"))
+        gpu = gpus[self.local_rank] if (self.world > 1 and len(gpus) > self.local_rank) else (
+            self.local_rank if self.world > 1 else gpus[0])
+        self.device = torch.device(f"cuda:{gpu}")
         self.ckpt_path = None
         self.websocket = websocket
         self.training_log = []
@@ -131,7 +141,6 @@ class _TrainerBase:
         self.logs_are_init = False
         self.dataset_id = self.dataset_input = self.dataset_output = None
         self.batch_size = self.force_stage = self.workers = None
-        self.local_rank = int(os.getenv("LOCAL_RANK", 0))
         self.JUST_FINISHED_STAGE = False
         self.END_OF_TRAINING = False
         self.graphs_json = None
@@ -140,7 +149,7 @@ class _TrainerBase:
     def print_and_log(self, line=None, end="\n", flush=False, save_to_file=False):
         if line is not None:
             self.training_log.append(f"{_now()} | {line}")
-        if save_to_file and self.local_rank == 0:
+        if save_to_file and self.rank == 0:
             with open(f"{save_to_file}/training.log", "w+") as f:
                 f.write("\n".join(self.training_log + [self.training_log_live_line]))
 
@@ -169,12 +178,22 @@ class _TrainerBase:
         self.logs_are_init = True
 
     def _write_graphs(self):
-        if self.local_rank == 0:
+        if self.rank == 0:
             with open(f"{self.dataset_output}/graphs.json", "w+") as f:
                 f.write(json.dumps(self.graphs_json))
 
+    def _dist_init(self):
+        """Join the NCCL process group when launched under torchrun (idempotent). -> world size"""
+        if self.world > 1:
+            import torch.distributed as dist
+            torch.cuda.set_device(self.device)
+            if not dist.is_initialized():
+                dist.init_process_group("nccl", device_id=self.device)
+            self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        return self.world
+
     async def _send(self, msg):
-        if self.websocket is not None and self.local_rank == 0:
+        if self.websocket is not None and self.rank == 0:
             r = self.websocket.send(msg)
             if asyncio.iscoroutine(r):
                 await r
@@ -216,29 +235,57 @@ class FastPitchTrainer(_TrainerBase):
             await self.iteration()
 
     async def init(self):
-        torch.manual_seed(1234 + self.local_rank)
-        self.model = fp.FastPitch(logger=self.logger, device=self.device, seed=1234)
-        self.criterion = fp.FastPitchLoss()
-        self.attention_kl_loss = fp.AttentionBinarizationLoss()                    # :342
+        world = self._dist_init()
+        torch.manual_seed(1234 + self.rank)
+        self.model = fp.FastPitch(logger=self.logger, device=self.device, seed=1234)   # same initial weights on every rank
+        self.model.seed = 1234 + self.rank                                         # per-rank dropout streams (:294-295)
+        self.criterion = fp.FastPitchLoss().set_distributed(world)
+        self.attention_kl_loss = fp.AttentionBinarizationLoss().set_distributed(world)   # :342
         self.optimizer = fp.Lamb(self.model, lr=0.1, betas=(0.9, 0.98), eps=1e-9, weight_decay=1e-6)
+        # gradient all-reduce overlapped with backward; losses are normalised by GLOBAL mask sums, so SUM is exact (8e)
+        self.sync = parallel.GradSync(self.model, world, mean=False) if world > 1 else None
         self.total_iter, self.epoch, self.avg_loss_per_epoch = 50000, 0, []       # new voices start at 40-50k (:304-335)
         self.start_iterations = self.total_iter
         stage = None
+        # xva_train.py:284-288: the newest checkpoint of THIS run wins; the user's base checkpoint is only the starting point
+        # of a run whose output folder has none yet (handleTrainer re-enters init() after every stage change and on resume).
         ck = self.last_checkpoint(self.dataset_output)
-        if self.checkpoint and os.path.isfile(str(self.checkpoint)):
+        if ck is None and self.checkpoint and os.path.isfile(str(self.checkpoint)):
             ck = self.checkpoint
+            self.print_and_log(f"Checkpoint: {ck}", save_to_file=self.dataset_output)
+        loaded_stage = None
         if ck:
-            stage, self.epoch, self.total_iter, self.avg_loss_per_epoch = self.load_checkpoint(ck)
+            loaded_stage, self.epoch, self.total_iter, self.avg_loss_per_epoch = self.load_checkpoint(ck)
             self.ckpt_path = ck
-        if self.force_stage:
+            stage = loaded_stage
+            # :356-359: a finished run (stage 5 on disk, or stage 5 forced) goes straight on to the vocoder
+            if (int(loaded_stage) == 5 and self.force_stage is None) or self.force_stage == 5:
+                self.END_OF_TRAINING = True
+                self.JUST_FINISHED_STAGE = True
+                raise StageFinished("FastPitch already finished: move to HiFi-GAN")
+        elif self.force_stage == 5:
+            self.END_OF_TRAINING = True
+            self.JUST_FINISHED_STAGE = True
+            raise StageFinished("stage 5 forced: move to HiFi-GAN")
+        if self.force_stage:                                                      # :361-366
+            self.print_and_log(f"Forcing stage: {self.force_stage}", save_to_file=self.dataset_output)
+            if loaded_stage is not None and int(loaded_stage) < self.force_stage and int(loaded_stage) != 3:
+                self.total_iter = self.start_iterations
+            self.avg_loss_per_epoch = []
             stage = self.force_stage
+        if ck and self.dataset_id not in str(ck):                                 # IS_NEW, :380-385: a base checkpoint of another voice
+            self.print_and_log("New voice", save_to_file=self.dataset_output)
+            stage = None                   # decided below: 1 when the batches carry the alignment prior (the reference's 1)
+            self.total_iter = self.start_iterations
+            self.avg_loss_per_epoch = []
+            self.epoch = 0
         source_key = (str(self.dataset_input), id(self.batch_source))
         if getattr(self, "_batches_key", None) == source_key:
             pass          # same trainer re-initialised for the next stage: keep the batches (and the extracted durations)
         elif self.batch_source is not None:
-            self.batches = list(self.batch_source)
+            self.batches = parallel.shard_batches(self.batch_source, self.rank, world)    # rank r: items r::W, drop_last
         elif str(self.dataset_input).startswith("synthetic:"):
-            self.batches = _synthetic_fastpitch_batches(self.dataset_input, self.device, 1234 + self.local_rank)
+            self.batches = _synthetic_fastpitch_batches(self.dataset_input, self.device, 1234 + self.rank)
         else:
             raise NotImplementedError("wav/text dataset loading is outside this build (SURVEY.md section 2 row 6): pass "
                                       "data['batch_source'] or dataset_path='synthetic:BxTtxTmxitems'")
@@ -246,23 +293,26 @@ class FastPitchTrainer(_TrainerBase):
         has_prior = all(b[0][7] is not None for b in self.batches)
         if stage is None:
             stage = 1 if has_prior else 2
-        stage = min(4, max(1, int(stage)))
+        stage = int(stage)
+        if stage not in (1, 2, 3, 4):
+            raise ValueError(f"training stage {stage} is not a FastPitch stage (1-4)")
         if stage == 1 and not has_prior:
             raise ValueError("training stage 1 needs batches that carry the alignment prior (inputs_x[7])")
         self.model.training_stage = self.criterion.training_stage = stage
-        num_data_lines = sum(int(b[0][0].shape[0]) for b in self.batches)           # utterances in the dataset (:380)
+        num_data_lines = world * sum(int(b[0][0].shape[0]) for b in self.batches)   # utterances in the dataset (:380)
         self.target_delta = get_target_delta(stage, num_data_lines)
         self.graphs_json["stages"][str(stage)]["target_delta"] = self.target_delta
         await self._send(f"Set stage to: {stage} ")
         mult = {1: 1.5, 2: 12, 3: 3.5, 4: 4}.get(stage, 1)                         # stage batch multipliers (:387-404)
         self.stage_batch = max(1, int(self.batch_size * mult))
-        self.gam = max(1, round(256 / self.stage_batch))                           # :407
+        self.gam = max(1, round(256 / (self.stage_batch * world)))                 # :403-407: global batch = W x per-GPU batch
         if stage == 1:
             self.print_and_log("Stage 1: Pre-training only the alignment.", save_to_file=self.dataset_output)   # :411-412
         self.model.train()
         self.EPOCH_AVG_SPAN, self.target_patience, self.target_patience_count = 20, 3, 0
         self.last_loss, self.iter_losses, self.avg_frames_s = None, [], []
         self.epoch_iter, self.micro, self.frames_acc = 0, 0, 0
+        self._window_loss = None
         self.batch_pos = 0
         self.avg_loss_per_epoch.append(0.0)
         self.step_t0 = time.perf_counter()
@@ -293,22 +343,39 @@ class FastPitchTrainer(_TrainerBase):
             meta["kl_loss"] = binarization_loss * kl_weight
             meta["loss"] = meta["loss"] + kl_weight * binarization_loss
             kl = (self.attention_kl_loss, kl_weight)
-        self.model.backward(self.criterion, 1.0 / self.gam, kl=kl)                                           # :806-813
         self.micro += 1
+        # the gradient exchange rides on the backward of the window's LAST micro-batch (the arena then holds the sum)
+        sync = self.sync if (self.sync is not None and self.micro % self.gam == 0) else None
+        self.model.backward(self.criterion, 1.0 / self.gam, grad_sync=sync, kl=kl)                           # :806-813
+        if sync is not None:
+            sync.finish()
         self.frames_acc += num_frames
         key = {3: "pitch_loss", 4: "mel_loss"}.get(stage, "loss")                                            # :815-820
         tracked = meta[key] * (0.1 if stage == 3 else 1.0)
+        if self.micro % self.gam != 0:
+            self._window_loss = tracked if self._window_loss is None else self._window_loss + tracked
         if self.micro % self.gam == 0:
+            # NaN / Inf guard BEFORE the update (xva_train.py:825-832 checks every micro-batch and skips): one host read per
+            # optimizer step of the tracked loss summed over the window and of the squared gradient norm of the arena, so
+            # a non-finite micro-batch anywhere in the accumulation window is seen. On a hit nothing is applied: gradients
+            # are cleared, moments, weights and their tf32 copy stay as they were.
+            self._window_loss = tracked if self._window_loss is None else self._window_loss + tracked
+            gsq = torch.linalg.vector_norm(self.model.arena.g).double()     # NaN / Inf propagate
+            val, gval = (float(v) for v in torch.stack([self._window_loss.double().reshape(()), gsq]).tolist())
+            val /= self.gam
+            self._window_loss = None
+            if not (math.isfinite(val) and math.isfinite(gval)):
+                self.model.zero_grad()
+                self.frames_acc = 0
+                self.step_t0 = time.perf_counter()
+                self.print_and_log("loss is NaN", save_to_file=self.dataset_output)
+                return
             self.optimizer.step()                                                                            # :855-862
             self.model.step_dropout()
             self.model.zero_grad()
-            val = float(tracked)                       # one host read per optimizer step (the reference does six)
-            if not math.isfinite(val):                 # NaN guard (:825-832): drop the step's contribution
-                self.print_and_log("NaN loss: step skipped", save_to_file=self.dataset_output)
-                return
             dt = time.perf_counter() - self.step_t0
             self.step_t0 = time.perf_counter()
-            frames_s = self.frames_acc / max(dt, 1e-9)
+            frames_s = self.world * self.frames_acc / max(dt, 1e-9)        # whole job (every rank holds the same frame count)
             self.frames_acc = 0
             self.avg_frames_s.append(frames_s)
             self.iter_losses.append(val)
@@ -377,7 +444,7 @@ class FastPitchTrainer(_TrainerBase):
     # reference: xva_train.py:979-1052
     def save_checkpoint(self, force_save=False, frames_s=0, total_iter=0, avg_loss=None, loss_delta=None,
                         avg_loss_per_epoch=(), fpath="out.pt", doPrintLog=True):
-        if self.local_rank != 0:
+        if self.rank != 0:
             return
         intermediate = self.epochs_per_checkpoint > 0 and self.epoch % self.epochs_per_checkpoint == 0
         if not intermediate and not force_save:
@@ -508,7 +575,8 @@ class HiFiTrainer(_TrainerBase):
         h = _Cfg(HIFI_CONFIG_V1)
         h.batch_size = int(self.batch_size * 1.4)                                     # :228
         self.h = h
-        torch.manual_seed(h.seed + self.local_rank)
+        world = self._dist_init()
+        torch.manual_seed(h.seed + self.rank)
         self.generator = hg.Generator(h, device=self.device)
         self.mpd = hg.MultiPeriodDiscriminator(device=self.device)
         self.msd = hg.MultiScaleDiscriminator(device=self.device)
@@ -530,19 +598,21 @@ class HiFiTrainer(_TrainerBase):
             self.steps, self.epoch = state_do["steps"] + 1, state_do["epoch"]
             self.avg_loss_per_epoch = list(state_do.get("avg_loss_per_epoch", []))
         self.generator.train(); self.mpd.train(); self.msd.train()
-        self.stepper = hg.HiFiGANStep(self.generator, self.mpd, self.msd, h)
+        self.stepper = hg.HiFiGANStep(self.generator, self.mpd, self.msd, h, world=world)
         if state_do and "optim_g" in state_do:
             for opt, key in ((self.stepper.optim_g, "optim_g"), (self.stepper.optim_d, "optim_d")):
-                st = state_do[key]
-                opt.m.copy_(st["m"]); opt.v.copy_(st["v"]); opt.steps = int(st["steps"]); opt.step_dev.fill_(opt.steps)
+                try:
+                    opt.load_state_dict(state_do[key])
+                except Exception:
+                    self.print_and_log(f"========== OPTIM NOT LOADED ({key}) ==========", save_to_file=self.dataset_output)
         self.lr = h.learning_rate * (h.lr_decay ** self.epoch)                        # ExponentialLR per epoch (:306-307)
         self.wav_segments = None
         if self.batch_source is not None:
-            self.batches = list(self.batch_source)
+            self.batches = parallel.shard_batches(self.batch_source, self.rank, world)
         elif str(self.dataset_input).startswith("synthetic:"):
             B, frames, items = (int(v) for v in self.dataset_input.split(":", 1)[1].split("x"))
             from . import hifigan as _hg
-            g = torch.Generator().manual_seed(1234 + self.local_rank)
+            g = torch.Generator().manual_seed(1234 + self.rank)
             mel_in = _hg.MelSpectrogram(fmax=h.fmax, device=self.device)
             mel_loss = _hg.MelSpectrogram(fmax=h.fmax_for_loss, device=self.device)
             self.batches = []
@@ -563,7 +633,9 @@ class HiFiTrainer(_TrainerBase):
         else:
             raise NotImplementedError("dataset_path must be a voice folder (metadata.csv + wavs/), 'synthetic:BxFRAMESxITEMS', "
                                       "or pass data['batch_source']")
-        self.graphs_json["stages"]["5"]["target_delta"] = 0.0002
+        self.target_delta, self.target_patience, self.target_patience_count = 0.0001, 3, 0     # :268-271
+        self.EPOCH_AVG_SPAN = 20
+        self.graphs_json["stages"]["5"]["target_delta"] = self.target_delta
         await self._send("Set stage to: 5 ")
         self.batch_pos, self.iter_losses = 0, []
         self.avg_loss_per_epoch.append(0.0)
@@ -593,40 +665,54 @@ class HiFiTrainer(_TrainerBase):
         for opt in (self.stepper.optim_g, self.stepper.optim_d):
             opt.param_groups[0]["lr"] = self.lr
         out = self.stepper.step(x, y, y_mel)                                          # :467-515
-        gen_loss = float(out["loss_gen_all"])
+        gen_loss, mel_error = (float(v) for v in torch.stack([out["loss_gen_all"].double(), out["mel_error"].double()]).tolist())
         its = 1.0 / max(time.perf_counter() - t0, 1e-9)
-        self.iter_losses.append(gen_loss)
-        self.avg_loss_per_epoch[-1] += gen_loss
+        mel_loss = int(mel_error * 1000) / 1000                                       # :518-523: the tracked quantity
+        self.iter_losses.append(mel_loss)
+        self.avg_loss_per_epoch[-1] += mel_loss
         self.training_log_live_line = (f"| Stage 5 | Epoch {self.epoch} | Steps {self.steps} | Gen loss {gen_loss:.3f} | "
-                                       f"Mel err {float(out['mel_error']):.4f} | {its * y.shape[0]:.1f} its/s")
+                                       f"Mel err {mel_error:.4f} | {its * y.shape[0]:.1f} its/s")
         self.print_and_log(save_to_file=self.dataset_output)                          # :517-545
         self.steps += 1
 
     def finish_epoch(self):                                                           # :607-649
         self.epoch += 1
-        self.avg_loss_per_epoch[-1] /= max(1, len(self.iter_losses))
         self.lr *= self.h.lr_decay
-        self.graphs_json["stages"]["5"]["loss"].append([self.steps, self.avg_loss_per_epoch[-1]])
-        deltas = [(a - b) / a for a, b in zip(self.avg_loss_per_epoch[:-1], self.avg_loss_per_epoch[1:]) if a]
-        if len(deltas) >= 2:
-            d = sum(deltas[-20:]) / len(deltas[-20:])
-            self.graphs_json["stages"]["5"]["loss_delta"].append([self.steps, d])
-        self._write_graphs()
         if self.epochs_per_checkpoint > 0 and self.epoch % self.epochs_per_checkpoint == 0:
             self.output_checkpoint()
-        if self.max_epochs and self.epoch >= self.max_epochs:
+        self.avg_loss_per_epoch[-1] /= max(1, len(self.iter_losses))
+        self.graphs_json["stages"]["5"]["loss"].append([self.steps, self.avg_loss_per_epoch[-1]])
+        deltas = [(a - b) / a for a, b in zip(self.avg_loss_per_epoch[:-1], self.avg_loss_per_epoch[1:]) if a]
+        done = False
+        if len(deltas) >= 2:
+            d = sum(deltas[-self.EPOCH_AVG_SPAN:]) / len(deltas[-self.EPOCH_AVG_SPAN:])
+            self.graphs_json["stages"]["5"]["loss_delta"].append([self.steps, d])
+            # :633-647: converged when the 20-epoch average relative improvement of the mel loss stays at or below
+            # 0.0001 for 3 consecutive epochs, with at least 25 deltas on record
+            if d <= self.target_delta and len(deltas) >= 25:
+                self.target_patience_count += 1
+                done = self.target_patience_count >= self.target_patience
+            else:
+                self.target_patience_count = 0
+        self._write_graphs()
+        if self.max_epochs and self.epoch >= self.max_epochs:                         # test hook
+            done = True
+        if done:
+            self.training_log_live_line = ""
+            self.print_and_log("HiFi-GAN training finished", save_to_file=self.dataset_output)
             self.output_checkpoint()
             self.END_OF_TRAINING = True
             raise StageFinished("HiFi-GAN finished")
 
     def output_checkpoint(self):                                                      # :570-604
-        if self.local_rank != 0:
+        if self.rank != 0:
             return
         gpath = f"{self.hifi_dir}/g_{self.steps:08d}"
         torch.save({"generator": self.generator.state_dict()}, gpath)
-        opt = lambda o: {"m": o.m.cpu(), "v": o.v.cpu(), "steps": o.steps}
-        torch.save({"mpd": self.mpd.state_dict(), "msd": self.msd.state_dict(), "optim_g": opt(self.stepper.optim_g),
-                    "optim_d": opt(self.stepper.optim_d), "steps": self.steps, "epoch": self.epoch,
+        # optim_g / optim_d in torch.optim.AdamW's own state_dict layout: the reference's do_ files load here and these
+        # load there (hifigan/xva_train.py:583-584)
+        torch.save({"mpd": self.mpd.state_dict(), "msd": self.msd.state_dict(), "optim_g": self.stepper.optim_g.state_dict(),
+                    "optim_d": self.stepper.optim_d.state_dict(), "steps": self.steps, "epoch": self.epoch,
                     "avg_loss_per_epoch": self.avg_loss_per_epoch, "ckpts_finetuned": True}, f"{self.hifi_dir}/do_{self.steps:08d}")
         torch.save({"generator": self.generator.state_dict()}, f"{self.dataset_output}/{self.dataset_id}.hg.pt")
         for prefix in ("g_", "do_"):                                                  # keep the last two (:592-597)
