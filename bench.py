@@ -37,7 +37,7 @@ def parse():
     ap.add_argument("--stage", type=int, default=3)
     ap.add_argument("--batch", type=int, default=B)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample-batch", type=int, default=4)
+    ap.add_argument("--cpu-sample-batch", type=int, default=0, help="reference arm / cpu_baseline batch (0: the full batch for --impl reference, 8 for the cpu_baseline leg)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--ragged", action="store_true", help="utterance lengths drawn below the maximum (realistic padding) "
                     "instead of the BASELINE config's full-length batch; frames/s then counts valid frames only")
@@ -47,9 +47,9 @@ def parse():
 
 
 def graph_ok(args, world):
-    """One CUDA-graph replay per step: always on one GPU; with N > 1 only when XVA_BENCH_GRAPH_NCCL=1 asks for the
-    (not yet measured) capture of the NCCL all-reduces inside the graph -- the default multi-GPU step launches eagerly."""
-    return (world == 1 or os.environ.get("XVA_BENCH_GRAPH_NCCL") == "1") and not args.no_graph
+    """One CUDA-graph replay per step. With N > 1 the NCCL all-reduces are captured inside the graph
+    (XVA_BENCH_GRAPH_NCCL=0 keeps the multi-GPU step on eager launches)."""
+    return (world == 1 or os.environ.get("XVA_BENCH_GRAPH_NCCL", "1") != "0") and not args.no_graph
 
 
 def config(args, world):
@@ -109,73 +109,139 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------- CPU reference / baseline
+def _median(v):
+    v = sorted(v)
+    return v[len(v) // 2]
+
+
+def ref_module():
+    """baseline/ref_step.py when the verbatim reference copy (baseline/_ref, git-ignored, made by baseline/make_ref.sh)
+    travelled with the tree; None otherwise (then the CPU numbers come from the oracle port)."""
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    try:
+        import ref_step
+    except Exception:
+        return None
+    return ref_step if ref_step.available() else None
+
+
 def cpu_step_rate(stage, batch, steps, warmup):
-    """frames/s of the CPU oracle's training step (oracle/fastpitch.py: forward, FastPitchLoss, autograd backward,
-    clip, LAMB; fp32, dropout on) on all host cores."""
+    """frames/s of the reference's FastPitch training step on all host cores (fp32, dropout on): the UNMODIFIED reference
+    modules driven through xva_train.py:784-862 (kind "reference") or, without baseline/_ref, the oracle's restatement
+    (kind "port"). Median of the timed steps. -> (rate, s/step, cores, frames, kind)"""
     import torch
-    from oracle import fastpitch as ofp
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    x, y = ofp.synthetic_batch(batch, TT, TM, seed=1234)
-    sd = ofp.make_state(1234, perturb=False)
-    opt = {}
-    frames = int(x[3].sum())
+    rs = ref_module()
+    if rs is not None:
+        x = rs.fastpitch_batch(batch, TT, TM, seed=1234)
+        r = rs.FastPitchRef("cpu", stage, "fp32")
+        fn = lambda: r.step(x)
+        frames, kind = batch * TM, "reference"
+    else:
+        from oracle import fastpitch as ofp
+
+        x, y = ofp.synthetic_batch(batch, TT, TM, seed=1234)
+        sd = ofp.make_state(1234, perturb=False)
+        opt, it = {}, [50000]
+
+        def fn():
+            it[0] += 1
+            ofp.train_step(sd, x, y, stage, ofp.noam_lr(it[0]), opt, drop=0.1, training=True)
+
+        frames, kind = int(x[3].sum()), "port"
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        ofp.train_step(sd, x, y, stage, ofp.noam_lr(50000 + i), opt, drop=0.1, training=True)
-        dt = time.perf_counter() - t0
+        fn()
         if i >= warmup:
-            times.append(dt)
-    per = sum(times) / len(times)
-    return frames / per, per, cores, frames
+            times.append(time.perf_counter() - t0)
+    per = _median(times)
+    return frames / per, per, cores, frames, kind
 
 
 def cpu_hifigan_rate(batch, steps, warmup):
-    """samples/s of the CPU oracle's HiFi-GAN training step (oracle/hifigan.py: D step + G step, AdamW; fp32) on all host
-    cores, on a bounded sample (batch x 8192 samples) of the batch-16 workload."""
+    """samples/s of the reference's HiFi-GAN training step (hifigan/xva_train.py:467-515: D step + G step, both AdamW;
+    fp32) on all host cores. -> (rate, s/step, cores, kind)"""
     import torch
-    from oracle import hifigan as ohg
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sd_g = ohg.make_generator_state(1234)
-    sd_p = ohg.make_disc_state(ohg.mpd_spec(), 21)
-    sd_s = ohg.make_disc_state(ohg.msd_spec(), 22)
-    x, y, y_mel = ohg.synthetic_batch(batch, 32, seed=1)
-    opt, times = {}, []
+    rs = ref_module()
+    if rs is not None:
+        hb = rs.hifigan_batch(batch)
+        r = rs.HiFiGANRef("cpu")
+        fn, kind = (lambda: r.step(*hb)), "reference"
+    else:
+        from oracle import hifigan as ohg
+
+        sd_g = ohg.make_generator_state(1234)
+        sd_p = ohg.make_disc_state(ohg.mpd_spec(), 21)
+        sd_s = ohg.make_disc_state(ohg.msd_spec(), 22)
+        x, y, y_mel = ohg.synthetic_batch(batch, 32, seed=1)
+        opt = {}
+        fn, kind = (lambda: ohg.train_step(sd_g, sd_p, sd_s, x, y, y_mel, opt)), "port"
+    times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        ohg.train_step(sd_g, sd_p, sd_s, x, y, y_mel, opt)
+        fn()
         if i >= warmup:
             times.append(time.perf_counter() - t0)
-    per = sum(times) / len(times)
-    return batch * 8192 / per, per, cores
+    per = _median(times)
+    return batch * 8192 / per, per, cores, kind
 
 
 def run_reference(args):
+    """The tier's reference arm: the reference's own CPU implementation of the path on this box's host cores, at the
+    config's full batch (32 utterances x 880 frames; 16 x 8192 samples), >= 3 timed steps, median."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    bs = args.cpu_sample_batch
-    steps, warm = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
-    rate, per, cores, frames = cpu_step_rate(args.stage, bs, steps, warm)
-    sample = (f"oracle train_step (PyTorch-CPU restatement of the reference step), batch {bs} x {TM} frames of the "
-              f"batch-{args.batch} workload, {warm} warm-up + {steps} timed steps, {cores} threads")
+    import warnings
+
+    warnings.filterwarnings("ignore")
+    bs = args.batch if args.cpu_sample_batch <= 0 else args.cpu_sample_batch
+    steps, warm = max(3, min(args.steps, 3)), 1
+    rate, per, cores, frames, kind = cpu_step_rate(args.stage, bs, steps, warm)
+    what = ("unmodified reference modules (baseline/_ref) through the trainer's loop body" if kind == "reference"
+            else "oracle train_step (PyTorch-CPU restatement of the reference step)")
+    sample = (f"{what}, batch {bs} x {TM} frames (the config's batch is {args.batch}), {warm} warm-up + {steps} timed steps, "
+              f"median, {cores} threads")
     hifi = None
     if not args.no_hifigan:
-        hr, hper, _ = cpu_hifigan_rate(2, 1, 1)
+        hb = 16
+        hr, hper, _, hkind = cpu_hifigan_rate(hb, 3, 1)
         hifi = {"metric": "audio-samples/s (HiFi-GAN v1 G+MPD+MSD train step)", "value": hr, "unit": "samples/s",
-                "ms_per_step": hper * 1e3, "cpu_baseline": {"value": hr, "unit": "samples/s", "cores": cores, "kind": "port",
-                "sample": f"oracle train_step, batch 2 x 8192 samples of the batch-16 workload, 1 warm-up + 1 timed step, {cores} threads"}}
+                "ms_per_step": hper * 1e3, "cpu_baseline": {"value": hr, "unit": "samples/s", "cores": cores, "kind": hkind,
+                "sample": f"batch {hb} x 8192 samples (the config's batch), 1 warm-up + 3 timed steps, median, {cores} threads"}}
+    cfg = config(args, 1)
+    cfg["launch"] = "PyTorch CPU, all host threads"
+    cfg["global_batch"] = bs
+    if bs != args.batch:
+        cfg["workload"] += f" -- timed on a batch-{bs} sample"
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": warm, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": config(args, 1),
-            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "dtype": "f32", "data": "synthetic", "config": cfg,
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "hifigan": hifi}
     print(json.dumps(line), flush=True)
+
+
+def eager_b200(local, want_hifigan):
+    """The kernel-for-kernel bar: the UNMODIFIED reference step under stock PyTorch eager on
+    this same GPU, in the trainer's own modes. None when baseline/_ref did not travel with the tree."""
+    rs = ref_module()
+    if rs is None:
+        return None
+    import warnings
+
+    warnings.filterwarnings("ignore")
+    try:
+        return rs.eager_b200(f"cuda:{local}", batch=B, stage=3, steps=5, warmup=2, hifigan=want_hifigan)
+    except Exception as e:      # the bar is a report, never a reason to lose the bench line
+        return {"unavailable": f"{type(e).__name__}: {e}"}
 
 
 # ---------------------------------------------------------------------------------------------- native arm
@@ -197,8 +263,7 @@ def run_hifigan(args, dev, world, rank, peak_tf32):
     roofline from one instrumented step. Returns the dict that goes under "hifigan" in the JSON line."""
     import torch
     import torch.distributed as dist
-    from oracle import hifigan as ohg           # synthetic batch generator only
-    from xva_trainer_b200 import capi, graph, hifigan as hg, ops
+    from xva_trainer_b200 import capi, graph, hifigan as hg, ops, synthetic
 
     Bh, frames = 16, 32
     h = _H(resblock="1", upsample_rates=[8, 8, 2, 2], upsample_kernel_sizes=[16, 16, 4, 4], upsample_initial_channel=512,
@@ -209,7 +274,7 @@ def run_hifigan(args, dev, world, rank, peak_tf32):
     mpd = hg.MultiPeriodDiscriminator(device=dev); mpd.train()
     msd = hg.MultiScaleDiscriminator(device=dev); msd.train()
     stepper = hg.HiFiGANStep(G, mpd, msd, h, world=world)
-    host = [t.pin_memory() for t in ohg.synthetic_batch(Bh, frames, seed=1 + rank)]
+    host = [t.cpu().pin_memory() for t in synthetic.hifigan_batch(Bh, frames, dev, seed=1 + rank)]
     h2d = sum(t.numel() * t.element_size() for t in host)
     x, y, y_mel = (t.to(dev, non_blocking=True) for t in host)
     steps = args.hifigan_steps
@@ -297,8 +362,7 @@ def run_native(args):
 
     import __graft_entry__ as ge
     ge.build()
-    from oracle import fastpitch as ofp  # synthetic batch generator + cpu_baseline leg only
-    from xva_trainer_b200 import capi, fastpitch as fp, graph, ops, parallel
+    from xva_trainer_b200 import capi, fastpitch as fp, graph, ops, parallel, synthetic
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -312,12 +376,13 @@ def run_native(args):
     model = fp.FastPitch(device=dev, seed=1234)          # identical weights on every rank
     model.training_stage = args.stage
     model.train()
-    crit = fp.FastPitchLoss()
+    model.seed = 1234 + rank                             # per-rank dropout streams
+    crit = fp.FastPitchLoss().set_distributed(world)     # global mask sums: the reference's multi-GPU loss
     crit.training_stage = args.stage
     opt = fp.Lamb(model, lr=0.1, betas=(0.9, 0.98), eps=1e-9, weight_decay=1e-6)
-    ddp = parallel.GradSync(model, world) if world > 1 else None
+    ddp = parallel.GradSync(model, world, mean=False) if world > 1 else None
 
-    x_cpu, y_cpu = ofp.synthetic_batch(args.batch, TT, TM, seed=1234 + rank, ragged=args.ragged)
+    x_cpu, y_cpu = synthetic.fastpitch_batch(args.batch, TT, TM, seed=1234 + rank, ragged=args.ragged)
     frames = int(x_cpu[3].sum())
     host_lens = (TM, int(x_cpu[3].max()))
     pin = [t.pin_memory() if torch.is_tensor(t) else t for t in x_cpu]
@@ -500,25 +565,37 @@ def run_native(args):
         hifi = run_hifigan(args, dev, world, rank, (pk["bf16_tflops_sustained"] if pk else 1400.0) / 2.0)
 
     if world > 1:
+        ft = torch.tensor([frames], device=dev, dtype=torch.float64)
+        dist.all_reduce(ft)
+        total_frames = int(ft.item())
         dist.barrier()
+    else:
+        total_frames = frames
     if rank != 0:
         if world > 1:
-            dist.destroy_process_group()
+            _leave(dist)
         return
 
+    eager = None
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        rate, per, cores, fr = cpu_step_rate(args.stage, args.cpu_sample_batch, 2, 1)
-        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"oracle train_step, batch {args.cpu_sample_batch} x {TM} frames of the batch-{args.batch} workload, "
-                         f"1 warm-up + 2 timed steps ({per:.1f} s/step), {cores} threads"}
+        # the kernel-for-kernel bar first (it needs the GPU this process still owns), then the bounded CPU sample
+        eager = eager_b200(local, hifi is not None)
+        del model, opt
+        torch.cuda.empty_cache()
+        cb = args.cpu_sample_batch if args.cpu_sample_batch > 0 else 8
+        rate, per, cores, fr, kind = cpu_step_rate(args.stage, cb, 2, 1)
+        what = "unmodified reference modules (baseline/_ref)" if kind == "reference" else "oracle train_step"
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": f"{what}, batch {cb} x {TM} frames of the batch-{args.batch} workload, 1 warm-up + 2 timed steps "
+                         f"({per:.1f} s/step, median), {cores} threads"}
         if hifi is not None:
-            hr, hper, _ = cpu_hifigan_rate(2, 1, 1)
-            hifi["cpu_baseline"] = {"value": hr, "unit": "samples/s", "cores": cores, "kind": "port",
-                                    "sample": f"oracle train_step, batch 2 x 8192 samples of the batch-16 workload, 1 warm-up + "
-                                              f"1 timed step ({hper:.1f} s/step), {cores} threads"}
+            hr, hper, _, hkind = cpu_hifigan_rate(4, 2, 1)
+            hifi["cpu_baseline"] = {"value": hr, "unit": "samples/s", "cores": cores, "kind": hkind,
+                                    "sample": f"{'unmodified reference modules' if hkind == 'reference' else 'oracle train_step'}, "
+                                              f"batch 4 x 8192 samples of the batch-16 workload, 1 warm-up + 2 timed steps "
+                                              f"({hper:.1f} s/step), {cores} threads"}
 
-    total_frames = frames * world  # every rank draws a batch with the same frame count (lengths are fixed)
     line = {"metric": METRIC, "value": total_frames * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32 (fp32 storage/accumulate)",
@@ -526,9 +603,24 @@ def run_native(args):
             "e2e": {"value": total_frames * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "loss": loss_host, "hifigan": hifi}
+    if eager is not None:
+        # the unmodified reference under PyTorch eager on this same B200 (ms/step, frames/s | samples/s per mode)
+        line["eager_b200"] = eager
     print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        _leave(dist)
+
+
+def _leave(dist):
+    """End of a multi-GPU run. With the all-reduces captured inside CUDA graphs, tearing the NCCL communicator down while
+    the graphs are still alive blocked for minutes on B200 (round-2 call B: the JSON line was out, the process was not);
+    every rank has passed the final barrier, so drain the device and leave without the teardown."""
+    import torch
+
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 def main():

@@ -135,7 +135,21 @@ typedef struct xva_gemm_args {
   const float* rowvec; /* XVA_GEMM_SOFTMAX_BWD: per-row scalar [Z*R] */
   int32_t drop_ld;     /* XVA_GEMM_SOFTMAX_BWD: row pitch of the dropout element index (0 = N) */
   int32_t _pad3;
+  /* Optional scratch for the stream-K schedule (mode 0/1): when the output tiles do not fill whole waves of SMs, the k
+     loop of the tiles of the fractional wave is cut over all SMs; pieces exchange fp32 partial accumulators through
+     sk_partials and count arrivals in sk_flags. Caller-owned like every buffer. sk_partials: at least
+     xva_gemm_sk_workspace_bytes(args) bytes, uninitialised, private to this launch. sk_flags: XVA_GEMM_SK_FLAGS uint32,
+     ZERO before the first launch that uses them; every launch leaves them zero, so one array serves all launches of a
+     stream -- but not launches that may run concurrently (one array per stream). NULL / too small: the launch falls
+     back to whole tiles per SM (same result up to the order of fp32 additions). */
+  float* sk_partials;
+  int64_t sk_partials_bytes;
+  uint32_t* sk_flags;
 } xva_gemm_args;
+
+#define XVA_GEMM_SK_FLAGS 4096
+/* Bytes of sk_partials this launch would use (0: it would not split any tile). No device work. */
+int64_t xva_gemm_sk_workspace_bytes(const xva_gemm_args* args);
 
 /* sizeof(xva_gemm_args) as compiled into the library, so a binding can verify its struct layout. */
 int xva_sizeof_gemm_args(void);
@@ -305,6 +319,8 @@ int xva_lens_mse_grad(const float* pred, const float* tgt, const int32_t* lens, 
  * CUDA block each; every chunk lies inside one tensor). norms is double[2*n_tensors], zeroed by the caller.
  * gnorm_sq (optional) = sum of squared gradients from xva_grad_sqnorm: gradients are scaled by
  * min(1, max_norm/(sqrt(gnorm_sq)+1e-6)) on the fly. lr is read from device memory (CUDA-graph friendly).
+ * A non-finite gnorm_sq (NaN / Inf anywhere in the gradients) makes the whole call a no-op on the device: the
+ * skip-the-step rule of xva_train.py:825-832 without a host round trip (p, m, v and p_tf32 are left untouched).
  * p_tf32 (optional, same layout as p) receives the updated parameters rounded to tf32: the copy the GEMMs read.
  * ---------------------------------------------------------------------------------------------------------- */
 int xva_grad_sqnorm(const float* g, const void* chunks, int n_chunks, double* out, void* stream);

@@ -224,7 +224,8 @@ def test_forward_matches_reference_golden(lib, stage):
     for k in ("loss", "mel_loss", "duration_predictor_loss", "pitch_loss", "energy_loss"):
         key = f"s{stage}/loss/{k}"
         if key in g.files:
-            assert abs(float(meta[k]) - float(g[key])) <= LOSS_TOL * abs(float(g[key])) + 1e-9, k
+            # (this fixture's batch is 3 x 14 tokens x 50 frames: few elements per loss term, bound as in round 1)
+            assert abs(float(meta[k]) - float(g[key])) <= 1e-3 * abs(float(g[key])) + 1e-9, (k, float(meta[k]), float(g[key]))
     m.zero_grad()
     m.backward(crit, 1.0)
     got = m.grads(fp.trainable_keys(stage))

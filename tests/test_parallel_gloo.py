@@ -101,3 +101,47 @@ def test_gradsync_stage1_slices_two_ranks_gloo():
     for rank, ok, buckets, elems in res:
         assert ok, f"rank {rank}: all-reduced arena is wrong"
         assert buckets == 2 and elems == 2000, (buckets, elems)   # only the two slices travel, not the arena between them
+
+
+def test_shard_batches_is_strided_and_drops_the_remainder():
+    sys.path.insert(0, ROOT)
+    from xva_trainer_b200.parallel import shard_batches
+
+    items = list(range(11))
+    shards = [shard_batches(items, r, 4) for r in range(4)]
+    assert shards == [[0, 4], [1, 5], [2, 6], [3, 7]]                 # 11 // 4 = 2 per rank, 3 items dropped
+    assert shard_batches(items, 0, 1) == items
+
+
+def _worker_mask_sums(rank, world, port, q):
+    """The criterion's {sum, count} pairs are all-reduced before the ratios: every rank then reports the loss of the
+    global batch, sum_global(err * mask) / sum_global(mask), not its local ratio."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from xva_trainer_b200.fastpitch import AttentionBinarizationLoss, FastPitchLoss
+
+    crit = FastPitchLoss().set_distributed(world)
+    acc = torch.tensor([[10.0 * (rank + 1), 100.0 + 50 * rank], [0.0, 0.0], [3.0 + rank, 7.0 - rank], [1.0, 2.0]], dtype=torch.float64)
+    crit._all_reduce(acc)
+    kl = AttentionBinarizationLoss().set_distributed(world)
+    q.put((rank, acc.tolist(), kl.world, FastPitchLoss().world))
+    dist.destroy_process_group()
+
+
+def test_loss_mask_sums_are_global_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + 7
+    procs = [ctx.Process(target=_worker_mask_sums, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = [[30.0, 250.0], [0.0, 0.0], [7.0, 13.0], [2.0, 4.0]]
+    for rank, acc, klw, default_world in out:
+        assert acc == want and klw == 2 and default_world == 1
+    # the global ratio differs from the mean of the per-rank ratios whenever the counts differ
+    assert abs(30.0 / 250.0 - 0.5 * (10.0 / 100.0 + 20.0 / 150.0)) > 1e-3

@@ -137,7 +137,12 @@ def test_hifigan_trainer_on_a_voice_folder(lib, tmp_path, monkeypatch):
     monkeypatch.setenv("XVA_B200_MAX_EPOCHS", "1")
     mm = trainers.ModelsManager(Log(), PROD=False)
     ws = FakeSocket()
-    data = {"dataset_path": str(voice), "output_path": str(tmp_path / "out"), "hifigan_checkpoint": None, "num_workers": 0,
+    # a real voice is always fine-tuned from a generator checkpoint ("Don't ever train from scratch",
+    # hifigan/xva_train.py:276-277): hand the trainer one in the reference's g_ file layout
+    from xva_trainer_b200 import hifigan as hg
+    base = tmp_path / "g_pretrained"
+    torch.save({"generator": hg.Generator(trainers._Cfg(trainers.HIFI_CONFIG_V1), device="cuda:0").state_dict()}, base)
+    data = {"dataset_path": str(voice), "output_path": str(tmp_path / "out"), "hifigan_checkpoint": str(base), "num_workers": 0,
             "batch_size": 3, "epochs_per_checkpoint": 1}
     os.makedirs(tmp_path / "out", exist_ok=True)
     res = asyncio.run(trainers.handleTrainerHiFi(mm, data, ws, [0]))

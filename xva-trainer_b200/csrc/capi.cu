@@ -35,6 +35,13 @@ int xva_gemm(const xva_gemm_args* args, void* stream) {
 
 int xva_gemm_debug_counters(long long* out8) { return gemm_debug_counters(out8); }
 
+int64_t xva_gemm_sk_workspace_bytes(const xva_gemm_args* args) {
+  if (args == nullptr) return 0;
+  long bytes = 0;
+  if (xva::gemm_tc_plan(*args, &bytes) != XVA_OK) return 0;
+  return static_cast<int64_t>(bytes);
+}
+
 int xva_gemm_ref(const xva_gemm_args* args, void* stream) {
   XVA_CHECK_ARG(args != nullptr, "xva_gemm_ref: null args");
   return gemm_ref_launch(*args, S(stream));

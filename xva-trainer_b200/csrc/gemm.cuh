@@ -51,6 +51,8 @@ inline GemmArgs gemm_args() {
 
 // tcgen05 + TMA implementation (the product path).
 int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream);
+// Host-only: bytes of stream-K scratch (GemmArgs::sk_partials) the launch of `g` would use; 0 = no tile is split.
+int gemm_tc_plan(const GemmArgs& g, long* sk_bytes);
 // Bring-up: cycle counters of CTA 0 from the last launch made with XVA_GEMM_DBG & 32 (see gemm_tc.cu).
 int gemm_debug_counters(long long* out8);
 // Plain fp32 SIMT implementation of the same contract; used by the tests to separate "descriptor/layout bug"

@@ -144,6 +144,10 @@ lamb_stage1_kernel(const float* __restrict__ p, const float* __restrict__ g, flo
                    float* __restrict__ v, const LambChunk* __restrict__ chunks, double* __restrict__ norms,
                    const double* __restrict__ gnorm_sq, float max_norm, float b1, float b2, float eps, float wd) {
   __shared__ double sh[8];
+  // A non-finite gradient norm (a NaN / Inf anywhere in the stage's gradients) turns the whole update into a no-op:
+  // the skip of xva_train.py:825-832 decided on the device, so weights, moments and the tf32 weight copy never see it
+  // and a captured step needs no host round trip before the optimizer.
+  if (gnorm_sq != nullptr && !isfinite(*gnorm_sq)) return;
   const LambChunk ck = chunks[blockIdx.x];
   const float coef = clip_coef(gnorm_sq, max_norm);
   double sp = 0.0, sr = 0.0;
@@ -171,7 +175,9 @@ lamb_stage1_kernel(const float* __restrict__ p, const float* __restrict__ g, flo
 __global__ void __launch_bounds__(256)
 lamb_stage2_kernel(float* __restrict__ p, const float* __restrict__ m, const float* __restrict__ v,
                    const LambChunk* __restrict__ chunks, const double* __restrict__ norms,
-                   const float* __restrict__ lr_dev, float eps, float wd, float* __restrict__ p_tf32) {
+                   const double* __restrict__ gnorm_sq, const float* __restrict__ lr_dev, float eps, float wd,
+                   float* __restrict__ p_tf32) {
+  if (gnorm_sq != nullptr && !isfinite(*gnorm_sq)) return;  // see stage 1
   const LambChunk ck = chunks[blockIdx.x];
   const float wn = fminf(static_cast<float>(sqrt(norms[2 * ck.tensor])), 10.0f);
   const float rn = static_cast<float>(sqrt(norms[2 * ck.tensor + 1]));
@@ -244,7 +250,7 @@ int lamb_step(float* p, const float* g, float* m, float* v, const void* chunks, 
   const LambChunk* ck = static_cast<const LambChunk*>(chunks);
   lamb_stage1_kernel<<<n_chunks, 256, 0, stream>>>(p, g, m, v, ck, norms, gnorm_sq, max_norm, b1, b2, eps, wd);
   XVA_CHECK_LAUNCH();
-  lamb_stage2_kernel<<<n_chunks, 256, 0, stream>>>(p, m, v, ck, norms, lr_dev, eps, wd, p_tf32);
+  lamb_stage2_kernel<<<n_chunks, 256, 0, stream>>>(p, m, v, ck, norms, gnorm_sq, lr_dev, eps, wd, p_tf32);
   XVA_CHECK_LAUNCH();
   return XVA_OK;
 }

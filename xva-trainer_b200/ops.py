@@ -31,9 +31,34 @@ def _check3(t, name):
                          f"{t.dtype} {tuple(t.shape)} strides {t.stride()}")
 
 
+_SK_FLAGS = {}   # (device index, stream handle) -> zeroed uint32[XVA_GEMM_SK_FLAGS]: stream-K arrival counters
+SK_SCRATCH = True   # False: hand no stream-K scratch to xva_gemm (whole tiles per SM); the tests' A/B switch
+
+
+def _sk_scratch(args):
+    """Stream-K scratch of one launch (xva_gemm_args.sk_*): the partial-accumulator buffer is a fresh allocation on the
+    launching stream (the caching allocator orders its reuse after the kernel), the arrival counters are one zeroed
+    array per (device, stream) -- launches of one stream run one after the other and each leaves them zero; launches on
+    different streams may overlap and must not share them. Returns the tensors to keep referenced until the launch."""
+    fn = getattr(capi.load(), "xva_gemm_sk_workspace_bytes", None) if SK_SCRATCH else None
+    need = int(fn(C.byref(args))) if fn is not None else 0
+    if need <= 0:
+        return None
+    dev = torch.cuda.current_device()
+    key = (dev, torch.cuda.current_stream().cuda_stream)
+    flags = _SK_FLAGS.get(key)
+    if flags is None:
+        flags = _SK_FLAGS[key] = torch.zeros(capi.XVA_GEMM_SK_FLAGS, device=f"cuda:{dev}", dtype=torch.int32)
+    part = torch.empty(need // 4, device=f"cuda:{dev}", dtype=torch.float32)
+    args.sk_partials, args.sk_partials_bytes, args.sk_flags = part.data_ptr(), need, flags.data_ptr()
+    return part, flags
+
+
 def gemm_launch(args, ref=False):
     """Launch one tap-GEMM described by a filled capi.GemmArgs."""
+    keep = None if ref else _sk_scratch(args)
     capi.call("xva_gemm_ref" if ref else "xva_gemm", C.byref(args), _stream())
+    del keep
 
 
 def _base_args(mode, shifts):
