@@ -43,6 +43,8 @@ def parse():
                     "instead of the BASELINE config's full-length batch; frames/s then counts valid frames only")
     ap.add_argument("--no-hifigan", action="store_true", help="skip the second half of the metric (HiFi-GAN samples/s)")
     ap.add_argument("--hifigan-steps", type=int, default=20)
+    ap.add_argument("--via-trainer", action="store_true", help="time the same workload through the trainer facade "
+                    "(FastPitchTrainer.iteration / HiFiTrainer.iteration: what the UI drives) instead of bench.py's own loop")
     return ap.parse_args()
 
 
@@ -484,7 +486,9 @@ def run_native(args):
     # ---- instrumented step: CUDA events around every tap-GEMM launch (after the timed regions)
     roof = None
     if rank != 0 and world > 1:
-        step(x_dev)          # the instrumented step below contains the gradient all-reduce: every rank must run it
+        opt.lr_on_device = False
+        eager_step(x_dev)    # the two eager steps below (allocator warm-up + instrumented) contain the gradient all-reduce:
+        eager_step(x_dev)    # every rank must run them
     if rank == 0:
         rec = []
         orig = ops.gemm_launch
@@ -496,10 +500,34 @@ def run_native(args):
             b.record()
             rec.append((a, b, gemm_flops(g), (g.mode, g.Z, g.R, g.M, g.N, g.K, g.taps, g.flags, g.split)))
 
+        # the fused attention kernels (csrc/attn_fused.cu) are timed the same way; algorithmic FLOPs: forward 2 products,
+        # backward 4 (dV, dP, dQ, dK) of 2 * B * T^2 * 64 each -- the recomputation of S in both backward kernels is not counted
+        att_rec = []
+        orig_af, orig_ab = ops.attn_fwd, ops.attn_bwd
+
+        def timed_attn(fn, n_products):
+            def run(qkv, *a, **k):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                out = fn(qkv, *a, **k)
+                e1.record()
+                att_rec.append((e0, e1, n_products * 2.0 * qkv.shape[0] * qkv.shape[1] ** 2 * 64))
+                return out
+            return run
+
+        ops.attn_fwd, ops.attn_bwd = timed_attn(orig_af, 2), timed_attn(orig_ab, 4)
         ops.gemm_launch = timed_launch
         opt.lr_on_device = False
         step = eager_step            # the instrumented step is launched eagerly (events between kernels)
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # one untimed eager step first: the timed region replays graphs, so the eager path's allocations (attention outputs,
+        # temporaries) would otherwise hit cudaMalloc between an event pair and count the host stall as kernel time
+        ops.gemm_launch, ops.attn_fwd, ops.attn_bwd = orig, orig_af, orig_ab
+        eager_step(x_dev)
+        ops.attn_fwd, ops.attn_bwd = timed_attn(orig_af, 2), timed_attn(orig_ab, 4)
+        ops.gemm_launch = timed_launch
+        rec.clear()
+        att_rec.clear()
         torch.cuda.synchronize()
         # park the GPU (~60 ms spin) so the host enqueues the whole step ahead of it: the event pairs then bracket
         # device time only, not host launch gaps
@@ -509,6 +537,7 @@ def run_native(args):
         s1.record()
         torch.cuda.synchronize()
         ops.gemm_launch = orig
+        ops.attn_fwd, ops.attn_bwd = orig_af, orig_ab
         gemm_ms = sum(r[0].elapsed_time(r[1]) for r in rec)
         flops = sum(r[2] for r in rec)
         table_path = os.environ.get("XVA_BENCH_GEMM_TABLE")
@@ -557,6 +586,16 @@ def run_native(args):
                 "share_of_step": gemm_ms / (ms / args.steps), "dominant_launch": dominant,
                 "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained / 2 (kind::tf32 runs at half the bf16 rate), "
                                 "of measured") if peaks else "fallback 1.4 PFLOP/s / 2, of fallback"}
+        if att_rec:
+            att_ms = sum(a.elapsed_time(b) for a, b, _ in att_rec)
+            att_fl = sum(f for _, _, f in att_rec)
+            roof["attention"] = {"kernel": "attn_fwd / attn_bwd_dq / attn_bwd_dkv (tcgen05 kind::tf32, S and P in tensor memory)",
+                                 "launches_per_step": len(att_rec), "flops_per_step": att_fl, "kernel_ms_per_step": att_ms,
+                                 "achieved": att_fl / (att_ms * 1e-3) / 1e12, "frac": att_fl / (att_ms * 1e-3) / 1e12 / peak,
+                                 "note": "algorithmic FLOPs (6 products per layer); the backward also recomputes S twice"}
+            roof["tensor_kernels_combined"] = {"flops_per_step": flops + att_fl, "kernel_ms_per_step": gemm_ms + att_ms,
+                                               "achieved": (flops + att_fl) / ((gemm_ms + att_ms) * 1e-3) / 1e12,
+                                               "frac": (flops + att_fl) / ((gemm_ms + att_ms) * 1e-3) / 1e12 / peak}
 
     hifi = None
     if not args.no_hifigan:
@@ -623,8 +662,89 @@ def _leave(dist):
     os._exit(0)
 
 
+def run_via_trainer(args):
+    """The configs[1] / configs[2] workloads driven through the reference-shaped entry points (trainers.FastPitchTrainer /
+    HiFiTrainer .iteration(), the methods the server's training thread loops over): same step, same kernels, plus the
+    facade's own bookkeeping (log line, TensorBoard scalars, one host read per optimizer step). Prints one JSON line; the
+    number to compare is bench.py's default `value` (batches are device-resident in both)."""
+    import asyncio
+    import tempfile
+
+    import torch
+
+    import __graft_entry__ as ge
+    ge.build()
+    from xva_trainer_b200 import trainers
+
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    torch.cuda.set_device(local)
+    out_dir = tempfile.mkdtemp(prefix="xva_bench_")
+    mm = trainers.ModelsManager(None, PROD=False)
+    W, K = max(args.warmup, 3), args.steps
+
+    async def drive(tr, data, n_warm, n_steps):
+        tr.running = True
+        if hasattr(tr, "force_stage"):
+            tr.force_stage = data.get("force_stage")
+        # what start() does before its `while self.running: await self.iteration()` loop
+        tr.dataset_input = data["dataset_path"]
+        tr.dataset_id = tr.dataset_input.replace(":", "_")
+        tr.dataset_output = os.path.join(out_dir, tr.dataset_id)
+        tr.checkpoint = None
+        tr.batch_size = int(data["batch_size"])
+        tr.epochs_per_checkpoint = 0
+        tr.batch_source = None
+        tr.max_epochs = 0
+        if isinstance(tr, trainers.FastPitchTrainer):
+            tr.workers, tr.learning_rate, tr.warmup_steps = 0, 0.1, 1000
+        else:
+            tr.hifi_dir = os.path.join(tr.dataset_output, "hifi")
+        tr.init_logs(tr.dataset_output)
+        for _ in range(n_warm):
+            await tr.iteration()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(n_steps):
+            await tr.iteration()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), time.perf_counter() - t0
+
+    # epochs never end inside the timed region: the synthetic dataset holds more batches than W + K iterations
+    fp_tr = trainers.FastPitchTrainer(None, False, list(range(max(world, 1))), mm)
+    n_items = args.batch * (W + K + 2)
+    ms, wall = asyncio.run(drive(fp_tr, {"dataset_path": f"synthetic:{args.batch}x{TT}x{TM}x{n_items}", "batch_size": 74,
+                                         "force_stage": args.stage}, W, K))
+    logged = [float(l.split("frames/s ")[1].split(" ")[0]) for l in [fp_tr.training_log_live_line] if "frames/s" in l]
+    frames = args.batch * TM * world
+    line = {"metric": METRIC, "via": "trainers.FastPitchTrainer.iteration", "value": frames * K / (ms * 1e-3), "unit": UNIT,
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "host_wall_ms_per_step": wall * 1e3 / K,
+            "logged_frames_per_s_last_step": logged[0] if logged else None, "gam": fp_tr.gam,
+            "graph": bool(fp_tr.use_graph), "config": config(args, world)}
+    del fp_tr
+    torch.cuda.empty_cache()
+    if not args.no_hifigan:
+        h_tr = trainers.HiFiTrainer(None, False, list(range(max(world, 1))), mm)
+        hs = args.hifigan_steps
+        hms, hwall = asyncio.run(drive(h_tr, {"dataset_path": f"synthetic:16x32x{16 * (W + hs + 2)}", "batch_size": 16}, W, hs))
+        line["hifigan"] = {"via": "trainers.HiFiTrainer.iteration", "value": 16 * 8192 * world * hs / (hms * 1e-3),
+                           "unit": "samples/s", "ms_per_step": hms / hs, "host_wall_ms_per_step": hwall * 1e3 / hs,
+                           "graph": bool(h_tr.use_graph)}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        _leave(dist)
+
+
 def main():
     args = parse()
+    if args.via_trainer:
+        return run_via_trainer(args)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -135,21 +135,7 @@ typedef struct xva_gemm_args {
   const float* rowvec; /* XVA_GEMM_SOFTMAX_BWD: per-row scalar [Z*R] */
   int32_t drop_ld;     /* XVA_GEMM_SOFTMAX_BWD: row pitch of the dropout element index (0 = N) */
   int32_t _pad3;
-  /* Optional scratch for the stream-K schedule (mode 0/1): when the output tiles do not fill whole waves of SMs, the k
-     loop of the tiles of the fractional wave is cut over all SMs; pieces exchange fp32 partial accumulators through
-     sk_partials and count arrivals in sk_flags. Caller-owned like every buffer. sk_partials: at least
-     xva_gemm_sk_workspace_bytes(args) bytes, uninitialised, private to this launch. sk_flags: XVA_GEMM_SK_FLAGS uint32,
-     ZERO before the first launch that uses them; every launch leaves them zero, so one array serves all launches of a
-     stream -- but not launches that may run concurrently (one array per stream). NULL / too small: the launch falls
-     back to whole tiles per SM (same result up to the order of fp32 additions). */
-  float* sk_partials;
-  int64_t sk_partials_bytes;
-  uint32_t* sk_flags;
 } xva_gemm_args;
-
-#define XVA_GEMM_SK_FLAGS 4096
-/* Bytes of sk_partials this launch would use (0: it would not split any tile). No device work. */
-int64_t xva_gemm_sk_workspace_bytes(const xva_gemm_args* args);
 
 /* sizeof(xva_gemm_args) as compiled into the library, so a binding can verify its struct layout. */
 int xva_sizeof_gemm_args(void);
@@ -183,13 +169,37 @@ int xva_average_pitch(const float* pitch, const float* durs, int B, int F, int T
  * (XVA_GEMM_SOFTMAX_BWD): sum_j P_d[r,j] * dP_d[r,j] = dO[r] . O[r] for O = P_d V. */
 int xva_rowdot2(const float* a, const float* b, int64_t rows, int C, int64_t a_ld, int64_t b_ld, float* out, void* stream);
 
+/* Fused single-head attention of an FFT block -- replaces the body of MultiHeadAttn._forward between the qkv projection
+ * and the output projection, fastpitch/transformer.py:113-133 (n_head = 1, d_head = 64): scores q.k^T * scale, key mask
+ * (keys >= lens[b]), softmax, attention dropout and the product with v in ONE kernel; the [B, T, T] score / probability
+ * tensors live only in tensor memory (tcgen05.mma accumulates S there, the softmax threads overwrite it with P, a second
+ * tcgen05.mma reads P from there). qkv [B, T, >= 192] fp32 holding tf32-rounded values, columns q 0..63 | k 64..127 |
+ * v 128..191, row stride rs, item stride zs (elements). out [B, T, 64] (strides o_rs, o_zs; stored tf32-rounded: it is the
+ * operand of the output projection), lse [B * T] = log sum_j exp(scale * q.k_j) over the unmasked keys (+inf for a row
+ * without any), what the backward recomputes P from. Dropout: element (b, row, key) is dropped by the shared counter
+ * hash of ((b * T + row) * drop_ld + key) with (seed, *seed_dev) -- the index the unfused xva_softmax kernels use. */
+int xva_attn_fwd(const float* qkv, int64_t rs, int64_t zs, int B, int T, const int32_t* lens, float scale, float drop_p,
+                 uint64_t seed, const uint64_t* seed_dev, int drop_ld, float* out, int64_t o_rs, int64_t o_zs, float* lse,
+                 void* stream);
+
+/* Backward of xva_attn_fwd (the autograd of transformer.py:113-133), two launches: dq per 128-row query tile, dk / dv per
+ * 128-key tile, both recomputing P = exp(scale * q.k - lse[row]) and the dropout mask, with S, dP, dS and P in tensor
+ * memory. dout [B, T, 64] = gradient of the attention output (strides d_rs, d_zs; tf32-rounded GEMM operand), lse from the
+ * forward, dsum [B * T] = dot(dout[row], out[row]) (xva_rowdot2). dqkv [B, T, >= 192] (strides g_rs, g_zs) receives
+ * dq | dk | dv in the column layout of qkv, tf32-rounded. Same dropout arguments as the forward call. */
+int xva_attn_bwd(const float* qkv, int64_t rs, int64_t zs, const float* dout, int64_t d_rs, int64_t d_zs, const float* lse,
+                 const float* dsum, int B, int T, const int32_t* lens, float scale, float drop_p, uint64_t seed,
+                 const uint64_t* seed_dev, int drop_ld, float* dqkv, int64_t g_rs, int64_t g_zs, void* stream);
+
 /* Monotonic alignment search -- replaces b_mas / mas_width1, fastpitch/alignment.py:79-118 (called through
  * FastPitch.binarize_attention_parallel, model.py:283-294, after a device->host copy; training stage 1): Viterbi path
  * through the soft alignment attn [B, Tm, Tt] (mel x text, the reference's [B, 1, Tm, Tt]) restricted to
  * [out_lens[b], in_lens[b]]. hard [B, Tm, Tt] gets the 0/1 alignment (zero elsewhere), durs [B, Tt] its column sums
  * (attn_hard.sum(2), model.py:318) as int32. is_log = 0: attn holds probabilities (the reference's input; log taken in
  * double and rounded to fp32); is_log = 1: attn holds fp32 log-probabilities and the path is bit-identical to the
- * reference recurrence on the same values. Tm x ceil(Tt/32) x 4 bytes of shared memory (<= 200 KiB). */
+ * reference recurrence on the same values. is_log | 2: the search of xVAPitch (maximum_path, xvapitch/util.py:14-53; SURVEY
+ * 8f rank 1) on the same layout -- log-likelihoods in, "stay" preferred on an exact tie (util.py:35) where FastPitch
+ * advances, no second mark in row 0. Tm x ceil(Tt/32) x 4 bytes of shared memory (<= 200 KiB). */
 int xva_mas_width1(const float* attn, const int32_t* in_lens, const int32_t* out_lens, int B, int Tm, int Tt, int is_log,
                    float* hard, int32_t* durs, void* stream);
 /* out[i] = (float) log((double) attn[i]), i < n: the logarithm xva_mas_width1 takes element by element with is_log = 0,

@@ -62,8 +62,6 @@ def record(streams=False):
         if isinstance(g, capi.GemmArgs):                           # byref(GemmArgs): every field but the pointers
             out = {}
             for name, typ in g._fields_:
-                if name.startswith("sk_"):     # caller-owned scratch of the stream-K schedule: not part of the launch's meaning
-                    continue
                 v = getattr(g, name)
                 if typ is C.c_void_p:
                     out[name] = None if v is None else "ptr"

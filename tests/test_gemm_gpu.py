@@ -432,87 +432,3 @@ def test_conv_wgrad_multi_tap_tiles(B, T, N, K, shifts):
     got_ref = ops.conv_wgrad(dy, x, shifts, ref=True)
     assert rel(got_ref, want.float()) < TOL_REF
     assert rel(got, want.float()) < TOL_TC
-
-
-# ------------------------------------------------------------------------------------------------ stream-K schedule
-def _sk_plan(ops_mod, fn):
-    """Bytes of stream-K scratch requested by the launches `fn` makes (0 = no tile was split)."""
-    from xva_trainer_b200 import capi
-
-    seen = []
-    orig = ops_mod._sk_scratch
-
-    def spy(args):
-        keep = orig(args)
-        seen.append(int(args.sk_partials_bytes))
-        return keep
-
-    ops_mod._sk_scratch = spy
-    try:
-        out = fn()
-    finally:
-        ops_mod._sk_scratch = orig
-    return out, seen
-
-
-@pytest.mark.parametrize("what,B,T,K,N,shifts", [
-    ("fwd", 32, 880, 1536, 384, (-1, 0, 1)),     # decoder ConvFF conv2: CTA pairs, 1.51 waves -> 38 tail tiles over 74 pairs
-    ("fwd", 32, 880, 384, 1536, (-1, 0, 1)),     # conv1: 9.08 waves, 6 tail tiles cut ~12 ways
-    ("dgrad", 32, 880, 384, 1536, (-1, 0, 1)),   # dgrad of conv2 (mode 1, MN-major weights)
-    ("dgrad", 32, 880, 1536, 384, (-1, 0, 1)),
-    ("fwd", 32, 160, 1536, 384, (-1, 0, 1)),     # encoder: sub-wave launch, every tile split
-    ("fwd", 32, 160, 384, 1536, (-1, 0, 1)),
-    ("dgrad", 32, 160, 384, 1536, (-1, 0, 1)),
-    ("fwd", 5, 333, 512, 200, (-2, 0, 2)),       # ragged everything: N not a multiple of 32, row tail, 2 segments
-])
-def test_stream_k_matches_whole_tiles_and_reference(what, B, T, K, N, shifts):
-    """The stream-K schedule (k loop of the fractional wave cut over all SMs, partial accumulators exchanged through
-    caller-owned scratch) gives the result of the whole-tile schedule up to the order of fp32 additions, for the launch
-    shapes of the bench; three launches in a row reuse the arrival counters (each launch must leave them zero)."""
-    ops = _ops()
-    if what == "fwd":
-        x, w = gen(B, T, K, seed=41), gen(len(shifts), N, K, seed=42, scale=K ** -0.5)
-        bias = gen(N, seed=43)
-        run = lambda **kw: ops.conv_fwd(x, w, shifts, bias=bias, relu=True, **kw)
-    else:
-        dy, w = gen(B, T, N, seed=44), gen(len(shifts), N, K, seed=45, scale=N ** -0.5)
-        h = gen(B, T, K, seed=46)
-        run = lambda **kw: ops.conv_dgrad(dy, w, shifts, gate=h, residual=h, **kw)
-    got, plan = _sk_plan(ops, run)
-    assert plan and plan[0] > 0, "this shape was expected to get a stream-K schedule"
-    again = [run() for _ in range(2)]
-    ops.SK_SCRATCH = False
-    try:
-        whole, plan0 = _sk_plan(ops, run)
-    finally:
-        ops.SK_SCRATCH = True
-    torch.cuda.synchronize()
-    assert plan0 == [0]
-    assert rel(got, whole) < 2e-6, rel(got, whole)
-    for a in again:
-        assert torch.equal(a, got)                  # deterministic: partials are added in a fixed order
-    flags = list(ops._SK_FLAGS.values())
-    assert flags and all(int(f.abs().sum()) == 0 for f in flags)
-    if B * T * N * K * len(shifts) < 4e10:         # the exact-fp32 checker on the smaller shapes
-        want = run(ref=True)
-        assert rel(got, want) < TOL_TC
-
-
-def test_stream_k_layernorm_epilogue_and_lens():
-    """EPI_LN owner pieces (temporal-predictor shape, sub-wave) and row-length masking."""
-    ops = _ops()
-    B, T, K, N = 32, 160, 384, 256
-    x, w, bias = gen(B, T, K, seed=51), gen(3, N, K, seed=52, scale=K ** -0.5), gen(N, seed=53)
-    gamma, beta = 1 + 0.1 * gen(N, seed=54), 0.1 * gen(N, seed=55)
-    lens = torch.randint(90, 161, (B,), device="cuda", dtype=torch.int32)
-    run = lambda **kw: ops.conv_fwd(x, w, (-1, 0, 1), bias=bias, relu=True, ln=(gamma, beta), lens=lens, **kw)
-    got, plan = _sk_plan(ops, run)
-    assert plan[0] > 0
-    want = run(ref=True)
-    ops.SK_SCRATCH = False
-    try:
-        whole = run()
-    finally:
-        ops.SK_SCRATCH = True
-    assert rel(got, whole) < 2e-6
-    assert rel(got, want) < TOL_TC

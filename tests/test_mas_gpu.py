@@ -54,3 +54,16 @@ def test_mas_full_size_properties(lib):
         tok = h[:ol[b]].argmax(1)
         assert tok[0] == 0 and tok[-1] == il[b] - 1 and (np.diff(tok) >= 0).all() and (np.diff(tok) <= 1).all()
         assert durs[b].sum() == ol[b] and np.array_equal(durs[b], h.sum(0).astype(np.int32))
+
+
+@pytest.mark.parametrize("case", ["small", "mid", "ties"])
+def test_xvapitch_maximum_path_matches_reference(lib, case):
+    """SURVEY 8f rank 1, first piece: xVAPitch's numpy maximum_path (python/xvapitch/util.py:14-53, recorded from the
+    unmodified reference by tests/golden/make_golden_xvapitch_mas.py) is xva_mas_width1 with the stay-on-tie flag --
+    identical paths, including the fixture made of exact ties."""
+    from xva_trainer_b200 import ops
+    g = np.load(os.path.join(GOLD, "xvapitch_mas.npz"))
+    val = torch.from_numpy(g[f"{case}/value"]).cuda()
+    xl, yl = torch.from_numpy(g[f"{case}/x_lens"]).cuda(), torch.from_numpy(g[f"{case}/y_lens"]).cuda()
+    path = ops.maximum_path(val, xl, yl)
+    assert torch.equal(path.cpu(), torch.from_numpy(g[f"{case}/path"]))

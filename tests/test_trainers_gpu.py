@@ -37,6 +37,7 @@ def test_fastpitch_handle_trainer_stages_and_files(lib, tmp_path, monkeypatch):
     out = tmp_path / "synthetic_4x24x64x16"
     names = sorted(os.listdir(out))
     assert "training.log" in names and "graphs.json" in names
+    assert any(n.startswith("events.out.tfevents") for n in names)                 # TensorBoard scalars (xva_train.py:297,841-899)
     assert "synthetic_4x24x64x16.pt" in names and "synthetic_4x24x64x16.json" in names
     assert sum(n.startswith("FastPitch_checkpoint_") for n in names) <= 2          # only the last two are kept
     assert {n.split("_")[1] for n in names if n.startswith("Stage_")} == {"2", "3", "4"}

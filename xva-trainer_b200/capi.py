@@ -49,7 +49,6 @@ class GemmArgs(C.Structure):
         ("a_col", C.c_int32 * XVA_MAX_TAPS), ("seed_dev", C.c_void_p),
         ("groups", C.c_int32), ("grp_step", C.c_int32),
         ("rowvec", C.c_void_p), ("drop_ld", C.c_int32), ("_pad3", C.c_int32),
-        ("sk_partials", C.c_void_p), ("sk_partials_bytes", C.c_int64), ("sk_flags", C.c_void_p),
     ]
 
 
@@ -66,7 +65,6 @@ class WnDesc(C.Structure):
 
 
 WN_TRANSPOSED, WN_NO_ROUND = 1, 2
-XVA_GEMM_SK_FLAGS = 4096
 
 # name -> (restype, argtypes); must list every symbol include/xva_b200.h declares (tests/test_abi.py checks it)
 _I, _F, _P, _U64, _I64 = C.c_int, C.c_float, C.c_void_p, C.c_uint64, C.c_int64
@@ -77,13 +75,14 @@ PROTOTYPES = {
     "xva_sizeof_gemm_args": (_I, []),
     "xva_gemm": (_I, [C.POINTER(GemmArgs), _P]),
     "xva_gemm_ref": (_I, [C.POINTER(GemmArgs), _P]),
-    "xva_gemm_sk_workspace_bytes": (_I64, [C.POINTER(GemmArgs)]),
     "xva_gemm_debug_counters": (_I, [C.POINTER(C.c_longlong * 8)]),
     "xva_regulate_len_scan": (_I, [_P, _I, _I, _F, _I, _P, _P, _P]),
     "xva_regulate_len_fwd": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "xva_regulate_len_bwd": (_I, [_P, _P, _I, _I, _I, _I, _P, _I, _P]),
     "xva_average_pitch": (_I, [_P, _P, _I, _I, _I, _I, _P, _I, _P]),
     "xva_rowdot2": (_I, [_P, _P, _I64, _I, _I64, _I64, _P, _P]),
+    "xva_attn_fwd": (_I, [_P, _I64, _I64, _I, _I, _P, _F, _F, _U64, _P, _I, _P, _I64, _I64, _P, _P]),
+    "xva_attn_bwd": (_I, [_P, _I64, _I64, _P, _I64, _I64, _P, _P, _I, _I, _P, _F, _F, _U64, _P, _I, _P, _I64, _I64, _P]),
     "xva_mas_width1": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "xva_attn_score_fwd": (_I, [_P, _I64, _P, _I64, _P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "xva_attn_score_bwd": (_I, [_P, _P, _P, _P, _I64, _P, _I64, _I, _I, _I, _I, _P, _P, _I64, _P, _I64, _P]),
@@ -172,8 +171,8 @@ def check(status, what=""):
 
 
 # kernels enqueued per successful call (everything not listed launches exactly one)
-_LAUNCHES = {"xva_lamb_step": 2, "xva_attn_score_bwd": 2, "xva_attn_ctc": 3, "xva_gemm_debug_counters": 0, "xva_set_operand_rounding": 0, "xva_abi_version": 0, "xva_last_error": 0, "xva_device_check": 0,
-             "xva_sizeof_gemm_args": 0, "xva_sizeof_wn_desc": 0, "xva_gemm_sk_workspace_bytes": 0}
+_LAUNCHES = {"xva_lamb_step": 2, "xva_attn_bwd": 2, "xva_attn_score_bwd": 2, "xva_attn_ctc": 3, "xva_gemm_debug_counters": 0, "xva_set_operand_rounding": 0, "xva_abi_version": 0, "xva_last_error": 0, "xva_device_check": 0,
+             "xva_sizeof_gemm_args": 0, "xva_sizeof_wn_desc": 0}
 _launch_count = 0
 
 

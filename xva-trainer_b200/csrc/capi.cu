@@ -35,13 +35,6 @@ int xva_gemm(const xva_gemm_args* args, void* stream) {
 
 int xva_gemm_debug_counters(long long* out8) { return gemm_debug_counters(out8); }
 
-int64_t xva_gemm_sk_workspace_bytes(const xva_gemm_args* args) {
-  if (args == nullptr) return 0;
-  long bytes = 0;
-  if (xva::gemm_tc_plan(*args, &bytes) != XVA_OK) return 0;
-  return static_cast<int64_t>(bytes);
-}
-
 int xva_gemm_ref(const xva_gemm_args* args, void* stream) {
   XVA_CHECK_ARG(args != nullptr, "xva_gemm_ref: null args");
   return gemm_ref_launch(*args, S(stream));
@@ -69,6 +62,21 @@ int xva_average_pitch(const float* pitch, const float* durs, int B, int F, int T
 
 int xva_rowdot2(const float* a, const float* b, int64_t rows, int C, int64_t a_ld, int64_t b_ld, float* out, void* stream) {
   return rowdot2(a, b, static_cast<long>(rows), C, static_cast<long>(a_ld), static_cast<long>(b_ld), out, S(stream));
+}
+
+int xva_attn_fwd(const float* qkv, int64_t rs, int64_t zs, int B, int T, const int32_t* lens, float scale, float drop_p,
+                 uint64_t seed, const uint64_t* seed_dev, int drop_ld, float* out, int64_t o_rs, int64_t o_zs, float* lse,
+                 void* stream) {
+  return attn_fused_fwd(qkv, static_cast<long>(rs), static_cast<long>(zs), B, T, lens, scale, drop_p, seed, seed_dev, drop_ld,
+                        out, static_cast<long>(o_rs), static_cast<long>(o_zs), lse, S(stream));
+}
+
+int xva_attn_bwd(const float* qkv, int64_t rs, int64_t zs, const float* dout, int64_t d_rs, int64_t d_zs, const float* lse,
+                 const float* dsum, int B, int T, const int32_t* lens, float scale, float drop_p, uint64_t seed,
+                 const uint64_t* seed_dev, int drop_ld, float* dqkv, int64_t g_rs, int64_t g_zs, void* stream) {
+  return attn_fused_bwd(qkv, static_cast<long>(rs), static_cast<long>(zs), dout, static_cast<long>(d_rs),
+                        static_cast<long>(d_zs), lse, dsum, B, T, lens, scale, drop_p, seed, seed_dev, drop_ld, dqkv,
+                        static_cast<long>(g_rs), static_cast<long>(g_zs), S(stream));
 }
 
 int xva_mas_width1(const float* attn, const int32_t* in_lens, const int32_t* out_lens, int B, int Tm, int Tt, int is_log,
@@ -136,6 +144,7 @@ int xva_set_operand_rounding(int on) {
   int rc;
   if ((rc = set_operand_rounding_gemm_tc(on)) != XVA_OK) return rc;
   if ((rc = set_operand_rounding_gemm_ref(on)) != XVA_OK) return rc;
+  if ((rc = set_operand_rounding_attn_fused(on)) != XVA_OK) return rc;
   if ((rc = set_operand_rounding_rowops(on)) != XVA_OK) return rc;
   if ((rc = set_operand_rounding_elemwise(on)) != XVA_OK) return rc;
   if ((rc = set_operand_rounding_melspec(on)) != XVA_OK) return rc;

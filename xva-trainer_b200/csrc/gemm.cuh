@@ -51,8 +51,11 @@ inline GemmArgs gemm_args() {
 
 // tcgen05 + TMA implementation (the product path).
 int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream);
-// Host-only: bytes of stream-K scratch (GemmArgs::sk_partials) the launch of `g` would use; 0 = no tile is split.
-int gemm_tc_plan(const GemmArgs& g, long* sk_bytes);
+// fp32 tensor map with zero out-of-bounds fill (cuTensorMapEncodeTiled): dims / strides in elements, innermost first,
+// strides[0] implicit; `map` points at a CUtensorMap; swizzle is a CUtensorMapSwizzle value. Shared with attn_fused.cu.
+int tma_encode_f32(void* map, const float* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
+                   const uint32_t* box, int swizzle);
+
 // Bring-up: cycle counters of CTA 0 from the last launch made with XVA_GEMM_DBG & 32 (see gemm_tc.cu).
 int gemm_debug_counters(long long* out8);
 // Plain fp32 SIMT implementation of the same contract; used by the tests to separate "descriptor/layout bug"

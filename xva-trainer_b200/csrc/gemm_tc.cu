@@ -93,19 +93,6 @@ struct GemmDev {
   const uint64_t* seed_dev;
   const float* rowvec;  // GEMM_SOFTMAX_BWD: per-row scalar
   int drop_ld;          // GEMM_SOFTMAX_BWD: row pitch of the dropout index
-  // Stream-K schedule of the fractional wave (mode 0/1). Tiles [sk_first, num_tiles) -- the ones that do not fill a whole
-  // wave of CTAs (every tile of a sub-wave launch) -- are laid end to end as sk_total = sk_tiles * iters k-iterations and
-  // cut into sk_ctas contiguous ranges of sk_ipc iterations, one per CTA, processed BEFORE the CTA's whole tiles. A range
-  // touches at most two tiles (sk_ipc <= iters): the piece that starts a tile (it0 == 0) OWNS it and runs its epilogue;
-  // a piece that starts inside a tile is always the FIRST thing its CTA does, so by the time the owner (who reaches that
-  // tile at the END of its own range) needs them, the other pieces' fp32 partial accumulators are in sk_part (one slot of
-  // 128 x n_tile floats per (tile, piece, CTA of the pair)) and their arrival counted in sk_flags (one counter per
-  // (tile, CTA of the pair, epilogue warp), reset by the owner: every launch leaves them zero).
-  int iters;       // k-iterations of one mode-0/1 tile (taps * k_chunks)
-  int sk_tiles, sk_first, sk_ipc, sk_ctas, sk_maxc;
-  long sk_total;
-  float* sk_part;
-  unsigned int* sk_flags;
   int dbg;     // bring-up knobs (XVA_GEMM_DBG): 1 = no epilogue stores, 2 = no TMA after the first ring fill, 4 = no MMA
   int vec_ok;  // every epilogue pointer is 16-byte aligned and every stride a multiple of 4: float4 accesses
   int round_on;  // host mirror of the operand-rounding test switch (xva_set_operand_rounding), read once per tile
@@ -177,53 +164,6 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmDev& p, int t, int ct
 __device__ __forceinline__ void seg_coord(const GemmDev& p, int S, int& z, int& r0) {
   z = S / p.segs;
   r0 = (S - z * p.segs) * p.seg;
-}
-
-// One unit of work of a CTA: a whole tile, or one piece [it0, it1) of a stream-K tile.
-struct Work {
-  int tile;       // tile index (decode_tile)
-  int it0, it1;   // k-iteration range; it1 < 0: the whole tile (its own iteration count)
-  int n_contrib;  // owner piece: partial accumulators to add before the epilogue
-  int piece;      // 0: whole tile / owner piece; > 0: contributor, partial slot piece - 1
-  int trel;       // stream-K tile index relative to sk_first
-};
-
-// idx-th unit of work of CTA `cta` (pair index under cta_group::2): stream-K pieces first, then whole tiles round-robin.
-__device__ __forceinline__ bool get_work(const GemmDev& p, int cta, int n_ctas, int idx, Work& w) {
-  int n_sk = 0;
-  if (p.sk_tiles > 0 && cta < p.sk_ctas) {
-    const long start = static_cast<long>(cta) * p.sk_ipc;
-    long end = start + p.sk_ipc;
-    if (end > p.sk_total) end = p.sk_total;
-    const int t0 = static_cast<int>(start / p.iters);
-    const long tile_end = static_cast<long>(t0 + 1) * p.iters;
-    const bool two = end > tile_end;
-    n_sk = two ? 2 : 1;
-    if (idx < n_sk) {
-      const int trel = t0 + idx;
-      const long a = idx == 0 ? start : tile_end;
-      const long b = (idx == 0 && two) ? tile_end : end;
-      const long T0 = static_cast<long>(trel) * p.iters;
-      const int first_cta = static_cast<int>(T0 / p.sk_ipc);
-      const int last_cta = static_cast<int>((T0 + p.iters - 1) / p.sk_ipc);
-      w.tile = p.sk_first + trel;
-      w.it0 = static_cast<int>(a - T0);
-      w.it1 = static_cast<int>(b - T0);
-      w.n_contrib = (w.it0 == 0) ? last_cta - first_cta : 0;
-      w.piece = cta - first_cta;
-      w.trel = trel;
-      return true;
-    }
-  }
-  const int tile = cta + (idx - n_sk) * n_ctas;
-  if (tile >= p.sk_first) return false;  // sk_first == num_tiles when the launch has no stream-K part
-  w.tile = tile;
-  w.it0 = 0;
-  w.it1 = -1;
-  w.n_contrib = 0;
-  w.piece = 0;
-  w.trel = 0;
-  return true;
 }
 
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout), version 1.
@@ -344,7 +284,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // ------------------------------------------------------------------ TMA producer, halo mode
     int s = 0, sa_i = 0;
     uint32_t ph = 0, pha = 0;
-    for (int tile = cta_id; tile < p.num_tiles; tile += n_ctas) {  // (halo launches have no stream-K part)
+    for (int tile = cta_id; tile < p.num_tiles; tile += n_ctas) {
       const TileCoord c = decode_tile<kCG>(p, tile, cta_rank);
       for (int kc = 0; kc < p.k_chunks; ++kc) {
         ptx::mbar_wait(&bar_aempty[sa_i], pha ^ 1);
@@ -404,9 +344,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     {
       int s = 0;
       uint32_t ph = 0;
-      Work wk;
-      for (int widx = 0; get_work(p, cta_id, n_ctas, widx, wk); ++widx) {
-        const int tile = wk.tile;
+      for (int tile = cta_id; tile < p.num_tiles; tile += n_ctas) {
         const TileCoord c = decode_tile<kCG>(p, tile, cta_rank);
         if (p.dbg & 16) continue;  // probe: raw MMA issue rate, no operand pipeline at all
         // outer index: tap (mode 0/1) or batch item of the reduced range (mode 2); inner: 32-wide k block
@@ -424,18 +362,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             if (sg < n_seg) seg_coord(p, c.s0 + sg, seg_z[sg], seg_r[sg]);
         }
         const int seg_bytes = p.seg * kBlockK * 4;
+        int it = 0;
         // Loop order. Mode 2: reduction unit outer, k-block inner. Mode 0/1 with p.tap_inner: k-block outer, TAP INNER --
         // the taps of one k-block re-read the same activation lines (shifted by a row) back to back, so they hit L2; with
         // the tap outer, a CTA streams its whole 128 x K row block once per tap and at K = 1536 the 148 CTAs push 116 MB
         // through the 126 MB L2 between two reads of a line (ncu: 459 MB read from DRAM for 223 MB of operands).
         const bool tap_inner = (p.mode != 2) && p.tap_inner;
         const int n1 = tap_inner ? p.k_chunks : n_outer, n2 = tap_inner ? n_outer : p.k_chunks;
-        // a stream-K piece runs iterations [it0, it1) of the same flat order
-        const int it_begin = wk.it0, it_end = wk.it1 < 0 ? c.iters : wk.it1;
-        int o1 = it_begin / n2, o2 = it_begin - o1 * n2;
-        (void)n1;
-        for (int it = it_begin; it < it_end; ++it) {
-          {
+        for (int o1 = 0; o1 < n1; ++o1) {
+          for (int o2 = 0; o2 < n2; ++o2, ++it) {
             const int jo = tap_inner ? o2 : o1, kc = tap_inner ? o1 : o2;
             const int shift_j = (p.mode != 2) ? p.shift[jo] : p.shift[c.j];
             const int acol_j = (p.mode != 2) ? p.a_col[jo] : 0;
@@ -495,10 +430,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               s = 0;
               ph ^= 1;
             }
-          }
-          if (++o2 == n2) {
-            o2 = 0;
-            ++o1;
           }
         }
       }
@@ -583,11 +514,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
           __syncwarp();
         }
-      } else {
-      Work wk;
-      for (int widx = 0; get_work(p, cta_id, n_ctas, widx, wk); ++widx, ++tile_iter) {
-        const TileCoord c = decode_tile<kCG>(p, wk.tile, 0);
-        const int it_begin = wk.it0, it_end = wk.it1 < 0 ? c.iters : wk.it1;
+      } else
+      for (int tile = cta_id; tile < p.num_tiles; tile += n_ctas, ++tile_iter) {
+        const TileCoord c = decode_tile<kCG>(p, tile, 0);
         const int acc = tile_iter % p.acc_stages;
         const uint32_t acc_ph = (tile_iter / p.acc_stages) & 1;
         long long t_a = clock64();
@@ -596,7 +525,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         long long t_b = clock64();
         cyc_wait_acc += t_b - t_a;
         const uint32_t tmem_acc = tmem_base + acc * 256;
-        for (int it = it_begin; it < it_end; ++it) {
+        for (int it = 0; it < c.iters; ++it) {
           if (!(dbg & 16)) {
             long long t_c = clock64();
             ptx::mbar_wait(&bar_full[s], ph);
@@ -607,7 +536,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             // straight-line issue: 4 k-slices x n_mma column halves, descriptors differ only in the address field
             const uint64_t da0 = da_hi | static_cast<uint64_t>(a_lo);
             const uint64_t db0 = db_hi | static_cast<uint64_t>(a_lo + (kATileBytes >> 4));
-            const uint32_t first = it > it_begin ? 1u : 0u;  // a stream-K piece starts its own accumulator
+            const uint32_t first = it > 0 ? 1u : 0u;
             if (dbg & 4) {
             } else if (n_mma == 1) {
               // (multi-tap weight gradient: the stage holds one B tile per tap of the group, each with its own accumulator)
@@ -658,7 +587,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
         __syncwarp();
       }
-      }
       if ((dbg & 32) && blockIdx.x == 0 && lane == 0) {
         const long long total = clock64() - t_start;
         g_gemm_dbg[0] = cyc_wait_acc;
@@ -687,30 +615,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const uint64_t seed = p.seed + (p.seed_dev ? __ldg(p.seed_dev) * 0xA24BAED4963EE407ull : 0ull);
     const bool vec = p.vec_ok != 0;
 
-    // stream-K owner piece: the other pieces' partial accumulators of the current tile (set per unit of work below)
-    const float* sk_src = nullptr;
-    int sk_n = 0;
-    long sk_slot_stride = 0;
-    auto load_chunk = [&](uint32_t taddr, float4 (&t)[8], int chunk) {
+    auto load_chunk = [&](uint32_t taddr, float4 (&t)[8]) {
       uint32_t v[32];
       ptx::tmem_ld32(taddr, v);
       ptx::tmem_wait_ld();
-      if (sk_n > 0) {  // + partials, stored by the contributing CTAs in this same (chunk, row) order: see dump_partial
-        const float* src = sk_src + (static_cast<long>(chunk) * kBlockM + (warp & 3) * 32 + lane) * 32;
-        for (int j = 0; j < sk_n; ++j, src += sk_slot_stride) {
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            float4 a;
-            asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];"
-                         : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w)
-                         : "l"(src + 4 * c));
-            v[4 * c] = __float_as_uint(__uint_as_float(v[4 * c]) + a.x);
-            v[4 * c + 1] = __float_as_uint(__uint_as_float(v[4 * c + 1]) + a.y);
-            v[4 * c + 2] = __float_as_uint(__uint_as_float(v[4 * c + 2]) + a.z);
-            v[4 * c + 3] = __float_as_uint(__uint_as_float(v[4 * c + 3]) + a.w);
-          }
-        }
-      }
       __syncwarp();  // everyone has finished reading the previous block out of tbuf
 #pragma unroll
       for (int c = 0; c < 8; ++c)
@@ -754,9 +662,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
     };
 
-    Work wk;
-    for (int widx = 0; get_work(p, cta_id, n_ctas, widx, wk); ++widx, ++tile_iter) {
-      const TileCoord c = decode_tile<kCG>(p, wk.tile, cta_rank);
+    for (int tile = cta_id; tile < p.num_tiles; tile += n_ctas, ++tile_iter) {
+      const TileCoord c = decode_tile<kCG>(p, tile, cta_rank);
       const int acc = tile_iter % p.acc_stages;
       const uint32_t acc_ph = (tile_iter / p.acc_stages) & 1;
       const long long t_e0 = clock64();
@@ -765,59 +672,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const long long t_e1 = clock64();
       epi_wait += t_e1 - t_e0;
       const uint32_t tacc = tmem_base + acc * 256 + lane_base;
-
-      // ---- stream-K pieces (see GemmDev::sk_*)
-      sk_n = 0;
-      if (p.sk_tiles > 0 && (wk.piece > 0 || wk.n_contrib > 0)) {
-        const long slot_floats = static_cast<long>(kBlockM) * p.n_tile;
-        const int n_chunks_sk = (p.n_tile + 31) / 32;
-        unsigned int* flag = p.sk_flags + (static_cast<long>(wk.trel) * kCG + cta_rank) * 8 + (warp - 4);
-        if (wk.piece > 0) {
-          // contributor: raw accumulator -> this piece's slot, then one arrival per epilogue warp; no epilogue, no output
-          float* dst = p.sk_part + ((static_cast<long>(wk.trel) * p.sk_maxc + (wk.piece - 1)) * kCG + cta_rank) * slot_floats;
-          const int q_ = warp & 3, half_ = (warp - 4) >> 2;
-          for (int ch = half_; ch < n_chunks_sk; ch += 2) {
-            uint32_t v[32];
-            ptx::tmem_ld32(tacc + ch * 32, v);
-            ptx::tmem_wait_ld();
-            float* d = dst + (static_cast<long>(ch) * kBlockM + q_ * 32 + lane) * 32;
-#pragma unroll
-            for (int c4i = 0; c4i < 8; ++c4i)
-              asm volatile("st.global.cg.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d + 4 * c4i), "r"(v[4 * c4i]),
-                           "r"(v[4 * c4i + 1]), "r"(v[4 * c4i + 2]), "r"(v[4 * c4i + 3])
-                           : "memory");
-          }
-          ptx::tc_fence_before();
-          __threadfence();
-          __syncwarp();
-          if (lane == 0) {
-            if (kCG == 2) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bar_tmem_empty[acc]), 0));
-            else ptx::mbar_arrive(&bar_tmem_empty[acc]);
-            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(flag) : "memory");
-          }
-          continue;
-        }
-        // owner: wait until every other piece of this tile has landed (they are the first thing their CTAs run)
-        if (lane == 0) {
-          unsigned int seen = 0;
-          long long spins = 0;
-          do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
-            if (seen >= static_cast<unsigned int>(wk.n_contrib)) break;
-            __nanosleep(64);
-            if (++spins > (1ll << 22)) {
-              printf("gemm_tc_kernel: stream-K owner of tile %d waited for %d partial(s), saw %u\n", wk.tile, wk.n_contrib, seen);
-              __trap();
-            }
-          } while (true);
-          *flag = 0;  // nobody else touches this counter again in this launch: leave it zero for the next one
-        }
-        __syncwarp();
-        __threadfence();
-        sk_src = p.sk_part + ((static_cast<long>(wk.trel) * p.sk_maxc) * kCG + cta_rank) * slot_floats;
-        sk_slot_stride = kCG * slot_floats;
-        sk_n = wk.n_contrib;
-      }
 
       int row_limit = (c.dup || (p.dbg & 1)) ? 0 : ((kEpi == EPI_WGRAD) ? p.M : p.R);
       const int n_cols = (p.N - c.n0) < p.n_tile ? (p.N - c.n0) : p.n_tile;  // valid columns of this tile
@@ -860,7 +714,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const int jj = qi / n_chunks, ch = qi - jj * n_chunks;  // tap of the group, 32-column chunk of its accumulator
           if (ch < ch_lo || ch >= ch_hi) continue;  // warp-uniform
           float4 t[8];
-          load_chunk(tacc + jj * p.n_tile + ch * 32, t, ch);
+          load_chunk(tacc + jj * p.n_tile + ch * 32, t);
           if (p.tp == 1 && ch == last_ch) release_tmem();
           obase = p.out + c.zo * p.o_zs + (c.j + jj) * p.o_js + c.n0;
           const int n = ch * 32 + 4 * c4;
@@ -996,7 +850,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const long ostep = 4L * p.o_rs;
           for (int ch = half; ch < n_chunks; ch += 2) {
             float4 t[8];
-            load_chunk(tacc + ch * 32, t, ch);
+            load_chunk(tacc + ch * 32, t);
             if (ch == last_ch) release_tmem();
             const int n = ch * 32 + 4 * c4;
             const int nv = n < n_cols ? ((n_cols - n) < 4 ? (n_cols - n) : 4) : 0;
@@ -1049,7 +903,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           int cnt = 0;  // columns this warp has accumulated per row
           for (int ch = half; ch < n_chunks; ch += 2) {
             float4 t[8];
-            load_chunk(tacc + ch * 32, t, ch);
+            load_chunk(tacc + ch * 32, t);
             if (ch == last_ch) release_tmem();
             const int n = ch * 32 + 4 * c4;
             const int nv = n < n_cols ? ((n_cols - n) < 4 ? (n_cols - n) : 4) : 0;
@@ -1239,48 +1093,17 @@ int encode_map(CUtensorMap* map, const float* base, int rank, const uint64_t* di
 
 }  // namespace
 
-namespace {
-bool sk_enabled() {
-  static const bool on = [] {
-    const char* e = getenv("XVA_GEMM_SK");
-    return !(e && e[0] == '0');
-  }();
-  return on;
+int tma_encode_f32(void* map, const float* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
+                   const uint32_t* box, int swizzle) {
+  return encode_map(static_cast<CUtensorMap*>(map), base, rank, dims, strides_elems, box, swizzle);
 }
-long tile_overhead() {  // SM clocks, see the n-tile cost model
-  static const long v = [] {
-    const char* e = getenv("XVA_GEMM_TILE_OVH");
-    return e ? atol(e) : 8000L;
-  }();
-  return v;
-}
-int sk_min_piece() {  // shortest stream-K piece in k-iterations (pipeline fill + a partial-accumulator round trip per piece)
-  static const int v = [] {
-    const char* e = getenv("XVA_GEMM_SK_MIN");
-    const int n = e ? atoi(e) : 0;
-    return n >= 1 ? n : 8;
-  }();
-  return v;
-}
-}  // namespace
 
 int gemm_debug_counters(long long* out8) {
   XVA_CHECK_CUDA(cudaMemcpyFromSymbol(out8, g_gemm_dbg, sizeof(long long) * 8));
   return XVA_OK;
 }
 
-static int gemm_tc_plan_or_launch(const GemmArgs& g, cudaStream_t stream, long* plan_sk_bytes);
-
-int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) { return gemm_tc_plan_or_launch(g, stream, nullptr); }
-
-int gemm_tc_plan(const GemmArgs& g, long* sk_bytes) {
-  *sk_bytes = 0;
-  return gemm_tc_plan_or_launch(g, nullptr, sk_bytes);
-}
-
-// plan_sk_bytes != nullptr: host-side planning only -- reports the stream-K scratch the launch would use and returns
-// before anything touches the device.
-static int gemm_tc_plan_or_launch(const GemmArgs& g, cudaStream_t stream, long* plan_sk_bytes) {
+int gemm_tc_launch(const GemmArgs& g, cudaStream_t stream) {
   XVA_CHECK_ARG(g.mode >= 0 && g.mode <= 2, "gemm: bad mode %d", g.mode);
   XVA_CHECK_ARG(g.taps >= 1 && g.taps <= kMaxTaps, "gemm: taps %d out of range", g.taps);
   XVA_CHECK_ARG(g.Z >= 1 && g.R >= 1 && g.N >= 1, "gemm: empty problem Z=%d R=%d N=%d", g.Z, g.R, g.N);
@@ -1393,14 +1216,8 @@ static int gemm_tc_plan_or_launch(const GemmArgs& g, cudaStream_t stream, long* 
         const int slots = pr ? num_sms() / 2 : num_sms();
         const int units = pr ? ceil_div(row_tiles, 2) : row_tiles;
         const long fetch = 256 + (pr ? nt : 2 * nt), mma = 2L * nt;
-        // waves in 1/1000: whole waves, or -- with the stream-K schedule splitting the fractional wave over all SMs -- the
-        // exact ratio plus ~8 % of a tile for the partial-accumulator exchange
-        const long u = static_cast<long>(units) * tn, tail = u % slots;
-        long w1000 = static_cast<long>(ceil_div(static_cast<int>(u), slots)) * 1000;
-        if (sk_enabled() && tail > 0 && tail * 10 < slots * 9L && iters >= 2L * sk_min_piece()) w1000 = u * 1000 / slots + 80;
-        // (+ a fixed cost per tile -- accumulator hand-over, pipeline ramp, epilogue tail: the measured time of a
-        // 192-column tile is 0.56, not 0.51, of a 384-column one at K = 3 x 1536)
-        const long cost = w1000 * (iters * (fetch > mma ? fetch : mma) + (nt > 256 ? 40L * nt : 0) + tile_overhead()) / 1000;
+        const long cost = static_cast<long>(ceil_div(units * tn, slots)) *
+                          (iters * (fetch > mma ? fetch : mma) + (nt > 256 ? 40L * nt : 0));
         if (best < 0 || cost < best) {
           best = cost;
           nt_max = cand;
@@ -1557,50 +1374,6 @@ static int gemm_tc_plan_or_launch(const GemmArgs& g, cudaStream_t stream, long* 
     p.split = ceil_div(p.ZR, p.zper);
     XVA_CHECK_ARG(p.split == 1 || (g.flags & GEMM_ATOMIC), "gemm: split > 1 needs GEMM_ATOMIC");
     p.num_tiles = (g.Z / g.ZR) * p.split * p.tgroups * p.tiles_m * p.tiles_n;
-  }
-
-  // ---- stream-K schedule of the fractional wave (GemmDev::sk_*)
-  p.iters = (g.mode != 2) ? g.taps * p.k_chunks : 0;
-  p.sk_tiles = 0;
-  p.sk_first = p.num_tiles;
-  p.sk_ipc = p.sk_ctas = p.sk_maxc = 0;
-  p.sk_total = 0;
-  p.sk_part = nullptr;
-  p.sk_flags = nullptr;
-  long sk_need = 0;
-  const int sk_slots = pair ? num_sms() / 2 : num_sms();
-  if (sk_enabled() && g.mode != 2 && !p.halo && G == 1 && p.dbg == 0 && p.iters >= 2 * sk_min_piece()) {
-    const int tail = p.num_tiles % sk_slots;
-    if (tail > 0 && tail * 10 < sk_slots * 9) {  // a last wave that is at least 90 % full is left alone
-      const long total = static_cast<long>(tail) * p.iters;
-      int ipc = static_cast<int>((total + sk_slots - 1) / sk_slots);
-      if (ipc < sk_min_piece()) ipc = sk_min_piece();
-      if (ipc < p.iters) {
-        p.sk_tiles = tail;
-        p.sk_first = p.num_tiles - tail;
-        p.sk_ipc = ipc;
-        p.sk_total = total;
-        p.sk_ctas = static_cast<int>((total + ipc - 1) / ipc);
-        p.sk_maxc = (p.iters - 1) / ipc + 1;
-        sk_need = static_cast<long>(tail) * p.sk_maxc * cg * kBlockM * p.n_tile * 4;
-      }
-    }
-  }
-  if (plan_sk_bytes) {
-    *plan_sk_bytes = sk_need;
-    return XVA_OK;
-  }
-  if (p.sk_tiles > 0) {
-    const bool have = g.sk_partials != nullptr && g.sk_flags != nullptr && g.sk_partials_bytes >= sk_need &&
-                      static_cast<long>(p.sk_tiles) * cg * 8 <= XVA_GEMM_SK_FLAGS &&
-                      (reinterpret_cast<uintptr_t>(g.sk_partials) & 15) == 0;
-    if (have) {
-      p.sk_part = g.sk_partials;
-      p.sk_flags = g.sk_flags;
-    } else {  // no scratch from the caller: whole tiles per SM, as before
-      p.sk_tiles = 0;
-      p.sk_first = p.num_tiles;
-    }
   }
 
   // MN-major tiles: SWIZZLE_128B_BASE32B descriptors + TMA 128B_ATOM_32B. XVA_MN_DEBUG=layout:lbo:sbo:tma_swizzle
@@ -1771,7 +1544,7 @@ static int gemm_tc_plan_or_launch(const GemmArgs& g, cudaStream_t stream, long* 
   cfg.attrs = attr;
   cfg.numAttrs = n_attr;
   if (!pair) {
-    cfg.gridDim = dim3((p.sk_tiles > 0 || p.num_tiles >= num_sms()) ? num_sms() : p.num_tiles);
+    cfg.gridDim = dim3(p.num_tiles < num_sms() ? p.num_tiles : num_sms());
     switch (epi) {
       case EPI_WGRAD: XVA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<EPI_WGRAD, 1>, map_a, map_b, p)); break;
       case EPI_LN: XVA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<EPI_LN, 1>, map_a, map_b, p)); break;
@@ -1780,7 +1553,7 @@ static int gemm_tc_plan_or_launch(const GemmArgs& g, cudaStream_t stream, long* 
     }
   } else {
     const int pairs = num_sms() / 2;
-    cfg.gridDim = dim3(2 * ((p.sk_tiles > 0 || p.num_tiles >= pairs) ? pairs : p.num_tiles));
+    cfg.gridDim = dim3(2 * (p.num_tiles < pairs ? p.num_tiles : pairs));
     switch (epi) {
       case EPI_LN: XVA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<EPI_LN, 2>, map_a, map_b, p)); break;
       case EPI_FULL: XVA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<EPI_FULL, 2>, map_a, map_b, p)); break;

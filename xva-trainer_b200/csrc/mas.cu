@@ -37,6 +37,11 @@ mas_kernel(const float* __restrict__ attn, const int* __restrict__ in_lens, cons
   // log of a probability: the reference takes np.log of the fp32 array (alignment.py:85); here the double-precision
   // logarithm rounded to fp32 (correctly rounded in all but ~1e-8 of cases), so near-ties resolve as they would with an
   // accurate libm. Pass is_log = 1 to hand in log-probabilities and make the path independent of any logarithm.
+  // is_log carries two flags: bit 0 = the input already holds log-probabilities; bit 1 = xVAPitch's maximum_path
+  // (python/xvapitch/util.py:14-53): on an exact tie between "stay" and "advance" it stays (v1 >= v0, :35) where
+  // FastPitch advances (alignment.py:96), and it has no extra mark in row 0 when the back-track stops short of token 0.
+  const bool stay_on_tie = (is_log & 2) != 0;
+  is_log &= 1;
   auto lg = [&](float v) { return is_log ? v : static_cast<float>(log(static_cast<double>(v))); };
   float* cur = row;
   float* nxt = row + (Tt + 1);
@@ -59,7 +64,7 @@ mas_kernel(const float* __restrict__ attn, const int* __restrict__ in_lens, cons
       if (j < n_txt) {
         const float la = lg(jb == 0 ? a_cur : a[static_cast<long>(i) * Tt + j]);
         const float stay = cur[j + 1], adv = cur[j];       // adv = log_p[i-1, j-1]
-        take_adv = (j >= 1) && (adv >= stay);              // alignment.py:96
+        take_adv = (j >= 1) && (stay_on_tie ? (adv > stay) : (adv >= stay));   // alignment.py:96 | util.py:35
         nxt[j + 1] = __fadd_rn(la, take_adv ? adv : stay);
       }
       const unsigned int m = __ballot_sync(0xffffffffu, take_adv);
@@ -87,7 +92,7 @@ mas_kernel(const float* __restrict__ attn, const int* __restrict__ in_lens, cons
     d[j] = run;
     // alignment.py:106-108: prev_ind[0, :] is 0, so after the loop curr_text_idx = 0 and opt[0, 0] is set as well -- a
     // second mark in row 0 when the back-track did not reach text position 0 (fewer mel frames than tokens)
-    if (h[0] == 0.0f) {
+    if (!stay_on_tie && h[0] == 0.0f) {
       h[0] = 1.0f;
       d[0] += 1;
     }

@@ -9,6 +9,7 @@ namespace xva {
 
 // ---- test switch for the tf32 operand rounding, one setter per translation unit (common.cuh)
 int set_operand_rounding_gemm_tc(int on);
+int set_operand_rounding_attn_fused(int on);
 int set_operand_rounding_gemm_ref(int on);
 int set_operand_rounding_rowops(int on);
 int set_operand_rounding_loss_optim(int on);
@@ -116,5 +117,13 @@ int grad_sqnorm(const float* g, const void* chunks, int n_chunks, double* out, c
 int lamb_step(float* p, const float* g, float* m, float* v, const void* chunks, int n_chunks, double* norms,
               const double* gnorm_sq, float max_norm, const float* lr_dev, float b1, float b2, float eps, float wd,
               float* p_tf32, cudaStream_t stream);
+
+// attn_fused.cu: fused single-head attention of the FFT blocks (scores, mask, softmax, dropout, P.V in tensor memory)
+int attn_fused_fwd(const float* qkv, long rs, long zs, int B, int T, const int* lens, float scale, float drop_p,
+                   uint64_t seed, const uint64_t* seed_dev, int drop_ld, float* out, long o_rs, long o_zs, float* lse,
+                   cudaStream_t stream);
+int attn_fused_bwd(const float* qkv, long rs, long zs, const float* dout, long d_rs, long d_zs, const float* lse,
+                   const float* dsum, int B, int T, const int* lens, float scale, float drop_p, uint64_t seed,
+                   const uint64_t* seed_dev, int drop_ld, float* dqkv, long g_rs, long g_zs, cudaStream_t stream);
 
 }  // namespace xva

@@ -188,6 +188,9 @@ class FastPitch(torch.nn.Module):
         # softmax backward inside the dP GEMM epilogue: parity-green but measured slower (13.84 vs 13.59 ms/step: the
         # epilogue-bound GEMM gets heavier than the HBM-speed row kernel it replaces), so off by default
         self.fuse_softmax_bwd = os.environ.get("XVA_FUSE_SOFTMAX_BWD", "0") == "1"
+        # one fused tcgen05 kernel per direction for scores / softmax / dropout / P.V (XVA_FUSED_ATTN=0: the unfused chain of
+        # six K = 64 GEMMs + softmax kernels with the [B, T, T] tensors in HBM, kept as the A/B and parity partner)
+        self.fused_attn = os.environ.get("XVA_FUSED_ATTN", "1") != "0"
         # EXPERIMENT, off by default, not yet measured (round-2 item): issue every FFT-block weight
         # gradient on a second stream. It only reads activations the forward saved and the layer's output gradient and
         # accumulates into the gradient arena, so it is independent of the input-gradient GEMM that follows it on the main
@@ -347,12 +350,18 @@ class FastPitch(torch.nn.Module):
         qkv = ops.conv_fwd(x, L.w.qkv_w, bias=L.w.qkv_b, round_out=True)
         q, k, v = qkv[..., :D_HEAD], qkv[..., D_HEAD:2 * D_HEAD], qkv[..., 2 * D_HEAD:]
         Tp = (T + 31) // 32 * 32
-        s = torch.empty(B, T, Tp, device=x.device, dtype=torch.float32)
-        ops.bmm_nt(q, k, alpha=1.0 / math.sqrt(D_HEAD), out=s[..., :T])
         p_att, seed_att = self._drop()
-        P, Pd = ops.softmax_fwd(s, lens, T, p_att, seed_att, sd)
-        del s
-        vec = ops.bmm_nn(Pd[..., :T], v, round_out=True)
+        P = Pd = lse = None
+        if self.fused_attn:
+            # scores, key mask, softmax, dropout and P.V in one kernel, S / P in tensor memory (csrc/attn_fused.cu); only
+            # the row log-sum-exp is kept for the backward, which recomputes P
+            vec, lse = ops.attn_fwd(qkv, lens, 1.0 / math.sqrt(D_HEAD), p_att, seed_att, sd, Tp)
+        else:
+            s = torch.empty(B, T, Tp, device=x.device, dtype=torch.float32)
+            ops.bmm_nt(q, k, alpha=1.0 / math.sqrt(D_HEAD), out=s[..., :T])
+            P, Pd = ops.softmax_fwd(s, lens, T, p_att, seed_att, sd)
+            del s
+            vec = ops.bmm_nn(Pd[..., :T], v, round_out=True)
         p1, seed1 = self._drop()
         # The post-LN of both sub-blocks is a separate HBM pass (xva_layernorm_fwd) over the pre-LN sum the GEMM epilogue
         # wrote (bias + dropout + residual): a 384-column LayerNorm epilogue needs the whole row in one accumulator, which
@@ -372,7 +381,7 @@ class FastPitch(torch.nn.Module):
             pre2 = ops.conv_fwd(h, L.w.w2, K3, bias=L.w.b2, residual=y1, drop_p=p2, seed=seed2, seed_dev=sd)
             y2, sv2 = ops.layernorm_fwd(pre2, L.w.ln2_g, L.w.ln2_b, lens)
         if save is not None:
-            save.append(_NS(x=x, qkv=qkv, P=P, Pd=Pd, vec=vec, sv1=sv1, y1=y1, h=h, sv2=sv2, T=T, att=(p_att, seed_att),
+            save.append(_NS(x=x, qkv=qkv, P=P, Pd=Pd, lse=lse, vec=vec, sv1=sv1, y1=y1, h=h, sv2=sv2, T=T, att=(p_att, seed_att),
                             d1=(p1, seed1), d2=(p2, seed2)))
         return y2
 
@@ -433,9 +442,12 @@ class FastPitch(torch.nn.Module):
         self._wgrad_side(lambda: ops.conv_wgrad(dbr1, c.vec, (0,), out=L.g.o_w, accumulate=True), dbr1)
         dvec = ops.conv_dgrad(dbr1, L.w.o_w, round_out=True)
         dqkv = torch.empty_like(qkv)
-        Tp = c.P.shape[2]
-        dP = torch.empty(B, T, Tp, device=x.device, dtype=torch.float32)
-        if self.fuse_softmax_bwd:
+        Tp = (T + 31) // 32 * 32
+        if c.lse is not None:
+            ops.attn_bwd(qkv, dvec, c.vec, c.lse, lens, 1.0 / math.sqrt(D_HEAD), c.att[0], c.att[1], sd, Tp, out=dqkv)
+            dP = None
+        elif self.fuse_softmax_bwd:
+            dP = torch.empty(B, T, Tp, device=x.device, dtype=torch.float32)
             # softmax + attention-dropout backward inside the epilogue of dP = dO.V^T: the row term sum_j P_d dP_d
             # equals dO.O (O = P_d V = vec), so dS is element-wise in the tile and the score-sized tensor is written
             # once instead of written, read twice and written again.
@@ -446,11 +458,13 @@ class FastPitch(torch.nn.Module):
                        softmax_bwd=(c.P, D, c.att[0], c.att[1], sd))
             ops.bmm_tn(c.Pd[..., :T], dvec, out=dqkv[..., 2 * D_HEAD:], round_out=True)
         else:
+            dP = torch.empty(B, T, Tp, device=x.device, dtype=torch.float32)
             ops.bmm_nt(dvec, v, out=dP[..., :T])
             ops.bmm_tn(c.Pd[..., :T], dvec, out=dqkv[..., 2 * D_HEAD:], round_out=True)
             ops.softmax_bwd_(c.P, dP, T, 1.0 / math.sqrt(D_HEAD), c.att[0], c.att[1], sd)
-        ops.bmm_nn(dP[..., :T], k, out=dqkv[..., :D_HEAD], round_out=True)
-        ops.bmm_tn(dP[..., :T], q, out=dqkv[..., D_HEAD:2 * D_HEAD], round_out=True)
+        if dP is not None:
+            ops.bmm_nn(dP[..., :T], k, out=dqkv[..., :D_HEAD], round_out=True)
+            ops.bmm_tn(dP[..., :T], q, out=dqkv[..., D_HEAD:2 * D_HEAD], round_out=True)
         del dP
         def qkv_grads():
             ops.conv_wgrad(dqkv, x, (0,), out=L.g.qkv_w, accumulate=True)
@@ -607,9 +621,10 @@ class FastPitch(torch.nn.Module):
         in_lens32 = input_lens.to(torch.int32)
 
         # ---- encoder (FFTransformer.forward, transformer.py:212-243)
-        x = ops.embed_pos(tokens, self.w.emb, None, None, self.inv_freq, B, Tt, D_MODEL)
-        for L in self.enc_layers:
-            x = self._layer_fwd(x, in_lens32, L, ctx.enc if ctx is not None else None)
+        with ops.nvtx("fastpitch.fwd.encoder"):
+            x = ops.embed_pos(tokens, self.w.emb, None, None, self.inv_freq, B, Tt, D_MODEL)
+            for L in self.enc_layers:
+                x = self._layer_fwd(x, in_lens32, L, ctx.enc if ctx is not None else None)
         enc_out = x
         dur_tgt = durs_padded
         if ctx is not None:
@@ -643,10 +658,11 @@ class FastPitch(torch.nn.Module):
         regulated = ops.regulate_gather(enc3, cum, T_out)
 
         # ---- decoder + projection
-        y = ops.embed_pos(None, None, regulated, dec_lens, self.inv_freq, B, T_out, D_MODEL)
-        for L in self.dec_layers:
-            y = self._layer_fwd(y, dec_lens, L, ctx.dec if ctx is not None else None)
-        mel_out = ops.conv_fwd(y, self.w.proj_w, bias=self.w.proj_b)
+        with ops.nvtx("fastpitch.fwd.decoder"):
+            y = ops.embed_pos(None, None, regulated, dec_lens, self.inv_freq, B, T_out, D_MODEL)
+            for L in self.dec_layers:
+                y = self._layer_fwd(y, dec_lens, L, ctx.dec if ctx is not None else None)
+            mel_out = ops.conv_fwd(y, self.w.proj_w, bias=self.w.proj_b)
         if ctx is not None:
             ctx.dec_out, ctx.cum, ctx.dec_lens, ctx.T_out = y, cum, dec_lens, T_out
             ctx.pitch_tgt, ctx.energy_tgt = pitch_tgt, energy_tgt
@@ -740,9 +756,10 @@ class FastPitch(torch.nn.Module):
             ops.conv_wgrad(dm, ctx.dec_out, (0,), out=self.g.proj_w, accumulate=True)
             ops.colsum_(B * T_out, N_MEL, dmel.shape[2], dmel, self.g.proj_b)
             dy = ops.conv_dgrad(dm, self.w.proj_w, lens=ctx.dec_lens)
-            for i, (L, c) in enumerate(zip(reversed(self.dec_layers), reversed(ctx.dec))):
-                dy = self._layer_bwd(dy, ctx.dec_lens, L, c)
-                ready(f"decoder.layers.{N_LAYERS - 1 - i}")
+            with ops.nvtx("fastpitch.bwd.decoder"):
+                for i, (L, c) in enumerate(zip(reversed(self.dec_layers), reversed(ctx.dec))):
+                    dy = self._layer_bwd(dy, ctx.dec_lens, L, c)
+                    ready(f"decoder.layers.{N_LAYERS - 1 - i}")
             d_enc = ops.regulate_scatter(dy, ctx.cum, Tt)         # pos-emb has no parameters: dy is d(regulated)
             del dy
             ops.scalar_conv_bwd_(d_enc, ctx.energy_tgt, self.g.energy_emb_w, self.g.energy_emb_b)
@@ -752,10 +769,11 @@ class FastPitch(torch.nn.Module):
                 d_enc = self._pred_bwd(seeds["pitch"], lens, self.pred["pitch"], ctx.preds["pitch"], residual=d_enc)
             # the tail of the arena (pitch/energy predictors + embeddings, proj) is final, touched or not
             ready("pitch_predictor", "pitch_emb", "energy_predictor", "energy_emb", "proj", flush=True)
-        for i, (L, c) in enumerate(zip(reversed(self.enc_layers), reversed(ctx.enc))):
-            d_enc = self._layer_bwd(d_enc, lens, L, c)
-            if i < N_LAYERS - 1:
-                ready(f"encoder.layers.{N_LAYERS - 1 - i}")
+        with ops.nvtx("fastpitch.bwd.encoder"):
+            for i, (L, c) in enumerate(zip(reversed(self.enc_layers), reversed(ctx.enc))):
+                d_enc = self._layer_bwd(d_enc, lens, L, c)
+                if i < N_LAYERS - 1:
+                    ready(f"encoder.layers.{N_LAYERS - 1 - i}")
         ops.embed_bwd_(ctx.tokens, d_enc, self.g.emb)
         ready("encoder.layers.0", "encoder.word_emb", flush=True)
         self._join_side()
@@ -949,6 +967,10 @@ class Lamb:
         self.model.zero_grad()
 
     def step(self, closure=None):
+        with ops.nvtx("fastpitch.lamb"):
+            return self._step()
+
+    def _step(self):
         A = self.model.arena
         g = self.param_groups[0]
         chunks, n_chunks, n_tensors = self._table(self.model.training_stage)

@@ -10,20 +10,25 @@ import torch
 
 
 class GraphedStep:
-    def __init__(self, fn, static_inputs, warmup=3):
-        """fn(*static_inputs) -> pytree of tensors; static_inputs: the tensors whose STORAGE the captured step reads."""
+    def __init__(self, fn, static_inputs, warmup=3, pool=None):
+        """fn(*static_inputs) -> pytree of tensors; static_inputs: the tensors whose STORAGE the captured step reads.
+        ``warmup`` eager executions precede the capture (0 when the caller has already run the step: a training step
+        has side effects). ``pool``: the memory pool of another GraphedStep whose replays never overlap this one's
+        (graphs of different batch shapes of one trainer), so their activations share memory."""
         self.fn, self.static_inputs = fn, list(static_inputs)
-        cur = torch.cuda.current_stream()
-        side = torch.cuda.Stream()
-        side.wait_stream(cur)
-        with torch.cuda.stream(side):
-            for _ in range(warmup):
-                fn(*self.static_inputs)
-        cur.wait_stream(side)
+        if warmup > 0:
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                for _ in range(warmup):
+                    fn(*self.static_inputs)
+            cur.wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, pool=pool):
             self.outputs = fn(*self.static_inputs)
+        self.pool = self.graph.pool()
 
     def load(self, *new_inputs):
         """Copy fresh values into the static input tensors (async on the current stream)."""

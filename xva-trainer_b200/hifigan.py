@@ -1222,19 +1222,21 @@ class HiFiGANStep:
         G, mpd, msd = self.generator, self.mpd, self.msd
         B = y.shape[0]
         y = y.reshape(B, -1).to(torch.float32).contiguous()
-        y_g_hat = G(x)                                                       # :479
-        wave = y_g_hat.reshape(B, -1)
-        mel_hat = self.mel(wave)                                             # :480, channels-last [B, F, 80]
+        with ops.nvtx("hifigan.generator.fwd"):
+            y_g_hat = G(x)                                                   # :479
+            wave = y_g_hat.reshape(B, -1)
+            mel_hat = self.mel(wave)                                         # :480, channels-last [B, F, 80]
         mel_tgt = y_mel.to(torch.float32).transpose(1, 2).contiguous()
 
         # ---- discriminators (:483-498); y_hat is detached: no gradient reaches the generator here
         self.optim_d.zero_grad()
-        rs, gs, _, _ = mpd(y, wave)
-        loss_disc_f = discriminator_loss_backward(mpd, rs, gs)
-        rs, gs, _, _ = msd(y, wave)
-        loss_disc_s = discriminator_loss_backward(msd, rs, gs)
-        self._all_reduce(self.optim_d.g)
-        self.optim_d.step()
+        with ops.nvtx("hifigan.d_step"):
+            rs, gs, _, _ = mpd(y, wave)
+            loss_disc_f = discriminator_loss_backward(mpd, rs, gs)
+            rs, gs, _, _ = msd(y, wave)
+            loss_disc_s = discriminator_loss_backward(msd, rs, gs)
+            self._all_reduce(self.optim_d.g)
+            self.optim_d.step()
 
         # ---- generator (:501-515)
         self.optim_g.zero_grad()
@@ -1243,13 +1245,15 @@ class HiFiGANStep:
         ops.reduce_l1(mel_tgt, mel_hat, acc)
         loss_mel = 45.0 * acc[0] / n
         dwave = self.mel.backward(ops.l1_grad(mel_tgt, mel_hat, 45.0 / n))
-        rs, gs, frs, fgs = mpd(y, wave, weight_grad=False)
-        loss_gen_f, loss_fm_f = generator_adv_loss_backward(mpd, gs, frs, fgs, dwave, pools=False)
-        rs, gs, frs, fgs = msd(y, wave, weight_grad=False)
-        loss_gen_s, loss_fm_s = generator_adv_loss_backward(msd, gs, frs, fgs, dwave, pools=True)
-        G.backward(dwave.view(B, 1, -1))
-        self._all_reduce(self.optim_g.g)
-        self.optim_g.step()
+        with ops.nvtx("hifigan.g_step.discriminators"):
+            rs, gs, frs, fgs = mpd(y, wave, weight_grad=False)
+            loss_gen_f, loss_fm_f = generator_adv_loss_backward(mpd, gs, frs, fgs, dwave, pools=False)
+            rs, gs, frs, fgs = msd(y, wave, weight_grad=False)
+            loss_gen_s, loss_fm_s = generator_adv_loss_backward(msd, gs, frs, fgs, dwave, pools=True)
+        with ops.nvtx("hifigan.g_step.generator_bwd"):
+            G.backward(dwave.view(B, 1, -1))
+            self._all_reduce(self.optim_g.g)
+            self.optim_g.step()
         self.steps += 1
         loss_gen_all = loss_gen_s + loss_gen_f + loss_fm_s + loss_fm_f + loss_mel
         return {"loss_gen_all": loss_gen_all, "loss_disc_all": loss_disc_s + loss_disc_f, "loss_mel": loss_mel,

@@ -17,6 +17,27 @@ def capturing():
     return torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
 
 
+class nvtx:
+    """NVTX range around one stage of a step (forward / loss / backward sections show up by name in nsys / ncu timelines).
+    XVA_NVTX=0 turns the ranges off; they cost ~1 us of host time each and nothing on the device."""
+    _on = None
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if nvtx._on is None:
+            import os
+            nvtx._on = os.environ.get("XVA_NVTX", "1") != "0" and torch.cuda.is_available()
+        if nvtx._on:
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        if nvtx._on:
+            torch.cuda.nvtx.range_pop()
+        return False
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -31,34 +52,9 @@ def _check3(t, name):
                          f"{t.dtype} {tuple(t.shape)} strides {t.stride()}")
 
 
-_SK_FLAGS = {}   # (device index, stream handle) -> zeroed uint32[XVA_GEMM_SK_FLAGS]: stream-K arrival counters
-SK_SCRATCH = True   # False: hand no stream-K scratch to xva_gemm (whole tiles per SM); the tests' A/B switch
-
-
-def _sk_scratch(args):
-    """Stream-K scratch of one launch (xva_gemm_args.sk_*): the partial-accumulator buffer is a fresh allocation on the
-    launching stream (the caching allocator orders its reuse after the kernel), the arrival counters are one zeroed
-    array per (device, stream) -- launches of one stream run one after the other and each leaves them zero; launches on
-    different streams may overlap and must not share them. Returns the tensors to keep referenced until the launch."""
-    fn = getattr(capi.load(), "xva_gemm_sk_workspace_bytes", None) if SK_SCRATCH else None
-    need = int(fn(C.byref(args))) if fn is not None else 0
-    if need <= 0:
-        return None
-    dev = torch.cuda.current_device()
-    key = (dev, torch.cuda.current_stream().cuda_stream)
-    flags = _SK_FLAGS.get(key)
-    if flags is None:
-        flags = _SK_FLAGS[key] = torch.zeros(capi.XVA_GEMM_SK_FLAGS, device=f"cuda:{dev}", dtype=torch.int32)
-    part = torch.empty(need // 4, device=f"cuda:{dev}", dtype=torch.float32)
-    args.sk_partials, args.sk_partials_bytes, args.sk_flags = part.data_ptr(), need, flags.data_ptr()
-    return part, flags
-
-
 def gemm_launch(args, ref=False):
     """Launch one tap-GEMM described by a filled capi.GemmArgs."""
-    keep = None if ref else _sk_scratch(args)
     capi.call("xva_gemm_ref" if ref else "xva_gemm", C.byref(args), _stream())
-    del keep
 
 
 def _base_args(mode, shifts):
@@ -327,9 +323,11 @@ def average_pitch(pitch, durs, log1p=False):
     return out
 
 
-def mas_width1(attn, in_lens, out_lens, is_log=False):
+def mas_width1(attn, in_lens, out_lens, is_log=False, stay_on_tie=False):
     """b_mas, fastpitch/alignment.py:110-118. attn [B, 1, Tm, Tt] (or [B, Tm, Tt]) soft alignment, in_lens / out_lens [B]
-    -> (attn_hard, same shape, 0/1 floats; durations int32 [B, Tt] = attn_hard.sum over mel)."""
+    -> (attn_hard, same shape, 0/1 floats; durations int32 [B, Tt] = attn_hard.sum over mel). stay_on_tie (with is_log):
+    xVAPitch's maximum_path (xvapitch/util.py:14-53) on [B, t_mel, t_text] log-likelihoods -- the reference's
+    value.transpose(1, 2); see maximum_path below."""
     shape = attn.shape
     a = attn.reshape(shape[0], shape[-2], shape[-1]).to(torch.float32).contiguous()
     B, Tm, Tt = a.shape
@@ -342,8 +340,16 @@ def mas_width1(attn, in_lens, out_lens, is_log=False):
         la = torch.empty_like(a)
         capi.call("xva_mas_log", _p(a), a.numel(), _p(la), _stream())
         a = la
-    capi.call("xva_mas_width1", _p(a), _p(il), _p(ol), B, Tm, Tt, 1, _p(hard), _p(durs), _stream())
+    capi.call("xva_mas_width1", _p(a), _p(il), _p(ol), B, Tm, Tt, 1 | (2 if stay_on_tie else 0), _p(hard), _p(durs), _stream())
     return hard.view(shape), durs
+
+
+def maximum_path(value, x_lens, y_lens):
+    """xVAPitch's monotonic alignment search, python/xvapitch/util.py:14-53, on the device (the reference copies `value` to
+    the host and runs a numpy loop at every training step, xvapitch/model.py:776): value [B, t_text, t_mel]
+    log-likelihoods, mask = (text < x_lens) & (mel < y_lens) -> path [B, t_text, t_mel] of 0 / 1."""
+    hard, _ = mas_width1(value.transpose(1, 2), x_lens, y_lens, is_log=True, stay_on_tie=True)
+    return hard.transpose(1, 2)
 
 
 def attn_score_fwd(q, k, prior, in_lens):
@@ -405,6 +411,34 @@ def attn_grad_combine(gctc, a, hard=None, soft=None, acc=None, bw=0.0, eps=1e-12
     capi.call("xva_attn_grad_combine", _p(gctc), _p(hard) if use_kl else None, _p(soft) if use_kl else None,
               _p(acc) if use_kl else None, float(a), float(bw), float(eps), gctc.numel() // Tt, Tt, _p(g), _stream())
     return g
+
+
+def attn_fwd(qkv, lens, scale, drop_p=0.0, seed=0, seed_dev=None, drop_ld=None):
+    """Fused attention of one FFT block (xva_attn_fwd): qkv [B, T, 192] (q | k | v, tf32-rounded) -> (vec [B, T, 64]
+    tf32-rounded, lse [B, T]). lens int32 [B] masks the keys >= lens[b]."""
+    _check3(qkv, "qkv")
+    B, T, C = qkv.shape
+    assert C == 192 and (lens is None or lens.dtype == torch.int32)
+    out = torch.empty(B, T, 64, device=qkv.device, dtype=torch.float32)
+    lse = torch.empty(B, T, device=qkv.device, dtype=torch.float32)
+    capi.call("xva_attn_fwd", _p(qkv), qkv.stride(1), qkv.stride(0), B, T, _p(lens), float(scale), float(drop_p),
+              int(seed) & 0xFFFFFFFFFFFFFFFF, _p(seed_dev), int(drop_ld if drop_ld else (T + 31) // 32 * 32), _p(out),
+              out.stride(1), out.stride(0), _p(lse), _stream())
+    return out, lse
+
+
+def attn_bwd(qkv, dvec, vec, lse, lens, scale, drop_p=0.0, seed=0, seed_dev=None, drop_ld=None, out=None):
+    """Backward of attn_fwd (xva_attn_bwd): -> dqkv [B, T, 192] = dq | dk | dv, tf32-rounded. dvec = gradient of the
+    attention output (tf32-rounded), vec / lse = what attn_fwd returned."""
+    _check3(qkv, "qkv")
+    _check3(dvec, "dvec")
+    B, T, _ = qkv.shape
+    dsum = rowdot2(dvec, vec)
+    dqkv = torch.empty_like(qkv) if out is None else out
+    capi.call("xva_attn_bwd", _p(qkv), qkv.stride(1), qkv.stride(0), _p(dvec), dvec.stride(1), dvec.stride(0), _p(lse),
+              _p(dsum), B, T, _p(lens), float(scale), float(drop_p), int(seed) & 0xFFFFFFFFFFFFFFFF, _p(seed_dev),
+              int(drop_ld if drop_ld else (T + 31) // 32 * 32), _p(dqkv), dqkv.stride(1), dqkv.stride(0), _stream())
+    return dqkv
 
 
 # ---------------------------------------------------------------------------------------------- row kernels

@@ -32,7 +32,9 @@ import traceback
 import torch
 
 from . import fastpitch as fp
+from . import graph
 from . import hifigan as hg
+from . import ops
 from . import parallel
 
 
@@ -182,6 +184,22 @@ class _TrainerBase:
             with open(f"{self.dataset_output}/graphs.json", "w+") as f:
                 f.write(json.dumps(self.graphs_json))
 
+    def _scalars(self, step, **named):
+        """TensorBoard scalars under the output folder, rank 0 only (SummaryWriter(log_dir=dataset_output, flush_secs=120),
+        xva_train.py:297; tags as xva_train.py:841-848,892-899,944-948 and hifigan/xva_train.py:554-557,628)."""
+        if self.rank != 0:
+            return
+        if getattr(self, "_tb", None) is None:
+            try:
+                from torch.utils.tensorboard import SummaryWriter
+                self._tb = SummaryWriter(log_dir=self.dataset_output, flush_secs=120)
+            except Exception:
+                self._tb = False
+        if self._tb:
+            for tag, v in named.items():
+                if v is not None:
+                    self._tb.add_scalar(tag, float(v), int(step))
+
     def _dist_init(self):
         """Join the NCCL process group when launched under torchrun (idempotent). -> world size"""
         if self.world > 1:
@@ -313,11 +331,90 @@ class FastPitchTrainer(_TrainerBase):
         self.last_loss, self.iter_losses, self.avg_frames_s = None, [], []
         self.epoch_iter, self.micro, self.frames_acc = 0, 0, 0
         self._window_loss = None
+        self.use_graph = os.environ.get("XVA_TRAINER_GRAPH", "1") != "0"
+        self._graphs, self._lens_cache, self._graph_pool = {}, {}, None    # per stage: init() runs again after a stage change
+        self.optimizer.lr_on_device = False
         self.batch_pos = 0
         self.avg_loss_per_epoch.append(0.0)
         self.step_t0 = time.perf_counter()
         self.model.zero_grad()
         self.is_init = True
+
+    # ---- CUDA-graph replay of the micro-step (stages 2-4). One graph per (stage, batch shape, last-of-window): the step is
+    # ~330 launches with static shapes, and issued one by one from Python it is host-bound (bench: 14.9 ms eager vs 13.7 ms
+    # replayed at 32 x 880 x 160; far worse at small batches). Everything that changes between replays lives on the device:
+    # the batch (copied into the graph's static input tensors), the learning rate (Lamb.lr_dev), the dropout counter, and the
+    # skip-on-non-finite decision (xva_lamb_step is a no-op when the gradient norm is not finite). Stage 1 stays eager: its
+    # binarization-loss weight changes every epoch and is a kernel argument.
+    GRAPH_CACHE = 8
+
+    def _host_lens(self, x):
+        """(mel_max_len, max decoder length) of a batch as Python ints, read once per batch and cached: FastPitch.forward
+        then needs no device->host read (model.py:330 and :75 make two per step)."""
+        key = (id(x), id(x[8]))
+        hit = self._lens_cache.get(key)
+        if hit is None:
+            mel_max = int(x[10][0].item())
+            _, dec = ops.duration_scan(x[8].to(torch.float32), 1.0, mel_max)
+            hit = self._lens_cache[key] = (mel_max, int(dec.max().item()))
+        return hit
+
+    def _micro_step(self, x, y, last, host_lens):
+        """forward + loss + backward of one micro-batch; with ``last`` also gradient exchange, LAMB, dropout counter and
+        zero_grad. Returns device scalars only (no host sync): tracked loss, gradient norm, the logged loss terms."""
+        stage = self.model.training_stage
+        y_pred = self.model(x, host_lens=host_lens)                                                          # :788
+        loss, meta = self.criterion(y_pred, y)                                                               # :790
+        sync = self.sync if last else None
+        self.model.backward(self.criterion, 1.0 / self.gam, grad_sync=sync)                                  # :806-813
+        if sync is not None:
+            sync.finish()
+        key = {3: "pitch_loss", 4: "mel_loss"}.get(stage, "loss")                                            # :815-820
+        tracked = (meta[key] * (0.1 if stage == 3 else 1.0)).double().reshape(())
+        names = ("loss", "mel_loss", "duration_predictor_loss", "pitch_loss", "energy_loss")
+        zero = torch.zeros((), device=tracked.device, dtype=torch.float64)
+        terms = [meta[k].double().reshape(()) if torch.is_tensor(meta.get(k)) else zero for k in names]
+        gsq = zero
+        if last:
+            gsq = torch.linalg.vector_norm(self.model.arena.g).double().reshape(())     # NaN / Inf propagate
+            self.optimizer.step()          # no-op on the device when the gradient norm is not finite (xva_lamb_step)      :855-862
+            self.model.step_dropout()
+            self.model.zero_grad()
+        return torch.stack([tracked, gsq] + terms)
+
+    def _graphed_micro_step(self, x, y, last):
+        stage = self.model.training_stage
+        hl = self._host_lens(x)
+        tensors = [i for i, t in enumerate(x) if torch.is_tensor(t)]
+        sig = (stage, bool(last), hl, tuple((i, tuple(x[i].shape), x[i].dtype) for i in tensors))
+        entry = self._graphs.get(sig)
+        if entry is None:
+            if len(self._graphs) >= self.GRAPH_CACHE:
+                return None                                   # shape not worth another graph: run it eagerly
+            static_x = [t.clone() if torch.is_tensor(t) else t for t in x]
+            static_y = [static_x[2], static_x[1], static_x[3], static_x[9]]
+            self.optimizer.lr_on_device = True
+
+            def run(*ts):
+                return self._micro_step(static_x, static_y, last, hl)
+
+            # warm-up executions inside GraphedStep would apply real optimizer steps: capture without warm-up, after one
+            # eager execution of this very micro-step (the caller's), so every lazily created buffer exists
+            entry = self._graphs[sig] = (None, static_x, tensors)
+            return None
+        gstep, static_x, tensors = entry
+        if gstep is None:
+            static_y = [static_x[2], static_x[1], static_x[3], static_x[9]]
+            self.optimizer.lr_on_device = True               # the captured LAMB reads lr_dev, filled before every replay
+            gstep = graph.GraphedStep(lambda: self._micro_step(static_x, static_y, last, hl), [], warmup=0, pool=self._graph_pool)
+            self._graph_pool = gstep.pool
+            self._graphs[sig] = (gstep, static_x, tensors)
+            # the capture itself does not execute: fall through to the replay below
+        for i in tensors:
+            if static_x[i] is not x[i]:
+                static_x[i].copy_(x[i], non_blocking=True)
+        self.optimizer.lr_dev.fill_(float(self.optimizer.param_groups[0]["lr"]))
+        return gstep()
 
     async def iteration(self):
         if not self.is_init:
@@ -328,6 +425,8 @@ class FastPitchTrainer(_TrainerBase):
             self.avg_loss_per_epoch.append(0.0)
             self.epoch_iter = 0
             self.iter_losses = []
+        if self.use_graph and self.model.training_stage != 1:
+            return await self._iteration_graphed()
         x, y, num_frames = self.batches[self.batch_pos]
         self.batch_pos += 1
         self.total_iter += 1
@@ -361,8 +460,11 @@ class FastPitchTrainer(_TrainerBase):
             # are cleared, moments, weights and their tf32 copy stay as they were.
             self._window_loss = tracked if self._window_loss is None else self._window_loss + tracked
             gsq = torch.linalg.vector_norm(self.model.arena.g).double()     # NaN / Inf propagate
-            val, gval = (float(v) for v in torch.stack([self._window_loss.double().reshape(()), gsq]).tolist())
-            val /= self.gam
+            names = ("loss", "mel_loss", "duration_predictor_loss", "pitch_loss", "energy_loss", "kl_loss")
+            zero = torch.zeros((), device=gsq.device, dtype=torch.float64)
+            terms = [meta[k].double().reshape(()) if k in meta else zero for k in names]
+            host = torch.stack([self._window_loss.double().reshape(()), gsq.reshape(())] + terms).tolist()
+            val, gval, logged = float(host[0]) / self.gam, float(host[1]), dict(zip(names, host[2:]))
             self._window_loss = None
             if not (math.isfinite(val) and math.isfinite(gval)):
                 self.model.zero_grad()
@@ -380,9 +482,64 @@ class FastPitchTrainer(_TrainerBase):
             self.avg_frames_s.append(frames_s)
             self.iter_losses.append(val)
             self.avg_loss_per_epoch[-1] += val
+            nz = lambda v: v if v else None             # the reference only writes the terms the stage trains (:839-848)
+            self._scalars(self.total_iter, **{"loss/loss": logged["loss"], "loss/mel": nz(logged["mel_loss"]),
+                                              "loss/dur": nz(logged["duration_predictor_loss"]), "loss/pitch": nz(logged["pitch_loss"]),
+                                              "loss/energy": nz(logged["energy_loss"]), "loss/kl": nz(logged["kl_loss"]),
+                                              "meta/frames/s": frames_s, "meta/lrate": self.optimizer.param_groups[0]["lr"]})
             self.training_log_live_line = (f"| Stage {stage} | Epoch {self.epoch} | iter {self.total_iter} | loss "
                                            f"{val:.5f} | frames/s {int(frames_s)} | lr {self.optimizer.param_groups[0]['lr']:.2e}")
             self.print_and_log(save_to_file=self.dataset_output)
+
+    async def _iteration_graphed(self):
+        """iteration() for stages 2-4 with the micro-step replayed from a CUDA graph (eager for the first two sightings of
+        a shape: one to create every lazily allocated buffer, one inside the capture's own bookkeeping)."""
+        x, y, num_frames = self.batches[self.batch_pos]
+        self.batch_pos += 1
+        self.total_iter += 1
+        self.epoch_iter += 1
+        fp.adjust_learning_rate(self.total_iter, self.optimizer, self.learning_rate, self.warmup_steps)     # :780
+        stage = self.model.training_stage
+        self.micro += 1
+        last = self.micro % self.gam == 0
+        steps_before = self.optimizer.steps      # host-side count of APPLIED updates (a capture or a replay does not run
+        out = self._graphed_micro_step(x, y, last)   # Lamb.step's Python; a skipped update must not count)
+        if out is None:
+            self.optimizer.lr_on_device = False
+            out = self._micro_step(x, y, last, self._host_lens(x))
+        self.optimizer.steps = steps_before
+        self.frames_acc += num_frames
+        # (out is the graph's static output tensor: the next replay overwrites it)
+        self._window_loss = out[0].clone() if self._window_loss is None else self._window_loss + out[0]
+        if not last:
+            return
+        host = torch.cat([self._window_loss.reshape(1), out[1:]]).tolist()          # the one host read of the optimizer step
+        self._window_loss = None
+        val, gval = float(host[0]) / self.gam, float(host[1])
+        logged = dict(zip(("loss", "mel_loss", "duration_predictor_loss", "pitch_loss", "energy_loss"), host[2:]))
+        if not (math.isfinite(val) and math.isfinite(gval)):
+            # the device already skipped the update (non-finite gradient norm); a NaN loss with finite gradients cannot
+            # happen (the loss is a function of the same activations), so there is nothing to undo
+            self.frames_acc = 0
+            self.step_t0 = time.perf_counter()
+            self.print_and_log("loss is NaN", save_to_file=self.dataset_output)
+            return
+        self.optimizer.steps = steps_before + 1
+        dt = time.perf_counter() - self.step_t0
+        self.step_t0 = time.perf_counter()
+        frames_s = self.world * self.frames_acc / max(dt, 1e-9)
+        self.frames_acc = 0
+        self.avg_frames_s.append(frames_s)
+        self.iter_losses.append(val)
+        self.avg_loss_per_epoch[-1] += val
+        nz = lambda v: v if v else None
+        self._scalars(self.total_iter, **{"loss/loss": logged["loss"], "loss/mel": nz(logged["mel_loss"]),
+                                          "loss/dur": nz(logged["duration_predictor_loss"]), "loss/pitch": nz(logged["pitch_loss"]),
+                                          "loss/energy": nz(logged["energy_loss"]),
+                                          "meta/frames/s": frames_s, "meta/lrate": self.optimizer.param_groups[0]["lr"]})
+        self.training_log_live_line = (f"| Stage {stage} | Epoch {self.epoch} | iter {self.total_iter} | loss "
+                                       f"{val:.5f} | frames/s {int(frames_s)} | lr {self.optimizer.param_groups[0]['lr']:.2e}")
+        self.print_and_log(save_to_file=self.dataset_output)
 
     # reference: xva_train.py:915-976
     def finish_epoch(self):
@@ -400,7 +557,10 @@ class FastPitchTrainer(_TrainerBase):
         frames_s = sum(self.avg_frames_s) / max(1, len(self.avg_frames_s))
         self.save_checkpoint(False, frames_s, self.total_iter, avg_loss, delta_avg, self.avg_loss_per_epoch, fpath)
         self.graphs_json["stages"][str(stage)]["loss"].append([self.total_iter, self.avg_loss_per_epoch[-1]])
+        if deltas:
+            self._scalars(self.total_iter, **{"meta/acc_epoch_delta": deltas[-1]})
         if delta_avg is not None:
+            self._scalars(self.total_iter, **{f"meta/stage_{stage}_acc_epoch_deltas_avg20": delta_avg})
             self.graphs_json["stages"][str(stage)]["loss_delta"].append([self.total_iter, delta_avg])
         self._write_graphs()
         done = False
@@ -639,6 +799,8 @@ class HiFiTrainer(_TrainerBase):
         await self._send("Set stage to: 5 ")
         self.batch_pos, self.iter_losses = 0, []
         self.avg_loss_per_epoch.append(0.0)
+        self.use_graph = os.environ.get("XVA_TRAINER_GRAPH", "1") != "0"
+        self._gstep, self._gstep_sig = None, None
         self.is_init = True
 
     def _wav_epoch(self):
@@ -662,11 +824,37 @@ class HiFiTrainer(_TrainerBase):
         x, y, y_mel = self.batches[self.batch_pos]
         self.batch_pos += 1
         t0 = time.perf_counter()
-        for opt in (self.stepper.optim_g, self.stepper.optim_d):
+        opts = (self.stepper.optim_g, self.stepper.optim_d)
+        for opt in opts:
             opt.param_groups[0]["lr"] = self.lr
-        out = self.stepper.step(x, y, y_mel)                                          # :467-515
+        sig = (tuple(x.shape), tuple(y.shape), tuple(y_mel.shape))
+        if self.use_graph and self._gstep is not None and self._gstep_sig == sig:
+            # one CUDA-graph replay per step (~1 000 launches; eager the step is host-bound: 41.7 vs 32.1 ms at 16 x 8192);
+            # learning rate and AdamW step count live on the device
+            for opt in opts:
+                opt.lr_dev.fill_(float(self.lr))
+            out = self._gstep(x, y, y_mel)
+            for opt in opts:
+                opt.steps += 1
+            self.stepper.steps += 1
+        else:
+            for opt in opts:
+                opt.lr_on_device = False
+            out = self.stepper.step(x, y, y_mel)                                      # :467-515
+            if self.use_graph and self._gstep is None:
+                # captured after this first eager step (every lazily created buffer now exists); capture does not execute
+                for opt in opts:
+                    opt.lr_on_device = True
+                statics = [x.clone(), y.clone(), y_mel.clone()]
+                self._gstep = graph.GraphedStep(lambda a, b, c: self.stepper.step(a, b, c), statics, warmup=0)
+                self._gstep_sig = sig
+                for opt in opts:          # the capture ran AdamW.step()'s host-side bookkeeping once without a launch
+                    opt.steps -= 1
+                self.stepper.steps -= 1
         gen_loss, mel_error = (float(v) for v in torch.stack([out["loss_gen_all"].double(), out["mel_error"].double()]).tolist())
         its = 1.0 / max(time.perf_counter() - t0, 1e-9)
+        self._scalars(self.steps, **{"training/gen_loss_total": gen_loss, "training/mel_spec_error": mel_error,
+                                     "training/d_lr": self.lr, "training/g_lr": self.lr})          # :554-557
         mel_loss = int(mel_error * 1000) / 1000                                       # :518-523: the tracked quantity
         self.iter_losses.append(mel_loss)
         self.avg_loss_per_epoch[-1] += mel_loss
@@ -686,6 +874,7 @@ class HiFiTrainer(_TrainerBase):
         done = False
         if len(deltas) >= 2:
             d = sum(deltas[-self.EPOCH_AVG_SPAN:]) / len(deltas[-self.EPOCH_AVG_SPAN:])
+            self._scalars(self.steps, **{"meta/stage_5_acc_epoch_deltas_avg20": d})              # :628
             self.graphs_json["stages"]["5"]["loss_delta"].append([self.steps, d])
             # :633-647: converged when the 20-epoch average relative improvement of the mel loss stays at or below
             # 0.0001 for 3 consecutive epochs, with at least 25 deltas on record
