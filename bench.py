@@ -572,7 +572,7 @@ def run_native(args):
         # DRAM bytes of the dominant launch from the committed ncu --set full capture of that exact shape (per launch)
         traffic = None
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_s5_dominant_launch_traffic.json")))
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r02_dominant_launch_traffic.json")))
             if all(dominant["shape"].get(k) == v for k, v in tr["shape"].items()):
                 traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
                 dominant["traffic"] = traffic

@@ -39,6 +39,11 @@ def _worker(rank, world, port, stage, out_q):
 
     B, Tt, Tm = 4, 40, 150
     x, _ = ofp.synthetic_batch(B, Tt, Tm, seed=11, ragged=True)
+    # every run pads to the GLOBAL lengths, as nn.DataParallel's replicas do (the shards below are slices of one padded
+    # batch; the decoder length is handed in): an utterance's last frames depend on the padded length of its batch --
+    # nothing masks between the two convolutions of PositionwiseConvFF -- so local padding would differ from the
+    # whole-batch run by ~1e-5 in the loss (measured: profiles/r02_ddp_nccl_stage3.json, r02_batch_invariance.txt)
+    hl = (Tm, int(x[3].max()))
     sd = ofp.make_state(1234)
     per = B // world
     to_dev = lambda xs: [t.to(dev) if torch.is_tensor(t) else t for t in xs]
@@ -61,7 +66,7 @@ def _worker(rank, world, port, stage, out_q):
     m, c = make()
     c.set_distributed(world)
     sync = parallel.GradSync(m, world, mean=False, min_bucket_elems=1 << 18)
-    loss, meta = c(m(xs), targets(xs))
+    loss, meta = c(m(xs, host_lens=hl), targets(xs))
     m.zero_grad()
     m.backward(c, 1.0, grad_sync=sync)
     sync.finish()
@@ -71,7 +76,7 @@ def _worker(rank, world, port, stage, out_q):
     # ---- (2) mean of per-rank ratios (what plain DDP would do)
     m2, c2 = make()
     sync2 = parallel.GradSync(m2, world, mean=True)
-    loss2, _ = c2(m2(xs), targets(xs))
+    loss2, _ = c2(m2(xs, host_lens=hl), targets(xs))
     m2.zero_grad()
     m2.backward(c2, 1.0, grad_sync=sync2)
     sync2.finish()
@@ -79,7 +84,7 @@ def _worker(rank, world, port, stage, out_q):
     # ---- (3) one process, whole batch (rank 0 computes, everyone compares against its broadcast)
     m3, c3 = make()
     xf = to_dev(x)
-    loss3, _ = c3(m3(xf), targets(xf))
+    loss3, _ = c3(m3(xf, host_lens=hl), targets(xf))
     m3.zero_grad()
     m3.backward(c3, 1.0)
     torch.cuda.synchronize()
@@ -96,7 +101,7 @@ def _worker(rank, world, port, stage, out_q):
     for i in range(5):
         fp.adjust_learning_rate(50000 + i, opt, 0.1, 1000)
         m4.zero_grad()
-        l4, _ = c4(m4(xs), targets(xs))
+        l4, _ = c4(m4(xs, host_lens=hl), targets(xs))
         m4.backward(c4, 1.0, grad_sync=sync4)
         sync4.finish()
         opt.step()

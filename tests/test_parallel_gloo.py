@@ -145,3 +145,47 @@ def test_loss_mask_sums_are_global_gloo():
         assert acc == want and klw == 2 and default_world == 1
     # the global ratio differs from the mean of the per-rank ratios whenever the counts differ
     assert abs(30.0 / 250.0 - 0.5 * (10.0 / 100.0 + 20.0 / 150.0)) > 1e-3
+
+
+def _worker_pad(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from xva_trainer_b200.parallel import pad_batches_to_global
+
+    def batch(B, Tt, Tm, prior):
+        x = [torch.ones(B, Tt, dtype=torch.long), torch.full((B,), Tt), torch.ones(B, 80, Tm), torch.full((B,), Tm),
+             torch.ones(B, 1, Tm), torch.ones(B, Tm), None, torch.ones(B, Tm, Tt) if prior else None, torch.ones(B, Tt),
+             torch.full((B,), float(Tt)), torch.full((B,), float(Tm)), ["u"] * B]
+        return (x, [x[2], x[1], x[3], x[9]], B * Tm)
+
+    mine = [batch(2, 10 + rank, 50 - 3 * rank, True), batch(2, 12, 40, False)]
+    out = pad_batches_to_global(mine, world)
+    shapes = [(tuple(b[0][0].shape), tuple(b[0][2].shape), tuple(b[0][4].shape), tuple(b[0][5].shape),
+               None if b[0][7] is None else tuple(b[0][7].shape), tuple(b[0][8].shape), float(b[0][9][0]), float(b[0][10][0]),
+               b[1][0] is b[0][2], int(b[0][1][0]), int(b[0][3][0]), float(b[0][2].sum()), float(b[0][0].sum())) for b in out]
+    q.put((rank, shapes))
+    dist.destroy_process_group()
+
+
+def test_pad_batches_to_global_gloo():
+    """Every rank's i-th batch ends up with the maximum text / mel length over ranks; lengths, sums (zero padding) and the
+    target list follow; a batch that is already at the maximum is returned untouched."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + 11
+    procs = [ctx.Process(target=_worker_pad, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank in (0, 1):
+        first, second = out[rank]
+        Tt, Tm = 10 + rank, 50 - 3 * rank
+        assert first[:6] == ((2, 11), (2, 80, 50), (2, 1, 50), (2, 50), (2, 50, 11), (2, 11))
+        assert first[6:9] == (11.0, 50.0, True)
+        assert first[9:11] == (Tt, Tm)                                   # the true lengths are not touched
+        assert first[11] == 2 * 80 * Tm and first[12] == 2 * Tt            # padding is zeros
+        assert second[:2] == ((2, 12), (2, 80, 40)) and second[4] is None

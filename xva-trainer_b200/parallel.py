@@ -92,3 +92,40 @@ def shard_batches(batches, rank, world):
     batches = list(batches)
     n = (len(batches) // world) * world
     return batches[rank:n:world]
+
+
+def pad_batches_to_global(batches, world, group=None):
+    """Pad the i-th batch of every rank to the same text and mel lengths (the maxima over ranks), in place of the
+    per-rank padding a collate produces. Why it matters for parity: in the reference nothing masks between the two
+    convolutions of PositionwiseConvFF (transformer.py:59-77), so the last valid frame of an utterance reads one frame of
+    its own padding -- a frame that exists when the utterance is shorter than its batch and is a zero boundary when it is
+    the longest. An utterance's output therefore depends (at the 1e-5 level in the loss) on the padded length of its
+    batch. nn.DataParallel pads the GLOBAL batch before scattering it; ranks that pad locally would differ from that, and
+    from one GPU running the global batch, by exactly this effect. ``batches``: list of (x, y, num_frames) in the layout
+    of batch_to_gpu (data_function.py:706-741). One all-reduce(MAX) of 2 ints per batch, once, at trainer start."""
+    import torch.nn.functional as F
+    if world <= 1 or not batches:
+        return batches
+    dev = batches[0][0][0].device
+    sizes = torch.tensor([[b[0][0].shape[1], b[0][2].shape[2]] for b in batches], device=dev, dtype=torch.int64)
+    dist.all_reduce(sizes, op=dist.ReduceOp.MAX, group=group)
+    out = []
+    for (x, y, n), (Tt, Tm) in zip(batches, sizes.tolist()):
+        dt, dm = Tt - x[0].shape[1], Tm - x[2].shape[2]
+        if dt or dm:
+            x = list(x)
+            x[0] = F.pad(x[0], (0, dt))                                   # text [B, Tt]
+            x[2] = F.pad(x[2], (0, dm))                                   # mel [B, 80, Tm]
+            if x[4] is not None:
+                x[4] = F.pad(x[4], (0, dm))                               # pitch [B, 1, Tm]
+            if x[5] is not None:
+                x[5] = F.pad(x[5], (0, dm))                               # energy [B, Tm]
+            if x[7] is not None:
+                x[7] = F.pad(x[7], (0, dt, 0, dm))                        # attn_prior [B, Tm, Tt]
+            if x[8] is not None:
+                x[8] = F.pad(x[8], (0, dt))                               # durations [B, Tt]
+            x[9] = torch.full_like(x[9], float(Tt))                       # max_inp_lengths
+            x[10] = torch.full_like(x[10], float(Tm))                     # max_mel_lengths
+            y = [x[2], x[1], x[3], x[9]]
+        out.append((x, y, n))
+    return out

@@ -252,6 +252,9 @@ class FastPitchTrainer(_TrainerBase):
         while self.running:
             await self.iteration()
 
+    def _batches_key_changed(self, key):
+        return getattr(self, "_batches_key", None) != key
+
     async def init(self):
         world = self._dist_init()
         torch.manual_seed(1234 + self.rank)
@@ -307,6 +310,8 @@ class FastPitchTrainer(_TrainerBase):
         else:
             raise NotImplementedError("wav/text dataset loading is outside this build (SURVEY.md section 2 row 6): pass "
                                       "data['batch_source'] or dataset_path='synthetic:BxTtxTmxitems'")
+        if self._batches_key_changed(source_key):
+            self.batches = parallel.pad_batches_to_global(self.batches, world)     # DataParallel pads the global batch (8e)
         self._batches_key = source_key
         has_prior = all(b[0][7] is not None for b in self.batches)
         if stage is None:
@@ -356,7 +361,13 @@ class FastPitchTrainer(_TrainerBase):
         if hit is None:
             mel_max = int(x[10][0].item())
             _, dec = ops.duration_scan(x[8].to(torch.float32), 1.0, mel_max)
-            hit = self._lens_cache[key] = (mel_max, int(dec.max().item()))
+            both = torch.stack([torch.tensor(mel_max, device=dec.device, dtype=torch.int64), dec.max().to(torch.int64)])
+            if self.world > 1:
+                # every rank runs its decoder at the GLOBAL maximum length, as the replicas of nn.DataParallel do: an
+                # utterance's last frames depend on the padded length of its batch (parallel.pad_batches_to_global)
+                import torch.distributed as dist
+                dist.all_reduce(both, op=dist.ReduceOp.MAX)
+            hit = self._lens_cache[key] = tuple(int(v) for v in both.tolist())
         return hit
 
     def _micro_step(self, x, y, last, host_lens):
@@ -432,9 +443,9 @@ class FastPitchTrainer(_TrainerBase):
         self.total_iter += 1
         self.epoch_iter += 1
         fp.adjust_learning_rate(self.total_iter, self.optimizer, self.learning_rate, self.warmup_steps)     # :780
-        y_pred = self.model(x)                                                                               # :788
-        loss, meta = self.criterion(y_pred, y)                                                               # :790
         stage = self.model.training_stage
+        y_pred = self.model(x) if stage == 1 else self.model(x, host_lens=self._host_lens(x))                # :788
+        loss, meta = self.criterion(y_pred, y)                                                               # :790
         kl = None
         if stage == 1 and self.KL_LOSS_START_EPOCH is not None and self.epoch >= self.KL_LOSS_START_EPOCH:   # :792-798
             binarization_loss = self.attention_kl_loss(y_pred[9], y_pred[8])
