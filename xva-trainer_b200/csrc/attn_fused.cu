@@ -16,6 +16,7 @@
 // index the unfused softmax kernels use, so both paths draw identical masks from one seed.
 #include <cuda.h>
 #include <cmath>
+#include <cstdlib>
 #include <mutex>
 #include "gemm.cuh"
 #include "ptx.cuh"
@@ -295,7 +296,7 @@ int g_attn_round_host = 1;
 // (xva_rowdot2). The A operand of every second-stage product is read from tensor memory; its B operand (K, Q or dO as
 // [d, rows]) is an MN-major tile, so those three tensors are staged twice per chunk: K-major for the first-stage
 // products and MN-major for the second. 256 threads: two warps per TMEM lane quarter split a row's 128 columns.
-constexpr int kBwdThreads = 256;
+constexpr int kBwdThreads = 512;   // 16 warps: four per TMEM lane quarter, each owns 32 of a chunk's 128 columns
 constexpr int kBwdTmemCols = 512;
 constexpr int kDqSmem = 6 * kTileBytes + 1024 + 128;     // Q, dO, K, V, K (MN-major) x 2
 constexpr int kDkvSmem = 6 * kTileBytes + 1024 + 128 + 2 * kAttnRows * 4;   // K, V, Q, dO, Q (MN), dO (MN) + lse / D of the chunk
@@ -427,9 +428,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_cons
     const int key0 = c * kAttnKeys;
     const int nvalid = (lim - key0) < kAttnKeys ? (lim - key0) : kAttnKeys;
     const uint64_t idx_row = (static_cast<uint64_t>(b) * T + row) * static_cast<uint64_t>(p.drop_ld) + key0;
-#pragma unroll 1
-    for (int blk = 0; blk < 2; ++blk) {
-      const int col0 = half * 64 + blk * 32;
+    {
+      const int col0 = half * 32;            // `half` is the warp's column part 0..3 here (16 warps)
       uint32_t s[32];
       if (col0 < nvalid) {
         uint32_t dp[32];
@@ -478,8 +478,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_cons
   }
 
   // ---- dQ -> dqkv[:, :, 0:64] (tf32-rounded: operand of the qkv weight gradient and input gradient)
-  float* dst = p.dqkv + static_cast<long>(b) * p.g_zs + static_cast<long>(row) * p.g_rs + half * 32;
-  if (n_chunks > 0) {
+  float* dst = p.dqkv + static_cast<long>(b) * p.g_zs + static_cast<long>(row) * p.g_rs + (half & 1) * 32;
+  if (half >= 2) {
+    // column parts 2, 3 have nothing to store (dQ is 64 wide)
+  } else if (n_chunks > 0) {
     uint32_t v[32];
     ptx::tmem_ld32(tdQ + half * 32, v);
     ptx::tmem_wait_ld();
@@ -629,9 +631,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_con
     if (warp == 0 && c + 1 < n_chunks && ptx::elect_one()) issue_qd(c + 1);
     __syncwarp();
 
-#pragma unroll 1
-    for (int blk = 0; blk < 2; ++blk) {
-      const int col0 = half * 64 + blk * 32;            // query columns of this pass
+    {
+      const int col0 = half * 32;                       // query columns of this warp (`half` = column part 0..3, 16 warps)
       uint32_t s[32], dp[32];
       ptx::tmem_ld32(tS + col0, s);
       ptx::tmem_ld32(tdP + col0, dp);
@@ -697,13 +698,14 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_con
     const bool store = key < T;
     float* dst = p.dqkv + static_cast<long>(b) * p.g_zs + static_cast<long>(store ? key : 0) * p.g_rs;
     if (n_chunks > 0) {
-#pragma unroll
-      for (int which = 0; which < 2; ++which) {   // 0: dK, 1: dV
+      // 16 warps, 2 x 64 output columns per row: column parts 0, 1 store dK, parts 2, 3 store dV, 32 columns each
+      {
+        const int which = half >> 1, hc = half & 1;
         uint32_t v[32];
-        ptx::tmem_ld32((which == 0 ? tdK : tdV) + half * 32, v);
+        ptx::tmem_ld32((which == 0 ? tdK : tdV) + hc * 32, v);
         ptx::tmem_wait_ld();
         if (store) {
-          float* d = dst + (which + 1) * kAttnD + half * 32;
+          float* d = dst + (which + 1) * kAttnD + hc * 32;
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
             uint4 o;
@@ -717,10 +719,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_con
       }
     } else if (store) {
 #pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        *reinterpret_cast<float4*>(dst + kAttnD + half * 32 + i) = make_float4(0.f, 0.f, 0.f, 0.f);
-        *reinterpret_cast<float4*>(dst + 2 * kAttnD + half * 32 + i) = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+      for (int i = 0; i < 32; i += 4)
+        *reinterpret_cast<float4*>(dst + kAttnD + half * 32 + i) = make_float4(0.f, 0.f, 0.f, 0.f);   // 4 parts x 32 = dK | dV
     }
   }
   ptx::tc_fence_before();
