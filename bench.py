@@ -85,9 +85,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, windows=None):
+        """``windows``: [(t0, t1), ...] host-clock intervals tried in order; the first one that holds at least two samples
+        is reported (the sampler is started before the warm-up: on an 8-GPU box nvidia-smi needs longer to produce its
+        first line than a 20-step timed region lasts)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -95,8 +98,14 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
+        rows, label = [r for _, r in self.rows], "whole run"
+        for name, (t0, t1) in (windows or []):
+            inside = [r for t, r in self.rows if t0 <= t <= t1]
+            if len(inside) >= 2:
+                rows, label = inside, name
+                break
         sm, mx, reasons = [], None, set()
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[0]))
                 mx = float(r[1])
@@ -107,7 +116,7 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": label}
 
 
 # ---------------------------------------------------------------------------------------------- CPU reference / baseline
@@ -443,25 +452,27 @@ def run_native(args):
                 gstep.load(*[x[i] for i in tensor_idx])
             return gstep()
 
-    # ---- warm-up
+    # ---- warm-up (the clock sampler starts here: same workload, GPU under the same load)
+    clocks = ClockSampler(local)
+    clocks.start()
+    t_warm = time.perf_counter()
     for _ in range(max(args.warmup, 3)):
         loss = step(x_dev)
     barrier()
 
     # ---- timed region 1: batch resident in HBM
-    clocks = ClockSampler(local)
-    clocks.start()
     capi.reset_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_r0 = time.perf_counter()
     e0.record()
     for _ in range(args.steps):
         loss = step(x_dev)
     e1.record()
     barrier()
+    t_r1 = time.perf_counter()
     ms = e0.elapsed_time(e1)
     launches = capi.launch_count() if launches_per_step is None else launches_per_step * args.steps
-    clk = clocks.stop()
 
     # ---- timed region 2: end to end from pinned host buffers, loss read back every step
     barrier()
@@ -474,7 +485,10 @@ def run_native(args):
         loss_host = float(loss)           # device -> host read of the step's result
     f1.record()
     barrier()
+    t_r2 = time.perf_counter()
     ms_e2e = f0.elapsed_time(f1)
+    clk = clocks.stop([("timed region (device-resident)", (t_r0, t_r1)), ("timed regions (device-resident + e2e)", (t_r0, t_r2)),
+                       ("warm-up + timed regions", (t_warm, t_r2))])
     if not (loss_host == loss_host):
         raise RuntimeError("loss is NaN")
 
