@@ -418,6 +418,10 @@ int xva_zero_tail_rows(float* x, int Z, int Lp, int Lvalid, int C, void* stream)
  * ---------------------------------------------------------------------------------------------------------- */
 #define XVA_WN_TRANSPOSED 1
 #define XVA_WN_NO_ROUND 2
+/* a plain (not weight-normed) convolution in the same table: w = v (g, dg unused, may be null), bwd: dv (+)= dW. The
+ * xVAPitch waveform decoder removes weight norm from conv_pre / conv_post and adds a plain cond_layer
+ * (python/xvapitch/hifigan.py:224-232, xvapitch/model.py:134-149). */
+#define XVA_WN_PLAIN 4
 typedef struct xva_wn_desc {
   const float* v;
   const float* g;

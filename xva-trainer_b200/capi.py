@@ -64,7 +64,7 @@ class WnDesc(C.Structure):
     ]
 
 
-WN_TRANSPOSED, WN_NO_ROUND = 1, 2
+WN_TRANSPOSED, WN_NO_ROUND, WN_PLAIN = 1, 2, 4
 
 # name -> (restype, argtypes); must list every symbol include/xva_b200.h declares (tests/test_abi.py checks it)
 _I, _F, _P, _U64, _I64 = C.c_int, C.c_float, C.c_void_p, C.c_uint64, C.c_int64

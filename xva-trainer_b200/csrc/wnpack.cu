@@ -62,7 +62,7 @@ wn_pack_fwd_kernel(const xva_wn_desc* __restrict__ table, int n_desc) {
     ss += x * x;
   }
   ss = block_sum_f(ss, red);  // (also orders the row_s writes before the reads below)
-  const float scale = d.g[r] / sqrtf(ss);
+  const float scale = (d.flags & XVA_WN_PLAIN) ? 1.0f : d.g[r] / sqrtf(ss);
   const bool rnd = !(d.flags & XVA_WN_NO_ROUND);
   for (int i = threadIdx.x; i < inner; i += kThreadsWn) {  // i = j * c2 + c: channel fastest in the packed matrices
     const int j = i / c2, c = i - j * c2;
@@ -93,13 +93,17 @@ wn_pack_bwd_kernel(const xva_wn_desc* __restrict__ table, int n_desc) {
     row_d[c * k + j] = d.ddst[dst_index(d, r, c, j)];
   }
   ss = block_sum_f(ss, red);
+  float* dv = d.dv + static_cast<long>(r) * inner;
+  if (d.flags & XVA_WN_PLAIN) {  // w = v: the packed gradient is the parameter's (block-uniform branch)
+    for (int i = threadIdx.x; i < inner; i += kThreadsWn) dv[i] += row_d[i];
+    return;
+  }
   float dot = 0.0f;
   for (int i = threadIdx.x; i < inner; i += kThreadsWn) dot += row_v[i] * row_d[i];
   dot = block_sum_f(dot, red);
   const float inv_norm = rsqrtf(ss);
   const float scale = d.g[r] * inv_norm;
   const float coef = scale * dot / ss;
-  float* dv = d.dv + static_cast<long>(r) * inner;
   for (int i = threadIdx.x; i < inner; i += kThreadsWn) dv[i] += scale * row_d[i] - coef * row_v[i];
   if (threadIdx.x == 0) d.dg[r] += dot * inv_norm;
 }

@@ -162,6 +162,42 @@ class _WNConv(nn.Module):
         return tuple((j - half) * self.dilation for j in range(self.k))
 
 
+class _PlainConv(nn.Module):
+    """Parameters of one Conv1d without weight norm, with torch's names (weight, bias): what remove_weight_norm leaves of
+    conv_pre / conv_post in the xVAPitch waveform decoder, and its cond_layer (python/xvapitch/hifigan.py:222-232)."""
+
+    transposed, stride = False, 1
+
+    def __init__(self, cin, cout, k, dilation=1, bias=True, bias_first=True):
+        """bias_first: state_dict order of a conv whose weight norm was removed (bias, weight -- remove_weight_norm
+        re-registers the weight last); a conv that never had one has torch's (weight, bias)."""
+        super().__init__()
+        self.cin, self.cout, self.k, self.dilation = cin, cout, k, dilation
+        if not bias_first:
+            self.weight = nn.Parameter(torch.zeros(cout, cin, k))
+        if bias:
+            self.bias = nn.Parameter(torch.zeros(cout))
+        else:
+            self.register_parameter("bias", None)
+        if bias_first:
+            self.weight = nn.Parameter(torch.zeros(cout, cin, k))
+
+    shifts = _WNConv.shifts
+
+
+def _wv(m):
+    """The parameter whose dim-0 rows the packer reads: weight_v, or the weight itself of a plain convolution."""
+    return m.weight if isinstance(m, _PlainConv) else m.weight_v
+
+
+def _eff_weight(m):
+    return m.weight if isinstance(m, _PlainConv) else m.weight()
+
+
+def _bias(m):
+    return None if m.bias is None else m.bias.detach()
+
+
 class _WnPacker:
     """Effective weights w = g * v / ||v|| of a set of weight-normed convolutions, written by ONE kernel launch
     (xva_wn_pack_fwd) into a flat arena in the layouts the tap-GEMM reads, and the way back (xva_wn_pack_bwd: gradient
@@ -188,7 +224,7 @@ class _WnPacker:
         taps = [0] * k
         for pos, j in enumerate(order):
             taps[j] = off + pos * cout * f * cg
-        self.items.append((m, 0, f * cg, og if og else cout, f, cg, taps))
+        self.items.append((m, capi.WN_PLAIN if isinstance(m, _PlainConv) else 0, f * cg, og if og else cout, f, cg, taps))
 
     def add_flat(self, key, m, cout, k):
         """First discriminator layer (one input channel): [cout, k], not rounded (it runs on CUDA cores in fp32)."""
@@ -218,27 +254,28 @@ class _WnPacker:
         self.garena = torch.zeros(self.size, device=device, dtype=torch.float32)
         view = lambda a: {k: tuple(a[o:o + int(math.prod(sh))].view(sh) for o, sh in v) for k, v in self.layout.items()}
         self.W, self.gW = view(self.arena), view(self.garena)
-        self.rows = sum(m.weight_v.shape[0] for m, *_ in self.items)
-        self.max_inner = max(m.weight_v.numel() // m.weight_v.shape[0] for m, *_ in self.items)
+        self.rows = sum(_wv(m).shape[0] for m, *_ in self.items)
+        self.max_inner = max(_wv(m).numel() // _wv(m).shape[0] for m, *_ in self.items)
 
     def _sync(self, grads):
         ptrs = []
         for m, *_ in self.items:
+            v, g = _wv(m), getattr(m, "weight_g", None)        # g is None: a plain convolution (XVA_WN_PLAIN)
             if grads:
-                for prm in (m.weight_v, m.weight_g):
-                    if prm.grad is None:
+                for prm in (v, g):
+                    if prm is not None and prm.grad is None:
                         prm.grad = torch.zeros_like(prm)
-            ptrs.append((m.weight_v.data_ptr(), m.weight_g.data_ptr(),
-                         m.weight_v.grad.data_ptr() if m.weight_v.grad is not None else 0,
-                         m.weight_g.grad.data_ptr() if m.weight_g.grad is not None else 0))
+            ptrs.append((v.data_ptr(), g.data_ptr() if g is not None else 0,
+                         v.grad.data_ptr() if v.grad is not None else 0,
+                         g.grad.data_ptr() if g is not None and g.grad is not None else 0))
         if ptrs == self._ptrs:
             return
         import ctypes as C
         arr = (capi.WnDesc * len(self.items))()
         row = 0
         for d, (m, flags, ld, og, f, cg, taps), (pv, pg, pdv, pdg) in zip(arr, self.items, ptrs):
-            v = m.weight_v
-            assert v.is_contiguous() and m.weight_g.is_contiguous()
+            v = _wv(m)
+            assert v.is_contiguous() and (pg == 0 or m.weight_g.is_contiguous())
             d.v, d.g, d.dv, d.dg = pv, pg, pdv, pdg
             d.dst, d.ddst = self.arena.data_ptr(), self.garena.data_ptr()
             d.rows, d.inner, d.k, d.flags = v.shape[0], v.numel() // v.shape[0], len(taps), flags
@@ -276,7 +313,10 @@ class ResBlock1(nn.Module):
 class Generator(nn.Module):
     """Drop-in for hifigan/models.py:81 ``Generator(h)`` (config_v1: resblock '1')."""
 
-    def __init__(self, h, device=None, seed=1234):
+    def __init__(self, h, device=None, seed=1234, in_channels=80, cond_channels=0, conv_pre_weight_norm=True,
+                 conv_post_weight_norm=True, conv_post_bias=True):
+        """The keyword arguments after `seed` are the xVAPitch waveform decoder's (HifiganGenerator below); their
+        defaults are hifigan/models.py's generator."""
         super().__init__()
         self.h = h
         self.num_kernels = len(h.resblock_kernel_sizes)
@@ -284,7 +324,9 @@ class Generator(nn.Module):
         if str(h.resblock) != "1":
             raise NotImplementedError("only ResBlock1 (config_v1.json) is built")
         c0 = h.upsample_initial_channel
-        self.conv_pre = _WNConv(80, c0, 7)
+        self.in_channels = int(in_channels)
+        self.in_cols = (self.in_channels + 31) // 32 * 32      # operand rows are whole 32-column chunks (zero tail)
+        self.conv_pre = _WNConv(self.in_channels, c0, 7) if conv_pre_weight_norm else _PlainConv(self.in_channels, c0, 7)
         self.ups = nn.ModuleList()
         for i, (u, k) in enumerate(zip(h.upsample_rates, h.upsample_kernel_sizes)):
             if k != 2 * u or u % 2:
@@ -295,7 +337,13 @@ class Generator(nn.Module):
             ch = c0 // 2 ** (i + 1)
             for k, d in zip(h.resblock_kernel_sizes, h.resblock_dilation_sizes):
                 self.resblocks.append(ResBlock1(h, ch, k, tuple(d)))
-        self.conv_post = _WNConv(ch, 1, 7)
+        self.conv_post = _WNConv(ch, 1, 7) if conv_post_weight_norm else _PlainConv(ch, 1, 7, bias=conv_post_bias)
+        if conv_post_weight_norm and not conv_post_bias:
+            raise NotImplementedError("a weight-normed conv_post without bias is not a configuration the reference uses")
+        if cond_channels > 0:
+            if cond_channels % 32:
+                raise NotImplementedError(f"cond_channels={cond_channels}: must be a multiple of 32")
+            self.cond_layer = _PlainConv(int(cond_channels), c0, 1, bias_first=False)
         self.reset_parameters(seed)
         dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         if dev.type != "cuda":
@@ -310,13 +358,13 @@ class Generator(nn.Module):
         if self._packer is None:
             pk = _WnPacker()
             for name, m in self.named_modules():
-                if not isinstance(m, _WNConv):
+                if not isinstance(m, (_WNConv, _PlainConv)):
                     continue
                 if m.transposed:
                     pk.add_transposed(name, m, m.cin, m.cout, m.stride)
                 else:
                     pk.add_conv(name, m, m.cout, m.cin, m.k)
-            pk.finalize(self.conv_pre.weight_v.device)
+            pk.finalize(_wv(self.conv_pre).device)
             self._packer = pk
         return self._packer
 
@@ -326,16 +374,19 @@ class Generator(nn.Module):
         g = torch.Generator().manual_seed(int(seed))
         with torch.no_grad():
             for name, m in self.named_modules():
-                if not isinstance(m, _WNConv):
+                if not isinstance(m, (_WNConv, _PlainConv)):
                     continue
-                fan_in = m.weight_v.shape[1] * m.weight_v.shape[2]
-                if name == "conv_pre":
+                v = _wv(m)
+                fan_in = v.shape[1] * v.shape[2]
+                if name in ("conv_pre", "cond_layer") or isinstance(m, _PlainConv):
                     bound = 1.0 / math.sqrt(fan_in)
-                    m.weight_v.copy_((torch.rand(m.weight_v.shape, generator=g) * 2 - 1) * bound)
+                    v.copy_((torch.rand(v.shape, generator=g) * 2 - 1) * bound)
                 else:
-                    m.weight_v.copy_(torch.randn(m.weight_v.shape, generator=g) * 0.01)
-                m.weight_g.copy_(m.weight_v.flatten(1).norm(dim=1).view(-1, 1, 1))
-                m.bias.copy_((torch.rand(m.bias.shape, generator=g) * 2 - 1) / math.sqrt(fan_in))
+                    v.copy_(torch.randn(v.shape, generator=g) * 0.01)
+                if isinstance(m, _WNConv):
+                    m.weight_g.copy_(v.flatten(1).norm(dim=1).view(-1, 1, 1))
+                if m.bias is not None:
+                    m.bias.copy_((torch.rand(m.bias.shape, generator=g) * 2 - 1) / math.sqrt(fan_in))
 
     # ------------------------------------------------------------------------------------------ weights
     def _pack(self):
@@ -344,9 +395,9 @@ class Generator(nn.Module):
         backward() can hand dL/d(packed) back to weight_g / weight_v."""
         packed = {}
         for name, m in self.named_modules():
-            if not isinstance(m, _WNConv):
+            if not isinstance(m, (_WNConv, _PlainConv)):
                 continue
-            w = m.weight()
+            w = _eff_weight(m)
             if not m.transposed:
                 packed[name] = (w.permute(2, 0, 1).contiguous(),)
             else:
@@ -366,24 +417,43 @@ class Generator(nn.Module):
         return out
 
     # ------------------------------------------------------------------------------------------ forward
-    def forward(self, x, cond_emb=None):
+    def forward(self, x, cond_emb=None, g=None):
         """Generator.forward, models.py:110-128. x [B, 80, T] -> [B, 1, 256 T]. In training mode the tensors backward()
-        needs are kept until the next forward()."""
+        needs are kept until the next forward(). g [B, cond_channels, 1]: the xVAPitch decoder's per-utterance
+        conditioning, cond_layer(g) added to conv_pre's output before the first leaky ReLU
+        (python/xvapitch/hifigan.py:248-250); ignored, as there, by a generator built without cond_channels."""
         if cond_emb is not None:
             raise NotImplementedError("USE_EMB_CONDITIONING is off in config_v1.json")
-        B, _, T = x.shape
+        B, cin, T = x.shape
+        if cin != self.in_channels:
+            raise ValueError(f"input has {cin} channels, the generator was built for {self.in_channels}")
         keep = self.training
         W = self._get_packer().pack()      # tf32-rounded effective weights of all 86 convolutions, one launch
         # [B, T, 80] channels-last operand in rows of 96 floats (zero tail): the weight-gradient GEMM reads it MN-major
         # in 32-column chunks
-        melp = torch.zeros(B, T, 96, device=x.device, dtype=torch.float32)
-        mel = melp[..., :80]
+        melp = torch.zeros(B, T, self.in_cols, device=x.device, dtype=torch.float32)
+        mel = melp[..., :cin]
         mel.copy_(x.to(torch.float32).transpose(1, 2))
         ops.round_tf32_(melp.reshape(-1), melp.reshape(-1))
-        ctx = {"mel": mel, "stages": [], "W": W, "B": B}
+        ctx = {"mel": mel, "stages": [], "W": W, "B": B, "cond": None}
         # conv_pre; only leaky_relu(conv_pre(x)) is ever read (models.py:111,115)
-        a = ops.conv_fwd(mel, W["conv_pre"][0], self.conv_pre.shifts, bias=self.conv_pre.bias.detach(),
-                         act_slope=LRELU_SLOPE, round_out=True)
+        if g is not None and hasattr(self, "cond_layer"):
+            # c = cond_layer(g) is one [B, cond] x [cond, C0] product (a 1-tap convolution over the B conditioning
+            # vectors taken as the rows of one item); conv_pre's epilogue adds it to every frame of its utterance
+            # through the residual slot read with row stride 0, and writes leaky_relu(.) as its second output
+            cl = self.cond_layer
+            if g.shape[0] != B or g.shape[1] != cl.cin or g.shape[2] != 1:
+                raise ValueError(f"g: expected [{B}, {cl.cin}, 1], got {tuple(g.shape)}")
+            gr = self._rounded(g.to(torch.float32).reshape(1, B, cl.cin).contiguous())
+            c = ops.conv_fwd(gr, W["cond_layer"][0], (0,), bias=cl.bias.detach())                     # [1, B, C0]
+            pre = torch.empty(B, T, cl.cout, device=x.device, dtype=torch.float32)
+            a = torch.empty_like(pre)
+            ops.conv_fwd(mel, W["conv_pre"][0], self.conv_pre.shifts, out=pre, bias=_bias(self.conv_pre),
+                         residual=c.view(B, 1, cl.cout).expand(B, T, cl.cout), out_act=a, out_act_slope=LRELU_SLOPE)
+            ctx["cond"] = gr
+        else:
+            a = ops.conv_fwd(mel, W["conv_pre"][0], self.conv_pre.shifts, bias=_bias(self.conv_pre),
+                             act_slope=LRELU_SLOPE, round_out=True)
         for i in range(self.num_upsamples):
             up = self.ups[i]
             u, p, cout = up.stride, up.stride // 2, up.cout
@@ -423,15 +493,16 @@ class Generator(nn.Module):
             slope = LRELU_SLOPE if i + 1 < self.num_upsamples else 0.01               # models.py:115 vs :124
             a = ops.mean3_lrelu(ys[0], ys[1], ys[2], slope)
             ctx["stages"].append(stage)
-        y = ops.conv_fwd(a, W["conv_post"][0], self.conv_post.shifts, bias=self.conv_post.bias.detach(), tanh=True)
+        y = ops.conv_fwd(a, W["conv_post"][0], self.conv_post.shifts, bias=_bias(self.conv_post), tanh=True)
         ctx["a_last"], ctx["y"] = a, y
         self._ctx = ctx if keep else None
         return y.view(B, 1, -1)
 
     # ------------------------------------------------------------------------------------------ backward
-    def backward(self, dy):
+    def backward(self, dy, need_input_grad=False):
         """dy = dL/d(output) [B, 1, 256 T]. Accumulates .grad of every parameter (bias directly, weight_g / weight_v
-        through the autograd graph of the weight-norm reparametrisation)."""
+        through the packer's weight-norm backward). need_input_grad: also return (dL/dx [B, in_channels, T], dL/dg
+        [B, cond_channels, 1] or None) -- the xVAPitch decoder's input is the posterior encoder's latent, which trains."""
         ctx = self._ctx
         if ctx is None:
             raise RuntimeError("backward() needs a forward() in training mode first")
@@ -441,6 +512,8 @@ class Generator(nn.Module):
 
         def bias_grad(name, d, cols, ld=None):
             b = mods[name].bias
+            if b is None:
+                return
             if b.grad is None:
                 b.grad = torch.zeros_like(b)
             _Side.run(lambda: ops.colsum_(d.shape[0] * d.shape[1], cols, ld if ld is not None else d.shape[2], d, b.grad), d)
@@ -498,10 +571,30 @@ class Generator(nn.Module):
         dpre0 = self._ups_dgrad(0, d_up, a, LRELU_SLOPE, W, alpha=1.0)
         wgrad(dpre0, ctx["mel"], self.conv_pre.shifts, gW["conv_pre"][0])
         bias_grad("conv_pre", dpre0, self.conv_pre.cout)
+        dx = dg = None
+        gr = ctx["cond"]
+        if gr is not None or need_input_grad:
+            T0 = dpre0.shape[1]
+        if gr is not None:
+            # d(cond_layer output)[b] = sum over the utterance's frames of dpre0: one column sum per item, then the
+            # layer's own gradients as the 1-tap convolution over [1, B, cond] that the forward ran
+            cl = self.cond_layer
+            dc = torch.zeros(1, B, cl.cout, device=dpre0.device, dtype=torch.float32)
+            for b in range(B):
+                ops.colsum_(T0, cl.cout, cl.cout, dpre0[b], dc[0, b])
+            bias_grad("cond_layer", dc, cl.cout)
+            dcr = self._rounded(dc)
+            wgrad(dcr, gr, (0,), gW["cond_layer"][0])
+            if need_input_grad:
+                dg = ops.conv_dgrad(dcr, W["cond_layer"][0], (0,)).view(B, cl.cin, 1)
+        if need_input_grad:
+            dx = ops.conv_dgrad(dpre0, W["conv_pre"][0], self.conv_pre.shifts)[..., :self.in_channels].transpose(1, 2)
 
         # packed-weight gradients -> weight_g / weight_v (.grad accumulated), one launch
         self._get_packer().unpack_grads()
         self._ctx = None
+        if need_input_grad:
+            return dx.contiguous(), dg
 
     def _ups_dgrad(self, i, d_up, a_in, slope, W, alpha=1.0 / 3.0):
         """Input gradient of ups[i] (two 2-tap dgrads, summed through the residual slot), times the derivative of the
@@ -516,6 +609,37 @@ class Generator(nn.Module):
         lo = ops.conv_dgrad(dv[..., :nlo], W[f"ups.{i}"][0], (0, -1), gate=a_in, gate_slope=slope, alpha=alpha)
         return ops.conv_dgrad(dv[..., nlo:], W[f"ups.{i}"][1], (1, 0), gate=a_in, gate_slope=slope, alpha=alpha,
                               residual=lo, round_out=True)
+
+
+class HifiganGenerator(Generator):
+    """Drop-in for python/xvapitch/hifigan.py:159 ``HifiganGenerator`` -- the xVAPitch waveform decoder
+    (xvapitch/model.py:134-149: 192 latent channels in, resblock '1', upsample factors (8, 8, 2, 2), plain conv_pre /
+    conv_post, no conv_post bias, cond_layer d_vector_dim -> 512). Same constructor arguments, parameter names
+    (conv_pre.weight, cond_layer.weight, ups.N.weight_g ...) and forward(x, g); the kernels are the HiFi-GAN v1
+    generator's. backward(dy, need_input_grad=True) returns the latent's and the conditioning vector's gradients."""
+
+    def __init__(self, in_channels, out_channels, resblock_type, resblock_dilation_sizes, resblock_kernel_sizes,
+                 upsample_kernel_sizes, upsample_initial_channel, upsample_factors, inference_padding=5, cond_channels=0,
+                 conv_pre_weight_norm=True, conv_post_weight_norm=True, conv_post_bias=True, device=None, seed=1234):
+        if out_channels != 1:
+            raise NotImplementedError("out_channels != 1: the reference only builds a mono waveform decoder")
+        from types import SimpleNamespace
+        h = SimpleNamespace(resblock=str(resblock_type), resblock_dilation_sizes=resblock_dilation_sizes,
+                            resblock_kernel_sizes=resblock_kernel_sizes, upsample_kernel_sizes=upsample_kernel_sizes,
+                            upsample_initial_channel=upsample_initial_channel, upsample_rates=upsample_factors)
+        super().__init__(h, device=device, seed=seed, in_channels=in_channels, cond_channels=cond_channels,
+                         conv_pre_weight_norm=conv_pre_weight_norm, conv_post_weight_norm=conv_post_weight_norm,
+                         conv_post_bias=conv_post_bias)
+        self.inference_padding = inference_padding
+
+    def forward(self, x, g=None):
+        return super().forward(x, g=g)
+
+    @torch.no_grad()
+    def inference(self, c):
+        """hifigan.py:264-279: replicate-pad the input by inference_padding frames on both sides, then forward."""
+        c = torch.nn.functional.pad(c.to(_wv(self.conv_pre).device), (self.inference_padding,) * 2, "replicate")
+        return self.forward(c)
 
 
 # ------------------------------------------------------------------------------------------------ mel spectrogram
