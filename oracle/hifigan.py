@@ -301,11 +301,11 @@ def discriminator_p(sd, pre, x, period, training=True, state=None):
     return torch.flatten(x, 1, -1), fmap
 
 
-def discriminator_s(sd, pre, x, training=True, state=None):
-    """DiscriminatorS.forward, models.py:218-228."""
+def discriminator_s(sd, pre, x, training=True, state=None, specs=None):
+    """DiscriminatorS.forward, models.py:218-228 (specs: another layer table, e.g. VITS_S_SPECS)."""
     state = {} if state is None else state
     fmap = []
-    for i, (cin, cout, k, s, p, g) in enumerate(S_SPECS):
+    for i, (cin, cout, k, s, p, g) in enumerate(S_SPECS if specs is None else specs):
         x = F.conv1d(x, _disc_weight(sd, f"{pre}.convs.{i}", training, state), sd[f"{pre}.convs.{i}.bias"], stride=s, padding=p, groups=g)
         x = F.leaky_relu(x, LRELU_SLOPE)
         fmap.append(x)
@@ -337,6 +337,43 @@ def msd(sd, y, y_hat, training=True, state=None):
         g_, fg = discriminator_s(sd, f"discriminators.{i}", y_hat, training, state)
         rs.append(r); gs.append(g_); frs.append(fr); fgs.append(fg)
     return rs, gs, frs, fgs
+
+
+# ---- xVAPitch discriminator
+VITS_S_SPECS = [(1, 16, 15, 1, 7, 1), (16, 64, 41, 4, 20, 4), (64, 256, 41, 4, 20, 16), (256, 1024, 41, 4, 20, 64),
+                (1024, 1024, 41, 4, 20, 256), (1024, 1024, 5, 1, 2, 1)]
+
+
+def vits_disc_spec():
+    """(key, shape) of VitsDiscriminator().state_dict() (python/xvapitch/model.py:1601-1607): nets.0 = the scale
+    discriminator with VITS widths (model.py:1558-1568), nets.1..5 = DiscriminatorP(2, 3, 5, 7, 11)
+    (xvapitch/hifigan.py:320-335, the layer table of hifigan/models.py's): 111 keys."""
+    spec = []
+    for name, (cin, cout, k, s, p, g) in [(f"convs.{i}", sp) for i, sp in enumerate(VITS_S_SPECS)] + [("conv_post", POST)]:
+        pre = f"nets.0.{name}"
+        spec += [(f"{pre}.bias", (cout,)), (f"{pre}.weight_g", (cout, 1, 1)), (f"{pre}.weight_v", (cout, cin // g, k))]
+    for d in range(len(PERIODS)):
+        for name, (cin, cout, k, s, p, g) in [(f"convs.{i}", sp) for i, sp in enumerate(P_SPECS)] + [("conv_post", POST)]:
+            pre = f"nets.{d + 1}.{name}"
+            spec += [(f"{pre}.bias", (cout,)), (f"{pre}.weight_g", (cout, 1, 1, 1)), (f"{pre}.weight_v", (cout, cin // g, k, 1))]
+    return spec
+
+
+def vits_discriminator(sd, x, x_hat=None):
+    """VitsDiscriminator.forward, python/xvapitch/model.py:1609-1631: x, x_hat [B, 1, T] -> (x_scores, x_feats,
+    x_hat_scores, x_hat_feats), every net on x and then on x_hat. Its losses are the LSGAN / feature-matching forms
+    below (xvapitch/losses.py:65-85, 329-342 are hifigan/models.py:263-294 again)."""
+    nets = [lambda w: discriminator_s(sd, "nets.0", w, specs=VITS_S_SPECS)]
+    nets += [lambda w, i=i, p=p: discriminator_p(sd, f"nets.{i + 1}", w, p) for i, p in enumerate(PERIODS)]
+    xs, xf = [], []
+    hs, hf = ([], []) if x_hat is not None else (None, None)
+    for net in nets:
+        s_, f_ = net(x)
+        xs.append(s_); xf.append(f_)
+        if x_hat is not None:
+            s_, f_ = net(x_hat)
+            hs.append(s_); hf.append(f_)
+    return xs, xf, hs, hf
 
 
 def feature_loss(fmap_r, fmap_g):

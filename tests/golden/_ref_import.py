@@ -63,3 +63,18 @@ def install():
                     normalize=lambda x, **k: x / (np.abs(x).max() + 1e-12))
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)
+
+
+def install_xvapitch():
+    """install() plus what python/xvapitch/model.py and losses.py import at module level and the build container lacks:
+    the text front end (unidecode, g2pc ... -- out of scope) and soundfile are stubs; np.bool is the
+    alias numpy >= 1.24 removed (xvapitch/util.py:28). scipy.signal is imported first because numpy.ma must not see the
+    alias while it initialises."""
+    import scipy.signal  # noqa: F401
+
+    np.bool = np.bool_
+    install()
+    text = types.ModuleType("python.xvapitch.text")
+    text.get_text_preprocessor, text.ALL_SYMBOLS, text.lang_names = None, list(range(200)), {}
+    sys.modules["python.xvapitch.text"] = text
+    sys.modules.setdefault("soundfile", types.ModuleType("soundfile"))

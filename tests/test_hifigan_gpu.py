@@ -512,3 +512,78 @@ def test_xvapitch_decoder_wiring_exact(lib, monkeypatch):
         assert rel(dz, zl.grad) < 2e-3 and rel(dg, gl.grad) < 2e-3, (rel(dz, zl.grad), rel(dg, gl.grad))
     finally:
         capi.call("xva_set_operand_rounding", 1)
+
+
+# ------------------------------------------------------------------------------------------------ xVAPitch discriminator
+def _vits_disc(lib):
+    from test_oracle_golden import _vits_disc_fixture
+    from xva_trainer_b200 import hifigan as hg
+
+    gold, spec, sd, x, x_hat = _vits_disc_fixture()
+    m = hg.VitsDiscriminator(device="cuda:0")
+    assert [(k, tuple(v.shape)) for k, v in m.state_dict().items()] == [(k, tuple(sh)) for k, sh in spec]
+    res = m.load_state_dict(sd)
+    assert not res.missing_keys and not res.unexpected_keys
+    m.train()
+    return hg, m, gold, spec, sd, x, x_hat
+
+
+def test_vits_discriminator_forward_matches_reference_golden(lib):
+    """python/xvapitch/model.py:1590-1631 recorded by tests/golden/make_golden_vits_discriminator.py: state_dict keys,
+    the six score maps on the real and the generated waveform (prime length: every period discriminator reflect-pads),
+    every feature map against the oracle (itself pinned to the same recording), zero padding channels / rows."""
+    hg, m, gold, spec, sd, x, x_hat = _vits_disc(lib)
+    with torch.no_grad():
+        xs, xf, hs, hf = m(x.cuda(), x_hat.cuda())
+    ors, ofr, ogs, ofg = ohg.vits_discriminator(sd, x, x_hat)
+    B = x.shape[0]
+    for i in range(6):
+        for got, key in ((xs[i], f"score_real/{i}"), (hs[i], f"score_fake/{i}")):
+            want = torch.from_numpy(gold[key])
+            got = _to_ref_layout(got, B).reshape(B, -1).cpu()
+            assert got.shape == want.shape and rel(got, want) < 3e-3, (key, got.shape, want.shape, rel(got, want))
+        for l, (f, of) in enumerate(zip(hf[i], ofg[i])):
+            C = of.shape[1]
+            full = _to_ref_layout(f, B)
+            got = full[:, :C, :of.shape[2]].cpu()
+            assert got.shape == of.shape, (i, l, got.shape, of.shape)
+            assert rel(got, of) < 3e-3, (i, l, rel(got, of))
+            assert float(full[:, C:].abs().max() if full.shape[1] > C else 0.0) == 0.0          # padding channels
+            assert float(f[:, of.shape[2]:].abs().max() if f.shape[1] > of.shape[2] else 0.0) == 0.0   # alignment rows
+
+
+def test_vits_discriminator_step_gradients(lib):
+    """D step: LSGAN loss and every parameter gradient (norms recorded from the reference's autograd, full tensors from
+    the oracle's); G step: adversarial + feature-matching loss and the gradient wrt the generated waveform, both
+    recorded from the reference (xvapitch/losses.py:65-85, 329-342)."""
+    hg, m, gold, spec, sd, x, x_hat = _vits_disc(lib)
+    B, T = x.shape[0], x.shape[2]
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    ors, _, ogs, _ = ohg.vits_discriminator(leaves, x, x_hat)
+    ohg.discriminator_loss(ors, ogs).backward()
+    m.zero_grad()
+    xs, xf, hs, hf = m(x.cuda(), x_hat.cuda())
+    loss = hg.discriminator_loss_backward(m, xs, hs)
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(gold["loss_disc"])) < 2e-3 * float(gold["loss_disc"]), (float(loss), float(gold["loss_disc"]))
+    num = den = 0.0
+    for (k, p), want_norm in zip(m.named_parameters(), gold["grad_norms"]):
+        w = leaves[k].grad
+        e = rel(p.grad, w)
+        assert e < 6e-2, (k, e)
+        assert abs(float(p.grad.double().norm()) - want_norm) < 3e-2 * want_norm, (k, float(p.grad.norm()), want_norm)
+        num += float((p.grad.cpu().double() - w.double()).pow(2).sum())
+        den += float(w.double().pow(2).sum())
+    assert (num / den) ** 0.5 < 2e-2, (num / den) ** 0.5
+    for k in ("nets.0.convs.1.weight_v", "nets.0.convs.0.weight_v", "nets.0.convs.0.bias"):       # the 4-channel groups
+        # same per-tensor bound as above, now against the reference's own tensors; convs.0 is the deepest (3.4e-2)
+        assert rel(dict(m.named_parameters())[k].grad, torch.from_numpy(gold[f"grad/{k}"])) < 6e-2, k
+    # ---- G step
+    xs, xf, hs, hf = m(x.cuda(), x_hat.cuda())
+    dwave = torch.zeros(B, T, device="cuda")
+    lg, lf = hg.generator_adv_loss_backward(m, hs, xf, hf, dwave, pools=0)
+    torch.cuda.synchronize()
+    assert abs(float(lg) - float(gold["loss_gen"])) < 2e-3 * float(gold["loss_gen"]), (float(lg), float(gold["loss_gen"]))
+    assert abs(float(lf) - float(gold["loss_feat"])) < 2e-3 * float(gold["loss_feat"]), (float(lf), float(gold["loss_feat"]))
+    want = torch.from_numpy(gold["dwave_gen"] + gold["dwave_feat"]).reshape(B, T)
+    assert rel(dwave.cpu(), want) < 3e-2, rel(dwave.cpu(), want)

@@ -755,6 +755,9 @@ class _DiscConv(nn.Module):
         super().__init__()
         self.cin, self.cout, self.k, self.stride, self.pad, self.groups = cin, cout, k, stride, pad, groups
         self.spectral, self.conv2d = spectral, conv2d
+        # channels of the activation buffer this layer writes: the real ones, or (first layer of the VITS scale
+        # discriminator, 16 channels) padded with zero channels to the 32-column granule of the next layer's operand
+        self.cout_phys = cout
         shape = (cout, cin // groups, k) + ((1,) if conv2d else ())
         self.bias = nn.Parameter(torch.zeros(cout))
         if spectral:
@@ -806,6 +809,11 @@ class _Disc(nn.Module):
         self.period = period
         self.convs = nn.ModuleList([_DiscConv(*s, spectral=spectral, conv2d=c2d) for s in specs])
         self.conv_post = _DiscConv(*post, spectral=spectral, conv2d=c2d)
+        m0 = self.convs[0]
+        if m0.cout % 32:
+            if spectral:
+                raise NotImplementedError("a spectral-normed first layer with a channel count that is not a multiple of 32")
+            m0.cout_phys = _round_up(m0.cout, 32)
 
     # geometry of the Z = B*P sequences inside the waveform [B, T]
     def _geom(self, T):
@@ -820,6 +828,10 @@ class _Disc(nn.Module):
         tensor core reads is 32 real channels wide and one launch covers the whole layer (xva_gemm_args.groups)."""
         G, Og, Cg = m.groups, m.cout // m.groups, m.cin // m.groups
         f = max(1, 32 // Cg) if G > 1 else 1
+        if G < f and G * Cg < 32 and 32 % Cg == 0:
+            # fewer groups than one 32-column block holds (VITS scale discriminator, 16 -> 64 in 4 groups): ONE dense
+            # launch over the input zero-padded to 32 channels (cout_phys of the layer before), block-diagonal filter
+            return 1, m.cout, Cg * f, f
         if G % f:
             raise NotImplementedError(f"groups={G} with {Cg} channels per group")
         return G // f, Og * f, Cg * f, f
@@ -831,7 +843,10 @@ class _Disc(nn.Module):
         for li, m in enumerate(list(self.convs) + [self.conv_post]):
             w = m.weight()
             if li == 0:
-                out.append(w.reshape(m.cout, m.k).contiguous())
+                w0 = w.reshape(m.cout, m.k)
+                if m.cout_phys != m.cout:
+                    w0 = torch.nn.functional.pad(w0, (0, 0, 0, m.cout_phys - m.cout))
+                out.append(w0.contiguous())
                 continue
             if getattr(m, "_order_idx", None) is None or m._order_idx.device != w.device:
                 m._order_idx = torch.tensor([j for j, _, _ in m.taps()], device=w.device, dtype=torch.long)
@@ -859,7 +874,7 @@ class _Disc(nn.Module):
         for li, m in enumerate(list(self.convs) + [self.conv_post]):
             key = f"{prefix}.{li}"
             if li == 0:
-                packer.add_flat(key, m, m.cout, m.k)
+                packer.add_flat(key, m, m.cout_phys, m.k)      # rows >= m.cout stay zero (the arena is zero-filled)
             else:
                 Gp, Ogp, Cgp, f = self._group_geom(m)
                 packer.add_conv(key, m, m.cout, m.cin // m.groups, m.k, order=[j for j, _, _ in m.taps()],
@@ -883,8 +898,15 @@ class _Disc(nn.Module):
         L0 = m0.out_len(L)
         nxt = layers[1].stride
         w0 = packed[0].detach() if W is None else W[0]
-        X = ops.conv_c1_fwd(wave, geom, w0, m0.bias.detach(), m0.k, m0.stride, m0.pad, Z, L0,
-                            _round_up(L0, nxt), m0.cout, LRELU_SLOPE)
+        b0 = m0.bias.detach()
+        if m0.cout_phys != m0.cout:
+            pad = self.__dict__.get("_bias_pad")
+            if pad is None or pad.device != b0.device:
+                pad = self.__dict__["_bias_pad"] = torch.zeros(m0.cout_phys, device=b0.device, dtype=torch.float32)
+            pad[:m0.cout].copy_(b0)
+            b0 = pad
+        X = ops.conv_c1_fwd(wave, geom, w0, b0, m0.k, m0.stride, m0.pad, Z, L0,
+                            _round_up(L0, nxt), m0.cout_phys, LRELU_SLOPE)
         acts, lens_v = [X], [L0]
         Wr = [w0]
         for li in range(1, len(layers)):
@@ -1001,10 +1023,13 @@ class _Disc(nn.Module):
         m0 = layers[0]
         w0 = Wr[0] if shared else ctx["packed"][0]
         if need_w:
-            dw0 = gW[0] if shared else torch.zeros(m0.cout, m0.k, device=dev, dtype=torch.float32)
+            dw0 = gW[0] if shared else torch.zeros(m0.cout_phys, m0.k, device=dev, dtype=torch.float32)
             if m0.bias.grad is None:
                 m0.bias.grad = torch.zeros_like(m0.bias)
-            ops.conv_c1_bwd_w(dpre, ctx["wave"], ctx["geom"], m0.k, m0.stride, m0.pad, lens_v[0], dw0, m0.bias.grad)
+            db0 = m0.bias.grad if m0.cout_phys == m0.cout else torch.zeros(m0.cout_phys, device=dev, dtype=torch.float32)
+            ops.conv_c1_bwd_w(dpre, ctx["wave"], ctx["geom"], m0.k, m0.stride, m0.pad, lens_v[0], dw0, db0)
+            if db0 is not m0.bias.grad:
+                m0.bias.grad.add_(db0[:m0.cout])
         if dwave is not None:
             ops.conv_c1_bwd_x(dpre, w0.detach(), ctx["geom"], m0.k, m0.stride, m0.pad, lens_v[0], wave_scale, dwave)
         if need_w and not shared:
@@ -1059,6 +1084,44 @@ class MultiScaleDiscriminator(nn.Module):
 
     def forward(self, y, y_hat, weight_grad=True):
         return _multi_forward(self, y, y_hat, pools=1, weight_grad=weight_grad)
+
+
+class VitsDiscriminatorS(_Disc):
+    """python/xvapitch/model.py:1548-1587: the scale discriminator with VITS channel widths (16, 64, 256, 1024, 1024,
+    1024; four input channels per group). The 16-channel first layer writes a 32-channel buffer with zero upper half,
+    and groups are merged eight at a time into block-diagonal 32-column super-groups (_group_geom)."""
+
+    def __init__(self, use_spectral_norm=False):
+        specs = [(1, 16, 15, 1, 7), (16, 64, 41, 4, 20, 4), (64, 256, 41, 4, 20, 16), (256, 1024, 41, 4, 20, 64),
+                 (1024, 1024, 41, 4, 20, 256), (1024, 1024, 5, 1, 2)]
+        super().__init__(specs, (1024, 1, 3, 1, 1), period=None, spectral=use_spectral_norm)
+
+
+class VitsDiscriminator(nn.Module):
+    """Drop-in for python/xvapitch/model.py:1590 ``VitsDiscriminator``: nets[0] the scale discriminator above, nets[1:]
+    DiscriminatorP(2, 3, 5, 7, 11) (xvapitch/hifigan.py:301-370 -- the layer table of hifigan/models.py's). Same
+    state_dict keys (nets.N.convs.M.weight_g ...). forward(x, x_hat) -> (x_scores, x_feats, x_hat_scores, x_hat_feats)
+    in the reference's order, feature maps channels-last [B*p, L, C]; discriminator_loss_backward /
+    generator_adv_loss_backward (pools=0) are its losses (xvapitch/losses.py:65-85, 329-342 restate
+    hifigan/models.py:263-294)."""
+
+    def __init__(self, use_spectral_norm=False, device=None, seed=1234):
+        super().__init__()
+        if use_spectral_norm:
+            raise NotImplementedError("the reference builds VitsDiscriminator(use_spectral_norm=False) (xvapitch/model.py:151)")
+        self.nets = nn.ModuleList([VitsDiscriminatorS()] + [DiscriminatorP(p) for p in (2, 3, 5, 7, 11)])
+        _init_disc(self, seed + 2, device)
+
+    @property
+    def discriminators(self):
+        return self.nets
+
+    def forward(self, x, x_hat=None, weight_grad=True):
+        if x_hat is None:
+            rs, _, frs, _ = _multi_forward(self, x, x, pools=0, weight_grad=weight_grad)
+            return rs, frs, None, None
+        rs, gs, frs, fgs = _multi_forward(self, x, x_hat, pools=0, weight_grad=weight_grad)
+        return rs, frs, gs, fgs
 
 
 def _init_disc(model, seed, device):
@@ -1194,7 +1257,8 @@ def generator_adv_loss_backward(model, y_d_gs, fmap_rs, fmap_gs, dwave, pools):
             dfeat = []
             n_act = len(cg["acts"])
             for l, (fr, fg) in enumerate(zip(fmap_rs[i], fmap_gs[i])):
-                valid = cg["Z"] * (cg["lens"][l] if l < n_act else cg["lens"][-1]) * fg.shape[2]
+                # elements of the reference's feature map (zero-padded channels of the buffer are not part of it)
+                valid = cg["Z"] * (cg["lens"][l] if l < n_act else cg["lens"][-1]) * (d.convs[l].cout if l < n_act else 1)
                 a = acc[16 * i + 1 + l:16 * i + 2 + l]
                 if l < n_act:
                     dfeat.append(ops.l1_loss_grad(fr, fg, 2.0 / valid, a, gate_slope=LRELU_SLOPE))   # loss term + gradient
