@@ -1,0 +1,153 @@
+"""CPU oracle for the xVAPitch ``--hifi_only`` training step: posterior encoder (WaveNet
+stack) + waveform decoder against the VITS discriminator. TEST INFRASTRUCTURE ONLY -- nothing in the product path may
+import this module; tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg are its only callers.
+
+A restatement in plain PyTorch (fp32, CPU, autograd) of
+
+    WN                         python/xvapitch/wavenet.py:6-106
+    PosteriorEncoder           python/xvapitch/model.py:1422-1475   (configured at model.py:93-101)
+    rand_segments / segment    python/xvapitch/util.py:145-178
+    TorchSTFT (log-mel)        python/xvapitch/audio.py:138-181, 194-195 (configured at xvapitch/losses.py:29-46)
+    hifi_only generator loss   python/xvapitch/losses.py:170-215  (feature_loss is CALLED with (fake, real) at :196 and
+                               detaches its first argument, :69: the feature-matching term reaches the discriminator's
+                               real-branch activations only, never the generator -- restated as the reference runs it)
+    step composition           python/xvapitch/model.py:650-678, 271-340, 385-399; xva_train.py:651-736;
+                               optimizers python/xvapitch/training_util.py:31-32, 66-67
+
+with the waveform decoder and the discriminator from oracle/hifigan.py (generator_vits, vits_discriminator). Parity is
+PINNED: tests/test_oracle_golden.py checks every function here against tests/golden/vits_hifi_only.npz, recorded from
+the unmodified reference modules by tests/golden/make_golden_vits_hifi_only.py."""
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import hifigan as ohg
+
+HIDDEN, LATENT, SPEC_BINS, COND, WN_LAYERS, WN_KERNEL = 192, 192, 513, 512, 16, 5
+SEGMENT, HOP = 32, 256
+MEL_ALPHA = 45.0
+LR_GEN, LR_DISC, ADAM_EPS = 0.000175, 0.0002, 1e-9
+
+
+def posterior_encoder_spec():
+    """(key, shape) of PosteriorEncoder(513, 192, 192, 5, 1, 16, cond_channels=512).named_parameters()."""
+    H = HIDDEN
+    spec = [("pre.weight", (H, SPEC_BINS, 1)), ("pre.bias", (H,))]
+    for i in range(WN_LAYERS):
+        spec += [(f"enc.in_layers.{i}.bias", (2 * H,)), (f"enc.in_layers.{i}.weight_g", (2 * H, 1, 1)),
+                 (f"enc.in_layers.{i}.weight_v", (2 * H, H, WN_KERNEL))]
+    for i in range(WN_LAYERS):
+        c = 2 * H if i < WN_LAYERS - 1 else H
+        spec += [(f"enc.res_skip_layers.{i}.bias", (c,)), (f"enc.res_skip_layers.{i}.weight_g", (c, 1, 1)),
+                 (f"enc.res_skip_layers.{i}.weight_v", (c, H, 1))]
+    spec += [("enc.cond_layer.bias", (2 * H * WN_LAYERS,)), ("enc.cond_layer.weight_g", (2 * H * WN_LAYERS, 1, 1)),
+             ("enc.cond_layer.weight_v", (2 * H * WN_LAYERS, COND, 1))]
+    spec += [("proj.weight", (2 * LATENT, H, 1)), ("proj.bias", (2 * LATENT,))]
+    return spec
+
+
+def sequence_mask(lengths, max_len):
+    """util.py:180-197: [B, max_len] bool, True where t < length."""
+    return torch.arange(max_len)[None, :] < torch.as_tensor(lengths)[:, None]
+
+
+def wn(sd, pre, x, x_mask, g, num_layers=WN_LAYERS, hidden=HIDDEN, kernel=WN_KERNEL, dilation_rate=1):
+    """WN.forward, wavenet.py:87-106 (dropout_p = 0). x [B, H, T], x_mask [B, 1, T], g [B, C, 1] or None."""
+    output = torch.zeros_like(x)
+    if g is not None:
+        g = F.conv1d(g, ohg.wn_weight(sd, f"{pre}.cond_layer"), sd[f"{pre}.cond_layer.bias"])
+    for i in range(num_layers):
+        d = dilation_rate ** i
+        x_in = F.conv1d(x, ohg.wn_weight(sd, f"{pre}.in_layers.{i}"), sd[f"{pre}.in_layers.{i}.bias"], dilation=d,
+                        padding=(kernel * d - d) // 2)
+        if g is not None:
+            x_in = x_in + g[:, i * 2 * hidden:(i + 1) * 2 * hidden, :]
+        acts = torch.tanh(x_in[:, :hidden]) * torch.sigmoid(x_in[:, hidden:])          # wavenet.py:6-13
+        rs = F.conv1d(acts, ohg.wn_weight(sd, f"{pre}.res_skip_layers.{i}"), sd[f"{pre}.res_skip_layers.{i}.bias"])
+        if i < num_layers - 1:
+            x = (x + rs[:, :hidden]) * x_mask
+            output = output + rs[:, hidden:]
+        else:
+            output = output + rs
+    return output * x_mask
+
+
+def posterior_encoder(sd, y, y_lengths, g, eps):
+    """PosteriorEncoder.forward, model.py:1462-1475, with the N(0, 1) draw of :1474 passed in. y [B, 513, T] ->
+    (z, mean, log_scale, mask [B, 1, T])."""
+    mask = sequence_mask(y_lengths, y.shape[2])[:, None, :].to(y.dtype)
+    x = F.conv1d(y, sd["pre.weight"], sd["pre.bias"]) * mask
+    x = wn(sd, "enc", x, mask, g)
+    stats = F.conv1d(x, sd["proj.weight"], sd["proj.bias"]) * mask
+    mean, log_scale = torch.split(stats, LATENT, dim=1)
+    z = (mean + eps * torch.exp(log_scale)) * mask
+    return z, mean, log_scale, mask
+
+
+def segment_starts(u, lengths, segment_size=SEGMENT):
+    """rand_segments' index rule, util.py:160-162: floor(u * (length - segment + 1)) with u ~ U[0, 1) per utterance."""
+    max_idxs = torch.as_tensor(lengths) - segment_size + 1
+    assert bool((max_idxs > 0).all()), "at least one sample is shorter than the segment size"
+    return (u.to(torch.float32) * max_idxs).long()
+
+
+def segment(x, starts, size):
+    """util.py:165-178: x [B, C, T] -> [B, C, size]."""
+    return torch.stack([x[i, :, int(s):int(s) + size] for i, s in enumerate(starts)])
+
+
+def torch_stft_mel(x, n_fft=1024, hop=256, win=1024, sr=22050, fmin=0, fmax=8000, n_mels=80):
+    """TorchSTFT(1024, 256, 1024, sample_rate=22050, mel_fmin=0, mel_fmax=8000, n_mels=80, use_mel=True,
+    do_amp_to_db=True).__call__, audio.py:138-181: centred reflect-padded STFT, sqrt(clamp(re^2 + im^2, 1e-8)), Slaney
+    mel, log(clamp(., 1e-5)). x [B, 1, T] or [B, T] -> [B, 80, T / hop + 1]."""
+    if x.dim() == 3:
+        x = x.squeeze(1)
+    o = torch.stft(x, n_fft, hop, win, torch.hann_window(win), center=True, pad_mode="reflect", normalized=False,
+                   onesided=True, return_complex=True)
+    s = torch.sqrt(torch.clamp(o.real ** 2 + o.imag ** 2, min=1e-8))
+    s = torch.matmul(ohg.mel_filterbank(sr, n_fft, n_mels, fmin, fmax), s)
+    return torch.log(torch.clamp(s, min=1e-5))
+
+
+def generator_losses(wav_hat, wav, scores_fake, feats_fake, feats_real):
+    """VitsGeneratorLoss.forward, hifi_only branch, losses.py:184-215 -> dict(loss, loss_gen, loss_feat, loss_mel)."""
+    loss_mel = F.l1_loss(torch_stft_mel(wav), torch_stft_mel(wav_hat)) * MEL_ALPHA
+    loss_gen = ohg.generator_loss(scores_fake)
+    loss_feat = ohg.feature_loss([[f.detach() for f in fs] for fs in feats_fake], feats_real)      # losses.py:196 + :69
+    return {"loss": loss_feat + loss_mel + loss_gen, "loss_gen": loss_gen, "loss_feat": loss_feat, "loss_mel": loss_mel}
+
+
+def hifi_only_step(sd_enc, sd_dec, sd_disc, linear, waveform, d_vectors, y_lengths, eps, u, opt_state, detail=None):
+    """One --hifi_only iteration. Updates the three state dicts in place (AdamW, eps 1e-9; generator-side lr 1.75e-4,
+    discriminator 2e-4) and returns the loss dict. linear [B, 513, T], waveform [B, 1, T * 256], d_vectors [B, 512]."""
+    enc = {k: v.clone().requires_grad_(True) for k, v in sd_enc.items()}
+    dec = {k: v.clone().requires_grad_(True) for k, v in sd_dec.items()}
+    disc = {k: v.clone().requires_grad_(True) for k, v in sd_disc.items()}
+    g = F.normalize(d_vectors).unsqueeze(-1)
+    z, m_q, logs_q, _ = posterior_encoder(enc, linear, y_lengths, g, eps)
+    starts = segment_starts(u, y_lengths)
+    o = ohg.generator_vits(dec, segment(z, starts, SEGMENT), g)
+    wav_seg = segment(waveform, starts * HOP, SEGMENT * HOP)
+    s_fake, f_fake, _, f_real = ohg.vits_discriminator(disc, o, wav_seg)
+    losses = generator_losses(o, wav_seg, s_fake, f_fake, f_real)
+    gen_leaves = list(enc.items()) + list(dec.items())
+    grads = torch.autograd.grad(losses["loss"], [v for _, v in gen_leaves])
+    g_gen = {("enc" if i < len(enc) else "dec", k): gr for i, ((k, _), gr) in enumerate(zip(gen_leaves, grads))}
+    # discriminator pass on the detached output
+    s_fake, _, s_real, _ = ohg.vits_discriminator(disc, o.detach(), wav_seg)
+    loss_disc = ohg.discriminator_loss(s_real, s_fake)
+    d_grads = torch.autograd.grad(loss_disc, list(disc.values()))
+    if detail is not None:
+        detail.update(z=z.detach(), m_q=m_q.detach(), logs_q=logs_q.detach(), o=o.detach(), wav_seg=wav_seg, starts=starts,
+                      grads_gen=g_gen, grads_disc=dict(zip(disc.keys(), d_grads)))
+    with torch.no_grad():
+        st = opt_state.setdefault("gen", {})
+        params = {("enc", k): sd_enc[k] for k in sd_enc}
+        params.update({("dec", k): sd_dec[k] for k in sd_dec})
+        ohg.adamw_step(params, g_gen, st, lr=LR_GEN, eps=ADAM_EPS)
+        ohg.adamw_step(sd_disc, dict(zip(disc.keys(), d_grads)), opt_state.setdefault("disc", {}), lr=LR_DISC, eps=ADAM_EPS)
+    out = {k: float(v) for k, v in losses.items()}
+    out["loss_disc"] = float(loss_disc)
+    return out
