@@ -351,6 +351,26 @@ int xva_lamb_step(float* p, const float* g, float* m, float* v, const void* chun
 int xva_mean3_lrelu(const float* y0, const float* y1, const float* y2, int64_t n, float slope, float* out, void* stream);
 int xva_sum3(const float* a, const float* b, const float* c, int64_t n, float* out, void* stream);
 int xva_tanh_bwd(const float* dy, const float* y, int64_t rows, int ld, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * xVAPitch posterior encoder, element-wise parts of its WaveNet stack.
+ *   xva_gated_act_fwd: acts[r, c] = tanh(x_in[r, c]) * sigmoid(x_in[r, H + c]), tf32-rounded -- replaces
+ *     fused_add_tanh_sigmoid_multiply (python/xvapitch/wavenet.py:6-13; the add of the conditioning slice is done by
+ *     the epilogue of the GEMM that produced x_in). x_in rows have pitch ld_in >= 2H, acts [rows, H]; H % 4 == 0.
+ *   xva_gated_act_bwd: dx_in [rows, 2H] = [d * s * (1 - t^2) | d * t * s * (1 - s)], t and s recomputed from x_in.
+ *   xva_vits_sample_fwd: z = (mean + eps * exp(log_scale)) on rows t < lens[b], 0 elsewhere, with stats [B, T, 2C] =
+ *     [mean | log_scale] (already masked by the projection's epilogue) and eps [B, T, C] the caller's N(0, 1) draw --
+ *     replaces python/xvapitch/model.py:1473-1474.  xva_vits_sample_bwd: dstats = [dz | dz * eps * exp(log_scale)].
+ *   xva_colsum_items: out[z * out_ld + c] += sum_t x[z * z_stride + t * ld + c] for z < Z, t < rows, c < C -- the
+ *     gradient of a per-utterance vector the forward broadcast over the frames (wavenet.py:99 g_l, hifigan.py:250).
+ * ---------------------------------------------------------------------------------------------------------- */
+int xva_gated_act_fwd(const float* x_in, int64_t rows, int H, int64_t ld_in, float* acts, void* stream);
+int xva_gated_act_bwd(const float* dacts, const float* x_in, int64_t rows, int H, int64_t ld_in, float* dx_in, void* stream);
+int xva_colsum_items(const float* x, int Z, int rows, int C, int64_t ld, int64_t z_stride, float* out, int64_t out_ld,
+                     void* stream);
+int xva_vits_sample_fwd(const float* stats, const float* eps, const int32_t* lens, int B, int T, int C, float* z, void* stream);
+int xva_vits_sample_bwd(const float* dz, const float* eps, const float* stats, const int32_t* lens, int B, int T, int C,
+                        float* dstats, void* stream);
 int xva_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, const float* lr_dev, float beta1, float beta2,
                    float eps, float weight_decay, int step, const uint64_t* step_dev, void* stream);
 
@@ -360,7 +380,8 @@ int xva_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, cons
  * over the [len/hop, hop] view of the padded signal, and a plain GEMM); these are the steps around them.
  *   reflect_pad : out[b, i] = y[b, reflect(i - pad)], length n + 2 pad (F.pad mode='reflect', meldataset.py:229), tf32
  *   spec_mag    : mag[r, c] = sqrt(re^2 + im^2 + eps) for c < nb, 0 for nb <= c < ld_m; spec rows hold re in columns
- *                 [0, nb) and im in [nb, 2 nb) (meldataset.py:235)
+ *                 [0, nb) and im in [nb, 2 nb) (meldataset.py:235). eps < 0 selects sqrt(max(re^2 + im^2, -eps)), the
+ *                 form of xVAPitch's TorchSTFT (python/xvapitch/audio.py:172; no gradient below the floor)
  *   log_clamp   : out = log(max(x, lo))  (spectral_normalize_torch, meldataset.py:238); bwd: dy / x where x >= lo
  *   reduce_loss : kind 0: acc += sum |a - b| (F.l1_loss, feature_loss models.py:263-269); kind 1: acc += sum (c - a)^2
  *                 (discriminator_loss / generator_loss, models.py:272-294). acc is a device double.

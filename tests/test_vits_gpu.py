@@ -1,0 +1,206 @@
+"""xVAPitch --hifi_only path (xva-trainer_b200/vits.py + hifigan.HifiganGenerator / VitsDiscriminator, all math through
+libxva_b200.so) vs the CPU oracle (oracle/vits.py, pinned to the reference by tests/test_oracle_golden.py) and vs the
+step recorded from the unmodified reference modules (tests/golden/vits_hifi_only.npz).
+
+Tolerances as for the HiFi-GAN path (tests/test_hifigan_gpu.py): tf32 tensor-core operands rounded to nearest, fp32
+accumulation; element-wise kernels 1e-6."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import hifigan as ohg
+from oracle import vits as ov
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def test_gated_activation_and_sample_kernels(lib):
+    from xva_trainer_b200 import capi, ops
+
+    capi.call("xva_set_operand_rounding", 0)
+    try:
+        g = torch.Generator().manual_seed(3)
+        B, T, H = 3, 37, 64
+        x_in = torch.randn(B, T, 2 * H, generator=g).requires_grad_(True)
+        d = torch.randn(B, T, H, generator=g)
+        want = torch.tanh(x_in[..., :H]) * torch.sigmoid(x_in[..., H:])
+        (want * d).sum().backward()
+        got = ops.gated_act(x_in.detach().cuda(), H)
+        assert rel(got, want) < 1e-6
+        assert rel(ops.gated_act_bwd(d.cuda(), x_in.detach().cuda(), H), x_in.grad) < 1e-6
+        # posterior sample
+        C = 32
+        stats = (torch.randn(B, T, 2 * C, generator=g) * 0.5).requires_grad_(True)
+        eps = torch.randn(B, T, C, generator=g)
+        lens = torch.tensor([37, 20, 1], dtype=torch.int32)
+        mask = (torch.arange(T)[None, :] < lens[:, None]).float().unsqueeze(-1)
+        z = (stats[..., :C] + eps * torch.exp(stats[..., C:])) * mask
+        dz = torch.randn(B, T, C, generator=g)
+        (z * dz).sum().backward()
+        got = ops.vits_sample(stats.detach().cuda(), eps.cuda(), lens.cuda())
+        assert rel(got, z) < 1e-6 and float(got[1, 20:].abs().max()) == 0.0
+        assert rel(ops.vits_sample_bwd(dz.cuda(), eps.cuda(), stats.detach().cuda(), lens.cuda()), stats.grad) < 1e-6
+        # per-item column sums, strided input and output views
+        x = torch.randn(B, T, 96, generator=g)
+        out = torch.ones(B, 200)
+        want = out.clone()
+        want[:, 40:104] += x[..., 16:80].sum(1)
+        xo, oo = x.cuda(), out.cuda()
+        ops.colsum_items_(xo[..., 16:80], oo[:, 40:104])
+        assert rel(oo, want) < 1e-6
+    finally:
+        capi.call("xva_set_operand_rounding", 1)
+
+
+def test_vits_mel_matches_reference_and_autograd(lib):
+    """MelSpectrogram.vits() = TorchSTFT(1024, 256, 1024, ..., use_mel, do_amp_to_db) of xvapitch/audio.py:138-181: the
+    log-mels recorded from the reference's own criterion.stft, and its backward vs autograd through the oracle."""
+    from xva_trainer_b200 import hifigan as hg
+
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vits_hifi_only.npz"))
+    mel = hg.MelSpectrogram.vits(device="cuda:0")
+    for wkey, mkey in (("wav_seg", "mel_real"), ("o", "mel_fake")):
+        w = torch.from_numpy(gold[wkey]).reshape(2, -1)
+        got = mel(w.cuda()).transpose(1, 2).cpu()
+        want = torch.from_numpy(gold[mkey])
+        assert got.shape == want.shape and rel(got, want) < 2e-3, (mkey, got.shape, rel(got, want))
+    w = torch.from_numpy(gold["o"]).reshape(2, -1).clone().requires_grad_(True)
+    d = torch.randn(2, 80, 33, generator=torch.Generator().manual_seed(5))
+    (ov.torch_stft_mel(w) * d).sum().backward()
+    mel(w.detach().cuda())
+    got = mel.backward(d.transpose(1, 2).contiguous().cuda())
+    assert rel(got, w.grad) < 5e-3, rel(got, w.grad)
+
+
+@pytest.mark.parametrize("with_g", [True, False])
+def test_wn_matches_oracle(lib, with_g):
+    """WN (python/xvapitch/wavenet.py:16-106) stand-alone: output, input / conditioning gradients and every parameter
+    gradient vs autograd through oracle.vits.wn, ragged mask."""
+    from xva_trainer_b200 import vits
+
+    H, L, K, C = 64, 3, 5, 64
+    m = vits.WN(H, H, K, 1, L, c_in_channels=C).to("cuda:0")
+    gen = torch.Generator().manual_seed(9)
+    sd = {}
+    for k, p in m.named_parameters():
+        if k.endswith("weight_v"):
+            sd[k] = torch.randn(p.shape, generator=gen) * 0.7 / np.sqrt(p.shape[1] * p.shape[2])
+        elif k.endswith("bias"):
+            sd[k] = (torch.rand(p.shape, generator=gen) * 2 - 1) * 0.05
+    for k, p in m.named_parameters():
+        if k.endswith("weight_g"):
+            sd[k] = sd[k[:-1] + "v"].flatten(1).norm(dim=1).view(p.shape) * (1 + 0.1 * torch.rand(p.shape, generator=gen))
+    assert not m.load_state_dict(sd).missing_keys
+    m.train()
+    B, T = 2, 45
+    x = torch.randn(B, H, T, generator=gen)
+    g = torch.nn.functional.normalize(torch.randn(B, C, 1, generator=gen), dim=1) if with_g else None
+    lens = [45, 31]
+    mask = ov.sequence_mask(lens, T)[:, None, :].float()
+    d = torch.randn(B, H, T, generator=gen)
+    leaves = {f"enc.{k}": v.clone().requires_grad_(True) for k, v in sd.items()}
+    xl = x.clone().requires_grad_(True)
+    gl = g.clone().requires_grad_(True) if with_g else None
+    want = ov.wn(leaves, "enc", xl, mask, gl, num_layers=L, hidden=H, kernel=K)
+    (want * d).sum().backward()
+    got = m(x.cuda(), mask.cuda(), g.cuda() if with_g else None)
+    assert rel(got, want) < 2e-3, rel(got, want)
+    m.zero_grad()
+    dx, dg = m.backward(d.cuda())
+    torch.cuda.synchronize()
+    assert rel(dx, xl.grad) < 5e-3, rel(dx, xl.grad)
+    if with_g:
+        assert rel(dg, gl.grad) < 5e-3, rel(dg, gl.grad)
+    for k, p in m.named_parameters():
+        if k.startswith("cond_layer") and not with_g:
+            continue
+        assert rel(p.grad, leaves[f"enc.{k}"].grad) < 1e-2, (k, rel(p.grad, leaves[f"enc.{k}"].grad))
+
+
+def _modules(lib):
+    from test_oracle_golden import _vits_hifi_only_fixture
+    from xva_trainer_b200 import hifigan as hg
+    from xva_trainer_b200 import vits
+
+    gold, specs, sds, linear, waveform, d_vectors = _vits_hifi_only_fixture()
+    enc = vits.PosteriorEncoder(513, 192, 192, kernel_size=5, dilation_rate=1, num_layers=16, cond_channels=512, device="cuda:0")
+    dec = hg.HifiganGenerator(192, 1, "1", [[1, 3, 5]] * 3, [3, 7, 11], [16, 16, 4, 4], 512, [8, 8, 2, 2], inference_padding=0,
+                              cond_channels=512, conv_pre_weight_norm=False, conv_post_weight_norm=False,
+                              conv_post_bias=False, device="cuda:0")
+    disc = hg.VitsDiscriminator(device="cuda:0")
+    for name, mod in (("enc", enc), ("dec", dec), ("disc", disc)):
+        assert [(k, tuple(v.shape)) for k, v in mod.state_dict().items()] == [(k, tuple(sh)) for k, sh in specs[name]], name
+        res = mod.load_state_dict(sds[name])
+        assert not res.missing_keys and not res.unexpected_keys
+        mod.train()
+    return gold, specs, sds, linear, waveform, d_vectors, enc, dec, disc
+
+
+def test_posterior_encoder_matches_reference_golden_and_oracle(lib):
+    """python/xvapitch/model.py:1422-1475 (513 -> 192, 16 WaveNet layers, conditioning 512): z / mean / log_scale recorded
+    from the reference module with its own N(0, 1) draw replayed, and every parameter gradient of sum(z * w) vs autograd
+    through the oracle."""
+    gold, specs, sds, linear, waveform, d_vectors, enc, dec, disc = _modules(lib)
+    g = torch.nn.functional.normalize(d_vectors).unsqueeze(-1)
+    eps = torch.from_numpy(gold["eps"])
+    lens = [int(v) for v in gold["y_lengths"]]
+    z, m_q, logs_q, mask = enc(linear.cuda(), lens, g=g.cuda(), eps=eps.cuda())
+    for got, key in ((z, "z"), (m_q, "m_q"), (logs_q, "logs_q")):
+        want = torch.from_numpy(gold[key])
+        assert got.shape == want.shape and rel(got, want) < 3e-3, (key, got.shape, rel(got, want))
+    assert float(z[1, :, 35:].abs().max()) == 0.0 and mask.shape == (2, 1, 40) and float(mask.sum()) == 75.0
+    w = torch.randn(2, 192, 40, generator=torch.Generator().manual_seed(4))
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sds["enc"].items()}
+    zo, _, _, _ = ov.posterior_encoder(leaves, linear, lens, g, eps)
+    (zo * w).sum().backward()
+    enc.zero_grad()
+    enc.backward(w.cuda())
+    torch.cuda.synchronize()
+    num = den = 0.0
+    for k, p in enc.named_parameters():
+        e = rel(p.grad, leaves[k].grad)
+        assert e < 3e-2, (k, e)
+        num += float((p.grad.double().cpu() - leaves[k].grad.double()).pow(2).sum())
+        den += float(leaves[k].grad.double().pow(2).sum())
+    assert (num / den) ** 0.5 < 1e-2, (num / den) ** 0.5
+
+
+def test_hifi_only_step_matches_reference_golden_and_oracle(lib):
+    """One --hifi_only iteration (vits.HifiOnlyStep) with the recorded random draws replayed: every loss of the step
+    recorded from the reference modules within 2e-3, the segment starts exactly, and all 447 updated parameter tensors
+    within 5e-3 of the oracle's (bound as in test_full_hifigan_step_matches_oracle: the first AdamW step is sign-like)
+    with the recorded norms of the updated tensors and of their change."""
+    from xva_trainer_b200 import vits
+
+    gold, specs, sds, linear, waveform, d_vectors, enc, dec, disc = _modules(lib)
+    before = {n: {k: v.clone() for k, v in sd.items()} for n, sd in sds.items()}
+    step = vits.HifiOnlyStep(enc, dec, disc)
+    eps, u = torch.from_numpy(gold["eps"]), torch.from_numpy(gold["u"])
+    lens = [int(v) for v in gold["y_lengths"]]
+    losses = step.step(linear, lens, waveform, d_vectors, eps=eps, u=u)
+    torch.cuda.synchronize()
+    assert losses["slice_ids"] == gold["slice_ids"].tolist()
+    for k in ("loss", "loss_gen", "loss_feat", "loss_mel", "loss_disc"):
+        a, b = float(losses[k]), float(gold[k])
+        assert abs(a - b) < 2e-3 * abs(b), (k, a, b)
+    want = ov.hifi_only_step(sds["enc"], sds["dec"], sds["disc"], linear, waveform, d_vectors, lens, eps, u, {})
+    for k in ("loss", "loss_gen", "loss_feat", "loss_mel", "loss_disc"):
+        assert abs(float(losses[k]) - want[k]) < 2e-3 * abs(want[k]), (k, float(losses[k]), want[k])
+    for name, mod in (("enc", enc), ("dec", dec), ("disc", disc)):
+        after = mod.state_dict()
+        moved = 0
+        for i, (k, _) in enumerate(specs[name]):
+            assert rel(after[k], sds[name][k]) < 5e-3, (name, k, rel(after[k], sds[name][k]))
+            moved += int(not torch.equal(after[k].cpu(), before[name][k]))
+            n_after = float(after[k].double().norm())
+            assert abs(n_after - gold[f"{name}/after_norms"][i]) < 1e-3 * gold[f"{name}/after_norms"][i] + 1e-9, (name, k)
+            delta = float((after[k].double().cpu() - before[name][k].double()).norm())
+            assert abs(delta - gold[f"{name}/delta_norms"][i]) < 0.1 * gold[f"{name}/delta_norms"][i] + 1e-9, (name, k, delta)
+        assert moved == len(specs[name]), (name, moved)

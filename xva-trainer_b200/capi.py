@@ -128,6 +128,11 @@ PROTOTYPES = {
     "xva_mean3_lrelu": (_I, [_P, _P, _P, _I64, _F, _P, _P]),
     "xva_sum3": (_I, [_P, _P, _P, _I64, _P, _P]),
     "xva_tanh_bwd": (_I, [_P, _P, _I64, _I, _P, _P]),
+    "xva_gated_act_fwd": (_I, [_P, _I64, _I, _I64, _P, _P]),
+    "xva_gated_act_bwd": (_I, [_P, _P, _I64, _I, _I64, _P, _P]),
+    "xva_colsum_items": (_I, [_P, _I, _I, _I, _I64, _I64, _P, _I64, _P]),
+    "xva_vits_sample_fwd": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
+    "xva_vits_sample_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P]),
     "xva_l1_loss_grad": (_I, [_P, _P, _I64, _F, _F, _P, _P, _P]),
     "xva_sizeof_wn_desc": (_I, []),
     "xva_wn_pack_fwd": (_I, [_P, _I, _I, _I, _P]),

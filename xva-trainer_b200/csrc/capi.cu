@@ -147,6 +147,7 @@ int xva_set_operand_rounding(int on) {
   if ((rc = set_operand_rounding_attn_fused(on)) != XVA_OK) return rc;
   if ((rc = set_operand_rounding_rowops(on)) != XVA_OK) return rc;
   if ((rc = set_operand_rounding_elemwise(on)) != XVA_OK) return rc;
+  if ((rc = set_operand_rounding_vits(on)) != XVA_OK) return rc;
   if ((rc = set_operand_rounding_melspec(on)) != XVA_OK) return rc;
   if ((rc = set_operand_rounding_disc(on)) != XVA_OK) return rc;
   if ((rc = set_operand_rounding_wnpack(on)) != XVA_OK) return rc;
@@ -231,6 +232,28 @@ int xva_mean3_lrelu(const float* y0, const float* y1, const float* y2, int64_t n
 
 int xva_sum3(const float* a, const float* b, const float* c, int64_t n, float* out, void* stream) {
   return sum3(a, b, c, static_cast<long>(n), out, S(stream));
+}
+
+int xva_gated_act_fwd(const float* x_in, int64_t rows, int H, int64_t ld_in, float* acts, void* stream) {
+  return gated_act_fwd(x_in, static_cast<long>(rows), H, static_cast<long>(ld_in), acts, S(stream));
+}
+
+int xva_gated_act_bwd(const float* dacts, const float* x_in, int64_t rows, int H, int64_t ld_in, float* dx_in, void* stream) {
+  return gated_act_bwd(dacts, x_in, static_cast<long>(rows), H, static_cast<long>(ld_in), dx_in, S(stream));
+}
+
+int xva_colsum_items(const float* x, int Z, int rows, int C, int64_t ld, int64_t z_stride, float* out, int64_t out_ld,
+                     void* stream) {
+  return colsum_items(x, Z, rows, C, static_cast<long>(ld), static_cast<long>(z_stride), out, static_cast<long>(out_ld), S(stream));
+}
+
+int xva_vits_sample_fwd(const float* stats, const float* eps, const int32_t* lens, int B, int T, int C, float* z, void* stream) {
+  return vits_sample_fwd(stats, eps, lens, B, T, C, z, S(stream));
+}
+
+int xva_vits_sample_bwd(const float* dz, const float* eps, const float* stats, const int32_t* lens, int B, int T, int C,
+                        float* dstats, void* stream) {
+  return vits_sample_bwd(dz, eps, stats, lens, B, T, C, dstats, S(stream));
 }
 
 int xva_tanh_bwd(const float* dy, const float* y, int64_t rows, int ld, float* out, void* stream) {

@@ -59,7 +59,9 @@ spec_mag_fwd_kernel(const float* __restrict__ spec, long rows, int nb, int ld_s,
     float v = 0.0f;
     if (c < nb) {
       const float re = spec[r * ld_s + c], im = spec[r * ld_s + nb + c];
-      v = tf32_rn(sqrtf(re * re + im * im + eps));  // operand of the mel projection
+      // eps >= 0: sqrt(p + eps); eps < 0: sqrt(max(p, -eps)) (xVAPitch's TorchSTFT clamps instead of adding)
+      const float p = re * re + im * im;
+      v = tf32_rn(sqrtf(eps >= 0.0f ? p + eps : fmaxf(p, -eps)));  // operand of the mel projection
     }
     mag[i] = v;
   }
@@ -77,8 +79,11 @@ spec_mag_bwd_kernel(const float* __restrict__ dmag, const float* __restrict__ sp
     if (c < 2 * nb) {
       const int bin = c < nb ? c : c - nb;
       const float re = spec[r * ld_s + bin], im = spec[r * ld_s + nb + bin];
-      const float m = sqrtf(re * re + im * im + eps);  // exact magnitude, not the tf32-rounded copy
-      v = tf32_rn(dmag[r * ld_m + bin] * spec[i] / m);
+      const float p = re * re + im * im;
+      if (eps >= 0.0f || p >= -eps) {  // the clamped variant passes no gradient below its floor
+        const float m = sqrtf(eps >= 0.0f ? p + eps : p);  // exact magnitude, not the tf32-rounded copy
+        v = tf32_rn(dmag[r * ld_m + bin] * spec[i] / m);
+      }
     }
     dspec[i] = v;
   }

@@ -14,6 +14,7 @@ int set_operand_rounding_gemm_ref(int on);
 int set_operand_rounding_rowops(int on);
 int set_operand_rounding_loss_optim(int on);
 int set_operand_rounding_elemwise(int on);
+int set_operand_rounding_vits(int on);
 int set_operand_rounding_melspec(int on);
 int set_operand_rounding_disc(int on);
 int set_operand_rounding_wnpack(int on);
@@ -71,6 +72,14 @@ int attn_ctc(const float* logprob, const int* in_lens, const int* out_lens, int 
 int attn_bin_loss(const float* hard, const float* soft, long rows, int Tt, float eps, double* acc, cudaStream_t stream);
 int attn_grad_combine(const float* gctc, const float* hard, const float* soft, const double* acc, float a, float bw,
                       float eps, long rows, int Tt, float* g, cudaStream_t stream);
+
+// ---- vits.cu
+int gated_act_fwd(const float* x_in, long rows, int H, long ld_in, float* acts, cudaStream_t stream);
+int gated_act_bwd(const float* dacts, const float* x_in, long rows, int H, long ld_in, float* dx_in, cudaStream_t stream);
+int colsum_items(const float* x, int Z, int rows, int C, long ld, long zs, float* out, long out_ld, cudaStream_t stream);
+int vits_sample_fwd(const float* stats, const float* eps, const int* lens, int B, int T, int C, float* z, cudaStream_t stream);
+int vits_sample_bwd(const float* dz, const float* eps, const float* stats, const int* lens, int B, int T, int C, float* dstats,
+                    cudaStream_t stream);
 
 // ---- elemwise.cu
 int mean3_lrelu(const float* y0, const float* y1, const float* y2, long n, float slope, float* out, cudaStream_t stream);

@@ -217,14 +217,17 @@ class _WnPacker:
         self.layout.setdefault(key, []).append((off, tuple(shape)))
         return off
 
-    def add_conv(self, key, m, cout, cg, k, order=None, og=None, f=1):
-        """Conv weight v [cout, cg, k] -> [k (in `order`), cout, f * cg] with group r's columns at ((r / og) % f) * cg."""
-        off = self._alloc(key, (k, cout, f * cg))
+    def add_conv(self, key, m, cout, cg, k, order=None, og=None, f=1, ld=None):
+        """Conv weight v [cout, cg, k] -> [k (in `order`), cout, f * cg] with group r's columns at ((r / og) % f) * cg.
+        ld > f * cg: rows padded with zero columns (an input width that is not a multiple of 32)."""
+        ld = f * cg if ld is None else int(ld)
+        assert ld >= f * cg
+        off = self._alloc(key, (k, cout, ld))
         order = list(range(k)) if order is None else list(order)
         taps = [0] * k
         for pos, j in enumerate(order):
-            taps[j] = off + pos * cout * f * cg
-        self.items.append((m, capi.WN_PLAIN if isinstance(m, _PlainConv) else 0, f * cg, og if og else cout, f, cg, taps))
+            taps[j] = off + pos * cout * ld
+        self.items.append((m, capi.WN_PLAIN if isinstance(m, _PlainConv) else 0, ld, og if og else cout, f, cg, taps))
 
     def add_flat(self, key, m, cout, k):
         """First discriminator layer (one input channel): [cout, k], not rounded (it runs on CUDA cores in fp32)."""
@@ -573,15 +576,12 @@ class Generator(nn.Module):
         bias_grad("conv_pre", dpre0, self.conv_pre.cout)
         dx = dg = None
         gr = ctx["cond"]
-        if gr is not None or need_input_grad:
-            T0 = dpre0.shape[1]
         if gr is not None:
             # d(cond_layer output)[b] = sum over the utterance's frames of dpre0: one column sum per item, then the
             # layer's own gradients as the 1-tap convolution over [1, B, cond] that the forward ran
             cl = self.cond_layer
             dc = torch.zeros(1, B, cl.cout, device=dpre0.device, dtype=torch.float32)
-            for b in range(B):
-                ops.colsum_(T0, cl.cout, cl.cout, dpre0[b], dc[0, b])
+            ops.colsum_items_(dpre0, dc[0])
             bias_grad("cond_layer", dc, cl.cout)
             dcr = self._rounded(dc)
             wgrad(dcr, gr, (0,), gW["cond_layer"][0])
@@ -731,6 +731,15 @@ class MelSpectrogram:
         -> [B, N / hop + 1, n_mels] (channels-last; the reference returns its transpose)."""
         return cls(filter_length, n_mel_channels, sampling_rate, hop_length, win_length, mel_fmin, mel_fmax, device=device,
                    pad=filter_length // 2, mag_eps=0.0)
+
+    @classmethod
+    def vits(cls, n_fft=1024, hop_length=256, win_length=1024, sample_rate=22050, mel_fmin=0, mel_fmax=8000, n_mels=80,
+             device="cuda"):
+        """TorchSTFT(n_fft, hop, win, sample_rate=..., use_mel=True, do_amp_to_db=True) of python/xvapitch/audio.py:40-195
+        as VitsGeneratorLoss builds it (xvapitch/losses.py:29-46): centred reflect padding (N / hop + 1 frames) and
+        sqrt(clamp(re^2 + im^2, 1e-8)) instead of an added epsilon."""
+        return cls(n_fft, n_mels, sample_rate, hop_length, win_length, mel_fmin, mel_fmax, device=device, pad=n_fft // 2,
+                   mag_eps=-1e-8)
 
     def backward(self, dmel):
         B, N, F_, spec, lin = self._ctx
@@ -1226,11 +1235,13 @@ def discriminator_loss_backward(model, y_d_rs, y_d_gs):
     return loss
 
 
-def generator_adv_loss_backward(model, y_d_gs, fmap_rs, fmap_gs, dwave, pools):
+def generator_adv_loss_backward(model, y_d_gs, fmap_rs, fmap_gs, dwave, pools, fm_grad=True):
     """generator_loss + feature_loss (models.py:263-269, 286-294) on the outputs of ``model(y, y_hat)`` and their
     gradient wrt the generated waveform, ACCUMULATED into dwave [B, T] (hifigan/xva_train.py:506-513). The
     discriminator weights get no gradient here: the reference computes and then discards it (its zero_grad at
-    :468-469 / :483 clears it before any optimizer step reads it)."""
+    :468-469 / :483 clears it before any optimizer step reads it). fm_grad=False: the feature-matching term is only
+    evaluated -- xVAPitch's generator loss detaches the generated features (python/xvapitch/losses.py:196 passes
+    (fake, real) to feature_loss(feats_real, feats_generated), which detaches its first argument, :69)."""
     dev = dwave.device
     n_d = len(y_d_gs)
     acc = torch.zeros(n_d * 16, device=dev, dtype=torch.float64)
@@ -1260,7 +1271,11 @@ def generator_adv_loss_backward(model, y_d_gs, fmap_rs, fmap_gs, dwave, pools):
                 # elements of the reference's feature map (zero-padded channels of the buffer are not part of it)
                 valid = cg["Z"] * (cg["lens"][l] if l < n_act else cg["lens"][-1]) * (d.convs[l].cout if l < n_act else 1)
                 a = acc[16 * i + 1 + l:16 * i + 2 + l]
-                if l < n_act:
+                if not fm_grad:
+                    ops.reduce_l1(fr, fg, a)
+                    if l < n_act:
+                        dfeat.append(None)
+                elif l < n_act:
                     dfeat.append(ops.l1_loss_grad(fr, fg, 2.0 / valid, a, gate_slope=LRELU_SLOPE))   # loss term + gradient
                 else:
                     ops.reduce_l1(fr, fg, a)

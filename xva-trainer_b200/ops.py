@@ -490,6 +490,50 @@ def colsum_(x2d_rows, C_, ld, x, out):
     capi.call("xva_colsum", _p(x), int(x2d_rows), int(C_), int(ld), _p(out), _stream())
 
 
+def colsum_items_(x, out):
+    """out[z, c] += sum_t x[z, t, c]; x [Z, T, C] (row / item strides free, contiguous columns), out [Z, C] view."""
+    _check3(x, "x")
+    Z, T, C_ = x.shape
+    assert out.shape == (Z, C_) and out.stride(1) == 1
+    capi.call("xva_colsum_items", _p(x), Z, T, C_, x.stride(1), x.stride(0), _p(out), out.stride(0), _stream())
+
+
+def gated_act(x_in, H):
+    """tanh(x_in[..., :H]) * sigmoid(x_in[..., H:2H]), tf32-rounded (python/xvapitch/wavenet.py:6-13)."""
+    _check3(x_in, "x_in")
+    B, T, W = x_in.shape
+    assert W >= 2 * H and x_in.stride(0) == T * x_in.stride(1)
+    out = torch.empty(B, T, H, device=x_in.device, dtype=torch.float32)
+    capi.call("xva_gated_act_fwd", _p(x_in), B * T, H, x_in.stride(1), _p(out), _stream())
+    return out
+
+
+def gated_act_bwd(dacts, x_in, H):
+    _check3(x_in, "x_in")
+    B, T, W = x_in.shape
+    assert dacts.is_contiguous() and dacts.shape == (B, T, H) and x_in.stride(0) == T * x_in.stride(1)
+    out = torch.empty(B, T, 2 * H, device=x_in.device, dtype=torch.float32)
+    capi.call("xva_gated_act_bwd", _p(dacts), _p(x_in), B * T, H, x_in.stride(1), _p(out), _stream())
+    return out
+
+
+def vits_sample(stats, eps, lens):
+    """z = (mean + eps * exp(log_scale)) * mask, stats [B, T, 2C] = [mean | log_scale] (xvapitch/model.py:1473-1474)."""
+    B, T, C2 = stats.shape
+    assert stats.is_contiguous() and eps.is_contiguous() and eps.shape == (B, T, C2 // 2) and lens.dtype == torch.int32
+    z = torch.empty(B, T, C2 // 2, device=stats.device, dtype=torch.float32)
+    capi.call("xva_vits_sample_fwd", _p(stats), _p(eps), _p(lens), B, T, C2 // 2, _p(z), _stream())
+    return z
+
+
+def vits_sample_bwd(dz, eps, stats, lens):
+    B, T, C2 = stats.shape
+    assert dz.is_contiguous() and dz.shape == (B, T, C2 // 2) and dz.dtype == torch.float32
+    out = torch.empty_like(stats)
+    capi.call("xva_vits_sample_bwd", _p(dz), _p(eps), _p(stats), _p(lens), B, T, C2 // 2, _p(out), _stream())
+    return out
+
+
 def embed_pos(tokens, emb, inp, lens, inv_freq, B, T, Cc):
     """inv_freq = None: the embedding lookup alone (no positional term)."""
     dev = inv_freq.device if inv_freq is not None else (emb if emb is not None else inp).device
