@@ -18,5 +18,10 @@ for f in models meldataset utils env; do
   cp "$SRC/python/hifigan/$f.py" "$DST/python/hifigan/"
 done
 cp "$SRC/python/hifigan/config_v1.json" "$DST/python/hifigan/"
+# xVAPitch --hifi_only step (posterior encoder, waveform decoder, discriminator, losses) and what those modules import
+mkdir -p "$DST/python/xvapitch"
+for f in model hifigan wavenet losses audio util glow_tts sdp; do
+  cp "$SRC/python/xvapitch/$f.py" "$DST/python/xvapitch/"
+done
 ( cd "$SRC" && git rev-parse HEAD 2>/dev/null || echo unknown ) > "$DST/REFERENCE_COMMIT"
 echo "baseline/_ref: $(find "$DST" -type f | wc -l) files"

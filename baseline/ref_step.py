@@ -256,6 +256,104 @@ class HiFiGANRef:
         return {"loss_disc_all": loss_disc_all.detach(), "loss_gen_all": loss_gen_all.detach(), "loss_mel": loss_mel.detach()}
 
 
+# ---------------------------------------------------------------------------------------------- xVAPitch --hifi_only
+def xvapitch_available():
+    return os.path.exists(os.path.join(REF, "python", "xvapitch", "model.py"))
+
+
+def install_xvapitch():
+    """install() plus what python/xvapitch/model.py and losses.py import at module level and this image lacks: the text
+    front end (out of scope) and soundfile are stubs; np.bool is the alias numpy >= 1.24 removed
+    (xvapitch/util.py:28); scipy.signal is imported first because numpy.ma must not see the alias while it initialises."""
+    import scipy.signal  # noqa: F401
+
+    np.bool = np.bool_
+    install()
+    if not xvapitch_available():
+        raise RuntimeError("baseline/_ref/python/xvapitch is missing: run baseline/make_ref.sh in the build container")
+    text = types.ModuleType("python.xvapitch.text")
+    text.get_text_preprocessor, text.ALL_SYMBOLS, text.lang_names = None, list(range(200)), {}
+    sys.modules["python.xvapitch.text"] = text
+    sys.modules.setdefault("soundfile", types.ModuleType("soundfile"))
+
+
+def vits_batch(B, T=256, seed=1):
+    """Synthetic --hifi_only batch: linear spectrogram [B, 513, T] (|N(0, 0.5)|), ragged lengths in [3T/4, T] (first = T),
+    waveform [B, 1, 256 T] = 0.9 tanh(N(0, 0.3)), d-vectors [B, 512]."""
+    g = torch.Generator().manual_seed(seed)
+    linear = torch.randn(B, 513, T, generator=g).abs() * 0.5
+    waveform = 0.9 * torch.tanh(torch.randn(B, 1, T * 256, generator=g) * 0.3)
+    d_vectors = torch.randn(B, 512, generator=g)
+    lens = torch.randint(3 * T // 4, T + 1, (B,), generator=g)
+    lens[0] = T
+    return linear, lens, waveform, d_vectors
+
+
+class VitsHifiOnlyRef:
+    """The reference's --hifi_only iteration from its own modules: xVAPitch.train_hifi_only (xvapitch/model.py:650-678),
+    xVAPitch.forward (model.py:271-340, 385-399), the trainer's loop body (xvapitch/xva_train.py:651-736) and optimizers
+    (training_util.py:31-32, 66-67). The full xVAPitch model is not instantiated (its text front end needs packages this
+    image lacks); the composition below is the one tests/golden/make_golden_vits_hifi_only.py recorded the golden step with."""
+
+    def __init__(self, device, mode="fp32", seed=1234):
+        install_xvapitch()
+        from python.xvapitch.hifigan import HifiganGenerator
+        from python.xvapitch.losses import VitsDiscriminatorLoss, VitsGeneratorLoss
+        from python.xvapitch.model import PosteriorEncoder, VitsDiscriminator
+        import python.xvapitch.util as ref_util
+
+        self.dev = torch.device(device)
+        self.amp = mode == "amp_fp16"
+        if self.dev.type == "cuda":
+            tf32 = mode != "fp32_strict"
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = False
+        torch.manual_seed(seed)
+        self.enc = PosteriorEncoder(513, 192, 192, kernel_size=5, dilation_rate=1, num_layers=16, cond_channels=512).to(self.dev)
+        self.dec = HifiganGenerator(192, 1, "1", [[1, 3, 5]] * 3, [3, 7, 11], [16, 16, 4, 4], 512, [8, 8, 2, 2],
+                                    inference_padding=0, cond_channels=512, conv_pre_weight_norm=False,
+                                    conv_post_weight_norm=False, conv_post_bias=False).to(self.dev)
+        self.disc = VitsDiscriminator().to(self.dev)
+        args = types.SimpleNamespace(hifi_only=True, analyze_loss=False, pitch=False, energy=False, mltts_rc=False)
+        self.crit_g, self.crit_d = VitsGeneratorLoss(args).to(self.dev), VitsDiscriminatorLoss().to(self.dev)
+        gen_params = list(self.enc.parameters()) + list(self.dec.parameters())
+        self.opt0 = torch.optim.AdamW(gen_params, lr=0.000175, betas=[0.8, 0.99], eps=1e-09, weight_decay=0.01)
+        self.opt1 = torch.optim.AdamW(self.disc.parameters(), lr=0.0002, betas=[0.8, 0.99], eps=1e-09, weight_decay=0.01)
+        self.scaler = torch.cuda.amp.GradScaler(enabled=self.amp)
+        self.util = ref_util
+        for m in (self.enc, self.dec, self.disc):
+            m.train()
+
+    def step(self, linear, lens, waveform, d_vectors):
+        import torch.nn.functional as F
+
+        ac = torch.autocast("cuda", dtype=torch.float16, enabled=self.amp) if self.dev.type == "cuda" else _Null()
+        self.opt0.zero_grad()
+        with ac:
+            g = F.normalize(d_vectors).unsqueeze(-1)
+            z, m_q, logs_q, y_mask = self.enc(linear, lens, g=g)
+            z_slice, slice_ids = self.util.rand_segments(z, lens, 32)
+            o = self.dec(z_slice, g=g)
+            wav_seg = self.util.segment(waveform, slice_ids * 256, 32 * 256)
+            scores_fake, feats_fake, _, feats_real = self.disc(o, wav_seg)
+            loss_dict = self.crit_g(waveform_hat=o.float(), waveform=wav_seg.float(), z_p=None, logs_q=None, m_p=None,
+                                    logs_p=None, z_mask=None, scores_disc_fake=scores_fake, feats_disc_fake=feats_fake,
+                                    feats_disc_real=feats_real, loss_duration=None)
+        self.scaler.scale(loss_dict["loss"].mean()).backward()
+        self.opt1.zero_grad()
+        with ac:
+            s_fake, _, s_real, _ = self.disc(o.detach(), wav_seg)
+            loss_d = self.crit_d(s_real, s_fake)
+        self.scaler.scale(loss_d["loss"].mean()).backward()
+        for opt in (self.opt0, self.opt1):                                  # xva_train.py:729-736
+            if self.amp:
+                self.scaler.step(opt)
+                self.scaler.update()
+            else:
+                opt.step()
+        return {"loss": loss_dict["loss"].detach(), "loss_disc": loss_d["loss"].detach()}
+
+
 # ---------------------------------------------------------------------------------------------- timing helpers
 def _median(v):
     v = sorted(v)
@@ -305,6 +403,16 @@ def eager_b200(device="cuda:0", batch=32, stage=3, steps=10, warmup=3, hifigan=T
             r = HiFiGANRef(device, mode)
             ms = time_cuda(lambda: r.step(*hb), warmup, steps)
             out["hifigan"][mode] = {"ms_per_step": ms, "samples_per_s": 16 * 8192 / (ms * 1e-3)}
+            del r
+            torch.cuda.empty_cache()
+    if hifigan and xvapitch_available():
+        out["xvapitch_hifi_only"] = {}
+        vb = [t.to(device) for t in vits_batch(16)]
+        for mode in ("amp_fp16", "fp32", "fp32_strict"):
+            r = VitsHifiOnlyRef(device, mode)
+            ms = time_cuda(lambda: r.step(*vb), warmup, steps)
+            out["xvapitch_hifi_only"][mode] = {"ms_per_step": ms, "samples_per_s": 16 * 8192 / (ms * 1e-3),
+                                               "spec_frames_per_s": float(vb[1].sum()) / (ms * 1e-3)}
             del r
             torch.cuda.empty_cache()
     out["modes"] = {"amp_fp16": "torch.autocast(fp16) + GradScaler: the trainer's default (xva_train.py:698,787)",

@@ -43,6 +43,8 @@ def parse():
                     "instead of the BASELINE config's full-length batch; frames/s then counts valid frames only")
     ap.add_argument("--no-hifigan", action="store_true", help="skip the second half of the metric (HiFi-GAN samples/s)")
     ap.add_argument("--hifigan-steps", type=int, default=20)
+    ap.add_argument("--no-xvapitch", action="store_true", help="skip the next-tier measurement (xVAPitch --hifi_only step, N=1 only)")
+    ap.add_argument("--xvapitch-only", action="store_true", help="(internal) run only the xVAPitch --hifi_only measurement and print its dict")
     ap.add_argument("--via-trainer", action="store_true", help="time the same workload through the trainer facade "
                     "(FastPitchTrainer.iteration / HiFiTrainer.iteration: what the UI drives) instead of bench.py's own loop")
     return ap.parse_args()
@@ -367,6 +369,147 @@ def run_hifigan(args, dev, world, rank, peak_tf32):
             "loss_gen_all": loss_host}
 
 
+def synthetic_vits_batch(B, T, seed):
+    """Same generator as baseline/ref_step.py vits_batch (the reference arm's inputs)."""
+    import torch
+
+    g = torch.Generator().manual_seed(seed)
+    linear = torch.randn(B, 513, T, generator=g).abs() * 0.5
+    waveform = 0.9 * torch.tanh(torch.randn(B, 1, T * 256, generator=g) * 0.3)
+    d_vectors = torch.randn(B, 512, generator=g)
+    lens = torch.randint(3 * T // 4, T + 1, (B,), generator=g)
+    lens[0] = T
+    return linear, lens.to(torch.int32), waveform, d_vectors
+
+
+def cpu_xvapitch_rate(batch, T, steps, warmup):
+    """samples/s of the reference's --hifi_only step on all host cores: the unmodified reference modules when
+    baseline/_ref holds them, else the oracle port. -> (rate, s/step, cores, kind)"""
+    import torch
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    rs = ref_module()
+    if rs is not None and rs.xvapitch_available():
+        b = rs.vits_batch(batch, T)
+        r = rs.VitsHifiOnlyRef("cpu")
+        fn, kind = (lambda: r.step(*b)), "reference"
+    else:
+        from oracle import hifigan as ohg, vits as ov
+
+        mk = lambda spec, seed: ohg.make_disc_state(spec, seed)
+        sd_e = mk(ov.posterior_encoder_spec(), 31)
+        sd_d = mk([(k, sh) for k, sh in ov.decoder_spec()], 32)
+        sd_c = mk(ohg.vits_disc_spec(), 33)
+        lin, lens, wav, dv = synthetic_vits_batch(batch, T, 1)
+        opt = {}
+        fn = lambda: ov.hifi_only_step(sd_e, sd_d, sd_c, lin, wav, dv, lens.tolist(), torch.randn(batch, 192, T),
+                                       torch.rand(batch), opt)
+        kind = "port"
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        fn()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    per = _median(times)
+    return batch * 8192 / per, per, cores, kind
+
+
+def run_xvapitch(args, dev, peak_tf32):
+    """Next-tier row: the xVAPitch --hifi_only training step -- posterior encoder (16-layer
+    WaveNet stack over the 513-bin spectrogram), random 32-frame latent segment, waveform decoder, VITS discriminator,
+    45 L1 log-mel + LSGAN losses, two AdamW updates -- at batch 16 x 256 spectrogram frames, 8192-sample segments.
+    Same protocol as the two halves of the headline metric: `value` with the batch resident in HBM, `e2e` from pinned
+    host buffers with a loss read back every step, tap-GEMM roofline from one instrumented eager step. N = 1 only."""
+    import torch
+    from xva_trainer_b200 import capi, graph, hifigan as hg, ops, vits
+
+    B, T = 16, 256
+    enc = vits.PosteriorEncoder(513, 192, 192, kernel_size=5, dilation_rate=1, num_layers=16, cond_channels=512, device=dev)
+    dec = hg.HifiganGenerator(192, 1, "1", [[1, 3, 5]] * 3, [3, 7, 11], [16, 16, 4, 4], 512, [8, 8, 2, 2], inference_padding=0,
+                              cond_channels=512, conv_pre_weight_norm=False, conv_post_weight_norm=False,
+                              conv_post_bias=False, device=dev)
+    disc = hg.VitsDiscriminator(device=dev)
+    for m in (enc, dec, disc):
+        m.train()
+    stepper = vits.HifiOnlyStep(enc, dec, disc)
+    host = [t.pin_memory() for t in synthetic_vits_batch(B, T, 1)]
+    h2d = sum(t.numel() * t.element_size() for t in host)
+    lin, lens, wav, dv = (t.to(dev, non_blocking=True) for t in host)
+    frames = int(host[1].sum())
+    steps = args.hifigan_steps
+    fn = lambda a, b, c, d: stepper.step(a, b, c, d)
+    capi.reset_launch_count()
+    use_graph = not args.no_graph
+    if use_graph:
+        stepper.optim_g.lr_on_device = stepper.optim_d.lr_on_device = True
+        gs = graph.GraphedStep(fn, [lin, lens, wav, dv], warmup=3)
+        per_step = capi.launch_count() // 4
+        run = lambda src=None: gs(*src) if src is not None else gs()
+    else:
+        for _ in range(3):
+            fn(lin, lens, wav, dv)
+        per_step = capi.launch_count() // 3
+        run = lambda src=None: fn(*[t.to(dev, non_blocking=True) for t in src]) if src is not None else fn(lin, lens, wav, dv)
+    for _ in range(3):
+        out = run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(steps):
+        out = run(host)
+        loss_host = float(out["loss"])
+    f1.record()
+    torch.cuda.synchronize()
+    ms_e2e = f0.elapsed_time(f1)
+    rec = []
+    orig = ops.gemm_launch
+
+    def timed_launch(g, ref=False):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        orig(g, ref)
+        b.record()
+        rec.append((a, b, gemm_flops(g)))
+
+    stepper.optim_g.lr_on_device = stepper.optim_d.lr_on_device = False
+    fn(lin, lens, wav, dv)                     # untimed eager step: allocator warm-up outside the instrumented one
+    ops.gemm_launch = timed_launch
+    torch.cuda.synchronize()
+    torch.cuda._sleep(int(0.3 * 1.9e9))
+    fn(lin, lens, wav, dv)
+    torch.cuda.synchronize()
+    ops.gemm_launch = orig
+    gemm_ms = sum(a.elapsed_time(b) for a, b, _ in rec)
+    flops = sum(f for _, _, f in rec)
+    achieved = flops / (gemm_ms * 1e-3) / 1e12
+    samples = B * 8192
+    return {"metric": "audio-samples/s (xVAPitch --hifi_only train step: posterior encoder + waveform decoder vs VITS discriminator)",
+            "value": samples * steps / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms / steps, "steps": steps, "n_gpus": 1,
+            "spec_frames_per_s": frames * steps / (ms * 1e-3),
+            "config": {"workload": f"xVAPitch --hifi_only step, batch {B} x {T} spectrogram frames (ragged, {frames} valid), "
+                                   "32-frame / 8192-sample segments, synthetic", "global_batch": B,
+                       "step": "posterior encoder fwd + segment + decoder fwd + one discriminator pass (real, fake) + D loss bwd "
+                               "+ 45 L1 mel + LSGAN bwd through decoder and encoder + 2 AdamW",
+                       "launch": "one CUDA-graph replay per step" if use_graph else "eager launches"},
+            "e2e": {"value": samples * steps / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e / steps},
+            "gpu_launches_per_step": per_step,
+            "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 kind::tf32 tap-GEMM)", "achieved": achieved,
+                         "peak": peak_tf32, "unit": "TFLOP/s", "frac": achieved / peak_tf32, "traffic": None,
+                         "launches_per_step": len(rec), "flops_per_step": flops, "kernel_ms_per_step": gemm_ms,
+                         "share_of_step": gemm_ms / (ms / steps)},
+            "loss": loss_host}
+
+
 def run_native(args):
     import torch
     import torch.distributed as dist
@@ -617,6 +760,21 @@ def run_native(args):
             os.path.join(ROOT, "MEASURED_PEAKS.json")) else None
         hifi = run_hifigan(args, dev, world, rank, (pk["bf16_tflops_sustained"] if pk else 1400.0) / 2.0)
 
+    xva = None
+    if not args.no_xvapitch and not args.no_hifigan and world == 1:
+        # in a child process: a next-tier measurement must not be able to take the headline line down with it
+        import subprocess
+
+        cmd = [sys.executable, os.path.abspath(__file__), "--xvapitch-only", "--hifigan-steps", str(args.hifigan_steps)]
+        if args.no_graph:
+            cmd.append("--no-graph")
+        try:
+            res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+            last = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
+            xva = json.loads(last[-1]) if res.returncode == 0 and last else {"error": (res.stderr or res.stdout)[-400:]}
+        except Exception as e:  # noqa: BLE001
+            xva = {"error": repr(e)[-400:]}
+
     if world > 1:
         ft = torch.tensor([frames], device=dev, dtype=torch.float64)
         dist.all_reduce(ft)
@@ -648,6 +806,12 @@ def run_native(args):
                                     "sample": f"{'unmodified reference modules' if hkind == 'reference' else 'oracle train_step'}, "
                                               f"batch 4 x 8192 samples of the batch-16 workload, 1 warm-up + 2 timed steps "
                                               f"({hper:.1f} s/step), {cores} threads"}
+        if xva is not None and "error" not in xva:
+            xr, xper, _, xkind = cpu_xvapitch_rate(4, 128, 2, 1)
+            xva["cpu_baseline"] = {"value": xr, "unit": "samples/s", "cores": cores, "kind": xkind,
+                                   "sample": f"{'unmodified reference modules' if xkind == 'reference' else 'oracle hifi_only_step'}, "
+                                             f"batch 4 x 128 frames of the batch-16 x 256 workload, 1 warm-up + 2 timed steps "
+                                             f"({xper:.1f} s/step), {cores} threads"}
 
     line = {"metric": METRIC, "value": total_frames * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
@@ -656,6 +820,8 @@ def run_native(args):
             "e2e": {"value": total_frames * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "loss": loss_host, "hifigan": hifi}
+    if xva is not None:
+        line["xvapitch_hifi_only"] = xva
     if eager is not None:
         # the unmodified reference under PyTorch eager on this same B200 (ms/step, frames/s | samples/s per mode)
         line["eager_b200"] = eager
@@ -757,6 +923,19 @@ def run_via_trainer(args):
 
 def main():
     args = parse()
+    if args.xvapitch_only:
+        import torch
+
+        sys.path.insert(0, ROOT)
+        import __graft_entry__ as ge
+
+        ge.build()
+        torch.cuda.set_device(0)
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
+            os.path.join(ROOT, "MEASURED_PEAKS.json")) else None
+        print(json.dumps(run_xvapitch(args, torch.device("cuda:0"), (pk["bf16_tflops_sustained"] if pk else 1400.0) / 2.0)),
+              flush=True)
+        return
     if args.via_trainer:
         return run_via_trainer(args)
     if args.impl == "reference":

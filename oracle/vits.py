@@ -48,6 +48,13 @@ def posterior_encoder_spec():
     return spec
 
 
+def decoder_spec():
+    """(key, shape) of the waveform decoder's named_parameters() (HifiganGenerator as configured at model.py:134-149)."""
+    mid = [(k, sh) for k, sh in ohg.generator_spec() if k.startswith(("ups.", "resblocks."))]
+    return ([("conv_pre.bias", (512,)), ("conv_pre.weight", (512, LATENT, 7))] + mid +
+            [("conv_post.weight", (1, 32, 7)), ("cond_layer.weight", (512, COND, 1)), ("cond_layer.bias", (512,))])
+
+
 def sequence_mask(lengths, max_len):
     """util.py:180-197: [B, max_len] bool, True where t < length."""
     return torch.arange(max_len)[None, :] < torch.as_tensor(lengths)[:, None]
@@ -148,6 +155,6 @@ def hifi_only_step(sd_enc, sd_dec, sd_disc, linear, waveform, d_vectors, y_lengt
         params.update({("dec", k): sd_dec[k] for k in sd_dec})
         ohg.adamw_step(params, g_gen, st, lr=LR_GEN, eps=ADAM_EPS)
         ohg.adamw_step(sd_disc, dict(zip(disc.keys(), d_grads)), opt_state.setdefault("disc", {}), lr=LR_DISC, eps=ADAM_EPS)
-    out = {k: float(v) for k, v in losses.items()}
-    out["loss_disc"] = float(loss_disc)
+    out = {k: float(v.detach()) for k, v in losses.items()}
+    out["loss_disc"] = float(loss_disc.detach())
     return out

@@ -320,24 +320,31 @@ class HifiOnlyStep:
         self.steps = 0
 
     def step(self, linear, y_lengths, waveform, d_vectors, eps=None, u=None):
+        """No host synchronisation when y_lengths (int32) and u are device tensors: the segment starts stay on the device
+        and the segments are gathered / scattered by index, so the whole iteration can be captured in a CUDA graph."""
         enc, dec, disc, S = self.enc, self.dec, self.disc, self.segment
         dev = next(dec.parameters()).device
         B, _, T = linear.shape
-        lens_host = [int(v) for v in torch.as_tensor(y_lengths).reshape(-1).tolist()]
-        if min(lens_host) - S + 1 <= 0:
-            raise ValueError(" [!] At least one sample is shorter than the segment size.")          # util.py:161
+        if not (torch.is_tensor(y_lengths) and y_lengths.is_cuda):
+            lens_host = [int(v) for v in torch.as_tensor(y_lengths).reshape(-1).tolist()]
+            if min(lens_host) - S + 1 <= 0:
+                raise ValueError(" [!] At least one sample is shorter than the segment size.")      # util.py:161
+            y_lengths = torch.tensor(lens_host, dtype=torch.int32, device=dev)
+        lens = y_lengths.reshape(-1).to(torch.int32)
         self.optim_g.zero_grad()
         self.optim_d.zero_grad()
         g = torch.nn.functional.normalize(d_vectors.to(device=dev, dtype=torch.float32)).unsqueeze(-1)    # model.py:920
-        enc(linear.to(dev), lens_host, g=g, eps=eps)
+        enc(linear.to(dev), lens, g=g, eps=eps)
         z = enc.z_cl                                                                         # [B, T, C]
         if u is None:
-            u = torch.rand(B)
-        starts = (u.to(torch.float32).cpu() * (torch.tensor(lens_host) - S + 1)).long().tolist()     # util.py:160-162
-        z_seg = torch.stack([z[b, s:s + S] for b, s in enumerate(starts)])                   # [B, S, C]
+            u = torch.rand(B, device=dev)
+        starts = (u.to(device=dev, dtype=torch.float32) * (lens - S + 1)).long()             # util.py:160-162
+        rows = torch.arange(B, device=dev)[:, None]
+        fidx = starts[:, None] + torch.arange(S, device=dev)[None, :]                        # frames of each segment
+        z_seg = z[rows, fidx]                                                                # [B, S, C]
         o = dec(z_seg.transpose(1, 2), g=g)                                                  # [B, 1, S * 256]
         wav = waveform.to(device=dev, dtype=torch.float32).reshape(B, -1)
-        wav_seg = torch.stack([wav[b, s * HOP:(s + S) * HOP] for b, s in enumerate(starts)]).contiguous()
+        wav_seg = wav.gather(1, starts[:, None] * HOP + torch.arange(S * HOP, device=dev)[None, :])    # util.py:165-178
         fake = o.reshape(B, -1)
         # ---- one discriminator pass over (real, fake); discriminator loss and its parameter gradients
         rs, frs, gs, fgs = disc(wav_seg, fake)
@@ -353,8 +360,7 @@ class HifiOnlyStep:
         loss_gen, loss_feat = generator_adv_loss_backward(disc, gs, frs, fgs, dwave, pools=0, fm_grad=False)
         dz_seg, _ = dec.backward(dwave.view(B, 1, -1), need_input_grad=True)                 # [B, C, S]
         dz = torch.zeros_like(z)
-        for b, s in enumerate(starts):
-            dz[b, s:s + S].copy_(dz_seg[b].transpose(0, 1))
+        dz[rows, fidx] = dz_seg.transpose(1, 2)
         enc.backward(dz, channels_last=True)
         self.optim_g.step()
         self.optim_d.step()
