@@ -93,6 +93,51 @@ def posterior_encoder(sd, y, y_lengths, g, eps):
     return z, mean, log_scale, mask
 
 
+FLOWS, FLOW_LAYERS = 4, 4
+
+
+def flow_spec():
+    """(key, shape) of ResidualCouplingBlocks(192, 192, 5, 1, 4, cond_channels=512).named_parameters() (model.py:103-112)."""
+    H, half = HIDDEN, LATENT // 2
+    spec = []
+    for f in range(FLOWS):
+        p = f"flows.{f}"
+        spec += [(f"{p}.pre.weight", (H, half, 1)), (f"{p}.pre.bias", (H,))]
+        for i in range(FLOW_LAYERS):
+            spec += [(f"{p}.enc.in_layers.{i}.bias", (2 * H,)), (f"{p}.enc.in_layers.{i}.weight_g", (2 * H, 1, 1)),
+                     (f"{p}.enc.in_layers.{i}.weight_v", (2 * H, H, WN_KERNEL))]
+        for i in range(FLOW_LAYERS):
+            c = 2 * H if i < FLOW_LAYERS - 1 else H
+            spec += [(f"{p}.enc.res_skip_layers.{i}.bias", (c,)), (f"{p}.enc.res_skip_layers.{i}.weight_g", (c, 1, 1)),
+                     (f"{p}.enc.res_skip_layers.{i}.weight_v", (c, H, 1))]
+        spec += [(f"{p}.enc.cond_layer.bias", (2 * H * FLOW_LAYERS,)), (f"{p}.enc.cond_layer.weight_g", (2 * H * FLOW_LAYERS, 1, 1)),
+                 (f"{p}.enc.cond_layer.weight_v", (2 * H * FLOW_LAYERS, COND, 1))]
+        spec += [(f"{p}.post.weight", (half, H, 1)), (f"{p}.post.bias", (half,))]
+    return spec
+
+
+def residual_coupling_blocks(sd, x, x_mask, g=None, reverse=False):
+    """ResidualCouplingBlocks.forward (model.py:1406-1421) over ResidualCouplingBlock.forward (:1516-1546, mean_only, no
+    projector): x [B, 192, T] -> the same shape; forward maps the posterior latent to the prior space, reverse inverts it."""
+    half = LATENT // 2
+
+    def block(f, x):
+        x0, x1 = x[:, :half], x[:, half:]
+        h = F.conv1d(x0, sd[f"flows.{f}.pre.weight"], sd[f"flows.{f}.pre.bias"]) * x_mask
+        h = wn(sd, f"flows.{f}.enc", h, x_mask, g, num_layers=FLOW_LAYERS)
+        m = F.conv1d(h, sd[f"flows.{f}.post.weight"], sd[f"flows.{f}.post.bias"]) * x_mask
+        x1 = (m + x1 * x_mask) if not reverse else (x1 - m) * x_mask
+        return torch.cat([x0, x1], 1)
+
+    if not reverse:
+        for f in range(FLOWS):
+            x = torch.flip(block(f, x), [1])
+    else:
+        for f in reversed(range(FLOWS)):
+            x = block(f, torch.flip(x, [1]))
+    return x
+
+
 def segment_starts(u, lengths, segment_size=SEGMENT):
     """rand_segments' index rule, util.py:160-162: floor(u * (length - segment + 1)) with u ~ U[0, 1) per utterance."""
     max_idxs = torch.as_tensor(lengths) - segment_size + 1

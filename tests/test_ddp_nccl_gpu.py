@@ -146,3 +146,86 @@ def test_two_ranks_equal_one_process_on_the_whole_batch(stage):
         assert res["buckets"] >= 2
     assert got[0]["loss_global"] == got[1]["loss_global"]
     assert got[0]["loss_local"] != got[1]["loss_local"]
+
+
+def _vits_worker(rank, world, port, out_q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    import __graft_entry__ as ge
+
+    ge.build()
+    from test_oracle_golden import _vits_hifi_only_fixture
+    from xva_trainer_b200 import hifigan as hg, vits
+
+    gold, specs, sds, linear, waveform, d_vectors = _vits_hifi_only_fixture()
+    eps, u = torch.from_numpy(gold["eps"]), torch.from_numpy(gold["u"])
+    lens = [int(v) for v in gold["y_lengths"]]
+
+    def make(world_):
+        enc = vits.PosteriorEncoder(513, 192, 192, kernel_size=5, dilation_rate=1, num_layers=16, cond_channels=512, device=dev)
+        dec = hg.HifiganGenerator(192, 1, "1", [[1, 3, 5]] * 3, [3, 7, 11], [16, 16, 4, 4], 512, [8, 8, 2, 2],
+                                  inference_padding=0, cond_channels=512, conv_pre_weight_norm=False,
+                                  conv_post_weight_norm=False, conv_post_bias=False, device=dev)
+        disc = hg.VitsDiscriminator(device=dev)
+        for name, mod in (("enc", enc), ("dec", dec), ("disc", disc)):
+            mod.load_state_dict(sds[name])
+            mod.train()
+        return vits.HifiOnlyStep(enc, dec, disc, world=world_)
+
+    # two ranks, one utterance each (the second padded to the batch's 40 frames, as a DataParallel replica sees it)
+    st = make(world)
+    sl = slice(rank, rank + 1)
+    losses = st.step(linear[sl], lens[rank:rank + 1], waveform[sl], d_vectors[sl], eps=eps[sl], u=u[sl])
+    torch.cuda.synchronize()
+    flat = lambda s_: torch.cat([s_.optim_g.p, s_.optim_d.p]).clone()
+    mine = flat(st)
+    other = mine.clone()
+    dist.broadcast(other, src=0)
+    res = {"replicas_equal": bool(torch.equal(mine, other)), "loss_disc": float(losses["loss_disc"]), "loss": float(losses["loss"])}
+    if rank == 0:
+        one = make(1)
+        l1 = one.step(linear, lens, waveform, d_vectors, eps=eps, u=u)
+        torch.cuda.synchronize()
+        ref = flat(one)
+        res["update_err"] = float((mine - ref).double().norm() / (ref - torch.cat([t.reshape(-1) for sd in (sds["enc"], sds["dec"], sds["disc"])
+                                                                                     for t in sd.values()]).to(dev)).double().norm())
+        res["param_err"] = float((mine - ref).double().norm() / ref.double().norm())
+        res["whole_batch"] = {k: float(l1[k]) for k in ("loss", "loss_disc")}
+    ls = torch.tensor([res["loss"], res["loss_disc"]], device=dev, dtype=torch.float64)
+    dist.all_reduce(ls)
+    res["mean_losses"] = (ls / world).tolist()
+    out_q.put((rank, res))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_vits_hifi_only_two_ranks_equal_one_process():
+    """xVAPitch --hifi_only step on 2 NCCL ranks x 1 utterance vs 1 process x 2 utterances (the recorded fixture): the
+    mean of the per-rank losses equals the whole-batch loss, both ranks hold identical parameters after the step without
+    a broadcast, and they are the one-process parameters up to tf32 / summation-order noise on a sign-like first AdamW
+    step (same bound as the oracle comparison of tests/test_vits_gpu.py)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 500) + 7
+    procs = [ctx.Process(target=_vits_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=600) for _ in range(2))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert got[0]["replicas_equal"] and got[1]["replicas_equal"]
+    r0 = got[0]
+    for i, k in enumerate(("loss", "loss_disc")):
+        assert abs(r0["mean_losses"][i] - r0["whole_batch"][k]) < 2e-3 * abs(r0["whole_batch"][k]), (k, r0)
+    assert r0["param_err"] < 5e-3, r0
+    import json
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(got[0], open(os.path.join(ROOT, "gpurun_out", "ddp_nccl_vits.json"), "w"), indent=1)

@@ -204,3 +204,37 @@ def test_hifi_only_step_matches_reference_golden_and_oracle(lib):
             delta = float((after[k].double().cpu() - before[name][k].double()).norm())
             assert abs(delta - gold[f"{name}/delta_norms"][i]) < 0.1 * gold[f"{name}/delta_norms"][i] + 1e-9, (name, k, delta)
         assert moved == len(specs[name]), (name, moved)
+
+
+def test_flow_matches_reference_golden_and_oracle(lib):
+    """vits.ResidualCouplingBlocks = python/xvapitch/model.py:1358-1421 (4 flows x 4-layer WN): forward and reverse outputs
+    recorded from the reference module, reverse(forward(x)) = x, input / conditioning gradients as recorded from its
+    autograd, every parameter gradient vs the oracle's and its recorded norm."""
+    from test_oracle_golden import _vits_flow_fixture
+    from xva_trainer_b200 import vits
+
+    gold, spec, sd = _vits_flow_fixture()
+    flow = vits.ResidualCouplingBlocks(192, 192, kernel_size=5, dilation_rate=1, num_layers=4, cond_channels=512, device="cuda:0")
+    assert [(k, tuple(v.shape)) for k, v in flow.state_dict().items()] == [(k, tuple(sh)) for k, sh in spec]
+    res = flow.load_state_dict(sd)
+    assert not res.missing_keys and not res.unexpected_keys
+    flow.train()
+    x, cond, w = (torch.from_numpy(gold[k]) for k in ("x", "g", "w"))
+    lens = [int(v) for v in gold["lens"]]
+    mask = ov.sequence_mask(lens, x.shape[2])[:, None, :].float()
+    z_p = flow(x.cuda(), mask.cuda(), g=cond.cuda())
+    assert rel(z_p, torch.from_numpy(gold["z_p"])) < 2e-3, rel(z_p, torch.from_numpy(gold["z_p"]))
+    flow.zero_grad()
+    dx, dg = flow.backward(w.cuda())
+    torch.cuda.synchronize()
+    assert rel(dx, torch.from_numpy(gold["dx"])) < 5e-3, rel(dx, torch.from_numpy(gold["dx"]))
+    assert rel(dg, torch.from_numpy(gold["dg"])) < 5e-3, rel(dg, torch.from_numpy(gold["dg"]))
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    (ov.residual_coupling_blocks(leaves, x, mask, cond) * w).sum().backward()
+    for (k, p), want_norm in zip(flow.named_parameters(), gold["grad_norms"]):
+        assert rel(p.grad, leaves[k].grad) < 2e-2, (k, rel(p.grad, leaves[k].grad))
+        assert abs(float(p.grad.double().norm()) - want_norm) < 1e-2 * want_norm + 1e-12, (k, float(p.grad.norm()), want_norm)
+    with torch.no_grad():
+        back = flow(z_p, mask.cuda(), g=cond.cuda(), reverse=True)
+    assert rel(back, torch.from_numpy(gold["reverse_of_z_p"])) < 2e-3
+    assert rel(back, x) < 2e-3, rel(back, x)

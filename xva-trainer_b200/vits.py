@@ -297,6 +297,148 @@ class PosteriorEncoder(nn.Module):
         self._ctx = None
 
 
+class ResidualCouplingBlock(nn.Module):
+    """Parameters of python/xvapitch/model.py:1476 ``ResidualCouplingBlock`` as xVAPitch builds it (mean_only, no
+    projector): pre 1x1 (C/2 -> H), WN, post 1x1 (H -> C/2). Run by ResidualCouplingBlocks below."""
+
+    def __init__(self, channels, hidden_channels, kernel_size, dilation_rate, num_layers, dropout_p=0, cond_channels=0,
+                 out_channels_override=None, mean_only=False):
+        assert channels % 2 == 0, "channels should be divisible by 2"
+        super().__init__()
+        if out_channels_override or not mean_only:
+            raise NotImplementedError("xVAPitch builds its flow with mean_only=True and no projector (model.py:1394-1403)")
+        if (channels // 2) % 32:
+            raise NotImplementedError("channels / 2 must be a multiple of 32")
+        self.half_channels, self.mean_only, self.conv1d_projector = channels // 2, mean_only, None
+        self.pre = _PlainConv(self.half_channels, hidden_channels, 1, bias_first=False)
+        self.enc = WN(hidden_channels, hidden_channels, kernel_size, dilation_rate, num_layers, dropout_p=dropout_p,
+                      c_in_channels=cond_channels)
+        self.post = _PlainConv(hidden_channels, self.half_channels, 1, bias_first=False)
+
+
+class ResidualCouplingBlocks(nn.Module):
+    """Drop-in for python/xvapitch/model.py:1358 ``ResidualCouplingBlocks`` (configured at model.py:103-112: 192 channels,
+    4 flows of a 4-layer WN, conditioning 512): ``forward(x [B, C, T], x_mask, g, reverse=False)`` -> [B, C, T]. Forward
+    (posterior latent -> prior space) keeps what ``backward(dz)`` needs in training mode and returns (dL/dx, dL/dg);
+    reverse is the inference / voice-conversion direction. The coupling x1 <- m + x1 * mask is the epilogue of the
+    ``post`` GEMM (x1 in the residual slot, the mask in the lens slot); the channel flip between flows is a copy."""
+
+    def __init__(self, channels, hidden_channels, kernel_size, dilation_rate, num_layers, num_flows=4, cond_channels=0,
+                 args=None, device=None, seed=1234):
+        super().__init__()
+        if args is not None and getattr(args, "expanded_flow", False):
+            raise NotImplementedError("expanded_flow")
+        self.channels, self.hidden_channels, self.kernel_size = channels, hidden_channels, kernel_size
+        self.dilation_rate, self.num_layers, self.num_flows, self.cond_channels = dilation_rate, num_layers, num_flows, cond_channels
+        self.flows = nn.ModuleList([ResidualCouplingBlock(channels, hidden_channels, kernel_size, dilation_rate, num_layers,
+                                                          cond_channels=cond_channels, mean_only=True) for _ in range(num_flows)])
+        gen = torch.Generator().manual_seed(int(seed))
+        with torch.no_grad():          # xavier_uniform_ on every weight (model.py:113-122), torch's default bias init
+            for m in self.modules():
+                if not isinstance(m, (_WNConv, _PlainConv)):
+                    continue
+                v = m.weight if isinstance(m, _PlainConv) else m.weight_v
+                fan_in, fan_out = v.shape[1] * v.shape[2], v.shape[0] * v.shape[2]
+                bound = math.sqrt(6.0 / (fan_in + fan_out))
+                v.copy_((torch.rand(v.shape, generator=gen) * 2 - 1) * bound)
+                if isinstance(m, _WNConv):
+                    m.weight_g.copy_(v.flatten(1).norm(dim=1).view(-1, 1, 1))
+                m.bias.copy_((torch.rand(m.bias.shape, generator=gen) * 2 - 1) / math.sqrt(fan_in))
+        self.to(_need_cuda(device))
+        self._packer = None
+        self._ctx = None
+
+    def _get_packer(self):
+        if self._packer is None:
+            pk = _WnPacker()
+            for i, f in enumerate(self.flows):
+                pk.add_conv(f"flows.{i}.pre", f.pre, f.pre.cout, f.pre.cin, 1)
+                f.enc.register_weights(pk, f"flows.{i}.enc.")
+                pk.add_conv(f"flows.{i}.post", f.post, f.post.cout, f.post.cin, 1)
+            pk.finalize(self.flows[0].pre.weight.device)
+            self._packer = pk
+        return self._packer
+
+    def forward(self, x, x_mask, g=None, reverse=False):
+        B, C, T = x.shape
+        dev = self.flows[0].pre.weight.device
+        h = C // 2
+        H = self.hidden_channels
+        lens = x_mask.reshape(B, T).to(dev).sum(1).to(torch.int32)
+        W = self._get_packer().pack()
+        xc = x.to(device=dev, dtype=torch.float32).transpose(1, 2).contiguous()
+        gr = None
+        if g is not None and self.cond_channels > 0:
+            gr = torch.empty(1, B, self.cond_channels, device=dev, dtype=torch.float32)
+            ops.round_tf32_(g.to(device=dev, dtype=torch.float32).reshape(-1).contiguous(), gr.reshape(-1))
+        keep = self.training and not reverse
+        saved = []
+        order = range(self.num_flows) if not reverse else reversed(range(self.num_flows))
+        for i in order:
+            f = self.flows[i]
+            if reverse:
+                xc = torch.flip(xc, [2])                                          # model.py:1419
+            xr = torch.empty_like(xc)
+            ops.round_tf32_(xc.reshape(-1), xr.reshape(-1))
+            hx, hr = torch.empty(B, T, H, device=dev, dtype=torch.float32), torch.empty(B, T, H, device=dev, dtype=torch.float32)
+            ops.conv_fwd(xr[..., :h], W[f"flows.{i}.pre"][0], (0,), out=hx, bias=_bias(f.pre), lens=lens, out_act=hr,
+                         out_act_slope=1.0)                                        # pre(x0) * mask, :1530
+            _, out_r = f.enc.forward_cl(hx, hr, lens, gr, W, f"flows.{i}.enc.", keep=keep)
+            xn = torch.empty_like(xc)
+            xn[..., :h].copy_(xc[..., :h])
+            if not reverse:    # x1 <- m + x1 * mask = (post(h) + x1) * mask, :1539
+                ops.conv_fwd(out_r, W[f"flows.{i}.post"][0], (0,), out=xn[..., h:], bias=_bias(f.post), residual=xc[..., h:],
+                             lens=lens)
+                xc = torch.flip(xn, [2])                                          # :1416
+            else:              # x1 <- (x1 - m) * mask, :1544
+                ops.conv_fwd(out_r, W[f"flows.{i}.post"][0], (0,), out=xn[..., h:], bias=-_bias(f.post), residual=xc[..., h:],
+                             lens=lens, alpha=-1.0)
+                xc = xn
+            if keep:
+                saved.append((xr, out_r))
+        self._ctx = (saved, lens, gr, W) if keep else None
+        return xc.transpose(1, 2)
+
+    def backward(self, dz):
+        """dz = dL/d(forward output) [B, C, T] -> (dL/dx [B, C, T], dL/dg [B, cond, 1] or None)."""
+        if self._ctx is None:
+            raise RuntimeError("backward() needs a forward() (not reverse) in training mode first")
+        saved, lens, gr, W = self._ctx
+        pk = self._get_packer()
+        gW = pk.zero_grads()
+        B, C, T = dz.shape
+        h, H = C // 2, self.hidden_channels
+        dev = dz.device
+        d = dz.to(torch.float32).transpose(1, 2).contiguous()
+        mask = (torch.arange(T, device=dev)[None, :] < lens[:, None]).to(torch.float32).unsqueeze(-1)
+        dg = None
+        for i in reversed(range(self.num_flows)):
+            f = self.flows[i]
+            xr, out_r = saved[i]
+            d = torch.flip(d, [2])
+            d1 = d[..., h:] * mask                                # gradient of both m (masked stats) and x1 * mask
+            d1r = torch.empty_like(d1)
+            ops.round_tf32_(d1.reshape(-1), d1r.reshape(-1))
+            _bias_grad_inline(f.post, d1r, f.post.cout)
+            _wgrad_inline(d1r, out_r, (0,), gW[f"flows.{i}.post"][0])
+            d_rs = torch.zeros(B, T, 2 * H, device=dev, dtype=torch.float32)
+            d_res = torch.zeros_like(d_rs)
+            ops.conv_dgrad(d1r, W[f"flows.{i}.post"][0], (0,), out=d_rs[..., H:], lens=lens, round_out=True)
+            dgi = f.enc.backward_cl(d_rs, d_res, gW, _bias_grad_inline, _wgrad_inline, mask_input_grad=True)
+            dh = d_rs[..., :H]
+            _bias_grad_inline(f.pre, dh, f.pre.cout)
+            _wgrad_inline(dh, xr[..., :h], (0,), gW[f"flows.{i}.pre"][0])
+            dn = torch.empty_like(d)
+            ops.conv_dgrad(dh, W[f"flows.{i}.pre"][0], (0,), out=dn[..., :h], residual=d[..., :h])
+            dn[..., h:].copy_(d1)
+            d = dn
+            if dgi is not None:
+                dg = dgi if dg is None else dg + dgi
+        pk.unpack_grads()
+        self._ctx = None
+        return d.transpose(1, 2).contiguous(), (None if dg is None else dg.reshape(B, -1, 1))
+
+
 class HifiOnlyStep:
     """One xVAPitch ``--hifi_only`` iteration (amp off, gam 1): posterior encoder -> random 32-frame latent segment ->
     waveform decoder -> VITS discriminator; generator-side loss = 45 * L1(log-mel) + LSGAN (the feature-matching term
@@ -310,14 +452,24 @@ class HifiOnlyStep:
     the posterior sample and the segment draw (model.py:1474, util.py:162). Returns the reference's loss dict."""
 
     def __init__(self, posterior_encoder, waveform_decoder, disc, lr=0.000175, disc_lr=0.0002, betas=(0.8, 0.99), eps=1e-9,
-                 weight_decay=0.01, segment=SPEC_SEGMENT):
+                 weight_decay=0.01, segment=SPEC_SEGMENT, world=1, group=None):
+        """world > 1: one process per GPU, each on its own utterances; the two gradient arenas are all-reduced (mean)
+        right before their optimizer steps -- the reference's nn.DataParallel semantics, whose criterion runs inside the
+        replicated forward and whose trainer averages the per-replica losses (xvapitch/xva_train.py:678-683)."""
         self.enc, self.dec, self.disc, self.segment = posterior_encoder, waveform_decoder, disc, int(segment)
+        self.world, self.group = int(world), group
         dev = next(waveform_decoder.parameters()).device
         self.mel = MelSpectrogram.vits(device=dev)
         self.optim_g = AdamW(list(posterior_encoder.parameters()) + list(waveform_decoder.parameters()), lr, betas, eps,
                              weight_decay)                                                  # training_util.py:31-32
         self.optim_d = AdamW(disc.parameters(), disc_lr, betas, eps, weight_decay)
         self.steps = 0
+
+    def _all_reduce(self, flat_grad):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=self.group)
+            flat_grad.mul_(1.0 / self.world)
 
     def step(self, linear, y_lengths, waveform, d_vectors, eps=None, u=None):
         """No host synchronisation when y_lengths (int32) and u are device tensors: the segment starts stay on the device
@@ -362,6 +514,8 @@ class HifiOnlyStep:
         dz = torch.zeros_like(z)
         dz[rows, fidx] = dz_seg.transpose(1, 2)
         enc.backward(dz, channels_last=True)
+        self._all_reduce(self.optim_d.g)
+        self._all_reduce(self.optim_g.g)
         self.optim_g.step()
         self.optim_d.step()
         self.steps += 1
