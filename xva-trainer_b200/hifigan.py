@@ -49,8 +49,9 @@ class _Side:
     input-gradient chain instead of serialising with it. Inputs are record_stream()-ed: their memory is not reused
     before the side stream is done with it; join() runs where the gradients are consumed (_WnPacker.unpack_grads)."""
     enabled = None          # None: by XVA_BWD_STREAMS (default auto); True / False: forced (tests)
-    stream = None
-    used = False
+    streams = {}            # launching stream (handle) -> its side stream
+    used = []
+    stream = None           # the side stream of the most recent run() (tests look at it)
 
     @classmethod
     def on(cls):
@@ -58,22 +59,33 @@ class _Side:
 
     @classmethod
     def run(cls, fn, *inputs):
+        """One side stream PER LAUNCHING STREAM: the weight gradients of the three ResBlock branches of a generator stage
+        (or of the eight sub-discriminators) do not queue behind each other on a single stream -- a weight-gradient
+        launch fills about a third of the SMs, and a step issues ~13 ms of them (profiles/r01_s5_hifigan_launches_summary
+        .txt). Launches from one branch stay ordered among themselves (two passes of a spectral-normed sub-discriminator
+        accumulate into the same bias gradients)."""
         if not cls.on():
             return fn()
-        if cls.stream is None:
-            cls.stream = torch.cuda.Stream()
-        cls.stream.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(cls.stream):
+        cur = torch.cuda.current_stream()
+        side = cls.streams.get(cur.cuda_stream)
+        if side is None:
+            side = cls.streams[cur.cuda_stream] = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
             fn()
         for t in inputs:
-            t.record_stream(cls.stream)
-        cls.used = True
+            t.record_stream(side)
+        if side not in cls.used:
+            cls.used.append(side)
+        cls.stream = side
 
     @classmethod
     def join(cls):
         if cls.used:
-            torch.cuda.current_stream().wait_stream(cls.stream)
-            cls.used = False
+            cur = torch.cuda.current_stream()
+            for side in cls.used:
+                cur.wait_stream(side)
+            cls.used = []
 
 
 class _Branches:
@@ -1079,8 +1091,8 @@ class MultiPeriodDiscriminator(nn.Module):
         self.discriminators = nn.ModuleList([DiscriminatorP(p) for p in (2, 3, 5, 7, 11)])
         _init_disc(self, seed, device)
 
-    def forward(self, y, y_hat, weight_grad=True):
-        return _multi_forward(self, y, y_hat, pools=0, weight_grad=weight_grad)
+    def forward(self, y, y_hat, weight_grad=True, join=True, stream_offset=0):
+        return _multi_forward(self, y, y_hat, pools=0, weight_grad=weight_grad, join=join, stream_offset=stream_offset)
 
 
 class MultiScaleDiscriminator(nn.Module):
@@ -1091,8 +1103,8 @@ class MultiScaleDiscriminator(nn.Module):
         self.discriminators = nn.ModuleList([DiscriminatorS(use_spectral_norm=True), DiscriminatorS(), DiscriminatorS()])
         _init_disc(self, seed + 1, device)
 
-    def forward(self, y, y_hat, weight_grad=True):
-        return _multi_forward(self, y, y_hat, pools=1, weight_grad=weight_grad)
+    def forward(self, y, y_hat, weight_grad=True, join=True, stream_offset=0):
+        return _multi_forward(self, y, y_hat, pools=1, weight_grad=weight_grad, join=join, stream_offset=stream_offset)
 
 
 class VitsDiscriminatorS(_Disc):
@@ -1156,8 +1168,11 @@ def _init_disc(model, seed, device):
     model.to(dev)
 
 
-def _multi_forward(model, y, y_hat, pools, weight_grad=True):
-    """Shared by MPD / MSD: every sub-discriminator on the real and the generated waveform ([B, 1, T] or [B, T]).
+def _multi_forward(model, y, y_hat, pools, weight_grad=True, join=True, stream_offset=0):
+    """join=False leaves the branch streams open (the caller joins after it has issued another model's branches too:
+    MPD and MSD are independent, HiFiGANStep runs their eight sub-discriminators side by side on streams
+    stream_offset + i); the waveforms the branches read then stay referenced on the model until its next forward.
+    Shared by MPD / MSD: every sub-discriminator on the real and the generated waveform ([B, 1, T] or [B, T]).
     Weight-normed sub-discriminators see both waveforms as ONE batch of 2B sequences (one launch per layer instead of
     two); the spectral-normed one (MSD scale 0) runs them one after the other because torch's spectral_norm hook does a
     power iteration per call, so the reference's two calls (models.py:251-252) use two different weights.
@@ -1183,7 +1198,7 @@ def _multi_forward(model, y, y_hat, pools, weight_grad=True):
         if pools and i != 0:
             both = ops.avgpool4(both)
             inputs.append(both)
-        with _Branches.branch(i):
+        with _Branches.branch(i + stream_offset):
             if any(m.spectral for m in d.convs):
                 sr, fr, cr = d(both[:B], weight_grad=weight_grad)
                 sg, fg, cg = d(both[B:], weight_grad=weight_grad)
@@ -1200,22 +1215,26 @@ def _multi_forward(model, y, y_hat, pools, weight_grad=True):
         fmap_rs.append(fr)
         fmap_gs.append(fg)
         model._ctx.append(passes)
-    _Branches.join()
+    model._branch_inputs = inputs
+    if join:
+        _Branches.join()
+        model._branch_inputs = None
     del inputs
     return y_d_rs, y_d_gs, fmap_rs, fmap_gs
 
 
 # ================================================================================================ losses / steps
-def discriminator_loss_backward(model, y_d_rs, y_d_gs):
+def discriminator_loss_backward(model, y_d_rs, y_d_gs, join=True, stream_offset=0):
     """discriminator_loss (models.py:272-283) on the outputs of ``model(y, y_hat.detach())`` plus the backward into the
-    discriminator's parameters (hifigan/xva_train.py:486-497). Returns the loss as a 0-dim device tensor."""
+    discriminator's parameters (hifigan/xva_train.py:486-497). Returns the loss as a 0-dim device tensor -- or, with
+    join=False, a function that returns it and must be called after _Branches.join() (it sums the per-branch terms and
+    unpacks the weight gradients, both of which need every branch finished)."""
     dev = y_d_rs[0].device
     acc = torch.zeros(2 * len(y_d_rs), device=dev, dtype=torch.float64)
-    loss = torch.zeros((), device=dev, dtype=torch.float64)
     model._packer.zero_grads()
     parts = []
     for i, (d, passes) in enumerate(zip(model.discriminators, model._ctx)):
-        with _Branches.branch(i):
+        with _Branches.branch(i + stream_offset):
             dr, dg = y_d_rs[i], y_d_gs[i]
             n = dr.numel()
             ops.reduce_sq(dr, 1.0, acc[2 * i:2 * i + 1])
@@ -1228,25 +1247,32 @@ def discriminator_loss_backward(model, y_d_rs, y_d_gs):
                 if gr is not None:
                     ops.sq_grad(dg, 0.0, 1.0 / n, out=dscore[gr[0]:gr[1]], accumulate=False)
                 d.backward(ctx, dscore, [None] * len(ctx["acts"]), need_w=True)
+
+    def finish():
+        loss = torch.zeros((), device=dev, dtype=torch.float64)
+        for part in parts:                # same summation order as one sub-discriminator after the other
+            loss = loss + part
+        model._packer.unpack_grads()      # packed-weight gradients -> weight_g / weight_v of every sub-discriminator
+        model._branch_inputs = None
+        return loss
+
+    if not join:
+        return finish
     _Branches.join()
-    for part in parts:                    # same summation order as one sub-discriminator after the other
-        loss = loss + part
-    model._packer.unpack_grads()          # packed-weight gradients -> weight_g / weight_v of every sub-discriminator
-    return loss
+    return finish()
 
 
-def generator_adv_loss_backward(model, y_d_gs, fmap_rs, fmap_gs, dwave, pools, fm_grad=True):
+def generator_adv_loss_backward(model, y_d_gs, fmap_rs, fmap_gs, dwave, pools, fm_grad=True, join=True, stream_offset=0):
     """generator_loss + feature_loss (models.py:263-269, 286-294) on the outputs of ``model(y, y_hat)`` and their
     gradient wrt the generated waveform, ACCUMULATED into dwave [B, T] (hifigan/xva_train.py:506-513). The
     discriminator weights get no gradient here: the reference computes and then discards it (its zero_grad at
     :468-469 / :483 clears it before any optimizer step reads it). fm_grad=False: the feature-matching term is only
     evaluated -- xVAPitch's generator loss detaches the generated features (python/xvapitch/losses.py:196 passes
-    (fake, real) to feature_loss(feats_real, feats_generated), which detaches its first argument, :69)."""
+    (fake, real) to feature_loss(feats_real, feats_generated), which detaches its first argument, :69). join=False: returns
+    a function to call after _Branches.join() that finishes the accumulation into dwave and returns the two losses."""
     dev = dwave.device
     n_d = len(y_d_gs)
     acc = torch.zeros(n_d * 16, device=dev, dtype=torch.float64)
-    loss_gen = torch.zeros((), device=dev, dtype=torch.float64)
-    loss_fm = torch.zeros((), device=dev, dtype=torch.float64)
     levels = [dwave]
     for i in range(1, n_d):
         if pools:
@@ -1254,7 +1280,7 @@ def generator_adv_loss_backward(model, y_d_gs, fmap_rs, fmap_gs, dwave, pools, f
             levels.append(torch.zeros(dwave.shape[0], L // 2 + 1, device=dev, dtype=torch.float32))
     gen_parts, fm_parts, own_dwave = [], [], []
     for i in reversed(range(n_d)):
-        with _Branches.branch(i):
+        with _Branches.branch(i + stream_offset):
             d = model.discriminators[i]
             cg = None
             for ctx, rr, gr in model._ctx[i]:      # the pass (or the half of the batched pass) of the generated waveform
@@ -1289,18 +1315,27 @@ def generator_adv_loss_backward(model, y_d_gs, fmap_rs, fmap_gs, dwave, pools, f
             else:
                 tgt = dwave
             d.backward(cg, dscore, dfeat, need_w=False, dwave=tgt)
+
+    def finish():
+        loss_gen = torch.zeros((), device=dev, dtype=torch.float64)
+        loss_fm = torch.zeros((), device=dev, dtype=torch.float64)
+        for part in gen_parts:            # same summation order as one sub-discriminator after the other
+            loss_gen = loss_gen + part
+        for part in fm_parts:
+            loss_fm = loss_fm + part
+        for t in own_dwave:
+            dwave.add_(t)
+        if pools:
+            for i in reversed(range(1, n_d)):
+                up = ops.avgpool4_bwd(levels[i], levels[i - 1].shape[1])
+                levels[i - 1].add_(up)
+        model._branch_inputs = None
+        return loss_gen, loss_fm
+
+    if not join:
+        return finish
     _Branches.join()
-    for part in gen_parts:                # same summation order as one sub-discriminator after the other
-        loss_gen = loss_gen + part
-    for part in fm_parts:
-        loss_fm = loss_fm + part
-    for t in own_dwave:
-        dwave.add_(t)
-    if pools:
-        for i in reversed(range(1, n_d)):
-            up = ops.avgpool4_bwd(levels[i], levels[i - 1].shape[1])
-            levels[i - 1].add_(up)
-    return loss_gen, loss_fm
+    return finish()
 
 
 class AdamW:
@@ -1433,11 +1468,15 @@ class HiFiGANStep:
 
         # ---- discriminators (:483-498); y_hat is detached: no gradient reaches the generator here
         self.optim_d.zero_grad()
+        # MPD and MSD are independent: their 5 + 3 sub-discriminators are issued side by side (streams 0-4 and 5-7 when
+        # the branch streams are on, i.e. inside a captured graph) and joined once
         with ops.nvtx("hifigan.d_step"):
-            rs, gs, _, _ = mpd(y, wave)
-            loss_disc_f = discriminator_loss_backward(mpd, rs, gs)
-            rs, gs, _, _ = msd(y, wave)
-            loss_disc_s = discriminator_loss_backward(msd, rs, gs)
+            rs_f, gs_f, _, _ = mpd(y, wave, join=False)
+            rs_s, gs_s, _, _ = msd(y, wave, join=False, stream_offset=5)
+            fin_f = discriminator_loss_backward(mpd, rs_f, gs_f, join=False)
+            fin_s = discriminator_loss_backward(msd, rs_s, gs_s, join=False, stream_offset=5)
+            _Branches.join()
+            loss_disc_f, loss_disc_s = fin_f(), fin_s()
             self._all_reduce(self.optim_d.g)
             self.optim_d.step()
 
@@ -1449,10 +1488,12 @@ class HiFiGANStep:
         loss_mel = 45.0 * acc[0] / n
         dwave = self.mel.backward(ops.l1_grad(mel_tgt, mel_hat, 45.0 / n))
         with ops.nvtx("hifigan.g_step.discriminators"):
-            rs, gs, frs, fgs = mpd(y, wave, weight_grad=False)
-            loss_gen_f, loss_fm_f = generator_adv_loss_backward(mpd, gs, frs, fgs, dwave, pools=False)
-            rs, gs, frs, fgs = msd(y, wave, weight_grad=False)
-            loss_gen_s, loss_fm_s = generator_adv_loss_backward(msd, gs, frs, fgs, dwave, pools=True)
+            _, gs_f, frs_f, fgs_f = mpd(y, wave, weight_grad=False, join=False)
+            _, gs_s, frs_s, fgs_s = msd(y, wave, weight_grad=False, join=False, stream_offset=5)
+            fin_f = generator_adv_loss_backward(mpd, gs_f, frs_f, fgs_f, dwave, pools=False, join=False)
+            fin_s = generator_adv_loss_backward(msd, gs_s, frs_s, fgs_s, dwave, pools=True, join=False, stream_offset=5)
+            _Branches.join()
+            (loss_gen_f, loss_fm_f), (loss_gen_s, loss_fm_s) = fin_f(), fin_s()
         with ops.nvtx("hifigan.g_step.generator_bwd"):
             G.backward(dwave.view(B, 1, -1))
             self._all_reduce(self.optim_g.g)
