@@ -183,7 +183,7 @@ def _vits_worker(rank, world, port, out_q):
     sl = slice(rank, rank + 1)
     losses = st.step(linear[sl], lens[rank:rank + 1], waveform[sl], d_vectors[sl], eps=eps[sl], u=u[sl])
     torch.cuda.synchronize()
-    flat = lambda s_: torch.cat([s_.optim_g.p, s_.optim_d.p]).clone()
+    flat = lambda s_: torch.cat([p.detach().reshape(-1) for p in s_.optim_g.params + s_.optim_d.params]).clone()
     mine = flat(st)
     other = mine.clone()
     dist.broadcast(other, src=0)

@@ -578,12 +578,35 @@ def test_vits_discriminator_step_gradients(lib):
     for k in ("nets.0.convs.1.weight_v", "nets.0.convs.0.weight_v", "nets.0.convs.0.bias"):       # the 4-channel groups
         # same per-tensor bound as above, now against the reference's own tensors; convs.0 is the deepest (3.4e-2)
         assert rel(dict(m.named_parameters())[k].grad, torch.from_numpy(gold[f"grad/{k}"])) < 6e-2, k
-    # ---- G step
+    # ---- G step. The feature-matching gradient back-propagates sign(fake - real) of every feature map, so elements whose
+    # difference is within tf32 rounding of zero flip the sign of their seed (about 1 % of them here): measured on B200
+    # (scripts/diag_vits_disc_dwave.py) 2.7-4.6 % per net for the adversarial term, up to 19 % for one net's
+    # feature-matching term, 2.3-5.1 % on the total depending on the last bit of the packed weights -- and 0.0000 for
+    # every net with the exact-fp32 checker GEMM, which is what pins the wiring below.
+    from xva_trainer_b200 import capi, ops
+
+    want_gen = torch.from_numpy(gold["dwave_gen"]).reshape(B, T)
+    want_all = torch.from_numpy(gold["dwave_gen"] + gold["dwave_feat"]).reshape(B, T)
     xs, xf, hs, hf = m(x.cuda(), x_hat.cuda())
     dwave = torch.zeros(B, T, device="cuda")
     lg, lf = hg.generator_adv_loss_backward(m, hs, xf, hf, dwave, pools=0)
     torch.cuda.synchronize()
     assert abs(float(lg) - float(gold["loss_gen"])) < 2e-3 * float(gold["loss_gen"]), (float(lg), float(gold["loss_gen"]))
     assert abs(float(lf) - float(gold["loss_feat"])) < 2e-3 * float(gold["loss_feat"]), (float(lf), float(gold["loss_feat"]))
-    want = torch.from_numpy(gold["dwave_gen"] + gold["dwave_feat"]).reshape(B, T)
-    assert rel(dwave.cpu(), want) < 3e-2, rel(dwave.cpu(), want)
+    assert rel(dwave.cpu(), want_all) < 1.5e-1, rel(dwave.cpu(), want_all)
+    xs, xf, hs, hf = m(x.cuda(), x_hat.cuda())
+    dwave = torch.zeros(B, T, device="cuda")
+    hg.generator_adv_loss_backward(m, hs, xf, hf, dwave, pools=0, fm_grad=False)
+    assert rel(dwave.cpu(), want_gen) < 6e-2, rel(dwave.cpu(), want_gen)
+    orig = ops.gemm_launch
+    ops.gemm_launch = lambda args, ref=False: orig(args, True)
+    capi.call("xva_set_operand_rounding", 0)
+    try:
+        xs, xf, hs, hf = m(x.cuda(), x_hat.cuda())
+        dwave = torch.zeros(B, T, device="cuda")
+        hg.generator_adv_loss_backward(m, hs, xf, hf, dwave, pools=0)
+        torch.cuda.synchronize()
+        assert rel(dwave.cpu(), want_all) < 1e-3, rel(dwave.cpu(), want_all)
+    finally:
+        ops.gemm_launch = orig
+        capi.call("xva_set_operand_rounding", 1)

@@ -1347,43 +1347,43 @@ class AdamW:
         self.params = [p for p in params]
         self.param_groups = [{"lr": lr, "betas": betas, "eps": eps, "weight_decay": weight_decay}]
         dev = self.params[0].device
-        n = sum(p.numel() for p in self.params)
-        self.p = torch.empty(n, device=dev, dtype=torch.float32)
+        # every parameter starts on a 16-byte boundary of the arena (a 1-element bias would otherwise misalign everything
+        # behind it and push the weight-pack kernels onto their scalar path); the pad elements stay zero
+        self.offsets, n = [], 0
+        for p in self.params:
+            self.offsets.append(n)
+            n += (p.numel() + 3) // 4 * 4
+        self.p = torch.zeros(n, device=dev, dtype=torch.float32)
         self.g = torch.zeros(n, device=dev, dtype=torch.float32)
         self.m = torch.zeros(n, device=dev, dtype=torch.float32)
         self.v = torch.zeros(n, device=dev, dtype=torch.float32)
         self.lr_dev = torch.full((1,), float(lr), device=dev, dtype=torch.float32)
         self.step_dev = torch.zeros(1, device=dev, dtype=torch.int64)   # device-side step count (graph replay)
         self.lr_on_device = False   # True: lr_dev is maintained by the caller (CUDA-graph replay), step() leaves it
-        off = 0
         with torch.no_grad():
-            for p in self.params:
+            for p, off in zip(self.params, self.offsets):
                 k = p.numel()
                 self.p[off:off + k].copy_(p.reshape(-1))
                 p.data = self.p[off:off + k].view(p.shape)
                 p.grad = self.g[off:off + k].view(p.shape)
-                off += k
         self.steps = 0
 
     def zero_grad(self, set_to_none=False):
         self.g.zero_()
-        off = 0
-        for p in self.params:       # re-bind in case something replaced a .grad tensor
+        for p, off in zip(self.params, self.offsets):       # re-bind in case something replaced a .grad tensor
             k = p.numel()
             if p.grad is None or p.grad.data_ptr() != self.g[off:off + k].data_ptr():
                 p.grad = self.g[off:off + k].view(p.shape)
-            off += k
 
     def state_dict(self):
         """torch.optim.AdamW.state_dict() layout: {'state': {i: {'step', 'exp_avg', 'exp_avg_sq'}}, 'param_groups': [...]}
         with parameter i = the i-th parameter handed to the constructor, tensors on the CPU in the parameters' shapes."""
-        st, off = {}, 0
-        for i, p in enumerate(self.params):
+        st = {}
+        for i, (p, off) in enumerate(zip(self.params, self.offsets)):
             k = p.numel()
             if self.steps > 0:
                 st[i] = {"step": torch.tensor(float(self.steps)), "exp_avg": self.m[off:off + k].view(p.shape).cpu().clone(),
                          "exp_avg_sq": self.v[off:off + k].view(p.shape).cpu().clone()}
-            off += k
         g = self.param_groups[0]
         group = {"lr": g["lr"], "betas": tuple(g["betas"]), "eps": g["eps"], "weight_decay": g["weight_decay"],
                  "amsgrad": False, "maximize": False, "foreach": None, "capturable": False, "differentiable": False,
@@ -1393,16 +1393,20 @@ class AdamW:
     def load_state_dict(self, sd):
         """Accepts torch.optim.AdamW's state_dict (what the reference's do_ checkpoints hold) or this class's round-1 flat
         layout ({'m', 'v', 'steps'})."""
-        if "m" in sd and "v" in sd and "state" not in sd:
-            self.m.copy_(sd["m"])
-            self.v.copy_(sd["v"])
+        if "m" in sd and "v" in sd and "state" not in sd:      # round-1 layout: parameters packed without padding
+            src = 0
+            for p, off in zip(self.params, self.offsets):
+                k = p.numel()
+                self.m[off:off + k].copy_(sd["m"][src:src + k])
+                self.v[off:off + k].copy_(sd["v"][src:src + k])
+                src += k
             self.steps = int(sd["steps"])
         else:
             state = sd["state"]
             if len(state) not in (0, len(self.params)):
                 raise ValueError(f"optimizer state holds {len(state)} parameters, this model has {len(self.params)}")
-            off, steps = 0, 0
-            for i, p in enumerate(self.params):
+            steps = 0
+            for i, (p, off) in enumerate(zip(self.params, self.offsets)):
                 k = p.numel()
                 e = state.get(i, state.get(str(i)))
                 if e is not None:
@@ -1411,7 +1415,6 @@ class AdamW:
                     self.m[off:off + k].copy_(e["exp_avg"].reshape(-1).to(torch.float32))
                     self.v[off:off + k].copy_(e["exp_avg_sq"].reshape(-1).to(torch.float32))
                     steps = max(steps, int(float(e["step"])))
-                off += k
             self.steps = steps
             if sd.get("param_groups"):
                 g0 = sd["param_groups"][0]
