@@ -457,6 +457,36 @@ typedef struct xva_wn_desc {
   int64_t tap_off[XVA_MAX_TAPS];
 } xva_wn_desc;
 int xva_sizeof_wn_desc(void);
+
+/* Spectral norm + packing of every convolution of a spectral-normed model -- replaces torch.nn.utils.spectral_norm's
+ * forward pre-hook (one power iteration per training forward, eps 1e-12; hifigan/models.py:207-215 with
+ * use_spectral_norm=True) plus the re-layout, and their autograd. With W = weight_orig [rows, inner]:
+ *   fwd, training: v <- normalize(W^T u); u <- normalize(W v); sigma = u . (W v); dst = W / sigma (packed, tf32-rounded).
+ *                  u / v (the module's buffers) are replaced by the new iterates, which are also stored in u_sav / v_sav.
+ *   fwd, eval:     sigma = u . (W v) with the stored vectors (copied to u_sav / v_sav).
+ *   bwd:           dw (+)= dW_eff / sigma - (<dW_eff, W> / sigma^2) u_sav v_sav^T, dW_eff gathered from ddst.
+ * Layout fields (k, flags, ld, og, f, cg, tap_off) as in xva_wn_desc. `work` is per-descriptor scratch of
+ * ceil(rows / 64) * inner + rows + 2 floats that must survive from a forward to its backward (it holds sigma).
+ * blk_start = sum over the preceding descriptors of ceil(inner / 256) * ceil(rows / 64); total_blocks = that sum over all. */
+typedef struct xva_sn_desc {
+  const float* w;
+  float* u;
+  float* v;
+  float* u_sav;
+  float* v_sav;
+  float* dw;          /* accumulated (bwd); may be null when no backward runs */
+  float* dst;
+  const float* ddst;
+  float* work;
+  int32_t rows, inner, k, flags;
+  int32_t ld, og, f, cg;
+  int32_t row_start, blk_start;
+  int64_t tap_off[XVA_MAX_TAPS];
+} xva_sn_desc;
+int xva_sizeof_sn_desc(void);
+int xva_sn_pack_fwd(const xva_sn_desc* table_dev, int n_desc, int total_rows, int total_blocks, int max_inner, int training,
+                    void* stream);
+int xva_sn_pack_bwd(const xva_sn_desc* table_dev, int n_desc, int total_rows, int total_blocks, int max_inner, void* stream);
 int xva_wn_pack_fwd(const xva_wn_desc* table_dev, int n_desc, int total_rows, int max_inner, void* stream);
 int xva_wn_pack_bwd(const xva_wn_desc* table_dev, int n_desc, int total_rows, int max_inner, void* stream);
 

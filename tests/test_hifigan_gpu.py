@@ -610,3 +610,58 @@ def test_vits_discriminator_step_gradients(lib):
     finally:
         ops.gemm_launch = orig
         capi.call("xva_set_operand_rounding", 1)
+
+
+def test_spectral_packer_matches_torch(lib):
+    """_SnPacker (xva_sn_pack_fwd / _bwd) vs the PyTorch restatement of torch.nn.utils.spectral_norm + re-packing that it
+    replaces (_DiscConv.weight / _Disc._packed): two consecutive training calls (the power iteration advances, each call
+    keeps its own weights), the u / v buffers after them, eval mode, and the gradient of weight_orig vs autograd."""
+    import copy
+
+    from xva_trainer_b200 import hifigan as hg
+
+    msd = hg.MultiScaleDiscriminator(device="cuda:0")
+    msd.load_state_dict(ohg.make_disc_state(ohg.msd_spec(), 22))
+    d0 = msd.discriminators[0]
+    d0.train()
+    dref = copy.deepcopy(d0)
+    dref.train()
+    sn = hg._SnPacker(slots=2)
+    d0.register_weights(sn, "0")
+    sn.finalize("cuda:0")
+    refs = []
+    for slot in range(2):
+        W = sn.pack(slot, True)
+        ref = dref._packed()                       # power iteration on dref's buffers + packed weights under autograd
+        refs.append(ref)
+        for li, want in enumerate(ref):
+            got = W[f"0.{li}"][0]
+            assert got.shape == want.shape, (li, got.shape, want.shape)
+            assert rel(got, want) < 5e-4, (slot, li, rel(got, want))
+        for m, mr in zip(list(d0.convs) + [d0.conv_post], list(dref.convs) + [dref.conv_post]):
+            assert rel(m.weight_u, mr.weight_u) < 1e-5 and rel(m.weight_v, mr.weight_v) < 1e-5
+    assert not torch.equal(sn.W[0]["0.3"][0], sn.W[1]["0.3"][0])          # the second call used its own sigma
+    # backward of the FIRST call (its u, v, sigma, not the buffers' current ones) vs autograd
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    sn.zero_grads()
+    grads = []
+    for li, t in enumerate(refs[0]):
+        g_ = sn.gW[0][f"0.{li}"][0]
+        g_.copy_(torch.randn(g_.shape, device="cuda", generator=gen))
+        grads.append(g_.clone())
+    params = [m.weight_orig for m in list(dref.convs) + [dref.conv_post]]
+    torch.autograd.backward(refs[0], grads)
+    for m in list(d0.convs) + [d0.conv_post]:
+        m.weight_orig.grad = None
+    sn.unpack_grads()
+    torch.cuda.synchronize()
+    for m, p_ in zip(list(d0.convs) + [d0.conv_post], params):
+        assert rel(m.weight_orig.grad, p_.grad) < 1e-4, (tuple(p_.shape), rel(m.weight_orig.grad, p_.grad))
+    # eval mode: no power iteration, sigma from the stored vectors
+    d0.eval(); dref.eval()
+    u_before = d0.convs[2].weight_u.clone()
+    W = sn.pack(0, False)
+    ref = dref._packed()
+    for li, want in enumerate(ref):
+        assert rel(W[f"0.{li}"][0], want) < 5e-4, (li, rel(W[f"0.{li}"][0], want))
+    assert torch.equal(d0.convs[2].weight_u, u_before)

@@ -64,6 +64,18 @@ class WnDesc(C.Structure):
     ]
 
 
+class SnDesc(C.Structure):
+    """Mirror of struct xva_sn_desc (include/xva_b200.h)."""
+    _fields_ = [
+        ("w", C.c_void_p), ("u", C.c_void_p), ("v", C.c_void_p), ("u_sav", C.c_void_p), ("v_sav", C.c_void_p),
+        ("dw", C.c_void_p), ("dst", C.c_void_p), ("ddst", C.c_void_p), ("work", C.c_void_p),
+        ("rows", C.c_int32), ("inner", C.c_int32), ("k", C.c_int32), ("flags", C.c_int32),
+        ("ld", C.c_int32), ("og", C.c_int32), ("f", C.c_int32), ("cg", C.c_int32),
+        ("row_start", C.c_int32), ("blk_start", C.c_int32),
+        ("tap_off", C.c_int64 * XVA_MAX_TAPS),
+    ]
+
+
 WN_TRANSPOSED, WN_NO_ROUND, WN_PLAIN = 1, 2, 4
 
 # name -> (restype, argtypes); must list every symbol include/xva_b200.h declares (tests/test_abi.py checks it)
@@ -135,6 +147,9 @@ PROTOTYPES = {
     "xva_vits_sample_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P]),
     "xva_l1_loss_grad": (_I, [_P, _P, _I64, _F, _F, _P, _P, _P]),
     "xva_sizeof_wn_desc": (_I, []),
+    "xva_sizeof_sn_desc": (_I, []),
+    "xva_sn_pack_fwd": (_I, [_P, _I, _I, _I, _I, _I, _P]),
+    "xva_sn_pack_bwd": (_I, [_P, _I, _I, _I, _I, _P]),
     "xva_wn_pack_fwd": (_I, [_P, _I, _I, _I, _P]),
     "xva_wn_pack_bwd": (_I, [_P, _I, _I, _I, _P]),
     "xva_adamw_step": (_I, [_P, _P, _P, _P, _I64, _P, _F, _F, _F, _F, _I, _P, _P]),
@@ -161,6 +176,8 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
+    if lib.xva_sizeof_sn_desc() != C.sizeof(SnDesc):
+        raise XvaError(f"xva_sn_desc layout mismatch: C {lib.xva_sizeof_sn_desc()} vs ctypes {C.sizeof(SnDesc)}")
     if lib.xva_sizeof_wn_desc() != C.sizeof(WnDesc):
         raise XvaError(f"xva_wn_desc layout mismatch: C {lib.xva_sizeof_wn_desc()} vs ctypes {C.sizeof(WnDesc)}")
     if lib.xva_sizeof_gemm_args() != C.sizeof(GemmArgs):
@@ -177,7 +194,7 @@ def check(status, what=""):
 
 # kernels enqueued per successful call (everything not listed launches exactly one)
 _LAUNCHES = {"xva_lamb_step": 2, "xva_attn_bwd": 2, "xva_attn_score_bwd": 2, "xva_attn_ctc": 3, "xva_gemm_debug_counters": 0, "xva_set_operand_rounding": 0, "xva_abi_version": 0, "xva_last_error": 0, "xva_device_check": 0,
-             "xva_sizeof_gemm_args": 0, "xva_sizeof_wn_desc": 0}
+             "xva_sizeof_gemm_args": 0, "xva_sizeof_wn_desc": 0, "xva_sizeof_sn_desc": 0, "xva_sn_pack_fwd": 5, "xva_sn_pack_bwd": 3}
 _launch_count = 0
 
 

@@ -267,6 +267,14 @@ int xva_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, cons
 }
 
 int xva_sizeof_wn_desc(void) { return static_cast<int>(sizeof(xva_wn_desc)); }
+int xva_sizeof_sn_desc(void) { return static_cast<int>(sizeof(xva_sn_desc)); }
+int xva_sn_pack_fwd(const xva_sn_desc* table_dev, int n_desc, int total_rows, int total_blocks, int max_inner, int training,
+                    void* stream) {
+  return sn_pack(table_dev, n_desc, total_rows, total_blocks, max_inner, training, 0, S(stream));
+}
+int xva_sn_pack_bwd(const xva_sn_desc* table_dev, int n_desc, int total_rows, int total_blocks, int max_inner, void* stream) {
+  return sn_pack(table_dev, n_desc, total_rows, total_blocks, max_inner, 0, 1, S(stream));
+}
 int xva_l1_loss_grad(const float* a, const float* b, int64_t n, float scale, float gate_slope, double* acc, float* out,
                      void* stream) {
   return l1_loss_grad(a, b, static_cast<long>(n), scale, gate_slope, acc, out, S(stream));

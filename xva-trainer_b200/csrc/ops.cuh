@@ -86,6 +86,8 @@ int mean3_lrelu(const float* y0, const float* y1, const float* y2, long n, float
 int sum3(const float* a, const float* b, const float* c, long n, float* out, cudaStream_t stream);
 int tanh_bwd(const float* dy, const float* y, long rows, int ld, float* out, cudaStream_t stream);
 int wn_pack(const xva_wn_desc* table_dev, int n_desc, int total_rows, int max_inner, int backward, cudaStream_t stream);
+int sn_pack(const xva_sn_desc* table_dev, int n_desc, int total_rows, int total_blocks, int max_inner, int training,
+            int backward, cudaStream_t stream);
 int l1_loss_grad(const float* a, const float* b, long n, float scale, float gate_slope, double* acc, float* out,
                  cudaStream_t stream);
 int adamw_step(float* p, const float* g, float* m, float* v, long n, const float* lr_dev, float b1, float b2, float eps,

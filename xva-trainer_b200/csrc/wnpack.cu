@@ -42,7 +42,8 @@ __device__ __forceinline__ const xva_wn_desc* find_desc(const xva_wn_desc* table
 }
 
 // offset of element (r, c, j) of v in the packed arena
-__device__ __forceinline__ long dst_index(const xva_wn_desc& d, int r, int c, int j) {
+template <class Desc>
+__device__ __forceinline__ long dst_index(const Desc& d, int r, int c, int j) {
   if (d.flags & XVA_WN_TRANSPOSED) return d.tap_off[j] + static_cast<long>(c) * d.ld + r;
   return d.tap_off[j] + static_cast<long>(r) * d.ld + ((r / d.og) % d.f) * d.cg + c;
 }
@@ -173,6 +174,203 @@ wn_pack_bwd_kernel(const xva_wn_desc* __restrict__ table, int n_desc, int allow_
   if (threadIdx.x == 0) d.dg[r] += dot * inv_norm;
 }
 
+
+// ================================================================================================ spectral norm
+// torch.nn.utils.spectral_norm (dim 0, one power iteration per training forward, eps 1e-12) + the same re-packing, for
+// the spectral-normed scale discriminator (hifigan/models.py:207-215 with use_spectral_norm): with W = weight_orig
+// reshaped [rows, inner], u [rows], v [inner]
+//     v <- normalize(W^T u),  u <- normalize(W v),  sigma = u . (W v),  w_eff = W / sigma
+// and, with u, v constants as in torch, dL/dW = dW_eff / sigma - (<dW_eff, W> / sigma^2) u v^T.
+// PyTorch eager spends ~14 launches per convolution and call on this (reshape, 3 mv, 2 normalize, clones, dot, div,
+// index_select, permute, mask, contiguous, round) plus their autograd mirror -- and the reference calls the
+// discriminator four times per step: ~450 launches, 3.2 ms of a 29.7 ms step (measured by replacing the spectral norm
+// with weight norm, profiles/r02_spectral_norm_ab.txt). Here a call is 5 launches for all 8 convolutions (3 in eval
+// mode), its backward 3; deterministic (two-stage sums, no floating-point atomics).
+constexpr int kSnRowChunk = 64;
+
+__device__ __forceinline__ const xva_sn_desc* find_sn_row(const xva_sn_desc* table, int n_desc, int row) {
+  int lo = 0, hi = n_desc - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (table[mid].row_start <= row) lo = mid;
+    else hi = mid - 1;
+  }
+  return table + lo;
+}
+__device__ __forceinline__ const xva_sn_desc* find_sn_blk(const xva_sn_desc* table, int n_desc, int blk) {
+  int lo = 0, hi = n_desc - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (table[mid].blk_start <= blk) lo = mid;
+    else hi = mid - 1;
+  }
+  return table + lo;
+}
+// scratch layout of one descriptor: [chunks * inner] partial column sums | [rows] row products | sigma, coef
+__device__ __forceinline__ int sn_chunks(const xva_sn_desc& d) { return (d.rows + kSnRowChunk - 1) / kSnRowChunk; }
+__device__ __forceinline__ float* sn_rowbuf(const xva_sn_desc& d) { return d.work + static_cast<long>(sn_chunks(d)) * d.inner; }
+__device__ __forceinline__ float* sn_scalars(const xva_sn_desc& d) { return sn_rowbuf(d) + d.rows; }
+
+// K1: partial[rc][c] = sum over the 64 rows of chunk rc of W[r, c] * u[r]
+__global__ void __launch_bounds__(kThreadsWn)
+sn_colsum_kernel(const xva_sn_desc* __restrict__ table, int n_desc) {
+  const xva_sn_desc& d = *find_sn_blk(table, n_desc, blockIdx.x);
+  const int local = blockIdx.x - d.blk_start;
+  const int ncc = (d.inner + kThreadsWn - 1) / kThreadsWn;
+  const int cc = local % ncc, rc = local / ncc;
+  const int c = cc * kThreadsWn + threadIdx.x;
+  if (c >= d.inner) return;
+  const int r0 = rc * kSnRowChunk, r1 = min(d.rows, r0 + kSnRowChunk);
+  const float* w = d.w + static_cast<long>(r0) * d.inner + c;
+  float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f, acc3 = 0.0f;
+  int r = r0;
+  for (; r + 4 <= r1; r += 4, w += 4L * d.inner) {  // four independent loads in flight per thread
+    acc0 += w[0] * d.u[r];
+    acc1 += w[d.inner] * d.u[r + 1];
+    acc2 += w[2L * d.inner] * d.u[r + 2];
+    acc3 += w[3L * d.inner] * d.u[r + 3];
+  }
+  for (; r < r1; ++r, w += d.inner) acc0 += w[0] * d.u[r];
+  d.work[static_cast<long>(rc) * d.inner + c] = (acc0 + acc1) + (acc2 + acc3);
+}
+
+// K2 (one block per descriptor): t = sum of the partials; v = t / max(||t||, eps) -> module buffer and the call's copy
+__global__ void __launch_bounds__(kThreadsWn)
+sn_normalize_v_kernel(const xva_sn_desc* __restrict__ table) {
+  __shared__ float red[kThreadsWn / 32];
+  const xva_sn_desc& d = table[blockIdx.x];
+  const int chunks = sn_chunks(d);
+  float ss = 0.0f;
+  for (int c = threadIdx.x; c < d.inner; c += kThreadsWn) {
+    float t = 0.0f;
+    for (int rc = 0; rc < chunks; ++rc) t += d.work[static_cast<long>(rc) * d.inner + c];
+    d.work[c] = t;  // (chunk 0's slot: read by this thread only)
+    ss += t * t;
+  }
+  ss = block_sum_f(ss, red);
+  const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+  for (int c = threadIdx.x; c < d.inner; c += kThreadsWn) {
+    const float x = d.work[c] * inv;
+    d.v[c] = x;
+    d.v_sav[c] = x;
+  }
+}
+
+// K3 (one block per row): s[r] = W[r, :] . v
+__global__ void __launch_bounds__(kThreadsWn)
+sn_rowdot_kernel(const xva_sn_desc* __restrict__ table, int n_desc, int training) {
+  __shared__ float red[kThreadsWn / 32];
+  const xva_sn_desc& d = *find_sn_row(table, n_desc, blockIdx.x);
+  const int r = blockIdx.x - d.row_start;
+  const float* w = d.w + static_cast<long>(r) * d.inner;
+  const float* v = training ? d.v_sav : d.v;
+  float acc = 0.0f;
+  for (int i = threadIdx.x; i < d.inner; i += kThreadsWn) acc += w[i] * v[i];
+  acc = block_sum_f(acc, red);
+  if (threadIdx.x == 0) sn_rowbuf(d)[r] = acc;
+}
+
+// K4 (one block per descriptor): training: u = s / max(||s||, eps); sigma = u . s.  eval: sigma = u . s with the stored u.
+__global__ void __launch_bounds__(kThreadsWn)
+sn_sigma_kernel(const xva_sn_desc* __restrict__ table, int training) {
+  __shared__ float red[kThreadsWn / 32];
+  const xva_sn_desc& d = table[blockIdx.x];
+  const float* s = sn_rowbuf(d);
+  float sigma;
+  if (training) {
+    float ss = 0.0f;
+    for (int r = threadIdx.x; r < d.rows; r += kThreadsWn) ss += s[r] * s[r];
+    ss = block_sum_f(ss, red);
+    const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+    float dot = 0.0f;
+    for (int r = threadIdx.x; r < d.rows; r += kThreadsWn) {
+      const float x = s[r] * inv;
+      d.u[r] = x;
+      d.u_sav[r] = x;
+      dot += x * s[r];
+    }
+    sigma = block_sum_f(dot, red);
+  } else {
+    float dot = 0.0f;
+    for (int r = threadIdx.x; r < d.rows; r += kThreadsWn) {
+      d.u_sav[r] = d.u[r];
+      dot += d.u[r] * s[r];
+    }
+    sigma = block_sum_f(dot, red);
+    for (int c = threadIdx.x; c < d.inner; c += kThreadsWn) d.v_sav[c] = d.v[c];
+  }
+  if (threadIdx.x == 0) sn_scalars(d)[0] = sigma;
+}
+
+// K5 (one block per row): dst = W[r, :] / sigma in the packed layout, tf32-rounded
+__global__ void __launch_bounds__(kThreadsWn)
+sn_pack_kernel(const xva_sn_desc* __restrict__ table, int n_desc) {
+  extern __shared__ float row_s[];
+  const xva_sn_desc& d = *find_sn_row(table, n_desc, blockIdx.x);
+  const int r = blockIdx.x - d.row_start;
+  const int inner = d.inner, k = d.k, c2 = inner / k;
+  const float* w = d.w + static_cast<long>(r) * inner;
+  for (int i = threadIdx.x; i < inner; i += kThreadsWn) row_s[i] = w[i];
+  __syncthreads();
+  const float scale = 1.0f / sn_scalars(d)[0];
+  const bool rnd = !(d.flags & XVA_WN_NO_ROUND);
+  for (int i = threadIdx.x; i < inner; i += kThreadsWn) {
+    const int j = i / c2, c = i - j * c2;
+    const float x = row_s[c * k + j] * scale;
+    d.dst[dst_index(d, r, c, j)] = rnd ? tf32_rn(x) : x;
+  }
+}
+
+// B1 (one block per row): rowdot[r] = <dW_eff[r, :], W[r, :]>
+__global__ void __launch_bounds__(kThreadsWn)
+sn_bwd_rowdot_kernel(const xva_sn_desc* __restrict__ table, int n_desc) {
+  __shared__ float red[kThreadsWn / 32];
+  const xva_sn_desc& d = *find_sn_row(table, n_desc, blockIdx.x);
+  const int r = blockIdx.x - d.row_start;
+  const int inner = d.inner, k = d.k, c2 = inner / k;
+  const float* w = d.w + static_cast<long>(r) * inner;
+  float acc = 0.0f;
+  for (int i = threadIdx.x; i < inner; i += kThreadsWn) {
+    const int j = i / c2, c = i - j * c2;
+    acc += d.ddst[dst_index(d, r, c, j)] * w[c * k + j];
+  }
+  acc = block_sum_f(acc, red);
+  if (threadIdx.x == 0) sn_rowbuf(d)[r] = acc;
+}
+
+// B2 (one block per descriptor): coef = <dW_eff, W> / sigma^2
+__global__ void __launch_bounds__(kThreadsWn)
+sn_bwd_coef_kernel(const xva_sn_desc* __restrict__ table) {
+  __shared__ float red[kThreadsWn / 32];
+  const xva_sn_desc& d = table[blockIdx.x];
+  const float* s = sn_rowbuf(d);
+  float acc = 0.0f;
+  for (int r = threadIdx.x; r < d.rows; r += kThreadsWn) acc += s[r];
+  acc = block_sum_f(acc, red);
+  if (threadIdx.x == 0) {
+    const float sigma = sn_scalars(d)[0];
+    sn_scalars(d)[1] = acc / (sigma * sigma);
+  }
+}
+
+// B3 (one block per row): dw[r, i] += dW_eff[r, i] / sigma - coef * u[r] * v[i]
+__global__ void __launch_bounds__(kThreadsWn)
+sn_bwd_apply_kernel(const xva_sn_desc* __restrict__ table, int n_desc) {
+  extern __shared__ float row_d[];
+  const xva_sn_desc& d = *find_sn_row(table, n_desc, blockIdx.x);
+  const int r = blockIdx.x - d.row_start;
+  const int inner = d.inner, k = d.k, c2 = inner / k;
+  for (int i = threadIdx.x; i < inner; i += kThreadsWn) {
+    const int j = i / c2, c = i - j * c2;
+    row_d[c * k + j] = d.ddst[dst_index(d, r, c, j)];
+  }
+  __syncthreads();
+  const float inv_sigma = 1.0f / sn_scalars(d)[0];
+  const float cu = sn_scalars(d)[1] * d.u_sav[r];
+  float* dw = d.dw + static_cast<long>(r) * inner;
+  for (int i = threadIdx.x; i < inner; i += kThreadsWn) dw[i] += row_d[i] * inv_sigma - cu * d.v_sav[i];
+}
+
 }  // namespace
 
 int wn_pack(const xva_wn_desc* table_dev, int n_desc, int total_rows, int max_inner, int backward, cudaStream_t stream) {
@@ -191,6 +389,34 @@ int wn_pack(const xva_wn_desc* table_dev, int n_desc, int total_rows, int max_in
   }();
   if (backward) wn_pack_bwd_kernel<<<total_rows, kThreadsWn, smem, stream>>>(table_dev, n_desc, allow_vec);
   else wn_pack_fwd_kernel<<<total_rows, kThreadsWn, smem, stream>>>(table_dev, n_desc, allow_vec);
+  XVA_CHECK_LAUNCH();
+  return XVA_OK;
+}
+
+int sn_pack(const xva_sn_desc* table_dev, int n_desc, int total_rows, int total_blocks, int max_inner, int training,
+            int backward, cudaStream_t stream) {
+  XVA_CHECK_ARG(table_dev && n_desc >= 1 && total_rows >= 1 && total_blocks >= 1, "sn_pack: empty table");
+  const size_t smem = static_cast<size_t>(max_inner) * sizeof(float);
+  XVA_CHECK_ARG(max_inner >= 1 && smem <= 96 * 1024, "sn_pack: max_inner=%d does not fit shared memory", max_inner);
+  static bool attr_done = false;
+  if (!attr_done) {
+    XVA_CHECK_CUDA(cudaFuncSetAttribute(sn_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    XVA_CHECK_CUDA(cudaFuncSetAttribute(sn_bwd_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    attr_done = true;
+  }
+  if (!backward) {
+    if (training) {
+      sn_colsum_kernel<<<total_blocks, kThreadsWn, 0, stream>>>(table_dev, n_desc);
+      sn_normalize_v_kernel<<<n_desc, kThreadsWn, 0, stream>>>(table_dev);
+    }
+    sn_rowdot_kernel<<<total_rows, kThreadsWn, 0, stream>>>(table_dev, n_desc, training);
+    sn_sigma_kernel<<<n_desc, kThreadsWn, 0, stream>>>(table_dev, training);
+    sn_pack_kernel<<<total_rows, kThreadsWn, smem, stream>>>(table_dev, n_desc);
+  } else {
+    sn_bwd_rowdot_kernel<<<total_rows, kThreadsWn, 0, stream>>>(table_dev, n_desc);
+    sn_bwd_coef_kernel<<<n_desc, kThreadsWn, 0, stream>>>(table_dev);
+    sn_bwd_apply_kernel<<<total_rows, kThreadsWn, smem, stream>>>(table_dev, n_desc);
+  }
   XVA_CHECK_LAUNCH();
   return XVA_OK;
 }

@@ -318,6 +318,97 @@ class _WnPacker:
         capi.call("xva_wn_pack_bwd", ops._p(self.table), len(self.items), self.rows, self.max_inner, ops._stream())
 
 
+class _SnPacker:
+    """Spectral-normed convolutions of a model (torch.nn.utils.spectral_norm: weight_orig, weight_u, weight_v): power
+    iteration, sigma, w = weight_orig / sigma and the re-packing for the tap-GEMM in 5 launches per call
+    (xva_sn_pack_fwd; 3 in eval mode), the way back to weight_orig.grad in 3 (xva_sn_pack_bwd). ``slots`` calls per
+    forward keep their own packed weights, gradient arena and (u, v, sigma): the reference runs the discriminator on the
+    real and on the generated waveform separately, each call advancing the power iteration (models.py:251-252)."""
+
+    def __init__(self, slots=2):
+        self.slots = slots
+        self.items = []
+        self.layout = {}
+        self.size = 0
+        self._tables = [None] * slots
+        self._ptrs = [None] * slots
+
+    _alloc = _WnPacker._alloc
+
+    def add_conv(self, key, m, cout, cg, k, order=None, og=None, f=1, ld=None):
+        ld = f * cg if ld is None else int(ld)
+        off = self._alloc(key, (k, cout, ld))
+        order = list(range(k)) if order is None else list(order)
+        taps = [0] * k
+        for pos, j in enumerate(order):
+            taps[j] = off + pos * cout * ld
+        self.items.append((m, 0, ld, og if og else cout, f, cg, taps))
+
+    def add_flat(self, key, m, cout, k):
+        off = self._alloc(key, (cout, k))
+        self.items.append((m, capi.WN_NO_ROUND, k, cout, 1, 0, [off + j for j in range(k)]))
+
+    def finalize(self, device):
+        z = lambda n: torch.zeros(n, device=device, dtype=torch.float32)
+        self.arena = [z(self.size) for _ in range(self.slots)]
+        self.garena = [z(self.size) for _ in range(self.slots)]
+        view = lambda a: {k: tuple(a[o:o + int(math.prod(sh))].view(sh) for o, sh in v) for k, v in self.layout.items()}
+        self.W, self.gW = [view(a) for a in self.arena], [view(a) for a in self.garena]
+        self.rows = sum(m.weight_orig.shape[0] for m, *_ in self.items)
+        geo = [(m.weight_orig.shape[0], m.weight_orig.numel() // m.weight_orig.shape[0]) for m, *_ in self.items]
+        self.max_inner = max(i for _, i in geo)
+        self.blocks = sum(((i + 255) // 256) * ((r + 63) // 64) for r, i in geo)
+        self.work = [[z(((r + 63) // 64) * i + r + 2) for r, i in geo] for _ in range(self.slots)]
+        self.u_sav = [[z(r) for r, _ in geo] for _ in range(self.slots)]
+        self.v_sav = [[z(i) for _, i in geo] for _ in range(self.slots)]
+
+    def _sync(self, slot, grads):
+        ptrs = []
+        for m, *_ in self.items:
+            if grads and m.weight_orig.grad is None:
+                m.weight_orig.grad = torch.zeros_like(m.weight_orig)
+            ptrs.append((m.weight_orig.data_ptr(), m.weight_u.data_ptr(), m.weight_v.data_ptr(),
+                         m.weight_orig.grad.data_ptr() if m.weight_orig.grad is not None else 0))
+        if ptrs == self._ptrs[slot]:
+            return
+        arr = (capi.SnDesc * len(self.items))()
+        row = blk = 0
+        for n, (d, (m, flags, ld, og, f, cg, taps), (pw, pu, pv, pdw)) in enumerate(zip(arr, self.items, ptrs)):
+            w = m.weight_orig
+            assert w.is_contiguous() and m.weight_u.is_contiguous() and m.weight_v.is_contiguous()
+            rows, inner = w.shape[0], w.numel() // w.shape[0]
+            d.w, d.u, d.v, d.dw = pw, pu, pv, pdw
+            d.u_sav, d.v_sav = self.u_sav[slot][n].data_ptr(), self.v_sav[slot][n].data_ptr()
+            d.dst, d.ddst, d.work = self.arena[slot].data_ptr(), self.garena[slot].data_ptr(), self.work[slot][n].data_ptr()
+            d.rows, d.inner, d.k, d.flags = rows, inner, len(taps), flags
+            d.ld, d.og, d.f, d.cg = ld, og, f, cg
+            d.row_start, d.blk_start = row, blk
+            row += rows
+            blk += ((inner + 255) // 256) * ((rows + 63) // 64)
+            for j, t in enumerate(taps):
+                d.tap_off[j] = t
+        host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+        self._tables[slot] = host.to(self.arena[slot].device)
+        self._ptrs[slot] = ptrs
+
+    def pack(self, slot, training):
+        self._sync(slot, False)
+        capi.call("xva_sn_pack_fwd", ops._p(self._tables[slot]), len(self.items), self.rows, self.blocks, self.max_inner,
+                  int(bool(training)), ops._stream())
+        return self.W[slot]
+
+    def zero_grads(self):
+        for a in self.garena:
+            a.zero_()
+
+    def unpack_grads(self):
+        _Side.join()
+        for slot in range(self.slots):
+            self._sync(slot, True)
+            capi.call("xva_sn_pack_bwd", ops._p(self._tables[slot]), len(self.items), self.rows, self.blocks, self.max_inner,
+                      ops._stream())
+
+
 class ResBlock1(nn.Module):
     def __init__(self, h, channels, kernel_size=3, dilation=(1, 3, 5)):
         super().__init__()
@@ -1100,7 +1191,8 @@ class MultiScaleDiscriminator(nn.Module):
 
     def __init__(self, device=None, seed=1234):
         super().__init__()
-        self.discriminators = nn.ModuleList([DiscriminatorS(use_spectral_norm=True), DiscriminatorS(), DiscriminatorS()])
+        sn = os.environ.get("XVA_DEBUG_NO_SPECTRAL", "0") != "1"     # diagnostic only: bounds what the spectral-norm path costs
+        self.discriminators = nn.ModuleList([DiscriminatorS(use_spectral_norm=sn), DiscriminatorS(), DiscriminatorS()])
         _init_disc(self, seed + 1, device)
 
     def forward(self, y, y_hat, weight_grad=True, join=True, stream_offset=0):
@@ -1191,6 +1283,14 @@ def _multi_forward(model, y, y_hat, pools, weight_grad=True, join=True, stream_o
         pk.finalize(both.device)
         model._packer = pk
     Wall = pk.pack()                      # every weight-normed convolution of the model: one launch
+    sn = getattr(model, "_sn", None)
+    if sn is None and os.environ.get("XVA_SN_NATIVE", "1") != "0" and any(m.spectral for d in model.discriminators for m in d.convs):
+        sn = _SnPacker(slots=2)
+        for i, d in enumerate(model.discriminators):
+            if any(m.spectral for m in d.convs):
+                d.register_weights(sn, str(i))
+        sn.finalize(both.device)
+        model._sn = sn
     n_layers = lambda d: len(d.convs) + 1
     y_d_rs, y_d_gs, fmap_rs, fmap_gs = [], [], [], []
     inputs = [both]                       # every pooled waveform stays referenced until the branches have been joined
@@ -1199,7 +1299,16 @@ def _multi_forward(model, y, y_hat, pools, weight_grad=True, join=True, stream_o
             both = ops.avgpool4(both)
             inputs.append(both)
         with _Branches.branch(i + stream_offset):
-            if any(m.spectral for m in d.convs):
+            if any(m.spectral for m in d.convs) and sn is not None:
+                # one power iteration + pack per call, real first (models.py:251-252), each call with its own weights
+                outs = []
+                for slot, part in ((0, both[:B]), (1, both[B:])):
+                    Ws = sn.pack(slot, model.training)
+                    outs.append(d(part, weight_grad=weight_grad, W=[Ws[f"{i}.{li}"][0] for li in range(n_layers(d))],
+                                  gW=[sn.gW[slot][f"{i}.{li}"][0] for li in range(n_layers(d))]))
+                (sr, fr, cr), (sg, fg, cg) = outs
+                passes = [(cr, (0, cr["Z"]), None), (cg, None, (0, cg["Z"]))]
+            elif any(m.spectral for m in d.convs):
                 sr, fr, cr = d(both[:B], weight_grad=weight_grad)
                 sg, fg, cg = d(both[B:], weight_grad=weight_grad)
                 passes = [(cr, (0, cr["Z"]), None), (cg, None, (0, cg["Z"]))]
@@ -1232,6 +1341,8 @@ def discriminator_loss_backward(model, y_d_rs, y_d_gs, join=True, stream_offset=
     dev = y_d_rs[0].device
     acc = torch.zeros(2 * len(y_d_rs), device=dev, dtype=torch.float64)
     model._packer.zero_grads()
+    if getattr(model, "_sn", None) is not None:
+        model._sn.zero_grads()
     parts = []
     for i, (d, passes) in enumerate(zip(model.discriminators, model._ctx)):
         with _Branches.branch(i + stream_offset):
@@ -1253,6 +1364,8 @@ def discriminator_loss_backward(model, y_d_rs, y_d_gs, join=True, stream_offset=
         for part in parts:                # same summation order as one sub-discriminator after the other
             loss = loss + part
         model._packer.unpack_grads()      # packed-weight gradients -> weight_g / weight_v of every sub-discriminator
+        if getattr(model, "_sn", None) is not None:
+            model._sn.unpack_grads()      # ... and -> weight_orig of the spectral-normed one
         model._branch_inputs = None
         return loss
 
