@@ -98,6 +98,18 @@ def main():
     lines.append("kernel time by name (all streams):")
     for n, t in byname.most_common(10):
         lines.append(f"  {t / 1e3:7.3f} ms  {n}")
+    nb = 40
+    lines.append(f"timeline in {nb} buckets of {span / nb:.2f} ms: average kernels in flight | the two kernels with most time in the bucket")
+    for b in range(nb):
+        lo, hi = t0 + (t1 - t0) * b / nb, t0 + (t1 - t0) * (b + 1) / nb
+        acc = collections.Counter()
+        for s_, e_, n in ker:
+            ov = min(e_, hi) - max(s_, lo)
+            if ov > 0:
+                acc[n.split("(")[0].replace("void ", "").replace("xva::", "").replace("anonymous namespace)::", "")[:44] + ("<" + n.split("<")[1].split(">")[0] + ">" if "gemm_tc_kernel<" in n else "")] += ov
+        tot = sum(acc.values())
+        top = ", ".join(f"{k} {100 * v / tot:.0f}%" for k, v in acc.most_common(2)) if tot else ""
+        lines.append(f"  {b:2d} {tot / (hi - lo):5.2f} | {top}")
     open(out, "w").write("\n".join(lines) + "\n")
     print("\n".join(lines))
 

@@ -75,6 +75,52 @@ conv_c1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, con
   }
 }
 
+
+// Register-tiled variant for the two filter shapes the discriminators use (k15 s1: scale discriminators; k5 s3: period
+// discriminators). The kernel above issues two shared-memory loads per FMA and runs at ~0.6 TB/s of output; here a
+// thread keeps its channel's K filter taps in registers and slides a register window of the input over 8 consecutive
+// output rows: (7 S + K) broadcast loads per 8 K FMAs. thread = (channel, row group), channel fastest: the [rows, Cout]
+// store stays fully coalesced.
+template <int K, int S>
+__global__ void __launch_bounds__(256)
+conv_c1_fwd_tiled_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, C1 p,
+                         int tiles_per_seq, float* __restrict__ out) {
+  constexpr int R = 8, WIN = (R - 1) * S + K;
+  __shared__ float xs[(kRowsFwd - 1) * S + K + WIN];  // (+ slack: a partial last chunk reads a full window)
+  const int z = blockIdx.x / tiles_per_seq, t0 = (blockIdx.x - z * tiles_per_seq) * kRowsFwd;
+  constexpr int win_tile = (kRowsFwd - 1) * S + K;
+  for (int i = threadIdx.x; i < win_tile + WIN; i += blockDim.x) {
+    const int q = t0 * S - p.pad + i;
+    xs[i] = (i < win_tile && q >= 0 && q < p.L) ? x[c1_src(p, z, q)] : 0.0f;
+  }
+  const int co = threadIdx.x % p.Cout, rg = threadIdx.x / p.Cout, groups = blockDim.x / p.Cout;
+  float wr[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) wr[j] = w[co * K + j];
+  const float b = bias[co];
+  __syncthreads();
+  if (rg >= groups) return;
+  const int rows = min(kRowsFwd, p.Lout_p - t0);
+  float* o = out + (static_cast<long>(z) * p.Lout_p + t0) * p.Cout + co;
+  for (int r0 = rg * R; r0 < rows; r0 += groups * R) {
+    float xw[WIN];
+#pragma unroll
+    for (int i = 0; i < WIN; ++i) xw[i] = xs[r0 * S + i];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (r0 + r >= rows) break;
+      float acc = 0.0f;
+      if (t0 + r0 + r < p.Lout) {  // alignment rows [Lout, Lout_p) stay zero
+        acc = b;
+#pragma unroll
+        for (int j = 0; j < K; ++j) acc = fmaf(wr[j], xw[r * S + j], acc);
+        acc = tf32_rn(acc > 0.0f ? acc : p.slope * acc);
+      }
+      o[static_cast<long>(r0 + r) * p.Cout] = acc;
+    }
+  }
+}
+
 // dw[co, j] += sum_rows dpre[row, co] * x(row, j) ; db[co] += sum_rows dpre[row, co].
 // A block owns kRowsBwdW rows of one sequence (input window in shared memory); thread = (channel, row slice): the
 // Cout channels are spread over the lanes (coalesced dpre rows), 256 / Cout row slices run in parallel and are summed
@@ -141,6 +187,50 @@ conv_c1_bwd_x_kernel(const float* __restrict__ dpre, const float* __restrict__ w
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   if (lane == 0) atomicAdd(dx + c1_src(p, z, q), scale * acc);
+}
+
+
+// Tiled variant: a block owns 64 consecutive input samples of one sequence; the dpre rows they touch and the filter
+// bank [k][Cout] sit in shared memory (the kernel above re-reads every dpre row k / s times from L2 with one dependent
+// load chain per warp: latency-bound at ~100 us for the 16 x 8192 x 128 scale discriminator). One warp per sample,
+// lanes over the channels.
+constexpr int kTileQ = 64;
+__global__ void __launch_bounds__(256)
+conv_c1_bwd_x_tiled_kernel(const float* __restrict__ dpre, const float* __restrict__ w, C1 p, int tiles_per_seq, int t_rows,
+                           float scale, float* __restrict__ dx) {
+  extern __shared__ float sm[];
+  float* ws = sm;                      // [k][Cout]
+  float* ds = sm + p.k * p.Cout;       // [t_rows][Cout]
+  const int z = blockIdx.x / tiles_per_seq, q0 = (blockIdx.x - z * tiles_per_seq) * kTileQ;
+  // first dpre row any sample of the tile can touch: t = ceil((q0 + pad - (k - 1)) / s), clamped at 0
+  const int lo_num = q0 + p.pad - (p.k - 1);
+  const int t_lo = lo_num <= 0 ? 0 : (lo_num + p.s - 1) / p.s;
+  for (int i = threadIdx.x; i < p.Cout * p.k; i += blockDim.x) {
+    const int co = i / p.k, j = i - co * p.k;
+    ws[j * p.Cout + co] = w[i];
+  }
+  const float* d = dpre + (static_cast<long>(z) * p.Lout_p + t_lo) * p.Cout;
+  const int valid = max(0, min(t_rows, p.Lout - t_lo));
+  for (int i = threadIdx.x; i < t_rows * p.Cout; i += blockDim.x) ds[i] = (i < valid * p.Cout) ? d[i] : 0.0f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int qq = warp; qq < kTileQ; qq += 8) {
+    const int q = q0 + qq;
+    if (q >= p.L) break;
+    float acc = 0.0f;
+    for (int j = 0; j < p.k; ++j) {
+      const int num = q + p.pad - j;
+      if (num < 0 || num % p.s) continue;
+      const int t = num / p.s - t_lo;
+      if (t < 0 || t >= valid) continue;
+      const float* dr = ds + t * p.Cout;
+      const float* wj = ws + j * p.Cout;
+      for (int co = lane; co < p.Cout; co += 32) acc = fmaf(dr[co], wj[co], acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) atomicAdd(dx + c1_src(p, z, q), scale * acc);
+  }
 }
 
 // AvgPool1d(4, 2, padding=2), count_include_pad: out[i] = (x[2i-2] + x[2i-1] + x[2i] + x[2i+1]) / 4
@@ -213,7 +303,14 @@ int conv_c1_fwd(const float* x, long xs_b, int xs_q, int xs_c, int P, int Lsrc, 
   if (rc != XVA_OK) return rc;
   XVA_CHECK_ARG(Cout <= 128 && s <= 4, "conv_c1 fwd: Cout=%d (max 128), stride=%d (max 4)", Cout, s);
   const int tiles = ceil_div(Lout_p, kRowsFwd);
-  conv_c1_fwd_kernel<<<Z * tiles, 256, 0, stream>>>(x, w, bias, p, tiles, out);
+  static const bool tiled = [] {  // XVA_C1_TILED=0: the original kernels (A/B and debugging)
+    const char* e = getenv("XVA_C1_TILED");
+    return !(e && e[0] == '0');
+  }();
+  const bool fits = tiled && Cout <= 256 && 256 % Cout == 0;
+  if (fits && k == 15 && s == 1) conv_c1_fwd_tiled_kernel<15, 1><<<Z * tiles, 256, 0, stream>>>(x, w, bias, p, tiles, out);
+  else if (fits && k == 5 && s == 3) conv_c1_fwd_tiled_kernel<5, 3><<<Z * tiles, 256, 0, stream>>>(x, w, bias, p, tiles, out);
+  else conv_c1_fwd_kernel<<<Z * tiles, 256, 0, stream>>>(x, w, bias, p, tiles, out);
   XVA_CHECK_LAUNCH();
   return XVA_OK;
 }
@@ -236,7 +333,24 @@ int conv_c1_bwd_x(const float* dpre, const float* w, long xs_b, int xs_q, int xs
   int rc = fill(&p, xs_b, xs_q, xs_c, P, Lsrc, L, k, s, pad, Lout, Lout_p, Cout, 0.0f);
   if (rc != XVA_OK) return rc;
   const long items = static_cast<long>(Z) * L;
-  conv_c1_bwd_x_kernel<<<static_cast<int>(ceil_div_l(items, 8)), 256, 0, stream>>>(dpre, w, p, items, scale, dx);
+  static const bool tiled = [] {
+    const char* e = getenv("XVA_C1_TILED");
+    return !(e && e[0] == '0');
+  }();
+  // dpre rows one tile of kTileQ samples can touch: ceil((kTileQ - 1 + k - 1) / s) + 1
+  const int t_rows = (kTileQ + k - 2) / s + 2;
+  const size_t smem = (static_cast<size_t>(k) + t_rows) * Cout * sizeof(float);
+  if (tiled && smem <= 64 * 1024) {
+    static bool attr_done = false;
+    if (!attr_done) {
+      XVA_CHECK_CUDA(cudaFuncSetAttribute(conv_c1_bwd_x_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      attr_done = true;
+    }
+    const int tiles = ceil_div(L, kTileQ);
+    conv_c1_bwd_x_tiled_kernel<<<Z * tiles, 256, smem, stream>>>(dpre, w, p, tiles, t_rows, scale, dx);
+  } else {
+    conv_c1_bwd_x_kernel<<<static_cast<int>(ceil_div_l(items, 8)), 256, 0, stream>>>(dpre, w, p, items, scale, dx);
+  }
   XVA_CHECK_LAUNCH();
   return XVA_OK;
 }
