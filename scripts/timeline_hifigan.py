@@ -18,6 +18,34 @@ from xva_trainer_b200 import graph, hifigan as hg, synthetic, vits
 
 
 def build(which, dev):
+    if which == "fastpitch":
+        from xva_trainer_b200 import fastpitch as fp
+
+        model = fp.FastPitch(device=dev, seed=1234)
+        model.training_stage = 3
+        model.train()
+        crit = fp.FastPitchLoss()
+        crit.training_stage = 3
+        opt = fp.Lamb(model, lr=0.1, betas=(0.9, 0.98), eps=1e-9, weight_decay=1e-6)
+        x_cpu, _ = synthetic.fastpitch_batch(32, 160, 880, seed=1234, ragged=False)
+        host_lens = (880, int(x_cpu[3].max()))
+        x_dev = [t.to(dev) if torch.is_tensor(t) else t for t in x_cpu]
+        idx = [i for i, t in enumerate(x_dev) if torch.is_tensor(t)]
+        opt.lr_on_device = True
+
+        def step(*tensors):
+            xs = list(x_dev)
+            for i, t in zip(idx, tensors):
+                xs[i] = t
+            model.zero_grad()
+            out = model(xs, host_lens=host_lens)
+            loss, _ = crit(out, [xs[2], xs[1], xs[3], xs[9]])
+            model.backward(crit, 1.0)
+            opt.step()
+            model.step_dropout()
+            return loss
+
+        return graph.GraphedStep(step, [x_dev[i] for i in idx], warmup=3)
     if which == "vits":
         enc = vits.PosteriorEncoder(513, 192, 192, kernel_size=5, dilation_rate=1, num_layers=16, cond_channels=512, device=dev)
         dec = hg.HifiganGenerator(192, 1, "1", [[1, 3, 5]] * 3, [3, 7, 11], [16, 16, 4, 4], 512, [8, 8, 2, 2],

@@ -25,10 +25,23 @@ class _FakeStream:
     def __init__(self, *a, **k):
         pass
 
+    cuda_stream = 0
+
     def wait_stream(self, other):
         _FakeStream.waits += 1
 
+    def wait_event(self, event):
+        _FakeStream.waits += 1
+
     def synchronize(self):
+        pass
+
+
+class _FakeEvent:
+    def __init__(self, *a, **k):
+        pass
+
+    def record(self, stream=None):
         pass
 
 
@@ -73,13 +86,15 @@ def record(streams=False):
         return None if a is None else "ptr"
 
     saved = (capi.load, capi.call, ops._stream, ops._check3, ops.duration_scan)
-    saved_cuda = (torch.cuda.Stream, torch.cuda.stream, torch.cuda.current_stream, getattr(torch.Tensor, "record_stream", None))
+    saved_cuda = (torch.cuda.Stream, torch.cuda.stream, torch.cuda.current_stream, getattr(torch.Tensor, "record_stream", None),
+                  torch.cuda.Event)
     saved_env = {k: os.environ.get(k) for k in ("XVA_BWD_STREAMS", "XVA_DISC_STREAMS", "XVA_GEN_STREAMS")}
     Tm = 40
     try:
         if streams:
             os.environ.update(XVA_BWD_STREAMS="1", XVA_DISC_STREAMS="4", XVA_GEN_STREAMS="1")
             torch.cuda.Stream = _FakeStream
+            torch.cuda.Event = _FakeEvent
             torch.cuda.stream = lambda s: _NullCtx()
             torch.cuda.current_stream = lambda *a, **k: _FakeStream()
             torch.Tensor.record_stream = lambda self, s: None
@@ -146,6 +161,7 @@ def record(streams=False):
     finally:
         capi.load, capi.call, ops._stream, ops._check3, ops.duration_scan = saved
         torch.cuda.Stream, torch.cuda.stream, torch.cuda.current_stream = saved_cuda[:3]
+        torch.cuda.Event = saved_cuda[4]
         if saved_cuda[3] is not None:
             torch.Tensor.record_stream = saved_cuda[3]
         for k, v in saved_env.items():

@@ -411,6 +411,12 @@ class FastPitch(torch.nn.Module):
             return ops.capturing()
         return v not in ("0", "false", "off")
 
+    def _pred_side(self):
+        """Stream of the pitch / energy predictors when they run next to the decoder (forward and backward)."""
+        if getattr(self, "_pred_stream", None) is None:
+            self._pred_stream = torch.cuda.Stream(device=self.device_)
+        return self._pred_stream
+
     def _join_side(self):
         """Before anything reads the gradient arena from the main stream: GradSync.ready, the end of backward()."""
         if self._side is not None and self._side_used:
@@ -638,11 +644,26 @@ class FastPitch(torch.nn.Module):
 
         # ---- get_pitch_energy, model.py:394-423
         durs = dur_tgt.to(torch.float32).contiguous()
-        pitch_pred = self._pred_fwd(enc_out, in_lens32, self.pred["pitch"], save("pitch")).view(B, 1, Tt)
+        # The two predictors read the encoder output and the TARGET pitch / energy only, and nothing but the loss reads
+        # their outputs: with the side streams on (inside a captured graph) they run next to the decoder instead of in
+        # front of it -- 12 launches over 160-frame rows, 0.35 ms during which 40 of 148 SMs had work
+        # (profiles/r02_timeline_fastpitch.txt). Only the stream changes: program order, launches and arguments are the
+        # same with the streams off (tests/test_launch_sequence.py).
+        pred_par = self._side_on() and ctx is not None and stage == 3 and os.environ.get("XVA_PRED_STREAM", "1") != "0"
+        ps = self._pred_side() if pred_par else None
+
+        def on_pred_stream(fn):
+            if not pred_par:
+                return fn()
+            ps.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(ps):
+                return fn()
+
+        pitch_pred = on_pred_stream(lambda: self._pred_fwd(enc_out, in_lens32, self.pred["pitch"], save("pitch")).view(B, 1, Tt))
         pitch_tgt = ops.average_pitch(pitch_dense, durs)                                    # [B,1,Tt]
         enc2 = enc_out.clone()
         ops.scalar_conv_add_(enc2, pitch_tgt, self.w.pitch_emb_w, self.w.pitch_emb_b, in_lens32)
-        energy_pred = self._pred_fwd(enc2, in_lens32, self.pred["energy"], save("energy"))
+        energy_pred = on_pred_stream(lambda: self._pred_fwd(enc2, in_lens32, self.pred["energy"], save("energy")))
         energy_tgt = ops.average_pitch(energy_dense.view(B, 1, -1), durs, log1p=True)       # [B,1,Tt]
         enc3 = enc2.clone()
         ops.scalar_conv_add_(enc3, energy_tgt, self.w.energy_emb_w, self.w.energy_emb_b, in_lens32)
@@ -666,6 +687,11 @@ class FastPitch(torch.nn.Module):
         if ctx is not None:
             ctx.dec_out, ctx.cum, ctx.dec_lens, ctx.T_out = y, cum, dec_lens, T_out
             ctx.pitch_tgt, ctx.energy_tgt = pitch_tgt, energy_tgt
+        if pred_par:       # the criterion reads the predictions on the launching stream
+            cur = torch.cuda.current_stream()
+            cur.wait_stream(ps)
+            pitch_pred.record_stream(cur)
+            energy_pred.record_stream(cur)
         self._ctx = ctx
         dec_mask = (torch.arange(T_out, device=dev)[None, :] < dec_lens[:, None]).unsqueeze(2)
         return [mel_out, dec_mask, None, None, pitch_pred, pitch_tgt, energy_pred, energy_tgt, None, None, dur_tgt, None,
@@ -753,6 +779,14 @@ class FastPitch(torch.nn.Module):
             dmel = seeds["mel"]                                   # [B,T_out,96], columns 80.. are zero
             dm = dmel[..., :N_MEL]
             T_out = ctx.T_out
+            # the predictors' backward needs only its loss seeds: with the streams on it is ordered after THIS point
+            # only (an event), so inside a captured graph it runs next to the decoder's backward although it is issued
+            # after it -- program order, launches and arguments do not depend on the switch
+            pred_par = self._side_on() and stage == 3 and os.environ.get("XVA_PRED_STREAM", "1") != "0"
+            if pred_par:
+                ps = self._pred_side()
+                ev_start = torch.cuda.Event()
+                ev_start.record(torch.cuda.current_stream())
             ops.conv_wgrad(dm, ctx.dec_out, (0,), out=self.g.proj_w, accumulate=True)
             ops.colsum_(B * T_out, N_MEL, dmel.shape[2], dmel, self.g.proj_b)
             dy = ops.conv_dgrad(dm, self.w.proj_w, lens=ctx.dec_lens)
@@ -764,9 +798,21 @@ class FastPitch(torch.nn.Module):
             del dy
             ops.scalar_conv_bwd_(d_enc, ctx.energy_tgt, self.g.energy_emb_w, self.g.energy_emb_b)
             if stage == 3:
-                d_enc = self._pred_bwd(seeds["energy"], lens, self.pred["energy"], ctx.preds["energy"], residual=d_enc)
+                if pred_par:
+                    ps.wait_event(ev_start)
+                    with torch.cuda.stream(ps):
+                        d_en = self._pred_bwd(seeds["energy"], lens, self.pred["energy"], ctx.preds["energy"])
+                        d_pi = self._pred_bwd(seeds["pitch"], lens, self.pred["pitch"], ctx.preds["pitch"])
+                    cur = torch.cuda.current_stream()
+                    cur.wait_stream(ps)
+                    d_en.record_stream(cur)
+                    d_pi.record_stream(cur)
+                else:
+                    d_en = self._pred_bwd(seeds["energy"], lens, self.pred["energy"], ctx.preds["energy"])
+                    d_pi = self._pred_bwd(seeds["pitch"], lens, self.pred["pitch"], ctx.preds["pitch"])
+                d_enc.add_(d_en)          # d(enc2) = d(enc3) + the energy predictor's input gradient
                 ops.scalar_conv_bwd_(d_enc, ctx.pitch_tgt, self.g.pitch_emb_w, self.g.pitch_emb_b)
-                d_enc = self._pred_bwd(seeds["pitch"], lens, self.pred["pitch"], ctx.preds["pitch"], residual=d_enc)
+                d_enc.add_(d_pi)
             # the tail of the arena (pitch/energy predictors + embeddings, proj) is final, touched or not
             ready("pitch_predictor", "pitch_emb", "energy_predictor", "energy_emb", "proj", flush=True)
         with ops.nvtx("fastpitch.bwd.encoder"):
