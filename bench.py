@@ -228,6 +228,14 @@ def run_reference(args):
         hifi = {"metric": "audio-samples/s (HiFi-GAN v1 G+MPD+MSD train step)", "value": hr, "unit": "samples/s",
                 "ms_per_step": hper * 1e3, "cpu_baseline": {"value": hr, "unit": "samples/s", "cores": cores, "kind": hkind,
                 "sample": f"batch {hb} x 8192 samples (the config's batch), 1 warm-up + 3 timed steps, median, {cores} threads"}}
+    xva = None
+    if not args.no_hifigan and not args.no_xvapitch:
+        xr, xper, _, xkind = cpu_xvapitch_rate(16, 256, 2, 1)
+        xva = {"metric": "audio-samples/s (xVAPitch --hifi_only train step: posterior encoder + waveform decoder vs VITS discriminator)",
+               "value": xr, "unit": "samples/s", "ms_per_step": xper * 1e3,
+               "cpu_baseline": {"value": xr, "unit": "samples/s", "cores": cores, "kind": xkind,
+                                "sample": f"batch 16 x 256 spectrogram frames (the native arm's workload), 1 warm-up + 2 timed steps, "
+                                          f"median, {cores} threads"}}
     cfg = config(args, 1)
     cfg["launch"] = "PyTorch CPU, all host threads"
     cfg["global_batch"] = bs
@@ -239,6 +247,8 @@ def run_reference(args):
             "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "hifigan": hifi}
+    if xva is not None:
+        line["xvapitch_hifi_only"] = xva
     print(json.dumps(line), flush=True)
 
 
