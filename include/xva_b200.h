@@ -361,6 +361,15 @@ int xva_tanh_bwd(const float* dy, const float* y, int64_t rows, int ld, float* o
  *   xva_vits_sample_fwd: z = (mean + eps * exp(log_scale)) on rows t < lens[b], 0 elsewhere, with stats [B, T, 2C] =
  *     [mean | log_scale] (already masked by the projection's epilogue) and eps [B, T, C] the caller's N(0, 1) draw --
  *     replaces python/xvapitch/model.py:1473-1474.  xva_vits_sample_bwd: dstats = [dz | dz * eps * exp(log_scale)].
+ *   xva_vits_logp_operands: the two operands of the alignment log-likelihood of xVAPitch.train_step
+ *     (python/xvapitch/model.py:766-771: four terms, two einsums) as ONE batched product of K = 2C + 32 columns:
+ *     tok [B, Tt, K] = [exp(-2 logs_p) | m_p exp(-2 logs_p) | r | 0..], r = sum_c(-log(2 pi)/2 - logs_p - m_p^2 exp(-2 logs_p)/2);
+ *     frm [B, Ts, K] = [-z_p^2 / 2 | z_p | 1 | 0..]; logp[b, j, i] = <frm[b, j], tok[b, i]> (xva_gemm_ref: exact fp32, the
+ *     path search that follows -- xva_mas_width1 -- compares these values). Inputs channels-last [B, T, C].
+ *   xva_vits_kl: VitsGeneratorLoss.kl_loss (python/xvapitch/losses.py:86-103) and its four gradients in one pass:
+ *     *acc += sum over valid frames and channels of logs_p - logs_q - 1/2 + (z_p - m_p)^2 exp(-2 logs_p) / 2 (divide by
+ *     sum(lens) for the loss); dz_p, dlogs_q, dm_p, dlogs_p = scale / sum(lens) times the partial derivatives, zero on
+ *     frames >= lens[b]. All tensors [B, T, C].
  *   xva_colsum_items: out[z * out_ld + c] += sum_t x[z * z_stride + t * ld + c] for z < Z, t < rows, c < C -- the
  *     gradient of a per-utterance vector the forward broadcast over the frames (wavenet.py:99 g_l, hifigan.py:250).
  * ---------------------------------------------------------------------------------------------------------- */
@@ -368,6 +377,10 @@ int xva_gated_act_fwd(const float* x_in, int64_t rows, int H, int64_t ld_in, flo
 int xva_gated_act_bwd(const float* dacts, const float* x_in, int64_t rows, int H, int64_t ld_in, float* dx_in, void* stream);
 int xva_colsum_items(const float* x, int Z, int rows, int C, int64_t ld, int64_t z_stride, float* out, int64_t out_ld,
                      void* stream);
+int xva_vits_logp_operands(const float* m_p, const float* logs_p, const float* z_p, int B, int Tt, int Ts, int C, float* tok,
+                            float* frm, void* stream);
+int xva_vits_kl(const float* z_p, const float* logs_q, const float* m_p, const float* logs_p, const int32_t* lens, int B, int T,
+                int C, float scale, double* acc, float* dz_p, float* dlogs_q, float* dm_p, float* dlogs_p, void* stream);
 int xva_vits_sample_fwd(const float* stats, const float* eps, const int32_t* lens, int B, int T, int C, float* z, void* stream);
 int xva_vits_sample_bwd(const float* dz, const float* eps, const float* stats, const int32_t* lens, int B, int T, int C,
                         float* dstats, void* stream);

@@ -138,6 +138,63 @@ def residual_coupling_blocks(sd, x, x_mask, g=None, reverse=False):
     return x
 
 
+# ------------------------------------------------------------------------------------------------ alignment, prior, KL
+def maximum_path(value, x_lens, y_lens):
+    """xVAPitch's monotonic alignment search, python/xvapitch/util.py:14-53, restated: value [B, t_x, t_y] (masked with
+    mask[b, i, j] = i < x_lens[b] and j < y_lens[b]); dynamic programme over the frames j with, for every token i, the
+    better of "stay on i" and "come from i - 1" -- ties stay (util.py:35: v1 >= v0) --, tokens i > j unreachable, then a
+    backtrack from token x_len - 1 at the last frame; fp32 scores as in the reference. -> path [B, t_x, t_y] of 0 / 1."""
+    val = value.detach().cpu().numpy().astype(np.float32)
+    B, tx, ty = val.shape
+    xl, yl = np.asarray(x_lens).astype(np.int64), np.asarray(y_lens).astype(np.int64)
+    mask = (np.arange(tx)[None, :, None] < xl[:, None, None]) & (np.arange(ty)[None, None, :] < yl[:, None, None])
+    val = val * mask
+    stay_dir = np.zeros((B, tx, ty), dtype=np.int64)
+    score = np.zeros((B, tx), dtype=np.float32)
+    for j in range(ty):
+        from_prev = np.concatenate([np.full((B, 1), -np.inf, dtype=np.float32), score[:, :-1]], axis=1)
+        keep = score >= from_prev
+        best = np.where(keep, score, from_prev)
+        stay_dir[:, :, j] = keep
+        score = np.where(np.arange(tx)[None, :] <= j, best + val[:, :, j], -np.inf).astype(np.float32)
+    stay_dir = np.where(mask, stay_dir, 1)
+    path = np.zeros((B, tx, ty), dtype=np.float32)
+    tok = mask[:, :, 0].sum(1).astype(np.int64) - 1
+    rows = np.arange(B)
+    for j in reversed(range(ty)):
+        path[rows, tok, j] = 1.0
+        tok = tok + stay_dir[rows, tok, j] - 1
+    return torch.from_numpy(path * mask)
+
+
+def alignment_logp(z_p, m_p, logs_p):
+    """Log-density of every latent frame under every token's diagonal Gaussian prior, in the four-term expansion the
+    reference evaluates (xvapitch/model.py:766-771). z_p [B, C, t_y], m_p / logs_p [B, C, t_x] -> [B, t_x, t_y]."""
+    o_scale = torch.exp(-2 * logs_p)
+    logp1 = torch.sum(-0.5 * math.log(2 * math.pi) - logs_p, [1]).unsqueeze(-1)
+    logp2 = torch.einsum("bct, bcs -> bts", o_scale, -0.5 * (z_p ** 2))
+    logp3 = torch.einsum("bct, bcs -> bts", m_p * o_scale, z_p)
+    logp4 = torch.sum(-0.5 * (m_p ** 2) * o_scale, [1]).unsqueeze(-1)
+    return logp2 + logp3 + logp1 + logp4
+
+
+def prior_alignment(z_p, m_p, logs_p, x_lens, y_lens):
+    """model.py:763-777 + :855-856: -> (logp, path [B, t_x, t_y], durations [B, t_x], m_p and logs_p expanded to the
+    frames [B, C, t_y])."""
+    with torch.no_grad():
+        logp = alignment_logp(z_p, m_p, logs_p)
+        path = maximum_path(logp, x_lens, y_lens)
+    expand = lambda t: torch.einsum("bts, bct -> bcs", path, t)
+    return logp, path, path.sum(2), expand(m_p), expand(logs_p)
+
+
+def kl_loss(z_p, logs_q, m_p, logs_p, z_mask):
+    """VitsGeneratorLoss.kl_loss, xvapitch/losses.py:86-103: KL(q || p) of diagonal Gaussians evaluated at the flow output,
+    summed over channels and valid frames, divided by the number of valid frames. z_mask [B, 1, t_y]."""
+    kl = logs_p - logs_q - 0.5 + 0.5 * (z_p - m_p) ** 2 * torch.exp(-2.0 * logs_p)
+    return torch.sum(kl * z_mask) / torch.sum(z_mask)
+
+
 def segment_starts(u, lengths, segment_size=SEGMENT):
     """rand_segments' index rule, util.py:160-162: floor(u * (length - segment + 1)) with u ~ U[0, 1) per utterance."""
     max_idxs = torch.as_tensor(lengths) - segment_size + 1

@@ -238,3 +238,93 @@ def test_flow_matches_reference_golden_and_oracle(lib):
         back = flow(z_p, mask.cuda(), g=cond.cuda(), reverse=True)
     assert rel(back, torch.from_numpy(gold["reverse_of_z_p"])) < 2e-3
     assert rel(back, x) < 2e-3, rel(back, x)
+
+
+def test_hifi_only_step_at_bench_shape(lib):
+    """The workload bench.py measures (batch 16 x 256 spectrogram frames, ragged, 8192-sample segments), one iteration
+    from the same seeded state on both sides with the same random draws: every loss within 2e-3 of the oracle's, all 447
+    updated tensors within 5e-3, and the size-independent properties of the step -- masked latent rows are exactly zero,
+    every segment start is inside its utterance, all parameters move."""
+    import bench
+    from xva_trainer_b200 import hifigan as hg, vits
+
+    B, T = 16, 256
+    gen = torch.Generator().manual_seed(77)
+    mk = lambda spec, scale: {k: v for k, v in _seeded_state(spec, gen, scale).items()}
+    sds = {"enc": mk(ov.posterior_encoder_spec(), 0.7), "dec": mk(ov.decoder_spec(), 0.7), "disc": mk(ohg.vits_disc_spec(), 1.0)}
+    enc = vits.PosteriorEncoder(513, 192, 192, kernel_size=5, dilation_rate=1, num_layers=16, cond_channels=512, device="cuda:0")
+    dec = hg.HifiganGenerator(192, 1, "1", [[1, 3, 5]] * 3, [3, 7, 11], [16, 16, 4, 4], 512, [8, 8, 2, 2], inference_padding=0,
+                              cond_channels=512, conv_pre_weight_norm=False, conv_post_weight_norm=False,
+                              conv_post_bias=False, device="cuda:0")
+    disc = hg.VitsDiscriminator(device="cuda:0")
+    for name, mod in (("enc", enc), ("dec", dec), ("disc", disc)):
+        res = mod.load_state_dict(sds[name])
+        assert not res.missing_keys and not res.unexpected_keys
+        mod.train()
+    linear, lens, waveform, d_vectors = bench.synthetic_vits_batch(B, T, 1)
+    eps, u = torch.randn(B, 192, T, generator=gen), torch.rand(B, generator=gen)
+    step = vits.HifiOnlyStep(enc, dec, disc)
+    before = {n: {k: v.clone() for k, v in sd.items()} for n, sd in sds.items()}
+    losses = step.step(linear, lens.tolist(), waveform, d_vectors, eps=eps, u=u)
+    torch.cuda.synchronize()
+    starts = losses["slice_ids"].tolist()
+    assert all(0 <= s and s + 32 <= int(n) for s, n in zip(starts, lens.tolist()))
+    z = enc.z_cl
+    for b, n in enumerate(lens.tolist()):
+        assert float(z[b, n:].abs().max() if n < T else 0.0) == 0.0
+    want = ov.hifi_only_step(sds["enc"], sds["dec"], sds["disc"], linear, waveform, d_vectors, lens.tolist(), eps, u, {})
+    for k in ("loss", "loss_gen", "loss_feat", "loss_mel", "loss_disc"):
+        assert abs(float(losses[k]) - want[k]) < 2e-3 * abs(want[k]), (k, float(losses[k]), want[k])
+    for name, mod in (("enc", enc), ("dec", dec), ("disc", disc)):
+        after = mod.state_dict()
+        for k, v in sds[name].items():
+            assert rel(after[k], v) < 5e-3, (name, k, rel(after[k], v))
+            assert not torch.equal(after[k].cpu(), before[name][k]), (name, k)
+
+
+def _seeded_state(spec, gen, scale):
+    sd = {k: torch.empty(sh) for k, sh in spec}
+    for k, sh in spec:
+        if k.endswith("weight_v") or k.endswith(".weight"):
+            sd[k].copy_(torch.randn(sh, generator=gen) * scale / np.sqrt(int(np.prod(sh[1:]))))
+        elif not k.endswith("weight_g"):
+            sd[k].copy_((torch.rand(sh, generator=gen) * 2 - 1) * 0.05)
+    for k, sh in spec:
+        if k.endswith("weight_g"):
+            v = sd[k[:-1] + "v"]
+            sd[k].copy_(v.flatten(1).norm(dim=1).view(sh) * (1.0 + 0.1 * torch.rand(sh, generator=gen)))
+    return sd
+
+
+def test_prior_alignment_and_kl_match_reference_golden(lib):
+    """vits.prior_alignment / kl_loss vs the recording made from the reference's own source lines
+    (tests/golden/make_golden_vits_alignment.py: model.py:763-777, 855-856, losses.py:86-103): log-likelihoods to fp32
+    rounding, the path and the durations BIT-EXACT, the expanded prior exact, the KL loss and its four gradients; and
+    the expansion's backward vs autograd through the oracle's einsum."""
+    from xva_trainer_b200 import vits
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vits_alignment.npz"))
+    t = lambda k: torch.from_numpy(g[k])
+    r = vits.prior_alignment(t("z_p").cuda(), t("m_p").cuda(), t("logs_p").cuda(), g["x_lens"], g["y_lens"])
+    torch.cuda.synchronize()
+    xl, yl = g["x_lens"], g["y_lens"]
+    for b in range(len(xl)):       # compared where the search reads them (the reference multiplies by the mask first)
+        got = r["logp"][b, :yl[b], :xl[b]].cpu().transpose(0, 1)
+        want = t("logp")[b, :xl[b], :yl[b]]
+        assert float((got - want).abs().max()) < 2e-4 * float(want.abs().max()), b
+    assert np.array_equal(r["attn"].squeeze(1).cpu().numpy().astype(np.int8), g["attn"])
+    assert np.array_equal(r["durations"].squeeze(1).cpu().numpy(), g["durations"])
+    assert torch.equal(r["m_p"].cpu(), t("m_p_expanded")) and torch.equal(r["logs_p"].cpu(), t("logs_p_expanded"))
+    loss, grads = vits.kl_loss(t("z_p").cuda(), t("logs_q").cuda(), r["m_p"], r["logs_p"], yl)
+    assert abs(float(loss) - float(g["loss_kl"])) < 1e-5 * abs(float(g["loss_kl"]))
+    for got, k in zip(grads, ("z_p", "logs_q", "m_p_expanded", "logs_p_expanded")):
+        assert rel(got, t(f"grad/{k}")) < 1e-5, (k, rel(got, t(f"grad/{k}")))
+    # backward of the expansion
+    gen = torch.Generator().manual_seed(3)
+    dm, dl = torch.randn(t("m_p_expanded").shape, generator=gen), torch.randn(t("m_p_expanded").shape, generator=gen)
+    ml, ll = t("m_p").clone().requires_grad_(True), t("logs_p").clone().requires_grad_(True)
+    path = t("attn").float()
+    (torch.einsum("bts, bct -> bcs", path, ml) * dm).sum().backward()
+    (torch.einsum("bts, bct -> bcs", path, ll) * dl).sum().backward()
+    got_m, got_l = vits.prior_expand_backward(dm.cuda(), dl.cuda(), r["cum"], t("m_p").shape[2])
+    assert rel(got_m, ml.grad) < 1e-6 and rel(got_l, ll.grad) < 1e-6

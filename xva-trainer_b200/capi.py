@@ -143,6 +143,8 @@ PROTOTYPES = {
     "xva_gated_act_fwd": (_I, [_P, _I64, _I, _I64, _P, _P]),
     "xva_gated_act_bwd": (_I, [_P, _P, _I64, _I, _I64, _P, _P]),
     "xva_colsum_items": (_I, [_P, _I, _I, _I, _I64, _I64, _P, _I64, _P]),
+    "xva_vits_logp_operands": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P]),
+    "xva_vits_kl": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P]),
     "xva_vits_sample_fwd": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
     "xva_vits_sample_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P]),
     "xva_l1_loss_grad": (_I, [_P, _P, _I64, _F, _F, _P, _P, _P]),
@@ -194,7 +196,7 @@ def check(status, what=""):
 
 # kernels enqueued per successful call (everything not listed launches exactly one)
 _LAUNCHES = {"xva_lamb_step": 2, "xva_attn_bwd": 2, "xva_attn_score_bwd": 2, "xva_attn_ctc": 3, "xva_gemm_debug_counters": 0, "xva_set_operand_rounding": 0, "xva_abi_version": 0, "xva_last_error": 0, "xva_device_check": 0,
-             "xva_sizeof_gemm_args": 0, "xva_sizeof_wn_desc": 0, "xva_sizeof_sn_desc": 0, "xva_sn_pack_fwd": 5, "xva_sn_pack_bwd": 3}
+             "xva_sizeof_gemm_args": 0, "xva_sizeof_wn_desc": 0, "xva_sizeof_sn_desc": 0, "xva_sn_pack_fwd": 5, "xva_sn_pack_bwd": 3, "xva_vits_logp_operands": 2}
 _launch_count = 0
 
 

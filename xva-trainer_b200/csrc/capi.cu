@@ -247,6 +247,16 @@ int xva_colsum_items(const float* x, int Z, int rows, int C, int64_t ld, int64_t
   return colsum_items(x, Z, rows, C, static_cast<long>(ld), static_cast<long>(z_stride), out, static_cast<long>(out_ld), S(stream));
 }
 
+int xva_vits_logp_operands(const float* m_p, const float* logs_p, const float* z_p, int B, int Tt, int Ts, int C, float* tok,
+                            float* frm, void* stream) {
+  return vits_logp_operands(m_p, logs_p, z_p, B, Tt, Ts, C, tok, frm, S(stream));
+}
+
+int xva_vits_kl(const float* z_p, const float* logs_q, const float* m_p, const float* logs_p, const int32_t* lens, int B, int T,
+                int C, float scale, double* acc, float* dz_p, float* dlogs_q, float* dm_p, float* dlogs_p, void* stream) {
+  return vits_kl(z_p, logs_q, m_p, logs_p, lens, B, T, C, scale, acc, dz_p, dlogs_q, dm_p, dlogs_p, S(stream));
+}
+
 int xva_vits_sample_fwd(const float* stats, const float* eps, const int32_t* lens, int B, int T, int C, float* z, void* stream) {
   return vits_sample_fwd(stats, eps, lens, B, T, C, z, S(stream));
 }

@@ -77,6 +77,10 @@ int attn_grad_combine(const float* gctc, const float* hard, const float* soft, c
 int gated_act_fwd(const float* x_in, long rows, int H, long ld_in, float* acts, cudaStream_t stream);
 int gated_act_bwd(const float* dacts, const float* x_in, long rows, int H, long ld_in, float* dx_in, cudaStream_t stream);
 int colsum_items(const float* x, int Z, int rows, int C, long ld, long zs, float* out, long out_ld, cudaStream_t stream);
+int vits_logp_operands(const float* m, const float* logs, const float* z, int B, int Tt, int Ts, int C, float* tok, float* frm,
+                       cudaStream_t stream);
+int vits_kl(const float* z, const float* lq, const float* m, const float* lp, const int* lens, int B, int T, int C, float scale,
+            double* acc, float* dz, float* dlq, float* dm, float* dlp, cudaStream_t stream);
 int vits_sample_fwd(const float* stats, const float* eps, const int* lens, int B, int T, int C, float* z, cudaStream_t stream);
 int vits_sample_bwd(const float* dz, const float* eps, const float* stats, const int* lens, int B, int T, int C, float* dstats,
                     cudaStream_t stream);

@@ -517,6 +517,33 @@ def gated_act_bwd(dacts, x_in, H):
     return out
 
 
+def vits_logp(z_p, m_p, logs_p):
+    """Alignment log-likelihoods of xVAPitch.train_step (xvapitch/model.py:766-771), channels-last inputs z_p [B, Ts, C],
+    m_p / logs_p [B, Tt, C] -> logp [B, Ts, Tt] (frames x tokens: the layout xva_mas_width1 searches), exact fp32."""
+    B, Ts, C_ = z_p.shape
+    Tt = m_p.shape[1]
+    assert z_p.is_contiguous() and m_p.is_contiguous() and logs_p.is_contiguous() and logs_p.shape == m_p.shape
+    K = 2 * C_ + 32
+    tok = torch.empty(B, Tt, K, device=z_p.device, dtype=torch.float32)
+    frm = torch.empty(B, Ts, K, device=z_p.device, dtype=torch.float32)
+    capi.call("xva_vits_logp_operands", _p(m_p), _p(logs_p), _p(z_p), B, Tt, Ts, C_, _p(tok), _p(frm), _stream())
+    return bmm_nt(frm, tok, ref=True)
+
+
+def vits_kl(z_p, logs_q, m_p, logs_p, lens, scale=1.0):
+    """VitsGeneratorLoss.kl_loss (xvapitch/losses.py:86-103) on channels-last [B, T, C] tensors -> (loss as a 0-dim device
+    double, (dz_p, dlogs_q, dm_p, dlogs_p) = scale * d loss / d input)."""
+    B, T, C_ = z_p.shape
+    for t in (z_p, logs_q, m_p, logs_p):
+        assert t.is_contiguous() and t.shape == z_p.shape and t.dtype == torch.float32
+    assert lens.dtype == torch.int32
+    acc = torch.zeros(1, device=z_p.device, dtype=torch.float64)
+    grads = tuple(torch.empty_like(z_p) for _ in range(4))
+    capi.call("xva_vits_kl", _p(z_p), _p(logs_q), _p(m_p), _p(logs_p), _p(lens), B, T, C_, float(scale), _p(acc),
+              *[_p(g) for g in grads], _stream())
+    return acc[0] / lens.sum().to(torch.float64), grads
+
+
 def vits_sample(stats, eps, lens):
     """z = (mean + eps * exp(log_scale)) * mask, stats [B, T, 2C] = [mean | log_scale] (xvapitch/model.py:1473-1474)."""
     B, T, C2 = stats.shape

@@ -439,6 +439,48 @@ class ResidualCouplingBlocks(nn.Module):
         return d.transpose(1, 2).contiguous(), (None if dg is None else dg.reshape(B, -1, 1))
 
 
+def prior_alignment(z_p, m_p, logs_p, x_lengths, y_lengths):
+    """The alignment block of xVAPitch.train_step (python/xvapitch/model.py:763-777, 855-856) on the device: prior
+    log-likelihood of every latent frame under every text token (one exact-fp32 batched product), the monotonic
+    alignment search (``xva_mas_width1``; the reference copies the [B, t_text, t_spec] matrix to the host and runs a numpy
+    loop, every step), the durations and the prior expanded to the frames (a gather by the path, not the reference's
+    one-hot einsum). Reference layouts in and out: z_p [B, C, Ts], m_p / logs_p [B, C, Tt] ->
+    dict(attn [B, 1, Tt, Ts], durations [B, 1, Tt], m_p [B, C, Ts], logs_p [B, C, Ts], cum) -- ``cum`` (int32 prefix sums
+    of the durations) is what ``prior_expand_backward`` needs."""
+    dev = z_p.device
+    B, C, Ts = z_p.shape
+    Tt = m_p.shape[2]
+    xl = torch.as_tensor(x_lengths).reshape(-1).to(device=dev, dtype=torch.int32)
+    yl = torch.as_tensor(y_lengths).reshape(-1).to(device=dev, dtype=torch.int32)
+    zc = z_p.detach().to(torch.float32).transpose(1, 2).contiguous()
+    mc = m_p.to(torch.float32).transpose(1, 2).contiguous()
+    lc = logs_p.to(torch.float32).transpose(1, 2).contiguous()
+    logp = ops.vits_logp(zc, mc.detach(), lc.detach())                                   # [B, Ts, Tt]
+    hard, durs = ops.mas_width1(logp, xl, yl, is_log=True, stay_on_tie=True)             # [B, Ts, Tt] 0 / 1, [B, Tt]
+    cum, _ = ops.duration_scan(durs.to(torch.float32), 1.0, Ts)
+    m_e = ops.regulate_gather(mc, cum, Ts)
+    l_e = ops.regulate_gather(lc, cum, Ts)
+    return {"attn": hard.transpose(1, 2).unsqueeze(1), "durations": durs.to(torch.float32).unsqueeze(1), "logp": logp,
+            "m_p": m_e.transpose(1, 2), "logs_p": l_e.transpose(1, 2), "cum": cum}
+
+
+def prior_expand_backward(d_m_p, d_logs_p, cum, t_text):
+    """Gradients of the expanded prior [B, C, Ts] back to the per-token prior [B, C, Tt] (the path is a constant)."""
+    dm = ops.regulate_scatter(d_m_p.transpose(1, 2).contiguous(), cum, t_text)
+    dl = ops.regulate_scatter(d_logs_p.transpose(1, 2).contiguous(), cum, t_text)
+    return dm.transpose(1, 2), dl.transpose(1, 2)
+
+
+def kl_loss(z_p, logs_q, m_p, logs_p, y_lengths, scale=1.0):
+    """VitsGeneratorLoss.kl_loss (python/xvapitch/losses.py:86-103) with a prefix mask given as lengths, and its gradients:
+    [B, C, T] tensors in -> (loss, (dz_p, dlogs_q, dm_p, dlogs_p) [B, C, T], already times ``scale``)."""
+    dev = z_p.device
+    yl = torch.as_tensor(y_lengths).reshape(-1).to(device=dev, dtype=torch.int32)
+    cl = lambda t: t.detach().to(torch.float32).transpose(1, 2).contiguous()
+    loss, grads = ops.vits_kl(cl(z_p), cl(logs_q), cl(m_p), cl(logs_p), yl, scale)
+    return loss, tuple(g.transpose(1, 2) for g in grads)
+
+
 class HifiOnlyStep:
     """One xVAPitch ``--hifi_only`` iteration (amp off, gam 1): posterior encoder -> random 32-frame latent segment ->
     waveform decoder -> VITS discriminator; generator-side loss = 45 * L1(log-mel) + LSGAN (the feature-matching term
