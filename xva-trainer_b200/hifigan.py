@@ -61,8 +61,8 @@ class _Side:
     def run(cls, fn, *inputs):
         """One side stream PER LAUNCHING STREAM: the weight gradients of the three ResBlock branches of a generator stage
         (or of the eight sub-discriminators) do not queue behind each other on a single stream -- a weight-gradient
-        launch fills about a third of the SMs, and a step issues ~13 ms of them (profiles/r01_s5_hifigan_launches_summary
-        .txt). Launches from one branch stay ordered among themselves (two passes of a spectral-normed sub-discriminator
+        launch fills one to two waves of CTAs, and a step issues ~10 ms of them (gemm_tc_kernel<0, 1> in
+        profiles/r02_timeline_hifigan_after.txt). Launches from one branch stay ordered among themselves (two passes of a spectral-normed sub-discriminator
         accumulate into the same bias gradients)."""
         if not cls.on():
             return fn()
