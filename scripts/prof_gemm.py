@@ -20,6 +20,24 @@ scores = torch.empty(B, T, 896, device="cuda")
 wo = r(1, 384, 64) * 0.1
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+if which.startswith("hg"):
+    # HiFi-GAN generator, last stage at B = 16 x 8192: 32 channels, kernel 11 (resblocks.11): forward with the leaky-ReLU
+    # epilogue, input gradient with the gate, weight gradient with the split the engine picks
+    Bh, Th, Ch = 16, 8192, 32
+    K11 = tuple(range(-5, 6))
+    xa = ops.round_tf32_(r(Bh, Th, Ch).reshape(-1), torch.empty(Bh * Th * Ch, device="cuda")).view(Bh, Th, Ch) if False else r(Bh, Th, Ch)
+    wa, ba = r(11, Ch, Ch) * 0.05, r(Ch)
+    gw = torch.zeros(11, Ch, Ch, device="cuda")
+    for _ in range(reps):
+        if which == "hg32":
+            ops.conv_fwd(xa, wa, K11, bias=ba, act_slope=0.1, round_out=True)
+        elif which == "hg32d":
+            ops.conv_dgrad(xa, wa, K11, gate=xa, gate_slope=0.1, round_out=True)
+        elif which == "hg32w":
+            ops.conv_wgrad(xa, xa, K11, out=gw, accumulate=True)
+    torch.cuda.synchronize()
+    print("done")
+    sys.exit(0)
 for _ in range(reps):
     if which in ("all", "conv1"):
         ops.conv_fwd(x, w1, K3, bias=b1, relu=True)
