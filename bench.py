@@ -363,6 +363,16 @@ def run_hifigan(args, dev, world, rank, peak_tf32):
     flops = sum(f for _, _, f in rec)
     achieved = flops / (gemm_ms * 1e-3) / 1e12
     samples = Bh * frames * 256 * world
+    # DRAM bytes of the step's characteristic launch (32-channel kernel-11 ResBlock convolution of the last generator
+    # stage; the step has no single dominant launch) from the committed ncu --set full capture, per launch
+    small = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r02_hifigan_ch32_traffic.json")))
+        small = {"shape": tr["shape"], "traffic": tr["dram_bytes_read"] + tr["dram_bytes_write"],
+                 "l2_to_sm_bytes": tr["l2_to_sm_bytes"], "algorithmic_bytes": sum(tr["algorithmic_bytes"].values()),
+                 "traffic_source": tr["source"]}
+    except Exception:
+        small = None
     return {"metric": "audio-samples/s (HiFi-GAN v1 G+MPD+MSD train step)", "value": samples * steps / (ms * 1e-3),
             "unit": "samples/s", "ms_per_step": ms / steps, "steps": steps, "n_gpus": world,
             "config": {"workload": "HiFi-GAN v1 G+MPD+MSD train step, batch=16/GPU, 8192-sample segments, synthetic "
@@ -373,7 +383,10 @@ def run_hifigan(args, dev, world, rank, peak_tf32):
                     "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e / steps},
             "gpu_launches_per_step": per_step,
             "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 kind::tf32 tap-GEMM)", "achieved": achieved,
-                         "peak": peak_tf32, "unit": "TFLOP/s", "frac": achieved / peak_tf32, "traffic": None,
+                         "peak": peak_tf32, "unit": "TFLOP/s", "frac": achieved / peak_tf32,
+                         "traffic": small["traffic"] if small else None,
+                         "traffic_of": "small_channel_launch (DRAM read + write bytes per launch, committed ncu --set full capture)" if small else None,
+                         "small_channel_launch": small,
                          "launches_per_step": len(rec), "flops_per_step": flops, "kernel_ms_per_step": gemm_ms,
                          "share_of_step": gemm_ms / (ms / steps)},
             "loss_gen_all": loss_host}
