@@ -138,6 +138,69 @@ def residual_coupling_blocks(sd, x, x_mask, g=None, reverse=False):
     return x
 
 
+# ------------------------------------------------------------------------------------------------ text encoder (oracle only)
+REL_WINDOW, TEXT_HEADS = 4, 2
+
+
+def relative_attention(sd, pre, x, mask, heads=TEXT_HEADS, window=REL_WINDOW):
+    """RelativePositionMultiHeadAttention.forward (self-attention, shared relative embeddings, no proximal bias),
+    python/xvapitch/glow_tts.py:159-214, written with explicit relative indices instead of the reference's pad / reshape
+    skewing (:260-292): with d = j - i,
+        score[i, j] = (q_i . k_j + [|d| <= w] q_i . E_k[d + w]) / sqrt(d_k),   masked_fill(-1e4) outside the mask,
+        out_i = sum_j p[i, j] (v_j + [|d| <= w] E_v[d + w]).
+    x [B, C, T], mask [B, 1, T] -> [B, C_out, T]."""
+    B, C, T = x.shape
+    dk = C // heads
+    proj = lambda name: F.conv1d(x, sd[f"{pre}.{name}.weight"], sd[f"{pre}.{name}.bias"]).view(B, heads, dk, T).transpose(2, 3)
+    q, k, v = proj("conv_q"), proj("conv_k"), proj("conv_v")                       # [B, H, T, dk]
+    e_k, e_v = sd[f"{pre}.emb_rel_k"][0], sd[f"{pre}.emb_rel_v"][0]                # [2w + 1, dk]
+    d = torch.arange(T)[None, :] - torch.arange(T)[:, None]                        # d[i, j] = j - i
+    near = d.abs() <= window
+    idx = (d + window).clamp(0, 2 * window)
+    rel_k = torch.einsum("bhid, ijd -> bhij", q, e_k[idx]) * near                  # q_i . E_k[j - i + w]
+    scores = (torch.matmul(q, k.transpose(-2, -1)) + rel_k) / math.sqrt(dk)
+    amask = mask.unsqueeze(2) * mask.unsqueeze(-1)                                 # [B, 1, T, T]
+    scores = scores.masked_fill(amask == 0, -1e4)
+    p = F.softmax(scores, dim=-1)
+    out = torch.matmul(p, v) + torch.einsum("bhij, ijd -> bhid", p * near, e_v[idx])
+    out = out.transpose(2, 3).contiguous().view(B, C, T)
+    return F.conv1d(out, sd[f"{pre}.conv_o.weight"], sd[f"{pre}.conv_o.bias"])
+
+
+def _layer_norm2(sd, pre, x):
+    """LayerNorm2 (glow_tts.py:34-56): layer norm over the channel dimension of [B, C, T]."""
+    return F.layer_norm(x.transpose(1, -1), (x.shape[1],), sd[f"{pre}.gamma"], sd[f"{pre}.beta"], 1e-5).transpose(1, -1)
+
+
+def relative_position_transformer(sd, pre, x, mask, num_layers, kernel=3):
+    """RelativePositionTransformer.forward, glow_tts.py:463-485 (dropout off; in = hidden = out channels, so no proj)."""
+    for i in range(num_layers):
+        x = x * mask
+        x = _layer_norm2(sd, f"{pre}.norm_layers_1.{i}", x + relative_attention(sd, f"{pre}.attn_layers.{i}", x, mask))
+        pad = ((kernel - 1) // 2, kernel // 2)
+        h = F.conv1d(F.pad(x * mask, pad), sd[f"{pre}.ffn_layers.{i}.conv_1.weight"], sd[f"{pre}.ffn_layers.{i}.conv_1.bias"])
+        h = torch.relu(h)
+        y = F.conv1d(F.pad(h * mask, pad), sd[f"{pre}.ffn_layers.{i}.conv_2.weight"], sd[f"{pre}.ffn_layers.{i}.conv_2.bias"]) * mask
+        x = _layer_norm2(sd, f"{pre}.norm_layers_2.{i}", x + y)
+    return x * mask
+
+
+def text_encoder(sd, tokens, x_lengths, lang_emb, num_layers):
+    """TextEncoder.forward(stats=False), xvapitch/model.py:1152-1168: scaled embedding, language embedding concatenated to
+    every token, transformer. tokens [B, T] -> (x [B, C + L, T], x_emb [B, T, C], mask [B, 1, T])."""
+    C = sd["emb.weight"].shape[1]
+    x_emb = F.embedding(tokens, sd["emb.weight"]) * math.sqrt(C)
+    x = torch.cat((x_emb, lang_emb.transpose(2, 1).expand(x_emb.size(0), x_emb.size(1), -1)), dim=-1).transpose(1, -1)
+    mask = sequence_mask(x_lengths, x.shape[2])[:, None, :].to(x.dtype)
+    return relative_position_transformer(sd, "encoder", x * mask, mask, num_layers), x_emb, mask
+
+
+def text_encoder_stats(sd, x, mask):
+    """TextEncoder.forward(stats=True), model.py:1147-1150: the prior's mean and log-scale per token."""
+    stats = F.conv1d(x, sd["proj.weight"], sd["proj.bias"]) * mask
+    return torch.split(stats, stats.shape[1] // 2, dim=1)
+
+
 # ------------------------------------------------------------------------------------------------ alignment, prior, KL
 def maximum_path(value, x_lens, y_lens):
     """xVAPitch's monotonic alignment search, python/xvapitch/util.py:14-53, restated: value [B, t_x, t_y] (masked with
