@@ -1,6 +1,6 @@
 """Host-orchestration fingerprint: the sequence of C-ABI calls (entry point, every scalar argument, the complete GEMM
-argument block except device pointers) that one FastPitch step of each training stage (3, 2, 4, 1) and one HiFi-GAN step
-emit, with the kernels stubbed out, on tiny seeded inputs. CPU only.
+argument block except device pointers) that one FastPitch step of each training stage (3, 2, 4, 1), one HiFi-GAN step and
+one xVAPitch --hifi_only step emit, with the kernels stubbed out, on tiny seeded inputs. CPU only.
 
 tests/golden/launch_sequence.json holds the fingerprint of a tree whose GPU parity suite was green
 (`python tests/launch_sequence.py --write` after such a run). tests/test_launch_sequence.py recomputes it: a refactor
@@ -158,6 +158,31 @@ def record(streams=False):
         msd.train()
         xx, yy, y_mel = ohg.synthetic_batch(2, 32, seed=1)
         hg.HiFiGANStep(G, mpd, msd, h).step(xx, yy, y_mel)
+
+        # the xVAPitch --hifi_only step (vits.py imports its building blocks from hifigan: hand it the dry-run copy)
+        real_hg = sys.modules.get("xva_trainer_b200.hifigan")
+        sys.modules["xva_trainer_b200.hifigan"] = hg
+        try:
+            vt = load("vits", [('if dev.type != "cuda":', "if False:"),
+                               ('dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")',
+                                'dev = torch.device("cpu")'),
+                               ('capi.call("xva_device_check", dev.index or 0)', "pass")])
+        finally:
+            if real_hg is not None:
+                sys.modules["xva_trainer_b200.hifigan"] = real_hg
+            else:
+                sys.modules.pop("xva_trainer_b200.hifigan", None)
+        enc = vt.PosteriorEncoder(513, 192, 192, kernel_size=5, dilation_rate=1, num_layers=16, cond_channels=512, device="cpu")
+        dec = hg.HifiganGenerator(192, 1, "1", [[1, 3, 5]] * 3, [3, 7, 11], [16, 16, 4, 4], 512, [8, 8, 2, 2],
+                                  inference_padding=0, cond_channels=512, conv_pre_weight_norm=False,
+                                  conv_post_weight_norm=False, conv_post_bias=False, device="cpu")
+        disc = hg.VitsDiscriminator(device="cpu")
+        for mod in (enc, dec, disc):
+            mod.train()
+        gen = torch.Generator().manual_seed(5)
+        vt.HifiOnlyStep(enc, dec, disc).step(torch.randn(2, 513, 40, generator=gen).abs(), [40, 35],
+                                              torch.randn(2, 1, 40 * 256, generator=gen), torch.randn(2, 512, generator=gen),
+                                              eps=torch.randn(2, 192, 40, generator=gen), u=torch.tensor([0.3, 0.6]))
     finally:
         capi.load, capi.call, ops._stream, ops._check3, ops.duration_scan = saved
         torch.cuda.Stream, torch.cuda.stream, torch.cuda.current_stream = saved_cuda[:3]
