@@ -328,3 +328,38 @@ def test_prior_alignment_and_kl_match_reference_golden(lib):
     (torch.einsum("bts, bct -> bcs", path, ll) * dl).sum().backward()
     got_m, got_l = vits.prior_expand_backward(dm.cuda(), dl.cuda(), r["cum"], t("m_p").shape[2])
     assert rel(got_m, ml.grad) < 1e-6 and rel(got_l, ll.grad) < 1e-6
+
+
+def test_hifi_only_step_same_with_streams(lib):
+    """The stream-level parallelism the step uses inside a captured graph (hifigan._Side: one weight-gradient stream per
+    launching stream; hifigan._Branches: the six discriminator nets / the three ResBlocks of an MRF stage side by side),
+    forced on for eagerly launched steps: the same two iterations from the same state give the same losses and weights up
+    to the order of the fp32 atomic additions of the split weight gradients (bounds as in
+    tests/test_hifigan_gpu.py::test_two_stream_backward_gives_the_same_step)."""
+    from xva_trainer_b200 import hifigan as hg, vits
+
+    gold, specs, sds, linear, waveform, d_vectors, *_ = _modules(lib)
+    eps, u = torch.from_numpy(gold["eps"]), torch.from_numpy(gold["u"])
+    lens = [int(v) for v in gold["y_lengths"]]
+    results = []
+    was = (hg._Side.enabled, hg._Branches.n, hg._Branches.n_gen)
+    try:
+        for flag in (False, True):
+            hg._Side.enabled = flag
+            hg._Branches.n = 8 if flag else 0
+            hg._Branches.n_gen = 3 if flag else 0
+            _, _, _, _, _, _, enc, dec, disc = _modules(lib)
+            step = vits.HifiOnlyStep(enc, dec, disc)
+            for _ in range(2):
+                losses = step.step(linear, lens, waveform, d_vectors, eps=eps, u=u)
+            torch.cuda.synchronize()
+            results.append(({k: float(v) for k, v in losses.items() if k != "slice_ids"},
+                            {n: {k: v.clone() for k, v in m.state_dict().items()} for n, m in (("enc", enc), ("dec", dec), ("disc", disc))}))
+    finally:
+        hg._Side.enabled, hg._Branches.n, hg._Branches.n_gen = was
+    (l0, s0), (l1, s1) = results
+    for k in l0:
+        assert abs(l0[k] - l1[k]) <= 1e-4 * abs(l0[k]) + 1e-7, (k, l0[k], l1[k])
+    for n in s0:
+        for k in s0[n]:
+            assert rel(s1[n][k], s0[n][k]) < 2e-3, (n, k, rel(s1[n][k], s0[n][k]))
