@@ -17,7 +17,7 @@ import torch
 import torch.nn as nn
 
 from . import capi, ops
-from .hifigan import (AdamW, MelSpectrogram, _PlainConv, _WNConv, _WnPacker, _bias, discriminator_loss_backward,
+from .hifigan import (AdamW, MelSpectrogram, _PlainConv, _Side, _WNConv, _WnPacker, _bias, discriminator_loss_backward,
                       generator_adv_loss_backward)
 
 SPEC_SEGMENT, HOP = 32, 256          # xvapitch/model.py:76, :662-663
@@ -100,18 +100,32 @@ class WN(nn.Module):
         """d_rs [B, T, 2H]: its upper half holds dL/d(output) (masked, tf32) on entry; d_res [B, T, 2H] is fp32 scratch
         of the same shape. On return the lower half of d_rs (tf32) / d_res (fp32) holds dL/dx of the stack's input
         (times the mask when mask_input_grad: the caller's input was x * mask). Parameter gradients go to gW (packed)
-        through ``wgrad`` and to the biases through ``bias_grad``. Returns dL/dg [1, B, C] (tf32) or None."""
+        through ``wgrad`` and to the biases through ``bias_grad``. Returns (dL/dg [1, B, C] (tf32) or None, the tf32 copy
+        of dL/dx [B, T, H] -- a view of d_rs or of its alternate buffer)."""
         saved, lens, g, W, prefix = self._ctx
         B, T, H2 = d_rs.shape
         H, L = H2 // 2, self.num_layers
         dG = None
         if g is not None:
             dG = torch.zeros(1, B, 2 * H * L, device=d_rs.device, dtype=torch.float32)
-        dxm_r, dxm = d_rs[..., :H], d_res[..., :H]
+        dxm = d_res[..., :H]
+        # With the weight-gradient side stream on (inside a captured graph) the weight / bias gradients of layer i read the
+        # gradient buffer of layer i while the launching stream already produces layer i - 1's: two buffers take turns
+        # (both carry dL/d(output) in their upper half), and a buffer is rewritten only after the side-stream work that
+        # read it two layers earlier has finished (an event; one whole layer of slack).
+        side = _Side.on()
+        bufs = [d_rs]
+        if side:
+            alt = torch.empty_like(d_rs)
+            alt[..., H:].copy_(d_rs[..., H:])
+            bufs.append(alt)
+        read_done = [None] * len(bufs)
+        cur = 0
         for i in reversed(range(L)):
             xr, x_in, acts = saved[i]
             m_in, m_rs = self.in_layers[i], self.res_skip_layers[i]
-            d_i = d_rs if i < L - 1 else d_rs[..., H:]          # gradient of res_skip_layers[i]'s output
+            src, nxt = bufs[cur], (cur + 1) % len(bufs)
+            d_i = src if i < L - 1 else src[..., H:]            # gradient of res_skip_layers[i]'s output
             bias_grad(m_rs, d_i, m_rs.cout)
             wgrad(d_i, acts, (0,), gW[f"{prefix}res_skip_layers.{i}"][0])
             d_acts = ops.conv_dgrad(d_i, W[f"{prefix}res_skip_layers.{i}"][0], (0,))
@@ -120,9 +134,15 @@ class WN(nn.Module):
                 ops.colsum_items_(d_xin, dG[0, :, i * 2 * H:(i + 1) * 2 * H])
             bias_grad(m_in, d_xin, m_in.cout)
             wgrad(d_xin, xr, m_in.shifts, gW[f"{prefix}in_layers.{i}"][0])
+            if side:
+                read_done[cur] = torch.cuda.Event()
+                read_done[cur].record(_Side.stream)
+                if read_done[nxt] is not None:
+                    torch.cuda.current_stream().wait_event(read_done[nxt])
             # dL/dx_i = dgrad + (the residual path of layers < L-1), then the mask that produced x_i
             ops.conv_dgrad(d_xin, W[f"{prefix}in_layers.{i}"][0], m_in.shifts, out=dxm, residual=dxm if i < L - 1 else None,
-                           lens=lens if (i > 0 or mask_input_grad) else None, out_act=dxm_r, out_act_slope=1.0)
+                           lens=lens if (i > 0 or mask_input_grad) else None, out_act=bufs[nxt][..., :H], out_act_slope=1.0)
+            cur = nxt
         dg = None
         if dG is not None:
             cl = self.cond_layer
@@ -132,7 +152,7 @@ class WN(nn.Module):
             wgrad(dGr, g, (0,), gW[f"{prefix}cond_layer"][0])
             dg = ops.conv_dgrad(dGr, W[f"{prefix}cond_layer"][0], (0,))
         self._ctx = None
-        return dg
+        return dg, bufs[cur][..., :H]
 
     # ------------------------------------------------------------------------------------------ stand-alone use
     def _own_packer(self):
@@ -176,21 +196,20 @@ class WN(nn.Module):
         d_rs[..., H:].copy_(d_out.to(torch.float32).transpose(1, 2))
         d_rs.mul_((torch.arange(T, device=d_out.device)[None, :] < lens[:, None]).to(torch.float32).unsqueeze(-1))   # * x_mask, :106
         ops.round_tf32_(d_rs.reshape(-1), d_rs.reshape(-1))
-        dg = self.backward_cl(d_rs, d_res, gW, _bias_grad_inline, _wgrad_inline, mask_input_grad=False)
+        dg, _ = self.backward_cl(d_rs, d_res, gW, _bias_grad_inline, _wgrad_inline, mask_input_grad=False)
         pk.unpack_grads()
         return d_res[..., :H].transpose(1, 2).contiguous(), (None if dg is None else dg.reshape(B, -1, 1))
 
 
-# gradient helpers on the launching stream (not hifigan._Side): the WaveNet backward reuses its two gradient buffers
-# in place, so nothing may still be reading them from another stream
+# weight / bias gradient launches: on hifigan._Side's stream when it is on (inside a captured graph), else in line
 def _bias_grad_inline(m, d, cols):
     if m.bias.grad is None:
         m.bias.grad = torch.zeros_like(m.bias)
-    ops.colsum_(d.shape[0] * d.shape[1], cols, d.stride(1), d, m.bias.grad)
+    _Side.run(lambda: ops.colsum_(d.shape[0] * d.shape[1], cols, d.stride(1), d, m.bias.grad), d)
 
 
 def _wgrad_inline(dy_, x_, shifts, out):
-    ops.conv_wgrad(dy_, x_, shifts, out=out, accumulate=True)
+    _Side.run(lambda: ops.conv_wgrad(dy_, x_, shifts, out=out, accumulate=True), dy_, x_)
 
 
 class PosteriorEncoder(nn.Module):
@@ -289,8 +308,7 @@ class PosteriorEncoder(nn.Module):
         d_rs = torch.zeros(B, T, 2 * H, device=yp.device, dtype=torch.float32)
         d_res = torch.zeros_like(d_rs)
         ops.conv_dgrad(dstats, W["proj"][0], (0,), out=d_rs[..., H:], lens=lens, round_out=True)       # dL/d(output), masked
-        self.enc.backward_cl(d_rs, d_res, gW, bias_grad, wgrad)
-        dx0 = d_rs[..., :H]
+        _, dx0 = self.enc.backward_cl(d_rs, d_res, gW, bias_grad, wgrad)
         bias_grad(self.pre, dx0, self.pre.cout)
         wgrad(dx0, yp, (0,), gW["pre"][0])
         pk.unpack_grads()
@@ -424,8 +442,7 @@ class ResidualCouplingBlocks(nn.Module):
             d_rs = torch.zeros(B, T, 2 * H, device=dev, dtype=torch.float32)
             d_res = torch.zeros_like(d_rs)
             ops.conv_dgrad(d1r, W[f"flows.{i}.post"][0], (0,), out=d_rs[..., H:], lens=lens, round_out=True)
-            dgi = f.enc.backward_cl(d_rs, d_res, gW, _bias_grad_inline, _wgrad_inline, mask_input_grad=True)
-            dh = d_rs[..., :H]
+            dgi, dh = f.enc.backward_cl(d_rs, d_res, gW, _bias_grad_inline, _wgrad_inline, mask_input_grad=True)
             _bias_grad_inline(f.pre, dh, f.pre.cout)
             _wgrad_inline(dh, xr[..., :h], (0,), gW[f"flows.{i}.pre"][0])
             dn = torch.empty_like(d)
