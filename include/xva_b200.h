@@ -388,6 +388,32 @@ int xva_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, cons
                    float eps, float weight_decay, int step, const uint64_t* step_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * xVAPitch text encoder: TextEncoder, python/xvapitch/model.py:1089-1170, over
+ * RelativePositionTransformer, python/xvapitch/glow_tts.py:373-485. Its convolutions, score / value products, softmax
+ * and LayerNorm are the xva_gemm / xva_softmax / xva_layernorm entries above; these are the remaining steps.
+ *   xva_text_embed_fwd : out[b, t, :] = [emb[tokens[b, t]] * scale | lang[b]] for t < lens[b], zero rows otherwise and zero
+ *                        in the pad columns [C + L, ld) -- model.py:1152-1165 (scale = sqrt(C), lang = the language
+ *                        embedding of the utterance, [B, L]); stored tf32-rounded (it is a GEMM operand). x_emb [B, T, C]
+ *                        (optional) = emb[tokens] * scale at EVERY position, the second value the reference returns.
+ *   xva_text_embed_bwd : demb[tokens[b, t], c] += scale * dout[b, t, c] for t < lens[b], c < C; dout has row pitch ld.
+ *                        (d lang = per-utterance column sums of dout[:, :, C : C + L): xva_colsum_items.)
+ *   xva_rel_band_add   : s[z, t, t + r - W] += rel[z, t, r] for r in [0, 2 W] with 0 <= t + r - W < T -- the relative-position
+ *                        logits q . E_k^T of glow_tts.py:178-186 added onto the scores (the reference pads and reshapes,
+ *                        :260-277); s [Z, T, ld], rel [Z, T, ldr]. The backward uses it on dP with rel = dO . E_v^T.
+ *   xva_rel_band_gather: out[z, t, r] = p[z, t, t + r - W] inside the band and the sequence, 0 elsewhere and for
+ *                        r in [2 W + 1, ldo) -- the attention weights in relative indexing, glow_tts.py:192-195 (:279-292);
+ *                        tf32-rounded: out is the operand of the product with E_v (and, on dS, with E_k).
+ *   xva_pad_cols       : dst [rows, ld] = src [rows, C] followed by zero columns (row pitch for MN-major GEMM operands).
+ * ---------------------------------------------------------------------------------------------------------- */
+int xva_text_embed_fwd(const int64_t* tokens, const float* emb, const float* lang, const int32_t* lens, int B, int T, int C,
+                       int L, int ld, float scale, float* out, float* x_emb, void* stream);
+int xva_text_embed_bwd(const int64_t* tokens, const float* dout, const int32_t* lens, int B, int T, int C, int ld, float scale,
+                       float* demb, void* stream);
+int xva_rel_band_add(float* s, const float* rel, int Z, int T, int W, int ld, int ldr, void* stream);
+int xva_rel_band_gather(const float* p, int Z, int T, int W, int ld, int ldo, float* out, void* stream);
+int xva_pad_cols(const float* src, int64_t rows, int C, int ld, float* dst, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Mel-spectrogram extractor -- mel_spectrogram(), hifigan/meldataset.py:217-240 (forward and the backward the 45 * L1
  * mel loss needs, hifigan/xva_train.py:480,504). The STFT and the mel projection are xva_gemm launches (a 4-tap GEMM
  * over the [len/hop, hop] view of the padded signal, and a plain GEMM); these are the steps around them.

@@ -147,6 +147,11 @@ PROTOTYPES = {
     "xva_vits_kl": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P]),
     "xva_vits_sample_fwd": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
     "xva_vits_sample_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P]),
+    "xva_text_embed_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P, _P]),
+    "xva_text_embed_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _F, _P, _P]),
+    "xva_rel_band_add": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
+    "xva_rel_band_gather": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
+    "xva_pad_cols": (_I, [_P, _I64, _I, _I, _P, _P]),
     "xva_l1_loss_grad": (_I, [_P, _P, _I64, _F, _F, _P, _P, _P]),
     "xva_sizeof_wn_desc": (_I, []),
     "xva_sizeof_sn_desc": (_I, []),

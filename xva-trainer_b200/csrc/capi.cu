@@ -152,6 +152,7 @@ int xva_set_operand_rounding(int on) {
   if ((rc = set_operand_rounding_disc(on)) != XVA_OK) return rc;
   if ((rc = set_operand_rounding_wnpack(on)) != XVA_OK) return rc;
   if ((rc = set_operand_rounding_align(on)) != XVA_OK) return rc;
+  if ((rc = set_operand_rounding_relattn(on)) != XVA_OK) return rc;
   return set_operand_rounding_loss_optim(on);
 }
 
@@ -264,6 +265,28 @@ int xva_vits_sample_fwd(const float* stats, const float* eps, const int32_t* len
 int xva_vits_sample_bwd(const float* dz, const float* eps, const float* stats, const int32_t* lens, int B, int T, int C,
                         float* dstats, void* stream) {
   return vits_sample_bwd(dz, eps, stats, lens, B, T, C, dstats, S(stream));
+}
+
+int xva_text_embed_fwd(const int64_t* tokens, const float* emb, const float* lang, const int32_t* lens, int B, int T, int C,
+                       int L, int ld, float scale, float* out, float* x_emb, void* stream) {
+  return text_embed_fwd(reinterpret_cast<const long long*>(tokens), emb, lang, lens, B, T, C, L, ld, scale, out, x_emb, S(stream));
+}
+
+int xva_text_embed_bwd(const int64_t* tokens, const float* dout, const int32_t* lens, int B, int T, int C, int ld, float scale,
+                       float* demb, void* stream) {
+  return text_embed_bwd(reinterpret_cast<const long long*>(tokens), dout, lens, B, T, C, ld, scale, demb, S(stream));
+}
+
+int xva_rel_band_add(float* s, const float* rel, int Z, int T, int W, int ld, int ldr, void* stream) {
+  return rel_band_add(s, rel, Z, T, W, ld, ldr, S(stream));
+}
+
+int xva_rel_band_gather(const float* p, int Z, int T, int W, int ld, int ldo, float* out, void* stream) {
+  return rel_band_gather(p, Z, T, W, ld, ldo, out, S(stream));
+}
+
+int xva_pad_cols(const float* src, int64_t rows, int C, int ld, float* dst, void* stream) {
+  return pad_cols(src, static_cast<long>(rows), C, ld, dst, S(stream));
 }
 
 int xva_tanh_bwd(const float* dy, const float* y, int64_t rows, int ld, float* out, void* stream) {

@@ -19,6 +19,7 @@ int set_operand_rounding_melspec(int on);
 int set_operand_rounding_disc(int on);
 int set_operand_rounding_wnpack(int on);
 int set_operand_rounding_align(int on);
+int set_operand_rounding_relattn(int on);
 
 // ---- regulate.cu
 int duration_scan(const float* durs, int B, int Tt, float pace, int mel_max_len, int* cum, int* dec_lens,
@@ -84,6 +85,15 @@ int vits_kl(const float* z, const float* lq, const float* m, const float* lp, co
 int vits_sample_fwd(const float* stats, const float* eps, const int* lens, int B, int T, int C, float* z, cudaStream_t stream);
 int vits_sample_bwd(const float* dz, const float* eps, const float* stats, const int* lens, int B, int T, int C, float* dstats,
                     cudaStream_t stream);
+
+// ---- relattn.cu (xVAPitch text encoder: embedding, relative-position band, padded copies)
+int text_embed_fwd(const long long* tokens, const float* emb, const float* lang, const int* lens, int B, int T, int C, int L,
+                   int ld, float scale, float* out, float* x_emb, cudaStream_t stream);
+int text_embed_bwd(const long long* tokens, const float* dout, const int* lens, int B, int T, int C, int ld, float scale,
+                   float* demb, cudaStream_t stream);
+int rel_band_add(float* s, const float* rel, int Z, int T, int W, int ld, int ldr, cudaStream_t stream);
+int rel_band_gather(const float* p, int Z, int T, int W, int ld, int ldo, float* out, cudaStream_t stream);
+int pad_cols(const float* src, long rows, int C, int ld, float* dst, cudaStream_t stream);
 
 // ---- elemwise.cu
 int mean3_lrelu(const float* y0, const float* y1, const float* y2, long n, float slope, float* out, cudaStream_t stream);
