@@ -1,0 +1,189 @@
+"""Host code of the xVAPitch text encoder (xva-trainer_b200/textenc.py) checked WITHOUT a GPU: every C-ABI call it makes
+is executed on host memory by tests/cabi_emu.py (the tap-GEMM / softmax / LayerNorm contracts of include/xva_b200.h,
+validated in tests/test_cabi_emu_cpu.py; the new element-wise kernels as the very functions of csrc/relattn_body.h compiled
+with g++). What is compared: the reference module's recorded outputs (tests/golden/vits_text_encoder.npz), the oracle
+(oracle.vits.text_encoder) and its autograd for every parameter gradient -- i.e. which operands, strides, taps, head
+slices, padded layouts and saved tensors the module hands to the kernels. What this cannot show -- the CUDA kernels
+producing the same numbers on the device -- is tests/test_vits_text_encoder_gpu.py. CPU only."""
+import ast
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+import cabi_emu  # noqa: E402
+from oracle import vits as ov  # noqa: E402
+from textenc_util import TE_PATCHES, golden_case, oracle_grads, rel, seeded_state  # noqa: E402
+
+
+def _build(te, sd, layers, lang=12, vocab=50, hidden=192, heads=2, ffn=768, k=3, p=0.0):
+    m = te.TextEncoder(vocab, hidden, hidden, ffn, heads, layers, k, p, language_emb_dim=lang, device="cpu")
+    m.load_state_dict(sd)
+    return m
+
+
+def test_forward_matches_the_reference_golden_and_state_dict_round_trips():
+    g, sd, tokens, lens, lang = golden_case()
+    with cabi_emu.installed():
+        te = cabi_emu.load_module("textenc", TE_PATCHES)
+        m = _build(te, sd, 3)
+        back = m.state_dict()
+        assert list(back) == list(sd)
+        for k_ in sd:
+            assert back[k_].shape == sd[k_].shape and torch.equal(back[k_], sd[k_]), k_
+        m.eval()
+        x, x_emb, mask = m(tokens, lens, lang_emb=lang)
+        m_p, logs_p = m(x, lens, stats=True, x_mask=mask)
+        used = set(cabi_emu.calls)
+    assert {"xva_text_embed_fwd", "xva_rel_band_add", "xva_rel_band_gather", "xva_gemm", "xva_softmax_fwd",
+            "xva_layernorm_fwd"} <= used
+    assert rel(x_emb, torch.from_numpy(g["x_emb"])) < 1e-6
+    assert rel(x, torch.from_numpy(g["x"])) < 2e-5
+    assert rel(m_p, torch.from_numpy(g["m_p"])) < 2e-5 and rel(logs_p, torch.from_numpy(g["logs_p"])) < 2e-5
+    assert float(x[1, :, 8:].abs().max()) == 0.0 and float(m_p[1, :, 8:].abs().max()) == 0.0
+    assert mask.shape == (2, 1, 13) and float(mask.sum()) == 21.0
+
+
+@pytest.mark.parametrize("T,lens,layers,cfg", [
+    (13, [13, 8], 3, dict()),                                   # the golden's shape
+    (3, [3, 2], 2, dict()),                                     # shorter than the relative window: the band is clipped
+    (37, [37, 20, 33], 2, dict(lang=4, hidden=64, ffn=96, heads=2)),   # 68 channels: another head / pad geometry, T > 32
+])
+def test_backward_matches_oracle_autograd(T, lens, layers, cfg):
+    lang_dim, hidden, vocab = cfg.get("lang", 12), cfg.get("hidden", 192), 50
+    sd = seeded_state(layers=layers, lang=lang_dim, hidden=hidden, ffn=cfg.get("ffn", 768), heads=cfg.get("heads", 2))
+    gen = torch.Generator().manual_seed(100 + T)
+    B = len(lens)
+    tokens = torch.randint(1, vocab, (B, T), generator=gen)
+    lang = torch.randn(B, lang_dim, 1, generator=gen)
+    C = hidden + lang_dim
+    rx, rm, rl = torch.randn(B, C, T, generator=gen), torch.randn(B, hidden, T, generator=gen), torch.randn(B, hidden, T, generator=gen)
+    re = torch.randn(B, T, hidden, generator=gen) * 0.1
+    want_out, want = oracle_grads(sd, tokens, lens, lang, layers, rx, rm, rl, re)
+
+    with cabi_emu.installed():
+        te = cabi_emu.load_module("textenc", TE_PATCHES)
+        m = _build(te, sd, layers, lang=lang_dim, hidden=hidden, ffn=cfg.get("ffn", 768), heads=cfg.get("heads", 2))
+        m.train()
+        m.zero_grad()
+        li = torch.tensor(lens, dtype=torch.int32)
+        x_cl, x_emb = m.forward_cl(tokens, li, lang.reshape(B, lang_dim).contiguous())
+        stats = m.stats_cl(x_cl, li)
+        dstats = torch.cat([rm, rl], 1).transpose(1, 2).contiguous()
+        dx_stats = m.stats_backward_cl(dstats)
+        dlang = m.backward_cl(rx.transpose(1, 2).contiguous() + dx_stats, dx_emb=re)
+        got = m.grads()
+        used = set(cabi_emu.calls)
+    assert {"xva_text_embed_bwd", "xva_pad_cols", "xva_softmax_bwd", "xva_layernorm_bwd", "xva_colsum_items"} <= used
+    assert rel(x_cl.transpose(1, 2), want_out["x"]) < 2e-5
+    assert rel(stats[..., :hidden].transpose(1, 2), want_out["m_p"]) < 2e-5
+    assert rel(dlang.unsqueeze(-1), want["lang"]) < 5e-5
+    # (conv_k.bias has no gradient in exact arithmetic -- a key bias shifts every score of a row alike -- so each tensor's
+    # error is taken relative to the larger of its own norm and 1e-4 of the largest gradient norm)
+    floor = 1e-4 * max(float(want[k_].norm()) for k_ in sd)
+    errs = sorted(((float((got[k_] - want[k_]).norm()) / max(float(want[k_].norm()), floor), k_) for k_ in sd), reverse=True)
+    assert errs[0][0] < 1e-4, errs[:5]
+    # the padded entries of the arena (head padding, relative rows 9..31, pitch columns) received exactly nothing
+    V = m._views(m.flat.grad)
+    for i in range(layers):
+        qw = V[f"l{i}.qkv_w"].view(3, m.num_heads, m.dkp, m.Cp)
+        assert float(qw[:, :, m.dk:].abs().max()) == 0.0 and float(qw[..., m.C:].abs().max()) == 0.0
+        assert float(V[f"l{i}.ek"][9:].abs().max()) == 0.0 and float(V[f"l{i}.ev"][:, m.dk:].abs().max()) == 0.0
+        assert float(V[f"l{i}.o_w"].view(m.C, m.num_heads, m.dkp)[:, :, m.dk:].abs().max()) == 0.0
+
+
+def _masked_reference(sd, tokens, lens, lang, layers, heads, p, seed, window=4):
+    """oracle.vits.text_encoder with the four dropout sites of a layer (glow_tts.py:193, 475, 355, 480) switched on, the
+    masks taken from the library's counter hash at the element indices its kernels use: softmax row (h B + b) T + t with
+    pitch Tp; GEMM epilogues (b T + t) N + n."""
+    import math
+    import torch.nn.functional as F
+    B, T = tokens.shape
+    Ce = sd["emb.weight"].shape[1]
+    x_emb = F.embedding(tokens, sd["emb.weight"]) * math.sqrt(Ce)
+    x = torch.cat((x_emb, lang.transpose(2, 1).expand(B, T, -1)), dim=-1)             # [B, T, C]
+    mask = ov.sequence_mask(lens, T)[:, :, None].to(x.dtype)                           # [B, T, 1]
+    x = x * mask
+    C = x.shape[2]
+    dk, Tp = C // heads, (T + 31) // 32 * 32
+    site = [0]
+
+    def scale(shape_idx):
+        site[0] += 1
+        sd_ = (seed * 0x9E3779B1 + site[0] * 0x85EBCA77) & 0xFFFFFFFFFFFF
+        return torch.from_numpy(cabi_emu.dropout_scale(sd_, None, shape_idx, p))
+
+    rows = (np.arange(B)[:, None] * T + np.arange(T)[None, :]).astype(np.uint64)       # b T + t
+    epi = lambda N: rows[:, :, None] * np.uint64(N) + np.arange(N, dtype=np.uint64)[None, None, :]
+    d = torch.arange(T)[None, :] - torch.arange(T)[:, None]
+    near, idx = (d.abs() <= window), (d + window).clamp(0, 2 * window)
+    for i in range(layers):
+        a = f"encoder.attn_layers.{i}"
+        lin = lambda n, t: t @ sd[f"{a}.conv_{n}.weight"][:, :, 0].T + sd[f"{a}.conv_{n}.bias"]
+        q, k, v = (lin(n, x).view(B, T, heads, dk).transpose(1, 2) for n in "qkv")      # [B, H, T, dk]
+        e_k, e_v = sd[f"{a}.emb_rel_k"][0], sd[f"{a}.emb_rel_v"][0]
+        sc = (q @ k.transpose(-2, -1) + torch.einsum("bhid, ijd -> bhij", q, e_k[idx]) * near) / math.sqrt(dk)
+        sc = sc.masked_fill((mask.transpose(1, 2) * mask)[:, None] == 0, -1e4)
+        pr = F.softmax(sc, dim=-1)
+        zrow = (np.arange(heads)[None, :, None] * B + np.arange(B)[:, None, None]) * T + np.arange(T)[None, None, :]   # [B, H, T]
+        sidx = zrow.astype(np.uint64)[..., None] * np.uint64(Tp) + np.arange(T, dtype=np.uint64)[None, None, None, :]
+        pr = pr * scale(sidx)
+        o = pr @ v + torch.einsum("bhij, ijd -> bhid", pr * near, e_v[idx])
+        y = lin("o", o.transpose(1, 2).reshape(B, T, C)) * scale(epi(C))
+        x = F.layer_norm(x + y, (C,), sd[f"encoder.norm_layers_1.{i}.gamma"], sd[f"encoder.norm_layers_1.{i}.beta"], 1e-5) * mask
+        f = f"encoder.ffn_layers.{i}"
+        conv = lambda n, t: F.conv1d(t.transpose(1, 2), sd[f"{f}.conv_{n}.weight"], sd[f"{f}.conv_{n}.bias"], padding=1).transpose(1, 2)
+        h = torch.relu(conv(1, x))
+        h = h * scale(epi(h.shape[2])) * mask
+        y = conv(2, h) * scale(epi(C))
+        x = F.layer_norm(x + y, (C,), sd[f"encoder.norm_layers_2.{i}.gamma"], sd[f"encoder.norm_layers_2.{i}.beta"], 1e-5) * mask
+    return x
+
+
+def test_dropout_masks_of_forward_and_backward_agree():
+    """With dropout on (p = 0.3, four sites per layer) the module's output and every parameter gradient equal those of
+    the oracle's arithmetic with the SAME masks applied through autograd -- the masks come from the library's counter
+    hash at the indices its kernels use, so a backward that re-derived a different mask than the forward drew, or a site
+    with the wrong seed, shows up as an O(1) gradient error."""
+    layers, T, lens, heads = 2, 9, [9, 6], 2
+    sd = seeded_state(layers=layers, lang=4, hidden=32, ffn=64, heads=heads)
+    gen = torch.Generator().manual_seed(5)
+    tokens = torch.randint(1, 50, (2, T), generator=gen)
+    lang = torch.randn(2, 4, 1, generator=gen)
+    r = torch.randn(2, T, 36, generator=gen)
+    li = torch.tensor(lens, dtype=torch.int32)
+    with cabi_emu.installed():
+        te = cabi_emu.load_module("textenc", TE_PATCHES)
+        m = te.TextEncoder(50, 32, 32, 64, heads, layers, 3, 0.3, language_emb_dim=4, device="cpu")
+        m.load_state_dict(sd)
+        m.train()
+        m.zero_grad()
+        x, _ = m.forward_cl(tokens, li, lang.reshape(2, 4).contiguous())
+        x_again, _ = m.forward_cl(tokens, li, lang.reshape(2, 4).contiguous())
+        assert torch.equal(x, x_again)                          # same counter, same masks
+        dlang = m.backward_cl(r.clone())
+        got = m.grads()
+        m.eval()
+        x_eval, _ = m.forward_cl(tokens, li, lang.reshape(2, 4).contiguous())
+        m.train()
+        m.step_dropout()
+        x_next, _ = m.forward_cl(tokens, li, lang.reshape(2, 4).contiguous())
+        seed = m.seed
+    assert rel(x, x_eval) > 0.05 and not torch.equal(x, x_next)   # dropout was on; the counter draws new masks
+    p = {k_: v.clone().requires_grad_(True) for k_, v in sd.items()}
+    lg = lang.clone().requires_grad_(True)
+    want_x = _masked_reference(p, tokens, lens, lg, layers, heads, 0.3, seed)
+    (want_x * r).sum().backward()
+    assert rel(x, want_x) < 2e-5
+    assert rel(dlang.unsqueeze(-1), lg.grad) < 1e-4
+    floor = 1e-4 * max(float(v.grad.norm()) for k_, v in p.items() if v.grad is not None)
+    for k_, v in p.items():
+        if v.grad is None:                                      # proj.*: not on this path
+            continue
+        assert float((got[k_] - v.grad).norm()) / max(float(v.grad.norm()), floor) < 2e-4, k_

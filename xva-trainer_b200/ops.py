@@ -791,3 +791,56 @@ def avgpool4_bwd(dout, L):
 def zero_tail_rows_(x, Lvalid):
     Z, Lp, Cc = x.shape
     capi.call("xva_zero_tail_rows", _p(x), Z, Lp, int(Lvalid), Cc, _stream())
+
+
+# ---------------------------------------------------------------------------------------------- xVAPitch text encoder
+def text_embed(tokens, emb, lang, lens, scale, ld, want_x_emb=True):
+    """TextEncoder.forward's input stage (python/xvapitch/model.py:1152-1165): tokens int64 [B, T], emb [V, C], lang [B, L]
+    or None, lens int32 [B] -> (x [B, T, ld] = [emb[tokens] * scale | lang | 0] on rows t < lens[b], zero rows after;
+    x_emb [B, T, C] = emb[tokens] * scale at every position, or None)."""
+    B, T = tokens.shape
+    V, C_ = emb.shape
+    L = 0 if lang is None else lang.shape[1]
+    assert tokens.dtype == torch.int64 and tokens.is_contiguous() and emb.is_contiguous() and lens.dtype == torch.int32
+    assert lang is None or (lang.is_contiguous() and lang.shape[0] == B)
+    out = torch.empty(B, T, ld, device=emb.device, dtype=torch.float32)
+    x_emb = torch.empty(B, T, C_, device=emb.device, dtype=torch.float32) if want_x_emb else None
+    capi.call("xva_text_embed_fwd", _p(tokens), _p(emb), _p(lang), _p(lens), B, T, C_, L, int(ld), float(scale), _p(out),
+              _p(x_emb), _stream())
+    return out, x_emb
+
+
+def text_embed_bwd_(tokens, dout, lens, C_, scale, demb):
+    """demb[tokens[b, t], :C] += scale * dout[b, t, :C] on rows t < lens[b] (lens None: every row). dout [B, T, >= C]."""
+    _check3(dout, "dout")
+    B, T, _ = dout.shape
+    assert dout.stride(0) == T * dout.stride(1) and demb.is_contiguous() and demb.shape[1] == C_
+    capi.call("xva_text_embed_bwd", _p(tokens), _p(dout), _p(lens), B, T, int(C_), dout.stride(1), float(scale), _p(demb),
+              _stream())
+
+
+def rel_band_add_(s, rel, T, W):
+    """s[z, t, t + r - W] += rel[z, t, r], r in [0, 2W], inside [0, T) (glow_tts.py:178-186). s [Z, T, ld], rel [Z, T, ldr]."""
+    Z, R, ld = s.shape
+    assert s.is_contiguous() and rel.is_contiguous() and rel.shape[:2] == (Z, R) and R == T
+    capi.call("xva_rel_band_add", _p(s), _p(rel), Z, int(T), int(W), ld, rel.shape[2], _stream())
+    return s
+
+
+def rel_band_gather(p, T, W, ldo=32):
+    """out[z, t, r] = p[z, t, t + r - W] inside the band and [0, T), zero elsewhere (glow_tts.py:192-195); p [Z, T, ld] ->
+    [Z, T, ldo], tf32-rounded."""
+    Z, R, ld = p.shape
+    assert p.is_contiguous() and R == T and ldo >= 2 * W + 1
+    out = torch.empty(Z, T, ldo, device=p.device, dtype=torch.float32)
+    capi.call("xva_rel_band_gather", _p(p), Z, int(T), int(W), ld, int(ldo), _p(out), _stream())
+    return out
+
+
+def pad_cols(x, ld):
+    """[.., C] contiguous -> [.., ld] with zero pad columns (a row pitch the MN-major GEMM operands accept)."""
+    assert x.is_contiguous() and ld >= x.shape[-1]
+    C_ = x.shape[-1]
+    out = torch.empty(*x.shape[:-1], ld, device=x.device, dtype=torch.float32)
+    capi.call("xva_pad_cols", _p(x), x.numel() // C_, C_, int(ld), _p(out), _stream())
+    return out

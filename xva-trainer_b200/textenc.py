@@ -1,0 +1,440 @@
+"""xVAPitch text encoder on the B200 engine.
+
+    TextEncoder   drop-in for python/xvapitch/model.py:1089 ``TextEncoder`` (same constructor arguments, ``forward`` with
+                  both of its calls -- stats=False: embedding + language embedding + transformer; stats=True: the 1x1
+                  projection to the prior's mean / log-scale --, same state_dict keys and shapes) over
+                  python/xvapitch/glow_tts.py:373-485 ``RelativePositionTransformer`` (relative-position multi-head
+                  attention with a window of 4, glow_tts.py:59-292; kernel-3 conv FFN, :324-372; LayerNorm2, :34-56).
+
+Every product (the q / k / v / o projections, q.k^T, q.E_k^T, P.v, P_band.E_v, the two FFN convolutions and all their
+input and weight gradients) is a launch of the tcgen05 tap-GEMM of libxva_b200.so on channels-last [B, T, C] tensors; the
+softmax, LayerNorm and column-sum kernels are the ones the FastPitch FFT block uses; the steps that are new here --
+embedding + language concat, adding the relative-position logits onto the score band, reading the band of the attention
+weights back in relative indexing, padded operand copies -- are csrc/relattn.cu.
+
+Layout decisions (all forced by operand alignment, none changes a result):
+  * C = hidden + language channels is 196 / 204 / 268 in the reference's configurations, so a head is 98 / 102 / 134 columns:
+    not a multiple of 4 floats, i.e. head h of a packed q | k | v row would not start on the 16 bytes a TMA operand base
+    needs. Each head is padded to dkp = 128 (160) columns in the projection's OUTPUT (zero weight rows and biases), in
+    E_k / E_v and in the input columns of conv_o; pad entries have zero gradients (every product that reaches them has a
+    zero factor), so AdamW leaves them zero.
+  * weights whose input dimension is C are stored with a row pitch of Cp = C rounded up to 32: the input-gradient GEMM
+    reads them MN-major in 32-column chunks. Activations are [B, T, C] contiguous (what the LayerNorm kernels take); the
+    four tensors per layer that a weight-gradient GEMM reads MN-major get a padded copy (xva_pad_cols) in the backward.
+  * all parameters live in ONE flat fp32 tensor in the layout the kernels read (``flat``; its ``.grad`` is the gradient
+    arena the weight-gradient GEMMs accumulate into), with a tf32-rounded copy refreshed by one launch per forward.
+    state_dict() / load_state_dict() convert to and from the reference's keys and shapes.
+There is no CPU path: the module raises without the library.
+"""
+import math
+from collections import OrderedDict
+
+import torch
+import torch.nn as nn
+
+from . import capi, ops
+
+REL_WINDOW = 4           # model.py:1137 rel_attn_window_size=4
+REL_COLS = 32            # the 2 W + 1 = 9 relative positions padded to one 32-column operand chunk
+
+
+def _need_cuda(device):
+    dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+    if dev.type != "cuda":
+        raise capi.XvaError("the xVAPitch modules (B200 build) need a CUDA device: there is no CPU path")
+    capi.load()
+    capi.call("xva_device_check", dev.index or 0)
+    return dev
+
+
+def _up(n, m):
+    return (n + m - 1) // m * m
+
+
+class _NS:
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+class TextEncoder(nn.Module):
+    def __init__(self, n_vocab, out_channels, hidden_channels, hidden_channels_ffn, num_heads, num_layers, kernel_size,
+                 dropout_p, language_emb_dim=None, device=None, seed=1234):
+        super().__init__()
+        self.n_vocab, self.out_channels, self.hidden_channels = int(n_vocab), int(out_channels), int(hidden_channels)
+        self.hidden_channels_ffn, self.num_heads, self.num_layers = int(hidden_channels_ffn), int(num_heads), int(num_layers)
+        self.kernel_size, self.dropout_p = int(kernel_size), float(dropout_p)
+        self.lang_dim = int(language_emb_dim or 0)
+        C = self.hidden_channels + self.lang_dim
+        if C % self.num_heads or C % 4 or C > 512:
+            raise NotImplementedError(f"{C} channels: need a multiple of 4 and of the head count, at most 512 (LayerNorm kernels)")
+        if self.hidden_channels_ffn % 32 or (2 * self.out_channels) % 32:
+            raise NotImplementedError("FFN channels and 2 * out_channels must be multiples of 32")
+        self.C, self.Cp = C, _up(C, 32)
+        self.dk = C // self.num_heads
+        self.dkp = _up(self.dk, 32)
+        self.W = REL_WINDOW
+        self.shifts = tuple(j - (self.kernel_size - 1) // 2 for j in range(self.kernel_size))    # glow_tts.py:354-361
+        dev = _need_cuda(device)
+        # ---- the arena: (name, kernel-layout shape), every tensor on a 64-float boundary
+        H, dkp, Cp, F, k = self.num_heads, self.dkp, self.Cp, self.hidden_channels_ffn, self.kernel_size
+        spec = [("emb", (self.n_vocab, self.hidden_channels))]
+        for i in range(self.num_layers):
+            spec += [(f"l{i}.qkv_w", (3 * H * dkp, Cp)), (f"l{i}.qkv_b", (3 * H * dkp,)), (f"l{i}.ek", (REL_COLS, dkp)),
+                     (f"l{i}.ev", (REL_COLS, dkp)), (f"l{i}.o_w", (C, H * dkp)), (f"l{i}.o_b", (C,)), (f"l{i}.ln1_g", (C,)),
+                     (f"l{i}.ln1_b", (C,)), (f"l{i}.w1", (k, F, Cp)), (f"l{i}.b1", (F,)), (f"l{i}.w2", (k, C, F)),
+                     (f"l{i}.b2", (C,)), (f"l{i}.ln2_g", (C,)), (f"l{i}.ln2_b", (C,))]
+        spec += [("proj_w", (2 * self.out_channels, Cp)), ("proj_b", (2 * self.out_channels,))]
+        self._spec, self._off, n = spec, {}, 0
+        for name, shape in spec:
+            self._off[name] = n
+            n += _up(int(math.prod(shape)), 64)
+        self.flat = nn.Parameter(torch.zeros(n, device=dev, dtype=torch.float32))
+        self.flat.grad = torch.zeros(n, device=dev, dtype=torch.float32)
+        self._w = torch.zeros(n, device=dev, dtype=torch.float32)          # tf32-rounded copy: what the GEMMs read
+        self.seed = int(seed)
+        self.step_counter = torch.zeros(1, device=dev, dtype=torch.int64)   # device-side dropout counter
+        self._site = 0
+        self._ctx = None
+        self._stats_ctx = None
+        self.reset_parameters(seed)
+
+    # ------------------------------------------------------------------------------------------ parameters
+    def _views(self, flat):
+        """{name: view of `flat` in the kernel layout} (flat: the parameters, their gradients or the rounded copy)."""
+        out = {}
+        for name, shape in self._spec:
+            o = self._off[name]
+            out[name] = flat[o:o + int(math.prod(shape))].view(shape)
+        return out
+
+    def _layer(self, V, i):
+        """Per-layer operand views of an arena view dict: weights as [taps, N, K] with K cut to the real channel count."""
+        C, H, dkp = self.C, self.num_heads, self.dkp
+        g = lambda n: V[f"l{i}.{n}"]
+        return _NS(qkv_w=g("qkv_w")[None, :, :C], qkv_b=g("qkv_b"), ek=g("ek")[None], ev=g("ev")[None], o_w=g("o_w")[None],
+                   o_b=g("o_b"), ln1_g=g("ln1_g"), ln1_b=g("ln1_b"), w1=g("w1")[..., :C], b1=g("b1"), w2=g("w2"), b2=g("b2"),
+                   ln2_g=g("ln2_g"), ln2_b=g("ln2_b"))
+
+    def _ref_spec(self):
+        """(key, shape) of the reference module's state_dict, in its order (model.py:1117-1141, glow_tts.py:131-146,
+        349-351, 420-447)."""
+        C, Ce, F, k, dk = self.C, self.hidden_channels, self.hidden_channels_ffn, self.kernel_size, self.dk
+        spec = [("emb.weight", (self.n_vocab, Ce))]
+        for i in range(self.num_layers):
+            a = f"encoder.attn_layers.{i}"
+            spec += [(f"{a}.emb_rel_k", (1, 2 * self.W + 1, dk)), (f"{a}.emb_rel_v", (1, 2 * self.W + 1, dk))]
+            for n in ("q", "k", "v", "o"):
+                spec += [(f"{a}.conv_{n}.weight", (C, C, 1)), (f"{a}.conv_{n}.bias", (C,))]
+        for i in range(self.num_layers):
+            spec += [(f"encoder.norm_layers_1.{i}.gamma", (C,)), (f"encoder.norm_layers_1.{i}.beta", (C,))]
+        for i in range(self.num_layers):
+            f = f"encoder.ffn_layers.{i}"
+            spec += [(f"{f}.conv_1.weight", (F, C, k)), (f"{f}.conv_1.bias", (F,)), (f"{f}.conv_2.weight", (C, F, k)),
+                     (f"{f}.conv_2.bias", (C,))]
+        for i in range(self.num_layers):
+            spec += [(f"encoder.norm_layers_2.{i}.gamma", (C,)), (f"encoder.norm_layers_2.{i}.beta", (C,))]
+        spec += [("proj.weight", (2 * self.out_channels, C, 1)), ("proj.bias", (2 * self.out_channels,))]
+        return spec
+
+    def _to_ref(self, V):
+        """Arena views (kernel layout, padded) -> {reference key: tensor in the reference's shape} (copies)."""
+        C, H, dk, dkp, NR = self.C, self.num_heads, self.dk, self.dkp, 2 * self.W + 1
+        out = OrderedDict()
+        out["emb.weight"] = V["emb"].clone()
+        for i in range(self.num_layers):
+            a, f = f"encoder.attn_layers.{i}", f"encoder.ffn_layers.{i}"
+            qw = V[f"l{i}.qkv_w"].view(3, H, dkp, self.Cp)[:, :, :dk, :C]
+            qb = V[f"l{i}.qkv_b"].view(3, H, dkp)[:, :, :dk]
+            out[f"{a}.emb_rel_k"] = V[f"l{i}.ek"][:NR, :dk].clone()[None]
+            out[f"{a}.emb_rel_v"] = V[f"l{i}.ev"][:NR, :dk].clone()[None]
+            for s, n in enumerate("qkv"):
+                out[f"{a}.conv_{n}.weight"] = qw[s].reshape(C, C, 1).clone()
+                out[f"{a}.conv_{n}.bias"] = qb[s].reshape(C).clone()
+            out[f"{a}.conv_o.weight"] = V[f"l{i}.o_w"].view(C, H, dkp)[:, :, :dk].reshape(C, C, 1).clone()
+            out[f"{a}.conv_o.bias"] = V[f"l{i}.o_b"].clone()
+            out[f"encoder.norm_layers_1.{i}.gamma"] = V[f"l{i}.ln1_g"].clone()
+            out[f"encoder.norm_layers_1.{i}.beta"] = V[f"l{i}.ln1_b"].clone()
+            out[f"{f}.conv_1.weight"] = V[f"l{i}.w1"][..., :C].permute(1, 2, 0).contiguous()
+            out[f"{f}.conv_1.bias"] = V[f"l{i}.b1"].clone()
+            out[f"{f}.conv_2.weight"] = V[f"l{i}.w2"].permute(1, 2, 0).contiguous()
+            out[f"{f}.conv_2.bias"] = V[f"l{i}.b2"].clone()
+            out[f"encoder.norm_layers_2.{i}.gamma"] = V[f"l{i}.ln2_g"].clone()
+            out[f"encoder.norm_layers_2.{i}.beta"] = V[f"l{i}.ln2_b"].clone()
+        out["proj.weight"] = V["proj_w"][:, :C].reshape(2 * self.out_channels, C, 1).clone()
+        out["proj.bias"] = V["proj_b"].clone()
+        return OrderedDict((k, out[k]) for k, _ in self._ref_spec())
+
+    def state_dict(self, *args, destination=None, prefix="", keep_vars=False):
+        out = OrderedDict() if destination is None else destination
+        for k, v in self._to_ref(self._views(self.flat.detach())).items():
+            out[prefix + k] = v
+        return out
+
+    def grads(self):
+        """{reference key: gradient in the reference's shape}."""
+        return self._to_ref(self._views(self.flat.grad))
+
+    def load_state_dict(self, state_dict, strict=True):
+        known = dict(self._ref_spec())
+        missing = [k for k in known if k not in state_dict]
+        unexpected = [k for k in state_dict if k not in known]
+        if strict and (missing or unexpected):
+            raise RuntimeError(f"load_state_dict: missing {missing[:5]} unexpected {unexpected[:5]}")
+        C, H, dk, dkp, NR = self.C, self.num_heads, self.dk, self.dkp, 2 * self.W + 1
+        V = self._views(self.flat.data)
+        get = lambda k: None if k not in state_dict else state_dict[k].detach().to(device=self.flat.device, dtype=torch.float32)
+        with torch.no_grad():
+            for k, t in state_dict.items():
+                if k in known and tuple(t.shape) != tuple(known[k]):
+                    raise RuntimeError(f"load_state_dict: {k} has shape {tuple(t.shape)}, expected {tuple(known[k])}")
+
+            def put(dst, key, fn=lambda t: t):
+                t = get(key)
+                if t is not None:
+                    dst.copy_(fn(t))
+
+            put(V["emb"], "emb.weight")
+            for i in range(self.num_layers):
+                a, f = f"encoder.attn_layers.{i}", f"encoder.ffn_layers.{i}"
+                qw = V[f"l{i}.qkv_w"].view(3, H, dkp, self.Cp)
+                qb = V[f"l{i}.qkv_b"].view(3, H, dkp)
+                put(V[f"l{i}.ek"][:NR, :dk], f"{a}.emb_rel_k", lambda t: t[0])
+                put(V[f"l{i}.ev"][:NR, :dk], f"{a}.emb_rel_v", lambda t: t[0])
+                for s, n in enumerate("qkv"):
+                    put(qw[s, :, :dk, :C], f"{a}.conv_{n}.weight", lambda t: t[:, :, 0].view(H, dk, C))
+                    put(qb[s, :, :dk], f"{a}.conv_{n}.bias", lambda t: t.view(H, dk))
+                put(V[f"l{i}.o_w"].view(C, H, dkp)[:, :, :dk], f"{a}.conv_o.weight", lambda t: t[:, :, 0].view(C, H, dk))
+                put(V[f"l{i}.o_b"], f"{a}.conv_o.bias")
+                put(V[f"l{i}.ln1_g"], f"encoder.norm_layers_1.{i}.gamma")
+                put(V[f"l{i}.ln1_b"], f"encoder.norm_layers_1.{i}.beta")
+                put(V[f"l{i}.w1"][..., :C], f"{f}.conv_1.weight", lambda t: t.permute(2, 0, 1))
+                put(V[f"l{i}.b1"], f"{f}.conv_1.bias")
+                put(V[f"l{i}.w2"], f"{f}.conv_2.weight", lambda t: t.permute(2, 0, 1))
+                put(V[f"l{i}.b2"], f"{f}.conv_2.bias")
+                put(V[f"l{i}.ln2_g"], f"encoder.norm_layers_2.{i}.gamma")
+                put(V[f"l{i}.ln2_b"], f"encoder.norm_layers_2.{i}.beta")
+            put(V["proj_w"][:, :C], "proj.weight", lambda t: t[:, :, 0])
+            put(V["proj_b"], "proj.bias")
+        return torch.nn.modules.module._IncompatibleKeys(missing, unexpected)
+
+    def reset_parameters(self, seed=1234):
+        """The reference constructor's initialisation, seeded and generated on the CPU (identical on every rank): emb ~
+        N(0, hidden^-1/2) (model.py:1119), emb_rel ~ N(0, d_k^-1/2), xavier-uniform conv_q / conv_k / conv_v
+        (glow_tts.py:139-157), torch's Conv1d default (U(+-1/sqrt(fan_in))) elsewhere, LayerNorm2 gamma = 1 / beta = 0."""
+        gen = torch.Generator().manual_seed(int(seed))
+        sd = OrderedDict()
+        for key, shape in self._ref_spec():
+            if key == "emb.weight":
+                t = torch.randn(shape, generator=gen) * self.hidden_channels ** -0.5
+            elif "emb_rel" in key:
+                t = torch.randn(shape, generator=gen) * self.dk ** -0.5
+            elif key.endswith("gamma"):
+                t = torch.ones(shape)
+            elif key.endswith("beta"):
+                t = torch.zeros(shape)
+            elif key.endswith(("conv_q.weight", "conv_k.weight", "conv_v.weight")):
+                bound = math.sqrt(6.0 / (shape[0] + shape[1]))
+                t = (torch.rand(shape, generator=gen) * 2 - 1) * bound
+            elif key.endswith(".weight"):
+                bound = 1.0 / math.sqrt(shape[1] * shape[2])
+                t = (torch.rand(shape, generator=gen) * 2 - 1) * bound
+            else:                                         # a convolution's bias: the same fan-in bound as its weight
+                wshape = dict(self._ref_spec())[key[:-4] + "weight"]
+                bound = 1.0 / math.sqrt(wshape[1] * wshape[2])
+                t = (torch.rand(shape, generator=gen) * 2 - 1) * bound
+            sd[key] = t
+        self.load_state_dict(sd)
+
+    def zero_grad(self, set_to_none=False):
+        if self.flat.grad is None:
+            self.flat.grad = torch.zeros_like(self.flat.data)
+        else:
+            self.flat.grad.zero_()
+
+    def _drop(self):
+        """(p, seed) of the next dropout site of this pass, numbered in call order (the backward re-derives the masks)."""
+        self._site += 1
+        p = self.dropout_p if self.training else 0.0
+        return p, (self.seed * 0x9E3779B1 + self._site * 0x85EBCA77) & 0xFFFFFFFFFFFF
+
+    def step_dropout(self):
+        """Advance the device-side dropout counter: call once per optimizer micro-step (fresh masks on a graph replay)."""
+        ops.counter_add_(self.step_counter, 1)
+
+    # ------------------------------------------------------------------------------------------ forward
+    def _weights(self):
+        ops.round_tf32_(self.flat.data, self._w)
+        return self._views(self._w), self._views(self.flat.data)
+
+    def forward_cl(self, tokens, lens, lang):
+        """tokens int64 [B, T], lens int32 [B], lang [B, L] or None -> (x [B, T, C] channels-last with zero rows past the
+        lengths, x_emb [B, T, hidden])."""
+        B, T = tokens.shape
+        C, H, dkp, Wd = self.C, self.num_heads, self.dkp, self.W
+        Wr, Wf = self._weights()                                 # GEMM operands (rounded) / fp32 biases and LayerNorm
+        keep = self.training
+        self._site = 0
+        sd = self.step_counter
+        scale = math.sqrt(self.hidden_channels)
+        x, x_emb = ops.text_embed(tokens, Wf["emb"], lang, lens, scale, C)
+        Tp = _up(T, 32)
+        lens_rep = lens.repeat(H)                                # one entry per (head, utterance): z = h * B + b
+        alpha = 1.0 / math.sqrt(self.dk)
+        saved = []
+        for i in range(self.num_layers):
+            L, Lf = self._layer(Wr, i), self._layer(Wf, i)
+            qkv = ops.conv_fwd(x, L.qkv_w, bias=Lf.qkv_b, round_out=True)                     # [B, T, 3 H dkp]
+            head = lambda s, h: qkv[..., (s * H + h) * dkp:(s * H + h + 1) * dkp]
+            s_ = torch.empty(H, B, T, Tp, device=x.device, dtype=torch.float32)
+            rel = torch.empty(H, B, T, REL_COLS, device=x.device, dtype=torch.float32)
+            for h in range(H):
+                ops.bmm_nt(head(0, h), head(1, h), alpha=alpha, out=s_[h][..., :T])          # q.k^T / sqrt(d_k)
+                ops.conv_fwd(head(0, h), L.ek, out=rel[h], alpha=alpha)                       # q.E_k^T / sqrt(d_k)
+            ops.rel_band_add_(s_.view(H * B, T, Tp), rel.view(H * B, T, REL_COLS), T, Wd)
+            p_att, seed_att = self._drop()
+            P, Pd = ops.softmax_fwd(s_.view(H * B, T, Tp), lens_rep, T, p_att, seed_att, sd)
+            del s_, rel
+            PB = ops.rel_band_gather(Pd, T, Wd, REL_COLS)                                     # [H B, T, 32]
+            vec = torch.empty(B, T, H * dkp, device=x.device, dtype=torch.float32)
+            Pd4, PB4 = Pd.view(H, B, T, Tp), PB.view(H, B, T, REL_COLS)
+            for h in range(H):
+                pv = ops.bmm_nn(Pd4[h][..., :T], head(2, h))                                  # P.v
+                ops.conv_dgrad(PB4[h], L.ev, out=vec[..., h * dkp:(h + 1) * dkp], residual=pv, round_out=True)  # + P_band.E_v
+            p1, seed1 = self._drop()
+            pre1 = ops.conv_fwd(vec, L.o_w, bias=Lf.o_b, residual=x, drop_p=p1, seed=seed1, seed_dev=sd)
+            y1, sv1 = ops.layernorm_fwd(pre1, Lf.ln1_g, Lf.ln1_b, lens)
+            pf, seedf = self._drop()
+            hdn = ops.conv_fwd(y1, L.w1, self.shifts, bias=Lf.b1, relu=True, lens=lens, drop_p=pf, seed=seedf, seed_dev=sd,
+                               round_out=True)
+            p2, seed2 = self._drop()
+            pre2 = ops.conv_fwd(hdn, L.w2, self.shifts, bias=Lf.b2, residual=y1, drop_p=p2, seed=seed2, seed_dev=sd)
+            y2, sv2 = ops.layernorm_fwd(pre2, Lf.ln2_g, Lf.ln2_b, lens)
+            if keep:
+                saved.append(_NS(x=x, qkv=qkv, P=P, Pd=Pd, PB=PB, vec=vec, sv1=sv1, y1=y1, h=hdn, sv2=sv2, att=(p_att, seed_att),
+                                 d1=(p1, seed1), df=(pf, seedf), d2=(p2, seed2)))
+            x = y2
+        self._ctx = _NS(saved=saved, tokens=tokens, lens=lens, lens_rep=lens_rep, lang=lang, T=T, B=B) if keep else None
+        return x, x_emb
+
+    def stats_cl(self, x, lens):
+        """TextEncoder.forward(stats=True), model.py:1147-1150: x [B, T, C] -> stats [B, T, 2 out] = [m | logs], masked."""
+        Wr, Wf = self._weights()
+        stats = ops.conv_fwd(x, Wr["proj_w"][None, :, :self.C], bias=Wf["proj_b"], lens=lens)
+        self._stats_ctx = (x, lens) if self.training else None
+        return stats
+
+    def forward(self, x, x_lengths, lang_emb=None, stats=False, x_mask=None, lang_emb_full=None):
+        """The reference's signature and layouts (model.py:1143-1168). stats=False: x = tokens [B, T] -> (x [B, C, T],
+        x_emb [B, T, hidden], x_mask [B, 1, T]). stats=True: x [B, C, T] -> (m, logs) [B, out, T]."""
+        dev = self.flat.device
+        if lang_emb_full is not None:
+            raise NotImplementedError("lang_emb_full (a per-token language embedding) is not built")
+        lens = torch.as_tensor(x_lengths).reshape(-1).to(device=dev, dtype=torch.int32)
+        if stats:
+            xc = x.to(device=dev, dtype=torch.float32).transpose(1, 2).contiguous()
+            st = self.stats_cl(xc, lens)
+            o = self.out_channels
+            return st[..., :o].transpose(1, 2), st[..., o:].transpose(1, 2)
+        tokens = x.to(device=dev, dtype=torch.int64).contiguous()
+        B, T = tokens.shape
+        lang = None
+        if self.lang_dim:
+            if lang_emb is None:
+                raise ValueError("this encoder was built with a language embedding: pass lang_emb [B, L, 1]")
+            lang = lang_emb.to(device=dev, dtype=torch.float32).reshape(B, self.lang_dim).contiguous()
+        xo, x_emb = self.forward_cl(tokens, lens, lang)
+        mask = (torch.arange(T, device=dev)[None, :] < lens[:, None]).to(torch.float32).unsqueeze(1)
+        return xo.transpose(1, 2), x_emb, mask
+
+    # ------------------------------------------------------------------------------------------ backward
+    def stats_backward_cl(self, dstats):
+        """dstats [B, T, 2 out] = dL/d[m | logs] (any values on the padded rows: they are masked here) -> dL/dx [B, T, C];
+        accumulates the projection's gradients."""
+        if self._stats_ctx is None:
+            raise RuntimeError("stats_backward_cl() needs a stats call in training mode first")
+        x, lens = self._stats_ctx
+        B, T, C = x.shape
+        Wr = self._views(self._w)
+        G = self._views(self.flat.grad)
+        # the forward multiplied by the mask (model.py:1148): zero the padded rows, and round -- d is a GEMM operand
+        mask = (torch.arange(T, device=x.device)[None, :] < lens[:, None]).to(torch.float32).unsqueeze(-1)
+        d = (dstats.to(torch.float32) * mask).contiguous()
+        ops.round_tf32_(d.view(-1), d.view(-1))
+        ops.colsum_(B * T, d.shape[2], d.shape[2], d, G["proj_b"])
+        xp = ops.pad_cols(x, self.Cp)
+        ops.conv_wgrad(d, xp[..., :C], (0,), out=G["proj_w"][None, :, :C], accumulate=True)
+        self._stats_ctx = None
+        return ops.conv_dgrad(d, Wr["proj_w"][None, :, :C])
+
+    def backward_cl(self, dx, dx_emb=None):
+        """dx [B, T, C] = dL/dx of forward_cl's first output (rows past the lengths are ignored), dx_emb [B, T, hidden]
+        (optional) = dL/dx_emb. Accumulates every parameter gradient into ``flat.grad``; returns dL/d(lang) [B, L] or None."""
+        c = self._ctx
+        if c is None:
+            raise RuntimeError("backward_cl() needs a forward in training mode first")
+        B, T, lens, lens_rep = c.B, c.T, c.lens, c.lens_rep
+        C, Cp, H, dkp, Wd, F = self.C, self.Cp, self.num_heads, self.dkp, self.W, self.hidden_channels_ffn
+        Wr, Wf = self._views(self._w), self._views(self.flat.data)
+        G = self._views(self.flat.grad)
+        sd = self.step_counter
+        Tp = _up(T, 32)
+        alpha = 1.0 / math.sqrt(self.dk)
+        dy = dx.to(torch.float32).contiguous()
+        for i in reversed(range(self.num_layers)):
+            s = c.saved[i]
+            L, Lf, g = self._layer(Wr, i), self._layer(Wf, i), self._layer(G, i)
+            head = lambda t, part, h: t[..., (part * H + h) * dkp:(part * H + h + 1) * dkp]
+            # ---- FeedForwardNetwork + LayerNorm2 (glow_tts.py:353-357, 481-482)
+            dx2, dbr2 = ops.layernorm_bwd(dy, s.sv2, Lf.ln2_g, lens, g.ln2_g, g.ln2_b, dbias=g.b2, want_drop=True,
+                                          drop_pre_p=s.d2[0], seed_pre=s.d2[1], seed_dev=sd)
+            ops.conv_wgrad(ops.pad_cols(dbr2, Cp)[..., :C], s.h, self.shifts, out=g.w2, accumulate=True)
+            dh = ops.conv_dgrad(dbr2, L.w2, self.shifts, gate=s.h, drop_p=s.df[0], seed=s.df[1], seed_dev=sd, round_out=True)
+            ops.conv_wgrad(dh, ops.pad_cols(s.y1, Cp)[..., :C], self.shifts, out=g.w1, accumulate=True)
+            ops.colsum_(B * T, F, F, dh, g.b1)
+            dy1 = ops.conv_dgrad(dh, L.w1, self.shifts, residual=dx2)
+            del dh, dx2, dbr2
+            # ---- RelativePositionMultiHeadAttention + LayerNorm1 (glow_tts.py:159-214, 476-478)
+            dx1, dbr1 = ops.layernorm_bwd(dy1, s.sv1, Lf.ln1_g, lens, g.ln1_g, g.ln1_b, dbias=g.o_b, want_drop=True,
+                                          drop_pre_p=s.d1[0], seed_pre=s.d1[1], seed_dev=sd)
+            ops.conv_wgrad(ops.pad_cols(dbr1, Cp)[..., :C], s.vec, (0,), out=g.o_w, accumulate=True)
+            dvec = ops.conv_dgrad(dbr1, L.o_w, round_out=True)                                 # [B, T, H dkp]
+            dqkv = torch.empty_like(s.qkv)
+            dP = torch.empty(H, B, T, Tp, device=dy.device, dtype=torch.float32)
+            dPB = torch.empty(H, B, T, REL_COLS, device=dy.device, dtype=torch.float32)
+            Pd4, PB4 = s.Pd.view(H, B, T, Tp), s.PB.view(H, B, T, REL_COLS)
+            for h in range(H):
+                dv_h = dvec[..., h * dkp:(h + 1) * dkp]
+                ops.bmm_nt(dv_h, head(s.qkv, 2, h), out=dP[h][..., :T])                       # dP = dO.v^T
+                ops.conv_fwd(dv_h, L.ev, out=dPB[h])                                           # band part: dO.E_v^T
+                ops.bmm_tn(Pd4[h][..., :T], dv_h, out=head(dqkv, 2, h), round_out=True)        # dv = P^T dO
+                ops.conv_wgrad(PB4[h], dv_h, (0,), out=g.ev, accumulate=True)                  # dE_v = P_band^T dO
+            ops.rel_band_add_(dP.view(H * B, T, Tp), dPB.view(H * B, T, REL_COLS), T, Wd)
+            ops.softmax_bwd_(s.P, dP.view(H * B, T, Tp), T, alpha, s.att[0], s.att[1], sd)     # dP <- dS / sqrt(d_k)
+            dR = ops.rel_band_gather(dP.view(H * B, T, Tp), T, Wd, REL_COLS).view(H, B, T, REL_COLS)
+            for h in range(H):
+                q_h, k_h = head(s.qkv, 0, h), head(s.qkv, 1, h)
+                dq = ops.bmm_nn(dP[h][..., :T], k_h)                                           # dS.k
+                ops.conv_dgrad(dR[h], L.ek, out=head(dqkv, 0, h), residual=dq, round_out=True)  # + dS_band.E_k
+                ops.bmm_tn(dP[h][..., :T], q_h, out=head(dqkv, 1, h), round_out=True)          # dk = dS^T q
+                ops.conv_wgrad(dR[h], q_h, (0,), out=g.ek, accumulate=True)                    # dE_k = dS_band^T q
+            del dP, dPB, dR, dvec
+            ops.conv_wgrad(dqkv, ops.pad_cols(s.x, Cp)[..., :C], (0,), out=g.qkv_w, accumulate=True)
+            ops.colsum_(B * T, dqkv.shape[2], dqkv.shape[2], dqkv, g.qkv_b)
+            dy = ops.conv_dgrad(dqkv, L.qkv_w, residual=dx1)
+            del dqkv, dx1, dbr1
+        # ---- embedding and language embedding (model.py:1152-1165)
+        scale = math.sqrt(self.hidden_channels)
+        ops.text_embed_bwd_(c.tokens, dy, lens, self.hidden_channels, scale, G["emb"])
+        if dx_emb is not None:
+            ops.text_embed_bwd_(c.tokens, dx_emb.to(torch.float32).contiguous(), None, self.hidden_channels, scale, G["emb"])
+        dlang = None
+        if self.lang_dim:
+            dlang = torch.zeros(B, self.lang_dim, device=dy.device, dtype=torch.float32)
+            ops.colsum_items_(dy[..., self.hidden_channels:], dlang)
+        self._ctx = None
+        return dlang
+
+    def backward(self, dx, dx_emb=None):
+        """dx [B, C, T] (the reference's layout) -> dL/d(lang_emb) [B, L, 1] or None."""
+        dlang = self.backward_cl(dx.transpose(1, 2), dx_emb)
+        return None if dlang is None else dlang.unsqueeze(-1)
