@@ -1,6 +1,7 @@
 """Host-orchestration fingerprint: the sequence of C-ABI calls (entry point, every scalar argument, the complete GEMM
-argument block except device pointers) that one FastPitch step of each training stage (3, 2, 4, 1), one HiFi-GAN step and
-one xVAPitch --hifi_only step emit, with the kernels stubbed out, on tiny seeded inputs. CPU only.
+argument block except device pointers) that one FastPitch step of each training stage (3, 2, 4, 1), one HiFi-GAN step, one
+xVAPitch --hifi_only step and one forward + backward of the xVAPitch text encoder emit, with the kernels stubbed out, on
+tiny seeded inputs. CPU only.
 
 tests/golden/launch_sequence.json holds the fingerprint of a tree whose GPU parity suite was green
 (`python tests/launch_sequence.py --write` after such a run). tests/test_launch_sequence.py recomputes it: a refactor
@@ -183,6 +184,18 @@ def record(streams=False):
         vt.HifiOnlyStep(enc, dec, disc).step(torch.randn(2, 513, 40, generator=gen).abs(), [40, 35],
                                               torch.randn(2, 1, 40 * 256, generator=gen), torch.randn(2, 512, generator=gen),
                                               eps=torch.randn(2, 192, 40, generator=gen), u=torch.tensor([0.3, 0.6]))
+
+        # the xVAPitch text encoder: embedding, 2 relative-position transformer layers, prior projection, and back
+        te = load("textenc", [('if dev.type != "cuda":', "if False:"),
+                              ('dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")',
+                               'dev = torch.device("cpu")')])
+        enc_t = te.TextEncoder(50, 192, 192, 768, 2, 2, 3, 0.1, language_emb_dim=12, device="cpu")
+        enc_t.train()
+        li = torch.tensor([13, 8], dtype=torch.int32)
+        xt, _ = enc_t.forward_cl(torch.randint(1, 50, (2, 13), generator=gen), li, torch.randn(2, 12, generator=gen))
+        enc_t.stats_cl(xt, li)
+        enc_t.backward_cl(torch.randn(2, 13, 204, generator=gen) + enc_t.stats_backward_cl(torch.randn(2, 13, 384, generator=gen)))
+        enc_t.step_dropout()
     finally:
         capi.load, capi.call, ops._stream, ops._check3, ops.duration_scan = saved
         torch.cuda.Stream, torch.cuda.stream, torch.cuda.current_stream = saved_cuda[:3]

@@ -6,9 +6,11 @@ Three layers of evidence, as for the FastPitch step (tests/test_fastpitch_gpu.py
   (1) the five new element-wise kernels one by one against torch, exact;
   (2) WIRING, exact arithmetic: every tap-GEMM routed to the fp32 checker kernel with operand rounding off -- forward
       <= 2e-5, every parameter gradient <= 2e-4 of the oracle's;
-  (3) the PRODUCT path (tcgen05 tap-GEMM, tf32 operands rounded to nearest): forward <= 3e-3, gradients <= 6e-2 per tensor
-      and <= 2e-2 over the whole gradient vector -- the bounds of the FastPitch FFT blocks at their toy shapes
-      (tests/test_fastpitch_gpu.py; measured there: 9e-4 / 3.4e-2 / 9e-3, profiles/r02_parity_table.txt).
+  (3) the PRODUCT path (tcgen05 tap-GEMM, tf32 operands rounded to nearest). Measured on B200 over the four cases below
+      (profiles/r02_textenc.txt, scripts/prof_textenc.py): forward 4.9e-4 .. 6.2e-4, d(lang_emb) 7.7e-3 .. 1.2e-2, gradient
+      vector 6.9e-3 .. 9.4e-3, worst tensor 1.8e-2 .. 2.9e-2 (an FFN conv_1 weight / bias; relative to the larger of its
+      own norm and 1 % of the largest gradient norm), median tensor 4e-3 .. 7.6e-3 -- the level of the FastPitch FFT
+      blocks at their toy shapes (9e-4 / 9e-3 / 3.4e-2, profiles/r02_parity_table.txt). Bounds = 2 x the measured maxima.
 The host code of the module is additionally checked on the CPU against the same oracle (tests/test_vits_text_encoder_cpu.py)."""
 import math
 import os
@@ -146,11 +148,11 @@ def test_product_path_matches_the_oracle(lib, T, lens, layers, cfg):
     out, got, dlang = _run(m, tokens, lens, lang, *seeds)
     assert rel(out["x_emb"], want_out["x_emb"]) < 1e-6
     for k in ("x", "m_p", "logs_p"):
-        assert rel(out[k], want_out[k]) < 3e-3, k
+        assert rel(out[k], want_out[k]) < 1.3e-3, k
     pad = out["x"].cpu()
     for b, n in enumerate(lens):
         assert float(pad[b, :, n:].abs().max()) == 0.0 if n < T else True
-    assert rel(dlang, want["lang"]) < 3e-2
+    assert rel(dlang, want["lang"]) < 2.4e-2
     floor = 1e-2 * max(float(want[k].norm()) for k in sd)
     num = sum(float((got[k].cpu() - want[k]).norm()) ** 2 for k in sd)
     den = sum(float(want[k].norm()) ** 2 for k in sd)
@@ -172,8 +174,8 @@ def test_forward_matches_the_reference_golden(lib):
     x, x_emb, mask = m(tokens, lens, lang_emb=lang)
     m_p, logs_p = m(x, lens, stats=True, x_mask=mask)
     assert rel(x_emb, torch.from_numpy(g["x_emb"])) < 1e-6
-    assert rel(x, torch.from_numpy(g["x"])) < 2e-3
-    assert rel(m_p, torch.from_numpy(g["m_p"])) < 2e-3 and rel(logs_p, torch.from_numpy(g["logs_p"])) < 2e-3
+    assert rel(x, torch.from_numpy(g["x"])) < 1.3e-3
+    assert rel(m_p, torch.from_numpy(g["m_p"])) < 1.3e-3 and rel(logs_p, torch.from_numpy(g["logs_p"])) < 1.3e-3
     assert float(x[1, :, 8:].abs().max()) == 0.0
     back = m.state_dict()
     assert list(back) == list(sd) and all(torch.equal(back[k].cpu(), sd[k]) for k in sd)
