@@ -533,6 +533,90 @@ def run_xvapitch(args, dev, peak_tf32):
             "loss": loss_host}
 
 
+def run_text_encoder(dev, steps=10):
+    """Next-tier row, second piece: one forward + backward of the xVAPitch text encoder
+    (xva-trainer_b200/textenc.py: embedding + language embedding, 10 layers of 2-head relative-position attention + k3
+    conv FFN, prior projection; every parameter gradient) at the full model's shape -- batch 32 x 160 tokens, 256 + 12
+    channels, dropout 0.1, ragged lengths -- replayed from a CUDA graph, launched eagerly, and the unmodified reference
+    module (python/xvapitch/model.py:1089 TextEncoder) under PyTorch eager on the same GPU. Device-resident inputs, CUDA
+    events, 3 warm-ups."""
+    import torch
+    from xva_trainer_b200 import capi, textenc
+
+    B, Tt, layers, hidden, lang_dim, vocab = 32, 160, 10, 256, 12, 200
+    gen = torch.Generator().manual_seed(1)
+    tokens = torch.randint(1, vocab, (B, Tt), generator=gen).to(dev)
+    lens_l = [Tt - (7 * i) % 60 for i in range(B)]
+    lens_l[0] = Tt
+    lens = torch.tensor(lens_l, dtype=torch.int32, device=dev)
+    lang = torch.randn(B, lang_dim, generator=gen).to(dev)
+    dx = torch.randn(B, Tt, hidden + lang_dim, generator=gen).to(dev)
+    dst = torch.randn(B, Tt, 2 * hidden, generator=gen).to(dev)
+    m = textenc.TextEncoder(vocab, hidden, hidden, 768, 2, layers, 3, 0.1, language_emb_dim=lang_dim, device=dev)
+    m.train()
+
+    def step():
+        m.zero_grad()
+        x, _ = m.forward_cl(tokens, lens, lang)
+        m.stats_cl(x, lens)
+        m.backward_cl(dx + m.stats_backward_cl(dst))
+        m.step_dropout()
+
+    def timed(fn, warm, n):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n
+
+    capi.reset_launch_count()
+    step()
+    launches = capi.launch_count()
+    out = {"metric": "tokens/s (xVAPitch text encoder, forward + backward)", "unit": "tokens/s", "n_gpus": 1, "steps": steps,
+           "config": {"workload": f"xVAPitch TextEncoder fwd + bwd, batch {B} x {Tt} tokens (ragged, {sum(lens_l)} valid), "
+                                  f"{layers} layers, {hidden} + {lang_dim} channels, ffn 768, 2 heads, window 4, dropout 0.1, synthetic"},
+           "gpu_launches_per_step": launches, "ms_per_step_eager": timed(step, 3, steps)}
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        step()
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        step()
+    ms = timed(g.replay, 3, steps)
+    out.update({"ms_per_step": ms, "value": B * Tt / (ms * 1e-3), "launch": "one CUDA-graph replay per step"})
+    try:
+        rs = ref_module()
+        if rs is not None and rs.xvapitch_available():
+            rs.install_xvapitch()
+            from python.xvapitch.model import TextEncoder as RefTE
+            torch.manual_seed(0)
+            r = RefTE(vocab, hidden, hidden, 768, 2, layers, 3, 0.1, language_emb_dim=lang_dim).to(dev).train()
+            lang3, lens64 = lang.unsqueeze(-1), lens.to(torch.int64)
+            rx, rst = dx.transpose(1, 2).contiguous(), dst.transpose(1, 2).contiguous()
+
+            def ref_fn(amp=False):
+                r.zero_grad(set_to_none=True)
+                with torch.autocast("cuda", dtype=torch.float16, enabled=amp):
+                    x, _, mask = r(tokens, lens64, lang_emb=lang3)
+                    mp, lp = r(x, lens64, stats=True, x_mask=mask)
+                    loss = (x.float() * rx).sum() + (torch.cat([mp, lp], 1).float() * rst).sum()
+                loss.backward()
+
+            out["eager_b200"] = {"fp32": {"ms_per_step": timed(ref_fn, 2, 5)},
+                                 "amp_fp16": {"ms_per_step": timed(lambda: ref_fn(True), 2, 5)},
+                                 "what": "unmodified reference TextEncoder, PyTorch eager, same GPU and shape"}
+    except Exception as e:  # noqa: BLE001
+        out["eager_b200"] = {"error": repr(e)[-300:]}
+    return out
+
+
 def run_native(args):
     import torch
     import torch.distributed as dist
@@ -956,8 +1040,12 @@ def main():
         torch.cuda.set_device(0)
         pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
             os.path.join(ROOT, "MEASURED_PEAKS.json")) else None
-        print(json.dumps(run_xvapitch(args, torch.device("cuda:0"), (pk["bf16_tflops_sustained"] if pk else 1400.0) / 2.0)),
-              flush=True)
+        res = run_xvapitch(args, torch.device("cuda:0"), (pk["bf16_tflops_sustained"] if pk else 1400.0) / 2.0)
+        try:                                   # second next-tier piece; its failure must not cost the first its numbers
+            res["text_encoder"] = run_text_encoder(torch.device("cuda:0"))
+        except Exception as e:  # noqa: BLE001
+            res["text_encoder"] = {"error": repr(e)[-400:]}
+        print(json.dumps(res), flush=True)
         return
     if args.via_trainer:
         return run_via_trainer(args)

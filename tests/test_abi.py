@@ -46,3 +46,4 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src, f"{f} mentions the oracle: the product path must not depend on it"
+                assert "cabi_emu" not in src, f"{f} mentions the CPU stand-in of the C ABI (tests/cabi_emu.py): test infrastructure only"

@@ -1,6 +1,6 @@
 // Element functions of the xVAPitch text-encoder kernels (csrc/relattn.cu): one call computes ONE output element, no
 // shared memory, no warp collectives. The __global__ kernels in relattn.cu are grid-stride loops over these functions.
-// The same functions compile as plain C++: the CPU tests build them with g++ (tests/cabi_emu.py) and run the loops on
+// The same functions compile as plain C++: the CPU tests build them with g++ (tests/relattn_host.cpp) and run the loops on
 // the host, so the index arithmetic below is checked against the CPU restatement of the reference without a GPU.
 //   XVA_HD          function qualifiers (__host__ __device__ __forceinline__ under nvcc, nothing under g++)
 //   XVA_RN(x)       store rounding of a GEMM operand (tf32_rn on the device; the host build rounds or not by a switch)
