@@ -267,7 +267,7 @@ int xva_layernorm_bwd(const float* dy, const float* x, const float* mean, const 
                       float* dbeta, float* dbias, float drop_post_p, uint64_t seed_post, float drop_pre_p,
                       uint64_t seed_pre, const uint64_t* seed_dev, int relu_gate, void* stream);
 
-/* nn.LayerNorm forward (transformer.py:75,148) on a stored pre-LN tensor x [Z,R,C] (C % 4 == 0, <= 512):
+/* nn.LayerNorm forward (transformer.py:75,148) on a stored pre-LN tensor x [Z,R,C] (C % 4 == 0, <= 1024):
  * y = ((x - mean) * rstd * gamma + beta) for rows r < lens[z] (lens optional), zero otherwise, stored tf32-rounded (it is
  * the next GEMM's operand); mean / rstd [Z*R] are saved for xva_layernorm_bwd. The FFT blocks use this after a GEMM
  * whose epilogue did bias + dropout + residual: un-fused, the GEMM keeps double-buffered accumulators. */

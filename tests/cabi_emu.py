@@ -414,3 +414,287 @@ def load_module(modname, patches, extra_modules=None):
             else:
                 sys.modules[k] = v
     return m
+
+
+# ------------------------------------------------------------------------------------------------ FastPitch-only entry points
+def _lens_mask(lens, Z, R):
+    if not _addr(lens):
+        return np.ones((Z, R), bool)
+    return np.arange(R)[None, :] < flat(lens, Z, np.int32)[:, None]
+
+
+def _embed_pos(tokens, emb, inp, lens, inv_freq, B, T, Cc, out, stream=None):
+    O = flat(out, B * T * Cc).reshape(B, T, Cc)
+    if _addr(tokens):
+        tok = flat(tokens, B * T, np.int64).reshape(B, T)
+        n_rows = int(tok.max()) + 1
+        v = flat(emb, n_rows * Cc).reshape(n_rows, Cc)[tok]
+        live = tok != 0
+    else:
+        v = flat(inp, B * T * Cc).reshape(B, T, Cc).copy()
+        live = _lens_mask(lens, B, T)
+    if _addr(inv_freq):
+        f = flat(inv_freq, Cc // 2)
+        ang = (np.arange(T, dtype=np.float32)[:, None] * f[None, :]).astype(np.float32)
+        pos = np.concatenate([np.sin(ang), np.cos(ang)], axis=1)
+        v = v + pos[None] * live[:, :, None]
+    O[...] = v.astype(np.float32)
+    return 0
+
+
+def _embed_bwd(tokens, dout, B, T, Cc, demb, stream=None):
+    tok = flat(tokens, B * T, np.int64)
+    D = flat(dout, B * T * Cc).reshape(B * T, Cc)
+    n_rows = int(tok.max()) + 1
+    E = flat(demb, n_rows * Cc).reshape(n_rows, Cc)
+    live = tok != 0
+    np.add.at(E, tok[live], D[live])
+    return 0
+
+
+def _scalar_conv_add(io, x, w, bias, lens, B, T, Cc, stream=None):
+    IO = flat(io, B * T * Cc).reshape(B, T, Cc)
+    X = flat(x, B * T).reshape(B, T)
+    Wt, bs = flat(w, Cc * 3).reshape(Cc, 3), flat(bias, Cc)
+    xp = np.pad(X, ((0, 0), (1, 1)))
+    add = bs[None, None, :] + xp[:, :-2, None] * Wt[None, None, :, 0] + X[:, :, None] * Wt[None, None, :, 1] + xp[:, 2:, None] * Wt[None, None, :, 2]
+    live = _lens_mask(lens, B, T)
+    IO[...] = np.where(live[:, :, None], IO + add, IO).astype(np.float32)
+    return 0
+
+
+def _scalar_conv_bwd(dout, x, B, T, Cc, dw, dbias, stream=None):
+    D = flat(dout, B * T * Cc).reshape(B, T, Cc).astype(np.float64)
+    X = flat(x, B * T).reshape(B, T).astype(np.float64)
+    xp = np.pad(X, ((0, 0), (1, 1)))
+    DW = flat(dw, Cc * 3).reshape(Cc, 3)
+    for j, xs in enumerate((xp[:, :-2], X, xp[:, 2:])):
+        DW[:, j] += np.einsum("btc,bt->c", D, xs).astype(np.float32)
+    flat(dbias, Cc)[...] += D.sum(axis=(0, 1)).astype(np.float32)
+    return 0
+
+
+def _rowdot_fwd(x, w, bias, lens, Z, R, Cc, out, stream=None):
+    X = flat(x, Z * R * Cc).reshape(Z, R, Cc).astype(np.float64)
+    v = X @ flat(w, Cc).astype(np.float64) + float(flat(bias, 1)[0])
+    flat(out, Z * R).reshape(Z, R)[...] = np.where(_lens_mask(lens, Z, R), v, 0.0).astype(np.float32)
+    return 0
+
+
+def _rowdot_bwd(dout, x, w, lens, Z, R, Cc, dx, dw, db, stream=None):
+    g = np.where(_lens_mask(lens, Z, R), flat(dout, Z * R).reshape(Z, R), 0.0).astype(np.float64)
+    X = flat(x, Z * R * Cc).reshape(Z, R, Cc).astype(np.float64)
+    flat(dx, Z * R * Cc).reshape(Z, R, Cc)[...] = (g[:, :, None] * flat(w, Cc)[None, None, :]).astype(np.float32)
+    flat(dw, Cc)[...] += np.einsum("zr,zrc->c", g, X).astype(np.float32)
+    flat(db, 1)[0] += np.float32(g.sum())
+    return 0
+
+
+def _regulate_scan(durs, B, Tt, pace, mel_max_len, cum, dec_lens, stream=None):
+    d = flat(durs, B * Tt).reshape(B, Tt)
+    reps = ((d * np.float32(pace)).astype(np.float32) + np.float32(0.5)).astype(np.float32).astype(np.int64)   # trunc toward zero
+    Cm = flat(cum, B * (Tt + 1), np.int32).reshape(B, Tt + 1)
+    Cm[:, 0] = 0
+    Cm[:, 1:] = np.cumsum(reps, axis=1)
+    tot = Cm[:, Tt]
+    flat(dec_lens, B, np.int32)[...] = np.where((mel_max_len >= 0) & (tot > mel_max_len), mel_max_len, tot)
+    return 0
+
+
+def _token_of_frame(Cm, T_out):
+    """idx[b, t] = j with cum[b, j] <= t < cum[b, j + 1], -1 past the total."""
+    B = Cm.shape[0]
+    idx = np.full((B, T_out), -1, np.int64)
+    for b in range(B):
+        t = np.arange(T_out)
+        j = np.searchsorted(Cm[b], t, side="right") - 1
+        ok = t < Cm[b, -1]
+        idx[b, ok] = j[ok]
+    return idx
+
+
+def _regulate_fwd(enc, cum, B, Tt, Cc, T_out, out, idx_out, stream=None):
+    Cm = flat(cum, B * (Tt + 1), np.int32).reshape(B, Tt + 1)
+    E = flat(enc, B * Tt * Cc).reshape(B, Tt, Cc)
+    idx = _token_of_frame(Cm, T_out)
+    O = flat(out, B * T_out * Cc).reshape(B, T_out, Cc)
+    for b in range(B):
+        O[b] = np.where((idx[b] >= 0)[:, None], E[b, np.clip(idx[b], 0, Tt - 1)], 0.0)
+    if _addr(idx_out):
+        flat(idx_out, B * T_out, np.int32).reshape(B, T_out)[...] = idx
+    return 0
+
+
+def _regulate_bwd(dout, cum, B, Tt, Cc, T_out, denc, accumulate, stream=None):
+    Cm = flat(cum, B * (Tt + 1), np.int32).reshape(B, Tt + 1)
+    D = flat(dout, B * T_out * Cc).reshape(B, T_out, Cc)
+    idx = _token_of_frame(Cm, T_out)
+    G = flat(denc, B * Tt * Cc).reshape(B, Tt, Cc)
+    for b in range(B):
+        acc = np.zeros((Tt, Cc), np.float64)
+        ok = idx[b] >= 0
+        np.add.at(acc, idx[b][ok], D[b][ok])
+        G[b] = (G[b] + acc if accumulate else acc).astype(np.float32)
+    return 0
+
+
+def _average_pitch(pitch, durs, B, Fn, Tm, Tt, out, log1p_out, stream=None):
+    P = flat(pitch, B * Fn * Tm).reshape(B, Fn, Tm)
+    d = flat(durs, B * Tt).reshape(B, Tt)
+    O = flat(out, B * Fn * Tt).reshape(B, Fn, Tt)
+    for b in range(B):
+        run = np.cumsum(d[b], dtype=np.float32)                       # fp32 running sum, truncated like cumsum(...).long()
+        cm = np.concatenate([[0], run.astype(np.int64)])
+        for j in range(Tt):
+            t0, t1 = min(cm[j], Tm), min(cm[j + 1], Tm)
+            seg = P[b, :, t0:t1]
+            cnt = (seg != 0).sum(axis=1)
+            mean = np.where(cnt > 0, seg.sum(axis=1, dtype=np.float32) / np.maximum(cnt, 1), 0.0).astype(np.float32)
+            O[b, :, j] = np.log(np.float32(1.0) + mean) if log1p_out else mean
+    return 0
+
+
+def _mel_mse(pred, tgt, B, T_out, Tm, Cc, acc, stream=None):
+    Pm = flat(pred, B * T_out * Cc).reshape(B, T_out, Cc)
+    Y = flat(tgt, B * Cc * Tm).reshape(B, Cc, Tm).transpose(0, 2, 1)          # [B, Tm, C]
+    Pf = np.zeros((B, Tm, Cc), np.float32)
+    Pf[:, :min(T_out, Tm)] = Pm[:, :min(T_out, Tm)]
+    m = Y != 0
+    A = flat(acc, 2, np.float64)
+    A[0] += float((((Pf - Y).astype(np.float32) ** 2).astype(np.float64) * m).sum())
+    A[1] += float(m.sum())
+    return 0
+
+
+def _mel_mse_grad(pred, tgt, B, T_out, Tm, Cc, ldd, acc, scale, dpred, stream=None):
+    Pm = flat(pred, B * T_out * Cc).reshape(B, T_out, Cc)
+    Y = flat(tgt, B * Cc * Tm).reshape(B, Cc, Tm).transpose(0, 2, 1)[:, :T_out]
+    k = np.float32(2.0 * scale / flat(acc, 2, np.float64)[1])
+    D = flat(dpred, B * T_out * ldd).reshape(B, T_out, ldd)
+    D[...] = 0.0
+    D[..., :Cc] = np.where(Y != 0, k * (Pm - Y), 0.0)
+    return 0
+
+
+def _lens_mse(pred, tgt, lens, B, T, log1p_tgt, acc, stream=None):
+    Pm, Y = flat(pred, B * T).reshape(B, T), flat(tgt, B * T).reshape(B, T)
+    if log1p_tgt:
+        Y = np.log(Y + np.float32(1.0))
+    m = _lens_mask(lens, B, T)
+    A = flat(acc, 2, np.float64)
+    A[0] += float((((Pm - Y).astype(np.float32) ** 2).astype(np.float64) * m).sum())
+    A[1] += float(m.sum())
+    return 0
+
+
+def _lens_mse_grad(pred, tgt, lens, B, T, log1p_tgt, acc, scale, dpred, stream=None):
+    Pm, Y = flat(pred, B * T).reshape(B, T), flat(tgt, B * T).reshape(B, T)
+    if log1p_tgt:
+        Y = np.log(Y + np.float32(1.0))
+    k = np.float32(2.0 * scale / flat(acc, 2, np.float64)[1])
+    flat(dpred, B * T).reshape(B, T)[...] = np.where(_lens_mask(lens, B, T), k * (Pm - Y), 0.0)
+    return 0
+
+
+_CHUNK = np.dtype([("start", np.int64), ("len", np.int32), ("tensor", np.int32)])
+
+
+def _chunks(p, n):
+    raw = np.ctypeslib.as_array(C.cast(_addr(p), C.POINTER(C.c_uint8)), shape=(int(n) * _CHUNK.itemsize,))
+    return raw.view(_CHUNK)
+
+
+def _grad_sqnorm(g, chunks, n_chunks, out, stream=None):
+    s = 0.0
+    for ck in _chunks(chunks, n_chunks):
+        v = flat(_addr(g) + 4 * int(ck["start"]), int(ck["len"])).astype(np.float64)
+        s += float((v * v).sum())
+    flat(out, 1, np.float64)[0] += s
+    return 0
+
+
+def _lamb_step(p, g, m, v, chunks, n_chunks, norms, gnorm_sq, max_norm, lr_dev, b1, b2, eps, wd, p_tf32, stream=None):
+    gs = flat(gnorm_sq, 1, np.float64)
+    if gs is not None and not np.isfinite(gs[0]):
+        return 0
+    coef = np.float32(1.0)
+    if gs is not None and max_norm > 0:
+        c = np.float32(max_norm) / (np.float32(np.sqrt(gs[0])) + np.float32(1e-6))
+        coef = min(c, np.float32(1.0))
+    cks = _chunks(chunks, n_chunks)
+    n_t = int(cks["tensor"].max()) + 1
+    N = flat(norms, 2 * n_t, np.float64)
+    b1, b2, eps, wd = (np.float32(x) for x in (b1, b2, eps, wd))
+    rs = []
+    for ck in cks:
+        a, n = int(ck["start"]), int(ck["len"])
+        P, G, M, V = (flat(_addr(q) + 4 * a, n) for q in (p, g, m, v))
+        gi = G * coef
+        M[...] = b1 * M + (np.float32(1.0) - b1) * gi
+        V[...] = b2 * V + (np.float32(1.0) - b2) * gi * gi
+        r = M / (np.sqrt(V) + eps) + wd * P
+        rs.append(r)
+        N[2 * ck["tensor"]] += float((P.astype(np.float64) ** 2).sum())
+        N[2 * ck["tensor"] + 1] += float((r.astype(np.float64) ** 2).sum())
+    lr = flat(lr_dev, 1)[0]
+    for ck, r in zip(cks, rs):
+        a, n = int(ck["start"]), int(ck["len"])
+        wn = min(np.float32(np.sqrt(N[2 * ck["tensor"]])), np.float32(10.0))
+        rn = np.float32(np.sqrt(N[2 * ck["tensor"] + 1]))
+        trust = np.float32(1.0) if (wn == 0 or rn == 0) else wn / rn
+        P = flat(_addr(p) + 4 * a, n)
+        P[...] = P - lr * trust * r
+        if _addr(p_tf32):
+            flat(_addr(p_tf32) + 4 * a, n)[...] = P
+    return 0
+
+
+def _attn_fwd(qkv, rs, zs, B, T, lens, scale, drop_p, seed, seed_dev, drop_ld, out, o_rs, o_zs, lse, stream=None):
+    """include/xva_b200.h xva_attn_fwd: single head, d_head 64, q | k | v in columns 0..191."""
+    X = strided(qkv, (B, T, 192), (zs, rs, 1)).astype(np.float64)
+    q, k, v = X[..., :64], X[..., 64:128], X[..., 128:]
+    s_ = np.float32(scale) * np.einsum("bid,bjd->bij", q, k)
+    keym = _lens_mask(lens, B, T)[:, None, :]
+    s_ = np.where(keym, s_, -np.inf)
+    mx = s_.max(axis=2, keepdims=True)
+    e = np.exp(s_ - mx)
+    den = e.sum(axis=2, keepdims=True)
+    P = e / den
+    idx = (np.arange(B, dtype=np.uint64)[:, None, None] * np.uint64(T) + np.arange(T, dtype=np.uint64)[None, :, None]) * np.uint64(drop_ld) \
+        + np.arange(T, dtype=np.uint64)[None, None, :]
+    Pd = P * dropout_scale(seed, seed_dev, idx, drop_p)
+    strided(out, (B, T, 64), (o_zs, o_rs, 1))[...] = np.einsum("bij,bjd->bid", Pd, v).astype(np.float32)
+    flat(lse, B * T).reshape(B, T)[...] = (mx + np.log(den))[..., 0].astype(np.float32)
+    return 0
+
+
+def _attn_bwd(qkv, rs, zs, dout, d_rs, d_zs, lse, dsum, B, T, lens, scale, drop_p, seed, seed_dev, drop_ld, dqkv, g_rs, g_zs,
+              stream=None):
+    X = strided(qkv, (B, T, 192), (zs, rs, 1)).astype(np.float64)
+    q, k, v = X[..., :64], X[..., 64:128], X[..., 128:]
+    dO = strided(dout, (B, T, 64), (d_zs, d_rs, 1)).astype(np.float64)
+    L = flat(lse, B * T).reshape(B, T, 1).astype(np.float64)
+    Ds = flat(dsum, B * T).reshape(B, T, 1).astype(np.float64)
+    sc = np.float64(np.float32(scale))
+    keym = _lens_mask(lens, B, T)[:, None, :]
+    P = np.where(keym, np.exp(sc * np.einsum("bid,bjd->bij", q, k) - L), 0.0)
+    idx = (np.arange(B, dtype=np.uint64)[:, None, None] * np.uint64(T) + np.arange(T, dtype=np.uint64)[None, :, None]) * np.uint64(drop_ld) \
+        + np.arange(T, dtype=np.uint64)[None, None, :]
+    dm = dropout_scale(seed, seed_dev, idx, drop_p)
+    dV = np.einsum("bij,bid->bjd", P * dm, dO)
+    dS = P * (np.einsum("bid,bjd->bij", dO, v) * dm - Ds)
+    G = strided(dqkv, (B, T, 192), (g_zs, g_rs, 1))
+    G[..., :64] = (sc * np.einsum("bij,bjd->bid", dS, k)).astype(np.float32)
+    G[..., 64:128] = (sc * np.einsum("bij,bid->bjd", dS, q)).astype(np.float32)
+    G[..., 128:] = dV.astype(np.float32)
+    return 0
+
+
+TABLE.update({
+    "xva_embed_pos": _embed_pos, "xva_embed_bwd": _embed_bwd, "xva_scalar_conv_add": _scalar_conv_add,
+    "xva_scalar_conv_bwd": _scalar_conv_bwd, "xva_rowdot_fwd": _rowdot_fwd, "xva_rowdot_bwd": _rowdot_bwd,
+    "xva_regulate_len_scan": _regulate_scan, "xva_regulate_len_fwd": _regulate_fwd, "xva_regulate_len_bwd": _regulate_bwd,
+    "xva_average_pitch": _average_pitch, "xva_mel_mse": _mel_mse, "xva_mel_mse_grad": _mel_mse_grad, "xva_lens_mse": _lens_mse,
+    "xva_lens_mse_grad": _lens_mse_grad, "xva_grad_sqnorm": _grad_sqnorm, "xva_lamb_step": _lamb_step,
+    "xva_attn_fwd": _attn_fwd, "xva_attn_bwd": _attn_bwd,
+})

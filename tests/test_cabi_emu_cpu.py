@@ -86,3 +86,66 @@ def test_dropout_hash_is_the_librarys():
         f = (h64(12345, i >> 2) >> (16 * (i & 3))) & 0xFFFF
         assert (s[i] > 0) == (f >= th)
     assert (cabi_emu.dropout_scale(1, None, idx, 0.0) == 1.0).all()
+
+
+@pytest.mark.parametrize("stage,fused", [(3, True), (2, False), (4, True)])
+def test_fastpitch_training_steps_through_the_emulator_match_the_oracle(stage, fused):
+    """The whole FastPitch micro-step of the product package -- forward (embedding, FFT stacks, predictors, pitch / energy
+    embeddings, length regulator, projection), FastPitchLoss, the hand-written backward, clip + LAMB -- executed on the CPU
+    through the emulated C ABI, two consecutive optimizer steps, against oracle.fastpitch.train_step: forward tensors,
+    every loss term, every parameter gradient, the weights after LAMB. (On the device the same comparison is
+    tests/test_fastpitch_gpu.py; here it pins the HOST code -- 330 launches per step and their arguments -- between GPU runs,
+    numerically rather than as a fingerprint.) fused = the fused-attention entry points (emulated from their contract in
+    include/xva_b200.h) or the six-launch chain."""
+    x, y = ofp.synthetic_batch(3, 12, 40, seed=7, ragged=True)
+    sd = ofp.make_state(1234)
+    with cabi_emu.installed():
+        fp = cabi_emu.load_module("fastpitch", FP_PATCHES)
+        m = fp.FastPitch(device="cpu")
+        m.load_state_dict({k: v.clone() for k, v in sd.items()})
+        m.training_stage = stage
+        m.train()
+        m.p_drop = 0.0
+        m.fused_attn = fused
+        crit = fp.FastPitchLoss()
+        crit.training_stage = stage
+        opt = fp.Lamb(m, lr=0.1, betas=(0.9, 0.98), eps=1e-9, weight_decay=1e-6)
+        osd, ostate = {k: v.clone() for k, v in sd.items()}, {}
+        keys = fp.trainable_keys(stage)
+        for it in (50000, 50001):
+            fp.adjust_learning_rate(it, opt, 0.1, 1000)
+            m.zero_grad()
+            out = m(x)
+            loss, meta = crit(out, y)
+            m.backward(crit, 1.0)
+            got_grads = {k: v.clone() for k, v in m.grads(keys).items()}
+            want_fwd = ofp.forward(osd, x, stage)
+            wmeta, wgrads = ofp.train_step(osd, x, y, stage, ofp.noam_lr(it), ostate, drop=0.0, training=False)
+            for name, g_, w_ in zip(("mel_out", "dec_mask", "dur_pred", "log_dur_pred", "pitch_pred", "pitch_tgt", "energy_pred",
+                                     "energy_tgt"), out[:8], want_fwd[:8]):
+                if w_ is None:
+                    continue
+                if w_.dtype == torch.bool:
+                    assert torch.equal(g_, w_), name
+                else:
+                    assert rel(g_.float(), w_.float()) < 2e-5, (it, name)
+            for k in ("loss", "mel_loss", "duration_predictor_loss", "pitch_loss", "energy_loss"):
+                a, b = float(meta[k]), float(wmeta[k])
+                assert abs(a - b) <= 2e-5 * max(abs(b), 1e-6), (it, k, a, b)
+            floor = 1e-4 * max(float(w.norm()) for w in wgrads.values() if w is not None)
+            for k in keys:
+                if wgrads[k] is None:
+                    assert float(got_grads[k].abs().max()) == 0.0, k
+                else:
+                    err = float((got_grads[k] - wgrads[k]).norm()) / max(float(wgrads[k].norm()), floor)
+                    assert err < 2e-4, (it, k, err)
+            opt.step()
+            m.step_dropout()
+            after = m.state_dict()
+            for k in keys:
+                assert rel(after[k], osd[k]) < 5e-5, (it, k)      # (LAMB divides by sqrt(v): tensors with ~0 gradients amplify rounding)
+        used = set(cabi_emu.calls)
+    want_used = {"xva_embed_pos", "xva_lamb_step", "xva_grad_sqnorm"} | (
+        {"xva_lens_mse", "xva_rowdot_bwd"} if stage == 2 else {"xva_regulate_len_fwd", "xva_regulate_len_bwd", "xva_mel_mse"})
+    assert want_used <= used, want_used - used
+    assert ("xva_attn_fwd" in used) == fused

@@ -53,7 +53,7 @@ def test_softmax_fwd_bwd(lib, Z, R, N):
     assert float(dpd[..., N:].abs().max() if ld > N else 0.0) == 0.0
 
 
-@pytest.mark.parametrize("Z,R,C", [(3, 50, 384), (2, 33, 256), (2, 17, 80)])
+@pytest.mark.parametrize("Z,R,C", [(3, 50, 384), (2, 33, 256), (2, 17, 80), (3, 41, 780), (2, 19, 708), (2, 9, 1024), (2, 21, 516)])
 def test_layernorm_fwd_bwd(lib, Z, R, C):
     from xva_trainer_b200 import ops
     x = gen(Z, R, C, seed=5) * 2 + 0.5

@@ -732,7 +732,7 @@ int layernorm_bwd(const float* dy, const float* x, const float* mean, const floa
                   const int* lens, int Z, int R, int C, float* dx, float* dx_drop, float* dgamma, float* dbeta,
                   float* dbias, float drop_post_p, uint64_t seed_post, float drop_pre_p, uint64_t seed_pre,
                   const uint64_t* seed_dev, int relu_gate, cudaStream_t stream) {
-  XVA_CHECK_ARG(C >= 1 && C <= 512, "layernorm bwd: C=%d (max 512)", C);
+  XVA_CHECK_ARG(C >= 1 && C <= 1024, "layernorm bwd: C=%d (max 1024)", C);
   uint32_t th_post, th_pre;
   float ik_post, ik_pre;
   drop_consts(drop_post_p, &th_post, &ik_post);
@@ -754,10 +754,12 @@ int layernorm_bwd(const float* dy, const float* x, const float* mean, const floa
   if (C % 4 == 0 && aligned16(dy) && aligned16(x) && aligned16(gamma) && aligned16(dx) && aligned16(dx_drop)) {
     if (C <= 256) XVA_LN_BWD4(2);
     else if (C <= 384) XVA_LN_BWD4(3);
-    else XVA_LN_BWD4(4);
+    else if (C <= 512) XVA_LN_BWD4(4);
+    else XVA_LN_BWD4(8);  // 513..1024 channels: the xVAPitch pitch predictor's 708 / 780 (python/xvapitch/model.py:154-168)
   } else if (C <= 256) XVA_LN_BWD(8);
   else if (C <= 384) XVA_LN_BWD(12);
-  else XVA_LN_BWD(16);
+  else if (C <= 512) XVA_LN_BWD(16);
+  else XVA_LN_BWD(32);
 #undef XVA_LN_BWD4
 #undef XVA_LN_BWD
   XVA_CHECK_LAUNCH();
@@ -766,13 +768,14 @@ int layernorm_bwd(const float* dy, const float* x, const float* mean, const floa
 
 int layernorm_fwd(const float* x, const float* gamma, const float* beta, const int* lens, int Z, int R, int C, float eps,
                   float* y, float* mean, float* rstd, cudaStream_t stream) {
-  XVA_CHECK_ARG(C >= 4 && C <= 512 && C % 4 == 0, "layernorm fwd: C=%d (multiple of 4, max 512)", C);
+  XVA_CHECK_ARG(C >= 4 && C <= 1024 && C % 4 == 0, "layernorm fwd: C=%d (multiple of 4, max 1024)", C);
   XVA_CHECK_ARG(aligned16(x) && aligned16(y) && aligned16(gamma) && aligned16(beta), "layernorm fwd: pointers must be 16-byte aligned");
   const long rows = static_cast<long>(Z) * R;
   if (rows == 0) return XVA_OK;
   if (C <= 256) layernorm_fwd_v4_kernel<2><<<row_blocks(rows), kWarpsPerBlock * 32, 0, stream>>>(x, gamma, beta, lens, R, C, rows, eps, y, mean, rstd);
   else if (C <= 384) layernorm_fwd_v4_kernel<3><<<row_blocks(rows), kWarpsPerBlock * 32, 0, stream>>>(x, gamma, beta, lens, R, C, rows, eps, y, mean, rstd);
-  else layernorm_fwd_v4_kernel<4><<<row_blocks(rows), kWarpsPerBlock * 32, 0, stream>>>(x, gamma, beta, lens, R, C, rows, eps, y, mean, rstd);
+  else if (C <= 512) layernorm_fwd_v4_kernel<4><<<row_blocks(rows), kWarpsPerBlock * 32, 0, stream>>>(x, gamma, beta, lens, R, C, rows, eps, y, mean, rstd);
+  else layernorm_fwd_v4_kernel<8><<<row_blocks(rows), kWarpsPerBlock * 32, 0, stream>>>(x, gamma, beta, lens, R, C, rows, eps, y, mean, rstd);
   XVA_CHECK_LAUNCH();
   return XVA_OK;
 }
