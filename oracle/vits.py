@@ -201,6 +201,32 @@ def text_encoder_stats(sd, x, mask):
     return torch.split(stats, stats.shape[1] // 2, dim=1)
 
 
+def pitch_predictor(sd, x, x_lengths, speaker_emb, num_layers, kernel=3):
+    """RelativePositioningPitchEnergyEncoder.forward, xvapitch/model.py:1310-1356 (built at :154-168 with out_channels = 1)
+    over RelativePositionTransformer.forward, glow_tts.py:463-485: x [B, T, hidden] (the text encoder's output, detached by
+    the caller, model.py:835), speaker_emb [B, 512, 1] -> pitch_pred [B, 1, T]. With out_channels = 1 the LAST layer keeps
+    its attention half only: its FFN is evaluated and thrown away (:479-483: `x = self.proj(x)` replaces `norm(x + y)`), so
+    ffn_layers[-1] and norm_layers_2[-1] never receive a gradient -- restated as the reference runs it, minus that dead
+    evaluation."""
+    B, T, _ = x.shape
+    h = torch.cat((x, speaker_emb.transpose(2, 1).expand(B, T, -1)), dim=-1).transpose(1, -1)      # [B, C, T]
+    mask = sequence_mask(x_lengths, T)[:, None, :].to(h.dtype)
+    h = h * mask
+    pre = "encoder"
+    pad = ((kernel - 1) // 2, kernel // 2)
+    for i in range(num_layers):
+        h = h * mask
+        h = _layer_norm2(sd, f"{pre}.norm_layers_1.{i}", h + relative_attention(sd, f"{pre}.attn_layers.{i}", h, mask))
+        if i + 1 == num_layers:
+            h = F.conv1d(h, sd[f"{pre}.proj.weight"], sd[f"{pre}.proj.bias"])
+        else:
+            f = F.conv1d(F.pad(h * mask, pad), sd[f"{pre}.ffn_layers.{i}.conv_1.weight"], sd[f"{pre}.ffn_layers.{i}.conv_1.bias"])
+            f = torch.relu(f)
+            y = F.conv1d(F.pad(f * mask, pad), sd[f"{pre}.ffn_layers.{i}.conv_2.weight"], sd[f"{pre}.ffn_layers.{i}.conv_2.bias"]) * mask
+            h = _layer_norm2(sd, f"{pre}.norm_layers_2.{i}", h + y)
+    return h * mask
+
+
 # ------------------------------------------------------------------------------------------------ alignment, prior, KL
 def maximum_path(value, x_lens, y_lens):
     """xVAPitch's monotonic alignment search, python/xvapitch/util.py:14-53, restated: value [B, t_x, t_y] (masked with

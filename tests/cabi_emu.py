@@ -690,7 +690,21 @@ def _attn_bwd(qkv, rs, zs, dout, d_rs, d_zs, lse, dsum, B, T, lens, scale, drop_
     return 0
 
 
+def _adamw_step(p, g, m, v, n, lr_dev, b1, b2, eps, wd, step, step_dev, stream=None):
+    """csrc/elemwise.cu adamw_kernel: torch.optim.AdamW over a flat arena."""
+    P, G, M, V = (flat(q, n) for q in (p, g, m, v))
+    lr = flat(lr_dev, 1)[0]
+    t = float(flat(step_dev, 1, np.uint64)[0]) if _addr(step_dev) else float(step)
+    b1, b2, eps, wd = (np.float32(x) for x in (b1, b2, eps, wd))
+    bc1, bc2 = np.float32(1.0 - float(b1) ** t), np.float32(1.0 - float(b2) ** t)
+    M[...] = b1 * M + (np.float32(1.0) - b1) * G
+    V[...] = b2 * V + (np.float32(1.0) - b2) * G * G
+    P[...] = P * (np.float32(1.0) - lr * wd) - (lr / bc1) * (M / (np.sqrt(V) / np.sqrt(bc2) + eps))
+    return 0
+
+
 TABLE.update({
+    "xva_adamw_step": _adamw_step,
     "xva_embed_pos": _embed_pos, "xva_embed_bwd": _embed_bwd, "xva_scalar_conv_add": _scalar_conv_add,
     "xva_scalar_conv_bwd": _scalar_conv_bwd, "xva_rowdot_fwd": _rowdot_fwd, "xva_rowdot_bwd": _rowdot_bwd,
     "xva_regulate_len_scan": _regulate_scan, "xva_regulate_len_fwd": _regulate_fwd, "xva_regulate_len_bwd": _regulate_bwd,

@@ -187,3 +187,136 @@ def test_dropout_masks_of_forward_and_backward_agree():
         if v.grad is None:                                      # proj.*: not on this path
             continue
         assert float((got[k_] - v.grad).norm()) / max(float(v.grad.norm()), floor) < 2e-4, k_
+
+
+# ------------------------------------------------------------------------------------------------ pitch predictor
+def _pitch_case():
+    from textenc_util import fill_pitch, pitch_ref_spec
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vits_pitch_predictor.npz"))
+    gen = torch.Generator().manual_seed(71)
+    sd = fill_pitch(pitch_ref_spec(), gen)
+    x = torch.randn(2, 13, 196, generator=gen)
+    spk = torch.nn.functional.normalize(torch.randn(2, 512, 1, generator=gen), dim=1)
+    r = torch.randn(2, 1, 13, generator=gen)
+    assert torch.equal(x, torch.from_numpy(g["x"])) and torch.equal(r, torch.from_numpy(g["r"]))
+    return g, sd, x, spk, r
+
+
+def test_pitch_predictor_matches_the_reference_golden_and_oracle_autograd():
+    """textenc.RelativePositioningPitchEnergyEncoder (xvapitch/model.py:1268-1356 as built at :154-168: 196 + 512 = 708
+    channels, 3 layers, out_channels = 1) through the emulated C ABI: output vs the reference recording, every gradient vs the
+    oracle's autograd and the reference's recorded gradient norms; the six parameters the reference never trains are state,
+    not optimizer parameters; state_dict round trip in the reference's keys."""
+    g, sd, x, spk, r = _pitch_case()
+    lens = [13, 8]
+    p = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    want = ov.pitch_predictor(p, x, lens, spk, num_layers=3)
+    (want * r).sum().backward()
+    with cabi_emu.installed():
+        te = cabi_emu.load_module("textenc", TE_PATCHES)
+        m = te.RelativePositioningPitchEnergyEncoder(1, 196, 768, 2, 3, 3, 0.0, conditioning_emb_dim=512, device="cpu")
+        m.load_state_dict(sd)
+        back = m.state_dict()
+        assert list(back) == list(sd) and all(torch.equal(back[k], sd[k]) for k in sd)
+        n_dead = sum(int(np.prod(sd[k].shape)) for k in m.dead_keys())
+        assert len(m.dead_keys()) == 6 and m.flat.numel() < sum(v.numel() for v in sd.values()) * 1.2 and n_dead > 1_000_000
+        m.train()
+        m.zero_grad()
+        pred = m(x, lens, speaker_emb=spk)
+        dxs = m.backward(r, need_input_grad=True)
+        got = m.grads()
+        used = set(cabi_emu.calls)
+    assert {"xva_gemm", "xva_layernorm_fwd", "xva_layernorm_bwd", "xva_rel_band_add", "xva_pad_cols", "xva_colsum_items"} <= used
+    assert pred.shape == (2, 1, 13)
+    assert rel(pred, torch.from_numpy(g["pitch_pred"])) < 2e-5 and rel(pred, want.detach()) < 2e-5
+    assert float(pred[1, :, 8:].abs().max()) == 0.0
+    assert set(got) == set(str(k) for k in g["has_grad"])            # exactly the parameters the reference gives a gradient
+    floor = 1e-4 * max(float(p[k].grad.norm()) for k in got)
+    for k in got:
+        assert float((got[k] - p[k].grad).norm()) / max(float(p[k].grad.norm()), floor) < 1e-4, k
+        assert abs(float(got[k].norm()) - float(g["gnorm/" + k])) <= 3e-4 * max(float(g["gnorm/" + k]), 10 * floor), k
+    # input gradients (not needed in training: the reference detaches x) against autograd of the oracle
+    xr, sr = x.clone().requires_grad_(True), spk.clone().requires_grad_(True)
+    (ov.pitch_predictor(sd, xr, lens, sr, num_layers=3) * r).sum().backward()
+    assert rel(dxs[0], xr.grad) < 1e-4 and rel(dxs[1].unsqueeze(-1), sr.grad) < 1e-4
+
+
+def test_pitch_predictor_big_model_shape():
+    """The other configuration xVAPitch builds (big = 1: 256 + 12 + 512 = 780 channels, heads of 390 padded to 416)."""
+    from textenc_util import fill_pitch, pitch_ref_spec
+
+    gen = torch.Generator().manual_seed(3)
+    sd = fill_pitch(pitch_ref_spec(layers=2, hidden=268), gen)
+    x = torch.randn(2, 9, 268, generator=gen)
+    spk = torch.randn(2, 512, 1, generator=gen)
+    r = torch.randn(2, 1, 9, generator=gen)
+    lens = [9, 4]
+    p = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    want = ov.pitch_predictor(p, x, lens, spk, num_layers=2)
+    (want * r).sum().backward()
+    with cabi_emu.installed():
+        te = cabi_emu.load_module("textenc", TE_PATCHES)
+        m = te.RelativePositioningPitchEnergyEncoder(1, 268, 768, 2, 2, 3, 0.0, conditioning_emb_dim=512, device="cpu")
+        m.load_state_dict(sd)
+        m.train()
+        m.zero_grad()
+        pred = m(x, lens, speaker_emb=spk)
+        m.backward(r)
+        got = m.grads()
+    assert (m.C, m.Cp, m.dk, m.dkp) == (780, 800, 390, 416)
+    assert rel(pred, want.detach()) < 2e-5
+    floor = 1e-4 * max(float(p[k].grad.norm()) for k in got)
+    for k in got:
+        assert float((got[k] - p[k].grad).norm()) / max(float(p[k].grad.norm()), floor) < 1e-4, k
+
+
+def test_adamw_over_the_flat_arenas_matches_torch_and_leaves_pad_and_dead_entries_alone():
+    """hifigan.AdamW([module.flat]) -- the optimizer of the xVAPitch generator (training_util.py:56-57: lr 1.75e-4, betas
+    0.8 / 0.99, eps 1e-9, weight decay 0.01) -- on the text encoder and the pitch predictor: after one step every
+    reference-shaped parameter equals torch.optim.AdamW's on the oracle's gradients, pad entries of the arena are still
+    exactly zero, and the pitch predictor's six untrained tensors are bit-identical (torch skips parameters without a
+    gradient, weight decay included)."""
+    from textenc_util import fill_pitch, pitch_ref_spec
+
+    gen = torch.Generator().manual_seed(71)
+    sd = fill_pitch(pitch_ref_spec(layers=2), gen)
+    x = torch.randn(2, 11, 196, generator=gen)
+    spk = torch.randn(2, 512, 1, generator=gen)
+    r = torch.randn(2, 1, 11, generator=gen)
+    lens = [11, 7]
+    p = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    topt = torch.optim.AdamW(list(p.values()), lr=1.75e-4, betas=(0.8, 0.99), eps=1e-9, weight_decay=0.01)
+    (ov.pitch_predictor(p, x, lens, spk, num_layers=2) * r).sum().backward()
+    topt.step()
+    with cabi_emu.installed():
+        te = cabi_emu.load_module("textenc", TE_PATCHES)
+        hg = cabi_emu.load_module("hifigan", [('if dev.type != "cuda":', "if False:")])
+        m = te.RelativePositioningPitchEnergyEncoder(1, 196, 768, 2, 2, 3, 0.0, conditioning_emb_dim=512, device="cpu")
+        m.load_state_dict(sd)
+        opt = hg.AdamW([m.flat], lr=1.75e-4, betas=(0.8, 0.99), eps=1e-9, weight_decay=0.01)
+        opt.zero_grad()
+        m.train()
+        m(x, lens, speaker_emb=spk)
+        m.backward(r)
+        opt.step()
+        after = m.state_dict()
+        V = m._views(m.flat.data)
+        for i in range(2):
+            qw = V[f"l{i}.qkv_w"].view(3, m.num_heads, m.dkp, m.Cp)
+            assert float(qw[:, :, m.dk:].abs().max()) == 0.0 and float(qw[..., m.C:].abs().max()) == 0.0
+            assert float(V[f"l{i}.ek"][9:].abs().max()) == 0.0 and float(V[f"l{i}.ev"][:, m.dk:].abs().max()) == 0.0
+        assert float(V["proj_w"][:, m.C:].abs().max()) == 0.0
+    for k in sd:
+        if k in m.dead_keys():
+            assert torch.equal(after[k], sd[k]) and p[k].grad is None, k
+        else:
+            # Adam's first step is lr * g / |g|: where a gradient is zero in exact arithmetic (the key bias, and the key
+            # weights' 512 speaker-embedding columns -- constant over the keys of an utterance, so softmax-invariant) both
+            # sides take a full-size step in the direction of their own rounding noise. Compare where the gradient is real.
+            gr = p[k].grad
+            real = gr.abs() > 1e-3 * gr.abs().max()
+            if k.endswith("conv_k.bias"):
+                continue
+            assert float(real.float().mean()) > 0.2, k
+            assert rel((after[k] - sd[k])[real], (p[k].detach() - sd[k])[real]) < 2e-3, k

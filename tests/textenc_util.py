@@ -89,3 +89,44 @@ def oracle_grads(sd, tokens, lens, lang, layers, rx, rm, rl, re):
     grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in p.items()}
     grads["lang"] = lg.grad
     return {"x": x.detach(), "x_emb": x_emb.detach(), "m_p": m_p.detach(), "logs_p": logs_p.detach()}, grads
+
+
+# ------------------------------------------------------------------------------------------------ pitch predictor
+def fill_pitch(spec, gen):
+    """Seeded fill of the pitch predictor's parameters (make_golden_vits_pitch_predictor.py): non-trivial LayerNorm
+    parameters and biases, weights scaled by 0.7 / sqrt(fan_in)."""
+    sd = {}
+    for k, sh in spec:
+        if k.endswith("gamma"):
+            sd[k] = 1.0 + 0.1 * torch.randn(sh, generator=gen)
+        elif k.endswith("beta") or k.endswith("bias"):
+            sd[k] = 0.05 * torch.randn(sh, generator=gen)
+        elif "emb_rel" in k:
+            sd[k] = torch.randn(sh, generator=gen) * 96 ** -0.5
+        else:
+            sd[k] = torch.randn(sh, generator=gen) * 0.7 / np.sqrt(int(np.prod(sh[1:])))
+    return sd
+
+
+def pitch_ref_spec(layers=3, hidden=196, cond=512, ffn=768, heads=2, k=3, window=4):
+    """(key, shape) of RelativePositioningPitchEnergyEncoder(out_channels=1, ...).named_parameters() in the reference's
+    registration order: the last layer's FFN / LayerNorm are built with out_channels = 1, encoder.proj after attn_layers[-1]."""
+    C = hidden + cond
+    dk = C // heads
+    spec = []
+    for i in range(layers):
+        a = f"encoder.attn_layers.{i}"
+        spec += [(f"{a}.emb_rel_k", (1, 2 * window + 1, dk)), (f"{a}.emb_rel_v", (1, 2 * window + 1, dk))]
+        for n in "qkvo":
+            spec += [(f"{a}.conv_{n}.weight", (C, C, 1)), (f"{a}.conv_{n}.bias", (C,))]
+    for i in range(layers):
+        spec += [(f"encoder.norm_layers_1.{i}.gamma", (C,)), (f"encoder.norm_layers_1.{i}.beta", (C,))]
+    for i in range(layers):
+        f, o = f"encoder.ffn_layers.{i}", (C if i + 1 < layers else 1)
+        spec += [(f"{f}.conv_1.weight", (ffn, C, k)), (f"{f}.conv_1.bias", (ffn,)), (f"{f}.conv_2.weight", (o, ffn, k)),
+                 (f"{f}.conv_2.bias", (o,))]
+    for i in range(layers):
+        o = C if i + 1 < layers else 1
+        spec += [(f"encoder.norm_layers_2.{i}.gamma", (o,)), (f"encoder.norm_layers_2.{i}.beta", (o,))]
+    spec += [("encoder.proj.weight", (1, C, 1)), ("encoder.proj.bias", (1,))]
+    return spec
