@@ -11,6 +11,10 @@ include/xva_b200.h. This module does that for the entry points below:
                                 groups > 1 is not emulated
     xva_softmax_fwd / _bwd, xva_layernorm_fwd / _bwd, xva_colsum, xva_colsum_items, xva_round_tf32, xva_counter_add,
     xva_rowdot2                 restated from csrc/rowops.cu / csrc/vits.cu
+    xva_embed_pos / _bwd, xva_scalar_conv_add / _bwd, xva_rowdot_fwd / _bwd, xva_regulate_len_scan / _fwd / _bwd,
+    xva_average_pitch, xva_mel_mse (+ _grad), xva_lens_mse (+ _grad), xva_grad_sqnorm, xva_lamb_step, xva_adamw_step
+                                restated from csrc/rowops.cu, regulate.cu, loss_optim.cu, elemwise.cu
+    xva_attn_fwd / _bwd         the fused attention, from its contract in include/xva_b200.h
     xva_text_embed_fwd / _bwd, xva_rel_band_add, xva_rel_band_gather, xva_pad_cols
                                 NOT restated: csrc/relattn_body.h (the per-element functions the CUDA kernels loop over)
                                 compiled for the host with g++ (tests/relattn_host.cpp) and run as is
@@ -20,7 +24,8 @@ xva_set_operand_rounding(0) test mode); dropout uses the library's counter hash 
 backward masks can be checked for consistency.
 
 The emulator itself is validated in tests/test_cabi_emu_cpu.py by running host code whose GPU parity is established --
-one FFT block of FastPitch, forward and backward, through the un-fused attention chain -- and comparing with the oracle.
+one FFT block of FastPitch through the un-fused attention chain, then whole FastPitch training steps (stages 2, 3, 4; forward,
+loss, backward, clip + LAMB, two consecutive steps) -- and comparing with the oracle.
 
 Usage:  with cabi_emu.installed():  ... build product modules on device="cpu" via cabi_emu.load_module(...)
 """
