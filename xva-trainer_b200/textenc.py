@@ -118,6 +118,10 @@ class _RelTransformer(nn.Module):
             ns.__dict__.update(w1=g("w1")[..., :C], b1=g("b1"), w2=g("w2"), b2=g("b2"), ln2_g=g("ln2_g"), ln2_b=g("ln2_b"))
         return ns
 
+    def to(self, *args, **kwargs):
+        """The device is fixed at construction (arena, gradient arena, operand copy and dropout counter live there)."""
+        return self
+
     def zero_grad(self, set_to_none=False):
         if self.flat.grad is None:
             self.flat.grad = torch.zeros_like(self.flat.data)
@@ -339,6 +343,11 @@ class _RelTransformer(nn.Module):
 
 
 class TextEncoder(_RelTransformer):
+    """Drop-in for python/xvapitch/model.py:1089 ``TextEncoder`` (see the module docstring): ``forward(tokens, x_lengths,
+    lang_emb)`` -> (x [B, C, T], x_emb [B, T, hidden], x_mask [B, 1, T]); ``forward(x, x_lengths, stats=True, x_mask=...)`` ->
+    (m_p, logs_p). Engine-facing entry points on channels-last tensors: ``forward_cl`` / ``stats_cl`` /
+    ``stats_backward_cl`` / ``backward_cl``. ``flat`` is the one parameter tensor an optimizer sees."""
+
     def __init__(self, n_vocab, out_channels, hidden_channels, hidden_channels_ffn, num_heads, num_layers, kernel_size,
                  dropout_p, language_emb_dim=None, device=None, seed=1234):
         super().__init__()
