@@ -107,11 +107,97 @@ from_flags = dict(RELU=1 << 0, LN=1 << 1, DROP_PRE=1 << 2, DROP_POST=1 << 3, ATO
                   TANH=1 << 7, SOFTMAX_BWD=1 << 8, HALO=1 << 9)
 
 
-def _gemm(ref, stream=None):
-    g = ref._obj
-    assert g.groups <= 1, "cabi_emu: grouped GEMMs are not emulated"
+def _gemm_grouped(g, G):
+    """xva_gemm_args.groups > 1 (DiscriminatorS's grouped convolutions in one launch), csrc/gemm_ref.cu ref_dot / wgrad:
+       mode 0: out[.., n] contracts A columns a_col[j] + grp * grp_step + [0, K) with B row n,            grp = n // (N / G)
+       mode 1: out[.., n] contracts A columns a_col[j] + grp * K + [0, K) with B rows grp * K + [0, K), column n - grp * N / G
+       mode 2: out[j, m, n] contracts A column m with B column a_col[j] + grp * grp_step + n,              grp = m // (M / G)
+    Epilogue (mode 0 / 1) as in the dense case without LayerNorm / softmax-backward."""
     Z, R, N, K, taps = g.Z, g.R, g.N, g.K, g.taps
     F = from_flags
+    assert not (g.flags & (F["LN"] | F["SOFTMAX_BWD"])) and g.b_batch_z == 0
+    if g.mode in (0, 1):
+        a_rows = g.a_rows or R
+        n_per = N // G
+        step = g.grp_step if g.mode == 0 else K
+        a_cols = max(g.a_col[j] for j in range(taps)) + (G - 1) * step + K
+        assert Z == 1 or g.a_zs != 0
+        A = strided(g.a, (Z, a_rows, a_cols), (g.a_zs, g.a_rs, 1))
+        n_zb = (taps - 1) * g.b_tap_z + 1
+        if g.mode == 0:
+            Bm = strided(g.b, (n_zb, N, K), (g.b_zs, g.b_rs, 1))
+        else:
+            Bm = strided(g.b, (n_zb, G * K, n_per), (g.b_zs, g.b_rs, 1))
+        acc = np.zeros((Z, R, N), np.float64)
+        for j in range(taps):
+            rr = np.arange(R) + g.shift[j]
+            ok = (rr >= 0) & (rr < a_rows)
+            if not ok.any():
+                continue
+            Bj = Bm[j * g.b_tap_z].astype(np.float64)
+            for grp in range(G):
+                Aj = np.zeros((Z, R, K), np.float64)
+                c0 = g.a_col[j] + grp * step
+                Aj[:, ok] = A[:, rr[ok], c0:c0 + K]
+                if g.mode == 0:
+                    acc[:, :, grp * n_per:(grp + 1) * n_per] += Aj @ Bj[grp * n_per:(grp + 1) * n_per].T
+                else:
+                    acc[:, :, grp * n_per:(grp + 1) * n_per] += Aj @ Bj[grp * K:(grp + 1) * K]
+        v = (np.float64(np.float32(g.alpha)) * acc).astype(np.float32)
+        view = lambda p, rs, zs: strided(p, (Z, R, N), (zs, rs, 1))
+        if g.bias:
+            v = v + flat(g.bias, N)[None, None, :]
+        if g.flags & F["RELU"]:
+            v = np.where(v > 0, v, np.float32(g.act_slope) * v)
+        if g.gate:
+            v = v * np.where(view(g.gate, g.g_rs, g.g_zs) > 0, np.float32(1.0), np.float32(g.gate_slope))
+        assert not ((g.flags & F["DROP_PRE"]) and g.drop_p > 0)
+        if g.residual:
+            v = v + view(g.residual, g.r_rs, g.r_zs)
+        if g.flags & F["TANH"]:
+            v = np.tanh(v)
+        if g.lens:
+            lens = flat(g.lens, Z, np.int32)
+            v = v * (np.arange(R)[None, :] < lens[:, None]).astype(np.float32)[:, :, None]
+        v = v.astype(np.float32)
+        if g.out_act:
+            view(g.out_act, g.o_rs, g.o_zs)[...] = np.where(v > 0, v, np.float32(g.out_act_slope) * v)
+        view(g.out, g.o_rs, g.o_zs)[...] = v
+        return 0
+    M, ZR = g.M, g.ZR
+    a_rows, b_rows = g.a_rows or R, g.b_rows or R
+    og = M // G
+    b_cols = max(g.a_col[j] for j in range(taps)) + (G - 1) * g.grp_step + N
+    tA = min(R, a_rows)
+    A = strided(g.a, (Z, tA, M), (g.a_zs, g.a_rs, 1)).astype(np.float64)
+    Bm = strided(g.b, (Z, b_rows, b_cols), (g.b_zs, g.b_rs, 1))
+    for zo in range(Z // ZR):
+        for j in range(taps):
+            bt = np.arange(tA) + g.shift[j]
+            ok = (bt >= 0) & (bt < b_rows)
+            acc = np.zeros((M, N), np.float64)
+            if ok.any():
+                for zr in range(ZR):
+                    z = zo * ZR + zr
+                    for grp in range(G):
+                        c0 = g.a_col[j] + grp * g.grp_step
+                        acc[grp * og:(grp + 1) * og] += A[z, ok][:, grp * og:(grp + 1) * og].T @ Bm[z, bt[ok], c0:c0 + N].astype(np.float64)
+            o = strided(_addr(g.out) + 4 * (zo * g.o_zs + j * g.o_js), (M, N), (g.o_rs, 1))
+            val = (np.float64(np.float32(g.alpha)) * acc).astype(np.float32)
+            if g.flags & F["ATOMIC"]:
+                o += val
+            else:
+                o[...] = val
+    return 0
+
+
+def _gemm(ref, stream=None):
+    g = ref._obj
+    Z, R, N, K, taps = g.Z, g.R, g.N, g.K, g.taps
+    F = from_flags
+    G = g.groups if g.groups > 1 else 1
+    if G > 1:
+        return _gemm_grouped(g, G)
     if g.mode in (0, 1):
         a_rows = g.a_rows or R
         a_cols = max(g.a_col[j] for j in range(taps)) + K
@@ -717,3 +803,347 @@ TABLE.update({
     "xva_lens_mse_grad": _lens_mse_grad, "xva_grad_sqnorm": _grad_sqnorm, "xva_lamb_step": _lamb_step,
     "xva_attn_fwd": _attn_fwd, "xva_attn_bwd": _attn_bwd,
 })
+
+
+# ------------------------------------------------------------------------------------------------ HiFi-GAN generator / WaveNet
+def _wn_table(table, n_desc):
+    from xva_trainer_b200 import capi
+    return (capi.WnDesc * int(n_desc)).from_address(_addr(table))
+
+
+def _wn_index(d, r, c, j):
+    if d.flags & 1:                                    # XVA_WN_TRANSPOSED
+        return d.tap_off[j] + c * d.ld + r
+    return d.tap_off[j] + r * d.ld + ((r // d.og) % d.f) * d.cg + c
+
+
+def _wn_pack_fwd(table, n_desc, total_rows, max_inner, stream=None):
+    """include/xva_b200.h xva_wn_pack_fwd: w = g * v / ||v|| per output row (w = v for XVA_WN_PLAIN), scattered into the
+    packed arena in the tap-GEMM layout."""
+    for d in _wn_table(table, n_desc):
+        rows, inner, k = d.rows, d.inner, d.k
+        c2 = inner // k
+        v = flat(d.v, rows * inner).reshape(rows, c2, k).astype(np.float64)
+        if d.flags & 4:                                # XVA_WN_PLAIN
+            w = v
+        else:
+            g = flat(d.g, rows).astype(np.float64)
+            w = v * (g / np.sqrt((v.reshape(rows, -1) ** 2).sum(axis=1)))[:, None, None]
+        r, c, j = np.meshgrid(np.arange(rows), np.arange(c2), np.arange(k), indexing="ij")
+        taps = np.array([d.tap_off[t] for t in range(k)], dtype=np.int64)
+        if d.flags & 1:
+            idx = taps[j] + c * d.ld + r
+        else:
+            idx = taps[j] + r * d.ld + ((r // d.og) % d.f) * d.cg + c
+        dst = flat(d.dst, int(idx.max()) + 1)
+        dst[idx.reshape(-1)] = w.reshape(-1).astype(np.float32)
+    return 0
+
+
+def _wn_pack_bwd(table, n_desc, total_rows, max_inner, stream=None):
+    for d in _wn_table(table, n_desc):
+        rows, inner, k = d.rows, d.inner, d.k
+        c2 = inner // k
+        v = flat(d.v, rows * inner).reshape(rows, c2, k).astype(np.float64)
+        r, c, j = np.meshgrid(np.arange(rows), np.arange(c2), np.arange(k), indexing="ij")
+        taps = np.array([d.tap_off[t] for t in range(k)], dtype=np.int64)
+        idx = (taps[j] + c * d.ld + r) if (d.flags & 1) else (taps[j] + r * d.ld + ((r // d.og) % d.f) * d.cg + c)
+        dW = flat(d.ddst, int(idx.max()) + 1)[idx.reshape(-1)].reshape(rows, c2, k).astype(np.float64)
+        dv = flat(d.dv, rows * inner).reshape(rows, c2, k)
+        if d.flags & 4:
+            dv += dW.astype(np.float32)
+            continue
+        ss = (v.reshape(rows, -1) ** 2).sum(axis=1)
+        dot = (v * dW).reshape(rows, -1).sum(axis=1)
+        g = flat(d.g, rows).astype(np.float64)
+        scale = g / np.sqrt(ss)
+        dv += (scale[:, None, None] * dW - (scale * dot / ss)[:, None, None] * v).astype(np.float32)
+        flat(d.dg, rows)[...] += (dot / np.sqrt(ss)).astype(np.float32)
+    return 0
+
+
+def _mean3_lrelu(y0, y1, y2, n, slope, out, stream=None):
+    m = ((flat(y0, n) + flat(y1, n)) + flat(y2, n)) * np.float32(1.0 / 3.0)
+    flat(out, n)[...] = np.where(m > 0, m, np.float32(slope) * m)
+    return 0
+
+
+def _sum3(a, b, c, n, out, stream=None):
+    flat(out, n)[...] = flat(a, n) + flat(b, n) + flat(c, n)
+    return 0
+
+
+def _tanh_bwd(dy, y, rows, ld, out, stream=None):
+    O = flat(out, rows * ld).reshape(rows, ld)
+    O[...] = 0.0
+    t = flat(y, rows)
+    O[:, 0] = flat(dy, rows) * (np.float32(1.0) - t * t)
+    return 0
+
+
+def _sig(x):
+    return 1.0 / (1.0 + np.exp(-x))
+
+
+def _gated_act_fwd(x_in, rows, H, ld_in, acts, stream=None):
+    X = strided(x_in, (rows, 2 * H), (ld_in, 1)).astype(np.float64)
+    flat(acts, rows * H).reshape(rows, H)[...] = (np.tanh(X[:, :H]) * _sig(X[:, H:])).astype(np.float32)
+    return 0
+
+
+def _gated_act_bwd(dacts, x_in, rows, H, ld_in, dx_in, stream=None):
+    X = strided(x_in, (rows, 2 * H), (ld_in, 1)).astype(np.float64)
+    d = flat(dacts, rows * H).reshape(rows, H).astype(np.float64)
+    t, sg = np.tanh(X[:, :H]), _sig(X[:, H:])
+    O = flat(dx_in, rows * 2 * H).reshape(rows, 2 * H)
+    O[:, :H] = (d * sg * (1.0 - t * t)).astype(np.float32)
+    O[:, H:] = (d * t * sg * (1.0 - sg)).astype(np.float32)
+    return 0
+
+
+def _vits_sample_fwd(stats, eps, lens, B, T, Cc, z, stream=None):
+    S = flat(stats, B * T * 2 * Cc).reshape(B, T, 2 * Cc)
+    E = flat(eps, B * T * Cc).reshape(B, T, Cc)
+    live = _lens_mask(lens, B, T)[:, :, None]
+    flat(z, B * T * Cc).reshape(B, T, Cc)[...] = np.where(live, S[..., :Cc] + E * np.exp(S[..., Cc:]), 0.0)
+    return 0
+
+
+def _vits_sample_bwd(dz, eps, stats, lens, B, T, Cc, dstats, stream=None):
+    S = flat(stats, B * T * 2 * Cc).reshape(B, T, 2 * Cc)
+    E = flat(eps, B * T * Cc).reshape(B, T, Cc)
+    D = flat(dz, B * T * Cc).reshape(B, T, Cc)
+    live = _lens_mask(lens, B, T)[:, :, None]
+    O = flat(dstats, B * T * 2 * Cc).reshape(B, T, 2 * Cc)
+    O[..., :Cc] = np.where(live, D, 0.0)
+    O[..., Cc:] = np.where(live, D * E * np.exp(S[..., Cc:]), 0.0)
+    return 0
+
+
+TABLE.update({"xva_wn_pack_fwd": _wn_pack_fwd, "xva_wn_pack_bwd": _wn_pack_bwd, "xva_mean3_lrelu": _mean3_lrelu, "xva_sum3": _sum3,
+              "xva_tanh_bwd": _tanh_bwd, "xva_gated_act_fwd": _gated_act_fwd, "xva_gated_act_bwd": _gated_act_bwd,
+              "xva_vits_sample_fwd": _vits_sample_fwd, "xva_vits_sample_bwd": _vits_sample_bwd})
+
+
+# ------------------------------------------------------------------------------------------------ discriminators, mel, GAN losses
+def _c1_src(z, q, xs_b, xs_q, xs_c, P, Lsrc):
+    b, c = z // P, z % P
+    idx = q * xs_q + c * xs_c
+    idx = np.where(idx >= Lsrc, 2 * (Lsrc - 1) - idx, idx)
+    return b * xs_b + idx
+
+
+def _c1_window(x, xs_b, xs_q, xs_c, P, Lsrc, L, k, s, pad, Z, Lout):
+    """xw[z, t, j] = sequence value at q = t * s - pad + j (zero outside [0, L)) and the flat source index of every q."""
+    n_src = (Z // P - 1) * xs_b + Lsrc
+    X = flat(x, n_src)
+    q = np.arange(Lout)[:, None] * s - pad + np.arange(k)[None, :]                   # [Lout, k]
+    ok = (q >= 0) & (q < L)
+    src = _c1_src(np.arange(Z)[:, None, None], np.clip(q, 0, L - 1)[None], xs_b, xs_q, xs_c, P, Lsrc)
+    return np.where(ok[None], X[src], 0.0).astype(np.float64), src, ok, X
+
+
+def _conv_c1_fwd(x, xs_b, xs_q, xs_c, P, Lsrc, L, w, bias, k, s, pad, Z, Lout, Lout_p, Cout, slope, out, stream=None):
+    xw, _, _, _ = _c1_window(x, xs_b, xs_q, xs_c, P, Lsrc, L, k, s, pad, Z, Lout)
+    Wt = flat(w, Cout * k).reshape(Cout, k).astype(np.float64)
+    v = (xw @ Wt.T + flat(bias, Cout)[None, None, :]).astype(np.float32)
+    O = flat(out, Z * Lout_p * Cout).reshape(Z, Lout_p, Cout)
+    O[...] = 0.0
+    O[:, :Lout] = np.where(v > 0, v, np.float32(slope) * v)
+    return 0
+
+
+def _conv_c1_bwd_w(dpre, x, xs_b, xs_q, xs_c, P, Lsrc, L, k, s, pad, Z, Lout, Lout_p, Cout, dw, db, stream=None):
+    xw, _, _, _ = _c1_window(x, xs_b, xs_q, xs_c, P, Lsrc, L, k, s, pad, Z, Lout)
+    D = flat(dpre, Z * Lout_p * Cout).reshape(Z, Lout_p, Cout)[:, :Lout].astype(np.float64)
+    flat(dw, Cout * k).reshape(Cout, k)[...] += np.einsum("ztc,ztj->cj", D, xw).astype(np.float32)
+    flat(db, Cout)[...] += D.sum(axis=(0, 1)).astype(np.float32)
+    return 0
+
+
+def _conv_c1_bwd_x(dpre, w, xs_b, xs_q, xs_c, P, Lsrc, L, k, s, pad, Z, Lout, Lout_p, Cout, scale, dx, stream=None):
+    D = flat(dpre, Z * Lout_p * Cout).reshape(Z, Lout_p, Cout)[:, :Lout].astype(np.float64)
+    Wt = flat(w, Cout * k).reshape(Cout, k).astype(np.float64)
+    contrib = np.einsum("ztc,cj->ztj", D, Wt)                                          # gradient wrt sequence value q = t s - pad + j
+    q = np.arange(Lout)[:, None] * s - pad + np.arange(k)[None, :]
+    ok = (q >= 0) & (q < L)
+    src = _c1_src(np.arange(Z)[:, None, None], np.clip(q, 0, L - 1)[None], xs_b, xs_q, xs_c, P, Lsrc)
+    n_src = (Z // P - 1) * xs_b + Lsrc
+    acc = np.zeros(n_src, np.float64)
+    np.add.at(acc, src[np.broadcast_to(ok[None], src.shape)], contrib[np.broadcast_to(ok[None], src.shape)])
+    flat(dx, n_src)[...] += (np.float32(scale) * acc).astype(np.float32)
+    return 0
+
+
+def _avgpool4_fwd(x, B, L, out, stream=None):
+    Lout = L // 2 + 1
+    X = np.pad(flat(x, B * L).reshape(B, L), ((0, 0), (2, 2)))
+    i = np.arange(Lout)
+    flat(out, B * Lout).reshape(B, Lout)[...] = np.float32(0.25) * (X[:, 2 * i] + X[:, 2 * i + 1] + X[:, 2 * i + 2] + X[:, 2 * i + 3])
+    return 0
+
+
+def _avgpool4_bwd(dout, B, L, dx, stream=None):
+    Lout = L // 2 + 1
+    D = flat(dout, B * Lout).reshape(B, Lout)
+    acc = np.zeros((B, L + 4), np.float32)
+    i = np.arange(Lout)
+    for d in range(4):
+        np.add.at(acc, (slice(None), 2 * i + d), np.float32(0.25) * D)
+    flat(dx, B * L).reshape(B, L)[...] = acc[:, 2:L + 2]
+    return 0
+
+
+def _zero_tail_rows(x, Z, Lp, Lvalid, Cc, stream=None):
+    flat(x, Z * Lp * Cc).reshape(Z, Lp, Cc)[:, Lvalid:] = 0.0
+    return 0
+
+
+def _sn_table(table, n_desc):
+    from xva_trainer_b200 import capi
+    return (capi.SnDesc * int(n_desc)).from_address(_addr(table))
+
+
+def _sn_idx(d):
+    rows, inner, k = d.rows, d.inner, d.k
+    c2 = inner // k
+    r, c, j = np.meshgrid(np.arange(rows), np.arange(c2), np.arange(k), indexing="ij")
+    taps = np.array([d.tap_off[t] for t in range(k)], dtype=np.int64)
+    return (taps[j] + c * d.ld + r) if (d.flags & 1) else (taps[j] + r * d.ld + ((r // d.og) % d.f) * d.cg + c)
+
+
+def _sn_pack_fwd(table, n_desc, total_rows, total_blocks, max_inner, training, stream=None):
+    """include/xva_b200.h xva_sn_pack_fwd: one power iteration (training), sigma = u . (W v), W / sigma packed."""
+    for d in _sn_table(table, n_desc):
+        rows, inner, k = d.rows, d.inner, d.k
+        Wm = flat(d.w, rows * inner).reshape(rows, inner).astype(np.float64)
+        u, v = flat(d.u, rows), flat(d.v, inner)
+        if training:
+            t = Wm.T @ u.astype(np.float64)
+            vn = (t / max(np.sqrt((t * t).sum()), 1e-12)).astype(np.float32)
+            v[...] = vn
+            s_ = Wm @ vn.astype(np.float64)
+            un = (s_ / max(np.sqrt((s_ * s_).sum()), 1e-12)).astype(np.float32)
+            u[...] = un
+            sigma = float((un.astype(np.float64) * s_).sum())
+        else:
+            s_ = Wm @ v.astype(np.float64)
+            sigma = float((u.astype(np.float64) * s_).sum())
+        flat(d.u_sav, rows)[...] = u
+        flat(d.v_sav, inner)[...] = v
+        chunks = (rows + 63) // 64
+        flat(d.work, chunks * inner + rows + 2)[chunks * inner + rows] = np.float32(sigma)
+        idx = _sn_idx(d)
+        dst = flat(d.dst, int(idx.max()) + 1)
+        dst[idx.reshape(-1)] = (Wm.reshape(rows, inner // k, k) / np.float32(sigma)).reshape(-1).astype(np.float32)
+    return 0
+
+
+def _sn_pack_bwd(table, n_desc, total_rows, total_blocks, max_inner, stream=None):
+    for d in _sn_table(table, n_desc):
+        rows, inner, k = d.rows, d.inner, d.k
+        Wm = flat(d.w, rows * inner).reshape(rows, inner).astype(np.float64)
+        chunks = (rows + 63) // 64
+        sigma = float(flat(d.work, chunks * inner + rows + 2)[chunks * inner + rows])
+        idx = _sn_idx(d)
+        dW = flat(d.ddst, int(idx.max()) + 1)[idx.reshape(-1)].reshape(rows, inner).astype(np.float64)
+        coef = float((dW * Wm).sum()) / (sigma * sigma)
+        u, v = flat(d.u_sav, rows).astype(np.float64), flat(d.v_sav, inner).astype(np.float64)
+        flat(d.dw, rows * inner).reshape(rows, inner)[...] += (dW / sigma - coef * np.outer(u, v)).astype(np.float32)
+    return 0
+
+
+def _reflect_index(t, n):
+    t = np.where(t < 0, -t, t)
+    return np.where(t >= n, 2 * (n - 1) - t, t)
+
+
+def _reflect_pad_fwd(y, B, n, pad, out, stream=None):
+    Y = flat(y, B * n).reshape(B, n)
+    flat(out, B * (n + 2 * pad)).reshape(B, n + 2 * pad)[...] = Y[:, _reflect_index(np.arange(n + 2 * pad) - pad, n)]
+    return 0
+
+
+def _reflect_pad_bwd(dyp, B, n, pad, dy, stream=None):
+    D = flat(dyp, B * (n + 2 * pad)).reshape(B, n + 2 * pad)
+    acc = np.zeros((B, n), np.float32)
+    np.add.at(acc, (slice(None), _reflect_index(np.arange(n + 2 * pad) - pad, n)), D)
+    flat(dy, B * n).reshape(B, n)[...] = acc
+    return 0
+
+
+def _spec_mag_fwd(spec, rows, nb, ld_s, ld_m, eps, mag, stream=None):
+    S = flat(spec, rows * ld_s).reshape(rows, ld_s)
+    p = S[:, :nb] ** 2 + S[:, nb:2 * nb] ** 2
+    M = flat(mag, rows * ld_m).reshape(rows, ld_m)
+    M[...] = 0.0
+    M[:, :nb] = np.sqrt(p + np.float32(eps) if eps >= 0 else np.maximum(p, np.float32(-eps)))
+    return 0
+
+
+def _spec_mag_bwd(dmag, spec, rows, nb, ld_s, ld_m, eps, dspec, stream=None):
+    S = flat(spec, rows * ld_s).reshape(rows, ld_s)
+    D = flat(dmag, rows * ld_m).reshape(rows, ld_m)[:, :nb]
+    p = S[:, :nb] ** 2 + S[:, nb:2 * nb] ** 2
+    if eps >= 0:
+        m, live = np.sqrt(p + np.float32(eps)), np.ones_like(p, bool)
+    else:
+        m, live = np.sqrt(np.maximum(p, 1e-30)), p >= np.float32(-eps)
+    O = flat(dspec, rows * ld_s).reshape(rows, ld_s)
+    O[...] = 0.0
+    O[:, :nb] = np.where(live, D * S[:, :nb] / m, 0.0)
+    O[:, nb:2 * nb] = np.where(live, D * S[:, nb:2 * nb] / m, 0.0)
+    return 0
+
+
+def _log_clamp_fwd(x, n, lo, out, stream=None):
+    flat(out, n)[...] = np.log(np.maximum(flat(x, n), np.float32(lo)))
+    return 0
+
+
+def _log_clamp_bwd(dy, x, n, lo, dx, stream=None):
+    X = flat(x, n)
+    flat(dx, n)[...] = np.where(X >= np.float32(lo), flat(dy, n) / np.where(X >= np.float32(lo), X, 1.0), 0.0)
+    return 0
+
+
+def _reduce_loss(a, b, n, kind, c, acc, stream=None):
+    A = flat(a, n)
+    if kind == 0:
+        flat(acc, 1, np.float64)[0] += float(np.abs(A - flat(b, n)).astype(np.float64).sum())
+    else:
+        dd = (np.float32(c) - A).astype(np.float32)
+        flat(acc, 1, np.float64)[0] += float((dd * dd).astype(np.float64).sum())
+    return 0
+
+
+def _l1_grad_values(a, b, n, scale, gate_slope):
+    A, Bv = flat(a, n), flat(b, n)
+    dd = Bv - A
+    g_ = np.where(dd > 0, np.float32(scale), np.where(dd < 0, np.float32(-scale), np.float32(0.0)))
+    return np.where(Bv > 0, g_, g_ * np.float32(gate_slope)).astype(np.float32), dd
+
+
+def _loss_grad(a, b, n, kind, c, scale, gate_slope, accumulate, out, stream=None):
+    if kind == 0:
+        g_, _ = _l1_grad_values(a, b, n, scale, gate_slope)
+    else:
+        g_ = (np.float32(scale) * np.float32(2.0) * (flat(a, n) - np.float32(c))).astype(np.float32)
+    O = flat(out, n)
+    O[...] = O + g_ if accumulate else g_
+    return 0
+
+
+def _l1_loss_grad(a, b, n, scale, gate_slope, acc, out, stream=None):
+    g_, dd = _l1_grad_values(a, b, n, scale, gate_slope)
+    flat(acc, 1, np.float64)[0] += float(np.abs(dd).astype(np.float64).sum())
+    flat(out, n)[...] = g_
+    return 0
+
+
+TABLE.update({"xva_conv_c1_fwd": _conv_c1_fwd, "xva_conv_c1_bwd_w": _conv_c1_bwd_w, "xva_conv_c1_bwd_x": _conv_c1_bwd_x,
+              "xva_avgpool4_fwd": _avgpool4_fwd, "xva_avgpool4_bwd": _avgpool4_bwd, "xva_zero_tail_rows": _zero_tail_rows,
+              "xva_sn_pack_fwd": _sn_pack_fwd, "xva_sn_pack_bwd": _sn_pack_bwd, "xva_reflect_pad_fwd": _reflect_pad_fwd,
+              "xva_reflect_pad_bwd": _reflect_pad_bwd, "xva_spec_mag_fwd": _spec_mag_fwd, "xva_spec_mag_bwd": _spec_mag_bwd,
+              "xva_log_clamp_fwd": _log_clamp_fwd, "xva_log_clamp_bwd": _log_clamp_bwd, "xva_reduce_loss": _reduce_loss,
+              "xva_loss_grad": _loss_grad, "xva_l1_loss_grad": _l1_loss_grad})

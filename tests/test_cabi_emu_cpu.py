@@ -149,3 +149,219 @@ def test_fastpitch_training_steps_through_the_emulator_match_the_oracle(stage, f
         {"xva_lens_mse", "xva_rowdot_bwd"} if stage == 2 else {"xva_regulate_len_fwd", "xva_regulate_len_bwd", "xva_mel_mse"})
     assert want_used <= used, want_used - used
     assert ("xva_attn_fwd" in used) == fused
+
+
+HG_PATCHES = [('if dev.type != "cuda":', "if False:")]
+VT_PATCHES = [('if dev.type != "cuda":', "if False:"),
+              ('dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")', 'dev = torch.device("cpu")'),
+              ('capi.call("xva_device_check", dev.index or 0)', "pass")]
+
+
+def test_hifigan_generator_through_the_emulator_matches_the_oracle():
+    """HiFi-GAN v1 Generator of the product package (hifigan/models.py:82-128: weight-norm packing of all 72 convolutions in
+    one call, conv_pre, 4 x [2-phase transposed convolution + 3 ResBlock1 + MRF mean], conv_post + tanh) forward and its
+    hand-written backward through the emulated C ABI vs oracle.hifigan.generator + autograd: output and all 234 parameter
+    gradients (weight_g / weight_v through the weight-norm backward)."""
+    from oracle import hifigan as ohg
+
+    class H(dict):
+        __getattr__ = dict.__getitem__
+
+    h = H(resblock="1", upsample_rates=[8, 8, 2, 2], upsample_kernel_sizes=[16, 16, 4, 4], upsample_initial_channel=512,
+          resblock_kernel_sizes=[3, 7, 11], resblock_dilation_sizes=[[1, 3, 5]] * 3)
+    sd = ohg.make_generator_state(11, scale=0.7)
+    gen = torch.Generator().manual_seed(11)
+    mel = torch.randn(1, 80, 4, generator=gen)
+    w = torch.randn(1, 1, 256 * 4, generator=gen)
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    want = ohg.generator(leaves, mel)
+    (want * w).sum().backward()
+    with cabi_emu.installed():
+        hg = cabi_emu.load_module("hifigan", HG_PATCHES)
+        G = hg.Generator(h, device="cpu")
+        res = G.load_state_dict(sd)
+        assert not res.missing_keys and not res.unexpected_keys
+        G.train()
+        y = G(mel)
+        G.zero_grad()
+        G.backward(w)
+        grads = {k: p.grad.detach().clone() for k, p in G.named_parameters()}
+        used = set(cabi_emu.calls)
+    assert {"xva_wn_pack_fwd", "xva_wn_pack_bwd", "xva_mean3_lrelu", "xva_sum3", "xva_tanh_bwd"} <= used
+    assert y.shape == want.shape and rel(y, want.detach()) < 1e-5
+    assert len(grads) == 234
+    # (single leaky-ReLU sign decisions on pre-activations within fp32 rounding of zero can differ: bound per tensor 1e-3)
+    worst = max((rel(grads[k], leaves[k].grad), k) for k in grads)
+    assert worst[0] < 1e-3, worst
+
+
+@pytest.mark.parametrize("with_g", [True, False])
+def test_wavenet_stack_through_the_emulator_matches_the_oracle(with_g):
+    """vits.WN (python/xvapitch/wavenet.py:16-106) stand-alone through the emulated C ABI: output, input and conditioning
+    gradients, every parameter gradient vs autograd through oracle.vits.wn, ragged mask."""
+    from oracle import vits as ov
+
+    Hc, L, K, Cc = 64, 3, 5, 64
+    gen = torch.Generator().manual_seed(9)
+    with cabi_emu.installed():
+        hg = cabi_emu.load_module("hifigan", HG_PATCHES)
+        vt = cabi_emu.load_module("vits", VT_PATCHES, extra_modules={"xva_trainer_b200.hifigan": hg})
+        m = vt.WN(Hc, Hc, K, 1, L, c_in_channels=Cc)
+        sd = {}
+        for k, p in m.named_parameters():
+            if k.endswith("weight_v"):
+                sd[k] = torch.randn(p.shape, generator=gen) * 0.7 / np.sqrt(p.shape[1] * p.shape[2])
+            elif k.endswith("bias"):
+                sd[k] = (torch.rand(p.shape, generator=gen) * 2 - 1) * 0.05
+        for k, p in m.named_parameters():
+            if k.endswith("weight_g"):
+                sd[k] = sd[k[:-1] + "v"].flatten(1).norm(dim=1).view(p.shape) * (1 + 0.1 * torch.rand(p.shape, generator=gen))
+        assert not m.load_state_dict(sd).missing_keys
+        m.train()
+        B, T = 2, 21
+        x = torch.randn(B, Hc, T, generator=gen)
+        g = torch.nn.functional.normalize(torch.randn(B, Cc, 1, generator=gen), dim=1) if with_g else None
+        lens = [21, 13]
+        mask = ov.sequence_mask(lens, T)[:, None, :].float()
+        d = torch.randn(B, Hc, T, generator=gen)
+        leaves = {f"enc.{k}": v.clone().requires_grad_(True) for k, v in sd.items()}
+        xl = x.clone().requires_grad_(True)
+        gl = g.clone().requires_grad_(True) if with_g else None
+        want = ov.wn(leaves, "enc", xl, mask, gl, num_layers=L, hidden=Hc, kernel=K)
+        (want * d).sum().backward()
+        got = m(x, mask, g)
+        m.zero_grad()
+        dx, dg = m.backward(d)
+        grads = {k: (p.grad.detach().clone() if p.grad is not None else None) for k, p in m.named_parameters()}
+    assert rel(got, want.detach()) < 1e-5 and rel(dx, xl.grad) < 1e-5
+    if with_g:
+        assert rel(dg, gl.grad) < 1e-5
+    for k, gr in grads.items():
+        if k.startswith("cond_layer") and not with_g:
+            continue
+        assert rel(gr, leaves[f"enc.{k}"].grad) < 1e-4, k
+
+
+def test_normalising_flow_through_the_emulator_matches_the_reference_recording():
+    """vits.ResidualCouplingBlocks (python/xvapitch/model.py:1358-1421: 4 flows x [1x1, 4-layer WaveNet, 1x1, coupling, flip])
+    through the emulated C ABI: forward and reverse outputs and the input / conditioning gradients as RECORDED from the
+    reference module (tests/golden/vits_flow.npz), every parameter gradient vs the oracle's autograd and the recorded norms,
+    reverse(forward(x)) = x."""
+    from oracle import vits as ov
+    from test_oracle_golden import _vits_flow_fixture
+
+    gold, spec, sd = _vits_flow_fixture()
+    x, cond, w = (torch.from_numpy(gold[k]) for k in ("x", "g", "w"))
+    lens = [int(v) for v in gold["lens"]]
+    mask = ov.sequence_mask(lens, x.shape[2])[:, None, :].float()
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    (ov.residual_coupling_blocks(leaves, x, mask, cond) * w).sum().backward()
+    with cabi_emu.installed():
+        hg = cabi_emu.load_module("hifigan", HG_PATCHES)
+        vt = cabi_emu.load_module("vits", VT_PATCHES, extra_modules={"xva_trainer_b200.hifigan": hg})
+        flow = vt.ResidualCouplingBlocks(192, 192, kernel_size=5, dilation_rate=1, num_layers=4, cond_channels=512, device="cpu")
+        assert [(k, tuple(v.shape)) for k, v in flow.state_dict().items()] == [(k, tuple(sh)) for k, sh in spec]
+        res = flow.load_state_dict(sd)
+        assert not res.missing_keys and not res.unexpected_keys
+        flow.train()
+        z_p = flow(x, mask, g=cond)
+        flow.zero_grad()
+        dx, dg = flow.backward(w)
+        grads = {k: p.grad.detach().clone() for k, p in flow.named_parameters()}
+        with torch.no_grad():
+            back = flow(z_p, mask, g=cond, reverse=True)
+    assert rel(z_p, torch.from_numpy(gold["z_p"])) < 2e-5
+    assert rel(dx, torch.from_numpy(gold["dx"])) < 5e-5 and rel(dg, torch.from_numpy(gold["dg"])) < 5e-5
+    for (k, gr), want_norm in zip(grads.items(), gold["grad_norms"]):
+        assert rel(gr, leaves[k].grad) < 2e-4, k
+        assert abs(float(gr.double().norm()) - want_norm) < 2e-4 * want_norm + 1e-12, k
+    assert rel(back, torch.from_numpy(gold["reverse_of_z_p"])) < 2e-5 and rel(back, x) < 2e-5
+
+
+def test_hifigan_training_step_through_the_emulator_matches_the_oracle():
+    """One HiFiTrainer.iteration body of the product package (hifigan.HiFiGANStep: generator forward, loss mel, D step over
+    MPD + MSD incl. the spectral-normed scale discriminator and the grouped convolutions, AdamW; G step with 45 L1 mel +
+    feature + adversarial losses, AdamW) through the emulated C ABI vs oracle.hifigan.train_step, which is pinned to two
+    steps recorded from the unmodified reference (tests/test_oracle_golden.py): every loss term and all 404 updated tensors.
+    The first AdamW step moves a weight by lr * sign(grad), so entries whose gradient is rounding noise may step the other
+    way: the weights are compared at 2e-3 of the tensor norm, the losses at 1e-5."""
+    from oracle import hifigan as ohg
+
+    class H(dict):
+        __getattr__ = dict.__getitem__
+
+    h = H(resblock="1", upsample_rates=[8, 8, 2, 2], upsample_kernel_sizes=[16, 16, 4, 4], upsample_initial_channel=512,
+          resblock_kernel_sizes=[3, 7, 11], resblock_dilation_sizes=[[1, 3, 5]] * 3, learning_rate=2e-4, adam_b1=0.8, adam_b2=0.99,
+          n_fft=1024, num_mels=80, sampling_rate=22050, hop_size=256, win_size=1024, fmin=0, fmax=8000, fmax_for_loss=None)
+    sd_g = ohg.make_generator_state(5, scale=0.7)
+    sd_p = ohg.make_disc_state(ohg.mpd_spec(), 21)
+    sd_s = ohg.make_disc_state(ohg.msd_spec(), 22)
+    x, y, y_mel = ohg.synthetic_batch(2, 8, seed=3)
+    og, op, os_ = ({k: v.clone() for k, v in d.items()} for d in (sd_g, sd_p, sd_s))
+    want, _ = ohg.train_step(og, op, os_, x, y, y_mel, {})
+    with cabi_emu.installed():
+        hg = cabi_emu.load_module("hifigan", HG_PATCHES)
+        G = hg.Generator(h, device="cpu"); G.load_state_dict(sd_g); G.train()
+        mpd = hg.MultiPeriodDiscriminator(device="cpu"); mpd.load_state_dict(sd_p); mpd.train()
+        msd = hg.MultiScaleDiscriminator(device="cpu"); msd.load_state_dict(sd_s); msd.train()
+        step = hg.HiFiGANStep(G, mpd, msd, h)
+        losses = step.step(x, y, y_mel)
+        after = {n: {k: v.clone() for k, v in m.state_dict().items()} for n, m in (("G", G), ("mpd", mpd), ("msd", msd))}
+        used = set(cabi_emu.calls)
+    assert {"xva_sn_pack_fwd", "xva_sn_pack_bwd", "xva_conv_c1_fwd", "xva_conv_c1_bwd_x", "xva_avgpool4_fwd", "xva_spec_mag_bwd",
+            "xva_l1_loss_grad", "xva_adamw_step"} <= used
+    for k in ("loss_disc_all", "loss_mel", "loss_fm", "loss_gen", "loss_gen_all"):
+        a, b = float(losses[k]), float(want[k])
+        assert abs(a - b) < 1e-5 * abs(b) + 1e-7, (k, a, b)
+    for name, ref, before in (("G", og, sd_g), ("mpd", op, sd_p), ("msd", os_, sd_s)):
+        moved = 0
+        for k, v in ref.items():
+            assert rel(after[name][k], v) < 2e-3, (name, k, rel(after[name][k], v))
+            moved += int(not torch.equal(after[name][k], before[k]))
+        assert moved >= len(ref) * 0.9, (name, moved, len(ref))
+
+
+def test_xvapitch_hifi_only_step_through_the_emulator_matches_the_reference_recording():
+    """One xVAPitch --hifi_only iteration of the product package (vits.HifiOnlyStep: posterior encoder with its 16-layer
+    WaveNet stack, segment draw, conditioned waveform decoder, VITS discriminator in one batched pass, TorchSTFT log-mels,
+    both losses, both AdamW) through the emulated C ABI, the reference's random draws replayed, vs the iteration RECORDED
+    from the unmodified reference modules (tests/golden/vits_hifi_only.npz): segment starts identical, every loss to 2e-5,
+    the norm of every one of the 447 updated tensors and of its change; and vs the oracle step tensor by tensor."""
+    from oracle import vits as ov
+    from test_oracle_golden import _vits_hifi_only_fixture
+
+    gold, specs, sds, linear, waveform, d_vectors = _vits_hifi_only_fixture()
+    before = {n: {k: v.clone() for k, v in sd.items()} for n, sd in sds.items()}
+    eps, u = torch.from_numpy(gold["eps"]), torch.from_numpy(gold["u"])
+    lens = [int(v) for v in gold["y_lengths"]]
+    with cabi_emu.installed():
+        hg = cabi_emu.load_module("hifigan", HG_PATCHES)
+        vt = cabi_emu.load_module("vits", VT_PATCHES, extra_modules={"xva_trainer_b200.hifigan": hg})
+        enc = vt.PosteriorEncoder(513, 192, 192, kernel_size=5, dilation_rate=1, num_layers=16, cond_channels=512, device="cpu")
+        dec = hg.HifiganGenerator(192, 1, "1", [[1, 3, 5]] * 3, [3, 7, 11], [16, 16, 4, 4], 512, [8, 8, 2, 2], inference_padding=0,
+                                  cond_channels=512, conv_pre_weight_norm=False, conv_post_weight_norm=False,
+                                  conv_post_bias=False, device="cpu")
+        disc = hg.VitsDiscriminator(device="cpu")
+        for name, mod in (("enc", enc), ("dec", dec), ("disc", disc)):
+            assert [(k, tuple(v.shape)) for k, v in mod.state_dict().items()] == [(k, tuple(sh)) for k, sh in specs[name]], name
+            res = mod.load_state_dict({k: v.clone() for k, v in sds[name].items()})
+            assert not res.missing_keys and not res.unexpected_keys
+            mod.train()
+        losses = vt.HifiOnlyStep(enc, dec, disc).step(linear, lens, waveform, d_vectors, eps=eps, u=u)
+        after = {n: {k: v.clone() for k, v in m.state_dict().items()} for n, m in (("enc", enc), ("dec", dec), ("disc", disc))}
+    assert losses["slice_ids"].tolist() == gold["slice_ids"].tolist()
+    for k in ("loss", "loss_gen", "loss_feat", "loss_mel", "loss_disc"):
+        a, b = float(losses[k]), float(gold[k])
+        assert abs(a - b) < 2e-5 * abs(b), (k, a, b)
+    osd = {n: {k: v.clone() for k, v in sd.items()} for n, sd in before.items()}
+    ov.hifi_only_step(osd["enc"], osd["dec"], osd["disc"], linear, waveform, d_vectors, lens, eps, u, {})
+    for name in ("enc", "dec", "disc"):
+        moved = 0
+        for i, (k, _) in enumerate(specs[name]):
+            assert rel(after[name][k], osd[name][k]) < 2e-3, (name, k, rel(after[name][k], osd[name][k]))
+            moved += int(not torch.equal(after[name][k], before[name][k]))
+            n_after = float(after[name][k].double().norm())
+            assert abs(n_after - gold[f"{name}/after_norms"][i]) < 1e-4 * gold[f"{name}/after_norms"][i] + 1e-9, (name, k)
+            delta = float((after[name][k].double() - before[name][k].double()).norm())
+            assert abs(delta - gold[f"{name}/delta_norms"][i]) < 0.05 * gold[f"{name}/delta_norms"][i] + 1e-9, (name, k, delta)
+        assert moved == len(specs[name]), (name, moved)
