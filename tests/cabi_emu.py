@@ -1,31 +1,43 @@
-"""CPU stand-in for part of libxva_b200's C ABI. TEST INFRASTRUCTURE ONLY (like oracle/): nothing in the product package
-may import it, and the product path still fails loudly without the CUDA library.
+"""CPU stand-in for libxva_b200's C ABI. TEST INFRASTRUCTURE ONLY (like oracle/): nothing in the product package may
+import it (tests/test_abi.py greps for it), and the product path still fails loudly without the CUDA library.
 
 Why it exists: the Python host side of the engine (which GEMM is launched with which operands, strides, taps, epilogue
-flags, in which order; what the backward saves and re-reads) is most of what can go wrong in a new module, and it can be
-checked without a GPU if every C-ABI call it makes is executed on host memory according to the contract written in
-include/xva_b200.h. This module does that for the entry points below:
+flags, in which order; what the backward saves and re-reads; how parameters are packed and un-packed) is most of what can
+go wrong in a module, and it can be checked without a GPU if every C-ABI call it makes is executed on host memory according
+to the contract written in include/xva_b200.h. This module does that for EVERY entry point that launches work (70 of the
+77; the rest are introspection calls -- tests/test_cabi_emu_cpu.py::test_every_compute_entry_point_of_the_abi_has_a_stand_in):
 
-    xva_gemm / xva_gemm_ref     the tap-GEMM contract exactly as csrc/gemm_ref.cu states it (modes 0 / 1 / 2, taps, row
-                                shifts, per-tap column offsets, batched / per-tap B, every epilogue step in order);
-                                groups > 1 is not emulated
-    xva_softmax_fwd / _bwd, xva_layernorm_fwd / _bwd, xva_colsum, xva_colsum_items, xva_round_tf32, xva_counter_add,
-    xva_rowdot2                 restated from csrc/rowops.cu / csrc/vits.cu
-    xva_embed_pos / _bwd, xva_scalar_conv_add / _bwd, xva_rowdot_fwd / _bwd, xva_regulate_len_scan / _fwd / _bwd,
-    xva_average_pitch, xva_mel_mse (+ _grad), xva_lens_mse (+ _grad), xva_grad_sqnorm, xva_lamb_step, xva_adamw_step
-                                restated from csrc/rowops.cu, regulate.cu, loss_optim.cu, elemwise.cu
+    xva_gemm / xva_gemm_ref     the tap-GEMM contract exactly as csrc/gemm_ref.cu states it: modes 0 / 1 / 2, taps, row
+                                shifts, per-tap column offsets, batched / per-tap B, grouped convolutions, every epilogue
+                                step in order (bias, (leaky) ReLU, gate, dropout, residual, LayerNorm, tanh, length mask,
+                                second output, the fused softmax backward)
+    row / element-wise kernels  softmax, LayerNorm, column sums, embeddings, scalar convolution, row dots, length regulator,
+                                average_pitch, masked MSE losses, LAMB, AdamW, gated activation, posterior sample, mel
+                                pieces (reflect pad, magnitude, log clamp), GAN losses, first discriminator convolution,
+                                pooling -- restated from csrc/rowops.cu, regulate.cu, loss_optim.cu, elemwise.cu, vits.cu,
+                                melspec.cu, disc.cu
+    xva_wn_pack_* / xva_sn_pack_*  weight-norm / spectral-norm re-parametrisation + packing from their descriptor tables
     xva_attn_fwd / _bwd         the fused attention, from its contract in include/xva_b200.h
+    xva_attn_score_*, xva_attn_bin_loss, xva_attn_grad_combine, xva_vits_logp_operands, xva_vits_kl
+                                restated from csrc/align.cu / vits.cu
+    xva_attn_ctc                NOT the kernel's recursion: torch.nn.functional.ctc_loss + autograd per utterance, as the
+                                reference computes it -- an independent implementation of the same contract
+    xva_mas_width1              the oracle's own searches (oracle.fastpitch.b_mas, oracle.vits.maximum_path): on the CPU
+                                these calls check the host code around the kernel only; the kernel is compared with the
+                                same functions bit for bit in tests/test_mas_gpu.py
     xva_text_embed_fwd / _bwd, xva_rel_band_add, xva_rel_band_gather, xva_pad_cols
                                 NOT restated: csrc/relattn_body.h (the per-element functions the CUDA kernels loop over)
                                 compiled for the host with g++ (tests/relattn_host.cpp) and run as is
 
-Arithmetic is exact fp32 inputs with float64 accumulation and no tf32 operand rounding (the library's
+Arithmetic is fp32 inputs with float64 accumulation and no tf32 operand rounding (the library's
 xva_set_operand_rounding(0) test mode); dropout uses the library's counter hash (csrc/common.cuh), so forward and
 backward masks can be checked for consistency.
 
-The emulator itself is validated in tests/test_cabi_emu_cpu.py by running host code whose GPU parity is established --
-one FFT block of FastPitch through the un-fused attention chain, then whole FastPitch training steps (stages 2, 3, 4; forward,
-loss, backward, clip + LAMB, two consecutive steps) -- and comparing with the oracle.
+The emulator is validated in tests/test_cabi_emu_cpu.py by running host code whose GPU parity is established against the
+oracle / the reference recordings: whole FastPitch training steps of all four stages (forward, loss, backward, clip + LAMB),
+the HiFi-GAN generator and one whole HiFi-GAN training step, the WaveNet stack, the normalising flow, the alignment block
+and one whole xVAPitch --hifi_only step. New host code is then checked the same way BEFORE it costs GPU time
+(tests/test_vits_text_encoder_cpu.py: the text encoder's first hardware run passed 12 of 12).
 
 Usage:  with cabi_emu.installed():  ... build product modules on device="cpu" via cabi_emu.load_module(...)
 """
@@ -466,7 +478,8 @@ def installed():
         sys.path.insert(0, ROOT)
     from xva_trainer_b200 import capi, ops
     saved = (capi.load, capi.call, ops._stream, ops._check3)
-    capi.load = lambda: types.SimpleNamespace()
+    capi.load = lambda: types.SimpleNamespace(
+        xva_attn_ctc_workspace_bytes=lambda B, T, Tt: 2 * B * T * (2 * Tt + 1) * 8 + B * 8 + (B * T * 4 + 7) // 8 * 8)
     capi.call = call
     ops._stream = lambda: None
 
@@ -1147,3 +1160,134 @@ TABLE.update({"xva_conv_c1_fwd": _conv_c1_fwd, "xva_conv_c1_bwd_w": _conv_c1_bwd
               "xva_reflect_pad_bwd": _reflect_pad_bwd, "xva_spec_mag_fwd": _spec_mag_fwd, "xva_spec_mag_bwd": _spec_mag_bwd,
               "xva_log_clamp_fwd": _log_clamp_fwd, "xva_log_clamp_bwd": _log_clamp_bwd, "xva_reduce_loss": _reduce_loss,
               "xva_loss_grad": _loss_grad, "xva_l1_loss_grad": _l1_loss_grad})
+
+
+# ------------------------------------------------------------------------------------------------ stage-1 aligner, xVAPitch alignment
+def _attn_score_fwd(q, ldq, k, ldk, prior, in_lens, B, Tm, Tt, Cc, logprob, soft, stream=None):
+    Q = strided(q, (B, Tm, Cc), (Tm * ldq, ldq, 1)).astype(np.float64)
+    Kk = strided(k, (B, Tt, Cc), (Tt * ldk, ldk, 1)).astype(np.float64)
+    Pr = flat(prior, B * Tm * Tt).reshape(B, Tm, Tt).astype(np.float64)
+    D = -0.0005 * ((Q[:, :, None, :] - Kk[:, None, :, :]) ** 2).sum(-1)
+    lse = np.log(np.exp(D - D.max(2, keepdims=True)).sum(2, keepdims=True)) + D.max(2, keepdims=True)
+    lp = (D - lse) + np.log(Pr + 1e-8)
+    flat(logprob, B * Tm * Tt).reshape(B, Tm, Tt)[...] = lp.astype(np.float32)
+    nk = np.clip(flat(in_lens, B, np.int32), 0, Tt)
+    live = np.arange(Tt)[None, None, :] < nk[:, None, None]
+    m = np.where(live, lp, -np.inf)
+    e = np.exp(m - m.max(2, keepdims=True)) * live
+    flat(soft, B * Tm * Tt).reshape(B, Tm, Tt)[...] = (e / e.sum(2, keepdims=True)).astype(np.float32)
+    return 0
+
+
+def _attn_score_bwd(g, logprob, prior, q, ldq, k, ldk, B, Tm, Tt, Cc, dD, dq, lddq, dk, lddk, stream=None):
+    Gm = flat(g, B * Tm * Tt).reshape(B, Tm, Tt).astype(np.float64)
+    sm = np.exp(flat(logprob, B * Tm * Tt).reshape(B, Tm, Tt).astype(np.float64)
+                - np.log(flat(prior, B * Tm * Tt).reshape(B, Tm, Tt).astype(np.float64) + 1e-8))
+    d = Gm - sm * Gm.sum(2, keepdims=True)
+    Q = strided(q, (B, Tm, Cc), (Tm * ldq, ldq, 1)).astype(np.float64)
+    Kk = strided(k, (B, Tt, Cc), (Tt * ldk, ldk, 1)).astype(np.float64)
+    flat(dD, B * Tm * Tt).reshape(B, Tm, Tt)[...] = d.astype(np.float32)            # (may alias g: written after it was read)
+    diff = Q[:, :, None, :] - Kk[:, None, :, :]                                      # q - k
+    strided(dq, (B, Tm, Cc), (Tm * lddq, lddq, 1))[...] = (-0.001 * np.einsum("btj,btjc->btc", d, diff)).astype(np.float32)
+    strided(dk, (B, Tt, Cc), (Tt * lddk, lddk, 1))[...] = (0.001 * np.einsum("btj,btjc->bjc", d, diff)).astype(np.float32)
+    return 0
+
+
+def _attn_ctc(logprob, in_lens, out_lens, B, Tm, Tt, blank_logprob, workspace, workspace_bytes, cost, grad, stream=None):
+    """AttentionCTCLoss (fastpitch/attn_loss_function.py:20-44) per utterance through torch's own CTC and autograd -- an
+    implementation independent of the kernel's fp64 recursion."""
+    import torch
+    import torch.nn.functional as Fn
+    LP = torch.from_numpy(flat(logprob, B * Tm * Tt).reshape(B, Tm, Tt).copy()).double().requires_grad_(True)
+    il, ol = flat(in_lens, B, np.int32), flat(out_lens, B, np.int32)
+    total = 0.0
+    costs = np.zeros(B)
+    for b in range(B):
+        L, T = int(il[b]), int(ol[b])
+        rows = torch.cat([torch.full((T, 1), float(blank_logprob), dtype=torch.float64), LP[b, :T, :L]], 1)
+        lsm = torch.log_softmax(rows, dim=1)[:, None, :]
+        c = Fn.ctc_loss(lsm, torch.arange(1, L + 1)[None], torch.tensor([T]), torch.tensor([L]), blank=0, reduction="mean",
+                        zero_infinity=True)
+        costs[b] = float(c.detach())
+        total = total + c / B
+    total.backward()
+    flat(cost, B, np.float64)[...] = costs
+    flat(grad, B * Tm * Tt).reshape(B, Tm, Tt)[...] = LP.grad.float().numpy()
+    return 0
+
+
+def _attn_bin_loss(hard, soft, rows, Tt, eps, acc, stream=None):
+    Hd, Sf = flat(hard, rows * Tt), flat(soft, rows * Tt)
+    A = flat(acc, 2, np.float64)
+    A[0] += float(np.log(np.maximum(Sf[Hd == 1], np.float32(eps)).astype(np.float64)).sum())
+    A[1] += float(Hd.astype(np.float64).sum())
+    return 0
+
+
+def _attn_grad_combine(gctc, hard, soft, acc, a, bw, eps, rows, Tt, g, stream=None):
+    Gc = flat(gctc, rows * Tt).reshape(rows, Tt)
+    out = np.float32(a) * Gc
+    if _addr(hard) and bw != 0.0:
+        Hd, Sf = flat(hard, rows * Tt).reshape(rows, Tt), flat(soft, rows * Tt).reshape(rows, Tt)
+        hp = Hd * (Sf >= np.float32(eps))
+        out = out + np.float32(bw / flat(acc, 2, np.float64)[1]) * (Sf * hp.sum(1, keepdims=True) - hp)
+    flat(g, rows * Tt).reshape(rows, Tt)[...] = out.astype(np.float32)
+    return 0
+
+
+def _mas_log(attn, n, out, stream=None):
+    with np.errstate(divide="ignore"):
+        flat(out, n)[...] = np.log(flat(attn, n).astype(np.float64)).astype(np.float32)
+    return 0
+
+
+def _mas_width1(attn, in_lens, out_lens, B, Tm, Tt, is_log, hard, durs, stream=None):
+    """The integer path is NOT restated a second time: it is the oracle's own search (oracle.fastpitch.b_mas, pinned to the
+    reference's numba b_mas; oracle.vits.maximum_path, pinned to xVAPitch's) -- on the CPU these calls only check the host
+    code around the kernel; the kernel itself is compared with the same functions bit for bit in tests/test_mas_gpu.py."""
+    import torch
+    from oracle import fastpitch as ofp, vits as ov
+    A = flat(attn, B * Tm * Tt).reshape(B, Tm, Tt)
+    il, ol = flat(in_lens, B, np.int32), flat(out_lens, B, np.int32)
+    if is_log & 2:
+        path = ov.maximum_path(torch.from_numpy(np.ascontiguousarray(A.transpose(0, 2, 1))), il, ol).numpy().transpose(0, 2, 1)
+    else:
+        path = ofp.b_mas(A[:, None].copy(), il, ol, is_log=bool(is_log & 1))[:, 0]
+    flat(hard, B * Tm * Tt).reshape(B, Tm, Tt)[...] = path
+    flat(durs, B * Tt, np.int32).reshape(B, Tt)[...] = path.sum(1).astype(np.int32)
+    return 0
+
+
+def _vits_logp_operands(m_p, logs_p, z_p, B, Tt, Ts, Cc, tok, frm, stream=None):
+    K = 2 * Cc + 32
+    M, Lg = (flat(t, B * Tt * Cc).reshape(B, Tt, Cc).astype(np.float64) for t in (m_p, logs_p))
+    Zp = flat(z_p, B * Ts * Cc).reshape(B, Ts, Cc).astype(np.float64)
+    o = np.exp(-2.0 * Lg)
+    Tk = flat(tok, B * Tt * K).reshape(B, Tt, K)
+    Tk[...] = 0.0
+    Tk[..., :Cc] = o
+    Tk[..., Cc:2 * Cc] = M * o
+    Tk[..., 2 * Cc] = (-0.5 * np.log(2 * np.pi) - Lg - 0.5 * M * M * o).sum(-1)
+    Fr = flat(frm, B * Ts * K).reshape(B, Ts, K)
+    Fr[...] = 0.0
+    Fr[..., :Cc] = -0.5 * Zp * Zp
+    Fr[..., Cc:2 * Cc] = Zp
+    Fr[..., 2 * Cc] = 1.0
+    return 0
+
+
+def _vits_kl(z_p, logs_q, m_p, logs_p, lens, B, T, Cc, scale, acc, dz_p, dlogs_q, dm_p, dlogs_p, stream=None):
+    Z, Lq, M, Lp = (flat(t, B * T * Cc).reshape(B, T, Cc).astype(np.float64) for t in (z_p, logs_q, m_p, logs_p))
+    live = _lens_mask(lens, B, T)[:, :, None]
+    e = np.exp(-2.0 * Lp)
+    d = Z - M
+    flat(acc, 1, np.float64)[0] += float(((Lp - Lq - 0.5 + 0.5 * d * d * e) * live).sum())
+    k = float(scale) / float(flat(lens, B, np.int32).sum())
+    for ptr, val in ((dz_p, d * e), (dlogs_q, -np.ones_like(d)), (dm_p, -d * e), (dlogs_p, 1.0 - d * d * e)):
+        flat(ptr, B * T * Cc).reshape(B, T, Cc)[...] = (k * val * live).astype(np.float32)
+    return 0
+
+
+TABLE.update({"xva_attn_score_fwd": _attn_score_fwd, "xva_attn_score_bwd": _attn_score_bwd, "xva_attn_ctc": _attn_ctc,
+              "xva_attn_bin_loss": _attn_bin_loss, "xva_attn_grad_combine": _attn_grad_combine, "xva_mas_log": _mas_log,
+              "xva_mas_width1": _mas_width1, "xva_vits_logp_operands": _vits_logp_operands, "xva_vits_kl": _vits_kl})

@@ -365,3 +365,103 @@ def test_xvapitch_hifi_only_step_through_the_emulator_matches_the_reference_reco
             delta = float((after[name][k].double() - before[name][k].double()).norm())
             assert abs(delta - gold[f"{name}/delta_norms"][i]) < 0.05 * gold[f"{name}/delta_norms"][i] + 1e-9, (name, k, delta)
         assert moved == len(specs[name]), (name, moved)
+
+
+def test_fastpitch_stage1_step_through_the_emulator_matches_the_oracle():
+    """Training stage 1 (the aligner) of the product package through the emulated C ABI -- ConvAttention's projection stacks
+    on the tap-GEMM, the score kernel, MAS, AttentionCTCLoss (here through torch's own CTC: an implementation independent
+    of the kernel's recursion), AttentionBinarizationLoss, the combined gradient and the backward through both stacks --
+    vs oracle.fastpitch: soft attention and log-probabilities, the hard alignment and durations, both losses, the gradient
+    of the 11 stage-1 tensors, zero gradient everywhere else."""
+    x, y = ofp.synthetic_batch(3, 14, 45, seed=21, ragged=True, prior=True)
+    x[2] = x[2] * 4.0
+    y[0] = x[2]
+    sd = ofp.make_state(4321)
+    klw = 0.5
+    with cabi_emu.installed():
+        fp = cabi_emu.load_module("fastpitch", FP_PATCHES)
+        m = fp.FastPitch(device="cpu")
+        m.load_state_dict({k: v.clone() for k, v in sd.items()})
+        m.training_stage = 1
+        m.train()
+        m.p_drop = 0.0
+        crit = fp.FastPitchLoss()
+        crit.training_stage = 1
+        kl = fp.AttentionBinarizationLoss()
+        out = m(x)
+        loss, meta = crit(out, y)
+        klv = kl(out[9], out[8])
+        m.zero_grad()
+        m.backward(crit, 1.0, kl=(kl, klw))
+        got = m.grads()
+        keys = fp.trainable_keys(1)
+        used = set(cabi_emu.calls)
+    assert {"xva_attn_score_fwd", "xva_attn_score_bwd", "xva_attn_ctc", "xva_mas_width1", "xva_attn_bin_loss",
+            "xva_attn_grad_combine"} <= used
+    want = ofp.forward(sd, x, 1)
+    assert rel(out[8], want[8]) < 2e-5 and rel(out[11], want[11]) < 2e-5
+    assert torch.equal(out[9], want[9]) and torch.equal(out[10], want[10])
+    wtotal, wmeta = ofp.loss(want, y, 1, kl_weight=klw)
+    assert abs(float(meta["attn_loss"]) - float(wmeta["attn_loss"])) <= 1e-5 * abs(float(wmeta["attn_loss"]))
+    assert abs(klw * float(klv) - float(wmeta["kl_loss"])) <= 1e-5 * abs(float(wmeta["kl_loss"])) + 1e-9
+    _, wgrads = ofp.train_step({k: v.clone() for k, v in sd.items()}, x, y, 1, 1e-3, {}, drop=0.0, training=False,
+                               kl_weight=klw, clip=1e9)
+    assert keys == ofp.trainable_keys(1) and len(keys) == 11
+    errs = []
+    for k, gr in got.items():
+        if k not in keys:
+            assert float(gr.abs().max()) == 0.0, k
+        else:
+            errs.append(rel(gr, wgrads[k]))
+            assert errs[-1] < 2e-2, (k, errs[-1])      # (a handful of ReLU gates within fp32 rounding of zero, as on the device)
+    assert sorted(errs)[len(errs) // 2] < 2e-5, sorted(errs)
+
+
+def test_xvapitch_alignment_block_through_the_emulator():
+    """vits.prior_alignment / prior_expand_backward / kl_loss (xvapitch/model.py:763-777, 855-856; losses.py:86-103) through
+    the emulated C ABI vs oracle.vits: log-likelihood matrix, path and durations, expanded prior and its backward, KL loss
+    and its four gradients."""
+    from oracle import vits as ov
+
+    gen = torch.Generator().manual_seed(4)
+    B, C, tx, ty = 2, 64, 7, 23
+    x_lens, y_lens = [7, 5], [23, 16]
+    z_p = torch.randn(B, C, ty, generator=gen)
+    m_p = torch.randn(B, C, tx, generator=gen)
+    logs_p = torch.randn(B, C, tx, generator=gen) * 0.3
+    logs_q = torch.randn(B, C, ty, generator=gen) * 0.3
+    d_m, d_l = torch.randn(B, C, ty, generator=gen), torch.randn(B, C, ty, generator=gen)
+    mp, lp = m_p.clone().requires_grad_(True), logs_p.clone().requires_grad_(True)
+    w_logp, w_path, w_durs, w_me, w_le = ov.prior_alignment(z_p, mp, lp, x_lens, y_lens)
+    ((w_me * d_m).sum() + (w_le * d_l).sum()).backward()
+    zq, lq, me, le = (t.clone().requires_grad_(True) for t in (z_p, logs_q, w_me.detach(), w_le.detach()))
+    z_mask = ov.sequence_mask(y_lens, ty)[:, None, :].float()
+    w_kl = ov.kl_loss(zq, lq, me, le, z_mask)
+    w_kl.backward()
+    with cabi_emu.installed():
+        hg = cabi_emu.load_module("hifigan", HG_PATCHES)
+        vt = cabi_emu.load_module("vits", VT_PATCHES, extra_modules={"xva_trainer_b200.hifigan": hg})
+        res = vt.prior_alignment(z_p, m_p, logs_p, x_lens, y_lens)
+        dm, dl = vt.prior_expand_backward(d_m, d_l, res["cum"], tx)
+        kl, grads = vt.kl_loss(z_p, logs_q, w_me.detach(), w_le.detach(), y_lens)
+        used = set(cabi_emu.calls)
+    assert {"xva_vits_logp_operands", "xva_mas_width1", "xva_regulate_len_fwd", "xva_regulate_len_bwd", "xva_vits_kl"} <= used
+    valid = (ov.sequence_mask(x_lens, tx)[:, :, None] & ov.sequence_mask(y_lens, ty)[:, None, :])
+    assert rel(res["logp"].transpose(1, 2) * valid, w_logp * valid) < 2e-6
+    assert torch.equal(res["attn"][:, 0], w_path) and torch.equal(res["durations"][:, 0], w_durs)
+    assert rel(res["m_p"], w_me) < 1e-6 and rel(res["logs_p"], w_le) < 1e-6
+    assert rel(dm, mp.grad) < 1e-6 and rel(dl, lp.grad) < 1e-6
+    assert abs(float(kl) - float(w_kl)) < 1e-6 * abs(float(w_kl))
+    for gr, w in zip(grads, (zq.grad, lq.grad, me.grad, le.grad)):
+        assert rel(gr, w) < 1e-5
+
+
+def test_every_compute_entry_point_of_the_abi_has_a_stand_in():
+    """include/xva_b200.h via capi.PROTOTYPES: everything that launches work is emulated (or, for csrc/relattn.cu, compiled
+    for the host); what is left are the library's introspection calls."""
+    from xva_trainer_b200 import capi
+
+    have = set(cabi_emu.TABLE) | set(cabi_emu.HOST_COMPILED)
+    missing = sorted(set(capi.PROTOTYPES) - have)
+    assert missing == ["xva_abi_version", "xva_attn_ctc_workspace_bytes", "xva_gemm_debug_counters", "xva_last_error",
+                       "xva_sizeof_gemm_args", "xva_sizeof_sn_desc", "xva_sizeof_wn_desc"], missing
