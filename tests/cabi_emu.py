@@ -222,16 +222,24 @@ def _gemm(ref, stream=None):
         else:
             kv = min(K, g.b_rows) if g.b_rows else K
             Bm = strided(g.b, (n_zb, kv, N), (g.b_zs, g.b_rs, 1))
+        # products in fp32 BLAS (what the exact checker kernel computes with fmaf), taps summed in float64
         acc = np.zeros((Z, R, N), np.float64)
         for j in range(taps):
             rr = np.arange(R) + g.shift[j]
             ok = (rr >= 0) & (rr < a_rows)
             if not ok.any():
                 continue
-            Aj = np.zeros((Z, R, K), np.float64)
+            Aj = np.zeros((Z, R, K), np.float32)
             Aj[:, ok] = A[:, rr[ok], g.a_col[j]:g.a_col[j] + K]
+            if g.b_batch_z == 0:
+                Bz = np.ascontiguousarray(Bm[j * g.b_tap_z])
+                if g.mode == 0:
+                    acc[:, :, :Bz.shape[0]] += (Aj.reshape(Z * R, K) @ Bz.T).reshape(Z, R, -1)
+                else:
+                    acc += (Aj.reshape(Z * R, K)[:, :Bz.shape[0]] @ Bz).reshape(Z, R, N)
+                continue
             for z in range(Z):
-                Bz = Bm[j * g.b_tap_z + z * g.b_batch_z].astype(np.float64)
+                Bz = Bm[j * g.b_tap_z + z * g.b_batch_z]
                 if g.mode == 0:
                     acc[z, :, :Bz.shape[0]] += Aj[z] @ Bz.T
                 else:
@@ -293,7 +301,7 @@ def _gemm(ref, stream=None):
     b_cols = max(g.a_col[j] for j in range(taps)) + N
     tA = min(R, a_rows)
     assert Z == 1 or (g.a_zs != 0 and g.b_zs != 0)
-    A = strided(g.a, (Z, tA, M), (g.a_zs, g.a_rs, 1)).astype(np.float64)
+    A = strided(g.a, (Z, tA, M), (g.a_zs, g.a_rs, 1))
     Bm = strided(g.b, (Z, b_rows, b_cols), (g.b_zs, g.b_rs, 1))
     for zo in range(Z // ZR):
         for j in range(taps):
@@ -303,7 +311,7 @@ def _gemm(ref, stream=None):
             if ok.any():
                 for zr in range(ZR):
                     z = zo * ZR + zr
-                    acc += A[z, ok].T @ Bm[z, bt[ok], g.a_col[j]:g.a_col[j] + N].astype(np.float64)
+                    acc += np.ascontiguousarray(A[z, ok].T) @ np.ascontiguousarray(Bm[z, bt[ok], g.a_col[j]:g.a_col[j] + N])
             o = strided(_addr(g.out) + 4 * (zo * g.o_zs + j * g.o_js), (M, N), (g.o_rs, 1))
             val = (np.float64(np.float32(g.alpha)) * acc).astype(np.float32)
             if g.flags & F["ATOMIC"]:
@@ -708,11 +716,23 @@ def _chunks(p, n):
     return raw.view(_CHUNK)
 
 
+def _merged(cks):
+    """Chunks of one tensor are consecutive: merge them into (start, len, tensor) runs (a few hundred instead of thousands)."""
+    runs = []
+    for ck in cks:
+        a, n, t = int(ck["start"]), int(ck["len"]), int(ck["tensor"])
+        if runs and runs[-1][2] == t and runs[-1][0] + runs[-1][1] == a:
+            runs[-1][1] += n
+        else:
+            runs.append([a, n, t])
+    return runs
+
+
 def _grad_sqnorm(g, chunks, n_chunks, out, stream=None):
     s = 0.0
-    for ck in _chunks(chunks, n_chunks):
-        v = flat(_addr(g) + 4 * int(ck["start"]), int(ck["len"])).astype(np.float64)
-        s += float((v * v).sum())
+    for a, n, _ in _merged(_chunks(chunks, n_chunks)):
+        v = flat(_addr(g) + 4 * a, n)
+        s += float(np.dot(v, v))                     # (BLAS sdot: blocked fp32 accumulation, ~1e-7 relative)
     flat(out, 1, np.float64)[0] += s
     return 0
 
@@ -726,25 +746,24 @@ def _lamb_step(p, g, m, v, chunks, n_chunks, norms, gnorm_sq, max_norm, lr_dev, 
         c = np.float32(max_norm) / (np.float32(np.sqrt(gs[0])) + np.float32(1e-6))
         coef = min(c, np.float32(1.0))
     cks = _chunks(chunks, n_chunks)
+    runs = _merged(cks)
     n_t = int(cks["tensor"].max()) + 1
     N = flat(norms, 2 * n_t, np.float64)
     b1, b2, eps, wd = (np.float32(x) for x in (b1, b2, eps, wd))
     rs = []
-    for ck in cks:
-        a, n = int(ck["start"]), int(ck["len"])
+    for a, n, t in runs:
         P, G, M, V = (flat(_addr(q) + 4 * a, n) for q in (p, g, m, v))
         gi = G * coef
         M[...] = b1 * M + (np.float32(1.0) - b1) * gi
         V[...] = b2 * V + (np.float32(1.0) - b2) * gi * gi
         r = M / (np.sqrt(V) + eps) + wd * P
         rs.append(r)
-        N[2 * ck["tensor"]] += float((P.astype(np.float64) ** 2).sum())
-        N[2 * ck["tensor"] + 1] += float((r.astype(np.float64) ** 2).sum())
+        N[2 * t] += float(np.dot(P, P))
+        N[2 * t + 1] += float(np.dot(r, r))
     lr = flat(lr_dev, 1)[0]
-    for ck, r in zip(cks, rs):
-        a, n = int(ck["start"]), int(ck["len"])
-        wn = min(np.float32(np.sqrt(N[2 * ck["tensor"]])), np.float32(10.0))
-        rn = np.float32(np.sqrt(N[2 * ck["tensor"] + 1]))
+    for (a, n, t), r in zip(runs, rs):
+        wn = min(np.float32(np.sqrt(N[2 * t])), np.float32(10.0))
+        rn = np.float32(np.sqrt(N[2 * t + 1]))
         trust = np.float32(1.0) if (wn == 0 or rn == 0) else wn / rn
         P = flat(_addr(p) + 4 * a, n)
         P[...] = P - lr * trust * r

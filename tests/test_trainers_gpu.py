@@ -9,6 +9,20 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
+# Device and synthetic FastPitch dataset of these tests. tests/test_trainers_cpu.py re-runs the host-logic ones on the CPU
+# through the emulated C ABI (tests/cabi_emu.py) with DEV = "cpu" and a smaller dataset.
+DEV = "cuda:0"
+FP_SPEC = "synthetic:4x24x64x16"          # B x tokens x frames x utterances
+
+
+def _fp_dir(spec=None):
+    return (spec or FP_SPEC).replace(":", "_")
+
+
+def _n_batches(spec=None):
+    b, _, _, items = (spec or FP_SPEC).split(":")[1].split("x")[:4]
+    return int(items) // int(b)
+
 
 class FakeSocket:
     def __init__(self):
@@ -29,16 +43,16 @@ def test_fastpitch_handle_trainer_stages_and_files(lib, tmp_path, monkeypatch):
     monkeypatch.setenv("XVA_B200_MAX_EPOCHS", "2")
     mm = trainers.ModelsManager(Log(), PROD=False)
     ws = FakeSocket()
-    data = {"dataset_path": "synthetic:4x24x64x16", "output_path": str(tmp_path), "checkpoint": None, "num_workers": 0,
+    data = {"dataset_path": FP_SPEC, "output_path": str(tmp_path), "checkpoint": None, "num_workers": 0,
             "batch_size": 64, "epochs_per_checkpoint": 1, "force_stage": None}
     res = asyncio.run(trainers.handleTrainer(mm, data, ws, [0]))
     assert res == "move to hifi"
     assert ws.sent == ["Set stage to: 2 ", "Set stage to: 3 ", "Set stage to: 4 "]
-    out = tmp_path / "synthetic_4x24x64x16"
+    out = tmp_path / _fp_dir()
     names = sorted(os.listdir(out))
     assert "training.log" in names and "graphs.json" in names
     assert any(n.startswith("events.out.tfevents") for n in names)                 # TensorBoard scalars (xva_train.py:297,841-899)
-    assert "synthetic_4x24x64x16.pt" in names and "synthetic_4x24x64x16.json" in names
+    assert f"{_fp_dir()}.pt" in names and f"{_fp_dir()}.json" in names
     assert sum(n.startswith("FastPitch_checkpoint_") for n in names) <= 2          # only the last two are kept
     assert {n.split("_")[1] for n in names if n.startswith("Stage_")} == {"2", "3", "4"}
     graphs = json.load(open(out / "graphs.json"))
@@ -48,7 +62,7 @@ def test_fastpitch_handle_trainer_stages_and_files(lib, tmp_path, monkeypatch):
     ck = torch.load(out / [n for n in names if n.startswith("FastPitch_checkpoint_")][-1], map_location="cpu")
     assert set(ck) == {"epoch", "iteration", "avg_loss_per_epoch", "training_stage", "state_dict", "optimizer"}
     assert len(ck["state_dict"]) == 185 and ck["state_dict"]["decoder.layers.0.pos_ff.CoreNet.0.weight"].shape == (1536, 384, 3)
-    half = torch.load(out / "synthetic_4x24x64x16.pt", map_location="cpu")
+    half = torch.load(out / f"{_fp_dir()}.pt", map_location="cpu")
     assert half["proj.weight"].dtype == torch.float16
     log = open(out / "training.log").read()
     assert "Stage: 2" in log and "frames/s" in log
@@ -65,7 +79,7 @@ def test_fastpitch_handle_trainer_starts_at_the_aligner(lib, tmp_path, monkeypat
     monkeypatch.setenv("XVA_B200_MAX_EPOCHS", "2")
     mm = trainers.ModelsManager(Log(), PROD=False)
     ws = FakeSocket()
-    data = {"dataset_path": "synthetic:4x24x64x16:prior", "output_path": str(tmp_path), "checkpoint": None,
+    data = {"dataset_path": FP_SPEC + ":prior", "output_path": str(tmp_path), "checkpoint": None,
             "num_workers": 0, "batch_size": 64, "epochs_per_checkpoint": 1, "force_stage": None}
     seen = {}
     orig = trainers.FastPitchTrainer.extract_durations
@@ -84,7 +98,7 @@ def test_fastpitch_handle_trainer_starts_at_the_aligner(lib, tmp_path, monkeypat
     assert seen["changed"]
     for s_, l_ in zip(seen["sums"], seen["mel_lens"]):
         assert torch.equal(s_.long(), l_)                       # a hard alignment: durations add up to the mel length
-    out = tmp_path / "synthetic_4x24x64x16_prior"
+    out = tmp_path / (_fp_dir() + "_prior")
     names = sorted(os.listdir(out))
     assert {n.split("_")[1] for n in names if n.startswith("Stage_")} == {"1", "2", "3", "4"}
     graphs = json.load(open(out / "graphs.json"))
@@ -142,7 +156,7 @@ def test_hifigan_trainer_on_a_voice_folder(lib, tmp_path, monkeypatch):
     # hifigan/xva_train.py:276-277): hand the trainer one in the reference's g_ file layout
     from xva_trainer_b200 import hifigan as hg
     base = tmp_path / "g_pretrained"
-    torch.save({"generator": hg.Generator(trainers._Cfg(trainers.HIFI_CONFIG_V1), device="cuda:0").state_dict()}, base)
+    torch.save({"generator": hg.Generator(trainers._Cfg(trainers.HIFI_CONFIG_V1), device=DEV).state_dict()}, base)
     data = {"dataset_path": str(voice), "output_path": str(tmp_path / "out"), "hifigan_checkpoint": str(base), "num_workers": 0,
             "batch_size": 3, "epochs_per_checkpoint": 1}
     os.makedirs(tmp_path / "out", exist_ok=True)
@@ -155,8 +169,8 @@ def test_hifigan_trainer_on_a_voice_folder(lib, tmp_path, monkeypatch):
 
 
 # ------------------------------------------------------------------------------------------------ round-1 advisor findings
-def _fp_data(tmp_path, spec="synthetic:4x24x64x16", **kw):
-    d = {"dataset_path": spec, "output_path": str(tmp_path), "checkpoint": None, "num_workers": 0, "batch_size": 64,
+def _fp_data(tmp_path, spec=None, **kw):
+    d = {"dataset_path": spec or FP_SPEC, "output_path": str(tmp_path), "checkpoint": None, "num_workers": 0, "batch_size": 64,
          "epochs_per_checkpoint": 1, "force_stage": None}
     d.update(kw)
     return d
@@ -172,17 +186,18 @@ def test_fastpitch_base_checkpoint_is_only_the_starting_point(lib, tmp_path, mon
     mm = trainers.ModelsManager(Log(), PROD=False)
     res = asyncio.run(trainers.handleTrainer(mm, _fp_data(tmp_path / "a"), FakeSocket(), [0]))
     assert res == "move to hifi"
-    a = tmp_path / "a" / "synthetic_4x24x64x16"
+    a = tmp_path / "a" / _fp_dir()
     base = [n for n in os.listdir(a) if n.startswith("Stage_2_DONE_")]
     assert len(base) == 1
     base_ck = torch.load(a / base[0], map_location="cpu")
     assert base_ck["training_stage"] == 3
     ws = FakeSocket()
-    data = _fp_data(tmp_path / "b", spec="synthetic:4x24x64x32", checkpoint=str(a / base[0]))
+    other = FP_SPEC.rsplit("x", 1)[0] + "x" + str(2 * int(FP_SPEC.rsplit("x", 1)[1]))     # another voice: twice the utterances
+    data = _fp_data(tmp_path / "b", spec=other, checkpoint=str(a / base[0]))
     res = asyncio.run(trainers.handleTrainer(mm, data, ws, [0]))
     assert res == "move to hifi"
     assert ws.sent == ["Set stage to: 2 ", "Set stage to: 3 ", "Set stage to: 4 "]
-    log = open(tmp_path / "b" / "synthetic_4x24x64x32" / "training.log").read()
+    log = open(tmp_path / "b" / _fp_dir(other) / "training.log").read()
     assert log.count("New voice") == 1 and log.count(f"Checkpoint: {a / base[0]}") == 1
     # a finished run on disk (training_stage 5) goes straight on to the vocoder (:356-359); so does force_stage 5
     ws2 = FakeSocket()
@@ -199,8 +214,8 @@ def test_fastpitch_nan_batch_is_skipped_before_the_update(lib, tmp_path, monkeyp
     from xva_trainer_b200 import trainers
 
     monkeypatch.setenv("XVA_B200_MAX_EPOCHS", "1")
-    batches = trainers._synthetic_fastpitch_batches("synthetic:4x24x64x16", torch.device("cuda:0"))
-    assert len(batches) == 4
+    batches = trainers._synthetic_fastpitch_batches(FP_SPEC, torch.device(DEV))
+    assert len(batches) == _n_batches() and len(batches) >= 2
     batches[1][0][2][0, 3, 5] = float("nan")          # one NaN in the mel target of the second batch
     mm = trainers.ModelsManager(Log(), PROD=False)
     seen = {}
@@ -219,8 +234,8 @@ def test_fastpitch_nan_batch_is_skipped_before_the_update(lib, tmp_path, monkeyp
         # force_stage stays 3 for every re-entry of this hand-driven call: stop after the first stage
         asyncio.run(_one_stage(trainers, mm, data))
     assert seen["finite"] and all(seen["finite"])
-    assert seen["steps"] == 3                          # 4 batches, gam = 1, one skipped
-    log = open(tmp_path / "synthetic_4x24x64x16" / "training.log").read()
+    assert seen["steps"] == _n_batches() - 1           # gam = 1, one batch skipped
+    log = open(tmp_path / _fp_dir() / "training.log").read()
     assert log.count("loss is NaN") == 1
 
 
