@@ -227,6 +227,116 @@ def pitch_predictor(sd, x, x_lengths, speaker_emb, num_layers, kernel=3):
     return h * mask
 
 
+# ------------------------------------------------------------------------------------------------ stochastic duration predictor
+# (oracle only: the engine-side module is not built. Groundwork for SURVEY.md section 8f rank 1, pinned to the reference
+# module by tests/golden/make_golden_vits_sdp.py.)
+SDP_BINS, SDP_TAIL = 10, 5.0
+
+
+def dds_conv(sd, pre, x, x_mask, num_layers=3, kernel=3, g=None):
+    """DilatedDepthSeparableConv.forward, python/xvapitch/sdp.py:77-93 (dropout off): per layer a depth-wise convolution with
+    dilation kernel^i on x * mask, LayerNorm over channels, GELU, 1x1 convolution, LayerNorm, GELU, residual add."""
+    if g is not None:
+        x = x + g
+    C = x.shape[1]
+    for i in range(num_layers):
+        d = kernel ** i
+        y = F.conv1d(x * x_mask, sd[f"{pre}.convs_sep.{i}.weight"], sd[f"{pre}.convs_sep.{i}.bias"], groups=C, dilation=d,
+                     padding=(kernel * d - d) // 2)
+        y = F.gelu(_layer_norm2(sd, f"{pre}.norms_1.{i}", y))
+        y = F.conv1d(y, sd[f"{pre}.convs_1x1.{i}.weight"], sd[f"{pre}.convs_1x1.{i}.bias"])
+        y = F.gelu(_layer_norm2(sd, f"{pre}.norms_2.{i}", y))
+        x = x + y
+    return x * x_mask
+
+
+def rq_spline_forward(x, w_un, h_un, d_un, tail=SDP_TAIL, min_w=1e-3, min_h=1e-3, min_d=1e-3):
+    """Forward direction of the monotonic rational-quadratic spline with linear tails (Durkan et al. 2019) as the reference
+    evaluates it (python/xvapitch/util.py:244-399, inverse=False): x [...], w_un / h_un [..., K], d_un [..., K - 1] ->
+    (y, log|dy/dx|). Outside [-tail, tail] the map is the identity. Written without boolean indexing: every element goes
+    through the spline arithmetic on a clamped copy and the tails are selected at the end."""
+    K = w_un.shape[-1]
+    inside = (x >= -tail) & (x <= tail)
+    xc = x.clamp(-tail, tail)
+    edge = math.log(math.exp(1 - min_d) - 1)                        # softplus^-1(1 - min_d): derivative 1 at both ends
+    d_un = F.pad(d_un, (1, 1), value=edge)
+
+    def knots(un, lo, hi, min_size):
+        size = min_size + (1 - min_size * K) * F.softmax(un, dim=-1)
+        cum = F.pad(torch.cumsum(size, dim=-1), (1, 0))
+        cum = (hi - lo) * cum + lo
+        cum = torch.cat([torch.full_like(cum[..., :1], lo), cum[..., 1:-1], torch.full_like(cum[..., :1], hi)], dim=-1)
+        return cum, cum[..., 1:] - cum[..., :-1]
+
+    cw, widths = knots(w_un, -tail, tail, min_w)
+    ch, heights = knots(h_un, -tail, tail, min_h)
+    deriv = min_d + F.softplus(d_un)
+    search = cw.clone()
+    search[..., -1] = search[..., -1] + 1e-6                        # util.py:239-241: the right edge belongs to the last bin
+    idx = (torch.sum(xc[..., None] >= search, dim=-1) - 1).clamp(0, K - 1)[..., None]
+    take = lambda t: t.gather(-1, idx)[..., 0]
+    x0, bw, y0, bh = take(cw), take(widths), take(ch), take(heights)
+    delta = take(heights / widths)
+    d0, d1 = take(deriv), take(deriv[..., 1:])
+    th = (xc - x0) / bw
+    tt = th * (1 - th)
+    den = delta + (d0 + d1 - 2 * delta) * tt
+    y = y0 + bh * (delta * th ** 2 + d0 * tt) / den
+    logdet = torch.log(delta ** 2 * (d1 * th ** 2 + 2 * delta * tt + d0 * (1 - th) ** 2)) - 2 * torch.log(den)
+    return torch.where(inside, y, x), torch.where(inside, logdet, torch.zeros_like(logdet))
+
+
+def conv_flow(sd, pre, x, x_mask, g, hidden=HIDDEN):
+    """ConvFlow.forward (forward direction), sdp.py:149-176: the first channel conditions a spline on the second."""
+    x0, x1 = x[:, :1], x[:, 1:]
+    h = F.conv1d(x0, sd[f"{pre}.pre.weight"], sd[f"{pre}.pre.bias"])
+    h = dds_conv(sd, f"{pre}.convs", h, x_mask, g=g)
+    h = F.conv1d(h, sd[f"{pre}.proj.weight"], sd[f"{pre}.proj.bias"]) * x_mask            # [B, 3 K - 1, T]
+    h = h.permute(0, 2, 1)[:, None]                                                        # [B, 1, T, 3 K - 1]
+    K = SDP_BINS
+    y1, logabsdet = rq_spline_forward(x1, h[..., :K] / math.sqrt(hidden), h[..., K:2 * K] / math.sqrt(hidden), h[..., 2 * K:])
+    return torch.cat([x0, y1], 1) * x_mask, torch.sum(logabsdet * x_mask, [1, 2])
+
+
+def _sdp_flows(sd, pre, z, x_mask, g, num_flows=4):
+    """ElementwiseAffine then num_flows x [ConvFlow, channel flip] (sdp.py:268-276, 292-297) -> (z, summed log-determinant)."""
+    z = (z * torch.exp(sd[f"{pre}.0.log_scale"]) + sd[f"{pre}.0.translation"]) * x_mask
+    logdet = torch.sum(sd[f"{pre}.0.log_scale"] * x_mask, [1, 2])
+    for i in range(1, num_flows + 1):
+        z, ld = conv_flow(sd, f"{pre}.{i}", z, x_mask, g)
+        logdet = logdet + ld
+        z = torch.flip(z, [1])
+    return z, logdet
+
+
+def sdp_nll(sd, x, x_mask, dr, g, lang_emb, noise):
+    """StochasticDurationPredictor.forward (training direction), sdp.py:241-300, with the N(0, 1) draw of :264 passed in:
+    x [B, C + L, T] (the text encoder's output, detached by the caller), dr [B, 1, T] durations, g [B, 512, 1],
+    lang_emb [B, L, 1], noise [B, 2, T] -> negative log-likelihood per utterance [B] (variational dequantisation + data
+    augmentation: a posterior flow conditioned on the durations, then the main flow on log(d - u))."""
+    x = F.conv1d(x, sd["pre.weight"], sd["pre.bias"])
+    if g is not None:
+        x = x + F.conv1d(g, sd["cond.weight"], sd["cond.bias"])
+    if lang_emb is not None:
+        x = x + F.conv1d(lang_emb, sd["cond_lang.weight"], sd["cond_lang.bias"])
+    x = dds_conv(sd, "convs", x, x_mask)
+    x = F.conv1d(x, sd["proj.weight"], sd["proj.bias"]) * x_mask
+    h = F.conv1d(dr, sd["post_pre.weight"], sd["post_pre.bias"])
+    h = dds_conv(sd, "post_convs", h, x_mask)
+    h = F.conv1d(h, sd["post_proj.weight"], sd["post_proj.bias"]) * x_mask
+    noise = noise * x_mask
+    z_q, logdet_q = _sdp_flows(sd, "post_flows", noise, x_mask, x + h)
+    z_u, z_v = z_q[:, :1], z_q[:, 1:]
+    u = torch.sigmoid(z_u) * x_mask
+    z0 = (dr - u) * x_mask
+    logdet_q = logdet_q + torch.sum((F.logsigmoid(z_u) + F.logsigmoid(-z_u)) * x_mask, [1, 2])
+    nll_post = torch.sum(-0.5 * (math.log(2 * math.pi) + noise ** 2) * x_mask, [1, 2]) - logdet_q
+    z0 = torch.log(torch.clamp_min(z0, 1e-5)) * x_mask
+    logdet = torch.sum(-z0, [1, 2])
+    z, ld = _sdp_flows(sd, "flows", torch.cat([z0, z_v], 1), x_mask, x)
+    return torch.sum(0.5 * (math.log(2 * math.pi) + z ** 2) * x_mask, [1, 2]) - (logdet + ld) + nll_post
+
+
 # ------------------------------------------------------------------------------------------------ alignment, prior, KL
 def maximum_path(value, x_lens, y_lens):
     """xVAPitch's monotonic alignment search, python/xvapitch/util.py:14-53, restated: value [B, t_x, t_y] (masked with

@@ -130,3 +130,17 @@ def pitch_ref_spec(layers=3, hidden=196, cond=512, ffn=768, heads=2, k=3, window
         spec += [(f"encoder.norm_layers_2.{i}.gamma", (o,)), (f"encoder.norm_layers_2.{i}.beta", (o,))]
     spec += [("encoder.proj.weight", (1, C, 1)), ("encoder.proj.bias", (1,))]
     return spec
+
+
+def fill_sdp(spec, gen):
+    """Seeded fill of the stochastic duration predictor's parameters (make_golden_vits_sdp.py): the reference zero-initialises
+    every ConvFlow projection (identity splines); here they get small random values so the splines are exercised."""
+    sd = {}
+    for k, sh in spec:
+        if k.endswith("gamma"):
+            sd[k] = 1.0 + 0.1 * torch.randn(sh, generator=gen)
+        elif k.endswith("beta") or k.endswith("bias") or k.endswith("translation") or k.endswith("log_scale"):
+            sd[k] = 0.1 * torch.randn(sh, generator=gen)
+        else:
+            sd[k] = torch.randn(sh, generator=gen) * 0.7 / np.sqrt(int(np.prod(sh[1:])))
+    return sd
