@@ -1,5 +1,9 @@
-"""xVAPitch text encoder on the B200 engine.
+"""xVAPitch text encoder and pitch predictor on the B200 engine.
 
+    RelativePositioningPitchEnergyEncoder
+                  drop-in for python/xvapitch/model.py:1268 as xVAPitch builds its pitch predictor (model.py:154-168): the
+                  same transformer layers over cat(text-encoder output, speaker embedding) = 708 / 780 channels, 3 layers,
+                  a 1-channel projection (class docstring below)
     TextEncoder   drop-in for python/xvapitch/model.py:1089 ``TextEncoder`` (same constructor arguments, ``forward`` with
                   both of its calls -- stats=False: embedding + language embedding + transformer; stats=True: the 1x1
                   projection to the prior's mean / log-scale --, same state_dict keys and shapes) over
