@@ -465,3 +465,25 @@ def test_every_compute_entry_point_of_the_abi_has_a_stand_in():
     missing = sorted(set(capi.PROTOTYPES) - have)
     assert missing == ["xva_abi_version", "xva_attn_ctc_workspace_bytes", "xva_gemm_debug_counters", "xva_last_error",
                        "xva_sizeof_gemm_args", "xva_sizeof_sn_desc", "xva_sizeof_wn_desc"], missing
+
+
+@pytest.mark.parametrize("case", ["free", "pace", "forced"])
+def test_fastpitch_infer_through_the_emulator_matches_the_reference_recording(case):
+    """FastPitch.infer of the product package (fastpitch/model.py:426-482) through the emulated C ABI vs the outputs
+    RECORDED from the reference's own FastPitch.infer (tests/golden/infer.npz): predicted durations / pitch / energy, frame
+    counts and the mel -- free-running, paced, and with forced durations + pitch."""
+    from test_infer_gpu import GOLD, infer_kwargs, infer_state
+
+    g = np.load(os.path.join(GOLD, "infer.npz"))
+    t = lambda k: torch.from_numpy(g[k])
+    kw = infer_kwargs(g, case)
+    with cabi_emu.installed():
+        fp = cabi_emu.load_module("fastpitch", FP_PATCHES)
+        m = fp.FastPitch(device="cpu")
+        m.load_state_dict(infer_state())
+        m.eval()
+        mel, dec_lens, dur_pred, pitch_pred, energy_pred = m.infer(t("text"), **kw)
+    assert rel(dur_pred, t(f"{case}/dur_pred")) < 2e-5
+    assert rel(pitch_pred, t(f"{case}/pitch_pred")) < 2e-5 and rel(energy_pred, t(f"{case}/energy_pred")) < 2e-5
+    assert torch.equal(dec_lens, t(f"{case}/dec_lens")) and dec_lens.dtype == torch.int64
+    assert tuple(mel.shape) == tuple(g[f"{case}/mel"].shape) and rel(mel, t(f"{case}/mel")) < 2e-5
