@@ -24,6 +24,20 @@ HG_PATCHES = [('if dev.type != "cuda":', "if False:")]
 TR_PATCHES = [('self.device = torch.device(f"cuda:{gpu}")', 'self.device = torch.device("cpu")')]
 
 
+@pytest.fixture(autouse=True)
+def _drop_checkpoints(tmp_path):
+    """A FastPitch checkpoint is 0.55 GB (weights + both LAMB moments) and every stage keeps several: delete them after
+    each test instead of leaving ~3 GB per test in pytest's retained temp directories."""
+    yield
+    for root, _, files in os.walk(tmp_path):
+        for f in files:
+            if f.endswith(".pt"):
+                try:
+                    os.remove(os.path.join(root, f))
+                except OSError:
+                    pass
+
+
 @pytest.fixture
 def emulated(monkeypatch):
     """xva_trainer_b200.trainers (and the fastpitch / hifigan modules it drives) as private copies with the CUDA-only checks
