@@ -487,3 +487,45 @@ def test_fastpitch_infer_through_the_emulator_matches_the_reference_recording(ca
     assert rel(pitch_pred, t(f"{case}/pitch_pred")) < 2e-5 and rel(energy_pred, t(f"{case}/energy_pred")) < 2e-5
     assert torch.equal(dec_lens, t(f"{case}/dec_lens")) and dec_lens.dtype == torch.int64
     assert tuple(mel.shape) == tuple(g[f"{case}/mel"].shape) and rel(mel, t(f"{case}/mel")) < 2e-5
+
+
+@pytest.mark.parametrize("stage", [3, 1])
+def test_gradient_accumulation_over_micro_batches_is_the_sum_of_their_gradients(stage):
+    """FastPitchTrainer accumulates `gam` micro-batches before one LAMB step (xva_train.py:806-813, 855-862: loss / gam,
+    backward, step every gam-th): backward(criterion, 1 / gam) must ADD into the gradient arena -- every weight-gradient
+    GEMM, column sum, LayerNorm / embedding / scalar-convolution gradient -- so that two micro-batches leave exactly
+    (g_1 + g_2) / 2 behind."""
+    xa, ya = ofp.synthetic_batch(2, 12, 40, seed=7, ragged=True, prior=(stage == 1))
+    xb, yb = ofp.synthetic_batch(2, 12, 40, seed=8, ragged=True, prior=(stage == 1))
+    sd = ofp.make_state(1234)
+    with cabi_emu.installed():
+        fp = cabi_emu.load_module("fastpitch", FP_PATCHES)
+        m = fp.FastPitch(device="cpu")
+        m.load_state_dict({k: v.clone() for k, v in sd.items()})
+        m.training_stage = stage
+        m.train()
+        m.p_drop = 0.0
+        crit = fp.FastPitchLoss()
+        crit.training_stage = stage
+        kl = fp.AttentionBinarizationLoss()
+
+        def micro(x, y, scale):
+            out = m(x)
+            crit(out, y)
+            if stage == 1:
+                kl(out[9], out[8])
+                m.backward(crit, scale, kl=(kl, 0.5))          # (the binarization weight; backward multiplies it by `scale`)
+            else:
+                m.backward(crit, scale)
+
+        singles = []
+        for x, y in ((xa, ya), (xb, yb)):
+            m.zero_grad()
+            micro(x, y, 1.0)
+            singles.append(m.arena.g.clone())
+        m.zero_grad()
+        micro(xa, ya, 0.5)
+        micro(xb, yb, 0.5)
+        both = m.arena.g.clone()
+    want = 0.5 * (singles[0] + singles[1])
+    assert float(want.norm()) > 0 and rel(both, want) < 1e-6
