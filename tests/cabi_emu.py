@@ -203,8 +203,48 @@ def _gemm_grouped(g, G):
     return 0
 
 
+def _up32(n):
+    return (n + 31) // 32 * 32
+
+
+def check_gemm_args(g):
+    """The argument checks of csrc/gemm_tc.cu (gemm_tc_launch / encode_map) that do not depend on the tile plan: a launch
+    the library would refuse with XVA_ERR_ARG must not pass on the CPU either. TMA needs 16-byte aligned operand bases and
+    row / item pitches; MN-major operands are fetched in 32-column chunks."""
+    assert 0 <= g.mode <= 2 and 1 <= g.taps <= 48 and g.Z >= 1 and g.R >= 1 and g.N >= 1, "gemm: empty / bad problem"
+    assert g.a and g.b and g.out, "gemm: null operand"
+    for name, ptr, rs, zs, nz in (("a", g.a, g.a_rs, g.a_zs, g.Z), ("b", g.b, g.b_rs, g.b_zs, g.b_nz if g.mode != 2 else g.Z)):
+        assert ptr % 16 == 0, f"gemm: operand {name} base {ptr:#x} is not 16-byte aligned (TMA)"
+        assert (rs * 4) % 16 == 0, f"gemm: operand {name} row pitch {rs} floats is not a multiple of 16 bytes"
+        assert nz <= 1 or zs == 0 or (zs * 4) % 16 == 0, f"gemm: operand {name} item pitch {zs} floats is not a multiple of 16 bytes"
+    G = g.groups if g.groups > 1 else 1
+    if g.mode != 2:
+        assert g.K >= 1
+        if g.flags & from_flags["LN"]:
+            assert g.N % 16 == 0 and g.N <= 512 and g.gamma and g.beta, f"gemm: LayerNorm epilogue needs N % 16 == 0, <= 512 (N={g.N})"
+        if g.mode == 1:
+            assert g.N % 32 == 0 or g.b_rs >= _up32(g.N), f"gemm: MN-major B with N={g.N} needs N % 32 == 0 or a row stride >= {_up32(g.N)} (got {g.b_rs})"
+        if G > 1:
+            assert not (g.flags & from_flags["LN"]) and g.b_batch_z == 0 and g.N % G == 0
+            if g.mode == 0:
+                assert (g.N // G) % 16 == 0 and g.N // G <= 256
+            else:
+                assert (g.N // G) % 32 == 0 and g.N // G <= 256 and g.K % 32 == 0
+    else:
+        assert g.M >= 1 and g.ZR >= 1 and g.Z % g.ZR == 0
+        assert g.M % 32 == 0 or g.a_rs >= _up32(g.M), f"gemm: MN-major A with M={g.M} needs M % 32 == 0 or a row stride >= {_up32(g.M)} (got {g.a_rs})"
+        assert g.N % 32 == 0 or g.b_rs >= _up32(g.N), f"gemm: MN-major B with N={g.N} needs N % 32 == 0 or a row stride >= {_up32(g.N)} (got {g.b_rs})"
+        for j in range(g.taps):
+            assert g.a_col[j] % 32 == 0, f"gemm: wgrad column offset {g.a_col[j]} of tap {j} is not a multiple of 32"
+        assert g.split <= 1 or (g.flags & from_flags["ATOMIC"]), "gemm: split > 1 needs GEMM_ATOMIC"
+        if G > 1:
+            og = g.M // G
+            assert g.M % G == 0 and og in (32, 64, 128) and g.grp_step == g.N and g.N % 32 == 0 and (128 // og) * g.N <= 256
+
+
 def _gemm(ref, stream=None):
     g = ref._obj
+    check_gemm_args(g)
     Z, R, N, K, taps = g.Z, g.R, g.N, g.K, g.taps
     F = from_flags
     G = g.groups if g.groups > 1 else 1
@@ -324,6 +364,7 @@ def _gemm(ref, stream=None):
 # ------------------------------------------------------------------------------------------------ row kernels
 def _softmax_fwd(s, lens, Z, R, N, ld, p_out, pd_out, drop_p, seed, seed_dev, stream=None):
     ld = ld if ld > 0 else N
+    assert N >= 1 and N <= ld <= 1024, f"softmax: N={N} ld={ld} out of range (max 1024)"
     rows = Z * R
     S = flat(s, rows * ld).reshape(rows, ld)
     nk = np.full(rows, N)
@@ -355,6 +396,8 @@ def _softmax_bwd(p, dpd, Z, R, N, ld, alpha, drop_p, seed, seed_dev, stream=None
 
 
 def _layernorm_fwd(x, gamma, beta, lens, Z, R, Cc, eps, y, mean, rstd, stream=None):
+    assert 4 <= Cc <= 1024 and Cc % 4 == 0, f"layernorm fwd: C={Cc} (multiple of 4, max 1024)"
+    assert all(_addr(q) % 16 == 0 for q in (x, y, gamma, beta)), "layernorm fwd: pointers must be 16-byte aligned"
     rows = Z * R
     X = flat(x, rows * Cc).reshape(rows, Cc).astype(np.float64)
     mu = X.mean(axis=1, keepdims=True)
@@ -370,6 +413,7 @@ def _layernorm_fwd(x, gamma, beta, lens, Z, R, Cc, eps, y, mean, rstd, stream=No
 
 def _layernorm_bwd(dy, x, mean, rstd, gamma, lens, Z, R, Cc, dx, dx_drop, dgamma, dbeta, dbias, drop_post_p, seed_post,
                    drop_pre_p, seed_pre, seed_dev, relu_gate, stream=None):
+    assert 1 <= Cc <= 1024, f"layernorm bwd: C={Cc} (max 1024)"
     rows = Z * R
     live = np.ones((rows, 1))
     if _addr(lens):
