@@ -87,6 +87,34 @@ def strided(p, shape, strides, dtype=np.float32):
     return np.lib.stride_tricks.as_strided(base, shape=tuple(int(s) for s in shape), strides=tuple(int(st) * item for st in strides))
 
 
+# ------------------------------------------------------------------------------------------------ tf32 operand model
+# TF32 = False (default): exact arithmetic, the library's xva_set_operand_rounding(0) test mode.
+# TF32 = True: the PRODUCT path's operand precision is modelled -- xva_gemm truncates its fp32 operands to tf32 (10-bit
+# mantissa) as the tensor cores do, and every kernel that stores a GEMM operand rounds it to nearest (csrc/common.cuh tf32_rn).
+# Supported for the entry points in TF32_MODELLED (the text encoder / pitch predictor / FFT-block path); any other call
+# raises in this mode rather than silently computing in a precision the device would not use. xva_gemm_ref stays exact.
+TF32 = False
+TF32_MODELLED = {"xva_gemm", "xva_gemm_ref", "xva_softmax_fwd", "xva_softmax_bwd", "xva_layernorm_fwd", "xva_layernorm_bwd",
+                 "xva_colsum", "xva_colsum_items", "xva_round_tf32", "xva_counter_add", "xva_rowdot2", "xva_device_check",
+                 "xva_set_operand_rounding", "xva_text_embed_fwd", "xva_text_embed_bwd", "xva_rel_band_add", "xva_rel_band_gather",
+                 "xva_pad_cols", "xva_adamw_step"}
+
+
+def tf32_rn(x):
+    """cvt.rna.tf32.f32: round to nearest, ties away from zero, low 13 mantissa bits cleared."""
+    u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
+    return ((u + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+def tf32_trunc(x):
+    u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
+    return (u & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+def _rn(x):
+    return tf32_rn(x) if TF32 else x
+
+
 # ------------------------------------------------------------------------------------------------ dropout hash
 def _hash_u64(seed, idx4):
     with np.errstate(over="ignore"):
@@ -242,9 +270,14 @@ def check_gemm_args(g):
             assert g.M % G == 0 and og in (32, 64, 128) and g.grp_step == g.N and g.N % 32 == 0 and (128 // og) * g.N <= 256
 
 
-def _gemm(ref, stream=None):
+def _gemm_ref(ref, stream=None):
+    return _gemm(ref, stream, exact=True)
+
+
+def _gemm(ref, stream=None, exact=False):
     g = ref._obj
     check_gemm_args(g)
+    tf = TF32 and not exact
     Z, R, N, K, taps = g.Z, g.R, g.N, g.K, g.taps
     F = from_flags
     G = g.groups if g.groups > 1 else 1
@@ -271,8 +304,12 @@ def _gemm(ref, stream=None):
                 continue
             Aj = np.zeros((Z, R, K), np.float32)
             Aj[:, ok] = A[:, rr[ok], g.a_col[j]:g.a_col[j] + K]
+            if tf:
+                Aj = tf32_trunc(Aj)
             if g.b_batch_z == 0:
                 Bz = np.ascontiguousarray(Bm[j * g.b_tap_z])
+                if tf:
+                    Bz = tf32_trunc(Bz)
                 if g.mode == 0:
                     acc[:, :, :Bz.shape[0]] += (Aj.reshape(Z * R, K) @ Bz.T).reshape(Z, R, -1)
                 else:
@@ -280,6 +317,8 @@ def _gemm(ref, stream=None):
                 continue
             for z in range(Z):
                 Bz = Bm[j * g.b_tap_z + z * g.b_batch_z]
+                if tf:
+                    Bz = tf32_trunc(Bz)
                 if g.mode == 0:
                     acc[z, :, :Bz.shape[0]] += Aj[z] @ Bz.T
                 else:
@@ -316,8 +355,8 @@ def _gemm(ref, stream=None):
                 v = np.tanh(v)
             v = v * keep_row
             if g.out_act:
-                view(g.out_act, g.o_rs, g.o_zs)[...] = np.where(v > 0, v, np.float32(g.out_act_slope) * v)
-            out[...] = v
+                view(g.out_act, g.o_rs, g.o_zs)[...] = _rn(np.where(v > 0, v, np.float32(g.out_act_slope) * v))
+            out[...] = _rn(v) if (g.flags & F["ROUND_OUT"]) else v
             return 0
         mean = v.astype(np.float64).mean(axis=2, keepdims=True)
         var = ((v - mean) ** 2).mean(axis=2, keepdims=True)
@@ -326,7 +365,7 @@ def _gemm(ref, stream=None):
         if (g.flags & F["DROP_POST"]) and g.drop_p > 0:
             di = rows_idx[:, :, None] * np.uint64(N) + np.arange(N, dtype=np.uint64)[None, None, :]
             y = y * dropout_scale(g.seed, g.seed_dev, di, g.drop_p)
-        out[...] = y * keep_row
+        out[...] = _rn(y * keep_row) if (g.flags & F["ROUND_OUT"]) else y * keep_row
         if g.out_pre:
             view(g.out_pre, g.o_rs, g.o_zs)[...] = v
         if g.ln_mean:
@@ -351,13 +390,14 @@ def _gemm(ref, stream=None):
             if ok.any():
                 for zr in range(ZR):
                     z = zo * ZR + zr
-                    acc += np.ascontiguousarray(A[z, ok].T) @ np.ascontiguousarray(Bm[z, bt[ok], g.a_col[j]:g.a_col[j] + N])
+                    At, Bt = np.ascontiguousarray(A[z, ok].T), np.ascontiguousarray(Bm[z, bt[ok], g.a_col[j]:g.a_col[j] + N])
+                    acc += (tf32_trunc(At) @ tf32_trunc(Bt)) if tf else (At @ Bt)
             o = strided(_addr(g.out) + 4 * (zo * g.o_zs + j * g.o_js), (M, N), (g.o_rs, 1))
             val = (np.float64(np.float32(g.alpha)) * acc).astype(np.float32)
             if g.flags & F["ATOMIC"]:
                 o += val
             else:
-                o[...] = val
+                o[...] = _rn(val) if (g.flags & F["ROUND_OUT"]) else val
     return 0
 
 
@@ -375,10 +415,11 @@ def _softmax_fwd(s, lens, Z, R, N, ld, p_out, pd_out, drop_p, seed, seed_dev, st
     v = np.where(live, S, -np.inf).astype(np.float64)
     v = np.exp(v - v.max(axis=1, keepdims=True)) * live
     p = (v / v.sum(axis=1, keepdims=True)).astype(np.float32)
+    p = _rn(p)                                           # both outputs are GEMM operands (P.V, dV = P^T dO)
     flat(p_out, rows * ld).reshape(rows, ld)[...] = p
     if _addr(pd_out):
         idx = np.arange(rows, dtype=np.uint64)[:, None] * np.uint64(ld) + np.arange(ld, dtype=np.uint64)[None, :]
-        flat(pd_out, rows * ld).reshape(rows, ld)[...] = p * dropout_scale(seed, seed_dev, idx, drop_p)
+        flat(pd_out, rows * ld).reshape(rows, ld)[...] = _rn(p * dropout_scale(seed, seed_dev, idx, drop_p))
     return 0
 
 
@@ -390,7 +431,7 @@ def _softmax_bwd(p, dpd, Z, R, N, ld, alpha, drop_p, seed, seed_dev, stream=None
     idx = np.arange(rows, dtype=np.uint64)[:, None] * np.uint64(ld) + np.arange(N, dtype=np.uint64)[None, :]
     gv = D[:, :N].astype(np.float64) * dropout_scale(seed, seed_dev, idx, drop_p)
     dot = (P * gv).sum(axis=1, keepdims=True)
-    D[:, :N] = (np.float32(alpha) * P * (gv - dot)).astype(np.float32)
+    D[:, :N] = _rn((np.float32(alpha) * P * (gv - dot)).astype(np.float32))
     D[:, N:] = 0.0
     return 0
 
@@ -405,7 +446,7 @@ def _layernorm_fwd(x, gamma, beta, lens, Z, R, Cc, eps, y, mean, rstd, stream=No
     live = np.ones((rows, 1))
     if _addr(lens):
         live = (np.tile(np.arange(R), Z) < np.repeat(flat(lens, Z, np.int32), R)).astype(np.float64)[:, None]
-    flat(y, rows * Cc).reshape(rows, Cc)[...] = (((X - mu) * rs * flat(gamma, Cc) + flat(beta, Cc)) * live).astype(np.float32)
+    flat(y, rows * Cc).reshape(rows, Cc)[...] = _rn((((X - mu) * rs * flat(gamma, Cc) + flat(beta, Cc)) * live).astype(np.float32))
     flat(mean, rows)[...] = mu[:, 0].astype(np.float32)
     flat(rstd, rows)[...] = rs[:, 0].astype(np.float32)
     return 0
@@ -433,11 +474,15 @@ def _layernorm_bwd(dy, x, mean, rstd, gamma, lens, Z, R, Cc, dx, dx_drop, dgamma
         flat(dgamma, Cc)[...] += (d * xh).sum(axis=0).astype(np.float32)
     if _addr(dbeta):
         flat(dbeta, Cc)[...] += d.sum(axis=0).astype(np.float32)
-    flat(dx, rows * Cc).reshape(rows, Cc)[...] = v.astype(np.float32)
+    # the tensor that feeds the dgrad / wgrad GEMMs (dx_drop if there is one, else dx) is stored tf32-rounded
     branch = v
     if _addr(dx_drop):
-        branch = v * dropout_scale(seed_pre, seed_dev, idx, drop_pre_p)
+        flat(dx, rows * Cc).reshape(rows, Cc)[...] = v.astype(np.float32)
+        branch = _rn((v * dropout_scale(seed_pre, seed_dev, idx, drop_pre_p)).astype(np.float32)).astype(np.float64)
         flat(dx_drop, rows * Cc).reshape(rows, Cc)[...] = branch.astype(np.float32)
+    else:
+        branch = _rn(v.astype(np.float32)).astype(np.float64)
+        flat(dx, rows * Cc).reshape(rows, Cc)[...] = branch.astype(np.float32)
     if _addr(dbias):
         flat(dbias, Cc)[...] += branch.sum(axis=0).astype(np.float32)
     return 0
@@ -456,7 +501,7 @@ def _colsum_items(x, Z, rows, Cc, ld, zs, out, out_ld, stream=None):
 
 
 def _round_tf32(src, dst, n, stream=None):
-    flat(dst, n)[...] = flat(src, n)                  # operand rounding off: a plain copy
+    flat(dst, n)[...] = _rn(flat(src, n))             # (a plain copy in the exact mode)
     return 0
 
 
@@ -495,6 +540,7 @@ def host_lib():
     for name in HOST_COMPILED:
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = capi.PROTOTYPES[name]
+    lib.xva_emu_set_rounding.restype, lib.xva_emu_set_rounding.argtypes = None, [C.c_int]
     _host_lib = lib
     return lib
 
@@ -502,7 +548,7 @@ def host_lib():
 HOST_COMPILED = ("xva_text_embed_fwd", "xva_text_embed_bwd", "xva_rel_band_add", "xva_rel_band_gather", "xva_pad_cols")
 
 TABLE = {
-    "xva_gemm": _gemm, "xva_gemm_ref": _gemm, "xva_softmax_fwd": _softmax_fwd, "xva_softmax_bwd": _softmax_bwd,
+    "xva_gemm": _gemm, "xva_gemm_ref": _gemm_ref, "xva_softmax_fwd": _softmax_fwd, "xva_softmax_bwd": _softmax_bwd,
     "xva_layernorm_fwd": _layernorm_fwd, "xva_layernorm_bwd": _layernorm_bwd, "xva_colsum": _colsum,
     "xva_colsum_items": _colsum_items, "xva_round_tf32": _round_tf32, "xva_counter_add": _counter_add, "xva_rowdot2": _rowdot2,
     "xva_device_check": lambda *a: 0, "xva_set_operand_rounding": lambda *a: 0,
@@ -513,7 +559,10 @@ calls = []          # names of the entry points executed since the last reset (t
 
 def call(name, *args):
     calls.append(name)
+    if TF32 and name not in TF32_MODELLED:
+        raise NotImplementedError(f"cabi_emu: {name} has no tf32 operand model (TF32 mode covers {sorted(TF32_MODELLED)})")
     if name in HOST_COMPILED:
+        host_lib().xva_emu_set_rounding(1 if TF32 else 0)
         rc = getattr(host_lib(), name)(*args)
     elif name in TABLE:
         rc = TABLE[name](*args)

@@ -5,13 +5,26 @@
 #include <string.h>
 
 #define XVA_HD static inline
-#define XVA_RN(x) (x)  // operand rounding off: the exact-arithmetic test mode (xva_set_operand_rounding(0))
+// Store rounding of GEMM operands: off = the exact-arithmetic test mode (xva_set_operand_rounding(0)); on = cvt.rna.tf32.f32
+// (round to nearest, ties away, 13 low mantissa bits cleared), the product path's precision.
+static int g_round = 0;
+static inline float emu_rn(float x) {
+  if (!g_round) return x;
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  u = (u + 0x1000u) & 0xFFFFE000u;
+  memcpy(&x, &u, 4);
+  return x;
+}
+#define XVA_RN(x) emu_rn(x)
 #define XVA_ADD(p, v) (*(p) += (v))
 #include "../xva-trainer_b200/csrc/relattn_body.h"
 
 using namespace xva::relattn;
 
 extern "C" {
+
+void xva_emu_set_rounding(int on) { g_round = on; }
 
 int xva_text_embed_fwd(const int64_t* tokens, const float* emb, const float* lang, const int32_t* lens, int B, int T, int C,
                        int L, int ld, float scale, float* out, float* x_emb, void*) {
