@@ -59,13 +59,17 @@ def emulated(monkeypatch):
         yield tr
 
 
+SLOW = pytest.mark.skipif(os.environ.get("XVA_TEST_SLOW", "0") != "1",
+                          reason="~50 s on the CPU (every stage writes 0.5 GB checkpoints): XVA_TEST_SLOW=1 runs it; the same test "
+                                 "runs on the GPU, and the base-checkpoint test below walks the same stage sequence")
+
+
+@SLOW
 def test_fastpitch_stages_files_and_protocol_strings(emulated, tmp_path, monkeypatch):
     T.test_fastpitch_handle_trainer_stages_and_files(None, tmp_path, monkeypatch)
 
 
-@pytest.mark.skipif(os.environ.get("XVA_TEST_SLOW", "0") != "1",
-                    reason="54 s on the CPU (four stages, each writing 0.5 GB checkpoints): XVA_TEST_SLOW=1 runs it; the stage-1 "
-                           "step itself is in tests/test_cabi_emu_cpu.py and the same test runs on the GPU")
+@SLOW
 def test_fastpitch_starts_at_the_aligner_and_extracts_durations(emulated, tmp_path, monkeypatch):
     T.test_fastpitch_handle_trainer_starts_at_the_aligner(None, tmp_path, monkeypatch)
 
