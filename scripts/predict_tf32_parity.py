@@ -1,4 +1,4 @@
-"""Predicts the product-path (tf32 operand) parity of the xVAPitch text encoder and pitch predictor ON THE CPU: the modules'
+"""Predicts the product-path (tf32 operand) parity of the xVAPitch text encoder, the pitch predictor and the FastPitch step ON THE CPU: the modules'
 host code through tests/cabi_emu.py with its tf32 operand model on (xva_gemm truncates operands as the tensor cores do,
 producers round to nearest) against the fp32 oracle -- the same comparison tests/test_vits_text_encoder_gpu.py makes on the
 device. For the text encoder the prediction can be held against the B200 measurement (profiles/r02_textenc.txt); for the
@@ -60,6 +60,41 @@ def main():
                 print(row, flush=True)
         finally:
             cabi_emu.TF32 = False
+    # ---- the FastPitch step at the toy shape of profiles/r02_parity_table.txt (4 x 40 x 150 ragged, seeds of tests/parity_util.py)
+    from oracle import fastpitch as ofp
+    from parity_util import FWD_NAMES, grad_summary
+    from test_cabi_emu_cpu import FP_PATCHES
+    out["fastpitch_toy"] = []
+    with cabi_emu.installed():
+        fp = cabi_emu.load_module("fastpitch", FP_PATCHES)
+        for stage in (3, 4):
+            x, y = ofp.synthetic_batch(4, 40, 150, seed=11, ragged=True)
+            sd = ofp.make_state(1234)
+            m = fp.FastPitch(device="cpu")
+            m.training_stage = stage
+            m.train()
+            m.p_drop = 0.0
+            crit = fp.FastPitchLoss()
+            crit.training_stage = stage
+            cabi_emu.TF32 = True
+            try:
+                m.load_state_dict({k: v.clone() for k, v in sd.items()})       # (the operand copy is rounded at load time)
+                o = m(x)
+                loss, meta = crit(o, y)
+                m.zero_grad()
+                m.backward(crit, 1.0)
+            finally:
+                cabi_emu.TF32 = False
+            want = ofp.forward(sd, x, stage)
+            wmeta, wgrads = ofp.train_step({k: v.clone() for k, v in sd.items()}, x, y, stage, 1e-3, {}, drop=0.0, training=False)
+            gs = grad_summary(m.grads(fp.trainable_keys(stage)), wgrads)
+            row = {"case": f"stage {stage}, 4 x 40 x 150 ragged"}
+            row.update({n: rel(g_.float(), w_.float()) for n, g_, w_ in zip(FWD_NAMES, o[:8], want[:8])
+                        if w_ is not None and w_.dtype != torch.bool and n in ("mel_out", "pitch_pred", "energy_pred")})
+            row.update(loss=abs(float(meta["loss"]) - float(wmeta["loss"])) / abs(float(wmeta["loss"])), grad_global=gs["global"],
+                       grad_median=gs["median"], grad_worst=gs["worst"], grad_worst_key=gs["worst_key"])
+            out["fastpitch_toy"].append(row)
+            print(row, flush=True)
     json.dump(out, open(os.path.join(ROOT, "profiles", "r02_tf32_parity_predicted.json"), "w"), indent=1)
 
 

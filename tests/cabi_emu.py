@@ -97,7 +97,12 @@ TF32 = False
 TF32_MODELLED = {"xva_gemm", "xva_gemm_ref", "xva_softmax_fwd", "xva_softmax_bwd", "xva_layernorm_fwd", "xva_layernorm_bwd",
                  "xva_colsum", "xva_colsum_items", "xva_round_tf32", "xva_counter_add", "xva_rowdot2", "xva_device_check",
                  "xva_set_operand_rounding", "xva_text_embed_fwd", "xva_text_embed_bwd", "xva_rel_band_add", "xva_rel_band_gather",
-                 "xva_pad_cols", "xva_adamw_step"}
+                 "xva_pad_cols", "xva_adamw_step",
+                 # the FastPitch stages 2-4 path
+                 "xva_embed_pos", "xva_embed_bwd", "xva_scalar_conv_add", "xva_scalar_conv_bwd", "xva_rowdot_fwd", "xva_rowdot_bwd",
+                 "xva_regulate_len_scan", "xva_regulate_len_fwd", "xva_regulate_len_bwd", "xva_average_pitch", "xva_mel_mse",
+                 "xva_mel_mse_grad", "xva_lens_mse", "xva_lens_mse_grad", "xva_grad_sqnorm", "xva_lamb_step", "xva_attn_fwd",
+                 "xva_attn_bwd"}
 
 
 def tf32_rn(x):
@@ -643,7 +648,7 @@ def _embed_pos(tokens, emb, inp, lens, inv_freq, B, T, Cc, out, stream=None):
         ang = (np.arange(T, dtype=np.float32)[:, None] * f[None, :]).astype(np.float32)
         pos = np.concatenate([np.sin(ang), np.cos(ang)], axis=1)
         v = v + pos[None] * live[:, :, None]
-    O[...] = v.astype(np.float32)
+    O[...] = _rn(v.astype(np.float32))                  # first GEMM operand of the FFT stack
     return 0
 
 
@@ -664,7 +669,7 @@ def _scalar_conv_add(io, x, w, bias, lens, B, T, Cc, stream=None):
     xp = np.pad(X, ((0, 0), (1, 1)))
     add = bs[None, None, :] + xp[:, :-2, None] * Wt[None, None, :, 0] + X[:, :, None] * Wt[None, None, :, 1] + xp[:, 2:, None] * Wt[None, None, :, 2]
     live = _lens_mask(lens, B, T)
-    IO[...] = np.where(live[:, :, None], IO + add, IO).astype(np.float32)
+    IO[...] = np.where(live[:, :, None], _rn((IO + add).astype(np.float32)), IO).astype(np.float32)
     return 0
 
 
@@ -777,7 +782,7 @@ def _mel_mse_grad(pred, tgt, B, T_out, Tm, Cc, ldd, acc, scale, dpred, stream=No
     k = np.float32(2.0 * scale / flat(acc, 2, np.float64)[1])
     D = flat(dpred, B * T_out * ldd).reshape(B, T_out, ldd)
     D[...] = 0.0
-    D[..., :Cc] = np.where(Y != 0, k * (Pm - Y), 0.0)
+    D[..., :Cc] = np.where(Y != 0, _rn((k * (Pm - Y)).astype(np.float32)), 0.0)      # operand of the proj dgrad / wgrad
     return 0
 
 
@@ -861,13 +866,14 @@ def _lamb_step(p, g, m, v, chunks, n_chunks, norms, gnorm_sq, max_norm, lr_dev, 
         P = flat(_addr(p) + 4 * a, n)
         P[...] = P - lr * trust * r
         if _addr(p_tf32):
-            flat(_addr(p_tf32) + 4 * a, n)[...] = P
+            flat(_addr(p_tf32) + 4 * a, n)[...] = _rn(P)
     return 0
 
 
 def _attn_fwd(qkv, rs, zs, B, T, lens, scale, drop_p, seed, seed_dev, drop_ld, out, o_rs, o_zs, lse, stream=None):
     """include/xva_b200.h xva_attn_fwd: single head, d_head 64, q | k | v in columns 0..191."""
-    X = strided(qkv, (B, T, 192), (zs, rs, 1)).astype(np.float64)
+    X = strided(qkv, (B, T, 192), (zs, rs, 1))
+    X = (tf32_trunc(X) if TF32 else X).astype(np.float64)          # tcgen05 kind::tf32 reads its fp32 operands truncated
     q, k, v = X[..., :64], X[..., 64:128], X[..., 128:]
     s_ = np.float32(scale) * np.einsum("bid,bjd->bij", q, k)
     keym = _lens_mask(lens, B, T)[:, None, :]
@@ -879,16 +885,20 @@ def _attn_fwd(qkv, rs, zs, B, T, lens, scale, drop_p, seed, seed_dev, drop_ld, o
     idx = (np.arange(B, dtype=np.uint64)[:, None, None] * np.uint64(T) + np.arange(T, dtype=np.uint64)[None, :, None]) * np.uint64(drop_ld) \
         + np.arange(T, dtype=np.uint64)[None, None, :]
     Pd = P * dropout_scale(seed, seed_dev, idx, drop_p)
-    strided(out, (B, T, 64), (o_zs, o_rs, 1))[...] = np.einsum("bij,bjd->bid", Pd, v).astype(np.float32)
+    if TF32:
+        Pd = tf32_rn(Pd.astype(np.float32)).astype(np.float64)     # P is written to tensor memory rounded: the A operand of P.V
+    strided(out, (B, T, 64), (o_zs, o_rs, 1))[...] = _rn(np.einsum("bij,bjd->bid", Pd, v).astype(np.float32))
     flat(lse, B * T).reshape(B, T)[...] = (mx + np.log(den))[..., 0].astype(np.float32)
     return 0
 
 
 def _attn_bwd(qkv, rs, zs, dout, d_rs, d_zs, lse, dsum, B, T, lens, scale, drop_p, seed, seed_dev, drop_ld, dqkv, g_rs, g_zs,
               stream=None):
-    X = strided(qkv, (B, T, 192), (zs, rs, 1)).astype(np.float64)
+    X = strided(qkv, (B, T, 192), (zs, rs, 1))
+    X = (tf32_trunc(X) if TF32 else X).astype(np.float64)
     q, k, v = X[..., :64], X[..., 64:128], X[..., 128:]
-    dO = strided(dout, (B, T, 64), (d_zs, d_rs, 1)).astype(np.float64)
+    dO = strided(dout, (B, T, 64), (d_zs, d_rs, 1))
+    dO = (tf32_trunc(dO) if TF32 else dO).astype(np.float64)
     L = flat(lse, B * T).reshape(B, T, 1).astype(np.float64)
     Ds = flat(dsum, B * T).reshape(B, T, 1).astype(np.float64)
     sc = np.float64(np.float32(scale))
@@ -897,12 +907,16 @@ def _attn_bwd(qkv, rs, zs, dout, d_rs, d_zs, lse, dsum, B, T, lens, scale, drop_
     idx = (np.arange(B, dtype=np.uint64)[:, None, None] * np.uint64(T) + np.arange(T, dtype=np.uint64)[None, :, None]) * np.uint64(drop_ld) \
         + np.arange(T, dtype=np.uint64)[None, None, :]
     dm = dropout_scale(seed, seed_dev, idx, drop_p)
-    dV = np.einsum("bij,bid->bjd", P * dm, dO)
+    Pdm = P * dm
     dS = P * (np.einsum("bid,bjd->bij", dO, v) * dm - Ds)
+    if TF32:                                                        # P and dS are MMA operands, rounded in tensor memory
+        Pdm = tf32_rn(Pdm.astype(np.float32)).astype(np.float64)
+        dS = tf32_rn(dS.astype(np.float32)).astype(np.float64)
+    dV = np.einsum("bij,bid->bjd", Pdm, dO)
     G = strided(dqkv, (B, T, 192), (g_zs, g_rs, 1))
-    G[..., :64] = (sc * np.einsum("bij,bjd->bid", dS, k)).astype(np.float32)
-    G[..., 64:128] = (sc * np.einsum("bij,bid->bjd", dS, q)).astype(np.float32)
-    G[..., 128:] = dV.astype(np.float32)
+    G[..., :64] = _rn((sc * np.einsum("bij,bjd->bid", dS, k)).astype(np.float32))
+    G[..., 64:128] = _rn((sc * np.einsum("bij,bid->bjd", dS, q)).astype(np.float32))
+    G[..., 128:] = _rn(dV.astype(np.float32))
     return 0
 
 
