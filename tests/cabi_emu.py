@@ -116,8 +116,43 @@ def tf32_trunc(x):
     return (u & np.uint32(0xFFFFE000)).view(np.float32)
 
 
+# What-if model for a 16-bit operand mode (tcgen05 kind::f16 at twice the MMA rate): with
+# OPERAND16 = "fp16" / "bf16" (and TF32 = True) producers store, and xva_gemm reads, operands in that type instead of tf32.
+# OPERAND_STATS, when a dict, collects per xva_gemm launch the magnitude range of both operands and the fraction of non-zero
+# elements below fp16's smallest normal / subnormal -- the numbers a loss scale has to fix.
+OPERAND16 = None
+OPERAND_STATS = None
+
+
+def to16(x):
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    if OPERAND16 == "fp16":
+        with np.errstate(over="ignore"):
+            return x.astype(np.float16).astype(np.float32)
+    u = x.view(np.uint32)                                # bf16: round to nearest even on the upper 16 bits
+    r = ((u >> np.uint32(16)) & np.uint32(1)) + np.uint32(0x7FFF)
+    return ((u + r) & np.uint32(0xFFFF0000)).view(np.float32)
+
+
 def _rn(x):
-    return tf32_rn(x) if TF32 else x
+    if not TF32:
+        return x
+    return to16(x) if OPERAND16 else tf32_rn(x)
+
+
+def _operand(x, which, g):
+    """The value the MMA reads for an fp32 operand element."""
+    if OPERAND_STATS is not None:
+        a = np.abs(x[x != 0])
+        if a.size:
+            key = (g.mode, which)
+            st = OPERAND_STATS.setdefault(key, {"n": 0, "min": np.inf, "max": 0.0, "below_normal": 0, "below_subnormal": 0, "over": 0})
+            st["n"] += a.size
+            st["min"], st["max"] = min(st["min"], float(a.min())), max(st["max"], float(a.max()))
+            st["below_normal"] += int((a < 6.1035e-5).sum())
+            st["below_subnormal"] += int((a < 5.96e-8).sum())
+            st["over"] += int((a > 65504.0).sum())
+    return to16(x) if OPERAND16 else tf32_trunc(x)
 
 
 # ------------------------------------------------------------------------------------------------ dropout hash
@@ -310,11 +345,11 @@ def _gemm(ref, stream=None, exact=False):
             Aj = np.zeros((Z, R, K), np.float32)
             Aj[:, ok] = A[:, rr[ok], g.a_col[j]:g.a_col[j] + K]
             if tf:
-                Aj = tf32_trunc(Aj)
+                Aj = _operand(Aj, "A", g)
             if g.b_batch_z == 0:
                 Bz = np.ascontiguousarray(Bm[j * g.b_tap_z])
                 if tf:
-                    Bz = tf32_trunc(Bz)
+                    Bz = _operand(Bz, "B", g)
                 if g.mode == 0:
                     acc[:, :, :Bz.shape[0]] += (Aj.reshape(Z * R, K) @ Bz.T).reshape(Z, R, -1)
                 else:
@@ -323,7 +358,7 @@ def _gemm(ref, stream=None, exact=False):
             for z in range(Z):
                 Bz = Bm[j * g.b_tap_z + z * g.b_batch_z]
                 if tf:
-                    Bz = tf32_trunc(Bz)
+                    Bz = _operand(Bz, "B", g)
                 if g.mode == 0:
                     acc[z, :, :Bz.shape[0]] += Aj[z] @ Bz.T
                 else:
@@ -396,7 +431,7 @@ def _gemm(ref, stream=None, exact=False):
                 for zr in range(ZR):
                     z = zo * ZR + zr
                     At, Bt = np.ascontiguousarray(A[z, ok].T), np.ascontiguousarray(Bm[z, bt[ok], g.a_col[j]:g.a_col[j] + N])
-                    acc += (tf32_trunc(At) @ tf32_trunc(Bt)) if tf else (At @ Bt)
+                    acc += (_operand(At, "A", g) @ _operand(Bt, "B", g)) if tf else (At @ Bt)
             o = strided(_addr(g.out) + 4 * (zo * g.o_zs + j * g.o_js), (M, N), (g.o_rs, 1))
             val = (np.float64(np.float32(g.alpha)) * acc).astype(np.float32)
             if g.flags & F["ATOMIC"]:
