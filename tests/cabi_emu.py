@@ -102,7 +102,13 @@ TF32_MODELLED = {"xva_gemm", "xva_gemm_ref", "xva_softmax_fwd", "xva_softmax_bwd
                  "xva_embed_pos", "xva_embed_bwd", "xva_scalar_conv_add", "xva_scalar_conv_bwd", "xva_rowdot_fwd", "xva_rowdot_bwd",
                  "xva_regulate_len_scan", "xva_regulate_len_fwd", "xva_regulate_len_bwd", "xva_average_pitch", "xva_mel_mse",
                  "xva_mel_mse_grad", "xva_lens_mse", "xva_lens_mse_grad", "xva_grad_sqnorm", "xva_lamb_step", "xva_attn_fwd",
-                 "xva_attn_bwd"}
+                 "xva_attn_bwd",
+                 # the HiFi-GAN / xVAPitch --hifi_only path
+                 "xva_wn_pack_fwd", "xva_wn_pack_bwd", "xva_sn_pack_fwd", "xva_sn_pack_bwd", "xva_mean3_lrelu", "xva_sum3",
+                 "xva_tanh_bwd", "xva_gated_act_fwd", "xva_gated_act_bwd", "xva_vits_sample_fwd", "xva_vits_sample_bwd",
+                 "xva_conv_c1_fwd", "xva_conv_c1_bwd_w", "xva_conv_c1_bwd_x", "xva_avgpool4_fwd", "xva_avgpool4_bwd",
+                 "xva_zero_tail_rows", "xva_reflect_pad_fwd", "xva_reflect_pad_bwd", "xva_spec_mag_fwd", "xva_spec_mag_bwd",
+                 "xva_log_clamp_fwd", "xva_log_clamp_bwd", "xva_reduce_loss", "xva_loss_grad", "xva_l1_loss_grad"}
 
 
 def tf32_rn(x):
@@ -214,11 +220,13 @@ def _gemm_grouped(g, G):
             ok = (rr >= 0) & (rr < a_rows)
             if not ok.any():
                 continue
-            Bj = Bm[j * g.b_tap_z].astype(np.float64)
+            Bj = Bm[j * g.b_tap_z]
+            Bj = (_operand(np.ascontiguousarray(Bj), "B", g) if TF32 else Bj).astype(np.float64)
             for grp in range(G):
-                Aj = np.zeros((Z, R, K), np.float64)
+                Aj = np.zeros((Z, R, K), np.float32)
                 c0 = g.a_col[j] + grp * step
                 Aj[:, ok] = A[:, rr[ok], c0:c0 + K]
+                Aj = (_operand(Aj, "A", g) if TF32 else Aj).astype(np.float64)
                 if g.mode == 0:
                     acc[:, :, grp * n_per:(grp + 1) * n_per] += Aj @ Bj[grp * n_per:(grp + 1) * n_per].T
                 else:
@@ -241,8 +249,8 @@ def _gemm_grouped(g, G):
             v = v * (np.arange(R)[None, :] < lens[:, None]).astype(np.float32)[:, :, None]
         v = v.astype(np.float32)
         if g.out_act:
-            view(g.out_act, g.o_rs, g.o_zs)[...] = np.where(v > 0, v, np.float32(g.out_act_slope) * v)
-        view(g.out, g.o_rs, g.o_zs)[...] = v
+            view(g.out_act, g.o_rs, g.o_zs)[...] = _rn(np.where(v > 0, v, np.float32(g.out_act_slope) * v).astype(np.float32))
+        view(g.out, g.o_rs, g.o_zs)[...] = _rn(v) if (g.flags & F["ROUND_OUT"]) else v
         return 0
     M, ZR = g.M, g.ZR
     a_rows, b_rows = g.a_rows or R, g.b_rows or R
@@ -261,7 +269,11 @@ def _gemm_grouped(g, G):
                     z = zo * ZR + zr
                     for grp in range(G):
                         c0 = g.a_col[j] + grp * g.grp_step
-                        acc[grp * og:(grp + 1) * og] += A[z, ok][:, grp * og:(grp + 1) * og].T @ Bm[z, bt[ok], c0:c0 + N].astype(np.float64)
+                        At = np.ascontiguousarray(A[z, ok][:, grp * og:(grp + 1) * og].T, dtype=np.float32)
+                        Bt = np.ascontiguousarray(Bm[z, bt[ok], c0:c0 + N], dtype=np.float32)
+                        if TF32:
+                            At, Bt = _operand(At, "A", g), _operand(Bt, "B", g)
+                        acc[grp * og:(grp + 1) * og] += At.astype(np.float64) @ Bt.astype(np.float64)
             o = strided(_addr(g.out) + 4 * (zo * g.o_zs + j * g.o_js), (M, N), (g.o_rs, 1))
             val = (np.float64(np.float32(g.alpha)) * acc).astype(np.float32)
             if g.flags & F["ATOMIC"]:
@@ -1010,7 +1022,8 @@ def _wn_pack_fwd(table, n_desc, total_rows, max_inner, stream=None):
         else:
             idx = taps[j] + r * d.ld + ((r // d.og) % d.f) * d.cg + c
         dst = flat(d.dst, int(idx.max()) + 1)
-        dst[idx.reshape(-1)] = w.reshape(-1).astype(np.float32)
+        wv = w.reshape(-1).astype(np.float32)
+        dst[idx.reshape(-1)] = wv if (d.flags & 2) else _rn(wv)          # XVA_WN_NO_ROUND: the fp32 first layer
     return 0
 
 
@@ -1038,12 +1051,12 @@ def _wn_pack_bwd(table, n_desc, total_rows, max_inner, stream=None):
 
 def _mean3_lrelu(y0, y1, y2, n, slope, out, stream=None):
     m = ((flat(y0, n) + flat(y1, n)) + flat(y2, n)) * np.float32(1.0 / 3.0)
-    flat(out, n)[...] = np.where(m > 0, m, np.float32(slope) * m)
+    flat(out, n)[...] = _rn(np.where(m > 0, m, np.float32(slope) * m).astype(np.float32))
     return 0
 
 
 def _sum3(a, b, c, n, out, stream=None):
-    flat(out, n)[...] = flat(a, n) + flat(b, n) + flat(c, n)
+    flat(out, n)[...] = _rn(flat(a, n) + flat(b, n) + flat(c, n))
     return 0
 
 
@@ -1051,7 +1064,7 @@ def _tanh_bwd(dy, y, rows, ld, out, stream=None):
     O = flat(out, rows * ld).reshape(rows, ld)
     O[...] = 0.0
     t = flat(y, rows)
-    O[:, 0] = flat(dy, rows) * (np.float32(1.0) - t * t)
+    O[:, 0] = _rn(flat(dy, rows) * (np.float32(1.0) - t * t))
     return 0
 
 
@@ -1061,7 +1074,7 @@ def _sig(x):
 
 def _gated_act_fwd(x_in, rows, H, ld_in, acts, stream=None):
     X = strided(x_in, (rows, 2 * H), (ld_in, 1)).astype(np.float64)
-    flat(acts, rows * H).reshape(rows, H)[...] = (np.tanh(X[:, :H]) * _sig(X[:, H:])).astype(np.float32)
+    flat(acts, rows * H).reshape(rows, H)[...] = _rn((np.tanh(X[:, :H]) * _sig(X[:, H:])).astype(np.float32))
     return 0
 
 
@@ -1070,8 +1083,8 @@ def _gated_act_bwd(dacts, x_in, rows, H, ld_in, dx_in, stream=None):
     d = flat(dacts, rows * H).reshape(rows, H).astype(np.float64)
     t, sg = np.tanh(X[:, :H]), _sig(X[:, H:])
     O = flat(dx_in, rows * 2 * H).reshape(rows, 2 * H)
-    O[:, :H] = (d * sg * (1.0 - t * t)).astype(np.float32)
-    O[:, H:] = (d * t * sg * (1.0 - sg)).astype(np.float32)
+    O[:, :H] = _rn((d * sg * (1.0 - t * t)).astype(np.float32))
+    O[:, H:] = _rn((d * t * sg * (1.0 - sg)).astype(np.float32))
     return 0
 
 
@@ -1089,8 +1102,8 @@ def _vits_sample_bwd(dz, eps, stats, lens, B, T, Cc, dstats, stream=None):
     D = flat(dz, B * T * Cc).reshape(B, T, Cc)
     live = _lens_mask(lens, B, T)[:, :, None]
     O = flat(dstats, B * T * 2 * Cc).reshape(B, T, 2 * Cc)
-    O[..., :Cc] = np.where(live, D, 0.0)
-    O[..., Cc:] = np.where(live, D * E * np.exp(S[..., Cc:]), 0.0)
+    O[..., :Cc] = _rn(np.where(live, D, 0.0).astype(np.float32))
+    O[..., Cc:] = _rn(np.where(live, D * E * np.exp(S[..., Cc:]), 0.0).astype(np.float32))
     return 0
 
 
@@ -1123,7 +1136,7 @@ def _conv_c1_fwd(x, xs_b, xs_q, xs_c, P, Lsrc, L, w, bias, k, s, pad, Z, Lout, L
     v = (xw @ Wt.T + flat(bias, Cout)[None, None, :]).astype(np.float32)
     O = flat(out, Z * Lout_p * Cout).reshape(Z, Lout_p, Cout)
     O[...] = 0.0
-    O[:, :Lout] = np.where(v > 0, v, np.float32(slope) * v)
+    O[:, :Lout] = _rn(np.where(v > 0, v, np.float32(slope) * v).astype(np.float32))      # operand of the next convolution
     return 0
 
 
@@ -1209,7 +1222,8 @@ def _sn_pack_fwd(table, n_desc, total_rows, total_blocks, max_inner, training, s
         flat(d.work, chunks * inner + rows + 2)[chunks * inner + rows] = np.float32(sigma)
         idx = _sn_idx(d)
         dst = flat(d.dst, int(idx.max()) + 1)
-        dst[idx.reshape(-1)] = (Wm.reshape(rows, inner // k, k) / np.float32(sigma)).reshape(-1).astype(np.float32)
+        wv = (Wm.reshape(rows, inner // k, k) / np.float32(sigma)).reshape(-1).astype(np.float32)
+        dst[idx.reshape(-1)] = wv if (d.flags & 2) else _rn(wv)
     return 0
 
 
@@ -1234,7 +1248,7 @@ def _reflect_index(t, n):
 
 def _reflect_pad_fwd(y, B, n, pad, out, stream=None):
     Y = flat(y, B * n).reshape(B, n)
-    flat(out, B * (n + 2 * pad)).reshape(B, n + 2 * pad)[...] = Y[:, _reflect_index(np.arange(n + 2 * pad) - pad, n)]
+    flat(out, B * (n + 2 * pad)).reshape(B, n + 2 * pad)[...] = _rn(Y[:, _reflect_index(np.arange(n + 2 * pad) - pad, n)])
     return 0
 
 
@@ -1251,7 +1265,7 @@ def _spec_mag_fwd(spec, rows, nb, ld_s, ld_m, eps, mag, stream=None):
     p = S[:, :nb] ** 2 + S[:, nb:2 * nb] ** 2
     M = flat(mag, rows * ld_m).reshape(rows, ld_m)
     M[...] = 0.0
-    M[:, :nb] = np.sqrt(p + np.float32(eps) if eps >= 0 else np.maximum(p, np.float32(-eps)))
+    M[:, :nb] = _rn(np.sqrt(p + np.float32(eps) if eps >= 0 else np.maximum(p, np.float32(-eps))).astype(np.float32))
     return 0
 
 
@@ -1265,8 +1279,8 @@ def _spec_mag_bwd(dmag, spec, rows, nb, ld_s, ld_m, eps, dspec, stream=None):
         m, live = np.sqrt(np.maximum(p, 1e-30)), p >= np.float32(-eps)
     O = flat(dspec, rows * ld_s).reshape(rows, ld_s)
     O[...] = 0.0
-    O[:, :nb] = np.where(live, D * S[:, :nb] / m, 0.0)
-    O[:, nb:2 * nb] = np.where(live, D * S[:, nb:2 * nb] / m, 0.0)
+    O[:, :nb] = _rn(np.where(live, D * S[:, :nb] / m, 0.0).astype(np.float32))
+    O[:, nb:2 * nb] = _rn(np.where(live, D * S[:, nb:2 * nb] / m, 0.0).astype(np.float32))
     return 0
 
 
@@ -1277,7 +1291,7 @@ def _log_clamp_fwd(x, n, lo, out, stream=None):
 
 def _log_clamp_bwd(dy, x, n, lo, dx, stream=None):
     X = flat(x, n)
-    flat(dx, n)[...] = np.where(X >= np.float32(lo), flat(dy, n) / np.where(X >= np.float32(lo), X, 1.0), 0.0)
+    flat(dx, n)[...] = _rn(np.where(X >= np.float32(lo), flat(dy, n) / np.where(X >= np.float32(lo), X, 1.0), 0.0).astype(np.float32))
     return 0
 
 
