@@ -140,8 +140,16 @@ def to16(x):
     return ((u + r) & np.uint32(0xFFFF0000)).view(np.float32)
 
 
-def _rn(x):
-    if not TF32:
+# Ablation switch for the operand model: which producers round. PHASE is set by the caller ("fwd" / "bwd") around the
+# forward and backward passes; ROUND_WHAT names the classes that round: "weights" (the operand copy of the parameters:
+# xva_round_tf32, the optimizers' p_tf32, the weight packers), "fwd" (operands produced by the forward pass), "bwd" (by the backward).
+PHASE = "fwd"
+ROUND_WHAT = {"weights", "fwd", "bwd"}
+MMA_TRUNCATES = True          # False (ablation only): the MMA reads un-rounded operands exactly
+
+
+def _rn(x, what=None):
+    if not TF32 or (what or PHASE) not in ROUND_WHAT:
         return x
     return to16(x) if OPERAND16 else tf32_rn(x)
 
@@ -158,7 +166,7 @@ def _operand(x, which, g):
             st["below_normal"] += int((a < 6.1035e-5).sum())
             st["below_subnormal"] += int((a < 5.96e-8).sum())
             st["over"] += int((a > 65504.0).sum())
-    return to16(x) if OPERAND16 else tf32_trunc(x)
+    return to16(x) if OPERAND16 else (tf32_trunc(x) if MMA_TRUNCATES else x)
 
 
 # ------------------------------------------------------------------------------------------------ dropout hash
@@ -553,7 +561,7 @@ def _colsum_items(x, Z, rows, Cc, ld, zs, out, out_ld, stream=None):
 
 
 def _round_tf32(src, dst, n, stream=None):
-    flat(dst, n)[...] = _rn(flat(src, n))             # (a plain copy in the exact mode)
+    flat(dst, n)[...] = _rn(flat(src, n), "weights")  # (a plain copy in the exact mode)
     return 0
 
 
@@ -913,7 +921,7 @@ def _lamb_step(p, g, m, v, chunks, n_chunks, norms, gnorm_sq, max_norm, lr_dev, 
         P = flat(_addr(p) + 4 * a, n)
         P[...] = P - lr * trust * r
         if _addr(p_tf32):
-            flat(_addr(p_tf32) + 4 * a, n)[...] = _rn(P)
+            flat(_addr(p_tf32) + 4 * a, n)[...] = _rn(P, "weights")
     return 0
 
 
@@ -1023,7 +1031,7 @@ def _wn_pack_fwd(table, n_desc, total_rows, max_inner, stream=None):
             idx = taps[j] + r * d.ld + ((r // d.og) % d.f) * d.cg + c
         dst = flat(d.dst, int(idx.max()) + 1)
         wv = w.reshape(-1).astype(np.float32)
-        dst[idx.reshape(-1)] = wv if (d.flags & 2) else _rn(wv)          # XVA_WN_NO_ROUND: the fp32 first layer
+        dst[idx.reshape(-1)] = wv if (d.flags & 2) else _rn(wv, "weights")   # XVA_WN_NO_ROUND: the fp32 first layer
     return 0
 
 
@@ -1223,7 +1231,7 @@ def _sn_pack_fwd(table, n_desc, total_rows, total_blocks, max_inner, training, s
         idx = _sn_idx(d)
         dst = flat(d.dst, int(idx.max()) + 1)
         wv = (Wm.reshape(rows, inner // k, k) / np.float32(sigma)).reshape(-1).astype(np.float32)
-        dst[idx.reshape(-1)] = wv if (d.flags & 2) else _rn(wv)
+        dst[idx.reshape(-1)] = wv if (d.flags & 2) else _rn(wv, "weights")
     return 0
 
 
