@@ -148,8 +148,17 @@ ROUND_WHAT = {"weights", "fwd", "bwd"}
 MMA_TRUNCATES = True          # False (ablation only): the MMA reads un-rounded operands exactly
 
 
+ROUNDING_ON = True            # the library's xva_set_operand_rounding switch (the tests' exact-arithmetic mode turns it off)
+
+
+def _set_operand_rounding(on):
+    global ROUNDING_ON
+    ROUNDING_ON = bool(on)
+    return 0
+
+
 def _rn(x, what=None):
-    if not TF32 or (what or PHASE) not in ROUND_WHAT:
+    if not TF32 or not ROUNDING_ON or (what or PHASE) not in ROUND_WHAT:
         return x
     return to16(x) if OPERAND16 else tf32_rn(x)
 
@@ -611,7 +620,7 @@ TABLE = {
     "xva_gemm": _gemm, "xva_gemm_ref": _gemm_ref, "xva_softmax_fwd": _softmax_fwd, "xva_softmax_bwd": _softmax_bwd,
     "xva_layernorm_fwd": _layernorm_fwd, "xva_layernorm_bwd": _layernorm_bwd, "xva_colsum": _colsum,
     "xva_colsum_items": _colsum_items, "xva_round_tf32": _round_tf32, "xva_counter_add": _counter_add, "xva_rowdot2": _rowdot2,
-    "xva_device_check": lambda *a: 0, "xva_set_operand_rounding": lambda *a: 0,
+    "xva_device_check": lambda *a: 0, "xva_set_operand_rounding": _set_operand_rounding,
 }
 
 calls = []          # names of the entry points executed since the last reset (the tests assert on coverage)
@@ -622,7 +631,7 @@ def call(name, *args):
     if TF32 and name not in TF32_MODELLED:
         raise NotImplementedError(f"cabi_emu: {name} has no tf32 operand model (TF32 mode covers {sorted(TF32_MODELLED)})")
     if name in HOST_COMPILED:
-        host_lib().xva_emu_set_rounding(1 if TF32 else 0)
+        host_lib().xva_emu_set_rounding(1 if (TF32 and ROUNDING_ON) else 0)
         rc = getattr(host_lib(), name)(*args)
     elif name in TABLE:
         rc = TABLE[name](*args)

@@ -362,3 +362,39 @@ def test_tf32_operand_model_reproduces_the_error_measured_on_the_b200():
     eg = math.sqrt(num / den)
     assert abs(ex - measured["x"]) < 0.05 * measured["x"], (ex, measured["x"])
     assert abs(eg - measured["grad_global"]) < 0.05 * measured["grad_global"], (eg, measured["grad_global"])
+
+
+def test_pitch_predictor_gpu_checks_hold_under_the_tf32_operand_model(monkeypatch):
+    """The pitch predictor's GPU tests have not run on hardware yet (tests/test_vits_zz_pitch_predictor_gpu.py). Their probe
+    (tests/pitch_predictor_gpu_probe.py) is executed here on the CPU instead, through the emulated C ABI with the tf32 operand
+    model on -- the model that reproduces the text encoder's measured errors -- and has to meet the very bounds the GPU tests
+    assert: exact-checker wiring 2e-5 / 2e-4, product path 3e-3 / 2e-2 / 6e-2, reference golden 3e-3, AMP-free AdamW step
+    leaving the six untrained tensors bit-identical."""
+    import json
+
+    import pitch_predictor_gpu_probe as P
+    import xva_trainer_b200
+
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    lines = []
+    monkeypatch.setattr("builtins.print", lambda *a, **k: lines.append(" ".join(str(x) for x in a)))
+    with cabi_emu.installed():
+        te = cabi_emu.load_module("textenc", TE_PATCHES)
+        hg = cabi_emu.load_module("hifigan", [('if dev.type != "cuda":', "if False:")])
+        for name, mod in (("textenc", te), ("hifigan", hg)):
+            monkeypatch.setitem(sys.modules, f"xva_trainer_b200.{name}", mod)
+            monkeypatch.setattr(xva_trainer_b200, name, mod, raising=False)
+        cabi_emu.TF32 = True
+        try:
+            P.main()
+        finally:
+            cabi_emu.TF32 = False
+            cabi_emu.ROUNDING_ON = True
+    out = json.loads([ln for ln in lines if ln.startswith("PITCH_PREDICTOR_PROBE ")][-1].split(" ", 1)[1])
+    for e in out["exact"]:
+        assert e["same_keys"] and e["fwd"] < 2e-5 and e["grad_worst"] < 2e-4, e
+    for e in out["product"]:
+        assert e["same_keys"] and e["pad_max"] == 0.0 and 1e-4 < e["fwd"] < 3e-3 and e["grad_global"] < 2e-2 and e["grad_worst"] < 6e-2, e
+    assert 1e-4 < out["golden_fwd"] < 3e-3
+    assert out["keys_in_reference_order"] and out["dead_untouched"] and out["moved"] == out["trainable"]
