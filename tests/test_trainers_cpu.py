@@ -80,3 +80,12 @@ def test_fastpitch_base_checkpoint_precedence_and_stage5_short_cut(emulated, tmp
 
 def test_fastpitch_nan_batch_is_skipped_before_the_update(emulated, tmp_path, monkeypatch):
     T.test_fastpitch_nan_batch_is_skipped_before_the_update(None, tmp_path, monkeypatch)
+
+
+@SLOW
+def test_hifigan_trainer_files_and_optimizer_state_resume(emulated, tmp_path, monkeypatch):
+    """HiFiTrainer through handleTrainerHiFi on the emulated ABI: g_ / do_ checkpoint files, the exported .hg.pt, websocket
+    strings, torch.optim.AdamW-format optimizer state and the resume from it (the two HiFi-GAN tests of the GPU suite; several
+    minutes on the CPU: every step is a whole G + MPD + MSD iteration)."""
+    T.test_hifigan_handle_trainer_files(None, tmp_path / "files", monkeypatch)
+    T.test_hifigan_optimizer_state_is_torch_adamw_format_and_resumes(None, tmp_path / "resume", monkeypatch)
