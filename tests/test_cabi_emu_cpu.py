@@ -24,6 +24,7 @@ FP_PATCHES = [('if self.device_.type != "cuda":', "if False:"),
 
 
 def rel(a, b):
+    a, b = a.detach(), b.detach()
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
 
 
