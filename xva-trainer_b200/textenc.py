@@ -122,6 +122,14 @@ class _RelTransformer(nn.Module):
             ns.__dict__.update(w1=g("w1")[..., :C], b1=g("b1"), w2=g("w2"), b2=g("b2"), ln2_g=g("ln2_g"), ln2_b=g("ln2_b"))
         return ns
 
+    @property
+    def arena(self):
+        """What parallel.GradSync reads: the gradient arena ``g``, the parameters ``p`` and where each tensor
+        lies. Every gradient of the module is in the one flat buffer, so the data-parallel exchange is all-reduces of its
+        slices -- ``GradSync(module, world).ready(["l2"])`` as soon as backward has finished layer 2, ``finish()`` before
+        the optimizer reads it; the pad entries stay zero on every rank (0 + 0)."""
+        return _NS(g=self.flat.grad, p=self.flat.data, offset=self._off, pshape=dict(self._spec))
+
     def to(self, *args, **kwargs):
         """The device is fixed at construction (arena, gradient arena, operand copy and dropout counter live there)."""
         return self
